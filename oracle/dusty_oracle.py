@@ -1,0 +1,555 @@
+"""CPU oracle for the DUSty-v2 G/D hot path.
+
+TEST INFRASTRUCTURE ONLY -- this file is the *checker*, never the product.  Only
+tests/, __graft_entry__.smoke() and bench.py's cpu_baseline / --impl reference
+legs may import it.  The shipped package (dusty_gan_v2_b200) never does; its ops
+raise when the CUDA library is missing.
+
+What it is: a plain fp32 PyTorch-on-CPU *restatement* (functional, state_dict
+driven, closed-form FIR / modulation algebra) of what the reference computes on
+CPU tensors, i.e. of the reference's own "ref" path.  Every
+function cites the reference file:line it follows.
+
+Parity pinning: the reference ships no tests or golden vectors (SURVEY.md
+section 4/8c).  The oracle is therefore pinned against outputs of the reference
+itself, imported in the build container from /root/reference by
+tests/golden/make_golden.py; the resulting small fixtures are committed under
+tests/golden/ and checked by tests/test_oracle_golden.py on every CPU run.
+"""
+from __future__ import annotations
+
+import math
+from typing import Dict, List, Optional, Sequence, Tuple
+
+import numpy as np
+import torch
+import torch.nn.functional as F
+
+Tensor = torch.Tensor
+SQRT2 = 2.0 ** 0.5
+
+# --------------------------------------------------------------------------------------
+# a3  fused bias + leaky-ReLU                      gans/models/ops/fused_act/fused_act.py
+# --------------------------------------------------------------------------------------
+
+
+def bias_act(x: Tensor, bias: Optional[Tensor] = None, slope: float = 0.2,
+             scale: float = SQRT2) -> Tensor:
+    """y = lrelu(x + b_c) * scale, bias broadcast over dim 1.
+
+    fused_act.py:112-124 (CPU branch) and fused_bias_act_kernel.cu:27-60
+    (act=3, grad=0).  NOTE the reference CPU branch hard-codes slope 0.2; the CUDA
+    kernel honours `alpha`.  Every caller passes 0.2 so the two agree.
+    """
+    if bias is not None:
+        shape = [1, -1] + [1] * (x.ndim - 2)
+        x = x + bias.reshape(shape)
+    return torch.where(x > 0, x, x * slope) * scale
+
+
+def bias_act_grad(dy: Tensor, out: Tensor, slope: float = 0.2,
+                  scale: float = SQRT2) -> Tuple[Tensor, Tensor]:
+    """First-order backward, gated by the saved *output* (fused_act.py:20-44,
+    kernel case 31): dx = dy * (out > 0 ? 1 : slope) * scale, db = sum over all
+    dims but 1."""
+    dx = torch.where(out > 0, dy, dy * slope) * scale
+    dims = [0] + list(range(2, dx.ndim))
+    return dx, dx.sum(dims)
+
+
+# --------------------------------------------------------------------------------------
+# a5  upfirdn2d                                    gans/models/ops/upfirdn2d/upfirdn2d.py
+# --------------------------------------------------------------------------------------
+
+
+def upfirdn2d_out_size(n_in: int, up: int, down: int, p0: int, p1: int, k: int) -> int:
+    """upfirdn2d.py:93-94 / upfirdn2d_kernel.cu:232-235."""
+    return (n_in * up + p0 + p1 - k + down) // down
+
+
+def upfirdn2d(x: Tensor, kernel: Tensor, up=1, down=1, pad=(0, 0)) -> Tensor:
+    """pad -> zero-insert upsample -> true convolution with `kernel` -> decimate.
+
+    Restates upfirdn2d_native (upfirdn2d.py:167-208) as an explicit polyphase
+    gather: out[my,mx] = sum_{ty,tx} K[kh-1-ty, kw-1-tx] * xu[my*dy+ty-py0, mx*dx+tx-px0]
+    where xu is the zero-inserted input (zero outside).  Argument order follows
+    the reference wrapper (upfirdn2d.py:148-164): up/down are (x, y), pad is
+    (x0, x1[, y0, y1]).
+    """
+    up_x, up_y = (up, up) if isinstance(up, int) else up
+    down_x, down_y = (down, down) if isinstance(down, int) else down
+    if len(pad) == 2:
+        pad = (pad[0], pad[1], pad[0], pad[1])
+    px0, px1, py0, py1 = pad
+    n, c, h, w = x.shape
+    kh, kw = kernel.shape
+    oh = upfirdn2d_out_size(h, up_y, down_y, py0, py1, kh)
+    ow = upfirdn2d_out_size(w, up_x, down_x, px0, px1, kw)
+    kflip = torch.flip(kernel, [0, 1]).to(x.dtype)
+    # zero-inserted signal on its own lattice
+    xu = x.new_zeros(n, c, h * up_y, w * up_x)
+    xu[:, :, ::up_y, ::up_x] = x
+    # explicit pad (positive) / crop (negative)
+    xu = F.pad(xu, (max(px0, 0), max(px1, 0), max(py0, 0), max(py1, 0)))
+    xu = xu[:, :, max(-py0, 0): xu.shape[2] - max(-py1, 0),
+            max(-px0, 0): xu.shape[3] - max(-px1, 0)]
+    full = F.conv2d(xu.reshape(n * c, 1, *xu.shape[2:]), kflip[None, None])
+    full = full[:, :, ::down_y, ::down_x]
+    assert full.shape[2] == oh and full.shape[3] == ow, (full.shape, oh, ow)
+    return full.reshape(n, c, oh, ow)
+
+
+# --------------------------------------------------------------------------------------
+# a4  Resample / BlurVH / filter2d / Pad                   gans/models/ops/common.py
+# --------------------------------------------------------------------------------------
+
+
+def resample_geometry(n_taps: int, up: int, down: int) -> Tuple[int, int]:
+    """(p0, p1) per axis as derived in Resample.__init__ (common.py:89-101)."""
+    if up > 1:
+        return (n_taps - up + 1) // 2 + up - 1, (n_taps - up) // 2
+    return (n_taps - down + 1) // 2, (n_taps - down) // 2
+
+
+def _boundary_index(idx: Tensor, n: int, circular: bool) -> Tensor:
+    return torch.remainder(idx, n) if circular else idx.clamp(0, n - 1)
+
+
+def _fir_axis(x: Tensor, taps: Tensor, up: int, down: int, p0: int, p1: int,
+              axis: int, circular: bool) -> Tensor:
+    """One separable pass: out[m] = sum_t taps[t] * xu[m*down + t - p0], where
+    xu[q] = X(q/up) if up | q else 0 and X() extends x circularly (ring, W axis)
+    or by edge replication (H axis).  This is the closed form of
+    margin-pad -> zero-insert -> crop -> depthwise correlate -> stride
+    (common.py:105-135)."""
+    n = x.shape[axis]
+    k = taps.numel()
+    n_out = (n * up + p0 + p1 - k) // down + 1
+    m = torch.arange(n_out)
+    out = None
+    for t in range(k):
+        q = m * down + t - p0
+        hit = (torch.remainder(q, up) == 0)
+        src = _boundary_index(torch.div(q, up, rounding_mode="floor"), n, circular)
+        term = x.index_select(axis, src)
+        shape = [1] * x.ndim
+        shape[axis] = n_out
+        term = term * (hit.to(x.dtype) * taps[t]).reshape(shape)
+        out = term if out is None else out + term
+    return out
+
+
+def resample(x: Tensor, up: int = 1, down: int = 1, window: Sequence[float] = (1, 3, 3, 1),
+             ring: bool = True, normalize: bool = True, direction: str = "hw") -> Tensor:
+    """Resample.forward (common.py:45-138): W pass first, then H pass
+    (common.py:126-128)."""
+    taps = torch.tensor(list(window), dtype=torch.float32)
+    if normalize:
+        taps = taps / taps.sum()
+    up_h = up if "h" in direction else 1
+    up_w = up if "w" in direction else 1
+    down_h = down if "h" in direction else 1
+    down_w = down if "w" in direction else 1
+    # kernel *= (up_h*up_w) ** (ndim/2), ndim == 1  (common.py:82)
+    taps = taps * float(up_h * up_w) ** 0.5
+    taps = taps.to(x.dtype)
+    y = x
+    if "w" in direction:
+        p0, p1 = resample_geometry(len(window), up_w, down_w)
+        y = _fir_axis(y, taps, up_w, down_w, p0, p1, axis=3, circular=ring)
+    if "h" in direction:
+        p0, p1 = resample_geometry(len(window), up_h, down_h)
+        y = _fir_axis(y, taps, up_h, down_h, p0, p1, axis=2, circular=False)
+    return y
+
+
+def blur_vh(x: Tensor, window: Sequence[float] = (1, 2, 1), ring: bool = True) -> Tensor:
+    """BlurVH (common.py:141-155): cat(vertical blur, horizontal blur) on dim 1."""
+    v = resample(x, window=window, ring=ring, direction="h")
+    h = resample(x, window=window, ring=ring, direction="w")
+    return torch.cat([v, h], dim=1)
+
+
+def pad2d(x: Tensor, padding, ring: bool = False, mode: str = "replicate") -> Tensor:
+    """Pad (common.py:10-24): W padded first (circular when ring), then H (`mode`)."""
+    if isinstance(padding, int):
+        padding = (padding,) * 4
+    left, right, top, bottom = padding
+    x = F.pad(x, (left, right, 0, 0), mode="circular" if ring else mode)
+    return F.pad(x, (0, 0, top, bottom), mode=mode)
+
+
+def filter2d(x: Tensor, kernel: Tensor, gain: float = 1.0) -> Tensor:
+    """filter2d (common.py:27-42): same-size separable blur, circular W / replicate H."""
+    k = kernel / kernel.sum()
+    k = k * (gain ** 0.5)
+    n = k.numel()
+    y = _fir_axis(x, k.to(x.dtype), 1, 1, n // 2, (n - 1) // 2, axis=3, circular=True)
+    return _fir_axis(y, k.to(x.dtype), 1, 1, n // 2, (n - 1) // 2, axis=2, circular=False)
+
+
+# --------------------------------------------------------------------------------------
+# a8  EqualLR / PixelNorm / MappingNetwork
+# --------------------------------------------------------------------------------------
+
+
+def equal_linear(x: Tensor, weight: Tensor, bias: Optional[Tensor], gain: float = 1.0,
+                 lr_mul: float = 1.0) -> Tensor:
+    """EqualLR(nn.Linear) (common.py:158-184): scales the *input* by 1/sqrt(fan_in),
+    applies the module (bias included), then multiplies by gain*lr_mul."""
+    scale = 1.0 / math.sqrt(weight[0].numel())
+    return F.linear(x * scale, weight, bias) * (gain * lr_mul)
+
+
+def equal_conv2d(x: Tensor, weight: Tensor, bias: Optional[Tensor] = None, stride: int = 1,
+                 gain: float = 1.0) -> Tensor:
+    scale = 1.0 / math.sqrt(weight[0].numel())
+    return F.conv2d(x * scale, weight, bias, stride=stride) * gain
+
+
+def pixel_norm(x: Tensor, alpha: float = 1e-8) -> Tensor:
+    """common.py:213-223."""
+    return x / x.pow(2.0).mean(dim=1, keepdim=True).add(alpha).sqrt()
+
+
+def mapping_network(sd: Dict[str, Tensor], z: Tensor, prefix: str = "mapping_network.",
+                    depth: int = 2) -> Tensor:
+    """MappingNetwork (dusty_v2.py:13-29): PixelNorm, then `depth` x
+    [EqualLR(Linear, gain sqrt2, lr_mul 0.01) + LeakyReLU(0.2)]."""
+    h = pixel_norm(z)
+    for i in range(1, depth + 1):
+        h = equal_linear(h, sd[f"{prefix}{i}.0.module.weight"], sd[f"{prefix}{i}.0.module.bias"],
+                         gain=SQRT2, lr_mul=0.01)
+        h = F.leaky_relu(h, 0.2)
+    return h
+
+
+# --------------------------------------------------------------------------------------
+# a2  FourierFeature                                   gans/models/ops/fourier.py:77-82
+# --------------------------------------------------------------------------------------
+
+
+def fourier_feature(angle: Tensor, freqs: Tensor, phase: Tensor) -> Tensor:
+    """coords = f_h*elev + f_w*azim + phase (a 1x1 conv), out = cat(sin, cos)."""
+    f = freqs.reshape(-1, 2).to(angle.dtype)
+    coords = (angle[:, 0:1] * f[:, 0].reshape(1, -1, 1, 1)
+              + angle[:, 1:2] * f[:, 1].reshape(1, -1, 1, 1)
+              + phase.reshape(1, -1, 1, 1))
+    return torch.cat([coords.sin(), coords.cos()], dim=1)
+
+
+# --------------------------------------------------------------------------------------
+# a1  ModConv2d (1x1)                                   gans/models/ops/style.py:68-126
+# --------------------------------------------------------------------------------------
+
+
+def modconv_weights(style_w: Tensor, weight: Tensor, mod_w: Tensor, mod_b: Tensor,
+                    ema_var: Tensor, demod: bool) -> Tensor:
+    """Per-sample effective 1x1 weights Wb[B,O,I] (never built as [B,O,I,1,1]):
+
+      s   = EqualLR-linear(style)                         style.py:72
+      W'  = scale*W / max|scale*W|   (demod only)         style.py:73-78
+      s'  = s / max_i|s_i| + 1 (demod)  or  s + 1         style.py:79-83
+      Wb  = W' * s'                                       style.py:93
+      Wb *= rsqrt(sum_i Wb^2 + 1e-8)  (demod)             style.py:96-98
+      Wb /= sqrt(ema_var) + 1e-8                          style.py:103
+    """
+    o, i = weight.shape[1], weight.shape[2]
+    w = weight.reshape(o, i) * (1.0 / math.sqrt(i))
+    s = equal_linear(style_w, mod_w, mod_b)
+    if demod:
+        w = w / w.abs().max()
+        s = s / s.abs().amax(dim=1, keepdim=True)
+    s = s + 1.0
+    wb = w[None] * s[:, None, :]
+    if demod:
+        wb = wb * torch.rsqrt(wb.pow(2).sum(dim=2, keepdim=True) + 1e-8)
+    return wb / (torch.sqrt(ema_var) + 1e-8)
+
+
+def modconv(x: Tensor, style_w: Tensor, weight: Tensor, mod_w: Tensor, mod_b: Tensor,
+            ema_var: Tensor, demod: bool = True, bias: Optional[Tensor] = None,
+            training: bool = False, ema_decay: float = 0.9989) -> Tuple[Tensor, Tensor]:
+    """Modulated 1x1 conv as a per-sample contraction Y_b = Wb_b @ X_b.
+    In training the EMA of mean(x^2) is updated *before* it is used
+    (style.py:99-103).  Returns (y, new_ema_var)."""
+    b, i, h, w_ = x.shape
+    if training:
+        var = x.detach().pow(2).mean()
+        ema_var = torch.lerp(ema_var, var, 1 - ema_decay)
+    wb = modconv_weights(style_w, weight, mod_w, mod_b, ema_var, demod)
+    y = torch.bmm(wb, x.reshape(b, i, h * w_)).reshape(b, -1, h, w_)
+    if bias is not None:
+        y = y + bias.reshape(1, -1, 1, 1)
+    return y, ema_var
+
+
+# --------------------------------------------------------------------------------------
+# a10  Gumbel-sigmoid raydrop               gans/models/ops/gumbel.py, gans/models/dusty_v1.py
+# --------------------------------------------------------------------------------------
+
+_EPS32 = float(torch.finfo(torch.float32).eps)
+_TINY32 = float(torch.finfo(torch.float32).tiny)
+
+
+def gumbel_sigmoid(logits: Tensor, u: Tensor, temperature: float = 1.0) -> Tuple[Tensor, Tensor]:
+    """Closed form of RelaxedBernoulli(T, logits).rsample() given the uniform draw
+    `u` (torch.distributions relaxed_bernoulli.py rsample + SigmoidTransform with
+    clamped probs), then the straight-through hard threshold (gumbel.py:23-29).
+    Returns (mask_with_soft_gradient, soft)."""
+    probs = torch.sigmoid(logits).clamp(_EPS32, 1 - _EPS32)
+    uu = u.clamp(_EPS32, 1 - _EPS32)
+    y = (uu.log() - (-uu).log1p() + probs.log() - (-probs).log1p()) / temperature
+    soft = torch.sigmoid(y).clamp(_TINY32, 1 - _EPS32)
+    hard = (soft > 0.5).to(logits.dtype)
+    return (hard - soft).detach() + soft, soft
+
+
+def raydrop(image: Tensor, logits: Tensor, u: Tensor, raydrop_const: float = -1.0,
+            temperature: float = 1.0) -> Dict[str, Tensor]:
+    """RayDropModel.forward (dusty_v1.py:20-25)."""
+    mask, _ = gumbel_sigmoid(logits, u, temperature)
+    const = torch.tensor(float(raydrop_const), dtype=image.dtype)
+    return {"raydrop_mask": mask, "image_orig": image,
+            "image": torch.lerp(image, const, 1 - mask)}
+
+
+# --------------------------------------------------------------------------------------
+# a14  CoordBridge                                                   gans/coords.py
+# --------------------------------------------------------------------------------------
+
+
+def angle_grid(angle_hw2: np.ndarray, num_ring: int, num_points: int) -> Tensor:
+    """CoordBridge.__init__ (coords.py:59-71): sin/cos -> tile x3 along W -> bilinear
+    resize -> centre crop -> atan2.  Bit-exact restatement (same torch CPU ops)."""
+    a = torch.from_numpy(np.ascontiguousarray(angle_hw2)).permute(2, 0, 1)[None]
+    per = torch.cat([a.sin(), a.cos()], dim=1)
+    per = torch.cat([per, per, per], dim=3)
+    per = F.interpolate(per, size=(num_ring, num_points * 3), mode="bilinear",
+                        align_corners=False)
+    per = per[..., num_points: 2 * num_points]
+    return torch.atan2(per[:, :2], per[:, 2:])
+
+
+def inv_depth_norm_to_depth(x: Tensor, min_depth: float, max_depth: float,
+                            tol: float = 1e-11) -> Tuple[Tensor, Tensor]:
+    """coords.py:143-147 + 73-81: valid = (x>tol) & (1/max <= x/min <= 1/min) & (x/min>0);
+    depth = valid / (x/min + tol).  Returns (depth, valid)."""
+    inv = x / min_depth
+    valid = (x > tol).float()
+    valid = valid * ((inv >= 1 / max_depth) & (inv <= 1 / min_depth) & (inv > 0.0)).float()
+    depth = 1 / (inv + tol) * valid
+    return depth, valid
+
+
+def depth_to_point_map(depth: Tensor, angle: Tensor) -> Tensor:
+    """coords.py:178-185: xyz = depth * [cos el cos az, cos el sin az, sin el]."""
+    c, s = torch.cos(angle), torch.sin(angle)
+    return torch.cat([depth * c[:, [0]] * c[:, [1]], depth * c[:, [0]] * s[:, [1]],
+                      depth * s[:, [0]]], dim=1)
+
+
+def inv_depth_norm_to_points(x: Tensor, angle: Tensor, min_depth: float, max_depth: float):
+    """convert(x, 'inv_depth_norm', 'point_map'/'point_set') (coords.py:139-155).
+    Returns (point_map[B,3,H,W], point_set[B,HW,3], valid_count int)."""
+    depth, valid = inv_depth_norm_to_depth(x, min_depth, max_depth)
+    pm = depth_to_point_map(depth, angle)
+    ps = pm.flatten(2).permute(0, 2, 1).contiguous()
+    return pm, ps, int(valid.sum().item())
+
+
+def depth_to_inv_depth_norm(depth: Tensor, min_depth: float, max_depth: float,
+                            tol: float = 1e-11) -> Tensor:
+    """convert(depth,'depth','inv_depth_norm') (coords.py:92-98,130-132)."""
+    valid = ((depth >= min_depth) & (depth <= max_depth) & (depth > 0.0)).float()
+    return (1 / (depth + tol) * valid) * min_depth
+
+
+def fetch_reals(depth: Tensor, mask: Tensor, min_depth: float, max_depth: float,
+                raydrop_const: float = -1.0) -> Tensor:
+    """Trainer.fetch_reals (trainer.py:211-217)."""
+    x = depth_to_inv_depth_norm(depth, min_depth, max_depth) * 2.0 - 1.0
+    return mask * x + (1 - mask) * raydrop_const
+
+
+# --------------------------------------------------------------------------------------
+# a12  MinibatchStdDev                                    gans/models/ops/common.py:226-253
+# --------------------------------------------------------------------------------------
+
+
+def minibatch_stddev(x: Tensor, group: int = 4, alpha: float = 1e-8) -> Tensor:
+    """features == 1.  Groups are *strided*: members {m, m+B/G, m+2B/G, ...}."""
+    b, c, h, w = x.shape
+    g = min(b, group)
+    y = x.reshape(g, b // g, c, h, w)
+    y = (y - y.mean(0, keepdim=True)).pow(2).mean(0)
+    y = torch.sqrt(y + alpha).mean(dim=(1, 2, 3))          # [B/G]
+    y = y.reshape(1, b // g, 1, 1, 1).expand(g, b // g, 1, h, w).reshape(b, 1, h, w)
+    return torch.cat([x, y], dim=1)
+
+
+# --------------------------------------------------------------------------------------
+# a7  aug-coords unshift                                 gans/models/dusty_v2.py:290-297
+# --------------------------------------------------------------------------------------
+
+
+def circular_unshift(v: Tensor, shift_rad: Tensor) -> Tensor:
+    """cat([v,v],W) -> affine_grid(translation shift/2pi on x) -> bilinear grid_sample
+    -> first W columns.  Same ATen calls as the reference so the fp32 coordinate
+    arithmetic is reproduced exactly."""
+    b, _, _, w = v.shape
+    t = shift_rad / (2 * np.pi)
+    theta = torch.zeros(b, 2, 3, dtype=v.dtype)
+    theta[:, 0, 0] = 1
+    theta[:, 1, 1] = 1
+    theta[:, 0, 2] = t
+    vv = torch.cat([v, v], dim=3)
+    grid = F.affine_grid(theta, vv.shape, align_corners=False)
+    return F.grid_sample(vv, grid, mode="bilinear", align_corners=False)[..., :w]
+
+
+# --------------------------------------------------------------------------------------
+# a7/a9  dusty_v2 generator                     gans/models/dusty_v2.py, gans/models/base.py
+# --------------------------------------------------------------------------------------
+
+
+def downsample_angle(angle: Tensor) -> Tensor:
+    """SynthesisBlock.downsample_angle (dusty_v2.py:135-140)."""
+    c = angle.shape[1]
+    per = resample(torch.cat([angle.sin(), angle.cos()], dim=1), down=2)
+    return torch.atan2(per[:, :c], per[:, c:])
+
+
+def _num_levels(sd: Dict[str, Tensor], prefix: str) -> int:
+    n = 0
+    while f"{prefix}layers.{n}.conv1.weight" in sd:
+        n += 1
+    return n
+
+
+def synthesis_network(sd: Dict[str, Tensor], ws: Tensor, angle: Tensor, training: bool = False,
+                      shifts_rad: Optional[Tensor] = None, output_scale: float = 0.25,
+                      prefix: str = "synthesis_network.",
+                      new_buffers: Optional[Dict[str, Tensor]] = None) -> Dict[str, Tensor]:
+    """SynthesisNetwork.forward (dusty_v2.py:261-308) with the per-block body of
+    SynthesisBlock.forward (dusty_v2.py:142-180).  `shifts_rad` [B] is the
+    aug-coords azimuth shift (already in radians) that the reference draws with
+    uniform_ (dusty_v2.py:266-274); None disables it (eval mode)."""
+    n_lv = _num_levels(sd, prefix)
+    if shifts_rad is not None:
+        sh = torch.zeros(ws.shape[0], 2, dtype=angle.dtype)
+        sh[:, 1] = shifts_rad
+        angle = angle + sh[..., None, None]
+    pyramid = [angle]
+    for _ in range(n_lv - 1):
+        pyramid.insert(0, downsample_angle(pyramid[0]))
+
+    def mc(x, style, name, demod, with_bias):
+        p = f"{prefix}{name}."
+        y, ev = modconv(x, style, sd[p + "weight"], sd[p + "mod.module.weight"],
+                        sd[p + "mod.module.bias"], sd[p + "ema_var"], demod=demod,
+                        bias=sd[p + "bias"] if with_bias else None, training=training)
+        if new_buffers is not None:
+            new_buffers[p + "ema_var"] = ev
+        return y
+
+    h, skip, i = None, None, 0
+    for l, ang in enumerate(pyramid):
+        lp = f"layers.{l}."
+        pe = fourier_feature(ang, sd[f"{prefix}{lp}pe.freqs"], sd[f"{prefix}{lp}pe.phase"])
+        if h is None:
+            h = pe
+        else:
+            h = torch.cat([resample(h, up=2), pe], dim=1)
+        h = bias_act(mc(h, ws[:, i], lp + "conv1", True, False), sd[f"{prefix}{lp}bias_act1.bias"])
+        n_conv = 1
+        if l > 0:
+            h = bias_act(mc(h, ws[:, i + 1], lp + "conv2", True, False),
+                         sd[f"{prefix}{lp}bias_act2.bias"])
+            n_conv = 2
+        out = {}
+        for name in ("image", "raydrop_logit"):
+            o = mc(h, ws[:, i + n_conv], f"{lp}head.heads.{name}", False, True)
+            if skip is not None:
+                o = o + resample(skip[name], up=2)
+            out[name] = o
+        skip = out
+        i += n_conv
+
+    if shifts_rad is not None:
+        skip = {k: circular_unshift(v, shifts_rad) for k, v in skip.items()}
+    skip = {k: v * output_scale for k, v in skip.items()}
+    skip["image"] = torch.tanh(skip["image"])
+    return skip
+
+
+def generator(sd: Dict[str, Tensor], z: Tensor, angle: Tensor, u: Tensor, training: bool = False,
+              shifts_rad: Optional[Tensor] = None, truncation_psi: float = 1.0,
+              input_w: bool = False, raydrop_const: float = -1.0, temperature: float = 1.0,
+              new_buffers: Optional[Dict[str, Tensor]] = None) -> Dict[str, Tensor]:
+    """base.Generator.forward (base.py:26-63) for dusty_v2.  `u` is the uniform
+    tensor RelaxedBernoulli would draw (shape of raydrop_logit)."""
+    n_styles = 2 * _num_levels(sd, "synthesis_network.")
+    if input_w:
+        w = z
+    else:
+        w = mapping_network(sd, z)
+        w = torch.stack([w] * n_styles, dim=1)
+    if training:
+        if new_buffers is not None:
+            new_buffers["w_avg"] = torch.lerp(sd["w_avg"], w[:, 0].mean(0, keepdim=True).detach(),
+                                              1 - 0.995)
+    elif truncation_psi != 1.0:
+        w = torch.lerp(sd["w_avg"][None].expand_as(w), w, truncation_psi)
+    o = synthesis_network(sd, w, angle, training, shifts_rad, new_buffers=new_buffers)
+    o["w"] = w
+    o.update(raydrop(o["image"], o["raydrop_logit"], u, raydrop_const, temperature))
+    return o
+
+
+# --------------------------------------------------------------------------------------
+# a11  dusty_v2 discriminator                          gans/models/dusty_v2.py:325-396
+# --------------------------------------------------------------------------------------
+
+
+def _conv_ring(x: Tensor, w: Tensor, stride: int, padding: int) -> Tensor:
+    """ops.Conv2d(bias=False, ring=True, equal_lr=True) (common.py:187-210)."""
+    if padding:
+        x = pad2d(x, padding, ring=True)
+    return equal_conv2d(x, w, None, stride)
+
+
+def discriminator(sd: Dict[str, Tensor], x: Tensor) -> Tensor:
+    h = blur_vh(x)
+    h = bias_act(_conv_ring(h, sd["layers.1.0.module.weight"], 1, 0), sd["layers.2.bias"])
+    l = 3
+    while f"layers.{l}.conv1.1.module.weight" in sd:
+        p = f"layers.{l}."
+        r = bias_act(_conv_ring(h, sd[p + "conv1.1.module.weight"], 1, 1), sd[p + "bias_act1.bias"])
+        r = bias_act(_conv_ring(resample(r), sd[p + "conv2.1.module.weight"], 2, 1),
+                     sd[p + "bias_act2.bias"])
+        s = _conv_ring(resample(h), sd[p + "skip.0.module.weight"], 2, 0)
+        h = (r + s) / SQRT2
+        l += 1
+    h = minibatch_stddev(h)
+    h = bias_act(_conv_ring(h, sd["epilogue.1.1.module.weight"], 1, 1), sd["epilogue.2.bias"])
+    h = h.flatten(1)
+    h = bias_act(equal_linear(h, sd["epilogue.4.module.weight"], None), sd["epilogue.5.bias"])
+    return equal_linear(h, sd["epilogue.6.module.weight"], sd["epilogue.6.module.bias"])
+
+
+# --------------------------------------------------------------------------------------
+# a13  losses                                   gans/models/loss.py, gans/trainer.py:426-447
+# --------------------------------------------------------------------------------------
+
+
+def nsgan_g(y_fake: Tensor) -> Tensor:
+    return F.softplus(-y_fake).mean()
+
+
+def nsgan_d(y_real: Tensor, y_fake: Tensor) -> Tensor:
+    return F.softplus(-y_real).mean() + F.softplus(y_fake).mean()
+
+
+def r1_penalty(grads: Tensor) -> Tensor:
+    return grads.pow(2).sum(dim=[1, 2, 3]).mean()

@@ -1,0 +1,194 @@
+"""Pins oracle/dusty_oracle.py against golden vectors produced by the unmodified
+reference (tests/golden/make_golden.py).  CPU only."""
+import hashlib
+import os
+
+import numpy as np
+import pytest
+import torch
+
+from oracle import dusty_oracle as O
+
+T = torch.from_numpy
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def close(a, b, rtol=1e-5, atol=1e-6):
+    a = a.detach().numpy() if isinstance(a, torch.Tensor) else a
+    np.testing.assert_allclose(a, b, rtol=rtol, atol=atol)
+
+
+def test_bias_act(g_ops):
+    x, b = T(g_ops["ba_x"]), T(g_ops["ba_b"])
+    y = O.bias_act(x, b)
+    close(y, g_ops["ba_y"])
+    dx, db = O.bias_act_grad(T(g_ops["ba_dy"]), y)
+    close(dx, g_ops["ba_dx"])
+    close(db, g_ops["ba_db"], rtol=1e-5, atol=1e-5)
+    close(O.bias_act(T(g_ops["ba2_x"]), T(g_ops["ba2_b"])), g_ops["ba2_y"])
+
+
+@pytest.mark.parametrize("name", ["ada_upx", "ada_upy", "ada_dnx", "ada_dny", "gen2d", "ident"])
+def test_upfirdn2d(g_ops, name):
+    cfg = g_ops[f"ufd_{name}_cfg"].tolist()
+    y = O.upfirdn2d(T(g_ops[f"ufd_{name}_x"]), T(g_ops[f"ufd_{name}_k"]), up=tuple(cfg[0:2]),
+                    down=tuple(cfg[2:4]), pad=tuple(cfg[4:8]))
+    assert tuple(y.shape) == g_ops[f"ufd_{name}_y"].shape
+    close(y, g_ops[f"ufd_{name}_y"], rtol=1e-5, atol=1e-6)
+
+
+def test_resample_family(g_ops):
+    x = T(g_ops["rs_x"])
+    close(O.resample(x, up=2), g_ops["rs_up2"])
+    close(O.resample(x, down=2), g_ops["rs_down2"])
+    close(O.resample(x), g_ops["rs_blur4"])
+    close(O.resample(x, window=(1, 2, 1), direction="h"), g_ops["rs_blur3_h"])
+    close(O.resample(x, window=(1, 2, 1), direction="w"), g_ops["rs_blur3_w"])
+    close(O.resample(x, up=2, ring=False), g_ops["rs_up2_noring"])
+    close(O.blur_vh(x), g_ops["rs_blurvh"])
+    close(O.pad2d(x, 1, ring=True), g_ops["rs_pad1"])
+    close(O.pad2d(x, 1, ring=True, mode="reflect"), g_ops["rs_pad1_reflect"])
+    close(O.filter2d(x, T(g_ops["rs_filter2d_k"])), g_ops["rs_filter2d"])
+
+
+@pytest.mark.parametrize("nm,kw", [("up2", dict(up=2)), ("down2", dict(down=2)), ("blur4", {})])
+def test_resample_grad(g_ops, nm, kw):
+    x = T(g_ops["rs_x"]).clone().requires_grad_()
+    y = O.resample(x, **kw)
+    (gx,) = torch.autograd.grad(y, x, T(g_ops[f"rs_{nm}_gy"]))
+    close(gx, g_ops[f"rs_{nm}_gx"], rtol=1e-5, atol=1e-6)
+
+
+def test_fourier(g_ops):
+    out = O.fourier_feature(T(g_ops["ff_angle"]), T(g_ops["ff_freqs"]), T(g_ops["ff_phase"]))
+    # |arg| ~ 1e2: one fp32 ulp of the argument is ~1e-5
+    close(out, g_ops["ff_out"], rtol=0, atol=3e-5)
+
+
+@pytest.mark.parametrize("tag,demod", [("dm", True), ("hd", False)])
+def test_modconv(g_ops, tag, demod):
+    g = lambda k: T(g_ops[f"mc_{tag}_{k}"])
+    sd = {k[len(f"mc_{tag}_sd_"):]: T(v) for k, v in g_ops.items() if k.startswith(f"mc_{tag}_sd_")}
+    x = g("x").clone().requires_grad_()
+    st = g("style").clone().requires_grad_()
+    w = sd["weight"].clone().requires_grad_()
+    mw = sd["mod.module.weight"].clone().requires_grad_()
+    mb = sd["mod.module.bias"].clone().requires_grad_()
+    bias = sd.get("bias")
+    y, ev = O.modconv(x, st, w, mw, mb, sd["ema_var"], demod=demod, bias=bias, training=False)
+    close(y, g_ops[f"mc_{tag}_y_eval"], rtol=1e-4, atol=1e-5)
+    assert float(ev) == float(sd["ema_var"])
+    grads = torch.autograd.grad(y, [x, st, w, mw, mb], g("gy"))
+    for nm, gr in zip(("gx", "gstyle", "gw", "gmodw", "gmodb"), grads):
+        ref = g_ops[f"mc_{tag}_{nm}"]
+        close(gr, ref, rtol=1e-3, atol=1e-4 * np.abs(ref).max())
+    y2, ev2 = O.modconv(x, st, w, mw, mb, sd["ema_var"], demod=demod, bias=bias, training=True)
+    close(y2, g_ops[f"mc_{tag}_y_train"], rtol=1e-4, atol=1e-5)
+    close(ev2, g_ops[f"mc_{tag}_ema_after"], rtol=1e-6, atol=0)
+
+
+def test_gumbel_raydrop(g_ops):
+    logit = T(g_ops["gs_logit"]).clone().requires_grad_()
+    img = T(g_ops["gs_img"]).clone().requires_grad_()
+    o = O.raydrop(img, logit, T(g_ops["gs_u"]))
+    # mask and count are integer-exact
+    assert np.array_equal(o["raydrop_mask"].detach().numpy(), g_ops["gs_mask"])
+    assert int(o["raydrop_mask"].sum().item()) == int(g_ops["gs_count"])
+    assert np.array_equal(o["image"].detach().numpy(), g_ops["gs_image"])
+    gl, gi = torch.autograd.grad(o["image"], [logit, img], T(g_ops["gs_gout"]))
+    close(gl, g_ops["gs_glogit"], rtol=1e-5, atol=1e-7)
+    close(gi, g_ops["gs_gimg"], rtol=1e-6, atol=0)
+
+
+def test_minibatch_std_pixelnorm(g_ops):
+    close(O.minibatch_stddev(T(g_ops["mb_x"])), g_ops["mb_y"], rtol=1e-5, atol=1e-6)
+    close(O.minibatch_stddev(T(g_ops["mb2_x"])), g_ops["mb2_y"], rtol=1e-5, atol=1e-6)
+    close(O.pixel_norm(T(g_ops["pn_x"])), g_ops["pn_y"], rtol=1e-6, atol=1e-7)
+
+
+def test_coords(g_coords):
+    raw = np.load(os.path.join(ROOT, "data", "coords", "kitti_raw.npy"))
+    assert hashlib.sha256(raw.tobytes()).hexdigest() == str(g_coords["raw_sha256"])
+    angle = O.angle_grid(raw, 64, 512)
+    # bit-exact: same ATen CPU ops in the same order
+    assert np.array_equal(angle.numpy(), g_coords["angle"])
+    xin = T(g_coords["xin"])
+    pm, ps, count = O.inv_depth_norm_to_points(xin, angle, 1.45, 80.0)
+    assert count == int(g_coords["valid_count"])
+    assert np.array_equal(pm.numpy()[:, :, ::4, ::8], g_coords["point_map"])
+    # pixel indexing: point_set[b, h*W + w] == point_map[b, :, h, w]
+    assert np.array_equal(ps.numpy()[:, :2048], g_coords["point_set_head"])
+    depth, _ = O.inv_depth_norm_to_depth(xin, 1.45, 80.0)
+    assert np.array_equal((depth / 80.0).numpy()[:, :, ::4, ::8], g_coords["depth_norm"])
+    reals = O.fetch_reals(T(g_coords["depth"]), T(g_coords["mask"]), 1.45, 80.0)
+    assert np.array_equal(reals.numpy(), g_coords["reals"])
+
+
+def _sd(g, prefix="sd_"):
+    return {k[len(prefix):]: T(v) for k, v in g.items() if k.startswith(prefix)}
+
+
+def test_generator_eval(g_gen):
+    sd = _sd(g_gen)
+    z, angle = T(g_gen["z"]), T(g_gen["angle"])
+    for tag, psi in (("eval", 1.0), ("psi", 0.7)):
+        o = O.generator(sd, z, angle, T(g_gen[f"{tag}_u"]), training=False, truncation_psi=psi)
+        close(o["w"][:, 0], g_gen[f"{tag}_w0"], rtol=1e-5, atol=1e-6)
+        for k in ("image_orig", "raydrop_logit"):
+            ref = g_gen[f"{tag}_{k}"]
+            close(o[k], ref, rtol=1e-3, atol=1e-4 * np.abs(ref).max())
+        # the hard mask may only differ where logit+noise is within float noise of 0
+        assert (o["raydrop_mask"].numpy() != g_gen[f"{tag}_raydrop_mask"]).mean() < 1e-3
+
+
+def test_generator_train_and_grads(g_gen):
+    sd = {k: v.clone().requires_grad_(v.dtype.is_floating_point and
+                                       not (k.endswith("ema_var") or k == "w_avg"
+                                            or "kernel" in k or "pe." in k or "raydrop_const" in k))
+          for k, v in _sd(g_gen).items()}
+    z, angle = T(g_gen["z"]), T(g_gen["angle"])
+    newb = {}
+    o = O.generator(sd, z, angle, T(g_gen["train_u"]), training=True,
+                    shifts_rad=T(g_gen["train_shift01"]) * (2 * np.pi), new_buffers=newb)
+    for k in ("image_orig", "raydrop_logit"):
+        ref = g_gen[f"train_{k}"]
+        close(o[k], ref, rtol=1e-3, atol=2e-4 * np.abs(ref).max())
+    for k, v in newb.items():
+        close(v, g_gen[f"after_{k}"], rtol=1e-5, atol=1e-7)
+    loss = (o["image"] * T(g_gen["train_gi"])).sum() + (o["raydrop_logit"] * T(g_gen["train_gl"])).sum()
+    names = [k for k, v in sd.items() if v.requires_grad]
+    grads = torch.autograd.grad(loss, [sd[k] for k in names], allow_unused=True)
+    checked = 0
+    for k, g in zip(names, grads):
+        key = f"grad_{k}"
+        if key in g_gen and g is not None:
+            ref = g_gen[key]
+            close(g, ref, rtol=2e-3, atol=2e-3 * max(np.abs(ref).max(), 1e-6))
+            checked += 1
+    assert checked > 40
+
+
+def test_discriminator_first_and_second_order(g_disc):
+    sd = {k: v.clone().requires_grad_("kernel" not in k) for k, v in _sd(g_disc).items()}
+    x = T(g_disc["x"]).clone().requires_grad_()
+    y = O.discriminator(sd, x)
+    close(y, g_disc["y"], rtol=1e-4, atol=1e-5)
+    names = [k for k, v in sd.items() if v.requires_grad]
+    loss = O.nsgan_g(y)
+    g1 = torch.autograd.grad(loss, [x] + [sd[k] for k in names], retain_graph=True)
+    close(g1[0], g_disc["gx_loss"], rtol=1e-3, atol=1e-6)
+    for k, g in zip(names, g1[1:]):
+        ref = g_disc[f"g1_{k}"]
+        close(g, ref, rtol=1e-3, atol=1e-4 * max(np.abs(ref).max(), 1e-8))
+    (gx,) = torch.autograd.grad(y.sum(), x, create_graph=True)
+    close(gx, g_disc["r1_gx"], rtol=1e-3, atol=1e-6)
+    r1 = O.r1_penalty(gx)
+    close(r1, g_disc["r1"], rtol=1e-4, atol=0)
+    g2 = torch.autograd.grad(r1, [sd[k] for k in names], allow_unused=True)
+    n = 0
+    for k, g in zip(names, g2):
+        if f"g2_{k}" in g_disc and g is not None:
+            ref = g_disc[f"g2_{k}"]
+            close(g, ref, rtol=2e-3, atol=2e-4 * max(np.abs(ref).max(), 1e-8))
+            n += 1
+    assert n >= 8

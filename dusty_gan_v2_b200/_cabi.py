@@ -1,0 +1,111 @@
+"""ctypes binding of libdusty_b200.so (the C ABI declared in include/dusty_b200.h).
+
+There is deliberately NO fallback: if the shared library is missing or a call fails the
+caller gets an exception.  PyTorch is used only for device memory and the current stream.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+
+import torch
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libdusty_b200.so")
+
+F32, BF16 = 0, 1
+PAD_ZERO, PAD_CIRCULAR, PAD_REPLICATE, PAD_REFLECT = 0, 1, 2, 3
+ABI_VERSION = 1
+
+_vp, _i, _i64, _f = C.c_void_p, C.c_int, C.c_int64, C.c_float
+
+# name -> argtypes; every entry returns int status unless listed in _RESTYPE
+SIGNATURES = {
+    "dusty_abi_version": [],
+    "dusty_last_error": [],
+    "dusty_query_sm": [],
+    "dusty_launch_count": [],
+    "dusty_bias_act": [_vp, _vp, _vp, _vp, _i64, _i, _i64, _i, _i, _f, _f, _i, _vp],
+    "dusty_bias_act_bwd": [_vp, _vp, _vp, _vp, _i64, _i, _i64, _f, _f, _i, _vp],
+    "dusty_fir2d": [_vp, _vp, _vp, _i, _i, _i, _i64] + [_i] * 13 + [_vp],
+    "dusty_fir2d_adj": [_vp, _vp, _vp, _i, _i, _i, _i64] + [_i] * 13 + [_vp],
+    "dusty_upfirdn2d": [_vp, _vp, _vp, _i64] + [_i] * 13 + [_vp],
+    "dusty_fourier": [_vp, _vp, _vp, _vp, _i, _i, _i64, _i, _vp],
+    "dusty_angle_down2": [_vp, _vp, _i, _i, _i, _vp],
+    "dusty_modconv_fwd": [_vp, _vp, _vp, _vp, _vp, _i, _i, _i, _i, _i, _i64, _i, _f, _f, _i, _i, _i, _vp],
+    "dusty_modconv_bwd_dx": [_vp, _vp, _vp, _i, _i, _i, _i, _i64, _i, _i, _i, _vp],
+    "dusty_modconv_bwd_dw": [_vp, _vp, _vp, _vp, _i, _i, _i, _i, _i, _i64, _i, _i, _vp],
+    "dusty_gumbel_raydrop_fwd": [_vp] * 7 + [_i64, _f, _f, _vp],
+    "dusty_gumbel_raydrop_bwd": [_vp] * 7 + [_i64, _f, _vp],
+    "dusty_point_project": [_vp, _vp, _vp, _vp, _i, _i64, _f, _f, _f, _i, _vp],
+    "dusty_minibatch_std_fwd": [_vp, _vp, _vp, _i, _i, _i64, _i, _f, _i, _vp],
+    "dusty_minibatch_std_bwd": [_vp, _vp, _vp, _vp, _i, _i, _i64, _i, _f, _i, _vp],
+    "dusty_sumsq_rows": [_vp, _vp, _i64, _i64, _i, _i, _vp],
+    "dusty_circular_shift": [_vp, _vp, _vp, _i, _i, _i, _i, _f, _i, _vp],
+}
+_RESTYPE = {"dusty_last_error": C.c_char_p, "dusty_launch_count": C.c_int64}
+
+_lib = None
+
+
+def load() -> C.CDLL:
+    """Load the library (once).  Raises if it has not been built."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(LIB_PATH):
+        raise RuntimeError(
+            f"{LIB_PATH} is missing: build it with `python -c 'import __graft_entry__ as g; g.build()'` "
+            "or `make -C dusty_gan_v2_b200/csrc`.  There is no CPU / PyTorch fallback.")
+    lib = C.CDLL(LIB_PATH)
+    for name, args in SIGNATURES.items():
+        fn = getattr(lib, name)  # AttributeError if the symbol is not exported
+        fn.argtypes = args
+        fn.restype = _RESTYPE.get(name, C.c_int)
+    ver = lib.dusty_abi_version()
+    if ver != ABI_VERSION:
+        raise RuntimeError(f"libdusty_b200 ABI version {ver} != expected {ABI_VERSION}")
+    _lib = lib
+    return lib
+
+
+def last_error() -> str:
+    return (load().dusty_last_error() or b"").decode()
+
+
+def launch_count() -> int:
+    return int(load().dusty_launch_count())
+
+
+def check(status: int, what: str):
+    if status != 0:
+        raise RuntimeError(f"{what} failed (status {status}): {last_error()}")
+
+
+def ptr(t):
+    """Device pointer of a tensor (None -> NULL)."""
+    return None if t is None else t.data_ptr()
+
+
+def stream_of(t: torch.Tensor):
+    return torch.cuda.current_stream(t.device).cuda_stream
+
+
+def dtype_code(t: torch.Tensor) -> int:
+    if t.dtype == torch.float32:
+        return F32
+    if t.dtype == torch.bfloat16:
+        return BF16
+    raise RuntimeError(f"dusty_b200 kernels support float32 and bfloat16 tensors, got {t.dtype}")
+
+
+def require_cuda(*tensors):
+    for t in tensors:
+        if t is not None and not t.is_cuda:
+            raise RuntimeError(
+                "dusty_b200 ops run on CUDA tensors only (no CPU fallback; the CPU restatement "
+                "lives in oracle/ and is test infrastructure)")
+
+
+def call(name: str, *args):
+    check(getattr(load(), name)(*args), name)

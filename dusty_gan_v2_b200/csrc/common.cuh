@@ -1,0 +1,106 @@
+// Shared helpers for libdusty_b200 (sm_100a only).
+#pragma once
+#include <cuda_bf16.h>
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stdio.h>
+
+#include "../../include/dusty_b200.h"
+
+namespace dusty {
+
+void set_error(const char *fmt, ...);
+void count_launch(int n = 1);
+int num_sms();
+
+#define DUSTY_CHECK_ARG(cond, msg)                                   \
+  do {                                                               \
+    if (!(cond)) {                                                   \
+      dusty::set_error("%s: %s", __func__, msg);                     \
+      return DUSTY_EINVAL;                                           \
+    }                                                                \
+  } while (0)
+
+#define DUSTY_LAUNCH_CHECK()                                                        \
+  do {                                                                              \
+    cudaError_t e__ = cudaGetLastError();                                           \
+    if (e__ != cudaSuccess) {                                                       \
+      dusty::set_error("%s: CUDA launch failed: %s", __func__, cudaGetErrorString(e__)); \
+      return DUSTY_ECUDA;                                                           \
+    }                                                                               \
+    dusty::count_launch();                                                          \
+  } while (0)
+
+template <typename T> __device__ __forceinline__ float to_f(T v);
+template <> __device__ __forceinline__ float to_f<float>(float v) { return v; }
+template <> __device__ __forceinline__ float to_f<__nv_bfloat16>(__nv_bfloat16 v) {
+  return __bfloat162float(v);
+}
+template <typename T> __device__ __forceinline__ T from_f(float v);
+template <> __device__ __forceinline__ float from_f<float>(float v) { return v; }
+template <> __device__ __forceinline__ __nv_bfloat16 from_f<__nv_bfloat16>(float v) {
+  return __float2bfloat16_rn(v);
+}
+
+// 16-byte vector of T
+template <typename T> struct Vec16;
+template <> struct Vec16<float> {
+  static constexpr int N = 4;
+  float4 raw;
+  __device__ __forceinline__ float get(int i) const { return (&raw.x)[i]; }
+  __device__ __forceinline__ void set(int i, float v) { (&raw.x)[i] = v; }
+};
+template <> struct Vec16<__nv_bfloat16> {
+  static constexpr int N = 8;
+  uint4 raw;
+  __device__ __forceinline__ float get(int i) const {
+    uint32_t w = (&raw.x)[i >> 1];
+    return __uint_as_float((i & 1) ? (w & 0xffff0000u) : (w << 16));
+  }
+  __device__ __forceinline__ void set(int i, float v) {
+    uint32_t b = (uint32_t)__bfloat16_as_ushort(__float2bfloat16_rn(v));
+    uint32_t &w = (&raw.x)[i >> 1];
+    w = (i & 1) ? ((w & 0x0000ffffu) | (b << 16)) : ((w & 0xffff0000u) | b);
+  }
+};
+
+template <typename T> __device__ __forceinline__ Vec16<T> ld16(const T *p) {
+  Vec16<T> v;
+  v.raw = *reinterpret_cast<const decltype(v.raw) *>(p);
+  return v;
+}
+template <typename T> __device__ __forceinline__ void st16(T *p, const Vec16<T> &v) {
+  *reinterpret_cast<decltype(v.raw) *>(p) = v.raw;
+}
+// streaming variants (read-once / write-once data: keep L2 for reusable tensors)
+template <typename T> __device__ __forceinline__ Vec16<T> ld16_stream(const T *p) {
+  Vec16<T> v;
+  v.raw = __ldcs(reinterpret_cast<const decltype(v.raw) *>(p));
+  return v;
+}
+template <typename T> __device__ __forceinline__ void st16_stream(T *p, const Vec16<T> &v) {
+  __stcs(reinterpret_cast<decltype(v.raw) *>(p), v.raw);
+}
+
+__device__ __forceinline__ float warp_sum(float v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+
+// Block-wide sum; result valid in thread 0.  `red` must hold >= 32 floats.
+__device__ __forceinline__ float block_sum(float v, float *red) {
+  v = warp_sum(v);
+  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+  __syncthreads();
+  if (lane == 0) red[wid] = v;
+  __syncthreads();
+  const int nw = (blockDim.x + 31) >> 5;
+  v = (threadIdx.x < nw) ? red[threadIdx.x] : 0.f;
+  if (wid == 0) v = warp_sum(v);
+  return v;
+}
+
+inline bool aligned16(const void *p) { return (reinterpret_cast<uintptr_t>(p) & 15u) == 0; }
+
+}  // namespace dusty

@@ -1,0 +1,85 @@
+// a1: C-ABI entry points of the modulated 1x1 contraction; dispatch between the SIMT fp32
+// kernel (exact parity path) and the tcgen05 tensor-core kernel (bf16 production path).
+#include "common.cuh"
+
+namespace dusty {
+int modconv_fwd_simt(const void *wb, const void *x1, const void *x2, const float *bias, void *y,
+                     int B, int O, int C1, int C2, int B2, int64_t P, int act, float alpha,
+                     float scale, int dtype, int wdtype, cudaStream_t st);
+int modconv_bwd_dx_simt(const void *wb, const void *dy, void *dx1, int B, int O, int C1, int K,
+                        int64_t P, int dtype, int wdtype, cudaStream_t st);
+int modconv_bwd_dw_simt(const void *dy, const void *x1, const void *x2, float *dwb, int B, int O,
+                        int C1, int C2, int B2, int64_t P, int dtype, cudaStream_t st);
+// tensor-core path (modconv_tc.cu); returns DUSTY_EUNSUPPORTED when the shape does not fit
+int modconv_fwd_tc(const void *wb, const void *x1, const void *x2, const float *bias, void *y,
+                   int B, int O, int C1, int C2, int B2, int64_t P, int act, float alpha,
+                   float scale, cudaStream_t st);
+bool modconv_fwd_tc_supported(int B, int O, int C1, int C2, int B2, int64_t P);
+}  // namespace dusty
+
+using namespace dusty;
+
+static bool dtype_ok(int d) { return d == DUSTY_F32 || d == DUSTY_BF16; }
+
+extern "C" int dusty_modconv_fwd(const void *wb, const void *x1, const void *x2, const float *bias,
+                                 void *y, int B, int O, int C1, int C2, int B2, int64_t P, int act,
+                                 float alpha, float scale, int dtype, int wdtype, int impl,
+                                 void *stream) {
+  DUSTY_CHECK_ARG(wb && y, "null pointer");
+  DUSTY_CHECK_ARG(B >= 1 && B <= 65535 && O >= 1 && C1 >= 0 && C2 >= 0 && C1 + C2 >= 1 && P >= 1,
+                  "bad shape");
+  DUSTY_CHECK_ARG((C1 == 0 || x1) && (C2 == 0 || x2), "missing source tensor");
+  DUSTY_CHECK_ARG(C2 == 0 || B2 == B || B2 == 1, "x2 batch must be B or 1");
+  DUSTY_CHECK_ARG(act == 1 || act == 3, "act must be 1 or 3");
+  DUSTY_CHECK_ARG(dtype_ok(dtype) && dtype_ok(wdtype), "bad dtype");
+  DUSTY_CHECK_ARG(impl >= 0 && impl <= 2, "impl must be 0 (auto), 1 (simt) or 2 (tcgen05)");
+  cudaStream_t st = (cudaStream_t)stream;
+  if (C1 == 0) x1 = x2;  // keep pointers valid for address arithmetic
+  if (C2 == 0) { x2 = x1; B2 = B; }
+  const bool tc_ok = dtype == DUSTY_BF16 && wdtype == DUSTY_BF16 &&
+                     modconv_fwd_tc_supported(B, O, C1, C2, B2, P);
+  if (impl == 2 && !tc_ok) {
+    set_error("dusty_modconv_fwd: tcgen05 path does not support this shape/dtype");
+    return DUSTY_EUNSUPPORTED;
+  }
+  int rc;
+  if (impl == 2 || (impl == 0 && tc_ok))
+    rc = modconv_fwd_tc(wb, x1, x2, bias, y, B, O, C1, C2, B2, P, act, alpha, scale, st);
+  else
+    rc = modconv_fwd_simt(wb, x1, x2, bias, y, B, O, C1, C2, B2, P, act, alpha, scale, dtype,
+                          wdtype, st);
+  if (rc) return rc;
+  DUSTY_LAUNCH_CHECK();
+  return DUSTY_OK;
+}
+
+extern "C" int dusty_modconv_bwd_dx(const void *wb, const void *dy, void *dx1, int B, int O, int C1,
+                                    int K, int64_t P, int dtype, int wdtype, int impl,
+                                    void *stream) {
+  DUSTY_CHECK_ARG(wb && dy && dx1, "null pointer");
+  DUSTY_CHECK_ARG(B >= 1 && B <= 65535 && O >= 1 && C1 >= 1 && K >= C1 && P >= 1, "bad shape");
+  DUSTY_CHECK_ARG(dtype_ok(dtype) && dtype_ok(wdtype), "bad dtype");
+  DUSTY_CHECK_ARG(impl == 0 || impl == 1, "only the SIMT implementation exists for dX");
+  int rc = modconv_bwd_dx_simt(wb, dy, dx1, B, O, C1, K, P, dtype, wdtype, (cudaStream_t)stream);
+  if (rc) return rc;
+  DUSTY_LAUNCH_CHECK();
+  return DUSTY_OK;
+}
+
+extern "C" int dusty_modconv_bwd_dw(const void *dy, const void *x1, const void *x2, float *dwb,
+                                    int B, int O, int C1, int C2, int B2, int64_t P, int dtype,
+                                    int impl, void *stream) {
+  DUSTY_CHECK_ARG(dy && dwb, "null pointer");
+  DUSTY_CHECK_ARG(B >= 1 && B <= 65535 && O >= 1 && C1 >= 0 && C2 >= 0 && C1 + C2 >= 1 && P >= 1,
+                  "bad shape");
+  DUSTY_CHECK_ARG((C1 == 0 || x1) && (C2 == 0 || x2), "missing source tensor");
+  DUSTY_CHECK_ARG(C2 == 0 || B2 == B || B2 == 1, "x2 batch must be B or 1");
+  DUSTY_CHECK_ARG(dtype_ok(dtype), "bad dtype");
+  DUSTY_CHECK_ARG(impl == 0 || impl == 1, "only the SIMT implementation exists for dW");
+  if (C1 == 0) x1 = x2;
+  if (C2 == 0) { x2 = x1; B2 = B; }
+  int rc = modconv_bwd_dw_simt(dy, x1, x2, dwb, B, O, C1, C2, B2, P, dtype, (cudaStream_t)stream);
+  if (rc) return rc;
+  DUSTY_LAUNCH_CHECK();
+  return DUSTY_OK;
+}

@@ -1,0 +1,306 @@
+// a1: modulated 1x1 convolution -- SIMT (CUDA-core, exact fp32 FMA) implementation.
+// This is the fp32 parity path (rtol 1e-3 against the oracle needs true fp32 products,
+// SURVEY 7.3-3); the bf16 production path is the tcgen05 kernel in modconv_tc.cu.
+//
+// Data layout: activations NCHW => per sample X_b is [K, P] with the pixel index
+// contiguous; per-sample effective weights wb_b are [O, K] row-major.  The channel axis of
+// X is the concatenation of two sources (upsampled features x1, Fourier features x2) that
+// are never concatenated in memory; x2 may be shared by the whole batch (B2 == 1).
+#include "common.cuh"
+
+namespace dusty {
+
+constexpr int BM = 64, BN = 64, BK = 16;
+
+template <typename T> struct Ld4 {};
+template <> struct Ld4<float> {
+  static __device__ __forceinline__ void ld(const float *p, float (&v)[4]) {
+    float4 t = *reinterpret_cast<const float4 *>(p);
+    v[0] = t.x; v[1] = t.y; v[2] = t.z; v[3] = t.w;
+  }
+};
+template <> struct Ld4<__nv_bfloat16> {
+  static __device__ __forceinline__ void ld(const __nv_bfloat16 *p, float (&v)[4]) {
+    uint2 t = *reinterpret_cast<const uint2 *>(p);
+    v[0] = __uint_as_float(t.x << 16); v[1] = __uint_as_float(t.x & 0xffff0000u);
+    v[2] = __uint_as_float(t.y << 16); v[3] = __uint_as_float(t.y & 0xffff0000u);
+  }
+};
+
+struct GemmNN {
+  // A(m,k) = a[b*a_bs + m*a_ms + k*a_ks]
+  const void *a; int64_t a_bs, a_ms, a_ks;
+  // B(k,n): k < K1 from b1 (batch stride b1_bs), else from b2 (batch stride b2_bs, 0 if shared)
+  const void *b1; const void *b2; int64_t b1_bs, b2_bs; int K1;
+  void *c; int64_t c_bs;
+  const float *bias;
+  int M, K; int64_t N;
+  int act; float alpha, scale;
+};
+
+// C[b] (M x N) = A[b] (M x K) * B[b] (K x N), fp32 accumulate, fused bias + lrelu epilogue.
+template <typename T, typename TA, bool A_KCONTIG>
+__global__ void __launch_bounds__(256)
+gemm_nn_kernel(GemmNN g) {
+  __shared__ __align__(16) float As[BK][BM + 4];
+  __shared__ __align__(16) float Bs[BK][BN + 4];
+  const int b = blockIdx.z;
+  const int m0 = blockIdx.y * BM;
+  const int64_t n0 = (int64_t)blockIdx.x * BN;
+  const int tid = threadIdx.x;
+  const int tx = tid & 15, ty = tid >> 4;
+  const TA *A = (const TA *)g.a + (int64_t)b * g.a_bs;
+  const T *B1 = (const T *)g.b1 + (int64_t)b * g.b1_bs;
+  const T *B2 = (const T *)g.b2 + (int64_t)b * g.b2_bs;
+  const bool n_vec = (g.N % 4 == 0);
+  float acc[4][4] = {};
+
+  for (int k0 = 0; k0 < g.K; k0 += BK) {
+    // ---- A tile -> As[k][m]
+    if (A_KCONTIG) {
+      const int m = tid >> 2, kq = (tid & 3) * 4;
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        const int gm = m0 + m, gk = k0 + kq + i;
+        As[kq + i][m] = (gm < g.M && gk < g.K) ? to_f(A[(int64_t)gm * g.a_ms + gk]) : 0.f;
+      }
+    } else {
+      const int k = tid >> 4, mq = (tid & 15) * 4;
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        const int gm = m0 + mq + i, gk = k0 + k;
+        As[k][mq + i] = (gm < g.M && gk < g.K) ? to_f(A[(int64_t)gm * g.a_ms + (int64_t)gk * g.a_ks]) : 0.f;
+      }
+    }
+    // ---- B tile -> Bs[k][n]
+    {
+      const int k = tid >> 4, nq = (tid & 15) * 4;
+      const int gk = k0 + k;
+      float v[4] = {0.f, 0.f, 0.f, 0.f};
+      if (gk < g.K) {
+        const T *src = (gk < g.K1) ? (B1 + (int64_t)gk * g.N) : (B2 + (int64_t)(gk - g.K1) * g.N);
+        const int64_t gn = n0 + nq;
+        if (n_vec && gn + 4 <= g.N) {
+          Ld4<T>::ld(src + gn, v);
+        } else {
+#pragma unroll
+          for (int i = 0; i < 4; ++i) if (gn + i < g.N) v[i] = to_f(src[gn + i]);
+        }
+      }
+      *reinterpret_cast<float4 *>(&Bs[k][nq]) = make_float4(v[0], v[1], v[2], v[3]);
+    }
+    __syncthreads();
+#pragma unroll
+    for (int k = 0; k < BK; ++k) {
+      const float4 av = *reinterpret_cast<const float4 *>(&As[k][ty * 4]);
+      const float4 bv = *reinterpret_cast<const float4 *>(&Bs[k][tx * 4]);
+      const float a[4] = {av.x, av.y, av.z, av.w};
+      const float bb[4] = {bv.x, bv.y, bv.z, bv.w};
+#pragma unroll
+      for (int i = 0; i < 4; ++i)
+#pragma unroll
+        for (int j = 0; j < 4; ++j) acc[i][j] = fmaf(a[i], bb[j], acc[i][j]);
+    }
+    __syncthreads();
+  }
+  // ---- epilogue
+  T *C = (T *)g.c + (int64_t)b * g.c_bs;
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const int gm = m0 + ty * 4 + i;
+    if (gm >= g.M) continue;
+    const float bv = g.bias ? g.bias[gm] : 0.f;
+    const int64_t gn = n0 + tx * 4;
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      if (gn + j >= g.N) continue;
+      float v = acc[i][j] + bv;
+      if (g.act == 3) v = (v > 0.f) ? v : v * g.alpha;
+      C[(int64_t)gm * g.N + gn + j] = from_f<T>(v * g.scale);
+    }
+  }
+}
+
+// Heads: O <= 4 outputs.  Pure streaming read of x (memory bound); weights in smem.
+template <typename T, typename TA, int OMAX>
+__global__ void __launch_bounds__(256)
+small_o_kernel(GemmNN g) {
+  extern __shared__ float sw[];  // [M][K]
+  const int b = blockIdx.y;
+  const TA *A = (const TA *)g.a + (int64_t)b * g.a_bs;
+  for (int i = threadIdx.x; i < g.M * g.K; i += blockDim.x) {
+    const int m = i / g.K, k = i - m * g.K;
+    sw[i] = to_f(A[(int64_t)m * g.a_ms + (int64_t)k * g.a_ks]);
+  }
+  __syncthreads();
+  const int64_t p0 = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) * 4;
+  if (p0 >= g.N) return;
+  const T *B1 = (const T *)g.b1 + (int64_t)b * g.b1_bs;
+  const T *B2 = (const T *)g.b2 + (int64_t)b * g.b2_bs;
+  const bool full = (g.N % 4 == 0) && (p0 + 4 <= g.N);
+  float acc[OMAX][4] = {};
+  for (int k = 0; k < g.K; ++k) {
+    const T *src = (k < g.K1) ? (B1 + (int64_t)k * g.N) : (B2 + (int64_t)(k - g.K1) * g.N);
+    float v[4] = {0.f, 0.f, 0.f, 0.f};
+    if (full) Ld4<T>::ld(src + p0, v);
+    else
+      for (int i = 0; i < 4; ++i) if (p0 + i < g.N) v[i] = to_f(src[p0 + i]);
+#pragma unroll
+    for (int m = 0; m < OMAX; ++m) {
+      if (m < g.M) {
+        const float w = sw[m * g.K + k];
+#pragma unroll
+        for (int i = 0; i < 4; ++i) acc[m][i] = fmaf(w, v[i], acc[m][i]);
+      }
+    }
+  }
+  T *C = (T *)g.c + (int64_t)b * g.c_bs;
+#pragma unroll
+  for (int m = 0; m < OMAX; ++m) {
+    if (m >= g.M) continue;
+    const float bv = g.bias ? g.bias[m] : 0.f;
+    for (int i = 0; i < 4; ++i) {
+      if (p0 + i >= g.N) continue;
+      float v = acc[m][i] + bv;
+      if (g.act == 3) v = (v > 0.f) ? v : v * g.alpha;
+      C[(int64_t)m * g.N + p0 + i] = from_f<T>(v * g.scale);
+    }
+  }
+}
+
+struct GemmNT {
+  const void *dy;  // [B, O, P]
+  const void *x1; const void *x2; int64_t x1_bs, x2_bs; int K1;
+  float *dw;       // [B, O, K]
+  int O, K; int64_t P;
+};
+
+// dw[b] (O x K) = dY[b] (O x P) * X[b]^T (P x K): both operands are pixel-contiguous.
+template <typename T>
+__global__ void __launch_bounds__(256)
+gemm_nt_kernel(GemmNT g) {
+  __shared__ __align__(16) float As[BK][BM + 4];  // [p][o]
+  __shared__ __align__(16) float Bs[BK][BN + 4];  // [p][k]
+  const int b = blockIdx.z;
+  const int o0 = blockIdx.y * BM, k0 = blockIdx.x * BN;
+  const int tid = threadIdx.x, tx = tid & 15, ty = tid >> 4;
+  const T *DY = (const T *)g.dy + (int64_t)b * g.O * g.P;
+  const T *X1 = (const T *)g.x1 + (int64_t)b * g.x1_bs;
+  const T *X2 = (const T *)g.x2 + (int64_t)b * g.x2_bs;
+  const bool p_vec = (g.P % 4 == 0);
+  float acc[4][4] = {};
+  const int r = tid >> 2, pq = (tid & 3) * 4;  // row within the tile, 4 consecutive pixels
+  for (int64_t p0 = 0; p0 < g.P; p0 += BK) {
+    {
+      float v[4] = {0.f, 0.f, 0.f, 0.f};
+      const int go = o0 + r;
+      if (go < g.O) {
+        const T *src = DY + (int64_t)go * g.P + p0 + pq;
+        if (p_vec && p0 + pq + 4 <= g.P) Ld4<T>::ld(src, v);
+        else
+          for (int i = 0; i < 4; ++i) if (p0 + pq + i < g.P) v[i] = to_f(src[i]);
+      }
+#pragma unroll
+      for (int i = 0; i < 4; ++i) As[pq + i][r] = v[i];
+    }
+    {
+      float v[4] = {0.f, 0.f, 0.f, 0.f};
+      const int gk = k0 + r;
+      if (gk < g.K) {
+        const T *src = ((gk < g.K1) ? (X1 + (int64_t)gk * g.P) : (X2 + (int64_t)(gk - g.K1) * g.P)) + p0 + pq;
+        if (p_vec && p0 + pq + 4 <= g.P) Ld4<T>::ld(src, v);
+        else
+          for (int i = 0; i < 4; ++i) if (p0 + pq + i < g.P) v[i] = to_f(src[i]);
+      }
+#pragma unroll
+      for (int i = 0; i < 4; ++i) Bs[pq + i][r] = v[i];
+    }
+    __syncthreads();
+#pragma unroll
+    for (int p = 0; p < BK; ++p) {
+      const float4 av = *reinterpret_cast<const float4 *>(&As[p][ty * 4]);
+      const float4 bv = *reinterpret_cast<const float4 *>(&Bs[p][tx * 4]);
+      const float a[4] = {av.x, av.y, av.z, av.w};
+      const float bb[4] = {bv.x, bv.y, bv.z, bv.w};
+#pragma unroll
+      for (int i = 0; i < 4; ++i)
+#pragma unroll
+        for (int j = 0; j < 4; ++j) acc[i][j] = fmaf(a[i], bb[j], acc[i][j]);
+    }
+    __syncthreads();
+  }
+  float *DW = g.dw + (int64_t)b * g.O * g.K;
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const int go = o0 + ty * 4 + i;
+    if (go >= g.O) continue;
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const int gk = k0 + tx * 4 + j;
+      if (gk < g.K) DW[(int64_t)go * g.K + gk] = acc[i][j];
+    }
+  }
+}
+
+template <typename T, typename TA>
+static int run_nn(const GemmNN &g, int B, bool a_kcontig, cudaStream_t st) {
+  if (g.M <= 4 && (size_t)g.M * g.K * sizeof(float) <= 48 * 1024) {
+    dim3 grid((unsigned)((g.N + 1023) / 1024), (unsigned)B);
+    small_o_kernel<T, TA, 4><<<grid, 256, (size_t)g.M * g.K * sizeof(float), st>>>(g);
+    return 0;
+  }
+  dim3 grid((unsigned)((g.N + BN - 1) / BN), (unsigned)((g.M + BM - 1) / BM), (unsigned)B);
+  if (a_kcontig) gemm_nn_kernel<T, TA, true><<<grid, 256, 0, st>>>(g);
+  else gemm_nn_kernel<T, TA, false><<<grid, 256, 0, st>>>(g);
+  return 0;
+}
+
+int modconv_fwd_simt(const void *wb, const void *x1, const void *x2, const float *bias, void *y,
+                     int B, int O, int C1, int C2, int B2, int64_t P, int act, float alpha,
+                     float scale, int dtype, int wdtype, cudaStream_t st) {
+  GemmNN g;
+  const int K = C1 + C2;
+  g.a = wb; g.a_bs = (int64_t)O * K; g.a_ms = K; g.a_ks = 1;
+  g.b1 = x1; g.b2 = x2; g.b1_bs = (int64_t)C1 * P; g.b2_bs = (B2 == 1) ? 0 : (int64_t)C2 * P;
+  g.K1 = C1; g.c = y; g.c_bs = (int64_t)O * P; g.bias = bias;
+  g.M = O; g.K = K; g.N = P; g.act = act; g.alpha = alpha; g.scale = scale;
+  if (dtype == DUSTY_F32) {
+    if (wdtype == DUSTY_F32) return run_nn<float, float>(g, B, true, st);
+    return run_nn<float, __nv_bfloat16>(g, B, true, st);
+  }
+  if (wdtype == DUSTY_F32) return run_nn<__nv_bfloat16, float>(g, B, true, st);
+  return run_nn<__nv_bfloat16, __nv_bfloat16>(g, B, true, st);
+}
+
+int modconv_bwd_dx_simt(const void *wb, const void *dy, void *dx1, int B, int O, int C1, int K,
+                        int64_t P, int dtype, int wdtype, cudaStream_t st) {
+  GemmNN g;
+  // A(m = k, kk = o) = wb[b, o, k]
+  g.a = wb; g.a_bs = (int64_t)O * K; g.a_ms = 1; g.a_ks = K;
+  g.b1 = dy; g.b2 = dy; g.b1_bs = (int64_t)O * P; g.b2_bs = 0; g.K1 = O;
+  g.c = dx1; g.c_bs = (int64_t)C1 * P; g.bias = nullptr;
+  g.M = C1; g.K = O; g.N = P; g.act = 1; g.alpha = 0.f; g.scale = 1.f;
+  dim3 grid((unsigned)((g.N + BN - 1) / BN), (unsigned)((g.M + BM - 1) / BM), (unsigned)B);
+  if (dtype == DUSTY_F32) {
+    if (wdtype == DUSTY_F32) gemm_nn_kernel<float, float, false><<<grid, 256, 0, st>>>(g);
+    else gemm_nn_kernel<float, __nv_bfloat16, false><<<grid, 256, 0, st>>>(g);
+  } else {
+    if (wdtype == DUSTY_F32) gemm_nn_kernel<__nv_bfloat16, float, false><<<grid, 256, 0, st>>>(g);
+    else gemm_nn_kernel<__nv_bfloat16, __nv_bfloat16, false><<<grid, 256, 0, st>>>(g);
+  }
+  return 0;
+}
+
+int modconv_bwd_dw_simt(const void *dy, const void *x1, const void *x2, float *dwb, int B, int O,
+                        int C1, int C2, int B2, int64_t P, int dtype, cudaStream_t st) {
+  GemmNT g;
+  g.dy = dy; g.x1 = x1; g.x2 = x2; g.x1_bs = (int64_t)C1 * P;
+  g.x2_bs = (B2 == 1) ? 0 : (int64_t)C2 * P; g.K1 = C1; g.dw = dwb;
+  g.O = O; g.K = C1 + C2; g.P = P;
+  dim3 grid((unsigned)((g.K + BN - 1) / BN), (unsigned)((g.O + BM - 1) / BM), (unsigned)B);
+  if (dtype == DUSTY_F32) gemm_nt_kernel<float><<<grid, 256, 0, st>>>(g);
+  else gemm_nt_kernel<__nv_bfloat16><<<grid, 256, 0, st>>>(g);
+  return 0;
+}
+
+}  // namespace dusty

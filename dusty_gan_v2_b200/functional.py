@@ -1,0 +1,510 @@
+"""Autograd-aware host wrappers around the C ABI (include/dusty_b200.h).
+
+PyTorch supplies device memory, the current stream and the autograd tape; every
+computation below is a kernel of libdusty_b200.so.  CPU tensors are rejected -- the CPU
+restatement of the reference lives in oracle/ and is test infrastructure only.
+
+Autograd conventions follow the reference: explicit Function pairs whose
+backward is itself a Function, so second order (the R1 penalty) works:
+  bias_act      <-> FusedLeakyReLUFunction / ...Backward   (fused_act.py:20-90)
+  fir2d / adj   <-> UpFirDn2d / UpFirDn2dBackward          (upfirdn2d.py:20-145)
+"""
+from __future__ import annotations
+
+import math
+from typing import Optional, Sequence, Tuple
+
+import torch
+from torch.autograd import Function
+from torch.autograd.function import once_differentiable
+
+from . import _cabi as K
+
+# --------------------------------------------------------------------------- precision
+_PRECISION = {"act": torch.float32, "modconv_impl": 0}
+
+
+def set_precision(name: str):
+    """'fp32': fp32 storage + exact-FMA SIMT contractions (parity mode).
+    'bf16': bf16 activations inside the blocks the reference runs under fp16 autocast
+    (dusty_v2.yaml num_fp16_layers: -1), fp32 master weights and accumulation."""
+    if name in ("fp32", "float32"):
+        _PRECISION["act"] = torch.float32
+    elif name in ("bf16", "bfloat16"):
+        _PRECISION["act"] = torch.bfloat16
+    else:
+        raise ValueError(f"unknown precision {name!r}")
+
+
+def act_dtype() -> torch.dtype:
+    return _PRECISION["act"]
+
+
+def set_modconv_impl(impl: int):
+    """0 auto, 1 SIMT, 2 tcgen05 (see dusty_modconv_fwd)."""
+    _PRECISION["modconv_impl"] = int(impl)
+
+
+def _contig(t: torch.Tensor) -> torch.Tensor:
+    return t if t.is_contiguous() else t.contiguous()
+
+
+# --------------------------------------------------------------------------- bias + act
+def _bias_act_raw(x, bias, ref, act, grad, alpha, scale):
+    K.require_cuda(x, bias, ref)
+    x = _contig(x)
+    y = torch.empty_like(x)
+    C = x.shape[1] if x.ndim >= 2 else 1
+    inner = 1
+    for s in x.shape[2:]:
+        inner *= s
+    if bias is not None:
+        if bias.numel() == 0:
+            bias = None
+        else:
+            bias = _contig(bias.to(x.dtype))
+            if bias.numel() != C:
+                raise RuntimeError(f"bias has {bias.numel()} elements, expected {C}")
+    if ref is not None and ref.numel() == 0:
+        ref = None
+    if ref is not None:
+        ref = _contig(ref)
+        if ref.shape != x.shape or ref.dtype != x.dtype:
+            raise RuntimeError("refer must match input shape and dtype")
+    K.call("dusty_bias_act", K.ptr(x), K.ptr(bias), K.ptr(ref), K.ptr(y), x.numel(), C, inner,
+           act, grad, alpha, scale, K.dtype_code(x), K.stream_of(x))
+    return y
+
+
+def fused_bias_act(input, bias, refer, act: int, grad: int, alpha: float, scale: float):
+    """Same contract as the reference's pybind `fused.fused_bias_act`
+    (fused_bias_act.cpp:18-32): empty `bias` / `refer` tensors mean "absent"."""
+    if not input.is_cuda:
+        raise RuntimeError("input must be a CUDA tensor")
+    if not input.is_contiguous():
+        raise RuntimeError("input must be contiguous")
+    return _bias_act_raw(input, bias, refer, act, grad, float(alpha), float(scale))
+
+
+class _BiasActBackward(Function):
+    @staticmethod
+    def forward(ctx, gy, out, has_bias, alpha, scale):
+        gy = _contig(gy)
+        gx = torch.empty_like(gy)
+        C = gy.shape[1]
+        inner = 1
+        for s in gy.shape[2:]:
+            inner *= s
+        db = torch.zeros(C, device=gy.device, dtype=torch.float32) if has_bias else None
+        K.call("dusty_bias_act_bwd", K.ptr(gy), K.ptr(out), K.ptr(gx), K.ptr(db), gy.shape[0], C,
+               inner, alpha, scale, K.dtype_code(gy), K.stream_of(gy))
+        ctx.save_for_backward(out)
+        ctx.alpha, ctx.scale = alpha, scale
+        return gx, db
+
+    @staticmethod
+    def backward(ctx, ggx, ggb):
+        (out,) = ctx.saved_tensors
+        b = None if ggb is None else ggb.to(ggx.dtype)
+        gg_out = _bias_act_raw(ggx, b, out, 3, 1, ctx.alpha, ctx.scale)
+        return gg_out, None, None, None, None
+
+
+class _BiasAct(Function):
+    @staticmethod
+    def forward(ctx, x, bias, alpha, scale):
+        out = _bias_act_raw(x, bias, None, 3, 0, alpha, scale)
+        ctx.save_for_backward(out)
+        ctx.has_bias = bias is not None
+        ctx.bias_dtype = bias.dtype if bias is not None else None
+        ctx.alpha, ctx.scale = alpha, scale
+        return out
+
+    @staticmethod
+    def backward(ctx, gy):
+        (out,) = ctx.saved_tensors
+        gx, db = _BiasActBackward.apply(gy, out, ctx.has_bias, ctx.alpha, ctx.scale)
+        if ctx.has_bias:
+            db = db.to(ctx.bias_dtype)
+        else:
+            db = None
+        return gx, db, None, None
+
+
+def bias_act(x, bias=None, negative_slope: float = 0.2, scale: float = 2 ** 0.5):
+    K.require_cuda(x, bias)
+    return _BiasAct.apply(_contig(x), bias, float(negative_slope), float(scale))
+
+
+# --------------------------------------------------------------------------- FIR family
+_TAPS_CACHE = {}
+
+
+def device_taps(taps2d: Sequence[Sequence[float]], device) -> torch.Tensor:
+    key = (tuple(tuple(float(v) for v in r) for r in taps2d), str(device))
+    t = _TAPS_CACHE.get(key)
+    if t is None:
+        t = torch.tensor(key[0], dtype=torch.float32, device=device)
+        _TAPS_CACHE[key] = t
+    return t
+
+
+class FirCfg:
+    """Geometry of one polyphase FIR (see dusty_fir2d in the header)."""
+    __slots__ = ("kh", "kw", "flip", "up_y", "up_x", "down_y", "down_x", "pad_y0", "pad_y1",
+                 "pad_x0", "pad_x1", "mode_y", "mode_x")
+
+    def __init__(self, kh, kw, flip=0, up=(1, 1), down=(1, 1), pad=(0, 0, 0, 0),
+                 mode=(K.PAD_ZERO, K.PAD_ZERO)):
+        self.kh, self.kw, self.flip = int(kh), int(kw), int(flip)
+        self.up_y, self.up_x = int(up[0]), int(up[1])
+        self.down_y, self.down_x = int(down[0]), int(down[1])
+        self.pad_y0, self.pad_y1, self.pad_x0, self.pad_x1 = (int(p) for p in pad)
+        self.mode_y, self.mode_x = int(mode[0]), int(mode[1])
+
+    def out_hw(self, h, w):
+        oh = (h * self.up_y + self.pad_y0 + self.pad_y1 - self.kh + self.down_y) // self.down_y
+        ow = (w * self.up_x + self.pad_x0 + self.pad_x1 - self.kw + self.down_x) // self.down_x
+        return oh, ow
+
+    def args(self):
+        return (self.up_y, self.up_x, self.down_y, self.down_x, self.pad_y0, self.pad_x0,
+                self.mode_y, self.mode_x)
+
+
+def _fir_raw(x, taps, cfg: FirCfg, adjoint: bool, in_hw=None):
+    K.require_cuda(x, taps)
+    x = _contig(x)
+    lead = x.shape[:-2]
+    n = 1
+    for s in lead:
+        n *= s
+    if not adjoint:
+        h, w = x.shape[-2:]
+        oh, ow = cfg.out_hw(h, w)
+        if oh < 0 or ow < 0:
+            raise RuntimeError("fir2d: negative output size")
+        y = torch.empty(*lead, oh, ow, device=x.device, dtype=x.dtype)
+        K.call("dusty_fir2d", K.ptr(x), K.ptr(y), K.ptr(taps), cfg.kh, cfg.kw, cfg.flip, n, h, w,
+               oh, ow, *cfg.args(), K.dtype_code(x), K.stream_of(x))
+        return y
+    h, w = in_hw
+    oh, ow = x.shape[-2:]
+    assert (oh, ow) == cfg.out_hw(h, w), "adjoint: gradient shape does not match geometry"
+    y = torch.empty(*lead, h, w, device=x.device, dtype=x.dtype)
+    K.call("dusty_fir2d_adj", K.ptr(x), K.ptr(y), K.ptr(taps), cfg.kh, cfg.kw, cfg.flip, n, h, w,
+           oh, ow, *cfg.args(), K.dtype_code(x), K.stream_of(x))
+    return y
+
+
+class _Fir(Function):
+    @staticmethod
+    def forward(ctx, x, taps, cfg):
+        ctx.cfg, ctx.in_hw = cfg, tuple(x.shape[-2:])
+        ctx.save_for_backward(taps)
+        return _fir_raw(x, taps, cfg, False)
+
+    @staticmethod
+    def backward(ctx, gy):
+        (taps,) = ctx.saved_tensors
+        return _FirAdj.apply(gy, taps, ctx.cfg, ctx.in_hw), None, None
+
+
+class _FirAdj(Function):
+    @staticmethod
+    def forward(ctx, gy, taps, cfg, in_hw):
+        ctx.cfg = cfg
+        ctx.save_for_backward(taps)
+        return _fir_raw(gy, taps, cfg, True, in_hw)
+
+    @staticmethod
+    def backward(ctx, ggx):
+        (taps,) = ctx.saved_tensors
+        return _Fir.apply(ggx, taps, ctx.cfg), None, None, None
+
+
+def fir2d(x: torch.Tensor, taps: torch.Tensor, cfg: FirCfg) -> torch.Tensor:
+    """x: [..., H, W]; taps: fp32 device tensor [kh, kw] (no gradient flows to the taps,
+    as in the reference: upfirdn2d.py:101,145)."""
+    if taps.dtype != torch.float32 or tuple(taps.shape) != (cfg.kh, cfg.kw):
+        raise RuntimeError("taps must be an fp32 [kh, kw] tensor")
+    return _Fir.apply(x, _contig(taps.detach()), cfg)
+
+
+# --------------------------------------------------------------------------- Fourier features
+def fourier_features(angle: torch.Tensor, freqs: torch.Tensor, phase: torch.Tensor,
+                     out_dtype: Optional[torch.dtype] = None) -> torch.Tensor:
+    """angle [Ba,2,H,W] fp32 -> [Ba, 2F, H, W]; no gradient (angles are data)."""
+    K.require_cuda(angle, freqs, phase)
+    angle = _contig(angle.detach().float())
+    f = _contig(freqs.detach().reshape(-1, 2).float())
+    ph = _contig(phase.detach().float())
+    ba, _, h, w = angle.shape
+    nf = f.shape[0]
+    out_dtype = out_dtype or torch.float32
+    out = torch.empty(ba, 2 * nf, h, w, device=angle.device, dtype=out_dtype)
+    K.call("dusty_fourier", K.ptr(angle), K.ptr(f), K.ptr(ph), K.ptr(out), ba, nf, h * w,
+           K.dtype_code(out), K.stream_of(angle))
+    return out
+
+
+def angle_down2(angle: torch.Tensor) -> torch.Tensor:
+    K.require_cuda(angle)
+    angle = _contig(angle.detach().float())
+    ba, c, h, w = angle.shape
+    assert c == 2
+    out = torch.empty(ba, 2, h // 2, w // 2, device=angle.device, dtype=torch.float32)
+    K.call("dusty_angle_down2", K.ptr(angle), K.ptr(out), ba, h, w, K.stream_of(angle))
+    return out
+
+
+# --------------------------------------------------------------------------- modulated 1x1 conv
+class _ModConvBmm(Function):
+    """y[b] = act(wb[b] @ cat(x1[b], x2[b or 0]) + bias) ; x2 (Fourier features) has no grad."""
+
+    @staticmethod
+    def forward(ctx, wb, x1, x2, bias, act, alpha, scale):
+        B, O, Kt = wb.shape
+        c1 = 0 if x1 is None else x1.shape[1]
+        c2 = 0 if x2 is None else x2.shape[1]
+        assert c1 + c2 == Kt, (c1, c2, Kt)
+        src = x1 if x1 is not None else x2
+        H, W = src.shape[-2:]
+        P = H * W
+        b2 = 1 if x2 is None else x2.shape[0]
+        y = torch.empty(B, O, H, W, device=src.device, dtype=src.dtype)
+        biasf = None if bias is None else _contig(bias.detach().float().reshape(-1))
+        K.call("dusty_modconv_fwd", K.ptr(wb), K.ptr(x1), K.ptr(x2), K.ptr(biasf), K.ptr(y), B, O,
+               c1, c2, b2, P, act, alpha, scale, K.dtype_code(src), K.dtype_code(wb),
+               _PRECISION["modconv_impl"], K.stream_of(src))
+        ctx.save_for_backward(wb, x1, x2, y if act == 3 else None)
+        ctx.cfg = (act, alpha, scale, bias is not None, None if bias is None else bias.shape,
+                   None if bias is None else bias.dtype)
+        return y
+
+    @staticmethod
+    @once_differentiable
+    def backward(ctx, gy):
+        wb, x1, x2, y = ctx.saved_tensors
+        act, alpha, scale, has_bias, bshape, bdtype = ctx.cfg
+        B, O, Kt = wb.shape
+        gy = _contig(gy)
+        H, W = gy.shape[-2:]
+        P = H * W
+        st = K.stream_of(gy)
+        dt = K.dtype_code(gy)
+        db = None
+        if act == 3:
+            gpre = torch.empty_like(gy)
+            dbf = torch.zeros(O, device=gy.device, dtype=torch.float32) if has_bias else None
+            K.call("dusty_bias_act_bwd", K.ptr(gy), K.ptr(y), K.ptr(gpre), K.ptr(dbf), B, O, P,
+                   alpha, scale, dt, st)
+            db = dbf
+        else:
+            gpre = gy if scale == 1.0 else gy * scale
+            if has_bias:
+                db = gpre.float().sum(dim=(0, 2, 3))
+        gx1 = None
+        c1 = 0 if x1 is None else x1.shape[1]
+        c2 = 0 if x2 is None else x2.shape[1]
+        b2 = 1 if x2 is None else x2.shape[0]
+        if x1 is not None and ctx.needs_input_grad[1]:
+            gx1 = torch.empty_like(x1)
+            K.call("dusty_modconv_bwd_dx", K.ptr(wb), K.ptr(gpre), K.ptr(gx1), B, O, c1, Kt, P, dt,
+                   K.dtype_code(wb), 0, st)
+        gwb = None
+        if ctx.needs_input_grad[0]:
+            gw32 = torch.empty(B, O, Kt, device=gy.device, dtype=torch.float32)
+            K.call("dusty_modconv_bwd_dw", K.ptr(gpre), K.ptr(x1), K.ptr(x2), K.ptr(gw32), B, O, c1,
+                   c2, b2, P, dt, 0, st)
+            gwb = gw32.to(wb.dtype)
+        if has_bias and ctx.needs_input_grad[3]:
+            db = db.reshape(bshape).to(bdtype)
+        else:
+            db = None
+        return gwb, gx1, None, db, None, None, None
+
+
+def modconv_bmm(wb, x1, x2=None, bias=None, act: int = 1, alpha: float = 0.2, scale: float = 1.0):
+    K.require_cuda(wb, x1, x2, bias)
+    wb = _contig(wb)
+    x1 = None if x1 is None else _contig(x1)
+    x2 = None if x2 is None else _contig(x2.detach())
+    return _ModConvBmm.apply(wb, x1, x2, bias, int(act), float(alpha), float(scale))
+
+
+def sumsq_total(x: torch.Tensor) -> torch.Tensor:
+    """sum(x^2) as a 0-dim fp32 device tensor (no grad): ModConv2d's EMA statistic."""
+    K.require_cuda(x)
+    x = _contig(x.detach())
+    out = torch.empty(1, device=x.device, dtype=torch.float32)
+    K.call("dusty_sumsq_rows", K.ptr(x), K.ptr(out), 1, x.numel(), 0, K.dtype_code(x),
+           K.stream_of(x))
+    return out[0]
+
+
+class _SumSqRows(Function):
+    @staticmethod
+    def forward(ctx, x):
+        x = _contig(x)
+        rows = x.shape[0]
+        out = torch.empty(rows, device=x.device, dtype=torch.float32)
+        K.call("dusty_sumsq_rows", K.ptr(x), K.ptr(out), rows, x.numel() // rows, 0,
+               K.dtype_code(x), K.stream_of(x))
+        ctx.save_for_backward(x)
+        return out
+
+    @staticmethod
+    def backward(ctx, g):
+        (x,) = ctx.saved_tensors
+        return x * (2.0 * g.reshape(-1, *([1] * (x.ndim - 1)))).to(x.dtype)
+
+
+def sumsq_rows(x: torch.Tensor) -> torch.Tensor:
+    """Per-sample sum of squares [B] (R1 penalty reduction, trainer.py:440)."""
+    K.require_cuda(x)
+    return _SumSqRows.apply(x)
+
+
+# --------------------------------------------------------------------------- raydrop
+class _Raydrop(Function):
+    @staticmethod
+    def forward(ctx, logit, image, u, rconst, temperature):
+        logit, image, u = _contig(logit.float()), _contig(image.float()), _contig(u.float())
+        mask = torch.empty_like(logit)
+        out = torch.empty_like(logit)
+        dsoft = torch.empty_like(logit)
+        K.call("dusty_gumbel_raydrop_fwd", K.ptr(logit), K.ptr(image), K.ptr(u), K.ptr(mask),
+               K.ptr(out), K.ptr(dsoft), None, logit.numel(), rconst, temperature,
+               K.stream_of(logit))
+        ctx.save_for_backward(image, mask, dsoft)
+        ctx.rconst = rconst
+        return mask, out
+
+    @staticmethod
+    @once_differentiable
+    def backward(ctx, g_mask, g_out):
+        image, mask, dsoft = ctx.saved_tensors
+        g_logit = torch.empty_like(image)
+        g_image = torch.empty_like(image)
+        g_out = None if g_out is None else _contig(g_out.float())
+        g_mask = None if g_mask is None else _contig(g_mask.float())
+        K.call("dusty_gumbel_raydrop_bwd", K.ptr(g_out), K.ptr(g_mask), K.ptr(image), K.ptr(mask),
+               K.ptr(dsoft), K.ptr(g_logit), K.ptr(g_image), image.numel(), ctx.rconst,
+               K.stream_of(image))
+        return g_logit, g_image, None, None, None
+
+
+def gumbel_raydrop(logit, image, u, rconst: float, temperature: float = 1.0):
+    """-> (mask with straight-through gradient, lerp(image, rconst, 1 - mask))."""
+    K.require_cuda(logit, image, u)
+    return _Raydrop.apply(logit, image, u, float(rconst), float(temperature))
+
+
+def raydrop_count(logit, image, u, rconst: float, temperature: float = 1.0):
+    """No-grad variant that also returns the integer number of kept rays."""
+    K.require_cuda(logit, image, u)
+    logit, image, u = _contig(logit.float()), _contig(image.float()), _contig(u.float())
+    mask, out, dsoft = torch.empty_like(logit), torch.empty_like(logit), torch.empty_like(logit)
+    count = torch.zeros(1, device=logit.device, dtype=torch.int32)
+    K.call("dusty_gumbel_raydrop_fwd", K.ptr(logit), K.ptr(image), K.ptr(u), K.ptr(mask),
+           K.ptr(out), K.ptr(dsoft), K.ptr(count), logit.numel(), float(rconst),
+           float(temperature), K.stream_of(logit))
+    return mask, out, count
+
+
+# --------------------------------------------------------------------------- projection
+def point_project(x: torch.Tensor, trig: torch.Tensor, min_depth: float, max_depth: float,
+                  tol: float = 1e-11, point_set: bool = False):
+    """x [B,1,H,W] inverse-depth-normalised -> (points, valid_count[int64 tensor]).
+    trig: [4, H*W] = cos el, sin el, cos az, sin az."""
+    K.require_cuda(x, trig)
+    x = _contig(x.detach().float())
+    B, _, H, W = x.shape
+    HW = H * W
+    out = torch.empty((B, HW, 3) if point_set else (B, 3, H, W), device=x.device,
+                      dtype=torch.float32)
+    count = torch.zeros(1, device=x.device, dtype=torch.int64)
+    K.call("dusty_point_project", K.ptr(x), K.ptr(trig), K.ptr(out), K.ptr(count), B, HW,
+           float(min_depth), float(max_depth), float(tol), 1 if point_set else 0, K.stream_of(x))
+    return out, count
+
+
+# --------------------------------------------------------------------------- minibatch stddev
+def _mbstd_composite_grad(gy, x, group, alpha):
+    """Analytic backward written with differentiable torch ops (used only when a second
+    derivative is being recorded, i.e. the R1 step)."""
+    B, C, H, W = x.shape
+    G = min(B, group)
+    M = B // G
+    xf = x.float().reshape(G, M, C, H, W)
+    mean = xf.mean(0, keepdim=True)
+    d = xf - mean
+    inv_sd = torch.rsqrt(d.pow(2).mean(0, keepdim=True) + alpha)
+    gstat = gy[:, C].float().reshape(G, M, H * W).sum(dim=(0, 2))      # [M]
+    coef = gstat.reshape(1, M, 1, 1, 1) / float(C * H * W * G)
+    gx = gy[:, :C].float().reshape(G, M, C, H, W) + coef * d * inv_sd
+    return gx.reshape(B, C, H, W).to(x.dtype)
+
+
+class _MbStd(Function):
+    @staticmethod
+    def forward(ctx, x, group, alpha):
+        x = _contig(x)
+        B, C, H, W = x.shape
+        G = min(B, group)
+        y = torch.empty(B, C + 1, H, W, device=x.device, dtype=x.dtype)
+        stat = torch.empty(B // G, device=x.device, dtype=torch.float32)
+        K.call("dusty_minibatch_std_fwd", K.ptr(x), K.ptr(y), K.ptr(stat), B, C, H * W, group,
+               alpha, K.dtype_code(x), K.stream_of(x))
+        ctx.save_for_backward(x)
+        ctx.group, ctx.alpha = group, alpha
+        return y
+
+    @staticmethod
+    def backward(ctx, gy):
+        (x,) = ctx.saved_tensors
+        if torch.is_grad_enabled():   # create_graph=True: stay differentiable
+            return _mbstd_composite_grad(gy, x, ctx.group, ctx.alpha), None, None
+        gy = _contig(gy)
+        B, C, H, W = x.shape
+        G = min(B, ctx.group)
+        gx = torch.empty_like(x)
+        dstat = torch.empty(B // G, device=x.device, dtype=torch.float32)
+        K.call("dusty_minibatch_std_bwd", K.ptr(gy), K.ptr(x), K.ptr(gx), K.ptr(dstat), B, C,
+               H * W, ctx.group, ctx.alpha, K.dtype_code(x), K.stream_of(x))
+        return gx, None, None
+
+
+def minibatch_stddev(x, group: int = 4, alpha: float = 1e-8):
+    K.require_cuda(x)
+    B = x.shape[0]
+    G = min(B, group)
+    if B % G != 0:
+        raise RuntimeError(f"batch {B} is not divisible by the group size {G}")
+    return _MbStd.apply(x, int(group), float(alpha))
+
+
+# --------------------------------------------------------------------------- circular un-shift
+class _CircShift(Function):
+    @staticmethod
+    def forward(ctx, v, shift01, scale, adjoint):
+        v = _contig(v.float())
+        B, C, H, W = v.shape
+        out = torch.empty_like(v)
+        K.call("dusty_circular_shift", K.ptr(v), K.ptr(shift01), K.ptr(out), B, C, H, W, scale,
+               adjoint, K.stream_of(v))
+        ctx.save_for_backward(shift01)
+        ctx.scale, ctx.adjoint = scale, adjoint
+        return out
+
+    @staticmethod
+    def backward(ctx, g):
+        (shift01,) = ctx.saved_tensors
+        return _CircShift.apply(g, shift01, ctx.scale, 1 - ctx.adjoint), None, None, None
+
+
+def circular_unshift(v, shift01, scale: float = 1.0):
+    """v [B,C,H,W] fp32, shift01 [B] fp32 in [0,1) (fraction of a full turn)."""
+    K.require_cuda(v, shift01)
+    return _CircShift.apply(v, _contig(shift01.detach().float()), float(scale), 0)

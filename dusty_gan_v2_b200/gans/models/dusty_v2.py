@@ -1,0 +1,309 @@
+"""Drop-in for gans/models/dusty_v2.py (reference 13-396): MappingNetwork, Head,
+SynthesisBlock, SynthesisNetwork, Generator, ResidualBlock, Discriminator with identical
+constructor arguments and state_dict keys (SURVEY.md section 8a footnote).
+
+What differs is the execution plan of a synthesis block:
+  reference:  resample -> FourierFeature -> torch.cat -> ~8 ATen kernels building
+              weight[B,O,I] -> grouped cuDNN conv -> fused_bias_act  (x2) -> two heads
+  here:       one FIR kernel (up2), one Fourier kernel (batch-shared when the angle grid
+              is), then per conv ONE contraction kernel reading [features | Fourier] as two
+              K ranges with bias+lrelu in its epilogue; the two 1-channel heads run as one
+              O=2 contraction.
+Precision: blocks flagged `use_fp16` by the reference run in the package's activation
+dtype (bf16 in production, fp32 in parity mode); head outputs and everything after them
+are fp32 like the reference (dusty_v2.py:174-178).
+"""
+import math
+
+import numpy as np
+import torch
+import torch.nn as nn
+from torch.nn.modules.utils import _pair
+
+from ... import functional as DF
+from . import base, dusty_v1, ops
+
+
+class MappingNetwork(nn.Sequential):
+    def __init__(self, in_ch, out_ch, depth=2):
+        self.in_ch, self.out_ch, self.depth = in_ch, out_ch, depth
+        stages, ch = [ops.PixelNorm()], in_ch
+        for _ in range(depth):
+            stages.append(nn.Sequential(
+                ops.EqualLR(nn.Linear(ch, out_ch), gain=math.sqrt(2), lr_mul=0.01),
+                nn.LeakyReLU(negative_slope=0.2)))
+            ch = out_ch
+        super().__init__(*stages)
+
+
+class _HeadOut(dict):
+    """name -> [B,1,H,W] views of one stacked [B,n,H,W] tensor (kept for the next level)."""
+    stacked = None
+
+
+class Head(nn.Module):
+    def __init__(self, in_ch, mod_ch, out_ch):
+        super().__init__()
+        self.in_ch, self.mod_ch, self.out_ch = in_ch, mod_ch, out_ch
+        self.heads = nn.ModuleDict()
+        for o in out_ch:
+            if o["ch"] == 0:
+                continue
+            if o["ch"] != 1:
+                raise NotImplementedError("heads with more than one channel")
+            self.heads[o["name"]] = ops.ModConv2d(out_ch=o["ch"], in_ch=in_ch, mod_ch=mod_ch,
+                                                  ksize=1, stride=1, padding=0, demod=False,
+                                                  ema=True)
+
+    def forward(self, x, style):
+        """All heads share x and the style: one contraction with O = number of heads."""
+        mods = list(self.heads.values())
+        if self.training:
+            total = DF.sumsq_total(x) / float(x.numel())
+            for m in mods:
+                with torch.no_grad():
+                    m.ema_var.lerp_(total.to(m.ema_var.dtype), 1 - m.ema_decay)
+        wb = torch.cat([m.effective_weights(style) for m in mods], dim=1)
+        bias = torch.cat([m.bias.reshape(-1) for m in mods])
+        y = DF.modconv_bmm(wb.to(x.dtype), x, None, bias, 1, 0.0, 1.0)
+        out = _HeadOut()
+        out.stacked = y
+        for i, name in enumerate(self.heads.keys()):
+            out[name] = y[:, i:i + 1]
+        return out
+
+
+class SynthesisBlock(nn.Module):
+    def __init__(self, in_ch, mid_ch, out_ch, mod_ch, resolution, up=2, resample_dir="hw",
+                 resample_window=[1, 3, 3, 1], use_noise=True, use_pe=True, pe_type="random",
+                 pe_ch=512, pe_scale_offset=(3, -1), ring=True):
+        super().__init__()
+        self.use_pe = use_pe
+        self.use_fp16 = False
+        self.is_first = in_ch == 0
+        self.num_conv = 0
+        if up > 1:
+            self.resample = ops.Resample(up=up, window=resample_window, ring=ring,
+                                         direction=resample_dir)
+            self.downsample = ops.Resample(down=up, window=resample_window, ring=ring,
+                                           direction=resample_dir)
+        else:
+            self.resample = nn.Identity()
+            self.downsample = None
+        if use_pe:
+            self.pe = ops.FourierFeature(resolution=resolution, basis_scale=pe_type,
+                                         num_freqs=pe_ch, L_offset=pe_scale_offset)
+            pe_ch = self.pe.out_ch
+        else:
+            pe_ch = 0
+        kw = dict(out_ch=mid_ch, mod_ch=mod_ch, ksize=1, stride=1, padding=0, bias=False, ema=True)
+        self.conv1 = ops.ModConv2d(in_ch=in_ch + pe_ch, **kw)
+        self.noise1 = ops.NoiseInjection() if use_noise else None
+        self.bias_act1 = ops.FusedLeakyReLU(mid_ch)
+        self.num_conv += 1
+        if not self.is_first:
+            self.conv2 = ops.ModConv2d(in_ch=mid_ch, **kw)
+            self.noise2 = ops.NoiseInjection() if use_noise else None
+            self.bias_act2 = ops.FusedLeakyReLU(mid_ch)
+            self.num_conv += 1
+        self.head = Head(mid_ch, mod_ch, out_ch)
+
+    def downsample_angle(self, angle):
+        if (isinstance(self.downsample, ops.Resample) and self.downsample.window == [1, 3, 3, 1]
+                and self.downsample.ring and self.downsample.direction == "hw"
+                and self.downsample.down_h == 2 and angle.shape[1] == 2):
+            return DF.angle_down2(angle)          # fused sin/cos -> FIR -> atan2
+        c = angle.shape[1]
+        per = self.downsample(torch.cat([angle.sin(), angle.cos()], dim=1))
+        return torch.atan2(per[:, :c], per[:, c:])
+
+    def _conv(self, conv, noise, act, h, style, pe=None):
+        if noise is None:
+            return conv(h, style, pe=pe, fused_act=act)
+        return act(noise(conv(h, style, pe=pe)))
+
+    def forward(self, h, skip, ws, angle):
+        ws = iter(ws)
+        dtype = DF.act_dtype() if (self.use_fp16 and angle.is_cuda) else torch.float32
+        if h is not None:
+            h = self.resample(h.to(dtype))
+        pe = self.pe(angle, out_dtype=dtype) if self.use_pe else None
+        h = self._conv(self.conv1, self.noise1, self.bias_act1, h, next(ws), pe)
+        if not self.is_first:
+            h = self._conv(self.conv2, self.noise2, self.bias_act2, h, next(ws))
+        o = self.head(h, next(ws))
+        y = o.stacked.float()
+        if skip is not None:
+            prev = skip.stacked if isinstance(skip, _HeadOut) else torch.cat(
+                [skip[k] for k in o.keys()], dim=1)
+            y = y + self.resample(prev)
+        out = _HeadOut()
+        out.stacked = y
+        for i, k in enumerate(o.keys()):
+            out[k] = y[:, i:i + 1]
+        return h, out
+
+    def extra_repr(self):
+        return f"use_fp16={self.use_fp16}"
+
+
+def _batch_shared(angle: torch.Tensor, cache: dict) -> bool:
+    """True when every sample carries the same angle grid (the trainer / demos always pass
+    CoordBridge.angle repeated B times).  The check costs one sync, so it is cached per
+    (storage, version, shape)."""
+    if angle.shape[0] == 1 or angle.stride(0) == 0:
+        return True
+    key = (angle.data_ptr(), angle._version, tuple(angle.shape))
+    hit = cache.get(key)
+    if hit is None:
+        hit = bool((angle[1:] == angle[:1]).all().item())
+        cache.clear()
+        cache[key] = hit
+    return hit
+
+
+class SynthesisNetwork(nn.Module):
+    def __init__(self, in_ch, out_ch, ch_base=64, ch_max=512, resolution=(64, 256), ring=True,
+                 layers=[2, 2, 2, 2], num_fp16_layers=-1, use_noise=True, pe_type="random",
+                 pe_scale_offset=(3, -1), aug_coords=True, aug_coords_blitting=False,
+                 output_scale=1 / 4.0):
+        super().__init__()
+        self.in_ch, self.out_ch = in_ch, out_ch
+        self.resolution_out = np.array(_pair(tuple(resolution) if not isinstance(resolution, int)
+                                             else resolution))
+        self.resolution_in = self.resolution_out // int(np.prod(layers))
+        n = len(layers)
+        width = [min(ch_base << (n - i), ch_max) for i in range(n + 1)]
+        self.layers = nn.ModuleList()
+        res = self.resolution_in.copy()
+        for i, scale in enumerate([1] + list(layers)):
+            res = res * scale
+            self.layers.append(SynthesisBlock(
+                in_ch=width[i - 1] if i else 0, mid_ch=width[i], out_ch=out_ch, mod_ch=in_ch,
+                resolution=res.copy(), up=scale, resample_window=[1, 3, 3, 1],
+                use_noise=use_noise, use_pe=(scale > 1 or i == 0), pe_type=pe_type,
+                pe_scale_offset=pe_scale_offset, ring=ring))
+        for i, blk in enumerate(reversed(self.layers)):
+            blk.use_fp16 = (num_fp16_layers == -1) or (i < num_fp16_layers)
+        self.num_styles = len(self.layers) * 2
+        self.aug_coords = aug_coords
+        self.aug_coords_blitting = aug_coords_blitting
+        self.output_scale = output_scale
+        acts = {}
+        for o in out_ch:
+            a = o["act"]
+            acts[o["name"]] = nn.Identity() if a is None else (eval(a)() if isinstance(a, str) else a())
+        self.output_acts = nn.ModuleDict(acts)
+        self._shared_cache = {}
+
+    @staticmethod
+    def translation_matrix(t):
+        t = t.div(2 * np.pi)
+        mat = torch.eye(3, device=t.device)[None].repeat_interleave(t.shape[0], dim=0)
+        mat[:, 0, 2] = t[:, 1]
+        mat[:, 1, 2] = t[:, 0]
+        return mat
+
+    def forward(self, ws, angle):
+        B, N, _ = ws.shape
+        if N != self.num_styles:
+            raise RuntimeError(f"{self.num_styles} != {N}")
+        aug = self.training and self.aug_coords
+        W = int(self.resolution_out[1])
+        shift01 = None
+        if aug:
+            # same RNG draw as the reference: one uniform per sample (dusty_v2.py:266-274)
+            shifts = torch.zeros((B, 2), device=ws.device)
+            shifts[:, 1].uniform_(0, 1)
+            if self.aug_coords_blitting:
+                shifts[:, 1].mul_(W).round_().div_(W)
+            shift01 = shifts[:, 1].contiguous()
+            angle = angle + shifts.mul(2 * np.pi)[..., None, None]
+        elif _batch_shared(angle, self._shared_cache):
+            angle = angle[:1]            # one pyramid + one Fourier block for the whole batch
+
+        pyramid = [angle]
+        for blk in self.layers[:0:-1]:
+            if blk.downsample is not None:
+                angle = blk.downsample_angle(angle)
+            pyramid.insert(0, angle)
+
+        h, skip, i = None, None, 0
+        for blk, ang in zip(self.layers, pyramid):
+            h, skip = blk(h, skip, (ws[:, i], ws[:, i + 1], ws[:, i + 2]), ang)
+            i += blk.num_conv
+
+        y = skip.stacked
+        if aug:      # cancel the azimuth shift in image space, output_scale folded in
+            y = DF.circular_unshift(y, shift01, self.output_scale)
+        else:
+            y = y * self.output_scale
+        out = {}
+        for j, k in enumerate(skip.keys()):
+            v = y[:, j:j + 1]
+            out[k] = self.output_acts[k](v) if k in self.output_acts else v
+        return out
+
+
+class Generator(base.Generator):
+    def __init__(self, mapping_kwargs, synthesis_kwargs, measurement_kwargs):
+        super().__init__(mapping_network=MappingNetwork(**mapping_kwargs),
+                         synthesis_network=SynthesisNetwork(**synthesis_kwargs),
+                         measurement_model=dusty_v1.RayDropModel(**measurement_kwargs))
+
+    def forward_synthesis(self, w, angle=None):
+        angle = self.angle if angle is None else angle
+        return self.synthesis_network(w, angle)
+
+
+class ResidualBlock(nn.Module):
+    def __init__(self, in_ch: int, out_ch: int):
+        super().__init__()
+        kw = dict(bias=False, ring=True, equal_lr=True)
+        self.conv1 = ops.Conv2d(in_ch, in_ch, 3, 1, 1, **kw)
+        self.bias_act1 = ops.FusedLeakyReLU(in_ch)
+        self.resample = ops.Resample(window=[1, 3, 3, 1], ring=True)
+        self.conv2 = ops.Conv2d(in_ch, out_ch, 3, 2, 1, **kw)
+        self.bias_act2 = ops.FusedLeakyReLU(out_ch)
+        self.skip = ops.Conv2d(in_ch, out_ch, 1, 2, 0, **kw)
+
+    def residual(self, x):
+        h = self.bias_act1(self.conv1(x))
+        return self.bias_act2(self.conv2(self.resample(h)))
+
+    def forward(self, x):
+        return (self.residual(x) + self.skip(self.resample(x))) * (1.0 / math.sqrt(2))
+
+
+class Discriminator(nn.Module):
+    def __init__(self, in_ch: int, ch_base: int = 32, ch_max: int = 512, mbdis_group: int = 4,
+                 mbdis_feat: int = 1, resolution=(64, 512), ring=True, num_fp16_layers=-1,
+                 pre_blur=True):
+        super().__init__()
+        res_in = _pair(256 if resolution is None else tuple(resolution))
+        n_down = int(np.log2(min(res_in) / 4))
+        res_out = tuple(r >> n_down for r in res_in)
+        ch = lambda i: min(ch_base << i, ch_max)
+        kw = dict(bias=False, ring=ring, equal_lr=True)
+        self.num_fp16_layers = num_fp16_layers
+        in_ch = in_ch * 2 if pre_blur else in_ch
+        stack = [ops.BlurVH(ring=ring)] if pre_blur else []
+        stack += [ops.Conv2d(in_ch, ch(0), 1, 1, 0, **kw), ops.FusedLeakyReLU(ch(0))]
+        stack += [ResidualBlock(ch(i), ch(i + 1)) for i in range(n_down)]
+        self.layers = nn.Sequential(*stack)
+        self.epilogue = nn.Sequential(
+            ops.MinibatchStdDev(group=mbdis_group, features=mbdis_feat),
+            ops.Conv2d(ch(4) + mbdis_feat, ch(4), 3, 1, 1, **kw),
+            ops.FusedLeakyReLU(ch(4)),
+            nn.Flatten(),
+            ops.EqualLR(nn.Linear(ch(4) * int(np.prod(res_out)), ch(4), bias=False)),
+            ops.FusedLeakyReLU(ch(4)),
+            ops.EqualLR(nn.Linear(ch(4), 1)),
+        )
+
+    def forward(self, h):
+        low = DF.act_dtype()
+        for i, layer in enumerate(self.layers):
+            use_low = ((self.num_fp16_layers > i) or (self.num_fp16_layers == -1)) and h.is_cuda
+            h = layer(h.to(low if use_low else torch.float32))
+        return self.epilogue(h.to(torch.float32))

@@ -1,0 +1,196 @@
+"""Drop-in for gans/models/ops/common.py: Pad, filter2d, Resample, BlurVH, EqualLR, Conv2d,
+PixelNorm, MinibatchStdDev -- same constructor arguments, attribute and state_dict names.
+
+All resampling / padding goes through one polyphase FIR kernel (dusty_fir2d) with the
+boundary extension folded into index math: no padded or zero-inserted tensor exists.
+The dense convolutions / linears themselves are library calls for now (cuDNN / cuBLAS via
+torch), with the EqualLR scale folded into the (small) weight instead of the activation.
+"""
+import math
+
+import numpy as np
+import torch
+import torch.nn as nn
+import torch.nn.functional as F
+from torch.nn.modules.utils import _pair, _quadruple
+
+from .... import _cabi as K
+from .... import functional as DF
+
+
+def _mode(name):
+    return {"replicate": K.PAD_REPLICATE, "reflect": K.PAD_REFLECT, "circular": K.PAD_CIRCULAR,
+            "zeros": K.PAD_ZERO, "constant": K.PAD_ZERO}[name]
+
+
+class Pad(nn.Module):
+    """reference common.py:10-24 -- W: circular when ring else `mode`; H: `mode`."""
+
+    def __init__(self, padding, ring=False, mode="replicate"):
+        super().__init__()
+        self.padding = _quadruple(padding)
+        self.horizontal = "circular" if ring else mode
+        self.vertical = mode
+
+    def forward(self, h):
+        left, right, top, bottom = self.padding
+        cfg = DF.FirCfg(1, 1, pad=(top, bottom, left, right),
+                        mode=(_mode(self.vertical), _mode(self.horizontal)))
+        return DF.fir2d(h, DF.device_taps([[1.0]], h.device), cfg)
+
+    def extra_repr(self):
+        return f"padding={self.padding}, horizontal={self.horizontal}, vertical={self.vertical}"
+
+
+def filter2d(x, kernel, gain=1):
+    """reference common.py:27-42: same-size separable blur, circular W / replicate H."""
+    assert kernel.ndim == 1
+    k = (kernel / kernel.sum()) * (gain ** 0.5)
+    n = len(k)
+    taps = torch.outer(k, k).to(device=x.device, dtype=torch.float32).contiguous()
+    cfg = DF.FirCfg(n, n, pad=(n // 2, (n - 1) // 2, n // 2, (n - 1) // 2),
+                    mode=(K.PAD_REPLICATE, K.PAD_CIRCULAR))
+    return DF.fir2d(x, taps, cfg)
+
+
+class Resample(nn.Module):
+    """reference common.py:45-138.  One launch per call: the H and W passes are applied as a
+    single separable 2-D tap set."""
+
+    def __init__(self, up=1, down=1, window=[1, 3, 3, 1], ring=True, normalize=True,
+                 direction="hw"):
+        super().__init__()
+        assert direction in ("h", "w", "hw")
+        self.up = np.asarray(_pair(up))
+        self.down = np.asarray(_pair(down))
+        self.window = list(window)
+        self.n_taps = len(window)
+        self.ring = ring
+        self.normalize = normalize
+        self.direction = direction
+        use_h, use_w = "h" in direction, "w" in direction
+        self.k_h = self.n_taps if use_h else 1
+        self.k_w = self.n_taps if use_w else 1
+        self.up_h, self.down_h = (int(self.up[0]), int(self.down[0])) if use_h else (1, 1)
+        self.up_w, self.down_w = (int(self.up[1]), int(self.down[1])) if use_w else (1, 1)
+
+        kernel = torch.tensor(self.window, dtype=torch.float32)
+        if normalize:
+            kernel = kernel / kernel.sum()
+        kernel = kernel * (self.up_h * self.up_w) ** 0.5
+        self.register_buffer("kernel", kernel)
+
+        def pads(k, u, d):
+            if u > 1:
+                return (k - u + 1) // 2 + u - 1, (k - u) // 2
+            return (k - d + 1) // 2, (k - d) // 2
+
+        self.ph0, self.ph1 = pads(self.k_h, self.up_h, self.down_h)
+        self.pw0, self.pw1 = pads(self.k_w, self.up_w, self.down_w)
+        self.margin = max(self.ph0, self.ph1, self.pw0, self.pw1)
+        self._cfg = DF.FirCfg(self.k_h, self.k_w, up=(self.up_h, self.up_w),
+                              down=(self.down_h, self.down_w),
+                              pad=(self.ph0, self.ph1, self.pw0, self.pw1),
+                              mode=(K.PAD_REPLICATE, K.PAD_CIRCULAR if ring else K.PAD_REPLICATE))
+        self._taps2d = None
+
+    def _taps(self, device):
+        t = self._taps2d
+        if t is None or t.device != device:
+            k = self.kernel.detach().float().to(device)
+            one = torch.ones(1, device=device)
+            t = torch.outer(k if self.k_h > 1 else one, k if self.k_w > 1 else one).contiguous()
+            self._taps2d = t
+        return t
+
+    def _apply(self, fn, *a, **kw):          # buffers may move / change: drop the cache
+        self._taps2d = None
+        return super()._apply(fn, *a, **kw)
+
+    def forward(self, h):
+        return DF.fir2d(h, self._taps(h.device), self._cfg)
+
+    def extra_repr(self):
+        return f'filter_type={self.window}, up={self.up}, down={self.down}, direction="{self.direction}"'
+
+
+class BlurVH(nn.Module):
+    """reference common.py:141-155."""
+
+    def __init__(self, window=[1, 2, 1], ring=True):
+        super().__init__()
+        self.blur_v = Resample(window=window, ring=ring, direction="h")
+        self.blur_h = Resample(window=window, ring=ring, direction="w")
+
+    def forward(self, x):
+        return torch.cat([self.blur_v(x), self.blur_h(x)], dim=1)
+
+
+class EqualLR(nn.Module):
+    """reference common.py:158-184.  y = module(x / sqrt(fan_in)) * gain * lr_mul, computed
+    with the scale folded into the weight (a [O, fan_in] tensor) rather than applied to the
+    activation tensor."""
+
+    def __init__(self, module, gain: float = 1.0, lr_mul=1.0):
+        super().__init__()
+        self.module = module
+        self.gain = gain
+        self.lr_mul = lr_mul
+        self.gain_ = gain * lr_mul
+        self.scale = 1.0 / math.sqrt(self.module.weight[0].numel())
+        nn.init.normal_(self.module.weight, 0.0, 1.0 / lr_mul)
+        if getattr(self.module, "bias", None) is not None:
+            nn.init.constant_(self.module.bias, 0.0)
+
+    def forward(self, x):
+        m = self.module
+        w = (m.weight * (self.scale * self.gain_)).to(x.dtype)
+        b = None if m.bias is None else (m.bias * self.gain_).to(x.dtype)
+        if isinstance(m, nn.Linear):
+            return F.linear(x, w, b)
+        if isinstance(m, nn.Conv2d):
+            return F.conv2d(x, w, b, m.stride, m.padding, m.dilation, m.groups)
+        if isinstance(m, nn.ConvTranspose2d):
+            return F.conv_transpose2d(x, w, b, m.stride, m.padding, m.output_padding, m.groups,
+                                      m.dilation)
+        return m(x * self.scale) * self.gain_
+
+    def extra_repr(self):
+        return f"gain={self.gain}, lr_mul={self.lr_mul}"
+
+
+class Conv2d(nn.Sequential):
+    """reference common.py:187-210: custom padding + Conv2d + EqualLR."""
+
+    def __init__(self, in_ch, out_ch, kernel_size, stride, padding, bias=True, ring=False,
+                 equal_lr=False, gain=1.0, lr_mul=1.0):
+        layers = []
+        if padding != 0:
+            layers.append(Pad(padding=padding, ring=ring))
+        conv = nn.Conv2d(in_ch, out_ch, kernel_size, stride, 0, bias=bias)
+        layers.append(EqualLR(conv, gain, lr_mul) if equal_lr else conv)
+        super().__init__(*layers)
+
+
+class PixelNorm(nn.Module):
+    """reference common.py:213-223 (on [B, 512] latents: negligible work, plain torch)."""
+
+    def forward(self, x, alpha: float = 1e-8):
+        return x / x.pow(2.0).mean(dim=1, keepdim=True).add(alpha).sqrt()
+
+
+class MinibatchStdDev(nn.Module):
+    """reference common.py:226-253; features == 1 only (all shipped configs)."""
+
+    def __init__(self, group=4, features=1):
+        super().__init__()
+        if features != 1:
+            raise NotImplementedError("MinibatchStdDev: only features == 1 is implemented")
+        self.group = group
+        self.features = features
+
+    def forward(self, x, alpha: float = 1e-8):
+        return DF.minibatch_stddev(x, self.group, alpha)
+
+    def extra_repr(self):
+        return f"group={self.group}, features={self.features}"

@@ -1,0 +1,119 @@
+"""Drop-in for gans/models/ops/style.py: ModConv2d (1x1) and NoiseInjection.
+
+ModConv2d.forward(x, style) keeps the reference contract (style.py:68-126) but never
+builds weight[B,O,I,1,1] x activations as a grouped conv: the modulation / demodulation /
+EMA normaliser are folded into small per-sample matrices wb[B,O,I] (fp32 math), and the
+heavy part is one batched contraction kernel (dusty_modconv_fwd) that
+  * reads its K axis from two tensors (features and Fourier features) so torch.cat of the
+    512 positional channels never happens,
+  * lets the Fourier operand be shared by the whole batch,
+  * applies bias + leaky-ReLU in its epilogue (FusedLeakyReLU fused).
+"""
+import math
+
+import numpy as np
+import torch
+import torch.nn as nn
+from torch.nn.modules.utils import _pair
+
+from .... import functional as DF
+from .common import EqualLR
+
+
+class ModConv2d(nn.Module):
+    def __init__(self, in_ch: int, out_ch: int, mod_ch: int, ksize: int = 3, stride: int = 1,
+                 padding: int = 1, demod: bool = True, bias: bool = True, gain: float = 1.0,
+                 transposed: bool = False, factorization_rank=None, ema=False,
+                 ema_decay=0.9989):
+        super().__init__()
+        self.in_ch, self.out_ch, self.mod_ch = in_ch, out_ch, mod_ch
+        self.ksize, self.stride, self.padding = _pair(ksize), _pair(stride), _pair(padding)
+        if self.ksize != (1, 1) or self.stride != (1, 1) or self.padding != (0, 0):
+            raise NotImplementedError(
+                "dusty_b200 ModConv2d implements the 1x1 / stride 1 / padding 0 case, the only one "
+                "dusty_v2 instantiates (dusty_v2.py:42-51,112-120)")
+        if transposed or factorization_rank is not None:
+            raise NotImplementedError("transposed / factorised ModConv2d are not on the hot path")
+        self.weight = nn.Parameter(torch.randn((1, out_ch, in_ch, 1, 1)))
+        self.transposed = transposed
+        self.bias = nn.Parameter(torch.zeros((1, out_ch, 1, 1))) if bias else None
+        self.gain = gain
+        self.scale = 1.0 / np.sqrt(in_ch)
+        self.factorization_rank = None
+        self.mod = EqualLR(nn.Linear(mod_ch, in_ch), gain=1.0)
+        self.demod = demod
+        self.ema = ema
+        self.ema_decay = ema_decay
+        self.register_buffer("ema_var", torch.tensor(1.0))
+
+    # -- small fp32 tensors: [B, O, I] at most 64 MiB for the widest layer, usually < 1 MiB
+    def effective_weights(self, style):
+        s = self.mod(style.float())
+        w = self.weight.float().reshape(self.out_ch, self.in_ch) * self.scale
+        if self.demod:
+            w = w / w.abs().amax()
+            s = s / s.abs().amax(dim=1, keepdim=True)
+        wb = w.unsqueeze(0) * (s + 1.0).unsqueeze(1)
+        if self.demod:
+            wb = wb * torch.rsqrt(wb.square().sum(dim=2, keepdim=True) + 1e-8)
+        if self.ema:
+            wb = wb / (torch.sqrt(self.ema_var) + 1e-8)
+        return wb
+
+    @torch.no_grad()
+    def update_ema(self, x, pe=None):
+        """ema_var <- lerp(ema_var, mean(x^2), 1 - decay) over the *whole* input, Fourier
+        channels included (style.py:99-102)."""
+        total = DF.sumsq_total(x) if x is not None else 0.0
+        numel = x.numel() if x is not None else 0
+        if pe is not None:
+            B = x.shape[0] if x is not None else pe.shape[0]
+            rep = B // pe.shape[0]
+            total = total + DF.sumsq_total(pe) * float(rep)
+            numel += pe.numel() * rep
+        self.ema_var.lerp_((total / float(numel)).to(self.ema_var.dtype), 1 - self.ema_decay)
+
+    def forward(self, x, style, pe=None, fused_act=None):
+        """x: [B, C1, H, W] (or None when the input is `pe` alone); pe: optional Fourier
+        block [B or 1, C2, H, W] appended on the channel axis; fused_act: a FusedLeakyReLU
+        module to apply in the epilogue."""
+        c1 = 0 if x is None else x.shape[1]
+        c2 = 0 if pe is None else pe.shape[1]
+        if c1 + c2 != self.in_ch:
+            raise RuntimeError(f"expected {self.in_ch} input channels, got {c1}+{c2}")
+        if self.ema and self.training:
+            self.update_ema(x, pe)
+        wb = self.effective_weights(style)
+        src = x if x is not None else pe
+        bias = self.bias
+        act, alpha, scale = 1, 0.0, float(self.gain)
+        if fused_act is not None:
+            assert bias is None and self.gain == 1.0
+            bias, act = fused_act.bias, 3
+            alpha, scale = float(fused_act.negative_slope), float(fused_act.scale)
+        elif bias is not None and self.gain != 1.0:
+            bias = bias * self.gain          # (h + b) * gain == h*gain + b*gain
+        return DF.modconv_bmm(wb.to(src.dtype), x, pe, bias, act, alpha, scale)
+
+    def extra_repr(self):
+        return (f"in_ch={self.in_ch}, out_ch={self.out_ch}, mod_ch={self.mod_ch}, "
+                f"ksize={self.ksize}, demod={self.demod}, gain={self.gain}")
+
+
+class NoiseInjection(nn.Module):
+    """reference style.py:136-160 (unused: use_noise false in every shipped config)."""
+
+    def __init__(self, ch: int = 1):
+        super().__init__()
+        self.ch = ch
+        self.weight = nn.Parameter(torch.zeros(1, self.ch, 1, 1))
+        self.fixed_noise = None
+
+    def forward(self, x):
+        B, _, H, W = x.shape
+        noise = (torch.randn((B, 1, H, W), device=x.device, dtype=x.dtype)
+                 if self.fixed_noise is None else self.fixed_noise.expand(B, -1, -1, -1))
+        return x + self.weight.to(x.dtype) * noise
+
+    def extra_repr(self):
+        return f"ch={self.ch}"

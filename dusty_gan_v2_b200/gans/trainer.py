@@ -1,0 +1,228 @@
+"""Host-side training step: mirror of gans/trainer.py `Trainer.step` (reference 247-482)
+with the same phase order, loss definitions, lazy regularisation and EMA schedule --
+
+    G step  : z -> G -> warmup -> ADA -> D -> softplus(-y) -> backward -> Adam(G)
+    D step  : G (no grad), real/fake -> warmup -> ADA -> D -> nsgan -> backward -> Adam(D)
+    R1      : every lazy.gp iterations, (gp*lazy/2) * mean ||grad_x D(ADA(warmup(x)))||^2
+    exit    : EMA of G, ADA p update every lazy.ada iterations, scalar reduction
+
+-- but without the host syncs of the reference: per-step scalars stay on the device in one
+packed tensor (one all_reduce instead of 6-9, no .item()), ADA transforms are sampled on
+the host, and the dataset (KITTI, out of scope) is replaced by any iterator of
+{"depth", "mask"} batches.  Multi-GPU: torch DDP (NCCL) on G and D gradient buckets only,
+exactly the collectives of the reference.
+"""
+import copy
+from collections import OrderedDict
+
+import numpy as np
+import torch
+import torch.distributed as dist
+
+from .. import functional as DF
+from .augment.adaptive_augment import AdaptiveAugment
+from .coords import CoordBridge
+from .models.builder import build_discriminator, build_generator
+from .models.loss import GANLoss
+from .models.ops.common import filter2d
+
+
+def set_requires_grad(net, requires_grad: bool = True):
+    for p in net.parameters():
+        p.requires_grad = requires_grad
+
+
+def sigmoid_to_tanh(x):
+    return x * 2.0 - 1.0
+
+
+def tanh_to_sigmoid(x):
+    return (x + 1.0) / 2.0
+
+
+@torch.no_grad()
+def ema_inplace(ema_model, new_model, decay):
+    """reference trainer.py:30-41, as two multi-tensor launches instead of ~240 tiny ones."""
+    ema_p = [p.data for p in ema_model.parameters()]
+    new_p = [p.data for p in new_model.parameters()]
+    torch._foreach_mul_(ema_p, decay)
+    torch._foreach_add_(ema_p, new_p, alpha=1 - decay)
+    for eb, nb in zip(ema_model.buffers(), new_model.buffers()):
+        eb.copy_(nb)
+
+
+class Trainer:
+    def __init__(self, cfg, batch_iter, device=None, rank=0, world_size=1,
+                 angle_file="data/coords/kitti_raw.npy", precision=None):
+        self.cfg = cfg
+        self.rank, self.world_size = rank, world_size
+        self.device = torch.device(device if device is not None else f"cuda:{rank}")
+        if precision is not None:
+            DF.set_precision(precision)
+        tr = cfg.training
+        self.resolution = cfg.model.generator.synthesis_kwargs.resolution
+        self.B = tr.batch_size // world_size
+        self.batch_iter = batch_iter
+
+        self.G = build_generator(cfg.model.generator).to(self.device)
+        self.G_ema = copy.deepcopy(self.G).eval()
+        self.D = build_discriminator(cfg.model.discriminator).to(self.device)
+        self.A = AdaptiveAugment(p_init=tr.augment.p_init, p_target=tr.augment.p_target,
+                                 kimg=tr.augment.kimg, **tr.augment.policy).to(self.device)
+        self.coord = CoordBridge(num_ring=self.resolution[0], num_points=self.resolution[1],
+                                 min_depth=cfg.dataset.min_depth, max_depth=cfg.dataset.max_depth,
+                                 angle_file=angle_file).eval().to(self.device)
+        self.G_module, self.D_module = self.G, self.D
+        if world_size > 1:
+            from torch.nn.parallel import DistributedDataParallel as DDP
+            kw = dict(device_ids=[self.device.index])
+            self.G = DDP(self.G, broadcast_buffers=True, **kw)
+            self.D = DDP(self.D, broadcast_buffers=False, **kw)
+        for m in (self.G, self.G_ema, self.D, self.A, self.coord):
+            m.requires_grad_(False)
+
+        self.auxin = {}
+        if "dusty_v2" in cfg.model.generator.arch:
+            # a stride-0 view: the synthesis network sees at once that the grid is batch-shared
+            self.auxin["angle"] = self.coord.angle.expand(self.B, -1, -1, -1)
+
+        self.adversarial_loss = GANLoss(tr.gan_objective).to(self.device)
+        self.gp_weight, self.gp_every = 0.0, 0
+        lazy_D = 1.0
+        if tr.loss.get("gp", 0) > 0:
+            self.gp_every = tr.lazy.gp
+            self.gp_weight = tr.loss.gp * tr.lazy.gp          # trainer.py:146
+            lazy_D = tr.lazy.gp / (tr.lazy.gp + 1.0)
+        if tr.loss.get("pl", 0) > 0:
+            raise NotImplementedError("path-length regularisation is dead code in the reference "
+                                      "(loss.pl = 0 in every config; the branch is broken)")
+        lr_g, lr_d = tr.lr.generator, tr.lr.discriminator
+        self.optim_G = torch.optim.Adam(self.G.parameters(), lr=lr_g.alpha,
+                                        betas=(lr_g.beta1, lr_g.beta2), fused=True)
+        self.optim_D = torch.optim.Adam(self.D.parameters(), lr=lr_d.alpha * lazy_D,
+                                        betas=(lr_d.beta1 ** lazy_D, lr_d.beta2 ** lazy_D),
+                                        fused=True)
+        self.z_dim = cfg.model.generator.mapping_kwargs.in_ch
+        self.warmup_fade_imgs = tr.warmup.fade_kimg * 1e3
+        self.blur_sigma = 0.0
+        self.dropout_ratio = 0.0
+        self.scalar_names = []
+
+    # ------------------------------------------------------------------ inputs
+    def sample_z(self, batch_size):
+        return torch.randn(batch_size, self.z_dim, device=self.device)
+
+    def fetch_reals(self, raw_batch):
+        """trainer.py:211-217: depth -> inverse depth in [-1, 1], dropped rays -> raydrop_const."""
+        depth = raw_batch["depth"].to(self.device, non_blocking=True)
+        mask = raw_batch["mask"].to(self.device, non_blocking=True)
+        x = sigmoid_to_tanh(self.coord.convert(depth, "depth", "inv_depth_norm"))
+        x = mask * x + (1 - mask) * self.cfg.dataset.raydrop_const
+        return {"image": x, "raydrop_mask": mask}
+
+    def set_warmup_params(self, iteration):
+        imgs = int(iteration * self.cfg.training.batch_size)
+        w = self.cfg.training.warmup
+        fade = max(1 - imgs / self.warmup_fade_imgs, 0) if self.warmup_fade_imgs > 0 else 0
+        self.blur_sigma = fade * w.blur_init_sigma
+        self.dropout_ratio = fade * w.dropout_init_ratio
+
+    def warmup(self, x):
+        """trainer.py:234-245: optional gaussian blur + bernoulli ray dropout, fading out."""
+        blur_size = np.floor(self.blur_sigma * 3)
+        if blur_size > 0:
+            k = torch.arange(-blur_size, blur_size + 1, device=x.device)
+            x = filter2d(x, k.div(self.blur_sigma).square().neg().exp2())
+        if self.dropout_ratio > 0:
+            keep = torch.bernoulli(torch.full_like(x, 1 - self.dropout_ratio))
+            x = keep * x + (1 - keep) * self.cfg.dataset.raydrop_const
+        return x
+
+    # ------------------------------------------------------------------ one iteration
+    def step(self, iteration):
+        tr = self.cfg.training
+        self.G.train()
+        self.set_warmup_params(iteration)
+        B = self.B
+        scalars = OrderedDict()
+        x_real = self.fetch_reals(next(self.batch_iter))["image"]
+
+        # ---- G step (trainer.py:262-301)
+        set_requires_grad(self.G, True)
+        self.optim_G.zero_grad(set_to_none=True)
+        x_fake = self.G(self.sample_z(B), **self.auxin)["image"]
+        y_fake = self.D(self.A(self.warmup(x_fake)))
+        loss_gan = self.adversarial_loss(None, y_fake, "G")
+        (tr.loss.gan * loss_gan).backward()
+        self.optim_G.step()
+        scalars["loss/G/adversarial"] = loss_gan.detach()
+        set_requires_grad(self.G, False)
+
+        # ---- D step (trainer.py:373-412)
+        set_requires_grad(self.D, True)
+        self.optim_D.zero_grad(set_to_none=True)
+        x_fake = self.G(self.sample_z(B), **self.auxin)["image"]
+        x_real_aug = self.A(self.warmup(x_real)).detach()
+        x_fake_aug = self.A(self.warmup(x_fake)).detach()
+        y_real, y_fake = self.D(x_real_aug), self.D(x_fake_aug)
+        self.A.cumulate(y_real)
+        loss_gan = self.adversarial_loss(y_real, y_fake, "D")
+        (tr.loss.gan * loss_gan).backward()
+        self.optim_D.step()
+        scalars["loss/D/output/real"] = y_real.mean().detach()
+        scalars["loss/D/output/fake"] = y_fake.mean().detach()
+        scalars["loss/D/adversarial"] = loss_gan.detach()
+
+        # ---- lazy R1 (trainer.py:419-451)
+        if self.gp_weight > 0 and iteration % self.gp_every == 0:
+            self.optim_D.zero_grad(set_to_none=True)
+            x_gp = x_real.detach().requires_grad_()
+            y_real = self.D(self.A(self.warmup(x_gp)))
+            (grads,) = torch.autograd.grad(outputs=[y_real.sum()], inputs=[x_gp], create_graph=True)
+            r1 = DF.sumsq_rows(grads).mean()
+            loss = (self.gp_weight / 2) * r1 + 0.0 * y_real.squeeze()[0]
+            loss.backward()
+            self.optim_D.step()
+            scalars["loss/D/gradient_penalty"] = r1.detach()
+        set_requires_grad(self.D, False)
+
+        # ---- exit (trainer.py:459-476)
+        ema_imgs = int(tr.ema_kimg * 1e3)
+        if tr.ema_rampup is not None:
+            ema_imgs = min(ema_imgs, iteration * tr.batch_size * tr.ema_rampup)
+        ema_decay = 0.5 ** (tr.batch_size / max(ema_imgs, 1e-8))
+        ema_inplace(self.G_ema, self.G_module, ema_decay)
+        if iteration % tr.lazy.ada == 0:
+            scalars["stats/ada_rt"] = self.A.update_p().detach().reshape(())
+            scalars["stats/ada_p"] = self.A.p.detach().reshape(())
+
+        packed = torch.stack([v.float().reshape(()) for v in scalars.values()])
+        if self.world_size > 1:
+            dist.all_reduce(packed)
+            packed /= self.world_size
+        self.scalar_names = list(scalars.keys())
+        self.last_stats = dict(ema_decay=ema_decay, blur_sigma=self.blur_sigma,
+                               dropout_ratio=self.dropout_ratio)
+        return packed            # device tensor; names in self.scalar_names
+
+    def scalars_to_host(self, packed):
+        vals = packed.detach().cpu().tolist()
+        out = dict(zip(self.scalar_names, vals))
+        out.update({f"stats/{k}": v for k, v in self.last_stats.items()})
+        return out
+
+    @torch.no_grad()
+    def sample(self, z, ema=True):
+        net = self.G_ema if ema else self.G_module
+        was = net.training
+        net.eval()
+        out = net(z, **{k: v[: z.shape[0]] for k, v in self.auxin.items()})
+        net.train(was)
+        return out
+
+    def state_dict(self, step):
+        """Checkpoint payload with the reference's keys (trainer.py:551-567)."""
+        return {"cfg": self.cfg, "step": step, "angle": self.coord.angle.detach().cpu(),
+                "G": self.G_module.state_dict(), "D": self.D_module.state_dict(),
+                "G_ema": self.G_ema.state_dict(), "A": self.A.state_dict(),
+                "optim_G": self.optim_G.state_dict(), "optim_D": self.optim_D.state_dict()}

@@ -1,0 +1,180 @@
+/*
+ * dusty_b200.h -- C ABI of libdusty_b200.so: the B200 (sm_100a) kernels behind the
+ * DUSty-v2 generator/discriminator hot path.
+ *
+ * Boundary rules:
+ *   - plain pointers and sizes only; no torch / ATen types;
+ *   - every pointer is a DEVICE pointer unless the name ends in _host;
+ *   - the caller owns every buffer (outputs and workspaces included) -- nothing
+ *     is allocated here;
+ *   - `stream` is a cudaStream_t passed as void*; launches are asynchronous;
+ *   - return value: 0 on success, negative DUSTY_E* on error, never throws.
+ *     dusty_last_error() gives a thread-local message.  The Python host turns a
+ *     non-zero status into RuntimeError, which is what the reference's
+ *     TORCH_CHECKs surface as (fused_bias_act.cpp:10-16, upfirdn2d.cpp:10-16);
+ *   - dtype is the storage type of activations (DUSTY_F32 / DUSTY_BF16);
+ *     accumulation is always fp32.
+ *
+ * Each entry cites the reference interface it replaces (paths relative to the
+ * reference repository root).
+ */
+#ifndef DUSTY_B200_H_
+#define DUSTY_B200_H_
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define DUSTY_ABI_VERSION 1
+
+enum { DUSTY_F32 = 0, DUSTY_BF16 = 1 };
+enum { DUSTY_OK = 0, DUSTY_EINVAL = -1, DUSTY_ECUDA = -2, DUSTY_EUNSUPPORTED = -3 };
+/* boundary extension used by the FIR family */
+enum { DUSTY_PAD_ZERO = 0, DUSTY_PAD_CIRCULAR = 1, DUSTY_PAD_REPLICATE = 2, DUSTY_PAD_REFLECT = 3 };
+
+/* ---- library queries -------------------------------------------------------------- */
+int dusty_abi_version(void);
+const char *dusty_last_error(void);
+/* compute capability major*10+minor of the current device, or <0 */
+int dusty_query_sm(void);
+/* number of kernels launched by this library in this process (all threads) */
+int64_t dusty_launch_count(void);
+
+/* ---- a3: fused bias + activation ------------------------------------------------------
+ * Replaces fused.fused_bias_act(input, bias, refer, act, grad, alpha, scale)
+ *   gans/models/ops/fused_act/fused_bias_act.cpp:18-32, fused_bias_act_kernel.cu:18-105.
+ * x viewed as [N, C, inner] contiguous; bias index = (i / inner) % C.
+ * bias == NULL / ref == NULL mean "absent" (the reference passes empty tensors).
+ * act: 1 linear, 3 leaky-relu.  grad: 0 forward, 1 first derivative gated by `ref`,
+ * 2 second derivative (zero).  y = f(x + b) * scale. */
+int dusty_bias_act(const void *x, const void *bias, const void *ref, void *y, int64_t n_elem,
+                   int C, int64_t inner, int act, int grad, float alpha, float scale, int dtype,
+                   void *stream);
+
+/* Fused backward: dx = dy * (out > 0 ? 1 : alpha) * scale and db[c] += sum dx (fp32, the
+ * caller zero-fills db).  Replaces FusedLeakyReLUFunctionBackward.forward
+ *   gans/models/ops/fused_act/fused_act.py:20-44 (kernel launch + ATen .sum(dim)).
+ * db may be NULL. */
+int dusty_bias_act_bwd(const void *dy, const void *out, void *dx, float *db, int64_t N, int C,
+                       int64_t inner, float alpha, float scale, int dtype, void *stream);
+
+/* ---- a4/a5: FIR family (upfirdn2d, Resample, BlurVH, filter2d, Pad) -------------------
+ * out[n,my,mx] = sum_{ty,tx} K[ty,tx] * XU(my*down_y + ty - pad_y0, mx*down_x + tx - pad_x0)
+ * XU(qy,qx) = X(qy/up_y, qx/up_x) when both divide exactly, else 0; X() extends x by
+ * mode_y / mode_x.  `taps` is a DEVICE fp32 [kh,kw] array; flip != 0 reads it reversed in
+ * both axes (true convolution, as upfirdn2d does).  x: [N, in_h, in_w], y: [N, out_h, out_w].
+ *
+ * With mode ZERO and flip=1 this is upfirdn2d_op.upfirdn2d (minor == 1)
+ *   gans/models/ops/upfirdn2d/upfirdn2d.cpp:17-31, upfirdn2d_kernel.cu:44-425
+ * with out_h = (in_h*up_y + pad_y0 + pad_y1 - kh + down_y) / down_y.
+ * With CIRCULAR (W) / REPLICATE (H) it is Resample.forward
+ *   gans/models/ops/common.py:105-135; with a 1x1 unit tap it is Pad.forward (:10-24). */
+int dusty_fir2d(const void *x, void *y, const float *taps, int kh, int kw, int flip, int64_t N,
+                int in_h, int in_w, int out_h, int out_w, int up_y, int up_x, int down_y,
+                int down_x, int pad_y0, int pad_x0, int mode_y, int mode_x, int dtype,
+                void *stream);
+/* Exact adjoint (transpose) of dusty_fir2d with the same parameters:
+ * dy: [N, out_h, out_w] -> dx: [N, in_h, in_w].  Serves backward of every FIR op and, the
+ * op being linear, dusty_fir2d itself serves the double backward
+ *   (UpFirDn2dBackward, gans/models/ops/upfirdn2d/upfirdn2d.py:20-85). */
+int dusty_fir2d_adj(const void *dy, void *dx, const float *taps, int kh, int kw, int flip,
+                    int64_t N, int in_h, int in_w, int out_h, int out_w, int up_y, int up_x,
+                    int down_y, int down_x, int pad_y0, int pad_x0, int mode_y, int mode_x,
+                    int dtype, void *stream);
+/* Reference-shaped convenience entry: zero padding, flipped taps, minor == 1. */
+int dusty_upfirdn2d(const void *x, const float *kernel, void *y, int64_t major, int in_h,
+                    int in_w, int kh, int kw, int up_x, int up_y, int down_x, int down_y,
+                    int pad_x0, int pad_x1, int pad_y0, int pad_y1, int dtype, void *stream);
+
+/* ---- a2: Fourier features --------------------------------------------------------------
+ * Replaces FourierFeature.forward gans/models/ops/fourier.py:77-82.
+ * angle: fp32 [Ba, 2, P] (elevation, azimuth); freqs: fp32 [F, 2]; phase: fp32 [F];
+ * out: [Ba, 2F, P] (sin block then cos block) in out_dtype. */
+int dusty_fourier(const float *angle, const float *freqs, const float *phase, void *out, int Ba,
+                  int F, int64_t P, int out_dtype, void *stream);
+
+/* angle pyramid step: cat(sin,cos) -> Resample(down=2, [1,3,3,1], ring) -> atan2
+ *   SynthesisBlock.downsample_angle gans/models/dusty_v2.py:135-140.
+ * in: fp32 [Ba, 2, H, W] -> out: fp32 [Ba, 2, H/2, W/2]. */
+int dusty_angle_down2(const float *angle_in, float *angle_out, int Ba, int H, int W, void *stream);
+
+/* ---- a1: modulated 1x1 convolution as a batched contraction ---------------------------
+ * Replaces the grouped conv of ModConv2d.forward gans/models/ops/style.py:106-121 (ksize 1).
+ * The per-sample effective weights wb[B, O, K] (modulation, demodulation and the EMA
+ * normaliser folded in, style.py:72-103) are produced by the host-side weight prep.
+ *
+ *   Y[b,o,p] = sum_k wb[b,o,k] * X(b,k,p),   X = x1 for k < C1, x2 (k - C1) otherwise
+ *
+ * x1: [B, C1, P] activations; x2: [B2, C2, P] Fourier features with B2 == B or 1 (batch
+ * shared); K = C1 + C2; either part may be empty (C == 0, pointer ignored).
+ * Epilogue: + bias[o] (fp32, may be NULL), then act (1 linear / 3 lrelu(alpha)) * scale.
+ * wb has dtype `wdtype`; x1/x2/y have dtype `dtype`.
+ * impl: 0 = auto, 1 = SIMT fp32-FMA kernel, 2 = tcgen05 tensor-core kernel (bf16 only). */
+int dusty_modconv_fwd(const void *wb, const void *x1, const void *x2, const float *bias, void *y,
+                      int B, int O, int C1, int C2, int B2, int64_t P, int act, float alpha,
+                      float scale, int dtype, int wdtype, int impl, void *stream);
+/* dX1[b,k,p] = sum_o wb[b,o,k] * dY[b,o,p]  for k < C1 (Fourier channels carry no grad). */
+int dusty_modconv_bwd_dx(const void *wb, const void *dy, void *dx1, int B, int O, int C1, int K,
+                         int64_t P, int dtype, int wdtype, int impl, void *stream);
+/* dwb[b,o,k] = sum_p dY[b,o,p] * X(b,k,p)  (fp32 output, overwritten). */
+int dusty_modconv_bwd_dw(const void *dy, const void *x1, const void *x2, float *dwb, int B, int O,
+                         int C1, int C2, int B2, int64_t P, int dtype, int impl, void *stream);
+
+/* ---- a10: Gumbel-sigmoid raydrop -------------------------------------------------------
+ * Replaces GumbelSigmoid.forward gans/models/ops/gumbel.py:23-29 (RelaxedBernoulli.rsample
+ * closed form, uniform draw supplied by the caller) + RayDropModel.forward
+ * gans/models/dusty_v1.py:20-25.  All fp32, n elements.
+ * Outputs: mask (hard 0/1), image_out = lerp(image, rconst, 1-mask), dsoft = d soft/d logit
+ * (saved for backward); count (int32, caller zero-fills, may be NULL) += sum(mask). */
+int dusty_gumbel_raydrop_fwd(const float *logit, const float *image, const float *u, float *mask,
+                             float *image_out, float *dsoft, int *count, int64_t n, float rconst,
+                             float temperature, void *stream);
+/* g_logit = (g_out*(image - rconst) + g_mask) * dsoft ; g_image = g_out * mask.
+ * g_mask may be NULL. */
+int dusty_gumbel_raydrop_bwd(const float *g_out, const float *g_mask, const float *image,
+                             const float *mask, const float *dsoft, float *g_logit,
+                             float *g_image, int64_t n, float rconst, void *stream);
+
+/* ---- a14: range image -> point cloud ---------------------------------------------------
+ * Replaces CoordBridge.convert(x, "inv_depth_norm", "point_map"|"point_set")
+ *   gans/coords.py:139-155,178-185.
+ * x: fp32 [B, HW] inverse depth (normalised).  trig: fp32 [4, HW] = cos(el), sin(el),
+ * cos(az), sin(az), computed once on the host from CoordBridge.angle.
+ * layout 0: out [B, 3, HW] (point_map); 1: out [B, HW, 3] (point_set, index h*W + w).
+ * valid_count (int64, caller zero-fills, may be NULL) += number of valid pixels. */
+int dusty_point_project(const float *x, const float *trig, float *out, long long *valid_count,
+                        int B, int64_t HW, float min_depth, float max_depth, float tol,
+                        int layout, void *stream);
+
+/* ---- a12: minibatch standard deviation --------------------------------------------------
+ * Replaces MinibatchStdDev.forward gans/models/ops/common.py:237-250 (features == 1).
+ * x: [B, C, HW] -> y: [B, C+1, HW]; stat: fp32 [B/G] workspace (overwritten). */
+int dusty_minibatch_std_fwd(const void *x, void *y, float *stat, int B, int C, int64_t HW,
+                            int group, float alpha, int dtype, void *stream);
+/* dx = dy[:, :C] + d stat path.  dstat: fp32 [B/G] workspace. */
+int dusty_minibatch_std_bwd(const void *dy, const void *x, void *dx, float *dstat, int B, int C,
+                            int64_t HW, int group, float alpha, int dtype, void *stream);
+
+/* ---- a13 / ema_var: row-wise sum of squares ---------------------------------------------
+ * out[r] (+)= sum_j x[r, j]^2, fp32.  accumulate == 0 overwrites (out must still be
+ * zero-filled by the caller when rows are split across CTAs: see implementation note --
+ * the entry zero-fills internally when accumulate == 0).
+ * Serves the R1 penalty gans/trainer.py:440 and ModConv2d's EMA statistic style.py:100. */
+int dusty_sumsq_rows(const void *x, float *out, int64_t rows, int64_t cols, int accumulate,
+                     int dtype, void *stream);
+
+/* ---- a7: aug-coords circular un-shift ---------------------------------------------------
+ * Replaces cat([v,v],3) -> affine_grid -> grid_sample -> [..., :W]
+ *   gans/models/dusty_v2.py:290-297.
+ * out[b,c,h,j] = (1-f_b) v[(j+n_b) % W] + f_b v[(j+n_b+1) % W], n_b + f_b = shift01[b]*W.
+ * adjoint != 0 applies the transpose (backward).  scale multiplies the result
+ * (output_scale, dusty_v2.py:299-301). fp32. */
+int dusty_circular_shift(const float *v, const float *shift01, float *out, int B, int C, int H,
+                         int W, float scale, int adjoint, void *stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* DUSTY_B200_H_ */

@@ -553,3 +553,117 @@ def nsgan_d(y_real: Tensor, y_fake: Tensor) -> Tensor:
 
 def r1_penalty(grads: Tensor) -> Tensor:
     return grads.pow(2).sum(dim=[1, 2, 3]).mean()
+
+
+# --------------------------------------------------------------------------------------
+# a6  AdaptiveAugment.forward, deterministic part       gans/augment/adaptive_augment.py:471-545
+# --------------------------------------------------------------------------------------
+
+SYM6 = (0.015404109327027373, 0.0034907120842174702, -0.11799011114819057,
+        -0.048311742585633, 0.4910559419267466, 0.787641141030194, 0.3379294217276218,
+        -0.07263752278646252, -0.021060292512300564, 0.04472490177066578,
+        0.0017677118642428036, -0.007800708325034148)
+
+
+def _m3(rows):
+    return torch.tensor(rows, dtype=torch.float32)
+
+
+def ada_padding(G_inv: Tensor, height: int, width: int, ksize: int):
+    """get_padding (adaptive_augment.py:271-291) -> (x1, x2, y1, y2) python ints."""
+    cx, cy = (width - 1) / 2, (height - 1) / 2
+    cp = G_inv @ _m3([(-cx, -cy, 1), (cx, -cy, 1), (cx, cy, 1), (-cx, cy, 1)]).T
+    pad_k = ksize // 4
+    pad = cp[:, :2, :].permute(1, 0, 2).flatten(1)
+    pad = torch.cat((-pad, pad)).max(1).values
+    pad = pad + _m3([pad_k * 2 - cx, pad_k * 2 - cy] * 2)
+    pad = pad.max(_m3([0, 0] * 2)).min(_m3([width - 1, height - 1] * 2))
+    x1, y1, x2, y2 = (int(v) for v in pad.ceil().to(torch.int32))
+    return x1, x2, y1, y2
+
+
+def ada_apply(img: Tensor, G_inv: Tensor, C: Tensor) -> Tensor:
+    """The deterministic body of AdaptiveAugment.forward for a given inverse geometric
+    transform G_inv [B,3,3] and colour matrix C [B,4,4]: circular-W / reflect-H pad,
+    SYM6 2x upsampling (W then H), bilinear affine warp, SYM6 2x downsampling, colour."""
+    B, ch, H, W = img.shape
+    k = torch.tensor(SYM6)
+    nk = k.numel()
+    x1, x2, y1, y2 = ada_padding(G_inv, H, W, nk)
+    img = F.pad(img, (x1, x2, 0, 0), mode="circular")
+    img = F.pad(img, (0, 0, y1, y2), mode="reflect")
+    G_inv = _m3([(1, 0, (x1 - x2) / 2), (0, 1, (y1 - y2) / 2), (0, 0, 1)]) @ G_inv
+    u0, u1 = (nk + 1) // 2, (nk - 2) // 2
+    img = upfirdn2d(img, k[None], up=(2, 1), pad=(u0, u1, 0, 0))
+    img = upfirdn2d(img, k[:, None], up=(1, 2), pad=(0, 0, u0, u1))
+    G_inv = _m3([(2, 0, 0), (0, 2, 0), (0, 0, 1)]) @ G_inv @ _m3([(.5, 0, 0), (0, .5, 0), (0, 0, 1)])
+    G_inv = (_m3([(1, 0, -.5), (0, 1, -.5), (0, 0, 1)]) @ G_inv
+             @ _m3([(1, 0, .5), (0, 1, .5), (0, 0, 1)]))
+    pad_k = nk // 4
+    shape = (B, ch, (H + pad_k * 2) * 2, (W + pad_k * 2) * 2)
+    G_inv = (_m3([(2 / img.shape[3], 0, 0), (0, 2 / img.shape[2], 0), (0, 0, 1)]) @ G_inv
+             @ _m3([(shape[3] / 2, 0, 0), (0, shape[2] / 2, 0), (0, 0, 1)]))
+    grid = F.affine_grid(G_inv[:, :2, :], shape, align_corners=False)
+    img = F.grid_sample(img, grid, mode="bilinear", padding_mode="zeros", align_corners=False)
+    d = -pad_k * 2
+    d0, d1 = d + (nk - 1) // 2, d + (nk - 2) // 2
+    kf = k.flip(0)
+    img = upfirdn2d(img, kf[None], down=(2, 1), pad=(d0, d1, 0, 0))
+    img = upfirdn2d(img, kf[:, None], down=(1, 2), pad=(0, 0, d0, d1))
+    img = img.reshape(B, ch, H * W)
+    if ch == 3:
+        img = C[:, :3, :3] @ img + C[:, :3, 3:]
+    else:
+        Cm = C[:, :3, :].mean(dim=1, keepdim=True)
+        img = img * Cm[:, :, :3].sum(dim=2, keepdim=True) + Cm[:, :, 3:]
+    return img.reshape(B, ch, H, W)
+
+
+# --------------------------------------------------------------------------------------
+# a16  one training iteration on the CPU (timing baseline + step-level parity)
+#      gans/trainer.py:247-451
+# --------------------------------------------------------------------------------------
+
+
+def warmup_dropout(x: Tensor, keep: Optional[Tensor], raydrop_const: float = -1.0) -> Tensor:
+    """Trainer.warmup with blur sigma 0 (trainer.py:241-244); `keep` is the Bernoulli draw."""
+    if keep is None:
+        return x
+    return keep * x + (1 - keep) * raydrop_const
+
+
+def train_iteration(sdG: Dict[str, Tensor], sdD: Dict[str, Tensor], x_real: Tensor, angle: Tensor,
+                    rnd: Dict[str, Tensor], with_r1: bool = True, gp_weight: float = 16.0):
+    """Losses and gradients of one iteration: G step, D step and (optionally) the R1 step,
+    with every random draw supplied in `rnd` (z_g, z_d, shift_g, shift_d, u_g, u_d, keep_*,
+    Ginv_*, C_*).  Returns dict(loss_G, loss_D, r1, grads_G, grads_D, grads_R1)."""
+    def aug(x, tag):
+        return ada_apply(warmup_dropout(x, rnd.get(f"keep_{tag}")), rnd[f"Ginv_{tag}"], rnd[f"C_{tag}"])
+
+    pG = {k: v for k, v in sdG.items() if v.requires_grad}
+    pD = {k: v for k, v in sdD.items() if v.requires_grad}
+    out = {}
+    # G step
+    fake = generator(sdG, rnd["z_g"], angle, rnd["u_g"], training=True,
+                     shifts_rad=rnd["shift_g"] * (2 * np.pi))["image"]
+    loss_g = nsgan_g(discriminator(sdD, aug(fake, "g_fake")))
+    out["loss_G"] = loss_g.detach()
+    out["grads_G"] = dict(zip(pG, torch.autograd.grad(loss_g, list(pG.values()), allow_unused=True)))
+    # D step
+    with torch.no_grad():
+        fake = generator(sdG, rnd["z_d"], angle, rnd["u_d"], training=True,
+                         shifts_rad=rnd["shift_d"] * (2 * np.pi))["image"]
+    y_real = discriminator(sdD, aug(x_real, "d_real").detach())
+    y_fake = discriminator(sdD, aug(fake, "d_fake").detach())
+    loss_d = nsgan_d(y_real, y_fake)
+    out["loss_D"] = loss_d.detach()
+    out["grads_D"] = dict(zip(pD, torch.autograd.grad(loss_d, list(pD.values()), allow_unused=True)))
+    if with_r1:
+        x_gp = x_real.detach().clone().requires_grad_()
+        y = discriminator(sdD, aug(x_gp, "r1"))
+        (gx,) = torch.autograd.grad(y.sum(), x_gp, create_graph=True)
+        r1 = r1_penalty(gx)
+        loss = (gp_weight / 2) * r1 + 0.0 * y.squeeze()[0]
+        out["r1"] = r1.detach()
+        out["grads_R1"] = dict(zip(pD, torch.autograd.grad(loss, list(pD.values()), allow_unused=True)))
+    return out

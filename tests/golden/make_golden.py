@@ -301,7 +301,30 @@ def golden_discriminator():
     save("d_small.npz", **out)
 
 
+def golden_ada():
+    """Reference AdaptiveAugment.forward with its samplers pinned to recorded matrices."""
+    seed(50)
+    ada = ref_ada.AdaptiveAugment(p_init=0.9, lr_flip=1, ud_flip=1, int_trans=1, iso_scale=1,
+                                  frac_trans=1, brightness=1, contrast=1, luma_flip=1, hue=1,
+                                  saturation=1)
+    B, H, W = 4, 16, 64
+    G = ada.sample_affine(B, H, W)
+    C = ada.sample_color(B)
+    G[0] = torch.eye(3)                      # keep one identity sample
+    ada.sample_affine = lambda *a, **k: G.clone()
+    ada.sample_color = lambda *a, **k: C.clone()
+    x = torch.tanh(torch.randn(B, 1, H, W)).requires_grad_()
+    y = ada(x)
+    gy = torch.randn_like(y)
+    (gx,) = torch.autograd.grad(y, x, gy)
+    save("ada.npz", G=npy(G), G_inv=npy(torch.inverse(G)), C=npy(C), x=npy(x), y=npy(y), gy=npy(gy),
+         gx=npy(gx))
+
+
 if __name__ == "__main__":
+    golden_ada()
+    if "--ada-only" in sys.argv:
+        sys.exit(0)
     golden_ops()
     golden_coords()
     golden_generator()

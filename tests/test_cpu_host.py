@@ -1,0 +1,137 @@
+"""CPU-side checks: the C-ABI library loads and exports every symbol the header declares,
+ops refuse CPU tensors (no fallback), host-side logic (configs, state_dict layout, ADA
+sampling, padding geometry) behaves, and the oracle never leaks into the product."""
+import os
+import re
+import subprocess
+import sys
+
+import numpy as np
+import pytest
+import torch
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def test_library_exports_every_declared_symbol():
+    from dusty_gan_v2_b200 import _cabi
+    lib = _cabi.load()
+    header = open(os.path.join(ROOT, "include", "dusty_b200.h")).read()
+    declared = set(re.findall(r"\b(dusty_[a-z0-9_]+)\s*\(", header))
+    assert len(declared) >= 20
+    for name in declared:
+        assert hasattr(lib, name), f"{name} declared in the header but not exported"
+    assert declared == set(_cabi.SIGNATURES), declared ^ set(_cabi.SIGNATURES)
+    assert lib.dusty_abi_version() == _cabi.ABI_VERSION
+
+
+def test_no_cpu_fallback():
+    import dusty_gan_v2_b200.functional as DF
+    from dusty_gan_v2_b200.gans.models import ops
+    from dusty_gan_v2_b200.gans.models.ops.upfirdn2d.upfirdn2d import upfirdn2d
+    x = torch.randn(2, 3, 8, 8)
+    with pytest.raises(RuntimeError, match="CUDA"):
+        DF.bias_act(x, torch.zeros(3))
+    with pytest.raises(RuntimeError, match="CUDA"):
+        ops.Resample(up=2)(x)
+    with pytest.raises(RuntimeError, match="CUDA"):
+        upfirdn2d(x, torch.ones(2, 2))
+    with pytest.raises(RuntimeError, match="CUDA"):
+        ops.MinibatchStdDev()(x)
+    with pytest.raises(RuntimeError, match="CUDA"):
+        ops.FourierFeature((8, 8), num_freqs=8)(torch.zeros(1, 2, 8, 8))
+
+
+def test_product_never_imports_oracle():
+    pkg = os.path.join(ROOT, "dusty_gan_v2_b200")
+    for d, _, files in os.walk(pkg):
+        for f in files:
+            if f.endswith((".py", ".cu", ".cuh", ".h")):
+                src = open(os.path.join(d, f)).read()
+                assert not re.search(r"^\s*(from|import)\s+oracle", src, re.M), os.path.join(d, f)
+    code = ("import sys; sys.path.insert(0, %r); import dusty_gan_v2_b200, "
+            "dusty_gan_v2_b200.gans.trainer; "
+            "assert not any(m == 'oracle' or m.startswith('oracle.') for m in sys.modules)" % ROOT)
+    subprocess.run([sys.executable, "-c", code], check=True)
+
+
+def test_missing_library_fails_loudly(monkeypatch):
+    from dusty_gan_v2_b200 import _cabi
+    monkeypatch.setattr(_cabi, "_lib", None)
+    monkeypatch.setattr(_cabi, "LIB_PATH", "/nonexistent/libdusty_b200.so")
+    with pytest.raises(RuntimeError, match="no CPU"):
+        _cabi.load()
+
+
+def test_state_dict_layout_matches_reference(g_gen, g_disc):
+    from dusty_gan_v2_b200.gans.models.builder import build_discriminator, build_generator
+    from small_cfgs import D_SMALL, G_SMALL
+    G, D = build_generator(G_SMALL), build_discriminator(D_SMALL)
+    ref_g = {k[3:]: v.shape for k, v in g_gen.items() if k.startswith("sd_")}
+    ref_d = {k[3:]: v.shape for k, v in g_disc.items() if k.startswith("sd_")}
+    assert {k: tuple(v.shape) for k, v in G.state_dict().items()} == ref_g
+    assert {k: tuple(v.shape) for k, v in D.state_dict().items()} == ref_d
+
+
+def test_full_size_parameter_counts_and_presets():
+    from dusty_gan_v2_b200.gans.models.builder import build_discriminator, build_generator
+    from dusty_gan_v2_b200.presets import preset
+    expect = {"dusty_v2": (4367594, 38445569), "dusty_v1": (36309954, 2821057),
+              "vanilla": (36308929, 2821057)}
+    for arch, (ng, nd) in expect.items():
+        cfg = preset(arch)
+        G, D = build_generator(cfg.model.generator), build_discriminator(cfg.model.discriminator)
+        assert sum(p.numel() for p in G.parameters()) == ng
+        assert sum(p.numel() for p in D.parameters()) == nd
+
+
+def test_fourier_init_consumes_rng_like_reference(g_ops):
+    from dusty_gan_v2_b200.gans.models.ops import FourierFeature
+    torch.manual_seed(11)
+    np.random.seed(11)
+    ff = FourierFeature(resolution=(8, 16), num_freqs=32)
+    assert np.array_equal(ff.freqs.numpy(), g_ops["ff_freqs"])
+    assert np.array_equal(ff.phase.numpy(), g_ops["ff_phase"])
+    assert [ff.L_h, ff.L_w] == g_ops["ff_L"].tolist()
+
+
+def test_coord_bridge_angle_bit_exact_on_host(g_coords):
+    from dusty_gan_v2_b200.gans.coords import CoordBridge
+    cb = CoordBridge(64, 512, 1.45, 80.0, os.path.join(ROOT, "data/coords/kitti_raw.npy"))
+    assert np.array_equal(cb.angle.numpy(), g_coords["angle"])
+    depth = torch.from_numpy(g_coords["depth"])
+    mask = torch.from_numpy(g_coords["mask"])
+    x = cb.convert(depth, "depth", "inv_depth_norm") * 2 - 1
+    assert np.array_equal((mask * x + (1 - mask) * -1.0).numpy(), g_coords["reals"])
+    ps = cb.convert(torch.arange(24.).reshape(1, 3, 2, 4), "point_map", "point_set")
+    assert ps.shape == (1, 8, 3) and float(ps[0, 5, 1]) == 8 + 5     # index h*W + w
+
+
+def test_ada_host_sampling_and_padding():
+    from dusty_gan_v2_b200.gans.augment import adaptive_augment as A
+    ada = A.AdaptiveAugment(p_init=0.0, lr_flip=1, ud_flip=1, int_trans=1, iso_scale=1, frac_trans=1,
+                            brightness=1, contrast=1, luma_flip=1, hue=1, saturation=1)
+    ada.generator = torch.Generator().manual_seed(0)
+    G = ada.sample_affine(5, 64, 512)
+    C = ada.sample_color(5)
+    assert torch.equal(G, torch.eye(3).repeat(5, 1, 1)) and torch.equal(C, torch.eye(4).repeat(5, 1, 1))
+    # identity transform needs only the filter margin (76 x 524 at p = 0)
+    px1, px2, py1, py2 = A.padding_for(torch.inverse(G), 64, 512, 12)
+    assert (64 + py1 + py2, 512 + px1 + px2) == (76, 524)
+    ada._p_host = 0.9
+    G = ada.sample_affine(64, 64, 512)
+    assert G.shape == (64, 3, 3) and float((G - torch.eye(3)).abs().sum()) > 0
+    assert torch.allclose(G[:, 2], torch.tensor([0.0, 0.0, 1.0]).expand(64, 3))
+    pads = A.padding_for(torch.inverse(G), 64, 512, 12)
+    assert all(0 <= p for p in pads) and pads[0] <= 511 and pads[2] <= 63
+    assert tuple(ada.Hz_fbank.shape) == (4, 43)
+
+
+def test_fir_geometry_matches_oracle_sizes():
+    from dusty_gan_v2_b200.functional import FirCfg
+    from oracle import dusty_oracle as O
+    for up, down, pad, k in [((2, 1), (1, 1), (0, 0, 6, 5), (1, 12)), ((1, 1), (2, 3), (1, 2, -1, 3), (4, 5))]:
+        cfg = FirCfg(k[0], k[1], 1, up=up, down=down, pad=pad)
+        oh, ow = cfg.out_hw(17, 23)
+        assert oh == O.upfirdn2d_out_size(17, up[0], down[0], pad[0], pad[1], k[0])
+        assert ow == O.upfirdn2d_out_size(23, up[1], down[1], pad[2], pad[3], k[1])

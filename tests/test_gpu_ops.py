@@ -1,0 +1,419 @@
+"""GPU parity tests: every kernel family, called through the host API (ctypes -> C ABI),
+against the CPU oracle on identical seeded inputs and against the reference-generated
+golden fixtures.  Tolerances: bit-exact for integer / index / mask-count results;
+rtol 1e-3 (fp32) and 2e-2 (bf16) for floating point, as BASELINE.json states."""
+import numpy as np
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+
+from oracle import dusty_oracle as O  # noqa: E402
+
+T = torch.from_numpy
+DEV = "cuda"
+
+
+def dev(a):
+    return (T(a) if isinstance(a, np.ndarray) else a).to(DEV)
+
+
+def close(a, b, rtol=1e-3, atol_rel=1e-4):
+    a = a.detach().float().cpu().numpy()
+    b = b.detach().float().cpu().numpy() if isinstance(b, torch.Tensor) else np.asarray(b)
+    atol = atol_rel * max(float(np.abs(b).max()), 1e-12)
+    np.testing.assert_allclose(a, b, rtol=rtol, atol=atol)
+
+
+@pytest.fixture(scope="module")
+def DF():
+    import dusty_gan_v2_b200.functional as DF
+    return DF
+
+
+@pytest.fixture(scope="module")
+def ops():
+    from dusty_gan_v2_b200.gans.models import ops
+    return ops
+
+
+# ----------------------------------------------------------------------------- a3 bias_act
+def test_bias_act_golden_and_grads(DF, g_ops):
+    x = dev(g_ops["ba_x"]).requires_grad_()
+    b = dev(g_ops["ba_b"]).requires_grad_()
+    y = DF.bias_act(x, b)
+    close(y, g_ops["ba_y"], rtol=1e-6, atol_rel=1e-7)
+    dx, db = torch.autograd.grad(y, [x, b], dev(g_ops["ba_dy"]))
+    close(dx, g_ops["ba_dx"], rtol=1e-6, atol_rel=1e-7)
+    close(db, g_ops["ba_db"], rtol=1e-5, atol_rel=1e-6)
+    close(DF.bias_act(dev(g_ops["ba2_x"]), dev(g_ops["ba2_b"])), g_ops["ba2_y"], 1e-6, 1e-7)
+
+
+@pytest.mark.parametrize("shape", [(3, 5, 7, 9), (2, 32, 64, 512), (4, 6), (1, 3, 5), (2, 8, 4, 4)])
+@pytest.mark.parametrize("dtype", [torch.float32, torch.bfloat16])
+def test_bias_act_vs_oracle_double_backward(DF, shape, dtype):
+    g = torch.Generator().manual_seed(1)
+    x = torch.randn(shape, generator=g)
+    b = torch.randn(shape[1], generator=g)
+    if dtype == torch.bfloat16:
+        x, b = x.bfloat16().float(), b.bfloat16().float()
+    xr, br = x.clone().requires_grad_(), b.clone().requires_grad_()
+    yr = O.bias_act(xr, br)
+    xg, bg = x.to(DEV, dtype).requires_grad_(), b.to(DEV).requires_grad_()
+    yg = DF.bias_act(xg, bg)
+    tol = dict(rtol=1e-3, atol_rel=1e-5) if dtype == torch.float32 else dict(rtol=2e-2, atol_rel=1e-2)
+    close(yg, yr, **tol)
+    gy = torch.randn(shape, generator=g)
+    (dxr, dbr) = torch.autograd.grad(yr, [xr, br], gy, create_graph=True)
+    (dxg, dbg) = torch.autograd.grad(yg, [xg, bg], gy.to(DEV, dtype), create_graph=True)
+    close(dxg, dxr, **tol)
+    close(dbg, dbr, rtol=tol["rtol"], atol_rel=max(tol["atol_rel"], 1e-4))
+    if dtype == torch.float32:
+        # second order: d/d(gy) of sum(dx * v) -- the R1 path
+        v = torch.randn(shape, generator=g)
+        # the oracle's bias_act is piecewise linear: grad-grad flows through gy only
+        gy_r = gy.clone().requires_grad_()
+        dx2 = torch.where(yr.detach() > 0, gy_r, gy_r * 0.2) * O.SQRT2
+        (ggr,) = torch.autograd.grad((dx2 * v).sum(), gy_r)
+        gy_g = gy.to(DEV).requires_grad_()
+        (dxg2,) = torch.autograd.grad(yg, xg, gy_g, create_graph=True)
+        (ggg,) = torch.autograd.grad((dxg2 * v.to(DEV)).sum(), gy_g)
+        close(ggg, ggr, rtol=1e-5, atol_rel=1e-6)
+
+
+def test_fused_bias_act_native_contract(ops):
+    from dusty_gan_v2_b200.gans.models.ops.fused_act.fused_act import fused
+    x = torch.randn(2, 3, 4, device=DEV)
+    empty = x.new_empty(0)
+    y = fused.fused_bias_act(x, empty, empty, 3, 0, 0.2, 1.0)
+    close(y, torch.nn.functional.leaky_relu(x, 0.2), 1e-6, 1e-7)
+    y2 = fused.fused_bias_act(x, empty, y, 3, 1, 0.2, 2.0)
+    close(y2, torch.where(y > 0, x, x * 0.2) * 2.0, 1e-6, 1e-7)
+    assert float(fused.fused_bias_act(x, empty, empty, 3, 2, 0.2, 1.0).abs().max()) == 0.0
+    with pytest.raises(RuntimeError):
+        fused.fused_bias_act(x.cpu(), empty.cpu(), empty.cpu(), 3, 0, 0.2, 1.0)
+    with pytest.raises(RuntimeError):
+        fused.fused_bias_act(x.transpose(0, 1), empty, empty, 3, 0, 0.2, 1.0)
+    with pytest.raises(RuntimeError):
+        ops.fused_leaky_relu(torch.randn(2, 3), torch.zeros(3))          # CPU: no fallback
+
+
+# ----------------------------------------------------------------------------- a5 upfirdn2d
+@pytest.mark.parametrize("name", ["ada_upx", "ada_upy", "ada_dnx", "ada_dny", "gen2d", "ident"])
+def test_upfirdn2d_golden(g_ops, name):
+    from dusty_gan_v2_b200.gans.models.ops.upfirdn2d.upfirdn2d import upfirdn2d, upfirdn2d_op
+    cfg = g_ops[f"ufd_{name}_cfg"].tolist()
+    x, k = dev(g_ops[f"ufd_{name}_x"]), dev(g_ops[f"ufd_{name}_k"])
+    y = upfirdn2d(x, k, up=tuple(cfg[0:2]), down=tuple(cfg[2:4]), pad=tuple(cfg[4:8]))
+    assert tuple(y.shape) == g_ops[f"ufd_{name}_y"].shape
+    close(y, g_ops[f"ufd_{name}_y"], rtol=1e-4, atol_rel=1e-6)
+    n, c, h, w = x.shape
+    y2 = upfirdn2d_op.upfirdn2d(x.reshape(-1, h, w, 1), k, *cfg)
+    close(y2.reshape(y.shape), g_ops[f"ufd_{name}_y"], rtol=1e-4, atol_rel=1e-6)
+
+
+@pytest.mark.parametrize("cfg", [((2, 1), (1, 1), (6, 5, 0, 0), (1, 12)), ((1, 2), (1, 1), (0, 0, 6, 5), (12, 1)),
+                                 ((1, 1), (2, 1), (-1, -1, 0, 0), (1, 12)), ((1, 1), (1, 2), (0, 0, -1, -1), (12, 1)),
+                                 ((2, 2), (1, 1), (2, 1, 2, 1), (4, 4)), ((1, 1), (2, 2), (1, 1, 1, 1), (4, 4)),
+                                 ((3, 2), (2, 3), (1, 4, -2, 3), (5, 3))])
+def test_upfirdn2d_grad_and_gradgrad_vs_oracle(cfg):
+    from dusty_gan_v2_b200.gans.models.ops.upfirdn2d.upfirdn2d import upfirdn2d
+    up, down, pad, kshape = cfg
+    g = torch.Generator().manual_seed(3)
+    x = torch.randn(2, 2, 13, 18, generator=g)
+    k = torch.randn(*kshape, generator=g)
+    xr = x.clone().requires_grad_()
+    yr = O.upfirdn2d(xr, k, up=up, down=down, pad=pad)
+    xg = x.to(DEV).requires_grad_()
+    yg = upfirdn2d(xg, k.to(DEV), up=up, down=down, pad=pad)
+    close(yg, yr, rtol=1e-4, atol_rel=1e-6)
+    gy = torch.randn(yr.shape, generator=g)
+    (gxr,) = torch.autograd.grad(yr, xr, gy)
+    gy_g = gy.to(DEV).requires_grad_()
+    (gxg,) = torch.autograd.grad(yg, xg, gy_g, create_graph=True)
+    close(gxg, gxr, rtol=1e-4, atol_rel=1e-6)
+    # the op is linear: grad-grad w.r.t. gy of <gx, v> is the forward applied to v
+    v = torch.randn(x.shape, generator=g)
+    (gg,) = torch.autograd.grad((gxg * v.to(DEV)).sum(), gy_g)
+    close(gg, O.upfirdn2d(v, k, up=up, down=down, pad=pad), rtol=1e-4, atol_rel=1e-6)
+
+
+# ----------------------------------------------------------------------------- a4 Resample family
+def test_resample_family_golden(ops, g_ops):
+    x = dev(g_ops["rs_x"])
+    close(ops.Resample(up=2).to(DEV)(x), g_ops["rs_up2"], 1e-5, 1e-6)
+    close(ops.Resample(down=2).to(DEV)(x), g_ops["rs_down2"], 1e-5, 1e-6)
+    close(ops.Resample().to(DEV)(x), g_ops["rs_blur4"], 1e-5, 1e-6)
+    close(ops.Resample(window=[1, 2, 1], direction="h").to(DEV)(x), g_ops["rs_blur3_h"], 1e-5, 1e-6)
+    close(ops.Resample(window=[1, 2, 1], direction="w").to(DEV)(x), g_ops["rs_blur3_w"], 1e-5, 1e-6)
+    close(ops.Resample(up=2, ring=False).to(DEV)(x), g_ops["rs_up2_noring"], 1e-5, 1e-6)
+    close(ops.BlurVH().to(DEV)(x), g_ops["rs_blurvh"], 1e-5, 1e-6)
+    assert np.array_equal(ops.Pad(1, ring=True)(x).cpu().numpy(), g_ops["rs_pad1"])
+    assert np.array_equal(ops.Pad(1, ring=True, mode="reflect")(x).cpu().numpy(), g_ops["rs_pad1_reflect"])
+    close(ops.filter2d(x, dev(g_ops["rs_filter2d_k"])), g_ops["rs_filter2d"], 1e-5, 1e-6)
+    for nm, mod in (("up2", ops.Resample(up=2)), ("down2", ops.Resample(down=2)), ("blur4", ops.Resample())):
+        xg = x.clone().requires_grad_()
+        (gx,) = torch.autograd.grad(mod.to(DEV)(xg), xg, dev(g_ops[f"rs_{nm}_gy"]))
+        close(gx, g_ops[f"rs_{nm}_gx"], 1e-5, 1e-6)
+
+
+@pytest.mark.parametrize("kw", [dict(up=2), dict(down=2), dict(), dict(window=[1, 2, 1], direction="h"),
+                                dict(window=[1, 2, 1], direction="w"), dict(up=2, ring=False)])
+@pytest.mark.parametrize("shape", [(2, 3, 4, 32), (1, 2, 64, 512), (2, 1, 6, 10)])
+@pytest.mark.parametrize("dtype", [torch.float32, torch.bfloat16])
+def test_resample_vs_oracle(ops, kw, shape, dtype):
+    g = torch.Generator().manual_seed(5)
+    x = torch.randn(shape, generator=g)
+    if dtype == torch.bfloat16:
+        x = x.bfloat16().float()
+    xr = x.clone().requires_grad_()
+    yr = O.resample(xr, **{k: (tuple(v) if isinstance(v, list) else v) for k, v in kw.items()})
+    xg = x.to(DEV, dtype).requires_grad_()
+    yg = ops.Resample(**kw).to(DEV)(xg)
+    tol = dict(rtol=1e-3, atol_rel=1e-5) if dtype == torch.float32 else dict(rtol=2e-2, atol_rel=1e-2)
+    close(yg, yr, **tol)
+    gy = torch.randn(yr.shape, generator=g)
+    (gxr,) = torch.autograd.grad(yr, xr, gy)
+    gy_g = gy.to(DEV, dtype).requires_grad_()
+    (gxg,) = torch.autograd.grad(yg, xg, gy_g, create_graph=True)
+    close(gxg, gxr, **tol)
+    if dtype == torch.float32:
+        v = torch.randn(shape, generator=g)
+        (gg,) = torch.autograd.grad((gxg * v.to(DEV)).sum(), gy_g)
+        close(gg, O.resample(v, **{k: (tuple(v2) if isinstance(v2, list) else v2) for k, v2 in kw.items()}),
+              rtol=1e-4, atol_rel=1e-6)
+
+
+@pytest.mark.parametrize("pad,ring,mode", [(1, True, "replicate"), (2, True, "reflect"), ((3, 0, 2, 1), False, "replicate"),
+                                           ((5, 7, 0, 0), True, "reflect")])
+def test_pad_fwd_bwd_exact(ops, pad, ring, mode):
+    g = torch.Generator().manual_seed(6)
+    x = torch.randn(2, 3, 6, 9, generator=g)
+    xr = x.clone().requires_grad_()
+    yr = O.pad2d(xr, pad, ring=ring, mode=mode)
+    xg = x.to(DEV).requires_grad_()
+    yg = ops.Pad(pad, ring=ring, mode=mode)(xg)
+    assert torch.equal(yg.cpu(), yr.detach())
+    gy = torch.randn(yr.shape, generator=g)
+    (gxr,) = torch.autograd.grad(yr, xr, gy)
+    (gxg,) = torch.autograd.grad(yg, xg, gy.to(DEV))
+    close(gxg, gxr, rtol=1e-5, atol_rel=1e-6)
+
+
+# ----------------------------------------------------------------------------- a2 Fourier features
+def test_fourier_golden_and_angle_pyramid(DF, g_ops):
+    out = DF.fourier_features(dev(g_ops["ff_angle"]), dev(g_ops["ff_freqs"]), dev(g_ops["ff_phase"]))
+    close(out, g_ops["ff_out"], rtol=0, atol_rel=5e-5)
+    ob = DF.fourier_features(dev(g_ops["ff_angle"]), dev(g_ops["ff_freqs"]), dev(g_ops["ff_phase"]),
+                             torch.bfloat16)
+    close(ob, g_ops["ff_out"], rtol=0, atol_rel=8e-3)
+    # angle pyramid step, incl. azimuth beyond +-pi (training-time shift)
+    g = torch.Generator().manual_seed(7)
+    el = torch.empty(3, 1, 16, 64).uniform_(-0.41, 0.05, generator=g)
+    az = (torch.linspace(3.1, -3.1, 64)[None, None, None].expand(3, 1, 16, 64)
+          + torch.tensor([0.0, 2.5, 6.0]).view(3, 1, 1, 1))
+    ang = torch.cat([el, az], 1).contiguous()
+    ref = O.downsample_angle(ang)
+    got = DF.angle_down2(ang.to(DEV)).cpu()
+    d = torch.remainder(got - ref + np.pi, 2 * np.pi) - np.pi        # compare modulo 2pi
+    assert float(d.abs().max()) < 2e-6
+
+
+@pytest.mark.parametrize("B,F,H,W", [(1, 256, 64, 512), (3, 256, 4, 32), (2, 5, 3, 7)])
+def test_fourier_vs_oracle_full_size(DF, B, F, H, W):
+    g = torch.Generator().manual_seed(8)
+    ang = torch.stack([torch.empty(B, H, W).uniform_(-0.41, 0.05, generator=g),
+                       torch.empty(B, H, W).uniform_(-3.14, 9.42, generator=g)], 1)
+    freqs = torch.stack([torch.empty(F).uniform_(-256, 256, generator=g),
+                         torch.randint(-7, 8, (F,), generator=g).float() * 16], 1)
+    phase = torch.rand(F, generator=g) * 2 * np.pi
+    ref = O.fourier_feature(ang, freqs, phase)
+    got = DF.fourier_features(ang.to(DEV), freqs.to(DEV), phase.to(DEV))
+    # identical fp32 argument arithmetic; device sincosf is within 2 ulp
+    assert float((got.cpu() - ref).abs().max()) < 1e-6
+
+
+# ----------------------------------------------------------------------------- a1 modulated conv
+@pytest.mark.parametrize("tag,demod", [("dm", True), ("hd", False)])
+def test_modconv_golden_module(ops, g_ops, tag, demod):
+    sd = {k[len(f"mc_{tag}_sd_"):]: T(v) for k, v in g_ops.items() if k.startswith(f"mc_{tag}_sd_")}
+    m = ops.ModConv2d(in_ch=12, out_ch=8 if demod else 1, mod_ch=16, ksize=1, stride=1, padding=0,
+                      demod=demod, bias=not demod, ema=True)
+    m.load_state_dict(sd)
+    m = m.to(DEV).eval()
+    x = dev(g_ops[f"mc_{tag}_x"]).requires_grad_()
+    st = dev(g_ops[f"mc_{tag}_style"]).requires_grad_()
+    y = m(x, st)
+    close(y, g_ops[f"mc_{tag}_y_eval"], rtol=1e-3, atol_rel=1e-5)
+    params = [x, st, m.weight, m.mod.module.weight, m.mod.module.bias]
+    grads = torch.autograd.grad(y, params, dev(g_ops[f"mc_{tag}_gy"]))
+    for nm, gr in zip(("gx", "gstyle", "gw", "gmodw", "gmodb"), grads):
+        close(gr, g_ops[f"mc_{tag}_{nm}"], rtol=1e-3, atol_rel=1e-4)
+    m.train()
+    y2 = m(x, st)
+    close(y2, g_ops[f"mc_{tag}_y_train"], rtol=1e-3, atol_rel=1e-5)
+    close(m.ema_var, g_ops[f"mc_{tag}_ema_after"], rtol=1e-5, atol_rel=0)
+
+
+@pytest.mark.parametrize("B,O,C1,C2,B2,HW,act", [
+    (2, 32, 64, 512, 2, (64, 512), 3),      # top-level conv1 shape (per-sample Fourier block)
+    (3, 32, 64, 512, 1, (8, 64), 3),        # batch-shared Fourier block
+    (2, 512, 0, 512, 1, (4, 32), 3),        # level 0: Fourier block only
+    (2, 64, 64, 0, 1, (32, 256), 3),        # conv2: features only
+    (2, 2, 32, 0, 1, (64, 512), 1),         # heads (O = 2)
+    (1, 70, 33, 19, 1, (5, 12), 1),         # ragged sizes
+])
+@pytest.mark.parametrize("dtype", [torch.float32, torch.bfloat16])
+def test_modconv_bmm_vs_oracle(DF, B, O, C1, C2, B2, HW, act, dtype):
+    g = torch.Generator().manual_seed(9)
+    H, W = HW
+    K = C1 + C2
+    wb = torch.randn(B, O, K, generator=g) / np.sqrt(K)
+    x1 = torch.randn(B, C1, H, W, generator=g) if C1 else None
+    x2 = torch.randn(B2, C2, H, W, generator=g) if C2 else None
+    bias = torch.randn(O, generator=g)
+    if dtype == torch.bfloat16:
+        wb = wb.bfloat16().float()
+        x1 = None if x1 is None else x1.bfloat16().float()
+        x2 = None if x2 is None else x2.bfloat16().float()
+    wr = wb.clone().requires_grad_()
+    x1r = None if x1 is None else x1.clone().requires_grad_()
+    parts = ([x1r] if C1 else []) + ([x2.expand(B, -1, -1, -1)] if C2 else [])
+    xin = torch.cat(parts, 1).reshape(B, K, H * W)
+    yr = torch.bmm(wr, xin).reshape(B, O, H, W) + bias.view(1, -1, 1, 1)
+    if act == 3:
+        yr = O_lrelu(yr)
+    wg = wb.to(DEV, dtype).requires_grad_()
+    x1g = None if x1 is None else x1.to(DEV, dtype).requires_grad_()
+    x2g = None if x2 is None else x2.to(DEV, dtype)
+    bg = bias.to(DEV).requires_grad_()
+    yg = DF.modconv_bmm(wg, x1g, x2g, bg, act, 0.2, O.SQRT2 if act == 3 else 1.0)
+    tol = dict(rtol=1e-3, atol_rel=2e-5) if dtype == torch.float32 else dict(rtol=2e-2, atol_rel=1e-2)
+    close(yg, yr, **tol)
+    gy = torch.randn(B, O, H, W, generator=g)
+    if dtype == torch.bfloat16:
+        gy = gy.bfloat16().float()
+    wanted_r = [wr] + ([x1r] if C1 else [])
+    gr = torch.autograd.grad(yr, wanted_r, gy)
+    wanted_g = [wg, bg] + ([x1g] if C1 else [])
+    gg = torch.autograd.grad(yg, wanted_g, gy.to(DEV, dtype))
+    close(gg[0], gr[0], **tol)
+    if C1:
+        close(gg[2], gr[1], **tol)
+    db_ref = (torch.where(yr.detach() > 0, gy, gy * 0.2) * O.SQRT2 if act == 3 else gy).sum((0, 2, 3))
+    close(gg[1], db_ref, rtol=tol["rtol"], atol_rel=max(tol["atol_rel"], 1e-4))
+
+
+def O_lrelu(y):
+    return torch.where(y > 0, y, y * 0.2) * O.SQRT2
+
+
+# ----------------------------------------------------------------------------- a10 raydrop
+def test_gumbel_raydrop_golden(DF, g_ops):
+    logit = dev(g_ops["gs_logit"]).requires_grad_()
+    img = dev(g_ops["gs_img"]).requires_grad_()
+    u = dev(g_ops["gs_u"])
+    mask, out = DF.gumbel_raydrop(logit, img, u, -1.0, 1.0)
+    ref_mask = g_ops["gs_mask"]
+    # device transcendentals differ in ulps: only near-ties (|logit + noise| ~ 0) may flip
+    lo = np.log(g_ops["gs_u"]) - np.log1p(-g_ops["gs_u"]) + g_ops["gs_logit"]
+    sure = np.abs(lo) > 1e-4
+    assert np.array_equal(mask.detach().cpu().numpy()[sure], ref_mask[sure])
+    assert np.array_equal(out.detach().cpu().numpy()[sure], g_ops["gs_image"][sure])
+    _, _, count = DF.raydrop_count(logit.detach(), img.detach(), u, -1.0, 1.0)
+    assert abs(int(count.item()) - int(g_ops["gs_count"])) <= int((~sure).sum())
+    gl, gi = torch.autograd.grad(out, [logit, img], dev(g_ops["gs_gout"]))
+    close(gl, g_ops["gs_glogit"], rtol=1e-3, atol_rel=1e-5)
+    close(gi, g_ops["gs_gimg"], rtol=1e-6, atol_rel=0)
+
+
+def test_gumbel_raydrop_full_size_count(DF):
+    g = torch.Generator().manual_seed(11)
+    logit = torch.randn(8, 1, 64, 512, generator=g) * 2
+    img = torch.tanh(torch.randn(8, 1, 64, 512, generator=g))
+    u = torch.rand(8, 1, 64, 512, generator=g)
+    ref = O.raydrop(img, logit, u)
+    mask, out, count = DF.raydrop_count(logit.to(DEV), img.to(DEV), u.to(DEV), -1.0, 1.0)
+    lo = u.clamp(1e-7, 1 - 1e-7).logit() + logit
+    sure = lo.abs() > 1e-4
+    assert torch.equal(mask.cpu()[sure], ref["raydrop_mask"][sure])
+    assert int(count.item()) == int(mask.sum().item())                 # kernel's own count
+    assert abs(int(count.item()) - int(ref["raydrop_mask"].sum().item())) <= int((~sure).sum())
+    assert torch.equal(out.cpu()[sure], ref["image"][sure])
+
+
+# ----------------------------------------------------------------------------- a14 projection
+def test_coord_bridge_bit_exact(g_coords):
+    from dusty_gan_v2_b200.gans.coords import CoordBridge
+    cb = CoordBridge(64, 512, 1.45, 80.0, "data/coords/kitti_raw.npy")
+    assert np.array_equal(cb.angle.numpy(), g_coords["angle"])          # angle grid: bit exact
+    cb = cb.to(DEV)
+    xin = dev(g_coords["xin"])
+    pm = cb.convert(xin, "inv_depth_norm", "point_map")
+    assert int(cb.last_valid_count.item()) == int(g_coords["valid_count"])    # mask count
+    ps = cb.convert(xin, "inv_depth_norm", "point_set")
+    assert int(cb.last_valid_count.item()) == int(g_coords["valid_count"])
+    # pixel indexing: point_set[b, h*W + w, :] == point_map[b, :, h, w]
+    assert torch.equal(ps, pm.flatten(2).permute(0, 2, 1))
+    # values: trig table comes from the host, products are plain fp32 -> bit exact
+    assert np.array_equal(pm.cpu().numpy()[:, :, ::4, ::8], g_coords["point_map"])
+    assert np.array_equal(ps.cpu().numpy()[:, :2048], g_coords["point_set_head"])
+    dn = cb.convert(xin, "inv_depth_norm", "depth_norm")
+    close(dn[:, :, ::4, ::8], g_coords["depth_norm"], rtol=1e-6, atol_rel=0)
+    with pytest.raises(RuntimeError):
+        cb.convert(xin.cpu(), "inv_depth_norm", "point_map")
+
+
+# ----------------------------------------------------------------------------- a12 minibatch stddev
+@pytest.mark.parametrize("shape", [(8, 6, 4, 4), (2, 6, 4, 4), (64, 512, 4, 32), (4, 3, 2, 2)])
+def test_minibatch_stddev(ops, g_ops, shape):
+    g = torch.Generator().manual_seed(12)
+    x = torch.randn(shape, generator=g)
+    xr = x.clone().requires_grad_()
+    yr = O.minibatch_stddev(xr)
+    xg = x.to(DEV).requires_grad_()
+    yg = ops.MinibatchStdDev(4, 1)(xg)
+    close(yg, yr, rtol=1e-4, atol_rel=1e-6)
+    gy = torch.randn(yr.shape, generator=g)
+    (gxr,) = torch.autograd.grad(yr, xr, gy, create_graph=True)
+    gy_g = gy.to(DEV)
+    (gx1,) = torch.autograd.grad(yg, xg, gy_g, retain_graph=True)           # fused kernel
+    close(gx1, gxr, rtol=1e-3, atol_rel=1e-5)
+    (gx2,) = torch.autograd.grad(yg, xg, gy_g, create_graph=True)           # differentiable path
+    close(gx2, gxr, rtol=1e-3, atol_rel=1e-5)
+    v = torch.randn(shape, generator=g)
+    (hr,) = torch.autograd.grad((gxr * v).sum(), xr)
+    (hg,) = torch.autograd.grad((gx2 * v.to(DEV)).sum(), xg)
+    close(hg, hr, rtol=2e-3, atol_rel=1e-4)
+    if shape == (8, 6, 4, 4):
+        close(ops.MinibatchStdDev(4, 1)(dev(g_ops["mb_x"])), g_ops["mb_y"], 1e-4, 1e-6)
+        close(ops.MinibatchStdDev(4, 1)(dev(g_ops["mb2_x"])), g_ops["mb2_y"], 1e-4, 1e-6)
+
+
+# ----------------------------------------------------------------------------- a13 / a7
+def test_sumsq_rows_and_r1_grad(DF):
+    g = torch.Generator().manual_seed(13)
+    x = torch.randn(6, 1, 64, 512, generator=g)
+    xg = x.to(DEV).requires_grad_()
+    s = DF.sumsq_rows(xg)
+    close(s, x.double().pow(2).sum((1, 2, 3)).float(), rtol=1e-5, atol_rel=0)
+    (gx,) = torch.autograd.grad(s.mean(), xg)
+    close(gx, 2 * x / 6, rtol=1e-6, atol_rel=0)
+    close(DF.sumsq_total(x.to(DEV).bfloat16()), x.bfloat16().double().pow(2).sum().float(), 1e-4, 0)
+
+
+def test_circular_unshift_vs_oracle(DF):
+    g = torch.Generator().manual_seed(14)
+    v = torch.randn(4, 2, 8, 64, generator=g)
+    s01 = torch.tensor([0.0, 0.25, 0.7303, 0.999])
+    vr = v.clone().requires_grad_()
+    ref = O.circular_unshift(vr, s01 * 2 * np.pi) * 0.25
+    vg = v.to(DEV).requires_grad_()
+    got = DF.circular_unshift(vg, s01.to(DEV), 0.25)
+    # the reference derives the sub-pixel offset through normalised fp32 grid coordinates
+    # (error ~ W * 2^-23 per unit slope): compare at that resolution
+    close(got, ref, rtol=1e-3, atol_rel=2e-4)
+    gy = torch.randn(ref.shape, generator=g)
+    (gr,) = torch.autograd.grad(ref, vr, gy)
+    (gg,) = torch.autograd.grad(got, vg, gy.to(DEV))
+    close(gg, gr, rtol=1e-3, atol_rel=2e-4)

@@ -192,3 +192,11 @@ def test_discriminator_first_and_second_order(g_disc):
             close(g, ref, rtol=2e-3, atol=2e-4 * max(np.abs(ref).max(), 1e-8))
             n += 1
     assert n >= 8
+
+
+def test_ada_apply(g_ada):
+    x = T(g_ada["x"]).clone().requires_grad_()
+    y = O.ada_apply(x, T(g_ada["G_inv"]), T(g_ada["C"]))
+    close(y, g_ada["y"], rtol=1e-4, atol=2e-5)
+    (gx,) = torch.autograd.grad(y, x, T(g_ada["gy"]))
+    close(gx, g_ada["gx"], rtol=1e-4, atol=2e-5)

@@ -1,0 +1,418 @@
+#!/usr/bin/env python
+"""Benchmark of the DUSty-v2 G+D training step (BASELINE.json metric:
+"dusty_v2 G+D train images/sec @64x512").
+
+    python bench.py --gpus N --steps K --warmup W            # this repo's B200 path
+    python bench.py --impl reference --gpus N --steps K ...   # reference CPU path (oracle port)
+
+One "step" = one training iteration of the reference's Trainer.step (G step, D step, R1 every
+16th iteration, EMA, ADA controller) at per-GPU batch 64 on synthetic 64x512 range images with
+random-init weights.  N>1 is launched by torchrun (one rank per GPU, NCCL, weak scaling:
+per-GPU batch fixed).  Rank 0 prints ONE JSON line.
+
+Timing: W warm-up steps, then exactly K steps bracketed by barrier + synchronize, CUDA events
+on the launching stream, max over ranks.  The working set of a step (GBs of activations)
+is far larger than the 126 MB L2, so no explicit flush is needed between steps; the isolated
+kernel measurements for the roofline block do flush L2 between launches.
+"""
+import argparse
+import json
+import os
+import statistics
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+for _p in (os.path.join(ROOT, "tests"), ROOT):
+    if _p not in sys.path:
+        sys.path.insert(0, _p)
+
+METRIC = "dusty_v2 G+D train images/sec @64x512"
+UNIT = "images/s"
+H, W = 64, 512
+
+
+def parse():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=32)
+    ap.add_argument("--warmup", type=int, default=4)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--precision", default="bf16", choices=["bf16", "fp32"])
+    ap.add_argument("--batch-per-gpu", type=int, default=64)
+    ap.add_argument("--arch", default="dusty_v2", choices=["dusty_v2", "dusty_v1", "vanilla"])
+    ap.add_argument("--ada-p", type=float, default=None, help="pin the ADA probability")
+    ap.add_argument("--cpu-batch", type=int, default=2, help="batch of the CPU baseline sample")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-roofline", action="store_true")
+    ap.add_argument("--no-e2e", action="store_true")
+    return ap.parse_args()
+
+
+# ------------------------------------------------------------------------------ helpers
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled DURING the timed region."""
+    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        self.rows, self.proc = [], None
+        try:
+            self.proc = subprocess.Popen(
+                ["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "200",
+                 "-i", str(index)], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.thread = threading.Thread(target=self._pump, daemon=True)
+            self.thread.start()
+        except Exception:
+            self.proc = None
+
+    def _pump(self):
+        for line in self.proc.stdout:
+            self.rows.append(line.strip())
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        sm, mx, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for r in self.rows:
+            f = [x.strip() for x in r.split(",")]
+            if len(f) < 7:
+                continue
+            try:
+                sm.append(float(f[0]))
+                mx.append(float(f[1]))
+            except ValueError:
+                continue
+            for n, v in zip(names, f[3:7]):
+                if v.lower().startswith("active"):
+                    reasons.add(n)
+        return {"sm_mhz": statistics.median(sm) if sm else None,
+                "sm_max_mhz": max(mx) if mx else None, "samples": len(sm),
+                "reasons": sorted(reasons)}
+
+
+def synthetic_batches(n, batch, seed, pinned=False, device=None):
+    """Synthetic reals: depth = 1.45 + 78.55*U(0,1), mask ~ Bernoulli(0.85)."""
+    import torch
+    g = torch.Generator().manual_seed(seed)
+    out = []
+    for _ in range(n):
+        depth = 1.45 + (80 - 1.45) * torch.rand(batch, 1, H, W, generator=g)
+        mask = (torch.rand(batch, 1, H, W, generator=g) < 0.85).float()
+        if pinned:
+            depth, mask = depth.pin_memory(), mask.pin_memory()
+        if device is not None:
+            depth, mask = depth.to(device), mask.to(device)
+        out.append({"depth": depth, "mask": mask})
+    return out
+
+
+def cycle(pool):
+    i = 0
+    while True:
+        yield pool[i % len(pool)]
+        i += 1
+
+
+# ------------------------------------------------------------------------------ CPU baseline
+def cpu_reference_run(args, steps, warmup, batch):
+    """Times the oracle's restatement of Trainer.step on the host cores.  Returns
+    (images_per_s, seconds_per_step, cores, description)."""
+    import numpy as np
+    import torch
+
+    from dusty_gan_v2_b200.gans.augment.adaptive_augment import AdaptiveAugment
+    from dusty_gan_v2_b200.gans.coords import CoordBridge
+    from dusty_gan_v2_b200.gans.models.builder import build_discriminator, build_generator
+    from dusty_gan_v2_b200.presets import preset
+    from oracle import dusty_oracle as O
+
+    cores = os.cpu_count() or 1
+    torch.set_num_threads(cores)
+    torch.manual_seed(0)
+    np.random.seed(0)
+    cfg = preset(args.arch, batch_size=batch)
+    G = build_generator(cfg.model.generator)            # parameter init only (CPU, no kernels)
+    D = build_discriminator(cfg.model.discriminator)
+    nograd = ("ema_var", "w_avg", "kernel", "pe.", "raydrop_const")
+    sdG = {k: v.clone().requires_grad_(not any(t in k for t in nograd)) for k, v in G.state_dict().items()}
+    sdD = {k: v.clone().requires_grad_("kernel" not in k) for k, v in D.state_dict().items()}
+    cb = CoordBridge(H, W, 1.45, 80.0, os.path.join(ROOT, "data/coords/kitti_raw.npy"))
+    angle = cb.angle.repeat_interleave(batch, dim=0)
+    ada = AdaptiveAugment(p_init=args.ada_p or 0.0, **cfg.training.augment.policy)
+    ada.generator = torch.Generator().manual_seed(7)
+    pool = synthetic_batches(2, batch, seed=2)
+    g = torch.Generator().manual_seed(1)
+
+    def draws():
+        r = {}
+        for tag in ("g", "d"):
+            r[f"z_{tag}"] = torch.randn(batch, 512, generator=g)
+            r[f"shift_{tag}"] = torch.rand(batch, generator=g)
+            r[f"u_{tag}"] = torch.rand(batch, 1, H, W, generator=g)
+        for tag in ("g_fake", "d_real", "d_fake", "r1"):
+            r[f"keep_{tag}"] = torch.bernoulli(torch.full((batch, 1, H, W), 0.5), generator=g)
+            r[f"Ginv_{tag}"] = torch.inverse(ada.sample_affine(batch, H, W))
+            r[f"C_{tag}"] = ada.sample_color(batch)
+        return r
+
+    lazy = 16 / 17.0
+    optG = torch.optim.Adam([v for v in sdG.values() if v.requires_grad], lr=0.002, betas=(0.0, 0.99))
+    optD = torch.optim.Adam([v for v in sdD.values() if v.requires_grad], lr=0.002 * lazy,
+                            betas=(0.0, 0.99 ** lazy))
+
+    def apply(opt, sd, grads):
+        for k, gr in grads.items():
+            sd[k].grad = gr
+        opt.step()
+        opt.zero_grad(set_to_none=True)
+
+    def one(it):
+        b = pool[it % len(pool)]
+        x_real = O.fetch_reals(b["depth"], b["mask"], 1.45, 80.0)
+        r = O.train_iteration(sdG, sdD, x_real, angle, draws(), with_r1=(it % 16 == 0))
+        apply(optG, sdG, r["grads_G"])
+        apply(optD, sdD, r["grads_D"])
+        if "grads_R1" in r:
+            apply(optD, sdD, r["grads_R1"])
+
+    for i in range(warmup):
+        one(i + 1)
+    t0 = time.perf_counter()
+    for i in range(steps):
+        one(i)
+    dt = time.perf_counter() - t0
+    desc = (f"oracle port of Trainer.step (G step + D step + R1 on every 16th step, ADA p="
+            f"{args.ada_p or 0.0}, warm-up dropout 0.5), fp32, batch {batch}, {steps} steps, "
+            f"Adam updates included (all three phases use the pre-step weights)")
+    return steps * batch / dt, dt / steps, cores, desc
+
+
+# ------------------------------------------------------------------------------ kernel roofline
+def kernel_rooflines(device, peaks):
+    """Isolated CUDA-event timings of this repo's kernels at the step's real shapes (B=64),
+    L2 flushed between launches.  Returns (dominant_contraction_entry, list_of_entries)."""
+    import torch
+
+    import dusty_gan_v2_b200.functional as DF
+    from dusty_gan_v2_b200 import _cabi as K
+    B = 64
+    flush = torch.empty(256 * 1024 * 1024, dtype=torch.uint8, device=device)
+
+    def timeit(fn, reps=5):
+        fn()
+        torch.cuda.synchronize()
+        ts = []
+        for _ in range(reps):
+            flush.zero_()
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            fn()
+            e1.record()
+            torch.cuda.synchronize()
+            ts.append(e0.elapsed_time(e1) * 1e-3)
+        return sum(ts) / len(ts)
+
+    bf = torch.bfloat16
+    hbm = peaks.get("hbm_gbs", 6650.0)
+    tflops = peaks.get("bf16_tflops", 1590.0)
+    src = "measured" if "hbm_gbs" in peaks else "fallback"
+    out = []
+
+    def mem_entry(name, fn, bytes_):
+        t = timeit(fn)
+        out.append({"kernel": name, "bound": "hbm", "achieved": bytes_ / t / 1e9, "peak": hbm,
+                    "unit": "GB/s", "frac": bytes_ / t / 1e9 / hbm, "traffic": None,
+                    "ms": t * 1e3, "peak_source": src})
+
+    # bias_act fwd on the D's first activation [64,32,64,512] bf16: read + write
+    x = torch.randn(B, 32, H, W, device=device, dtype=bf)
+    b = torch.zeros(32, device=device)
+    mem_entry("bias_act_fwd[64,32,64,512]bf16", lambda: DF._bias_act_raw(x, b, None, 3, 0, 0.2, 1.41), 2 * x.numel() * 2)
+    y = DF._bias_act_raw(x, b, None, 3, 0, 0.2, 1.41)
+    gx = torch.empty_like(x)
+    db = torch.zeros(32, device=device)
+    mem_entry("bias_act_bwd[64,32,64,512]bf16",
+              lambda: K.call("dusty_bias_act_bwd", K.ptr(x), K.ptr(y), K.ptr(gx), K.ptr(db), B, 32, H * W,
+                             0.2, 1.41, K.BF16, K.stream_of(x)), 3 * x.numel() * 2)
+    # Resample up2 on the level-3 features [64,64,32,256] -> [64,64,64,512]
+    from dusty_gan_v2_b200.gans.models.ops import Resample
+    up = Resample(up=2).to(device)
+    h = torch.randn(B, 64, 32, 256, device=device, dtype=bf)
+    mem_entry("resample_up2[64,64,32,256]bf16", lambda: up(h), 5 * h.numel() * 2)
+    blur = Resample().to(device)
+    mem_entry("resample_blur[64,32,64,512]bf16", lambda: blur(x), 2 * x.numel() * 2)
+    # Fourier features, per-sample block at the top level: write-bound
+    ang = torch.rand(B, 2, H, W, device=device)
+    fr = torch.randn(256, 2, device=device)
+    ph = torch.rand(256, device=device)
+    mem_entry("fourier[64,512,64,512]bf16", lambda: DF.fourier_features(ang, fr, ph, bf),
+              B * H * W * (8 + 512 * 2))
+    del x, y, gx, h
+    # top-level conv1 contraction: [64, 32, 576] x [64, 576, 32768]
+    O_, C1, C2, P = 32, 64, 512, H * W
+    wb = (torch.randn(B, O_, C1 + C2, device=device) / 24).to(bf)
+    x1 = torch.randn(B, C1, H, W, device=device, dtype=bf)
+    x2 = DF.fourier_features(ang[:1], fr, ph, bf)
+    bias = torch.zeros(O_, device=device)
+    t = timeit(lambda: DF.modconv_bmm(wb, x1, x2, bias, 3, 0.2, 1.41))
+    flops = 2.0 * B * O_ * (C1 + C2) * P
+    dom = {"kernel": "modconv_fwd[B=64,O=32,K=64+512,P=32768]bf16", "bound": "tensor",
+           "achieved": flops / t / 1e12, "peak": tflops, "unit": "TFLOP/s",
+           "frac": flops / t / 1e12 / tflops, "traffic": None, "ms": t * 1e3, "peak_source": src}
+    # the same launch seen as a memory stream (it is HBM-bound at N=32: AI ~ 60 flop/B)
+    byts = (x1.numel() + B * O_ * P) * 2 + x2.numel() * 2
+    out.append({"kernel": dom["kernel"] + " (as stream)", "bound": "hbm", "achieved": byts / t / 1e9,
+                "peak": hbm, "unit": "GB/s", "frac": byts / t / 1e9 / hbm, "traffic": None,
+                "ms": t * 1e3, "peak_source": src})
+    return dom, out
+
+
+# ------------------------------------------------------------------------------ main
+def main():
+    args = parse()
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+
+    if args.impl == "reference":
+        if rank != 0:
+            return
+        ips, spt, cores, desc = cpu_reference_run(args, args.steps, args.warmup, args.cpu_batch)
+        line = {"impl": "reference", "metric": METRIC, "value": ips, "unit": UNIT, "n_gpus": args.gpus,
+                "steps": args.steps, "warmup": args.warmup, "ms_per_step": spt * 1e3,
+                "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
+                "data": "synthetic",
+                "config": {"workload": f"{args.arch} G+D training step (nsgan + lazy R1), 64x512, CPU sample "
+                                       f"batch {args.cpu_batch}", "global_batch": args.cpu_batch,
+                           "parallelism": "cpu"},
+                "cpu_baseline": {"value": ips, "unit": UNIT, "cores": cores, "kind": "port", "sample": desc},
+                "e2e": {"value": ips, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+        print(json.dumps(line))
+        return
+
+    import torch
+    import torch.distributed as dist
+
+    import dusty_gan_v2_b200 as pkg
+    from dusty_gan_v2_b200.gans.trainer import Trainer
+    from dusty_gan_v2_b200.presets import preset
+
+    assert torch.cuda.is_available(), "bench.py needs a GPU (no CPU fallback)"
+    torch.cuda.set_device(local_rank)
+    device = torch.device("cuda", local_rank)
+    if world > 1:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", device_id=device)
+    pkg.set_precision(args.precision)
+    torch.backends.cudnn.benchmark = True        # the reference sets it (gans/utils.py:29-30)
+    torch.manual_seed(0 + rank)
+    import numpy as np
+    np.random.seed(0 + rank)
+
+    B = args.batch_per_gpu
+    cfg = preset(args.arch, batch_size=B * world)
+    if args.ada_p is not None:
+        cfg.training.augment.p_init = args.ada_p
+        cfg.training.augment.p_target = None
+    pool_dev = synthetic_batches(4, B, seed=2 + rank, device=device)
+    tr = Trainer(cfg, cycle(pool_dev), device=device, rank=rank, world_size=world,
+                 angle_file=os.path.join(ROOT, "data/coords/kitti_raw.npy"))
+    tr.A.generator = torch.Generator().manual_seed(100 + rank)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def run(first_it, n):
+        for i in range(n):
+            last = tr.step(first_it + i)
+        return last
+
+    # warm-up: iteration 0 carries an R1 step, so every phase is warmed
+    run(0, args.warmup)
+    gp = max(tr.gp_every, 1)
+    start = ((args.warmup + gp - 1) // gp) * gp          # timed region starts on an R1 iteration
+    barrier()
+    clocks = ClockSampler(local_rank) if rank == 0 else None
+    n0 = pkg.launch_count()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    run(start, args.steps)
+    e1.record()
+    barrier()
+    launches = pkg.launch_count() - n0
+    ms = torch.tensor([e0.elapsed_time(e1)], device=device)
+    if world > 1:
+        dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+    ms = float(ms.item())
+    clk = clocks.stop() if clocks else None
+    value = args.steps * B * world / (ms * 1e-3)
+    r1_steps = len([i for i in range(start, start + args.steps) if tr.gp_every and i % tr.gp_every == 0])
+
+    # ---- end to end: pinned host batches in, step scalars out, every step
+    e2e = None
+    if not args.no_e2e:
+        pool_host = synthetic_batches(4, B, seed=2 + rank, pinned=True)
+        tr.batch_iter = cycle(pool_host)
+        h2d = sum(t.numel() * t.element_size() for t in pool_host[0].values())
+        run(start + args.steps, 2)
+        barrier()
+        t0 = time.perf_counter()
+        d2h = 0
+        for i in range(args.steps):
+            packed = tr.step(start + args.steps + 2 + i)
+            host = packed.cpu()                       # device -> host read of the step's scalars
+            d2h = host.numel() * host.element_size()
+        barrier()
+        dt = torch.tensor([time.perf_counter() - t0], device=device)
+        if world > 1:
+            dist.all_reduce(dt, op=dist.ReduceOp.MAX)
+        e2e = {"value": args.steps * B * world / float(dt.item()), "unit": UNIT,
+               "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h}
+        tr.batch_iter = cycle(pool_dev)
+
+    line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": ms / args.steps, "higher_is_better": True,
+            "scaling": "weak", "vs_baseline": None, "dtype": "bf16" if args.precision == "bf16" else "f32",
+            "data": "synthetic",
+            "config": {"workload": f"{args.arch} full G+D training step (nsgan + R1 every 16th step, ADA, "
+                                   f"warm-up dropout, EMA, Adam), 64x512 range images, random-init weights",
+                       "global_batch": B * world, "per_gpu_batch": B, "parallelism": f"dp{world}",
+                       "r1_steps_timed": r1_steps, "ada_p": "adaptive from 0.0" if args.ada_p is None else args.ada_p,
+                       "l2": "no flush: per-step working set (GBs) >> 126 MB L2",
+                       "dense_convs": "D 3x3/1x1 convs and linears via cuDNN/cuBLAS (library, interim)"},
+            "clocks": clk, "gpu_launches": launches, "e2e": e2e}
+
+    if rank == 0 and world == 1:
+        peaks = {}
+        try:
+            peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+        except Exception:
+            pass
+        if not args.no_roofline:
+            del tr
+            torch.cuda.empty_cache()
+            dom, kernels = kernel_rooflines(device, peaks)
+            line["roofline"] = {k: dom[k] for k in ("bound", "achieved", "peak", "unit", "frac", "traffic")}
+            line["roofline"]["kernel"] = dom["kernel"]
+            line["roofline"]["peak_source"] = dom["peak_source"]
+            line["kernels"] = kernels
+        if not args.no_cpu_baseline:
+            ips, spt, cores, desc = cpu_reference_run(args, 2, 1, args.cpu_batch)
+            line["cpu_baseline"] = {"value": ips, "unit": UNIT, "cores": cores, "kind": "port",
+                                    "sample": desc}
+    if rank == 0:
+        print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

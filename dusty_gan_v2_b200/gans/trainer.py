@@ -98,9 +98,9 @@ class Trainer:
                                       "(loss.pl = 0 in every config; the branch is broken)")
         lr_g, lr_d = tr.lr.generator, tr.lr.discriminator
         self.optim_G = torch.optim.Adam(self.G.parameters(), lr=lr_g.alpha,
-                                        betas=(lr_g.beta1, lr_g.beta2), fused=True)
+                                        betas=(float(lr_g.beta1), float(lr_g.beta2)), fused=True)
         self.optim_D = torch.optim.Adam(self.D.parameters(), lr=lr_d.alpha * lazy_D,
-                                        betas=(lr_d.beta1 ** lazy_D, lr_d.beta2 ** lazy_D),
+                                        betas=(float(lr_d.beta1 ** lazy_D), float(lr_d.beta2 ** lazy_D)),
                                         fused=True)
         self.z_dim = cfg.model.generator.mapping_kwargs.in_ch
         self.warmup_fade_imgs = tr.warmup.fade_kimg * 1e3

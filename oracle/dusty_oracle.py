@@ -582,6 +582,28 @@ def ada_padding(G_inv: Tensor, height: int, width: int, ksize: int):
     return x1, x2, y1, y2
 
 
+def bilinear_warp(img: Tensor, grid: Tensor) -> Tensor:
+    """F.grid_sample(mode="bilinear", padding_mode="zeros", align_corners=False) written
+    with gather so that it is differentiable to any order (ATen's grid_sampler backward
+    is not; the reference wraps it in GridSampleForward/Backward,
+    adaptive_augment.py:49-96, for the same reason)."""
+    B, C, H, W = img.shape
+    ix = ((grid[..., 0] + 1) * W - 1) / 2
+    iy = ((grid[..., 1] + 1) * H - 1) / 2
+    x0, y0 = torch.floor(ix), torch.floor(iy)
+    fx, fy = ix - x0, iy - y0
+    flat = img.reshape(B, C, H * W)
+    out = 0
+    for dy, wy in ((0, 1 - fy), (1, fy)):
+        for dx, wx in ((0, 1 - fx), (1, fx)):
+            xi, yi = x0 + dx, y0 + dy
+            ok = ((xi >= 0) & (xi < W) & (yi >= 0) & (yi < H)).to(img.dtype)
+            idx = (yi.clamp(0, H - 1) * W + xi.clamp(0, W - 1)).long().reshape(B, 1, -1)
+            val = torch.gather(flat, 2, idx.expand(B, C, -1)).reshape(B, C, *grid.shape[1:3])
+            out = out + val * (wy * wx * ok).unsqueeze(1)
+    return out
+
+
 def ada_apply(img: Tensor, G_inv: Tensor, C: Tensor) -> Tensor:
     """The deterministic body of AdaptiveAugment.forward for a given inverse geometric
     transform G_inv [B,3,3] and colour matrix C [B,4,4]: circular-W / reflect-H pad,
@@ -604,7 +626,7 @@ def ada_apply(img: Tensor, G_inv: Tensor, C: Tensor) -> Tensor:
     G_inv = (_m3([(2 / img.shape[3], 0, 0), (0, 2 / img.shape[2], 0), (0, 0, 1)]) @ G_inv
              @ _m3([(shape[3] / 2, 0, 0), (0, shape[2] / 2, 0), (0, 0, 1)]))
     grid = F.affine_grid(G_inv[:, :2, :], shape, align_corners=False)
-    img = F.grid_sample(img, grid, mode="bilinear", padding_mode="zeros", align_corners=False)
+    img = bilinear_warp(img, grid)
     d = -pad_k * 2
     d0, d1 = d + (nk - 1) // 2, d + (nk - 2) // 2
     kf = k.flip(0)
@@ -640,15 +662,19 @@ def train_iteration(sdG: Dict[str, Tensor], sdD: Dict[str, Tensor], x_real: Tens
     def aug(x, tag):
         return ada_apply(warmup_dropout(x, rnd.get(f"keep_{tag}")), rnd[f"Ginv_{tag}"], rnd[f"C_{tag}"])
 
+    import time
     pG = {k: v for k, v in sdG.items() if v.requires_grad}
     pD = {k: v for k, v in sdD.items() if v.requires_grad}
     out = {}
+    t0 = time.perf_counter()
     # G step
     fake = generator(sdG, rnd["z_g"], angle, rnd["u_g"], training=True,
                      shifts_rad=rnd["shift_g"] * (2 * np.pi))["image"]
     loss_g = nsgan_g(discriminator(sdD, aug(fake, "g_fake")))
     out["loss_G"] = loss_g.detach()
     out["grads_G"] = dict(zip(pG, torch.autograd.grad(loss_g, list(pG.values()), allow_unused=True)))
+    out["t_G"] = time.perf_counter() - t0
+    t0 = time.perf_counter()
     # D step
     with torch.no_grad():
         fake = generator(sdG, rnd["z_d"], angle, rnd["u_d"], training=True,
@@ -658,7 +684,9 @@ def train_iteration(sdG: Dict[str, Tensor], sdD: Dict[str, Tensor], x_real: Tens
     loss_d = nsgan_d(y_real, y_fake)
     out["loss_D"] = loss_d.detach()
     out["grads_D"] = dict(zip(pD, torch.autograd.grad(loss_d, list(pD.values()), allow_unused=True)))
+    out["t_D"] = time.perf_counter() - t0
     if with_r1:
+        t0 = time.perf_counter()
         x_gp = x_real.detach().clone().requires_grad_()
         y = discriminator(sdD, aug(x_gp, "r1"))
         (gx,) = torch.autograd.grad(y.sum(), x_gp, create_graph=True)
@@ -666,4 +694,5 @@ def train_iteration(sdG: Dict[str, Tensor], sdD: Dict[str, Tensor], x_real: Tens
         loss = (gp_weight / 2) * r1 + 0.0 * y.squeeze()[0]
         out["r1"] = r1.detach()
         out["grads_R1"] = dict(zip(pD, torch.autograd.grad(loss, list(pD.values()), allow_unused=True)))
+        out["t_R1"] = time.perf_counter() - t0
     return out

@@ -167,7 +167,7 @@ def test_full_size_generator_vs_oracle(precision, tol):
     cbd = cb.to(DEV)
     inv = (out["image"].float() + 1) / 2
     pts = cbd.convert(inv, "inv_depth_norm", "point_set")
-    _, _, count = O.inv_depth_norm_to_points(inv.cpu(), cb.angle, 1.45, 80.0)
+    _, _, count = O.inv_depth_norm_to_points(inv.cpu(), cb.angle.cpu(), 1.45, 80.0)
     assert int(cbd.last_valid_count.item()) == count
     assert pts.shape == (B, 64 * 512, 3)
 

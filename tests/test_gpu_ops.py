@@ -64,6 +64,8 @@ def test_bias_act_vs_oracle_double_backward(DF, shape, dtype):
     tol = dict(rtol=1e-3, atol_rel=1e-5) if dtype == torch.float32 else dict(rtol=2e-2, atol_rel=1e-2)
     close(yg, yr, **tol)
     gy = torch.randn(shape, generator=g)
+    if dtype == torch.bfloat16:
+        gy = gy.bfloat16().float()
     (dxr, dbr) = torch.autograd.grad(yr, [xr, br], gy, create_graph=True)
     (dxg, dbg) = torch.autograd.grad(yg, [xg, bg], gy.to(DEV, dtype), create_graph=True)
     close(dxg, dxr, **tol)
@@ -120,7 +122,7 @@ def test_upfirdn2d_grad_and_gradgrad_vs_oracle(cfg):
     from dusty_gan_v2_b200.gans.models.ops.upfirdn2d.upfirdn2d import upfirdn2d
     up, down, pad, kshape = cfg
     g = torch.Generator().manual_seed(3)
-    x = torch.randn(2, 2, 13, 18, generator=g)
+    x = torch.randn(2, 2, 26, 28, generator=g)
     k = torch.randn(*kshape, generator=g)
     xr = x.clone().requires_grad_()
     yr = O.upfirdn2d(xr, k, up=up, down=down, pad=pad)
@@ -255,7 +257,7 @@ def test_modconv_golden_module(ops, g_ops, tag, demod):
     close(m.ema_var, g_ops[f"mc_{tag}_ema_after"], rtol=1e-5, atol_rel=0)
 
 
-@pytest.mark.parametrize("B,O,C1,C2,B2,HW,act", [
+@pytest.mark.parametrize("B,Oc,C1,C2,B2,HW,act", [
     (2, 32, 64, 512, 2, (64, 512), 3),      # top-level conv1 shape (per-sample Fourier block)
     (3, 32, 64, 512, 1, (8, 64), 3),        # batch-shared Fourier block
     (2, 512, 0, 512, 1, (4, 32), 3),        # level 0: Fourier block only
@@ -264,14 +266,14 @@ def test_modconv_golden_module(ops, g_ops, tag, demod):
     (1, 70, 33, 19, 1, (5, 12), 1),         # ragged sizes
 ])
 @pytest.mark.parametrize("dtype", [torch.float32, torch.bfloat16])
-def test_modconv_bmm_vs_oracle(DF, B, O, C1, C2, B2, HW, act, dtype):
+def test_modconv_bmm_vs_oracle(DF, B, Oc, C1, C2, B2, HW, act, dtype):
     g = torch.Generator().manual_seed(9)
     H, W = HW
     K = C1 + C2
-    wb = torch.randn(B, O, K, generator=g) / np.sqrt(K)
+    wb = torch.randn(B, Oc, K, generator=g) / np.sqrt(K)
     x1 = torch.randn(B, C1, H, W, generator=g) if C1 else None
     x2 = torch.randn(B2, C2, H, W, generator=g) if C2 else None
-    bias = torch.randn(O, generator=g)
+    bias = torch.randn(Oc, generator=g)
     if dtype == torch.bfloat16:
         wb = wb.bfloat16().float()
         x1 = None if x1 is None else x1.bfloat16().float()
@@ -280,7 +282,7 @@ def test_modconv_bmm_vs_oracle(DF, B, O, C1, C2, B2, HW, act, dtype):
     x1r = None if x1 is None else x1.clone().requires_grad_()
     parts = ([x1r] if C1 else []) + ([x2.expand(B, -1, -1, -1)] if C2 else [])
     xin = torch.cat(parts, 1).reshape(B, K, H * W)
-    yr = torch.bmm(wr, xin).reshape(B, O, H, W) + bias.view(1, -1, 1, 1)
+    yr = torch.bmm(wr, xin).reshape(B, Oc, H, W) + bias.view(1, -1, 1, 1)
     if act == 3:
         yr = O_lrelu(yr)
     wg = wb.to(DEV, dtype).requires_grad_()
@@ -290,7 +292,7 @@ def test_modconv_bmm_vs_oracle(DF, B, O, C1, C2, B2, HW, act, dtype):
     yg = DF.modconv_bmm(wg, x1g, x2g, bg, act, 0.2, O.SQRT2 if act == 3 else 1.0)
     tol = dict(rtol=1e-3, atol_rel=2e-5) if dtype == torch.float32 else dict(rtol=2e-2, atol_rel=1e-2)
     close(yg, yr, **tol)
-    gy = torch.randn(B, O, H, W, generator=g)
+    gy = torch.randn(B, Oc, H, W, generator=g)
     if dtype == torch.bfloat16:
         gy = gy.bfloat16().float()
     wanted_r = [wr] + ([x1r] if C1 else [])
@@ -384,7 +386,8 @@ def test_minibatch_stddev(ops, g_ops, shape):
     v = torch.randn(shape, generator=g)
     (hr,) = torch.autograd.grad((gxr * v).sum(), xr)
     (hg,) = torch.autograd.grad((gx2 * v.to(DEV)).sum(), xg)
-    close(hg, hr, rtol=2e-3, atol_rel=1e-4)
+    np.testing.assert_allclose(hg.cpu().numpy(), hr.numpy(), rtol=2e-3,
+                               atol=max(1e-4 * float(hr.abs().max()), 2e-6))
     if shape == (8, 6, 4, 4):
         close(ops.MinibatchStdDev(4, 1)(dev(g_ops["mb_x"])), g_ops["mb_y"], 1e-4, 1e-6)
         close(ops.MinibatchStdDev(4, 1)(dev(g_ops["mb2_x"])), g_ops["mb2_y"], 1e-4, 1e-6)

@@ -38,7 +38,11 @@ __device__ __forceinline__ int posmod(int a, int b) {
 
 // extended coordinate -> stored index, or -1 when it reads as zero
 __device__ __forceinline__ int bmap(int i, int n, int mode) {
-  if (mode == DUSTY_PAD_CIRCULAR) return posmod(i, n);
+  if (mode == DUSTY_PAD_CIRCULAR) {
+    if (i < 0) { i += n; if (i < 0) i = posmod(i, n); }
+    else if (i >= n) { i -= n; if (i >= n) i = posmod(i, n); }
+    return i;
+  }
   if (mode == DUSTY_PAD_REPLICATE) return i < 0 ? 0 : (i >= n ? n - 1 : i);
   if (mode == DUSTY_PAD_REFLECT) {
     if (i < 0) i = -i;
@@ -52,25 +56,25 @@ __device__ __forceinline__ float tap_at(const float *sk, const FirParams &p, int
   return p.flip ? sk[(p.kh - 1 - ty) * p.kw + (p.kw - 1 - tx)] : sk[ty * p.kw + tx];
 }
 
+// grid = (ceil(out_w / 256), out_h, min(N, 65535)): no per-element div/mod
 template <typename T>
 __global__ void __launch_bounds__(256)
 fir2d_fwd_kernel(const T *__restrict__ x, T *__restrict__ y, const float *__restrict__ taps,
-                 FirParams p, int64_t total) {
+                 FirParams p, int64_t N) {
   __shared__ float sk[kMaxTaps];
   for (int i = threadIdx.x; i < p.kh * p.kw; i += blockDim.x) sk[i] = taps[i];
   __syncthreads();
-  const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+  const int mx = blockIdx.x * blockDim.x + threadIdx.x;
+  const int my = blockIdx.y;
+  if (mx >= p.out_w) return;
   const int64_t in_plane = (int64_t)p.in_h * p.in_w;
-  for (int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += stride) {
-    const int mx = (int)(idx % p.out_w);
-    const int64_t t = idx / p.out_w;
-    const int my = (int)(t % p.out_h);
-    const int64_t n = t / p.out_h;
+  const int64_t out_plane = (int64_t)p.out_h * p.out_w;
+  const int by = my * p.down_y - p.pad_y0;
+  const int bx = mx * p.down_x - p.pad_x0;
+  const int ty0 = posmod(-by, p.up_y);
+  const int tx0 = posmod(-bx, p.up_x);
+  for (int64_t n = blockIdx.z; n < N; n += gridDim.z) {
     const T *xp = x + n * in_plane;
-    const int by = my * p.down_y - p.pad_y0;
-    const int bx = mx * p.down_x - p.pad_x0;
-    const int ty0 = posmod(-by, p.up_y);
-    const int tx0 = posmod(-bx, p.up_x);
     float acc = 0.f;
     for (int ty = ty0; ty < p.kh; ty += p.up_y) {
       const int iy = bmap((by + ty) / p.up_y, p.in_h, p.mode_y);
@@ -84,7 +88,7 @@ fir2d_fwd_kernel(const T *__restrict__ x, T *__restrict__ y, const float *__rest
       }
       acc += racc;
     }
-    y[idx] = from_f<T>(acc);
+    y[n * out_plane + (int64_t)my * p.out_w + mx] = from_f<T>(acc);
   }
 }
 
@@ -127,17 +131,16 @@ __device__ __forceinline__ int preimage(int c, int i, int n, int mode, int lo, i
 template <typename T>
 __global__ void __launch_bounds__(256)
 fir2d_adj_kernel(const T *__restrict__ dy, T *__restrict__ dx, const float *__restrict__ taps,
-                 FirParams p, int64_t total) {
+                 FirParams p, int64_t N) {
   __shared__ float sk[kMaxTaps];
   for (int i = threadIdx.x; i < p.kh * p.kw; i += blockDim.x) sk[i] = taps[i];
   __syncthreads();
-  const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+  const int ix = blockIdx.x * blockDim.x + threadIdx.x;
+  const int iy = blockIdx.y;
+  if (ix >= p.in_w) return;
   const int64_t out_plane = (int64_t)p.out_h * p.out_w;
-  for (int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += stride) {
-    const int ix = (int)(idx % p.in_w);
-    const int64_t t = idx / p.in_w;
-    const int iy = (int)(t % p.in_h);
-    const int64_t n = t / p.in_h;
+  const int64_t in_plane = (int64_t)p.in_h * p.in_w;
+  for (int64_t n = blockIdx.z; n < N; n += gridDim.z) {
     const T *gp = dy + n * out_plane;
     float acc = 0.f;
     for (int cy = 0;; ++cy) {
@@ -162,7 +165,7 @@ fir2d_adj_kernel(const T *__restrict__ dy, T *__restrict__ dx, const float *__re
         }
       }
     }
-    dx[idx] = from_f<T>(acc);
+    dx[n * in_plane + (int64_t)iy * p.in_w + ix] = from_f<T>(acc);
   }
 }
 
@@ -202,11 +205,8 @@ static int fill_params(FirParams &p, int kh, int kw, int flip, int in_h, int in_
   return 0;
 }
 
-static unsigned grid_for(int64_t total) {
-  int64_t blocks = (total + 255) / 256;
-  const int64_t cap = (int64_t)num_sms() * 8;
-  if (blocks > cap) blocks = cap;
-  return (unsigned)(blocks < 1 ? 1 : blocks);
+static dim3 grid_for(int w, int h, int64_t N) {
+  return dim3((unsigned)((w + 255) / 256), (unsigned)h, (unsigned)(N > 65535 ? 65535 : N));
 }
 
 }  // namespace dusty
@@ -223,15 +223,15 @@ extern "C" int dusty_fir2d(const void *x, void *y, const float *taps, int kh, in
   int rc = fill_params(p, kh, kw, flip, in_h, in_w, out_h, out_w, up_y, up_x, down_y, down_x,
                        pad_y0, pad_x0, mode_y, mode_x);
   if (rc) return rc;
-  const int64_t total = N * out_h * out_w;
-  if (total <= 0) return DUSTY_OK;
+  if (N <= 0 || out_h <= 0 || out_w <= 0) return DUSTY_OK;
+  DUSTY_CHECK_ARG(out_h <= 65535, "out_h too large");
   cudaStream_t st = (cudaStream_t)stream;
   if (dtype == DUSTY_F32)
-    fir2d_fwd_kernel<float><<<grid_for(total), 256, 0, st>>>((const float *)x, (float *)y, taps, p,
-                                                             total);
+    fir2d_fwd_kernel<float><<<grid_for(out_w, out_h, N), 256, 0, st>>>((const float *)x, (float *)y,
+                                                                      taps, p, N);
   else
-    fir2d_fwd_kernel<__nv_bfloat16><<<grid_for(total), 256, 0, st>>>(
-        (const __nv_bfloat16 *)x, (__nv_bfloat16 *)y, taps, p, total);
+    fir2d_fwd_kernel<__nv_bfloat16><<<grid_for(out_w, out_h, N), 256, 0, st>>>(
+        (const __nv_bfloat16 *)x, (__nv_bfloat16 *)y, taps, p, N);
   DUSTY_LAUNCH_CHECK();
   return DUSTY_OK;
 }
@@ -246,15 +246,15 @@ extern "C" int dusty_fir2d_adj(const void *dy, void *dx, const float *taps, int 
   int rc = fill_params(p, kh, kw, flip, in_h, in_w, out_h, out_w, up_y, up_x, down_y, down_x,
                        pad_y0, pad_x0, mode_y, mode_x);
   if (rc) return rc;
-  const int64_t total = N * in_h * in_w;
-  if (total <= 0) return DUSTY_OK;
+  if (N <= 0) return DUSTY_OK;
+  DUSTY_CHECK_ARG(in_h <= 65535, "in_h too large");
   cudaStream_t st = (cudaStream_t)stream;
   if (dtype == DUSTY_F32)
-    fir2d_adj_kernel<float><<<grid_for(total), 256, 0, st>>>((const float *)dy, (float *)dx, taps,
-                                                             p, total);
+    fir2d_adj_kernel<float><<<grid_for(in_w, in_h, N), 256, 0, st>>>((const float *)dy, (float *)dx,
+                                                                    taps, p, N);
   else
-    fir2d_adj_kernel<__nv_bfloat16><<<grid_for(total), 256, 0, st>>>(
-        (const __nv_bfloat16 *)dy, (__nv_bfloat16 *)dx, taps, p, total);
+    fir2d_adj_kernel<__nv_bfloat16><<<grid_for(in_w, in_h, N), 256, 0, st>>>(
+        (const __nv_bfloat16 *)dy, (__nv_bfloat16 *)dx, taps, p, N);
   DUSTY_LAUNCH_CHECK();
   return DUSTY_OK;
 }

@@ -1,13 +1,356 @@
 // a1: tcgen05 tensor-core implementation of the modulated 1x1 contraction (bf16 operands,
-// fp32 accumulation in TMEM).  Placeholder until the kernel lands: reports "unsupported" so
-// the dispatcher keeps using the SIMT kernel.
+// fp32 accumulation in TMEM) -- forward.
+//
+//   Y[b, o, p] = act( sum_k wb[b, o, k] * X(b, k, p) + bias[o] ) * scale
+//
+// Mapping onto UMMA (cta_group::1, kind::f16):
+//   M = 128 pixels        A tile = X_b[k0:k0+64, p0:p0+128]   pixel-contiguous  -> MN-major
+//   N = BN out channels   B tile = wb_b[n0:n0+BN, k0:k0+64]   k-contiguous      -> K-major
+//   K = 64 channels per pipeline stage = 4 x (UMMA_K = 16)
+//   D = fp32 [128 lanes x BN columns] in TMEM
+// Putting pixels on M keeps the instruction shape full (M = 128) even where O shrinks to 32
+// at the 64x512 level, and lets NCHW activations be consumed as they are: the A operand is
+// a "transposed" (MN-major) shared-memory tile, which TMA writes directly with the 128-byte
+// swizzle the UMMA descriptor expects -- two boxes of [64 channels x 64 pixels] per stage.
+// The K axis is the concatenation [features | Fourier features]; each 64-channel block
+// comes from one of two tensor maps, and the Fourier map may be batch-shared (L2 resident).
+//
+// Warp roles (192 threads): warp 0 = TMA producer, warp 1 = TMEM allocator + MMA issuer
+// (one elected thread), warps 2..5 = epilogue (tcgen05.ld 32x32b: one pixel row per thread,
+// bias + leaky-ReLU fused, coalesced stores along the pixel axis).
+#include <cuda.h>
+
 #include "common.cuh"
 
 namespace dusty {
-bool modconv_fwd_tc_supported(int, int, int, int, int, int64_t) { return false; }
-int modconv_fwd_tc(const void *, const void *, const void *, const float *, void *, int, int, int,
-                   int, int, int64_t, int, float, float, cudaStream_t) {
-  set_error("modconv_fwd_tc: not built");
-  return DUSTY_EUNSUPPORTED;
+
+// ------------------------------------------------------------------ PTX wrappers
+__device__ __forceinline__ uint32_t smem_u32(const void *p) {
+  return (uint32_t)__cvta_generic_to_shared(p);
 }
+__device__ __forceinline__ void mbar_init(uint64_t *bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t *bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)),
+               "r"(bytes)
+               : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity) {
+  asm volatile(
+      "{\n"
+      ".reg .pred p;\n"
+      "WAIT_LOOP:\n"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+      "@p bra DONE;\n"
+      "bra WAIT_LOOP;\n"
+      "DONE:\n"
+      "}\n" ::"r"(smem_u32(bar)),
+      "r"(parity)
+      : "memory");
+}
+__device__ __forceinline__ void fence_barrier_init() {
+  asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+}
+__device__ __forceinline__ void fence_proxy_async() {
+  asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+}
+__device__ __forceinline__ void tma_load_3d(void *smem_dst, const CUtensorMap *map, uint64_t *bar,
+                                            int c0, int c1, int c2) {
+  asm volatile(
+      "cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes"
+      " [%0], [%1, {%3, %4, %5}], [%2];" ::"r"(smem_u32(smem_dst)),
+      "l"(map), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2)
+      : "memory");
+}
+__device__ __forceinline__ void tmem_alloc(uint32_t *dst_smem, uint32_t cols) {
+  asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(
+                   smem_u32(dst_smem)),
+               "r"(cols)
+               : "memory");
+  asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void tmem_dealloc(uint32_t taddr, uint32_t cols) {
+  asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(taddr), "r"(cols)
+               : "memory");
+}
+__device__ __forceinline__ void tc_fence_before() {
+  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+}
+__device__ __forceinline__ void tc_fence_after() {
+  asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+}
+__device__ __forceinline__ void umma_bf16(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc,
+                                          uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n"
+      ".reg .pred p;\n"
+      "setp.ne.b32 p, %4, 0;\n"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n"
+      "}\n" ::"r"(tmem_d),
+      "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+// arrive on an mbarrier when all previously issued MMAs of this thread have completed
+__device__ __forceinline__ void umma_commit(uint64_t *bar) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(
+                   smem_u32(bar))
+               : "memory");
+}
+__device__ __forceinline__ void tmem_ld16(uint32_t taddr, uint32_t (&r)[16]) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x16.b32 "
+      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]),
+        "=r"(r[7]), "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]),
+        "=r"(r[14]), "=r"(r[15])
+      : "r"(taddr)
+      : "memory");
+}
+__device__ __forceinline__ void tmem_ld_wait() {
+  asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+}
+
+// ------------------------------------------------------------------ descriptors
+// 64-bit shared-memory matrix descriptor (cute::UMMA::SmemDescriptor bit layout):
+//   [0,14) start >> 4 | [16,30) LBO >> 4 | [32,46) SBO >> 4 | [46,48) version = 1 |
+//   [61,64) layout type (2 = SWIZZLE_128B)
+__device__ __forceinline__ uint64_t make_desc(uint32_t saddr, uint32_t lbo_bytes,
+                                              uint32_t sbo_bytes) {
+  uint64_t d = 0;
+  d |= (uint64_t)((saddr & 0x3FFFF) >> 4);
+  d |= (uint64_t)((lbo_bytes >> 4) & 0x3FFF) << 16;
+  d |= (uint64_t)((sbo_bytes >> 4) & 0x3FFF) << 32;
+  d |= (uint64_t)1 << 46;
+  d |= (uint64_t)2 << 61;
+  return d;
+}
+// 32-bit instruction descriptor (cute::UMMA::InstrDescriptor): D = F32, A = B = BF16,
+// A MN-major ("transposed"), B K-major, dense, no negate.
+__host__ __device__ constexpr uint32_t make_idesc(int M, int N) {
+  return (1u << 4) | (1u << 7) | (1u << 10) | (1u << 15) | (0u << 16) | ((uint32_t)(N >> 3) << 17) |
+         ((uint32_t)(M >> 4) << 24);
+}
+
+constexpr int kBM = 128;          // pixels per tile (UMMA M)
+constexpr int kBK = 64;           // channels per stage (one 128-byte swizzle atom of bf16)
+constexpr int kABytes = kBM * kBK * 2;   // 16 KiB
+constexpr int kThreads = 192;
+
+struct TcParams {
+  int O, C1, K, B2;       // K = C1 + C2 rounded up to kBK by TMA zero fill
+  int64_t P;
+  const float *bias;
+  __nv_bfloat16 *y;
+  int act;
+  float alpha, scale;
+};
+
+template <int BN, int STAGES>
+__global__ void __launch_bounds__(kThreads)
+modconv_fwd_tc_kernel(const __grid_constant__ CUtensorMap map_x1,
+                      const __grid_constant__ CUtensorMap map_x2,
+                      const __grid_constant__ CUtensorMap map_w, TcParams prm) {
+  extern __shared__ __align__(1024) uint8_t smem_raw[];
+  // 1024-byte alignment for the 128B swizzle atoms
+  uint8_t *smem = (uint8_t *)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
+  constexpr int kBBytes = BN * kBK * 2;
+  constexpr int kStageBytes = kABytes + kBBytes;
+  uint8_t *a_base = smem;
+  uint8_t *b_base = smem + STAGES * kABytes;
+  uint64_t *full = (uint64_t *)(smem + STAGES * kStageBytes);
+  uint64_t *empty = full + STAGES;
+  uint64_t *acc_full = empty + STAGES;
+  uint32_t *tmem_slot = (uint32_t *)(acc_full + 1);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int p0 = blockIdx.x * kBM;
+  const int n0 = blockIdx.y * BN;
+  const int b = blockIdx.z;
+  const int num_kb = (prm.K + kBK - 1) / kBK;
+
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < STAGES; ++s) {
+      mbar_init(&full[s], 1);
+      mbar_init(&empty[s], 1);
+    }
+    mbar_init(acc_full, 1);
+    fence_barrier_init();
+  }
+  if (warp == 1) tmem_alloc(tmem_slot, BN);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_acc = *tmem_slot;
+
+  if (warp == 0) {
+    // ===================== TMA producer =====================
+    if (lane == 0) {
+      for (int kb = 0; kb < num_kb; ++kb) {
+        const int s = kb % STAGES;
+        const uint32_t ph = (kb / STAGES) & 1;
+        mbar_wait(&empty[s], ph ^ 1);
+        mbar_expect_tx(&full[s], kStageBytes);
+        const int c0 = kb * kBK;
+        uint8_t *a_dst = a_base + s * kABytes;
+        if (c0 < prm.C1) {
+          tma_load_3d(a_dst, &map_x1, &full[s], p0, c0, b);
+          tma_load_3d(a_dst + kABytes / 2, &map_x1, &full[s], p0 + 64, c0, b);
+        } else {
+          const int bb = prm.B2 == 1 ? 0 : b;
+          tma_load_3d(a_dst, &map_x2, &full[s], p0, c0 - prm.C1, bb);
+          tma_load_3d(a_dst + kABytes / 2, &map_x2, &full[s], p0 + 64, c0 - prm.C1, bb);
+        }
+        tma_load_3d(b_base + s * kBBytes, &map_w, &full[s], c0, n0, b);
+      }
+    }
+  } else if (warp == 1) {
+    // ===================== MMA issuer =====================
+    if (lane == 0) {
+      constexpr uint32_t idesc = make_idesc(kBM, BN);
+      for (int kb = 0; kb < num_kb; ++kb) {
+        const int s = kb % STAGES;
+        const uint32_t ph = (kb / STAGES) & 1;
+        mbar_wait(&full[s], ph);
+        tc_fence_after();
+        const uint32_t a_addr = smem_u32(a_base + s * kABytes);
+        const uint32_t b_addr = smem_u32(b_base + s * kBBytes);
+#pragma unroll
+        for (int k16 = 0; k16 < kBK / 16; ++k16) {
+          // A (MN-major, SW128): 16 channel rows = 2 KiB per UMMA_K step; LBO = next 64-pixel
+          // block (8 KiB), SBO = next group of 8 channel rows (1 KiB)
+          const uint64_t adesc = make_desc(a_addr + k16 * 2048, kABytes / 2, 1024);
+          // B (K-major, SW128): 32 bytes per UMMA_K step inside the swizzle atom; SBO = next
+          // group of 8 out-channel rows (1 KiB)
+          const uint64_t bdesc = make_desc(b_addr + k16 * 32, 16, 1024);
+          umma_bf16(tmem_acc, adesc, bdesc, idesc, (kb > 0 || k16 > 0) ? 1u : 0u);
+        }
+        umma_commit(&empty[s]);            // smem slot reusable once these MMAs retire
+      }
+      umma_commit(acc_full);               // accumulator complete
+    }
+  } else {
+    // ===================== epilogue (warps 2..5) =====================
+    const int q = warp & 3;                // TMEM lane quarter this warp may access
+    const int row = q * 32 + lane;         // pixel row inside the tile
+    mbar_wait(acc_full, 0);
+    tc_fence_after();
+    const int64_t p = (int64_t)p0 + row;
+    __nv_bfloat16 *yb = prm.y + (int64_t)b * prm.O * prm.P + p;
+#pragma unroll 1
+    for (int c = 0; c < BN; c += 16) {
+      uint32_t r[16];
+      tmem_ld16(tmem_acc + ((uint32_t)(q * 32) << 16) + (uint32_t)c, r);
+      tmem_ld_wait();
+#pragma unroll
+      for (int j = 0; j < 16; ++j) {
+        const int o = n0 + c + j;
+        if (o < prm.O && p < prm.P) {
+          float v = __uint_as_float(r[j]);
+          if (prm.bias) v += __ldg(prm.bias + o);
+          if (prm.act == 3) v = v > 0.f ? v : v * prm.alpha;
+          yb[(int64_t)o * prm.P] = __float2bfloat16_rn(v * prm.scale);
+        }
+      }
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    tmem_dealloc(tmem_acc, BN);
+  }
+}
+
+// ------------------------------------------------------------------ host side
+typedef CUresult (*EncodeTiledFn)(CUtensorMap *, CUtensorMapDataType, cuuint32_t, void *,
+                                  const cuuint64_t *, const cuuint64_t *, const cuuint32_t *,
+                                  const cuuint32_t *, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+static EncodeTiledFn get_encode() {
+  static EncodeTiledFn fn = nullptr;
+  static bool tried = false;
+  if (!tried) {
+    tried = true;
+    void *p = nullptr;
+    cudaDriverEntryPointQueryResult qres;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &qres) ==
+            cudaSuccess &&
+        qres == cudaDriverEntryPointSuccess)
+      fn = (EncodeTiledFn)p;
+  }
+  return fn;
+}
+
+// 3-D bf16 tensor [d2, d1, d0] (d0 contiguous), box [1, box1, box0], 128-byte swizzle
+static bool make_map3(CUtensorMap *m, const void *ptr, uint64_t d0, uint64_t d1, uint64_t d2,
+                      uint32_t box0, uint32_t box1) {
+  EncodeTiledFn enc = get_encode();
+  if (!enc) return false;
+  cuuint64_t dims[3] = {d0, d1, d2};
+  cuuint64_t strides[2] = {d0 * 2, d0 * d1 * 2};
+  cuuint32_t box[3] = {box0, box1, 1};
+  cuuint32_t estr[3] = {1, 1, 1};
+  CUresult r = enc(m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 3, const_cast<void *>(ptr), dims, strides,
+                   box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
+                   CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  return r == CUDA_SUCCESS;
+}
+
+bool modconv_fwd_tc_supported(int B, int O, int C1, int C2, int B2, int64_t P) {
+  if (get_encode() == nullptr) return false;
+  if (O < 32 || O % 16 != 0) return false;               // heads (O <= 4) use the streaming kernel
+  if (C1 % kBK != 0 && C2 != 0) return false;            // a K block must not straddle the sources
+  if (P % kBM != 0 || P > 0x7fffffff) return false;
+  if ((C1 % 8) || (C2 % 8)) return false;                // 16-byte global strides for TMA
+  (void)B; (void)B2;
+  return true;
+}
+
+template <int BN, int STAGES>
+static int launch_tc(const CUtensorMap &mx1, const CUtensorMap &mx2, const CUtensorMap &mw,
+                     const TcParams &prm, int B, cudaStream_t st) {
+  constexpr int kStageBytes = kABytes + BN * kBK * 2;
+  constexpr int smem = STAGES * kStageBytes + (2 * STAGES + 1) * 8 + 16 + 1024;
+  static bool configured = false;
+  if (!configured) {
+    if (cudaFuncSetAttribute(modconv_fwd_tc_kernel<BN, STAGES>,
+                             cudaFuncAttributeMaxDynamicSharedMemorySize, smem) != cudaSuccess) {
+      set_error("modconv_fwd_tc: cannot reserve %d bytes of shared memory", smem);
+      return DUSTY_ECUDA;
+    }
+    configured = true;
+  }
+  dim3 grid((unsigned)(prm.P / kBM), (unsigned)((prm.O + BN - 1) / BN), (unsigned)B);
+  modconv_fwd_tc_kernel<BN, STAGES><<<grid, kThreads, smem, st>>>(mx1, mx2, mw, prm);
+  return 0;
+}
+
+int modconv_fwd_tc(const void *wb, const void *x1, const void *x2, const float *bias, void *y,
+                   int B, int O, int C1, int C2, int B2, int64_t P, int act, float alpha,
+                   float scale, cudaStream_t st) {
+  const int K = C1 + C2;
+  const int BN = O >= 256 ? 256 : (O >= 128 ? 128 : (O >= 64 ? 64 : 32));
+  CUtensorMap mx1, mx2, mw;
+  const bool ok1 = make_map3(&mx1, x1, (uint64_t)P, (uint64_t)(C1 ? C1 : C2), (uint64_t)(C1 ? B : B2),
+                             64, kBK);
+  const bool ok2 = make_map3(&mx2, x2, (uint64_t)P, (uint64_t)(C2 ? C2 : C1), (uint64_t)(C2 ? B2 : B),
+                             64, kBK);
+  const bool ok3 = make_map3(&mw, wb, (uint64_t)K, (uint64_t)O, (uint64_t)B, kBK, (uint32_t)BN);
+  if (!(ok1 && ok2 && ok3)) {
+    set_error("modconv_fwd_tc: cuTensorMapEncodeTiled failed");
+    return DUSTY_ECUDA;
+  }
+  TcParams prm;
+  prm.O = O; prm.C1 = C1; prm.K = K; prm.B2 = B2; prm.P = P; prm.bias = bias;
+  prm.y = (__nv_bfloat16 *)y; prm.act = act; prm.alpha = alpha; prm.scale = scale;
+  switch (BN) {
+    case 256: return launch_tc<256, 4>(mx1, mx2, mw, prm, B, st);
+    case 128: return launch_tc<128, 3>(mx1, mx2, mw, prm, B, st);
+    case 64: return launch_tc<64, 4>(mx1, mx2, mw, prm, B, st);
+    default: return launch_tc<32, 5>(mx1, mx2, mw, prm, B, st);
+  }
+}
+
 }  // namespace dusty

@@ -231,6 +231,50 @@ def fir2d(x: torch.Tensor, taps: torch.Tensor, cfg: FirCfg) -> torch.Tensor:
     return _Fir.apply(x, _contig(taps.detach()), cfg)
 
 
+# 4-tap separable fast path (blur / 2x upsample, circular W, replicate H)
+def _resample4_raw(x, taps4, up, adjoint):
+    x = _contig(x)
+    lead = x.shape[:-2]
+    n = 1
+    for s_ in lead:
+        n *= s_
+    h, w = x.shape[-2:]
+    if adjoint:
+        H, W = h // up, w // up
+        y = torch.empty(*lead, H, W, device=x.device, dtype=x.dtype)
+    else:
+        H, W = h, w
+        y = torch.empty(*lead, H * up, W * up, device=x.device, dtype=x.dtype)
+    K.call("dusty_resample4", K.ptr(x), K.ptr(y), taps4[0], taps4[1], taps4[2], taps4[3], n, H, W,
+           up, 1 if adjoint else 0, K.dtype_code(x), K.stream_of(x))
+    return y
+
+
+class _Resample4(Function):
+    @staticmethod
+    def forward(ctx, x, taps4, up, adjoint):
+        ctx.cfg = (taps4, up, adjoint)
+        return _resample4_raw(x, taps4, up, adjoint)
+
+    @staticmethod
+    def backward(ctx, g):
+        taps4, up, adjoint = ctx.cfg
+        return _Resample4.apply(g, taps4, up, not adjoint), None, None, None
+
+
+def resample4_supported(x: torch.Tensor, up: int) -> bool:
+    if x.ndim < 3 or not x.is_cuda or x.dtype not in (torch.float32, torch.bfloat16):
+        return False
+    vec = 16 // x.element_size()
+    return x.shape[-1] % vec == 0 and x.shape[-2] >= 2 and x.shape[-1] >= 4 and up in (1, 2)
+
+
+def resample4(x: torch.Tensor, taps4, up: int) -> torch.Tensor:
+    """Blur (up=1) or 2x upsample (up=2) with per-axis taps `taps4` (python floats)."""
+    K.require_cuda(x)
+    return _Resample4.apply(x, tuple(float(t) for t in taps4), int(up), False)
+
+
 # --------------------------------------------------------------------------- Fourier features
 def fourier_features(angle: torch.Tensor, freqs: torch.Tensor, phase: torch.Tensor,
                      out_dtype: Optional[torch.dtype] = None) -> torch.Tensor:

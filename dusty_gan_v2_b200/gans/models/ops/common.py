@@ -93,6 +93,12 @@ class Resample(nn.Module):
                               pad=(self.ph0, self.ph1, self.pw0, self.pw1),
                               mode=(K.PAD_REPLICATE, K.PAD_CIRCULAR if ring else K.PAD_REPLICATE))
         self._taps2d = None
+        # 4-tap ring "hw" blur / 2x upsample: specialised kernel (dusty_resample4)
+        self._fast_up = None
+        if (self.n_taps == 4 and ring and direction == "hw" and self.down_h == 1 and self.down_w == 1
+                and self.up_h == self.up_w and self.up_h in (1, 2)):
+            self._fast_up = self.up_h
+        self._taps_host = None
 
     def _taps(self, device):
         t = self._taps2d
@@ -103,11 +109,21 @@ class Resample(nn.Module):
             self._taps2d = t
         return t
 
-    def _apply(self, fn, *a, **kw):          # buffers may move / change: drop the cache
+    def _apply(self, fn, *a, **kw):          # buffers may move / change: drop the caches
         self._taps2d = None
+        self._taps_host = None
         return super()._apply(fn, *a, **kw)
 
+    def _load_from_state_dict(self, *a, **kw):
+        self._taps2d = None
+        self._taps_host = None
+        return super()._load_from_state_dict(*a, **kw)
+
     def forward(self, h):
+        if self._fast_up is not None and DF.resample4_supported(h, self._fast_up):
+            if self._taps_host is None:      # one-time host copy of the 4 taps
+                self._taps_host = tuple(self.kernel.detach().float().cpu().tolist())
+            return DF.resample4(h, self._taps_host, self._fast_up)
         return DF.fir2d(h, self._taps(h.device), self._cfg)
 
     def extra_repr(self):

@@ -88,6 +88,15 @@ int dusty_upfirdn2d(const void *x, const float *kernel, void *y, int64_t major, 
                     int in_w, int kh, int kw, int up_x, int up_y, int down_x, int down_y,
                     int pad_x0, int pad_x1, int pad_y0, int pad_y1, int dtype, void *stream);
 
+/* Fast path of Resample.forward (gans/models/ops/common.py:105-135) for 4-tap separable
+ * windows, ring=True, direction "hw": up == 1 is the same-size blur (pads 2,1; ResidualBlock
+ * dusty_v2.py:331), up == 2 the 2x upsampling (SynthesisBlock.resample dusty_v2.py:85-90).
+ * k0..k3 are the per-axis taps exactly as stored in the module's `kernel` buffer.
+ * x: [N, H, W] -> y: [N, up*H, up*W]; adjoint != 0 applies the exact transpose
+ * (y-shaped input -> x-shaped output).  W must be a multiple of 16 bytes / sizeof(T). */
+int dusty_resample4(const void *x, void *y, float k0, float k1, float k2, float k3, int64_t N,
+                    int H, int W, int up, int adjoint, int dtype, void *stream);
+
 /* ---- a2: Fourier features --------------------------------------------------------------
  * Replaces FourierFeature.forward gans/models/ops/fourier.py:77-82.
  * angle: fp32 [Ba, 2, P] (elevation, azimuth); freqs: fp32 [F, 2]; phase: fp32 [F];

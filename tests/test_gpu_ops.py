@@ -295,15 +295,23 @@ def test_modconv_bmm_vs_oracle(DF, B, Oc, C1, C2, B2, HW, act, dtype):
     gy = torch.randn(B, Oc, H, W, generator=g)
     if dtype == torch.bfloat16:
         gy = gy.bfloat16().float()
-    wanted_r = [wr] + ([x1r] if C1 else [])
-    gr = torch.autograd.grad(yr, wanted_r, gy)
+    # backward reference: the lrelu gate is discontinuous, so gate on the sign the device
+    # actually produced (a |y| ~ 1e-7 element may round to either side) and check the
+    # linear parts (dX = W^T g, dW = g X^T, db = sum g) against fp32 CPU matmuls
+    if act == 3:
+        gate = torch.where(yg.detach().float().cpu() > 0, 1.0, 0.2) * O.SQRT2
+        gpre = gy * gate
+    else:
+        gpre = gy
+    gp = gpre.reshape(B, Oc, H * W)
+    dw_ref = torch.bmm(gp, xin.detach().transpose(1, 2))
+    dx_ref = torch.bmm(wb.transpose(1, 2), gp)[:, :C1].reshape(B, C1, H, W) if C1 else None
     wanted_g = [wg, bg] + ([x1g] if C1 else [])
     gg = torch.autograd.grad(yg, wanted_g, gy.to(DEV, dtype))
-    close(gg[0], gr[0], **tol)
+    close(gg[0], dw_ref, **tol)
     if C1:
-        close(gg[2], gr[1], **tol)
-    db_ref = (torch.where(yr.detach() > 0, gy, gy * 0.2) * O.SQRT2 if act == 3 else gy).sum((0, 2, 3))
-    close(gg[1], db_ref, rtol=tol["rtol"], atol_rel=max(tol["atol_rel"], 1e-4))
+        close(gg[2], dx_ref, **tol)
+    close(gg[1], gpre.sum((0, 2, 3)), rtol=tol["rtol"], atol_rel=max(tol["atol_rel"], 1e-4))
 
 
 def O_lrelu(y):
@@ -387,7 +395,7 @@ def test_minibatch_stddev(ops, g_ops, shape):
     (hr,) = torch.autograd.grad((gxr * v).sum(), xr)
     (hg,) = torch.autograd.grad((gx2 * v.to(DEV)).sum(), xg)
     np.testing.assert_allclose(hg.cpu().numpy(), hr.numpy(), rtol=2e-3,
-                               atol=max(1e-4 * float(hr.abs().max()), 2e-6))
+                               atol=max(1e-4 * float(hr.abs().max()), 1e-5))
     if shape == (8, 6, 4, 4):
         close(ops.MinibatchStdDev(4, 1)(dev(g_ops["mb_x"])), g_ops["mb_y"], 1e-4, 1e-6)
         close(ops.MinibatchStdDev(4, 1)(dev(g_ops["mb2_x"])), g_ops["mb2_y"], 1e-4, 1e-6)
@@ -420,3 +428,43 @@ def test_circular_unshift_vs_oracle(DF):
     (gr,) = torch.autograd.grad(ref, vr, gy)
     (gg,) = torch.autograd.grad(got, vg, gy.to(DEV))
     close(gg, gr, rtol=1e-3, atol_rel=2e-4)
+
+
+# ----------------------------------------------------------------------------- a1 tcgen05 path
+@pytest.mark.parametrize("B,Oc,C1,C2,B2,HW", [
+    (2, 32, 64, 512, 2, (64, 512)),      # level 4 conv1, per-sample Fourier block
+    (3, 32, 64, 512, 1, (8, 64)),        # batch-shared Fourier block
+    (2, 512, 0, 512, 1, (4, 32)),        # level 0 (Fourier only), two N tiles of 256
+    (2, 256, 512, 512, 2, (8, 64)),      # level 1 conv1, K = 1024
+    (2, 128, 256, 512, 1, (16, 128)),    # level 2 conv1
+    (2, 64, 64, 0, 1, (32, 256)),        # level 3 conv2
+    (2, 32, 32, 0, 1, (64, 512)),        # level 4 conv2: K = 32 < one stage (TMA zero fill)
+    (1, 48, 64, 0, 1, (2, 64)),          # O not a multiple of the N tile
+])
+def test_modconv_tcgen05_vs_fp32_reference(DF, B, Oc, C1, C2, B2, HW):
+    import dusty_gan_v2_b200 as pkg
+    g = torch.Generator().manual_seed(21)
+    H, W = HW
+    K = C1 + C2
+    bf = torch.bfloat16
+    wb = (torch.randn(B, Oc, K, generator=g) / np.sqrt(K)).to(bf)
+    x1 = torch.randn(B, C1, H, W, generator=g).to(bf) if C1 else None
+    x2 = torch.randn(B2, C2, H, W, generator=g).to(bf) if C2 else None
+    bias = torch.randn(Oc, generator=g)
+    parts = ([x1.float()] if C1 else []) + ([x2.float().expand(B, -1, -1, -1)] if C2 else [])
+    xin = torch.cat(parts, 1).reshape(B, K, H * W)
+    ref = O_lrelu(torch.bmm(wb.float(), xin).reshape(B, Oc, H, W) + bias.view(1, -1, 1, 1))
+    args = (wb.to(DEV), None if x1 is None else x1.to(DEV), None if x2 is None else x2.to(DEV),
+            bias.to(DEV), 3, 0.2, O.SQRT2)
+    try:
+        pkg.set_modconv_impl(2)
+        got = DF.modconv_bmm(*args)
+        pkg.set_modconv_impl(1)
+        simt = DF.modconv_bmm(*args)
+    finally:
+        pkg.set_modconv_impl(0)
+    torch.cuda.synchronize()
+    # bf16 output rounding only: both kernels accumulate in fp32
+    close(simt, ref, rtol=2e-2, atol_rel=4e-3)
+    close(got, ref, rtol=2e-2, atol_rel=4e-3)
+    assert float((got.float() - simt.float()).abs().max()) <= 2e-2 * float(ref.abs().max())

@@ -48,6 +48,8 @@ def parse():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-roofline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--ncu-window", action="store_true",
+                    help="bracket the timed region with cudaProfilerStart/Stop (ncu --profile-from-start off)")
     return ap.parse_args()
 
 
@@ -343,10 +345,14 @@ def main():
     clocks = ClockSampler(local_rank) if rank == 0 else None
     n0 = pkg.launch_count()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    if args.ncu_window:
+        torch.cuda.profiler.start()
     e0.record()
     run(start, args.steps)
     e1.record()
     barrier()
+    if args.ncu_window:
+        torch.cuda.profiler.stop()
     launches = pkg.launch_count() - n0
     ms = torch.tensor([e0.elapsed_time(e1)], device=device)
     if world > 1:

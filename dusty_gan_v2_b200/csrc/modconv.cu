@@ -15,6 +15,12 @@ int modconv_fwd_tc(const void *wb, const void *x1, const void *x2, const float *
                    int B, int O, int C1, int C2, int B2, int64_t P, int act, float alpha,
                    float scale, cudaStream_t st);
 bool modconv_fwd_tc_supported(int B, int O, int C1, int C2, int B2, int64_t P);
+int modconv_dx_tc(const void *wb, const void *dy, void *dx1, int B, int O, int C1, int K, int64_t P,
+                  cudaStream_t st);
+bool modconv_dx_tc_supported(int B, int O, int C1, int K, int64_t P);
+int modconv_dw_tc(const void *dy, const void *x1, const void *x2, float *dwb, int B, int O, int C1,
+                  int C2, int B2, int64_t P, cudaStream_t st);
+bool modconv_dw_tc_supported(int B, int O, int C1, int C2, int B2, int64_t P);
 }  // namespace dusty
 
 using namespace dusty;
@@ -59,8 +65,17 @@ extern "C" int dusty_modconv_bwd_dx(const void *wb, const void *dy, void *dx1, i
   DUSTY_CHECK_ARG(wb && dy && dx1, "null pointer");
   DUSTY_CHECK_ARG(B >= 1 && B <= 65535 && O >= 1 && C1 >= 1 && K >= C1 && P >= 1, "bad shape");
   DUSTY_CHECK_ARG(dtype_ok(dtype) && dtype_ok(wdtype), "bad dtype");
-  DUSTY_CHECK_ARG(impl == 0 || impl == 1, "only the SIMT implementation exists for dX");
-  int rc = modconv_bwd_dx_simt(wb, dy, dx1, B, O, C1, K, P, dtype, wdtype, (cudaStream_t)stream);
+  DUSTY_CHECK_ARG(impl >= 0 && impl <= 2, "impl must be 0 (auto), 1 (simt) or 2 (tcgen05)");
+  const bool tc_ok = dtype == DUSTY_BF16 && wdtype == DUSTY_BF16 && modconv_dx_tc_supported(B, O, C1, K, P);
+  if (impl == 2 && !tc_ok) {
+    set_error("dusty_modconv_bwd_dx: tcgen05 path does not support this shape/dtype");
+    return DUSTY_EUNSUPPORTED;
+  }
+  int rc;
+  if (impl == 2 || (impl == 0 && tc_ok))
+    rc = modconv_dx_tc(wb, dy, dx1, B, O, C1, K, P, (cudaStream_t)stream);
+  else
+    rc = modconv_bwd_dx_simt(wb, dy, dx1, B, O, C1, K, P, dtype, wdtype, (cudaStream_t)stream);
   if (rc) return rc;
   DUSTY_LAUNCH_CHECK();
   return DUSTY_OK;
@@ -75,10 +90,19 @@ extern "C" int dusty_modconv_bwd_dw(const void *dy, const void *x1, const void *
   DUSTY_CHECK_ARG((C1 == 0 || x1) && (C2 == 0 || x2), "missing source tensor");
   DUSTY_CHECK_ARG(C2 == 0 || B2 == B || B2 == 1, "x2 batch must be B or 1");
   DUSTY_CHECK_ARG(dtype_ok(dtype), "bad dtype");
-  DUSTY_CHECK_ARG(impl == 0 || impl == 1, "only the SIMT implementation exists for dW");
+  DUSTY_CHECK_ARG(impl >= 0 && impl <= 2, "impl must be 0 (auto), 1 (simt) or 2 (tcgen05)");
   if (C1 == 0) x1 = x2;
   if (C2 == 0) { x2 = x1; B2 = B; }
-  int rc = modconv_bwd_dw_simt(dy, x1, x2, dwb, B, O, C1, C2, B2, P, dtype, (cudaStream_t)stream);
+  const bool tc_ok = dtype == DUSTY_BF16 && modconv_dw_tc_supported(B, O, C1, C2, B2, P);
+  if (impl == 2 && !tc_ok) {
+    set_error("dusty_modconv_bwd_dw: tcgen05 path does not support this shape/dtype");
+    return DUSTY_EUNSUPPORTED;
+  }
+  int rc;
+  if (impl == 2 || (impl == 0 && tc_ok))
+    rc = modconv_dw_tc(dy, x1, x2, dwb, B, O, C1, C2, B2, P, (cudaStream_t)stream);
+  else
+    rc = modconv_bwd_dw_simt(dy, x1, x2, dwb, B, O, C1, C2, B2, P, dtype, (cudaStream_t)stream);
   if (rc) return rc;
   DUSTY_LAUNCH_CHECK();
   return DUSTY_OK;

@@ -242,6 +242,62 @@ gemm_nt_kernel(GemmNT g) {
   }
 }
 
+// dW for the heads (O <= 4): a streaming reduction over pixels.  Each CTA owns KB input
+// channels of one sample; every thread strides over the pixel axis with 4-wide loads, the
+// O x KB partial sums are reduced by warp shuffles + one smem pass.  x is read once.
+constexpr int kSmallKB = 8;
+template <typename T, int OMAX>
+__global__ void __launch_bounds__(256)
+small_o_dw_kernel(GemmNT g) {
+  __shared__ float red[8][kSmallKB * OMAX];
+  const int b = blockIdx.y;
+  const int k0 = blockIdx.x * kSmallKB;
+  const T *DY = (const T *)g.dy + (int64_t)b * g.O * g.P;
+  const T *X1 = (const T *)g.x1 + (int64_t)b * g.x1_bs;
+  const T *X2 = (const T *)g.x2 + (int64_t)b * g.x2_bs;
+  float acc[kSmallKB][OMAX] = {};
+  const bool p_vec = (g.P % 4 == 0);
+  for (int64_t p = (int64_t)threadIdx.x * 4; p < g.P; p += 256 * 4) {
+    float gv[OMAX][4];
+#pragma unroll
+    for (int o = 0; o < OMAX; ++o) {
+      if (o < g.O) {
+        if (p_vec) Ld4<T>::ld(DY + (int64_t)o * g.P + p, gv[o]);
+        else for (int i = 0; i < 4; ++i) gv[o][i] = (p + i < g.P) ? to_f(DY[(int64_t)o * g.P + p + i]) : 0.f;
+      } else {
+        gv[o][0] = gv[o][1] = gv[o][2] = gv[o][3] = 0.f;
+      }
+    }
+#pragma unroll
+    for (int kk = 0; kk < kSmallKB; ++kk) {
+      const int k = k0 + kk;
+      if (k >= g.K) break;
+      const T *src = ((k < g.K1) ? (X1 + (int64_t)k * g.P) : (X2 + (int64_t)(k - g.K1) * g.P)) + p;
+      float xv[4] = {0.f, 0.f, 0.f, 0.f};
+      if (p_vec) Ld4<T>::ld(src, xv);
+      else for (int i = 0; i < 4; ++i) if (p + i < g.P) xv[i] = to_f(src[i]);
+#pragma unroll
+      for (int o = 0; o < OMAX; ++o)
+        acc[kk][o] += xv[0] * gv[o][0] + xv[1] * gv[o][1] + xv[2] * gv[o][2] + xv[3] * gv[o][3];
+    }
+  }
+  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+#pragma unroll
+  for (int kk = 0; kk < kSmallKB; ++kk)
+#pragma unroll
+    for (int o = 0; o < OMAX; ++o) {
+      const float v = warp_sum(acc[kk][o]);
+      if (lane == 0) red[wid][kk * OMAX + o] = v;
+    }
+  __syncthreads();
+  if (threadIdx.x < kSmallKB * OMAX) {
+    float v = 0.f;
+    for (int w = 0; w < 8; ++w) v += red[w][threadIdx.x];
+    const int kk = threadIdx.x / OMAX, o = threadIdx.x % OMAX;
+    if (k0 + kk < g.K && o < g.O) g.dw[((int64_t)b * g.O + o) * g.K + k0 + kk] = v;
+  }
+}
+
 template <typename T, typename TA>
 static int run_nn(const GemmNN &g, int B, bool a_kcontig, cudaStream_t st) {
   if (g.M <= 4 && (size_t)g.M * g.K * sizeof(float) <= 48 * 1024) {
@@ -297,6 +353,12 @@ int modconv_bwd_dw_simt(const void *dy, const void *x1, const void *x2, float *d
   g.dy = dy; g.x1 = x1; g.x2 = x2; g.x1_bs = (int64_t)C1 * P;
   g.x2_bs = (B2 == 1) ? 0 : (int64_t)C2 * P; g.K1 = C1; g.dw = dwb;
   g.O = O; g.K = C1 + C2; g.P = P;
+  if (O <= 4) {
+    dim3 grid((unsigned)((g.K + kSmallKB - 1) / kSmallKB), (unsigned)B);
+    if (dtype == DUSTY_F32) small_o_dw_kernel<float, 4><<<grid, 256, 0, st>>>(g);
+    else small_o_dw_kernel<__nv_bfloat16, 4><<<grid, 256, 0, st>>>(g);
+    return 0;
+  }
   dim3 grid((unsigned)((g.K + BN - 1) / BN), (unsigned)((g.O + BM - 1) / BM), (unsigned)B);
   if (dtype == DUSTY_F32) gemm_nt_kernel<float><<<grid, 256, 0, st>>>(g);
   else gemm_nt_kernel<__nv_bfloat16><<<grid, 256, 0, st>>>(g);

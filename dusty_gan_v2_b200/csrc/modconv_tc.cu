@@ -126,10 +126,10 @@ __device__ __forceinline__ uint64_t make_desc(uint32_t saddr, uint32_t lbo_bytes
   return d;
 }
 // 32-bit instruction descriptor (cute::UMMA::InstrDescriptor): D = F32, A = B = BF16,
-// A MN-major ("transposed"), B K-major, dense, no negate.
-__host__ __device__ constexpr uint32_t make_idesc(int M, int N) {
-  return (1u << 4) | (1u << 7) | (1u << 10) | (1u << 15) | (0u << 16) | ((uint32_t)(N >> 3) << 17) |
-         ((uint32_t)(M >> 4) << 24);
+// per-operand major-ness (MN-major = "transposed"), dense, no negate.
+__host__ __device__ constexpr uint32_t make_idesc(int M, int N, bool a_mn, bool b_mn) {
+  return (1u << 4) | (1u << 7) | (1u << 10) | ((a_mn ? 1u : 0u) << 15) | ((b_mn ? 1u : 0u) << 16) |
+         ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
 }
 
 constexpr int kBM = 128;          // pixels per tile (UMMA M)
@@ -146,7 +146,10 @@ struct TcParams {
   float alpha, scale;
 };
 
-template <int BN, int STAGES>
+// B_MN == false: forward (B = wb tile [BN out-channels x 64 k], K-major)
+// B_MN == true : dX      (A = dY, contraction over out-channels; B = wb tile
+//                         [64 out-channels x BN in-channels], in-channel contiguous = MN-major)
+template <int BN, int STAGES, bool B_MN>
 __global__ void __launch_bounds__(kThreads)
 modconv_fwd_tc_kernel(const __grid_constant__ CUtensorMap map_x1,
                       const __grid_constant__ CUtensorMap map_x2,
@@ -201,13 +204,19 @@ modconv_fwd_tc_kernel(const __grid_constant__ CUtensorMap map_x1,
           tma_load_3d(a_dst, &map_x2, &full[s], p0, c0 - prm.C1, bb);
           tma_load_3d(a_dst + kABytes / 2, &map_x2, &full[s], p0 + 64, c0 - prm.C1, bb);
         }
-        tma_load_3d(b_base + s * kBBytes, &map_w, &full[s], c0, n0, b);
+        if (!B_MN) {
+          tma_load_3d(b_base + s * kBBytes, &map_w, &full[s], c0, n0, b);
+        } else {
+#pragma unroll
+          for (int j = 0; j < BN / 64; ++j)
+            tma_load_3d(b_base + s * kBBytes + j * 8192, &map_w, &full[s], n0 + 64 * j, c0, b);
+        }
       }
     }
   } else if (warp == 1) {
     // ===================== MMA issuer =====================
     if (lane == 0) {
-      constexpr uint32_t idesc = make_idesc(kBM, BN);
+      constexpr uint32_t idesc = make_idesc(kBM, BN, true, B_MN);
       for (int kb = 0; kb < num_kb; ++kb) {
         const int s = kb % STAGES;
         const uint32_t ph = (kb / STAGES) & 1;
@@ -222,7 +231,9 @@ modconv_fwd_tc_kernel(const __grid_constant__ CUtensorMap map_x1,
           const uint64_t adesc = make_desc(a_addr + k16 * 2048, kABytes / 2, 1024);
           // B (K-major, SW128): 32 bytes per UMMA_K step inside the swizzle atom; SBO = next
           // group of 8 out-channel rows (1 KiB)
-          const uint64_t bdesc = make_desc(b_addr + k16 * 32, 16, 1024);
+          // (MN-major B, dX: same geometry as A -- 2 KiB per step, LBO = next 64-column block)
+          const uint64_t bdesc = B_MN ? make_desc(b_addr + k16 * 2048, 8192, 1024)
+                                      : make_desc(b_addr + k16 * 32, 16, 1024);
           umma_bf16(tmem_acc, adesc, bdesc, idesc, (kb > 0 || k16 > 0) ? 1u : 0u);
         }
         umma_commit(&empty[s]);            // smem slot reusable once these MMAs retire
@@ -251,6 +262,118 @@ modconv_fwd_tc_kernel(const __grid_constant__ CUtensorMap map_x1,
           if (prm.act == 3) v = v > 0.f ? v : v * prm.alpha;
           yb[(int64_t)o * prm.P] = __float2bfloat16_rn(v * prm.scale);
         }
+      }
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    tmem_dealloc(tmem_acc, BN);
+  }
+}
+
+// ------------------------------------------------------------------ dW kernel
+// dwb[b, o, k] = sum_p dY[b, o, p] * X(b, k, p): both operands are pixel-contiguous, i.e.
+// K-major for a contraction over pixels.  M = 128 input channels (two 64-channel boxes,
+// each from the feature or the Fourier tensor map), N = BN out-channels, K = 64 pixels per
+// stage; the accumulator row is the in-channel index, so the fp32 result is stored with the
+// in-channel axis contiguous (coalesced), no atomics.
+struct DwParams {
+  int O, C1, K, B2;
+  int64_t P;
+  float *dw;
+};
+
+template <int BN, int STAGES>
+__global__ void __launch_bounds__(kThreads)
+modconv_dw_tc_kernel(const __grid_constant__ CUtensorMap map_x1,
+                     const __grid_constant__ CUtensorMap map_x2,
+                     const __grid_constant__ CUtensorMap map_g, DwParams prm) {
+  extern __shared__ __align__(1024) uint8_t smem_raw[];
+  uint8_t *smem = (uint8_t *)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
+  constexpr int kBBytes = BN * kBK * 2;
+  constexpr int kStageBytes = kABytes + kBBytes;
+  uint8_t *a_base = smem;
+  uint8_t *b_base = smem + STAGES * kABytes;
+  uint64_t *full = (uint64_t *)(smem + STAGES * kStageBytes);
+  uint64_t *empty = full + STAGES;
+  uint64_t *acc_full = empty + STAGES;
+  uint32_t *tmem_slot = (uint32_t *)(acc_full + 1);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int m0 = blockIdx.x * kBM;       // in-channel tile
+  const int n0 = blockIdx.y * BN;        // out-channel tile
+  const int b = blockIdx.z;
+  const int num_pb = (int)(prm.P / kBK);
+
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < STAGES; ++s) {
+      mbar_init(&full[s], 1);
+      mbar_init(&empty[s], 1);
+    }
+    mbar_init(acc_full, 1);
+    fence_barrier_init();
+  }
+  if (warp == 1) tmem_alloc(tmem_slot, BN);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_acc = *tmem_slot;
+
+  if (warp == 0) {
+    if (lane == 0) {
+      const int bb = prm.B2 == 1 ? 0 : b;
+      for (int pb = 0; pb < num_pb; ++pb) {
+        const int s = pb % STAGES;
+        const uint32_t ph = (pb / STAGES) & 1;
+        mbar_wait(&empty[s], ph ^ 1);
+        mbar_expect_tx(&full[s], kStageBytes);
+        uint8_t *a_dst = a_base + s * kABytes;
+#pragma unroll
+        for (int half = 0; half < 2; ++half) {
+          const int c = m0 + 64 * half;
+          if (c < prm.C1) tma_load_3d(a_dst + half * 8192, &map_x1, &full[s], pb * kBK, c, b);
+          else tma_load_3d(a_dst + half * 8192, &map_x2, &full[s], pb * kBK, c - prm.C1, bb);
+        }
+        tma_load_3d(b_base + s * kBBytes, &map_g, &full[s], pb * kBK, n0, b);
+      }
+    }
+  } else if (warp == 1) {
+    if (lane == 0) {
+      constexpr uint32_t idesc = make_idesc(kBM, BN, false, false);
+      for (int pb = 0; pb < num_pb; ++pb) {
+        const int s = pb % STAGES;
+        const uint32_t ph = (pb / STAGES) & 1;
+        mbar_wait(&full[s], ph);
+        tc_fence_after();
+        const uint32_t a_addr = smem_u32(a_base + s * kABytes);
+        const uint32_t b_addr = smem_u32(b_base + s * kBBytes);
+#pragma unroll
+        for (int k16 = 0; k16 < kBK / 16; ++k16) {
+          const uint64_t adesc = make_desc(a_addr + k16 * 32, 16, 1024);
+          const uint64_t bdesc = make_desc(b_addr + k16 * 32, 16, 1024);
+          umma_bf16(tmem_acc, adesc, bdesc, idesc, (pb > 0 || k16 > 0) ? 1u : 0u);
+        }
+        umma_commit(&empty[s]);
+      }
+      umma_commit(acc_full);
+    }
+  } else {
+    const int q = warp & 3;
+    const int k = m0 + q * 32 + lane;      // in-channel index of this thread's accumulator row
+    mbar_wait(acc_full, 0);
+    tc_fence_after();
+    float *dwb = prm.dw + (int64_t)b * prm.O * prm.K + k;
+#pragma unroll 1
+    for (int c = 0; c < BN; c += 16) {
+      uint32_t r[16];
+      tmem_ld16(tmem_acc + ((uint32_t)(q * 32) << 16) + (uint32_t)c, r);
+      tmem_ld_wait();
+#pragma unroll
+      for (int j = 0; j < 16; ++j) {
+        const int o = n0 + c + j;
+        if (o < prm.O && k < prm.K) dwb[(int64_t)o * prm.K] = __uint_as_float(r[j]);
       }
     }
   }
@@ -298,6 +421,23 @@ static bool make_map3(CUtensorMap *m, const void *ptr, uint64_t d0, uint64_t d1,
   return r == CUDA_SUCCESS;
 }
 
+template <typename KernelT>
+static int set_smem(KernelT kernel, int smem, bool *configured) {
+  if (*configured) return 0;
+  if (cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem) !=
+      cudaSuccess) {
+    set_error("modconv_tc: cannot reserve %d bytes of shared memory", smem);
+    return DUSTY_ECUDA;
+  }
+  *configured = true;
+  return 0;
+}
+
+template <int BN, int STAGES>
+constexpr int tc_smem_bytes() {
+  return STAGES * (kABytes + BN * kBK * 2) + (2 * STAGES + 1) * 8 + 16 + 1024;
+}
+
 bool modconv_fwd_tc_supported(int B, int O, int C1, int C2, int B2, int64_t P) {
   if (get_encode() == nullptr) return false;
   if (O < 32 || O % 16 != 0) return false;               // heads (O <= 4) use the streaming kernel
@@ -308,22 +448,32 @@ bool modconv_fwd_tc_supported(int B, int O, int C1, int C2, int B2, int64_t P) {
   return true;
 }
 
-template <int BN, int STAGES>
+bool modconv_dx_tc_supported(int B, int O, int C1, int K, int64_t P) {
+  if (get_encode() == nullptr) return false;
+  if (O % 8 || K % 8 || C1 % 8 || C1 < 32) return false;
+  if (P % kBM != 0 || P > 0x7fffffff) return false;
+  (void)B;
+  return true;
+}
+
+bool modconv_dw_tc_supported(int B, int O, int C1, int C2, int B2, int64_t P) {
+  if (get_encode() == nullptr) return false;
+  if (O < 32 || O % 16 != 0) return false;
+  if (C1 % kBK != 0 && C2 != 0) return false;            // 64-channel boxes must not straddle
+  if (P % kBK != 0 || P > 0x7fffffff) return false;
+  if ((C1 % 8) || (C2 % 8)) return false;
+  (void)B; (void)B2;
+  return true;
+}
+
+template <int BN, int STAGES, bool B_MN>
 static int launch_tc(const CUtensorMap &mx1, const CUtensorMap &mx2, const CUtensorMap &mw,
                      const TcParams &prm, int B, cudaStream_t st) {
-  constexpr int kStageBytes = kABytes + BN * kBK * 2;
-  constexpr int smem = STAGES * kStageBytes + (2 * STAGES + 1) * 8 + 16 + 1024;
+  constexpr int smem = tc_smem_bytes<BN, STAGES>();
   static bool configured = false;
-  if (!configured) {
-    if (cudaFuncSetAttribute(modconv_fwd_tc_kernel<BN, STAGES>,
-                             cudaFuncAttributeMaxDynamicSharedMemorySize, smem) != cudaSuccess) {
-      set_error("modconv_fwd_tc: cannot reserve %d bytes of shared memory", smem);
-      return DUSTY_ECUDA;
-    }
-    configured = true;
-  }
+  if (int rc = set_smem(modconv_fwd_tc_kernel<BN, STAGES, B_MN>, smem, &configured)) return rc;
   dim3 grid((unsigned)(prm.P / kBM), (unsigned)((prm.O + BN - 1) / BN), (unsigned)B);
-  modconv_fwd_tc_kernel<BN, STAGES><<<grid, kThreads, smem, st>>>(mx1, mx2, mw, prm);
+  modconv_fwd_tc_kernel<BN, STAGES, B_MN><<<grid, kThreads, smem, st>>>(mx1, mx2, mw, prm);
   return 0;
 }
 
@@ -346,10 +496,68 @@ int modconv_fwd_tc(const void *wb, const void *x1, const void *x2, const float *
   prm.O = O; prm.C1 = C1; prm.K = K; prm.B2 = B2; prm.P = P; prm.bias = bias;
   prm.y = (__nv_bfloat16 *)y; prm.act = act; prm.alpha = alpha; prm.scale = scale;
   switch (BN) {
-    case 256: return launch_tc<256, 4>(mx1, mx2, mw, prm, B, st);
-    case 128: return launch_tc<128, 3>(mx1, mx2, mw, prm, B, st);
-    case 64: return launch_tc<64, 4>(mx1, mx2, mw, prm, B, st);
-    default: return launch_tc<32, 5>(mx1, mx2, mw, prm, B, st);
+    case 256: return launch_tc<256, 4, false>(mx1, mx2, mw, prm, B, st);
+    case 128: return launch_tc<128, 3, false>(mx1, mx2, mw, prm, B, st);
+    case 64: return launch_tc<64, 4, false>(mx1, mx2, mw, prm, B, st);
+    default: return launch_tc<32, 5, false>(mx1, mx2, mw, prm, B, st);
+  }
+}
+
+// dX1[b, c, p] = sum_o wb[b, o, c] * dY[b, o, p], c < C1
+int modconv_dx_tc(const void *wb, const void *dy, void *dx1, int B, int O, int C1, int K, int64_t P,
+                  cudaStream_t st) {
+  const int BN = C1 > 128 ? 256 : (C1 > 64 ? 128 : 64);
+  CUtensorMap mg, mw;
+  const bool ok1 = make_map3(&mg, dy, (uint64_t)P, (uint64_t)O, (uint64_t)B, 64, kBK);
+  // wb viewed with the in-channel axis innermost: box = [64 out-channels x 64 in-channels]
+  const bool ok2 = make_map3(&mw, wb, (uint64_t)K, (uint64_t)O, (uint64_t)B, 64, kBK);
+  if (!(ok1 && ok2)) {
+    set_error("modconv_dx_tc: cuTensorMapEncodeTiled failed");
+    return DUSTY_ECUDA;
+  }
+  TcParams prm;
+  prm.O = C1;            // output channels of this contraction = input channels of the layer
+  prm.C1 = O;            // the whole contraction axis (out-channels) comes from the dY map
+  prm.K = O; prm.B2 = B; prm.P = P; prm.bias = nullptr;
+  prm.y = (__nv_bfloat16 *)dx1; prm.act = 1; prm.alpha = 0.f; prm.scale = 1.f;
+  switch (BN) {
+    case 256: return launch_tc<256, 4, true>(mg, mg, mw, prm, B, st);
+    case 128: return launch_tc<128, 3, true>(mg, mg, mw, prm, B, st);
+    default: return launch_tc<64, 4, true>(mg, mg, mw, prm, B, st);
+  }
+}
+
+template <int BN, int STAGES>
+static int launch_dw(const CUtensorMap &mx1, const CUtensorMap &mx2, const CUtensorMap &mg,
+                     const DwParams &prm, int B, cudaStream_t st) {
+  constexpr int smem = tc_smem_bytes<BN, STAGES>();
+  static bool configured = false;
+  if (int rc = set_smem(modconv_dw_tc_kernel<BN, STAGES>, smem, &configured)) return rc;
+  dim3 grid((unsigned)((prm.K + kBM - 1) / kBM), (unsigned)((prm.O + BN - 1) / BN), (unsigned)B);
+  modconv_dw_tc_kernel<BN, STAGES><<<grid, kThreads, smem, st>>>(mx1, mx2, mg, prm);
+  return 0;
+}
+
+int modconv_dw_tc(const void *dy, const void *x1, const void *x2, float *dwb, int B, int O, int C1,
+                  int C2, int B2, int64_t P, cudaStream_t st) {
+  const int BN = O >= 256 ? 256 : (O >= 128 ? 128 : (O >= 64 ? 64 : 32));
+  CUtensorMap mx1, mx2, mg;
+  const bool ok1 = make_map3(&mx1, x1, (uint64_t)P, (uint64_t)(C1 ? C1 : C2), (uint64_t)(C1 ? B : B2),
+                             kBK, 64);
+  const bool ok2 = make_map3(&mx2, x2, (uint64_t)P, (uint64_t)(C2 ? C2 : C1), (uint64_t)(C2 ? B2 : B),
+                             kBK, 64);
+  const bool ok3 = make_map3(&mg, dy, (uint64_t)P, (uint64_t)O, (uint64_t)B, kBK, (uint32_t)BN);
+  if (!(ok1 && ok2 && ok3)) {
+    set_error("modconv_dw_tc: cuTensorMapEncodeTiled failed");
+    return DUSTY_ECUDA;
+  }
+  DwParams prm;
+  prm.O = O; prm.C1 = C1; prm.K = C1 + C2; prm.B2 = B2; prm.P = P; prm.dw = dwb;
+  switch (BN) {
+    case 256: return launch_dw<256, 4>(mx1, mx2, mg, prm, B, st);
+    case 128: return launch_dw<128, 4>(mx1, mx2, mg, prm, B, st);
+    case 64: return launch_dw<64, 4>(mx1, mx2, mg, prm, B, st);
+    default: return launch_dw<32, 5>(mx1, mx2, mg, prm, B, st);
   }
 }
 

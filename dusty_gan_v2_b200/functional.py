@@ -275,6 +275,65 @@ def resample4(x: torch.Tensor, taps4, up: int) -> torch.Tensor:
     return _Resample4.apply(x, tuple(float(t) for t in taps4), int(up), False)
 
 
+# small-halo padding fast path
+def _pad_raw(x, pads, modes, adjoint, in_hw=None):
+    x = _contig(x)
+    lead = x.shape[:-2]
+    n = 1
+    for s_ in lead:
+        n *= s_
+    pt, pb, pl, pr = pads
+    if adjoint:
+        H, W = in_hw
+        y = torch.empty(*lead, H, W, device=x.device, dtype=x.dtype)
+    else:
+        H, W = x.shape[-2:]
+        y = torch.empty(*lead, H + pt + pb, W + pl + pr, device=x.device, dtype=x.dtype)
+    K.call("dusty_pad2d", K.ptr(x), K.ptr(y), n, H, W, pt, pb, pl, pr, modes[0], modes[1],
+           1 if adjoint else 0, K.dtype_code(x), K.stream_of(x))
+    return y
+
+
+class _Pad(Function):
+    @staticmethod
+    def forward(ctx, x, pads, modes):
+        ctx.cfg = (pads, modes, tuple(x.shape[-2:]))
+        return _pad_raw(x, pads, modes, False)
+
+    @staticmethod
+    def backward(ctx, g):
+        pads, modes, in_hw = ctx.cfg
+        return _PadAdj.apply(g, pads, modes, in_hw), None, None
+
+
+class _PadAdj(Function):
+    @staticmethod
+    def forward(ctx, g, pads, modes, in_hw):
+        ctx.cfg = (pads, modes)
+        return _pad_raw(g, pads, modes, True, in_hw)
+
+    @staticmethod
+    def backward(ctx, gg):
+        pads, modes = ctx.cfg
+        return _Pad.apply(gg, pads, modes), None, None, None
+
+
+def pad2d_supported(x, pads, modes) -> bool:
+    if not x.is_cuda or x.ndim < 3 or x.dtype not in (torch.float32, torch.bfloat16):
+        return False
+    H, W = x.shape[-2:]
+    pt, pb, pl, pr = pads
+    return (all(0 <= p <= 4 for p in pads) and max(pt, pb) < H and max(pl, pr) < W
+            and modes[0] in (K.PAD_REPLICATE, K.PAD_REFLECT)
+            and modes[1] in (K.PAD_CIRCULAR, K.PAD_REPLICATE, K.PAD_REFLECT))
+
+
+def pad2d(x, pads, modes):
+    """pads = (top, bottom, left, right); modes = (mode_y, mode_x)."""
+    K.require_cuda(x)
+    return _Pad.apply(x, tuple(int(p) for p in pads), tuple(int(m) for m in modes))
+
+
 # --------------------------------------------------------------------------- Fourier features
 def fourier_features(angle: torch.Tensor, freqs: torch.Tensor, phase: torch.Tensor,
                      out_dtype: Optional[torch.dtype] = None) -> torch.Tensor:
@@ -355,12 +414,12 @@ class _ModConvBmm(Function):
         if x1 is not None and ctx.needs_input_grad[1]:
             gx1 = torch.empty_like(x1)
             K.call("dusty_modconv_bwd_dx", K.ptr(wb), K.ptr(gpre), K.ptr(gx1), B, O, c1, Kt, P, dt,
-                   K.dtype_code(wb), 0, st)
+                   K.dtype_code(wb), _PRECISION["modconv_impl"], st)
         gwb = None
         if ctx.needs_input_grad[0]:
             gw32 = torch.empty(B, O, Kt, device=gy.device, dtype=torch.float32)
             K.call("dusty_modconv_bwd_dw", K.ptr(gpre), K.ptr(x1), K.ptr(x2), K.ptr(gw32), B, O, c1,
-                   c2, b2, P, dt, 0, st)
+                   c2, b2, P, dt, _PRECISION["modconv_impl"], st)
             gwb = gw32.to(wb.dtype)
         if has_bias and ctx.needs_input_grad[3]:
             db = db.reshape(bshape).to(bdtype)

@@ -34,6 +34,9 @@ class Pad(nn.Module):
 
     def forward(self, h):
         left, right, top, bottom = self.padding
+        modes = (_mode(self.vertical), _mode(self.horizontal))
+        if DF.pad2d_supported(h, (top, bottom, left, right), modes):
+            return DF.pad2d(h, (top, bottom, left, right), modes)
         cfg = DF.FirCfg(1, 1, pad=(top, bottom, left, right),
                         mode=(_mode(self.vertical), _mode(self.horizontal)))
         return DF.fir2d(h, DF.device_taps([[1.0]], h.device), cfg)

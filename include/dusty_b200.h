@@ -97,6 +97,12 @@ int dusty_upfirdn2d(const void *x, const float *kernel, void *y, int64_t major, 
 int dusty_resample4(const void *x, void *y, float k0, float k1, float k2, float k3, int64_t N,
                     int H, int W, int up, int adjoint, int dtype, void *stream);
 
+/* Fast path of Pad.forward (gans/models/ops/common.py:10-24) for halos up to 4 pixels:
+ * x: [N, H, W] -> y: [N, H+pt+pb, W+pl+pr]; mode_y in {REPLICATE, REFLECT}, mode_x in
+ * {CIRCULAR, REPLICATE, REFLECT}.  adjoint != 0: y-shaped gradient in, x-shaped out. */
+int dusty_pad2d(const void *x, void *y, int64_t N, int H, int W, int pt, int pb, int pl, int pr,
+                int mode_y, int mode_x, int adjoint, int dtype, void *stream);
+
 /* ---- a2: Fourier features --------------------------------------------------------------
  * Replaces FourierFeature.forward gans/models/ops/fourier.py:77-82.
  * angle: fp32 [Ba, 2, P] (elevation, azimuth); freqs: fp32 [F, 2]; phase: fp32 [F];

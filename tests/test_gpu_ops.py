@@ -454,17 +454,30 @@ def test_modconv_tcgen05_vs_fp32_reference(DF, B, Oc, C1, C2, B2, HW):
     parts = ([x1.float()] if C1 else []) + ([x2.float().expand(B, -1, -1, -1)] if C2 else [])
     xin = torch.cat(parts, 1).reshape(B, K, H * W)
     ref = O_lrelu(torch.bmm(wb.float(), xin).reshape(B, Oc, H, W) + bias.view(1, -1, 1, 1))
-    args = (wb.to(DEV), None if x1 is None else x1.to(DEV), None if x2 is None else x2.to(DEV),
-            bias.to(DEV), 3, 0.2, O.SQRT2)
+    gy = torch.randn(B, Oc, H, W, generator=g).to(bf)
+    res = {}
     try:
-        pkg.set_modconv_impl(2)
-        got = DF.modconv_bmm(*args)
-        pkg.set_modconv_impl(1)
-        simt = DF.modconv_bmm(*args)
+        for impl in (2, 1):
+            pkg.set_modconv_impl(impl)
+            wg = wb.to(DEV).requires_grad_()
+            x1g = None if x1 is None else x1.to(DEV).requires_grad_()
+            out = DF.modconv_bmm(wg, x1g, None if x2 is None else x2.to(DEV), bias.to(DEV), 3, 0.2,
+                                 O.SQRT2)
+            grads = torch.autograd.grad(out, [wg] + ([x1g] if C1 else []), gy.to(DEV))
+            res[impl] = (out.detach(), grads)
     finally:
         pkg.set_modconv_impl(0)
     torch.cuda.synchronize()
+    got, simt = res[2][0], res[1][0]
     # bf16 output rounding only: both kernels accumulate in fp32
     close(simt, ref, rtol=2e-2, atol_rel=4e-3)
     close(got, ref, rtol=2e-2, atol_rel=4e-3)
     assert float((got.float() - simt.float()).abs().max()) <= 2e-2 * float(ref.abs().max())
+    # backward: fp32 reference gated on the tensor-core forward's own sign pattern
+    gate = torch.where(got.float().cpu() > 0, 1.0, 0.2) * O.SQRT2
+    gp = (gy.float() * gate).to(bf).float().reshape(B, Oc, H * W)        # g_pre is stored in bf16
+    dw_ref = torch.bmm(gp, xin.transpose(1, 2))
+    close(res[2][1][0], dw_ref, rtol=2e-2, atol_rel=1e-2)
+    if C1:
+        dx_ref = torch.bmm(wb.float().transpose(1, 2), gp)[:, :C1].reshape(B, C1, H, W)
+        close(res[2][1][1], dx_ref, rtol=2e-2, atol_rel=1e-2)

@@ -197,12 +197,14 @@ def cpu_reference_run(args, steps, warmup, batch):
 
 # ------------------------------------------------------------------------------ kernel roofline
 def kernel_rooflines(device, peaks):
-    """Isolated CUDA-event timings of this repo's kernels at the step's real shapes (B=64),
-    L2 flushed between launches.  Returns (dominant_contraction_entry, list_of_entries)."""
+    """Isolated CUDA-event timings of this repo's kernels at the step's real shapes (B=64,
+    bf16), L2 flushed between launches.  `achieved` uses ALGORITHMIC bytes / flops (DESIGN.md
+    section 4).  Returns (dominant_contraction_entry, list_of_entries)."""
     import torch
 
     import dusty_gan_v2_b200.functional as DF
     from dusty_gan_v2_b200 import _cabi as K
+    from dusty_gan_v2_b200.gans.models.ops import Pad, Resample
     B = 64
     flush = torch.empty(256 * 1024 * 1024, dtype=torch.uint8, device=device)
 
@@ -232,7 +234,15 @@ def kernel_rooflines(device, peaks):
                     "unit": "GB/s", "frac": bytes_ / t / 1e9 / hbm, "traffic": None,
                     "ms": t * 1e3, "peak_source": src})
 
-    # bias_act fwd on the D's first activation [64,32,64,512] bf16: read + write
+    def tc_entry(name, fn, flops, bytes_):
+        t = timeit(fn)
+        e = {"kernel": name, "bound": "tensor", "achieved": flops / t / 1e12, "peak": tflops,
+             "unit": "TFLOP/s", "frac": flops / t / 1e12 / tflops, "traffic": None, "ms": t * 1e3,
+             "peak_source": src, "hbm_gbs": bytes_ / t / 1e9, "hbm_frac": bytes_ / t / 1e9 / hbm}
+        out.append(e)
+        return e
+
+    # ---- memory-bound kernels
     x = torch.randn(B, 32, H, W, device=device, dtype=bf)
     b = torch.zeros(32, device=device)
     mem_entry("bias_act_fwd[64,32,64,512]bf16", lambda: DF._bias_act_raw(x, b, None, 3, 0, 0.2, 1.41), 2 * x.numel() * 2)
@@ -242,36 +252,74 @@ def kernel_rooflines(device, peaks):
     mem_entry("bias_act_bwd[64,32,64,512]bf16",
               lambda: K.call("dusty_bias_act_bwd", K.ptr(x), K.ptr(y), K.ptr(gx), K.ptr(db), B, 32, H * W,
                              0.2, 1.41, K.BF16, K.stream_of(x)), 3 * x.numel() * 2)
-    # Resample up2 on the level-3 features [64,64,32,256] -> [64,64,64,512]
-    from dusty_gan_v2_b200.gans.models.ops import Resample
     up = Resample(up=2).to(device)
     h = torch.randn(B, 64, 32, 256, device=device, dtype=bf)
     mem_entry("resample_up2[64,64,32,256]bf16", lambda: up(h), 5 * h.numel() * 2)
+    gup = torch.randn(B, 64, 64, 512, device=device, dtype=bf)
+    taps = tuple(up.kernel.tolist())
+    mem_entry("resample_up2_adjoint[64,64,64,512]bf16", lambda: DF._resample4_raw(gup, taps, 2, True),
+              5 * h.numel() * 2)
     blur = Resample().to(device)
     mem_entry("resample_blur[64,32,64,512]bf16", lambda: blur(x), 2 * x.numel() * 2)
-    # Fourier features, per-sample block at the top level: write-bound
+    btaps = tuple(blur.kernel.tolist())
+    mem_entry("resample_blur_adjoint[64,32,64,512]bf16", lambda: DF._resample4_raw(x, btaps, 1, True),
+              2 * x.numel() * 2)
+    pad = Pad(1, ring=True)
+    mem_entry("pad_ring1[64,32,64,512]bf16", lambda: pad(x), (x.numel() + B * 32 * 66 * 514) * 2)
+    gp = torch.randn(B, 32, 66, 514, device=device, dtype=bf)
+    mem_entry("pad_ring1_adjoint[64,32,66,514]bf16",
+              lambda: DF._pad_raw(gp, (1, 1, 1, 1), (K.PAD_REPLICATE, K.PAD_CIRCULAR), True, (H, W)),
+              (x.numel() + gp.numel()) * 2)
     ang = torch.rand(B, 2, H, W, device=device)
     fr = torch.randn(256, 2, device=device)
     ph = torch.rand(256, device=device)
     mem_entry("fourier[64,512,64,512]bf16", lambda: DF.fourier_features(ang, fr, ph, bf),
               B * H * W * (8 + 512 * 2))
-    del x, y, gx, h
-    # top-level conv1 contraction: [64, 32, 576] x [64, 576, 32768]
-    O_, C1, C2, P = 32, 64, 512, H * W
-    wb = (torch.randn(B, O_, C1 + C2, device=device) / 24).to(bf)
-    x1 = torch.randn(B, C1, H, W, device=device, dtype=bf)
-    x2 = DF.fourier_features(ang[:1], fr, ph, bf)
-    bias = torch.zeros(O_, device=device)
-    t = timeit(lambda: DF.modconv_bmm(wb, x1, x2, bias, 3, 0.2, 1.41))
-    flops = 2.0 * B * O_ * (C1 + C2) * P
-    dom = {"kernel": "modconv_fwd[B=64,O=32,K=64+512,P=32768]bf16", "bound": "tensor",
-           "achieved": flops / t / 1e12, "peak": tflops, "unit": "TFLOP/s",
-           "frac": flops / t / 1e12 / tflops, "traffic": None, "ms": t * 1e3, "peak_source": src}
-    # the same launch seen as a memory stream (it is HBM-bound at N=32: AI ~ 60 flop/B)
-    byts = (x1.numel() + B * O_ * P) * 2 + x2.numel() * 2
-    out.append({"kernel": dom["kernel"] + " (as stream)", "bound": "hbm", "achieved": byts / t / 1e9,
-                "peak": hbm, "unit": "GB/s", "frac": byts / t / 1e9 / hbm, "traffic": None,
-                "ms": t * 1e3, "peak_source": src})
+    mem_entry("sumsq[64,64,64,512]bf16", lambda: DF.sumsq_total(gup), gup.numel() * 2)
+    lg = torch.randn(B, 1, H, W, device=device)
+    im = torch.tanh(torch.randn(B, 1, H, W, device=device))
+    u = torch.rand(B, 1, H, W, device=device)
+    mem_entry("gumbel_raydrop_fwd[64,1,64,512]f32", lambda: DF.raydrop_count(lg, im, u, -1.0, 1.0),
+              lg.numel() * 4 * 6)
+    trig = torch.rand(4, H * W, device=device)
+    inv = torch.rand(B, 1, H, W, device=device)
+    mem_entry("point_project[64,1,64,512]f32", lambda: DF.point_project(inv, trig, 1.45, 80.0),
+              inv.numel() * 4 * 4)
+    k12 = torch.randn(1, 12, device=device)
+    from dusty_gan_v2_b200.gans.models.ops.upfirdn2d.upfirdn2d import upfirdn2d
+    xa = torch.randn(B, 1, 76, 524, device=device)
+    mem_entry("upfirdn2d_ada_up_x[64,1,76,524]f32", lambda: upfirdn2d(xa, k12, up=(2, 1), pad=(6, 5, 0, 0)),
+              xa.numel() * 4 * 3)
+    del x, y, gx, h, gup, gp
+    # ---- contractions (tcgen05): level-4 conv1 (HBM/L2 bound: N = 32) and level-1 conv1
+    def contraction(tag, O_, C1, C2, hh, ww, shared):
+        P = hh * ww
+        wb = (torch.randn(B, O_, C1 + C2, device=device) / (C1 + C2) ** 0.5).to(bf)
+        x1 = torch.randn(B, C1, hh, ww, device=device, dtype=bf)
+        a = torch.rand(1 if shared else B, 2, hh, ww, device=device)
+        x2 = DF.fourier_features(a, fr, ph, bf)
+        bias = torch.zeros(O_, device=device)
+        flops = 2.0 * B * O_ * (C1 + C2) * P
+        byts = (x1.numel() + B * O_ * P + wb.numel() + x2.numel()) * 2
+        e = tc_entry(f"modconv_fwd[{tag} B=64,O={O_},K={C1}+{C2},P={P},pe={'shared' if shared else 'per-sample'}]bf16",
+                     lambda: DF.modconv_bmm(wb, x1, x2, bias, 3, 0.2, 1.41), flops, byts)
+        g = torch.randn(B, O_, hh, ww, device=device, dtype=bf)
+        gw = torch.empty(B, O_, C1 + C2, device=device)
+        tc_entry(f"modconv_dw[{tag}]bf16",
+                 lambda: K.call("dusty_modconv_bwd_dw", K.ptr(g), K.ptr(x1), K.ptr(x2), K.ptr(gw), B, O_, C1, C2,
+                                x2.shape[0], P, K.BF16, 0, K.stream_of(g)),
+                 flops, (x1.numel() + g.numel() + x2.numel() * (1 if shared else 1)) * 2 + gw.numel() * 4)
+        gx1 = torch.empty_like(x1)
+        tc_entry(f"modconv_dx[{tag}]bf16",
+                 lambda: K.call("dusty_modconv_bwd_dx", K.ptr(wb), K.ptr(g), K.ptr(gx1), B, O_, C1, C1 + C2, P,
+                                K.BF16, K.BF16, 0, K.stream_of(g)),
+                 2.0 * B * O_ * C1 * P, (g.numel() + gx1.numel() + wb.numel()) * 2)
+        return e
+
+    dom = contraction("L4.conv1", 32, 64, 512, H, W, True)
+    contraction("L4.conv1", 32, 64, 512, H, W, False)
+    contraction("L1.conv1", 256, 512, 512, 8, 64, True)
+    contraction("L2.conv1", 128, 256, 512, 16, 128, True)
     return dom, out
 
 
@@ -313,6 +361,8 @@ def main():
         dist.init_process_group("nccl", device_id=device)
     pkg.set_precision(args.precision)
     torch.backends.cudnn.benchmark = True        # the reference sets it (gans/utils.py:29-30)
+    if args.precision == "bf16":                 # fp32 epilogue GEMMs of D on the tensor cores
+        torch.backends.cuda.matmul.allow_tf32 = True
     torch.manual_seed(0 + rank)
     import numpy as np
     np.random.seed(0 + rank)
@@ -407,6 +457,8 @@ def main():
             torch.cuda.empty_cache()
             dom, kernels = kernel_rooflines(device, peaks)
             line["roofline"] = {k: dom[k] for k in ("bound", "achieved", "peak", "unit", "frac", "traffic")}
+            line["roofline"]["hbm_gbs"] = dom["hbm_gbs"]
+            line["roofline"]["hbm_frac"] = dom["hbm_frac"]
             line["roofline"]["kernel"] = dom["kernel"]
             line["roofline"]["peak_source"] = dom["peak_source"]
             line["kernels"] = kernels

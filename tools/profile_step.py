@@ -33,6 +33,7 @@ def main():
     dev = torch.device("cuda", 0)
     pkg.set_precision(args.precision)
     torch.backends.cudnn.benchmark = True
+    torch.backends.cuda.matmul.allow_tf32 = args.precision == "bf16"
     torch.manual_seed(0)
     cfg = preset("dusty_v2", batch_size=args.batch)
     pool = bench.synthetic_batches(2, args.batch, seed=2, device=dev)

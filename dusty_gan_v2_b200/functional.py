@@ -436,6 +436,45 @@ def modconv_bmm(wb, x1, x2=None, bias=None, act: int = 1, alpha: float = 0.2, sc
     return _ModConvBmm.apply(wb, x1, x2, bias, int(act), float(alpha), float(scale))
 
 
+class _ModPrep(Function):
+    @staticmethod
+    def forward(ctx, slin, weight, ema_var, scale, demod, out_dtype):
+        slin = _contig(slin.float())
+        w2 = _contig(weight.float().reshape(weight.shape[-4], weight.shape[-3]) if weight.ndim == 5
+                     else weight.float())
+        B, I = slin.shape
+        O = w2.shape[0]
+        wb = torch.empty(B, O, I, device=slin.device, dtype=out_dtype)
+        stats = torch.empty(B + 2 + B * O, device=slin.device, dtype=torch.float32)
+        ev = None if ema_var is None else ema_var.detach().float().reshape(1)
+        K.call("dusty_modprep_fwd", K.ptr(slin), K.ptr(w2), K.ptr(ev), K.ptr(wb), K.ptr(stats), B, O,
+               I, scale, 1 if demod else 0, K.dtype_code(wb), K.stream_of(slin))
+        ctx.save_for_backward(slin, w2, stats)
+        ctx.cfg = (scale, demod, tuple(weight.shape), weight.dtype)
+        return wb
+
+    @staticmethod
+    @once_differentiable
+    def backward(ctx, gwb):
+        slin, w2, stats = ctx.saved_tensors
+        scale, demod, wshape, wdtype = ctx.cfg
+        B, I = slin.shape
+        O = w2.shape[0]
+        gwb = _contig(gwb.float())
+        dslin = torch.empty_like(slin)
+        dw = torch.empty_like(w2)
+        work = torch.empty(B * O + B * I + O * I, device=slin.device, dtype=torch.float32)
+        K.call("dusty_modprep_bwd", K.ptr(gwb), K.ptr(slin), K.ptr(w2), K.ptr(stats), K.ptr(dslin),
+               K.ptr(dw), K.ptr(work), B, O, I, scale, 1 if demod else 0, K.stream_of(slin))
+        return dslin, dw.reshape(wshape).to(wdtype), None, None, None, None
+
+
+def modprep(slin, weight, ema_var, scale: float, demod: bool, out_dtype=torch.float32):
+    """Per-sample effective weights wb[B,O,I] of a modulated 1x1 conv (see dusty_modprep_fwd)."""
+    K.require_cuda(slin, weight, ema_var)
+    return _ModPrep.apply(slin, weight, ema_var, float(scale), bool(demod), out_dtype)
+
+
 def sumsq_total(x: torch.Tensor) -> torch.Tensor:
     """sum(x^2) as a 0-dim fp32 device tensor (no grad): ModConv2d's EMA statistic."""
     K.require_cuda(x)

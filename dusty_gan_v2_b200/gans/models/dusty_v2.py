@@ -63,9 +63,9 @@ class Head(nn.Module):
             for m in mods:
                 with torch.no_grad():
                     m.ema_var.lerp_(total.to(m.ema_var.dtype), 1 - m.ema_decay)
-        wb = torch.cat([m.effective_weights(style) for m in mods], dim=1)
+        wb = torch.cat([m.effective_weights(style, x.dtype) for m in mods], dim=1)
         bias = torch.cat([m.bias.reshape(-1) for m in mods])
-        y = DF.modconv_bmm(wb.to(x.dtype), x, None, bias, 1, 0.0, 1.0)
+        y = DF.modconv_bmm(wb, x, None, bias, 1, 0.0, 1.0)
         out = _HeadOut()
         out.stacked = y
         for i, name in enumerate(self.heads.keys()):

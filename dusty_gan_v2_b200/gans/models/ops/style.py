@@ -47,8 +47,17 @@ class ModConv2d(nn.Module):
         self.register_buffer("ema_var", torch.tensor(1.0))
 
     # -- small fp32 tensors: [B, O, I] at most 64 MiB for the widest layer, usually < 1 MiB
-    def effective_weights(self, style):
+    def effective_weights(self, style, out_dtype=torch.float32):
+        """wb[B,O,I]: one fused kernel pair (dusty_modprep_fwd/bwd) on CUDA."""
         s = self.mod(style.float())
+        if s.is_cuda:
+            return DF.modprep(s, self.weight, self.ema_var if self.ema else None, self.scale,
+                              self.demod, out_dtype)
+        return self._effective_weights_composite(s).to(out_dtype)
+
+    def _effective_weights_composite(self, s):
+        """The same algebra in plain tensor ops (host-side reference of the fused kernel; used
+        by the tests and for shape inference on the CPU, never on the training path)."""
         w = self.weight.float().reshape(self.out_ch, self.in_ch) * self.scale
         if self.demod:
             w = w / w.abs().amax()
@@ -83,8 +92,8 @@ class ModConv2d(nn.Module):
             raise RuntimeError(f"expected {self.in_ch} input channels, got {c1}+{c2}")
         if self.ema and self.training:
             self.update_ema(x, pe)
-        wb = self.effective_weights(style)
         src = x if x is not None else pe
+        wb = self.effective_weights(style, src.dtype)
         bias = self.bias
         act, alpha, scale = 1, 0.0, float(self.gain)
         if fused_act is not None:
@@ -93,7 +102,7 @@ class ModConv2d(nn.Module):
             alpha, scale = float(fused_act.negative_slope), float(fused_act.scale)
         elif bias is not None and self.gain != 1.0:
             bias = bias * self.gain          # (h + b) * gain == h*gain + b*gain
-        return DF.modconv_bmm(wb.to(src.dtype), x, pe, bias, act, alpha, scale)
+        return DF.modconv_bmm(wb, x, pe, bias, act, alpha, scale)
 
     def extra_repr(self):
         return (f"in_ch={self.in_ch}, out_ch={self.out_ch}, mod_ch={self.mod_ch}, "

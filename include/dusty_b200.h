@@ -137,6 +137,20 @@ int dusty_modconv_bwd_dx(const void *wb, const void *dy, void *dx1, int B, int O
 int dusty_modconv_bwd_dw(const void *dy, const void *x1, const void *x2, float *dwb, int B, int O,
                          int C1, int C2, int B2, int64_t P, int dtype, int impl, void *stream);
 
+/* Per-sample effective weights (modulation, pre-normalisation, demodulation, EMA
+ * normaliser) -- the part of ModConv2d.forward before the grouped conv, style.py:72-103.
+ * slin: fp32 [B, I] = mod(style) (the EqualLR linear stays a library GEMM); weight: fp32
+ * [O, I]; ema_var: device scalar or NULL; wb: [B, O, I] in wdtype.
+ * stats: fp32 workspace of B + 2 + B*O floats, kept for the backward. */
+int dusty_modprep_fwd(const float *slin, const float *weight, const float *ema_var, void *wb,
+                      float *stats, int B, int O, int I, float scale, int demod, int wdtype,
+                      void *stream);
+/* Analytic backward: gwb fp32 [B, O, I] -> dslin [B, I], dweight [O, I].
+ * work: fp32 workspace of B*O + B*I + O*I floats. */
+int dusty_modprep_bwd(const float *gwb, const float *slin, const float *weight, const float *stats,
+                      float *dslin, float *dweight, float *work, int B, int O, int I, float scale,
+                      int demod, void *stream);
+
 /* ---- a10: Gumbel-sigmoid raydrop -------------------------------------------------------
  * Replaces GumbelSigmoid.forward gans/models/ops/gumbel.py:23-29 (RelaxedBernoulli.rsample
  * closed form, uniform draw supplied by the caller) + RayDropModel.forward

@@ -481,3 +481,27 @@ def test_modconv_tcgen05_vs_fp32_reference(DF, B, Oc, C1, C2, B2, HW):
     if C1:
         dx_ref = torch.bmm(wb.float().transpose(1, 2), gp)[:, :C1].reshape(B, C1, H, W)
         close(res[2][1][1], dx_ref, rtol=2e-2, atol_rel=1e-2)
+
+
+@pytest.mark.parametrize("demod", [True, False])
+@pytest.mark.parametrize("B,Oc,I", [(3, 8, 12), (64, 32, 576), (5, 256, 1024), (4, 1, 32)])
+def test_modprep_fused_vs_composite(ops, demod, B, Oc, I):
+    """Fused weight-prep kernels (value + analytic gradient) against the same algebra in
+    autograd-traced tensor ops."""
+    torch.manual_seed(31)
+    m = ops.ModConv2d(in_ch=I, out_ch=Oc, mod_ch=16, ksize=1, stride=1, padding=0, demod=demod,
+                      bias=False, ema=True).to(DEV)
+    m.mod.module.bias.data.normal_(0, 0.3)
+    m.ema_var.fill_(0.8)
+    style = torch.randn(B, 16, device=DEV, requires_grad=True)
+    params = [style, m.weight, m.mod.module.weight, m.mod.module.bias]
+    wb = m.effective_weights(style)
+    ref = m._effective_weights_composite(m.mod(style.float()))
+    close(wb, ref, rtol=1e-4, atol_rel=1e-6)
+    gw = torch.randn_like(ref)
+    g_fused = torch.autograd.grad(wb, params, gw)
+    g_ref = torch.autograd.grad(ref, params, gw)
+    for a, b_ in zip(g_fused, g_ref):
+        close(a, b_, rtol=2e-3, atol_rel=2e-4)
+    wb16 = m.effective_weights(style, torch.bfloat16)
+    close(wb16, ref, rtol=1e-2, atol_rel=4e-3)

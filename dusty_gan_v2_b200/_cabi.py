@@ -32,6 +32,10 @@ SIGNATURES = {
     "dusty_upfirdn2d": [_vp, _vp, _vp, _i64] + [_i] * 13 + [_vp],
     "dusty_resample4": [_vp, _vp, _f, _f, _f, _f, _i64, _i, _i, _i, _i, _i, _vp],
     "dusty_pad2d": [_vp, _vp, _i64] + [_i] * 10 + [_vp],
+    "dusty_bias_act_cl": [_vp, _vp, _vp, _vp, _i64, _i, _i, _i, _f, _f, _i, _vp],
+    "dusty_bias_act_bwd_cl": [_vp, _vp, _vp, _vp, _i64, _i, _f, _f, _i, _vp],
+    "dusty_pad2d_cl": [_vp, _vp] + [_i] * 12 + [_vp],
+    "dusty_blur4_cl": [_vp, _vp, _f, _f, _f, _f] + [_i] * 6 + [_vp],
     "dusty_fourier": [_vp, _vp, _vp, _vp, _i, _i, _i64, _i, _vp],
     "dusty_angle_down2": [_vp, _vp, _i, _i, _i, _vp],
     "dusty_modconv_fwd": [_vp, _vp, _vp, _vp, _vp, _i, _i, _i, _i, _i, _i64, _i, _f, _f, _i, _i, _i, _vp],

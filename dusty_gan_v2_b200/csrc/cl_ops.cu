@@ -1,0 +1,365 @@
+// Channels-last (NHWC) variants of the discriminator's memory-bound ops.  The dense
+// convolutions of D are library calls whose fast sm_100 kernels want NHWC; keeping the whole
+// residual trunk in NHWC removes every NCHW<->NHWC conversion pass, and makes padding and
+// blurring fully vectorisable: the channel axis is contiguous, so each thread moves 16 bytes
+// (8 bf16 / 4 fp32 channels) per access.
+//   bias_act_cl      a3  (bias index = channel = fastest axis)
+//   pad2d_cl         a4/a11  ring padding, forward + adjoint
+//   blur4_cl         a4  4-tap separable blur (circular W, replicate H), forward + adjoint
+#include "common.cuh"
+
+namespace dusty {
+
+// ------------------------------------------------------------------ bias + act (NHWC)
+template <typename T, int ACT, int GRAD>
+__global__ void __launch_bounds__(256)
+bias_act_cl_kernel(const T *__restrict__ x, const T *__restrict__ bias, const T *__restrict__ ref,
+                   T *__restrict__ y, int64_t n_vec, int cv, float alpha, float scale) {
+  constexpr int V = Vec16<T>::N;
+  const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n_vec; i += stride) {
+    Vec16<T> vx = ld16_stream(x + i * V);
+    Vec16<T> vr, vb, vy;
+    if (GRAD == 1) vr = ld16_stream(ref + i * V);
+    if (bias != nullptr) vb = ld16(bias + (int)(i % cv) * V);
+#pragma unroll
+    for (int j = 0; j < V; ++j) {
+      float v = vx.get(j) + (bias != nullptr ? vb.get(j) : 0.f);
+      const float gate = (GRAD == 1) ? vr.get(j) : v;
+      float r = (ACT == 3) ? ((gate > 0.f) ? v : v * alpha) : v;
+      if (GRAD == 2) r = 0.f;
+      vy.set(j, r * scale);
+    }
+    st16(y + i * V, vy);
+  }
+}
+
+// dx = dy * gate(out) * scale ; db[c] += column sums.  Block = (256 / cv) rows x cv vectors.
+template <typename T>
+__global__ void __launch_bounds__(256)
+bias_act_bwd_cl_kernel(const T *__restrict__ dy, const T *__restrict__ out, T *__restrict__ dx,
+                       float *__restrict__ db, int64_t rows, int cv, int64_t rows_per_block,
+                       float alpha, float scale) {
+  constexpr int V = Vec16<T>::N;
+  __shared__ float red[256 * Vec16<T>::N];
+  const int j = threadIdx.x % cv, r = threadIdx.x / cv, R = blockDim.x / cv;
+  const int64_t r0 = (int64_t)blockIdx.x * rows_per_block;
+  int64_t r1 = r0 + rows_per_block;
+  if (r1 > rows) r1 = rows;
+  float acc[V];
+#pragma unroll
+  for (int k = 0; k < V; ++k) acc[k] = 0.f;
+  for (int64_t row = r0 + r; row < r1; row += R) {
+    const int64_t off = (row * cv + j) * V;
+    Vec16<T> g = ld16_stream(dy + off), o = ld16_stream(out + off), d;
+#pragma unroll
+    for (int k = 0; k < V; ++k) {
+      const float gv = g.get(k);
+      const float v = ((o.get(k) > 0.f) ? gv : gv * alpha) * scale;
+      d.set(k, v);
+      acc[k] += v;
+    }
+    st16(dx + off, d);
+  }
+  if (db == nullptr) return;
+#pragma unroll
+  for (int k = 0; k < V; ++k) red[threadIdx.x * V + k] = acc[k];
+  __syncthreads();
+  // threads 0 .. cv*V-1 each own one channel: sum over the R row-lanes
+  for (int c = threadIdx.x; c < cv * V; c += blockDim.x) {
+    const int jj = c / V, k = c % V;
+    float s = 0.f;
+    for (int rr = 0; rr < R; ++rr) s += red[(rr * cv + jj) * V + k];
+    atomicAdd(db + c, s);
+  }
+}
+
+// ------------------------------------------------------------------ pad (NHWC)
+struct PadCL {
+  int H, W, Ho, Wo, pt, pb, pl, pr, mode_y, mode_x, cv;   // cv = C / V
+};
+
+__device__ __forceinline__ int cl_map(int i, int n, int mode) {
+  if (mode == DUSTY_PAD_CIRCULAR) return i < 0 ? i + n : (i >= n ? i - n : i);
+  if (mode == DUSTY_PAD_REFLECT) return i < 0 ? -i : (i >= n ? 2 * (n - 1) - i : i);
+  return i < 0 ? 0 : (i >= n ? n - 1 : i);
+}
+
+// grid = (ceil(Wo*cv / 256), Ho, B)
+template <typename T>
+__global__ void __launch_bounds__(256)
+pad2d_cl_fwd_kernel(const T *__restrict__ x, T *__restrict__ y, PadCL p) {
+  constexpr int V = Vec16<T>::N;
+  const int v = blockIdx.x * blockDim.x + threadIdx.x;
+  if (v >= p.Wo * p.cv) return;
+  const int ox = v / p.cv, j = v - ox * p.cv;
+  const int oy = blockIdx.y, b = blockIdx.z;
+  const int iy = cl_map(oy - p.pt, p.H, p.mode_y), ix = cl_map(ox - p.pl, p.W, p.mode_x);
+  const int64_t src = ((((int64_t)b * p.H + iy) * p.W + ix) * p.cv + j) * V;
+  const int64_t dst = ((((int64_t)b * p.Ho + oy) * p.Wo + ox) * p.cv + j) * V;
+  st16(y + dst, ld16(x + src));
+}
+
+__device__ __forceinline__ int cl_preimages(int i, int n, int p0, int p1, int mode, int *out) {
+  int c = 0;
+  out[c++] = i + p0;
+  if (mode == DUSTY_PAD_CIRCULAR) {
+    if (i >= n - p0) out[c++] = i - (n - p0);
+    if (i < p1) out[c++] = p0 + n + i;
+  } else if (mode == DUSTY_PAD_REFLECT) {
+    if (i >= 1 && i <= p0) out[c++] = p0 - i;
+    if (i <= n - 2 && i >= n - 1 - p1) out[c++] = p0 + 2 * (n - 1) - i;
+  } else {
+    if (i == 0) for (int k = 0; k < p0; ++k) out[c++] = k;
+    if (i == n - 1) for (int k = 0; k < p1; ++k) out[c++] = p0 + n + k;
+  }
+  return c;
+}
+
+// grid = (ceil(W*cv / 256), H, B)
+template <typename T>
+__global__ void __launch_bounds__(256)
+pad2d_cl_adj_kernel(const T *__restrict__ dy, T *__restrict__ dx, PadCL p) {
+  constexpr int V = Vec16<T>::N;
+  const int v = blockIdx.x * blockDim.x + threadIdx.x;
+  if (v >= p.W * p.cv) return;
+  const int ix = v / p.cv, j = v - ix * p.cv;
+  const int iy = blockIdx.y, b = blockIdx.z;
+  int ys[10], xs[10];
+  const int ny = cl_preimages(iy, p.H, p.pt, p.pb, p.mode_y, ys);
+  const int nx = cl_preimages(ix, p.W, p.pl, p.pr, p.mode_x, xs);
+  float acc[V];
+#pragma unroll
+  for (int k = 0; k < V; ++k) acc[k] = 0.f;
+  for (int a = 0; a < ny; ++a)
+    for (int c = 0; c < nx; ++c) {
+      Vec16<T> g = ld16(dy + ((((int64_t)b * p.Ho + ys[a]) * p.Wo + xs[c]) * p.cv + j) * V);
+#pragma unroll
+      for (int k = 0; k < V; ++k) acc[k] += g.get(k);
+    }
+  Vec16<T> o;
+#pragma unroll
+  for (int k = 0; k < V; ++k) o.set(k, acc[k]);
+  st16(dx + ((((int64_t)b * p.H + iy) * p.W + ix) * p.cv + j) * V, o);
+}
+
+// ------------------------------------------------------------------ blur4 (NHWC)
+struct Taps4CL { float k[4]; };
+
+// thread -> (b, x, channel vector); slides over a strip of rows.
+// ADJ == false: out[y] = sum_t k[t] h[clamp(y+t-2)],  h[r][x] = sum_t k[t] in[r][wrap(x+t-2)]
+// ADJ == true : transpose (see resample4.cu): g[e] = sum_t k[t] Gh[e+2-t], Gh from d[wrap(x+2-t)],
+//               rows e in [-2, H] folded onto clamp(e)
+template <typename T, bool ADJ>
+__global__ void __launch_bounds__(128)
+blur4_cl_kernel(const T *__restrict__ x, T *__restrict__ y, Taps4CL t, int H, int W, int cv,
+                int strip, int64_t n_threads) {
+  constexpr int V = Vec16<T>::N;
+  const int64_t tid = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (tid >= n_threads) return;
+  const int j = (int)(tid % cv);
+  const int64_t q = tid / cv;
+  const int xx = (int)(q % W);
+  const int64_t b = q / W;
+  const T *img = x + b * (int64_t)H * W * cv * V;
+  T *out = y + b * (int64_t)H * W * cv * V;
+  // wrapped neighbour columns for the 4 horizontal taps
+  int xc[4];
+#pragma unroll
+  for (int s = 0; s < 4; ++s) {
+    int c = ADJ ? (xx + 2 - s) : (xx + s - 2);
+    xc[s] = c < 0 ? c + W : (c >= W ? c - W : c);
+  }
+  auto hpass = [&](int r, float *dst) {
+    if (ADJ) {
+      if (r < 0 || r >= H) {
+#pragma unroll
+        for (int k = 0; k < V; ++k) dst[k] = 0.f;
+        return;
+      }
+    } else {
+      r = r < 0 ? 0 : (r >= H ? H - 1 : r);
+    }
+    const T *row = img + (int64_t)r * W * cv * V;
+#pragma unroll
+    for (int k = 0; k < V; ++k) dst[k] = 0.f;
+#pragma unroll
+    for (int s = 0; s < 4; ++s) {
+      Vec16<T> v = ld16(row + ((int64_t)xc[s] * cv + j) * V);
+#pragma unroll
+      for (int k = 0; k < V; ++k) dst[k] = fmaf(t.k[s], v.get(k), dst[k]);
+    }
+  };
+  const int y0 = blockIdx.y * strip;
+  const int y1 = min(y0 + strip, H);
+  float a[V], bb[V], c[V], d[V];
+  if (!ADJ) {
+    hpass(y0 - 2, a); hpass(y0 - 1, bb); hpass(y0, c);
+    for (int r = y0; r < y1; ++r) {
+      hpass(r + 1, d);
+      Vec16<T> o;
+#pragma unroll
+      for (int k = 0; k < V; ++k) {
+        o.set(k, fmaf(t.k[3], d[k], fmaf(t.k[2], c[k], fmaf(t.k[1], bb[k], t.k[0] * a[k]))));
+        a[k] = bb[k]; bb[k] = c[k]; c[k] = d[k];
+      }
+      st16(out + (((int64_t)r * W + xx) * cv + j) * V, o);
+    }
+  } else {
+    const int e_lo = (y0 == 0) ? -2 : y0;
+    const int e_hi = (y1 == H) ? H : y1 - 1;
+    hpass(e_lo - 1, a); hpass(e_lo, bb); hpass(e_lo + 1, c);
+    float acc[V];
+#pragma unroll
+    for (int k = 0; k < V; ++k) acc[k] = 0.f;
+    for (int e = e_lo; e <= e_hi; ++e) {
+      hpass(e + 2, d);
+#pragma unroll
+      for (int k = 0; k < V; ++k) {
+        acc[k] += fmaf(t.k[0], d[k], fmaf(t.k[1], c[k], fmaf(t.k[2], bb[k], t.k[3] * a[k])));
+        a[k] = bb[k]; bb[k] = c[k]; c[k] = d[k];
+      }
+      const int i = e < 0 ? 0 : (e >= H ? H - 1 : e);
+      const int i_next = (e + 1) < 0 ? 0 : ((e + 1) >= H ? H - 1 : (e + 1));
+      if (e == e_hi || i_next != i) {
+        Vec16<T> o;
+#pragma unroll
+        for (int k = 0; k < V; ++k) { o.set(k, acc[k]); acc[k] = 0.f; }
+        st16(out + (((int64_t)i * W + xx) * cv + j) * V, o);
+      }
+    }
+  }
+}
+
+static unsigned cl_flat_grid(int64_t work) {
+  int64_t blocks = (work + 255) / 256;
+  const int64_t cap = (int64_t)num_sms() * 16;
+  if (blocks > cap) blocks = cap;
+  return (unsigned)(blocks < 1 ? 1 : blocks);
+}
+
+template <typename T>
+static int launch_bias_act_cl(const void *x, const void *bias, const void *ref, void *y,
+                              int64_t n_elem, int C, int act, int grad, float alpha, float scale,
+                              cudaStream_t st) {
+  constexpr int V = Vec16<T>::N;
+  const int64_t n_vec = n_elem / V;
+  const int cv = C / V;
+  const unsigned g = cl_flat_grid(n_vec);
+  const T *xp = (const T *)x, *bp = (const T *)bias, *rp = (const T *)ref;
+  T *yp = (T *)y;
+  if (grad == 2) bias_act_cl_kernel<T, 1, 2><<<g, 256, 0, st>>>(xp, bp, rp, yp, n_vec, cv, alpha, scale);
+  else if (act == 1) bias_act_cl_kernel<T, 1, 0><<<g, 256, 0, st>>>(xp, bp, rp, yp, n_vec, cv, alpha, scale);
+  else if (grad == 0) bias_act_cl_kernel<T, 3, 0><<<g, 256, 0, st>>>(xp, bp, rp, yp, n_vec, cv, alpha, scale);
+  else bias_act_cl_kernel<T, 3, 1><<<g, 256, 0, st>>>(xp, bp, rp, yp, n_vec, cv, alpha, scale);
+  return 0;
+}
+
+}  // namespace dusty
+
+using namespace dusty;
+
+static bool cl_channels_ok(int C, int dtype) {
+  const int V = dtype == DUSTY_F32 ? 4 : 8;
+  const int cv = C / V;
+  return C % V == 0 && cv >= 1 && cv <= 256 && (256 % cv) == 0;
+}
+
+extern "C" int dusty_bias_act_cl(const void *x, const void *bias, const void *ref, void *y,
+                                 int64_t n_elem, int C, int act, int grad, float alpha, float scale,
+                                 int dtype, void *stream) {
+  DUSTY_CHECK_ARG(x && y, "null tensor");
+  DUSTY_CHECK_ARG(act == 1 || act == 3, "act must be 1 or 3");
+  DUSTY_CHECK_ARG(grad >= 0 && grad <= 2, "grad must be 0, 1 or 2");
+  DUSTY_CHECK_ARG(grad != 1 || act != 3 || ref != nullptr, "grad=1 needs ref");
+  DUSTY_CHECK_ARG(dtype == DUSTY_F32 || dtype == DUSTY_BF16, "bad dtype");
+  DUSTY_CHECK_ARG(cl_channels_ok(C, dtype) && n_elem % C == 0, "channel count not vectorisable");
+  DUSTY_CHECK_ARG(aligned16(x) && aligned16(y) && (!bias || aligned16(bias)), "16-byte alignment");
+  if (n_elem == 0) return DUSTY_OK;
+  cudaStream_t st = (cudaStream_t)stream;
+  if (dtype == DUSTY_F32) launch_bias_act_cl<float>(x, bias, ref, y, n_elem, C, act, grad, alpha, scale, st);
+  else launch_bias_act_cl<__nv_bfloat16>(x, bias, ref, y, n_elem, C, act, grad, alpha, scale, st);
+  DUSTY_LAUNCH_CHECK();
+  return DUSTY_OK;
+}
+
+extern "C" int dusty_bias_act_bwd_cl(const void *dy, const void *out, void *dx, float *db,
+                                     int64_t rows, int C, float alpha, float scale, int dtype,
+                                     void *stream) {
+  DUSTY_CHECK_ARG(dy && out && dx, "null tensor");
+  DUSTY_CHECK_ARG(dtype == DUSTY_F32 || dtype == DUSTY_BF16, "bad dtype");
+  DUSTY_CHECK_ARG(cl_channels_ok(C, dtype) && rows >= 1, "channel count not vectorisable");
+  cudaStream_t st = (cudaStream_t)stream;
+  const int V = dtype == DUSTY_F32 ? 4 : 8;
+  const int cv = C / V;
+  int64_t blocks = (int64_t)num_sms() * 8;
+  int64_t rpb = (rows + blocks - 1) / blocks;
+  const int R = 256 / cv;
+  if (rpb < R * 4) rpb = R * 4;
+  blocks = (rows + rpb - 1) / rpb;
+  if (dtype == DUSTY_F32)
+    bias_act_bwd_cl_kernel<float><<<(unsigned)blocks, 256, 0, st>>>(
+        (const float *)dy, (const float *)out, (float *)dx, db, rows, cv, rpb, alpha, scale);
+  else
+    bias_act_bwd_cl_kernel<__nv_bfloat16><<<(unsigned)blocks, 256, 0, st>>>(
+        (const __nv_bfloat16 *)dy, (const __nv_bfloat16 *)out, (__nv_bfloat16 *)dx, db, rows, cv, rpb,
+        alpha, scale);
+  DUSTY_LAUNCH_CHECK();
+  return DUSTY_OK;
+}
+
+extern "C" int dusty_pad2d_cl(const void *x, void *y, int B, int H, int W, int C, int pt, int pb,
+                              int pl, int pr, int mode_y, int mode_x, int adjoint, int dtype,
+                              void *stream) {
+  DUSTY_CHECK_ARG(x && y, "null pointer");
+  DUSTY_CHECK_ARG(B >= 1 && B <= 65535 && H >= 1 && W >= 1, "bad shape");
+  DUSTY_CHECK_ARG(pt >= 0 && pb >= 0 && pl >= 0 && pr >= 0 && pt <= 4 && pb <= 4 && pl <= 4 && pr <= 4,
+                  "pads must be in [0, 4]");
+  DUSTY_CHECK_ARG(pt < H && pb < H && pl < W && pr < W, "pad must be smaller than the image");
+  DUSTY_CHECK_ARG(mode_y == DUSTY_PAD_REPLICATE || mode_y == DUSTY_PAD_REFLECT, "bad mode_y");
+  DUSTY_CHECK_ARG(mode_x >= DUSTY_PAD_CIRCULAR && mode_x <= DUSTY_PAD_REFLECT, "bad mode_x");
+  DUSTY_CHECK_ARG(dtype == DUSTY_F32 || dtype == DUSTY_BF16, "bad dtype");
+  const int V = dtype == DUSTY_F32 ? 4 : 8;
+  DUSTY_CHECK_ARG(C % V == 0, "C must be a multiple of the 16-byte vector width");
+  PadCL p{H, W, H + pt + pb, W + pl + pr, pt, pb, pl, pr, mode_y, mode_x, C / V};
+  DUSTY_CHECK_ARG(p.Ho <= 65535, "image too tall");
+  cudaStream_t st = (cudaStream_t)stream;
+  if (!adjoint) {
+    dim3 grid((unsigned)((p.Wo * p.cv + 255) / 256), (unsigned)p.Ho, (unsigned)B);
+    if (dtype == DUSTY_F32) pad2d_cl_fwd_kernel<float><<<grid, 256, 0, st>>>((const float *)x, (float *)y, p);
+    else pad2d_cl_fwd_kernel<__nv_bfloat16><<<grid, 256, 0, st>>>((const __nv_bfloat16 *)x, (__nv_bfloat16 *)y, p);
+  } else {
+    dim3 grid((unsigned)((W * p.cv + 255) / 256), (unsigned)H, (unsigned)B);
+    if (dtype == DUSTY_F32) pad2d_cl_adj_kernel<float><<<grid, 256, 0, st>>>((const float *)x, (float *)y, p);
+    else pad2d_cl_adj_kernel<__nv_bfloat16><<<grid, 256, 0, st>>>((const __nv_bfloat16 *)x, (__nv_bfloat16 *)y, p);
+  }
+  DUSTY_LAUNCH_CHECK();
+  return DUSTY_OK;
+}
+
+extern "C" int dusty_blur4_cl(const void *x, void *y, float k0, float k1, float k2, float k3, int B,
+                              int H, int W, int C, int adjoint, int dtype, void *stream) {
+  DUSTY_CHECK_ARG(x && y, "null pointer");
+  DUSTY_CHECK_ARG(B >= 1 && H >= 2 && W >= 4, "bad shape");
+  DUSTY_CHECK_ARG(dtype == DUSTY_F32 || dtype == DUSTY_BF16, "bad dtype");
+  const int V = dtype == DUSTY_F32 ? 4 : 8;
+  DUSTY_CHECK_ARG(C % V == 0, "C must be a multiple of the 16-byte vector width");
+  Taps4CL t;
+  t.k[0] = k0; t.k[1] = k1; t.k[2] = k2; t.k[3] = k3;
+  const int cv = C / V;
+  const int64_t n_threads = (int64_t)B * W * cv;
+  int strip = H;
+  const int64_t ctas_x = (n_threads + 127) / 128;
+  while (strip > 8 && ctas_x * ((H + strip - 1) / strip) < (int64_t)num_sms() * 8) strip = (strip + 1) / 2;
+  dim3 grid((unsigned)ctas_x, (unsigned)((H + strip - 1) / strip));
+  cudaStream_t st = (cudaStream_t)stream;
+  if (dtype == DUSTY_F32) {
+    if (adjoint) blur4_cl_kernel<float, true><<<grid, 128, 0, st>>>((const float *)x, (float *)y, t, H, W, cv, strip, n_threads);
+    else blur4_cl_kernel<float, false><<<grid, 128, 0, st>>>((const float *)x, (float *)y, t, H, W, cv, strip, n_threads);
+  } else {
+    if (adjoint) blur4_cl_kernel<__nv_bfloat16, true><<<grid, 128, 0, st>>>((const __nv_bfloat16 *)x, (__nv_bfloat16 *)y, t, H, W, cv, strip, n_threads);
+    else blur4_cl_kernel<__nv_bfloat16, false><<<grid, 128, 0, st>>>((const __nv_bfloat16 *)x, (__nv_bfloat16 *)y, t, H, W, cv, strip, n_threads);
+  }
+  DUSTY_LAUNCH_CHECK();
+  return DUSTY_OK;
+}

@@ -49,12 +49,61 @@ def _contig(t: torch.Tensor) -> torch.Tensor:
     return t if t.is_contiguous() else t.contiguous()
 
 
+_CL = torch.channels_last
+
+
+def _is_cl(t: torch.Tensor) -> bool:
+    """Stored NHWC (torch.channels_last) and not simultaneously NCHW-contiguous."""
+    return t.ndim == 4 and (not t.is_contiguous()) and t.is_contiguous(memory_format=_CL)
+
+
+def _cl_vec_ok(t: torch.Tensor, pow2: bool = False) -> bool:
+    v = 16 // t.element_size()
+    c = t.shape[1]
+    if c % v:
+        return False
+    cv = c // v
+    return (not pow2) or (cv <= 256 and 256 % cv == 0)
+
+
+def _canon(t: torch.Tensor, need_pow2: bool = False) -> torch.Tensor:
+    """Keep NCHW-contiguous and supported NHWC tensors as they are; copy anything else to NCHW."""
+    if t.is_contiguous():
+        return t
+    if _is_cl(t) and t.dtype in (torch.float32, torch.bfloat16) and _cl_vec_ok(t, need_pow2):
+        return t
+    return t.contiguous()
+
+
+def _like(t: torch.Tensor, ref: torch.Tensor) -> torch.Tensor:
+    """t in the memory format of ref (NHWC or NCHW)."""
+    if _is_cl(ref):
+        return t if _is_cl(t) else t.contiguous(memory_format=_CL)
+    return _contig(t)
+
+
 # --------------------------------------------------------------------------- bias + act
 def _bias_act_raw(x, bias, ref, act, grad, alpha, scale):
     K.require_cuda(x, bias, ref)
-    x = _contig(x)
+    x = _canon(x, need_pow2=True)
     y = torch.empty_like(x)
     C = x.shape[1] if x.ndim >= 2 else 1
+    if _is_cl(x):
+        if bias is not None and bias.numel() == 0:
+            bias = None
+        if bias is not None:
+            bias = _contig(bias.to(x.dtype))
+            if bias.numel() != C:
+                raise RuntimeError(f"bias has {bias.numel()} elements, expected {C}")
+        if ref is not None and ref.numel() == 0:
+            ref = None
+        if ref is not None:
+            if ref.shape != x.shape or ref.dtype != x.dtype:
+                raise RuntimeError("refer must match input shape and dtype")
+            ref = _like(ref, x)
+        K.call("dusty_bias_act_cl", K.ptr(x), K.ptr(bias), K.ptr(ref), K.ptr(y), x.numel(), C, act,
+               grad, alpha, scale, K.dtype_code(x), K.stream_of(x))
+        return y
     inner = 1
     for s in x.shape[2:]:
         inner *= s
@@ -89,15 +138,19 @@ def fused_bias_act(input, bias, refer, act: int, grad: int, alpha: float, scale:
 class _BiasActBackward(Function):
     @staticmethod
     def forward(ctx, gy, out, has_bias, alpha, scale):
-        gy = _contig(gy)
+        gy = _like(gy, out)
         gx = torch.empty_like(gy)
         C = gy.shape[1]
         inner = 1
         for s in gy.shape[2:]:
             inner *= s
         db = torch.zeros(C, device=gy.device, dtype=torch.float32) if has_bias else None
-        K.call("dusty_bias_act_bwd", K.ptr(gy), K.ptr(out), K.ptr(gx), K.ptr(db), gy.shape[0], C,
-               inner, alpha, scale, K.dtype_code(gy), K.stream_of(gy))
+        if _is_cl(out):
+            K.call("dusty_bias_act_bwd_cl", K.ptr(gy), K.ptr(out), K.ptr(gx), K.ptr(db),
+                   gy.numel() // C, C, alpha, scale, K.dtype_code(gy), K.stream_of(gy))
+        else:
+            K.call("dusty_bias_act_bwd", K.ptr(gy), K.ptr(out), K.ptr(gx), K.ptr(db), gy.shape[0], C,
+                   inner, alpha, scale, K.dtype_code(gy), K.stream_of(gy))
         ctx.save_for_backward(out)
         ctx.alpha, ctx.scale = alpha, scale
         return gx, db
@@ -133,7 +186,7 @@ class _BiasAct(Function):
 
 def bias_act(x, bias=None, negative_slope: float = 0.2, scale: float = 2 ** 0.5):
     K.require_cuda(x, bias)
-    return _BiasAct.apply(_contig(x), bias, float(negative_slope), float(scale))
+    return _BiasAct.apply(_canon(x, need_pow2=True), bias, float(negative_slope), float(scale))
 
 
 # --------------------------------------------------------------------------- FIR family
@@ -233,6 +286,12 @@ def fir2d(x: torch.Tensor, taps: torch.Tensor, cfg: FirCfg) -> torch.Tensor:
 
 # 4-tap separable fast path (blur / 2x upsample, circular W, replicate H)
 def _resample4_raw(x, taps4, up, adjoint):
+    if up == 1 and _is_cl(x) and _cl_vec_ok(x):
+        y = torch.empty_like(x)
+        B, C, H, W = x.shape
+        K.call("dusty_blur4_cl", K.ptr(x), K.ptr(y), taps4[0], taps4[1], taps4[2], taps4[3], B, H, W,
+               C, 1 if adjoint else 0, K.dtype_code(x), K.stream_of(x))
+        return y
     x = _contig(x)
     lead = x.shape[:-2]
     n = 1
@@ -266,6 +325,8 @@ def resample4_supported(x: torch.Tensor, up: int) -> bool:
     if x.ndim < 3 or not x.is_cuda or x.dtype not in (torch.float32, torch.bfloat16):
         return False
     vec = 16 // x.element_size()
+    if up == 1 and _is_cl(x) and _cl_vec_ok(x) and x.shape[-2] >= 2 and x.shape[-1] >= 4:
+        return True
     return x.shape[-1] % vec == 0 and x.shape[-2] >= 2 and x.shape[-1] >= 4 and up in (1, 2)
 
 
@@ -277,6 +338,15 @@ def resample4(x: torch.Tensor, taps4, up: int) -> torch.Tensor:
 
 # small-halo padding fast path
 def _pad_raw(x, pads, modes, adjoint, in_hw=None):
+    if _is_cl(x) and _cl_vec_ok(x):
+        B, C = x.shape[:2]
+        pt, pb, pl, pr = pads
+        H, W = in_hw if adjoint else x.shape[-2:]
+        oshape = (B, C, H, W) if adjoint else (B, C, H + pt + pb, W + pl + pr)
+        y = torch.empty(oshape, device=x.device, dtype=x.dtype, memory_format=_CL)
+        K.call("dusty_pad2d_cl", K.ptr(x), K.ptr(y), B, H, W, C, pt, pb, pl, pr, modes[0], modes[1],
+               1 if adjoint else 0, K.dtype_code(x), K.stream_of(x))
+        return y
     x = _contig(x)
     lead = x.shape[:-2]
     n = 1

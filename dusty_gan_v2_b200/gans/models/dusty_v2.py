@@ -286,6 +286,9 @@ class Discriminator(nn.Module):
         ch = lambda i: min(ch_base << i, ch_max)
         kw = dict(bias=False, ring=ring, equal_lr=True)
         self.num_fp16_layers = num_fp16_layers
+        # keep the residual trunk in NHWC on CUDA: the dense convs (library) run their sm_100
+        # kernels without layout-conversion passes, and pad / blur / bias_act vectorise over C
+        self.channels_last = True
         in_ch = in_ch * 2 if pre_blur else in_ch
         stack = [ops.BlurVH(ring=ring)] if pre_blur else []
         stack += [ops.Conv2d(in_ch, ch(0), 1, 1, 0, **kw), ops.FusedLeakyReLU(ch(0))]
@@ -306,4 +309,6 @@ class Discriminator(nn.Module):
         for i, layer in enumerate(self.layers):
             use_low = ((self.num_fp16_layers > i) or (self.num_fp16_layers == -1)) and h.is_cuda
             h = layer(h.to(low if use_low else torch.float32))
-        return self.epilogue(h.to(torch.float32))
+            if i == 0 and self.channels_last and h.is_cuda:
+                h = h.contiguous(memory_format=torch.channels_last)
+        return self.epilogue(h.to(torch.float32).contiguous())

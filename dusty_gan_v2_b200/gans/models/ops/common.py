@@ -176,7 +176,8 @@ class _Conv2dBwdFn(torch.autograd.Function):
     def forward(ctx, gy, x, w, stride, need_x, need_w):
         ctx.save_for_backward(gy, x, w)
         ctx.stride, ctx.need = stride, (need_x, need_w)
-        gx, gw = _conv_grads(gy.contiguous(), x, w, stride, need_x, need_w)
+        gy = gy.contiguous(memory_format=torch.channels_last) if DF._is_cl(x) else gy.contiguous()
+        gx, gw = _conv_grads(gy, x, w, stride, need_x, need_w)
         return gx, gw
 
     @staticmethod
@@ -186,7 +187,7 @@ class _Conv2dBwdFn(torch.autograd.Function):
         need_gy, need_x, need_w = ctx.needs_input_grad[:3]
         g_gy = g_x = g_w = None
         if ggx is not None:
-            ggx = ggx.contiguous()
+            ggx = ggx.contiguous(memory_format=torch.channels_last) if DF._is_cl(x) else ggx.contiguous()
             if need_gy:
                 g_gy = _Conv2dFn.apply(ggx, w, s)                       # fprop
             if need_w:
@@ -231,6 +232,8 @@ class EqualLR(nn.Module):
         if isinstance(m, nn.Linear):
             return F.linear(x, w, b)
         if isinstance(m, nn.Conv2d):
+            if DF._is_cl(x):            # NHWC activations: hand cuDNN an NHWC filter too
+                w = w.contiguous(memory_format=torch.channels_last)
             if b is None and m.padding == (0, 0) and m.dilation == (1, 1) and m.groups == 1:
                 return conv2d_valid(x, w, m.stride)
             return F.conv2d(x, w, b, m.stride, m.padding, m.dilation, m.groups)

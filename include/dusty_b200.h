@@ -103,6 +103,19 @@ int dusty_resample4(const void *x, void *y, float k0, float k1, float k2, float 
 int dusty_pad2d(const void *x, void *y, int64_t N, int H, int W, int pt, int pb, int pl, int pr,
                 int mode_y, int mode_x, int adjoint, int dtype, void *stream);
 
+/* ---- channels-last (NHWC) variants used by the discriminator trunk ---------------------
+ * Same semantics as dusty_bias_act / dusty_bias_act_bwd / dusty_pad2d / dusty_resample4(up=1)
+ * on tensors stored [B, H, W, C] (torch.channels_last); C must be a multiple of the 16-byte
+ * vector width (and C / width a power of two <= 256 for the bias kernels). */
+int dusty_bias_act_cl(const void *x, const void *bias, const void *ref, void *y, int64_t n_elem,
+                      int C, int act, int grad, float alpha, float scale, int dtype, void *stream);
+int dusty_bias_act_bwd_cl(const void *dy, const void *out, void *dx, float *db, int64_t rows, int C,
+                          float alpha, float scale, int dtype, void *stream);
+int dusty_pad2d_cl(const void *x, void *y, int B, int H, int W, int C, int pt, int pb, int pl,
+                   int pr, int mode_y, int mode_x, int adjoint, int dtype, void *stream);
+int dusty_blur4_cl(const void *x, void *y, float k0, float k1, float k2, float k3, int B, int H,
+                   int W, int C, int adjoint, int dtype, void *stream);
+
 /* ---- a2: Fourier features --------------------------------------------------------------
  * Replaces FourierFeature.forward gans/models/ops/fourier.py:77-82.
  * angle: fp32 [Ba, 2, P] (elevation, azimuth); freqs: fp32 [F, 2]; phase: fp32 [F];

@@ -505,3 +505,47 @@ def test_modprep_fused_vs_composite(ops, demod, B, Oc, I):
         close(a, b_, rtol=2e-3, atol_rel=2e-4)
     wb16 = m.effective_weights(style, torch.bfloat16)
     close(wb16, ref, rtol=1e-2, atol_rel=4e-3)
+
+
+# ----------------------------------------------------------------------------- NHWC variants
+@pytest.mark.parametrize("dtype,C", [(torch.float32, 4), (torch.float32, 32), (torch.bfloat16, 32),
+                                     (torch.bfloat16, 256)])
+def test_channels_last_ops_match_nchw(DF, ops, dtype, C):
+    """bias_act / pad / blur on NHWC-stored tensors give the NCHW results (values, first and
+    second order), and keep the NHWC layout."""
+    g = torch.Generator().manual_seed(41)
+    x = torch.randn(3, C, 8, 16, generator=g).to(DEV, dtype)
+    b = torch.randn(C, generator=g).to(DEV)
+    CL = torch.channels_last
+    tol = dict(rtol=1e-5, atol_rel=1e-6) if dtype == torch.float32 else dict(rtol=2e-2, atol_rel=1e-2)
+
+    def run(fn, xin):
+        xin = xin.clone().requires_grad_()
+        y = fn(xin)
+        gy = torch.randn(y.shape, generator=torch.Generator().manual_seed(5)).to(DEV, dtype)
+        gy = gy.contiguous(memory_format=CL) if DF._is_cl(xin) else gy
+        gy = gy.requires_grad_()
+        (gx,) = torch.autograd.grad(y, xin, gy, create_graph=True)
+        v = torch.randn(xin.shape, generator=torch.Generator().manual_seed(6)).to(DEV, dtype)
+        (gg,) = torch.autograd.grad((gx.float() * v.float()).sum(), gy)
+        return y, gx, gg
+
+    blur, pad = ops.Resample().to(DEV), ops.Pad(1, ring=True)
+    for name, fn in (("bias_act", lambda t: DF.bias_act(t, b)), ("pad", pad), ("blur", blur)):
+        ref = run(fn, x)
+        got = run(fn, x.contiguous(memory_format=CL))
+        assert DF._is_cl(got[0]), name
+        for a, r in zip(got, ref):
+            if name == "pad":
+                assert torch.equal(a.contiguous(), r.contiguous()), name
+            else:
+                close(a, r, **tol)
+    # bias gradient through the NHWC reduction
+    bb = b.clone().requires_grad_()
+    xc = x.contiguous(memory_format=CL)
+    y = DF.bias_act(xc, bb)
+    gy = torch.randn(y.shape, generator=torch.Generator().manual_seed(7)).to(DEV, dtype)
+    (db,) = torch.autograd.grad(y, bb, gy.contiguous(memory_format=CL))
+    bb2 = b.clone().requires_grad_()
+    (db2,) = torch.autograd.grad(DF.bias_act(x, bb2), bb2, gy)
+    close(db, db2, rtol=1e-3, atol_rel=1e-3)

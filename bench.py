@@ -48,6 +48,7 @@ def parse():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-roofline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--no-cudnn-benchmark", action="store_true")
     ap.add_argument("--ncu-window", action="store_true",
                     help="bracket the timed region with cudaProfilerStart/Stop (ncu --profile-from-start off)")
     return ap.parse_args()
@@ -360,7 +361,7 @@ def main():
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
         dist.init_process_group("nccl", device_id=device)
     pkg.set_precision(args.precision)
-    torch.backends.cudnn.benchmark = True        # the reference sets it (gans/utils.py:29-30)
+    torch.backends.cudnn.benchmark = not args.no_cudnn_benchmark   # the reference sets it (gans/utils.py:29-30)
     if args.precision == "bf16":                 # fp32 epilogue GEMMs of D on the tensor cores
         torch.backends.cuda.matmul.allow_tf32 = True
     torch.manual_seed(0 + rank)

@@ -54,6 +54,7 @@ SIGNATURES = {
 _RESTYPE = {"dusty_last_error": C.c_char_p, "dusty_launch_count": C.c_int64}
 
 _lib = None
+_fns = {}
 
 
 def load() -> C.CDLL:
@@ -74,6 +75,8 @@ def load() -> C.CDLL:
     if ver != ABI_VERSION:
         raise RuntimeError(f"libdusty_b200 ABI version {ver} != expected {ABI_VERSION}")
     _lib = lib
+    for name in SIGNATURES:
+        _fns[name] = getattr(lib, name)
     return lib
 
 
@@ -95,7 +98,13 @@ def ptr(t):
     return None if t is None else t.data_ptr()
 
 
+_raw_stream = getattr(torch._C, "_cuda_getCurrentRawStream", None)
+
+
 def stream_of(t: torch.Tensor):
+    """Raw cudaStream_t of torch's current stream on t's device (fast path: no Stream object)."""
+    if _raw_stream is not None:
+        return _raw_stream(t.device.index or 0)
     return torch.cuda.current_stream(t.device).cuda_stream
 
 
@@ -116,4 +125,10 @@ def require_cuda(*tensors):
 
 
 def call(name: str, *args):
-    check(getattr(load(), name)(*args), name)
+    fn = _fns.get(name)
+    if fn is None:
+        load()
+        fn = _fns[name]
+    status = fn(*args)
+    if status != 0:
+        check(status, name)

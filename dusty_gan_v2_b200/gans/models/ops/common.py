@@ -227,6 +227,11 @@ class EqualLR(nn.Module):
 
     def forward(self, x):
         m = self.module
+        if isinstance(m, nn.Linear) and x.dtype == m.weight.dtype and x.numel() <= m.weight.numel():
+            # small activations (style / latent vectors): scale x, not the weight -- one tiny
+            # launch, exactly the reference's order of operations (common.py:180-181)
+            y = F.linear(x * self.scale, m.weight, m.bias)
+            return y if self.gain_ == 1.0 else y * self.gain_
         w = (m.weight * (self.scale * self.gain_)).to(x.dtype)
         b = None if m.bias is None else (m.bias * self.gain_).to(x.dtype)
         if isinstance(m, nn.Linear):

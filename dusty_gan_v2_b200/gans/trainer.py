@@ -28,7 +28,8 @@ from .models.ops.common import filter2d
 
 
 def set_requires_grad(net, requires_grad: bool = True):
-    for p in net.parameters():
+    params = net if isinstance(net, (list, tuple)) else net.parameters()
+    for p in params:
         p.requires_grad = requires_grad
 
 
@@ -47,8 +48,7 @@ def ema_inplace(ema_model, new_model, decay):
     new_p = [p.data for p in new_model.parameters()]
     torch._foreach_mul_(ema_p, decay)
     torch._foreach_add_(ema_p, new_p, alpha=1 - decay)
-    for eb, nb in zip(ema_model.buffers(), new_model.buffers()):
-        eb.copy_(nb)
+    torch._foreach_copy_(list(ema_model.buffers()), list(new_model.buffers()))
 
 
 class Trainer:
@@ -102,6 +102,8 @@ class Trainer:
         self.optim_D = torch.optim.Adam(self.D.parameters(), lr=lr_d.alpha * lazy_D,
                                         betas=(float(lr_d.beta1 ** lazy_D), float(lr_d.beta2 ** lazy_D)),
                                         fused=True)
+        self._G_params = list(self.G.parameters())     # cached: no module-tree walk per step
+        self._D_params = list(self.D.parameters())
         self.z_dim = cfg.model.generator.mapping_kwargs.in_ch
         self.warmup_fade_imgs = tr.warmup.fade_kimg * 1e3
         self.blur_sigma = 0.0
@@ -141,14 +143,15 @@ class Trainer:
     # ------------------------------------------------------------------ one iteration
     def step(self, iteration):
         tr = self.cfg.training
-        self.G.train()
+        if not self.G.training:
+            self.G.train()
         self.set_warmup_params(iteration)
         B = self.B
         scalars = OrderedDict()
         x_real = self.fetch_reals(next(self.batch_iter))["image"]
 
         # ---- G step (trainer.py:262-301)
-        set_requires_grad(self.G, True)
+        set_requires_grad(self._G_params, True)
         self.optim_G.zero_grad(set_to_none=True)
         x_fake = self.G(self.sample_z(B), **self.auxin)["image"]
         y_fake = self.D(self.A(self.warmup(x_fake)))
@@ -156,10 +159,10 @@ class Trainer:
         (tr.loss.gan * loss_gan).backward()
         self.optim_G.step()
         scalars["loss/G/adversarial"] = loss_gan.detach()
-        set_requires_grad(self.G, False)
+        set_requires_grad(self._G_params, False)
 
         # ---- D step (trainer.py:373-412)
-        set_requires_grad(self.D, True)
+        set_requires_grad(self._D_params, True)
         self.optim_D.zero_grad(set_to_none=True)
         x_fake = self.G(self.sample_z(B), **self.auxin)["image"]
         x_real_aug = self.A(self.warmup(x_real)).detach()
@@ -184,7 +187,7 @@ class Trainer:
             loss.backward()
             self.optim_D.step()
             scalars["loss/D/gradient_penalty"] = r1.detach()
-        set_requires_grad(self.D, False)
+        set_requires_grad(self._D_params, False)
 
         # ---- exit (trainer.py:459-476)
         ema_imgs = int(tr.ema_kimg * 1e3)

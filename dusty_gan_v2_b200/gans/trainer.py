@@ -53,7 +53,7 @@ def ema_inplace(ema_model, new_model, decay):
 
 class Trainer:
     def __init__(self, cfg, batch_iter, device=None, rank=0, world_size=1,
-                 angle_file="data/coords/kitti_raw.npy", precision=None):
+                 angle_file="data/coords/kitti_raw.npy", precision=None, cuda_graphs=True):
         self.cfg = cfg
         self.rank, self.world_size = rank, world_size
         self.device = torch.device(device if device is not None else f"cuda:{rank}")
@@ -105,6 +105,14 @@ class Trainer:
         self._G_params = list(self.G.parameters())     # cached: no module-tree walk per step
         self._D_params = list(self.D.parameters())
         self.z_dim = cfg.model.generator.mapping_kwargs.in_ch
+        # CUDA graphs for the static-shape segments (the step is launch-bound at B=64):
+        #   * the no-grad generator forward of the D step (z drawn inside the graph)
+        # ADA (data-dependent padding) and the discriminator stay eager.
+        self.cuda_graphs = bool(cuda_graphs) and self.device.type == "cuda"
+        self._g_graph = None
+        self._g_graph_out = None
+        self._g_graph_launches = 0
+        self.graph_replayed_launches = 0
         self.warmup_fade_imgs = tr.warmup.fade_kimg * 1e3
         self.blur_sigma = 0.0
         self.dropout_ratio = 0.0
@@ -140,6 +148,40 @@ class Trainer:
             x = keep * x + (1 - keep) * self.cfg.dataset.raydrop_const
         return x
 
+    # ------------------------------------------------------------------ graphed G forward
+    def _sync_G_buffers(self):
+        """DDP(broadcast_buffers=True) semantics for the graphed path: rank 0's buffers win."""
+        if self.world_size > 1:
+            bufs = [b for b in self.G_module.buffers() if b.is_floating_point()]
+            flat = torch.cat([b.reshape(-1).float() for b in bufs])
+            dist.broadcast(flat, 0)
+            torch._foreach_copy_(bufs, [c.reshape(b.shape).to(b.dtype)
+                                        for b, c in zip(bufs, flat.split([b.numel() for b in bufs]))])
+
+    def _fake_images_nograd(self, B):
+        """x_fake for the D step (no graph of G is needed: trainer.py:380-383)."""
+        if not self.cuda_graphs:
+            with torch.no_grad():
+                return self.G(self.sample_z(B), **self.auxin)["image"]
+        from .. import _cabi
+        self._sync_G_buffers()
+        if self._g_graph is None:
+            side = torch.cuda.Stream(device=self.device)
+            side.wait_stream(torch.cuda.current_stream(self.device))
+            with torch.cuda.stream(side), torch.no_grad():
+                for _ in range(2):          # warm-up outside capture (lazy inits, autotune)
+                    self.G_module(self.sample_z(B), **self.auxin)
+            torch.cuda.current_stream(self.device).wait_stream(side)
+            graph = torch.cuda.CUDAGraph()
+            n0 = _cabi.launch_count()
+            with torch.no_grad(), torch.cuda.graph(graph):
+                out = self.G_module(self.sample_z(B), **self.auxin)["image"]
+            self._g_graph_launches = _cabi.launch_count() - n0
+            self._g_graph, self._g_graph_out = graph, out
+        self._g_graph.replay()
+        self.graph_replayed_launches += self._g_graph_launches
+        return self._g_graph_out
+
     # ------------------------------------------------------------------ one iteration
     def step(self, iteration):
         tr = self.cfg.training
@@ -164,7 +206,7 @@ class Trainer:
         # ---- D step (trainer.py:373-412)
         set_requires_grad(self._D_params, True)
         self.optim_D.zero_grad(set_to_none=True)
-        x_fake = self.G(self.sample_z(B), **self.auxin)["image"]
+        x_fake = self._fake_images_nograd(B)
         x_real_aug = self.A(self.warmup(x_real)).detach()
         x_fake_aug = self.A(self.warmup(x_fake)).detach()
         y_real, y_fake = self.D(x_real_aug), self.D(x_fake_aug)

@@ -57,7 +57,9 @@ __device__ __forceinline__ float tap_at(const float *sk, const FirParams &p, int
 }
 
 // grid = (ceil(out_w / 256), out_h, min(N, 65535)): no per-element div/mod
-template <typename T>
+// UPX / UPY: compile-time up factors (1 or 2) so the polyphase index math needs no integer
+// division; 0 = run-time value (generic).
+template <typename T, int UPX, int UPY>
 __global__ void __launch_bounds__(256)
 fir2d_fwd_kernel(const T *__restrict__ x, T *__restrict__ y, const float *__restrict__ taps,
                  FirParams p, int64_t N) {
@@ -71,18 +73,21 @@ fir2d_fwd_kernel(const T *__restrict__ x, T *__restrict__ y, const float *__rest
   const int64_t out_plane = (int64_t)p.out_h * p.out_w;
   const int by = my * p.down_y - p.pad_y0;
   const int bx = mx * p.down_x - p.pad_x0;
-  const int ty0 = posmod(-by, p.up_y);
-  const int tx0 = posmod(-bx, p.up_x);
+  const int up_y = UPY ? UPY : p.up_y, up_x = UPX ? UPX : p.up_x;
+  const int ty0 = UPY == 1 ? 0 : (UPY == 2 ? (by & 1) : posmod(-by, up_y));
+  const int tx0 = UPX == 1 ? 0 : (UPX == 2 ? (bx & 1) : posmod(-bx, up_x));
   for (int64_t n = blockIdx.z; n < N; n += gridDim.z) {
     const T *xp = x + n * in_plane;
     float acc = 0.f;
-    for (int ty = ty0; ty < p.kh; ty += p.up_y) {
-      const int iy = bmap((by + ty) / p.up_y, p.in_h, p.mode_y);
+    for (int ty = ty0; ty < p.kh; ty += up_y) {
+      const int qy = by + ty;                     // exact multiple of up_y
+      const int iy = bmap(UPY == 1 ? qy : (UPY == 2 ? (qy >> 1) : qy / up_y), p.in_h, p.mode_y);
       if (iy < 0) continue;
       const T *row = xp + (int64_t)iy * p.in_w;
       float racc = 0.f;
-      for (int tx = tx0; tx < p.kw; tx += p.up_x) {
-        const int ix = bmap((bx + tx) / p.up_x, p.in_w, p.mode_x);
+      for (int tx = tx0; tx < p.kw; tx += up_x) {
+        const int qx = bx + tx;
+        const int ix = bmap(UPX == 1 ? qx : (UPX == 2 ? (qx >> 1) : qx / up_x), p.in_w, p.mode_x);
         if (ix < 0) continue;
         racc = fmaf(tap_at(sk, p, ty, tx), to_f(row[ix]), racc);
       }
@@ -128,7 +133,7 @@ __device__ __forceinline__ int preimage(int c, int i, int n, int mode, int lo, i
   }
 }
 
-template <typename T>
+template <typename T, int DNX, int DNY>
 __global__ void __launch_bounds__(256)
 fir2d_adj_kernel(const T *__restrict__ dy, T *__restrict__ dx, const float *__restrict__ taps,
                  FirParams p, int64_t N) {
@@ -148,8 +153,9 @@ fir2d_adj_kernel(const T *__restrict__ dy, T *__restrict__ dx, const float *__re
       if (ey == INT_MIN) break;
       if (ey == INT_MIN + 1) continue;
       const int ny = ey * p.up_y + p.pad_y0;  // = my*down_y + ty
-      for (int ty = posmod(ny, p.down_y); ty < p.kh; ty += p.down_y) {
-        const int my = (ny - ty) / p.down_y;
+      const int down_y = DNY ? DNY : p.down_y, down_x = DNX ? DNX : p.down_x;
+      for (int ty = (DNY == 1 ? 0 : (DNY == 2 ? (ny & 1) : posmod(ny, down_y))); ty < p.kh; ty += down_y) {
+        const int my = DNY == 1 ? (ny - ty) : (DNY == 2 ? ((ny - ty) >> 1) : (ny - ty) / down_y);
         if (ny - ty < 0 || my >= p.out_h) continue;
         const T *grow = gp + (int64_t)my * p.out_w;
         for (int cx = 0;; ++cx) {
@@ -157,8 +163,8 @@ fir2d_adj_kernel(const T *__restrict__ dy, T *__restrict__ dx, const float *__re
           if (ex == INT_MIN) break;
           if (ex == INT_MIN + 1) continue;
           const int nx = ex * p.up_x + p.pad_x0;
-          for (int tx = posmod(nx, p.down_x); tx < p.kw; tx += p.down_x) {
-            const int mx = (nx - tx) / p.down_x;
+          for (int tx = (DNX == 1 ? 0 : (DNX == 2 ? (nx & 1) : posmod(nx, down_x))); tx < p.kw; tx += down_x) {
+            const int mx = DNX == 1 ? (nx - tx) : (DNX == 2 ? ((nx - tx) >> 1) : (nx - tx) / down_x);
             if (nx - tx < 0 || mx >= p.out_w) continue;
             acc = fmaf(tap_at(sk, p, ty, tx), to_f(grow[mx]), acc);
           }
@@ -226,12 +232,21 @@ extern "C" int dusty_fir2d(const void *x, void *y, const float *taps, int kh, in
   if (N <= 0 || out_h <= 0 || out_w <= 0) return DUSTY_OK;
   DUSTY_CHECK_ARG(out_h <= 65535, "out_h too large");
   cudaStream_t st = (cudaStream_t)stream;
-  if (dtype == DUSTY_F32)
-    fir2d_fwd_kernel<float><<<grid_for(out_w, out_h, N), 256, 0, st>>>((const float *)x, (float *)y,
-                                                                      taps, p, N);
-  else
-    fir2d_fwd_kernel<__nv_bfloat16><<<grid_for(out_w, out_h, N), 256, 0, st>>>(
-        (const __nv_bfloat16 *)x, (__nv_bfloat16 *)y, taps, p, N);
+  const dim3 grid = grid_for(out_w, out_h, N);
+#define FIR_FWD(T, UX, UY) \
+  fir2d_fwd_kernel<T, UX, UY><<<grid, 256, 0, st>>>((const T *)x, (T *)y, taps, p, N)
+#define FIR_FWD_DISPATCH(T)                                   \
+  do {                                                        \
+    if (up_x == 1 && up_y == 1) FIR_FWD(T, 1, 1);             \
+    else if (up_x == 2 && up_y == 1) FIR_FWD(T, 2, 1);        \
+    else if (up_x == 1 && up_y == 2) FIR_FWD(T, 1, 2);        \
+    else if (up_x == 2 && up_y == 2) FIR_FWD(T, 2, 2);        \
+    else FIR_FWD(T, 0, 0);                                    \
+  } while (0)
+  if (dtype == DUSTY_F32) FIR_FWD_DISPATCH(float);
+  else FIR_FWD_DISPATCH(__nv_bfloat16);
+#undef FIR_FWD_DISPATCH
+#undef FIR_FWD
   DUSTY_LAUNCH_CHECK();
   return DUSTY_OK;
 }
@@ -249,12 +264,21 @@ extern "C" int dusty_fir2d_adj(const void *dy, void *dx, const float *taps, int 
   if (N <= 0) return DUSTY_OK;
   DUSTY_CHECK_ARG(in_h <= 65535, "in_h too large");
   cudaStream_t st = (cudaStream_t)stream;
-  if (dtype == DUSTY_F32)
-    fir2d_adj_kernel<float><<<grid_for(in_w, in_h, N), 256, 0, st>>>((const float *)dy, (float *)dx,
-                                                                    taps, p, N);
-  else
-    fir2d_adj_kernel<__nv_bfloat16><<<grid_for(in_w, in_h, N), 256, 0, st>>>(
-        (const __nv_bfloat16 *)dy, (__nv_bfloat16 *)dx, taps, p, N);
+  const dim3 grid = grid_for(in_w, in_h, N);
+#define FIR_ADJ(T, DX, DY) \
+  fir2d_adj_kernel<T, DX, DY><<<grid, 256, 0, st>>>((const T *)dy, (T *)dx, taps, p, N)
+#define FIR_ADJ_DISPATCH(T)                                       \
+  do {                                                            \
+    if (down_x == 1 && down_y == 1) FIR_ADJ(T, 1, 1);             \
+    else if (down_x == 2 && down_y == 1) FIR_ADJ(T, 2, 1);        \
+    else if (down_x == 1 && down_y == 2) FIR_ADJ(T, 1, 2);        \
+    else if (down_x == 2 && down_y == 2) FIR_ADJ(T, 2, 2);        \
+    else FIR_ADJ(T, 0, 0);                                        \
+  } while (0)
+  if (dtype == DUSTY_F32) FIR_ADJ_DISPATCH(float);
+  else FIR_ADJ_DISPATCH(__nv_bfloat16);
+#undef FIR_ADJ_DISPATCH
+#undef FIR_ADJ
   DUSTY_LAUNCH_CHECK();
   return DUSTY_OK;
 }

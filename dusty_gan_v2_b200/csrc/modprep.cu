@@ -113,96 +113,82 @@ __device__ __forceinline__ float prep_dt(const PrepCtx &c, float gw, float t, fl
 // ds'[b,i] = sum_o dt * w'      thread per (b, i)
 __global__ void __launch_bounds__(128)
 modprep_ds_kernel(PrepCtx c, const float *__restrict__ gwb, const float *__restrict__ cbo,
-                  float *__restrict__ dsp) {
+                  float *__restrict__ dsp, float *__restrict__ sums) {
+  __shared__ float red[32];
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   const int b = blockIdx.y;
-  if (i >= c.I) return;
-  const float inv_w = 1.f / c.wmax(), inv_s = 1.f / c.smax(b);
-  const float sp = c.sp(b, i, inv_s);
-  float acc = 0.f;
-  for (int o = 0; o < c.O; ++o) {
-    const float wp = c.wp(o, i, inv_w);
-    const float dt = prep_dt(c, gwb[((int64_t)b * c.O + o) * c.I + i], wp * sp, c.d(b, o),
-                             c.demod ? cbo[(int64_t)b * c.O + o] : 0.f);
-    acc = fmaf(dt, wp, acc);
+  float acc = 0.f, dot = 0.f;
+  if (i < c.I) {
+    const float inv_w = 1.f / c.wmax(), inv_s = 1.f / c.smax(b);
+    const float sp = c.sp(b, i, inv_s);
+    for (int o = 0; o < c.O; ++o) {
+      const float wp = c.wp(o, i, inv_w);
+      const float dt = prep_dt(c, gwb[((int64_t)b * c.O + o) * c.I + i], wp * sp, c.d(b, o),
+                               c.demod ? cbo[(int64_t)b * c.O + o] : 0.f);
+      acc = fmaf(dt, wp, acc);
+    }
+    dsp[(int64_t)b * c.I + i] = acc;
+    dot = acc * c.slin[(int64_t)b * c.I + i];
   }
-  dsp[(int64_t)b * c.I + i] = acc;
+  if (c.demod) {       // sum_j ds'_j s_j, needed by the inf-norm term of the finish pass
+    dot = block_sum(dot, red);
+    if (threadIdx.x == 0) atomicAdd(sums + b, dot);
+  }
 }
 
 // dw'[o,i] = sum_b dt * s'      thread per (o, i)
 __global__ void __launch_bounds__(128)
 modprep_dw_kernel(PrepCtx c, const float *__restrict__ gwb, const float *__restrict__ cbo,
-                  float *__restrict__ dwp) {
+                  float *__restrict__ dwp, float *__restrict__ sums) {
+  __shared__ float red[32];
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   const int o = blockIdx.y;
-  if (i >= c.I) return;
-  const float inv_w = 1.f / c.wmax();
-  const float wp = c.wp(o, i, inv_w);
-  float acc = 0.f;
-  for (int b = 0; b < c.B; ++b) {
-    const float sp = c.sp(b, i, 1.f / c.smax(b));
-    const float dt = prep_dt(c, gwb[((int64_t)b * c.O + o) * c.I + i], wp * sp, c.d(b, o),
-                             c.demod ? cbo[(int64_t)b * c.O + o] : 0.f);
-    acc = fmaf(dt, sp, acc);
+  float acc = 0.f, dot = 0.f;
+  if (i < c.I) {
+    const float inv_w = 1.f / c.wmax();
+    const float wp = c.wp(o, i, inv_w);
+    for (int b = 0; b < c.B; ++b) {
+      const float sp = c.sp(b, i, 1.f / c.smax(b));
+      const float dt = prep_dt(c, gwb[((int64_t)b * c.O + o) * c.I + i], wp * sp, c.d(b, o),
+                               c.demod ? cbo[(int64_t)b * c.O + o] : 0.f);
+      acc = fmaf(dt, sp, acc);
+    }
+    dwp[(int64_t)o * c.I + i] = acc;
+    dot = acc * c.W[(int64_t)o * c.I + i] * c.scale;
   }
-  dwp[(int64_t)o * c.I + i] = acc;
+  if (c.demod) {
+    dot = block_sum(dot, red);
+    if (threadIdx.x == 0) atomicAdd(sums + c.B, dot);
+  }
 }
 
-// grid = B + 1 blocks.  Blocks [0,B): ds[b,:] from ds'; block B: dW from dw'.
-// v = x / max|x| (+1):  dx_i = dv_i / m  -  [i == argmax] * sign(x_i) * (sum_j dv_j x_j) / m^2
+// Elementwise finish over the B*I style entries and the O*I weight entries.
+// v = x / max|x| (+1):  dx_i = dv_i / m  -  [|x_i| == m] * sign(x_i) * (sum_j dv_j x_j) / m^2
+// (the arg-max element is recognised by equality with the stored maximum).
 __global__ void __launch_bounds__(256)
 modprep_finish_kernel(PrepCtx c, const float *__restrict__ dsp, const float *__restrict__ dwp,
-                      float *__restrict__ dslin, float *__restrict__ dW) {
-  __shared__ float red_s[8];
-  __shared__ float red_m[8];
-  __shared__ int red_i[8];
-  __shared__ float bc_sum;
-  __shared__ int bc_idx;
-  const bool is_w = (int)blockIdx.x == c.B;
-  const int64_t n = is_w ? (int64_t)c.O * c.I : c.I;
-  const float *x = is_w ? c.W : c.slin + (int64_t)blockIdx.x * c.I;
-  const float *dv = is_w ? dwp : dsp + (int64_t)blockIdx.x * c.I;
-  float *dx = is_w ? dW : dslin + (int64_t)blockIdx.x * c.I;
-  const float pre = is_w ? c.scale : 1.f;          // x enters as pre*x
-  if (!c.demod) {
-    for (int64_t i = threadIdx.x; i < n; i += blockDim.x) dx[i] = dv[i] * pre;
-    return;
-  }
-  const float m = is_w ? c.wmax() : c.smax(blockIdx.x);
-  float s = 0.f, best = -1.f;
-  int64_t bi = 0;
-  for (int64_t i = threadIdx.x; i < n; i += blockDim.x) {
-    const float xv = x[i] * pre;
-    s = fmaf(dv[i], xv, s);
-    if (fabsf(xv) > best) { best = fabsf(xv); bi = i; }
-  }
-  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
-  s = warp_sum(s);
-#pragma unroll
-  for (int o = 16; o > 0; o >>= 1) {
-    const float ob = __shfl_xor_sync(0xffffffffu, best, o);
-    const int oi = __shfl_xor_sync(0xffffffffu, (int)bi, o);
-    if (ob > best || (ob == best && oi < (int)bi)) { best = ob; bi = oi; }
-  }
-  if (lane == 0) { red_s[wid] = s; red_m[wid] = best; red_i[wid] = (int)bi; }
-  __syncthreads();
-  if (threadIdx.x == 0) {
-    float ts = 0.f, tb = -1.f;
-    int ti = 0;
-    for (int w = 0; w < (int)(blockDim.x >> 5); ++w) {
-      ts += red_s[w];
-      if (red_m[w] > tb || (red_m[w] == tb && red_i[w] < ti)) { tb = red_m[w]; ti = red_i[w]; }
+                      const float *__restrict__ sums, float *__restrict__ dslin,
+                      float *__restrict__ dW) {
+  const int64_t ns = (int64_t)c.B * c.I, nw = (int64_t)c.O * c.I;
+  for (int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; t < ns + nw;
+       t += (int64_t)gridDim.x * blockDim.x) {
+    const bool is_w = t >= ns;
+    const int64_t i = is_w ? t - ns : t;
+    const float pre = is_w ? c.scale : 1.f;
+    const float dv = is_w ? dwp[i] : dsp[i];
+    float *dst = is_w ? dW + i : dslin + i;
+    if (!c.demod) {
+      *dst = dv * pre;
+      continue;
     }
-    bc_sum = ts;
-    bc_idx = ti;
-  }
-  __syncthreads();
-  const float inv_m = 1.f / m;
-  const float corr = bc_sum * inv_m * inv_m;
-  for (int64_t i = threadIdx.x; i < n; i += blockDim.x) {
-    float g = dv[i] * inv_m;
-    if (i == bc_idx) g -= (x[i] >= 0.f ? corr : -corr);
-    dx[i] = g * pre;
+    const int b = is_w ? 0 : (int)(i / c.I);
+    const float m = is_w ? c.wmax() : c.smax(b);
+    const float sum = is_w ? sums[c.B] : sums[b];
+    const float xv = (is_w ? c.W[i] : c.slin[i]) * pre;
+    const float inv_m = 1.f / m;
+    float g = dv * inv_m;
+    if (fabsf(xv) == m) g -= (xv >= 0.f ? 1.f : -1.f) * sum * inv_m * inv_m;
+    *dst = g * pre;
   }
 }
 
@@ -241,14 +227,20 @@ extern "C" int dusty_modprep_bwd(const float *gwb, const float *slin, const floa
   float *cbo = work;                         // [B*O]
   float *dsp = work + (int64_t)B * O;        // [B*I]
   float *dwp = dsp + (int64_t)B * I;         // [O*I]
+  float *sums = dwp + (int64_t)O * I;        // [B + 1]
+  if (cudaMemsetAsync(sums, 0, sizeof(float) * (B + 1), st) != cudaSuccess) return DUSTY_ECUDA;
   if (demod) {
     dim3 grid((unsigned)((O + 3) / 4), (unsigned)B);
     modprep_c_kernel<<<grid, 128, 0, st>>>(c, gwb, cbo);
     count_launch(1);
   }
-  modprep_ds_kernel<<<dim3((unsigned)((I + 127) / 128), (unsigned)B), 128, 0, st>>>(c, gwb, cbo, dsp);
-  modprep_dw_kernel<<<dim3((unsigned)((I + 127) / 128), (unsigned)O), 128, 0, st>>>(c, gwb, cbo, dwp);
-  modprep_finish_kernel<<<B + 1, 256, 0, st>>>(c, dsp, dwp, dslin, dweight);
+  modprep_ds_kernel<<<dim3((unsigned)((I + 127) / 128), (unsigned)B), 128, 0, st>>>(c, gwb, cbo, dsp, sums);
+  modprep_dw_kernel<<<dim3((unsigned)((I + 127) / 128), (unsigned)O), 128, 0, st>>>(c, gwb, cbo, dwp, sums);
+  {
+    int64_t nb = (((int64_t)B + O) * I + 255) / 256;
+    if (nb > 1184) nb = 1184;
+    modprep_finish_kernel<<<(unsigned)nb, 256, 0, st>>>(c, dsp, dwp, sums, dslin, dweight);
+  }
   DUSTY_LAUNCH_CHECK();
   count_launch(2);
   return DUSTY_OK;

@@ -533,7 +533,7 @@ class _ModPrep(Function):
         gwb = _contig(gwb.float())
         dslin = torch.empty_like(slin)
         dw = torch.empty_like(w2)
-        work = torch.empty(B * O + B * I + O * I, device=slin.device, dtype=torch.float32)
+        work = torch.empty(B * O + B * I + O * I + B + 1, device=slin.device, dtype=torch.float32)
         K.call("dusty_modprep_bwd", K.ptr(gwb), K.ptr(slin), K.ptr(w2), K.ptr(stats), K.ptr(dslin),
                K.ptr(dw), K.ptr(work), B, O, I, scale, 1 if demod else 0, K.stream_of(slin))
         return dslin, dw.reshape(wshape).to(wdtype), None, None, None, None

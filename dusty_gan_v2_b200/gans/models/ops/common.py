@@ -178,6 +178,8 @@ class _Conv2dBwdFn(torch.autograd.Function):
         ctx.stride, ctx.need = stride, (need_x, need_w)
         gy = gy.contiguous(memory_format=torch.channels_last) if DF._is_cl(x) else gy.contiguous()
         gx, gw = _conv_grads(gy, x, w, stride, need_x, need_w)
+        if gw is not None and not gw.is_contiguous():
+            gw = gw.contiguous()           # NHWC filter grads -> parameter (NCHW) layout
         return gx, gw
 
     @staticmethod
@@ -232,6 +234,13 @@ class EqualLR(nn.Module):
             # launch, exactly the reference's order of operations (common.py:180-181)
             y = F.linear(x * self.scale, m.weight, m.bias)
             return y if self.gain_ == 1.0 else y * self.gain_
+        if (isinstance(m, nn.Linear) and x.is_cuda and x.dtype == torch.float32
+                and DF.act_dtype() == torch.bfloat16 and m.weight.numel() >= (1 << 22)):
+            # the 65536 -> 512 linear of D's epilogue: bf16 operands on the tensor cores with
+            # fp32 accumulation in low-precision mode (an fp32 SIMT/TF32 GEMM costs ~0.6 ms)
+            w16 = (m.weight * (self.scale * self.gain_)).to(torch.bfloat16)
+            y = F.linear(x.to(torch.bfloat16), w16).float()
+            return y if m.bias is None else y + m.bias * self.gain_
         w = (m.weight * (self.scale * self.gain_)).to(x.dtype)
         b = None if m.bias is None else (m.bias * self.gain_).to(x.dtype)
         if isinstance(m, nn.Linear):
@@ -280,8 +289,16 @@ class MinibatchStdDev(nn.Module):
             raise NotImplementedError("MinibatchStdDev: only features == 1 is implemented")
         self.group = group
         self.features = features
+        # number of independent mini-batches stacked along dim 0 (the trainer evaluates real and
+        # fake images in one pass; statistics must not mix them)
+        self.sub_batches = 1
 
     def forward(self, x, alpha: float = 1e-8):
+        if self.sub_batches > 1:
+            if x.shape[0] % self.sub_batches:
+                raise RuntimeError("batch is not divisible by sub_batches")
+            return torch.cat([DF.minibatch_stddev(c, self.group, alpha)
+                              for c in x.chunk(self.sub_batches, dim=0)], dim=0)
         return DF.minibatch_stddev(x, self.group, alpha)
 
     def extra_repr(self):

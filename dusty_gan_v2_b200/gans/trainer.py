@@ -41,14 +41,22 @@ def tanh_to_sigmoid(x):
     return (x + 1.0) / 2.0
 
 
+_EMA_LISTS = {}
+
+
 @torch.no_grad()
 def ema_inplace(ema_model, new_model, decay):
-    """reference trainer.py:30-41, as two multi-tensor launches instead of ~240 tiny ones."""
-    ema_p = [p.data for p in ema_model.parameters()]
-    new_p = [p.data for p in new_model.parameters()]
-    torch._foreach_mul_(ema_p, decay)
-    torch._foreach_add_(ema_p, new_p, alpha=1 - decay)
-    torch._foreach_copy_(list(ema_model.buffers()), list(new_model.buffers()))
+    """reference trainer.py:30-41, as multi-tensor launches instead of ~240 tiny ones:
+    params lerp towards the new weights, buffers are copied."""
+    key = (id(ema_model), id(new_model))
+    lists = _EMA_LISTS.get(key)
+    if lists is None:
+        lists = ([p.data for p in ema_model.parameters()], [p.data for p in new_model.parameters()],
+                 list(ema_model.buffers()), list(new_model.buffers()))
+        _EMA_LISTS[key] = lists
+    ema_p, new_p, ema_b, new_b = lists
+    torch._foreach_lerp_(ema_p, new_p, 1 - decay)
+    torch._foreach_copy_(ema_b, new_b)
 
 
 class Trainer:
@@ -182,6 +190,20 @@ class Trainer:
         self.graph_replayed_launches += self._g_graph_launches
         return self._g_graph_out
 
+    def _D_two_halves(self, x_both):
+        mb = getattr(self, "_mbstd_modules", None)
+        if mb is None:
+            mb = self._mbstd_modules = [m for m in self.D_module.modules()
+                                        if hasattr(m, "sub_batches")]
+        for m in mb:
+            m.sub_batches = 2
+        try:
+            y = self.D(x_both)
+        finally:
+            for m in mb:
+                m.sub_batches = 1
+        return y.chunk(2, dim=0)
+
     # ------------------------------------------------------------------ one iteration
     def step(self, iteration):
         tr = self.cfg.training
@@ -207,9 +229,10 @@ class Trainer:
         set_requires_grad(self._D_params, True)
         self.optim_D.zero_grad(set_to_none=True)
         x_fake = self._fake_images_nograd(B)
-        x_real_aug = self.A(self.warmup(x_real)).detach()
-        x_fake_aug = self.A(self.warmup(x_fake)).detach()
-        y_real, y_fake = self.D(x_real_aug), self.D(x_fake_aug)
+        # real and fake go through warm-up, ADA and D as ONE stacked batch (per-sample
+        # transforms, per-half minibatch statistics): same math, half the launches
+        x_both = self.A(self.warmup(torch.cat([x_real, x_fake], dim=0))).detach()
+        y_real, y_fake = self._D_two_halves(x_both)
         self.A.cumulate(y_real)
         loss_gan = self.adversarial_loss(y_real, y_fake, "D")
         (tr.loss.gan * loss_gan).backward()

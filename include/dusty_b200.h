@@ -159,7 +159,7 @@ int dusty_modprep_fwd(const float *slin, const float *weight, const float *ema_v
                       float *stats, int B, int O, int I, float scale, int demod, int wdtype,
                       void *stream);
 /* Analytic backward: gwb fp32 [B, O, I] -> dslin [B, I], dweight [O, I].
- * work: fp32 workspace of B*O + B*I + O*I floats. */
+ * work: fp32 workspace of B*O + B*I + O*I + B + 1 floats. */
 int dusty_modprep_bwd(const float *gwb, const float *slin, const float *weight, const float *stats,
                       float *dslin, float *dweight, float *work, int B, int O, int I, float scale,
                       int demod, void *stream);

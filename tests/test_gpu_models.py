@@ -247,3 +247,22 @@ def test_training_step_runs_and_matches_oracle_losses():
     assert float(tr.A.p) == 0.0 or float(tr.A.p) > 0
     out = tr.sample(torch.randn(2, 16, device=DEV))
     assert out["image"].shape == (2, 1, 16, 64)
+
+
+def test_discriminator_stacked_halves_equals_two_passes(g_disc):
+    """D(cat(real, fake)) with per-half minibatch statistics == (D(real), D(fake))."""
+    from dusty_gan_v2_b200.gans.models.builder import build_discriminator
+    D = build_discriminator(D_SMALL)
+    D.load_state_dict(_sd(g_disc), strict=True)
+    D = D.to(DEV)
+    g = torch.Generator().manual_seed(9)
+    a = torch.tanh(torch.randn(8, 1, 16, 64, generator=g)).to(DEV)
+    b = torch.tanh(torch.randn(8, 1, 16, 64, generator=g)).to(DEV)
+    with torch.no_grad():
+        ya, yb = D(a), D(b)
+        for m in D.modules():
+            if hasattr(m, "sub_batches"):
+                m.sub_batches = 2
+        yab = D(torch.cat([a, b], 0))
+    close(yab[:8], ya, rtol=1e-4, atol_rel=1e-5)
+    close(yab[8:], yb, rtol=1e-4, atol_rel=1e-5)

@@ -41,5 +41,8 @@ for i in range(8):
 pr.disable()
 torch.cuda.synchronize()
 s = io.StringIO()
-pstats.Stats(pr, stream=s).sort_stats("tottime").print_stats(45)
+pstats.Stats(pr, stream=s).sort_stats("tottime").print_stats(40)
+print(s.getvalue()[:7000])
+s = io.StringIO()
+pstats.Stats(pr, stream=s).sort_stats("cumtime").print_stats("dusty_gan_v2_b200|optim|run_backward", 45)
 print(s.getvalue()[:9000])

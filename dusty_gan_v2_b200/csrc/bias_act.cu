@@ -73,7 +73,7 @@ static int launch_bias_act(const void *x, const void *bias, const void *ref, voi
 }
 
 // Backward over rows r = n*C + c of `inner` contiguous elements.
-// grid = (chunks, rows); each CTA handles one chunk of one row, so its partial bias
+// grid = (rows, chunks); each CTA handles one chunk of one row, so its partial bias
 // gradient belongs to a single channel.
 template <typename T, bool VEC>
 __global__ void __launch_bounds__(256)
@@ -82,9 +82,9 @@ bias_act_bwd_kernel(const T *__restrict__ dy, const T *__restrict__ out, T *__re
                     float scale) {
   __shared__ float red[32];
   constexpr int V = VEC ? Vec16<T>::N : 1;
-  const int64_t row = blockIdx.y;
+  const int64_t row = blockIdx.x;
   const int64_t base = row * inner;
-  const int64_t lo = (int64_t)blockIdx.x * chunk;
+  const int64_t lo = (int64_t)blockIdx.y * chunk;
   int64_t hi = lo + chunk;
   if (hi > inner) hi = inner;
   float acc = 0.f;
@@ -148,11 +148,12 @@ static int launch_bias_act_bwd(const void *dy, const void *out, void *dx, float 
   int64_t chunk = 256 * V * 4;  // 4 vectors per thread
   if (chunk > inner) chunk = ((inner + V - 1) / V) * V;
   const int64_t chunks = (inner + chunk - 1) / chunk;
-  if (rows > 65535) {
-    set_error("dusty_bias_act_bwd: N*C = %lld exceeds 65535", (long long)rows);
+  if (rows > 0x7fffffff || chunks > 65535) {
+    set_error("dusty_bias_act_bwd: tensor too large (rows %lld, chunks %lld)", (long long)rows,
+              (long long)chunks);
     return DUSTY_EUNSUPPORTED;
   }
-  dim3 grid((unsigned)chunks, (unsigned)rows);
+  dim3 grid((unsigned)rows, (unsigned)chunks);
   if (vec)
     bias_act_bwd_kernel<T, true><<<grid, 256, 0, st>>>((const T *)dy, (const T *)out, (T *)dx, db,
                                                        C, inner, chunk, alpha, scale);

@@ -55,6 +55,12 @@ struct PrepCtx {
   const float *slin, *W, *stats;
   int B, O, I, demod;
   float scale;
+  // optional per-sample rotation of the Fourier columns (azimuth-shift identity, see header):
+  // rot[b, f] = cos(psi_bf), rot[b, F + f] = sin(psi_bf); columns [C1, C1+F) are the sin block,
+  // [C1+F, C1+2F) the cos block.  rot == nullptr: none.
+  const float *rot;
+  int C1, F;
+  __device__ __forceinline__ bool rotated(int i) const { return rot != nullptr && i >= C1; }
   __device__ __forceinline__ float smax(int b) const { return stats[b]; }
   __device__ __forceinline__ float wmax() const { return demod ? stats[B] : 1.f; }
   __device__ __forceinline__ float g() const { return stats[B + 1]; }
@@ -86,7 +92,36 @@ modprep_wb_kernel(PrepCtx c, float *__restrict__ stats_w, T *__restrict__ wb) {
   if (lane == 0) stats_w[c.B + 2 + (int64_t)b * c.O + o] = d;
   const float dg = d * c.g();
   T *row = wb + ((int64_t)b * c.O + o) * c.I;
-  for (int i = lane; i < c.I; i += 32) row[i] = from_f<T>(c.wp(o, i, inv_w) * c.sp(b, i, inv_s) * dg);
+  if (c.rot == nullptr) {
+    for (int i = lane; i < c.I; i += 32) row[i] = from_f<T>(c.wp(o, i, inv_w) * c.sp(b, i, inv_s) * dg);
+  } else {
+    // rotation preserves sum t^2, so d above is unaffected
+    for (int i = lane; i < c.C1 + c.F; i += 32) {
+      const float ts = c.wp(o, i, inv_w) * c.sp(b, i, inv_s) * dg;
+      if (i < c.C1) {
+        row[i] = from_f<T>(ts);
+      } else {
+        const int f = i - c.C1;
+        const float tc = c.wp(o, i + c.F, inv_w) * c.sp(b, i + c.F, inv_s) * dg;
+        const float cs = c.rot[(int64_t)b * 2 * c.F + f], sn = c.rot[(int64_t)b * 2 * c.F + c.F + f];
+        row[i] = from_f<T>(ts * cs - tc * sn);
+        row[i + c.F] = from_f<T>(ts * sn + tc * cs);
+      }
+    }
+  }
+}
+
+// incoming gradient w.r.t. the UN-rotated weights (transpose of the rotation above)
+__device__ __forceinline__ float prep_gw(const PrepCtx &c, const float *__restrict__ gwb, int b,
+                                         int o, int i) {
+  const float *row = gwb + ((int64_t)b * c.O + o) * c.I;
+  if (!c.rotated(i)) return row[i];
+  const int r = i - c.C1;
+  const bool is_cos = r >= c.F;
+  const int f = is_cos ? r - c.F : r;
+  const float gs = row[c.C1 + f], gc = row[c.C1 + c.F + f];
+  const float cs = c.rot[(int64_t)b * 2 * c.F + f], sn = c.rot[(int64_t)b * 2 * c.F + c.F + f];
+  return is_cos ? (gc * cs - gs * sn) : (gs * cs + gc * sn);
 }
 
 // c[b,o] = sum_i gwb * g * t      (demod only)
@@ -97,9 +132,9 @@ modprep_c_kernel(PrepCtx c, const float *__restrict__ gwb, float *__restrict__ c
   const int b = blockIdx.y;
   if (o >= c.O) return;
   const float inv_w = 1.f / c.wmax(), inv_s = 1.f / c.smax(b);
-  const float *grow = gwb + ((int64_t)b * c.O + o) * c.I;
   float acc = 0.f;
-  for (int i = lane; i < c.I; i += 32) acc = fmaf(grow[i], c.wp(o, i, inv_w) * c.sp(b, i, inv_s), acc);
+  for (int i = lane; i < c.I; i += 32)
+    acc = fmaf(prep_gw(c, gwb, b, o, i), c.wp(o, i, inv_w) * c.sp(b, i, inv_s), acc);
   acc = warp_sum(acc);
   if (lane == 0) cbo[(int64_t)b * c.O + o] = acc * c.g();
 }
@@ -123,7 +158,7 @@ modprep_ds_kernel(PrepCtx c, const float *__restrict__ gwb, const float *__restr
     const float sp = c.sp(b, i, inv_s);
     for (int o = 0; o < c.O; ++o) {
       const float wp = c.wp(o, i, inv_w);
-      const float dt = prep_dt(c, gwb[((int64_t)b * c.O + o) * c.I + i], wp * sp, c.d(b, o),
+      const float dt = prep_dt(c, prep_gw(c, gwb, b, o, i), wp * sp, c.d(b, o),
                                c.demod ? cbo[(int64_t)b * c.O + o] : 0.f);
       acc = fmaf(dt, wp, acc);
     }
@@ -149,7 +184,7 @@ modprep_dw_kernel(PrepCtx c, const float *__restrict__ gwb, const float *__restr
     const float wp = c.wp(o, i, inv_w);
     for (int b = 0; b < c.B; ++b) {
       const float sp = c.sp(b, i, 1.f / c.smax(b));
-      const float dt = prep_dt(c, gwb[((int64_t)b * c.O + o) * c.I + i], wp * sp, c.d(b, o),
+      const float dt = prep_dt(c, prep_gw(c, gwb, b, o, i), wp * sp, c.d(b, o),
                                c.demod ? cbo[(int64_t)b * c.O + o] : 0.f);
       acc = fmaf(dt, sp, acc);
     }
@@ -198,8 +233,10 @@ using namespace dusty;
 
 extern "C" int dusty_modprep_fwd(const float *slin, const float *weight, const float *ema_var,
                                  void *wb, float *stats, int B, int O, int I, float scale,
-                                 int demod, int wdtype, void *stream) {
+                                 int demod, int wdtype, const float *rot, int C1, int F,
+                                 void *stream) {
   DUSTY_CHECK_ARG(slin && weight && wb && stats, "null pointer");
+  DUSTY_CHECK_ARG(rot == nullptr || (C1 >= 0 && F >= 1 && C1 + 2 * F == I), "bad rotation layout");
   DUSTY_CHECK_ARG(B >= 1 && B <= 65535 && O >= 1 && I >= 1, "bad shape");
   DUSTY_CHECK_ARG(wdtype == DUSTY_F32 || wdtype == DUSTY_BF16, "bad dtype");
   cudaStream_t st = (cudaStream_t)stream;
@@ -208,7 +245,7 @@ extern "C" int dusty_modprep_fwd(const float *slin, const float *weight, const f
   if (nw > 64) nw = 64;
   if (nw < 1) nw = 1;
   modprep_stats_kernel<<<B + nw, 256, 0, st>>>(slin, weight, ema_var, stats, B, O, I, scale, demod);
-  PrepCtx c{slin, weight, stats, B, O, I, demod, scale};
+  PrepCtx c{slin, weight, stats, B, O, I, demod, scale, rot, C1, F};
   dim3 grid((unsigned)((O + 3) / 4), (unsigned)B);
   if (wdtype == DUSTY_F32) modprep_wb_kernel<float><<<grid, 128, 0, st>>>(c, stats, (float *)wb);
   else modprep_wb_kernel<__nv_bfloat16><<<grid, 128, 0, st>>>(c, stats, (__nv_bfloat16 *)wb);
@@ -219,11 +256,13 @@ extern "C" int dusty_modprep_fwd(const float *slin, const float *weight, const f
 
 extern "C" int dusty_modprep_bwd(const float *gwb, const float *slin, const float *weight,
                                  const float *stats, float *dslin, float *dweight, float *work,
-                                 int B, int O, int I, float scale, int demod, void *stream) {
+                                 int B, int O, int I, float scale, int demod, const float *rot,
+                                 int C1, int F, void *stream) {
   DUSTY_CHECK_ARG(gwb && slin && weight && stats && dslin && dweight && work, "null pointer");
+  DUSTY_CHECK_ARG(rot == nullptr || (C1 >= 0 && F >= 1 && C1 + 2 * F == I), "bad rotation layout");
   DUSTY_CHECK_ARG(B >= 1 && B <= 65535 && O >= 1 && O <= 65535 && I >= 1, "bad shape");
   cudaStream_t st = (cudaStream_t)stream;
-  PrepCtx c{slin, weight, stats, B, O, I, demod, scale};
+  PrepCtx c{slin, weight, stats, B, O, I, demod, scale, rot, C1, F};
   float *cbo = work;                         // [B*O]
   float *dsp = work + (int64_t)B * O;        // [B*I]
   float *dwp = dsp + (int64_t)B * I;         // [O*I]

@@ -508,7 +508,7 @@ def modconv_bmm(wb, x1, x2=None, bias=None, act: int = 1, alpha: float = 0.2, sc
 
 class _ModPrep(Function):
     @staticmethod
-    def forward(ctx, slin, weight, ema_var, scale, demod, out_dtype):
+    def forward(ctx, slin, weight, ema_var, scale, demod, out_dtype, rot, c1):
         slin = _contig(slin.float())
         w2 = _contig(weight.float().reshape(weight.shape[-4], weight.shape[-3]) if weight.ndim == 5
                      else weight.float())
@@ -517,17 +517,23 @@ class _ModPrep(Function):
         wb = torch.empty(B, O, I, device=slin.device, dtype=out_dtype)
         stats = torch.empty(B + 2 + B * O, device=slin.device, dtype=torch.float32)
         ev = None if ema_var is None else ema_var.detach().float().reshape(1)
+        nf = 0
+        if rot is not None:
+            rot = _contig(rot.detach().float())
+            nf = rot.shape[1] // 2
+            if rot.shape[0] != B or c1 + 2 * nf != I:
+                raise RuntimeError("rotation table does not match the layer")
         K.call("dusty_modprep_fwd", K.ptr(slin), K.ptr(w2), K.ptr(ev), K.ptr(wb), K.ptr(stats), B, O,
-               I, scale, 1 if demod else 0, K.dtype_code(wb), K.stream_of(slin))
-        ctx.save_for_backward(slin, w2, stats)
-        ctx.cfg = (scale, demod, tuple(weight.shape), weight.dtype)
+               I, scale, 1 if demod else 0, K.dtype_code(wb), K.ptr(rot), c1, nf, K.stream_of(slin))
+        ctx.save_for_backward(slin, w2, stats, rot)
+        ctx.cfg = (scale, demod, tuple(weight.shape), weight.dtype, c1, nf)
         return wb
 
     @staticmethod
     @once_differentiable
     def backward(ctx, gwb):
-        slin, w2, stats = ctx.saved_tensors
-        scale, demod, wshape, wdtype = ctx.cfg
+        slin, w2, stats, rot = ctx.saved_tensors
+        scale, demod, wshape, wdtype, c1, nf = ctx.cfg
         B, I = slin.shape
         O = w2.shape[0]
         gwb = _contig(gwb.float())
@@ -535,14 +541,17 @@ class _ModPrep(Function):
         dw = torch.empty_like(w2)
         work = torch.empty(B * O + B * I + O * I + B + 1, device=slin.device, dtype=torch.float32)
         K.call("dusty_modprep_bwd", K.ptr(gwb), K.ptr(slin), K.ptr(w2), K.ptr(stats), K.ptr(dslin),
-               K.ptr(dw), K.ptr(work), B, O, I, scale, 1 if demod else 0, K.stream_of(slin))
-        return dslin, dw.reshape(wshape).to(wdtype), None, None, None, None
+               K.ptr(dw), K.ptr(work), B, O, I, scale, 1 if demod else 0, K.ptr(rot), c1, nf,
+               K.stream_of(slin))
+        return dslin, dw.reshape(wshape).to(wdtype), None, None, None, None, None, None
 
 
-def modprep(slin, weight, ema_var, scale: float, demod: bool, out_dtype=torch.float32):
-    """Per-sample effective weights wb[B,O,I] of a modulated 1x1 conv (see dusty_modprep_fwd)."""
-    K.require_cuda(slin, weight, ema_var)
-    return _ModPrep.apply(slin, weight, ema_var, float(scale), bool(demod), out_dtype)
+def modprep(slin, weight, ema_var, scale: float, demod: bool, out_dtype=torch.float32, rot=None,
+            c1: int = 0):
+    """Per-sample effective weights wb[B,O,I] of a modulated 1x1 conv (see dusty_modprep_fwd).
+    rot: optional [B, 2F] (cos | sin) rotation of the Fourier columns starting at c1."""
+    K.require_cuda(slin, weight, ema_var, rot)
+    return _ModPrep.apply(slin, weight, ema_var, float(scale), bool(demod), out_dtype, rot, int(c1))
 
 
 def sumsq_total(x: torch.Tensor) -> torch.Tensor:

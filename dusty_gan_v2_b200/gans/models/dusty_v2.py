@@ -117,18 +117,25 @@ class SynthesisBlock(nn.Module):
         per = self.downsample(torch.cat([angle.sin(), angle.cos()], dim=1))
         return torch.atan2(per[:, :c], per[:, c:])
 
-    def _conv(self, conv, noise, act, h, style, pe=None):
+    def _conv(self, conv, noise, act, h, style, pe=None, pe_rot=None):
         if noise is None:
-            return conv(h, style, pe=pe, fused_act=act)
-        return act(noise(conv(h, style, pe=pe)))
+            return conv(h, style, pe=pe, fused_act=act, pe_rot=pe_rot)
+        return act(noise(conv(h, style, pe=pe, pe_rot=pe_rot)))
 
-    def forward(self, h, skip, ws, angle):
+    def pe_rotation(self, shift_rad):
+        """[B, 2F] table (cos | sin) of psi[b,f] = f_w[f] * shift_b for this block's basis."""
+        f_w = self.pe.freqs[:, 1].reshape(1, -1).float()
+        psi = shift_rad.reshape(-1, 1).float() * f_w
+        return torch.cat([psi.cos(), psi.sin()], dim=1)
+
+    def forward(self, h, skip, ws, angle, shift_rad=None):
         ws = iter(ws)
         dtype = DF.act_dtype() if (self.use_fp16 and angle.is_cuda) else torch.float32
         if h is not None:
             h = self.resample(h.to(dtype))
         pe = self.pe(angle, out_dtype=dtype) if self.use_pe else None
-        h = self._conv(self.conv1, self.noise1, self.bias_act1, h, next(ws), pe)
+        rot = self.pe_rotation(shift_rad) if (shift_rad is not None and pe is not None) else None
+        h = self._conv(self.conv1, self.noise1, self.bias_act1, h, next(ws), pe, rot)
         if not self.is_first:
             h = self._conv(self.conv2, self.noise2, self.bias_act2, h, next(ws))
         o = self.head(h, next(ws))
@@ -195,6 +202,25 @@ class SynthesisNetwork(nn.Module):
             acts[o["name"]] = nn.Identity() if a is None else (eval(a)() if isinstance(a, str) else a())
         self.output_acts = nn.ModuleDict(acts)
         self._shared_cache = {}
+        self._int_freq_cache = {}
+        self.shared_pe_in_training = "auto"     # "auto" (bf16 mode only) | True | False
+
+    def _can_rotate(self, angle):
+        """Shared-Fourier-block training path: low-precision mode, batch-shared angle grid and
+        integer horizontal frequencies at every level (true for the 'random' basis,
+        fourier.py:33-36).  fp32 mode keeps the literal per-sample evaluation for parity."""
+        if self.shared_pe_in_training is False or not angle.is_cuda:
+            return False
+        if self.shared_pe_in_training == "auto" and DF.act_dtype() == torch.float32:
+            return False
+        if not _batch_shared(angle, self._shared_cache):
+            return False
+        key = tuple(blk.pe.freqs._version for blk in self.layers if blk.use_pe)
+        if self._int_freq_cache.get("key") != key:
+            ok = all(bool((blk.pe.freqs[:, 1] == blk.pe.freqs[:, 1].round()).all().item())
+                     for blk in self.layers if blk.use_pe) and all(blk.use_pe for blk in self.layers)
+            self._int_freq_cache = {"key": key, "ok": ok}
+        return self._int_freq_cache["ok"]
 
     @staticmethod
     def translation_matrix(t):
@@ -211,6 +237,7 @@ class SynthesisNetwork(nn.Module):
         aug = self.training and self.aug_coords
         W = int(self.resolution_out[1])
         shift01 = None
+        shift_rad = None
         if aug:
             # same RNG draw as the reference: one uniform per sample (dusty_v2.py:266-274)
             shifts = torch.zeros((B, 2), device=ws.device)
@@ -218,7 +245,13 @@ class SynthesisNetwork(nn.Module):
             if self.aug_coords_blitting:
                 shifts[:, 1].mul_(W).round_().div_(W)
             shift01 = shifts[:, 1].contiguous()
-            angle = angle + shifts.mul(2 * np.pi)[..., None, None]
+            if self._can_rotate(angle):
+                # integer horizontal frequencies: PE(angle + shift) = Rot(f_w * shift) PE(angle),
+                # so keep ONE Fourier block for the batch and rotate the per-sample weights
+                angle = angle[:1]
+                shift_rad = shift01 * (2 * np.pi)
+            else:
+                angle = angle + shifts.mul(2 * np.pi)[..., None, None]
         elif _batch_shared(angle, self._shared_cache):
             angle = angle[:1]            # one pyramid + one Fourier block for the whole batch
 
@@ -230,7 +263,7 @@ class SynthesisNetwork(nn.Module):
 
         h, skip, i = None, None, 0
         for blk, ang in zip(self.layers, pyramid):
-            h, skip = blk(h, skip, (ws[:, i], ws[:, i + 1], ws[:, i + 2]), ang)
+            h, skip = blk(h, skip, (ws[:, i], ws[:, i + 1], ws[:, i + 2]), ang, shift_rad)
             i += blk.num_conv
 
         y = skip.stacked

@@ -47,12 +47,15 @@ class ModConv2d(nn.Module):
         self.register_buffer("ema_var", torch.tensor(1.0))
 
     # -- small fp32 tensors: [B, O, I] at most 64 MiB for the widest layer, usually < 1 MiB
-    def effective_weights(self, style, out_dtype=torch.float32):
-        """wb[B,O,I]: one fused kernel pair (dusty_modprep_fwd/bwd) on CUDA."""
+    def effective_weights(self, style, out_dtype=torch.float32, pe_rot=None, c1=0):
+        """wb[B,O,I]: one fused kernel pair (dusty_modprep_fwd/bwd) on CUDA.  pe_rot [B, 2F]
+        rotates the Fourier columns (batch-shared Fourier block under an azimuth shift)."""
         s = self.mod(style.float())
         if s.is_cuda:
             return DF.modprep(s, self.weight, self.ema_var if self.ema else None, self.scale,
-                              self.demod, out_dtype)
+                              self.demod, out_dtype, pe_rot, c1)
+        if pe_rot is not None:
+            raise RuntimeError("pe_rot needs the CUDA path")
         return self._effective_weights_composite(s).to(out_dtype)
 
     def _effective_weights_composite(self, s):
@@ -82,7 +85,7 @@ class ModConv2d(nn.Module):
             numel += pe.numel() * rep
         self.ema_var.lerp_((total / float(numel)).to(self.ema_var.dtype), 1 - self.ema_decay)
 
-    def forward(self, x, style, pe=None, fused_act=None):
+    def forward(self, x, style, pe=None, fused_act=None, pe_rot=None):
         """x: [B, C1, H, W] (or None when the input is `pe` alone); pe: optional Fourier
         block [B or 1, C2, H, W] appended on the channel axis; fused_act: a FusedLeakyReLU
         module to apply in the epilogue."""
@@ -93,7 +96,7 @@ class ModConv2d(nn.Module):
         if self.ema and self.training:
             self.update_ema(x, pe)
         src = x if x is not None else pe
-        wb = self.effective_weights(style, src.dtype)
+        wb = self.effective_weights(style, src.dtype, pe_rot, c1)
         bias = self.bias
         act, alpha, scale = 1, 0.0, float(self.gain)
         if fused_act is not None:

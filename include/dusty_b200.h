@@ -155,14 +155,19 @@ int dusty_modconv_bwd_dw(const void *dy, const void *x1, const void *x2, float *
  * slin: fp32 [B, I] = mod(style) (the EqualLR linear stays a library GEMM); weight: fp32
  * [O, I]; ema_var: device scalar or NULL; wb: [B, O, I] in wdtype.
  * stats: fp32 workspace of B + 2 + B*O floats, kept for the backward. */
+/* rot (optional, fp32 [B, 2F] = cos | sin of psi[b,f] = f_w[f] * shift_b): per-sample rotation
+ * of the Fourier columns [C1, C1+F) (sin block) / [C1+F, C1+2F) (cos block).  The training-time
+ * aug-coords azimuth shift (dusty_v2.py:266-274) with integer horizontal frequencies is
+ * exactly this rotation of a batch-SHARED Fourier block (angle-addition identity), so the
+ * contraction can read one L2-resident Fourier operand for the whole batch. */
 int dusty_modprep_fwd(const float *slin, const float *weight, const float *ema_var, void *wb,
                       float *stats, int B, int O, int I, float scale, int demod, int wdtype,
-                      void *stream);
+                      const float *rot, int C1, int F, void *stream);
 /* Analytic backward: gwb fp32 [B, O, I] -> dslin [B, I], dweight [O, I].
  * work: fp32 workspace of B*O + B*I + O*I + B + 1 floats. */
 int dusty_modprep_bwd(const float *gwb, const float *slin, const float *weight, const float *stats,
                       float *dslin, float *dweight, float *work, int B, int O, int I, float scale,
-                      int demod, void *stream);
+                      int demod, const float *rot, int C1, int F, void *stream);
 
 /* ---- a10: Gumbel-sigmoid raydrop -------------------------------------------------------
  * Replaces GumbelSigmoid.forward gans/models/ops/gumbel.py:23-29 (RelaxedBernoulli.rsample

@@ -266,3 +266,36 @@ def test_discriminator_stacked_halves_equals_two_passes(g_disc):
         yab = D(torch.cat([a, b], 0))
     close(yab[:8], ya, rtol=1e-4, atol_rel=1e-5)
     close(yab[8:], yb, rtol=1e-4, atol_rel=1e-5)
+
+
+def test_shared_fourier_rotation_matches_literal_shift(g_gen, monkeypatch):
+    """Training-time aug-coords shift: rotating the per-sample weights over ONE batch-shared
+    Fourier block (angle-addition identity, integer horizontal frequencies) reproduces the
+    literal per-sample evaluation -- outputs, EMA buffers and every parameter gradient."""
+    shift = torch.tensor([0.0, 0.3127, 0.5, 0.9391])
+    u = torch.rand(4, 1, 16, 64, generator=torch.Generator().manual_seed(3))
+    gi = torch.randn(4, 1, 16, 64, generator=torch.Generator().manual_seed(4)).to(DEV)
+    gl = torch.randn(4, 1, 16, 64, generator=torch.Generator().manual_seed(5)).to(DEV)
+    z = T(g_gen["z"]).to(DEV)
+    angle = T(g_gen["angle"]).to(DEV)[:1].expand(4, -1, -1, -1)      # batch-shared grid
+    monkeypatch.setattr(torch.Tensor, "uniform_",
+                        lambda self, a=0, b=1, **k: self.copy_(shift.to(self.device)), raising=True)
+    res = {}
+    for mode in (False, True):
+        G = _build_G(g_gen).train()
+        G.synthesis_network.shared_pe_in_training = mode
+        for p in G.parameters():
+            p.requires_grad_(True)
+        real_rand = torch.rand
+        monkeypatch.setattr(torch, "rand", lambda *a, **k: u.to(k.get("device", "cpu")))
+        o = G(z, angle=angle)
+        monkeypatch.setattr(torch, "rand", real_rand)
+        ((o["image_orig"] * gi).sum() + (o["raydrop_logit"] * gl).sum()).backward()
+        res[mode] = (o, {n: p.grad.clone() for n, p in G.named_parameters()},
+                     {n: b.clone() for n, b in G.named_buffers() if n.endswith("ema_var")})
+    for k in ("image_orig", "raydrop_logit"):
+        close(res[True][0][k], res[False][0][k], rtol=2e-3, atol_rel=1e-3)
+    for n, b in res[False][2].items():
+        close(res[True][2][n], b, rtol=1e-4, atol_rel=0)
+    for n, g in res[False][1].items():
+        close(res[True][1][n], g, rtol=1e-2, atol_rel=5e-3)

@@ -278,11 +278,12 @@ def test_shared_fourier_rotation_matches_literal_shift(g_gen, monkeypatch):
     gl = torch.randn(4, 1, 16, 64, generator=torch.Generator().manual_seed(5)).to(DEV)
     z = T(g_gen["z"]).to(DEV)
     angle = T(g_gen["angle"]).to(DEV)[:1].expand(4, -1, -1, -1)      # batch-shared grid
+    models = {mode: _build_G(g_gen).train() for mode in (False, True)}
     monkeypatch.setattr(torch.Tensor, "uniform_",
                         lambda self, a=0, b=1, **k: self.copy_(shift.to(self.device)), raising=True)
     res = {}
     for mode in (False, True):
-        G = _build_G(g_gen).train()
+        G = models[mode]
         G.synthesis_network.shared_pe_in_training = mode
         for p in G.parameters():
             p.requires_grad_(True)

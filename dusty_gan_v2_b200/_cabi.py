@@ -36,6 +36,8 @@ SIGNATURES = {
     "dusty_bias_act_bwd_cl": [_vp, _vp, _vp, _vp, _i64, _i, _f, _f, _i, _vp],
     "dusty_pad2d_cl": [_vp, _vp] + [_i] * 12 + [_vp],
     "dusty_blur4_cl": [_vp, _vp, _f, _f, _f, _f] + [_i] * 6 + [_vp],
+    "dusty_fir1d": [_vp, _vp, _vp, _i, _i, _i64] + [_i] * 7 + [_vp],
+    "dusty_affine_warp": [_vp, _vp, _vp] + [_i] * 7 + [_vp],
     "dusty_fourier": [_vp, _vp, _vp, _vp, _i, _i, _i64, _i, _vp],
     "dusty_angle_down2": [_vp, _vp, _i, _i, _i, _vp],
     "dusty_modconv_fwd": [_vp, _vp, _vp, _vp, _vp, _i, _i, _i, _i, _i, _i64, _i, _f, _f, _i, _i, _i, _vp],
@@ -49,6 +51,7 @@ SIGNATURES = {
     "dusty_minibatch_std_fwd": [_vp, _vp, _vp, _i, _i, _i64, _i, _f, _i, _vp],
     "dusty_minibatch_std_bwd": [_vp, _vp, _vp, _vp, _i, _i, _i64, _i, _f, _i, _vp],
     "dusty_sumsq_rows": [_vp, _vp, _i64, _i64, _i, _i, _vp],
+    "dusty_ema_lerp": [_vp, _vp, _vp, _f, _f, _f, _vp],
     "dusty_circular_shift": [_vp, _vp, _vp, _i, _i, _i, _i, _f, _i, _vp],
 }
 _RESTYPE = {"dusty_last_error": C.c_char_p, "dusty_launch_count": C.c_int64}

@@ -1,0 +1,178 @@
+// a5/a6: the band-limited geometric pipeline of AdaptiveAugment
+// (adaptive_augment.py:496-535): SYM6 2x up-sampling in x then y, bilinear affine warp,
+// 2x down-sampling in x then y -- as lean single-axis FIR kernels plus one warp kernel.
+//
+//  * fir1d: zero-padded polyphase FIR along ONE axis (upfirdn2d with a [1,k] or [k,1]
+//    kernel), up/down factors compile-time (no integer division), flipped taps staged once
+//    in shared memory; the x variant also stages its input row segment (+halo) in shared
+//    memory, the y variant reads whole rows coalesced (neighbouring output rows re-use them
+//    through L1).  The adjoint of such an op is the same op with up<->down swapped and the
+//    taps reversed (UpFirDn2dBackward, upfirdn2d.py:20-59), so one kernel serves all orders.
+//  * affine_warp: out = bilinear(img, theta * [x_n, y_n, 1]) with zero padding,
+//    align_corners=False -- F.affine_grid + F.grid_sample fused: the sampling grid
+//    (B x H x W x 2 floats, 150 MB at B=128) and the batched [HW,3]x[3,2] GEMM that builds it
+//    never exist.  The adjoint scatters with red.global.add.f32.
+#include "common.cuh"
+
+namespace dusty {
+
+constexpr int kMaxTaps1d = 64;
+
+struct Fir1d {
+  int n_in, n_out;     // extent along the filtered axis
+  int other;           // extent of the other image axis
+  int k, p0, flip;
+};
+
+// ---- along x: grid = (ceil(n_out / 256), other (rows), N)
+template <int U, int D>
+__global__ void __launch_bounds__(256)
+fir1d_x_kernel(const float *__restrict__ x, float *__restrict__ y, const float *__restrict__ taps,
+               Fir1d p) {
+  __shared__ float sk[kMaxTaps1d];
+  __shared__ float sx[256 * D / U + kMaxTaps1d + 4];
+  if (threadIdx.x < p.k) sk[threadIdx.x] = taps[p.flip ? p.k - 1 - threadIdx.x : threadIdx.x];
+  const int m0 = blockIdx.x * 256;
+  const float *row = x + ((int64_t)blockIdx.z * p.other + blockIdx.y) * p.n_in;
+  // input span needed by outputs [m0, m0 + 256): q in [m0*D - p0, (m0+255)*D - p0 + k - 1]
+  const int q_lo = m0 * D - p.p0;
+  const int i_lo = (q_lo >= 0 ? q_lo : q_lo - (U - 1)) / U;          // floor(q_lo / U)
+  const int span = (255 * D + p.k - 1) / U + 2;
+  for (int j = threadIdx.x; j < span; j += 256) {
+    const int i = i_lo + j;
+    sx[j] = (i >= 0 && i < p.n_in) ? row[i] : 0.f;
+  }
+  __syncthreads();
+  const int m = m0 + threadIdx.x;
+  if (m >= p.n_out) return;
+  const int b = m * D - p.p0;                 // q = b + t
+  const int t0 = (U == 1) ? 0 : ((-b) & (U - 1));
+  float acc = 0.f;
+  for (int t = t0; t < p.k; t += U) {
+    const int q = b + t;                      // multiple of U
+    const int i = (U == 1) ? q : (q >> 1);
+    acc = fmaf(sk[t], sx[i - i_lo], acc);
+  }
+  y[((int64_t)blockIdx.z * p.other + blockIdx.y) * p.n_out + m] = acc;
+}
+
+// ---- along y: grid = (ceil(other / 256), n_out (rows), N); thread = one column
+template <int U, int D>
+__global__ void __launch_bounds__(256)
+fir1d_y_kernel(const float *__restrict__ x, float *__restrict__ y, const float *__restrict__ taps,
+               Fir1d p) {
+  __shared__ float sk[kMaxTaps1d];
+  if (threadIdx.x < p.k) sk[threadIdx.x] = taps[p.flip ? p.k - 1 - threadIdx.x : threadIdx.x];
+  __syncthreads();
+  const int col = blockIdx.x * 256 + threadIdx.x;
+  if (col >= p.other) return;
+  const int m = blockIdx.y;
+  const float *img = x + (int64_t)blockIdx.z * p.n_in * p.other + col;
+  const int b = m * D - p.p0;
+  const int t0 = (U == 1) ? 0 : ((-b) & (U - 1));
+  float acc = 0.f;
+  for (int t = t0; t < p.k; t += U) {
+    const int q = b + t;
+    const int i = (U == 1) ? q : (q >> 1);
+    if (i >= 0 && i < p.n_in) acc = fmaf(sk[t], img[(int64_t)i * p.other], acc);
+  }
+  y[((int64_t)blockIdx.z * p.n_out + m) * p.other + col] = acc;
+}
+
+// ------------------------------------------------------------------ affine warp
+// theta: [N, 2, 3] row-major.  grid = (ceil(Wo/256), Ho, N*C)
+template <bool ADJ>
+__global__ void __launch_bounds__(256)
+affine_warp_kernel(const float *__restrict__ src, float *__restrict__ dst,
+                   const float *__restrict__ theta, int C, int Hi, int Wi, int Ho, int Wo) {
+  const int ox = blockIdx.x * 256 + threadIdx.x;
+  if (ox >= Wo) return;
+  const int oy = blockIdx.y;
+  const int nc = blockIdx.z, n = nc / C;
+  const float *th = theta + (int64_t)n * 6;
+  // base grid of affine_grid (align_corners=False): (2j + 1) / W - 1
+  const float xn = (2.f * ox + 1.f) / Wo - 1.f, yn = (2.f * oy + 1.f) / Ho - 1.f;
+  const float gx = th[0] * xn + th[1] * yn + th[2];
+  const float gy = th[3] * xn + th[4] * yn + th[5];
+  // grid_sample un-normalisation (align_corners=False)
+  const float ix = ((gx + 1.f) * Wi - 1.f) * 0.5f, iy = ((gy + 1.f) * Hi - 1.f) * 0.5f;
+  const float fx0 = floorf(ix), fy0 = floorf(iy);
+  const float ax = ix - fx0, ay = iy - fy0;
+  const int x0 = (int)fx0, y0 = (int)fy0;
+  const float w00 = (1.f - ax) * (1.f - ay), w01 = ax * (1.f - ay), w10 = (1.f - ax) * ay, w11 = ax * ay;
+  const bool vx0 = x0 >= 0 && x0 < Wi, vx1 = x0 + 1 >= 0 && x0 + 1 < Wi;
+  const bool vy0 = y0 >= 0 && y0 < Hi, vy1 = y0 + 1 >= 0 && y0 + 1 < Hi;
+  const int64_t in_base = (int64_t)nc * Hi * Wi;
+  const int64_t out_idx = ((int64_t)nc * Ho + oy) * Wo + ox;
+  if (!ADJ) {
+    const float *im = src + in_base;
+    float v = 0.f;
+    if (vy0 && vx0) v = fmaf(w00, im[(int64_t)y0 * Wi + x0], v);
+    if (vy0 && vx1) v = fmaf(w01, im[(int64_t)y0 * Wi + x0 + 1], v);
+    if (vy1 && vx0) v = fmaf(w10, im[(int64_t)(y0 + 1) * Wi + x0], v);
+    if (vy1 && vx1) v = fmaf(w11, im[(int64_t)(y0 + 1) * Wi + x0 + 1], v);
+    dst[out_idx] = v;
+  } else {
+    const float g = src[out_idx];              // gradient w.r.t. the warped image
+    float *gi = dst + in_base;                 // zero-filled by the caller
+    if (vy0 && vx0) atomicAdd(gi + (int64_t)y0 * Wi + x0, w00 * g);
+    if (vy0 && vx1) atomicAdd(gi + (int64_t)y0 * Wi + x0 + 1, w01 * g);
+    if (vy1 && vx0) atomicAdd(gi + (int64_t)(y0 + 1) * Wi + x0, w10 * g);
+    if (vy1 && vx1) atomicAdd(gi + (int64_t)(y0 + 1) * Wi + x0 + 1, w11 * g);
+  }
+}
+
+}  // namespace dusty
+
+using namespace dusty;
+
+extern "C" int dusty_fir1d(const float *x, float *y, const float *taps, int k, int flip, int64_t N,
+                           int in_h, int in_w, int axis, int up, int down, int pad0, int pad1,
+                           void *stream) {
+  DUSTY_CHECK_ARG(x && y && taps, "null pointer");
+  DUSTY_CHECK_ARG(k >= 1 && k <= kMaxTaps1d, "tap count must be in [1, 64]");
+  DUSTY_CHECK_ARG((up == 1 || up == 2) && (down == 1 || down == 2), "up/down must be 1 or 2");
+  DUSTY_CHECK_ARG(axis == 0 || axis == 1, "axis must be 0 (y) or 1 (x)");
+  DUSTY_CHECK_ARG(N >= 1 && N <= 65535 && in_h >= 1 && in_w >= 1, "bad shape");
+  const int n_in = axis ? in_w : in_h, other = axis ? in_h : in_w;
+  const int n_out = (n_in * up + pad0 + pad1 - k + down) / down;
+  DUSTY_CHECK_ARG(n_out >= 1 && n_out <= (axis ? 0x7fffffff : 65535) && other <= (axis ? 65535 : 0x7fffffff),
+                  "bad output size");
+  Fir1d p{n_in, n_out, other, k, pad0, flip ? 1 : 0};
+  cudaStream_t st = (cudaStream_t)stream;
+#define LAUNCH(KERN, GRID)                                                      \
+  do {                                                                          \
+    if (up == 1 && down == 1) KERN<1, 1><<<GRID, 256, 0, st>>>(x, y, taps, p);  \
+    else if (up == 2 && down == 1) KERN<2, 1><<<GRID, 256, 0, st>>>(x, y, taps, p); \
+    else if (up == 1 && down == 2) KERN<1, 2><<<GRID, 256, 0, st>>>(x, y, taps, p); \
+    else KERN<2, 2><<<GRID, 256, 0, st>>>(x, y, taps, p);                       \
+  } while (0)
+  if (axis == 1) {
+    dim3 grid((unsigned)((n_out + 255) / 256), (unsigned)other, (unsigned)N);
+    LAUNCH(fir1d_x_kernel, grid);
+  } else {
+    dim3 grid((unsigned)((other + 255) / 256), (unsigned)n_out, (unsigned)N);
+    LAUNCH(fir1d_y_kernel, grid);
+  }
+#undef LAUNCH
+  DUSTY_LAUNCH_CHECK();
+  return DUSTY_OK;
+}
+
+extern "C" int dusty_affine_warp(const float *src, float *dst, const float *theta, int N, int C,
+                                 int Hi, int Wi, int Ho, int Wo, int adjoint, void *stream) {
+  DUSTY_CHECK_ARG(src && dst && theta, "null pointer");
+  DUSTY_CHECK_ARG(N >= 1 && C >= 1 && (int64_t)N * C <= 65535 && Hi >= 1 && Wi >= 1 && Ho >= 1 &&
+                      Ho <= 65535 && Wo >= 1, "bad shape");
+  cudaStream_t st = (cudaStream_t)stream;
+  dim3 grid((unsigned)((Wo + 255) / 256), (unsigned)Ho, (unsigned)(N * C));
+  if (!adjoint) {
+    affine_warp_kernel<false><<<grid, 256, 0, st>>>(src, dst, theta, C, Hi, Wi, Ho, Wo);
+  } else {
+    if (cudaMemsetAsync(dst, 0, sizeof(float) * (size_t)N * C * Hi * Wi, st) != cudaSuccess)
+      return DUSTY_ECUDA;
+    affine_warp_kernel<true><<<grid, 256, 0, st>>>(src, dst, theta, C, Hi, Wi, Ho, Wo);
+  }
+  DUSTY_LAUNCH_CHECK();
+  return DUSTY_OK;
+}

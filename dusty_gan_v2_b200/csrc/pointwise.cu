@@ -236,6 +236,17 @@ circ_shift_kernel(const float *__restrict__ v, const float *__restrict__ shift01
   }
 }
 
+// ema <- lerp(ema, (sum_a + rep_b * sum_b) / numel, weight): ModConv2d's running input power
+__global__ void ema_lerp_kernel(float *ema, const float *sum_a, const float *sum_b, float rep_b,
+                                float inv_numel, float weight) {
+  if (threadIdx.x == 0 && blockIdx.x == 0) {
+    float total = (sum_a ? *sum_a : 0.f) + (sum_b ? rep_b * *sum_b : 0.f);
+    const float var = total * inv_numel;
+    const float e = *ema;
+    *ema = e + weight * (var - e);
+  }
+}
+
 static unsigned flat_grid(int64_t total, int per_sm = 8) {
   int64_t blocks = (total + 255) / 256;
   const int64_t cap = (int64_t)num_sms() * per_sm;
@@ -383,6 +394,14 @@ extern "C" int dusty_circular_shift(const float *v, const float *shift01, float 
   const int64_t total = (int64_t)B * C * H * W;
   circ_shift_kernel<<<flat_grid(total), 256, 0, (cudaStream_t)stream>>>(v, shift01, out, C, H, W,
                                                                        scale, adjoint, total);
+  DUSTY_LAUNCH_CHECK();
+  return DUSTY_OK;
+}
+
+extern "C" int dusty_ema_lerp(float *ema_var, const float *sum_a, const float *sum_b, float rep_b,
+                              float inv_numel, float weight, void *stream) {
+  DUSTY_CHECK_ARG(ema_var && (sum_a || sum_b), "null pointer");
+  ema_lerp_kernel<<<1, 32, 0, (cudaStream_t)stream>>>(ema_var, sum_a, sum_b, rep_b, inv_numel, weight);
   DUSTY_LAUNCH_CHECK();
   return DUSTY_OK;
 }

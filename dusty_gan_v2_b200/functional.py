@@ -336,6 +336,89 @@ def resample4(x: torch.Tensor, taps4, up: int) -> torch.Tensor:
     return _Resample4.apply(x, tuple(float(t) for t in taps4), int(up), False)
 
 
+# single-axis zero-padded FIR (ADA's SYM6 passes) and the fused affine warp
+class _Fir1d(Function):
+    @staticmethod
+    def forward(ctx, x, taps, axis, up, down, pad0, pad1, flip):
+        x = _contig(x.float())
+        lead = x.shape[:-2]
+        n = 1
+        for s_ in lead:
+            n *= s_
+        h, w = x.shape[-2:]
+        k = taps.numel()
+        n_in = w if axis == 1 else h
+        n_out = (n_in * up + pad0 + pad1 - k + down) // down
+        if n_out < 1:
+            raise RuntimeError("fir1d: empty output")
+        y = torch.empty(*lead, *((h, n_out) if axis == 1 else (n_out, w)), device=x.device,
+                        dtype=torch.float32)
+        K.call("dusty_fir1d", K.ptr(x), K.ptr(y), K.ptr(taps), k, flip, n, h, w, axis, up, down,
+               pad0, pad1, K.stream_of(x))
+        ctx.save_for_backward(taps)
+        ctx.cfg = (axis, up, down, pad0, pad1, flip, n_in, n_out, k)
+        return y
+
+    @staticmethod
+    def backward(ctx, g):
+        (taps,) = ctx.saved_tensors
+        axis, up, down, pad0, pad1, flip, n_in, n_out, k = ctx.cfg
+        gp0 = k - pad0 - 1
+        gp1 = n_in * up - n_out * down + pad0 - up + 1
+        return (_Fir1d.apply(g, taps, axis, down, up, gp0, gp1, 1 - flip),) + (None,) * 7
+
+
+def fir1d_supported(x, kernel, up, down, pad) -> bool:
+    """upfirdn2d call that is a single-axis FIR with up/down in {1,2} on an fp32 CUDA tensor."""
+    if not (x.is_cuda and x.dtype == torch.float32 and kernel.ndim == 2):
+        return False
+    kh, kw = kernel.shape
+    (ux, uy), (dx, dy), (px0, px1, py0, py1) = up, down, pad
+    if kh == 1 and kw <= 64:
+        return uy == 1 and dy == 1 and py0 == 0 and py1 == 0 and ux in (1, 2) and dx in (1, 2)
+    if kw == 1 and kh <= 64:
+        return ux == 1 and dx == 1 and px0 == 0 and px1 == 0 and uy in (1, 2) and dy in (1, 2)
+    return False
+
+
+def fir1d(x, kernel, up, down, pad):
+    """upfirdn2d(x, kernel[1,k] or [k,1], up=(ux,uy), down=(dx,dy), pad=(px0,px1,py0,py1))."""
+    kh, kw = kernel.shape
+    taps = _contig(kernel.detach().float().reshape(-1))
+    if kh == 1:
+        return _Fir1d.apply(x, taps, 1, int(up[0]), int(down[0]), int(pad[0]), int(pad[1]), 1)
+    return _Fir1d.apply(x, taps, 0, int(up[1]), int(down[1]), int(pad[2]), int(pad[3]), 1)
+
+
+class _AffineWarp(Function):
+    @staticmethod
+    def forward(ctx, img, theta, out_hw, in_hw, adjoint):
+        img = _contig(img.float())
+        theta = _contig(theta.detach().float())
+        N, C = img.shape[:2]
+        (Ho, Wo), (Hi, Wi) = out_hw, in_hw
+        out = torch.empty((N, C, Hi, Wi) if adjoint else (N, C, Ho, Wo), device=img.device,
+                          dtype=torch.float32)
+        K.call("dusty_affine_warp", K.ptr(img), K.ptr(out), K.ptr(theta), N, C, Hi, Wi, Ho, Wo,
+               1 if adjoint else 0, K.stream_of(img))
+        ctx.save_for_backward(theta)
+        ctx.cfg = (out_hw, in_hw, adjoint)
+        return out
+
+    @staticmethod
+    def backward(ctx, g):
+        (theta,) = ctx.saved_tensors
+        out_hw, in_hw, adjoint = ctx.cfg
+        return _AffineWarp.apply(g, theta, out_hw, in_hw, not adjoint), None, None, None, None
+
+
+def affine_warp(img, theta, out_hw):
+    """grid_sample(img, affine_grid(theta, [N,C,*out_hw])), bilinear / zeros /
+    align_corners=False, linear in img (first and higher orders through the adjoint)."""
+    K.require_cuda(img, theta)
+    return _AffineWarp.apply(img, theta, tuple(out_hw), tuple(img.shape[-2:]), False)
+
+
 # small-halo padding fast path
 def _pad_raw(x, pads, modes, adjoint, in_hw=None):
     if _is_cl(x) and _cl_vec_ok(x):
@@ -562,6 +645,25 @@ def sumsq_total(x: torch.Tensor) -> torch.Tensor:
     K.call("dusty_sumsq_rows", K.ptr(x), K.ptr(out), 1, x.numel(), 0, K.dtype_code(x),
            K.stream_of(x))
     return out[0]
+
+
+def sumsq_buffer(x: torch.Tensor) -> torch.Tensor:
+    """sum(x^2) as a 1-element fp32 device tensor (no grad)."""
+    K.require_cuda(x)
+    x = _canon(x.detach())
+    out = torch.empty(1, device=x.device, dtype=torch.float32)
+    K.call("dusty_sumsq_rows", K.ptr(x), K.ptr(out), 1, x.numel(), 0, K.dtype_code(x),
+           K.stream_of(x))
+    return out
+
+
+def ema_lerp_(ema_var: torch.Tensor, sum_a, sum_b, rep_b: float, numel: int, weight: float):
+    """In place: ema_var <- lerp(ema_var, (sum_a + rep_b*sum_b)/numel, weight); sums are the
+    1-element tensors of sumsq_buffer (either may be None)."""
+    if ema_var.dtype != torch.float32 or not ema_var.is_cuda:
+        raise RuntimeError("ema_var must be an fp32 CUDA tensor")
+    K.call("dusty_ema_lerp", K.ptr(ema_var), K.ptr(sum_a), K.ptr(sum_b), float(rep_b),
+           1.0 / float(numel), float(weight), K.stream_of(ema_var))
 
 
 class _SumSqRows(Function):

@@ -262,9 +262,8 @@ class AdaptiveAugment(torch.nn.Module):
         shape = (B, ch, (H + pad_k * 2) * 2, (W + pad_k * 2) * 2)
         G_inv = (_single([(2 / img.shape[3], 0, 0), (0, 2 / img.shape[2], 0), (0, 0, 1)]) @ G_inv
                  @ _single([(shape[3] / 2, 0, 0), (0, shape[2] / 2, 0), (0, 0, 1)]))
-        theta = G_inv[:, :2, :].to(device, non_blocking=True)
-        grid = F.affine_grid(theta, shape, align_corners=False)
-        img = grid_sample(img, grid)
+        theta = G_inv[:, :2, :].contiguous().to(device, non_blocking=True)
+        img = DF.affine_warp(img, theta, shape[2:])      # affine_grid + grid_sample, fused
 
         d_p = -pad_k * 2
         dn0, dn1 = d_p + (nk - 1) // 2, d_p + (nk - 2) // 2

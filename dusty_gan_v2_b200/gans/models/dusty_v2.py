@@ -59,10 +59,9 @@ class Head(nn.Module):
         """All heads share x and the style: one contraction with O = number of heads."""
         mods = list(self.heads.values())
         if self.training:
-            total = DF.sumsq_total(x) / float(x.numel())
+            total = DF.sumsq_buffer(x)
             for m in mods:
-                with torch.no_grad():
-                    m.ema_var.lerp_(total.to(m.ema_var.dtype), 1 - m.ema_decay)
+                DF.ema_lerp_(m.ema_var, total, None, 1, x.numel(), 1 - m.ema_decay)
         wb = torch.cat([m.effective_weights(style, x.dtype) for m in mods], dim=1)
         bias = torch.cat([m.bias.reshape(-1) for m in mods])
         y = DF.modconv_bmm(wb, x, None, bias, 1, 0.0, 1.0)

@@ -75,15 +75,16 @@ class ModConv2d(nn.Module):
     @torch.no_grad()
     def update_ema(self, x, pe=None):
         """ema_var <- lerp(ema_var, mean(x^2), 1 - decay) over the *whole* input, Fourier
-        channels included (style.py:99-102)."""
-        total = DF.sumsq_total(x) if x is not None else 0.0
+        channels included (style.py:99-102): two reductions + one scalar kernel."""
+        sa = DF.sumsq_buffer(x) if x is not None else None
         numel = x.numel() if x is not None else 0
+        sb, rep = None, 1
         if pe is not None:
             B = x.shape[0] if x is not None else pe.shape[0]
             rep = B // pe.shape[0]
-            total = total + DF.sumsq_total(pe) * float(rep)
+            sb = DF.sumsq_buffer(pe)
             numel += pe.numel() * rep
-        self.ema_var.lerp_((total / float(numel)).to(self.ema_var.dtype), 1 - self.ema_decay)
+        DF.ema_lerp_(self.ema_var, sa, sb, rep, numel, 1 - self.ema_decay)
 
     def forward(self, x, style, pe=None, fused_act=None, pe_rot=None):
         """x: [B, C1, H, W] (or None when the input is `pe` alone); pe: optional Fourier

@@ -46,6 +46,8 @@ def upfirdn2d(input, kernel, up=1, down=1, pad=(0, 0)):
         pad = (pad[0], pad[1], pad[0], pad[1])
     if kernel.ndim != 2:
         raise RuntimeError("kernel must be 2-D [kh, kw]")
+    if DF.fir1d_supported(input, kernel, up, down, pad):     # single-axis fast path (ADA)
+        return DF.fir1d(input, kernel.to(input.device), up, down, pad)
     cfg = _cfg(kernel, up[0], up[1], down[0], down[1], *pad)
     taps = kernel.detach().to(device=input.device, dtype=torch.float32).contiguous()
     return DF.fir2d(input, taps, cfg)

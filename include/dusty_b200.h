@@ -116,6 +116,21 @@ int dusty_pad2d_cl(const void *x, void *y, int B, int H, int W, int C, int pt, i
 int dusty_blur4_cl(const void *x, void *y, float k0, float k1, float k2, float k3, int B, int H,
                    int W, int C, int adjoint, int dtype, void *stream);
 
+/* ---- a5/a6: AdaptiveAugment's geometric pipeline ------------------------------------------
+ * Single-axis zero-padded polyphase FIR: upfirdn2d with a [1,k] (axis 1 = x) or [k,1]
+ * (axis 0 = y) kernel, fp32, up/down in {1,2}:
+ *   n_out = (n_in*up + pad0 + pad1 - k + down) / down  along the filtered axis.
+ * flip != 0 applies the taps reversed (true convolution, as upfirdn2d does).  The adjoint is
+ * the same entry with up<->down, flip toggled and the reference's g_pad
+ * (gans/models/ops/upfirdn2d/upfirdn2d.py:108-116). */
+int dusty_fir1d(const float *x, float *y, const float *taps, int k, int flip, int64_t N, int in_h,
+                int in_w, int axis, int up, int down, int pad0, int pad1, void *stream);
+/* F.affine_grid(theta, [N,C,Ho,Wo], align_corners=False) + F.grid_sample(bilinear, zeros,
+ * align_corners=False) fused (adaptive_augment.py:523-524).  theta: fp32 [N,2,3].
+ * adjoint != 0: src is the [N,C,Ho,Wo] gradient, dst the [N,C,Hi,Wi] image gradient. */
+int dusty_affine_warp(const float *src, float *dst, const float *theta, int N, int C, int Hi,
+                      int Wi, int Ho, int Wo, int adjoint, void *stream);
+
 /* ---- a2: Fourier features --------------------------------------------------------------
  * Replaces FourierFeature.forward gans/models/ops/fourier.py:77-82.
  * angle: fp32 [Ba, 2, P] (elevation, azimuth); freqs: fp32 [F, 2]; phase: fp32 [F];
@@ -211,6 +226,11 @@ int dusty_minibatch_std_bwd(const void *dy, const void *x, void *dx, float *dsta
  * Serves the R1 penalty gans/trainer.py:440 and ModConv2d's EMA statistic style.py:100. */
 int dusty_sumsq_rows(const void *x, float *out, int64_t rows, int64_t cols, int accumulate,
                      int dtype, void *stream);
+
+/* ModConv2d's EMA side effect (style.py:99-102) from device-side sums, one tiny launch:
+ * ema_var <- lerp(ema_var, (sum_a + rep_b * sum_b) * inv_numel, weight).  Either sum may be NULL. */
+int dusty_ema_lerp(float *ema_var, const float *sum_a, const float *sum_b, float rep_b,
+                   float inv_numel, float weight, void *stream);
 
 /* ---- a7: aug-coords circular un-shift ---------------------------------------------------
  * Replaces cat([v,v],3) -> affine_grid -> grid_sample -> [..., :W]

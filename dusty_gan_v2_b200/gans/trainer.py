@@ -59,6 +59,19 @@ def ema_inplace(ema_model, new_model, decay):
     torch._foreach_copy_(ema_b, new_b)
 
 
+class _GImage(torch.nn.Module):
+    """z -> G(z, angle)["image"]: the tensor-in / tensor-out view of the generator that CUDA
+    graph capture needs (the dict of outputs stays internal)."""
+
+    def __init__(self, G, auxin):
+        super().__init__()
+        self.G = G
+        self._auxin = auxin
+
+    def forward(self, z):
+        return self.G(z, **self._auxin)["image"]
+
+
 class Trainer:
     def __init__(self, cfg, batch_iter, device=None, rank=0, world_size=1,
                  angle_file="data/coords/kitti_raw.npy", precision=None, cuda_graphs=True):
@@ -81,10 +94,14 @@ class Trainer:
                                  min_depth=cfg.dataset.min_depth, max_depth=cfg.dataset.max_depth,
                                  angle_file=angle_file).eval().to(self.device)
         self.G_module, self.D_module = self.G, self.D
+        self.cuda_graphs = bool(cuda_graphs) and self.device.type == "cuda"
         if world_size > 1:
             from torch.nn.parallel import DistributedDataParallel as DDP
             kw = dict(device_ids=[self.device.index])
-            self.G = DDP(self.G, broadcast_buffers=True, **kw)
+            if not self.cuda_graphs:
+                self.G = DDP(self.G, broadcast_buffers=True, **kw)
+            # graphed generator: its 17.5 MB of gradients are all-reduced as one flat bucket
+            # after backward and its buffers broadcast before forward (same collectives as DDP)
             self.D = DDP(self.D, broadcast_buffers=False, **kw)
         for m in (self.G, self.G_ema, self.D, self.A, self.coord):
             m.requires_grad_(False)
@@ -116,8 +133,8 @@ class Trainer:
         # CUDA graphs for the static-shape segments (the step is launch-bound at B=64):
         #   * the no-grad generator forward of the D step (z drawn inside the graph)
         # ADA (data-dependent padding) and the discriminator stay eager.
-        self.cuda_graphs = bool(cuda_graphs) and self.device.type == "cuda"
         self._g_graph = None
+        self._G_train_callable = None         # graphed forward+backward of the G step
         self._g_graph_out = None
         self._g_graph_launches = 0
         self.graph_replayed_launches = 0
@@ -165,6 +182,38 @@ class Trainer:
             dist.broadcast(flat, 0)
             torch._foreach_copy_(bufs, [c.reshape(b.shape).to(b.dtype)
                                         for b, c in zip(bufs, flat.split([b.numel() for b in bufs]))])
+
+    def _G_train_forward(self, z):
+        """x_fake for the G step, with autograd.  With CUDA graphs: forward and backward of
+        the whole generator are two graph launches (torch.cuda.make_graphed_callables)."""
+        if not self.cuda_graphs:
+            return self.G(z, **self.auxin)["image"]
+        self._sync_G_buffers()
+        if self._G_train_callable is None:
+            from .. import _cabi
+            wrapper = _GImage(self.G_module, self.auxin)
+            n0 = _cabi.launch_count()
+            try:
+                self._G_train_callable = torch.cuda.make_graphed_callables(wrapper, (z.clone(),))
+                # 3 warm-up passes + 1 capture, each forward + backward
+                self._G_train_launches = (_cabi.launch_count() - n0) // 4
+            except Exception as exc:           # capture not possible: stay eager, loudly
+                import warnings
+                warnings.warn(f"CUDA-graph capture of the generator step failed ({exc!r}); "
+                              "running it eagerly")
+                self._G_train_callable = wrapper
+                self._G_train_launches = 0
+        self.graph_replayed_launches += self._G_train_launches
+        return self._G_train_callable(z)
+
+    def _allreduce_G_grads(self):
+        if self.world_size > 1 and self.G is self.G_module:
+            grads = [p.grad for p in self._G_params if p.grad is not None]
+            flat = torch.cat([g.reshape(-1) for g in grads])
+            dist.all_reduce(flat)
+            flat /= self.world_size
+            torch._foreach_copy_(grads, [c.reshape(g.shape) for g, c in
+                                         zip(grads, flat.split([g.numel() for g in grads]))])
 
     def _fake_images_nograd(self, B):
         """x_fake for the D step (no graph of G is needed: trainer.py:380-383)."""
@@ -217,10 +266,11 @@ class Trainer:
         # ---- G step (trainer.py:262-301)
         set_requires_grad(self._G_params, True)
         self.optim_G.zero_grad(set_to_none=True)
-        x_fake = self.G(self.sample_z(B), **self.auxin)["image"]
+        x_fake = self._G_train_forward(self.sample_z(B))
         y_fake = self.D(self.A(self.warmup(x_fake)))
         loss_gan = self.adversarial_loss(None, y_fake, "G")
         (tr.loss.gan * loss_gan).backward()
+        self._allreduce_G_grads()
         self.optim_G.step()
         scalars["loss/G/adversarial"] = loss_gan.detach()
         set_requires_grad(self._G_params, False)

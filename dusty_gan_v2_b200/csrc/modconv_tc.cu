@@ -138,6 +138,7 @@ constexpr int kABytes = kBM * kBK * 2;   // 16 KiB
 constexpr int kThreads = 192;
 
 struct TcParams {
+  int MT, NT, total_tiles, tiles_per_cta;   // tile schedule (pixel tiles, channel tiles)
   int O, C1, K, B2;       // K = C1 + C2 rounded up to kBK by TMA zero fill
   int64_t P;
   const float *bias;
@@ -146,6 +147,18 @@ struct TcParams {
   float alpha, scale;
 };
 
+__device__ __forceinline__ void mbar_arrive(uint64_t *bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+
+// Multi-tile ("persistent") kernel.  Each CTA owns a contiguous range of output tiles
+// (128 pixels x BN channels); the TMA producer streams the k-blocks of successive tiles
+// through one shared-memory ring without draining it between tiles, the MMA thread
+// alternates between TWO TMEM accumulators, and the epilogue warps drain accumulator i
+// while the MMAs of tile i+1 are already running.  This matters most where the layer is
+// thin (64x512 level: K = 32..64 per tile, i.e. one or two k-blocks): a one-tile CTA there
+// is all prologue and epilogue.
+//
 // B_MN == false: forward (B = wb tile [BN out-channels x 64 k], K-major)
 // B_MN == true : dX      (A = dY, contraction over out-channels; B = wb tile
 //                         [64 out-channels x BN in-channels], in-channel contiguous = MN-major)
@@ -163,53 +176,70 @@ modconv_fwd_tc_kernel(const __grid_constant__ CUtensorMap map_x1,
   uint8_t *b_base = smem + STAGES * kABytes;
   uint64_t *full = (uint64_t *)(smem + STAGES * kStageBytes);
   uint64_t *empty = full + STAGES;
-  uint64_t *acc_full = empty + STAGES;
-  uint32_t *tmem_slot = (uint32_t *)(acc_full + 1);
+  uint64_t *acc_full = empty + STAGES;      // [2]
+  uint64_t *acc_empty = acc_full + 2;       // [2]
+  uint32_t *tmem_slot = (uint32_t *)(acc_empty + 2);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int p0 = blockIdx.x * kBM;
-  const int n0 = blockIdx.y * BN;
-  const int b = blockIdx.z;
   const int num_kb = (prm.K + kBK - 1) / kBK;
+  const int t_begin = blockIdx.x * prm.tiles_per_cta;
+  const int t_end = min(t_begin + prm.tiles_per_cta, prm.total_tiles);
 
   if (threadIdx.x == 0) {
     for (int s = 0; s < STAGES; ++s) {
       mbar_init(&full[s], 1);
       mbar_init(&empty[s], 1);
     }
-    mbar_init(acc_full, 1);
+    for (int a = 0; a < 2; ++a) {
+      mbar_init(&acc_full[a], 1);
+      mbar_init(&acc_empty[a], 4);          // one arrival per epilogue warp
+    }
     fence_barrier_init();
   }
-  if (warp == 1) tmem_alloc(tmem_slot, BN);
+  if (warp == 1) tmem_alloc(tmem_slot, 2 * BN);
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
-  const uint32_t tmem_acc = *tmem_slot;
+  const uint32_t tmem_base = *tmem_slot;
+
+  // tile -> (sample b, channel tile n0, pixel tile p0); pixel tiles of a sample are adjacent
+  auto decode = [&](int tile, int &b, int &n0, int &p0) {
+    const int mt = tile % prm.MT;
+    const int r = tile / prm.MT;
+    p0 = mt * kBM;
+    n0 = (r % prm.NT) * BN;
+    b = r / prm.NT;
+  };
 
   if (warp == 0) {
     // ===================== TMA producer =====================
     if (lane == 0) {
-      for (int kb = 0; kb < num_kb; ++kb) {
-        const int s = kb % STAGES;
-        const uint32_t ph = (kb / STAGES) & 1;
-        mbar_wait(&empty[s], ph ^ 1);
-        mbar_expect_tx(&full[s], kStageBytes);
-        const int c0 = kb * kBK;
-        uint8_t *a_dst = a_base + s * kABytes;
-        if (c0 < prm.C1) {
-          tma_load_3d(a_dst, &map_x1, &full[s], p0, c0, b);
-          tma_load_3d(a_dst + kABytes / 2, &map_x1, &full[s], p0 + 64, c0, b);
-        } else {
-          const int bb = prm.B2 == 1 ? 0 : b;
-          tma_load_3d(a_dst, &map_x2, &full[s], p0, c0 - prm.C1, bb);
-          tma_load_3d(a_dst + kABytes / 2, &map_x2, &full[s], p0 + 64, c0 - prm.C1, bb);
-        }
-        if (!B_MN) {
-          tma_load_3d(b_base + s * kBBytes, &map_w, &full[s], c0, n0, b);
-        } else {
+      int it = 0;
+      for (int tile = t_begin; tile < t_end; ++tile) {
+        int b, n0, p0;
+        decode(tile, b, n0, p0);
+        for (int kb = 0; kb < num_kb; ++kb, ++it) {
+          const int s = it % STAGES;
+          const uint32_t ph = (it / STAGES) & 1;
+          mbar_wait(&empty[s], ph ^ 1);
+          mbar_expect_tx(&full[s], kStageBytes);
+          const int c0 = kb * kBK;
+          uint8_t *a_dst = a_base + s * kABytes;
+          if (c0 < prm.C1) {
+            tma_load_3d(a_dst, &map_x1, &full[s], p0, c0, b);
+            tma_load_3d(a_dst + kABytes / 2, &map_x1, &full[s], p0 + 64, c0, b);
+          } else {
+            const int bb = prm.B2 == 1 ? 0 : b;
+            tma_load_3d(a_dst, &map_x2, &full[s], p0, c0 - prm.C1, bb);
+            tma_load_3d(a_dst + kABytes / 2, &map_x2, &full[s], p0 + 64, c0 - prm.C1, bb);
+          }
+          if (!B_MN) {
+            tma_load_3d(b_base + s * kBBytes, &map_w, &full[s], c0, n0, b);
+          } else {
 #pragma unroll
-          for (int j = 0; j < BN / 64; ++j)
-            tma_load_3d(b_base + s * kBBytes + j * 8192, &map_w, &full[s], n0 + 64 * j, c0, b);
+            for (int j = 0; j < BN / 64; ++j)
+              tma_load_3d(b_base + s * kBBytes + j * 8192, &map_w, &full[s], n0 + 64 * j, c0, b);
+          }
         }
       }
     }
@@ -217,59 +247,75 @@ modconv_fwd_tc_kernel(const __grid_constant__ CUtensorMap map_x1,
     // ===================== MMA issuer =====================
     if (lane == 0) {
       constexpr uint32_t idesc = make_idesc(kBM, BN, true, B_MN);
-      for (int kb = 0; kb < num_kb; ++kb) {
-        const int s = kb % STAGES;
-        const uint32_t ph = (kb / STAGES) & 1;
-        mbar_wait(&full[s], ph);
+      int it = 0, lt = 0;
+      for (int tile = t_begin; tile < t_end; ++tile, ++lt) {
+        const int a = lt & 1;
+        mbar_wait(&acc_empty[a], ((lt >> 1) & 1) ^ 1);     // epilogue has drained this accumulator
         tc_fence_after();
-        const uint32_t a_addr = smem_u32(a_base + s * kABytes);
-        const uint32_t b_addr = smem_u32(b_base + s * kBBytes);
+        const uint32_t tmem_acc = tmem_base + (uint32_t)(a * BN);
+        for (int kb = 0; kb < num_kb; ++kb, ++it) {
+          const int s = it % STAGES;
+          const uint32_t ph = (it / STAGES) & 1;
+          mbar_wait(&full[s], ph);
+          tc_fence_after();
+          const uint32_t a_addr = smem_u32(a_base + s * kABytes);
+          const uint32_t b_addr = smem_u32(b_base + s * kBBytes);
 #pragma unroll
-        for (int k16 = 0; k16 < kBK / 16; ++k16) {
-          // A (MN-major, SW128): 16 channel rows = 2 KiB per UMMA_K step; LBO = next 64-pixel
-          // block (8 KiB), SBO = next group of 8 channel rows (1 KiB)
-          const uint64_t adesc = make_desc(a_addr + k16 * 2048, kABytes / 2, 1024);
-          // B (K-major, SW128): 32 bytes per UMMA_K step inside the swizzle atom; SBO = next
-          // group of 8 out-channel rows (1 KiB)
-          // (MN-major B, dX: same geometry as A -- 2 KiB per step, LBO = next 64-column block)
-          const uint64_t bdesc = B_MN ? make_desc(b_addr + k16 * 2048, 8192, 1024)
-                                      : make_desc(b_addr + k16 * 32, 16, 1024);
-          umma_bf16(tmem_acc, adesc, bdesc, idesc, (kb > 0 || k16 > 0) ? 1u : 0u);
+          for (int k16 = 0; k16 < kBK / 16; ++k16) {
+            // A (MN-major, SW128): 16 channel rows = 2 KiB per UMMA_K step; LBO = next
+            // 64-pixel block (8 KiB), SBO = next group of 8 channel rows (1 KiB)
+            const uint64_t adesc = make_desc(a_addr + k16 * 2048, kABytes / 2, 1024);
+            // B K-major (SW128): 32 bytes per UMMA_K step inside the swizzle atom, SBO = next
+            // group of 8 out-channel rows; B MN-major (dX): same geometry as A
+            const uint64_t bdesc = B_MN ? make_desc(b_addr + k16 * 2048, 8192, 1024)
+                                        : make_desc(b_addr + k16 * 32, 16, 1024);
+            umma_bf16(tmem_acc, adesc, bdesc, idesc, (kb > 0 || k16 > 0) ? 1u : 0u);
+          }
+          umma_commit(&empty[s]);            // smem slot reusable once these MMAs retire
         }
-        umma_commit(&empty[s]);            // smem slot reusable once these MMAs retire
+        umma_commit(&acc_full[a]);           // accumulator of this tile complete
       }
-      umma_commit(acc_full);               // accumulator complete
     }
   } else {
     // ===================== epilogue (warps 2..5) =====================
-    const int q = warp & 3;                // TMEM lane quarter this warp may access
-    const int row = q * 32 + lane;         // pixel row inside the tile
-    mbar_wait(acc_full, 0);
-    tc_fence_after();
-    const int64_t p = (int64_t)p0 + row;
-    __nv_bfloat16 *yb = prm.y + (int64_t)b * prm.O * prm.P + p;
+    const int q = warp & 3;                  // TMEM lane quarter this warp may access
+    const int row = q * 32 + lane;           // pixel row inside the tile
+    int lt = 0;
+    for (int tile = t_begin; tile < t_end; ++tile, ++lt) {
+      int b, n0, p0;
+      decode(tile, b, n0, p0);
+      const int a = lt & 1;
+      mbar_wait(&acc_full[a], (lt >> 1) & 1);
+      tc_fence_after();
+      const int64_t p = (int64_t)p0 + row;
+      __nv_bfloat16 *yb = prm.y + (int64_t)b * prm.O * prm.P + p;
+      const uint32_t tmem_acc = tmem_base + (uint32_t)(a * BN) + ((uint32_t)(q * 32) << 16);
 #pragma unroll 1
-    for (int c = 0; c < BN; c += 16) {
-      uint32_t r[16];
-      tmem_ld16(tmem_acc + ((uint32_t)(q * 32) << 16) + (uint32_t)c, r);
-      tmem_ld_wait();
+      for (int c = 0; c < BN; c += 16) {
+        uint32_t r[16];
+        tmem_ld16(tmem_acc + (uint32_t)c, r);
+        tmem_ld_wait();
 #pragma unroll
-      for (int j = 0; j < 16; ++j) {
-        const int o = n0 + c + j;
-        if (o < prm.O && p < prm.P) {
-          float v = __uint_as_float(r[j]);
-          if (prm.bias) v += __ldg(prm.bias + o);
-          if (prm.act == 3) v = v > 0.f ? v : v * prm.alpha;
-          yb[(int64_t)o * prm.P] = __float2bfloat16_rn(v * prm.scale);
+        for (int j = 0; j < 16; ++j) {
+          const int o = n0 + c + j;
+          if (o < prm.O && p < prm.P) {
+            float v = __uint_as_float(r[j]);
+            if (prm.bias) v += __ldg(prm.bias + o);
+            if (prm.act == 3) v = v > 0.f ? v : v * prm.alpha;
+            yb[(int64_t)o * prm.P] = __float2bfloat16_rn(v * prm.scale);
+          }
         }
       }
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&acc_empty[a]);   // this warp is done reading accumulator a
     }
   }
   tc_fence_before();
   __syncthreads();
   if (warp == 1) {
     tc_fence_after();
-    tmem_dealloc(tmem_acc, BN);
+    tmem_dealloc(tmem_base, 2 * BN);
   }
 }
 
@@ -435,7 +481,7 @@ static int set_smem(KernelT kernel, int smem, bool *configured) {
 
 template <int BN, int STAGES>
 constexpr int tc_smem_bytes() {
-  return STAGES * (kABytes + BN * kBK * 2) + (2 * STAGES + 1) * 8 + 16 + 1024;
+  return STAGES * (kABytes + BN * kBK * 2) + (2 * STAGES + 4) * 8 + 16 + 1024;
 }
 
 bool modconv_fwd_tc_supported(int B, int O, int C1, int C2, int B2, int64_t P) {
@@ -468,12 +514,24 @@ bool modconv_dw_tc_supported(int B, int O, int C1, int C2, int B2, int64_t P) {
 
 template <int BN, int STAGES, bool B_MN>
 static int launch_tc(const CUtensorMap &mx1, const CUtensorMap &mx2, const CUtensorMap &mw,
-                     const TcParams &prm, int B, cudaStream_t st) {
+                     TcParams prm, int B, cudaStream_t st) {
   constexpr int smem = tc_smem_bytes<BN, STAGES>();
   static bool configured = false;
   if (int rc = set_smem(modconv_fwd_tc_kernel<BN, STAGES, B_MN>, smem, &configured)) return rc;
-  dim3 grid((unsigned)(prm.P / kBM), (unsigned)((prm.O + BN - 1) / BN), (unsigned)B);
-  modconv_fwd_tc_kernel<BN, STAGES, B_MN><<<grid, kThreads, smem, st>>>(mx1, mx2, mw, prm);
+  prm.MT = (int)(prm.P / kBM);
+  prm.NT = (prm.O + BN - 1) / BN;
+  const int64_t total = (int64_t)prm.MT * prm.NT * B;
+  if (total > 0x7fffffff) {
+    set_error("modconv_tc: too many tiles");
+    return DUSTY_EUNSUPPORTED;
+  }
+  prm.total_tiles = (int)total;
+  // CTAs that can be co-resident: 2 per SM unless the stage ring fills shared memory
+  const int resident = num_sms() * ((smem <= 110 * 1024 && 2 * BN * 2 <= 512) ? 2 : 1);
+  int ctas = prm.total_tiles < resident ? prm.total_tiles : resident;
+  prm.tiles_per_cta = (prm.total_tiles + ctas - 1) / ctas;
+  ctas = (prm.total_tiles + prm.tiles_per_cta - 1) / prm.tiles_per_cta;
+  modconv_fwd_tc_kernel<BN, STAGES, B_MN><<<ctas, kThreads, smem, st>>>(mx1, mx2, mw, prm);
   return 0;
 }
 

@@ -179,6 +179,7 @@ modconv_fwd_tc_kernel(const __grid_constant__ CUtensorMap map_x1,
   uint64_t *acc_full = empty + STAGES;      // [2]
   uint64_t *acc_empty = acc_full + 2;       // [2]
   uint32_t *tmem_slot = (uint32_t *)(acc_empty + 2);
+  uint8_t *epi_base = smem + STAGES * kStageBytes + 128;   // 2 x 8 KiB staging, 16-B aligned
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int num_kb = (prm.K + kBK - 1) / kBK;
@@ -278,37 +279,57 @@ modconv_fwd_tc_kernel(const __grid_constant__ CUtensorMap map_x1,
     }
   } else {
     // ===================== epilogue (warps 2..5) =====================
+    // TMEM -> registers (one pixel row per thread) -> bias/act -> bf16 -> shared-memory
+    // staging tile [32 channels][128 pixels] -> 16-byte global stores along the pixel axis
+    // (a direct store from the accumulator layout would be 2 bytes per lane).
     const int q = warp & 3;                  // TMEM lane quarter this warp may access
     const int row = q * 32 + lane;           // pixel row inside the tile
-    int lt = 0;
+    const int et = threadIdx.x - 64;         // 0..127 among the epilogue threads
+    __nv_bfloat16 *stage = reinterpret_cast<__nv_bfloat16 *>(epi_base);   // 2 x [32][128]
+    int lt = 0, chunk_id = 0;
     for (int tile = t_begin; tile < t_end; ++tile, ++lt) {
       int b, n0, p0;
       decode(tile, b, n0, p0);
       const int a = lt & 1;
       mbar_wait(&acc_full[a], (lt >> 1) & 1);
       tc_fence_after();
-      const int64_t p = (int64_t)p0 + row;
-      __nv_bfloat16 *yb = prm.y + (int64_t)b * prm.O * prm.P + p;
       const uint32_t tmem_acc = tmem_base + (uint32_t)(a * BN) + ((uint32_t)(q * 32) << 16);
+      __nv_bfloat16 *yt = prm.y + (int64_t)b * prm.O * prm.P + p0;
 #pragma unroll 1
-      for (int c = 0; c < BN; c += 16) {
-        uint32_t r[16];
-        tmem_ld16(tmem_acc + (uint32_t)c, r);
+      for (int c = 0; c < BN; c += 32, ++chunk_id) {
+        __nv_bfloat16 *buf = stage + (chunk_id & 1) * (32 * kBM);
+        uint32_t r0[16], r1[16];
+        tmem_ld16(tmem_acc + (uint32_t)c, r0);
+        tmem_ld16(tmem_acc + (uint32_t)(c + 16), r1);
         tmem_ld_wait();
+        if (c + 32 >= BN) {                  // accumulator fully read: hand it back to the MMA
+          tc_fence_before();
+          __syncwarp();
+          if (lane == 0) mbar_arrive(&acc_empty[a]);
+        }
 #pragma unroll
-        for (int j = 0; j < 16; ++j) {
+        for (int j = 0; j < 32; ++j) {
           const int o = n0 + c + j;
-          if (o < prm.O && p < prm.P) {
-            float v = __uint_as_float(r[j]);
-            if (prm.bias) v += __ldg(prm.bias + o);
-            if (prm.act == 3) v = v > 0.f ? v : v * prm.alpha;
-            yb[(int64_t)o * prm.P] = __float2bfloat16_rn(v * prm.scale);
+          float v = __uint_as_float(j < 16 ? r0[j] : r1[j - 16]);
+          if (prm.bias && o < prm.O) v += __ldg(prm.bias + o);
+          if (prm.act == 3) v = v > 0.f ? v : v * prm.alpha;
+          buf[j * kBM + row] = __float2bfloat16_rn(v * prm.scale);
+        }
+        asm volatile("bar.sync 1, 128;" ::: "memory");
+        // 32 channel rows x 256 bytes = 512 vectors of 16 bytes, 4 per thread
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+          const int v = i * 128 + et;
+          const int ch = v >> 4, seg = v & 15;
+          const int o = n0 + c + ch;
+          if (o < prm.O) {
+            const uint4 val = *reinterpret_cast<const uint4 *>(buf + ch * kBM + seg * 8);
+            *reinterpret_cast<uint4 *>(yt + (int64_t)o * prm.P + seg * 8) = val;
           }
         }
+        // the other staging buffer is used next; this one is rewritten two chunks later,
+        // after the next bar.sync has ordered these reads before those writes
       }
-      tc_fence_before();
-      __syncwarp();
-      if (lane == 0) mbar_arrive(&acc_empty[a]);   // this warp is done reading accumulator a
     }
   }
   tc_fence_before();
@@ -481,7 +502,8 @@ static int set_smem(KernelT kernel, int smem, bool *configured) {
 
 template <int BN, int STAGES>
 constexpr int tc_smem_bytes() {
-  return STAGES * (kABytes + BN * kBK * 2) + (2 * STAGES + 4) * 8 + 16 + 1024;
+  // stage ring + barrier block (128 B) + epilogue staging (2 x 32 x 128 bf16) + alignment slack
+  return STAGES * (kABytes + BN * kBK * 2) + 128 + 2 * 32 * kBM * 2 + 1024;
 }
 
 bool modconv_fwd_tc_supported(int B, int O, int C1, int C2, int B2, int64_t P) {
@@ -527,7 +549,7 @@ static int launch_tc(const CUtensorMap &mx1, const CUtensorMap &mx2, const CUten
   }
   prm.total_tiles = (int)total;
   // CTAs that can be co-resident: 2 per SM unless the stage ring fills shared memory
-  const int resident = num_sms() * ((smem <= 110 * 1024 && 2 * BN * 2 <= 512) ? 2 : 1);
+  const int resident = num_sms() * ((2 * smem <= 225 * 1024 && 2 * BN * 2 <= 512) ? 2 : 1);
   int ctas = prm.total_tiles < resident ? prm.total_tiles : resident;
   prm.tiles_per_cta = (prm.total_tiles + ctas - 1) / ctas;
   ctas = (prm.total_tiles + prm.tiles_per_cta - 1) / prm.tiles_per_cta;
@@ -555,9 +577,9 @@ int modconv_fwd_tc(const void *wb, const void *x1, const void *x2, const float *
   prm.y = (__nv_bfloat16 *)y; prm.act = act; prm.alpha = alpha; prm.scale = scale;
   switch (BN) {
     case 256: return launch_tc<256, 4, false>(mx1, mx2, mw, prm, B, st);
-    case 128: return launch_tc<128, 3, false>(mx1, mx2, mw, prm, B, st);
-    case 64: return launch_tc<64, 4, false>(mx1, mx2, mw, prm, B, st);
-    default: return launch_tc<32, 5, false>(mx1, mx2, mw, prm, B, st);
+    case 128: return launch_tc<128, 5, false>(mx1, mx2, mw, prm, B, st);
+    case 64: return launch_tc<64, 3, false>(mx1, mx2, mw, prm, B, st);
+    default: return launch_tc<32, 4, false>(mx1, mx2, mw, prm, B, st);
   }
 }
 
@@ -580,8 +602,8 @@ int modconv_dx_tc(const void *wb, const void *dy, void *dx1, int B, int O, int C
   prm.y = (__nv_bfloat16 *)dx1; prm.act = 1; prm.alpha = 0.f; prm.scale = 1.f;
   switch (BN) {
     case 256: return launch_tc<256, 4, true>(mg, mg, mw, prm, B, st);
-    case 128: return launch_tc<128, 3, true>(mg, mg, mw, prm, B, st);
-    default: return launch_tc<64, 4, true>(mg, mg, mw, prm, B, st);
+    case 128: return launch_tc<128, 5, true>(mg, mg, mw, prm, B, st);
+    default: return launch_tc<64, 3, true>(mg, mg, mw, prm, B, st);
   }
 }
 

@@ -610,7 +610,7 @@ int modconv_dx_tc(const void *wb, const void *dy, void *dx1, int B, int O, int C
 template <int BN, int STAGES>
 static int launch_dw(const CUtensorMap &mx1, const CUtensorMap &mx2, const CUtensorMap &mg,
                      const DwParams &prm, int B, cudaStream_t st) {
-  constexpr int smem = tc_smem_bytes<BN, STAGES>();
+  constexpr int smem = STAGES * (kABytes + BN * kBK * 2) + 128 + 1024;   // no epilogue staging
   static bool configured = false;
   if (int rc = set_smem(modconv_dw_tc_kernel<BN, STAGES>, smem, &configured)) return rc;
   dim3 grid((unsigned)((prm.K + kBM - 1) / kBM), (unsigned)((prm.O + BN - 1) / BN), (unsigned)B);

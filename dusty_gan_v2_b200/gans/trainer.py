@@ -72,6 +72,27 @@ class _GImage(torch.nn.Module):
         return self.G(z, **self._auxin)["image"]
 
 
+class _DLogits(torch.nn.Module):
+    """x -> D(x): separate wrapper instances are graph-captured for the two ways the
+    discriminator is used (frozen with a differentiable input in the G step; trainable with
+    a detached, real+fake stacked input in the D step)."""
+
+    def __init__(self, D, sub_batches=1):
+        super().__init__()
+        self.D = D
+        self._sub = sub_batches
+        self._mb = [m for m in D.modules() if hasattr(m, "sub_batches")]
+
+    def forward(self, x):
+        for m in self._mb:
+            m.sub_batches = self._sub
+        try:
+            return self.D(x)
+        finally:
+            for m in self._mb:
+                m.sub_batches = 1
+
+
 class Trainer:
     def __init__(self, cfg, batch_iter, device=None, rank=0, world_size=1,
                  angle_file="data/coords/kitti_raw.npy", precision=None, cuda_graphs=True):
@@ -100,9 +121,10 @@ class Trainer:
             kw = dict(device_ids=[self.device.index])
             if not self.cuda_graphs:
                 self.G = DDP(self.G, broadcast_buffers=True, **kw)
-            # graphed generator: its 17.5 MB of gradients are all-reduced as one flat bucket
-            # after backward and its buffers broadcast before forward (same collectives as DDP)
-            self.D = DDP(self.D, broadcast_buffers=False, **kw)
+                self.D = DDP(self.D, broadcast_buffers=False, **kw)
+            # graphed path: gradients of G (17.5 MB) and D (154 MB) are all-reduced as flat
+            # NCCL buckets right after each backward, G buffers broadcast before its forward
+            # -- the same collectives DDP would issue (graph replays bypass DDP's hooks)
         for m in (self.G, self.G_ema, self.D, self.A, self.coord):
             m.requires_grad_(False)
 
@@ -135,6 +157,8 @@ class Trainer:
         # ADA (data-dependent padding) and the discriminator stay eager.
         self._g_graph = None
         self._G_train_callable = None         # graphed forward+backward of the G step
+        self._D_callables = {}                # graphed D: "frozen" (G step) / "train" (D step)
+        self._D_launches = {}
         self._g_graph_out = None
         self._g_graph_launches = 0
         self.graph_replayed_launches = 0
@@ -206,6 +230,44 @@ class Trainer:
         self.graph_replayed_launches += self._G_train_launches
         return self._G_train_callable(z)
 
+    def _D_forward(self, x, mode):
+        """mode 'frozen': D frozen, x differentiable (G step); 'train': D trainable, x is the
+        detached real+fake stack (D step).  Graph-captured per mode; the R1 step (double
+        backward) always runs eagerly."""
+        sub = 2 if mode == "train" else 1
+        if not self.cuda_graphs:
+            fn = self._D_callables.get(mode)
+            if fn is None:
+                fn = self._D_callables[mode] = _DLogits(self.D, sub)
+            return fn(x)
+        fn = self._D_callables.get(mode)
+        if fn is None:
+            from .. import _cabi
+            wrapper = _DLogits(self.D_module, sub)
+            n0 = _cabi.launch_count()
+            try:
+                sample = x.detach().clone().requires_grad_(x.requires_grad)
+                fn = torch.cuda.make_graphed_callables(wrapper, (sample,))
+                self._D_launches[mode] = (_cabi.launch_count() - n0) // 4
+            except Exception as exc:
+                import warnings
+                warnings.warn(f"CUDA-graph capture of the discriminator ({mode}) failed ({exc!r}); "
+                              "running it eagerly")
+                fn = wrapper
+                self._D_launches[mode] = 0
+            self._D_callables[mode] = fn
+        self.graph_replayed_launches += self._D_launches[mode]
+        return fn(x)
+
+    def _allreduce_grads(self, params):
+        if self.world_size > 1 and self.cuda_graphs:
+            grads = [p.grad for p in params if p.grad is not None]
+            flat = torch.cat([g.reshape(-1) for g in grads])
+            dist.all_reduce(flat)
+            flat /= self.world_size
+            torch._foreach_copy_(grads, [c.reshape(g.shape) for g, c in
+                                         zip(grads, flat.split([g.numel() for g in grads]))])
+
     def _allreduce_G_grads(self):
         if self.world_size > 1 and self.G is self.G_module:
             grads = [p.grad for p in self._G_params if p.grad is not None]
@@ -239,20 +301,6 @@ class Trainer:
         self.graph_replayed_launches += self._g_graph_launches
         return self._g_graph_out
 
-    def _D_two_halves(self, x_both):
-        mb = getattr(self, "_mbstd_modules", None)
-        if mb is None:
-            mb = self._mbstd_modules = [m for m in self.D_module.modules()
-                                        if hasattr(m, "sub_batches")]
-        for m in mb:
-            m.sub_batches = 2
-        try:
-            y = self.D(x_both)
-        finally:
-            for m in mb:
-                m.sub_batches = 1
-        return y.chunk(2, dim=0)
-
     # ------------------------------------------------------------------ one iteration
     def step(self, iteration):
         tr = self.cfg.training
@@ -267,7 +315,7 @@ class Trainer:
         set_requires_grad(self._G_params, True)
         self.optim_G.zero_grad(set_to_none=True)
         x_fake = self._G_train_forward(self.sample_z(B))
-        y_fake = self.D(self.A(self.warmup(x_fake)))
+        y_fake = self._D_forward(self.A(self.warmup(x_fake)), "frozen")
         loss_gan = self.adversarial_loss(None, y_fake, "G")
         (tr.loss.gan * loss_gan).backward()
         self._allreduce_G_grads()
@@ -282,10 +330,11 @@ class Trainer:
         # real and fake go through warm-up, ADA and D as ONE stacked batch (per-sample
         # transforms, per-half minibatch statistics): same math, half the launches
         x_both = self.A(self.warmup(torch.cat([x_real, x_fake], dim=0))).detach()
-        y_real, y_fake = self._D_two_halves(x_both)
+        y_real, y_fake = self._D_forward(x_both, "train").chunk(2, dim=0)
         self.A.cumulate(y_real)
         loss_gan = self.adversarial_loss(y_real, y_fake, "D")
         (tr.loss.gan * loss_gan).backward()
+        self._allreduce_grads(self._D_params)
         self.optim_D.step()
         scalars["loss/D/output/real"] = y_real.mean().detach()
         scalars["loss/D/output/fake"] = y_fake.mean().detach()
@@ -300,6 +349,7 @@ class Trainer:
             r1 = DF.sumsq_rows(grads).mean()
             loss = (self.gp_weight / 2) * r1 + 0.0 * y_real.squeeze()[0]
             loss.backward()
+            self._allreduce_grads(self._D_params)
             self.optim_D.step()
             scalars["loss/D/gradient_penalty"] = r1.detach()
         set_requires_grad(self._D_params, False)

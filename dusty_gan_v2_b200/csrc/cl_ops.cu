@@ -150,26 +150,51 @@ struct Taps4CL { float k[4]; };
 // ADJ == false: out[y] = sum_t k[t] h[clamp(y+t-2)],  h[r][x] = sum_t k[t] in[r][wrap(x+t-2)]
 // ADJ == true : transpose (see resample4.cu): g[e] = sum_t k[t] Gh[e+2-t], Gh from d[wrap(x+2-t)],
 //               rows e in [-2, H] folded onto clamp(e)
-template <typename T, bool ADJ>
+// PAD == true fuses the ring padding (1 pixel, circular W / replicate H) that follows the blur
+// in the residual blocks (conv2 input): forward writes the blurred image straight into the
+// padded [H+2, W+2] tensor; the adjoint reads the padded gradient and folds the halo on load.
+template <typename T, bool ADJ, bool PAD>
 __global__ void __launch_bounds__(128)
 blur4_cl_kernel(const T *__restrict__ x, T *__restrict__ y, Taps4CL t, int H, int W, int cv,
                 int strip, int64_t n_threads) {
   constexpr int V = Vec16<T>::N;
+  const int Wx = (PAD && !ADJ) ? W + 2 : W;      // columns covered by threads
   const int64_t tid = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (tid >= n_threads) return;
   const int j = (int)(tid % cv);
   const int64_t q = tid / cv;
-  const int xx = (int)(q % W);
-  const int64_t b = q / W;
-  const T *img = x + b * (int64_t)H * W * cv * V;
-  T *out = y + b * (int64_t)H * W * cv * V;
-  // wrapped neighbour columns for the 4 horizontal taps
+  const int xo = (int)(q % Wx);                  // output column (padded coordinates if PAD fwd)
+  const int64_t b = q / Wx;
+  int xx = xo;                                   // image column this thread evaluates
+  if (PAD && !ADJ) { xx = xo - 1; xx = xx < 0 ? xx + W : (xx >= W ? xx - W : xx); }
+  const int Hp = H + 2, Wp = W + 2;
+  const int64_t in_img = (int64_t)((PAD && ADJ) ? Hp * Wp : H * W) * cv * V;
+  const int64_t out_img = (int64_t)((PAD && !ADJ) ? Hp * Wp : H * W) * cv * V;
+  const T *img = x + b * in_img;
+  T *out = y + b * out_img;
   int xc[4];
 #pragma unroll
   for (int s = 0; s < 4; ++s) {
     int c = ADJ ? (xx + 2 - s) : (xx + s - 2);
     xc[s] = c < 0 ? c + W : (c >= W ? c - W : c);
   }
+  // gradient element (r, c) of the un-padded image = sum of the padded-gradient elements that
+  // the padding copied it to
+  auto load_folded = [&](int r, int c, float *acc, float w) {
+    const int rows[3] = {r + 1, r == 0 ? 0 : -1, r == H - 1 ? H + 1 : -1};
+    const int cols[3] = {c + 1, c == 0 ? W + 1 : -1, c == W - 1 ? 0 : -1};
+#pragma unroll
+    for (int a = 0; a < 3; ++a) {
+      if (rows[a] < 0) continue;
+#pragma unroll
+      for (int e = 0; e < 3; ++e) {
+        if (cols[e] < 0) continue;
+        Vec16<T> v = ld16(img + (((int64_t)rows[a] * Wp + cols[e]) * cv + j) * V);
+#pragma unroll
+        for (int k = 0; k < V; ++k) acc[k] = fmaf(w, v.get(k), acc[k]);
+      }
+    }
+  };
   auto hpass = [&](int r, float *dst) {
     if (ADJ) {
       if (r < 0 || r >= H) {
@@ -180,14 +205,19 @@ blur4_cl_kernel(const T *__restrict__ x, T *__restrict__ y, Taps4CL t, int H, in
     } else {
       r = r < 0 ? 0 : (r >= H ? H - 1 : r);
     }
-    const T *row = img + (int64_t)r * W * cv * V;
 #pragma unroll
     for (int k = 0; k < V; ++k) dst[k] = 0.f;
+    if (PAD && ADJ) {
 #pragma unroll
-    for (int s = 0; s < 4; ++s) {
-      Vec16<T> v = ld16(row + ((int64_t)xc[s] * cv + j) * V);
+      for (int s = 0; s < 4; ++s) load_folded(r, xc[s], dst, t.k[s]);
+    } else {
+      const T *row = img + (int64_t)r * W * cv * V;
 #pragma unroll
-      for (int k = 0; k < V; ++k) dst[k] = fmaf(t.k[s], v.get(k), dst[k]);
+      for (int s = 0; s < 4; ++s) {
+        Vec16<T> v = ld16(row + ((int64_t)xc[s] * cv + j) * V);
+#pragma unroll
+        for (int k = 0; k < V; ++k) dst[k] = fmaf(t.k[s], v.get(k), dst[k]);
+      }
     }
   };
   const int y0 = blockIdx.y * strip;
@@ -203,7 +233,13 @@ blur4_cl_kernel(const T *__restrict__ x, T *__restrict__ y, Taps4CL t, int H, in
         o.set(k, fmaf(t.k[3], d[k], fmaf(t.k[2], c[k], fmaf(t.k[1], bb[k], t.k[0] * a[k]))));
         a[k] = bb[k]; bb[k] = c[k]; c[k] = d[k];
       }
-      st16(out + (((int64_t)r * W + xx) * cv + j) * V, o);
+      if (PAD) {
+        st16(out + (((int64_t)(r + 1) * Wp + xo) * cv + j) * V, o);
+        if (r == 0) st16(out + (((int64_t)0 * Wp + xo) * cv + j) * V, o);
+        if (r == H - 1) st16(out + (((int64_t)(H + 1) * Wp + xo) * cv + j) * V, o);
+      } else {
+        st16(out + (((int64_t)r * W + xx) * cv + j) * V, o);
+      }
     }
   } else {
     const int e_lo = (y0 == 0) ? -2 : y0;
@@ -338,28 +374,36 @@ extern "C" int dusty_pad2d_cl(const void *x, void *y, int B, int H, int W, int C
 }
 
 extern "C" int dusty_blur4_cl(const void *x, void *y, float k0, float k1, float k2, float k3, int B,
-                              int H, int W, int C, int adjoint, int dtype, void *stream) {
+                              int H, int W, int C, int adjoint, int pad, int dtype, void *stream) {
   DUSTY_CHECK_ARG(x && y, "null pointer");
   DUSTY_CHECK_ARG(B >= 1 && H >= 2 && W >= 4, "bad shape");
+  DUSTY_CHECK_ARG(pad == 0 || pad == 1, "pad must be 0 or 1");
   DUSTY_CHECK_ARG(dtype == DUSTY_F32 || dtype == DUSTY_BF16, "bad dtype");
   const int V = dtype == DUSTY_F32 ? 4 : 8;
   DUSTY_CHECK_ARG(C % V == 0, "C must be a multiple of the 16-byte vector width");
   Taps4CL t;
   t.k[0] = k0; t.k[1] = k1; t.k[2] = k2; t.k[3] = k3;
   const int cv = C / V;
-  const int64_t n_threads = (int64_t)B * W * cv;
+  const int Wx = (pad && !adjoint) ? W + 2 : W;
+  const int64_t n_threads = (int64_t)B * Wx * cv;
   int strip = H;
   const int64_t ctas_x = (n_threads + 127) / 128;
   while (strip > 8 && ctas_x * ((H + strip - 1) / strip) < (int64_t)num_sms() * 8) strip = (strip + 1) / 2;
   dim3 grid((unsigned)ctas_x, (unsigned)((H + strip - 1) / strip));
   cudaStream_t st = (cudaStream_t)stream;
-  if (dtype == DUSTY_F32) {
-    if (adjoint) blur4_cl_kernel<float, true><<<grid, 128, 0, st>>>((const float *)x, (float *)y, t, H, W, cv, strip, n_threads);
-    else blur4_cl_kernel<float, false><<<grid, 128, 0, st>>>((const float *)x, (float *)y, t, H, W, cv, strip, n_threads);
-  } else {
-    if (adjoint) blur4_cl_kernel<__nv_bfloat16, true><<<grid, 128, 0, st>>>((const __nv_bfloat16 *)x, (__nv_bfloat16 *)y, t, H, W, cv, strip, n_threads);
-    else blur4_cl_kernel<__nv_bfloat16, false><<<grid, 128, 0, st>>>((const __nv_bfloat16 *)x, (__nv_bfloat16 *)y, t, H, W, cv, strip, n_threads);
-  }
+#define BLUR_CL(T, A, P) \
+  blur4_cl_kernel<T, A, P><<<grid, 128, 0, st>>>((const T *)x, (T *)y, t, H, W, cv, strip, n_threads)
+#define BLUR_CL_DISPATCH(T)                       \
+  do {                                            \
+    if (adjoint && pad) BLUR_CL(T, true, true);   \
+    else if (adjoint) BLUR_CL(T, true, false);    \
+    else if (pad) BLUR_CL(T, false, true);        \
+    else BLUR_CL(T, false, false);                \
+  } while (0)
+  if (dtype == DUSTY_F32) BLUR_CL_DISPATCH(float);
+  else BLUR_CL_DISPATCH(__nv_bfloat16);
+#undef BLUR_CL_DISPATCH
+#undef BLUR_CL
   DUSTY_LAUNCH_CHECK();
   return DUSTY_OK;
 }

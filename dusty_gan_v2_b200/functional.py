@@ -290,7 +290,7 @@ def _resample4_raw(x, taps4, up, adjoint):
         y = torch.empty_like(x)
         B, C, H, W = x.shape
         K.call("dusty_blur4_cl", K.ptr(x), K.ptr(y), taps4[0], taps4[1], taps4[2], taps4[3], B, H, W,
-               C, 1 if adjoint else 0, K.dtype_code(x), K.stream_of(x))
+               C, 1 if adjoint else 0, 0, K.dtype_code(x), K.stream_of(x))
         return y
     x = _contig(x)
     lead = x.shape[:-2]
@@ -319,6 +319,40 @@ class _Resample4(Function):
     def backward(ctx, g):
         taps4, up, adjoint = ctx.cfg
         return _Resample4.apply(g, taps4, up, not adjoint), None, None, None
+
+
+class _BlurPadCL(Function):
+    """blur (4-tap, ring) followed by Pad(1, ring) on an NHWC tensor, one kernel each way."""
+
+    @staticmethod
+    def forward(ctx, x, taps4, adjoint):
+        B, C = x.shape[:2]
+        if adjoint:
+            H, W = x.shape[2] - 2, x.shape[3] - 2
+            x = x if _is_cl(x) else x.contiguous(memory_format=_CL)
+            y = torch.empty((B, C, H, W), device=x.device, dtype=x.dtype, memory_format=_CL)
+        else:
+            H, W = x.shape[2:]
+            y = torch.empty((B, C, H + 2, W + 2), device=x.device, dtype=x.dtype, memory_format=_CL)
+        K.call("dusty_blur4_cl", K.ptr(x), K.ptr(y), taps4[0], taps4[1], taps4[2], taps4[3], B, H, W,
+               C, 1 if adjoint else 0, 1, K.dtype_code(x), K.stream_of(x))
+        ctx.cfg = (taps4, adjoint)
+        return y
+
+    @staticmethod
+    def backward(ctx, g):
+        taps4, adjoint = ctx.cfg
+        return _BlurPadCL.apply(g, taps4, not adjoint), None, None
+
+
+def blur_pad_cl_supported(x: torch.Tensor) -> bool:
+    return (x.is_cuda and _is_cl(x) and _cl_vec_ok(x) and x.dtype in (torch.float32, torch.bfloat16)
+            and x.shape[-2] >= 2 and x.shape[-1] >= 4)
+
+
+def blur_pad_cl(x: torch.Tensor, taps4) -> torch.Tensor:
+    """Pad(1, ring)(Resample([k0..k3], ring)(x)) for an NHWC tensor."""
+    return _BlurPadCL.apply(x, tuple(float(t) for t in taps4), False)
 
 
 def resample4_supported(x: torch.Tensor, up: int) -> bool:

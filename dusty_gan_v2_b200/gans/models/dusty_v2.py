@@ -299,9 +299,21 @@ class ResidualBlock(nn.Module):
         self.bias_act2 = ops.FusedLeakyReLU(out_ch)
         self.skip = ops.Conv2d(in_ch, out_ch, 1, 2, 0, **kw)
 
+    def _blur_pad_conv2(self, h):
+        """conv2(resample(h)) with the blur and conv2's ring padding as one kernel (NHWC)."""
+        pad = self.conv2[0] if len(self.conv2) == 2 else None
+        rs = self.resample
+        if (pad is not None and isinstance(pad, ops.Pad) and pad.padding == (1, 1, 1, 1)
+                and pad.horizontal == "circular" and pad.vertical == "replicate"
+                and getattr(rs, "_fast_up", None) == 1 and DF.blur_pad_cl_supported(h)):
+            if rs._taps_host is None:
+                rs._taps_host = tuple(rs.kernel.detach().float().cpu().tolist())
+            return self.conv2[1](DF.blur_pad_cl(h, rs._taps_host))
+        return self.conv2(rs(h))
+
     def residual(self, x):
         h = self.bias_act1(self.conv1(x))
-        return self.bias_act2(self.conv2(self.resample(h)))
+        return self.bias_act2(self._blur_pad_conv2(h))
 
     def forward(self, x):
         return (self.residual(x) + self.skip(self.resample(x))) * (1.0 / math.sqrt(2))

@@ -113,8 +113,11 @@ int dusty_bias_act_bwd_cl(const void *dy, const void *out, void *dx, float *db, 
                           float alpha, float scale, int dtype, void *stream);
 int dusty_pad2d_cl(const void *x, void *y, int B, int H, int W, int C, int pt, int pb, int pl,
                    int pr, int mode_y, int mode_x, int adjoint, int dtype, void *stream);
+/* pad == 1 fuses the 1-pixel ring padding that follows the blur in ResidualBlock.residual
+ * (dusty_v2.py:337: conv2(resample(h)), conv2 = Pad(1, ring) + conv): forward writes
+ * [B, H+2, W+2, C]; the adjoint takes that padded gradient and folds the halo on load. */
 int dusty_blur4_cl(const void *x, void *y, float k0, float k1, float k2, float k3, int B, int H,
-                   int W, int C, int adjoint, int dtype, void *stream);
+                   int W, int C, int adjoint, int pad, int dtype, void *stream);
 
 /* ---- a5/a6: AdaptiveAugment's geometric pipeline ------------------------------------------
  * Single-axis zero-padded polyphase FIR: upfirdn2d with a [1,k] (axis 1 = x) or [k,1]

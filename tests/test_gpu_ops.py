@@ -549,3 +549,29 @@ def test_channels_last_ops_match_nchw(DF, ops, dtype, C):
     bb2 = b.clone().requires_grad_()
     (db2,) = torch.autograd.grad(DF.bias_act(x, bb2), bb2, gy)
     close(db, db2, rtol=1e-3, atol_rel=1e-3)
+
+
+@pytest.mark.parametrize("dtype,C", [(torch.float32, 8), (torch.bfloat16, 32)])
+def test_fused_blur_pad_nhwc(DF, ops, dtype, C):
+    """blur + ring pad as one NHWC kernel == Pad(1, ring)(Resample()(x)); value, adjoint and
+    second order (the op is linear)."""
+    g = torch.Generator().manual_seed(43)
+    CL = torch.channels_last
+    x = torch.randn(2, C, 8, 16, generator=g).to(DEV, dtype)
+    blur, pad = ops.Resample().to(DEV), ops.Pad(1, ring=True)
+    taps = tuple(blur.kernel.tolist())
+    tol = dict(rtol=1e-5, atol_rel=1e-6) if dtype == torch.float32 else dict(rtol=2e-2, atol_rel=1e-2)
+    xr = x.clone().requires_grad_()
+    ref = pad(blur(xr))
+    xf = x.contiguous(memory_format=CL).requires_grad_()
+    got = DF.blur_pad_cl(xf, taps)
+    assert got.shape == ref.shape and DF._is_cl(got)
+    close(got, ref, **tol)
+    gy = torch.randn(ref.shape, generator=g).to(DEV, dtype)
+    (gr,) = torch.autograd.grad(ref, xr, gy)
+    gyf = gy.contiguous(memory_format=CL).requires_grad_()
+    (gf,) = torch.autograd.grad(got, xf, gyf, create_graph=True)
+    close(gf, gr, **tol)
+    v = torch.randn(x.shape, generator=g).to(DEV, dtype)
+    (gg,) = torch.autograd.grad((gf.float() * v.float()).sum(), gyf)
+    close(gg, pad(blur(v)), **tol)

@@ -121,11 +121,14 @@ gemm_nn_kernel(GemmNN g) {
   }
 }
 
-// Heads: O <= 4 outputs.  Pure streaming read of x (memory bound); weights in smem.
+// Heads: O <= 4 outputs.  Pure streaming read of x (memory bound); weights in smem.  Each
+// thread owns one 16-byte pixel group (8 bf16 / 4 fp32) and walks the channel axis with four
+// independent loads in flight.
 template <typename T, typename TA, int OMAX>
 __global__ void __launch_bounds__(256)
 small_o_kernel(GemmNN g) {
   extern __shared__ float sw[];  // [M][K]
+  constexpr int V = Vec16<T>::N;
   const int b = blockIdx.y;
   const TA *A = (const TA *)g.a + (int64_t)b * g.a_bs;
   for (int i = threadIdx.x; i < g.M * g.K; i += blockDim.x) {
@@ -133,37 +136,74 @@ small_o_kernel(GemmNN g) {
     sw[i] = to_f(A[(int64_t)m * g.a_ms + (int64_t)k * g.a_ks]);
   }
   __syncthreads();
-  const int64_t p0 = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) * 4;
+  const int64_t p0 = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) * V;
   if (p0 >= g.N) return;
   const T *B1 = (const T *)g.b1 + (int64_t)b * g.b1_bs;
   const T *B2 = (const T *)g.b2 + (int64_t)b * g.b2_bs;
-  const bool full = (g.N % 4 == 0) && (p0 + 4 <= g.N);
-  float acc[OMAX][4] = {};
-  for (int k = 0; k < g.K; ++k) {
-    const T *src = (k < g.K1) ? (B1 + (int64_t)k * g.N) : (B2 + (int64_t)(k - g.K1) * g.N);
-    float v[4] = {0.f, 0.f, 0.f, 0.f};
-    if (full) Ld4<T>::ld(src + p0, v);
-    else
-      for (int i = 0; i < 4; ++i) if (p0 + i < g.N) v[i] = to_f(src[p0 + i]);
+  const bool full = (g.N % V == 0) && (p0 + V <= g.N) &&
+                    ((reinterpret_cast<uintptr_t>(B1) | reinterpret_cast<uintptr_t>(B2)) & 15u) == 0;
+  float acc[OMAX][V] = {};
+  auto src_of = [&](int k) {
+    return ((k < g.K1) ? (B1 + (int64_t)k * g.N) : (B2 + (int64_t)(k - g.K1) * g.N)) + p0;
+  };
+  auto fma_k = [&](int k, const float *v) {
 #pragma unroll
     for (int m = 0; m < OMAX; ++m) {
       if (m < g.M) {
         const float w = sw[m * g.K + k];
 #pragma unroll
-        for (int i = 0; i < 4; ++i) acc[m][i] = fmaf(w, v[i], acc[m][i]);
+        for (int i = 0; i < V; ++i) acc[m][i] = fmaf(w, v[i], acc[m][i]);
       }
     }
+  };
+  int k = 0;
+  if (full) {
+    for (; k + 4 <= g.K; k += 4) {
+      Vec16<T> v0 = ld16_stream(src_of(k)), v1 = ld16_stream(src_of(k + 1));
+      Vec16<T> v2 = ld16_stream(src_of(k + 2)), v3 = ld16_stream(src_of(k + 3));
+      float f[V];
+#pragma unroll
+      for (int i = 0; i < V; ++i) f[i] = v0.get(i);
+      fma_k(k, f);
+#pragma unroll
+      for (int i = 0; i < V; ++i) f[i] = v1.get(i);
+      fma_k(k + 1, f);
+#pragma unroll
+      for (int i = 0; i < V; ++i) f[i] = v2.get(i);
+      fma_k(k + 2, f);
+#pragma unroll
+      for (int i = 0; i < V; ++i) f[i] = v3.get(i);
+      fma_k(k + 3, f);
+    }
+  }
+  for (; k < g.K; ++k) {
+    const T *src = src_of(k);
+    float f[V];
+#pragma unroll
+    for (int i = 0; i < V; ++i) f[i] = (p0 + i < g.N) ? to_f(src[i]) : 0.f;
+    fma_k(k, f);
   }
   T *C = (T *)g.c + (int64_t)b * g.c_bs;
 #pragma unroll
   for (int m = 0; m < OMAX; ++m) {
     if (m >= g.M) continue;
     const float bv = g.bias ? g.bias[m] : 0.f;
-    for (int i = 0; i < 4; ++i) {
-      if (p0 + i >= g.N) continue;
+    float o[V];
+#pragma unroll
+    for (int i = 0; i < V; ++i) {
       float v = acc[m][i] + bv;
       if (g.act == 3) v = (v > 0.f) ? v : v * g.alpha;
-      C[(int64_t)m * g.N + p0 + i] = from_f<T>(v * g.scale);
+      o[i] = v * g.scale;
+    }
+    T *dst = C + (int64_t)m * g.N + p0;
+    if (full && (reinterpret_cast<uintptr_t>(dst) & 15u) == 0) {
+      Vec16<T> ov;
+#pragma unroll
+      for (int i = 0; i < V; ++i) ov.set(i, o[i]);
+      st16(dst, ov);
+    } else {
+#pragma unroll
+      for (int i = 0; i < V; ++i) if (p0 + i < g.N) dst[i] = from_f<T>(o[i]);
     }
   }
 }
@@ -301,7 +341,8 @@ small_o_dw_kernel(GemmNT g) {
 template <typename T, typename TA>
 static int run_nn(const GemmNN &g, int B, bool a_kcontig, cudaStream_t st) {
   if (g.M <= 4 && (size_t)g.M * g.K * sizeof(float) <= 48 * 1024) {
-    dim3 grid((unsigned)((g.N + 1023) / 1024), (unsigned)B);
+    constexpr int V = Vec16<T>::N;
+    dim3 grid((unsigned)((g.N + 256 * V - 1) / (256 * V)), (unsigned)B);
     small_o_kernel<T, TA, 4><<<grid, 256, (size_t)g.M * g.K * sizeof(float), st>>>(g);
     return 0;
   }

@@ -696,3 +696,54 @@ def train_iteration(sdG: Dict[str, Tensor], sdD: Dict[str, Tensor], x_real: Tens
         out["grads_R1"] = dict(zip(pD, torch.autograd.grad(loss, list(pD.values()), allow_unused=True)))
         out["t_R1"] = time.perf_counter() - t0
     return out
+
+
+# --------------------------------------------------------------------------------------
+# a15  vanilla / dusty_v1 baselines                 gans/models/vanilla.py, dusty_v1.py:31-41
+# --------------------------------------------------------------------------------------
+
+
+def _equal_convT(x: Tensor, w: Tensor, b: Optional[Tensor], stride: int, padding: int) -> Tensor:
+    """EqualLR(nn.ConvTranspose2d): the runtime scale is 1/sqrt(weight[0].numel()) -- for a
+    transposed conv weight [in, out, kh, kw] that is out*kh*kw (common.py:171-172)."""
+    scale = 1.0 / math.sqrt(w[0].numel())
+    return F.conv_transpose2d(x * scale, w, b, stride=stride, padding=padding)
+
+
+def vanilla_synthesis(sd: Dict[str, Tensor], w: Tensor, prefix: str = "synthesis_network.",
+                      image_tanh: bool = False) -> Dict[str, Tensor]:
+    """vanilla.SynthesisNetwork (vanilla.py:49-69): Projection, 3x Upsample, Head."""
+    h = w.reshape(w.shape[0], -1, 1, 1)                                    # "B 1 C -> B C 1 1"
+    h = bias_act(_equal_convT(h, sd[f"{prefix}0.1.module.weight"], None, 1, 0), sd[f"{prefix}0.2.bias"])
+    for i in (1, 2, 3):
+        h = pad2d(h, 1, ring=True, mode="reflect")
+        h = bias_act(_equal_convT(h, sd[f"{prefix}{i}.1.module.weight"], None, 2, 3),
+                     sd[f"{prefix}{i}.2.bias"])
+    out = {}
+    for name in ("image", "raydrop_logit"):
+        key = f"{prefix}4.heads.{name}.1.module.weight"
+        if key in sd:
+            o = _equal_convT(pad2d(h, 1, ring=True, mode="reflect"), sd[key],
+                             sd[f"{prefix}4.heads.{name}.1.module.bias"], 2, 3)
+            out[name] = torch.tanh(o) if (image_tanh and name == "image") else o
+    return out
+
+
+def vanilla_generator(sd: Dict[str, Tensor], z: Tensor, u: Optional[Tensor] = None,
+                      raydrop_const: float = -1.0, image_tanh: bool = False) -> Dict[str, Tensor]:
+    """vanilla.Generator / dusty_v1.Generator in eval mode (mapping = Identity, one style)."""
+    o = vanilla_synthesis(sd, z[:, None, :], image_tanh=image_tanh)
+    o["w"] = z[:, None, :]
+    if "raydrop_logit" in o and u is not None:
+        o.update(raydrop(o["image"], o["raydrop_logit"], u, raydrop_const))
+    return o
+
+
+def vanilla_discriminator(sd: Dict[str, Tensor], x: Tensor) -> Tensor:
+    """vanilla.Discriminator (vanilla.py:94-105): BlurVH, 4x [Pad(1,reflect) + conv4x4 s2 +
+    FusedLeakyReLU], full-size conv to one logit."""
+    h = blur_vh(x)
+    for i in (1, 2, 3, 4):
+        h = pad2d(h, 1, ring=True, mode="reflect")
+        h = bias_act(equal_conv2d(h, sd[f"{i}.1.module.weight"], None, 2), sd[f"{i}.2.bias"])
+    return equal_conv2d(h, sd["5.module.weight"], sd["5.module.bias"], 1)

@@ -57,3 +57,8 @@ def g_disc():
 @pytest.fixture(scope="session")
 def g_ada():
     return load_golden("ada.npz")
+
+
+@pytest.fixture(scope="session")
+def g_vanilla():
+    return load_golden("vanilla_small.npz")

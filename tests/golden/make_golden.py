@@ -321,7 +321,55 @@ def golden_ada():
          gx=npy(gx))
 
 
+V_SYN = dict(in_ch=16, ch_base=4, ch_max=16, resolution=[32, 64], ring=True)
+V1_SMALL = dict(arch="dusty_v1", synthesis_kwargs=dict(V_SYN, out_ch=[
+    dict(name="image", ch=1, act=None), dict(name="raydrop_logit", ch=1, act=None)]),
+    measurement_kwargs=dict(raydrop_const=-1, gumbel_temperature=1))
+VD_SMALL = dict(arch="vanilla", layer_kwargs=dict(in_ch=1, ring=True, ch_base=4, ch_max=16,
+                                                  resolution=[32, 64]))
+
+
+def golden_vanilla():
+    """dusty_v1 generator (vanilla synthesis + raydrop) and vanilla discriminator."""
+    seed(60)
+    G = build_generator(ref_import.to_attr(V1_SMALL)).eval()
+    D = build_discriminator(ref_import.to_attr(VD_SMALL))
+    with torch.no_grad():
+        for n, p_ in list(G.named_parameters()) + list(D.named_parameters()):
+            if "bias" in n:
+                p_.normal_(0, 0.2)
+    out = {f"sdG_{k}": npy(v).copy() for k, v in G.state_dict().items()}
+    out.update({f"sdD_{k}": npy(v).copy() for k, v in D.state_dict().items()})
+    B = 4
+    z = torch.randn(B, 16, requires_grad=True)
+    for p_ in list(G.parameters()) + list(D.parameters()):
+        p_.requires_grad_(True)
+    torch.manual_seed(61)
+    o = G(z)
+    torch.manual_seed(61)
+    u = torch.rand(B, 1, 32, 64)
+    y = D(o["image"])
+    loss = torch.nn.functional.softplus(-y).mean()
+    namesG = [n for n, _ in G.named_parameters()]
+    namesD = [n for n, _ in D.named_parameters()]
+    grads = torch.autograd.grad(loss, [z] + list(G.parameters()) + list(D.parameters()),
+                                allow_unused=True)
+    out.update(z=npy(z), u=npy(u), image=npy(o["image"]), image_orig=npy(o["image_orig"]),
+               raydrop_logit=npy(o["raydrop_logit"]), raydrop_mask=npy(o["raydrop_mask"]),
+               y=npy(y), gz=npy(grads[0]))
+    for n, g in zip(namesG, grads[1:1 + len(namesG)]):
+        if g is not None:
+            out[f"gG_{n}"] = npy(g)
+    for n, g in zip(namesD, grads[1 + len(namesG):]):
+        if g is not None:
+            out[f"gD_{n}"] = npy(g)
+    save("vanilla_small.npz", **out)
+
+
 if __name__ == "__main__":
+    if "--vanilla-only" in sys.argv:
+        golden_vanilla()
+        sys.exit(0)
     golden_ada()
     if "--ada-only" in sys.argv:
         sys.exit(0)
@@ -329,3 +377,4 @@ if __name__ == "__main__":
     golden_coords()
     golden_generator()
     golden_discriminator()
+    golden_vanilla()

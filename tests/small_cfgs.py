@@ -13,3 +13,10 @@ G_SMALL = dict(
 D_SMALL = dict(arch="dusty_v2", layer_kwargs=dict(in_ch=1, ring=True, ch_base=4, ch_max=8,
                                                   resolution=[16, 64], mbdis_group=4, mbdis_feat=1,
                                                   num_fp16_layers=-1, pre_blur=True))
+
+V_SYN = dict(in_ch=16, ch_base=4, ch_max=16, resolution=[32, 64], ring=True)
+V1_SMALL = dict(arch="dusty_v1", synthesis_kwargs=dict(V_SYN, out_ch=[
+    dict(name="image", ch=1, act=None), dict(name="raydrop_logit", ch=1, act=None)]),
+    measurement_kwargs=dict(raydrop_const=-1, gumbel_temperature=1))
+VD_SMALL = dict(arch="vanilla", layer_kwargs=dict(in_ch=1, ring=True, ch_base=4, ch_max=16,
+                                                  resolution=[32, 64]))

@@ -300,3 +300,76 @@ def test_shared_fourier_rotation_matches_literal_shift(g_gen, monkeypatch):
         close(res[True][2][n], b, rtol=1e-4, atol_rel=0)
     for n, g in res[False][1].items():
         close(res[True][1][n], g, rtol=1e-2, atol_rel=5e-3)
+
+
+def test_vanilla_and_dusty_v1_golden(g_vanilla):
+    """BASELINE config 3 architectures: dusty_v1 generator (transposed-conv synthesis + raydrop)
+    and vanilla discriminator, same state_dict as the reference, outputs and gradients."""
+    from dusty_gan_v2_b200.gans.models.builder import build_discriminator, build_generator
+    from small_cfgs import V1_SMALL, VD_SMALL
+    G, D = build_generator(V1_SMALL).eval(), build_discriminator(VD_SMALL)
+    G.load_state_dict({k[4:]: T(v) for k, v in g_vanilla.items() if k.startswith("sdG_")}, strict=True)
+    D.load_state_dict({k[4:]: T(v) for k, v in g_vanilla.items() if k.startswith("sdD_")}, strict=True)
+    G, D = G.to(DEV), D.to(DEV)
+    for p in list(G.parameters()) + list(D.parameters()):
+        p.requires_grad_(True)
+    z = T(g_vanilla["z"]).to(DEV).requires_grad_()
+    u = T(g_vanilla["u"])
+    real_rand = torch.rand
+    torch.rand = lambda *a, **k: u.to(k.get("device", "cpu"))
+    try:
+        o = G(z)
+    finally:
+        torch.rand = real_rand
+    for k in ("image_orig", "raydrop_logit"):
+        close(o[k], g_vanilla[k], rtol=1e-3, atol_rel=2e-4)
+    assert (o["raydrop_mask"].cpu().numpy() != g_vanilla["raydrop_mask"]).mean() < 2e-3
+    y = D(o["image"])
+    close(y, g_vanilla["y"], rtol=2e-3, atol_rel=1e-3)
+    loss = torch.nn.functional.softplus(-y).mean()
+    loss.backward()
+    close(z.grad, g_vanilla["gz"], rtol=5e-3, atol_rel=5e-3)
+    n = 0
+    for tag, net in (("gG_", G), ("gD_", D)):
+        for name, p in net.named_parameters():
+            if tag + name in g_vanilla:
+                close(p.grad, g_vanilla[tag + name], rtol=5e-3, atol_rel=5e-3)
+                n += 1
+    assert n >= 15
+
+
+def test_inversion_style_latent_gradient_vs_oracle(g_gen):
+    """BASELINE config 5 (gans/inversion.py usage): eval-mode G driven by per-layer styles w
+    (input_w=True), masked L1-type loss on the converted depth, gradient w.r.t. w only; plus
+    the integer valid-point count of the projected cloud."""
+    G = _build_G(g_gen).eval()
+    sd = _sd(g_gen)
+    B = 4
+    g = torch.Generator().manual_seed(17)
+    w = torch.randn(B, 10, 16, generator=g) * 0.5
+    angle = T(g_gen["angle"])
+    u = torch.rand(B, 1, 16, 64, generator=g)
+    target = torch.rand(B, 1, 16, 64, generator=g)
+    tmask = (torch.rand(B, 1, 16, 64, generator=g) < 0.8).float()
+
+    def loss_fn(out):
+        depth = (out["image_orig"] + 1) / 2                      # tanh_to_sigmoid
+        tm = tmask.to(depth.device)
+        l1 = ((depth - target.to(depth.device)).abs() * tm).sum() / tm.sum()
+        return l1 + 0.1 * torch.nn.functional.softplus(-out["raydrop_logit"] * (2 * tm - 1)).mean()
+
+    wr = w.clone().requires_grad_()
+    ref = O.generator(sd, wr, angle, u, training=False, input_w=True)
+    loss_fn(ref).backward()
+    wg = w.to(DEV).requires_grad_()
+    real_rand = torch.rand
+    torch.rand = lambda *a, **k: u.to(k.get("device", "cpu"))
+    try:
+        out = G(wg, angle=angle.to(DEV), input_w=True)
+    finally:
+        torch.rand = real_rand
+    lg = loss_fn(out)
+    lg.backward()
+    close(out["image_orig"], ref["image_orig"], rtol=1e-3, atol_rel=5e-4)
+    close(wg.grad, wr.grad, rtol=5e-3, atol_rel=5e-3)
+    assert all(p.grad is None for p in G.parameters())           # G frozen: no weight grads

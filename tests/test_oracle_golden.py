@@ -200,3 +200,35 @@ def test_ada_apply(g_ada):
     close(y, g_ada["y"], rtol=1e-4, atol=2e-5)
     (gx,) = torch.autograd.grad(y, x, T(g_ada["gy"]))
     close(gx, g_ada["gx"], rtol=1e-4, atol=2e-5)
+
+
+def test_vanilla_and_dusty_v1(g_vanilla):
+    sdG = {k[4:]: T(v).clone().requires_grad_(v.dtype.kind == "f" and "kernel" not in k and "raydrop_const" not in k and "w_avg" not in k)
+           for k, v in g_vanilla.items() if k.startswith("sdG_")}
+    sdD = {k[4:]: T(v).clone().requires_grad_("kernel" not in k) for k, v in g_vanilla.items()
+           if k.startswith("sdD_")}
+    z = T(g_vanilla["z"]).clone().requires_grad_()
+    o = O.vanilla_generator(sdG, z, T(g_vanilla["u"]))
+    for k in ("image_orig", "raydrop_logit"):
+        close(o[k], g_vanilla[k], rtol=1e-4, atol=1e-5)
+    assert np.array_equal(o["raydrop_mask"].detach().numpy(), g_vanilla["raydrop_mask"])
+    y = O.vanilla_discriminator(sdD, o["image"])
+    close(y, g_vanilla["y"], rtol=1e-4, atol=1e-5)
+    loss = O.nsgan_g(y)
+    namesG = [k for k, v in sdG.items() if v.requires_grad]
+    namesD = [k for k, v in sdD.items() if v.requires_grad]
+    grads = torch.autograd.grad(loss, [z] + [sdG[k] for k in namesG] + [sdD[k] for k in namesD],
+                                allow_unused=True)
+    close(grads[0], g_vanilla["gz"], rtol=1e-3, atol=1e-7)
+    n = 0
+    for k, g in zip(namesG, grads[1:1 + len(namesG)]):
+        if f"gG_{k}" in g_vanilla and g is not None:
+            ref = g_vanilla[f"gG_{k}"]
+            close(g, ref, rtol=2e-3, atol=1e-4 * max(np.abs(ref).max(), 1e-8))
+            n += 1
+    for k, g in zip(namesD, grads[1 + len(namesG):]):
+        if f"gD_{k}" in g_vanilla and g is not None:
+            ref = g_vanilla[f"gD_{k}"]
+            close(g, ref, rtol=2e-3, atol=1e-4 * max(np.abs(ref).max(), 1e-8))
+            n += 1
+    assert n >= 15

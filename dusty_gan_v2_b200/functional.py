@@ -327,9 +327,9 @@ class _BlurPadCL(Function):
     @staticmethod
     def forward(ctx, x, taps4, adjoint):
         B, C = x.shape[:2]
+        x = x if _is_cl(x) else x.contiguous(memory_format=_CL)     # any layout may arrive here
         if adjoint:
             H, W = x.shape[2] - 2, x.shape[3] - 2
-            x = x if _is_cl(x) else x.contiguous(memory_format=_CL)
             y = torch.empty((B, C, H, W), device=x.device, dtype=x.dtype, memory_format=_CL)
         else:
             H, W = x.shape[2:]

@@ -218,6 +218,8 @@ def kernel_rooflines(device, peaks):
         are the cross-check."""
         fn()
         torch.cuda.synchronize()
+        if os.environ.get("DUSTY_KB_ONCE"):      # one launch per kernel: for `ncu --set full`
+            return 1.0
         ts = []
         for _ in range(reps):
             flush.zero_()
@@ -278,6 +280,33 @@ def kernel_rooflines(device, peaks):
     mem_entry("pad_ring1_adjoint[64,32,66,514]bf16",
               lambda: DF._pad_raw(gp, (1, 1, 1, 1), (K.PAD_REPLICATE, K.PAD_CIRCULAR), True, (H, W)),
               (x.numel() + gp.numel()) * 2)
+    # NHWC variants (what the discriminator trunk actually runs)
+    CL = torch.channels_last
+    xc = x.contiguous(memory_format=CL)
+    mem_entry("bias_act_fwd_nhwc[64,32,64,512]bf16", lambda: DF._bias_act_raw(xc, b, None, 3, 0, 0.2, 1.41),
+              2 * x.numel() * 2)
+    yc = DF._bias_act_raw(xc, b, None, 3, 0, 0.2, 1.41)
+    gxc = torch.empty_like(xc)
+    mem_entry("bias_act_bwd_nhwc[64,32,64,512]bf16",
+              lambda: K.call("dusty_bias_act_bwd_cl", K.ptr(xc), K.ptr(yc), K.ptr(gxc), K.ptr(db), B * H * W, 32,
+                             0.2, 1.41, K.BF16, K.stream_of(xc)), 3 * x.numel() * 2)
+    mem_entry("resample_blur_nhwc[64,32,64,512]bf16", lambda: blur(xc), 2 * x.numel() * 2)
+    mem_entry("blur+pad_fused_nhwc[64,32,64,512]bf16", lambda: DF.blur_pad_cl(xc, btaps),
+              (x.numel() + B * 32 * 66 * 514) * 2)
+    gpc = gp.contiguous(memory_format=CL)
+    mem_entry("blur+pad_fused_adjoint_nhwc[64,32,66,514]bf16", lambda: DF._BlurPadCL.apply(gpc, btaps, True),
+              (x.numel() + gp.numel()) * 2)
+    mem_entry("pad_ring1_nhwc[64,32,64,512]bf16", lambda: pad(xc), (x.numel() + gp.numel()) * 2)
+    mem_entry("pad_ring1_adjoint_nhwc[64,32,66,514]bf16",
+              lambda: DF._pad_raw(gpc, (1, 1, 1, 1), (K.PAD_REPLICATE, K.PAD_CIRCULAR), True, (H, W)),
+              (x.numel() + gp.numel()) * 2)
+    del xc, yc, gxc, gpc
+    hd = torch.randn(B, 32, H, W, device=device, dtype=bf)
+    wh = (torch.randn(B, 2, 32, device=device) / 6).to(bf)
+    bh = torch.zeros(2, device=device)
+    mem_entry("heads_fwd[O=2,C=32,64x512]bf16", lambda: DF.modconv_bmm(wh, hd, None, bh, 1, 0.0, 1.0),
+              (hd.numel() + B * 2 * H * W) * 2)
+    del hd
     ang = torch.rand(B, 2, H, W, device=device)
     fr = torch.randn(256, 2, device=device)
     ph = torch.rand(256, device=device)

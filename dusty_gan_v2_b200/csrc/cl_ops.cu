@@ -154,10 +154,10 @@ struct Taps4CL { float k[4]; };
 // in the residual blocks (conv2 input): forward writes the blurred image straight into the
 // padded [H+2, W+2] tensor; the adjoint reads the padded gradient and folds the halo on load.
 template <typename T, bool ADJ, bool PAD>
-__global__ void __launch_bounds__(128)
+__global__ void __launch_bounds__(128, 8)
 blur4_cl_kernel(const T *__restrict__ x, T *__restrict__ y, Taps4CL t, int H, int W, int cv,
                 int strip, int64_t n_threads) {
-  constexpr int V = Vec16<T>::N;
+  constexpr int V = Vec8<T>::N;       // 8-byte channel groups: half the window registers
   const int Wx = (PAD && !ADJ) ? W + 2 : W;      // columns covered by threads
   const int64_t tid = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (tid >= n_threads) return;
@@ -178,20 +178,24 @@ blur4_cl_kernel(const T *__restrict__ x, T *__restrict__ y, Taps4CL t, int H, in
     int c = ADJ ? (xx + 2 - s) : (xx + s - 2);
     xc[s] = c < 0 ? c + W : (c >= W ? c - W : c);
   }
-  // gradient element (r, c) of the un-padded image = sum of the padded-gradient elements that
-  // the padding copied it to
-  auto load_folded = [&](int r, int c, float *acc, float w) {
-    const int rows[3] = {r + 1, r == 0 ? 0 : -1, r == H - 1 ? H + 1 : -1};
-    const int cols[3] = {c + 1, c == 0 ? W + 1 : -1, c == W - 1 ? 0 : -1};
+  // PAD adjoint: gradient element (r, c) of the un-padded image = sum of the padded-gradient
+  // elements the padding copied it to: column c+1, plus the opposite halo column when c is a
+  // border column; row r+1, plus the halo row when r is a border row.
+  int xe[4];                                     // extra (halo) padded column per tap, or -1
+  if (PAD && ADJ) {
 #pragma unroll
-    for (int a = 0; a < 3; ++a) {
-      if (rows[a] < 0) continue;
+    for (int s = 0; s < 4; ++s) xe[s] = xc[s] == 0 ? W + 1 : (xc[s] == W - 1 ? 0 : -1);
+  }
+  auto add_row = [&](const T *prow, float *dst) {    // one padded gradient row, 4 taps
 #pragma unroll
-      for (int e = 0; e < 3; ++e) {
-        if (cols[e] < 0) continue;
-        Vec16<T> v = ld16(img + (((int64_t)rows[a] * Wp + cols[e]) * cv + j) * V);
+    for (int s = 0; s < 4; ++s) {
+      Vec8<T> v = ld8(prow + ((int64_t)(xc[s] + 1) * cv + j) * V);
 #pragma unroll
-        for (int k = 0; k < V; ++k) acc[k] = fmaf(w, v.get(k), acc[k]);
+      for (int k = 0; k < V; ++k) dst[k] = fmaf(t.k[s], v.get(k), dst[k]);
+      if (xe[s] >= 0) {
+        Vec8<T> e = ld8(prow + ((int64_t)xe[s] * cv + j) * V);
+#pragma unroll
+        for (int k = 0; k < V; ++k) dst[k] = fmaf(t.k[s], e.get(k), dst[k]);
       }
     }
   };
@@ -208,13 +212,15 @@ blur4_cl_kernel(const T *__restrict__ x, T *__restrict__ y, Taps4CL t, int H, in
 #pragma unroll
     for (int k = 0; k < V; ++k) dst[k] = 0.f;
     if (PAD && ADJ) {
-#pragma unroll
-      for (int s = 0; s < 4; ++s) load_folded(r, xc[s], dst, t.k[s]);
+      const int64_t pitch = (int64_t)Wp * cv * V;
+      add_row(img + (int64_t)(r + 1) * pitch, dst);
+      if (r == 0) add_row(img, dst);
+      if (r == H - 1) add_row(img + (int64_t)(H + 1) * pitch, dst);
     } else {
       const T *row = img + (int64_t)r * W * cv * V;
 #pragma unroll
       for (int s = 0; s < 4; ++s) {
-        Vec16<T> v = ld16(row + ((int64_t)xc[s] * cv + j) * V);
+        Vec8<T> v = ld8(row + ((int64_t)xc[s] * cv + j) * V);
 #pragma unroll
         for (int k = 0; k < V; ++k) dst[k] = fmaf(t.k[s], v.get(k), dst[k]);
       }
@@ -227,18 +233,18 @@ blur4_cl_kernel(const T *__restrict__ x, T *__restrict__ y, Taps4CL t, int H, in
     hpass(y0 - 2, a); hpass(y0 - 1, bb); hpass(y0, c);
     for (int r = y0; r < y1; ++r) {
       hpass(r + 1, d);
-      Vec16<T> o;
+      Vec8<T> o;
 #pragma unroll
       for (int k = 0; k < V; ++k) {
         o.set(k, fmaf(t.k[3], d[k], fmaf(t.k[2], c[k], fmaf(t.k[1], bb[k], t.k[0] * a[k]))));
         a[k] = bb[k]; bb[k] = c[k]; c[k] = d[k];
       }
       if (PAD) {
-        st16(out + (((int64_t)(r + 1) * Wp + xo) * cv + j) * V, o);
-        if (r == 0) st16(out + (((int64_t)0 * Wp + xo) * cv + j) * V, o);
-        if (r == H - 1) st16(out + (((int64_t)(H + 1) * Wp + xo) * cv + j) * V, o);
+        st8(out + (((int64_t)(r + 1) * Wp + xo) * cv + j) * V, o);
+        if (r == 0) st8(out + (((int64_t)0 * Wp + xo) * cv + j) * V, o);
+        if (r == H - 1) st8(out + (((int64_t)(H + 1) * Wp + xo) * cv + j) * V, o);
       } else {
-        st16(out + (((int64_t)r * W + xx) * cv + j) * V, o);
+        st8(out + (((int64_t)r * W + xx) * cv + j) * V, o);
       }
     }
   } else {
@@ -258,10 +264,10 @@ blur4_cl_kernel(const T *__restrict__ x, T *__restrict__ y, Taps4CL t, int H, in
       const int i = e < 0 ? 0 : (e >= H ? H - 1 : e);
       const int i_next = (e + 1) < 0 ? 0 : ((e + 1) >= H ? H - 1 : (e + 1));
       if (e == e_hi || i_next != i) {
-        Vec16<T> o;
+        Vec8<T> o;
 #pragma unroll
         for (int k = 0; k < V; ++k) { o.set(k, acc[k]); acc[k] = 0.f; }
-        st16(out + (((int64_t)i * W + xx) * cv + j) * V, o);
+        st8(out + (((int64_t)i * W + xx) * cv + j) * V, o);
       }
     }
   }
@@ -379,8 +385,8 @@ extern "C" int dusty_blur4_cl(const void *x, void *y, float k0, float k1, float 
   DUSTY_CHECK_ARG(B >= 1 && H >= 2 && W >= 4, "bad shape");
   DUSTY_CHECK_ARG(pad == 0 || pad == 1, "pad must be 0 or 1");
   DUSTY_CHECK_ARG(dtype == DUSTY_F32 || dtype == DUSTY_BF16, "bad dtype");
-  const int V = dtype == DUSTY_F32 ? 4 : 8;
-  DUSTY_CHECK_ARG(C % V == 0, "C must be a multiple of the 16-byte vector width");
+  const int V = dtype == DUSTY_F32 ? 2 : 4;    // the stencil kernel works on 8-byte channel groups
+  DUSTY_CHECK_ARG(C % V == 0, "C must be a multiple of the 8-byte vector width");
   Taps4CL t;
   t.k[0] = k0; t.k[1] = k1; t.k[2] = k2; t.k[3] = k3;
   const int cv = C / V;

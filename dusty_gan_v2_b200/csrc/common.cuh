@@ -64,6 +64,36 @@ template <> struct Vec16<__nv_bfloat16> {
   }
 };
 
+// 8-byte vector of T (register-lean variant for the sliding-window stencils)
+template <typename T> struct Vec8;
+template <> struct Vec8<float> {
+  static constexpr int N = 2;
+  float2 raw;
+  __device__ __forceinline__ float get(int i) const { return i ? raw.y : raw.x; }
+  __device__ __forceinline__ void set(int i, float v) { if (i) raw.y = v; else raw.x = v; }
+};
+template <> struct Vec8<__nv_bfloat16> {
+  static constexpr int N = 4;
+  uint2 raw;
+  __device__ __forceinline__ float get(int i) const {
+    uint32_t w = (i >> 1) ? raw.y : raw.x;
+    return __uint_as_float((i & 1) ? (w & 0xffff0000u) : (w << 16));
+  }
+  __device__ __forceinline__ void set(int i, float v) {
+    uint32_t b = (uint32_t)__bfloat16_as_ushort(__float2bfloat16_rn(v));
+    uint32_t &w = (i >> 1) ? raw.y : raw.x;
+    w = (i & 1) ? ((w & 0x0000ffffu) | (b << 16)) : ((w & 0xffff0000u) | b);
+  }
+};
+template <typename T> __device__ __forceinline__ Vec8<T> ld8(const T *p) {
+  Vec8<T> v;
+  v.raw = *reinterpret_cast<const decltype(v.raw) *>(p);
+  return v;
+}
+template <typename T> __device__ __forceinline__ void st8(T *p, const Vec8<T> &v) {
+  *reinterpret_cast<decltype(v.raw) *>(p) = v.raw;
+}
+
 template <typename T> __device__ __forceinline__ Vec16<T> ld16(const T *p) {
   Vec16<T> v;
   v.raw = *reinterpret_cast<const decltype(v.raw) *>(p);

@@ -53,8 +53,13 @@ SIGNATURES = {
     "dusty_sumsq_rows": [_vp, _vp, _i64, _i64, _i, _i, _vp],
     "dusty_ema_lerp": [_vp, _vp, _vp, _f, _f, _f, _vp],
     "dusty_circular_shift": [_vp, _vp, _vp, _i, _i, _i, _i, _f, _i, _vp],
+    "dusty_conv2d_tc": [_vp, _vp, _vp, _vp] + [_i] * 9 + [_vp, _vp, _i, _i, _i]
+                       + [C.c_longlong] * 4 + [_i, _f, _f, _vp],
+    "dusty_conv2d_wgrad_tc_workspace": [_i] * 7,
+    "dusty_conv2d_wgrad_tc": [_vp, _vp, _vp, _vp, C.c_longlong] + [_i] * 11 + [_vp],
 }
-_RESTYPE = {"dusty_last_error": C.c_char_p, "dusty_launch_count": C.c_int64}
+_RESTYPE = {"dusty_last_error": C.c_char_p, "dusty_launch_count": C.c_int64,
+            "dusty_conv2d_wgrad_tc_workspace": C.c_longlong}
 
 _lib = None
 _fns = {}

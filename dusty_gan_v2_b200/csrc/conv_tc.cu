@@ -1,0 +1,604 @@
+// a11: dense 2-D convolutions of the discriminator trunk on tcgen05 (bf16 operands, fp32
+// accumulation in TMEM), NHWC activations.  Implicit GEMM without an im2col buffer: the K axis
+// of the contraction is walked as "groups" of 64-wide chunks, and every chunk is one TMA box
+// of the activation tensor at shifted coordinates.
+//
+//   y[b, oh, ow, n] = sum_g sum_k  A_g[b, oh, ow, k] * wpk[g, n, k]
+//
+// Two ways of addressing A_g (chosen by the host):
+//  * "window" (forward / wgrad of a valid convolution over an explicitly padded input): the S
+//    taps of one filter row are CONTIGUOUS in NHWC memory -- x[b, h, w:w+S, :] is a run of
+//    S*C elements -- so filter row r is ONE group with K_g = S*C "virtual channels", read
+//    through a tensor map whose pixel strides overlap the window (stride C per pixel, the
+//    convolution stride folded into the map strides).  3 groups for a 3x3 filter, each tap row
+//    read once, no zero padding needed.
+//  * "tap" (dgrad: correlation of dY with the flipped filter, zero padded): one group per
+//    filter tap, K_g = channels of dY, coordinates shifted by the tap offset; out-of-range
+//    rows/columns are zero-filled by TMA.  A strided dgrad is 4 such launches (one per output
+//    parity class) writing through strided output pointers.
+//
+// UMMA mapping (cta_group::1, kind::f16): M = 128 output pixels (TH x TW patch of one sample),
+// N = BN output channels, K = 64 per stage.  A tile = [128 pixels][64 k] K-major SW128 (what
+// the TMA box [64, TW, TH, 1] lands), B tile = wpk[g, n0:n0+BN, k0:k0+64] K-major SW128.
+// Same warp-specialised multi-tile pipeline as modconv_tc.cu (TMA warp, MMA warp, 4 epilogue
+// warps, two TMEM accumulators).  The accumulator row is a pixel and its columns are the
+// output channels, which are contiguous in NHWC: the epilogue stores 16-byte vectors straight
+// from registers (bias + leaky-ReLU optional).
+//
+// wgrad: dwp[r, m, n] = sum_{b,oh,ow} x_window_r[b, oh, ow, m] * dY[b, oh, ow, n]; M = 128
+// virtual channels (s, c) of filter row r, N = BN output channels, K = 64 pixels per stage,
+// both operands MN-major (channel-contiguous).  Split over pixel ranges; partials in a
+// caller-provided fp32 workspace, reduced by a second kernel.
+#include "tc_common.cuh"
+
+namespace dusty {
+
+namespace {
+
+constexpr int kCM = 128;                 // UMMA M
+constexpr int kCK = 64;                  // K elements per stage
+constexpr int kCABytes = kCM * kCK * 2;  // 16 KiB
+constexpr int kCThreads = 192;
+constexpr int kMaxGroups = 16;
+
+struct ConvMaps {
+  CUtensorMap a[4];
+  CUtensorMap w;
+};
+
+struct ConvParams {
+  int G, KC;                               // groups, 64-wide chunks per group
+  int amap[kMaxGroups], aw[kMaxGroups], ah[kMaxGroups];
+  int TW, TH, tiles_w, tiles_h, NT, total_tiles, tiles_per_cta;
+  int H_out, W_out, O;
+  long long y_off, y_sb, y_sh, y_sw;       // element strides of the output view
+  const float *bias;
+  __nv_bfloat16 *y;
+  int act;
+  float alpha, scale;
+};
+
+template <int BN, int STAGES>
+__global__ void __launch_bounds__(kCThreads)
+conv_fwd_tc_kernel(const __grid_constant__ ConvMaps maps, const __grid_constant__ ConvParams prm) {
+  extern __shared__ __align__(1024) uint8_t smem_raw[];
+  uint8_t *smem = (uint8_t *)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
+  constexpr int kBBytes = BN * kCK * 2;
+  constexpr int kStageBytes = kCABytes + kBBytes;
+  uint8_t *a_base = smem;
+  uint8_t *b_base = smem + STAGES * kCABytes;
+  uint64_t *full = (uint64_t *)(smem + STAGES * kStageBytes);
+  uint64_t *empty = full + STAGES;
+  uint64_t *acc_full = empty + STAGES;
+  uint64_t *acc_empty = acc_full + 2;
+  uint32_t *tmem_slot = (uint32_t *)(acc_empty + 2);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int num_kb = prm.G * prm.KC;
+  const int t_begin = blockIdx.x * prm.tiles_per_cta;
+  const int t_end = min(t_begin + prm.tiles_per_cta, prm.total_tiles);
+
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < STAGES; ++s) {
+      mbar_init(&full[s], 1);
+      mbar_init(&empty[s], 1);
+    }
+    for (int a = 0; a < 2; ++a) {
+      mbar_init(&acc_full[a], 1);
+      mbar_init(&acc_empty[a], 4);
+    }
+    fence_barrier_init();
+  }
+  if (warp == 1) tmem_alloc(tmem_slot, 2 * BN);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  // tile -> (sample, patch row, patch column, channel tile); channel tiles of a patch adjacent
+  auto decode = [&](int tile, int &b, int &oh0, int &ow0, int &n0) {
+    n0 = (tile % prm.NT) * BN;
+    int r = tile / prm.NT;
+    ow0 = (r % prm.tiles_w) * prm.TW;
+    r /= prm.tiles_w;
+    oh0 = (r % prm.tiles_h) * prm.TH;
+    b = r / prm.tiles_h;
+  };
+
+  if (warp == 0) {
+    if (lane == 0) {
+      int it = 0;
+      for (int tile = t_begin; tile < t_end; ++tile) {
+        int b, oh0, ow0, n0;
+        decode(tile, b, oh0, ow0, n0);
+        for (int g = 0; g < prm.G; ++g) {
+          const CUtensorMap *am = &maps.a[prm.amap[g]];
+          const int cw = ow0 + prm.aw[g], ch = oh0 + prm.ah[g];
+          for (int kc = 0; kc < prm.KC; ++kc, ++it) {
+            const int s = it % STAGES;
+            const uint32_t ph = (it / STAGES) & 1;
+            mbar_wait(&empty[s], ph ^ 1);
+            mbar_expect_tx(&full[s], kStageBytes);
+            tma_load_4d(a_base + s * kCABytes, am, &full[s], kc * kCK, cw, ch, b);
+            tma_load_3d(b_base + s * kBBytes, &maps.w, &full[s], kc * kCK, n0, g);
+          }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    if (lane == 0) {
+      constexpr uint32_t idesc = make_idesc(kCM, BN, false, false);
+      int it = 0, lt = 0;
+      for (int tile = t_begin; tile < t_end; ++tile, ++lt) {
+        const int a = lt & 1;
+        mbar_wait(&acc_empty[a], ((lt >> 1) & 1) ^ 1);
+        tc_fence_after();
+        const uint32_t tmem_acc = tmem_base + (uint32_t)(a * BN);
+        for (int kb = 0; kb < num_kb; ++kb, ++it) {
+          const int s = it % STAGES;
+          const uint32_t ph = (it / STAGES) & 1;
+          mbar_wait(&full[s], ph);
+          tc_fence_after();
+          const uint32_t a_addr = smem_u32(a_base + s * kCABytes);
+          const uint32_t b_addr = smem_u32(b_base + s * kBBytes);
+#pragma unroll
+          for (int k16 = 0; k16 < kCK / 16; ++k16) {
+            // K-major SW128 on both sides: 32 bytes per UMMA_K step inside the swizzle atom,
+            // SBO = next group of 8 rows (1 KiB)
+            const uint64_t adesc = make_desc(a_addr + k16 * 32, 16, 1024);
+            const uint64_t bdesc = make_desc(b_addr + k16 * 32, 16, 1024);
+            umma_bf16(tmem_acc, adesc, bdesc, idesc, (kb > 0 || k16 > 0) ? 1u : 0u);
+          }
+          umma_commit(&empty[s]);
+        }
+        umma_commit(&acc_full[a]);
+      }
+    }
+  } else {
+    const int q = warp & 3;
+    const int row = q * 32 + lane;
+    const int th = row / prm.TW, tw = row % prm.TW;
+    int lt = 0;
+    for (int tile = t_begin; tile < t_end; ++tile, ++lt) {
+      int b, oh0, ow0, n0;
+      decode(tile, b, oh0, ow0, n0);
+      const int a = lt & 1;
+      mbar_wait(&acc_full[a], (lt >> 1) & 1);
+      tc_fence_after();
+      const uint32_t tmem_acc = tmem_base + (uint32_t)(a * BN) + ((uint32_t)(q * 32) << 16);
+      const int oh = oh0 + th, ow = ow0 + tw;
+      const bool pix_ok = oh < prm.H_out && ow < prm.W_out;
+      __nv_bfloat16 *yp = prm.y + prm.y_off + (long long)b * prm.y_sb + (long long)oh * prm.y_sh +
+                          (long long)ow * prm.y_sw + n0;
+#pragma unroll 1
+      for (int c = 0; c < BN; c += 16) {
+        uint32_t r[16];
+        tmem_ld16(tmem_acc + (uint32_t)c, r);
+        tmem_ld_wait();
+        if (c + 16 >= BN) {
+          tc_fence_before();
+          __syncwarp();
+          if (lane == 0) mbar_arrive(&acc_empty[a]);
+        }
+        if (pix_ok) {
+#pragma unroll
+          for (int h8 = 0; h8 < 2; ++h8) {
+            const int o = n0 + c + h8 * 8;
+            if (o < prm.O) {
+              uint32_t pk[4];
+#pragma unroll
+              for (int j = 0; j < 4; ++j) {
+                float v0 = __uint_as_float(r[h8 * 8 + 2 * j]);
+                float v1 = __uint_as_float(r[h8 * 8 + 2 * j + 1]);
+                if (prm.bias) {
+                  v0 += __ldg(prm.bias + o + 2 * j);
+                  v1 += __ldg(prm.bias + o + 2 * j + 1);
+                }
+                if (prm.act == 3) {
+                  v0 = v0 > 0.f ? v0 : v0 * prm.alpha;
+                  v1 = v1 > 0.f ? v1 : v1 * prm.alpha;
+                }
+                const uint32_t lo = __bfloat16_as_ushort(__float2bfloat16_rn(v0 * prm.scale));
+                const uint32_t hi = __bfloat16_as_ushort(__float2bfloat16_rn(v1 * prm.scale));
+                pk[j] = lo | (hi << 16);
+              }
+              *reinterpret_cast<uint4 *>(yp + c + h8 * 8) = make_uint4(pk[0], pk[1], pk[2], pk[3]);
+            }
+          }
+        }
+      }
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, 2 * BN);
+  }
+}
+
+// ------------------------------------------------------------------ wgrad
+struct WgMaps {
+  CUtensorMap a[4];    // x window of filter row r
+  CUtensorMap g;       // dY
+};
+
+struct WgParams {
+  int tiles_w, tiles_h, TW, TH;   // 64-pixel patches
+  int total_pb, pb_per_split;
+  int MT, NT;                     // 128-wide virtual-channel tiles, BN-wide out-channel tiles
+  int SC, O;                      // S*C, out channels
+  float *out;                     // [splits][R][SC][O]
+  long long split_stride;
+};
+
+template <int BN, int STAGES>
+__global__ void __launch_bounds__(kCThreads)
+conv_wgrad_tc_kernel(const __grid_constant__ WgMaps maps, const __grid_constant__ WgParams prm) {
+  extern __shared__ __align__(1024) uint8_t smem_raw[];
+  uint8_t *smem = (uint8_t *)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
+  constexpr int kBBytes = BN * kCK * 2;
+  constexpr int kStageBytes = kCABytes + kBBytes;
+  uint8_t *a_base = smem;
+  uint8_t *b_base = smem + STAGES * kCABytes;
+  uint64_t *full = (uint64_t *)(smem + STAGES * kStageBytes);
+  uint64_t *empty = full + STAGES;
+  uint64_t *acc_full = empty + STAGES;
+  uint32_t *tmem_slot = (uint32_t *)(acc_full + 1);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int split = blockIdx.x;
+  const int m0 = (blockIdx.y % prm.MT) * kCM;
+  const int n0 = (blockIdx.y / prm.MT) * BN;
+  const int r = blockIdx.z;
+  const int pb_begin = split * prm.pb_per_split;
+  const int pb_end = min(pb_begin + prm.pb_per_split, prm.total_pb);
+
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < STAGES; ++s) {
+      mbar_init(&full[s], 1);
+      mbar_init(&empty[s], 1);
+    }
+    mbar_init(acc_full, 1);
+    fence_barrier_init();
+  }
+  if (warp == 1) tmem_alloc(tmem_slot, BN < 32 ? 32 : BN);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_acc = *tmem_slot;
+
+  if (warp == 0) {
+    if (lane == 0) {
+      const CUtensorMap *am = &maps.a[r];
+      for (int pb = pb_begin, it = 0; pb < pb_end; ++pb, ++it) {
+        const int s = it % STAGES;
+        const uint32_t ph = (it / STAGES) & 1;
+        int t = pb;
+        const int ow0 = (t % prm.tiles_w) * prm.TW;
+        t /= prm.tiles_w;
+        const int oh0 = (t % prm.tiles_h) * prm.TH;
+        const int b = t / prm.tiles_h;
+        mbar_wait(&empty[s], ph ^ 1);
+        mbar_expect_tx(&full[s], kStageBytes);
+        uint8_t *a_dst = a_base + s * kCABytes;
+        tma_load_4d(a_dst, am, &full[s], m0, ow0, oh0, b);
+        tma_load_4d(a_dst + 8192, am, &full[s], m0 + 64, ow0, oh0, b);
+#pragma unroll
+        for (int j = 0; j < BN / 64; ++j)
+          tma_load_4d(b_base + s * kBBytes + j * 8192, &maps.g, &full[s], n0 + 64 * j, ow0, oh0, b);
+      }
+    }
+  } else if (warp == 1) {
+    if (lane == 0) {
+      constexpr uint32_t idesc = make_idesc(kCM, BN, true, true);
+      for (int pb = pb_begin, it = 0; pb < pb_end; ++pb, ++it) {
+        const int s = it % STAGES;
+        const uint32_t ph = (it / STAGES) & 1;
+        mbar_wait(&full[s], ph);
+        tc_fence_after();
+        const uint32_t a_addr = smem_u32(a_base + s * kCABytes);
+        const uint32_t b_addr = smem_u32(b_base + s * kBBytes);
+#pragma unroll
+        for (int k16 = 0; k16 < kCK / 16; ++k16) {
+          // MN-major SW128: 16 pixel rows = 2 KiB per UMMA_K step; LBO = next 64-channel
+          // block (8 KiB), SBO = next group of 8 pixel rows (1 KiB)
+          const uint64_t adesc = make_desc(a_addr + k16 * 2048, 8192, 1024);
+          const uint64_t bdesc = make_desc(b_addr + k16 * 2048, 8192, 1024);
+          umma_bf16(tmem_acc, adesc, bdesc, idesc, (it > 0 || k16 > 0) ? 1u : 0u);
+        }
+        umma_commit(&empty[s]);
+      }
+      umma_commit(acc_full);
+    }
+  } else {
+    const int q = warp & 3;
+    const int m = m0 + q * 32 + lane;
+    mbar_wait(acc_full, 0);
+    tc_fence_after();
+    float *op = prm.out + (long long)split * prm.split_stride +
+                ((long long)r * prm.SC + m) * prm.O + n0;
+    const bool have = pb_end > pb_begin;
+#pragma unroll 1
+    for (int c = 0; c < BN; c += 16) {
+      uint32_t v[16];
+      tmem_ld16(tmem_acc + ((uint32_t)(q * 32) << 16) + (uint32_t)c, v);
+      tmem_ld_wait();
+      if (m < prm.SC) {
+#pragma unroll
+        for (int j4 = 0; j4 < 4; ++j4) {
+          if (n0 + c + j4 * 4 < prm.O) {
+            float4 o4;
+            o4.x = have ? __uint_as_float(v[j4 * 4 + 0]) : 0.f;
+            o4.y = have ? __uint_as_float(v[j4 * 4 + 1]) : 0.f;
+            o4.z = have ? __uint_as_float(v[j4 * 4 + 2]) : 0.f;
+            o4.w = have ? __uint_as_float(v[j4 * 4 + 3]) : 0.f;
+            *reinterpret_cast<float4 *>(op + c + j4 * 4) = o4;
+          }
+        }
+      }
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    tmem_dealloc(tmem_acc, BN < 32 ? 32 : BN);
+  }
+}
+
+__global__ void wgrad_reduce_kernel(const float *__restrict__ ws, float *__restrict__ out,
+                                    long long n4, int splits, long long split_stride4) {
+  const float4 *w4 = reinterpret_cast<const float4 *>(ws);
+  float4 *o4 = reinterpret_cast<float4 *>(out);
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n4;
+       i += (long long)gridDim.x * blockDim.x) {
+    float4 acc = w4[i];
+    for (int s = 1; s < splits; ++s) {
+      const float4 v = w4[i + s * split_stride4];
+      acc.x += v.x; acc.y += v.y; acc.z += v.z; acc.w += v.w;
+    }
+    o4[i] = acc;
+  }
+}
+
+// 4-D bf16 tensor map, 128-byte swizzle, zero fill out of range
+bool make_map4(CUtensorMap *m, const void *ptr, const uint64_t dims[4], const uint64_t strides_b[3],
+               const uint32_t box[4]) {
+  EncodeTiledFn enc = get_encode();
+  if (!enc) return false;
+  cuuint64_t d[4] = {dims[0], dims[1], dims[2], dims[3]};
+  cuuint64_t s[3] = {strides_b[0], strides_b[1], strides_b[2]};
+  cuuint32_t bx[4] = {box[0], box[1], box[2], box[3]};
+  cuuint32_t es[4] = {1, 1, 1, 1};
+  return enc(m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, const_cast<void *>(ptr), d, s, bx, es,
+             CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
+             CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
+}
+
+bool make_map3w(CUtensorMap *m, const void *ptr, uint64_t d0, uint64_t d1, uint64_t d2,
+                uint32_t box0, uint32_t box1) {
+  EncodeTiledFn enc = get_encode();
+  if (!enc) return false;
+  cuuint64_t dims[3] = {d0, d1, d2};
+  cuuint64_t strides[2] = {d0 * 2, d0 * d1 * 2};
+  cuuint32_t box[3] = {box0, box1, 1};
+  cuuint32_t estr[3] = {1, 1, 1};
+  return enc(m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 3, const_cast<void *>(ptr), dims, strides, box,
+             estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
+             CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
+}
+
+template <int BN, int STAGES>
+constexpr int conv_smem_bytes() {
+  return STAGES * (kCABytes + BN * kCK * 2) + 128 + 1024;
+}
+
+template <int BN, int STAGES>
+int launch_conv(const ConvMaps &maps, ConvParams prm, cudaStream_t st) {
+  constexpr int smem = conv_smem_bytes<BN, STAGES>();
+  static bool configured = false;
+  if (int rc = set_smem(conv_fwd_tc_kernel<BN, STAGES>, smem, &configured)) return rc;
+  const int resident = num_sms() * ((2 * smem <= 225 * 1024 && 2 * BN * 2 <= 512) ? 2 : 1);
+  int ctas = prm.total_tiles < resident ? prm.total_tiles : resident;
+  prm.tiles_per_cta = (prm.total_tiles + ctas - 1) / ctas;
+  ctas = (prm.total_tiles + prm.tiles_per_cta - 1) / prm.tiles_per_cta;
+  conv_fwd_tc_kernel<BN, STAGES><<<ctas, kCThreads, smem, st>>>(maps, prm);
+  return 0;
+}
+
+template <int BN, int STAGES>
+int launch_wgrad(const WgMaps &maps, const WgParams &prm, int splits, int R, cudaStream_t st) {
+  constexpr int smem = conv_smem_bytes<BN, STAGES>();
+  static bool configured = false;
+  if (int rc = set_smem(conv_wgrad_tc_kernel<BN, STAGES>, smem, &configured)) return rc;
+  dim3 grid((unsigned)splits, (unsigned)(prm.MT * prm.NT), (unsigned)R);
+  conv_wgrad_tc_kernel<BN, STAGES><<<grid, kCThreads, smem, st>>>(maps, prm);
+  return 0;
+}
+
+// pixel patch of `n` pixels (n = 128 or 64): widest power-of-two row segment with the least
+// padding waste over a W x H output
+void pick_patch(int W, int H, int n, int *TW, int *TH) {
+  long long best = -1;
+  for (int tw = n; tw >= 1; tw >>= 1) {
+    const int th = n / tw;
+    const long long cover = (long long)((W + tw - 1) / tw) * tw * ((H + th - 1) / th) * th;
+    if (best < 0 || cover < best) {
+      best = cover;
+      *TW = tw;
+      *TH = th;
+    }
+  }
+}
+
+}  // namespace
+
+}  // namespace dusty
+
+using namespace dusty;
+
+extern "C" int dusty_conv2d_tc(const void *x, const void *wpk, const float *bias, void *y, int B,
+                               int H_in, int W_in, int C, int H_out, int W_out, int O, int mode,
+                               int G, const int *tap_dh, const int *tap_dw, int S, int stride_h,
+                               int stride_w, long long y_off, long long y_sb, long long y_sh,
+                               long long y_sw, int act, float alpha, float scale, void *stream) {
+  DUSTY_CHECK_ARG(x && wpk && y, "null pointer");
+  DUSTY_CHECK_ARG(get_encode() != nullptr, "cuTensorMapEncodeTiled unavailable");
+  DUSTY_CHECK_ARG(B > 0 && H_in > 0 && W_in > 0 && H_out > 0 && W_out > 0, "empty tensor");
+  DUSTY_CHECK_ARG(C % 8 == 0 && O % 8 == 0, "channel counts must be multiples of 8");
+  DUSTY_CHECK_ARG(G >= 1 && G <= kMaxGroups, "1..16 groups");
+  DUSTY_CHECK_ARG(mode == 0 || mode == 1, "mode: 0 = tap, 1 = window");
+  DUSTY_CHECK_ARG(mode == 1 ? (G <= 4 && S >= 1) : (stride_h == 1 && stride_w == 1),
+                  "window mode: at most 4 filter rows; tap mode: unit stride");
+  DUSTY_CHECK_ARG(aligned16(x) && aligned16(wpk) && aligned16(y), "16-byte alignment");
+  DUSTY_CHECK_ARG((y_off % 8 == 0) && (y_sb % 8 == 0) && (y_sh % 8 == 0) && (y_sw % 8 == 0),
+                  "output strides must keep 16-byte alignment");
+  cudaStream_t st = (cudaStream_t)stream;
+  const int Kg = mode == 1 ? S * C : C;
+  ConvMaps maps;
+  ConvParams prm;
+  prm.G = G;
+  prm.KC = (Kg + kCK - 1) / kCK;
+  pick_patch(W_out, H_out, kCM, &prm.TW, &prm.TH);
+  const uint32_t box[4] = {(uint32_t)kCK, (uint32_t)prm.TW, (uint32_t)prm.TH, 1u};
+  const __nv_bfloat16 *xb = (const __nv_bfloat16 *)x;
+  bool ok = true;
+  if (mode == 1) {
+    for (int g = 0; g < G; ++g) {
+      const int dh = tap_dh[g], dw = tap_dw[g];
+      DUSTY_CHECK_ARG(dh >= 0 && dw >= 0 && (long long)(H_out - 1) * stride_h + dh < H_in &&
+                          (long long)(W_out - 1) * stride_w + dw + S <= W_in,
+                      "window outside the input");
+      const uint64_t dims[4] = {(uint64_t)Kg, (uint64_t)W_out, (uint64_t)H_out, (uint64_t)B};
+      const uint64_t strides[3] = {(uint64_t)stride_w * C * 2, (uint64_t)stride_h * W_in * C * 2,
+                                   (uint64_t)H_in * W_in * C * 2};
+      ok = ok && make_map4(&maps.a[g], xb + ((long long)dh * W_in + dw) * C, dims, strides, box);
+      prm.amap[g] = g; prm.aw[g] = 0; prm.ah[g] = 0;
+    }
+    for (int g = G; g < 4; ++g) maps.a[g] = maps.a[0];
+  } else {
+    const uint64_t dims[4] = {(uint64_t)C, (uint64_t)W_in, (uint64_t)H_in, (uint64_t)B};
+    const uint64_t strides[3] = {(uint64_t)C * 2, (uint64_t)W_in * C * 2, (uint64_t)H_in * W_in * C * 2};
+    ok = make_map4(&maps.a[0], xb, dims, strides, box);
+    for (int g = 1; g < 4; ++g) maps.a[g] = maps.a[0];
+    for (int g = 0; g < G; ++g) { prm.amap[g] = 0; prm.aw[g] = tap_dw[g]; prm.ah[g] = tap_dh[g]; }
+  }
+  for (int g = G; g < kMaxGroups; ++g) { prm.amap[g] = 0; prm.aw[g] = 0; prm.ah[g] = 0; }
+  const int BN = O > 128 ? 256 : (O > 64 ? 128 : (O > 32 ? 64 : 32));
+  ok = ok && make_map3w(&maps.w, wpk, (uint64_t)Kg, (uint64_t)O, (uint64_t)G, kCK, (uint32_t)BN);
+  if (!ok) {
+    set_error("dusty_conv2d_tc: cuTensorMapEncodeTiled failed");
+    return DUSTY_ECUDA;
+  }
+  prm.tiles_w = (W_out + prm.TW - 1) / prm.TW;
+  prm.tiles_h = (H_out + prm.TH - 1) / prm.TH;
+  prm.NT = (O + BN - 1) / BN;
+  const long long total = (long long)prm.tiles_w * prm.tiles_h * prm.NT * B;
+  DUSTY_CHECK_ARG(total <= 0x7fffffff, "too many tiles");
+  prm.total_tiles = (int)total;
+  prm.H_out = H_out; prm.W_out = W_out; prm.O = O;
+  prm.y_off = y_off; prm.y_sb = y_sb; prm.y_sh = y_sh; prm.y_sw = y_sw;
+  prm.bias = bias; prm.y = (__nv_bfloat16 *)y; prm.act = act; prm.alpha = alpha; prm.scale = scale;
+  int rc;
+  switch (BN) {
+    case 256: rc = launch_conv<256, 4>(maps, prm, st); break;
+    case 128: rc = launch_conv<128, 5>(maps, prm, st); break;
+    case 64: rc = launch_conv<64, 4>(maps, prm, st); break;
+    default: rc = launch_conv<32, 4>(maps, prm, st); break;
+  }
+  if (rc) return rc;
+  DUSTY_LAUNCH_CHECK();
+  return DUSTY_OK;
+}
+
+static int wgrad_splits(int B, int H_out, int W_out, int C, int O, int R, int S) {
+  int TW, TH;
+  pick_patch(W_out, H_out, kCK, &TW, &TH);
+  const long long total_pb = (long long)((W_out + TW - 1) / TW) * ((H_out + TH - 1) / TH) * B;
+  const int BN = O > 128 ? 256 : (O > 64 ? 128 : 64);
+  const int tile_ctas = ((S * C + kCM - 1) / kCM) * ((O + BN - 1) / BN) * R;
+  long long splits = (2 * num_sms() + tile_ctas - 1) / tile_ctas;
+  if (splits > total_pb) splits = total_pb;
+  return splits < 1 ? 1 : (int)splits;
+}
+
+extern "C" long long dusty_conv2d_wgrad_tc_workspace(int B, int H_out, int W_out, int C, int O,
+                                                     int R, int S) {
+  const int splits = wgrad_splits(B, H_out, W_out, C, O, R, S);
+  return splits > 1 ? (long long)R * S * C * O * splits : 0;
+}
+
+extern "C" int dusty_conv2d_wgrad_tc(const void *x, const void *dy, float *dwp, float *ws,
+                                     long long ws_elems, int B, int H_in, int W_in, int C,
+                                     int H_out, int W_out, int O, int R, int S, int stride_h,
+                                     int stride_w, void *stream) {
+  DUSTY_CHECK_ARG(x && dy && dwp, "null pointer");
+  DUSTY_CHECK_ARG(get_encode() != nullptr, "cuTensorMapEncodeTiled unavailable");
+  DUSTY_CHECK_ARG(C % 8 == 0 && O % 8 == 0, "channel counts must be multiples of 8");
+  DUSTY_CHECK_ARG(R >= 1 && R <= 4 && S >= 1, "1..4 filter rows");
+  DUSTY_CHECK_ARG((long long)(H_out - 1) * stride_h + R <= H_in &&
+                      (long long)(W_out - 1) * stride_w + S <= W_in,
+                  "window outside the input");
+  DUSTY_CHECK_ARG(aligned16(x) && aligned16(dy) && aligned16(dwp), "16-byte alignment");
+  cudaStream_t st = (cudaStream_t)stream;
+  const int SC = S * C;
+  WgMaps maps;
+  WgParams prm;
+  pick_patch(W_out, H_out, kCK, &prm.TW, &prm.TH);
+  const uint32_t box[4] = {64u, (uint32_t)prm.TW, (uint32_t)prm.TH, 1u};
+  const __nv_bfloat16 *xb = (const __nv_bfloat16 *)x;
+  bool ok = true;
+  for (int r = 0; r < R; ++r) {
+    const uint64_t dims[4] = {(uint64_t)SC, (uint64_t)W_out, (uint64_t)H_out, (uint64_t)B};
+    const uint64_t strides[3] = {(uint64_t)stride_w * C * 2, (uint64_t)stride_h * W_in * C * 2,
+                                 (uint64_t)H_in * W_in * C * 2};
+    ok = ok && make_map4(&maps.a[r], xb + (long long)r * W_in * C, dims, strides, box);
+  }
+  for (int r = R; r < 4; ++r) maps.a[r] = maps.a[0];
+  {
+    const uint64_t dims[4] = {(uint64_t)O, (uint64_t)W_out, (uint64_t)H_out, (uint64_t)B};
+    const uint64_t strides[3] = {(uint64_t)O * 2, (uint64_t)W_out * O * 2, (uint64_t)H_out * W_out * O * 2};
+    ok = ok && make_map4(&maps.g, dy, dims, strides, box);
+  }
+  if (!ok) {
+    set_error("dusty_conv2d_wgrad_tc: cuTensorMapEncodeTiled failed");
+    return DUSTY_ECUDA;
+  }
+  const int BN = O > 128 ? 256 : (O > 64 ? 128 : 64);
+  prm.tiles_w = (W_out + prm.TW - 1) / prm.TW;
+  prm.tiles_h = (H_out + prm.TH - 1) / prm.TH;
+  const long long total_pb = (long long)prm.tiles_w * prm.tiles_h * B;
+  DUSTY_CHECK_ARG(total_pb <= 0x7fffffff, "too many pixel blocks");
+  prm.total_pb = (int)total_pb;
+  prm.MT = (SC + kCM - 1) / kCM;
+  prm.NT = (O + BN - 1) / BN;
+  prm.SC = SC; prm.O = O;
+  const long long n = (long long)R * SC * O;
+  int splits = wgrad_splits(B, H_out, W_out, C, O, R, S);
+  if (splits > 1 && (ws == nullptr || ws_elems < n * splits)) {
+    // shrink to what the workspace holds
+    splits = ws ? (int)(ws_elems / n) : 1;
+    if (splits < 1) splits = 1;
+  }
+  prm.pb_per_split = (prm.total_pb + splits - 1) / splits;
+  splits = (prm.total_pb + prm.pb_per_split - 1) / prm.pb_per_split;
+  prm.out = splits > 1 ? ws : dwp;
+  prm.split_stride = n;
+  int rc;
+  switch (BN) {
+    case 256: rc = launch_wgrad<256, 4>(maps, prm, splits, R, st); break;
+    case 128: rc = launch_wgrad<128, 4>(maps, prm, splits, R, st); break;
+    default: rc = launch_wgrad<64, 4>(maps, prm, splits, R, st); break;
+  }
+  if (rc) return rc;
+  DUSTY_LAUNCH_CHECK();
+  if (splits > 1) {
+    const long long n4 = n / 4;
+    int blocks = (int)((n4 + 255) / 256);
+    if (blocks > 8 * num_sms()) blocks = 8 * num_sms();
+    wgrad_reduce_kernel<<<blocks, 256, 0, st>>>(ws, dwp, n4, splits, n / 4);
+    DUSTY_LAUNCH_CHECK();
+  }
+  return DUSTY_OK;
+}

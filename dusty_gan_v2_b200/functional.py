@@ -865,3 +865,106 @@ def circular_unshift(v, shift01, scale: float = 1.0):
     """v [B,C,H,W] fp32, shift01 [B] fp32 in [0,1) (fraction of a full turn)."""
     K.require_cuda(v, shift01)
     return _CircShift.apply(v, _contig(shift01.detach().float()), float(scale), 0)
+
+
+# ---- a11: dense NHWC convolutions on tcgen05 (conv_tc.cu) --------------------------------
+_CONV_IMPL = {"mode": "auto"}      # "auto": own kernels where the shape qualifies; "library": cuDNN
+
+
+def set_conv_impl(mode: str):
+    """'auto' (tcgen05 kernels for bf16 NHWC shapes that qualify) or 'library' (cuDNN)."""
+    if mode not in ("auto", "library"):
+        raise ValueError(mode)
+    _CONV_IMPL["mode"] = mode
+
+
+def conv_tc_supported(x: torch.Tensor, w: torch.Tensor, stride) -> bool:
+    """bf16 NHWC activations, channel counts multiples of 8 (16-byte TMA strides), filters of at
+    most 4x4 taps, strides 1 or 2."""
+    if _CONV_IMPL["mode"] != "auto" or not x.is_cuda or x.dim() != 4:
+        return False
+    if x.dtype != torch.bfloat16 or w.dtype != torch.bfloat16:
+        return False
+    O, C, R, S = w.shape
+    if C != x.shape[1] or C % 8 or O % 8 or C < 16 or R > 4 or S > 4:
+        return False
+    if stride[0] not in (1, 2) or stride[1] not in (1, 2):
+        return False
+    return x.shape[2] >= R and x.shape[3] >= S
+
+
+def _nhwc(x: torch.Tensor) -> torch.Tensor:
+    return x.contiguous(memory_format=torch.channels_last)
+
+
+def _ints(vals):
+    return (K.C.c_int * len(vals))(*vals)
+
+
+def conv2d_fprop_tc(x, w, stride, bias=None, act: int = 1, alpha: float = 0.2, scale: float = 1.0):
+    """y = conv2d(x, w, stride) (valid, no padding) [+ bias, leaky-ReLU, scale]; NHWC in/out."""
+    K.require_cuda(x, w)
+    x = _nhwc(x)
+    B, C, H, W = x.shape
+    O, _, R, S = w.shape
+    sh, sw = stride
+    Ho, Wo = (H - R) // sh + 1, (W - S) // sw + 1
+    wpk = w.permute(2, 0, 3, 1).reshape(R, O, S * C).contiguous()
+    y = torch.empty((B, O, Ho, Wo), dtype=x.dtype, device=x.device,
+                    memory_format=torch.channels_last)
+    K.call("dusty_conv2d_tc", K.ptr(x), K.ptr(wpk), K.ptr(bias), K.ptr(y),
+               B, H, W, C, Ho, Wo, O, 1, R, _ints(list(range(R))), _ints([0] * R), S, sh, sw,
+               0, Ho * Wo * O, Wo * O, O, act, alpha, scale, K.stream_of(x))
+    return y
+
+
+def conv2d_dgrad_tc(gy, w, stride, in_hw):
+    """Gradient of the valid convolution w.r.t. its input ([B, C, H, W] NHWC)."""
+    K.require_cuda(gy, w)
+    gy = _nhwc(gy)
+    B, O, Ho, Wo = gy.shape
+    _, C, R, S = w.shape
+    H, W = in_hw
+    sh, sw = stride
+    wt = w.permute(2, 3, 1, 0)                       # [R, S, C, O]
+    classes = []
+    for ph in range(sh):
+        rs = [r for r in range(R) if r % sh == ph]
+        for pw in range(sw):
+            ss = [s for s in range(S) if s % sw == pw]
+            classes.append((ph, pw, rs, ss))
+    full = all(rs and ss for _, _, rs, ss in classes)
+    alloc = torch.empty if full else torch.zeros
+    gx = alloc((B, C, H, W), dtype=gy.dtype, device=gy.device, memory_format=torch.channels_last)
+    st = K.stream_of(gy)
+    for ph, pw, rs, ss in classes:
+        if not (rs and ss):
+            continue
+        Hc, Wc = (H - ph + sh - 1) // sh, (W - pw + sw - 1) // sw
+        if Hc <= 0 or Wc <= 0:
+            continue
+        taps = [(r, s) for r in rs for s in ss]
+        wpk = torch.stack([wt[r, s] for r, s in taps]).contiguous() if len(taps) != R * S \
+            else wt.reshape(R * S, C, O).contiguous()
+        dh = [(ph - r) // sh for r, _ in taps]
+        dw = [(pw - s) // sw for _, s in taps]
+        K.call("dusty_conv2d_tc", K.ptr(gy), K.ptr(wpk), None, K.ptr(gx),
+                   B, Ho, Wo, O, Hc, Wc, C, 0, len(taps), _ints(dh), _ints(dw), 1, 1, 1,
+                   (ph * W + pw) * C, H * W * C, sh * W * C, sw * C, 1, 0.0, 1.0, st)
+    return gx
+
+
+def conv2d_wgrad_tc(gy, x, stride, w_shape, out_dtype):
+    """Gradient of the valid convolution w.r.t. its filter ([O, C, R, S], contiguous)."""
+    K.require_cuda(gy, x)
+    gy, x = _nhwc(gy), _nhwc(x)
+    B, C, H, W = x.shape
+    O, _, R, S = w_shape
+    _, _, Ho, Wo = gy.shape
+    sh, sw = stride
+    n_ws = int(K.load().dusty_conv2d_wgrad_tc_workspace(B, Ho, Wo, C, O, R, S))
+    ws = torch.empty(max(n_ws, 1), dtype=torch.float32, device=x.device)
+    dwp = torch.empty((R, S, C, O), dtype=torch.float32, device=x.device)
+    K.call("dusty_conv2d_wgrad_tc", K.ptr(x), K.ptr(gy), K.ptr(dwp), K.ptr(ws),
+               n_ws, B, H, W, C, Ho, Wo, O, R, S, sh, sw, K.stream_of(x))
+    return dwp.permute(3, 2, 0, 1).to(out_dtype).contiguous()

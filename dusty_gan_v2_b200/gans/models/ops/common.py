@@ -146,11 +146,22 @@ class BlurVH(nn.Module):
 
 
 # ---- dense convolution with an explicit first / second order ------------------------------
-# The library call itself is cuDNN (interim); what is ours is the autograd
-# wiring: PyTorch's generic convolution double-backward falls onto slow grouped / SIMT conv
+# bf16 NHWC shapes run on our tcgen05 implicit-GEMM kernels (conv_tc.cu: fprop / dgrad /
+# wgrad); fp32 (parity mode), NCHW and odd channel counts stay library calls.  The autograd
+# wiring is ours either way: PyTorch's generic convolution double-backward falls onto slow grouped / SIMT conv
 # formulations (~100 ms per R1 step at B=64), whereas conv is bilinear in (x, w) so every
 # derivative of every order is again one of fprop / dgrad / wgrad.
+def _conv_fprop(x, w, stride):
+    if DF.conv_tc_supported(x, w, stride):
+        return DF.conv2d_fprop_tc(x, w, stride)
+    return F.conv2d(x, w, None, stride)
+
+
 def _conv_grads(gy, x, w, stride, need_x, need_w):
+    if DF.conv_tc_supported(x, w, stride) and gy.dtype == x.dtype:
+        gx = DF.conv2d_dgrad_tc(gy, w, stride, x.shape[2:]) if need_x else None
+        gw = DF.conv2d_wgrad_tc(gy, x, stride, w.shape, w.dtype) if need_w else None
+        return gx, gw
     gx, gw, _ = torch.ops.aten.convolution_backward(
         gy, x, w, None, stride, (0, 0), (1, 1), False, (0, 0), 1, (need_x, need_w, False))
     return gx, gw
@@ -161,7 +172,7 @@ class _Conv2dFn(torch.autograd.Function):
     def forward(ctx, x, w, stride):
         ctx.save_for_backward(x, w)
         ctx.stride = stride
-        return F.conv2d(x, w, None, stride)
+        return _conv_fprop(x, w, stride)
 
     @staticmethod
     def backward(ctx, gy):

@@ -244,6 +244,36 @@ int dusty_ema_lerp(float *ema_var, const float *sum_a, const float *sum_b, float
 int dusty_circular_shift(const float *v, const float *shift01, float *out, int B, int C, int H,
                          int W, float scale, int adjoint, void *stream);
 
+/* ---- a11: dense convolutions of the discriminator trunk (tcgen05, NHWC bf16) ---------------
+ * Replaces F.conv2d / cuDNN behind Conv2d + EqualLR, gans/models/ops/common.py:187-210, for
+ * the ResidualBlock convolutions gans/models/dusty_v2.py:347-396 (SURVEY 8b dusty_conv2d_*).
+ *
+ * dusty_conv2d_tc is the implicit-GEMM primitive
+ *   y[b,oh,ow,n] = act(sum_g sum_k A_g[b,oh,ow,k] * wpk[g,n,k] + bias[n]) * scale
+ * x is [B,H_in,W_in,C] (NHWC), y is written through the element strides (y_off,y_sb,y_sh,y_sw)
+ * with n contiguous; wpk is [G][O][K_g] bf16.
+ *   mode 1 ("window", valid conv fprop): G filter rows; group g reads the S*C contiguous
+ *     elements starting at x[b, oh*stride_h + tap_dh[g], ow*stride_w + tap_dw[g], 0]
+ *     (K_g = S*C, wpk[g][n][s*C+c] = w[n][c][g][s]).
+ *   mode 0 ("tap", dgrad): G taps; group g reads x[b, oh + tap_dh[g], ow + tap_dw[g], :]
+ *     (K_g = C), rows / columns outside x contribute zero; unit stride only -- a strided
+ *     dgrad is one call per output parity class with y_sh / y_sw doubled.
+ * tap_dh / tap_dw are HOST arrays of G ints.  bias may be NULL; act: 1 linear, 3 leaky-ReLU. */
+int dusty_conv2d_tc(const void *x, const void *wpk, const float *bias, void *y, int B, int H_in,
+                    int W_in, int C, int H_out, int W_out, int O, int mode, int G,
+                    const int *tap_dh, const int *tap_dw, int S, int stride_h, int stride_w,
+                    long long y_off, long long y_sb, long long y_sh, long long y_sw, int act,
+                    float alpha, float scale, void *stream);
+
+/* Filter gradient of the valid convolution above:
+ *   dwp[r][s*C+c][n] = sum_{b,oh,ow} x[b, oh*stride_h + r, ow*stride_w + s, c] * dy[b,oh,ow,n]
+ * fp32 output [R][S*C][O].  ws: caller-owned fp32 workspace of at least
+ * dusty_conv2d_wgrad_tc_workspace(...) elements (split-K partials; may be NULL if that is 0). */
+long long dusty_conv2d_wgrad_tc_workspace(int B, int H_out, int W_out, int C, int O, int R, int S);
+int dusty_conv2d_wgrad_tc(const void *x, const void *dy, float *dwp, float *ws, long long ws_elems,
+                          int B, int H_in, int W_in, int C, int H_out, int W_out, int O, int R,
+                          int S, int stride_h, int stride_w, void *stream);
+
 #ifdef __cplusplus
 }
 #endif

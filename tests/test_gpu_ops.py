@@ -575,3 +575,73 @@ def test_fused_blur_pad_nhwc(DF, ops, dtype, C):
     v = torch.randn(x.shape, generator=g).to(DEV, dtype)
     (gg,) = torch.autograd.grad((gf.float() * v.float()).sum(), gyf)
     close(gg, pad(blur(v)), **tol)
+
+
+# ----------------------------------------------------------------------------- a11 dense convs
+@pytest.mark.parametrize("B,C,Oc,H,W,k,stride", [
+    (2, 32, 32, 18, 66, 3, 1),       # RB0 conv1 shape family (C = O = 32, K_g = 96 -> zero-filled chunk)
+    (2, 32, 64, 19, 67, 3, 2),       # strided 3x3, odd padded size
+    (1, 64, 64, 34, 258, 3, 1),      # several 128-pixel patches per row
+    (2, 64, 128, 18, 130, 3, 2),
+    (2, 128, 128, 18, 34, 3, 1),     # patch = 4 rows x 32
+    (1, 256, 512, 10, 66, 3, 2),     # two N tiles of 256
+    (2, 256, 256, 6, 34, 3, 1),
+    (2, 32, 64, 16, 64, 1, 2),       # skip branch: 1x1 stride 2
+    (2, 48, 40, 9, 21, 3, 1),        # channel counts that are not powers of two
+    (1, 16, 24, 7, 9, 2, 1),
+])
+def test_conv2d_tcgen05_fprop_dgrad_wgrad(DF, B, C, Oc, H, W, k, stride):
+    """Own implicit-GEMM convolution vs the oracle's F.conv2d (fp32, CPU) on bf16-rounded
+    operands; tolerance = bf16 output rounding (rtol 2e-2)."""
+    g = torch.Generator().manual_seed(33)
+    bf = torch.bfloat16
+    x = torch.randn(B, C, H, W, generator=g).to(bf)
+    w = (torch.randn(Oc, C, k, k, generator=g) / np.sqrt(C * k * k)).to(bf)
+    xr = x.float().requires_grad_()
+    wr = w.float().requires_grad_()
+    ref = torch.nn.functional.conv2d(xr, wr, None, stride)
+    gy = torch.randn(ref.shape, generator=g).to(bf)
+    gx_ref, gw_ref = torch.autograd.grad(ref, [xr, wr], gy.float())
+
+    xd = x.to(DEV).contiguous(memory_format=torch.channels_last)
+    wd = w.to(DEV)
+    s2 = (stride, stride)
+    assert DF.conv_tc_supported(xd, wd, s2)
+    y = DF.conv2d_fprop_tc(xd, wd, s2)
+    assert y.shape == ref.shape and y.is_contiguous(memory_format=torch.channels_last)
+    close(y, ref, rtol=2e-2, atol_rel=4e-3)
+    gx = DF.conv2d_dgrad_tc(gy.to(DEV), wd, s2, (H, W))
+    close(gx, gx_ref, rtol=2e-2, atol_rel=4e-3)
+    gw = DF.conv2d_wgrad_tc(gy.to(DEV), xd, s2, w.shape, torch.float32)
+    assert gw.shape == w.shape
+    close(gw, gw_ref, rtol=2e-2, atol_rel=4e-3)
+    # fused bias + leaky-ReLU epilogue
+    bias = torch.randn(Oc, generator=g)
+    yb = DF.conv2d_fprop_tc(xd, wd, s2, bias.to(DEV), 3, 0.2, O.SQRT2)
+    close(yb, O_lrelu(ref.detach() + bias.view(1, -1, 1, 1)), rtol=2e-2, atol_rel=4e-3)
+
+
+def test_conv2d_valid_autograd_routes_through_tcgen05(DF, ops):
+    """conv2d_valid: first and second order through the own kernels agree with the library path."""
+    from dusty_gan_v2_b200.gans.models.ops.common import conv2d_valid
+    g = torch.Generator().manual_seed(34)
+    bf = torch.bfloat16
+    x = torch.randn(2, 32, 12, 36, generator=g).to(bf).to(DEV).contiguous(memory_format=torch.channels_last)
+    w = (torch.randn(64, 32, 3, 3, generator=g) / 17.0).to(bf).to(DEV)
+    gy = torch.randn(2, 64, 5, 17, generator=g).to(bf).to(DEV)
+    res = {}
+    for mode in ("auto", "library"):
+        DF.set_conv_impl(mode)
+        try:
+            xg, wg = x.clone().requires_grad_(), w.clone().requires_grad_()
+            n0 = DF.K.launch_count()
+            y = conv2d_valid(xg, wg, (2, 2))
+            gx, gw = torch.autograd.grad(y, [xg, wg], gy, create_graph=True)
+            r1 = gx.float().pow(2).sum()
+            ggw, = torch.autograd.grad(r1, [wg])
+            res[mode] = (y.detach(), gx.detach(), gw.detach(), ggw.detach(), DF.K.launch_count() - n0)
+        finally:
+            DF.set_conv_impl("auto")
+    assert res["auto"][4] >= 6 and res["library"][4] == 0
+    for a, b in zip(res["auto"][:4], res["library"][:4]):
+        close(a, b, rtol=3e-2, atol_rel=1e-2)

@@ -934,8 +934,10 @@ def conv2d_dgrad_tc(gy, w, stride, in_hw):
             ss = [s for s in range(S) if s % sw == pw]
             classes.append((ph, pw, rs, ss))
     full = all(rs and ss for _, _, rs, ss in classes)
-    alloc = torch.empty if full else torch.zeros
-    gx = alloc((B, C, H, W), dtype=gy.dtype, device=gy.device, memory_format=torch.channels_last)
+    gx = torch.empty((B, C, H, W), dtype=gy.dtype, device=gy.device,
+                     memory_format=torch.channels_last)
+    if not full:
+        gx.zero_()
     st = K.stream_of(gy)
     for ph, pw, rs, ss in classes:
         if not (rs and ss):

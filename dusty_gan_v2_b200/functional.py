@@ -868,20 +868,24 @@ def circular_unshift(v, shift01, scale: float = 1.0):
 
 
 # ---- a11: dense NHWC convolutions on tcgen05 (conv_tc.cu) --------------------------------
-_CONV_IMPL = {"mode": "auto"}      # "auto": own kernels where the shape qualifies; "library": cuDNN
+_CONV_IMPL = {"mode": "auto"}
 
 
 def set_conv_impl(mode: str):
-    """'auto' (tcgen05 kernels for bf16 NHWC shapes that qualify) or 'library' (cuDNN)."""
-    if mode not in ("auto", "library"):
+    """'tc': own tcgen05 kernels for every bf16 NHWC shape that qualifies; 'library': cuDNN;
+    'auto' (default): own kernels where they measured faster than cuDNN at the step's shapes
+    (profiles/r01_conv_layers.json: the 32-channel 64x512 layers' strided dgrad and wgrad),
+    cuDNN elsewhere."""
+    if mode not in ("auto", "tc", "library"):
         raise ValueError(mode)
     _CONV_IMPL["mode"] = mode
 
 
-def conv_tc_supported(x: torch.Tensor, w: torch.Tensor, stride) -> bool:
+def conv_tc_supported(x: torch.Tensor, w: torch.Tensor, stride, op: str = "fprop") -> bool:
     """bf16 NHWC activations, channel counts multiples of 8 (16-byte TMA strides), filters of at
     most 4x4 taps, strides 1 or 2."""
-    if _CONV_IMPL["mode"] != "auto" or not x.is_cuda or x.dim() != 4:
+    mode = _CONV_IMPL["mode"]
+    if mode == "library" or not x.is_cuda or x.dim() != 4:
         return False
     if x.dtype != torch.bfloat16 or w.dtype != torch.bfloat16:
         return False
@@ -890,7 +894,12 @@ def conv_tc_supported(x: torch.Tensor, w: torch.Tensor, stride) -> bool:
         return False
     if stride[0] not in (1, 2) or stride[1] not in (1, 2):
         return False
-    return x.shape[2] >= R and x.shape[3] >= S
+    if x.shape[2] < R or x.shape[3] < S:
+        return False
+    if mode == "auto":
+        strided = stride[0] == 2 or stride[1] == 2
+        return C <= 32 and ((op == "dgrad" and strided) or (op == "wgrad" and R * S > 1))
+    return True
 
 
 def _nhwc(x: torch.Tensor) -> torch.Tensor:

@@ -146,8 +146,9 @@ class BlurVH(nn.Module):
 
 
 # ---- dense convolution with an explicit first / second order ------------------------------
-# bf16 NHWC shapes run on our tcgen05 implicit-GEMM kernels (conv_tc.cu: fprop / dgrad /
-# wgrad); fp32 (parity mode), NCHW and odd channel counts stay library calls.  The autograd
+# bf16 NHWC shapes can run on our tcgen05 implicit-GEMM kernels (conv_tc.cu: fprop / dgrad /
+# wgrad; DF.set_conv_impl selects "tc" / "auto" / "library"); fp32 (parity mode), NCHW and odd
+# channel counts are library calls.  The autograd
 # wiring is ours either way: PyTorch's generic convolution double-backward falls onto slow grouped / SIMT conv
 # formulations (~100 ms per R1 step at B=64), whereas conv is bilinear in (x, w) so every
 # derivative of every order is again one of fprop / dgrad / wgrad.
@@ -158,12 +159,17 @@ def _conv_fprop(x, w, stride):
 
 
 def _conv_grads(gy, x, w, stride, need_x, need_w):
-    if DF.conv_tc_supported(x, w, stride) and gy.dtype == x.dtype:
-        gx = DF.conv2d_dgrad_tc(gy, w, stride, x.shape[2:]) if need_x else None
-        gw = DF.conv2d_wgrad_tc(gy, x, stride, w.shape, w.dtype) if need_w else None
-        return gx, gw
-    gx, gw, _ = torch.ops.aten.convolution_backward(
-        gy, x, w, None, stride, (0, 0), (1, 1), False, (0, 0), 1, (need_x, need_w, False))
+    gx = gw = None
+    same = gy.dtype == x.dtype
+    if need_x and same and DF.conv_tc_supported(x, w, stride, "dgrad"):
+        gx, need_x = DF.conv2d_dgrad_tc(gy, w, stride, x.shape[2:]), False
+    if need_w and same and DF.conv_tc_supported(x, w, stride, "wgrad"):
+        gw, need_w = DF.conv2d_wgrad_tc(gy, x, stride, w.shape, w.dtype), False
+    if need_x or need_w:
+        lx, lw, _ = torch.ops.aten.convolution_backward(
+            gy, x, w, None, stride, (0, 0), (1, 1), False, (0, 0), 1, (need_x, need_w, False))
+        gx = lx if need_x else gx
+        gw = lw if need_w else gw
     return gx, gw
 
 

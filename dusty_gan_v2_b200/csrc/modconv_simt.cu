@@ -121,26 +121,30 @@ gemm_nn_kernel(GemmNN g) {
   }
 }
 
-// Heads: O <= 4 outputs.  Pure streaming read of x (memory bound); weights in smem.  Each
-// thread owns one 16-byte pixel group (8 bf16 / 4 fp32) and walks the channel axis with four
-// independent loads in flight.
+// Heads: O <= 4 outputs.  Pure streaming read of x (memory bound); weights in smem.  Block =
+// PG pixel groups (16 bytes of pixels each) x KS slices of the channel axis: at the coarse
+// levels there are few pixels and many channels, and one thread walking all of K is pure load
+// latency.  Partial sums meet in shared memory; slice 0 applies bias / activation and stores.
 template <typename T, typename TA, int OMAX>
 __global__ void __launch_bounds__(256)
-small_o_kernel(GemmNN g) {
-  extern __shared__ float sw[];  // [M][K]
+small_o_kernel(GemmNN g, int PG) {
+  extern __shared__ float sw[];  // [M][K] weights, then [256][OMAX * V] partials
   constexpr int V = Vec16<T>::N;
+  float *part = sw + g.M * g.K;
   const int b = blockIdx.y;
+  const int KS = blockDim.x / PG;
+  const int tx = threadIdx.x % PG, ty = threadIdx.x / PG;
   const TA *A = (const TA *)g.a + (int64_t)b * g.a_bs;
   for (int i = threadIdx.x; i < g.M * g.K; i += blockDim.x) {
     const int m = i / g.K, k = i - m * g.K;
     sw[i] = to_f(A[(int64_t)m * g.a_ms + (int64_t)k * g.a_ks]);
   }
   __syncthreads();
-  const int64_t p0 = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) * V;
-  if (p0 >= g.N) return;
+  const int64_t p0 = ((int64_t)blockIdx.x * PG + tx) * V;
+  const bool active = p0 < g.N;
   const T *B1 = (const T *)g.b1 + (int64_t)b * g.b1_bs;
   const T *B2 = (const T *)g.b2 + (int64_t)b * g.b2_bs;
-  const bool full = (g.N % V == 0) && (p0 + V <= g.N) &&
+  const bool full = active && (g.N % V == 0) && (p0 + V <= g.N) &&
                     ((reinterpret_cast<uintptr_t>(B1) | reinterpret_cast<uintptr_t>(B2)) & 15u) == 0;
   float acc[OMAX][V] = {};
   auto src_of = [&](int k) {
@@ -156,33 +160,52 @@ small_o_kernel(GemmNN g) {
       }
     }
   };
-  int k = 0;
-  if (full) {
-    for (; k + 4 <= g.K; k += 4) {
-      Vec16<T> v0 = ld16_stream(src_of(k)), v1 = ld16_stream(src_of(k + 1));
-      Vec16<T> v2 = ld16_stream(src_of(k + 2)), v3 = ld16_stream(src_of(k + 3));
+  if (active) {
+    int k = ty;
+    if (full) {
+      for (; k + 3 * KS < g.K; k += 4 * KS) {
+        Vec16<T> v0 = ld16_stream(src_of(k)), v1 = ld16_stream(src_of(k + KS));
+        Vec16<T> v2 = ld16_stream(src_of(k + 2 * KS)), v3 = ld16_stream(src_of(k + 3 * KS));
+        float f[V];
+#pragma unroll
+        for (int i = 0; i < V; ++i) f[i] = v0.get(i);
+        fma_k(k, f);
+#pragma unroll
+        for (int i = 0; i < V; ++i) f[i] = v1.get(i);
+        fma_k(k + KS, f);
+#pragma unroll
+        for (int i = 0; i < V; ++i) f[i] = v2.get(i);
+        fma_k(k + 2 * KS, f);
+#pragma unroll
+        for (int i = 0; i < V; ++i) f[i] = v3.get(i);
+        fma_k(k + 3 * KS, f);
+      }
+    }
+    for (; k < g.K; k += KS) {
+      const T *src = src_of(k);
       float f[V];
 #pragma unroll
-      for (int i = 0; i < V; ++i) f[i] = v0.get(i);
+      for (int i = 0; i < V; ++i) f[i] = (p0 + i < g.N) ? to_f(src[i]) : 0.f;
       fma_k(k, f);
-#pragma unroll
-      for (int i = 0; i < V; ++i) f[i] = v1.get(i);
-      fma_k(k + 1, f);
-#pragma unroll
-      for (int i = 0; i < V; ++i) f[i] = v2.get(i);
-      fma_k(k + 2, f);
-#pragma unroll
-      for (int i = 0; i < V; ++i) f[i] = v3.get(i);
-      fma_k(k + 3, f);
     }
   }
-  for (; k < g.K; ++k) {
-    const T *src = src_of(k);
-    float f[V];
+  if (KS > 1) {
+    if (ty > 0) {
 #pragma unroll
-    for (int i = 0; i < V; ++i) f[i] = (p0 + i < g.N) ? to_f(src[i]) : 0.f;
-    fma_k(k, f);
+      for (int m = 0; m < OMAX; ++m)
+#pragma unroll
+        for (int i = 0; i < V; ++i) part[(m * V + i) * 256 + threadIdx.x] = acc[m][i];
+    }
+    __syncthreads();
+    if (ty > 0) return;
+    for (int s2 = 1; s2 < KS; ++s2) {
+#pragma unroll
+      for (int m = 0; m < OMAX; ++m)
+#pragma unroll
+        for (int i = 0; i < V; ++i) acc[m][i] += part[(m * V + i) * 256 + s2 * PG + tx];
+    }
   }
+  if (!active) return;
   T *C = (T *)g.c + (int64_t)b * g.c_bs;
 #pragma unroll
   for (int m = 0; m < OMAX; ++m) {
@@ -204,6 +227,71 @@ small_o_kernel(GemmNN g) {
     } else {
 #pragma unroll
       for (int i = 0; i < V; ++i) if (p0 + i < g.N) dst[i] = from_f<T>(o[i]);
+    }
+  }
+}
+
+// dX of the heads: dx[b, c, p] = sum_{o < O} wb[b, o, c] * dy[b, o, p], O <= 4.  Streaming
+// write of C x P per sample; each thread keeps its 16-byte pixel group of dY in registers and
+// walks a chunk of the channel axis.
+template <typename T, typename TA, int OMAX>
+__global__ void __launch_bounds__(256)
+small_o_dx_kernel(GemmNN g, int c_chunk) {
+  extern __shared__ float sw[];  // [O][c_chunk]
+  constexpr int V = Vec16<T>::N;
+  const int b = blockIdx.y;
+  const int c0 = blockIdx.z * c_chunk;
+  const int nc = min(c_chunk, g.M - c0);
+  const TA *A = (const TA *)g.a + (int64_t)b * g.a_bs;
+  for (int i = threadIdx.x; i < g.K * nc; i += blockDim.x) {
+    const int o = i / nc, c = i - o * nc;
+    sw[o * c_chunk + c] = to_f(A[(int64_t)(c0 + c) * g.a_ms + (int64_t)o * g.a_ks]);
+  }
+  __syncthreads();
+  const int64_t p0 = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) * V;
+  if (p0 >= g.N) return;
+  const T *DY = (const T *)g.b1 + (int64_t)b * g.b1_bs;
+  T *C = (T *)g.c + (int64_t)b * g.c_bs;
+  const bool full = (g.N % V == 0) && (p0 + V <= g.N) &&
+                    ((reinterpret_cast<uintptr_t>(DY) | reinterpret_cast<uintptr_t>(C)) & 15u) == 0;
+  float gv[OMAX][V];
+#pragma unroll
+  for (int o = 0; o < OMAX; ++o) {
+    if (o < g.K) {
+      if (full) {
+        Vec16<T> v = ld16_stream(DY + (int64_t)o * g.N + p0);
+#pragma unroll
+        for (int i = 0; i < V; ++i) gv[o][i] = v.get(i);
+      } else {
+#pragma unroll
+        for (int i = 0; i < V; ++i) gv[o][i] = (p0 + i < g.N) ? to_f(DY[(int64_t)o * g.N + p0 + i]) : 0.f;
+      }
+    } else {
+#pragma unroll
+      for (int i = 0; i < V; ++i) gv[o][i] = 0.f;
+    }
+  }
+  for (int c = 0; c < nc; ++c) {
+    float o8[V];
+#pragma unroll
+    for (int i = 0; i < V; ++i) o8[i] = 0.f;
+#pragma unroll
+    for (int o = 0; o < OMAX; ++o) {
+      if (o < g.K) {
+        const float w = sw[o * c_chunk + c];
+#pragma unroll
+        for (int i = 0; i < V; ++i) o8[i] = fmaf(w, gv[o][i], o8[i]);
+      }
+    }
+    T *dst = C + (int64_t)(c0 + c) * g.N + p0;
+    if (full) {
+      Vec16<T> ov;
+#pragma unroll
+      for (int i = 0; i < V; ++i) ov.set(i, o8[i]);
+      st16(dst, ov);
+    } else {
+#pragma unroll
+      for (int i = 0; i < V; ++i) if (p0 + i < g.N) dst[i] = from_f<T>(o8[i]);
     }
   }
 }
@@ -297,7 +385,12 @@ small_o_dw_kernel(GemmNT g) {
   const T *X2 = (const T *)g.x2 + (int64_t)b * g.x2_bs;
   float acc[kSmallKB][OMAX] = {};
   const bool p_vec = (g.P % 4 == 0);
-  for (int64_t p = (int64_t)threadIdx.x * 4; p < g.P; p += 256 * 4) {
+  // grid.z slices of the pixel axis (multiples of 1024 pixels); partial sums meet in dw by
+  // atomics when there is more than one slice (the host zero-fills dw then)
+  const int64_t p_per = (((g.P + gridDim.z - 1) / gridDim.z) + 1023) / 1024 * 1024;
+  const int64_t p_lo = (int64_t)blockIdx.z * p_per;
+  const int64_t p_hi = p_lo + p_per < g.P ? p_lo + p_per : g.P;
+  for (int64_t p = p_lo + (int64_t)threadIdx.x * 4; p < p_hi; p += 256 * 4) {
     float gv[OMAX][4];
 #pragma unroll
     for (int o = 0; o < OMAX; ++o) {
@@ -334,7 +427,11 @@ small_o_dw_kernel(GemmNT g) {
     float v = 0.f;
     for (int w = 0; w < 8; ++w) v += red[w][threadIdx.x];
     const int kk = threadIdx.x / OMAX, o = threadIdx.x % OMAX;
-    if (k0 + kk < g.K && o < g.O) g.dw[((int64_t)b * g.O + o) * g.K + k0 + kk] = v;
+    if (k0 + kk < g.K && o < g.O) {
+      float *dst = g.dw + ((int64_t)b * g.O + o) * g.K + k0 + kk;
+      if (gridDim.z > 1) atomicAdd(dst, v);
+      else *dst = v;
+    }
   }
 }
 
@@ -342,8 +439,20 @@ template <typename T, typename TA>
 static int run_nn(const GemmNN &g, int B, bool a_kcontig, cudaStream_t st) {
   if (g.M <= 4 && (size_t)g.M * g.K * sizeof(float) <= 48 * 1024) {
     constexpr int V = Vec16<T>::N;
-    dim3 grid((unsigned)((g.N + 256 * V - 1) / (256 * V)), (unsigned)B);
-    small_o_kernel<T, TA, 4><<<grid, 256, (size_t)g.M * g.K * sizeof(float), st>>>(g);
+    // pixel groups per block: 32 (8 channel slices) unless the channel axis is short
+    const int64_t groups = (g.N + V - 1) / V;
+    int PG = 32;
+    while (PG < 256 && g.K < 4 * (256 / PG)) PG <<= 1;      // >= 4 channels per slice
+    while (PG > 8 && groups < PG) PG >>= 1;
+    dim3 grid((unsigned)((groups + PG - 1) / PG), (unsigned)B);
+    const size_t smem = ((size_t)g.M * g.K + 256 * 4 * V) * sizeof(float);
+    static bool configured = false;
+    if (!configured) {
+      cudaFuncSetAttribute(small_o_kernel<T, TA, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                           96 * 1024);
+      configured = true;
+    }
+    small_o_kernel<T, TA, 4><<<grid, 256, smem, st>>>(g, PG);
     return 0;
   }
   dim3 grid((unsigned)((g.N + BN - 1) / BN), (unsigned)((g.M + BM - 1) / BM), (unsigned)B);
@@ -377,6 +486,24 @@ int modconv_bwd_dx_simt(const void *wb, const void *dy, void *dx1, int B, int O,
   g.b1 = dy; g.b2 = dy; g.b1_bs = (int64_t)O * P; g.b2_bs = 0; g.K1 = O;
   g.c = dx1; g.c_bs = (int64_t)C1 * P; g.bias = nullptr;
   g.M = C1; g.K = O; g.N = P; g.act = 1; g.alpha = 0.f; g.scale = 1.f;
+  if (O <= 4) {
+    const int V = dtype == DUSTY_F32 ? 4 : 8;
+    const int64_t groups = (P + V - 1) / V;
+    // enough CTAs to fill the machine: split the channel axis when there are few pixels
+    int c_chunk = C1;
+    while (c_chunk > 16 && ((groups + 255) / 256) * B * ((C1 + c_chunk - 1) / c_chunk) < 2 * num_sms())
+      c_chunk = (c_chunk + 1) / 2;
+    dim3 grid((unsigned)((groups + 255) / 256), (unsigned)B, (unsigned)((C1 + c_chunk - 1) / c_chunk));
+    const size_t smem = (size_t)O * c_chunk * sizeof(float);
+    if (dtype == DUSTY_F32) {
+      if (wdtype == DUSTY_F32) small_o_dx_kernel<float, float, 4><<<grid, 256, smem, st>>>(g, c_chunk);
+      else small_o_dx_kernel<float, __nv_bfloat16, 4><<<grid, 256, smem, st>>>(g, c_chunk);
+    } else {
+      if (wdtype == DUSTY_F32) small_o_dx_kernel<__nv_bfloat16, float, 4><<<grid, 256, smem, st>>>(g, c_chunk);
+      else small_o_dx_kernel<__nv_bfloat16, __nv_bfloat16, 4><<<grid, 256, smem, st>>>(g, c_chunk);
+    }
+    return 0;
+  }
   dim3 grid((unsigned)((g.N + BN - 1) / BN), (unsigned)((g.M + BM - 1) / BM), (unsigned)B);
   if (dtype == DUSTY_F32) {
     if (wdtype == DUSTY_F32) gemm_nn_kernel<float, float, false><<<grid, 256, 0, st>>>(g);
@@ -395,7 +522,13 @@ int modconv_bwd_dw_simt(const void *dy, const void *x1, const void *x2, float *d
   g.x2_bs = (B2 == 1) ? 0 : (int64_t)C2 * P; g.K1 = C1; g.dw = dwb;
   g.O = O; g.K = C1 + C2; g.P = P;
   if (O <= 4) {
-    dim3 grid((unsigned)((g.K + kSmallKB - 1) / kSmallKB), (unsigned)B);
+    const int kt = (g.K + kSmallKB - 1) / kSmallKB;
+    int ps = 1;
+    while (ps < 32 && (int64_t)kt * B * ps < 4 * num_sms() && P / (ps * 2) >= 2048) ps *= 2;
+    if (ps > 1 &&
+        cudaMemsetAsync(dwb, 0, sizeof(float) * (size_t)B * O * g.K, st) != cudaSuccess)
+      return DUSTY_ECUDA;
+    dim3 grid((unsigned)kt, (unsigned)B, (unsigned)ps);
     if (dtype == DUSTY_F32) small_o_dw_kernel<float, 4><<<grid, 256, 0, st>>>(g);
     else small_o_dw_kernel<__nv_bfloat16, 4><<<grid, 256, 0, st>>>(g);
     return 0;

@@ -124,7 +124,7 @@ __device__ __forceinline__ float prep_gw(const PrepCtx &c, const float *__restri
   return is_cos ? (gc * cs - gs * sn) : (gs * cs + gc * sn);
 }
 
-// c[b,o] = sum_i gwb * g * t      (demod only)
+// c[b,o] = sum_i gwb * g * t      (demod only); one warp per (b, o) row
 __global__ void __launch_bounds__(128)
 modprep_c_kernel(PrepCtx c, const float *__restrict__ gwb, float *__restrict__ cbo) {
   const int lane = threadIdx.x & 31;
@@ -132,10 +132,17 @@ modprep_c_kernel(PrepCtx c, const float *__restrict__ gwb, float *__restrict__ c
   const int b = blockIdx.y;
   if (o >= c.O) return;
   const float inv_w = 1.f / c.wmax(), inv_s = 1.f / c.smax(b);
-  float acc = 0.f;
-  for (int i = lane; i < c.I; i += 32)
-    acc = fmaf(prep_gw(c, gwb, b, o, i), c.wp(o, i, inv_w) * c.sp(b, i, inv_s), acc);
-  acc = warp_sum(acc);
+  float acc0 = 0.f, acc1 = 0.f, acc2 = 0.f, acc3 = 0.f;
+  int i = lane;
+  for (; i + 96 < c.I; i += 128) {      // four independent load groups in flight
+    acc0 = fmaf(prep_gw(c, gwb, b, o, i), c.wp(o, i, inv_w) * c.sp(b, i, inv_s), acc0);
+    acc1 = fmaf(prep_gw(c, gwb, b, o, i + 32), c.wp(o, i + 32, inv_w) * c.sp(b, i + 32, inv_s), acc1);
+    acc2 = fmaf(prep_gw(c, gwb, b, o, i + 64), c.wp(o, i + 64, inv_w) * c.sp(b, i + 64, inv_s), acc2);
+    acc3 = fmaf(prep_gw(c, gwb, b, o, i + 96), c.wp(o, i + 96, inv_w) * c.sp(b, i + 96, inv_s), acc3);
+  }
+  for (; i < c.I; i += 32)
+    acc0 = fmaf(prep_gw(c, gwb, b, o, i), c.wp(o, i, inv_w) * c.sp(b, i, inv_s), acc0);
+  const float acc = warp_sum((acc0 + acc1) + (acc2 + acc3));
   if (lane == 0) cbo[(int64_t)b * c.O + o] = acc * c.g();
 }
 
@@ -145,55 +152,80 @@ __device__ __forceinline__ float prep_dt(const PrepCtx &c, float gw, float t, fl
   return c.demod ? (u * d - cbo * d * d * d * t) : u;
 }
 
-// ds'[b,i] = sum_o dt * w'      thread per (b, i)
-__global__ void __launch_bounds__(128)
+constexpr int kRedY = 8;     // threads along the reduced axis per block (block = 32 x kRedY)
+
+// ds'[b,i] = sum_o dt * w'.  Block = 32 columns i x 8 slices of the o axis; the serial
+// version (one thread per (b, i), O dependent iterations) was pure load latency.
+__global__ void __launch_bounds__(32 * kRedY)
 modprep_ds_kernel(PrepCtx c, const float *__restrict__ gwb, const float *__restrict__ cbo,
                   float *__restrict__ dsp, float *__restrict__ sums) {
-  __shared__ float red[32];
-  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  __shared__ float part[kRedY][33];
+  const int tx = threadIdx.x, ty = threadIdx.y;
+  const int i = blockIdx.x * 32 + tx;
   const int b = blockIdx.y;
-  float acc = 0.f, dot = 0.f;
+  float acc = 0.f;
   if (i < c.I) {
     const float inv_w = 1.f / c.wmax(), inv_s = 1.f / c.smax(b);
     const float sp = c.sp(b, i, inv_s);
-    for (int o = 0; o < c.O; ++o) {
+#pragma unroll 4
+    for (int o = ty; o < c.O; o += kRedY) {
       const float wp = c.wp(o, i, inv_w);
       const float dt = prep_dt(c, prep_gw(c, gwb, b, o, i), wp * sp, c.d(b, o),
                                c.demod ? cbo[(int64_t)b * c.O + o] : 0.f);
       acc = fmaf(dt, wp, acc);
     }
-    dsp[(int64_t)b * c.I + i] = acc;
-    dot = acc * c.slin[(int64_t)b * c.I + i];
   }
-  if (c.demod) {       // sum_j ds'_j s_j, needed by the inf-norm term of the finish pass
-    dot = block_sum(dot, red);
-    if (threadIdx.x == 0) atomicAdd(sums + b, dot);
+  part[ty][tx] = acc;
+  __syncthreads();
+  if (ty == 0) {
+#pragma unroll
+    for (int k = 1; k < kRedY; ++k) acc += part[k][tx];
+    float dot = 0.f;
+    if (i < c.I) {
+      dsp[(int64_t)b * c.I + i] = acc;
+      dot = acc * c.slin[(int64_t)b * c.I + i];
+    }
+    if (c.demod) {       // sum_j ds'_j s_j, needed by the inf-norm term of the finish pass
+      dot = warp_sum(dot);
+      if (tx == 0) atomicAdd(sums + b, dot);
+    }
   }
 }
 
-// dw'[o,i] = sum_b dt * s'      thread per (o, i)
-__global__ void __launch_bounds__(128)
+// dw'[o,i] = sum_b dt * s'.  Block = 32 columns i x 8 slices of the batch axis.
+__global__ void __launch_bounds__(32 * kRedY)
 modprep_dw_kernel(PrepCtx c, const float *__restrict__ gwb, const float *__restrict__ cbo,
                   float *__restrict__ dwp, float *__restrict__ sums) {
-  __shared__ float red[32];
-  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  __shared__ float part[kRedY][33];
+  const int tx = threadIdx.x, ty = threadIdx.y;
+  const int i = blockIdx.x * 32 + tx;
   const int o = blockIdx.y;
-  float acc = 0.f, dot = 0.f;
+  float acc = 0.f;
   if (i < c.I) {
     const float inv_w = 1.f / c.wmax();
     const float wp = c.wp(o, i, inv_w);
-    for (int b = 0; b < c.B; ++b) {
+#pragma unroll 4
+    for (int b = ty; b < c.B; b += kRedY) {
       const float sp = c.sp(b, i, 1.f / c.smax(b));
       const float dt = prep_dt(c, prep_gw(c, gwb, b, o, i), wp * sp, c.d(b, o),
                                c.demod ? cbo[(int64_t)b * c.O + o] : 0.f);
       acc = fmaf(dt, sp, acc);
     }
-    dwp[(int64_t)o * c.I + i] = acc;
-    dot = acc * c.W[(int64_t)o * c.I + i] * c.scale;
   }
-  if (c.demod) {
-    dot = block_sum(dot, red);
-    if (threadIdx.x == 0) atomicAdd(sums + c.B, dot);
+  part[ty][tx] = acc;
+  __syncthreads();
+  if (ty == 0) {
+#pragma unroll
+    for (int k = 1; k < kRedY; ++k) acc += part[k][tx];
+    float dot = 0.f;
+    if (i < c.I) {
+      dwp[(int64_t)o * c.I + i] = acc;
+      dot = acc * c.W[(int64_t)o * c.I + i] * c.scale;
+    }
+    if (c.demod) {
+      dot = warp_sum(dot);
+      if (tx == 0) atomicAdd(sums + c.B, dot);
+    }
   }
 }
 
@@ -273,8 +305,9 @@ extern "C" int dusty_modprep_bwd(const float *gwb, const float *slin, const floa
     modprep_c_kernel<<<grid, 128, 0, st>>>(c, gwb, cbo);
     count_launch(1);
   }
-  modprep_ds_kernel<<<dim3((unsigned)((I + 127) / 128), (unsigned)B), 128, 0, st>>>(c, gwb, cbo, dsp, sums);
-  modprep_dw_kernel<<<dim3((unsigned)((I + 127) / 128), (unsigned)O), 128, 0, st>>>(c, gwb, cbo, dwp, sums);
+  const dim3 rblock(32, kRedY);
+  modprep_ds_kernel<<<dim3((unsigned)((I + 31) / 32), (unsigned)B), rblock, 0, st>>>(c, gwb, cbo, dsp, sums);
+  modprep_dw_kernel<<<dim3((unsigned)((I + 31) / 32), (unsigned)O), rblock, 0, st>>>(c, gwb, cbo, dwp, sums);
   {
     int64_t nb = (((int64_t)B + O) * I + 255) / 256;
     if (nb > 1184) nb = 1184;

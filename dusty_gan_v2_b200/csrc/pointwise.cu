@@ -172,7 +172,7 @@ mbstd_bwd_kernel(const T *__restrict__ dy, const T *__restrict__ x, const float 
     const float inv_sd = rsqrtf(var / (float)G + alpha);
     for (int g = 0; g < G; ++g) {
       const int64_t b = (int64_t)g * M + m;
-      const float gpass = to_f(dy[b * (C + 1) * HW + j]);
+      const float gpass = dy ? to_f(dy[b * (C + 1) * HW + j]) : 0.f;
       dx[b * CHW + j] = from_f<T>(gpass + coef * (v[g] - mean) * inv_sd);
     }
   }
@@ -305,7 +305,7 @@ extern "C" int dusty_point_project(const float *x, const float *trig, float *out
 extern "C" int dusty_minibatch_std_fwd(const void *x, void *y, float *stat, int B, int C,
                                        int64_t HW, int group, float alpha, int dtype,
                                        void *stream) {
-  DUSTY_CHECK_ARG(x && y && stat, "null pointer");
+  DUSTY_CHECK_ARG(x && stat, "null pointer");
   DUSTY_CHECK_ARG(B >= 1 && C >= 1 && HW >= 1 && group >= 1, "bad shape");
   const int G = B < group ? B : group;
   DUSTY_CHECK_ARG(B % G == 0 && G <= 8, "batch must be divisible by the group (<= 8)");
@@ -314,6 +314,18 @@ extern "C" int dusty_minibatch_std_fwd(const void *x, void *y, float *stat, int 
   const int64_t CHW = (int64_t)C * HW;
   cudaStream_t st = (cudaStream_t)stream;
   if (cudaMemsetAsync(stat, 0, sizeof(float) * M, st) != cudaSuccess) return DUSTY_ECUDA;
+  if (y == nullptr) {       // statistic only (any per-sample element order)
+    int64_t bx1 = (CHW + 255) / 256;
+    if (bx1 > 64) bx1 = 64;
+    dim3 grid1((unsigned)bx1, (unsigned)M);
+    if (dtype == DUSTY_F32)
+      mbstd_stat_kernel<float><<<grid1, 256, 0, st>>>((const float *)x, stat, G, M, CHW, alpha);
+    else
+      mbstd_stat_kernel<__nv_bfloat16><<<grid1, 256, 0, st>>>((const __nv_bfloat16 *)x, stat, G, M,
+                                                              CHW, alpha);
+    DUSTY_LAUNCH_CHECK();
+    return DUSTY_OK;
+  }
   int64_t bx = (CHW + 255) / 256;
   if (bx > 64) bx = 64;
   dim3 grid((unsigned)bx, (unsigned)M);
@@ -336,7 +348,7 @@ extern "C" int dusty_minibatch_std_fwd(const void *x, void *y, float *stat, int 
 extern "C" int dusty_minibatch_std_bwd(const void *dy, const void *x, void *dx, float *dstat,
                                        int B, int C, int64_t HW, int group, float alpha, int dtype,
                                        void *stream) {
-  DUSTY_CHECK_ARG(dy && x && dx && dstat, "null pointer");
+  DUSTY_CHECK_ARG(x && dx && dstat, "null pointer");
   DUSTY_CHECK_ARG(B >= 1 && C >= 1 && HW >= 1 && group >= 1, "bad shape");
   const int G = B < group ? B : group;
   DUSTY_CHECK_ARG(B % G == 0 && G <= 8, "batch must be divisible by the group (<= 8)");
@@ -347,6 +359,16 @@ extern "C" int dusty_minibatch_std_bwd(const void *dy, const void *x, void *dx, 
   int64_t bx = (CHW + 255) / 256;
   if (bx > 64) bx = 64;
   dim3 grid((unsigned)bx, (unsigned)M);
+  if (dy == nullptr) {      // statistic-only variant: dstat is the incoming gradient
+    if (dtype == DUSTY_F32)
+      mbstd_bwd_kernel<float><<<grid, 256, 0, st>>>(nullptr, (const float *)x, dstat, (float *)dx, G,
+                                                    M, C, HW, alpha);
+    else
+      mbstd_bwd_kernel<__nv_bfloat16><<<grid, 256, 0, st>>>(nullptr, (const __nv_bfloat16 *)x, dstat,
+                                                            (__nv_bfloat16 *)dx, G, M, C, HW, alpha);
+    DUSTY_LAUNCH_CHECK();
+    return DUSTY_OK;
+  }
   if (dtype == DUSTY_F32) {
     mbstd_dstat_kernel<float><<<M, 256, 0, st>>>((const float *)dy, dstat, B, C, HW, M);
     mbstd_bwd_kernel<float><<<grid, 256, 0, st>>>((const float *)dy, (const float *)x, dstat,

@@ -842,6 +842,53 @@ def minibatch_stddev(x, group: int = 4, alpha: float = 1e-8):
     return _MbStd.apply(x, int(group), float(alpha))
 
 
+class _MbStdStat(Function):
+    """stat[m] of MinibatchStdDev only (the appended channel is constant over C, H, W, so the
+    consumer can fold it in analytically); x in any dense per-sample layout."""
+
+    @staticmethod
+    def forward(ctx, x, group, alpha):
+        B, C, H, W = x.shape
+        G = min(B, group)
+        stat = torch.empty(B // G, device=x.device, dtype=torch.float32)
+        K.call("dusty_minibatch_std_fwd", K.ptr(x), None, K.ptr(stat), B, C, H * W, group, alpha,
+               K.dtype_code(x), K.stream_of(x))
+        ctx.save_for_backward(x)
+        ctx.group, ctx.alpha = group, alpha
+        return stat
+
+    @staticmethod
+    def backward(ctx, gstat):
+        (x,) = ctx.saved_tensors
+        B, C, H, W = x.shape
+        G = min(B, ctx.group)
+        M = B // G
+        if torch.is_grad_enabled():   # create_graph=True (R1): differentiable composite
+            xf = x.float().reshape(G, M, C, H, W)
+            d = xf - xf.mean(0, keepdim=True)
+            inv_sd = torch.rsqrt(d.pow(2).mean(0, keepdim=True) + ctx.alpha)
+            coef = gstat.float().reshape(1, M, 1, 1, 1) / float(C * H * W * G)
+            gx = (coef * d * inv_sd).reshape(B, C, H, W).to(x.dtype)
+            return (gx.contiguous(memory_format=torch.channels_last) if _is_cl(x) else gx), None, None
+        gx = torch.empty_like(x)
+        K.call("dusty_minibatch_std_bwd", None, K.ptr(x), K.ptr(gx), K.ptr(gstat.float().contiguous()),
+               B, C, H * W, ctx.group, ctx.alpha, K.dtype_code(x), K.stream_of(x))
+        return gx, None, None
+
+
+def minibatch_std_stat(x, group: int = 4, alpha: float = 1e-8):
+    """Per-sample value of MinibatchStdDev's appended channel, [B] fp32 (sample b of a group
+    slot m = b % (B/G) carries stat[m], common.py:237-250)."""
+    K.require_cuda(x)
+    B = x.shape[0]
+    G = min(B, group)
+    if B % G != 0:
+        raise RuntimeError(f"batch {B} is not divisible by the group size {G}")
+    if not (x.is_contiguous() or x.is_contiguous(memory_format=torch.channels_last)):
+        x = x.contiguous()
+    return _MbStdStat.apply(x, int(group), float(alpha)).repeat(G)
+
+
 # --------------------------------------------------------------------------- circular un-shift
 class _CircShift(Function):
     @staticmethod

@@ -355,4 +355,33 @@ class Discriminator(nn.Module):
             h = layer(h.to(low if use_low else torch.float32))
             if i == 0 and self.channels_last and h.is_cuda:
                 h = h.contiguous(memory_format=torch.channels_last)
+        if self._fast_epilogue_ok(h, low):
+            return self._epilogue_low_precision(h)
         return self.epilogue(h.to(torch.float32).contiguous())
+
+    def _fast_epilogue_ok(self, h, low):
+        mb = self.epilogue[0]
+        return (h.is_cuda and low == torch.bfloat16 and h.dtype == torch.bfloat16 and mb.features == 1
+                and h.shape[0] % (mb.sub_batches * min(h.shape[0] // mb.sub_batches, mb.group)) == 0)
+
+    def _epilogue_low_precision(self, h):
+        """Same arithmetic as `self.epilogue`, arranged for the NHWC bf16 trunk: the appended
+        MinibatchStdDev channel is constant over (H, W) and stays constant under the ring
+        padding, so its contribution to the 3x3 convolution is stat_b * sum_{r,s} w[o, C, r, s]
+        -- a per-sample bias.  The 512-channel remainder of the filter runs as an ordinary NHWC
+        convolution; nothing with 513 channels (odd strides, fp32 NCHW pads) is materialised."""
+        mb, conv, act1, _, lin1, act2, lin2 = self.epilogue
+        pad, eq = conv[0], conv[1]
+        C = h.shape[1]
+        if mb.sub_batches > 1:
+            stat = torch.cat([DF.minibatch_std_stat(c, mb.group) for c in h.chunk(mb.sub_batches, 0)])
+        else:
+            stat = DF.minibatch_std_stat(h, mb.group)
+        w = eq.module.weight * (eq.scale * eq.gain_)                   # [O, C + 1, 3, 3] fp32
+        w_main = w[:, :C].to(h.dtype).contiguous(memory_format=torch.channels_last)
+        w_stat = w[:, C].sum(dim=(1, 2))                               # [O]
+        y = ops.conv2d_valid(pad(h), w_main, eq.module.stride)
+        y = y + (stat[:, None] * w_stat[None, :]).to(y.dtype)[:, :, None, None]
+        y = act1(y)
+        y = lin1(y.flatten(1))              # logical (c, h, w) order, as nn.Flatten on NCHW
+        return lin2(act2(y.float()))

@@ -251,7 +251,7 @@ class EqualLR(nn.Module):
             # launch, exactly the reference's order of operations (common.py:180-181)
             y = F.linear(x * self.scale, m.weight, m.bias)
             return y if self.gain_ == 1.0 else y * self.gain_
-        if (isinstance(m, nn.Linear) and x.is_cuda and x.dtype == torch.float32
+        if (isinstance(m, nn.Linear) and x.is_cuda and x.dtype in (torch.float32, torch.bfloat16)
                 and DF.act_dtype() == torch.bfloat16 and m.weight.numel() >= (1 << 22)):
             # the 65536 -> 512 linear of D's epilogue: bf16 operands on the tensor cores with
             # fp32 accumulation in low-precision mode (an fp32 SIMT/TF32 GEMM costs ~0.6 ms)

@@ -215,10 +215,13 @@ int dusty_point_project(const float *x, const float *trig, float *out, long long
 
 /* ---- a12: minibatch standard deviation --------------------------------------------------
  * Replaces MinibatchStdDev.forward gans/models/ops/common.py:237-250 (features == 1).
- * x: [B, C, HW] -> y: [B, C+1, HW]; stat: fp32 [B/G] workspace (overwritten). */
+ * x: [B, C, HW] -> y: [B, C+1, HW]; stat: fp32 [B/G] (overwritten) = the appended value per
+ * group slot.  y == NULL: statistic only (x may then be in any per-sample element order, e.g.
+ * NHWC -- the statistic is a mean over all C*HW positions). */
 int dusty_minibatch_std_fwd(const void *x, void *y, float *stat, int B, int C, int64_t HW,
                             int group, float alpha, int dtype, void *stream);
-/* dx = dy[:, :C] + d stat path.  dstat: fp32 [B/G] workspace. */
+/* dx = dy[:, :C] + d stat path.  dstat: fp32 [B/G] workspace.  dy == NULL: statistic-only
+ * variant, dstat is then the INPUT gradient w.r.t. stat and dx holds only that path. */
 int dusty_minibatch_std_bwd(const void *dy, const void *x, void *dx, float *dstat, int B, int C,
                             int64_t HW, int group, float alpha, int dtype, void *stream);
 

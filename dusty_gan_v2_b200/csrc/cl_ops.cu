@@ -154,10 +154,10 @@ struct Taps4CL { float k[4]; };
 // in the residual blocks (conv2 input): forward writes the blurred image straight into the
 // padded [H+2, W+2] tensor; the adjoint reads the padded gradient and folds the halo on load.
 template <typename T, bool ADJ, bool PAD>
-__global__ void __launch_bounds__(128, 8)
+__global__ void __launch_bounds__(128, (ADJ && PAD) ? 4 : 5)
 blur4_cl_kernel(const T *__restrict__ x, T *__restrict__ y, Taps4CL t, int H, int W, int cv,
                 int strip, int64_t n_threads) {
-  constexpr int V = Vec8<T>::N;       // 8-byte channel groups: half the window registers
+  constexpr int V = Vec16<T>::N;      // 16-byte channel groups
   const int Wx = (PAD && !ADJ) ? W + 2 : W;      // columns covered by threads
   const int64_t tid = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (tid >= n_threads) return;
@@ -172,90 +172,116 @@ blur4_cl_kernel(const T *__restrict__ x, T *__restrict__ y, Taps4CL t, int H, in
   const int64_t out_img = (int64_t)((PAD && !ADJ) ? Hp * Wp : H * W) * cv * V;
   const T *img = x + b * in_img;
   T *out = y + b * out_img;
-  int xc[4];
+  // element offsets of the four horizontal taps inside one (padded) input row
+  int64_t xoff[4];
+  int xe[4];                                     // PAD adjoint: extra (halo) padded column, or -1
 #pragma unroll
   for (int s = 0; s < 4; ++s) {
     int c = ADJ ? (xx + 2 - s) : (xx + s - 2);
-    xc[s] = c < 0 ? c + W : (c >= W ? c - W : c);
+    c = c < 0 ? c + W : (c >= W ? c - W : c);
+    xoff[s] = ((int64_t)(c + ((PAD && ADJ) ? 1 : 0)) * cv + j) * V;
+    xe[s] = (PAD && ADJ) ? (c == 0 ? W + 1 : (c == W - 1 ? 0 : -1)) : -1;
   }
-  // PAD adjoint: gradient element (r, c) of the un-padded image = sum of the padded-gradient
-  // elements the padding copied it to: column c+1, plus the opposite halo column when c is a
-  // border column; row r+1, plus the halo row when r is a border row.
-  int xe[4];                                     // extra (halo) padded column per tap, or -1
-  if (PAD && ADJ) {
+  const int64_t pitch = (int64_t)((PAD && ADJ) ? Wp : W) * cv * V;
+
+  // A row of raw operands in flight: the loads of row r+1 are issued before row r is reduced,
+  // so every thread keeps two rows (8 x 16 bytes) of requests outstanding.
+  struct Row {
+    Vec16<T> v[4];
+    int r;          // image row (un-padded coordinates); < 0: contributes zero
+  };
+  auto issue = [&](int r, Row &row) {
+    if (ADJ) {
+      if (r < 0 || r >= H) { row.r = -1; return; }
+    } else {
+      r = r < 0 ? 0 : (r >= H ? H - 1 : r);
+    }
+    row.r = r;
+    const T *prow = img + (int64_t)(r + ((PAD && ADJ) ? 1 : 0)) * pitch;
 #pragma unroll
-    for (int s = 0; s < 4; ++s) xe[s] = xc[s] == 0 ? W + 1 : (xc[s] == W - 1 ? 0 : -1);
-  }
-  auto add_row = [&](const T *prow, float *dst) {    // one padded gradient row, 4 taps
+    for (int s = 0; s < 4; ++s) row.v[s] = ld16(prow + xoff[s]);
+  };
+  // PAD adjoint: fold the halo copies of a padded gradient row onto dst (rare: border threads
+  // and border rows only)
+  auto add_halo_cols = [&](const T *prow, float *dst) {
 #pragma unroll
     for (int s = 0; s < 4; ++s) {
-      Vec8<T> v = ld8(prow + ((int64_t)(xc[s] + 1) * cv + j) * V);
-#pragma unroll
-      for (int k = 0; k < V; ++k) dst[k] = fmaf(t.k[s], v.get(k), dst[k]);
       if (xe[s] >= 0) {
-        Vec8<T> e = ld8(prow + ((int64_t)xe[s] * cv + j) * V);
+        Vec16<T> e = ld16(prow + ((int64_t)xe[s] * cv + j) * V);
 #pragma unroll
         for (int k = 0; k < V; ++k) dst[k] = fmaf(t.k[s], e.get(k), dst[k]);
       }
     }
   };
-  auto hpass = [&](int r, float *dst) {
-    if (ADJ) {
-      if (r < 0 || r >= H) {
+  auto add_full_row = [&](const T *prow, float *dst) {
 #pragma unroll
-        for (int k = 0; k < V; ++k) dst[k] = 0.f;
-        return;
-      }
-    } else {
-      r = r < 0 ? 0 : (r >= H ? H - 1 : r);
+    for (int s = 0; s < 4; ++s) {
+      Vec16<T> v = ld16(prow + xoff[s]);
+#pragma unroll
+      for (int k = 0; k < V; ++k) dst[k] = fmaf(t.k[s], v.get(k), dst[k]);
     }
+    add_halo_cols(prow, dst);
+  };
+  auto reduce = [&](const Row &row, float *dst) {
 #pragma unroll
     for (int k = 0; k < V; ++k) dst[k] = 0.f;
+    if (ADJ && row.r < 0) return;
+#pragma unroll
+    for (int s = 0; s < 4; ++s)
+#pragma unroll
+      for (int k = 0; k < V; ++k) dst[k] = fmaf(t.k[s], row.v[s].get(k), dst[k]);
     if (PAD && ADJ) {
-      const int64_t pitch = (int64_t)Wp * cv * V;
-      add_row(img + (int64_t)(r + 1) * pitch, dst);
-      if (r == 0) add_row(img, dst);
-      if (r == H - 1) add_row(img + (int64_t)(H + 1) * pitch, dst);
-    } else {
-      const T *row = img + (int64_t)r * W * cv * V;
-#pragma unroll
-      for (int s = 0; s < 4; ++s) {
-        Vec8<T> v = ld8(row + ((int64_t)xc[s] * cv + j) * V);
-#pragma unroll
-        for (int k = 0; k < V; ++k) dst[k] = fmaf(t.k[s], v.get(k), dst[k]);
-      }
+      add_halo_cols(img + (int64_t)(row.r + 1) * pitch, dst);
+      if (row.r == 0) add_full_row(img, dst);
+      if (row.r == H - 1) add_full_row(img + (int64_t)(H + 1) * pitch, dst);
     }
   };
+
   const int y0 = blockIdx.y * strip;
   const int y1 = min(y0 + strip, H);
   float a[V], bb[V], c[V], d[V];
+  Row cur, nxt;
   if (!ADJ) {
-    hpass(y0 - 2, a); hpass(y0 - 1, bb); hpass(y0, c);
+    issue(y0 - 2, cur); issue(y0 - 1, nxt);
+    reduce(cur, a);
+    issue(y0, cur);
+    reduce(nxt, bb);
+    issue(y0 + 1, nxt);
+    reduce(cur, c);
     for (int r = y0; r < y1; ++r) {
-      hpass(r + 1, d);
-      Vec8<T> o;
+      cur = nxt;                         // row r+1 (already in flight)
+      issue(r + 2, nxt);                 // prefetch the row of the next iteration
+      reduce(cur, d);
+      Vec16<T> o;
 #pragma unroll
       for (int k = 0; k < V; ++k) {
         o.set(k, fmaf(t.k[3], d[k], fmaf(t.k[2], c[k], fmaf(t.k[1], bb[k], t.k[0] * a[k]))));
         a[k] = bb[k]; bb[k] = c[k]; c[k] = d[k];
       }
       if (PAD) {
-        st8(out + (((int64_t)(r + 1) * Wp + xo) * cv + j) * V, o);
-        if (r == 0) st8(out + (((int64_t)0 * Wp + xo) * cv + j) * V, o);
-        if (r == H - 1) st8(out + (((int64_t)(H + 1) * Wp + xo) * cv + j) * V, o);
+        st16(out + (((int64_t)(r + 1) * Wp + xo) * cv + j) * V, o);
+        if (r == 0) st16(out + (((int64_t)0 * Wp + xo) * cv + j) * V, o);
+        if (r == H - 1) st16(out + (((int64_t)(H + 1) * Wp + xo) * cv + j) * V, o);
       } else {
-        st8(out + (((int64_t)r * W + xx) * cv + j) * V, o);
+        st16(out + (((int64_t)r * W + xx) * cv + j) * V, o);
       }
     }
   } else {
     const int e_lo = (y0 == 0) ? -2 : y0;
     const int e_hi = (y1 == H) ? H : y1 - 1;
-    hpass(e_lo - 1, a); hpass(e_lo, bb); hpass(e_lo + 1, c);
+    issue(e_lo - 1, cur); issue(e_lo, nxt);
+    reduce(cur, a);
+    issue(e_lo + 1, cur);
+    reduce(nxt, bb);
+    issue(e_lo + 2, nxt);
+    reduce(cur, c);
     float acc[V];
 #pragma unroll
     for (int k = 0; k < V; ++k) acc[k] = 0.f;
     for (int e = e_lo; e <= e_hi; ++e) {
-      hpass(e + 2, d);
+      cur = nxt;                         // row e+2
+      issue(e + 3, nxt);
+      reduce(cur, d);
 #pragma unroll
       for (int k = 0; k < V; ++k) {
         acc[k] += fmaf(t.k[0], d[k], fmaf(t.k[1], c[k], fmaf(t.k[2], bb[k], t.k[3] * a[k])));
@@ -264,13 +290,141 @@ blur4_cl_kernel(const T *__restrict__ x, T *__restrict__ y, Taps4CL t, int H, in
       const int i = e < 0 ? 0 : (e >= H ? H - 1 : e);
       const int i_next = (e + 1) < 0 ? 0 : ((e + 1) >= H ? H - 1 : (e + 1));
       if (e == e_hi || i_next != i) {
-        Vec8<T> o;
+        Vec16<T> o;
 #pragma unroll
         for (int k = 0; k < V; ++k) { o.set(k, acc[k]); acc[k] = 0.f; }
-        st8(out + (((int64_t)i * W + xx) * cv + j) * V, o);
+        st16(out + (((int64_t)i * W + xx) * cv + j) * V, o);
       }
     }
   }
+}
+
+// ------------------------------------------------------------------ blur4 + 2x decimation (NHWC)
+// Skip branch of the residual blocks: conv1x1_stride2(blur(x)) only ever reads the blurred
+// image at even rows / columns, so the blur is evaluated there and nowhere else:
+//   out[i][j] = sum_{r,s} k[r] k[s] x[clamp(2i + r - 2)][wrap(2j + s - 2)]
+// (input read once, a quarter written; the 1x1 convolution then runs at unit stride).
+// thread -> (b, j, channel vector), slides over a strip of output rows; two new input rows per
+// step, the next two already in flight.
+template <typename T>
+__global__ void __launch_bounds__(128, 4)
+blur4_down2_cl_kernel(const T *__restrict__ x, T *__restrict__ y, Taps4CL t, int H, int W, int cv,
+                      int strip, int64_t n_threads) {
+  constexpr int V = Vec16<T>::N;
+  const int H2 = H >> 1, W2 = W >> 1;
+  const int64_t tid = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (tid >= n_threads) return;
+  const int j = (int)(tid % cv);
+  const int64_t q = tid / cv;
+  const int xo = (int)(q % W2);
+  const int64_t b = q / W2;
+  const T *img = x + b * (int64_t)H * W * cv * V;
+  T *out = y + b * (int64_t)H2 * W2 * cv * V;
+  int64_t xoff[4];
+#pragma unroll
+  for (int s = 0; s < 4; ++s) {
+    int c = 2 * xo + s - 2;
+    c = c < 0 ? c + W : (c >= W ? c - W : c);
+    xoff[s] = ((int64_t)c * cv + j) * V;
+  }
+  const int64_t pitch = (int64_t)W * cv * V;
+  struct Row { Vec16<T> v[4]; };
+  auto issue = [&](int r, Row &row) {
+    r = r < 0 ? 0 : (r >= H ? H - 1 : r);
+    const T *prow = img + (int64_t)r * pitch;
+#pragma unroll
+    for (int s = 0; s < 4; ++s) row.v[s] = ld16(prow + xoff[s]);
+  };
+  auto reduce = [&](const Row &row, float *dst) {
+#pragma unroll
+    for (int k = 0; k < V; ++k) dst[k] = 0.f;
+#pragma unroll
+    for (int s = 0; s < 4; ++s)
+#pragma unroll
+      for (int k = 0; k < V; ++k) dst[k] = fmaf(t.k[s], row.v[s].get(k), dst[k]);
+  };
+  const int i0 = blockIdx.y * strip;
+  const int i1 = min(i0 + strip, H2);
+  float a[V], bb[V], c[V], d[V];
+  Row r0, r1;
+  issue(2 * i0 - 2, r0); issue(2 * i0 - 1, r1);
+  reduce(r0, a);
+  issue(2 * i0, r0);
+  reduce(r1, bb);
+  issue(2 * i0 + 1, r1);
+  for (int i = i0; i < i1; ++i) {
+    reduce(r0, c);
+    issue(2 * i + 2, r0);
+    reduce(r1, d);
+    issue(2 * i + 3, r1);
+    Vec16<T> o;
+#pragma unroll
+    for (int k = 0; k < V; ++k) {
+      o.set(k, fmaf(t.k[3], d[k], fmaf(t.k[2], c[k], fmaf(t.k[1], bb[k], t.k[0] * a[k]))));
+      a[k] = c[k]; bb[k] = d[k];
+    }
+    st16(out + (((int64_t)i * W2 + xo) * cv + j) * V, o);
+  }
+}
+
+// adjoint (gather form): dx[y][x] = sum over the (i, r), (j, s) with clamp(2i+r-2) == y and
+// wrap(2j+s-2) == x of k[r] k[s] g[i][j] -- two taps per axis (same parity as the coordinate),
+// plus the two rows folded onto y == 0 by the clamp.
+template <typename T>
+__global__ void __launch_bounds__(256)
+blur4_down2_cl_adj_kernel(const T *__restrict__ g, T *__restrict__ dx, Taps4CL t, int H, int W,
+                          int cv, int64_t n_threads) {
+  constexpr int V = Vec16<T>::N;
+  const int H2 = H >> 1, W2 = W >> 1;
+  const int64_t tid = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (tid >= n_threads) return;
+  const int j = (int)(tid % cv);
+  int64_t q = tid / cv;
+  const int xc = (int)(q % W);
+  q /= W;
+  const int yr = (int)(q % H);
+  const int64_t b = q / H;
+  const T *gi = g + b * (int64_t)H2 * W2 * cv * V;
+  // horizontal taps s = p, p + 2 (p = x & 1): 2j + s - 2 == x (mod W)
+  const int p = xc & 1;
+  int jc[2];
+  float kx[2];
+#pragma unroll
+  for (int u = 0; u < 2; ++u) {
+    const int s = p + 2 * u;
+    int jj = (xc + 2 - s) >> 1;                  // in [0, W2]
+    jc[u] = jj >= W2 ? jj - W2 : jj;
+    kx[u] = t.k[s];
+  }
+  float acc[V];
+#pragma unroll
+  for (int k = 0; k < V; ++k) acc[k] = 0.f;
+  auto add = [&](int i, float ky) {
+    const T *row = gi + (int64_t)i * W2 * cv * V;
+#pragma unroll
+    for (int u = 0; u < 2; ++u) {
+      Vec16<T> v = ld16(row + ((int64_t)jc[u] * cv + j) * V);
+      const float w = ky * kx[u];
+#pragma unroll
+      for (int k = 0; k < V; ++k) acc[k] = fmaf(w, v.get(k), acc[k]);
+    }
+  };
+  const int pq = yr & 1;
+#pragma unroll
+  for (int u = 0; u < 2; ++u) {
+    const int r = pq + 2 * u;
+    const int i = (yr + 2 - r) >> 1;
+    if (i >= 0 && i < H2) add(i, t.k[r]);
+  }
+  if (yr == 0) {           // rows e = -2 (i = 0, r = 0) and e = -1 (i = 0, r = 1) clamp to 0
+    // (e = -2 has even parity and is not produced by the loop above for y = 0: r = 0 -> i = 1)
+    add(0, t.k[0]);
+    add(0, t.k[1]);
+  }
+  Vec16<T> o;
+#pragma unroll
+  for (int k = 0; k < V; ++k) o.set(k, acc[k]);
+  st16(dx + tid * V, o);
 }
 
 static unsigned cl_flat_grid(int64_t work) {
@@ -385,8 +539,8 @@ extern "C" int dusty_blur4_cl(const void *x, void *y, float k0, float k1, float 
   DUSTY_CHECK_ARG(B >= 1 && H >= 2 && W >= 4, "bad shape");
   DUSTY_CHECK_ARG(pad == 0 || pad == 1, "pad must be 0 or 1");
   DUSTY_CHECK_ARG(dtype == DUSTY_F32 || dtype == DUSTY_BF16, "bad dtype");
-  const int V = dtype == DUSTY_F32 ? 2 : 4;    // the stencil kernel works on 8-byte channel groups
-  DUSTY_CHECK_ARG(C % V == 0, "C must be a multiple of the 8-byte vector width");
+  const int V = dtype == DUSTY_F32 ? 4 : 8;    // 16-byte channel groups
+  DUSTY_CHECK_ARG(C % V == 0, "C must be a multiple of the 16-byte vector width");
   Taps4CL t;
   t.k[0] = k0; t.k[1] = k1; t.k[2] = k2; t.k[3] = k3;
   const int cv = C / V;
@@ -410,6 +564,42 @@ extern "C" int dusty_blur4_cl(const void *x, void *y, float k0, float k1, float 
   else BLUR_CL_DISPATCH(__nv_bfloat16);
 #undef BLUR_CL_DISPATCH
 #undef BLUR_CL
+  DUSTY_LAUNCH_CHECK();
+  return DUSTY_OK;
+}
+
+extern "C" int dusty_blur4_down2_cl(const void *x, void *y, float k0, float k1, float k2, float k3,
+                                    int B, int H, int W, int C, int adjoint, int dtype,
+                                    void *stream) {
+  DUSTY_CHECK_ARG(x && y, "null pointer");
+  DUSTY_CHECK_ARG(B >= 1 && H >= 2 && W >= 4 && H % 2 == 0 && W % 2 == 0, "bad shape");
+  DUSTY_CHECK_ARG(dtype == DUSTY_F32 || dtype == DUSTY_BF16, "bad dtype");
+  const int V = dtype == DUSTY_F32 ? 4 : 8;
+  DUSTY_CHECK_ARG(C % V == 0, "C must be a multiple of the 16-byte vector width");
+  Taps4CL t;
+  t.k[0] = k0; t.k[1] = k1; t.k[2] = k2; t.k[3] = k3;
+  const int cv = C / V;
+  cudaStream_t st = (cudaStream_t)stream;
+  if (!adjoint) {
+    const int H2 = H / 2;
+    const int64_t n_threads = (int64_t)B * (W / 2) * cv;
+    int strip = H2;
+    const int64_t ctas_x = (n_threads + 127) / 128;
+    while (strip > 4 && ctas_x * ((H2 + strip - 1) / strip) < (int64_t)num_sms() * 8) strip = (strip + 1) / 2;
+    dim3 grid((unsigned)ctas_x, (unsigned)((H2 + strip - 1) / strip));
+    if (dtype == DUSTY_F32)
+      blur4_down2_cl_kernel<float><<<grid, 128, 0, st>>>((const float *)x, (float *)y, t, H, W, cv, strip, n_threads);
+    else
+      blur4_down2_cl_kernel<__nv_bfloat16><<<grid, 128, 0, st>>>((const __nv_bfloat16 *)x, (__nv_bfloat16 *)y, t, H, W, cv, strip, n_threads);
+  } else {
+    const int64_t n_threads = (int64_t)B * H * W * cv;
+    const int64_t blocks = (n_threads + 255) / 256;
+    DUSTY_CHECK_ARG(blocks <= 0x7fffffff, "tensor too large");
+    if (dtype == DUSTY_F32)
+      blur4_down2_cl_adj_kernel<float><<<(unsigned)blocks, 256, 0, st>>>((const float *)x, (float *)y, t, H, W, cv, n_threads);
+    else
+      blur4_down2_cl_adj_kernel<__nv_bfloat16><<<(unsigned)blocks, 256, 0, st>>>((const __nv_bfloat16 *)x, (__nv_bfloat16 *)y, t, H, W, cv, n_threads);
+  }
   DUSTY_LAUNCH_CHECK();
   return DUSTY_OK;
 }

@@ -355,6 +355,39 @@ def blur_pad_cl(x: torch.Tensor, taps4) -> torch.Tensor:
     return _BlurPadCL.apply(x, tuple(float(t) for t in taps4), False)
 
 
+class _BlurDown2CL(Function):
+    """Resample([k0..k3], ring)(x)[:, :, ::2, ::2] on an NHWC tensor without evaluating the
+    discarded positions (skip branch of the residual blocks), and its adjoint."""
+
+    @staticmethod
+    def forward(ctx, x, taps4, adjoint):
+        B, C = x.shape[:2]
+        x = x if _is_cl(x) else x.contiguous(memory_format=_CL)
+        if adjoint:
+            H, W = x.shape[2] * 2, x.shape[3] * 2
+            y = torch.empty((B, C, H, W), device=x.device, dtype=x.dtype, memory_format=_CL)
+        else:
+            H, W = x.shape[2:]
+            y = torch.empty((B, C, H // 2, W // 2), device=x.device, dtype=x.dtype, memory_format=_CL)
+        K.call("dusty_blur4_down2_cl", K.ptr(x), K.ptr(y), taps4[0], taps4[1], taps4[2], taps4[3],
+               B, H, W, C, 1 if adjoint else 0, K.dtype_code(x), K.stream_of(x))
+        ctx.cfg = (taps4, adjoint)
+        return y
+
+    @staticmethod
+    def backward(ctx, g):
+        taps4, adjoint = ctx.cfg
+        return _BlurDown2CL.apply(g, taps4, not adjoint), None, None
+
+
+def blur_down2_cl_supported(x: torch.Tensor) -> bool:
+    return (blur_pad_cl_supported(x) and x.shape[-2] % 2 == 0 and x.shape[-1] % 2 == 0)
+
+
+def blur_down2_cl(x: torch.Tensor, taps4) -> torch.Tensor:
+    return _BlurDown2CL.apply(x, tuple(float(t) for t in taps4), False)
+
+
 def resample4_supported(x: torch.Tensor, up: int) -> bool:
     if x.ndim < 3 or not x.is_cuda or x.dtype not in (torch.float32, torch.bfloat16):
         return False

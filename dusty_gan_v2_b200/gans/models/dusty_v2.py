@@ -315,8 +315,24 @@ class ResidualBlock(nn.Module):
         h = self.bias_act1(self.conv1(x))
         return self.bias_act2(self._blur_pad_conv2(h))
 
+    def _skip(self, x):
+        """skip(resample(x)): the 1x1 stride-2 convolution reads the blurred image at even
+        positions only, so on the NHWC path the blur is evaluated there alone and the
+        convolution runs at unit stride on the quarter-size tensor."""
+        rs, eq = self.resample, self.skip[-1]
+        conv = getattr(eq, "module", None)
+        if (len(self.skip) == 1 and isinstance(eq, ops.EqualLR) and isinstance(conv, nn.Conv2d)
+                and conv.kernel_size == (1, 1) and conv.stride == (2, 2) and conv.bias is None
+                and getattr(rs, "_fast_up", None) == 1 and DF.blur_down2_cl_supported(x)):
+            if rs._taps_host is None:
+                rs._taps_host = tuple(rs.kernel.detach().float().cpu().tolist())
+            w = (conv.weight * (eq.scale * eq.gain_)).to(x.dtype)
+            w = w.contiguous(memory_format=torch.channels_last)
+            return ops.conv2d_valid(DF.blur_down2_cl(x, rs._taps_host), w, (1, 1))
+        return self.skip(rs(x))
+
     def forward(self, x):
-        return (self.residual(x) + self.skip(self.resample(x))) * (1.0 / math.sqrt(2))
+        return (self.residual(x) + self._skip(x)) * (1.0 / math.sqrt(2))
 
 
 class Discriminator(nn.Module):

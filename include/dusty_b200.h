@@ -119,6 +119,13 @@ int dusty_pad2d_cl(const void *x, void *y, int B, int H, int W, int C, int pt, i
 int dusty_blur4_cl(const void *x, void *y, float k0, float k1, float k2, float k3, int B, int H,
                    int W, int C, int adjoint, int pad, int dtype, void *stream);
 
+/* Skip branch of ResidualBlock (dusty_v2.py:387-396): conv1x1_stride2(Resample(x)) only reads
+ * the blurred image at even rows / columns.  y[b,i,j,:] = blur4(x)[b,2i,2j,:], y is
+ * [B,H/2,W/2,C]; adjoint != 0: x is the [B,H/2,W/2,C] gradient, y the [B,H,W,C] result.
+ * H, W even; C a multiple of the 16-byte vector width. */
+int dusty_blur4_down2_cl(const void *x, void *y, float k0, float k1, float k2, float k3, int B,
+                         int H, int W, int C, int adjoint, int dtype, void *stream);
+
 /* ---- a5/a6: AdaptiveAugment's geometric pipeline ------------------------------------------
  * Single-axis zero-padded polyphase FIR: upfirdn2d with a [1,k] (axis 1 = x) or [k,1]
  * (axis 0 = y) kernel, fp32, up/down in {1,2}:

@@ -401,6 +401,33 @@ def test_minibatch_stddev(ops, g_ops, shape):
         close(ops.MinibatchStdDev(4, 1)(dev(g_ops["mb2_x"])), g_ops["mb2_y"], 1e-4, 1e-6)
 
 
+@pytest.mark.parametrize("shape,cl", [((8, 6, 4, 4), False), ((8, 16, 4, 32), True), ((2, 8, 4, 4), True)])
+def test_minibatch_std_stat_only(DF, shape, cl):
+    """Statistic-only variant (D's NHWC epilogue): value of the appended channel and its
+    gradient, first order (kernel) and differentiable (R1) paths, vs the oracle."""
+    g = torch.Generator().manual_seed(13)
+    x = torch.randn(shape, generator=g)
+    xr = x.clone().requires_grad_()
+    stat_r = O.minibatch_stddev(xr)[:, -1, 0, 0]                 # [B]
+    xg = x.to(DEV)
+    if cl:
+        xg = xg.contiguous(memory_format=torch.channels_last)
+    xg.requires_grad_()
+    stat_g = DF.minibatch_std_stat(xg, 4)
+    close(stat_g, stat_r, rtol=1e-4, atol_rel=1e-6)
+    gs = torch.randn(shape[0], generator=g)
+    (gxr,) = torch.autograd.grad(stat_r, xr, gs, create_graph=True)
+    (gx1,) = torch.autograd.grad(stat_g, xg, gs.to(DEV), retain_graph=True)
+    close(gx1, gxr, rtol=1e-3, atol_rel=1e-5)
+    (gx2,) = torch.autograd.grad(stat_g, xg, gs.to(DEV), create_graph=True)
+    close(gx2, gxr, rtol=1e-3, atol_rel=1e-5)
+    v = torch.randn(shape, generator=g)
+    (hr,) = torch.autograd.grad((gxr * v).sum(), xr)
+    (hg,) = torch.autograd.grad((gx2 * v.to(DEV)).sum(), xg)
+    np.testing.assert_allclose(hg.cpu().numpy(), hr.numpy(), rtol=2e-3,
+                               atol=max(1e-4 * float(hr.abs().max()), 1e-5))
+
+
 # ----------------------------------------------------------------------------- a13 / a7
 def test_sumsq_rows_and_r1_grad(DF):
     g = torch.Generator().manual_seed(13)
@@ -575,6 +602,34 @@ def test_fused_blur_pad_nhwc(DF, ops, dtype, C):
     v = torch.randn(x.shape, generator=g).to(DEV, dtype)
     (gg,) = torch.autograd.grad((gf.float() * v.float()).sum(), gyf)
     close(gg, pad(blur(v)), **tol)
+
+
+@pytest.mark.parametrize("dtype,C,H,W", [(torch.float32, 8, 8, 16), (torch.bfloat16, 32, 6, 20),
+                                         (torch.bfloat16, 64, 2, 4), (torch.float32, 4, 64, 512)])
+def test_blur_down2_nhwc(DF, ops, dtype, C, H, W):
+    """blur evaluated at even positions only == Resample()(x)[:, :, ::2, ::2] (what the 1x1
+    stride-2 skip convolution reads); value, adjoint and second order."""
+    g = torch.Generator().manual_seed(44)
+    CL = torch.channels_last
+    x = torch.randn(2, C, H, W, generator=g).to(DEV, dtype)
+    blur = ops.Resample().to(DEV)
+    taps = tuple(blur.kernel.tolist())
+    tol = dict(rtol=1e-5, atol_rel=1e-6) if dtype == torch.float32 else dict(rtol=2e-2, atol_rel=1e-2)
+    xr = x.clone().requires_grad_()
+    ref = blur(xr)[:, :, ::2, ::2]
+    xf = x.contiguous(memory_format=CL).requires_grad_()
+    assert DF.blur_down2_cl_supported(xf)
+    got = DF.blur_down2_cl(xf, taps)
+    assert got.shape == ref.shape and DF._is_cl(got)
+    close(got, ref, **tol)
+    gy = torch.randn(ref.shape, generator=g).to(DEV, dtype)
+    (gr,) = torch.autograd.grad(ref, xr, gy)
+    gyf = gy.contiguous(memory_format=CL).requires_grad_()
+    (gf,) = torch.autograd.grad(got, xf, gyf, create_graph=True)
+    close(gf, gr, **tol)
+    v = torch.randn(x.shape, generator=g).to(DEV, dtype)
+    (gg,) = torch.autograd.grad((gf.float() * v.float()).sum(), gyf)
+    close(gg, blur(v)[:, :, ::2, ::2], **tol)
 
 
 # ----------------------------------------------------------------------------- a11 dense convs

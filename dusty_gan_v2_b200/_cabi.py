@@ -57,6 +57,8 @@ SIGNATURES = {
     "dusty_conv2d_tc": [_vp, _vp, _vp, _vp] + [_i] * 9 + [_vp, _vp, _i, _i, _i]
                        + [C.c_longlong] * 4 + [_i, _f, _f, _vp],
     "dusty_conv2d_wgrad_tc_workspace": [_i] * 7,
+    "dusty_conv2d_halo_supported": [_i] * 4,
+    "dusty_conv2d_halo_tc": [_vp, _vp, _vp, _vp] + [_i] * 11 + [C.c_longlong] * 4 + [_i, _f, _f, _vp],
     "dusty_conv2d_wgrad_tc": [_vp, _vp, _vp, _vp, C.c_longlong] + [_i] * 11 + [_vp],
 }
 _RESTYPE = {"dusty_last_error": C.c_char_p, "dusty_launch_count": C.c_int64,

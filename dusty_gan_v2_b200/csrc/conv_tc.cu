@@ -217,6 +217,201 @@ conv_fwd_tc_kernel(const __grid_constant__ ConvMaps maps, const __grid_constant_
   }
 }
 
+// ------------------------------------------------------------------ halo-resident 3x3 (C = 32 / 64)
+// The thin, wide layers (32 / 64 channels at 64x512 / 32x256) are bound by operand delivery, not
+// by the tensor pipe: an implicit GEMM that lands every filter tap as its own shared-memory tile
+// moves each input pixel 9 times from L2.  Here every input pixel is landed ONCE: a CTA loads a
+// (TH + R - 1) x PW pixel patch (rows of C channels = 64 or 128 bytes, K-major, 64B / 128B
+// swizzle) with a single TMA box, and the A operand of tap (r, s) is the SAME buffer read
+// through a descriptor whose start address is advanced by r * PW + s pixel rows.  That relies
+// on the swizzle being a function of the absolute shared-memory address (start addresses that
+// are not multiples of the 8-row swizzle atom, base-offset field 0) -- measured on sm_100a by
+// tools/experiments/umma_rowshift.cu for both swizzle widths.  M = 128 consecutive "virtual
+// pixels" of the patch (pitch PW); the PW - TW virtual pixels per row whose window crosses the
+// row end are computed and discarded.  All R*S filter taps stay resident in shared memory.
+// fprop of a valid conv: patch origin = tile origin.  dgrad (unit stride): the same kernel on
+// dY with the patch origin moved by -(R-1), -(S-1) (TMA zero-fills outside dY) and the filter
+// flipped / transposed by the host.
+struct HaloMaps {
+  CUtensorMap x, w;
+};
+
+struct HaloParams {
+  int T, S;                 // taps, taps per filter row
+  int PW, TH, TWo;          // patch pitch (pixels), output rows per tile, output columns per tile
+  int MB;                   // 128-pixel M blocks per tile = TH * PW / 128
+  int org_h, org_w;         // patch origin relative to the tile origin
+  int tiles_w, tiles_h, total_tiles, tiles_per_cta;
+  int H_out, W_out, O;
+  int patch_bytes;          // bytes landed per patch
+  long long y_off, y_sb, y_sh, y_sw;
+  const float *bias;
+  __nv_bfloat16 *y;
+  int act;
+  float alpha, scale;
+};
+
+template <int ROWB, int BN, int NBUF>
+__global__ void __launch_bounds__(kCThreads)
+conv_halo_tc_kernel(const __grid_constant__ HaloMaps maps, const __grid_constant__ HaloParams prm,
+                    int buf_stride) {
+  extern __shared__ __align__(1024) uint8_t smem_raw[];
+  uint8_t *smem = (uint8_t *)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
+  constexpr uint64_t kLayout = ROWB == 64 ? 4 : 2;          // SWIZZLE_64B : SWIZZLE_128B
+  constexpr int kWTap = BN * ROWB;                          // bytes of one filter tap [BN][C]
+  uint8_t *w_base = smem;
+  uint8_t *p_base = smem + ((prm.T * kWTap + 1023) & ~1023);
+  uint64_t *full = (uint64_t *)(p_base + NBUF * buf_stride);
+  uint64_t *empty = full + NBUF;
+  uint64_t *acc_full = empty + NBUF;
+  uint64_t *acc_empty = acc_full + 2;
+  uint64_t *w_full = acc_empty + 2;
+  uint32_t *tmem_slot = (uint32_t *)(w_full + 1);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int t_begin = blockIdx.x * prm.tiles_per_cta;
+  const int t_end = min(t_begin + prm.tiles_per_cta, prm.total_tiles);
+
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < NBUF; ++s) {
+      mbar_init(&full[s], 1);
+      mbar_init(&empty[s], 1);
+    }
+    for (int a = 0; a < 2; ++a) {
+      mbar_init(&acc_full[a], 1);
+      mbar_init(&acc_empty[a], 4);
+    }
+    mbar_init(w_full, 1);
+    fence_barrier_init();
+  }
+  if (warp == 1) tmem_alloc(tmem_slot, 2 * BN < 32 ? 32 : 2 * BN);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  auto decode = [&](int tile, int &b, int &oh0, int &ow0) {
+    ow0 = (tile % prm.tiles_w) * prm.TWo;
+    int r = tile / prm.tiles_w;
+    oh0 = (r % prm.tiles_h) * prm.TH;
+    b = r / prm.tiles_h;
+  };
+
+  if (warp == 0) {
+    if (lane == 0) {
+      mbar_expect_tx(w_full, prm.T * kWTap);
+      for (int t = 0; t < prm.T; ++t) tma_load_3d(w_base + t * kWTap, &maps.w, w_full, 0, 0, t);
+      int it = 0;
+      for (int tile = t_begin; tile < t_end; ++tile, ++it) {
+        int b, oh0, ow0;
+        decode(tile, b, oh0, ow0);
+        const int s = it % NBUF;
+        mbar_wait(&empty[s], ((it / NBUF) & 1) ^ 1);
+        mbar_expect_tx(&full[s], prm.patch_bytes);
+        tma_load_4d(p_base + s * buf_stride, &maps.x, &full[s], 0, ow0 + prm.org_w, oh0 + prm.org_h, b);
+      }
+    }
+  } else if (warp == 1) {
+    if (lane == 0) {
+      constexpr uint32_t idesc = make_idesc(kCM, BN, false, false);
+      mbar_wait(w_full, 0);
+      int it = 0, lt = 0;
+      for (int tile = t_begin; tile < t_end; ++tile, ++it) {
+        const int s = it % NBUF;
+        mbar_wait(&full[s], (it / NBUF) & 1);
+        tc_fence_after();
+        const uint32_t p_addr = smem_u32(p_base + s * buf_stride);
+        const uint32_t w_addr = smem_u32(w_base);
+        for (int mb = 0; mb < prm.MB; ++mb, ++lt) {
+          const int a = lt & 1;
+          mbar_wait(&acc_empty[a], ((lt >> 1) & 1) ^ 1);
+          tc_fence_after();
+          const uint32_t tmem_acc = tmem_base + (uint32_t)(a * BN);
+          uint32_t first = 0;
+          for (int t = 0; t < prm.T; ++t) {
+            const int shift = (t / prm.S) * prm.PW + (t % prm.S);
+            const uint32_t a_addr = p_addr + (uint32_t)((mb * kCM + shift) * ROWB);
+#pragma unroll
+            for (int k16 = 0; k16 < ROWB / 32; ++k16) {
+              uint64_t adesc = make_desc(a_addr + k16 * 32, 16, 8 * ROWB);
+              uint64_t bdesc = make_desc(w_addr + t * kWTap + k16 * 32, 16, 8 * ROWB);
+              adesc = (adesc & ~((uint64_t)7 << 61)) | (kLayout << 61);
+              bdesc = (bdesc & ~((uint64_t)7 << 61)) | (kLayout << 61);
+              umma_bf16(tmem_acc, adesc, bdesc, idesc, first);
+              first = 1u;
+            }
+          }
+          umma_commit(&acc_full[a]);
+        }
+        umma_commit(&empty[s]);              // patch buffer reusable once these MMAs retire
+      }
+    }
+  } else {
+    const int q = warp & 3;
+    const int row = q * 32 + lane;
+    int lt = 0;
+    for (int tile = t_begin; tile < t_end; ++tile) {
+      int b, oh0, ow0;
+      decode(tile, b, oh0, ow0);
+      for (int mb = 0; mb < prm.MB; ++mb, ++lt) {
+        const int a = lt & 1;
+        mbar_wait(&acc_full[a], (lt >> 1) & 1);
+        tc_fence_after();
+        const uint32_t tmem_acc = tmem_base + (uint32_t)(a * BN) + ((uint32_t)(q * 32) << 16);
+        const int m = mb * kCM + row;                 // virtual pixel inside the patch
+        const int hh = m / prm.PW, ww = m - hh * prm.PW;
+        const int oh = oh0 + hh, ow = ow0 + ww;
+        const bool pix_ok = ww < prm.TWo && oh < prm.H_out && ow < prm.W_out;
+        __nv_bfloat16 *yp = prm.y + prm.y_off + (long long)b * prm.y_sb + (long long)oh * prm.y_sh +
+                            (long long)ow * prm.y_sw;
+#pragma unroll 1
+        for (int c = 0; c < BN; c += 16) {
+          uint32_t r[16];
+          tmem_ld16(tmem_acc + (uint32_t)c, r);
+          tmem_ld_wait();
+          if (c + 16 >= BN) {
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&acc_empty[a]);
+          }
+          if (pix_ok) {
+#pragma unroll
+            for (int h8 = 0; h8 < 2; ++h8) {
+              const int o = c + h8 * 8;
+              if (o < prm.O) {
+                uint32_t pk[4];
+#pragma unroll
+                for (int j = 0; j < 4; ++j) {
+                  float v0 = __uint_as_float(r[h8 * 8 + 2 * j]);
+                  float v1 = __uint_as_float(r[h8 * 8 + 2 * j + 1]);
+                  if (prm.bias) {
+                    v0 += __ldg(prm.bias + o + 2 * j);
+                    v1 += __ldg(prm.bias + o + 2 * j + 1);
+                  }
+                  if (prm.act == 3) {
+                    v0 = v0 > 0.f ? v0 : v0 * prm.alpha;
+                    v1 = v1 > 0.f ? v1 : v1 * prm.alpha;
+                  }
+                  const uint32_t lo = __bfloat16_as_ushort(__float2bfloat16_rn(v0 * prm.scale));
+                  const uint32_t hi = __bfloat16_as_ushort(__float2bfloat16_rn(v1 * prm.scale));
+                  pk[j] = lo | (hi << 16);
+                }
+                *reinterpret_cast<uint4 *>(yp + o) = make_uint4(pk[0], pk[1], pk[2], pk[3]);
+              }
+            }
+          }
+        }
+      }
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, 2 * BN < 32 ? 32 : 2 * BN);
+  }
+}
+
 // ------------------------------------------------------------------ wgrad
 struct WgMaps {
   CUtensorMap a[4];    // x window of filter row r
@@ -387,6 +582,42 @@ bool make_map3w(CUtensorMap *m, const void *ptr, uint64_t d0, uint64_t d1, uint6
   return enc(m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 3, const_cast<void *>(ptr), dims, strides, box,
              estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
              CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
+}
+
+bool make_map_sw(CUtensorMap *m, const void *ptr, int rank, const uint64_t *dims,
+                 const uint64_t *strides_b, const uint32_t *box, bool sw64) {
+  EncodeTiledFn enc = get_encode();
+  if (!enc) return false;
+  cuuint64_t d[4];
+  cuuint64_t s[3];
+  cuuint32_t bx[4], es[4];
+  for (int i = 0; i < rank; ++i) { d[i] = dims[i]; bx[i] = box[i]; es[i] = 1; }
+  for (int i = 0; i + 1 < rank; ++i) s[i] = strides_b[i];
+  return enc(m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, rank, const_cast<void *>(ptr), d, s, bx, es,
+             CU_TENSOR_MAP_INTERLEAVE_NONE,
+             sw64 ? CU_TENSOR_MAP_SWIZZLE_64B : CU_TENSOR_MAP_SWIZZLE_128B,
+             CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
+}
+
+template <int ROWB, int BN, int NBUF>
+int launch_halo(const HaloMaps &maps, HaloParams prm, int buf_stride, cudaStream_t st) {
+  const int smem = ((prm.T * BN * ROWB + 1023) & ~1023) + NBUF * buf_stride + 256 + 1024;
+  static int configured = 0;
+  if (smem > configured) {
+    if (cudaFuncSetAttribute(conv_halo_tc_kernel<ROWB, BN, NBUF>,
+                             cudaFuncAttributeMaxDynamicSharedMemorySize, smem) != cudaSuccess) {
+      set_error("conv_halo_tc: cannot reserve %d bytes of shared memory", smem);
+      return DUSTY_ECUDA;
+    }
+    configured = smem;
+  }
+  const int per_sm = (2 * smem <= 225 * 1024 && 4 * BN <= 512) ? 2 : 1;
+  const int resident = num_sms() * per_sm;
+  int ctas = prm.total_tiles < resident ? prm.total_tiles : resident;
+  prm.tiles_per_cta = (prm.total_tiles + ctas - 1) / ctas;
+  ctas = (prm.total_tiles + prm.tiles_per_cta - 1) / prm.tiles_per_cta;
+  conv_halo_tc_kernel<ROWB, BN, NBUF><<<ctas, kCThreads, smem, st>>>(maps, prm, buf_stride);
+  return 0;
 }
 
 template <int BN, int STAGES>
@@ -600,5 +831,81 @@ extern "C" int dusty_conv2d_wgrad_tc(const void *x, const void *dy, float *dwp, 
     wgrad_reduce_kernel<<<blocks, 256, 0, st>>>(ws, dwp, n4, splits, n / 4);
     DUSTY_LAUNCH_CHECK();
   }
+  return DUSTY_OK;
+}
+
+extern "C" int dusty_conv2d_halo_supported(int C, int O, int R, int S) {
+  return (C == 32 || C == 64) && O % 8 == 0 && O >= 8 && O <= 128 && R >= 1 && R <= 3 && S >= 1 &&
+         S <= 3 && get_encode() != nullptr;
+}
+
+extern "C" int dusty_conv2d_halo_tc(const void *x, const void *wpk, const float *bias, void *y,
+                                    int B, int H_in, int W_in, int C, int H_out, int W_out, int O,
+                                    int R, int S, int org_h, int org_w, long long y_off,
+                                    long long y_sb, long long y_sh, long long y_sw, int act,
+                                    float alpha, float scale, void *stream) {
+  DUSTY_CHECK_ARG(x && wpk && y, "null pointer");
+  DUSTY_CHECK_ARG(dusty_conv2d_halo_supported(C, O, R, S), "shape not supported by the halo kernel");
+  DUSTY_CHECK_ARG(B > 0 && H_in > 0 && W_in > 0 && H_out > 0 && W_out > 0, "empty tensor");
+  DUSTY_CHECK_ARG(aligned16(x) && aligned16(wpk) && aligned16(y), "16-byte alignment");
+  DUSTY_CHECK_ARG((y_off % 8 == 0) && (y_sb % 8 == 0) && (y_sh % 8 == 0) && (y_sw % 8 == 0),
+                  "output strides must keep 16-byte alignment");
+  cudaStream_t st = (cudaStream_t)stream;
+  const int ROWB = C * 2;
+  const int BN = O > 64 ? 128 : (O > 32 ? 64 : 32);
+  HaloParams prm;
+  prm.T = R * S; prm.S = S;
+  // patch pitch: 64 pixels, or 32 when that wastes fewer columns on a narrow image
+  auto cover = [&](int pw) { const int two = pw - (S - 1); return (long long)((W_out + two - 1) / two) * pw; };
+  prm.PW = cover(32) < cover(64) ? 32 : 64;
+  prm.TWo = prm.PW - (S - 1);
+  // rows per tile: as many as a 48 / 64 KiB patch allows, in multiples that make TH * PW % 128 == 0
+  const int th_step = 128 / prm.PW;
+  int th = th_step;
+  const int patch_cap = ROWB == 64 ? 48 * 1024 : 64 * 1024;
+  while ((th + th_step + R - 1) * prm.PW * ROWB <= patch_cap && th + th_step <= 16 &&
+         th < H_out) th += th_step;
+  prm.TH = th;
+  prm.MB = prm.TH * prm.PW / 128;
+  prm.org_h = org_h; prm.org_w = org_w;
+  prm.tiles_w = (W_out + prm.TWo - 1) / prm.TWo;
+  prm.tiles_h = (H_out + prm.TH - 1) / prm.TH;
+  const long long total = (long long)prm.tiles_w * prm.tiles_h * B;
+  DUSTY_CHECK_ARG(total <= 0x7fffffff, "too many tiles");
+  prm.total_tiles = (int)total;
+  prm.H_out = H_out; prm.W_out = W_out; prm.O = O;
+  const int prow = prm.TH + R - 1;
+  prm.patch_bytes = prow * prm.PW * ROWB;
+  // the last taps of the last M block read up to S - 1 rows past the patch: keep them inside
+  // the buffer (their values only reach discarded virtual pixels)
+  const int buf_stride = (prm.patch_bytes + (S - 1) * ROWB + 1023) & ~1023;
+  prm.y_off = y_off; prm.y_sb = y_sb; prm.y_sh = y_sh; prm.y_sw = y_sw;
+  prm.bias = bias; prm.y = (__nv_bfloat16 *)y; prm.act = act; prm.alpha = alpha; prm.scale = scale;
+  HaloMaps maps;
+  {
+    const uint64_t dims[4] = {(uint64_t)C, (uint64_t)W_in, (uint64_t)H_in, (uint64_t)B};
+    const uint64_t strides[3] = {(uint64_t)C * 2, (uint64_t)W_in * C * 2, (uint64_t)H_in * W_in * C * 2};
+    const uint32_t box[4] = {(uint32_t)C, (uint32_t)prm.PW, (uint32_t)prow, 1u};
+    const uint64_t wdims[3] = {(uint64_t)C, (uint64_t)O, (uint64_t)prm.T};
+    const uint64_t wstr[2] = {(uint64_t)C * 2, (uint64_t)O * C * 2};
+    const uint32_t wbox[3] = {(uint32_t)C, (uint32_t)BN, 1u};
+    if (!make_map_sw(&maps.x, x, 4, dims, strides, box, ROWB == 64) ||
+        !make_map_sw(&maps.w, wpk, 3, wdims, wstr, wbox, ROWB == 64)) {
+      set_error("dusty_conv2d_halo_tc: cuTensorMapEncodeTiled failed");
+      return DUSTY_ECUDA;
+    }
+  }
+  int rc;
+  if (ROWB == 64) {
+    if (BN == 32) rc = launch_halo<64, 32, 2>(maps, prm, buf_stride, st);
+    else if (BN == 64) rc = launch_halo<64, 64, 2>(maps, prm, buf_stride, st);
+    else rc = launch_halo<64, 128, 2>(maps, prm, buf_stride, st);
+  } else {
+    if (BN == 32) rc = launch_halo<128, 32, 2>(maps, prm, buf_stride, st);
+    else if (BN == 64) rc = launch_halo<128, 64, 2>(maps, prm, buf_stride, st);
+    else rc = launch_halo<128, 128, 2>(maps, prm, buf_stride, st);
+  }
+  if (rc) return rc;
+  DUSTY_LAUNCH_CHECK();
   return DUSTY_OK;
 }

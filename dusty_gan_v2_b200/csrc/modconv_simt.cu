@@ -441,9 +441,12 @@ static int run_nn(const GemmNN &g, int B, bool a_kcontig, cudaStream_t st) {
     constexpr int V = Vec16<T>::N;
     // pixel groups per block: 32 (8 channel slices) unless the channel axis is short
     const int64_t groups = (g.N + V - 1) / V;
-    int PG = 32;
-    while (PG < 256 && g.K < 4 * (256 / PG)) PG <<= 1;      // >= 4 channels per slice
-    while (PG > 8 && groups < PG) PG >>= 1;
+    // one slice (PG = 256) when the pixel axis alone fills the machine; otherwise halve PG
+    // (double the channel slices) while a slice keeps >= 8 channels
+    int PG = 256;
+    while (PG > 8 && ((groups + PG - 1) / PG) * B < 4 * (int64_t)num_sms() &&
+           g.K / (256 / (PG / 2)) >= 8)
+      PG >>= 1;
     dim3 grid((unsigned)((groups + PG - 1) / PG), (unsigned)B);
     const size_t smem = ((size_t)g.M * g.K + 256 * 4 * V) * sizeof(float);
     static bool configured = false;

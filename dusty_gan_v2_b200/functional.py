@@ -948,7 +948,12 @@ def circular_unshift(v, shift01, scale: float = 1.0):
 
 
 # ---- a11: dense NHWC convolutions on tcgen05 (conv_tc.cu) --------------------------------
-_CONV_IMPL = {"mode": "auto"}
+_CONV_IMPL = {"mode": "auto", "halo": True}
+
+
+def set_conv_halo(enabled: bool):
+    """Allow / forbid the halo-resident kernel (tests exercise both formulations)."""
+    _CONV_IMPL["halo"] = bool(enabled)
 
 
 def set_conv_impl(mode: str):
@@ -978,8 +983,20 @@ def conv_tc_supported(x: torch.Tensor, w: torch.Tensor, stride, op: str = "fprop
         return False
     if mode == "auto":
         strided = stride[0] == 2 or stride[1] == 2
+        if not strided and op in ("fprop", "dgrad") and conv_halo_ok(w, op):
+            return True
         return C <= 32 and ((op == "dgrad" and strided) or (op == "wgrad" and R * S > 1))
     return True
+
+
+def conv_halo_ok(w: torch.Tensor, op: str) -> bool:
+    """Unit-stride fprop / dgrad of a thin layer: the halo-resident kernel (each input pixel
+    landed in shared memory once) applies when the contracted channel count is 32 or 64."""
+    if not _CONV_IMPL["halo"]:
+        return False
+    O, C, R, S = w.shape
+    cin, cout = (C, O) if op == "fprop" else (O, C)
+    return R <= 3 and S <= 3 and cin in (32, 64) and cout % 8 == 0 and 8 <= cout <= 128
 
 
 def _nhwc(x: torch.Tensor) -> torch.Tensor:
@@ -998,9 +1015,14 @@ def conv2d_fprop_tc(x, w, stride, bias=None, act: int = 1, alpha: float = 0.2, s
     O, _, R, S = w.shape
     sh, sw = stride
     Ho, Wo = (H - R) // sh + 1, (W - S) // sw + 1
-    wpk = w.permute(2, 0, 3, 1).reshape(R, O, S * C).contiguous()
     y = torch.empty((B, O, Ho, Wo), dtype=x.dtype, device=x.device,
                     memory_format=torch.channels_last)
+    if sh == 1 and sw == 1 and conv_halo_ok(w, "fprop"):
+        wpk = w.permute(2, 3, 0, 1).reshape(R * S, O, C).contiguous()
+        K.call("dusty_conv2d_halo_tc", K.ptr(x), K.ptr(wpk), K.ptr(bias), K.ptr(y), B, H, W, C,
+               Ho, Wo, O, R, S, 0, 0, 0, Ho * Wo * O, Wo * O, O, act, alpha, scale, K.stream_of(x))
+        return y
+    wpk = w.permute(2, 0, 3, 1).reshape(R, O, S * C).contiguous()
     K.call("dusty_conv2d_tc", K.ptr(x), K.ptr(wpk), K.ptr(bias), K.ptr(y),
                B, H, W, C, Ho, Wo, O, 1, R, _ints(list(range(R))), _ints([0] * R), S, sh, sw,
                0, Ho * Wo * O, Wo * O, O, act, alpha, scale, K.stream_of(x))
@@ -1015,6 +1037,13 @@ def conv2d_dgrad_tc(gy, w, stride, in_hw):
     _, C, R, S = w.shape
     H, W = in_hw
     sh, sw = stride
+    if sh == 1 and sw == 1 and conv_halo_ok(w, "dgrad"):
+        gx = torch.empty((B, C, H, W), dtype=gy.dtype, device=gy.device,
+                         memory_format=torch.channels_last)
+        wpk = w.flip(2, 3).permute(2, 3, 1, 0).reshape(R * S, C, O).contiguous()
+        K.call("dusty_conv2d_halo_tc", K.ptr(gy), K.ptr(wpk), None, K.ptr(gx), B, Ho, Wo, O, H, W,
+               C, R, S, -(R - 1), -(S - 1), 0, H * W * C, W * C, C, 1, 0.0, 1.0, K.stream_of(gy))
+        return gx
     wt = w.permute(2, 3, 1, 0)                       # [R, S, C, O]
     classes = []
     for ph in range(sh):

@@ -284,6 +284,19 @@ int dusty_conv2d_wgrad_tc(const void *x, const void *dy, float *dwp, float *ws, 
                           int B, int H_in, int W_in, int C, int H_out, int W_out, int O, int R,
                           int S, int stride_h, int stride_w, void *stream);
 
+/* Halo-resident variant for the thin layers (C = 32 or 64 input channels, O <= 128, filters up
+ * to 3x3, unit stride): every input pixel is landed in shared memory once and the R*S taps are
+ * shifted views of that patch (see conv_tc.cu).  y[b,oh,ow,n] = act(sum_{a,b',c}
+ * x[b, oh + org_h + a, ow + org_w + b', c] * wpk[a*S + b'][n][c] + bias[n]) * scale, rows /
+ * columns outside x read as zero.  fprop of a valid conv: org = (0, 0), wpk[t][n][c] =
+ * w[n][c][r][s]; dgrad: x := dY, org = (-(R-1), -(S-1)), wpk[a*S+b'][c][n] = w[n][c][R-1-a][S-1-b'].
+ * dusty_conv2d_halo_supported returns non-zero when the shape qualifies. */
+int dusty_conv2d_halo_supported(int C, int O, int R, int S);
+int dusty_conv2d_halo_tc(const void *x, const void *wpk, const float *bias, void *y, int B,
+                         int H_in, int W_in, int C, int H_out, int W_out, int O, int R, int S,
+                         int org_h, int org_w, long long y_off, long long y_sb, long long y_sh,
+                         long long y_sw, int act, float alpha, float scale, void *stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -644,8 +644,13 @@ def test_blur_down2_nhwc(DF, ops, dtype, C, H, W):
     (2, 32, 64, 16, 64, 1, 2),       # skip branch: 1x1 stride 2
     (2, 48, 40, 9, 21, 3, 1),        # channel counts that are not powers of two
     (1, 16, 24, 7, 9, 2, 1),
+    (2, 40, 64, 12, 70, 3, 1),       # halo kernel on the dgrad side only (contracts 64 channels)
+    (2, 32, 32, 10, 20, 3, 1),       # narrow image: 32-pixel patch pitch
+    (2, 32, 64, 8, 32, 1, 1),        # skip branch after the decimating blur: 1x1, unit stride
+    (3, 64, 128, 11, 131, 3, 1),     # odd sizes, several tiles with ragged edges
 ])
-def test_conv2d_tcgen05_fprop_dgrad_wgrad(DF, B, C, Oc, H, W, k, stride):
+@pytest.mark.parametrize("halo", [True, False])
+def test_conv2d_tcgen05_fprop_dgrad_wgrad(DF, B, C, Oc, H, W, k, stride, halo):
     """Own implicit-GEMM convolution vs the oracle's F.conv2d (fp32, CPU) on bf16-rounded
     operands; tolerance = bf16 output rounding (rtol 2e-2)."""
     g = torch.Generator().manual_seed(33)
@@ -661,11 +666,19 @@ def test_conv2d_tcgen05_fprop_dgrad_wgrad(DF, B, C, Oc, H, W, k, stride):
     xd = x.to(DEV).contiguous(memory_format=torch.channels_last)
     wd = w.to(DEV)
     s2 = (stride, stride)
+    if halo and not (stride == 1 and (DF.conv_halo_ok(wd, "fprop") or DF.conv_halo_ok(wd, "dgrad"))):
+        pytest.skip("shape does not take the halo-resident kernel")
     DF.set_conv_impl("tc")
+    DF.set_conv_halo(halo)
     try:
         assert DF.conv_tc_supported(xd, wd, s2)
+        _conv_checks(DF, xd, wd, w, s2, ref, gy, gx_ref, gw_ref, g, Oc, H, W)
     finally:
         DF.set_conv_impl("auto")
+        DF.set_conv_halo(True)
+
+
+def _conv_checks(DF, xd, wd, w, s2, ref, gy, gx_ref, gw_ref, g, Oc, H, W):
     y = DF.conv2d_fprop_tc(xd, wd, s2)
     assert y.shape == ref.shape and y.is_contiguous(memory_format=torch.channels_last)
     close(y, ref, rtol=2e-2, atol_rel=4e-3)

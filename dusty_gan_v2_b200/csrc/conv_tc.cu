@@ -128,6 +128,11 @@ conv_fwd_tc_kernel(const __grid_constant__ ConvMaps maps, const __grid_constant_
   } else if (warp == 1) {
     if (lane == 0) {
       constexpr uint32_t idesc = make_idesc(kCM, BN, false, false);
+      // K-major SW128 on both sides: 32 bytes per UMMA_K step inside the swizzle atom, SBO =
+      // next group of 8 rows (1 KiB); constant high word, low word advanced by adds
+      const uint32_t d_hi = desc_hi(1024, 2);
+      const uint32_t a_lo0 = desc_lo(smem_u32(a_base), 16);
+      const uint32_t b_lo0 = desc_lo(smem_u32(b_base), 16);
       int it = 0, lt = 0;
       for (int tile = t_begin; tile < t_end; ++tile, ++lt) {
         const int a = lt & 1;
@@ -139,16 +144,12 @@ conv_fwd_tc_kernel(const __grid_constant__ ConvMaps maps, const __grid_constant_
           const uint32_t ph = (it / STAGES) & 1;
           mbar_wait(&full[s], ph);
           tc_fence_after();
-          const uint32_t a_addr = smem_u32(a_base + s * kCABytes);
-          const uint32_t b_addr = smem_u32(b_base + s * kBBytes);
+          const uint32_t a_lo = a_lo0 + (uint32_t)s * (kCABytes >> 4);
+          const uint32_t b_lo = b_lo0 + (uint32_t)s * (kBBytes >> 4);
 #pragma unroll
-          for (int k16 = 0; k16 < kCK / 16; ++k16) {
-            // K-major SW128 on both sides: 32 bytes per UMMA_K step inside the swizzle atom,
-            // SBO = next group of 8 rows (1 KiB)
-            const uint64_t adesc = make_desc(a_addr + k16 * 32, 16, 1024);
-            const uint64_t bdesc = make_desc(b_addr + k16 * 32, 16, 1024);
-            umma_bf16(tmem_acc, adesc, bdesc, idesc, (kb > 0 || k16 > 0) ? 1u : 0u);
-          }
+          for (int k16 = 0; k16 < kCK / 16; ++k16)
+            umma_bf16_lh(tmem_acc, a_lo + k16 * 2, d_hi, b_lo + k16 * 2, d_hi, idesc,
+                         (kb > 0 || k16 > 0) ? 1u : 0u);
           umma_commit(&empty[s]);
         }
         umma_commit(&acc_full[a]);
@@ -315,31 +316,35 @@ conv_halo_tc_kernel(const __grid_constant__ HaloMaps maps, const __grid_constant
     if (lane == 0) {
       constexpr uint32_t idesc = make_idesc(kCM, BN, false, false);
       mbar_wait(w_full, 0);
+      const uint32_t d_hi = desc_hi(8 * ROWB, (uint32_t)kLayout);
+      const uint32_t p_lo0 = desc_lo(smem_u32(p_base), 16);
+      const uint32_t w_lo0 = desc_lo(smem_u32(w_base), 16);
+      constexpr uint32_t kRow16 = ROWB >> 4;            // descriptor units per pixel row
       int it = 0, lt = 0;
       for (int tile = t_begin; tile < t_end; ++tile, ++it) {
         const int s = it % NBUF;
         mbar_wait(&full[s], (it / NBUF) & 1);
         tc_fence_after();
-        const uint32_t p_addr = smem_u32(p_base + s * buf_stride);
-        const uint32_t w_addr = smem_u32(w_base);
+        const uint32_t p_lo = p_lo0 + (uint32_t)s * (uint32_t)(buf_stride >> 4);
         for (int mb = 0; mb < prm.MB; ++mb, ++lt) {
           const int a = lt & 1;
           mbar_wait(&acc_empty[a], ((lt >> 1) & 1) ^ 1);
           tc_fence_after();
           const uint32_t tmem_acc = tmem_base + (uint32_t)(a * BN);
           uint32_t first = 0;
+          // tap (r, s2): A = the patch read from pixel row mb*128 + r*PW + s2 onwards
+          uint32_t a_row = p_lo + (uint32_t)(mb * kCM) * kRow16;
+          uint32_t w_lo = w_lo0;
+          int s2 = 0;
           for (int t = 0; t < prm.T; ++t) {
-            const int shift = (t / prm.S) * prm.PW + (t % prm.S);
-            const uint32_t a_addr = p_addr + (uint32_t)((mb * kCM + shift) * ROWB);
 #pragma unroll
             for (int k16 = 0; k16 < ROWB / 32; ++k16) {
-              uint64_t adesc = make_desc(a_addr + k16 * 32, 16, 8 * ROWB);
-              uint64_t bdesc = make_desc(w_addr + t * kWTap + k16 * 32, 16, 8 * ROWB);
-              adesc = (adesc & ~((uint64_t)7 << 61)) | (kLayout << 61);
-              bdesc = (bdesc & ~((uint64_t)7 << 61)) | (kLayout << 61);
-              umma_bf16(tmem_acc, adesc, bdesc, idesc, first);
+              umma_bf16_lh(tmem_acc, a_row + (uint32_t)s2 * kRow16 + k16 * 2, d_hi, w_lo + k16 * 2,
+                           d_hi, idesc, first);
               first = 1u;
             }
+            w_lo += kWTap >> 4;
+            if (++s2 == prm.S) { s2 = 0; a_row += (uint32_t)prm.PW * kRow16; }
           }
           umma_commit(&acc_full[a]);
         }
@@ -487,21 +492,22 @@ conv_wgrad_tc_kernel(const __grid_constant__ WgMaps maps, const __grid_constant_
   } else if (warp == 1) {
     if (lane == 0) {
       constexpr uint32_t idesc = make_idesc(kCM, BN, true, true);
+      // MN-major SW128: 16 pixel rows = 2 KiB per UMMA_K step; LBO = next 64-channel block
+      // (8 KiB), SBO = next group of 8 pixel rows (1 KiB)
+      const uint32_t d_hi = desc_hi(1024, 2);
+      const uint32_t a_lo0 = desc_lo(smem_u32(a_base), 8192);
+      const uint32_t b_lo0 = desc_lo(smem_u32(b_base), 8192);
       for (int pb = pb_begin, it = 0; pb < pb_end; ++pb, ++it) {
         const int s = it % STAGES;
         const uint32_t ph = (it / STAGES) & 1;
         mbar_wait(&full[s], ph);
         tc_fence_after();
-        const uint32_t a_addr = smem_u32(a_base + s * kCABytes);
-        const uint32_t b_addr = smem_u32(b_base + s * kBBytes);
+        const uint32_t a_lo = a_lo0 + (uint32_t)s * (kCABytes >> 4);
+        const uint32_t b_lo = b_lo0 + (uint32_t)s * (kBBytes >> 4);
 #pragma unroll
-        for (int k16 = 0; k16 < kCK / 16; ++k16) {
-          // MN-major SW128: 16 pixel rows = 2 KiB per UMMA_K step; LBO = next 64-channel
-          // block (8 KiB), SBO = next group of 8 pixel rows (1 KiB)
-          const uint64_t adesc = make_desc(a_addr + k16 * 2048, 8192, 1024);
-          const uint64_t bdesc = make_desc(b_addr + k16 * 2048, 8192, 1024);
-          umma_bf16(tmem_acc, adesc, bdesc, idesc, (it > 0 || k16 > 0) ? 1u : 0u);
-        }
+        for (int k16 = 0; k16 < kCK / 16; ++k16)
+          umma_bf16_lh(tmem_acc, a_lo + k16 * (2048 >> 4), d_hi, b_lo + k16 * (2048 >> 4), d_hi, idesc,
+                       (it > 0 || k16 > 0) ? 1u : 0u);
         umma_commit(&empty[s]);
       }
       umma_commit(acc_full);
@@ -835,8 +841,9 @@ extern "C" int dusty_conv2d_wgrad_tc(const void *x, const void *dy, float *dwp, 
 }
 
 extern "C" int dusty_conv2d_halo_supported(int C, int O, int R, int S) {
+  const int BN = O > 64 ? 128 : (O > 32 ? 64 : 32);
   return (C == 32 || C == 64) && O % 8 == 0 && O >= 8 && O <= 128 && R >= 1 && R <= 3 && S >= 1 &&
-         S <= 3 && get_encode() != nullptr;
+         S <= 3 && R * S * BN * C * 2 <= 72 * 1024 && get_encode() != nullptr;
 }
 
 extern "C" int dusty_conv2d_halo_tc(const void *x, const void *wpk, const float *bias, void *y,

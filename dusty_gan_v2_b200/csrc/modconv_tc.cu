@@ -134,6 +134,14 @@ modconv_fwd_tc_kernel(const __grid_constant__ CUtensorMap map_x1,
     // ===================== MMA issuer =====================
     if (lane == 0) {
       constexpr uint32_t idesc = make_idesc(kBM, BN, true, B_MN);
+      // A (MN-major, SW128): 16 channel rows = 2 KiB per UMMA_K step; LBO = next 64-pixel block
+      // (8 KiB), SBO = next group of 8 channel rows (1 KiB).  B K-major (SW128): 32 bytes per
+      // UMMA_K step inside the swizzle atom, SBO = next group of 8 out-channel rows; B MN-major
+      // (dX): same geometry as A.  High words are constant, low words advance by adds.
+      const uint32_t d_hi = desc_hi(1024, 2);
+      const uint32_t a_lo0 = desc_lo(smem_u32(a_base), kABytes / 2);
+      const uint32_t b_lo0 = desc_lo(smem_u32(b_base), B_MN ? 8192 : 16);
+      constexpr uint32_t kBStep = (B_MN ? 2048 : 32) >> 4;
       int it = 0, lt = 0;
       for (int tile = t_begin; tile < t_end; ++tile, ++lt) {
         const int a = lt & 1;
@@ -145,19 +153,12 @@ modconv_fwd_tc_kernel(const __grid_constant__ CUtensorMap map_x1,
           const uint32_t ph = (it / STAGES) & 1;
           mbar_wait(&full[s], ph);
           tc_fence_after();
-          const uint32_t a_addr = smem_u32(a_base + s * kABytes);
-          const uint32_t b_addr = smem_u32(b_base + s * kBBytes);
+          const uint32_t a_lo = a_lo0 + (uint32_t)s * (kABytes >> 4);
+          const uint32_t b_lo = b_lo0 + (uint32_t)s * (kBBytes >> 4);
 #pragma unroll
-          for (int k16 = 0; k16 < kBK / 16; ++k16) {
-            // A (MN-major, SW128): 16 channel rows = 2 KiB per UMMA_K step; LBO = next
-            // 64-pixel block (8 KiB), SBO = next group of 8 channel rows (1 KiB)
-            const uint64_t adesc = make_desc(a_addr + k16 * 2048, kABytes / 2, 1024);
-            // B K-major (SW128): 32 bytes per UMMA_K step inside the swizzle atom, SBO = next
-            // group of 8 out-channel rows; B MN-major (dX): same geometry as A
-            const uint64_t bdesc = B_MN ? make_desc(b_addr + k16 * 2048, 8192, 1024)
-                                        : make_desc(b_addr + k16 * 32, 16, 1024);
-            umma_bf16(tmem_acc, adesc, bdesc, idesc, (kb > 0 || k16 > 0) ? 1u : 0u);
-          }
+          for (int k16 = 0; k16 < kBK / 16; ++k16)
+            umma_bf16_lh(tmem_acc, a_lo + k16 * (2048 >> 4), d_hi, b_lo + k16 * kBStep, d_hi, idesc,
+                         (kb > 0 || k16 > 0) ? 1u : 0u);
           umma_commit(&empty[s]);            // smem slot reusable once these MMAs retire
         }
         umma_commit(&acc_full[a]);           // accumulator of this tile complete
@@ -295,19 +296,20 @@ modconv_dw_tc_kernel(const __grid_constant__ CUtensorMap map_x1,
   } else if (warp == 1) {
     if (lane == 0) {
       constexpr uint32_t idesc = make_idesc(kBM, BN, false, false);
+      const uint32_t d_hi = desc_hi(1024, 2);
+      const uint32_t a_lo0 = desc_lo(smem_u32(a_base), 16);
+      const uint32_t b_lo0 = desc_lo(smem_u32(b_base), 16);
       for (int pb = 0; pb < num_pb; ++pb) {
         const int s = pb % STAGES;
         const uint32_t ph = (pb / STAGES) & 1;
         mbar_wait(&full[s], ph);
         tc_fence_after();
-        const uint32_t a_addr = smem_u32(a_base + s * kABytes);
-        const uint32_t b_addr = smem_u32(b_base + s * kBBytes);
+        const uint32_t a_lo = a_lo0 + (uint32_t)s * (kABytes >> 4);
+        const uint32_t b_lo = b_lo0 + (uint32_t)s * (kBBytes >> 4);
 #pragma unroll
-        for (int k16 = 0; k16 < kBK / 16; ++k16) {
-          const uint64_t adesc = make_desc(a_addr + k16 * 32, 16, 1024);
-          const uint64_t bdesc = make_desc(b_addr + k16 * 32, 16, 1024);
-          umma_bf16(tmem_acc, adesc, bdesc, idesc, (pb > 0 || k16 > 0) ? 1u : 0u);
-        }
+        for (int k16 = 0; k16 < kBK / 16; ++k16)
+          umma_bf16_lh(tmem_acc, a_lo + k16 * 2, d_hi, b_lo + k16 * 2, d_hi, idesc,
+                       (pb > 0 || k16 > 0) ? 1u : 0u);
         umma_commit(&empty[s]);
       }
       umma_commit(acc_full);

@@ -108,6 +108,34 @@ __device__ __forceinline__ uint64_t make_desc(uint32_t saddr, uint32_t lbo_bytes
   d |= (uint64_t)2 << 61;
   return d;
 }
+// Split form of the descriptor for the MMA-issuing thread: that single thread's ALU chain is
+// the issue bottleneck of thin tiles (a 128xNx16 UMMA with N <= 64 is 16-32 tensor cycles, a
+// rebuilt 64-bit descriptor is ~20 dependent instructions), so the constant high word is built
+// once and the low word (start address | LBO) is advanced with one 32-bit add per step:
+// byte offset `off` -> lo + (off >> 4) (shared-memory addresses fit the 14-bit field).
+__device__ __forceinline__ uint32_t desc_lo(uint32_t saddr, uint32_t lbo_bytes) {
+  return ((saddr & 0x3FFFF) >> 4) | (((lbo_bytes >> 4) & 0x3FFF) << 16);
+}
+// layout: 2 = SWIZZLE_128B, 4 = SWIZZLE_64B
+__device__ __forceinline__ uint32_t desc_hi(uint32_t sbo_bytes, uint32_t layout) {
+  return ((sbo_bytes >> 4) & 0x3FFF) | (1u << 14) | (layout << 29);
+}
+__device__ __forceinline__ void umma_bf16_lh(uint32_t tmem_d, uint32_t alo, uint32_t ahi,
+                                             uint32_t blo, uint32_t bhi, uint32_t idesc,
+                                             uint32_t accumulate) {
+  asm volatile(
+      "{\n"
+      ".reg .pred p;\n"
+      ".reg .b64 da, db;\n"
+      "setp.ne.b32 p, %6, 0;\n"
+      "mov.b64 da, {%1, %2};\n"
+      "mov.b64 db, {%3, %4};\n"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], da, db, %5, p;\n"
+      "}\n" ::"r"(tmem_d),
+      "r"(alo), "r"(ahi), "r"(blo), "r"(bhi), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+
 // 32-bit instruction descriptor (cute::UMMA::InstrDescriptor): D = F32, A = B = BF16,
 // per-operand major-ness (MN-major = "transposed"), dense, no negate.
 __host__ __device__ constexpr uint32_t make_idesc(int M, int N, bool a_mn, bool b_mn) {

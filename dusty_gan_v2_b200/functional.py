@@ -996,7 +996,9 @@ def conv_halo_ok(w: torch.Tensor, op: str) -> bool:
         return False
     O, C, R, S = w.shape
     cin, cout = (C, O) if op == "fprop" else (O, C)
-    return R <= 3 and S <= 3 and cin in (32, 64) and cout % 8 == 0 and 8 <= cout <= 128
+    bn = 128 if cout > 64 else (64 if cout > 32 else 32)      # resident filter: <= 72 KiB
+    return (R <= 3 and S <= 3 and cin in (32, 64) and cout % 8 == 0 and 8 <= cout <= 128
+            and R * S * bn * cin * 2 <= 72 * 1024)
 
 
 def _nhwc(x: torch.Tensor) -> torch.Tensor:

@@ -13,7 +13,7 @@ int modconv_bwd_dw_simt(const void *dy, const void *x1, const void *x2, float *d
 // tensor-core path (modconv_tc.cu); returns DUSTY_EUNSUPPORTED when the shape does not fit
 int modconv_fwd_tc(const void *wb, const void *x1, const void *x2, const float *bias, void *y,
                    int B, int O, int C1, int C2, int B2, int64_t P, int act, float alpha,
-                   float scale, cudaStream_t st);
+                   float scale, bool batch_fused, cudaStream_t st);
 bool modconv_fwd_tc_supported(int B, int O, int C1, int C2, int B2, int64_t P);
 int modconv_dx_tc(const void *wb, const void *dy, void *dx1, int B, int O, int C1, int K, int64_t P,
                   cudaStream_t st);
@@ -38,19 +38,20 @@ extern "C" int dusty_modconv_fwd(const void *wb, const void *x1, const void *x2,
   DUSTY_CHECK_ARG(C2 == 0 || B2 == B || B2 == 1, "x2 batch must be B or 1");
   DUSTY_CHECK_ARG(act == 1 || act == 3, "act must be 1 or 3");
   DUSTY_CHECK_ARG(dtype_ok(dtype) && dtype_ok(wdtype), "bad dtype");
-  DUSTY_CHECK_ARG(impl >= 0 && impl <= 2, "impl must be 0 (auto), 1 (simt) or 2 (tcgen05)");
+  DUSTY_CHECK_ARG(impl >= 0 && impl <= 3,
+                  "impl must be 0 (auto), 1 (simt), 2 (tcgen05) or 3 (tcgen05, per-sample tiles only)");
   cudaStream_t st = (cudaStream_t)stream;
   if (C1 == 0) x1 = x2;  // keep pointers valid for address arithmetic
   if (C2 == 0) { x2 = x1; B2 = B; }
   const bool tc_ok = dtype == DUSTY_BF16 && wdtype == DUSTY_BF16 &&
                      modconv_fwd_tc_supported(B, O, C1, C2, B2, P);
-  if (impl == 2 && !tc_ok) {
+  if (impl >= 2 && !tc_ok) {
     set_error("dusty_modconv_fwd: tcgen05 path does not support this shape/dtype");
     return DUSTY_EUNSUPPORTED;
   }
   int rc;
-  if (impl == 2 || (impl == 0 && tc_ok))
-    rc = modconv_fwd_tc(wb, x1, x2, bias, y, B, O, C1, C2, B2, P, act, alpha, scale, st);
+  if (impl >= 2 || (impl == 0 && tc_ok))
+    rc = modconv_fwd_tc(wb, x1, x2, bias, y, B, O, C1, C2, B2, P, act, alpha, scale, impl != 3, st);
   else
     rc = modconv_fwd_simt(wb, x1, x2, bias, y, B, O, C1, C2, B2, P, act, alpha, scale, dtype,
                           wdtype, st);
@@ -65,14 +66,14 @@ extern "C" int dusty_modconv_bwd_dx(const void *wb, const void *dy, void *dx1, i
   DUSTY_CHECK_ARG(wb && dy && dx1, "null pointer");
   DUSTY_CHECK_ARG(B >= 1 && B <= 65535 && O >= 1 && C1 >= 1 && K >= C1 && P >= 1, "bad shape");
   DUSTY_CHECK_ARG(dtype_ok(dtype) && dtype_ok(wdtype), "bad dtype");
-  DUSTY_CHECK_ARG(impl >= 0 && impl <= 2, "impl must be 0 (auto), 1 (simt) or 2 (tcgen05)");
+  DUSTY_CHECK_ARG(impl >= 0 && impl <= 3, "impl must be 0 (auto), 1 (simt), 2 or 3 (tcgen05)");
   const bool tc_ok = dtype == DUSTY_BF16 && wdtype == DUSTY_BF16 && modconv_dx_tc_supported(B, O, C1, K, P);
-  if (impl == 2 && !tc_ok) {
+  if (impl >= 2 && !tc_ok) {
     set_error("dusty_modconv_bwd_dx: tcgen05 path does not support this shape/dtype");
     return DUSTY_EUNSUPPORTED;
   }
   int rc;
-  if (impl == 2 || (impl == 0 && tc_ok))
+  if (impl >= 2 || (impl == 0 && tc_ok))
     rc = modconv_dx_tc(wb, dy, dx1, B, O, C1, K, P, (cudaStream_t)stream);
   else
     rc = modconv_bwd_dx_simt(wb, dy, dx1, B, O, C1, K, P, dtype, wdtype, (cudaStream_t)stream);
@@ -90,16 +91,16 @@ extern "C" int dusty_modconv_bwd_dw(const void *dy, const void *x1, const void *
   DUSTY_CHECK_ARG((C1 == 0 || x1) && (C2 == 0 || x2), "missing source tensor");
   DUSTY_CHECK_ARG(C2 == 0 || B2 == B || B2 == 1, "x2 batch must be B or 1");
   DUSTY_CHECK_ARG(dtype_ok(dtype), "bad dtype");
-  DUSTY_CHECK_ARG(impl >= 0 && impl <= 2, "impl must be 0 (auto), 1 (simt) or 2 (tcgen05)");
+  DUSTY_CHECK_ARG(impl >= 0 && impl <= 3, "impl must be 0 (auto), 1 (simt), 2 or 3 (tcgen05)");
   if (C1 == 0) x1 = x2;
   if (C2 == 0) { x2 = x1; B2 = B; }
   const bool tc_ok = dtype == DUSTY_BF16 && modconv_dw_tc_supported(B, O, C1, C2, B2, P);
-  if (impl == 2 && !tc_ok) {
+  if (impl >= 2 && !tc_ok) {
     set_error("dusty_modconv_bwd_dw: tcgen05 path does not support this shape/dtype");
     return DUSTY_EUNSUPPORTED;
   }
   int rc;
-  if (impl == 2 || (impl == 0 && tc_ok))
+  if (impl >= 2 || (impl == 0 && tc_ok))
     rc = modconv_dw_tc(dy, x1, x2, dwb, B, O, C1, C2, B2, P, (cudaStream_t)stream);
   else
     rc = modconv_bwd_dw_simt(dy, x1, x2, dwb, B, O, C1, C2, B2, P, dtype, (cudaStream_t)stream);

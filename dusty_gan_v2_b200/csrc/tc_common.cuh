@@ -46,6 +46,65 @@ __device__ __forceinline__ void tma_load_3d(void *smem_dst, const CUtensorMap *m
       "l"(map), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2)
       : "memory");
 }
+// L2 prefetch of a tensor-map box (no shared-memory destination, no barrier): issued a tile or
+// two ahead by the producer of a persistent kernel, it turns the HBM latency of the activation
+// stream into L2 latency for the ring loads, whose depth (bytes in flight) shared memory bounds.
+__device__ __forceinline__ void tma_prefetch_3d(const CUtensorMap *map, int c0, int c1, int c2) {
+  asm volatile("cp.async.bulk.prefetch.tensor.3d.L2.global [%0, {%1, %2, %3}];" ::"l"(map), "r"(c0),
+               "r"(c1), "r"(c2)
+               : "memory");
+}
+// One elected lane of a fully converged warp (the same lane every time for a full mask).  The
+// producer and MMA warps keep WARP-UNIFORM control flow -- every lane runs the loops and waits
+// on the barriers, only the TMA / UMMA / commit instructions sit under this predicate -- so
+// that the compiler keeps addresses and descriptors in uniform registers.  Inside an
+// `if (lane == 0)` region the same code is divergent: every UTMALDG / UTCHMMA operand is moved
+// to the uniform file with its own ELECT + R2UR.BROADCAST sequence and the single issuing
+// thread becomes the bottleneck of the whole CTA (ncu source page: ~150 dependent
+// instructions per 4-UMMA stage, tensor pipe 37 % active).
+__device__ __forceinline__ bool elect_one_sync() {
+  uint32_t pred = 0;
+  asm volatile(
+      "{\n"
+      ".reg .b32 rx;\n"
+      ".reg .pred px;\n"
+      "elect.sync rx|px, 0xffffffff;\n"
+      "@px mov.s32 %0, 1;\n"
+      "}\n"
+      : "+r"(pred));
+  return pred != 0;
+}
+// ring position (slot, phase parity) advanced without divisions
+struct RingPos {
+  int s;
+  uint32_t ph;
+  __device__ __forceinline__ RingPos() : s(0), ph(0) {}
+  template <int STAGES>
+  __device__ __forceinline__ void advance() {
+    if (++s == STAGES) { s = 0; ph ^= 1; }
+  }
+};
+// TMA store of a dense (un-swizzled) shared-memory tile, bulk-group completion
+__device__ __forceinline__ void tma_store_3d(const CUtensorMap *map, uint32_t smem_src, int c0,
+                                             int c1, int c2) {
+  asm volatile("cp.async.bulk.tensor.3d.global.shared::cta.bulk_group [%0, {%2, %3, %4}], [%1];" ::"l"(map),
+               "r"(smem_src), "r"(c0), "r"(c1), "r"(c2)
+               : "memory");
+}
+__device__ __forceinline__ void tma_store_commit() {
+  asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+}
+// all but the newest `N` committed store groups of this thread have finished READING shared memory
+template <int N>
+__device__ __forceinline__ void tma_store_wait_read() {
+  asm volatile("cp.async.bulk.wait_group.read %0;" ::"n"(N) : "memory");
+}
+__device__ __forceinline__ void st_shared_b16(uint32_t addr, uint16_t v) {
+  asm volatile("st.shared.b16 [%0], %1;" ::"r"(addr), "h"(v) : "memory");
+}
+__device__ __forceinline__ void named_bar_sync(int id, int threads) {
+  asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(threads) : "memory");
+}
 __device__ __forceinline__ void tmem_alloc(uint32_t *dst_smem, uint32_t cols) {
   asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(
                    smem_u32(dst_smem)),

@@ -41,7 +41,7 @@ def act_dtype() -> torch.dtype:
 
 
 def set_modconv_impl(impl: int):
-    """0 auto, 1 SIMT, 2 tcgen05 (see dusty_modconv_fwd)."""
+    """0 auto, 1 SIMT, 2 tcgen05, 3 tcgen05 without the batch-fused tiles (see dusty_modconv_fwd)."""
     _PRECISION["modconv_impl"] = int(impl)
 
 

@@ -164,7 +164,9 @@ int dusty_angle_down2(const float *angle_in, float *angle_out, int Ba, int H, in
  * shared); K = C1 + C2; either part may be empty (C == 0, pointer ignored).
  * Epilogue: + bias[o] (fp32, may be NULL), then act (1 linear / 3 lrelu(alpha)) * scale.
  * wb has dtype `wdtype`; x1/x2/y have dtype `dtype`.
- * impl: 0 = auto, 1 = SIMT fp32-FMA kernel, 2 = tcgen05 tensor-core kernel (bf16 only). */
+ * impl: 0 = auto, 1 = SIMT fp32-FMA kernel, 2 = tcgen05 tensor-core kernel (bf16 only; with a
+ * batch-shared x2 the Fourier half runs as one dense GEMM over the [(B*O), K] weight matrix,
+ * several samples side by side in one accumulator), 3 = tcgen05 with per-sample tiles only. */
 int dusty_modconv_fwd(const void *wb, const void *x1, const void *x2, const float *bias, void *y,
                       int B, int O, int C1, int C2, int B2, int64_t P, int act, float alpha,
                       float scale, int dtype, int wdtype, int impl, void *stream);

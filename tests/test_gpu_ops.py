@@ -467,6 +467,11 @@ def test_circular_unshift_vs_oracle(DF):
     (2, 64, 64, 0, 1, (32, 256)),        # level 3 conv2
     (2, 32, 32, 0, 1, (64, 512)),        # level 4 conv2: K = 32 < one stage (TMA zero fill)
     (1, 48, 64, 0, 1, (2, 64)),          # O not a multiple of the N tile
+    (8, 32, 64, 512, 1, (16, 128)),      # batch-fused tiles: 8 samples side by side (BN = 256)
+    (16, 32, 64, 512, 1, (8, 64)),       # ... two column tiles
+    (6, 32, 64, 512, 1, (8, 64)),        # ... group of 6 (BN = 192)
+    (4, 64, 128, 512, 1, (16, 128)),     # level 3 conv1, 4 samples per tile
+    (4, 128, 256, 512, 1, (8, 64)),      # level 2 conv1, 2 samples per tile
 ])
 def test_modconv_tcgen05_vs_fp32_reference(DF, B, Oc, C1, C2, B2, HW):
     import dusty_gan_v2_b200 as pkg

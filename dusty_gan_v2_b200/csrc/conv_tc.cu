@@ -38,7 +38,8 @@ namespace {
 constexpr int kCM = 128;                 // UMMA M
 constexpr int kCK = 64;                  // K elements per stage
 constexpr int kCABytes = kCM * kCK * 2;  // 16 KiB
-constexpr int kCThreads = 192;
+constexpr int kCThreads = 64 + 256;   // TMA warp, MMA warp, 8 epilogue warps (fprop / dgrad)
+constexpr int kWgThreads = 192;        // wgrad: one epilogue pass per CTA, 4 warps
 constexpr int kMaxGroups = 16;
 
 struct ConvMaps {
@@ -85,7 +86,7 @@ conv_fwd_tc_kernel(const __grid_constant__ ConvMaps maps, const __grid_constant_
     }
     for (int a = 0; a < 2; ++a) {
       mbar_init(&acc_full[a], 1);
-      mbar_init(&acc_empty[a], 4);
+      mbar_init(&acc_empty[a], 8);
     }
     fence_barrier_init();
   }
@@ -106,44 +107,46 @@ conv_fwd_tc_kernel(const __grid_constant__ ConvMaps maps, const __grid_constant_
   };
 
   if (warp == 0) {
-    if (lane == 0) {
-      int it = 0;
-      for (int tile = t_begin; tile < t_end; ++tile) {
-        int b, oh0, ow0, n0;
-        decode(tile, b, oh0, ow0, n0);
-        for (int g = 0; g < prm.G; ++g) {
-          const CUtensorMap *am = &maps.a[prm.amap[g]];
-          const int cw = ow0 + prm.aw[g], ch = oh0 + prm.ah[g];
-          for (int kc = 0; kc < prm.KC; ++kc, ++it) {
-            const int s = it % STAGES;
-            const uint32_t ph = (it / STAGES) & 1;
-            mbar_wait(&empty[s], ph ^ 1);
+    // warp-uniform loop, elected lane issues (see elect_one_sync)
+    RingPos r;
+    for (int tile = t_begin; tile < t_end; ++tile) {
+      int b, oh0, ow0, n0;
+      decode(tile, b, oh0, ow0, n0);
+      for (int g = 0; g < prm.G; ++g) {
+        const CUtensorMap *am = &maps.a[prm.amap[g]];
+        const int cw = ow0 + prm.aw[g], ch = oh0 + prm.ah[g];
+        for (int kc = 0; kc < prm.KC; ++kc) {
+          const int s = r.s;
+          mbar_wait(&empty[s], r.ph ^ 1);
+          if (elect_one_sync()) {
             mbar_expect_tx(&full[s], kStageBytes);
             tma_load_4d(a_base + s * kCABytes, am, &full[s], kc * kCK, cw, ch, b);
             tma_load_3d(b_base + s * kBBytes, &maps.w, &full[s], kc * kCK, n0, g);
           }
+          __syncwarp();
+          r.template advance<STAGES>();
         }
       }
     }
   } else if (warp == 1) {
-    if (lane == 0) {
-      constexpr uint32_t idesc = make_idesc(kCM, BN, false, false);
-      // K-major SW128 on both sides: 32 bytes per UMMA_K step inside the swizzle atom, SBO =
-      // next group of 8 rows (1 KiB); constant high word, low word advanced by adds
-      const uint32_t d_hi = desc_hi(1024, 2);
-      const uint32_t a_lo0 = desc_lo(smem_u32(a_base), 16);
-      const uint32_t b_lo0 = desc_lo(smem_u32(b_base), 16);
-      int it = 0, lt = 0;
-      for (int tile = t_begin; tile < t_end; ++tile, ++lt) {
-        const int a = lt & 1;
-        mbar_wait(&acc_empty[a], ((lt >> 1) & 1) ^ 1);
+    constexpr uint32_t idesc = make_idesc(kCM, BN, false, false);
+    // K-major SW128 on both sides: 32 bytes per UMMA_K step inside the swizzle atom, SBO =
+    // next group of 8 rows (1 KiB); constant high word, low word advanced by adds
+    const uint32_t d_hi = desc_hi(1024, 2);
+    const uint32_t a_lo0 = desc_lo(smem_u32(a_base), 16);
+    const uint32_t b_lo0 = desc_lo(smem_u32(b_base), 16);
+    RingPos r;
+    int lt = 0;
+    for (int tile = t_begin; tile < t_end; ++tile, ++lt) {
+      const int a = lt & 1;
+      mbar_wait(&acc_empty[a], ((lt >> 1) & 1) ^ 1);
+      tc_fence_after();
+      const uint32_t tmem_acc = tmem_base + (uint32_t)(a * BN);
+      for (int kb = 0; kb < num_kb; ++kb) {
+        const int s = r.s;
+        mbar_wait(&full[s], r.ph);
         tc_fence_after();
-        const uint32_t tmem_acc = tmem_base + (uint32_t)(a * BN);
-        for (int kb = 0; kb < num_kb; ++kb, ++it) {
-          const int s = it % STAGES;
-          const uint32_t ph = (it / STAGES) & 1;
-          mbar_wait(&full[s], ph);
-          tc_fence_after();
+        if (elect_one_sync()) {
           const uint32_t a_lo = a_lo0 + (uint32_t)s * (kCABytes >> 4);
           const uint32_t b_lo = b_lo0 + (uint32_t)s * (kBBytes >> 4);
 #pragma unroll
@@ -152,11 +155,15 @@ conv_fwd_tc_kernel(const __grid_constant__ ConvMaps maps, const __grid_constant_
                          (kb > 0 || k16 > 0) ? 1u : 0u);
           umma_commit(&empty[s]);
         }
-        umma_commit(&acc_full[a]);
+        __syncwarp();
+        r.template advance<STAGES>();
       }
+      if (elect_one_sync()) umma_commit(&acc_full[a]);
+      __syncwarp();
     }
   } else {
     const int q = warp & 3;
+    const int grp = (warp - 2) >> 2;
     const int row = q * 32 + lane;
     const int th = row / prm.TW, tw = row % prm.TW;
     int lt = 0;
@@ -171,12 +178,14 @@ conv_fwd_tc_kernel(const __grid_constant__ ConvMaps maps, const __grid_constant_
       const bool pix_ok = oh < prm.H_out && ow < prm.W_out;
       __nv_bfloat16 *yp = prm.y + prm.y_off + (long long)b * prm.y_sb + (long long)oh * prm.y_sh +
                           (long long)ow * prm.y_sw + n0;
+      // the two groups of four epilogue warps take alternate 16-column chunks
+      constexpr int kLastMine = BN - 32;      // + 16 * grp: last chunk a group reads (BN >= 32)
 #pragma unroll 1
-      for (int c = 0; c < BN; c += 16) {
+      for (int c = 16 * grp; c < BN; c += 32) {
         uint32_t r[16];
         tmem_ld16(tmem_acc + (uint32_t)c, r);
         tmem_ld_wait();
-        if (c + 16 >= BN) {
+        if (c >= kLastMine) {
           tc_fence_before();
           __syncwarp();
           if (lane == 0) mbar_arrive(&acc_empty[a]);
@@ -280,7 +289,7 @@ conv_halo_tc_kernel(const __grid_constant__ HaloMaps maps, const __grid_constant
     }
     for (int a = 0; a < 2; ++a) {
       mbar_init(&acc_full[a], 1);
-      mbar_init(&acc_empty[a], 4);
+      mbar_init(&acc_empty[a], 8);
     }
     mbar_init(w_full, 1);
     fence_barrier_init();
@@ -299,37 +308,43 @@ conv_halo_tc_kernel(const __grid_constant__ HaloMaps maps, const __grid_constant
   };
 
   if (warp == 0) {
-    if (lane == 0) {
+    if (elect_one_sync()) {
       mbar_expect_tx(w_full, prm.T * kWTap);
       for (int t = 0; t < prm.T; ++t) tma_load_3d(w_base + t * kWTap, &maps.w, w_full, 0, 0, t);
-      int it = 0;
-      for (int tile = t_begin; tile < t_end; ++tile, ++it) {
-        int b, oh0, ow0;
-        decode(tile, b, oh0, ow0);
-        const int s = it % NBUF;
-        mbar_wait(&empty[s], ((it / NBUF) & 1) ^ 1);
+    }
+    __syncwarp();
+    RingPos r;
+    for (int tile = t_begin; tile < t_end; ++tile) {
+      int b, oh0, ow0;
+      decode(tile, b, oh0, ow0);
+      const int s = r.s;
+      mbar_wait(&empty[s], r.ph ^ 1);
+      if (elect_one_sync()) {
         mbar_expect_tx(&full[s], prm.patch_bytes);
         tma_load_4d(p_base + s * buf_stride, &maps.x, &full[s], 0, ow0 + prm.org_w, oh0 + prm.org_h, b);
       }
+      __syncwarp();
+      r.template advance<NBUF>();
     }
   } else if (warp == 1) {
-    if (lane == 0) {
-      constexpr uint32_t idesc = make_idesc(kCM, BN, false, false);
-      mbar_wait(w_full, 0);
-      const uint32_t d_hi = desc_hi(8 * ROWB, (uint32_t)kLayout);
-      const uint32_t p_lo0 = desc_lo(smem_u32(p_base), 16);
-      const uint32_t w_lo0 = desc_lo(smem_u32(w_base), 16);
-      constexpr uint32_t kRow16 = ROWB >> 4;            // descriptor units per pixel row
-      int it = 0, lt = 0;
-      for (int tile = t_begin; tile < t_end; ++tile, ++it) {
-        const int s = it % NBUF;
-        mbar_wait(&full[s], (it / NBUF) & 1);
+    constexpr uint32_t idesc = make_idesc(kCM, BN, false, false);
+    mbar_wait(w_full, 0);
+    const uint32_t d_hi = desc_hi(8 * ROWB, (uint32_t)kLayout);
+    const uint32_t p_lo0 = desc_lo(smem_u32(p_base), 16);
+    const uint32_t w_lo0 = desc_lo(smem_u32(w_base), 16);
+    constexpr uint32_t kRow16 = ROWB >> 4;            // descriptor units per pixel row
+    RingPos r;
+    int lt = 0;
+    for (int tile = t_begin; tile < t_end; ++tile) {
+      const int s = r.s;
+      mbar_wait(&full[s], r.ph);
+      tc_fence_after();
+      const uint32_t p_lo = p_lo0 + (uint32_t)s * (uint32_t)(buf_stride >> 4);
+      for (int mb = 0; mb < prm.MB; ++mb, ++lt) {
+        const int a = lt & 1;
+        mbar_wait(&acc_empty[a], ((lt >> 1) & 1) ^ 1);
         tc_fence_after();
-        const uint32_t p_lo = p_lo0 + (uint32_t)s * (uint32_t)(buf_stride >> 4);
-        for (int mb = 0; mb < prm.MB; ++mb, ++lt) {
-          const int a = lt & 1;
-          mbar_wait(&acc_empty[a], ((lt >> 1) & 1) ^ 1);
-          tc_fence_after();
+        if (elect_one_sync()) {
           const uint32_t tmem_acc = tmem_base + (uint32_t)(a * BN);
           uint32_t first = 0;
           // tap (r, s2): A = the patch read from pixel row mb*128 + r*PW + s2 onwards
@@ -348,11 +363,15 @@ conv_halo_tc_kernel(const __grid_constant__ HaloMaps maps, const __grid_constant
           }
           umma_commit(&acc_full[a]);
         }
-        umma_commit(&empty[s]);              // patch buffer reusable once these MMAs retire
+        __syncwarp();
       }
+      if (elect_one_sync()) umma_commit(&empty[s]);   // patch buffer reusable once these MMAs retire
+      __syncwarp();
+      r.template advance<NBUF>();
     }
   } else {
     const int q = warp & 3;
+    const int grp = (warp - 2) >> 2;
     const int row = q * 32 + lane;
     int lt = 0;
     for (int tile = t_begin; tile < t_end; ++tile) {
@@ -369,12 +388,13 @@ conv_halo_tc_kernel(const __grid_constant__ HaloMaps maps, const __grid_constant
         const bool pix_ok = ww < prm.TWo && oh < prm.H_out && ow < prm.W_out;
         __nv_bfloat16 *yp = prm.y + prm.y_off + (long long)b * prm.y_sb + (long long)oh * prm.y_sh +
                             (long long)ow * prm.y_sw;
+        constexpr int kLastMine = BN - 32;    // + 16 * grp: last chunk a group reads (BN >= 32)
 #pragma unroll 1
-        for (int c = 0; c < BN; c += 16) {
+        for (int c = 16 * grp; c < BN; c += 32) {
           uint32_t r[16];
           tmem_ld16(tmem_acc + (uint32_t)c, r);
           tmem_ld_wait();
-          if (c + 16 >= BN) {
+          if (c >= kLastMine) {
             tc_fence_before();
             __syncwarp();
             if (lane == 0) mbar_arrive(&acc_empty[a]);
@@ -433,7 +453,7 @@ struct WgParams {
 };
 
 template <int BN, int STAGES>
-__global__ void __launch_bounds__(kCThreads)
+__global__ void __launch_bounds__(kWgThreads)
 conv_wgrad_tc_kernel(const __grid_constant__ WgMaps maps, const __grid_constant__ WgParams prm) {
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   uint8_t *smem = (uint8_t *)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
@@ -469,17 +489,17 @@ conv_wgrad_tc_kernel(const __grid_constant__ WgMaps maps, const __grid_constant_
   const uint32_t tmem_acc = *tmem_slot;
 
   if (warp == 0) {
-    if (lane == 0) {
-      const CUtensorMap *am = &maps.a[r];
-      for (int pb = pb_begin, it = 0; pb < pb_end; ++pb, ++it) {
-        const int s = it % STAGES;
-        const uint32_t ph = (it / STAGES) & 1;
-        int t = pb;
-        const int ow0 = (t % prm.tiles_w) * prm.TW;
-        t /= prm.tiles_w;
-        const int oh0 = (t % prm.tiles_h) * prm.TH;
-        const int b = t / prm.tiles_h;
-        mbar_wait(&empty[s], ph ^ 1);
+    const CUtensorMap *am = &maps.a[r];
+    RingPos rp;
+    for (int pb = pb_begin; pb < pb_end; ++pb) {
+      const int s = rp.s;
+      int t = pb;
+      const int ow0 = (t % prm.tiles_w) * prm.TW;
+      t /= prm.tiles_w;
+      const int oh0 = (t % prm.tiles_h) * prm.TH;
+      const int b = t / prm.tiles_h;
+      mbar_wait(&empty[s], rp.ph ^ 1);
+      if (elect_one_sync()) {
         mbar_expect_tx(&full[s], kStageBytes);
         uint8_t *a_dst = a_base + s * kCABytes;
         tma_load_4d(a_dst, am, &full[s], m0, ow0, oh0, b);
@@ -488,30 +508,35 @@ conv_wgrad_tc_kernel(const __grid_constant__ WgMaps maps, const __grid_constant_
         for (int j = 0; j < BN / 64; ++j)
           tma_load_4d(b_base + s * kBBytes + j * 8192, &maps.g, &full[s], n0 + 64 * j, ow0, oh0, b);
       }
+      __syncwarp();
+      rp.template advance<STAGES>();
     }
   } else if (warp == 1) {
-    if (lane == 0) {
-      constexpr uint32_t idesc = make_idesc(kCM, BN, true, true);
-      // MN-major SW128: 16 pixel rows = 2 KiB per UMMA_K step; LBO = next 64-channel block
-      // (8 KiB), SBO = next group of 8 pixel rows (1 KiB)
-      const uint32_t d_hi = desc_hi(1024, 2);
-      const uint32_t a_lo0 = desc_lo(smem_u32(a_base), 8192);
-      const uint32_t b_lo0 = desc_lo(smem_u32(b_base), 8192);
-      for (int pb = pb_begin, it = 0; pb < pb_end; ++pb, ++it) {
-        const int s = it % STAGES;
-        const uint32_t ph = (it / STAGES) & 1;
-        mbar_wait(&full[s], ph);
-        tc_fence_after();
+    constexpr uint32_t idesc = make_idesc(kCM, BN, true, true);
+    // MN-major SW128: 16 pixel rows = 2 KiB per UMMA_K step; LBO = next 64-channel block
+    // (8 KiB), SBO = next group of 8 pixel rows (1 KiB)
+    const uint32_t d_hi = desc_hi(1024, 2);
+    const uint32_t a_lo0 = desc_lo(smem_u32(a_base), 8192);
+    const uint32_t b_lo0 = desc_lo(smem_u32(b_base), 8192);
+    RingPos rp;
+    for (int pb = pb_begin; pb < pb_end; ++pb) {
+      const int s = rp.s;
+      mbar_wait(&full[s], rp.ph);
+      tc_fence_after();
+      if (elect_one_sync()) {
         const uint32_t a_lo = a_lo0 + (uint32_t)s * (kCABytes >> 4);
         const uint32_t b_lo = b_lo0 + (uint32_t)s * (kBBytes >> 4);
 #pragma unroll
         for (int k16 = 0; k16 < kCK / 16; ++k16)
           umma_bf16_lh(tmem_acc, a_lo + k16 * (2048 >> 4), d_hi, b_lo + k16 * (2048 >> 4), d_hi, idesc,
-                       (it > 0 || k16 > 0) ? 1u : 0u);
+                       (pb > pb_begin || k16 > 0) ? 1u : 0u);
         umma_commit(&empty[s]);
       }
-      umma_commit(acc_full);
+      __syncwarp();
+      rp.template advance<STAGES>();
     }
+    if (elect_one_sync()) umma_commit(acc_full);
+    __syncwarp();
   } else {
     const int q = warp & 3;
     const int m = m0 + q * 32 + lane;
@@ -650,7 +675,7 @@ int launch_wgrad(const WgMaps &maps, const WgParams &prm, int splits, int R, cud
   static bool configured = false;
   if (int rc = set_smem(conv_wgrad_tc_kernel<BN, STAGES>, smem, &configured)) return rc;
   dim3 grid((unsigned)splits, (unsigned)(prm.MT * prm.NT), (unsigned)R);
-  conv_wgrad_tc_kernel<BN, STAGES><<<grid, kCThreads, smem, st>>>(maps, prm);
+  conv_wgrad_tc_kernel<BN, STAGES><<<grid, kWgThreads, smem, st>>>(maps, prm);
   return 0;
 }
 

@@ -238,17 +238,37 @@ def kernel_rooflines(device, peaks):
     src = "measured" if "hbm_gbs" in peaks else "fallback"
     out = []
 
+    # DRAM bytes per launch (dram__bytes_read.sum + dram__bytes_write.sum) of the same kernels
+    # from the committed `ncu --set full` capture (profiles/ncu_traffic.json, written by
+    # tools/ncu_traffic.py from the .ncu-rep); None where the capture has no such launch.
+    try:
+        traffic_db = json.load(open(os.path.join(ROOT, "profiles", "ncu_traffic.json")))["kernels"]
+    except Exception:
+        traffic_db = {}
+
+    def traffic_of(name):
+        e = traffic_db.get(name)
+        return None if e is None else int(e["dram_bytes"])
+
     def mem_entry(name, fn, bytes_):
         t = timeit(fn)
         out.append({"kernel": name, "bound": "hbm", "achieved": bytes_ / t / 1e9, "peak": hbm,
-                    "unit": "GB/s", "frac": bytes_ / t / 1e9 / hbm, "traffic": None,
-                    "ms": t * 1e3, "peak_source": src})
+                    "unit": "GB/s", "frac": bytes_ / t / 1e9 / hbm, "traffic": traffic_of(name),
+                    "algorithmic_bytes": bytes_, "ms": t * 1e3, "peak_source": src})
 
     def tc_entry(name, fn, flops, bytes_):
+        """A contraction is reported against the roof that bounds it: the larger of
+        flops / bf16 peak and algorithmic bytes / HBM peak (thin layers: O = 32 moves 438 MB
+        for 77 GFLOP, i.e. 67 us of HBM time against 47 us of tensor time)."""
         t = timeit(fn)
-        e = {"kernel": name, "bound": "tensor", "achieved": flops / t / 1e12, "peak": tflops,
-             "unit": "TFLOP/s", "frac": flops / t / 1e12 / tflops, "traffic": None, "ms": t * 1e3,
-             "peak_source": src, "hbm_gbs": bytes_ / t / 1e9, "hbm_frac": bytes_ / t / 1e9 / hbm}
+        tf, gb = flops / t / 1e12, bytes_ / t / 1e9
+        hbm_bound = bytes_ / (hbm * 1e9) > flops / (tflops * 1e12)
+        e = {"kernel": name, "bound": "hbm" if hbm_bound else "tensor",
+             "achieved": gb if hbm_bound else tf, "peak": hbm if hbm_bound else tflops,
+             "unit": "GB/s" if hbm_bound else "TFLOP/s",
+             "frac": gb / hbm if hbm_bound else tf / tflops, "traffic": traffic_of(name),
+             "algorithmic_bytes": bytes_, "algorithmic_flops": flops, "ms": t * 1e3, "peak_source": src,
+             "tflops": tf, "tensor_frac": tf / tflops, "hbm_gbs": gb, "hbm_frac": gb / hbm}
         out.append(e)
         return e
 
@@ -482,7 +502,10 @@ def main():
                        "global_batch": B * world, "per_gpu_batch": B, "parallelism": f"dp{world}",
                        "r1_steps_timed": r1_steps, "ada_p": "adaptive from 0.0" if args.ada_p is None else args.ada_p,
                        "l2": "no flush: per-step working set (GBs) >> 126 MB L2",
-                       "dense_convs": "D 3x3/1x1 convs and linears via cuDNN/cuBLAS (library, interim)"},
+                       "dense_convs": ("D convs: own tcgen05 kernels where they measured faster than cuDNN at these "
+                                       "shapes (unit-stride 3x3 fprop/dgrad of the 32/64-channel layers: "
+                                       "halo-resident kernel; strided dgrad and 3x3 wgrad of the 32-channel "
+                                       "layers), cuDNN elsewhere, cuBLAS linears (profiles/r01_conv_layers.json)")},
             "clocks": clk, "gpu_launches": launches, "e2e": e2e}
 
     if rank == 0 and world == 1:
@@ -496,10 +519,9 @@ def main():
             torch.cuda.empty_cache()
             dom, kernels = kernel_rooflines(device, peaks)
             line["roofline"] = {k: dom[k] for k in ("bound", "achieved", "peak", "unit", "frac", "traffic")}
-            line["roofline"]["hbm_gbs"] = dom["hbm_gbs"]
-            line["roofline"]["hbm_frac"] = dom["hbm_frac"]
-            line["roofline"]["kernel"] = dom["kernel"]
-            line["roofline"]["peak_source"] = dom["peak_source"]
+            for k in ("kernel", "peak_source", "algorithmic_bytes", "algorithmic_flops", "tflops",
+                      "tensor_frac", "hbm_gbs", "hbm_frac", "ms"):
+                line["roofline"][k] = dom[k]
             line["kernels"] = kernels
         if not args.no_cpu_baseline:
             ips, spt, cores, desc = cpu_reference_run(args, 2, 1, args.cpu_batch)

@@ -203,33 +203,40 @@ blur4_cl_kernel(const T *__restrict__ x, T *__restrict__ y, Taps4CL t, int H, in
   };
   // PAD adjoint: fold the halo copies of a padded gradient row onto dst (rare: border threads
   // and border rows only)
-  auto add_halo_cols = [&](const T *prow, float *dst) {
+  // all arithmetic on element PAIRS (float2: FFMA2 / FMUL2, one F2FP per packed pair)
+  constexpr int VP = V / 2;
+  auto add_halo_cols = [&](const T *prow, float2 *dst) {
 #pragma unroll
     for (int s = 0; s < 4; ++s) {
       if (xe[s] >= 0) {
         Vec16<T> e = ld16(prow + ((int64_t)xe[s] * cv + j) * V);
 #pragma unroll
-        for (int k = 0; k < V; ++k) dst[k] = fmaf(t.k[s], e.get(k), dst[k]);
+        for (int k = 0; k < VP; ++k) dst[k] = fma2(t.k[s], get2(e, k), dst[k]);
       }
     }
   };
-  auto add_full_row = [&](const T *prow, float *dst) {
+  auto add_full_row = [&](const T *prow, float2 *dst) {
 #pragma unroll
     for (int s = 0; s < 4; ++s) {
       Vec16<T> v = ld16(prow + xoff[s]);
 #pragma unroll
-      for (int k = 0; k < V; ++k) dst[k] = fmaf(t.k[s], v.get(k), dst[k]);
+      for (int k = 0; k < VP; ++k) dst[k] = fma2(t.k[s], get2(v, k), dst[k]);
     }
     add_halo_cols(prow, dst);
   };
-  auto reduce = [&](const Row &row, float *dst) {
+  auto reduce = [&](const Row &row, float2 *dst) {
+    if (ADJ && row.r < 0) {
 #pragma unroll
-    for (int k = 0; k < V; ++k) dst[k] = 0.f;
-    if (ADJ && row.r < 0) return;
+      for (int k = 0; k < VP; ++k) dst[k] = make_float2(0.f, 0.f);
+      return;
+    }
 #pragma unroll
-    for (int s = 0; s < 4; ++s)
+    for (int k = 0; k < VP; ++k) {
+      float2 h = mul2(t.k[0], get2(row.v[0], k));
 #pragma unroll
-      for (int k = 0; k < V; ++k) dst[k] = fmaf(t.k[s], row.v[s].get(k), dst[k]);
+      for (int s = 1; s < 4; ++s) h = fma2(t.k[s], get2(row.v[s], k), h);
+      dst[k] = h;
+    }
     if (PAD && ADJ) {
       add_halo_cols(img + (int64_t)(row.r + 1) * pitch, dst);
       if (row.r == 0) add_full_row(img, dst);
@@ -239,7 +246,7 @@ blur4_cl_kernel(const T *__restrict__ x, T *__restrict__ y, Taps4CL t, int H, in
 
   const int y0 = blockIdx.y * strip;
   const int y1 = min(y0 + strip, H);
-  float a[V], bb[V], c[V], d[V];
+  float2 a[VP], bb[VP], c[VP], d[VP];
   Row cur, nxt;
   if (!ADJ) {
     issue(y0 - 2, cur); issue(y0 - 1, nxt);
@@ -248,14 +255,15 @@ blur4_cl_kernel(const T *__restrict__ x, T *__restrict__ y, Taps4CL t, int H, in
     reduce(nxt, bb);
     issue(y0 + 1, nxt);
     reduce(cur, c);
-    for (int r = y0; r < y1; ++r) {
+#pragma unroll 4
+    for (int r = y0; r < y1; ++r) {      // unrolled: the window rotates by renaming, not by moves
       cur = nxt;                         // row r+1 (already in flight)
       issue(r + 2, nxt);                 // prefetch the row of the next iteration
       reduce(cur, d);
       Vec16<T> o;
 #pragma unroll
-      for (int k = 0; k < V; ++k) {
-        o.set(k, fmaf(t.k[3], d[k], fmaf(t.k[2], c[k], fmaf(t.k[1], bb[k], t.k[0] * a[k]))));
+      for (int k = 0; k < VP; ++k) {
+        set2(o, k, fma2(t.k[3], d[k], fma2(t.k[2], c[k], fma2(t.k[1], bb[k], mul2(t.k[0], a[k])))));
         a[k] = bb[k]; bb[k] = c[k]; c[k] = d[k];
       }
       if (PAD) {
@@ -275,16 +283,17 @@ blur4_cl_kernel(const T *__restrict__ x, T *__restrict__ y, Taps4CL t, int H, in
     reduce(nxt, bb);
     issue(e_lo + 2, nxt);
     reduce(cur, c);
-    float acc[V];
+    float2 acc[VP];
 #pragma unroll
-    for (int k = 0; k < V; ++k) acc[k] = 0.f;
+    for (int k = 0; k < VP; ++k) acc[k] = make_float2(0.f, 0.f);
+#pragma unroll 4
     for (int e = e_lo; e <= e_hi; ++e) {
       cur = nxt;                         // row e+2
       issue(e + 3, nxt);
       reduce(cur, d);
 #pragma unroll
-      for (int k = 0; k < V; ++k) {
-        acc[k] += fmaf(t.k[0], d[k], fmaf(t.k[1], c[k], fmaf(t.k[2], bb[k], t.k[3] * a[k])));
+      for (int k = 0; k < VP; ++k) {
+        acc[k] = fma2(t.k[0], d[k], fma2(t.k[1], c[k], fma2(t.k[2], bb[k], fma2(t.k[3], a[k], acc[k]))));
         a[k] = bb[k]; bb[k] = c[k]; c[k] = d[k];
       }
       const int i = e < 0 ? 0 : (e >= H ? H - 1 : e);
@@ -292,7 +301,7 @@ blur4_cl_kernel(const T *__restrict__ x, T *__restrict__ y, Taps4CL t, int H, in
       if (e == e_hi || i_next != i) {
         Vec16<T> o;
 #pragma unroll
-        for (int k = 0; k < V; ++k) { o.set(k, acc[k]); acc[k] = 0.f; }
+        for (int k = 0; k < VP; ++k) { set2(o, k, acc[k]); acc[k] = make_float2(0.f, 0.f); }
         st16(out + (((int64_t)i * W + xx) * cv + j) * V, o);
       }
     }
@@ -335,23 +344,26 @@ blur4_down2_cl_kernel(const T *__restrict__ x, T *__restrict__ y, Taps4CL t, int
 #pragma unroll
     for (int s = 0; s < 4; ++s) row.v[s] = ld16(prow + xoff[s]);
   };
-  auto reduce = [&](const Row &row, float *dst) {
+  constexpr int VP = V / 2;           // arithmetic on element pairs (FFMA2)
+  auto reduce = [&](const Row &row, float2 *dst) {
 #pragma unroll
-    for (int k = 0; k < V; ++k) dst[k] = 0.f;
+    for (int k = 0; k < VP; ++k) {
+      float2 h = mul2(t.k[0], get2(row.v[0], k));
 #pragma unroll
-    for (int s = 0; s < 4; ++s)
-#pragma unroll
-      for (int k = 0; k < V; ++k) dst[k] = fmaf(t.k[s], row.v[s].get(k), dst[k]);
+      for (int s = 1; s < 4; ++s) h = fma2(t.k[s], get2(row.v[s], k), h);
+      dst[k] = h;
+    }
   };
   const int i0 = blockIdx.y * strip;
   const int i1 = min(i0 + strip, H2);
-  float a[V], bb[V], c[V], d[V];
+  float2 a[VP], bb[VP], c[VP], d[VP];
   Row r0, r1;
   issue(2 * i0 - 2, r0); issue(2 * i0 - 1, r1);
   reduce(r0, a);
   issue(2 * i0, r0);
   reduce(r1, bb);
   issue(2 * i0 + 1, r1);
+#pragma unroll 2
   for (int i = i0; i < i1; ++i) {
     reduce(r0, c);
     issue(2 * i + 2, r0);
@@ -359,8 +371,8 @@ blur4_down2_cl_kernel(const T *__restrict__ x, T *__restrict__ y, Taps4CL t, int
     issue(2 * i + 3, r1);
     Vec16<T> o;
 #pragma unroll
-    for (int k = 0; k < V; ++k) {
-      o.set(k, fmaf(t.k[3], d[k], fmaf(t.k[2], c[k], fmaf(t.k[1], bb[k], t.k[0] * a[k]))));
+    for (int k = 0; k < VP; ++k) {
+      set2(o, k, fma2(t.k[3], d[k], fma2(t.k[2], c[k], fma2(t.k[1], bb[k], mul2(t.k[0], a[k])))));
       a[k] = c[k]; bb[k] = d[k];
     }
     st16(out + (((int64_t)i * W2 + xo) * cv + j) * V, o);
@@ -396,9 +408,10 @@ blur4_down2_cl_adj_kernel(const T *__restrict__ g, T *__restrict__ dx, Taps4CL t
     jc[u] = jj >= W2 ? jj - W2 : jj;
     kx[u] = t.k[s];
   }
-  float acc[V];
+  constexpr int VP = V / 2;
+  float2 acc[VP];
 #pragma unroll
-  for (int k = 0; k < V; ++k) acc[k] = 0.f;
+  for (int k = 0; k < VP; ++k) acc[k] = make_float2(0.f, 0.f);
   auto add = [&](int i, float ky) {
     const T *row = gi + (int64_t)i * W2 * cv * V;
 #pragma unroll
@@ -406,7 +419,7 @@ blur4_down2_cl_adj_kernel(const T *__restrict__ g, T *__restrict__ dx, Taps4CL t
       Vec16<T> v = ld16(row + ((int64_t)jc[u] * cv + j) * V);
       const float w = ky * kx[u];
 #pragma unroll
-      for (int k = 0; k < V; ++k) acc[k] = fmaf(w, v.get(k), acc[k]);
+      for (int k = 0; k < VP; ++k) acc[k] = fma2(w, get2(v, k), acc[k]);
     }
   };
   const int pq = yr & 1;
@@ -423,7 +436,7 @@ blur4_down2_cl_adj_kernel(const T *__restrict__ g, T *__restrict__ dx, Taps4CL t
   }
   Vec16<T> o;
 #pragma unroll
-  for (int k = 0; k < V; ++k) o.set(k, acc[k]);
+  for (int k = 0; k < VP; ++k) set2(o, k, acc[k]);
   st16(dx + tid * V, o);
 }
 

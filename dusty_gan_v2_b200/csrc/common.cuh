@@ -64,6 +64,29 @@ template <> struct Vec16<__nv_bfloat16> {
   }
 };
 
+// Pair access (elements 2i, 2i+1) for the packed fp32 pipe of sm_100 (FFMA2 / FADD2 / FMUL2: two
+// fp32 operations per issued instruction).  The stencils are issue-bound, not HBM-bound, when
+// written one element at a time (~27 instructions per bf16 output element in blur4_cl).
+__device__ __forceinline__ float2 get2(const Vec16<float> &v, int i) {
+  return i ? make_float2(v.raw.z, v.raw.w) : make_float2(v.raw.x, v.raw.y);
+}
+__device__ __forceinline__ void set2(Vec16<float> &v, int i, float2 p) {
+  if (i) { v.raw.z = p.x; v.raw.w = p.y; } else { v.raw.x = p.x; v.raw.y = p.y; }
+}
+__device__ __forceinline__ float2 get2(const Vec16<__nv_bfloat16> &v, int i) {
+  const uint32_t w = (&v.raw.x)[i];
+  return make_float2(__uint_as_float(w << 16), __uint_as_float(w & 0xffff0000u));
+}
+__device__ __forceinline__ void set2(Vec16<__nv_bfloat16> &v, int i, float2 p) {
+  const __nv_bfloat162 b = __floats2bfloat162_rn(p.x, p.y);      // one F2FP for the pair
+  (&v.raw.x)[i] = *reinterpret_cast<const uint32_t *>(&b);
+}
+__device__ __forceinline__ float2 fma2(float k, float2 v, float2 acc) {
+  return __ffma2_rn(make_float2(k, k), v, acc);
+}
+__device__ __forceinline__ float2 mul2(float k, float2 v) { return __fmul2_rn(make_float2(k, k), v); }
+__device__ __forceinline__ float2 add2(float2 a, float2 b) { return __fadd2_rn(a, b); }
+
 // 8-byte vector of T (register-lean variant for the sliding-window stencils)
 template <typename T> struct Vec8;
 template <> struct Vec8<float> {

@@ -27,7 +27,7 @@ namespace dusty {
 // DUSTY_TC_PREFETCH=<tiles> overrides the L2 prefetch distance (0 disables); experiments only
 static int g_tc_prefetch = [] {
   const char *e = getenv("DUSTY_TC_PREFETCH");
-  return e ? atoi(e) : -1;
+  return e ? atoi(e) : 0;   // default off: measured slower (L4 conv1 102 -> 132 us)
 }();
 
 constexpr int kBM = 128;          // pixels per tile (UMMA M)
@@ -237,12 +237,13 @@ modconv_fwd_tc_kernel(const __grid_constant__ CUtensorMap map_x1,
           const int c0 = kb * kBK;
           uint8_t *a_dst = a_base + s * kABytes;
           if (c0 < prm.C1) {
-            tma_load_3d(a_dst, &map_x1, &full[s], p0, c0, b);
-            tma_load_3d(a_dst + kABytes / 2, &map_x1, &full[s], p0 + 64, c0, b);
+            tma_load_3d_hint(a_dst, &map_x1, &full[s], p0, c0, b, kEvictFirst);
+            tma_load_3d_hint(a_dst + kABytes / 2, &map_x1, &full[s], p0 + 64, c0, b, kEvictFirst);
           } else {
             const int bb = prm.B2 == 1 ? 0 : b;
-            tma_load_3d(a_dst, &map_x2, &full[s], p0, c0 - prm.C1, bb);
-            tma_load_3d(a_dst + kABytes / 2, &map_x2, &full[s], p0 + 64, c0 - prm.C1, bb);
+            const uint64_t pol = prm.B2 == 1 ? kEvictLast : kEvictFirst;
+            tma_load_3d_hint(a_dst, &map_x2, &full[s], p0, c0 - prm.C1, bb, pol);
+            tma_load_3d_hint(a_dst + kABytes / 2, &map_x2, &full[s], p0 + 64, c0 - prm.C1, bb, pol);
           }
           if (!B_MN) {
             tma_load_3d(b_base + s * kBBytes, &map_w, &full[s], c0, n0, b);
@@ -412,9 +413,10 @@ modconv_fwd_shared_tc_kernel(const __grid_constant__ CUtensorMap map_x1,
           if (elect_one_sync()) {
             mbar_expect_tx(&full[s], kABytes + prm.BN * kBK * 2);
             uint8_t *a_dst = a_base + s * kABytes;
-            tma_load_3d(a_dst, &map_pe, &full[s], p0, pi * kBK, 0);
-            tma_load_3d(a_dst + kABytes / 2, &map_pe, &full[s], p0 + 64, pi * kBK, 0);
-            tma_load_3d(b_base + s * kShBBytes, &map_wp, &full[s], prm.C1 + pi * kBK, nt * prm.BN, 0);
+            tma_load_3d_hint(a_dst, &map_pe, &full[s], p0, pi * kBK, 0, kEvictLast);
+            tma_load_3d_hint(a_dst + kABytes / 2, &map_pe, &full[s], p0 + 64, pi * kBK, 0, kEvictLast);
+            tma_load_3d_hint(b_base + s * kShBBytes, &map_wp, &full[s], prm.C1 + pi * kBK, nt * prm.BN, 0,
+                             kEvictLast);
           }
           __syncwarp();
           r.advance<STAGES>();
@@ -428,9 +430,9 @@ modconv_fwd_shared_tc_kernel(const __grid_constant__ CUtensorMap map_x1,
             if (leader) {
               const int b = nt * prm.NS + j, c0 = kbx * kBK;
               uint8_t *a_dst = u ? b_base + s * kShBBytes + 16384 : a_base + s * kABytes;
-              tma_load_3d(a_dst, &map_x1, &full[s], p0, c0, b);
-              tma_load_3d(a_dst + kABytes / 2, &map_x1, &full[s], p0 + 64, c0, b);
-              tma_load_3d(b_base + s * kShBBytes + u * 8192, &map_ws, &full[s], c0, 0, b);
+              tma_load_3d_hint(a_dst, &map_x1, &full[s], p0, c0, b, kEvictFirst);
+              tma_load_3d_hint(a_dst + kABytes / 2, &map_x1, &full[s], p0 + 64, c0, b, kEvictFirst);
+              tma_load_3d_hint(b_base + s * kShBBytes + u * 8192, &map_ws, &full[s], c0, 0, b, kEvictLast);
             }
             if (++kbx == kb1) { kbx = 0; ++j; }
           }

@@ -105,6 +105,19 @@ __device__ __forceinline__ void st_shared_b16(uint32_t addr, uint16_t v) {
 __device__ __forceinline__ void named_bar_sync(int id, int threads) {
   asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(threads) : "memory");
 }
+// L2 eviction-priority hints for TMA loads (the encodings CUTLASS's TMA::CacheHintSm90 uses):
+// stream-once activations must not push the batch-shared operands (Fourier block, weights)
+// out of L2 -- ncu showed 420 MB of DRAM reads for 304 MB of algorithmic reads without them.
+constexpr uint64_t kEvictFirst = 0x12F0000000000000ull;
+constexpr uint64_t kEvictLast = 0x14F0000000000000ull;
+__device__ __forceinline__ void tma_load_3d_hint(void *smem_dst, const CUtensorMap *map, uint64_t *bar,
+                                                 int c0, int c1, int c2, uint64_t policy) {
+  asm volatile(
+      "cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes.L2::cache_hint"
+      " [%0], [%1, {%3, %4, %5}], [%2], %6;" ::"r"(smem_u32(smem_dst)),
+      "l"(map), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2), "l"(policy)
+      : "memory");
+}
 __device__ __forceinline__ void tmem_alloc(uint32_t *dst_smem, uint32_t cols) {
   asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(
                    smem_u32(dst_smem)),

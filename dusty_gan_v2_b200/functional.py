@@ -947,6 +947,83 @@ def circular_unshift(v, shift01, scale: float = 1.0):
     return _CircShift.apply(v, _contig(shift01.detach().float()), float(scale), 0)
 
 
+# ---- a11: discriminator stem (BlurVH -> 1x1 conv 2 -> O -> bias + leaky ReLU), stem.cu -------
+class _Stem(Function):
+    """y (bf16, NHWC) = lrelu(conv1x1(cat(blur_v(x), blur_h(x)), w) + bias) * gain in one pass.
+    First order: one fused backward pass (+ a small adjoint-blur kernel when x needs a
+    gradient).  Under create_graph=True (the R1 penalty) the backward is re-expressed through
+    `composite`, the same math built from the differentiable ops of this module, so every
+    higher-order term stays exact."""
+
+    @staticmethod
+    def forward(ctx, x, w, bias, taps, alpha, scale, composite):
+        B, _, H, W = x.shape
+        O = w.shape[0]
+        xin = _contig(x.detach())
+        if xin.dtype not in (torch.float32, torch.bfloat16):
+            xin = xin.float()
+        wf = _contig(w.detach().float().reshape(O, 2))
+        bf = None if bias is None else _contig(bias.detach().float().reshape(O))
+        y = torch.empty((B, O, H, W), dtype=torch.bfloat16, device=x.device,
+                        memory_format=torch.channels_last)
+        K.call("dusty_stem_fwd", K.ptr(xin), K.ptr(wf), K.ptr(bf), K.ptr(y), B, H, W, O, taps[0], taps[1],
+               taps[2], alpha, scale, K.dtype_code(xin), K.stream_of(xin))
+        ctx.save_for_backward(x, w, bias, y)
+        ctx.cfg = (taps, alpha, scale, composite)
+        return y
+
+    @staticmethod
+    def backward(ctx, gy):
+        x, w, bias, y = ctx.saved_tensors
+        taps, alpha, scale, composite = ctx.cfg
+        need_x, need_w, need_b = ctx.needs_input_grad[:3]
+        if torch.is_grad_enabled():
+            with torch.enable_grad():
+                wanted = [t for t, n in ((x, need_x), (w, need_w), (bias, need_b)) if n and t is not None]
+                yc = composite(x, w, bias)
+                grads = list(torch.autograd.grad(yc, wanted, gy.to(yc.dtype), create_graph=True,
+                                                 allow_unused=True))
+            out = []
+            for t, n in ((x, need_x), (w, need_w), (bias, need_b)):
+                out.append(grads.pop(0) if (n and t is not None) else None)
+            return out[0], out[1], out[2], None, None, None, None
+        B, _, H, W = x.shape
+        O = w.shape[0]
+        gy = gy.contiguous(memory_format=torch.channels_last)
+        if gy.dtype != torch.bfloat16:
+            gy = gy.to(torch.bfloat16)
+        xin = _contig(x.detach())
+        if xin.dtype not in (torch.float32, torch.bfloat16):
+            xin = xin.float()
+        wf = _contig(w.detach().float().reshape(O, 2))
+        dvh = torch.empty((B, 2, H, W), dtype=torch.float32, device=x.device) if need_x else None
+        dwb = torch.empty((O, 3), dtype=torch.float32, device=x.device)
+        st = K.stream_of(gy)
+        K.call("dusty_stem_bwd", K.ptr(gy), K.ptr(y), K.ptr(xin), K.ptr(wf), K.ptr(dvh), K.ptr(dwb), B, H, W,
+               O, taps[0], taps[1], taps[2], alpha, scale, K.dtype_code(xin), st)
+        gx = None
+        if need_x:
+            gx = torch.empty((B, 1, H, W), dtype=torch.float32, device=x.device)
+            K.call("dusty_stem_dx", K.ptr(dvh), K.ptr(gx), B, H, W, taps[0], taps[1], taps[2], st)
+            gx = gx.to(x.dtype)
+        gw = dwb[:, :2].reshape(w.shape).to(w.dtype) if need_w else None
+        gb = dwb[:, 2].reshape(bias.shape).to(bias.dtype) if (need_b and bias is not None) else None
+        return gx, gw, gb, None, None, None, None
+
+
+def stem_supported(x: torch.Tensor, out_ch: int) -> bool:
+    return (x.is_cuda and x.dim() == 4 and x.shape[1] == 1 and x.shape[2] >= 2 and x.shape[3] >= 2
+            and out_ch in (8, 16, 32, 64) and _PRECISION["act"] == torch.bfloat16)
+
+
+def stem(x, w, bias, taps, composite, negative_slope: float = 0.2, scale: float = 2 ** 0.5):
+    """Fused discriminator stem; `composite(x, w, bias)` must compute the same function from
+    differentiable ops (used only for second-order gradients)."""
+    K.require_cuda(x, w, bias)
+    return _Stem.apply(x, w, bias, tuple(float(t) for t in taps), float(negative_slope), float(scale),
+                       composite)
+
+
 # ---- a11: dense NHWC convolutions on tcgen05 (conv_tc.cu) --------------------------------
 _CONV_IMPL = {"mode": "auto", "halo": True}
 

@@ -335,6 +335,14 @@ class ResidualBlock(nn.Module):
         return (self.residual(x) + self._skip(x)) * (1.0 / math.sqrt(2))
 
 
+class _ActView:
+    """Stand-in `self` for FusedLeakyReLU.forward with an explicit bias tensor (the composite
+    form of the fused stem differentiates w.r.t. the bias it was handed)."""
+
+    def __init__(self, bias, negative_slope, scale):
+        self.bias, self.negative_slope, self.scale = bias, negative_slope, scale
+
+
 class Discriminator(nn.Module):
     def __init__(self, in_ch: int, ch_base: int = 32, ch_max: int = 512, mbdis_group: int = 4,
                  mbdis_feat: int = 1, resolution=(64, 512), ring=True, num_fp16_layers=-1,
@@ -349,6 +357,8 @@ class Discriminator(nn.Module):
         # keep the residual trunk in NHWC on CUDA: the dense convs (library) run their sm_100
         # kernels without layout-conversion passes, and pad / blur / bias_act vectorise over C
         self.channels_last = True
+        self.fused_stem = True          # BlurVH + 1x1 conv + bias/lrelu as one kernel (bf16 mode)
+        self._stem_taps = None
         in_ch = in_ch * 2 if pre_blur else in_ch
         stack = [ops.BlurVH(ring=ring)] if pre_blur else []
         stack += [ops.Conv2d(in_ch, ch(0), 1, 1, 0, **kw), ops.FusedLeakyReLU(ch(0))]
@@ -364,8 +374,54 @@ class Discriminator(nn.Module):
             ops.EqualLR(nn.Linear(ch(4), 1)),
         )
 
+    def _fused_stem(self, x, low):
+        """layers[0:3] = BlurVH -> 1x1 Conv2d(2 -> C0) -> FusedLeakyReLU as one kernel (bf16 NHWC
+        output); None when the configuration does not match."""
+        if not (self.fused_stem and len(self.layers) >= 3 and low == torch.bfloat16 and x.is_cuda):
+            return None
+        blur, conv, act = self.layers[0], self.layers[1], self.layers[2]
+        if not (isinstance(blur, ops.BlurVH) and isinstance(conv, ops.Conv2d) and len(conv) == 1
+                and isinstance(act, ops.FusedLeakyReLU) and self.num_fp16_layers in (-1,)):
+            return None
+        eq = conv[0]
+        m = getattr(eq, "module", None)
+        if not (isinstance(eq, ops.EqualLR) and isinstance(m, nn.Conv2d) and m.kernel_size == (1, 1)
+                and m.stride == (1, 1) and m.bias is None and m.in_channels == 2
+                and DF.stem_supported(x, m.out_channels)):
+            return None
+        kv, kh = blur.blur_v, blur.blur_h
+        if not (kv.window == [1, 2, 1] and kh.window == [1, 2, 1] and kv.ring and kh.ring
+                and getattr(kv, "up_h", 1) == 1 and getattr(kv, "down_h", 1) == 1):
+            return None
+        if self._stem_taps is None:
+            tv = kv.kernel.detach().float().cpu().reshape(-1).tolist()
+            th = kh.kernel.detach().float().cpu().reshape(-1).tolist()
+            if len(tv) != 3 or any(abs(a - b) > 1e-7 for a, b in zip(tv, th)):
+                self._stem_taps = False
+            else:
+                self._stem_taps = tuple(tv)
+        if not self._stem_taps:
+            return None
+        w = m.weight.reshape(m.out_channels, 2) * (eq.scale * eq.gain_)
+
+        def composite(xc, wc, bc):
+            hc = blur(xc.to(low))
+            yc = ops.conv2d_valid(hc, wc.reshape(-1, 2, 1, 1).to(hc.dtype), (1, 1)) if hc.is_cuda \
+                else torch.nn.functional.conv2d(hc, wc.reshape(-1, 2, 1, 1))
+            return act.__class__.forward(_ActView(bc, act.negative_slope, act.scale), yc)
+
+        return DF.stem(x, w, act.bias, self._stem_taps, composite, act.negative_slope, act.scale)
+
     def forward(self, h):
         low = DF.act_dtype()
+        y = self._fused_stem(h, low) if h.dim() == 4 and h.shape[1] == 1 else None
+        if y is not None:
+            h = y
+            for layer in self.layers[3:]:
+                h = layer(h)
+            if self._fast_epilogue_ok(h, low):
+                return self._epilogue_low_precision(h)
+            return self.epilogue(h.to(torch.float32).contiguous())
         for i, layer in enumerate(self.layers):
             use_low = ((self.num_fp16_layers > i) or (self.num_fp16_layers == -1)) and h.is_cuda
             h = layer(h.to(low if use_low else torch.float32))

@@ -256,6 +256,25 @@ int dusty_ema_lerp(float *ema_var, const float *sum_a, const float *sum_b, float
 int dusty_circular_shift(const float *v, const float *shift01, float *out, int B, int C, int H,
                          int W, float scale, int adjoint, void *stream);
 
+/* ---- a11: discriminator stem -------------------------------------------------------------
+ * Replaces BlurVH -> Conv2d(2 -> O, 1x1, EqualLR, no bias) -> FusedLeakyReLU(O), the first three
+ * layers of Discriminator.layers, gans/models/dusty_v2.py:352-354 (BlurVH common.py:141-155,
+ * fused_leaky_relu fused_act.py:93-129), as one pass.
+ * x: [B, 1, H, W] (fp32 or bf16); w: fp32 [O, 2] effective weights (EqualLR scale folded in);
+ * bias: fp32 [O] or NULL; y: bf16 NHWC [B, H, W, O]; taps k0..k2 of the 3-tap blur (vertical
+ * pass clamps rows, horizontal pass wraps columns).  O in {8, 16, 32, 64}. */
+int dusty_stem_fwd(const void *x, const float *w, const float *bias, void *y, int B, int H, int W,
+                   int O, float k0, float k1, float k2, float alpha, float scale, int x_dtype,
+                   void *stream);
+/* One pass over (dy, y): dwb fp32 [O, 3] = (dW[o,0], dW[o,1], db[o]) (overwritten); dvh: fp32
+ * [B, 2, H, W] gradient w.r.t. the blurred pair, or NULL when the input needs no gradient. */
+int dusty_stem_bwd(const void *dy, const void *y, const void *x, const float *w, float *dvh,
+                   float *dwb, int B, int H, int W, int O, float k0, float k1, float k2, float alpha,
+                   float scale, int x_dtype, void *stream);
+/* dx [B, 1, H, W] fp32 = adjoint of the two blurs applied to dvh. */
+int dusty_stem_dx(const float *dvh, float *dx, int B, int H, int W, float k0, float k1, float k2,
+                  void *stream);
+
 /* ---- a11: dense convolutions of the discriminator trunk (tcgen05, NHWC bf16) ---------------
  * Replaces F.conv2d / cuDNN behind Conv2d + EqualLR, gans/models/ops/common.py:187-210, for
  * the ResidualBlock convolutions gans/models/dusty_v2.py:347-396 (SURVEY 8b dusty_conv2d_*).

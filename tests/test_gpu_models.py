@@ -373,3 +373,90 @@ def test_inversion_style_latent_gradient_vs_oracle(g_gen):
     close(out["image_orig"], ref["image_orig"], rtol=1e-3, atol_rel=5e-4)
     close(wg.grad, wr.grad, rtol=5e-3, atol_rel=5e-3)
     assert all(p.grad is None for p in G.parameters())           # G frozen: no weight grads
+
+
+def test_fused_discriminator_stem_matches_composite_and_oracle():
+    """bf16 mode: BlurVH + 1x1 conv + bias/lrelu as one kernel (stem.cu) against the same layers
+    run one by one, first order (x, weight, bias gradients) and the R1-style second order, and
+    the whole discriminator against the fp32 CPU oracle."""
+    import dusty_gan_v2_b200 as pkg
+    from dusty_gan_v2_b200.gans.models.builder import build_discriminator
+    from dusty_gan_v2_b200.presets import preset
+    pkg.set_precision("bf16")
+    torch.manual_seed(3)
+    D = build_discriminator(preset("dusty_v2").model.discriminator)
+    with torch.no_grad():
+        D.layers[2].bias.normal_(0, 0.5)
+    sd = {k: v.clone() for k, v in D.state_dict().items()}
+    B = 4
+    x = torch.tanh(torch.randn(B, 1, 64, 512, generator=torch.Generator().manual_seed(5)))
+    with torch.no_grad():
+        ref = O.discriminator(sd, x)
+    D = D.to(DEV)
+    params = [D.layers[1][0].module.weight, D.layers[2].bias]
+    for p in D.parameters():
+        p.requires_grad_(True)
+    res = {}
+    for fused in (True, False):
+        D.fused_stem = fused
+        xg = x.to(DEV).requires_grad_()
+        # the stem alone, first order
+        if fused:
+            h = D._fused_stem(xg, torch.bfloat16)
+            assert h is not None and h.dtype == torch.bfloat16
+        else:
+            h = xg.to(torch.bfloat16)
+            for layer in D.layers[:3]:
+                h = layer(h)
+        gh = torch.randn(h.shape, generator=torch.Generator().manual_seed(7)).to(DEV, torch.bfloat16)
+        g1 = torch.autograd.grad(h, [xg] + params, gh)
+        # whole network, R1-style second order
+        xg2 = x.to(DEV).requires_grad_()
+        y = D(xg2)
+        (gx,) = torch.autograd.grad(y.sum(), xg2, create_graph=True)
+        r1 = gx.float().square().sum()
+        g2 = torch.autograd.grad(r1, params)
+        res[fused] = (h.detach().float(), [g.detach().float() for g in g1], y.detach().float(),
+                      gx.detach().float(), [g.detach().float() for g in g2])
+    D.fused_stem = True
+    f, c = res[True], res[False]
+    def rel_l2(a, b):
+        return float((a - b).norm() / b.norm().clamp_min(1e-12))
+
+    # (1) the fused kernels against an fp32 CPU restatement of the same three layers, the
+    # leaky-ReLU gate taken from the fused forward's own output (the op is discontinuous there:
+    # a pre-activation of ~0 may round to either side in bf16)
+    import torch.nn.functional as F
+    w_eff = (sd["layers.1.0.module.weight"].reshape(32, 2) / np.sqrt(2.0)).clone().requires_grad_()
+    b_cpu = sd["layers.2.bias"].clone().requires_grad_()
+    x_cpu = x.clone().requires_grad_()
+    k = torch.tensor([0.25, 0.5, 0.25])
+    xv = F.pad(x_cpu, (0, 0, 1, 1), mode="replicate")
+    xh = F.pad(x_cpu, (1, 1, 0, 0), mode="circular")
+    v = sum(k[i] * xv[:, :, i:i + 64, :] for i in range(3))
+    hh = sum(k[i] * xh[:, :, :, i:i + 512] for i in range(3))
+    pre = w_eff[:, 0].view(1, -1, 1, 1) * v + w_eff[:, 1].view(1, -1, 1, 1) * hh + b_cpu.view(1, -1, 1, 1)
+    gate = torch.where(res[True][0].cpu() > 0, 1.0, 0.2) * np.sqrt(2.0)
+    close(res[True][0], F.leaky_relu(pre, 0.2) * np.sqrt(2.0), rtol=1e-2, atol_rel=5e-3)
+    gh_cpu = torch.randn(res[True][0].shape, generator=torch.Generator().manual_seed(7)).bfloat16().float()
+    gx_ref, gw_ref, gb_ref = torch.autograd.grad(pre * gate, [x_cpu, w_eff, b_cpu], gh_cpu)
+    close(res[True][1][0], gx_ref, rtol=1e-2, atol_rel=2e-3)                                  # d/dx
+    close(res[True][1][1].reshape(32, 2) * np.sqrt(2.0), gw_ref, rtol=1e-2, atol_rel=2e-3)    # d/dW
+    close(res[True][1][2], gb_ref, rtol=1e-2, atol_rel=2e-3)                                  # d/dbias
+
+    # (2) against the layer-by-layer bf16 path (several extra bf16 roundings and its own gate
+    # pattern: agreement in the large), the oracle, and the R1-style second order
+    close(f[0], c[0], rtol=2e-2, atol_rel=1e-2)
+    for a, b in zip(f[1], c[1]):
+        assert rel_l2(a, b) < 1e-1
+    # D(x) vs the fp32 oracle: random-init logits are ~0.05 against O(1) activations, so the
+    # bf16 trunk's rounding shows up at the several-percent level in BOTH paths; the fused
+    # stem must not be the worse one
+    e_f, e_c = rel_l2(f[2].cpu(), ref), rel_l2(c[2].cpu(), ref)
+    assert e_f < 0.15 and e_c < 0.15, (e_f, e_c)
+    assert e_f < 2 * e_c + 2e-2, (e_f, e_c)
+    assert rel_l2(f[3], c[3]) < 1e-1                                  # grad_x D (bf16 trunk)
+    # d r1 / d(stem weight).  (The bias is not compared: the network is piecewise linear, so
+    # grad_x D depends on a bias only through MinibatchStdDev -- a tiny, noise-dominated term.)
+    assert rel_l2(f[4][0], c[4][0]) < 1.5e-1
+    assert torch.isfinite(f[4][1]).all()

@@ -34,6 +34,8 @@ SIGNATURES = {
     "dusty_pad2d": [_vp, _vp, _i64] + [_i] * 10 + [_vp],
     "dusty_bias_act_cl": [_vp, _vp, _vp, _vp, _i64, _i, _i, _i, _f, _f, _i, _vp],
     "dusty_bias_act_bwd_cl": [_vp, _vp, _vp, _vp, _i64, _i, _f, _f, _i, _vp],
+    "dusty_bias_act_add_cl": [_vp, _vp, _vp, _vp, _i64, _i, _f, _f, _f, _i, _vp],
+    "dusty_bias_act_add_bwd_cl": [_vp, _vp, _vp, _vp, _vp, _vp, _i64, _i, _f, _f, _f, _i, _vp],
     "dusty_pad2d_cl": [_vp, _vp] + [_i] * 12 + [_vp],
     "dusty_blur4_cl": [_vp, _vp, _f, _f, _f, _f] + [_i] * 7 + [_vp],
     "dusty_blur4_down2_cl": [_vp, _vp, _f, _f, _f, _f] + [_i] * 6 + [_vp],

@@ -74,6 +74,77 @@ bias_act_bwd_cl_kernel(const T *__restrict__ dy, const T *__restrict__ out, T *_
   }
 }
 
+// ------------------------------------------------------------------ residual tail (NHWC)
+// End of a discriminator ResidualBlock (dusty_v2.py:387-396 of the reference):
+//   y = ( lrelu(x + b) * gain + skip ) * c            (c = 1/sqrt(2))
+// as ONE pass (2 reads + 1 write) instead of bias_act (1r 1w), add (2r 1w), mul (1r 1w).
+template <typename T>
+__global__ void __launch_bounds__(256)
+bias_act_add_cl_kernel(const T *__restrict__ x, const T *__restrict__ bias, const T *__restrict__ skip,
+                       T *__restrict__ y, int64_t n_vec, int cv, float alpha, float gain, float c) {
+  constexpr int V = Vec16<T>::N;
+  const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n_vec; i += stride) {
+    const Vec16<T> vx = ld16_stream(x + i * V), vs = ld16_stream(skip + i * V);
+    Vec16<T> vb, vy;
+    if (bias != nullptr) vb = ld16(bias + (int)(i % cv) * V);
+#pragma unroll
+    for (int j = 0; j < V; ++j) {
+      const float v = vx.get(j) + (bias != nullptr ? vb.get(j) : 0.f);
+      const float a = (v > 0.f ? v : v * alpha) * gain;
+      vy.set(j, (a + vs.get(j)) * c);
+    }
+    st16(y + i * V, vy);
+  }
+}
+
+// backward: g = dy * c;  dskip = g;  dx = g * gate(x + b) * gain;  db[ch] += column sums of dx.
+// The gate is re-derived from the saved PRE-activation (the activated tensor never exists).
+template <typename T>
+__global__ void __launch_bounds__(256)
+bias_act_add_bwd_cl_kernel(const T *__restrict__ dy, const T *__restrict__ x, const T *__restrict__ bias,
+                           T *__restrict__ dx, T *__restrict__ dskip, float *__restrict__ db,
+                           int64_t rows, int cv, int64_t rows_per_block, float alpha, float gain,
+                           float c) {
+  constexpr int V = Vec16<T>::N;
+  __shared__ float red[256 * Vec16<T>::N];
+  const int j = threadIdx.x % cv, r = threadIdx.x / cv, R = blockDim.x / cv;
+  const int64_t r0 = (int64_t)blockIdx.x * rows_per_block;
+  int64_t r1 = r0 + rows_per_block;
+  if (r1 > rows) r1 = rows;
+  Vec16<T> vb;
+  if (bias != nullptr) vb = ld16(bias + j * V);
+  float acc[V];
+#pragma unroll
+  for (int k = 0; k < V; ++k) acc[k] = 0.f;
+  for (int64_t row = r0 + r; row < r1; row += R) {
+    const int64_t off = (row * cv + j) * V;
+    const Vec16<T> g = ld16_stream(dy + off), xv = ld16_stream(x + off);
+    Vec16<T> d, ds;
+#pragma unroll
+    for (int k = 0; k < V; ++k) {
+      const float gs = g.get(k) * c;
+      const float pre = xv.get(k) + (bias != nullptr ? vb.get(k) : 0.f);
+      const float v = (pre > 0.f ? gs : gs * alpha) * gain;
+      ds.set(k, gs);
+      d.set(k, v);
+      acc[k] += v;
+    }
+    st16(dx + off, d);
+    if (dskip != nullptr) st16(dskip + off, ds);
+  }
+  if (db == nullptr) return;
+#pragma unroll
+  for (int k = 0; k < V; ++k) red[threadIdx.x * V + k] = acc[k];
+  __syncthreads();
+  for (int ch = threadIdx.x; ch < cv * V; ch += blockDim.x) {
+    const int jj = ch / V, k = ch % V;
+    float s = 0.f;
+    for (int rr = 0; rr < R; ++rr) s += red[(rr * cv + jj) * V + k];
+    atomicAdd(db + ch, s);
+  }
+}
+
 // ------------------------------------------------------------------ pad (NHWC)
 struct PadCL {
   int H, W, Ho, Wo, pt, pb, pl, pr, mode_y, mode_x, cv;   // cv = C / V
@@ -513,6 +584,56 @@ extern "C" int dusty_bias_act_bwd_cl(const void *dy, const void *out, void *dx, 
     bias_act_bwd_cl_kernel<__nv_bfloat16><<<(unsigned)blocks, 256, 0, st>>>(
         (const __nv_bfloat16 *)dy, (const __nv_bfloat16 *)out, (__nv_bfloat16 *)dx, db, rows, cv, rpb,
         alpha, scale);
+  DUSTY_LAUNCH_CHECK();
+  return DUSTY_OK;
+}
+
+extern "C" int dusty_bias_act_add_cl(const void *x, const void *bias, const void *skip, void *y,
+                                     int64_t n_elem, int C, float alpha, float gain, float c, int dtype,
+                                     void *stream) {
+  DUSTY_CHECK_ARG(x && skip && y, "null tensor");
+  DUSTY_CHECK_ARG(dtype == DUSTY_F32 || dtype == DUSTY_BF16, "bad dtype");
+  DUSTY_CHECK_ARG(cl_channels_ok(C, dtype) && n_elem % C == 0, "channel count not vectorisable");
+  DUSTY_CHECK_ARG(aligned16(x) && aligned16(y) && aligned16(skip) && (!bias || aligned16(bias)),
+                  "16-byte alignment");
+  if (n_elem == 0) return DUSTY_OK;
+  cudaStream_t st = (cudaStream_t)stream;
+  const int V = dtype == DUSTY_F32 ? 4 : 8;
+  const int64_t n_vec = n_elem / V;
+  const unsigned g = cl_flat_grid(n_vec);
+  if (dtype == DUSTY_F32)
+    bias_act_add_cl_kernel<float><<<g, 256, 0, st>>>((const float *)x, (const float *)bias, (const float *)skip,
+                                                     (float *)y, n_vec, C / V, alpha, gain, c);
+  else
+    bias_act_add_cl_kernel<__nv_bfloat16><<<g, 256, 0, st>>>(
+        (const __nv_bfloat16 *)x, (const __nv_bfloat16 *)bias, (const __nv_bfloat16 *)skip, (__nv_bfloat16 *)y,
+        n_vec, C / V, alpha, gain, c);
+  DUSTY_LAUNCH_CHECK();
+  return DUSTY_OK;
+}
+
+extern "C" int dusty_bias_act_add_bwd_cl(const void *dy, const void *x, const void *bias, void *dx,
+                                         void *dskip, float *db, int64_t rows, int C, float alpha,
+                                         float gain, float c, int dtype, void *stream) {
+  DUSTY_CHECK_ARG(dy && x && dx, "null tensor");
+  DUSTY_CHECK_ARG(dtype == DUSTY_F32 || dtype == DUSTY_BF16, "bad dtype");
+  DUSTY_CHECK_ARG(cl_channels_ok(C, dtype) && rows >= 1, "channel count not vectorisable");
+  cudaStream_t st = (cudaStream_t)stream;
+  const int V = dtype == DUSTY_F32 ? 4 : 8;
+  const int cv = C / V;
+  int64_t blocks = (int64_t)num_sms() * 8;
+  int64_t rpb = (rows + blocks - 1) / blocks;
+  const int R = 256 / cv;
+  if (rpb < R * 4) rpb = R * 4;
+  blocks = (rows + rpb - 1) / rpb;
+  if (dtype == DUSTY_F32)
+    bias_act_add_bwd_cl_kernel<float><<<(unsigned)blocks, 256, 0, st>>>(
+        (const float *)dy, (const float *)x, (const float *)bias, (float *)dx, (float *)dskip, db, rows, cv,
+        rpb, alpha, gain, c);
+  else
+    bias_act_add_bwd_cl_kernel<__nv_bfloat16><<<(unsigned)blocks, 256, 0, st>>>(
+        (const __nv_bfloat16 *)dy, (const __nv_bfloat16 *)x, (const __nv_bfloat16 *)bias, (__nv_bfloat16 *)dx,
+        (__nv_bfloat16 *)dskip, db, rows, cv, rpb, alpha, gain, c);
   DUSTY_LAUNCH_CHECK();
   return DUSTY_OK;
 }

@@ -189,6 +189,60 @@ def bias_act(x, bias=None, negative_slope: float = 0.2, scale: float = 2 ** 0.5)
     return _BiasAct.apply(_canon(x, need_pow2=True), bias, float(negative_slope), float(scale))
 
 
+class _ResidualTail(Function):
+    """y = (lrelu(x + bias) * gain + skip) * c, NHWC, one pass each way (cl_ops.cu).  Saves the
+    pre-activation x (the activated tensor is never materialised).  Under create_graph=True
+    the backward is re-expressed through the differentiable single ops."""
+
+    @staticmethod
+    def forward(ctx, x, bias, skip, alpha, gain, c):
+        xc = _canon(x, need_pow2=True)
+        sk = _like(skip, xc)
+        C = xc.shape[1]
+        b = None if bias is None else _contig(bias.detach().to(xc.dtype))
+        y = torch.empty_like(xc)
+        K.call("dusty_bias_act_add_cl", K.ptr(xc), K.ptr(b), K.ptr(sk), K.ptr(y), xc.numel(), C, alpha,
+               gain, c, K.dtype_code(xc), K.stream_of(xc))
+        ctx.save_for_backward(x, bias, skip)
+        ctx.cfg = (alpha, gain, c)
+        return y
+
+    @staticmethod
+    def backward(ctx, gy):
+        x, bias, skip = ctx.saved_tensors
+        alpha, gain, c = ctx.cfg
+        need_x, need_b, need_s = ctx.needs_input_grad[:3]
+        if torch.is_grad_enabled():
+            with torch.enable_grad():
+                yc = (bias_act(x, bias, alpha, gain) + skip) * c
+                wanted = [t for t, n in ((x, need_x), (bias, need_b), (skip, need_s)) if n and t is not None]
+                grads = list(torch.autograd.grad(yc, wanted, gy, create_graph=True, allow_unused=True))
+            out = [grads.pop(0) if (n and t is not None) else None
+                   for t, n in ((x, need_x), (bias, need_b), (skip, need_s))]
+            return out[0], out[1], out[2], None, None, None
+        xc = _canon(x.detach(), need_pow2=True)
+        g = _like(gy, xc)
+        C = xc.shape[1]
+        b = None if bias is None else _contig(bias.detach().to(xc.dtype))
+        dx = torch.empty_like(xc)
+        dskip = torch.empty_like(xc) if need_s else None
+        db = torch.zeros(C, device=xc.device, dtype=torch.float32) if (need_b and bias is not None) else None
+        K.call("dusty_bias_act_add_bwd_cl", K.ptr(g), K.ptr(xc), K.ptr(b), K.ptr(dx), K.ptr(dskip), K.ptr(db),
+               xc.numel() // C, C, alpha, gain, c, K.dtype_code(xc), K.stream_of(xc))
+        return (dx if need_x else None, None if db is None else db.to(bias.dtype), dskip, None, None, None)
+
+
+def residual_tail_supported(x: torch.Tensor, skip: torch.Tensor) -> bool:
+    return (x.is_cuda and x.dim() == 4 and _is_cl(x) and _cl_vec_ok(x, pow2=True) and skip.shape == x.shape
+            and skip.dtype == x.dtype)
+
+
+def residual_tail(x, bias, skip, negative_slope: float = 0.2, gain: float = 2 ** 0.5,
+                  c: float = 2 ** -0.5):
+    K.require_cuda(x, bias, skip)
+    return _ResidualTail.apply(x, bias, skip, float(negative_slope), float(gain), float(c))
+
+
 # --------------------------------------------------------------------------- FIR family
 _TAPS_CACHE = {}
 

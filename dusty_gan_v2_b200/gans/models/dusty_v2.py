@@ -331,8 +331,31 @@ class ResidualBlock(nn.Module):
             return ops.conv2d_valid(DF.blur_down2_cl(x, rs._taps_host), w, (1, 1))
         return self.skip(rs(x))
 
+    def _conv1_act(self, x):
+        """bias_act1(conv1(x)); on the halo-resident tcgen05 kernel the bias / leaky ReLU run in
+        the convolution's epilogue."""
+        seq, act = self.conv1, self.bias_act1
+        eq = seq[-1]
+        conv = getattr(eq, "module", None)
+        if (len(seq) == 2 and isinstance(seq[0], ops.Pad) and isinstance(eq, ops.EqualLR)
+                and isinstance(conv, nn.Conv2d) and conv.bias is None and conv.stride == (1, 1)
+                and x.is_cuda and x.dtype == torch.bfloat16):
+            w = (conv.weight * (eq.scale * eq.gain_)).to(x.dtype).contiguous(memory_format=torch.channels_last)
+            xp = seq[0](x)
+            if ops.conv_bias_act_supported(xp, w, (1, 1)):
+                return ops.conv_bias_act(xp, w, act.bias, (1, 1), act.negative_slope, act.scale)
+            return act(ops.conv2d_valid(xp, w, (1, 1)))
+        return act(seq(x))
+
     def forward(self, x):
-        return (self.residual(x) + self._skip(x)) * (1.0 / math.sqrt(2))
+        skip = self._skip(x)
+        pre = self._blur_pad_conv2(self._conv1_act(x))                # conv2 output, before bias_act2
+        act = self.bias_act2
+        if DF.residual_tail_supported(pre, skip):
+            # bias_act2, the residual sum and the 1/sqrt(2) as one NHWC pass
+            return DF.residual_tail(pre, act.bias, skip, act.negative_slope, act.scale,
+                                    1.0 / math.sqrt(2))
+        return (act(pre) + skip) * (1.0 / math.sqrt(2))
 
 
 class _ActView:

@@ -220,6 +220,51 @@ class _Conv2dBwdFn(torch.autograd.Function):
         return g_gy, g_x, g_w, None, None, None
 
 
+class _ConvBiasActFn(torch.autograd.Function):
+    """y = lrelu(conv2d_valid(x, w) + bias) * gain with the bias / activation in the epilogue of
+    our tcgen05 convolution (one write of y instead of write + read + write).  First-order
+    backward = the fused bias_act backward followed by dgrad / wgrad; under create_graph=True it
+    is re-expressed through the differentiable single ops."""
+
+    @staticmethod
+    def forward(ctx, x, w, bias, stride, alpha, gain):
+        bf = None if bias is None else bias.detach().float().contiguous()
+        y = DF.conv2d_fprop_tc(x, w, stride, bf, 3, alpha, gain)
+        ctx.save_for_backward(x, w, bias, y)
+        ctx.cfg = (stride, alpha, gain)
+        return y
+
+    @staticmethod
+    def backward(ctx, gy):
+        x, w, bias, y = ctx.saved_tensors
+        stride, alpha, gain = ctx.cfg
+        need_x, need_w, need_b = ctx.needs_input_grad[:3]
+        if torch.is_grad_enabled():
+            with torch.enable_grad():
+                yc = DF.bias_act(conv2d_valid(x, w, stride), bias, alpha, gain)
+                wanted = [t for t, n in ((x, need_x), (w, need_w), (bias, need_b)) if n and t is not None]
+                grads = list(torch.autograd.grad(yc, wanted, gy, create_graph=True, allow_unused=True))
+            out = [grads.pop(0) if (n and t is not None) else None
+                   for t, n in ((x, need_x), (w, need_w), (bias, need_b))]
+            return out[0], out[1], out[2], None, None, None
+        gpre, db = DF._BiasActBackward.apply(gy, y, bias is not None, alpha, gain)
+        gx, gw = _Conv2dBwdFn.apply(gpre, x, w, stride, need_x, need_w)
+        gb = db.to(bias.dtype) if (need_b and bias is not None) else None
+        return gx, gw, gb, None, None, None
+
+
+def conv_bias_act_supported(x, w, stride) -> bool:
+    """The fused epilogue exists on the halo-resident kernel (unit-stride 3x3 of the thin layers)."""
+    stride = tuple(stride) if isinstance(stride, (tuple, list)) else (stride, stride)
+    return (x.is_cuda and stride == (1, 1) and DF._is_cl(x) and DF.conv_tc_supported(x, w, stride, "fprop")
+            and DF.conv_halo_ok(w, "fprop"))
+
+
+def conv_bias_act(x, w, bias, stride, negative_slope=0.2, gain=2 ** 0.5):
+    stride = tuple(stride) if isinstance(stride, (tuple, list)) else (stride, stride)
+    return _ConvBiasActFn.apply(x, w, bias, stride, float(negative_slope), float(gain))
+
+
 def conv2d_valid(x, w, stride):
     """Un-padded, bias-free 2-D convolution with analytic higher-order gradients."""
     stride = tuple(stride) if isinstance(stride, (tuple, list)) else (stride, stride)

@@ -111,6 +111,16 @@ int dusty_bias_act_cl(const void *x, const void *bias, const void *ref, void *y,
                       int C, int act, int grad, float alpha, float scale, int dtype, void *stream);
 int dusty_bias_act_bwd_cl(const void *dy, const void *out, void *dx, float *db, int64_t rows, int C,
                           float alpha, float scale, int dtype, void *stream);
+
+/* End of a ResidualBlock (gans/models/dusty_v2.py:387-396: bias_act2, + skip, / sqrt 2) as one
+ * NHWC pass:  y = (lrelu(x + bias[c]) * gain + skip) * c.  bias has the activation dtype. */
+int dusty_bias_act_add_cl(const void *x, const void *bias, const void *skip, void *y, int64_t n_elem,
+                          int C, float alpha, float gain, float c, int dtype, void *stream);
+/* g = dy * c; dskip = g (may be NULL); dx = g * gate(x + bias) * gain; db fp32 [C] += sum dx
+ * (may be NULL; the caller zeroes it). */
+int dusty_bias_act_add_bwd_cl(const void *dy, const void *x, const void *bias, void *dx, void *dskip,
+                              float *db, int64_t rows, int C, float alpha, float gain, float c,
+                              int dtype, void *stream);
 int dusty_pad2d_cl(const void *x, void *y, int B, int H, int W, int C, int pt, int pb, int pl,
                    int pr, int mode_y, int mode_x, int adjoint, int dtype, void *stream);
 /* pad == 1 fuses the 1-pixel ring padding that follows the blur in ResidualBlock.residual

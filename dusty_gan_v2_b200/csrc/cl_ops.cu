@@ -6,6 +6,8 @@
 //   bias_act_cl      a3  (bias index = channel = fastest axis)
 //   pad2d_cl         a4/a11  ring padding, forward + adjoint
 //   blur4_cl         a4  4-tap separable blur (circular W, replicate H), forward + adjoint
+#include <stdlib.h>
+
 #include "common.cuh"
 
 namespace dusty {
@@ -379,6 +381,219 @@ blur4_cl_kernel(const T *__restrict__ x, T *__restrict__ y, Taps4CL t, int H, in
   }
 }
 
+// ------------------------------------------------------------------ blur4, shared-memory row ring
+// The register-window kernel above asks for every input vector four times (once per horizontal
+// tap, from four different threads) and holds those requests in registers: ~10 KB of UNIQUE
+// bytes in flight per SM, latency-bound at ~50 % of HBM.  Here a CTA owns a tile of TP = 128/cv
+// output pixels x a strip of rows and streams the input rows through a ring in shared memory
+// with cp.async: every thread fetches only its own pixel's vector (plus 3 halo pixels per row,
+// and the 2 folded ring columns for the padded adjoint), LA rows ahead of the one being
+// reduced, so each input byte is fetched once per CTA and the requests cost no registers.
+// The horizontal taps are then four conflict-free 16-byte shared-memory reads.
+// Row schedule: a table of source rows built once per CTA (clamped rows for the forward blur,
+// zero rows and the two folded ring rows for the adjoint); entry q is consumed LA iterations
+// after it was issued; D = LA + 2 slots make slot reuse safe with one barrier per row.
+constexpr int kRingLA = 6;
+constexpr int kRingD = kRingLA + 2;
+constexpr int kRingMaxEntries = 160;
+
+__device__ __forceinline__ void cp_async16(uint32_t dst, const void *src) {
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst), "l"(src) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int N>
+__device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
+
+template <typename T, bool ADJ, bool PAD>
+__global__ void __launch_bounds__(128)
+blur4_ring_cl_kernel(const T *__restrict__ x, T *__restrict__ y, Taps4CL t, int H, int W, int cv,
+                     int strip) {
+  constexpr int V = Vec16<T>::N;
+  constexpr int VP = V / 2;
+  extern __shared__ __align__(16) uint8_t ring_raw[];
+  __shared__ int entries[kRingMaxEntries];           // source row (in the SOURCE tensor), -1: zero row;
+                                                     // bit 30: fold into the next entry
+  __shared__ int n_entries;
+  const int TP = 128 / cv;                           // output pixels per tile
+  const int cols = TP + 3 + ((PAD && ADJ) ? 2 : 0);  // ring columns per row
+  const int slot_bytes = cols * cv * 16;
+  const int j = threadIdx.x % cv, p = threadIdx.x / cv;
+  const int Wx = (PAD && !ADJ) ? W + 2 : W;          // output columns covered by tiles
+  const int xo0 = blockIdx.x * TP;
+  const int xo = xo0 + p;
+  const int b = blockIdx.z;
+  const int Hs = (PAD && ADJ) ? H + 2 : H, Ws = (PAD && ADJ) ? W + 2 : W;   // source extents
+  const T *img = x + (int64_t)b * Hs * Ws * cv * V;
+  const int64_t out_img = (int64_t)((PAD && !ADJ) ? (H + 2) * (W + 2) : H * W) * cv * V;
+  T *out = y + (int64_t)b * out_img;
+  const int y0 = blockIdx.y * strip, y1 = min(y0 + strip, H);
+
+  // ---- row schedule
+  int rho0, n_main;                                  // first image row of the stream, main entries
+  if (!ADJ) { rho0 = y0 - 2; n_main = (y1 - y0) + 3; }
+  else {
+    const int e_lo = (y0 == 0) ? -2 : y0, e_hi = (y1 == H) ? H : y1 - 1;
+    rho0 = e_lo - 1; n_main = (e_hi - e_lo + 1) + 3;
+  }
+  if (threadIdx.x == 0) {
+    int n = 0;
+    for (int q = 0; q < n_main; ++q) {
+      const int rho = rho0 + q;
+      if (!ADJ) {
+        entries[n++] = rho < 0 ? 0 : (rho >= H ? H - 1 : rho);
+      } else if (rho < 0 || rho >= H) {
+        entries[n++] = -1;
+      } else {
+        if (PAD && rho == 0) entries[n++] = 0 | (1 << 30);            // padded ring row 0
+        if (PAD && rho == H - 1) entries[n++] = (H + 1) | (1 << 30);  // padded ring row H+1
+        entries[n++] = PAD ? rho + 1 : rho;
+      }
+    }
+    n_entries = n;
+  }
+  __syncthreads();
+  const int n = n_entries;
+
+  // ---- per-thread source columns (in the source tensor) and smem addresses
+  // ring column c <-> image column wrap(cbase + c); forward taps read c = p + s, adjoint c = p + 3 - s
+  const int x_img0 = (PAD && !ADJ) ? xo0 - 1 : xo0;  // image column of this tile's first output
+  const int cbase = ADJ ? x_img0 - 1 : x_img0 - 2;
+  auto src_col = [&](int c) {
+    int ic = (cbase + c) % W;
+    if (ic < 0) ic += W;
+    return ic + ((PAD && ADJ) ? 1 : 0);
+  };
+  const int64_t own_off = ((int64_t)src_col(p) * cv + j) * V;
+  const int64_t halo_off = p < 3 ? ((int64_t)src_col(TP + p) * cv + j) * V : 0;
+  // padded adjoint: ring columns TP+3 / TP+4 hold padded column W+1 (folds onto image column 0)
+  // and padded column 0 (folds onto image column W-1)
+  const int64_t fold_off = (PAD && ADJ && (p == 3 || p == 4)) ? ((int64_t)(p == 3 ? W + 1 : 0) * cv + j) * V : 0;
+  const int64_t pitch = (int64_t)Ws * cv * V;
+  const uint32_t ring = smem_addr_u32(ring_raw);
+  const uint32_t own_dst = (uint32_t)((p * cv + j) * 16);
+  const uint32_t halo_dst = (uint32_t)(((TP + p) * cv + j) * 16);
+  const uint32_t fold_dst = (uint32_t)(((TP + 3 + (p - 3)) * cv + j) * 16);
+  uint32_t tap_src[4];                               // byte offsets of this thread's 4 taps in a slot
+  int fold_sel[4];                                   // padded adjoint: 0 none, 1 add E0, 2 add E1
+#pragma unroll
+  for (int s2 = 0; s2 < 4; ++s2) {
+    const int c = ADJ ? p + 3 - s2 : p + s2;
+    tap_src[s2] = (uint32_t)((c * cv + j) * 16);
+    fold_sel[s2] = 0;
+    if (PAD && ADJ) {
+      int ic = (cbase + c) % W;
+      if (ic < 0) ic += W;
+      fold_sel[s2] = ic == 0 ? 1 : (ic == W - 1 ? 2 : 0);
+    }
+  }
+  const uint32_t e0_src = (uint32_t)(((TP + 3) * cv + j) * 16), e1_src = (uint32_t)(((TP + 4) * cv + j) * 16);
+
+  auto issue = [&](int q) {
+    if (q < n) {
+      const int e = entries[q];
+      if (e >= 0) {
+        const T *prow = img + (int64_t)(e & 0xffff) * pitch;
+        const uint32_t base = ring + (uint32_t)((q % kRingD) * slot_bytes);
+        cp_async16(base + own_dst, prow + own_off);
+        if (p < 3) cp_async16(base + halo_dst, prow + halo_off);
+        if (PAD && ADJ && (p == 3 || p == 4)) cp_async16(base + fold_dst, prow + fold_off);
+      }
+    }
+    cp_async_commit();
+  };
+  auto lds16 = [&](uint32_t addr) {
+    Vec16<T> v;
+    uint32_t a0, a1, a2, a3;
+    asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];" : "=r"(a0), "=r"(a1), "=r"(a2), "=r"(a3) : "r"(addr));
+    uint4 u = make_uint4(a0, a1, a2, a3);
+    v.raw = *reinterpret_cast<decltype(v.raw) *>(&u);
+    return v;
+  };
+  // horizontal reduction of ring slot q into dst (+= when acc)
+  auto hreduce = [&](int q, float2 *dst, bool acc) {
+    const uint32_t base = ring + (uint32_t)((q % kRingD) * slot_bytes);
+    Vec16<T> v[4];
+#pragma unroll
+    for (int s2 = 0; s2 < 4; ++s2) v[s2] = lds16(base + tap_src[s2]);
+#pragma unroll
+    for (int k = 0; k < VP; ++k) {
+      float2 h = acc ? fma2(t.k[0], get2(v[0], k), dst[k]) : mul2(t.k[0], get2(v[0], k));
+#pragma unroll
+      for (int s2 = 1; s2 < 4; ++s2) h = fma2(t.k[s2], get2(v[s2], k), h);
+      dst[k] = h;
+    }
+    if (PAD && ADJ) {
+#pragma unroll
+      for (int s2 = 0; s2 < 4; ++s2) {
+        if (fold_sel[s2]) {
+          const Vec16<T> e = lds16(base + (fold_sel[s2] == 1 ? e0_src : e1_src));
+#pragma unroll
+          for (int k = 0; k < VP; ++k) dst[k] = fma2(t.k[s2], get2(e, k), dst[k]);
+        }
+      }
+    }
+  };
+
+  for (int q = 0; q < kRingLA; ++q) issue(q);
+  float2 a[VP], bb[VP], c[VP], d[VP], acc[VP];
+#pragma unroll
+  for (int k = 0; k < VP; ++k) a[k] = bb[k] = c[k] = d[k] = acc[k] = make_float2(0.f, 0.f);
+  const bool col_ok = xo < Wx;
+  int m = 0;                                         // main entries consumed so far
+  bool pending = false;                              // d holds a folded ring row awaiting its image row
+  for (int q = 0; q < n; ++q) {
+    issue(q + kRingLA);
+    cp_async_wait<kRingLA>();
+    __syncthreads();
+    const int e = entries[q];
+    if (e < 0) {
+#pragma unroll
+      for (int k = 0; k < VP; ++k) d[k] = make_float2(0.f, 0.f);
+    } else {
+      hreduce(q, d, pending);
+    }
+    if (e >= 0 && (e & (1 << 30))) { pending = true; continue; }
+    pending = false;
+    ++m;
+    if (m >= 4) {
+      if (!ADJ) {
+        const int r = y0 + (m - 4);
+        Vec16<T> o;
+#pragma unroll
+        for (int k = 0; k < VP; ++k)
+          set2(o, k, fma2(t.k[3], d[k], fma2(t.k[2], c[k], fma2(t.k[1], bb[k], mul2(t.k[0], a[k])))));
+        if (col_ok) {
+          if (PAD) {
+            const int Wp = W + 2;
+            st16(out + (((int64_t)(r + 1) * Wp + xo) * cv + j) * V, o);
+            if (r == 0) st16(out + ((int64_t)xo * cv + j) * V, o);
+            if (r == H - 1) st16(out + (((int64_t)(H + 1) * Wp + xo) * cv + j) * V, o);
+          } else {
+            st16(out + (((int64_t)r * W + xo) * cv + j) * V, o);
+          }
+        }
+      } else {
+        const int e_lo = (y0 == 0) ? -2 : y0, e_hi = (y1 == H) ? H : y1 - 1;
+        const int er = e_lo + (m - 4);               // row e of the un-clamped adjoint
+#pragma unroll
+        for (int k = 0; k < VP; ++k)
+          acc[k] = fma2(t.k[0], d[k], fma2(t.k[1], c[k], fma2(t.k[2], bb[k], fma2(t.k[3], a[k], acc[k]))));
+        const int i = er < 0 ? 0 : (er >= H ? H - 1 : er);
+        const int i_next = (er + 1) < 0 ? 0 : ((er + 1) >= H ? H - 1 : (er + 1));
+        if (er == e_hi || i_next != i) {
+          Vec16<T> o;
+#pragma unroll
+          for (int k = 0; k < VP; ++k) { set2(o, k, acc[k]); acc[k] = make_float2(0.f, 0.f); }
+          if (col_ok) st16(out + (((int64_t)i * W + xo) * cv + j) * V, o);
+        }
+      }
+    }
+#pragma unroll
+    for (int k = 0; k < VP; ++k) { a[k] = bb[k]; bb[k] = c[k]; c[k] = d[k]; }
+  }
+  cp_async_wait<0>();
+}
+
 // ------------------------------------------------------------------ blur4 + 2x decimation (NHWC)
 // Skip branch of the residual blocks: conv1x1_stride2(blur(x)) only ever reads the blurred
 // image at even rows / columns, so the blur is evaluated there and nowhere else:
@@ -679,12 +894,44 @@ extern "C" int dusty_blur4_cl(const void *x, void *y, float k0, float k1, float 
   t.k[0] = k0; t.k[1] = k1; t.k[2] = k2; t.k[3] = k3;
   const int cv = C / V;
   const int Wx = (pad && !adjoint) ? W + 2 : W;
+  cudaStream_t st = (cudaStream_t)stream;
+  // shared-memory row-ring variant: MEASURED SLOWER than the register-window kernel (64x512x32
+  // bf16: 101 vs 71 us forward, 138 vs 122 us padded adjoint -- one barrier per 16-byte output
+  // row costs more than the deeper prefetch buys; both are issue-bound at ~130 instructions
+  // per row).  Kept as an opt-in experiment (DUSTY_BLUR_RING=1), covered by the same tests.
+  static const bool ring_on = [] { const char *e = getenv("DUSTY_BLUR_RING"); return e && atoi(e) != 0; }();
+  if (ring_on && cv <= 8 && 128 % cv == 0 && B <= 65535) {
+    const int TP = 128 / cv;
+    const int tiles = (Wx + TP - 1) / TP;
+    int rstrip = H;
+    while (rstrip > 16 && (int64_t)tiles * B * ((H + rstrip - 1) / rstrip) < (int64_t)num_sms() * 8)
+      rstrip = (rstrip + 1) / 2;
+    if (rstrip + 8 <= kRingMaxEntries) {
+      const int cols = TP + 3 + ((pad && adjoint) ? 2 : 0);
+      const int smem = kRingD * cols * cv * 16;
+      dim3 rgrid((unsigned)tiles, (unsigned)((H + rstrip - 1) / rstrip), (unsigned)B);
+#define BLUR_RING(T, A, P) \
+  blur4_ring_cl_kernel<T, A, P><<<rgrid, 128, smem, st>>>((const T *)x, (T *)y, t, H, W, cv, rstrip)
+#define BLUR_RING_DISPATCH(T)                      \
+  do {                                             \
+    if (adjoint && pad) BLUR_RING(T, true, true);  \
+    else if (adjoint) BLUR_RING(T, true, false);   \
+    else if (pad) BLUR_RING(T, false, true);       \
+    else BLUR_RING(T, false, false);               \
+  } while (0)
+      if (dtype == DUSTY_F32) BLUR_RING_DISPATCH(float);
+      else BLUR_RING_DISPATCH(__nv_bfloat16);
+#undef BLUR_RING_DISPATCH
+#undef BLUR_RING
+      DUSTY_LAUNCH_CHECK();
+      return DUSTY_OK;
+    }
+  }
   const int64_t n_threads = (int64_t)B * Wx * cv;
   int strip = H;
   const int64_t ctas_x = (n_threads + 127) / 128;
   while (strip > 8 && ctas_x * ((H + strip - 1) / strip) < (int64_t)num_sms() * 8) strip = (strip + 1) / 2;
   dim3 grid((unsigned)ctas_x, (unsigned)((H + strip - 1) / strip));
-  cudaStream_t st = (cudaStream_t)stream;
 #define BLUR_CL(T, A, P) \
   blur4_cl_kernel<T, A, P><<<grid, 128, 0, st>>>((const T *)x, (T *)y, t, H, W, cv, strip, n_threads)
 #define BLUR_CL_DISPATCH(T)                       \

@@ -154,6 +154,10 @@ __device__ __forceinline__ float block_sum(float v, float *red) {
   return v;
 }
 
+__device__ __forceinline__ uint32_t smem_addr_u32(const void *p) {
+  return (uint32_t)__cvta_generic_to_shared(p);
+}
+
 inline bool aligned16(const void *p) { return (reinterpret_cast<uintptr_t>(p) & 15u) == 0; }
 
 }  // namespace dusty

@@ -46,14 +46,15 @@ stem_fwd_kernel(const TX *__restrict__ x, const float *__restrict__ w, const flo
     b[j] = bias != nullptr ? __ldg(bias + og * 8 + j) : 0.f;
   }
   const int ppb = blockDim.x / OG;                       // pixels per block per sweep
-  const int64_t stride = (int64_t)gridDim.x * ppb;
-  const int64_t hw = (int64_t)H * W;
-  for (int64_t p = (int64_t)blockIdx.x * ppb + threadIdx.x / OG; p < n_pix; p += stride) {
-    const int64_t bi = p / hw;
-    const int r = (int)(p - bi * hw);
+  const int stride = (int)gridDim.x * ppb;               // n_pix < 2^31 (checked by the host):
+  const int hw = H * W;                                  // 32-bit index math, no 64-bit divisions
+  const int np = (int)n_pix;
+  for (int p = (int)blockIdx.x * ppb + threadIdx.x / OG; p < np; p += stride) {
+    const int bi = p / hw;
+    const int r = p - bi * hw;
     const int yy = r / W, xx = r - yy * W;
     float v, h;
-    stem_vh(x + bi * hw, yy, xx, H, W, t, v, h);
+    stem_vh(x + (int64_t)bi * hw, yy, xx, H, W, t, v, h);
     Vec16<__nv_bfloat16> o;
 #pragma unroll
     for (int j = 0; j < 4; ++j) {
@@ -63,7 +64,7 @@ stem_fwd_kernel(const TX *__restrict__ x, const float *__restrict__ w, const flo
       a1 = (a1 > 0.f ? a1 : a1 * alpha) * scale;
       set2(o, j, make_float2(a0, a1));
     }
-    st16_stream(y + (p * OG + og) * 8, o);
+    st16_stream(y + ((int64_t)p * OG + og) * 8, o);
   }
 }
 
@@ -85,23 +86,35 @@ stem_bwd_kernel(const __nv_bfloat16 *__restrict__ dy, const __nv_bfloat16 *__res
 #pragma unroll
   for (int j = 0; j < 8; ++j) sb[j] = s0[j] = s1[j] = 0.f;
   const int ppb = blockDim.x / OG;
-  const int64_t stride = (int64_t)gridDim.x * ppb;
-  const int64_t hw = (int64_t)H * W;
-  // every thread of a warp runs the same number of sweeps (shuffles below need full warps)
-  const int64_t p_first = (int64_t)blockIdx.x * ppb + threadIdx.x / OG;
-  const int64_t sweeps = (n_pix + stride - 1) / stride;
-  for (int64_t it = 0; it < sweeps; ++it) {
-    const int64_t p = p_first + it * stride;
-    const bool live = p < n_pix;
+  const int stride = (int)gridDim.x * ppb;               // n_pix < 2^31: 32-bit index math
+  const int hw = H * W;
+  const int np = (int)n_pix;
+  // every thread of a warp runs the same number of sweeps (shuffles below need full warps);
+  // the two 16-byte vectors of sweep it+1 are requested before sweep it is reduced
+  const int p_first = (int)blockIdx.x * ppb + threadIdx.x / OG;
+  const int sweeps = (np + stride - 1) / stride;
+  Vec16<__nv_bfloat16> g_n, o_n;
+  if (p_first < np) {
+    g_n = ld16_stream(dy + ((int64_t)p_first * OG + og) * 8);
+    o_n = ld16_stream(y + ((int64_t)p_first * OG + og) * 8);
+  }
+  for (int it = 0; it < sweeps; ++it) {
+    const int p = p_first + it * stride;
+    const bool live = p < np;
+    const Vec16<__nv_bfloat16> g = g_n, o = o_n;
+    const int pn = p + stride;
+    if (it + 1 < sweeps && pn < np) {
+      g_n = ld16_stream(dy + ((int64_t)pn * OG + og) * 8);
+      o_n = ld16_stream(y + ((int64_t)pn * OG + og) * 8);
+    }
     float dv = 0.f, dh = 0.f;
+    int bi = 0, r = 0;
     if (live) {
-      const int64_t bi = p / hw;
-      const int r = (int)(p - bi * hw);
+      bi = p / hw;
+      r = p - bi * hw;
       const int yy = r / W, xx = r - yy * W;
       float v, h;
-      stem_vh(x + bi * hw, yy, xx, H, W, t, v, h);
-      const Vec16<__nv_bfloat16> g = ld16_stream(dy + (p * OG + og) * 8);
-      const Vec16<__nv_bfloat16> o = ld16_stream(y + (p * OG + og) * 8);
+      stem_vh(x + (int64_t)bi * hw, yy, xx, H, W, t, v, h);
 #pragma unroll
       for (int j = 0; j < 8; ++j) {
         const float gp = g.get(j) * (o.get(j) > 0.f ? 1.f : alpha) * scale;
@@ -118,10 +131,8 @@ stem_bwd_kernel(const __nv_bfloat16 *__restrict__ dy, const __nv_bfloat16 *__res
         dh += __shfl_xor_sync(0xffffffffu, dh, m);
       }
       if (live && og == 0) {
-        const int64_t bi = p / hw;
-        const int64_t r = p - bi * hw;
-        dvh[(bi * 2) * hw + r] = dv;
-        dvh[(bi * 2 + 1) * hw + r] = dh;
+        dvh[((int64_t)bi * 2) * hw + r] = dv;
+        dvh[((int64_t)bi * 2 + 1) * hw + r] = dh;
       }
     }
   }
@@ -192,6 +203,7 @@ using namespace dusty;
 
 static bool stem_shape_ok(int B, int H, int W, int O) {
   const int og = O / 8;
+  if ((int64_t)B * H * W * (og > 0 ? og : 1) >= 0x7fffffffLL) return false;   // 32-bit pixel indices
   return B >= 1 && H >= 2 && W >= 2 && O >= 8 && O % 8 == 0 && og <= 8 && (og & (og - 1)) == 0;
 }
 
@@ -232,7 +244,7 @@ extern "C" int dusty_stem_bwd(const void *dy, const void *y, const void *x, cons
     set_error("dusty_stem_bwd: memset failed");
     return DUSTY_ECUDA;
   }
-  int64_t blocks = (int64_t)num_sms() * 4;
+  int64_t blocks = (int64_t)num_sms() * 8;
   const int ppb = 256 / OG;
   if (blocks * ppb > n_pix) blocks = (n_pix + ppb - 1) / ppb;
   if (x_dtype == DUSTY_F32)

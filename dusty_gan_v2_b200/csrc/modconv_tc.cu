@@ -586,10 +586,15 @@ modconv_dw_tc_kernel(const __grid_constant__ CUtensorMap map_x1,
 #pragma unroll
         for (int half = 0; half < 2; ++half) {
           const int c = m0 + 64 * half;
-          if (c < prm.C1) tma_load_3d(a_dst + half * 8192, &map_x1, &full[s], pb * kBK, c, b);
-          else tma_load_3d(a_dst + half * 8192, &map_x2, &full[s], pb * kBK, c - prm.C1, bb);
+          // stream-once activations must not evict the batch-shared Fourier block, which every
+          // sample's CTAs re-read (without hints: 2.6 GB of DRAM reads for 0.44 GB algorithmic)
+          if (c < prm.C1)
+            tma_load_3d_hint(a_dst + half * 8192, &map_x1, &full[s], pb * kBK, c, b, kEvictFirst);
+          else
+            tma_load_3d_hint(a_dst + half * 8192, &map_x2, &full[s], pb * kBK, c - prm.C1, bb,
+                             prm.B2 == 1 ? kEvictLast : kEvictFirst);
         }
-        tma_load_3d(b_base + s * kBBytes, &map_g, &full[s], pb * kBK, n0, b);
+        tma_load_3d_hint(b_base + s * kBBytes, &map_g, &full[s], pb * kBK, n0, b, kEvictFirst);
       }
       __syncwarp();
       r.template advance<STAGES>();

@@ -56,6 +56,8 @@ SIGNATURES = {
     "dusty_sumsq_rows": [_vp, _vp, _i64, _i64, _i, _i, _vp],
     "dusty_ema_lerp": [_vp, _vp, _vp, _f, _f, _f, _vp],
     "dusty_circular_shift": [_vp, _vp, _vp, _i, _i, _i, _i, _f, _i, _vp],
+    "dusty_weight_prep": [_vp, _vp, _i, _i, _i, _f, _i, _vp],
+    "dusty_weight_prep_adj": [_vp, _vp, _i, _i, _i, _f, _i, _i, _vp],
     "dusty_stem_fwd": [_vp, _vp, _vp, _vp, _i, _i, _i, _i, _f, _f, _f, _f, _f, _i, _vp],
     "dusty_stem_bwd": [_vp, _vp, _vp, _vp, _vp, _vp, _i, _i, _i, _i, _f, _f, _f, _f, _f, _i, _vp],
     "dusty_stem_dx": [_vp, _vp, _i, _i, _i, _f, _f, _f, _vp],

@@ -427,3 +427,72 @@ extern "C" int dusty_ema_lerp(float *ema_var, const float *sum_a, const float *s
   DUSTY_LAUNCH_CHECK();
   return DUSTY_OK;
 }
+
+// ------------------------------------------------------------------ a11: EqualLR weight preparation
+// Conv2d + EqualLR (gans/models/ops/common.py:158-184 of the reference) multiplies by
+// 1/sqrt(fan_in); folded into the weight that is scale, cast and NCHW -> NHWC filter layout:
+// three ATen kernels per convolution per pass (and four on the way back).  One kernel each way:
+//   fwd: out[o][rs][c] (bf16 / fp32) = w[o][c][rs] (fp32 master) * scale
+//   adj: gw[o][c][rs] (fp32)         = g[o][rs][c] or g[o][c][rs] (bf16 / fp32) * scale
+namespace dusty {
+template <typename TO>
+__global__ void __launch_bounds__(256)
+weight_prep_fwd_kernel(const float *__restrict__ w, TO *__restrict__ out, int64_t n, int C, int RS,
+                       float scale) {
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+    const int c = (int)(i % C);
+    const int64_t t = i / C;
+    const int rs = (int)(t % RS);
+    const int64_t o = t / RS;
+    out[i] = from_f<TO>(__ldg(w + (o * C + c) * RS + rs) * scale);
+  }
+}
+template <typename TI>
+__global__ void __launch_bounds__(256)
+weight_prep_adj_kernel(const TI *__restrict__ g, float *__restrict__ gw, int64_t n, int C, int RS,
+                       float scale, int nhwc) {
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+    const int rs = (int)(i % RS);
+    const int64_t t = i / RS;
+    const int c = (int)(t % C);
+    const int64_t o = t / C;
+    const int64_t src = nhwc ? (o * RS + rs) * C + c : i;
+    gw[i] = to_f(g[src]) * scale;
+  }
+}
+}  // namespace dusty
+
+extern "C" int dusty_weight_prep(const float *w, void *out, int O, int C, int RS, float scale,
+                                 int out_dtype, void *stream) {
+  DUSTY_CHECK_ARG(w && out, "null pointer");
+  DUSTY_CHECK_ARG(O >= 1 && C >= 1 && RS >= 1, "bad shape");
+  DUSTY_CHECK_ARG(out_dtype == DUSTY_F32 || out_dtype == DUSTY_BF16, "bad dtype");
+  const int64_t n = (int64_t)O * C * RS;
+  int64_t blocks = (n + 255) / 256;
+  if (blocks > (int64_t)num_sms() * 16) blocks = (int64_t)num_sms() * 16;
+  cudaStream_t st = (cudaStream_t)stream;
+  if (out_dtype == DUSTY_F32)
+    weight_prep_fwd_kernel<float><<<(unsigned)blocks, 256, 0, st>>>(w, (float *)out, n, C, RS, scale);
+  else
+    weight_prep_fwd_kernel<__nv_bfloat16><<<(unsigned)blocks, 256, 0, st>>>(w, (__nv_bfloat16 *)out, n, C, RS, scale);
+  DUSTY_LAUNCH_CHECK();
+  return DUSTY_OK;
+}
+
+extern "C" int dusty_weight_prep_adj(const void *g, float *gw, int O, int C, int RS, float scale,
+                                     int g_dtype, int g_nhwc, void *stream) {
+  DUSTY_CHECK_ARG(g && gw, "null pointer");
+  DUSTY_CHECK_ARG(O >= 1 && C >= 1 && RS >= 1, "bad shape");
+  DUSTY_CHECK_ARG(g_dtype == DUSTY_F32 || g_dtype == DUSTY_BF16, "bad dtype");
+  const int64_t n = (int64_t)O * C * RS;
+  int64_t blocks = (n + 255) / 256;
+  if (blocks > (int64_t)num_sms() * 16) blocks = (int64_t)num_sms() * 16;
+  cudaStream_t st = (cudaStream_t)stream;
+  if (g_dtype == DUSTY_F32)
+    weight_prep_adj_kernel<float><<<(unsigned)blocks, 256, 0, st>>>((const float *)g, gw, n, C, RS, scale, g_nhwc);
+  else
+    weight_prep_adj_kernel<__nv_bfloat16><<<(unsigned)blocks, 256, 0, st>>>((const __nv_bfloat16 *)g, gw, n, C, RS,
+                                                                           scale, g_nhwc);
+  DUSTY_LAUNCH_CHECK();
+  return DUSTY_OK;
+}

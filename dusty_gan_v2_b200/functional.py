@@ -1001,6 +1001,59 @@ def circular_unshift(v, shift01, scale: float = 1.0):
     return _CircShift.apply(v, _contig(shift01.detach().float()), float(scale), 0)
 
 
+# ---- a11: EqualLR weight preparation (scale + cast + OIHW -> OHWI), one kernel each way -------
+class _WeightPrep(Function):
+    """fp32 master filter [O, C, R, S] -> scaled filter in `dtype`, channels_last memory.  A
+    linear map: its backward is the adjoint kernel, whose backward is this kernel again, so
+    second-order terms (R1) flow through exactly."""
+
+    @staticmethod
+    def forward(ctx, w, scale, dtype):
+        O, C, R, S = w.shape
+        wf = _contig(w.detach().float())
+        out = torch.empty((O, C, R, S), dtype=dtype, device=w.device, memory_format=torch.channels_last)
+        K.call("dusty_weight_prep", K.ptr(wf), K.ptr(out), O, C, R * S, scale, K.dtype_code(out),
+               K.stream_of(wf))
+        ctx.cfg = (scale, w.dtype)
+        return out
+
+    @staticmethod
+    def backward(ctx, g):
+        scale, wdtype = ctx.cfg
+        return _WeightPrepAdj.apply(g, scale).to(wdtype), None, None
+
+
+class _WeightPrepAdj(Function):
+    @staticmethod
+    def forward(ctx, g, scale):
+        O, C, R, S = g.shape
+        nhwc = 1
+        if g.dtype not in (torch.float32, torch.bfloat16):
+            g = g.float()
+        if g.is_contiguous(memory_format=torch.channels_last):
+            gsrc = g
+        elif g.is_contiguous():
+            gsrc, nhwc = g, 0
+        else:
+            gsrc = g.contiguous(memory_format=torch.channels_last)
+        gw = torch.empty((O, C, R, S), dtype=torch.float32, device=g.device)
+        K.call("dusty_weight_prep_adj", K.ptr(gsrc), K.ptr(gw), O, C, R * S, scale, K.dtype_code(gsrc), nhwc,
+               K.stream_of(gsrc))
+        ctx.cfg = (scale, g.dtype)
+        return gw
+
+    @staticmethod
+    def backward(ctx, gg):
+        scale, gdtype = ctx.cfg
+        return _WeightPrep.apply(gg, scale, gdtype), None
+
+
+def prep_conv_weight(w: torch.Tensor, scale: float, dtype: torch.dtype) -> torch.Tensor:
+    """EqualLR-scaled convolution filter in `dtype` and channels_last memory."""
+    K.require_cuda(w)
+    return _WeightPrep.apply(w, float(scale), dtype)
+
+
 # ---- a11: discriminator stem (BlurVH -> 1x1 conv 2 -> O -> bias + leaky ReLU), stem.cu -------
 class _Stem(Function):
     """y (bf16, NHWC) = lrelu(conv1x1(cat(blur_v(x), blur_h(x)), w) + bias) * gain in one pass.

@@ -195,8 +195,9 @@ class _Conv2dBwdFn(torch.autograd.Function):
         ctx.stride, ctx.need = stride, (need_x, need_w)
         gy = gy.contiguous(memory_format=torch.channels_last) if DF._is_cl(x) else gy.contiguous()
         gx, gw = _conv_grads(gy, x, w, stride, need_x, need_w)
-        if gw is not None and not gw.is_contiguous():
-            gw = gw.contiguous()           # NHWC filter grads -> parameter (NCHW) layout
+        if (gw is not None and not gw.is_contiguous()
+                and not (DF._is_cl(w) and gw.is_contiguous(memory_format=torch.channels_last))):
+            gw = gw.contiguous()           # odd strides -> dense (an NHWC filter keeps NHWC grads)
         return gx, gw
 
     @staticmethod
@@ -345,6 +346,9 @@ class EqualLR(nn.Module):
             # passes per forward/backward pair); TF32 keeps 3 more mantissa bits than bf16.
             y = _TF32Linear.apply(x.float(), m.weight) * (self.scale * self.gain_)
             return y if m.bias is None else y + m.bias * self.gain_
+        if (isinstance(m, nn.Conv2d) and x.is_cuda and x.dtype == torch.bfloat16 and DF._is_cl(x)
+                and m.bias is None and m.padding == (0, 0) and m.dilation == (1, 1) and m.groups == 1):
+            return conv2d_valid(x, self.prepared_weight(x.dtype), m.stride)
         w = (m.weight * (self.scale * self.gain_)).to(x.dtype)
         b = None if m.bias is None else (m.bias * self.gain_).to(x.dtype)
         if isinstance(m, nn.Linear):
@@ -359,6 +363,14 @@ class EqualLR(nn.Module):
             return F.conv_transpose2d(x, w, b, m.stride, m.padding, m.output_padding, m.groups,
                                       m.dilation)
         return m(x * self.scale) * self.gain_
+
+    def prepared_weight(self, dtype):
+        """Scaled conv filter in `dtype`, channels_last memory: one kernel (scale + cast + layout)
+        forward, one backward (DF.prep_conv_weight) instead of three / four ATen kernels."""
+        m = self.module
+        if m.weight.is_cuda and m.weight.dim() == 4:
+            return DF.prep_conv_weight(m.weight, self.scale * self.gain_, dtype)
+        return (m.weight * (self.scale * self.gain_)).to(dtype).contiguous(memory_format=torch.channels_last)
 
     def extra_repr(self):
         return f"gain={self.gain}, lr_mul={self.lr_mul}"

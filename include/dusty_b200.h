@@ -266,6 +266,16 @@ int dusty_ema_lerp(float *ema_var, const float *sum_a, const float *sum_b, float
 int dusty_circular_shift(const float *v, const float *shift01, float *out, int B, int C, int H,
                          int W, float scale, int adjoint, void *stream);
 
+/* ---- a11: EqualLR weight preparation -----------------------------------------------------
+ * Replaces the weight side of EqualLR + Conv2d, gans/models/ops/common.py:158-184,187-210: the
+ * 1/sqrt(fan_in) scale folded into the filter, cast to the activation dtype, OIHW -> OHWI.
+ * w: fp32 [O, C, RS] master weight; out: [O, RS, C] (bf16 or fp32) = w * scale. */
+int dusty_weight_prep(const float *w, void *out, int O, int C, int RS, float scale, int out_dtype,
+                      void *stream);
+/* Adjoint: gw fp32 [O, C, RS] = g * scale, g in [O, RS, C] (g_nhwc = 1) or [O, C, RS] order. */
+int dusty_weight_prep_adj(const void *g, float *gw, int O, int C, int RS, float scale, int g_dtype,
+                          int g_nhwc, void *stream);
+
 /* ---- a11: discriminator stem -------------------------------------------------------------
  * Replaces BlurVH -> Conv2d(2 -> O, 1x1, EqualLR, no bias) -> FusedLeakyReLU(O), the first three
  * layers of Discriminator.layers, gans/models/dusty_v2.py:352-354 (BlurVH common.py:141-155,

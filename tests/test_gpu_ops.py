@@ -783,3 +783,27 @@ def test_conv_bias_act_epilogue_vs_single_ops(ops, DF):
     close(res[0][0], ref, rtol=2e-2, atol_rel=5e-3)
     for a, b_ in zip(res[0][1], res[1][1]):        # two gate patterns (bf16 rounding of ~0 values)
         assert rel_l2(a, b_) < 5e-2
+
+
+@pytest.mark.parametrize("shape", [(64, 32, 3, 3), (128, 64, 1, 1), (24, 40, 3, 3)])
+def test_equal_lr_weight_prep_kernel(DF, shape):
+    """scale + cast + OIHW -> OHWI in one kernel against the three tensor ops, with its adjoint
+    (first order) and the adjoint's adjoint (second order: the map is linear)."""
+    g = torch.Generator().manual_seed(47)
+    w = torch.randn(*shape, generator=g).to(DEV).requires_grad_()
+    s = 0.37
+    CL = torch.channels_last
+    out = DF.prep_conv_weight(w, s, torch.bfloat16)
+    ref = (w * s).to(torch.bfloat16).contiguous(memory_format=CL)
+    assert out.is_contiguous(memory_format=CL) and out.dtype == torch.bfloat16
+    assert torch.equal(out.detach().float().cpu(), ref.detach().float().cpu())
+    for fmt in (CL, torch.contiguous_format):
+        gy = torch.randn(*shape, generator=g).to(DEV, torch.bfloat16).contiguous(memory_format=fmt)
+        (gw,) = torch.autograd.grad(out, w, gy, retain_graph=True)
+        close(gw, gy.float() * s, rtol=1e-6, atol_rel=1e-7)
+    # second order: d/dg of <prep_adj(g), v> = prep(v)
+    gyr = torch.randn(*shape, generator=g).to(DEV, torch.bfloat16).contiguous(memory_format=CL).requires_grad_()
+    (gw,) = torch.autograd.grad(out, w, gyr, create_graph=True)
+    v = torch.randn(*shape, generator=g).to(DEV)
+    (gg,) = torch.autograd.grad(gw, gyr, v)
+    close(gg, (v * s).to(torch.bfloat16), rtol=1e-2, atol_rel=1e-3)

@@ -29,7 +29,7 @@ for _p in (os.path.join(ROOT, "tests"), ROOT):
     if _p not in sys.path:
         sys.path.insert(0, _p)
 
-METRIC = "dusty_v2 G+D train images/sec @64x512"
+METRIC = "dusty_v2 G+D train images/sec @64x512"       # --arch dusty_v1 / vanilla substitute their name
 UNIT = "images/s"
 H, W = 64, 512
 
@@ -50,6 +50,9 @@ def parse():
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cudnn-benchmark", action="store_true")
     ap.add_argument("--no-cuda-graphs", action="store_true")
+    ap.add_argument("--conv-impl", default="tc", choices=["tc", "auto", "library"],
+                    help="D convolutions: own tcgen05 kernels everywhere (default), own-or-cuDNN by "
+                         "measured speed, or cuDNN")
     ap.add_argument("--ncu-window", action="store_true",
                     help="bracket the timed region with cudaProfilerStart/Stop (ncu --profile-from-start off)")
     return ap.parse_args()
@@ -417,6 +420,8 @@ def main():
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
         dist.init_process_group("nccl", device_id=device)
     pkg.set_precision(args.precision)
+    import dusty_gan_v2_b200.functional as DFm
+    DFm.set_conv_impl(args.conv_impl)
     torch.backends.cudnn.benchmark = not args.no_cudnn_benchmark   # the reference sets it (gans/utils.py:29-30)
     if args.precision == "bf16":                 # fp32 epilogue GEMMs of D on the tensor cores
         torch.backends.cuda.matmul.allow_tf32 = True
@@ -493,7 +498,8 @@ def main():
                "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h}
         tr.batch_iter = cycle(pool_dev)
 
-    line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
+    line = {"metric": METRIC.replace("dusty_v2", args.arch), "value": value, "unit": UNIT, "n_gpus": world,
+            "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": ms / args.steps, "higher_is_better": True,
             "scaling": "weak", "vs_baseline": None, "dtype": "bf16" if args.precision == "bf16" else "f32",
             "data": "synthetic",
@@ -502,10 +508,13 @@ def main():
                        "global_batch": B * world, "per_gpu_batch": B, "parallelism": f"dp{world}",
                        "r1_steps_timed": r1_steps, "ada_p": "adaptive from 0.0" if args.ada_p is None else args.ada_p,
                        "l2": "no flush: per-step working set (GBs) >> 126 MB L2",
-                       "dense_convs": ("D convs: own tcgen05 kernels where they measured faster than cuDNN at these "
-                                       "shapes (unit-stride 3x3 fprop/dgrad of the 32/64-channel layers: "
-                                       "halo-resident kernel; strided dgrad and 3x3 wgrad of the 32-channel "
-                                       "layers), cuDNN elsewhere, cuBLAS linears (profiles/r01_conv_layers.json)")},
+                       "dense_convs": {
+                           "tc": "all D residual-block / epilogue convolutions on own tcgen05 kernels "
+                                 "(fprop, dgrad, wgrad), fused stem kernel; cuBLAS for the two linears",
+                           "auto": "own tcgen05 kernels where they measured faster than cuDNN "
+                                   "(profiles/r01_conv_layers.json), cuDNN elsewhere; cuBLAS linears",
+                           "library": "cuDNN convolutions, cuBLAS linears"}[args.conv_impl],
+                       "conv_impl": args.conv_impl},
             "clocks": clk, "gpu_launches": launches, "e2e": e2e}
 
     if rank == 0 and world == 1:

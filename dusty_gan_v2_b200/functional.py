@@ -1132,7 +1132,7 @@ def stem(x, w, bias, taps, composite, negative_slope: float = 0.2, scale: float 
 
 
 # ---- a11: dense NHWC convolutions on tcgen05 (conv_tc.cu) --------------------------------
-_CONV_IMPL = {"mode": "auto", "halo": True}
+_CONV_IMPL = {"mode": "tc", "halo": True}
 
 
 def set_conv_halo(enabled: bool):
@@ -1141,10 +1141,11 @@ def set_conv_halo(enabled: bool):
 
 
 def set_conv_impl(mode: str):
-    """'tc': own tcgen05 kernels for every bf16 NHWC shape that qualifies; 'library': cuDNN;
-    'auto' (default): own kernels where they measured faster than cuDNN at the step's shapes
-    (profiles/r01_conv_layers.json: the 32-channel 64x512 layers' strided dgrad and wgrad),
-    cuDNN elsewhere."""
+    """'tc' (default): own tcgen05 kernels for every bf16 NHWC shape that qualifies (all of
+    D's residual-block convolutions); 'library': cuDNN; 'auto': own kernels where they measured
+    faster than cuDNN at the step's shapes (profiles/r01_conv_layers.json: the thin 64x512 /
+    32x256 layers), cuDNN elsewhere -- 6 % faster per training iteration than 'tc' today
+    (18.9 vs 20.0 ms, all-cuDNN 19.3 ms; profiles/r01_conv_impl_modes.json)."""
     if mode not in ("auto", "tc", "library"):
         raise ValueError(mode)
     _CONV_IMPL["mode"] = mode

@@ -679,7 +679,7 @@ def test_conv2d_tcgen05_fprop_dgrad_wgrad(DF, B, C, Oc, H, W, k, stride, halo):
         assert DF.conv_tc_supported(xd, wd, s2)
         _conv_checks(DF, xd, wd, w, s2, ref, gy, gx_ref, gw_ref, g, Oc, H, W)
     finally:
-        DF.set_conv_impl("auto")
+        DF.set_conv_impl("tc")
         DF.set_conv_halo(True)
 
 
@@ -718,7 +718,7 @@ def test_conv2d_valid_autograd_routes_through_tcgen05(DF, ops):
             ggw, = torch.autograd.grad(r1, [wg])
             res[mode] = (y.detach(), gx.detach(), gw.detach(), ggw.detach(), DF.K.launch_count() - n0)
         finally:
-            DF.set_conv_impl("auto")
+            DF.set_conv_impl("tc")
     assert res["tc"][4] >= 6 and res["library"][4] == 0
     for a, b in zip(res["tc"][:4], res["library"][:4]):
         close(a, b, rtol=3e-2, atol_rel=1e-2)

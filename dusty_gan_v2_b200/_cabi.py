@@ -56,16 +56,18 @@ SIGNATURES = {
     "dusty_sumsq_rows": [_vp, _vp, _i64, _i64, _i, _i, _vp],
     "dusty_ema_lerp": [_vp, _vp, _vp, _f, _f, _f, _vp],
     "dusty_circular_shift": [_vp, _vp, _vp, _i, _i, _i, _i, _f, _i, _vp],
-    "dusty_weight_prep": [_vp, _vp, _i, _i, _i, _f, _i, _vp],
+    "dusty_weight_prep": [_vp, _vp, _vp, _i, _i, _i, _f, _i, _vp],
     "dusty_weight_prep_adj": [_vp, _vp, _i, _i, _i, _f, _i, _i, _vp],
+    "dusty_filter_rsco_to_ohwi": [_vp, _vp, _i, _i, _i, _i, _vp],
     "dusty_stem_fwd": [_vp, _vp, _vp, _vp, _i, _i, _i, _i, _f, _f, _f, _f, _f, _i, _vp],
     "dusty_stem_bwd": [_vp, _vp, _vp, _vp, _vp, _vp, _i, _i, _i, _i, _f, _f, _f, _f, _f, _i, _vp],
     "dusty_stem_dx": [_vp, _vp, _i, _i, _i, _f, _f, _f, _vp],
     "dusty_conv2d_tc": [_vp, _vp, _vp, _vp] + [_i] * 9 + [_vp, _vp, _i, _i, _i]
-                       + [C.c_longlong] * 4 + [_i, _f, _f, _vp],
+                       + [C.c_longlong] * 4 + [_i, _f, _f, C.c_longlong, C.c_longlong, _vp, _i, _vp],
     "dusty_conv2d_wgrad_tc_workspace": [_i] * 7,
     "dusty_conv2d_halo_supported": [_i] * 4,
-    "dusty_conv2d_halo_tc": [_vp, _vp, _vp, _vp] + [_i] * 11 + [C.c_longlong] * 4 + [_i, _f, _f, _vp],
+    "dusty_conv2d_halo_tc": [_vp, _vp, _vp, _vp] + [_i] * 11 + [C.c_longlong] * 4
+                            + [_i, _f, _f, C.c_longlong, C.c_longlong, _i, _vp],
     "dusty_conv2d_wgrad_tc": [_vp, _vp, _vp, _vp, C.c_longlong] + [_i] * 11 + [_vp],
 }
 _RESTYPE = {"dusty_last_error": C.c_char_p, "dusty_launch_count": C.c_int64,

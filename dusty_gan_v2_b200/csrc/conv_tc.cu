@@ -52,6 +52,7 @@ struct ConvMaps {
 struct ConvParams {
   int G, KC;                               // groups, 64-wide chunks per group
   int amap[kMaxGroups], aw[kMaxGroups], ah[kMaxGroups];
+  int wtap[kMaxGroups];                    // index of group g's filter block in the weight tensor
   int TW, TH, tiles_w, tiles_h, NT, total_tiles, tiles_per_cta;
   int H_out, W_out, O;
   long long y_off, y_sb, y_sh, y_sw;       // element strides of the output view
@@ -123,7 +124,7 @@ conv_fwd_tc_kernel(const __grid_constant__ ConvMaps maps, const __grid_constant_
           if (elect_one_sync()) {
             mbar_expect_tx(&full[s], kStageBytes);
             tma_load_4d(a_base + s * kCABytes, am, &full[s], kc * kCK, cw, ch, b);
-            tma_load_3d(b_base + s * kBBytes, &maps.w, &full[s], kc * kCK, n0, g);
+            tma_load_3d(b_base + s * kBBytes, &maps.w, &full[s], kc * kCK, n0, prm.wtap[g]);
           }
           __syncwarp();
           r.template advance<STAGES>();
@@ -250,6 +251,7 @@ struct HaloMaps {
 
 struct HaloParams {
   int T, S;                 // taps, taps per filter row
+  int flip;                 // read the filter blocks in reverse tap order (dgrad of a correlation)
   int PW, TH, TWo;          // patch pitch (pixels), output rows per tile, output columns per tile
   int MB;                   // 128-pixel M blocks per tile = TH * PW / 128
   int org_h, org_w;         // patch origin relative to the tile origin
@@ -312,7 +314,8 @@ conv_halo_tc_kernel(const __grid_constant__ HaloMaps maps, const __grid_constant
   if (warp == 0) {
     if (elect_one_sync()) {
       mbar_expect_tx(w_full, prm.T * kWTap);
-      for (int t = 0; t < prm.T; ++t) tma_load_3d(w_base + t * kWTap, &maps.w, w_full, 0, 0, t);
+      for (int t = 0; t < prm.T; ++t)
+        tma_load_3d(w_base + t * kWTap, &maps.w, w_full, 0, 0, prm.flip ? prm.T - 1 - t : t);
     }
     __syncwarp();
     RingPos r;
@@ -611,11 +614,11 @@ bool make_map4(CUtensorMap *m, const void *ptr, const uint64_t dims[4], const ui
 }
 
 bool make_map3w(CUtensorMap *m, const void *ptr, uint64_t d0, uint64_t d1, uint64_t d2,
-                uint32_t box0, uint32_t box1) {
+                uint32_t box0, uint32_t box1, uint64_t s1_elems = 0, uint64_t s2_elems = 0) {
   EncodeTiledFn enc = get_encode();
   if (!enc) return false;
   cuuint64_t dims[3] = {d0, d1, d2};
-  cuuint64_t strides[2] = {d0 * 2, d0 * d1 * 2};
+  cuuint64_t strides[2] = {(s1_elems ? s1_elems : d0) * 2, (s2_elems ? s2_elems : d0 * d1) * 2};
   cuuint32_t box[3] = {box0, box1, 1};
   cuuint32_t estr[3] = {1, 1, 1};
   return enc(m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 3, const_cast<void *>(ptr), dims, strides, box,
@@ -712,12 +715,15 @@ extern "C" int dusty_conv2d_tc(const void *x, const void *wpk, const float *bias
                                int H_in, int W_in, int C, int H_out, int W_out, int O, int mode,
                                int G, const int *tap_dh, const int *tap_dw, int S, int stride_h,
                                int stride_w, long long y_off, long long y_sb, long long y_sh,
-                               long long y_sw, int act, float alpha, float scale, void *stream) {
+                               long long y_sw, int act, float alpha, float scale, long long w_sn,
+                               long long w_sg, const int *wtap, int w_taps, void *stream) {
   DUSTY_CHECK_ARG(x && wpk && y, "null pointer");
   DUSTY_CHECK_ARG(get_encode() != nullptr, "cuTensorMapEncodeTiled unavailable");
   DUSTY_CHECK_ARG(B > 0 && H_in > 0 && W_in > 0 && H_out > 0 && W_out > 0, "empty tensor");
   DUSTY_CHECK_ARG(C % 8 == 0 && O % 8 == 0, "channel counts must be multiples of 8");
   DUSTY_CHECK_ARG(G >= 1 && G <= kMaxGroups, "1..16 groups");
+  DUSTY_CHECK_ARG(w_sn >= 0 && w_sg >= 0 && w_sn % 8 == 0 && w_sg % 8 == 0, "weight strides: multiples of 8");
+  DUSTY_CHECK_ARG(w_taps >= 0 && (wtap == nullptr || w_taps >= 1), "w_taps: filter blocks in the weight tensor");
   DUSTY_CHECK_ARG(mode == 0 || mode == 1, "mode: 0 = tap, 1 = window");
   DUSTY_CHECK_ARG(mode == 1 ? (G <= 4 && S >= 1) : (stride_h == 1 && stride_w == 1),
                   "window mode: at most 4 filter rows; tap mode: unit stride");
@@ -756,7 +762,11 @@ extern "C" int dusty_conv2d_tc(const void *x, const void *wpk, const float *bias
   }
   for (int g = G; g < kMaxGroups; ++g) { prm.amap[g] = 0; prm.aw[g] = 0; prm.ah[g] = 0; }
   const int BN = O > 128 ? 256 : (O > 64 ? 128 : (O > 32 ? 64 : 32));
-  ok = ok && make_map3w(&maps.w, wpk, (uint64_t)Kg, (uint64_t)O, (uint64_t)G, kCK, (uint32_t)BN);
+  const int Gw = wtap ? w_taps : G;          // filter blocks present in the weight tensor
+  for (int g = 0; g < kMaxGroups; ++g) prm.wtap[g] = (wtap && g < G) ? wtap[g] : (g < G ? g : 0);
+  for (int g = 0; g < G; ++g) DUSTY_CHECK_ARG(prm.wtap[g] >= 0 && prm.wtap[g] < Gw, "wtap out of range");
+  ok = ok && make_map3w(&maps.w, wpk, (uint64_t)Kg, (uint64_t)O, (uint64_t)Gw, kCK, (uint32_t)BN,
+                        (uint64_t)w_sn, (uint64_t)w_sg);
   if (!ok) {
     set_error("dusty_conv2d_tc: cuTensorMapEncodeTiled failed");
     return DUSTY_ECUDA;
@@ -899,8 +909,10 @@ extern "C" int dusty_conv2d_halo_tc(const void *x, const void *wpk, const float 
                                     int B, int H_in, int W_in, int C, int H_out, int W_out, int O,
                                     int R, int S, int org_h, int org_w, long long y_off,
                                     long long y_sb, long long y_sh, long long y_sw, int act,
-                                    float alpha, float scale, void *stream) {
+                                    float alpha, float scale, long long w_sn, long long w_sg, int flip,
+                                    void *stream) {
   DUSTY_CHECK_ARG(x && wpk && y, "null pointer");
+  DUSTY_CHECK_ARG(w_sn >= 0 && w_sg >= 0 && w_sn % 8 == 0 && w_sg % 8 == 0, "weight strides: multiples of 8");
   DUSTY_CHECK_ARG(dusty_conv2d_halo_supported(C, O, R, S), "shape not supported by the halo kernel");
   DUSTY_CHECK_ARG(B > 0 && H_in > 0 && W_in > 0 && H_out > 0 && W_out > 0, "empty tensor");
   DUSTY_CHECK_ARG(aligned16(x) && aligned16(wpk) && aligned16(y), "16-byte alignment");
@@ -910,7 +922,7 @@ extern "C" int dusty_conv2d_halo_tc(const void *x, const void *wpk, const float 
   const int ROWB = C * 2;
   const int BN = O > 64 ? 128 : (O > 32 ? 64 : 32);
   HaloParams prm;
-  prm.T = R * S; prm.S = S;
+  prm.T = R * S; prm.S = S; prm.flip = flip ? 1 : 0;
   // patch pitch: 64 pixels, or 32 when that wastes fewer columns on a narrow image
   auto cover = [&](int pw) { const int two = pw - (S - 1); return (long long)((W_out + two - 1) / two) * pw; };
   prm.PW = cover(32) < cover(64) ? 32 : 64;
@@ -943,7 +955,7 @@ extern "C" int dusty_conv2d_halo_tc(const void *x, const void *wpk, const float 
     const uint64_t strides[3] = {(uint64_t)C * 2, (uint64_t)W_in * C * 2, (uint64_t)H_in * W_in * C * 2};
     const uint32_t box[4] = {(uint32_t)C, (uint32_t)prm.PW, (uint32_t)prow, 1u};
     const uint64_t wdims[3] = {(uint64_t)C, (uint64_t)O, (uint64_t)prm.T};
-    const uint64_t wstr[2] = {(uint64_t)C * 2, (uint64_t)O * C * 2};
+    const uint64_t wstr[2] = {(uint64_t)(w_sn ? w_sn : C) * 2, (uint64_t)(w_sg ? w_sg : (long long)O * C) * 2};
     const uint32_t wbox[3] = {(uint32_t)C, (uint32_t)BN, 1u};
     if (!make_map_sw(&maps.x, x, 4, dims, strides, box, ROWB == 64) ||
         !make_map_sw(&maps.w, wpk, 3, wdims, wstr, wbox, ROWB == 64)) {

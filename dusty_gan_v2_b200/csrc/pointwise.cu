@@ -437,14 +437,23 @@ extern "C" int dusty_ema_lerp(float *ema_var, const float *sum_a, const float *s
 namespace dusty {
 template <typename TO>
 __global__ void __launch_bounds__(256)
-weight_prep_fwd_kernel(const float *__restrict__ w, TO *__restrict__ out, int64_t n, int C, int RS,
-                       float scale) {
+weight_prep_fwd_kernel(const float *__restrict__ w, TO *__restrict__ out, TO *__restrict__ out_tco,
+                       int64_t n, int O, int C, int RS, float scale) {
   for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
     const int c = (int)(i % C);
     const int64_t t = i / C;
     const int rs = (int)(t % RS);
     const int64_t o = t / RS;
     out[i] = from_f<TO>(__ldg(w + (o * C + c) * RS + rs) * scale);
+  }
+  if (out_tco == nullptr) return;
+  // second layout for the data-gradient kernels: [tap][c][o], o contiguous
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+    const int o = (int)(i % O);
+    const int64_t t = i / O;
+    const int c = (int)(t % C);
+    const int64_t rs = t / C;
+    out_tco[i] = from_f<TO>(__ldg(w + ((int64_t)o * C + c) * RS + rs) * scale);
   }
 }
 template <typename TI>
@@ -462,8 +471,8 @@ weight_prep_adj_kernel(const TI *__restrict__ g, float *__restrict__ gw, int64_t
 }
 }  // namespace dusty
 
-extern "C" int dusty_weight_prep(const float *w, void *out, int O, int C, int RS, float scale,
-                                 int out_dtype, void *stream) {
+extern "C" int dusty_weight_prep(const float *w, void *out, void *out_tco, int O, int C, int RS,
+                                 float scale, int out_dtype, void *stream) {
   DUSTY_CHECK_ARG(w && out, "null pointer");
   DUSTY_CHECK_ARG(O >= 1 && C >= 1 && RS >= 1, "bad shape");
   DUSTY_CHECK_ARG(out_dtype == DUSTY_F32 || out_dtype == DUSTY_BF16, "bad dtype");
@@ -472,9 +481,11 @@ extern "C" int dusty_weight_prep(const float *w, void *out, int O, int C, int RS
   if (blocks > (int64_t)num_sms() * 16) blocks = (int64_t)num_sms() * 16;
   cudaStream_t st = (cudaStream_t)stream;
   if (out_dtype == DUSTY_F32)
-    weight_prep_fwd_kernel<float><<<(unsigned)blocks, 256, 0, st>>>(w, (float *)out, n, C, RS, scale);
+    weight_prep_fwd_kernel<float><<<(unsigned)blocks, 256, 0, st>>>(w, (float *)out, (float *)out_tco, n, O, C, RS,
+                                                                    scale);
   else
-    weight_prep_fwd_kernel<__nv_bfloat16><<<(unsigned)blocks, 256, 0, st>>>(w, (__nv_bfloat16 *)out, n, C, RS, scale);
+    weight_prep_fwd_kernel<__nv_bfloat16><<<(unsigned)blocks, 256, 0, st>>>(
+        w, (__nv_bfloat16 *)out, (__nv_bfloat16 *)out_tco, n, O, C, RS, scale);
   DUSTY_LAUNCH_CHECK();
   return DUSTY_OK;
 }
@@ -493,6 +504,41 @@ extern "C" int dusty_weight_prep_adj(const void *g, float *gw, int O, int C, int
   else
     weight_prep_adj_kernel<__nv_bfloat16><<<(unsigned)blocks, 256, 0, st>>>((const __nv_bfloat16 *)g, gw, n, C, RS,
                                                                            scale, g_nhwc);
+  DUSTY_LAUNCH_CHECK();
+  return DUSTY_OK;
+}
+
+// filter gradient as the wgrad kernel produces it, fp32 [RS][C][O], -> OHWI [O][RS][C] in the
+// activation dtype (the layout / dtype of the prepared filter whose gradient it is): one
+// kernel instead of a permuted cast + a layout copy
+namespace dusty {
+template <typename TO>
+__global__ void __launch_bounds__(256)
+filter_rsco_to_ohwi_kernel(const float *__restrict__ src, TO *__restrict__ dst, int64_t n, int O, int C,
+                           int RS) {
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+    const int c = (int)(i % C);
+    const int64_t t = i / C;
+    const int rs = (int)(t % RS);
+    const int64_t o = t / RS;
+    dst[i] = from_f<TO>(__ldg(src + ((int64_t)rs * C + c) * O + o));
+  }
+}
+}  // namespace dusty
+
+extern "C" int dusty_filter_rsco_to_ohwi(const float *src, void *dst, int O, int C, int RS, int dst_dtype,
+                                         void *stream) {
+  DUSTY_CHECK_ARG(src && dst, "null pointer");
+  DUSTY_CHECK_ARG(O >= 1 && C >= 1 && RS >= 1, "bad shape");
+  DUSTY_CHECK_ARG(dst_dtype == DUSTY_F32 || dst_dtype == DUSTY_BF16, "bad dtype");
+  const int64_t n = (int64_t)O * C * RS;
+  int64_t blocks = (n + 255) / 256;
+  if (blocks > (int64_t)num_sms() * 16) blocks = (int64_t)num_sms() * 16;
+  cudaStream_t st = (cudaStream_t)stream;
+  if (dst_dtype == DUSTY_F32)
+    filter_rsco_to_ohwi_kernel<float><<<(unsigned)blocks, 256, 0, st>>>(src, (float *)dst, n, O, C, RS);
+  else
+    filter_rsco_to_ohwi_kernel<__nv_bfloat16><<<(unsigned)blocks, 256, 0, st>>>(src, (__nv_bfloat16 *)dst, n, O, C, RS);
   DUSTY_LAUNCH_CHECK();
   return DUSTY_OK;
 }

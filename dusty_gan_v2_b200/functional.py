@@ -1003,24 +1003,29 @@ def circular_unshift(v, shift01, scale: float = 1.0):
 
 # ---- a11: EqualLR weight preparation (scale + cast + OIHW -> OHWI), one kernel each way -------
 class _WeightPrep(Function):
-    """fp32 master filter [O, C, R, S] -> scaled filter in `dtype`, channels_last memory.  A
-    linear map: its backward is the adjoint kernel, whose backward is this kernel again, so
-    second-order terms (R1) flow through exactly."""
+    """fp32 master filter [O, C, R, S] -> scaled filter in `dtype`, channels_last memory, plus
+    (non-differentiable second output) the same filter as [R*S][C][O] for the data-gradient
+    kernels -- both written by one launch.  A linear map: its backward is the adjoint kernel,
+    whose backward is this kernel again, so second-order terms (R1) flow through exactly."""
 
     @staticmethod
-    def forward(ctx, w, scale, dtype):
+    def forward(ctx, w, scale, dtype, with_tco):
         O, C, R, S = w.shape
         wf = _contig(w.detach().float())
         out = torch.empty((O, C, R, S), dtype=dtype, device=w.device, memory_format=torch.channels_last)
-        K.call("dusty_weight_prep", K.ptr(wf), K.ptr(out), O, C, R * S, scale, K.dtype_code(out),
-               K.stream_of(wf))
+        tco = torch.empty((R * S, C, O), dtype=dtype, device=w.device) if with_tco else None
+        K.call("dusty_weight_prep", K.ptr(wf), K.ptr(out), K.ptr(tco), O, C, R * S, scale,
+               K.dtype_code(out), K.stream_of(wf))
         ctx.cfg = (scale, w.dtype)
+        if with_tco:
+            ctx.mark_non_differentiable(tco)
+            return out, tco
         return out
 
     @staticmethod
-    def backward(ctx, g):
+    def backward(ctx, g, *unused):
         scale, wdtype = ctx.cfg
-        return _WeightPrepAdj.apply(g, scale).to(wdtype), None, None
+        return _WeightPrepAdj.apply(g, scale).to(wdtype), None, None, None
 
 
 class _WeightPrepAdj(Function):
@@ -1045,13 +1050,14 @@ class _WeightPrepAdj(Function):
     @staticmethod
     def backward(ctx, gg):
         scale, gdtype = ctx.cfg
-        return _WeightPrep.apply(gg, scale, gdtype), None
+        return _WeightPrep.apply(gg, scale, gdtype, False), None
 
 
-def prep_conv_weight(w: torch.Tensor, scale: float, dtype: torch.dtype) -> torch.Tensor:
-    """EqualLR-scaled convolution filter in `dtype` and channels_last memory."""
+def prep_conv_weight(w: torch.Tensor, scale: float, dtype: torch.dtype, with_tco: bool = False):
+    """EqualLR-scaled convolution filter in `dtype` and channels_last memory; with_tco=True
+    also returns its [R*S][C][O] form (see _WeightPrep)."""
     K.require_cuda(w)
-    return _WeightPrep.apply(w, float(scale), dtype)
+    return _WeightPrep.apply(w, float(scale), dtype, bool(with_tco))
 
 
 # ---- a11: discriminator stem (BlurVH -> 1x1 conv 2 -> O -> bias + leaky ReLU), stem.cu -------
@@ -1194,8 +1200,23 @@ def _ints(vals):
     return (K.C.c_int * len(vals))(*vals)
 
 
+def _ohwi(w: torch.Tensor) -> torch.Tensor:
+    """The filter with OHWI memory ([O][R][S][C], what channels_last gives): no copy when it is
+    already laid out that way (prepared weights are)."""
+    return w if w.is_contiguous(memory_format=torch.channels_last) else \
+        w.contiguous(memory_format=torch.channels_last)
+
+
+def filter_tco(w: torch.Tensor) -> torch.Tensor:
+    """[R*S][C][O] copy of a filter (O contiguous): the layout of the data-gradient kernels.
+    Prepared weights carry it already (one kernel makes both layouts); this is the fallback."""
+    O, C, R, S = w.shape
+    return w.permute(2, 3, 1, 0).reshape(R * S, C, O).contiguous()
+
+
 def conv2d_fprop_tc(x, w, stride, bias=None, act: int = 1, alpha: float = 0.2, scale: float = 1.0):
-    """y = conv2d(x, w, stride) (valid, no padding) [+ bias, leaky-ReLU, scale]; NHWC in/out."""
+    """y = conv2d(x, w, stride) (valid, no padding) [+ bias, leaky-ReLU, scale]; NHWC in/out.
+    The filter is read in place from its OHWI memory through strided tensor maps."""
     K.require_cuda(x, w)
     x = _nhwc(x)
     B, C, H, W = x.shape
@@ -1204,46 +1225,47 @@ def conv2d_fprop_tc(x, w, stride, bias=None, act: int = 1, alpha: float = 0.2, s
     Ho, Wo = (H - R) // sh + 1, (W - S) // sw + 1
     y = torch.empty((B, O, Ho, Wo), dtype=x.dtype, device=x.device,
                     memory_format=torch.channels_last)
+    wo = _ohwi(w)
     if sh == 1 and sw == 1 and conv_halo_ok(w, "fprop"):
-        wpk = w.permute(2, 3, 0, 1).reshape(R * S, O, C).contiguous()
-        K.call("dusty_conv2d_halo_tc", K.ptr(x), K.ptr(wpk), K.ptr(bias), K.ptr(y), B, H, W, C,
-               Ho, Wo, O, R, S, 0, 0, 0, Ho * Wo * O, Wo * O, O, act, alpha, scale, K.stream_of(x))
+        # element (t, n, c) at  n * (R*S*C) + t * C + c
+        K.call("dusty_conv2d_halo_tc", K.ptr(x), K.ptr(wo), K.ptr(bias), K.ptr(y), B, H, W, C,
+               Ho, Wo, O, R, S, 0, 0, 0, Ho * Wo * O, Wo * O, O, act, alpha, scale,
+               R * S * C, C, 0, K.stream_of(x))
         return y
-    wpk = w.permute(2, 0, 3, 1).reshape(R, O, S * C).contiguous()
-    K.call("dusty_conv2d_tc", K.ptr(x), K.ptr(wpk), K.ptr(bias), K.ptr(y),
-               B, H, W, C, Ho, Wo, O, 1, R, _ints(list(range(R))), _ints([0] * R), S, sh, sw,
-               0, Ho * Wo * O, Wo * O, O, act, alpha, scale, K.stream_of(x))
+    # window mode: group r, element (n, s*C + c) at  n * (R*S*C) + r * (S*C) + s*C + c
+    K.call("dusty_conv2d_tc", K.ptr(x), K.ptr(wo), K.ptr(bias), K.ptr(y),
+           B, H, W, C, Ho, Wo, O, 1, R, _ints(list(range(R))), _ints([0] * R), S, sh, sw,
+           0, Ho * Wo * O, Wo * O, O, act, alpha, scale, R * S * C, S * C, None, 0, K.stream_of(x))
     return y
 
 
-def conv2d_dgrad_tc(gy, w, stride, in_hw):
-    """Gradient of the valid convolution w.r.t. its input ([B, C, H, W] NHWC)."""
+def conv2d_dgrad_tc(gy, w, stride, in_hw, w_tco=None):
+    """Gradient of the valid convolution w.r.t. its input ([B, C, H, W] NHWC).  Every variant
+    (halo-resident, unit stride, the parity classes of a strided convolution) reads the same
+    [R*S][C][O] filter tensor `w_tco` through tap-index maps: no flipping / stacking copies."""
     K.require_cuda(gy, w)
     gy = _nhwc(gy)
     B, O, Ho, Wo = gy.shape
     _, C, R, S = w.shape
     H, W = in_hw
     sh, sw = stride
+    if w_tco is None or w_tco.dtype != gy.dtype or tuple(w_tco.shape) != (R * S, C, O):
+        w_tco = filter_tco(w)
+    gx = torch.empty((B, C, H, W), dtype=gy.dtype, device=gy.device,
+                     memory_format=torch.channels_last)
+    st = K.stream_of(gy)
     if sh == 1 and sw == 1 and conv_halo_ok(w, "dgrad"):
-        gx = torch.empty((B, C, H, W), dtype=gy.dtype, device=gy.device,
-                         memory_format=torch.channels_last)
-        wpk = w.flip(2, 3).permute(2, 3, 1, 0).reshape(R * S, C, O).contiguous()
-        K.call("dusty_conv2d_halo_tc", K.ptr(gy), K.ptr(wpk), None, K.ptr(gx), B, Ho, Wo, O, H, W,
-               C, R, S, -(R - 1), -(S - 1), 0, H * W * C, W * C, C, 1, 0.0, 1.0, K.stream_of(gy))
+        K.call("dusty_conv2d_halo_tc", K.ptr(gy), K.ptr(w_tco), None, K.ptr(gx), B, Ho, Wo, O, H, W,
+               C, R, S, -(R - 1), -(S - 1), 0, H * W * C, W * C, C, 1, 0.0, 1.0, 0, 0, 1, st)
         return gx
-    wt = w.permute(2, 3, 1, 0)                       # [R, S, C, O]
     classes = []
     for ph in range(sh):
         rs = [r for r in range(R) if r % sh == ph]
         for pw in range(sw):
             ss = [s for s in range(S) if s % sw == pw]
             classes.append((ph, pw, rs, ss))
-    full = all(rs and ss for _, _, rs, ss in classes)
-    gx = torch.empty((B, C, H, W), dtype=gy.dtype, device=gy.device,
-                     memory_format=torch.channels_last)
-    if not full:
+    if not all(rs and ss for _, _, rs, ss in classes):
         gx.zero_()
-    st = K.stream_of(gy)
     for ph, pw, rs, ss in classes:
         if not (rs and ss):
             continue
@@ -1251,13 +1273,12 @@ def conv2d_dgrad_tc(gy, w, stride, in_hw):
         if Hc <= 0 or Wc <= 0:
             continue
         taps = [(r, s) for r in rs for s in ss]
-        wpk = torch.stack([wt[r, s] for r, s in taps]).contiguous() if len(taps) != R * S \
-            else wt.reshape(R * S, C, O).contiguous()
         dh = [(ph - r) // sh for r, _ in taps]
         dw = [(pw - s) // sw for _, s in taps]
-        K.call("dusty_conv2d_tc", K.ptr(gy), K.ptr(wpk), None, K.ptr(gx),
-                   B, Ho, Wo, O, Hc, Wc, C, 0, len(taps), _ints(dh), _ints(dw), 1, 1, 1,
-                   (ph * W + pw) * C, H * W * C, sh * W * C, sw * C, 1, 0.0, 1.0, st)
+        wtap = [r * S + s for r, s in taps]
+        K.call("dusty_conv2d_tc", K.ptr(gy), K.ptr(w_tco), None, K.ptr(gx),
+               B, Ho, Wo, O, Hc, Wc, C, 0, len(taps), _ints(dh), _ints(dw), 1, 1, 1,
+               (ph * W + pw) * C, H * W * C, sh * W * C, sw * C, 1, 0.0, 1.0, 0, 0, _ints(wtap), R * S, st)
     return gx
 
 
@@ -1274,4 +1295,10 @@ def conv2d_wgrad_tc(gy, x, stride, w_shape, out_dtype):
     dwp = torch.empty((R, S, C, O), dtype=torch.float32, device=x.device)
     K.call("dusty_conv2d_wgrad_tc", K.ptr(x), K.ptr(gy), K.ptr(dwp), K.ptr(ws),
                n_ws, B, H, W, C, Ho, Wo, O, R, S, sh, sw, K.stream_of(x))
+    if out_dtype in (torch.float32, torch.bfloat16):
+        # [R,S,C,O] fp32 -> [O,C,R,S] in out_dtype with OHWI (channels_last) memory, one kernel
+        gw = torch.empty((O, C, R, S), dtype=out_dtype, device=x.device, memory_format=torch.channels_last)
+        K.call("dusty_filter_rsco_to_ohwi", K.ptr(dwp), K.ptr(gw), O, C, R * S, K.dtype_code(gw),
+               K.stream_of(x))
+        return gw
     return dwp.permute(3, 2, 0, 1).to(out_dtype).contiguous()

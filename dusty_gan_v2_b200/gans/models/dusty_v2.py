@@ -326,7 +326,8 @@ class ResidualBlock(nn.Module):
                 and getattr(rs, "_fast_up", None) == 1 and DF.blur_down2_cl_supported(x)):
             if rs._taps_host is None:
                 rs._taps_host = tuple(rs.kernel.detach().float().cpu().tolist())
-            return ops.conv2d_valid(DF.blur_down2_cl(x, rs._taps_host), eq.prepared_weight(x.dtype), (1, 1))
+            w, w_tco = eq.prepared_weight(x.dtype, with_tco=True)
+            return ops.conv2d_valid(DF.blur_down2_cl(x, rs._taps_host), w, (1, 1), w_tco)
         return self.skip(rs(x))
 
     def _conv1_act(self, x):
@@ -338,11 +339,11 @@ class ResidualBlock(nn.Module):
         if (len(seq) == 2 and isinstance(seq[0], ops.Pad) and isinstance(eq, ops.EqualLR)
                 and isinstance(conv, nn.Conv2d) and conv.bias is None and conv.stride == (1, 1)
                 and x.is_cuda and x.dtype == torch.bfloat16):
-            w = eq.prepared_weight(x.dtype)
+            w, w_tco = eq.prepared_weight(x.dtype, with_tco=True)
             xp = seq[0](x)
             if ops.conv_bias_act_supported(xp, w, (1, 1)):
-                return ops.conv_bias_act(xp, w, act.bias, (1, 1), act.negative_slope, act.scale)
-            return act(ops.conv2d_valid(xp, w, (1, 1)))
+                return ops.conv_bias_act(xp, w, act.bias, (1, 1), act.negative_slope, act.scale, w_tco)
+            return act(ops.conv2d_valid(xp, w, (1, 1), w_tco))
         return act(seq(x))
 
     def forward(self, x):

@@ -158,11 +158,11 @@ def _conv_fprop(x, w, stride):
     return F.conv2d(x, w, None, stride)
 
 
-def _conv_grads(gy, x, w, stride, need_x, need_w):
+def _conv_grads(gy, x, w, stride, need_x, need_w, w_tco=None):
     gx = gw = None
     same = gy.dtype == x.dtype
     if need_x and same and DF.conv_tc_supported(x, w, stride, "dgrad"):
-        gx, need_x = DF.conv2d_dgrad_tc(gy, w, stride, x.shape[2:]), False
+        gx, need_x = DF.conv2d_dgrad_tc(gy, w, stride, x.shape[2:], w_tco), False
     if need_w and same and DF.conv_tc_supported(x, w, stride, "wgrad"):
         gw, need_w = DF.conv2d_wgrad_tc(gy, x, stride, w.shape, w.dtype), False
     if need_x or need_w:
@@ -174,30 +174,34 @@ def _conv_grads(gy, x, w, stride, need_x, need_w):
 
 
 class _Conv2dFn(torch.autograd.Function):
+    """w_tco: optional [R*S][C][O] copy of w for the data-gradient kernels (a representation of
+    the same values, not a separate autograd input)."""
+
     @staticmethod
-    def forward(ctx, x, w, stride):
+    def forward(ctx, x, w, stride, w_tco=None):
         ctx.save_for_backward(x, w)
         ctx.stride = stride
+        ctx.w_tco = w_tco
         return _conv_fprop(x, w, stride)
 
     @staticmethod
     def backward(ctx, gy):
         x, w = ctx.saved_tensors
         gx, gw = _Conv2dBwdFn.apply(gy, x, w, ctx.stride, ctx.needs_input_grad[0],
-                                    ctx.needs_input_grad[1])
-        return gx, gw, None
+                                    ctx.needs_input_grad[1], ctx.w_tco)
+        return gx, gw, None, None
 
 
 class _Conv2dBwdFn(torch.autograd.Function):
     @staticmethod
-    def forward(ctx, gy, x, w, stride, need_x, need_w):
+    def forward(ctx, gy, x, w, stride, need_x, need_w, w_tco=None):
         ctx.save_for_backward(gy, x, w)
         ctx.stride, ctx.need = stride, (need_x, need_w)
         gy = gy.contiguous(memory_format=torch.channels_last) if DF._is_cl(x) else gy.contiguous()
-        gx, gw = _conv_grads(gy, x, w, stride, need_x, need_w)
+        gx, gw = _conv_grads(gy, x, w, stride, need_x, need_w, w_tco)
         if (gw is not None and not gw.is_contiguous()
-                and not (DF._is_cl(w) and gw.is_contiguous(memory_format=torch.channels_last))):
-            gw = gw.contiguous()           # odd strides -> dense (an NHWC filter keeps NHWC grads)
+                and not gw.is_contiguous(memory_format=torch.channels_last)):
+            gw = gw.contiguous()           # odd strides -> dense (OHWI filter grads stay OHWI)
         return gx, gw
 
     @staticmethod
@@ -218,7 +222,7 @@ class _Conv2dBwdFn(torch.autograd.Function):
                 g_gy = t if g_gy is None else g_gy + t
             if need_x:
                 g_x = _conv_grads(gy, x, ggw.contiguous(), s, True, False)[0]   # dgrad(gy, ggw)
-        return g_gy, g_x, g_w, None, None, None
+        return g_gy, g_x, g_w, None, None, None, None
 
 
 class _ConvBiasActFn(torch.autograd.Function):
@@ -228,11 +232,12 @@ class _ConvBiasActFn(torch.autograd.Function):
     is re-expressed through the differentiable single ops."""
 
     @staticmethod
-    def forward(ctx, x, w, bias, stride, alpha, gain):
+    def forward(ctx, x, w, bias, stride, alpha, gain, w_tco=None):
         bf = None if bias is None else bias.detach().float().contiguous()
         y = DF.conv2d_fprop_tc(x, w, stride, bf, 3, alpha, gain)
         ctx.save_for_backward(x, w, bias, y)
         ctx.cfg = (stride, alpha, gain)
+        ctx.w_tco = w_tco
         return y
 
     @staticmethod
@@ -247,11 +252,11 @@ class _ConvBiasActFn(torch.autograd.Function):
                 grads = list(torch.autograd.grad(yc, wanted, gy, create_graph=True, allow_unused=True))
             out = [grads.pop(0) if (n and t is not None) else None
                    for t, n in ((x, need_x), (w, need_w), (bias, need_b))]
-            return out[0], out[1], out[2], None, None, None
+            return out[0], out[1], out[2], None, None, None, None
         gpre, db = DF._BiasActBackward.apply(gy, y, bias is not None, alpha, gain)
-        gx, gw = _Conv2dBwdFn.apply(gpre, x, w, stride, need_x, need_w)
+        gx, gw = _Conv2dBwdFn.apply(gpre, x, w, stride, need_x, need_w, ctx.w_tco)
         gb = db.to(bias.dtype) if (need_b and bias is not None) else None
-        return gx, gw, gb, None, None, None
+        return gx, gw, gb, None, None, None, None
 
 
 def conv_bias_act_supported(x, w, stride) -> bool:
@@ -261,16 +266,16 @@ def conv_bias_act_supported(x, w, stride) -> bool:
             and DF.conv_halo_ok(w, "fprop"))
 
 
-def conv_bias_act(x, w, bias, stride, negative_slope=0.2, gain=2 ** 0.5):
+def conv_bias_act(x, w, bias, stride, negative_slope=0.2, gain=2 ** 0.5, w_tco=None):
     stride = tuple(stride) if isinstance(stride, (tuple, list)) else (stride, stride)
-    return _ConvBiasActFn.apply(x, w, bias, stride, float(negative_slope), float(gain))
+    return _ConvBiasActFn.apply(x, w, bias, stride, float(negative_slope), float(gain), w_tco)
 
 
-def conv2d_valid(x, w, stride):
+def conv2d_valid(x, w, stride, w_tco=None):
     """Un-padded, bias-free 2-D convolution with analytic higher-order gradients."""
     stride = tuple(stride) if isinstance(stride, (tuple, list)) else (stride, stride)
     if x.is_cuda and w.shape[1] == x.shape[1]:
-        return _Conv2dFn.apply(x, w, stride)
+        return _Conv2dFn.apply(x, w, stride, w_tco)
     return F.conv2d(x, w, None, stride)
 
 
@@ -348,7 +353,8 @@ class EqualLR(nn.Module):
             return y if m.bias is None else y + m.bias * self.gain_
         if (isinstance(m, nn.Conv2d) and x.is_cuda and x.dtype == torch.bfloat16 and DF._is_cl(x)
                 and m.bias is None and m.padding == (0, 0) and m.dilation == (1, 1) and m.groups == 1):
-            return conv2d_valid(x, self.prepared_weight(x.dtype), m.stride)
+            w, w_tco = self.prepared_weight(x.dtype, with_tco=True)
+            return conv2d_valid(x, w, m.stride, w_tco)
         w = (m.weight * (self.scale * self.gain_)).to(x.dtype)
         b = None if m.bias is None else (m.bias * self.gain_).to(x.dtype)
         if isinstance(m, nn.Linear):
@@ -364,13 +370,20 @@ class EqualLR(nn.Module):
                                       m.dilation)
         return m(x * self.scale) * self.gain_
 
-    def prepared_weight(self, dtype):
+    def prepared_weight(self, dtype, with_tco=False):
         """Scaled conv filter in `dtype`, channels_last memory: one kernel (scale + cast + layout)
-        forward, one backward (DF.prep_conv_weight) instead of three / four ATen kernels."""
+        forward, one backward (DF.prep_conv_weight) instead of three / four ATen kernels.
+        with_tco=True: (w, w_tco) with the [R*S][C][O] form the data-gradient kernels read (made
+        by the same launch when our tcgen05 convolutions are in use, else None)."""
         m = self.module
         if m.weight.is_cuda and m.weight.dim() == 4:
-            return DF.prep_conv_weight(m.weight, self.scale * self.gain_, dtype)
-        return (m.weight * (self.scale * self.gain_)).to(dtype).contiguous(memory_format=torch.channels_last)
+            want = with_tco and DF._CONV_IMPL["mode"] != "library" and m.weight.requires_grad is not None
+            r = DF.prep_conv_weight(m.weight, self.scale * self.gain_, dtype, want)
+            if with_tco:
+                return r if want else (r, None)
+            return r
+        w = (m.weight * (self.scale * self.gain_)).to(dtype).contiguous(memory_format=torch.channels_last)
+        return (w, None) if with_tco else w
 
     def extra_repr(self):
         return f"gain={self.gain}, lr_mul={self.lr_mul}"

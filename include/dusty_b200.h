@@ -270,11 +270,18 @@ int dusty_circular_shift(const float *v, const float *shift01, float *out, int B
  * Replaces the weight side of EqualLR + Conv2d, gans/models/ops/common.py:158-184,187-210: the
  * 1/sqrt(fan_in) scale folded into the filter, cast to the activation dtype, OIHW -> OHWI.
  * w: fp32 [O, C, RS] master weight; out: [O, RS, C] (bf16 or fp32) = w * scale. */
-int dusty_weight_prep(const float *w, void *out, int O, int C, int RS, float scale, int out_dtype,
-                      void *stream);
+int dusty_weight_prep(const float *w, void *out, void *out_tco, int O, int C, int RS, float scale,
+                      int out_dtype, void *stream);
+/* out_tco (may be NULL): the same scaled filter as [RS, C, O] (O contiguous), the layout the
+ * data-gradient kernels read (dusty_conv2d_tc tap mode / dusty_conv2d_halo_tc with flip). */
 /* Adjoint: gw fp32 [O, C, RS] = g * scale, g in [O, RS, C] (g_nhwc = 1) or [O, C, RS] order. */
 int dusty_weight_prep_adj(const void *g, float *gw, int O, int C, int RS, float scale, int g_dtype,
                           int g_nhwc, void *stream);
+
+/* Filter gradient from dusty_conv2d_wgrad_tc's fp32 [RS, C, O] order to OHWI [O, RS, C] in
+ * dst_dtype (the layout and dtype of the prepared filter it is the gradient of). */
+int dusty_filter_rsco_to_ohwi(const float *src, void *dst, int O, int C, int RS, int dst_dtype,
+                              void *stream);
 
 /* ---- a11: discriminator stem -------------------------------------------------------------
  * Replaces BlurVH -> Conv2d(2 -> O, 1x1, EqualLR, no bias) -> FusedLeakyReLU(O), the first three
@@ -309,12 +316,18 @@ int dusty_stem_dx(const float *dvh, float *dx, int B, int H, int W, float k0, fl
  *   mode 0 ("tap", dgrad): G taps; group g reads x[b, oh + tap_dh[g], ow + tap_dw[g], :]
  *     (K_g = C), rows / columns outside x contribute zero; unit stride only -- a strided
  *     dgrad is one call per output parity class with y_sh / y_sw doubled.
- * tap_dh / tap_dw are HOST arrays of G ints.  bias may be NULL; act: 1 linear, 3 leaky-ReLU. */
+ * tap_dh / tap_dw are HOST arrays of G ints.  bias may be NULL; act: 1 linear, 3 leaky-ReLU.
+ * Weight addressing (so that no per-call repacking is needed): element (g, n, k) of the filter
+ * is read at wpk[wtap[g] * w_sg + n * w_sn + k]; w_sn = 0 / w_sg = 0 mean the dense strides
+ * K_g / O * K_g, wtap = NULL means wtap[g] = g; w_taps = number of filter blocks in the tensor
+ * (used with wtap).  E.g. window mode straight from an OHWI filter: w_sn = R*S*C, w_sg = S*C;
+ * a dgrad parity class from a [R*S][C][O] tensor: wtap[g] = r*S + s of the class's taps. */
 int dusty_conv2d_tc(const void *x, const void *wpk, const float *bias, void *y, int B, int H_in,
                     int W_in, int C, int H_out, int W_out, int O, int mode, int G,
                     const int *tap_dh, const int *tap_dw, int S, int stride_h, int stride_w,
                     long long y_off, long long y_sb, long long y_sh, long long y_sw, int act,
-                    float alpha, float scale, void *stream);
+                    float alpha, float scale, long long w_sn, long long w_sg, const int *wtap,
+                    int w_taps, void *stream);
 
 /* Filter gradient of the valid convolution above:
  *   dwp[r][s*C+c][n] = sum_{b,oh,ow} x[b, oh*stride_h + r, ow*stride_w + s, c] * dy[b,oh,ow,n]
@@ -331,12 +344,16 @@ int dusty_conv2d_wgrad_tc(const void *x, const void *dy, float *dwp, float *ws, 
  * x[b, oh + org_h + a, ow + org_w + b', c] * wpk[a*S + b'][n][c] + bias[n]) * scale, rows /
  * columns outside x read as zero.  fprop of a valid conv: org = (0, 0), wpk[t][n][c] =
  * w[n][c][r][s]; dgrad: x := dY, org = (-(R-1), -(S-1)), wpk[a*S+b'][c][n] = w[n][c][R-1-a][S-1-b'].
- * dusty_conv2d_halo_supported returns non-zero when the shape qualifies. */
+ * dusty_conv2d_halo_supported returns non-zero when the shape qualifies.
+ * Weight addressing: element (t, n, c) at wpk[t' * w_sg + n * w_sn + c], t' = flip ? T-1-t : t;
+ * w_sn = 0 / w_sg = 0 mean dense (C / O*C).  fprop straight from an OHWI filter: w_sn = R*S*C,
+ * w_sg = C; dgrad from an un-flipped [R*S][C][O] tensor: flip = 1. */
 int dusty_conv2d_halo_supported(int C, int O, int R, int S);
 int dusty_conv2d_halo_tc(const void *x, const void *wpk, const float *bias, void *y, int B,
                          int H_in, int W_in, int C, int H_out, int W_out, int O, int R, int S,
                          int org_h, int org_w, long long y_off, long long y_sb, long long y_sh,
-                         long long y_sw, int act, float alpha, float scale, void *stream);
+                         long long y_sw, int act, float alpha, float scale, long long w_sn,
+                         long long w_sg, int flip, void *stream);
 
 #ifdef __cplusplus
 }

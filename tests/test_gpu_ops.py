@@ -797,6 +797,10 @@ def test_equal_lr_weight_prep_kernel(DF, shape):
     ref = (w * s).to(torch.bfloat16).contiguous(memory_format=CL)
     assert out.is_contiguous(memory_format=CL) and out.dtype == torch.bfloat16
     assert torch.equal(out.detach().float().cpu(), ref.detach().float().cpu())
+    out2, tco = DF.prep_conv_weight(w, s, torch.bfloat16, with_tco=True)
+    assert torch.equal(out2.detach().float().cpu(), ref.detach().float().cpu()) and not tco.requires_grad
+    O_, C_, R_, S_ = shape
+    assert torch.equal(tco.float().cpu(), ref.detach().permute(2, 3, 1, 0).reshape(R_ * S_, C_, O_).float().cpu())
     for fmt in (CL, torch.contiguous_format):
         gy = torch.randn(*shape, generator=g).to(DEV, torch.bfloat16).contiguous(memory_format=fmt)
         (gw,) = torch.autograd.grad(out, w, gy, retain_graph=True)

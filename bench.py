@@ -323,12 +323,37 @@ def kernel_rooflines(device, peaks):
     mem_entry("pad_ring1_adjoint_nhwc[64,32,66,514]bf16",
               lambda: DF._pad_raw(gpc, (1, 1, 1, 1), (K.PAD_REPLICATE, K.PAD_CIRCULAR), True, (H, W)),
               (x.numel() + gp.numel()) * 2)
+    # discriminator stem (BlurVH + 1x1 conv 2->32 + bias/lrelu) and residual tail, fused kernels
+    xs = torch.tanh(torch.randn(B, 1, H, W, device=device))
+    ws_ = torch.randn(32, 2, device=device) / 1.4
+    bs_ = torch.zeros(32, device=device)
+    ys_ = torch.empty((B, 32, H, W), dtype=bf, device=device, memory_format=CL)
+    mem_entry("stem_fwd[64,1->32,64,512]bf16",
+              lambda: K.call("dusty_stem_fwd", K.ptr(xs), K.ptr(ws_), K.ptr(bs_), K.ptr(ys_), B, H, W, 32, 0.25, 0.5,
+                             0.25, 0.2, 1.41, K.F32, K.stream_of(xs)), xs.numel() * 4 + ys_.numel() * 2)
+    dvh_ = torch.empty(B, 2, H, W, device=device)
+    dwb_ = torch.empty(32, 3, device=device)
+    mem_entry("stem_bwd[64,1->32,64,512]bf16",
+              lambda: K.call("dusty_stem_bwd", K.ptr(xc), K.ptr(ys_), K.ptr(xs), K.ptr(ws_), K.ptr(dvh_), K.ptr(dwb_),
+                             B, H, W, 32, 0.25, 0.5, 0.25, 0.2, 1.41, K.F32, K.stream_of(xs)),
+              xs.numel() * 4 + 2 * ys_.numel() * 2 + dvh_.numel() * 4)
+    sk_ = torch.randn(B, 64, 32, 256, device=device, dtype=bf).contiguous(memory_format=CL)
+    pr_ = torch.randn(B, 64, 32, 256, device=device, dtype=bf).contiguous(memory_format=CL)
+    b64 = torch.zeros(64, device=device)
+    mem_entry("residual_tail_fwd[64,64,32,256]bf16", lambda: DF.residual_tail(pr_, b64, sk_), 3 * sk_.numel() * 2)
+    del xs, ys_, dvh_, sk_, pr_
     del xc, yc, gxc, gpc
     hd = torch.randn(B, 32, H, W, device=device, dtype=bf)
     wh = (torch.randn(B, 2, 32, device=device) / 6).to(bf)
     bh = torch.zeros(2, device=device)
     mem_entry("heads_fwd[O=2,C=32,64x512]bf16", lambda: DF.modconv_bmm(wh, hd, None, bh, 1, 0.0, 1.0),
               (hd.numel() + B * 2 * H * W) * 2)
+    gh_ = torch.randn(B, 2, H, W, device=device, dtype=bf)
+    gwh_ = torch.empty(B, 2, 32, device=device)
+    mem_entry("heads_dw[O=2,C=32,64x512]bf16",
+              lambda: K.call("dusty_modconv_bwd_dw", K.ptr(gh_), K.ptr(hd), None, K.ptr(gwh_), B, 2, 32, 0, 1,
+                             H * W, K.BF16, 0, K.stream_of(hd)), (hd.numel() + gh_.numel()) * 2)
+    del gh_
     del hd
     ang = torch.rand(B, 2, H, W, device=device)
     fr = torch.randn(256, 2, device=device)

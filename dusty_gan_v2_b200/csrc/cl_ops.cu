@@ -198,6 +198,15 @@ pad2d_cl_adj_kernel(const T *__restrict__ dy, T *__restrict__ dx, PadCL p) {
   if (v >= p.W * p.cv) return;
   const int ix = v / p.cv, j = v - ix * p.cv;
   const int iy = blockIdx.y, b = blockIdx.z;
+  // interior pixels (all but a ring of width max(pad)) have exactly one pre-image: a plain
+  // 16-byte copy.  The generic pre-image enumeration below cost ~80 instructions per vector
+  // and made the kernel issue-bound (ncu: issue slots 62 % busy at 36 % of DRAM bandwidth).
+  const int my = p.pt > p.pb ? p.pt : p.pb, mx = p.pl > p.pr ? p.pl : p.pr;   // safe for every pad mode
+  if (iy > my && iy < p.H - 1 - my && ix > mx && ix < p.W - 1 - mx) {
+    st16(dx + ((((int64_t)b * p.H + iy) * p.W + ix) * p.cv + j) * V,
+         ld16_stream(dy + ((((int64_t)b * p.Ho + iy + p.pt) * p.Wo + ix + p.pl) * p.cv + j) * V));
+    return;
+  }
   int ys[10], xs[10];
   const int ny = cl_preimages(iy, p.H, p.pt, p.pb, p.mode_y, ys);
   const int nx = cl_preimages(ix, p.W, p.pl, p.pr, p.mode_x, xs);

@@ -390,12 +390,13 @@ def kernel_rooflines(device, peaks):
                      lambda: DF.modconv_bmm(wb, x1, x2, bias, 3, 0.2, 1.41), flops, byts)
         g = torch.randn(B, O_, hh, ww, device=device, dtype=bf)
         gw = torch.empty(B, O_, C1 + C2, device=device)
-        tc_entry(f"modconv_dw[{tag}]bf16",
+        pe_tag = "shared" if shared else "per-sample"
+        tc_entry(f"modconv_dw[{tag},pe={pe_tag}]bf16",
                  lambda: K.call("dusty_modconv_bwd_dw", K.ptr(g), K.ptr(x1), K.ptr(x2), K.ptr(gw), B, O_, C1, C2,
                                 x2.shape[0], P, K.BF16, 0, K.stream_of(g)),
                  flops, (x1.numel() + g.numel() + x2.numel() * (1 if shared else 1)) * 2 + gw.numel() * 4)
         gx1 = torch.empty_like(x1)
-        tc_entry(f"modconv_dx[{tag}]bf16",
+        tc_entry(f"modconv_dx[{tag},pe={pe_tag}]bf16",
                  lambda: K.call("dusty_modconv_bwd_dx", K.ptr(wb), K.ptr(g), K.ptr(gx1), B, O_, C1, C1 + C2, P,
                                 K.BF16, K.BF16, 0, K.stream_of(g)),
                  2.0 * B * O_ * C1 * P, (g.numel() + gx1.numel() + wb.numel()) * 2)

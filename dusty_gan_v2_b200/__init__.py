@@ -28,7 +28,7 @@ _MIRRORED = [
     "gans.models.ops.gumbel", "gans.models.ops.fused_act", "gans.models.ops.fused_act.fused_act",
     "gans.models.ops.upfirdn2d", "gans.models.ops.upfirdn2d.upfirdn2d", "gans.models.base",
     "gans.models.dusty_v1", "gans.models.dusty_v2", "gans.models.vanilla", "gans.models.builder",
-    "gans.models.loss", "gans.augment", "gans.augment.adaptive_augment",
+    "gans.models.loss", "gans.augment", "gans.augment.adaptive_augment", "gans.inversion",
 ]
 
 

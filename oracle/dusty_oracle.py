@@ -747,3 +747,62 @@ def vanilla_discriminator(sd: Dict[str, Tensor], x: Tensor) -> Tensor:
         h = pad2d(h, 1, ring=True, mode="reflect")
         h = bias_act(equal_conv2d(h, sd[f"{i}.1.module.weight"], None, 2), sd[f"{i}.2.bias"])
     return equal_conv2d(h, sd["5.module.weight"], sd["5.module.bias"], 1)
+
+
+# ---- BASELINE config 5: GAN inversion losses (reference gans/inversion.py) -----------------
+def masked_loss(img_ref: Tensor, img_gen: Tensor, mask: Tensor, loss: str = "l1",
+                relative: bool = True) -> Tensor:
+    """inversion.py:23-30 -- per-sample masked (relative) L1 / L2."""
+    d = (img_ref - img_gen).abs() if loss == "l1" else (img_ref - img_gen).square()
+    if relative:
+        d = (d * mask) / (img_ref + 1e-11)
+    d = (d * mask).sum(dim=(1, 2, 3))
+    return d / (mask.sum(dim=(1, 2, 3)) + 1e-8)
+
+
+def _blurpool3(x: Tensor, taps: Tensor) -> Tensor:
+    """Pad(1, replicate H, circular W) + depthwise 3x3 stride-2 correlation
+    (inversion.py:52-64)."""
+    xp = pad2d(x, 1, ring=True, mode="replicate")
+    C = x.shape[1]
+    return F.conv2d(xp, taps[None, None].repeat(C, 1, 1, 1), stride=2, groups=C)
+
+
+def multiscale_masked_loss(gen: Tensor, ref: Tensor, mask: Tensor, level: Optional[int] = None,
+                           loss: str = "l1", relative: bool = True) -> Tensor:
+    """MultiScaleMaskedLoss.forward (inversion.py:66-80): masked loss on a blur-pool pyramid;
+    the mask is pooled with a box filter, renormalised by 9 / (number of valid pixels) and
+    re-binarised at every level."""
+    H = gen.shape[2]
+    level = int(np.log2(H)) if level is None else level
+    k1 = torch.tensor([1.0, 2.0, 1.0])
+    blur = torch.outer(k1, k1)
+    blur = blur / blur.sum()
+    ones = torch.ones(3, 3)
+    total = 0
+    for _ in range(max(1, level)):
+        total = total + masked_loss(ref, gen, mask, loss, relative)
+        cnt = _blurpool3(mask, ones)
+        norm = 9.0 / cnt.masked_fill(cnt == 0, 1.0)
+        new_mask = torch.ones_like(cnt).masked_fill(cnt == 0, 0.0)
+        gen = _blurpool3(gen * mask, blur) * norm
+        ref = _blurpool3(ref * mask, blur) * norm
+        mask = new_mask
+    return total
+
+
+def geocross_loss(latents: Tensor) -> Tensor:
+    """inversion.py:83-91 (PULSE geodesic cross loss on [B, N, D] latents)."""
+    Bn, N, D = latents.shape
+    X, Y = latents.view(Bn, 1, N, D), latents.view(Bn, N, 1, D)
+    A = ((X - Y).pow(2).sum(-1) + 1e-9).sqrt()
+    Bm = ((X + Y).pow(2).sum(-1) + 1e-9).sqrt()
+    Dm = 2 * torch.atan2(A, Bm)
+    return (Dm.pow(2) * Dm).mean((1, 2)) / 8.0
+
+
+def spherical_project_(param: Tensor) -> Tensor:
+    """SphericalOptimizer.step's projection (inversion.py:17-19): unit RMS along the last axis."""
+    with torch.no_grad():
+        param.div_(param.pow(2).mean(dim=-1, keepdim=True).add(1e-9).sqrt())
+    return param

@@ -62,3 +62,8 @@ def g_ada():
 @pytest.fixture(scope="session")
 def g_vanilla():
     return load_golden("vanilla_small.npz")
+
+
+@pytest.fixture(scope="session")
+def g_inv():
+    return load_golden("inversion.npz")

@@ -460,3 +460,36 @@ def test_fused_discriminator_stem_matches_composite_and_oracle():
     # grad_x D depends on a bias only through MinibatchStdDev -- a tiny, noise-dominated term.)
     assert rel_l2(f[4][0], c[4][0]) < 1.5e-1
     assert torch.isfinite(f[4][1]).all()
+
+
+@pytest.mark.parametrize("tag,loss_fn,level,relative", [
+    ("l1_rel_full", "l1", None, True), ("l1_rel_l2", "l1", 2, True), ("l2_abs_l3", "l2", 3, False)])
+def test_inversion_losses_golden(g_inv, tag, loss_fn, level, relative):
+    """BASELINE config 5: MultiScaleMaskedLoss / geocross_loss / SphericalOptimizer of the mirror
+    (blur-pool pyramid on the package's FIR kernel) against the reference's own outputs."""
+    import torch.nn.functional as F
+    from dusty_gan_v2_b200.gans import inversion as inv
+    fn = F.l1_loss if loss_fn == "l1" else F.mse_loss
+    crit = inv.MultiScaleMaskedLoss(fn, level=level, relative=relative).to(DEV)
+    gen = T(g_inv["gen"]).to(DEV).requires_grad_()
+    loss = crit(gen, T(g_inv["ref"]).to(DEV), T(g_inv["mask"]).to(DEV))
+    close(loss, g_inv[f"{tag}_loss"], rtol=1e-4, atol_rel=1e-5)
+    (g,) = torch.autograd.grad(loss.sum(), gen)
+    close(g, g_inv[f"{tag}_grad"], rtol=1e-3, atol_rel=1e-5)
+    with pytest.raises(RuntimeError):
+        crit.cpu()(T(g_inv["gen"]), T(g_inv["ref"]), T(g_inv["mask"]))
+
+
+def test_inversion_geocross_and_spherical_optimizer_golden(g_inv):
+    from dusty_gan_v2_b200.gans import inversion as inv
+    lat = T(g_inv["lat"]).to(DEV).requires_grad_()
+    gl = inv.geocross_loss(lat)
+    close(gl, g_inv["geocross"], rtol=1e-4, atol_rel=1e-5)
+    (g,) = torch.autograd.grad(gl.sum(), lat)
+    close(g, g_inv["geocross_grad"], rtol=1e-3, atol_rel=1e-5)
+    p = torch.nn.Parameter(T(g_inv["sph_p0"]).to(DEV))
+    opt = inv.SphericalOptimizer([p], lr=0.1, betas=(0.9, 0.999))
+    for i in range(2):
+        p.grad = T(g_inv[f"sph_g{i}"]).to(DEV)
+        opt.step()
+        close(p, g_inv[f"sph_p{i + 1}"], rtol=1e-4, atol_rel=1e-5)

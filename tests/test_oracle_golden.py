@@ -232,3 +232,31 @@ def test_vanilla_and_dusty_v1(g_vanilla):
             close(g, ref, rtol=2e-3, atol=1e-4 * max(np.abs(ref).max(), 1e-8))
             n += 1
     assert n >= 15
+
+
+# ----------------------------------------------------------------------------- config 5
+@pytest.mark.parametrize("tag,kw", [("l1_rel_full", dict(level=None, loss="l1", relative=True)),
+                                    ("l1_rel_l2", dict(level=2, loss="l1", relative=True)),
+                                    ("l2_abs_l3", dict(level=3, loss="l2", relative=False))])
+def test_inversion_multiscale_masked_loss(g_inv, tag, kw):
+    gen = T(g_inv["gen"]).requires_grad_()
+    loss = O.multiscale_masked_loss(gen, T(g_inv["ref"]), T(g_inv["mask"]), **kw)
+    close(loss, g_inv[f"{tag}_loss"], rtol=1e-5, atol=1e-6)
+    (g,) = torch.autograd.grad(loss.sum(), gen)
+    close(g, g_inv[f"{tag}_grad"], rtol=1e-4, atol=1e-6)
+
+
+def test_inversion_geocross_and_spherical_projection(g_inv):
+    lat = T(g_inv["lat"]).requires_grad_()
+    gl = O.geocross_loss(lat)
+    close(gl, g_inv["geocross"], rtol=1e-5, atol=1e-7)
+    (g,) = torch.autograd.grad(gl.sum(), lat)
+    close(g, g_inv["geocross_grad"], rtol=1e-4, atol=1e-7)
+    # Adam (lr 0.1, betas 0.9 / 0.999) + projection to unit RMS, two steps with fixed gradients
+    p = torch.nn.Parameter(T(g_inv["sph_p0"]).clone())
+    opt = torch.optim.Adam([p], lr=0.1, betas=(0.9, 0.999))
+    for i in range(2):
+        p.grad = T(g_inv[f"sph_g{i}"]).clone()
+        opt.step()
+        O.spherical_project_(p.data)
+        close(p, g_inv[f"sph_p{i + 1}"], rtol=1e-5, atol=1e-6)

@@ -135,3 +135,24 @@ def test_fir_geometry_matches_oracle_sizes():
         oh, ow = cfg.out_hw(17, 23)
         assert oh == O.upfirdn2d_out_size(17, up[0], down[0], pad[0], pad[1], k[0])
         assert ow == O.upfirdn2d_out_size(23, up[1], down[1], pad[2], pad[3], k[1])
+
+
+def test_c_abi_argument_errors_are_status_codes_not_crashes():
+    """Error behaviour of the C ABI (no GPU needed: arguments are validated before any CUDA
+    call): bad arguments return a negative status and set dusty_last_error()."""
+    from dusty_gan_v2_b200 import _cabi as K
+    lib = K.load()
+    one = torch.zeros(64)
+    p = one.data_ptr()
+    rc = lib.dusty_stem_fwd(p, p, None, p, 1, 8, 8, 12, 0.25, 0.5, 0.25, 0.2, 1.41, K.F32, None)   # O = 12
+    assert rc != 0 and "O must be" in K.last_error()
+    rc = lib.dusty_weight_prep(None, p, None, 4, 4, 9, 1.0, K.BF16, None)
+    assert rc != 0 and "null" in K.last_error()
+    rc = lib.dusty_bias_act_add_cl(p, None, p, p, 64, 12, 0.2, 1.41, 0.7, K.BF16, None)           # C % 8 != 0
+    assert rc != 0 and "channel" in K.last_error()
+    rc = lib.dusty_modconv_fwd(p, p, p, None, p, 2, 32, 64, 0, 1, 128, 3, 0.2, 1.0, K.BF16, K.BF16, 7, None)
+    assert rc != 0 and "impl" in K.last_error()
+    rc = lib.dusty_filter_rsco_to_ohwi(p, p, 0, 4, 9, K.BF16, None)
+    assert rc != 0 and "shape" in K.last_error()
+    with pytest.raises(RuntimeError, match="status"):
+        K.call("dusty_pad2d_cl", p, p, 1, 8, 8, 8, 9, 0, 0, 0, K.PAD_REPLICATE, K.PAD_CIRCULAR, 0, K.BF16, None)

@@ -458,15 +458,22 @@ struct WgParams {
   int atomic;                     // partial tiles are added into `out` with 16-byte reductions
 };
 
-template <int BN, int STAGES>
+// NR = filter rows accumulated by one CTA.  NR == 1: one row per CTA (grid.z = R), every CTA
+// streams its own copy of dY.  NR == 3 (3x3 filters of the thin / mid layers, O <= 128): the
+// three row-windows of x share ONE landing of the dY tile per stage and feed three TMEM
+// accumulators -- dY crosses L2->SM once instead of three times (the 32-channel 64x512 layers
+// are bound by exactly that traffic: 1.6 GB per call for 0.54 GB of tensors).
+template <int BN, int STAGES, int NR>
 __global__ void __launch_bounds__(kWgThreads)
 conv_wgrad_tc_kernel(const __grid_constant__ WgMaps maps, const __grid_constant__ WgParams prm) {
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   uint8_t *smem = (uint8_t *)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
   constexpr int kBBytes = BN * kCK * 2;
-  constexpr int kStageBytes = kCABytes + kBBytes;
+  constexpr int kASlot = NR * kCABytes;
+  constexpr int kStageBytes = kASlot + kBBytes;
+  constexpr int kTmemCols = NR * BN <= 32 ? 32 : (NR * BN <= 64 ? 64 : (NR * BN <= 128 ? 128 : (NR * BN <= 256 ? 256 : 512)));
   uint8_t *a_base = smem;
-  uint8_t *b_base = smem + STAGES * kCABytes;
+  uint8_t *b_base = smem + STAGES * kASlot;
   uint64_t *full = (uint64_t *)(smem + STAGES * kStageBytes);
   uint64_t *empty = full + STAGES;
   uint64_t *acc_full = empty + STAGES;
@@ -476,7 +483,7 @@ conv_wgrad_tc_kernel(const __grid_constant__ WgMaps maps, const __grid_constant_
   const int split = blockIdx.x;
   const int m0 = (blockIdx.y % prm.MT) * kCM;
   const int n0 = (blockIdx.y / prm.MT) * BN;
-  const int r = blockIdx.z;
+  const int r_first = NR == 1 ? (int)blockIdx.z : 0;     // filter rows [r_first, r_first + NR)
   const int pb_begin = split * prm.pb_per_split;
   const int pb_end = min(pb_begin + prm.pb_per_split, prm.total_pb);
 
@@ -488,14 +495,13 @@ conv_wgrad_tc_kernel(const __grid_constant__ WgMaps maps, const __grid_constant_
     mbar_init(acc_full, 1);
     fence_barrier_init();
   }
-  if (warp == 1) tmem_alloc(tmem_slot, BN < 32 ? 32 : BN);
+  if (warp == 1) tmem_alloc(tmem_slot, kTmemCols);
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_acc = *tmem_slot;
 
   if (warp == 0) {
-    const CUtensorMap *am = &maps.a[r];
     RingPos rp;
     for (int pb = pb_begin; pb < pb_end; ++pb) {
       const int s = rp.s;
@@ -507,9 +513,13 @@ conv_wgrad_tc_kernel(const __grid_constant__ WgMaps maps, const __grid_constant_
       mbar_wait(&empty[s], rp.ph ^ 1);
       if (elect_one_sync()) {
         mbar_expect_tx(&full[s], kStageBytes);
-        uint8_t *a_dst = a_base + s * kCABytes;
-        tma_load_4d(a_dst, am, &full[s], m0, ow0, oh0, b);
-        tma_load_4d(a_dst + 8192, am, &full[s], m0 + 64, ow0, oh0, b);
+#pragma unroll
+        for (int rr = 0; rr < NR; ++rr) {
+          const CUtensorMap *am = &maps.a[r_first + rr];
+          uint8_t *a_dst = a_base + s * kASlot + rr * kCABytes;
+          tma_load_4d(a_dst, am, &full[s], m0, ow0, oh0, b);
+          tma_load_4d(a_dst + 8192, am, &full[s], m0 + 64, ow0, oh0, b);
+        }
 #pragma unroll
         for (int j = 0; j < BN / 64; ++j)
           tma_load_4d(b_base + s * kBBytes + j * 8192, &maps.g, &full[s], n0 + 64 * j, ow0, oh0, b);
@@ -530,12 +540,15 @@ conv_wgrad_tc_kernel(const __grid_constant__ WgMaps maps, const __grid_constant_
       mbar_wait(&full[s], rp.ph);
       tc_fence_after();
       if (elect_one_sync()) {
-        const uint32_t a_lo = a_lo0 + (uint32_t)s * (kCABytes >> 4);
         const uint32_t b_lo = b_lo0 + (uint32_t)s * (kBBytes >> 4);
 #pragma unroll
-        for (int k16 = 0; k16 < kCK / 16; ++k16)
-          umma_bf16_lh(tmem_acc, a_lo + k16 * (2048 >> 4), d_hi, b_lo + k16 * (2048 >> 4), d_hi, idesc,
-                       (pb > pb_begin || k16 > 0) ? 1u : 0u);
+        for (int rr = 0; rr < NR; ++rr) {
+          const uint32_t a_lo = a_lo0 + (uint32_t)s * (kASlot >> 4) + (uint32_t)rr * (kCABytes >> 4);
+#pragma unroll
+          for (int k16 = 0; k16 < kCK / 16; ++k16)
+            umma_bf16_lh(tmem_acc + (uint32_t)(rr * BN), a_lo + k16 * (2048 >> 4), d_hi,
+                         b_lo + k16 * (2048 >> 4), d_hi, idesc, (pb > pb_begin || k16 > 0) ? 1u : 0u);
+        }
         umma_commit(&empty[s]);
       }
       __syncwarp();
@@ -548,28 +561,31 @@ conv_wgrad_tc_kernel(const __grid_constant__ WgMaps maps, const __grid_constant_
     const int m = m0 + q * 32 + lane;
     mbar_wait(acc_full, 0);
     tc_fence_after();
-    float *op = prm.out + (long long)split * prm.split_stride +
-                ((long long)r * prm.SC + m) * prm.O + n0;
     const bool have = pb_end > pb_begin;
     const bool atomic = prm.atomic != 0;    // split-K partials meet in the (zeroed) result
 #pragma unroll 1
-    for (int c = 0; c < BN; c += 16) {
-      uint32_t v[16];
-      tmem_ld16(tmem_acc + ((uint32_t)(q * 32) << 16) + (uint32_t)c, v);
-      tmem_ld_wait();
-      if (m < prm.SC) {
+    for (int rr = 0; rr < NR; ++rr) {
+      float *op = prm.out + (long long)split * prm.split_stride +
+                  ((long long)(r_first + rr) * prm.SC + m) * prm.O + n0;
+#pragma unroll 1
+      for (int c = 0; c < BN; c += 16) {
+        uint32_t v[16];
+        tmem_ld16(tmem_acc + ((uint32_t)(q * 32) << 16) + (uint32_t)(rr * BN + c), v);
+        tmem_ld_wait();
+        if (m < prm.SC) {
 #pragma unroll
-        for (int j4 = 0; j4 < 4; ++j4) {
-          if (n0 + c + j4 * 4 < prm.O) {
-            float4 o4;
-            o4.x = have ? __uint_as_float(v[j4 * 4 + 0]) : 0.f;
-            o4.y = have ? __uint_as_float(v[j4 * 4 + 1]) : 0.f;
-            o4.z = have ? __uint_as_float(v[j4 * 4 + 2]) : 0.f;
-            o4.w = have ? __uint_as_float(v[j4 * 4 + 3]) : 0.f;
-            if (atomic) {
-              if (have) atomicAdd(reinterpret_cast<float4 *>(op + c + j4 * 4), o4);   // 16-byte red (sm_90+)
-            } else {
-              *reinterpret_cast<float4 *>(op + c + j4 * 4) = o4;
+          for (int j4 = 0; j4 < 4; ++j4) {
+            if (n0 + c + j4 * 4 < prm.O) {
+              float4 o4;
+              o4.x = have ? __uint_as_float(v[j4 * 4 + 0]) : 0.f;
+              o4.y = have ? __uint_as_float(v[j4 * 4 + 1]) : 0.f;
+              o4.z = have ? __uint_as_float(v[j4 * 4 + 2]) : 0.f;
+              o4.w = have ? __uint_as_float(v[j4 * 4 + 3]) : 0.f;
+              if (atomic) {
+                if (have) atomicAdd(reinterpret_cast<float4 *>(op + c + j4 * 4), o4);   // 16-byte red (sm_90+)
+              } else {
+                *reinterpret_cast<float4 *>(op + c + j4 * 4) = o4;
+              }
             }
           }
         }
@@ -580,7 +596,7 @@ conv_wgrad_tc_kernel(const __grid_constant__ WgMaps maps, const __grid_constant_
   __syncthreads();
   if (warp == 1) {
     tc_fence_after();
-    tmem_dealloc(tmem_acc, BN < 32 ? 32 : BN);
+    tmem_dealloc(tmem_acc, kTmemCols);
   }
 }
 
@@ -680,13 +696,13 @@ int launch_conv(const ConvMaps &maps, ConvParams prm, cudaStream_t st) {
   return 0;
 }
 
-template <int BN, int STAGES>
+template <int BN, int STAGES, int NR>
 int launch_wgrad(const WgMaps &maps, const WgParams &prm, int splits, int R, cudaStream_t st) {
-  constexpr int smem = conv_smem_bytes<BN, STAGES>();
+  constexpr int smem = STAGES * (NR * kCABytes + BN * kCK * 2) + 256 + 1024;
   static bool configured = false;
-  if (int rc = set_smem(conv_wgrad_tc_kernel<BN, STAGES>, smem, &configured)) return rc;
-  dim3 grid((unsigned)splits, (unsigned)(prm.MT * prm.NT), (unsigned)R);
-  conv_wgrad_tc_kernel<BN, STAGES><<<grid, kWgThreads, smem, st>>>(maps, prm);
+  if (int rc = set_smem(conv_wgrad_tc_kernel<BN, STAGES, NR>, smem, &configured)) return rc;
+  dim3 grid((unsigned)splits, (unsigned)(prm.MT * prm.NT), (unsigned)(NR == 1 ? R : 1));
+  conv_wgrad_tc_kernel<BN, STAGES, NR><<<grid, kWgThreads, smem, st>>>(maps, prm);
   return 0;
 }
 
@@ -792,12 +808,18 @@ extern "C" int dusty_conv2d_tc(const void *x, const void *wpk, const float *bias
   return DUSTY_OK;
 }
 
+// three filter rows per CTA (shared dY tile): 3-row filters whose N tile is at most 128 wide
+static bool wgrad_rows_merged(int O, int R) {
+  static const bool off = [] { const char *e = getenv("DUSTY_WGRAD_ROWS"); return e && atoi(e) == 1; }();
+  return !off && R == 3 && O <= 128;
+}
+
 static int wgrad_splits(int B, int H_out, int W_out, int C, int O, int R, int S) {
   int TW, TH;
   pick_patch(W_out, H_out, kCK, &TW, &TH);
   const long long total_pb = (long long)((W_out + TW - 1) / TW) * ((H_out + TH - 1) / TH) * B;
   const int BN = O > 128 ? 256 : (O > 64 ? 128 : 64);
-  const int tile_ctas = ((S * C + kCM - 1) / kCM) * ((O + BN - 1) / BN) * R;
+  const int tile_ctas = ((S * C + kCM - 1) / kCM) * ((O + BN - 1) / BN) * (wgrad_rows_merged(O, R) ? 1 : R);
   long long splits = (2 * num_sms() + tile_ctas - 1) / tile_ctas;
   if (splits > total_pb) splits = total_pb;
   return splits < 1 ? 1 : (int)splits;
@@ -882,10 +904,15 @@ extern "C" int dusty_conv2d_wgrad_tc(const void *x, const void *dy, float *dwp, 
     return DUSTY_ECUDA;
   }
   int rc;
-  switch (BN) {
-    case 256: rc = launch_wgrad<256, 4>(maps, prm, splits, R, st); break;
-    case 128: rc = launch_wgrad<128, 4>(maps, prm, splits, R, st); break;
-    default: rc = launch_wgrad<64, 4>(maps, prm, splits, R, st); break;
+  if (wgrad_rows_merged(O, R)) {
+    rc = BN == 128 ? launch_wgrad<128, 3, 3>(maps, prm, splits, R, st)
+                   : launch_wgrad<64, 3, 3>(maps, prm, splits, R, st);
+  } else {
+    switch (BN) {
+      case 256: rc = launch_wgrad<256, 4, 1>(maps, prm, splits, R, st); break;
+      case 128: rc = launch_wgrad<128, 4, 1>(maps, prm, splits, R, st); break;
+      default: rc = launch_wgrad<64, 4, 1>(maps, prm, splits, R, st); break;
+    }
   }
   if (rc) return rc;
   DUSTY_LAUNCH_CHECK();

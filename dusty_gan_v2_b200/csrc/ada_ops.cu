@@ -25,57 +25,68 @@ struct Fir1d {
 };
 
 constexpr int kFirR = 4;      // outputs per thread (independent accumulators: loads in flight)
+constexpr int kFirRows = 4;   // image rows per block of the x kernel
 
-// ---- along x: grid = (ceil(n_out / (256 * kFirR)), other (rows), N)
-template <int U, int D>
+// ---- along x: grid = (ceil(n_out / (256 * R)), ceil(rows / kFirRows), N).  R is picked so that
+// one block spans a whole row when it can (ADA's rows are 512 - 1048 outputs: with R fixed at
+// 4 every second block held 24 live outputs), and a block walks kFirRows rows so that the tap
+// load and the block launch are amortised -- the first version launched 20-40 k blocks of one
+// short row segment each and ran at 12-30 % of HBM on these 1-channel images.
+template <int U, int D, int R>
 __global__ void __launch_bounds__(256)
 fir1d_x_kernel(const float *__restrict__ x, float *__restrict__ y, const float *__restrict__ taps,
                Fir1d p) {
-  constexpr int kOut = 256 * kFirR;
+  constexpr int kOut = 256 * R;
   __shared__ float sk[kMaxTaps1d];
   __shared__ float sx[kOut * D / U + kMaxTaps1d + 4];
   if (threadIdx.x < p.k) sk[threadIdx.x] = taps[p.flip ? p.k - 1 - threadIdx.x : threadIdx.x];
   const int m0 = blockIdx.x * kOut;
-  const float *row = x + ((int64_t)blockIdx.z * p.other + blockIdx.y) * p.n_in;
   // input span needed by outputs [m0, m0 + kOut): q in [m0*D - p0, (m0+kOut-1)*D - p0 + k - 1]
   const int q_lo = m0 * D - p.p0;
   const int i_lo = (q_lo >= 0 ? q_lo : q_lo - (U - 1)) / U;          // floor(q_lo / U)
   const int span = ((kOut - 1) * D + p.k - 1) / U + 2;
-  for (int j = threadIdx.x; j < span; j += 256) {
-    const int i = i_lo + j;
-    sx[j] = (i >= 0 && i < p.n_in) ? row[i] : 0.f;
-  }
-  __syncthreads();
-  float acc[kFirR];
-  int base[kFirR], t0[kFirR];
+  int base[R], t0[R];
 #pragma unroll
-  for (int r = 0; r < kFirR; ++r) {
+  for (int r = 0; r < R; ++r) {
     const int m = m0 + threadIdx.x + 256 * r;
     base[r] = m * D - p.p0;                   // q = base + t
     t0[r] = (U == 1) ? 0 : ((-base[r]) & (U - 1));
-    acc[r] = 0.f;
   }
-  for (int t = 0; t < p.k; t += U) {
+  const int row_end = min((int)(blockIdx.y + 1) * kFirRows, p.other);
+  for (int rowi = blockIdx.y * kFirRows; rowi < row_end; ++rowi) {
+    const float *row = x + ((int64_t)blockIdx.z * p.other + rowi) * p.n_in;
+    __syncthreads();                          // previous row's reads of sx are done (and sk is set)
+    for (int j = threadIdx.x; j < span; j += 256) {
+      const int i = i_lo + j;
+      sx[j] = (i >= 0 && i < p.n_in) ? __ldg(row + i) : 0.f;
+    }
+    __syncthreads();
+    float acc[R];
 #pragma unroll
-    for (int r = 0; r < kFirR; ++r) {
-      const int tt = t + t0[r];
-      if (tt < p.k) {
-        const int q = base[r] + tt;           // multiple of U
-        const int i = (U == 1) ? q : (q >> 1);
-        acc[r] = fmaf(sk[tt], sx[i - i_lo], acc[r]);
+    for (int r = 0; r < R; ++r) acc[r] = 0.f;
+    for (int t = 0; t < p.k; t += U) {
+#pragma unroll
+      for (int r = 0; r < R; ++r) {
+        const int tt = t + t0[r];
+        if (tt < p.k) {
+          const int q = base[r] + tt;           // multiple of U
+          const int i = (U == 1) ? q : (q >> 1);
+          acc[r] = fmaf(sk[tt], sx[i - i_lo], acc[r]);
+        }
       }
     }
-  }
-  float *orow = y + ((int64_t)blockIdx.z * p.other + blockIdx.y) * p.n_out;
+    float *orow = y + ((int64_t)blockIdx.z * p.other + rowi) * p.n_out;
 #pragma unroll
-  for (int r = 0; r < kFirR; ++r) {
-    const int m = m0 + threadIdx.x + 256 * r;
-    if (m < p.n_out) orow[m] = acc[r];
+    for (int r = 0; r < R; ++r) {
+      const int m = m0 + threadIdx.x + 256 * r;
+      if (m < p.n_out) orow[m] = acc[r];
+    }
   }
 }
 
-// ---- along y: grid = (ceil(other / 256), ceil(n_out / kFirR), N); thread = one column,
-// kFirR consecutive output rows
+// ---- along y: threads are a flat index over (row group, column): grid = (ceil(other * groups /
+// 256), 1, N), so no block is a mostly-empty column remainder; thread = one column, kFirR
+// consecutive output rows
 template <int U, int D>
 __global__ void __launch_bounds__(256)
 fir1d_y_kernel(const float *__restrict__ x, float *__restrict__ y, const float *__restrict__ taps,
@@ -83,14 +94,17 @@ fir1d_y_kernel(const float *__restrict__ x, float *__restrict__ y, const float *
   __shared__ float sk[kMaxTaps1d];
   if (threadIdx.x < p.k) sk[threadIdx.x] = taps[p.flip ? p.k - 1 - threadIdx.x : threadIdx.x];
   __syncthreads();
-  const int col = blockIdx.x * 256 + threadIdx.x;
-  if (col >= p.other) return;
+  const int groups = (p.n_out + kFirR - 1) / kFirR;
+  const int64_t gid = (int64_t)blockIdx.x * 256 + threadIdx.x;
+  if (gid >= (int64_t)groups * p.other) return;
+  const int grp = (int)(gid / p.other);
+  const int col = (int)(gid - (int64_t)grp * p.other);
   const float *img = x + (int64_t)blockIdx.z * p.n_in * p.other + col;
   float acc[kFirR];
   int base[kFirR], t0[kFirR];
 #pragma unroll
   for (int r = 0; r < kFirR; ++r) {
-    const int m = blockIdx.y * kFirR + r;
+    const int m = grp * kFirR + r;
     base[r] = m * D - p.p0;
     t0[r] = (U == 1) ? 0 : ((-base[r]) & (U - 1));
     acc[r] = 0.f;
@@ -106,7 +120,7 @@ fir1d_y_kernel(const float *__restrict__ x, float *__restrict__ y, const float *
   }
 #pragma unroll
   for (int r = 0; r < kFirR; ++r) {
-    const int m = blockIdx.y * kFirR + r;
+    const int m = grp * kFirR + r;
     if (m < p.n_out) y[((int64_t)blockIdx.z * p.n_out + m) * p.other + col] = acc[r];
   }
 }
@@ -200,21 +214,30 @@ extern "C" int dusty_fir1d(const float *x, float *y, const float *taps, int k, i
                   "bad output size");
   Fir1d p{n_in, n_out, other, k, pad0, flip ? 1 : 0};
   cudaStream_t st = (cudaStream_t)stream;
-#define LAUNCH(KERN, GRID)                                                      \
-  do {                                                                          \
-    if (up == 1 && down == 1) KERN<1, 1><<<GRID, 256, 0, st>>>(x, y, taps, p);  \
-    else if (up == 2 && down == 1) KERN<2, 1><<<GRID, 256, 0, st>>>(x, y, taps, p); \
-    else if (up == 1 && down == 2) KERN<1, 2><<<GRID, 256, 0, st>>>(x, y, taps, p); \
-    else KERN<2, 2><<<GRID, 256, 0, st>>>(x, y, taps, p);                       \
+#define LAUNCH_X(R)                                                                                   \
+  do {                                                                                                  \
+    dim3 grid((unsigned)((n_out + 256 * R - 1) / (256 * R)), (unsigned)((other + kFirRows - 1) / kFirRows), \
+              (unsigned)N);                                                                             \
+    if (up == 1 && down == 1) fir1d_x_kernel<1, 1, R><<<grid, 256, 0, st>>>(x, y, taps, p);             \
+    else if (up == 2 && down == 1) fir1d_x_kernel<2, 1, R><<<grid, 256, 0, st>>>(x, y, taps, p);        \
+    else if (up == 1 && down == 2) fir1d_x_kernel<1, 2, R><<<grid, 256, 0, st>>>(x, y, taps, p);        \
+    else fir1d_x_kernel<2, 2, R><<<grid, 256, 0, st>>>(x, y, taps, p);                                  \
   } while (0)
   if (axis == 1) {
-    dim3 grid((unsigned)((n_out + 256 * kFirR - 1) / (256 * kFirR)), (unsigned)other, (unsigned)N);
-    LAUNCH(fir1d_x_kernel, grid);
+    // outputs per thread: the smallest of {2, 3, 4, 5} that lets one block span the row, else 4
+    if (n_out <= 512) LAUNCH_X(2);
+    else if (n_out <= 768) LAUNCH_X(3);
+    else if (n_out <= 1024 || n_out > 1280) LAUNCH_X(4);
+    else LAUNCH_X(5);
   } else {
-    dim3 grid((unsigned)((other + 255) / 256), (unsigned)((n_out + kFirR - 1) / kFirR), (unsigned)N);
-    LAUNCH(fir1d_y_kernel, grid);
+    const int64_t groups = (n_out + kFirR - 1) / kFirR;
+    dim3 grid((unsigned)((groups * other + 255) / 256), 1u, (unsigned)N);
+    if (up == 1 && down == 1) fir1d_y_kernel<1, 1><<<grid, 256, 0, st>>>(x, y, taps, p);
+    else if (up == 2 && down == 1) fir1d_y_kernel<2, 1><<<grid, 256, 0, st>>>(x, y, taps, p);
+    else if (up == 1 && down == 2) fir1d_y_kernel<1, 2><<<grid, 256, 0, st>>>(x, y, taps, p);
+    else fir1d_y_kernel<2, 2><<<grid, 256, 0, st>>>(x, y, taps, p);
   }
-#undef LAUNCH
+#undef LAUNCH_X
   DUSTY_LAUNCH_CHECK();
   return DUSTY_OK;
 }

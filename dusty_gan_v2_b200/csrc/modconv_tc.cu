@@ -177,7 +177,7 @@ modconv_fwd_tc_kernel(const __grid_constant__ CUtensorMap map_x1,
   uint32_t *tmem_slot = (uint32_t *)(acc_empty + 2);
   uint8_t *epi_base = smem + STAGES * kStageBytes + 128;   // 2 x 8 KiB staging, 16-B aligned
 
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int warp = threadIdx.x >> 5;
   const int num_kb = (prm.K + kBK - 1) / kBK;
   const int t_begin = blockIdx.x * prm.tiles_per_cta;
   const int t_end = min(t_begin + prm.tiles_per_cta, prm.total_tiles);
@@ -363,7 +363,7 @@ modconv_fwd_shared_tc_kernel(const __grid_constant__ CUtensorMap map_x1,
   uint32_t *tmem_slot = (uint32_t *)(acc_empty + 2);
   uint8_t *epi_base = smem + STAGES * kStageBytes + 128;
 
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int warp = threadIdx.x >> 5;
   const int kb1 = prm.C1 / kBK;             // feature k-blocks per sample
   const int nX = prm.NS * kb1;              // per-sample stages of a tile
   const int nP = prm.C2 / kBK;              // Fourier stages of a tile

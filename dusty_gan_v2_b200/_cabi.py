@@ -39,6 +39,7 @@ SIGNATURES = {
     "dusty_pad2d_cl": [_vp, _vp] + [_i] * 12 + [_vp],
     "dusty_blur4_cl": [_vp, _vp, _f, _f, _f, _f] + [_i] * 7 + [_vp],
     "dusty_blur4_down2_cl": [_vp, _vp, _f, _f, _f, _f] + [_i] * 6 + [_vp],
+    "dusty_residual_fork_bwd_cl": [_vp, _vp, _vp, _f, _f, _f, _f] + [_i] * 5 + [_vp],
     "dusty_fir1d": [_vp, _vp, _vp, _i, _i, _i64] + [_i] * 7 + [_vp],
     "dusty_affine_warp": [_vp, _vp, _vp] + [_i] * 7 + [_vp],
     "dusty_fourier": [_vp, _vp, _vp, _vp, _i, _i, _i64, _i, _vp],

@@ -735,6 +735,87 @@ blur4_down2_cl_adj_kernel(const T *__restrict__ g, T *__restrict__ dx, Taps4CL t
   st16(dx + tid * V, o);
 }
 
+// ResidualBlock input fork, backward: x feeds Pad(1, ring) (conv1 branch) and the decimating
+// blur (skip branch); dx = pad_adjoint(g_pad) + blur4_down2_adjoint(g_down) as ONE gather pass
+// (was: two adjoint kernels + the autograd engine's accumulation add = 6.25 tensor passes, now
+// 2.25).  Pad geometry is fixed: one pixel, replicate in H, circular in W.
+template <typename T>
+__global__ void __launch_bounds__(256)
+residual_fork_bwd_cl_kernel(const T *__restrict__ gp, const T *__restrict__ g, T *__restrict__ dx,
+                            Taps4CL t, int H, int W, int cv, int64_t n_threads) {
+  constexpr int V = Vec16<T>::N;
+  const int H2 = H >> 1, W2 = W >> 1;
+  const int64_t tid = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (tid >= n_threads) return;
+  const int j = (int)(tid % cv);
+  int64_t q = tid / cv;
+  const int xc = (int)(q % W);
+  q /= W;
+  const int yr = (int)(q % H);
+  const int64_t b = q / H;
+  constexpr int VP = V / 2;
+  float2 acc[VP];
+  // ---- pad adjoint: padded (py, px) with clampH(py - 1) == yr, wrapW(px - 1) == xc
+  const int Wp = W + 2;
+  const T *gpi = gp + b * (int64_t)(H + 2) * Wp * cv * V;
+  {
+    Vec16<T> v = ld16(gpi + (((int64_t)(yr + 1) * Wp + (xc + 1)) * cv + j) * V);
+#pragma unroll
+    for (int k = 0; k < VP; ++k) acc[k] = get2(v, k);
+  }
+  const int px2 = xc == 0 ? W + 1 : (xc == W - 1 ? 0 : -1);     // second pre-image column
+  const int py2 = yr == 0 ? 0 : (yr == H - 1 ? H + 1 : -1);     // second pre-image row
+  if (px2 >= 0 || py2 >= 0) {
+    auto addp = [&](int py, int px) {
+      Vec16<T> v = ld16(gpi + (((int64_t)py * Wp + px) * cv + j) * V);
+#pragma unroll
+      for (int k = 0; k < VP; ++k) { float2 w = get2(v, k); acc[k].x += w.x; acc[k].y += w.y; }
+    };
+    if (px2 >= 0) addp(yr + 1, px2);
+    if (py2 >= 0) {
+      addp(py2, xc + 1);
+      if (px2 >= 0) addp(py2, px2);
+    }
+  }
+  // ---- decimating-blur adjoint (same gather as blur4_down2_cl_adj_kernel)
+  const T *gi = g + b * (int64_t)H2 * W2 * cv * V;
+  const int p = xc & 1;
+  int jc[2];
+  float kx[2];
+#pragma unroll
+  for (int u = 0; u < 2; ++u) {
+    const int s = p + 2 * u;
+    int jj = (xc + 2 - s) >> 1;
+    jc[u] = jj >= W2 ? jj - W2 : jj;
+    kx[u] = t.k[s];
+  }
+  auto add = [&](int i, float ky) {
+    const T *row = gi + (int64_t)i * W2 * cv * V;
+#pragma unroll
+    for (int u = 0; u < 2; ++u) {
+      Vec16<T> v = ld16(row + ((int64_t)jc[u] * cv + j) * V);
+      const float w = ky * kx[u];
+#pragma unroll
+      for (int k = 0; k < VP; ++k) acc[k] = fma2(w, get2(v, k), acc[k]);
+    }
+  };
+  const int pq = yr & 1;
+#pragma unroll
+  for (int u = 0; u < 2; ++u) {
+    const int r = pq + 2 * u;
+    const int i = (yr + 2 - r) >> 1;
+    if (i >= 0 && i < H2) add(i, t.k[r]);
+  }
+  if (yr == 0) {
+    add(0, t.k[0]);
+    add(0, t.k[1]);
+  }
+  Vec16<T> o;
+#pragma unroll
+  for (int k = 0; k < VP; ++k) set2(o, k, acc[k]);
+  st16(dx + tid * V, o);
+}
+
 static unsigned cl_flat_grid(int64_t work) {
   int64_t blocks = (work + 255) / 256;
   const int64_t cap = (int64_t)num_sms() * 16;
@@ -990,6 +1071,32 @@ extern "C" int dusty_blur4_down2_cl(const void *x, void *y, float k0, float k1, 
     else
       blur4_down2_cl_adj_kernel<__nv_bfloat16><<<(unsigned)blocks, 256, 0, st>>>((const __nv_bfloat16 *)x, (__nv_bfloat16 *)y, t, H, W, cv, n_threads);
   }
+  DUSTY_LAUNCH_CHECK();
+  return DUSTY_OK;
+}
+
+extern "C" int dusty_residual_fork_bwd_cl(const void *g_pad, const void *g_down, void *dx, float k0,
+                                          float k1, float k2, float k3, int B, int H, int W, int C,
+                                          int dtype, void *stream) {
+  DUSTY_CHECK_ARG(g_pad && g_down && dx, "null pointer");
+  DUSTY_CHECK_ARG(B >= 1 && H >= 2 && W >= 4 && H % 2 == 0 && W % 2 == 0, "bad shape");
+  DUSTY_CHECK_ARG(dtype == DUSTY_F32 || dtype == DUSTY_BF16, "bad dtype");
+  const int V = dtype == DUSTY_F32 ? 4 : 8;
+  DUSTY_CHECK_ARG(C % V == 0, "C must be a multiple of the 16-byte vector width");
+  Taps4CL t;
+  t.k[0] = k0; t.k[1] = k1; t.k[2] = k2; t.k[3] = k3;
+  const int cv = C / V;
+  cudaStream_t st = (cudaStream_t)stream;
+  const int64_t n_threads = (int64_t)B * H * W * cv;
+  const int64_t blocks = (n_threads + 255) / 256;
+  DUSTY_CHECK_ARG(blocks <= 0x7fffffff, "tensor too large");
+  if (dtype == DUSTY_F32)
+    residual_fork_bwd_cl_kernel<float><<<(unsigned)blocks, 256, 0, st>>>(
+        (const float *)g_pad, (const float *)g_down, (float *)dx, t, H, W, cv, n_threads);
+  else
+    residual_fork_bwd_cl_kernel<__nv_bfloat16><<<(unsigned)blocks, 256, 0, st>>>(
+        (const __nv_bfloat16 *)g_pad, (const __nv_bfloat16 *)g_down, (__nv_bfloat16 *)dx, t, H, W, cv,
+        n_threads);
   DUSTY_LAUNCH_CHECK();
   return DUSTY_OK;
 }

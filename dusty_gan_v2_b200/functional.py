@@ -442,6 +442,55 @@ def blur_down2_cl(x: torch.Tensor, taps4) -> torch.Tensor:
     return _BlurDown2CL.apply(x, tuple(float(t) for t in taps4), False)
 
 
+class _ResidualFork(Function):
+    """ResidualBlock input fork on an NHWC tensor: x -> (Pad(1, ring)(x), blur_down2(x)).  Both
+    consumers' gradients arrive in ONE backward, which evaluates pad_adjoint + blur adjoint as a
+    single gather pass (dusty_residual_fork_bwd_cl) instead of two adjoint launches and the
+    autograd engine's accumulation add.  Under create_graph (R1) the backward is re-expressed
+    through the differentiable single ops."""
+
+    @staticmethod
+    def forward(ctx, x, taps4):
+        x = x if _is_cl(x) else x.contiguous(memory_format=_CL)
+        B, C, H, W = x.shape
+        xp = _pad_raw(x, _FORK_PADS, _FORK_MODES, False)
+        xd = torch.empty((B, C, H // 2, W // 2), device=x.device, dtype=x.dtype, memory_format=_CL)
+        K.call("dusty_blur4_down2_cl", K.ptr(x), K.ptr(xd), taps4[0], taps4[1], taps4[2], taps4[3],
+               B, H, W, C, 0, K.dtype_code(x), K.stream_of(x))
+        ctx.cfg = (taps4, (H, W))
+        ctx.set_materialize_grads(False)
+        return xp, xd
+
+    @staticmethod
+    def backward(ctx, g_pad, g_down):
+        taps4, (H, W) = ctx.cfg
+        if g_pad is None and g_down is None:
+            return None, None
+        if g_pad is None:
+            return _BlurDown2CL.apply(g_down, taps4, True), None
+        if g_down is None:
+            return _PadAdj.apply(g_pad, _FORK_PADS, _FORK_MODES, (H, W)), None
+        if torch.is_grad_enabled():      # create_graph=True: stay differentiable
+            return (_PadAdj.apply(g_pad, _FORK_PADS, _FORK_MODES, (H, W))
+                    + _BlurDown2CL.apply(g_down, taps4, True)), None
+        g_pad = g_pad if _is_cl(g_pad) else g_pad.contiguous(memory_format=_CL)
+        g_down = g_down if _is_cl(g_down) else g_down.contiguous(memory_format=_CL)
+        B, C = g_down.shape[:2]
+        dx = torch.empty((B, C, H, W), device=g_pad.device, dtype=g_pad.dtype, memory_format=_CL)
+        K.call("dusty_residual_fork_bwd_cl", K.ptr(g_pad), K.ptr(g_down), K.ptr(dx), taps4[0],
+               taps4[1], taps4[2], taps4[3], B, H, W, C, K.dtype_code(dx), K.stream_of(dx))
+        return dx, None
+
+
+def residual_fork_supported(x: torch.Tensor) -> bool:
+    return blur_down2_cl_supported(x) and pad2d_supported(x, _FORK_PADS, _FORK_MODES)
+
+
+def residual_fork(x: torch.Tensor, taps4):
+    """(Pad(1, ring)(x), Resample([k0..k3], ring)(x)[:, :, ::2, ::2]) for an NHWC tensor."""
+    return _ResidualFork.apply(x, tuple(float(t) for t in taps4))
+
+
 def resample4_supported(x: torch.Tensor, up: int) -> bool:
     if x.ndim < 3 or not x.is_cuda or x.dtype not in (torch.float32, torch.bfloat16):
         return False
@@ -541,6 +590,8 @@ def affine_warp(img, theta, out_hw):
 
 
 # small-halo padding fast path
+_FORK_PADS = (1, 1, 1, 1)                       # (top, bottom, left, right)
+_FORK_MODES = (K.PAD_REPLICATE, K.PAD_CIRCULAR)   # (mode_y, mode_x): Pad(1, ring=True)
 def _pad_raw(x, pads, modes, adjoint, in_hw=None):
     if _is_cl(x) and _cl_vec_ok(x):
         B, C = x.shape[:2]

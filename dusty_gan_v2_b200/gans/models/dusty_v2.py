@@ -298,6 +298,7 @@ class ResidualBlock(nn.Module):
         self.conv2 = ops.Conv2d(in_ch, out_ch, 3, 2, 1, **kw)
         self.bias_act2 = ops.FusedLeakyReLU(out_ch)
         self.skip = ops.Conv2d(in_ch, out_ch, 1, 2, 0, **kw)
+        self.fused_fork = True          # one backward kernel for the input's two consumers (NHWC)
 
     def _blur_pad_conv2(self, h):
         """conv2(resample(h)) with the blur and conv2's ring padding as one kernel (NHWC)."""
@@ -315,40 +316,69 @@ class ResidualBlock(nn.Module):
         h = self.bias_act1(self.conv1(x))
         return self.bias_act2(self._blur_pad_conv2(h))
 
-    def _skip(self, x):
-        """skip(resample(x)): the 1x1 stride-2 convolution reads the blurred image at even
-        positions only, so on the NHWC path the blur is evaluated there alone and the
-        convolution runs at unit stride on the quarter-size tensor."""
+    def _skip_fast(self, x):
         rs, eq = self.resample, self.skip[-1]
         conv = getattr(eq, "module", None)
-        if (len(self.skip) == 1 and isinstance(eq, ops.EqualLR) and isinstance(conv, nn.Conv2d)
+        return (len(self.skip) == 1 and isinstance(eq, ops.EqualLR) and isinstance(conv, nn.Conv2d)
                 and conv.kernel_size == (1, 1) and conv.stride == (2, 2) and conv.bias is None
-                and getattr(rs, "_fast_up", None) == 1 and DF.blur_down2_cl_supported(x)):
+                and getattr(rs, "_fast_up", None) == 1 and DF.blur_down2_cl_supported(x))
+
+    def _skip(self, x, xd=None):
+        """skip(resample(x)): the 1x1 stride-2 convolution reads the blurred image at even
+        positions only, so on the NHWC path the blur is evaluated there alone and the
+        convolution runs at unit stride on the quarter-size tensor (`xd`: that tensor when the
+        fused input fork already produced it)."""
+        rs, eq = self.resample, self.skip[-1]
+        if xd is not None or self._skip_fast(x):
             if rs._taps_host is None:
                 rs._taps_host = tuple(rs.kernel.detach().float().cpu().tolist())
             w, w_tco = eq.prepared_weight(x.dtype, with_tco=True)
-            return ops.conv2d_valid(DF.blur_down2_cl(x, rs._taps_host), w, (1, 1), w_tco)
+            if xd is None:
+                xd = DF.blur_down2_cl(x, rs._taps_host)
+            return ops.conv2d_valid(xd, w, (1, 1), w_tco)
         return self.skip(rs(x))
 
-    def _conv1_act(self, x):
-        """bias_act1(conv1(x)); on the halo-resident tcgen05 kernel the bias / leaky ReLU run in
-        the convolution's epilogue."""
-        seq, act = self.conv1, self.bias_act1
+    def _conv1_fast(self, x):
+        seq = self.conv1
         eq = seq[-1]
         conv = getattr(eq, "module", None)
-        if (len(seq) == 2 and isinstance(seq[0], ops.Pad) and isinstance(eq, ops.EqualLR)
+        return (len(seq) == 2 and isinstance(seq[0], ops.Pad) and isinstance(eq, ops.EqualLR)
                 and isinstance(conv, nn.Conv2d) and conv.bias is None and conv.stride == (1, 1)
-                and x.is_cuda and x.dtype == torch.bfloat16):
+                and x.is_cuda and x.dtype == torch.bfloat16)
+
+    def _conv1_act(self, x, xp=None):
+        """bias_act1(conv1(x)); on the halo-resident tcgen05 kernel the bias / leaky ReLU run in
+        the convolution's epilogue (`xp`: the ring-padded input when the fused input fork
+        already produced it)."""
+        seq, act = self.conv1, self.bias_act1
+        eq = seq[-1]
+        if xp is not None or self._conv1_fast(x):
             w, w_tco = eq.prepared_weight(x.dtype, with_tco=True)
-            xp = seq[0](x)
+            if xp is None:
+                xp = seq[0](x)
             if ops.conv_bias_act_supported(xp, w, (1, 1)):
                 return ops.conv_bias_act(xp, w, act.bias, (1, 1), act.negative_slope, act.scale, w_tco)
             return act(ops.conv2d_valid(xp, w, (1, 1), w_tco))
         return act(seq(x))
 
+    def _fork(self, x):
+        """(Pad(1, ring)(x), blur_down2(x)) through one autograd node, so that the two
+        branches' input gradients are folded and summed by one kernel; (None, None) when
+        either branch is not on its NHWC fast path."""
+        pad = self.conv1[0]
+        if (self.fused_fork and self._conv1_fast(x) and self._skip_fast(x)
+                and pad.padding == (1, 1, 1, 1) and pad.horizontal == "circular"
+                and pad.vertical == "replicate" and DF.residual_fork_supported(x)):
+            rs = self.resample
+            if rs._taps_host is None:
+                rs._taps_host = tuple(rs.kernel.detach().float().cpu().tolist())
+            return DF.residual_fork(x, rs._taps_host)
+        return None, None
+
     def forward(self, x):
-        skip = self._skip(x)
-        pre = self._blur_pad_conv2(self._conv1_act(x))                # conv2 output, before bias_act2
+        xp, xd = self._fork(x)
+        skip = self._skip(x, xd)
+        pre = self._blur_pad_conv2(self._conv1_act(x, xp))            # conv2 output, before bias_act2
         act = self.bias_act2
         if DF.residual_tail_supported(pre, skip):
             # bias_act2, the residual sum and the 1/sqrt(2) as one NHWC pass

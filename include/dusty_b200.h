@@ -136,6 +136,14 @@ int dusty_blur4_cl(const void *x, void *y, float k0, float k1, float k2, float k
 int dusty_blur4_down2_cl(const void *x, void *y, float k0, float k1, float k2, float k3, int B,
                          int H, int W, int C, int adjoint, int dtype, void *stream);
 
+/* Backward of the ResidualBlock input fork (dusty_v2.py:387-396: x feeds conv1 = Pad(1, ring) +
+ * conv AND skip = conv1x1_stride2(Resample(x))): dx = pad_adjoint(g_pad) + blur4_down2_adjoint(
+ * g_down) in one pass, replacing two adjoint launches plus the autograd accumulation add.
+ * g_pad [B,H+2,W+2,C] (replicate H / circular W, one pixel), g_down [B,H/2,W/2,C], dx [B,H,W,C]. */
+int dusty_residual_fork_bwd_cl(const void *g_pad, const void *g_down, void *dx, float k0, float k1,
+                               float k2, float k3, int B, int H, int W, int C, int dtype,
+                               void *stream);
+
 /* ---- a5/a6: AdaptiveAugment's geometric pipeline ------------------------------------------
  * Single-axis zero-padded polyphase FIR: upfirdn2d with a [1,k] (axis 1 = x) or [k,1]
  * (axis 0 = y) kernel, fp32, up/down in {1,2}:

@@ -806,3 +806,60 @@ def spherical_project_(param: Tensor) -> Tensor:
     with torch.no_grad():
         param.div_(param.pow(2).mean(dim=-1, keepdim=True).add(1e-9).sqrt())
     return param
+
+
+def inv_depth_norm_to_depth_norm(x: Tensor, min_depth: float, max_depth: float,
+                                 tol: float = 1e-11) -> Tensor:
+    """convert(x, 'inv_depth_norm', 'depth_norm') (coords.py:139-144 -> 127-135 -> 101-103):
+    inv = x/min; depth = mask(inv) / (inv + tol); depth / max.  (The `x > tol` flag computed at
+    coords.py:141 is unused on this branch.)"""
+    inv = x / min_depth
+    valid = ((inv >= 1 / max_depth) & (inv <= 1 / min_depth) & (inv > 0.0)).float()
+    return (1 / (inv + tol) * valid) / max_depth
+
+
+def inversion_targets(depth: Tensor, mask: Tensor, min_depth: float, max_depth: float):
+    """demo_inversion.py:89-94: metric depth + mask -> (t_depth [depth_norm], t_inv_depth
+    [inv_depth_norm, masked])."""
+    t_depth = depth / max_depth
+    t_inv = depth_to_inv_depth_norm(t_depth * max_depth, min_depth, max_depth) * mask
+    return t_depth, t_inv
+
+
+def inversion_lr_schedule(iteration: int, num_steps: int, rampup: float = 0.05,
+                          rampdown: float = 0.25) -> float:
+    """demo_inversion.py:140-146 (StyleGAN2 projector schedule)."""
+    t = iteration / num_steps
+    gamma = min(1.0, (1.0 - t) / rampdown)
+    gamma = 0.5 - 0.5 * math.cos(gamma * math.pi)
+    return gamma * min(1.0, t / rampup)
+
+
+def inversion_forward(sdG: Dict[str, Tensor], z: Tensor, angle: Tensor, t_depth: Tensor,
+                      t_inv_depth: Tensor, t_mask: Tensor, min_depth: float, max_depth: float,
+                      latent_type: str = "w", phase: Optional[Tensor] = None,
+                      u: Optional[Tensor] = None):
+    """One evaluation of the inversion objective, demo_inversion.py:149-191 (perturb_z off):
+    eval-mode G driven by styles (input_w=True) at angle + phase, tanh_to_sigmoid, the
+    multi-scale masked relative-L1 loss (level 2) on depth_norm and on inv_depth_norm, plus
+    5e-3 * geocross for 'w+'.  Returns (outputs, per-sample loss [B])."""
+    n_styles = 2 * _num_levels(sdG, "synthesis_network.")
+    w = torch.stack([z] * n_styles, dim=1) if latent_type == "w" else z
+    B = w.shape[0]
+    ang = angle if phase is None else angle + phase
+    if ang.shape[0] != B:
+        ang = ang.expand(B, -1, -1, -1)
+    if u is None:
+        u = torch.full((B, 1) + tuple(angle.shape[-2:]), 0.5)
+    imgs = generator(sdG, w, ang, u, training=False, input_w=True)
+    inv_orig = (imgs["image_orig"] + 1.0) / 2.0
+    g_depth = inv_depth_norm_to_depth_norm(inv_orig, min_depth, max_depth)
+    loss = 0
+    if latent_type == "w+":
+        loss = loss + 5e-3 * geocross_loss(w)
+    loss = loss + multiscale_masked_loss(g_depth, t_depth, t_mask, level=2)
+    loss = loss + multiscale_masked_loss(inv_orig, t_inv_depth, t_mask, level=2)
+    out = dict(inv_depth=(imgs["image"] + 1.0) / 2.0, inv_depth_orig=inv_orig,
+               raydrop_prob=torch.sigmoid(imgs["raydrop_logit"]), g_depth=g_depth,
+               raydrop_logit=imgs["raydrop_logit"], raydrop_mask=imgs["raydrop_mask"])
+    return out, loss

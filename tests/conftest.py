@@ -67,3 +67,8 @@ def g_vanilla():
 @pytest.fixture(scope="session")
 def g_inv():
     return load_golden("inversion.npz")
+
+
+@pytest.fixture(scope="session")
+def g_invloop():
+    return load_golden("inversion_loop.npz")

@@ -493,3 +493,53 @@ def test_inversion_geocross_and_spherical_optimizer_golden(g_inv):
         p.grad = T(g_inv[f"sph_g{i}"]).to(DEV)
         opt.step()
         close(p, g_inv[f"sph_p{i + 1}"], rtol=1e-4, atol_rel=1e-5)
+
+
+@pytest.mark.parametrize("latent_type", ["w", "w+"])
+def test_latent_inversion_loop_golden(g_gen, g_invloop, latent_type):
+    """BASELINE config 5, the loop itself (demo_inversion.py:89-217): targets, objective, Adam +
+    LambdaLR schedule of `LatentInversion` against three steps recorded from the reference's own
+    Generator / CoordBridge / MultiScaleMaskedLoss / geocross_loss; plus the integer counts of
+    the projected result."""
+    import os
+    from dusty_gan_v2_b200.gans.coords import CoordBridge
+    from dusty_gan_v2_b200.gans.inversion import LatentInversion, lr_schedule
+    g = g_invloop
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    G = _build_G(g_gen).eval()
+    coord = CoordBridge(16, 64, 1.45, 80.0, os.path.join(root, "data/coords/kitti_raw.npy")).to(DEV)
+    assert np.array_equal(coord.angle.cpu().numpy(), g["angle"])                  # bit-exact grid
+    depth, mask = T(g["depth"]).to(DEV), T(g["mask"]).to(DEV)
+    inv = LatentInversion(G, coord, depth, mask, latent_type=latent_type, num_steps_1st=3,
+                          num_steps_2nd=0, num_z_samples=256)
+    assert np.array_equal(inv.t_depth.cpu().numpy(), g["t_depth"])
+    close(inv.t_inv_depth, g["t_inv_depth"], rtol=1e-6, atol_rel=1e-7)
+    assert tuple(inv.z.shape) == g[f"{latent_type}_z0"].shape
+    # the device RNG draws other z samples than the CPU one: the initial latent is statistically,
+    # not numerically, the reference's -- continue from the recorded one
+    assert float((inv.z[0].reshape(-1, 16)[0].cpu() - T(g["z_avg"])[0]).abs().max()) < 0.2
+    inv.z.data.copy_(T(g[f"{latent_type}_z0"]).to(DEV))
+    for step in range(3):
+        assert abs(5e-2 * lr_schedule(step, 3) - float(g[f"{latent_type}_lr{step}"])) < 1e-12
+        out, loss = inv.step_1st(step)
+        if step == 0:
+            close(out["inv_depth_orig"], g[f"{latent_type}_inv_depth_orig0"], rtol=1e-3, atol_rel=2e-4)
+            close(out["raydrop_prob"], torch.sigmoid(T(g[f"{latent_type}_raydrop_logit0"])), rtol=1e-3,
+                  atol_rel=2e-4)
+        close(loss, g[f"{latent_type}_loss{step}"], rtol=2e-3, atol_rel=1e-4)
+        close(inv.z.grad, g[f"{latent_type}_grad{step}"], rtol=5e-3, atol_rel=5e-3)
+        # Adam normalises the step: entries whose gradient is ~0 may move the other way
+        dz = (inv.z.detach().cpu() - T(g[f"{latent_type}_z{step + 1}"])).abs()
+        assert float((dz < 2e-3).float().mean()) > 0.98, float(dz.max())
+    assert all(p.grad is None for p in G.parameters())                            # stage 1: G frozen
+    # stage 2 (pivotal tuning): generator weights receive gradients and move
+    inv.num_steps_2nd = 2
+    w_before = G.synthesis_network.layers[0].conv1.weight.detach().clone()
+    _, loss2 = inv.step_2nd(0)
+    assert torch.isfinite(loss2).all()
+    assert not torch.equal(w_before, G.synthesis_network.layers[0].conv1.weight.detach())
+    # projection of the result: valid-point count is the integer the oracle computes
+    pts = inv.point_cloud(out, "inv_depth_orig")
+    _, ps, cnt = O.inv_depth_norm_to_points(out["inv_depth_orig"].detach().cpu(), T(g["angle"]), 1.45, 80.0)
+    assert int(inv.last_valid_count) == cnt
+    close(pts, ps, rtol=1e-5, atol_rel=1e-6)

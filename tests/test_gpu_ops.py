@@ -637,6 +637,55 @@ def test_blur_down2_nhwc(DF, ops, dtype, C, H, W):
     close(gg, blur(v)[:, :, ::2, ::2], **tol)
 
 
+@pytest.mark.parametrize("dtype,C,H,W", [(torch.float32, 8, 8, 16), (torch.bfloat16, 32, 6, 20),
+                                         (torch.bfloat16, 64, 2, 4), (torch.float32, 4, 64, 512),
+                                         (torch.bfloat16, 128, 16, 128)])
+def test_residual_fork_nhwc(DF, ops, dtype, C, H, W):
+    """ResidualBlock input fork (dusty_v2.py:387-396): (Pad(1, ring)(x), blur(x)[::2, ::2]) from one
+    autograd node whose backward folds both gradients in one kernel; against the oracle's
+    pad2d / resample, first order (one and both consumers) and the R1-style second order."""
+    g = torch.Generator().manual_seed(45)
+    CL = torch.channels_last
+    x = torch.randn(2, C, H, W, generator=g)
+    if dtype == torch.bfloat16:
+        x = x.bfloat16().float()
+    tol = dict(rtol=1e-5, atol_rel=1e-6) if dtype == torch.float32 else dict(rtol=2e-2, atol_rel=1e-2)
+    xr = x.clone().requires_grad_()
+    ref_p = O.pad2d(xr, 1, ring=True, mode="replicate")
+    ref_d = O.resample(xr)[:, :, ::2, ::2]
+    taps = tuple(ops.Resample().kernel.tolist())
+    xf = x.to(DEV, dtype).contiguous(memory_format=CL).requires_grad_()
+    assert DF.residual_fork_supported(xf)
+    xp, xd = DF.residual_fork(xf, taps)
+    assert DF._is_cl(xp) and DF._is_cl(xd)
+    close(xp, ref_p, rtol=0, atol_rel=0)            # padding copies values: bit-exact
+    close(xd, ref_d, **tol)
+    gp = torch.randn(ref_p.shape, generator=g)
+    gd = torch.randn(ref_d.shape, generator=g)
+    if dtype == torch.bfloat16:
+        gp, gd = gp.bfloat16().float(), gd.bfloat16().float()
+    (gr,) = torch.autograd.grad([ref_p, ref_d], xr, [gp, gd], retain_graph=True)
+    gpf = gp.to(DEV, dtype).contiguous(memory_format=CL).requires_grad_()
+    gdf = gd.to(DEV, dtype).contiguous(memory_format=CL).requires_grad_()
+    (gf,) = torch.autograd.grad([xp, xd], xf, [gpf, gdf], retain_graph=True)     # fused kernel
+    assert DF._is_cl(gf)
+    close(gf, gr, **tol)
+    # one consumer only
+    (g1,) = torch.autograd.grad(xp, xf, gpf, retain_graph=True)
+    close(g1, torch.autograd.grad(ref_p, xr, gp, retain_graph=True)[0], **tol)
+    (g2,) = torch.autograd.grad(xd, xf, gdf, retain_graph=True)
+    close(g2, torch.autograd.grad(ref_d, xr, gd, retain_graph=True)[0], **tol)
+    # second order: d/d(gp, gd) of <backward(gp, gd), v> = (pad(v), blur_down2(v))
+    (gc,) = torch.autograd.grad([xp, xd], xf, [gpf, gdf], create_graph=True)
+    close(gc, gr, **tol)
+    v = torch.randn(x.shape, generator=g)
+    if dtype == torch.bfloat16:
+        v = v.bfloat16().float()
+    ggp, ggd = torch.autograd.grad((gc.float() * v.to(DEV)).sum(), [gpf, gdf])
+    close(ggp, O.pad2d(v, 1, ring=True, mode="replicate"), **tol)
+    close(ggd, O.resample(v)[:, :, ::2, ::2], **tol)
+
+
 # ----------------------------------------------------------------------------- a11 dense convs
 @pytest.mark.parametrize("B,C,Oc,H,W,k,stride", [
     (2, 32, 32, 18, 66, 3, 1),       # RB0 conv1 shape family (C = O = 32, K_g = 96 -> zero-filled chunk)

@@ -260,3 +260,42 @@ def test_inversion_geocross_and_spherical_projection(g_inv):
         opt.step()
         O.spherical_project_(p.data)
         close(p, g_inv[f"sph_p{i + 1}"], rtol=1e-5, atol=1e-6)
+
+
+@pytest.mark.parametrize("latent_type", ["w", "w+"])
+def test_inversion_loop_against_reference(g_gen, g_invloop, latent_type):
+    """demo_inversion.py's stage-1 loop (targets, latent init, objective, Adam + LambdaLR):
+    three steps of the oracle against the trajectory recorded from the reference's parts."""
+    g, sd = g_invloop, _sd(g_gen)
+    MIN_D, MAX_D, STEPS = 1.45, 80.0, 3
+    depth, mask, angle = T(g["depth"]), T(g["mask"]), T(g["angle"])
+    close(O.angle_grid(np.load(os.path.join(ROOT, "data/coords/kitti_raw.npy")), 16, 64), g["angle"],
+          rtol=0, atol=0)
+    t_depth, t_inv = O.inversion_targets(depth, mask, MIN_D, MAX_D)
+    close(t_depth, g["t_depth"], rtol=0, atol=0)
+    close(t_inv, g["t_inv_depth"], rtol=1e-6, atol=1e-8)
+    # latent initialisation (demo_inversion.py:99-107)
+    torch.manual_seed(0)
+    ws = O.mapping_network(sd, torch.randn(256, 16))
+    z_avg = ws.mean(dim=0, keepdim=True)
+    close(z_avg, g["z_avg"], rtol=1e-5, atol=1e-6)
+    close((((ws - z_avg) ** 2).sum() / 256).sqrt(), g["z_std"], rtol=1e-5)
+    z = torch.nn.Parameter(T(g[f"{latent_type}_z0"]).clone())
+    opt = torch.optim.Adam([z], lr=5e-2)
+    for step in range(STEPS):
+        lr = 5e-2 * O.inversion_lr_schedule(step, STEPS)
+        assert abs(lr - float(g[f"{latent_type}_lr{step}"])) < 1e-12
+        for grp in opt.param_groups:
+            grp["lr"] = lr
+        out, loss = O.inversion_forward(sd, z, angle, t_depth, t_inv, mask, MIN_D, MAX_D, latent_type)
+        opt.zero_grad(set_to_none=True)
+        loss.backward(gradient=torch.ones_like(loss))
+        if step == 0:
+            close(out["inv_depth_orig"], g[f"{latent_type}_inv_depth_orig0"], rtol=1e-4, atol=1e-6)
+            close(out["g_depth"], g[f"{latent_type}_g_depth0"], rtol=1e-4, atol=1e-6)
+            close(out["raydrop_logit"], g[f"{latent_type}_raydrop_logit0"], rtol=1e-4, atol=1e-5)
+        ref_g = g[f"{latent_type}_grad{step}"]
+        close(loss, g[f"{latent_type}_loss{step}"], rtol=1e-4, atol=1e-6)
+        close(z.grad, ref_g, rtol=2e-3, atol=2e-4 * np.abs(ref_g).max())
+        opt.step()
+        close(z, g[f"{latent_type}_z{step + 1}"], rtol=1e-3, atol=2e-3)

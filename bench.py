@@ -292,6 +292,7 @@ def kernel_rooflines(device, peaks):
     taps = tuple(up.kernel.tolist())
     mem_entry("resample_up2_adjoint[64,64,64,512]bf16", lambda: DF._resample4_raw(gup, taps, 2, True),
               5 * h.numel() * 2)
+    mem_entry("resample_up2+sumsq[64,64,32,256]bf16", lambda: DF.up2_with_sumsq(h, taps), 5 * h.numel() * 2)
     blur = Resample().to(device)
     mem_entry("resample_blur[64,32,64,512]bf16", lambda: blur(x), 2 * x.numel() * 2)
     btaps = tuple(blur.kernel.tolist())
@@ -323,6 +324,13 @@ def kernel_rooflines(device, peaks):
     mem_entry("pad_ring1_adjoint_nhwc[64,32,66,514]bf16",
               lambda: DF._pad_raw(gpc, (1, 1, 1, 1), (K.PAD_REPLICATE, K.PAD_CIRCULAR), True, (H, W)),
               (x.numel() + gp.numel()) * 2)
+    gdc = torch.randn(B, 32, H // 2, W // 2, device=device, dtype=bf).contiguous(memory_format=CL)
+    dxc = torch.empty_like(xc)
+    mem_entry("residual_fork_bwd_nhwc[64,32,64,512]bf16",
+              lambda: K.call("dusty_residual_fork_bwd_cl", K.ptr(gpc), K.ptr(gdc), K.ptr(dxc), btaps[0], btaps[1],
+                             btaps[2], btaps[3], B, H, W, 32, K.BF16, K.stream_of(xc)),
+              (gpc.numel() + gdc.numel() + dxc.numel()) * 2)
+    del gdc, dxc
     # discriminator stem (BlurVH + 1x1 conv 2->32 + bias/lrelu) and residual tail, fused kernels
     xs = torch.tanh(torch.randn(B, 1, H, W, device=device))
     ws_ = torch.randn(32, 2, device=device) / 1.4
@@ -539,7 +547,10 @@ def main():
                                  "(fprop, dgrad, wgrad), fused stem kernel; cuBLAS for the two linears",
                            "auto": "own tcgen05 kernels where they measured faster than cuDNN "
                                    "(profiles/r01_conv_layers.json), cuDNN elsewhere; cuBLAS linears",
-                           "library": "cuDNN convolutions, cuBLAS linears"}[args.conv_impl],
+                           "library": "cuDNN convolutions, cuBLAS linears"}[args.conv_impl]
+                       if args.arch == "dusty_v2" else
+                       "dense 4x4 (transposed) convolutions of the vanilla / dusty_v1 networks are cuDNN calls; "
+                       "pad, blur, bias_act, raydrop, ADA on own kernels",
                        "conv_impl": args.conv_impl},
             "clocks": clk, "gpu_launches": launches, "e2e": e2e}
 

@@ -31,6 +31,7 @@ SIGNATURES = {
     "dusty_fir2d_adj": [_vp, _vp, _vp, _i, _i, _i, _i64] + [_i] * 13 + [_vp],
     "dusty_upfirdn2d": [_vp, _vp, _vp, _i64] + [_i] * 13 + [_vp],
     "dusty_resample4": [_vp, _vp, _f, _f, _f, _f, _i64, _i, _i, _i, _i, _i, _vp],
+    "dusty_up2_sumsq": [_vp, _vp, _vp, _f, _f, _f, _f, _i64, _i, _i, _i, _vp],
     "dusty_pad2d": [_vp, _vp, _i64] + [_i] * 10 + [_vp],
     "dusty_bias_act_cl": [_vp, _vp, _vp, _vp, _i64, _i, _i, _i, _f, _f, _i, _vp],
     "dusty_bias_act_bwd_cl": [_vp, _vp, _vp, _vp, _i64, _i, _f, _f, _i, _vp],

@@ -739,81 +739,114 @@ blur4_down2_cl_adj_kernel(const T *__restrict__ g, T *__restrict__ dx, Taps4CL t
 // blur (skip branch); dx = pad_adjoint(g_pad) + blur4_down2_adjoint(g_down) as ONE gather pass
 // (was: two adjoint kernels + the autograd engine's accumulation add = 6.25 tensor passes, now
 // 2.25).  Pad geometry is fixed: one pixel, replicate in H, circular in W.
+// thread -> one 2x2 block of dx for one channel vector: rows 2i, 2i+1 and columns 2j, 2j+1 all
+// read the same four g_down vectors (rows i, i+1 x columns j, j+1), so the block costs 4 + 4
+// loads for 4 stores (the one-output-per-thread form issued 5 loads per store).  Blur adjoint per
+// axis: even coordinate 2i <- k[2] g[i] + k[0] g[i+1], odd 2i+1 <- k[3] g[i] + k[1] g[i+1]
+// (g[H2] absent; column j+1 wraps), plus (k[0] + k[1]) g[0] folded onto row 0 by the clamp.
 template <typename T>
-__global__ void __launch_bounds__(256)
+__global__ void __launch_bounds__(128)
 residual_fork_bwd_cl_kernel(const T *__restrict__ gp, const T *__restrict__ g, T *__restrict__ dx,
-                            Taps4CL t, int H, int W, int cv, int64_t n_threads) {
+                            Taps4CL t, int H, int W, int cv) {
   constexpr int V = Vec16<T>::N;
-  const int H2 = H >> 1, W2 = W >> 1;
-  const int64_t tid = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-  if (tid >= n_threads) return;
-  const int j = (int)(tid % cv);
-  int64_t q = tid / cv;
-  const int xc = (int)(q % W);
-  q /= W;
-  const int yr = (int)(q % H);
-  const int64_t b = q / H;
   constexpr int VP = V / 2;
-  float2 acc[VP];
-  // ---- pad adjoint: padded (py, px) with clampH(py - 1) == yr, wrapW(px - 1) == xc
+  const int H2 = H >> 1, W2 = W >> 1;
+  const int v = blockIdx.x * blockDim.x + threadIdx.x;
+  if (v >= W2 * cv) return;
+  const int jv = v % cv;
+  const int j = v / cv;
+  const int i = blockIdx.y;
+  const int64_t b = blockIdx.z;
   const int Wp = W + 2;
   const T *gpi = gp + b * (int64_t)(H + 2) * Wp * cv * V;
-  {
-    Vec16<T> v = ld16(gpi + (((int64_t)(yr + 1) * Wp + (xc + 1)) * cv + j) * V);
-#pragma unroll
-    for (int k = 0; k < VP; ++k) acc[k] = get2(v, k);
-  }
-  const int px2 = xc == 0 ? W + 1 : (xc == W - 1 ? 0 : -1);     // second pre-image column
-  const int py2 = yr == 0 ? 0 : (yr == H - 1 ? H + 1 : -1);     // second pre-image row
-  if (px2 >= 0 || py2 >= 0) {
-    auto addp = [&](int py, int px) {
-      Vec16<T> v = ld16(gpi + (((int64_t)py * Wp + px) * cv + j) * V);
-#pragma unroll
-      for (int k = 0; k < VP; ++k) { float2 w = get2(v, k); acc[k].x += w.x; acc[k].y += w.y; }
-    };
-    if (px2 >= 0) addp(yr + 1, px2);
-    if (py2 >= 0) {
-      addp(py2, xc + 1);
-      if (px2 >= 0) addp(py2, px2);
-    }
-  }
-  // ---- decimating-blur adjoint (same gather as blur4_down2_cl_adj_kernel)
   const T *gi = g + b * (int64_t)H2 * W2 * cv * V;
-  const int p = xc & 1;
-  int jc[2];
-  float kx[2];
+  T *out = dx + b * (int64_t)H * W * cv * V;
+  const int j1 = j + 1 == W2 ? 0 : j + 1;
+  const bool has_i1 = i + 1 < H2;
+  // ---- all eight loads first
+  Vec16<T> p[2][2], q[2][2];
 #pragma unroll
-  for (int u = 0; u < 2; ++u) {
-    const int s = p + 2 * u;
-    int jj = (xc + 2 - s) >> 1;
-    jc[u] = jj >= W2 ? jj - W2 : jj;
-    kx[u] = t.k[s];
+  for (int a = 0; a < 2; ++a)
+#pragma unroll
+    for (int c = 0; c < 2; ++c)
+      p[a][c] = ld16(gpi + (((int64_t)(2 * i + a + 1) * Wp + (2 * j + c + 1)) * cv + jv) * V);
+  q[0][0] = ld16(gi + (((int64_t)i * W2 + j) * cv + jv) * V);
+  q[0][1] = ld16(gi + (((int64_t)i * W2 + j1) * cv + jv) * V);
+  if (has_i1) {
+    q[1][0] = ld16(gi + (((int64_t)(i + 1) * W2 + j) * cv + jv) * V);
+    q[1][1] = ld16(gi + (((int64_t)(i + 1) * W2 + j1) * cv + jv) * V);
   }
-  auto add = [&](int i, float ky) {
-    const T *row = gi + (int64_t)i * W2 * cv * V;
+  float2 acc[2][2][VP];
 #pragma unroll
-    for (int u = 0; u < 2; ++u) {
-      Vec16<T> v = ld16(row + ((int64_t)jc[u] * cv + j) * V);
-      const float w = ky * kx[u];
+  for (int a = 0; a < 2; ++a)
 #pragma unroll
-      for (int k = 0; k < VP; ++k) acc[k] = fma2(w, get2(v, k), acc[k]);
+    for (int c = 0; c < 2; ++c)
+#pragma unroll
+      for (int k = 0; k < VP; ++k) acc[a][c][k] = get2(p[a][c], k);
+  // ---- pad adjoint, folded halo (block touches a border)
+  auto addp = [&](int a, int c, int py, int px) {
+    Vec16<T> w = ld16(gpi + (((int64_t)py * Wp + px) * cv + jv) * V);
+#pragma unroll
+    for (int k = 0; k < VP; ++k) {
+      float2 u = get2(w, k);
+      acc[a][c][k].x += u.x;
+      acc[a][c][k].y += u.y;
     }
   };
-  const int pq = yr & 1;
-#pragma unroll
-  for (int u = 0; u < 2; ++u) {
-    const int r = pq + 2 * u;
-    const int i = (yr + 2 - r) >> 1;
-    if (i >= 0 && i < H2) add(i, t.k[r]);
+  // j == 0 folds padded column W+1 onto x = 0; j == W2-1 folds padded column 0 onto x = W-1
+  // (W >= 4, so the two are different blocks); i == 0 / i == H2-1 fold padded rows 0 / H+1
+  if (j == 0) { addp(0, 0, 2 * i + 1, W + 1); addp(1, 0, 2 * i + 2, W + 1); }
+  if (j == W2 - 1) { addp(0, 1, 2 * i + 1, 0); addp(1, 1, 2 * i + 2, 0); }
+  if (i == 0 || i == H2 - 1) {
+    if (i == 0) {
+      addp(0, 0, 0, 2 * j + 1); addp(0, 1, 0, 2 * j + 2);
+      if (j == 0) addp(0, 0, 0, W + 1);
+      if (j == W2 - 1) addp(0, 1, 0, 0);
+    }
+    if (i == H2 - 1) {
+      addp(1, 0, H + 1, 2 * j + 1); addp(1, 1, H + 1, 2 * j + 2);
+      if (j == 0) addp(1, 0, H + 1, W + 1);
+      if (j == W2 - 1) addp(1, 1, H + 1, 0);
+    }
   }
-  if (yr == 0) {
-    add(0, t.k[0]);
-    add(0, t.k[1]);
-  }
-  Vec16<T> o;
+  // ---- decimating-blur adjoint, separable on the 2x2 block
+  // horizontal: hc[row][c] = kx[c][col j] * q[row][0] + kx[c][col j+1] * q[row][1]
+  //   c = 0 (x even): k[2] (col j), k[0] (col j+1);  c = 1 (x odd): k[3], k[1]
 #pragma unroll
-  for (int k = 0; k < VP; ++k) set2(o, k, acc[k]);
-  st16(dx + tid * V, o);
+  for (int k = 0; k < VP; ++k) {
+    float2 h0[2], h1[2];
+    {
+      const float2 a0 = get2(q[0][0], k), a1 = get2(q[0][1], k);
+      h0[0] = fma2(t.k[0], a1, mul2(t.k[2], a0));
+      h0[1] = fma2(t.k[1], a1, mul2(t.k[3], a0));
+    }
+    if (has_i1) {
+      const float2 b0 = get2(q[1][0], k), b1 = get2(q[1][1], k);
+      h1[0] = fma2(t.k[0], b1, mul2(t.k[2], b0));
+      h1[1] = fma2(t.k[1], b1, mul2(t.k[3], b0));
+    } else {
+      h1[0] = h1[1] = make_float2(0.f, 0.f);
+    }
+    // vertical: row 2i <- k[2] h(i) + k[0] h(i+1) (+ (k[0]+k[1]) h(0) when i == 0);
+    //           row 2i+1 <- k[3] h(i) + k[1] h(i+1)
+    const float ky_even = i == 0 ? t.k[2] + t.k[0] + t.k[1] : t.k[2];
+#pragma unroll
+    for (int c = 0; c < 2; ++c) {
+      acc[0][c][k] = fma2(ky_even, h0[c], acc[0][c][k]);
+      acc[0][c][k] = fma2(t.k[0], h1[c], acc[0][c][k]);
+      acc[1][c][k] = fma2(t.k[3], h0[c], acc[1][c][k]);
+      acc[1][c][k] = fma2(t.k[1], h1[c], acc[1][c][k]);
+    }
+  }
+#pragma unroll
+  for (int a = 0; a < 2; ++a)
+#pragma unroll
+    for (int c = 0; c < 2; ++c) {
+      Vec16<T> o;
+#pragma unroll
+      for (int k = 0; k < VP; ++k) set2(o, k, acc[a][c][k]);
+      st16(out + (((int64_t)(2 * i + a) * W + (2 * j + c)) * cv + jv) * V, o);
+    }
 }
 
 static unsigned cl_flat_grid(int64_t work) {
@@ -1087,16 +1120,15 @@ extern "C" int dusty_residual_fork_bwd_cl(const void *g_pad, const void *g_down,
   t.k[0] = k0; t.k[1] = k1; t.k[2] = k2; t.k[3] = k3;
   const int cv = C / V;
   cudaStream_t st = (cudaStream_t)stream;
-  const int64_t n_threads = (int64_t)B * H * W * cv;
-  const int64_t blocks = (n_threads + 255) / 256;
-  DUSTY_CHECK_ARG(blocks <= 0x7fffffff, "tensor too large");
+  DUSTY_CHECK_ARG(B <= 65535 && H / 2 <= 65535, "B and H/2 must fit the grid's y / z extents");
+  const int row_vecs = (W / 2) * cv;
+  dim3 grid((unsigned)((row_vecs + 127) / 128), (unsigned)(H / 2), (unsigned)B);
   if (dtype == DUSTY_F32)
-    residual_fork_bwd_cl_kernel<float><<<(unsigned)blocks, 256, 0, st>>>(
-        (const float *)g_pad, (const float *)g_down, (float *)dx, t, H, W, cv, n_threads);
+    residual_fork_bwd_cl_kernel<float><<<grid, 128, 0, st>>>(
+        (const float *)g_pad, (const float *)g_down, (float *)dx, t, H, W, cv);
   else
-    residual_fork_bwd_cl_kernel<__nv_bfloat16><<<(unsigned)blocks, 256, 0, st>>>(
-        (const __nv_bfloat16 *)g_pad, (const __nv_bfloat16 *)g_down, (__nv_bfloat16 *)dx, t, H, W, cv,
-        n_threads);
+    residual_fork_bwd_cl_kernel<__nv_bfloat16><<<grid, 128, 0, st>>>(
+        (const __nv_bfloat16 *)g_pad, (const __nv_bfloat16 *)g_down, (__nv_bfloat16 *)dx, t, H, W, cv);
   DUSTY_LAUNCH_CHECK();
   return DUSTY_OK;
 }

@@ -154,13 +154,17 @@ blur4_adj_kernel(const T *__restrict__ dy, T *__restrict__ dx, Taps4 t, int H, i
 
 // ------------------------------------------------------------------ up2 forward
 // thread -> (image, input vector column); strip of INPUT rows [r0, r1) -> output rows 2r, 2r+1
-template <typename T>
+// SUMSQ: also accumulate sum(y^2) (fp32, of the un-rounded outputs) into *sumsq -- the statistic
+// ModConv2d's EMA normaliser takes of its input (style.py:99-102), which for conv1 of a synthesis
+// block IS this kernel's output: one atomicAdd per CTA instead of a second pass over 4N elements.
+template <typename T, bool SUMSQ>
 __global__ void __launch_bounds__(128)
 up2_fwd_kernel(const T *__restrict__ x, T *__restrict__ y, Taps4 t, int H, int W, int strip,
-               int64_t n_threads) {
+               int64_t n_threads, float *__restrict__ sumsq) {
   constexpr int V = RowIO<T>::V;
   const int64_t tid = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-  if (tid >= n_threads) return;
+  float ss = 0.f;
+  if (tid < n_threads) {
   const int vpr = W / V;
   const int vc = (int)(tid % vpr);
   const int64_t n = tid / vpr;
@@ -188,16 +192,29 @@ up2_fwd_kernel(const T *__restrict__ x, T *__restrict__ y, Taps4 t, int H, int W
     hpass(r + 1, c);
     float o[2 * V];
 #pragma unroll
-    for (int j = 0; j < 2 * V; ++j) o[j] = fmaf(t.k[2], b[j], t.k[0] * a[j]);
+    for (int j = 0; j < 2 * V; ++j) {
+      o[j] = fmaf(t.k[2], b[j], t.k[0] * a[j]);
+      if (SUMSQ) ss = fmaf(o[j], o[j], ss);
+    }
     RowIO<T>::store(out + (int64_t)(2 * r) * W2, 2 * x0, o);
     RowIO<T>::store(out + (int64_t)(2 * r) * W2, 2 * x0 + V, o + V);
 #pragma unroll
     for (int j = 0; j < 2 * V; ++j) {
       o[j] = fmaf(t.k[3], c[j], t.k[1] * b[j]);
+      if (SUMSQ) ss = fmaf(o[j], o[j], ss);
       a[j] = b[j]; b[j] = c[j];
     }
     RowIO<T>::store(out + (int64_t)(2 * r + 1) * W2, 2 * x0, o);
     RowIO<T>::store(out + (int64_t)(2 * r + 1) * W2, 2 * x0 + V, o + V);
+  }
+  }
+  if (SUMSQ) {
+    __shared__ float part[4];
+#pragma unroll
+    for (int d = 16; d > 0; d >>= 1) ss += __shfl_xor_sync(0xffffffffu, ss, d);
+    if ((threadIdx.x & 31) == 0) part[threadIdx.x >> 5] = ss;
+    __syncthreads();
+    if (threadIdx.x == 0) atomicAdd(sumsq, (part[0] + part[1]) + (part[2] + part[3]));
   }
 }
 
@@ -270,7 +287,7 @@ up2_adj_kernel(const T *__restrict__ dy, T *__restrict__ dx, Taps4 t, int H, int
 
 template <typename T>
 static int launch_resample4(const void *x, void *y, Taps4 t, int64_t N, int H, int W, int up,
-                            int adjoint, cudaStream_t st) {
+                            int adjoint, cudaStream_t st, float *sumsq = nullptr) {
   constexpr int V = Vec16<T>::N;
   const int64_t n_threads = N * (W / V);
   // strips: enough CTAs to fill the GPU, at least 8 rows per strip to amortise the halo
@@ -282,7 +299,8 @@ static int launch_resample4(const void *x, void *y, Taps4 t, int64_t N, int H, i
   T *yp = (T *)y;
   if (up == 1 && !adjoint) blur4_fwd_kernel<T><<<grid, 128, 0, st>>>(xp, yp, t, H, W, strip, n_threads);
   else if (up == 1) blur4_adj_kernel<T><<<grid, 128, 0, st>>>(xp, yp, t, H, W, strip, n_threads);
-  else if (!adjoint) up2_fwd_kernel<T><<<grid, 128, 0, st>>>(xp, yp, t, H, W, strip, n_threads);
+  else if (!adjoint && sumsq) up2_fwd_kernel<T, true><<<grid, 128, 0, st>>>(xp, yp, t, H, W, strip, n_threads, sumsq);
+  else if (!adjoint) up2_fwd_kernel<T, false><<<grid, 128, 0, st>>>(xp, yp, t, H, W, strip, n_threads, nullptr);
   else up2_adj_kernel<T><<<grid, 128, 0, st>>>(xp, yp, t, H, W, strip, n_threads);
   return 0;
 }
@@ -306,6 +324,24 @@ extern "C" int dusty_resample4(const void *x, void *y, float k0, float k1, float
   cudaStream_t st = (cudaStream_t)stream;
   int rc = dtype == DUSTY_F32 ? launch_resample4<float>(x, y, t, N, H, W, up, adjoint, st)
                               : launch_resample4<__nv_bfloat16>(x, y, t, N, H, W, up, adjoint, st);
+  if (rc) return rc;
+  DUSTY_LAUNCH_CHECK();
+  return DUSTY_OK;
+}
+
+extern "C" int dusty_up2_sumsq(const void *x, void *y, float *sumsq, float k0, float k1, float k2,
+                               float k3, int64_t N, int H, int W, int dtype, void *stream) {
+  DUSTY_CHECK_ARG(x && y && sumsq, "null pointer");
+  DUSTY_CHECK_ARG(dtype == DUSTY_F32 || dtype == DUSTY_BF16, "bad dtype");
+  DUSTY_CHECK_ARG(N >= 1 && H >= 2 && W >= 4, "bad shape");
+  const int V = dtype == DUSTY_F32 ? 4 : 8;
+  DUSTY_CHECK_ARG(W % V == 0, "W must be a multiple of the 16-byte vector width");
+  DUSTY_CHECK_ARG(aligned16(x) && aligned16(y), "tensors must be 16-byte aligned");
+  Taps4 t;
+  t.k[0] = k0; t.k[1] = k1; t.k[2] = k2; t.k[3] = k3;
+  cudaStream_t st = (cudaStream_t)stream;
+  int rc = dtype == DUSTY_F32 ? launch_resample4<float>(x, y, t, N, H, W, 2, 0, st, sumsq)
+                              : launch_resample4<__nv_bfloat16>(x, y, t, N, H, W, 2, 0, st, sumsq);
   if (rc) return rc;
   DUSTY_LAUNCH_CHECK();
   return DUSTY_OK;

@@ -506,6 +506,37 @@ def resample4(x: torch.Tensor, taps4, up: int) -> torch.Tensor:
     return _Resample4.apply(x, tuple(float(t) for t in taps4), int(up), False)
 
 
+class _Up2SumSq(Function):
+    """2x upsampling (dusty_resample4 up=2) whose forward also yields sum(y^2) as a 1-element
+    fp32 buffer (no grad): the EMA statistic of the ModConv2d that consumes y."""
+
+    @staticmethod
+    def forward(ctx, x, taps4):
+        x = _contig(x)
+        lead = x.shape[:-2]
+        n = 1
+        for s_ in lead:
+            n *= s_
+        H, W = x.shape[-2:]
+        y = torch.empty(*lead, 2 * H, 2 * W, device=x.device, dtype=x.dtype)
+        ss = torch.zeros(1, device=x.device, dtype=torch.float32)
+        K.call("dusty_up2_sumsq", K.ptr(x), K.ptr(y), K.ptr(ss), taps4[0], taps4[1], taps4[2],
+               taps4[3], n, H, W, K.dtype_code(x), K.stream_of(x))
+        ctx.cfg = taps4
+        ctx.mark_non_differentiable(ss)
+        return y, ss
+
+    @staticmethod
+    def backward(ctx, g, _g_ss):
+        return _Resample4.apply(g, ctx.cfg, 2, True), None
+
+
+def up2_with_sumsq(x: torch.Tensor, taps4):
+    """(Resample(up=2)(x), sum of its squares) in one launch."""
+    K.require_cuda(x)
+    return _Up2SumSq.apply(x, tuple(float(t) for t in taps4))
+
+
 # single-axis zero-padded FIR (ADA's SYM6 passes) and the fused affine warp
 class _Fir1d(Function):
     @staticmethod

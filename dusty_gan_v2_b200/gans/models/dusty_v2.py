@@ -116,10 +116,10 @@ class SynthesisBlock(nn.Module):
         per = self.downsample(torch.cat([angle.sin(), angle.cos()], dim=1))
         return torch.atan2(per[:, :c], per[:, c:])
 
-    def _conv(self, conv, noise, act, h, style, pe=None, pe_rot=None):
+    def _conv(self, conv, noise, act, h, style, pe=None, pe_rot=None, x_sumsq=None):
         if noise is None:
-            return conv(h, style, pe=pe, fused_act=act, pe_rot=pe_rot)
-        return act(noise(conv(h, style, pe=pe, pe_rot=pe_rot)))
+            return conv(h, style, pe=pe, fused_act=act, pe_rot=pe_rot, x_sumsq=x_sumsq)
+        return act(noise(conv(h, style, pe=pe, pe_rot=pe_rot, x_sumsq=x_sumsq)))
 
     def pe_rotation(self, shift_rad):
         """[B, 2F] table (cos | sin) of psi[b,f] = f_w[f] * shift_b for this block's basis."""
@@ -130,11 +130,16 @@ class SynthesisBlock(nn.Module):
     def forward(self, h, skip, ws, angle, shift_rad=None):
         ws = iter(ws)
         dtype = DF.act_dtype() if (self.use_fp16 and angle.is_cuda) else torch.float32
+        h_ss = None
         if h is not None:
-            h = self.resample(h.to(dtype))
+            if self.training and self.conv1.ema and isinstance(self.resample, ops.Resample):
+                # conv1's EMA statistic of the upsampled tensor comes out of the upsampling kernel
+                h, h_ss = self.resample.forward_with_sumsq(h.to(dtype))
+            else:
+                h = self.resample(h.to(dtype))
         pe = self.pe(angle, out_dtype=dtype) if self.use_pe else None
         rot = self.pe_rotation(shift_rad) if (shift_rad is not None and pe is not None) else None
-        h = self._conv(self.conv1, self.noise1, self.bias_act1, h, next(ws), pe, rot)
+        h = self._conv(self.conv1, self.noise1, self.bias_act1, h, next(ws), pe, rot, h_ss)
         if not self.is_first:
             h = self._conv(self.conv2, self.noise2, self.bias_act2, h, next(ws))
         o = self.head(h, next(ws))

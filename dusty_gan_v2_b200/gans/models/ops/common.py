@@ -129,6 +129,15 @@ class Resample(nn.Module):
             return DF.resample4(h, self._taps_host, self._fast_up)
         return DF.fir2d(h, self._taps(h.device), self._cfg)
 
+    def forward_with_sumsq(self, h):
+        """(forward(h), sum(forward(h)^2) as a 1-element fp32 device buffer or None): the 2x
+        upsampling kernel can emit the statistic the following ModConv2d's EMA needs."""
+        if self._fast_up == 2 and DF.resample4_supported(h, 2):
+            if self._taps_host is None:
+                self._taps_host = tuple(self.kernel.detach().float().cpu().tolist())
+            return DF.up2_with_sumsq(h, self._taps_host)
+        return self.forward(h), None
+
     def extra_repr(self):
         return f'filter_type={self.window}, up={self.up}, down={self.down}, direction="{self.direction}"'
 

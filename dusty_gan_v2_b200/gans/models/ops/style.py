@@ -73,10 +73,11 @@ class ModConv2d(nn.Module):
         return wb
 
     @torch.no_grad()
-    def update_ema(self, x, pe=None):
+    def update_ema(self, x, pe=None, x_sumsq=None):
         """ema_var <- lerp(ema_var, mean(x^2), 1 - decay) over the *whole* input, Fourier
-        channels included (style.py:99-102): two reductions + one scalar kernel."""
-        sa = DF.sumsq_buffer(x) if x is not None else None
+        channels included (style.py:99-102): two reductions + one scalar kernel (`x_sumsq`:
+        sum(x^2) when the kernel that produced x already accumulated it)."""
+        sa = x_sumsq if x_sumsq is not None else (DF.sumsq_buffer(x) if x is not None else None)
         numel = x.numel() if x is not None else 0
         sb, rep = None, 1
         if pe is not None:
@@ -86,7 +87,7 @@ class ModConv2d(nn.Module):
             numel += pe.numel() * rep
         DF.ema_lerp_(self.ema_var, sa, sb, rep, numel, 1 - self.ema_decay)
 
-    def forward(self, x, style, pe=None, fused_act=None, pe_rot=None):
+    def forward(self, x, style, pe=None, fused_act=None, pe_rot=None, x_sumsq=None):
         """x: [B, C1, H, W] (or None when the input is `pe` alone); pe: optional Fourier
         block [B or 1, C2, H, W] appended on the channel axis; fused_act: a FusedLeakyReLU
         module to apply in the epilogue."""
@@ -95,7 +96,7 @@ class ModConv2d(nn.Module):
         if c1 + c2 != self.in_ch:
             raise RuntimeError(f"expected {self.in_ch} input channels, got {c1}+{c2}")
         if self.ema and self.training:
-            self.update_ema(x, pe)
+            self.update_ema(x, pe, x_sumsq)
         src = x if x is not None else pe
         wb = self.effective_weights(style, src.dtype, pe_rot, c1)
         bias = self.bias

@@ -97,6 +97,13 @@ int dusty_upfirdn2d(const void *x, const float *kernel, void *y, int64_t major, 
 int dusty_resample4(const void *x, void *y, float k0, float k1, float k2, float k3, int64_t N,
                     int H, int W, int up, int adjoint, int dtype, void *stream);
 
+/* dusty_resample4(up = 2, forward) that also adds sum(y^2) to *sumsq (fp32 device scalar, zeroed by
+ * the caller): SynthesisBlock feeds the upsampled tensor straight into conv1, whose training-mode
+ * EMA normaliser needs mean(x^2) of its input (gans/models/ops/style.py:99-102) -- the statistic
+ * comes out of the producing kernel instead of a second pass over the 4N outputs. */
+int dusty_up2_sumsq(const void *x, void *y, float *sumsq, float k0, float k1, float k2, float k3,
+                    int64_t N, int H, int W, int dtype, void *stream);
+
 /* Fast path of Pad.forward (gans/models/ops/common.py:10-24) for halos up to 4 pixels:
  * x: [N, H, W] -> y: [N, H+pt+pb, W+pl+pr]; mode_y in {REPLICATE, REFLECT}, mode_x in
  * {CIRCULAR, REPLICATE, REFLECT}.  adjoint != 0: y-shaped gradient in, x-shaped out. */

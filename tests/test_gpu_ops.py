@@ -637,6 +637,35 @@ def test_blur_down2_nhwc(DF, ops, dtype, C, H, W):
     close(gg, blur(v)[:, :, ::2, ::2], **tol)
 
 
+@pytest.mark.parametrize("dtype,shape", [(torch.float32, (2, 3, 4, 8)), (torch.bfloat16, (2, 5, 6, 16)),
+                                         (torch.float32, (3, 16, 32, 256)),
+                                         (torch.bfloat16, (4, 64, 32, 256))])
+def test_up2_with_sumsq(DF, ops, dtype, shape):
+    """2x upsampling that also emits sum(y^2) (ModConv2d's EMA statistic, style.py:99-102): same y
+    as the plain kernel bit for bit, statistic against the oracle, same adjoint."""
+    g = torch.Generator().manual_seed(46)
+    x = torch.randn(shape, generator=g)
+    if dtype == torch.bfloat16:
+        x = x.bfloat16().float()
+    up = ops.Resample(up=2).to(DEV)
+    taps = tuple(up.kernel.tolist())
+    ref = O.resample(x, up=2)
+    xd = x.to(DEV, dtype).requires_grad_()
+    y, ss = DF.up2_with_sumsq(xd, taps)
+    assert torch.equal(y, DF.resample4(xd.detach(), taps, 2))
+    assert not ss.requires_grad and tuple(ss.shape) == (1,) and ss.dtype == torch.float32
+    close(ss, ref.double().square().sum().float().reshape(1), rtol=1e-4 if dtype == torch.float32 else 2e-3,
+          atol_rel=0)
+    y2, ss2 = up.forward_with_sumsq(xd.detach())
+    assert torch.equal(y2, y.detach())
+    close(ss2, ss, rtol=1e-5, atol_rel=0)          # float atomics: summation order varies
+    gy = torch.randn(ref.shape, generator=g).to(DEV, dtype)
+    (gx,) = torch.autograd.grad(y, xd, gy)
+    xr = xd.detach().clone().requires_grad_()
+    (gr,) = torch.autograd.grad(DF.resample4(xr, taps, 2), xr, gy)
+    assert torch.equal(gx, gr)
+
+
 @pytest.mark.parametrize("dtype,C,H,W", [(torch.float32, 8, 8, 16), (torch.bfloat16, 32, 6, 20),
                                          (torch.bfloat16, 64, 2, 4), (torch.float32, 4, 64, 512),
                                          (torch.bfloat16, 128, 16, 128)])

@@ -35,6 +35,8 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--precision", default="bf16", choices=["bf16", "fp32"])
     ap.add_argument("--latent-type", default="w+", choices=["w", "w+"])
+    ap.add_argument("--schedule-steps", type=int, default=500,
+                    help="length of the learning-rate schedule (demo default); the bench runs its first steps")
     ap.add_argument("--cpu", action="store_true", help="also time the oracle on the host (batch 2)")
     ap.add_argument("--json", default=os.path.join(ROOT, "gpurun_out", "inversion_bench.json"))
     args = ap.parse_args()
@@ -50,7 +52,8 @@ def main():
     pool = bench.synthetic_batches(n_chunks, args.batch, seed=2, device=dev)
     total = args.steps + args.warmup
     jobs = [LatentInversion(G, coord, b["depth"] * b["mask"], b["mask"], latent_type=args.latent_type,
-                            num_steps_1st=total, num_steps_2nd=0, num_z_samples=10_000)
+                            num_steps_1st=max(total, args.schedule_steps), num_steps_2nd=0,
+                            num_z_samples=10_000)
             for b in pool]
     losses = []
     for s in range(args.warmup):

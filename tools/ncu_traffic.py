@@ -25,7 +25,7 @@ HINTS = [  # bench entry prefix -> substring of the kernel name that carries the
     ("blur+pad_fused", "blur4_cl_kernel"), ("pad_ring1_adjoint_nhwc", "pad2d_cl_adj_kernel"),
     ("pad_ring1_nhwc", "pad2d_cl_fwd_kernel"), ("pad_ring1_adjoint", "pad2d_adj_kernel"),
     ("pad_ring1", "pad2d_fwd_kernel"), ("stem_fwd", "stem_fwd_kernel"), ("stem_bwd", "stem_bwd_kernel"),
-    ("residual_tail_fwd", "bias_act_add_cl_kernel"), ("heads_fwd", "small_o_kernel"),
+    ("residual_fork_bwd", "residual_fork_bwd_cl_kernel"), ("residual_tail_fwd", "bias_act_add_cl_kernel"), ("heads_fwd", "small_o_kernel"),
     ("heads_dw", "heads_dw_bf16_kernel"), ("fourier", "fourier_kernel"),
     ("sumsq", "sumsq_rows_kernel"), ("gumbel_raydrop", "raydrop"), ("point_project", "point_project"),
     ("upfirdn2d_ada", "fir1d"), ("modconv_fwd", "modconv_fwd"), ("modconv_dw", "modconv_dw"),

@@ -34,16 +34,39 @@ def main():
     flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
 
     def timeit(fn, reps=6, inner=4):
+        """Median device time per call in us.  The `inner` calls are captured into a CUDA graph
+        and replayed, so that the host cost of either side's Python / pybind wrapper (20-40 us,
+        more than some of these kernels take) stays out of the number."""
         for _ in range(3):
             fn()
+        torch.cuda.synchronize()
+        graph = None
+        try:
+            side = torch.cuda.Stream()
+            side.wait_stream(torch.cuda.current_stream())
+            with torch.cuda.stream(side):
+                fn()
+                gr = torch.cuda.CUDAGraph()
+                with torch.cuda.graph(gr, stream=side):
+                    for _ in range(inner):
+                        fn()
+            torch.cuda.current_stream().wait_stream(side)
+            torch.cuda.synchronize()
+            graph = gr
+        except Exception as e:          # fall back to eager launches
+            print(f"graph capture failed ({type(e).__name__}); eager timing", file=sys.stderr)
+            torch.cuda.synchronize()
         best = []
         for _ in range(reps):
             flush.zero_()
             torch.cuda.synchronize()
             e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
             e0.record()
-            for _ in range(inner):
-                fn()
+            if graph is not None:
+                graph.replay()
+            else:
+                for _ in range(inner):
+                    fn()
             e1.record()
             torch.cuda.synchronize()
             best.append(e0.elapsed_time(e1) / inner)
@@ -92,7 +115,8 @@ def main():
         row(f"upfirdn2d_{name}[64,1,{hw[0]},{hw[1]}]f32", lambda: ufd.upfirdn2d(x4, kk, *a),
             lambda: upfirdn2d(x, kk, up=up, down=down, pad=pad), (x.numel() + out.numel()) * 4)
     res = {"device": torch.cuda.get_device_name(0), "note": "reference kernels = sm_100 builds of the "
-           "reference's own .cu files (oracle/_ref); median of 6 groups of 4 launches, L2 flushed", "rows": rows}
+           "reference's own .cu files (oracle/_ref); median of 6 graph replays of 4 launches (device time, no host "
+           "wrapper cost), L2 flushed before each replay", "rows": rows}
     os.makedirs(os.path.dirname(args.json), exist_ok=True)
     json.dump(res, open(args.json, "w"), indent=1)
     print(json.dumps(res))

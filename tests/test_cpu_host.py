@@ -156,3 +156,54 @@ def test_c_abi_argument_errors_are_status_codes_not_crashes():
     assert rc != 0 and "shape" in K.last_error()
     with pytest.raises(RuntimeError, match="status"):
         K.call("dusty_pad2d_cl", p, p, 1, 8, 8, 8, 9, 0, 0, 0, K.PAD_REPLICATE, K.PAD_CIRCULAR, 0, K.BF16, None)
+
+
+def test_inversion_host_logic_and_no_cpu_fallback():
+    """gans/inversion.py mirror: the learning-rate schedule is the oracle's (demo_inversion.py:140-146),
+    the losses and the loop refuse CPU tensors, SphericalOptimizer / geocross are plain torch."""
+    from dusty_gan_v2_b200.gans import inversion as inv
+    from oracle import dusty_oracle as O
+    for n in (3, 13, 500):
+        for i in range(0, n, max(1, n // 7)):
+            assert inv.lr_schedule(i, n) == pytest.approx(O.inversion_lr_schedule(i, n), abs=1e-15)
+    assert inv.lr_schedule(0, 500) == 0.0 and inv.lr_schedule(25, 500) == pytest.approx(1.0)
+    x = torch.rand(2, 1, 16, 64) + 0.1
+    with pytest.raises(RuntimeError, match="CUDA"):
+        inv.MultiScaleMaskedLoss(torch.nn.functional.l1_loss, level=2)(x, x, torch.ones_like(x))
+    with pytest.raises(RuntimeError, match="CUDA"):
+        inv.LatentInversion(None, None, x, torch.ones_like(x))
+    with pytest.raises(ValueError):
+        inv.LatentInversion(None, None, x, torch.ones_like(x), latent_type="q")
+    lat = torch.randn(2, 10, 16)
+    assert torch.allclose(inv.geocross_loss(lat), O.geocross_loss(lat))
+    assert torch.equal(inv.tanh_to_sigmoid(torch.tensor([-1.0, 0.0, 1.0])), torch.tensor([0.0, 0.5, 1.0]))
+
+
+def test_reference_extension_recipe():
+    """oracle/build_ref.py: compiles the reference's sources where they lie (no copy in the repo),
+    outputs only under oracle/_ref (git-ignored, not gpurun-ignored), loader returns None when a
+    module is not there."""
+    from oracle import build_ref
+    assert build_ref.load_built("no_such_module") is None
+    for srcs in build_ref.MODULES.values():
+        for f in srcs:
+            assert not os.path.abspath(f).startswith(ROOT + os.sep), f
+    assert build_ref.OUT == os.path.join(ROOT, "oracle", "_ref")
+    ignore = open(os.path.join(ROOT, ".gitignore")).read().split()
+    assert "oracle/_ref/" in ignore
+    gpurunignore = os.path.join(ROOT, ".gpurunignore")
+    if os.path.exists(gpurunignore):
+        assert "oracle/_ref" not in open(gpurunignore).read()
+    # no reference source file was copied into the tree
+    for d, _, files in os.walk(ROOT):
+        if ".git" in d.split(os.sep) or os.sep + "_ref" in d:
+            continue
+        assert not {"fused_bias_act_kernel.cu", "upfirdn2d_kernel.cu"} & set(files), d
+
+
+def test_ncu_window_summary_tool():
+    csv_path = os.path.join(ROOT, "profiles", "r01_ncu_launches_window.csv")
+    out = subprocess.run([sys.executable, os.path.join(ROOT, "tools", "ncu_window_summary.py"), csv_path],
+                         check=True, capture_output=True, text=True).stdout
+    head = out.splitlines()[0]
+    assert "2500 launches" in head and "dusty:: kernels" in head

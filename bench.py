@@ -53,6 +53,9 @@ def parse():
     ap.add_argument("--conv-impl", default="tc", choices=["tc", "auto", "library"],
                     help="D convolutions: own tcgen05 kernels everywhere (default), own-or-cuDNN by "
                          "measured speed, or cuDNN")
+    ap.add_argument("--ref-kernels-only", action="store_true",
+                    help="time the reference's own CUDA kernels (oracle/_ref) beside ours, print JSON, exit")
+    ap.add_argument("--no-ref-kernels", action="store_true")
     ap.add_argument("--ncu-window", action="store_true",
                     help="bracket the timed region with cudaProfilerStart/Stop (ncu --profile-from-start off)")
     return ap.parse_args()
@@ -418,11 +421,147 @@ def kernel_rooflines(device, peaks):
 
 
 # ------------------------------------------------------------------------------ main
+# ------------------------------------------------------- reference's own CUDA kernels (oracle/_ref)
+def reference_kernel_baseline():
+    """Kernel-level reference arm: the REFERENCE'S OWN two CUDA kernels (fused_bias_act_kernel.cu,
+    upfirdn2d_kernel.cu; sm_100 builds made in place from /root/reference by oracle/build_ref.py,
+    shipped as oracle/_ref/*.so) timed beside ours on the same tensors at the training step's
+    shapes.  Device time of CUDA-graph replays (the 20-40 us of host wrapper cost per call on
+    either side would hide kernels of this size), L2 flushed before each replay.  Returns a dict."""
+    import torch
+
+    if not torch.cuda.is_available():
+        return {"unavailable": "no CUDA device"}
+    from oracle import build_ref      # the checker / reference arm; never imported by the package
+    import dusty_gan_v2_b200.functional as DF
+    from dusty_gan_v2_b200.gans.models.ops.upfirdn2d.upfirdn2d import upfirdn2d
+    fused = build_ref.load_built("dusty_ref_fused")
+    ufd = build_ref.load_built("dusty_ref_upfirdn2d")
+    if fused is None or ufd is None:
+        return {"unavailable": "oracle/_ref not built (python oracle/build_ref.py in the build container)"}
+    dev = torch.device("cuda", 0)
+    flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
+
+    def timeit(fn, reps=6, inner=4):
+        """Median device time per call in us.  The `inner` calls are captured into a CUDA graph
+        and replayed, so that the host cost of either side's Python / pybind wrapper (20-40 us,
+        more than some of these kernels take) stays out of the number."""
+        for _ in range(3):
+            fn()
+        torch.cuda.synchronize()
+        graph = None
+        try:
+            side = torch.cuda.Stream()
+            side.wait_stream(torch.cuda.current_stream())
+            with torch.cuda.stream(side):
+                fn()
+                gr = torch.cuda.CUDAGraph()
+                with torch.cuda.graph(gr, stream=side):
+                    for _ in range(inner):
+                        fn()
+            torch.cuda.current_stream().wait_stream(side)
+            torch.cuda.synchronize()
+            graph = gr
+        except Exception as e:          # fall back to eager launches
+            print(f"graph capture failed ({type(e).__name__}); eager timing", file=sys.stderr)
+            torch.cuda.synchronize()
+        best = []
+        for _ in range(reps):
+            flush.zero_()
+            torch.cuda.synchronize()
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            if graph is not None:
+                graph.replay()
+            else:
+                for _ in range(inner):
+                    fn()
+            e1.record()
+            torch.cuda.synchronize()
+            best.append(e0.elapsed_time(e1) / inner)
+        best.sort()
+        return best[len(best) // 2] * 1e3          # us
+
+    rows = []
+
+    def row(name, ref_fn, our_fn, bytes_):
+        r, o = timeit(ref_fn), timeit(our_fn)
+        rows.append({"kernel": name, "reference_us": round(r, 1), "ours_us": round(o, 1),
+                     "speedup": round(r / o, 2), "algorithmic_bytes": bytes_,
+                     "reference_gbs": round(bytes_ / r / 1e3, 1), "ours_gbs": round(bytes_ / o / 1e3, 1)})
+
+    B, H, W = 64, 64, 512
+    for dt_ref, dt_our, tag in ((torch.float32, torch.float32, "f32"), (torch.float16, torch.bfloat16, "f16|bf16")):
+        x = torch.randn(B, 32, H, W, device=dev)
+        b = torch.randn(32, device=dev)
+        xr, br, xo, bo = x.to(dt_ref), b.to(dt_ref), x.to(dt_our), b.to(dt_our)
+        er, eo = xr.new_empty(0), xo.new_empty(0)
+        es = x.element_size() if dt_ref == torch.float32 else 2
+        row(f"bias_act_fwd[64,32,64,512]{tag}", lambda: fused.fused_bias_act(xr, br, er, 3, 0, 0.2, 1.41),
+            lambda: DF.fused_bias_act(xo, bo, eo, 3, 0, 0.2, 1.41), 2 * x.numel() * es)
+        yr = fused.fused_bias_act(xr, br, er, 3, 0, 0.2, 1.41)
+        yo = DF.fused_bias_act(xo, bo, eo, 3, 0, 0.2, 1.41)
+        # the reference's backward = the gradient kernel + a separate ATen reduction for db
+        # (fused_act.py:28-40); ours produces dx and db in one pass
+        row(f"bias_act_bwd+db[64,32,64,512]{tag}",
+            lambda: fused.fused_bias_act(xr, er, yr, 3, 1, 0.2, 1.41).sum((0, 2, 3)),
+            lambda: DF._BiasActBackward.apply(xo, yo, True, 0.2, 1.41), 3 * x.numel() * es)
+        del x, xr, xo, yr, yo
+    # AdaptiveAugment's four separable passes (adaptive_augment.py:497-545), 1-channel fp32
+    k = torch.tensor([0.015404109327027373, 0.0034907120842174702, -0.11799011114819057,
+                      -0.048311742585633, 0.4910559419267466, 0.787641141030194, 0.3379294217276218,
+                      -0.07263752278646252, -0.021060292512300564, 0.04472490177066578,
+                      0.0017677118642428036, -0.007800708325034148], device=dev)
+    for name, hw, ks, up, down, pad in (("ada_up_x", (76, 524), (1, 12), (2, 1), (1, 1), (6, 5, 0, 0)),
+                                        ("ada_up_y", (76, 1048), (12, 1), (1, 2), (1, 1), (0, 0, 6, 5)),
+                                        ("ada_down_x", (140, 1036), (1, 12), (1, 1), (2, 1), (-1, -1, 0, 0)),
+                                        ("ada_down_y", (140, 512), (12, 1), (1, 1), (1, 2), (0, 0, -1, -1))):
+        x = torch.randn(B, 1, hw[0], hw[1], device=dev)
+        kk = k.reshape(ks).contiguous()
+        x4 = x.reshape(B, hw[0], hw[1], 1)
+        a = (up[0], up[1], down[0], down[1], pad[0], pad[1], pad[2], pad[3])
+        out = ufd.upfirdn2d(x4, kk, *a)
+        row(f"upfirdn2d_{name}[64,1,{hw[0]},{hw[1]}]f32", lambda: ufd.upfirdn2d(x4, kk, *a),
+            lambda: upfirdn2d(x, kk, up=up, down=down, pad=pad), (x.numel() + out.numel()) * 4)
+    res = {"device": torch.cuda.get_device_name(0), "note": "reference kernels = sm_100 builds of the "
+           "reference's own .cu files (oracle/_ref); median of 6 graph replays of 4 launches (device time, no host "
+           "wrapper cost), L2 flushed before each replay", "rows": rows}
+    return res
+
+
+def inversion_cpu_baseline(sdG, z0, angle, depth, mask, latent_type, min_depth=1.45, max_depth=80.0):
+    """CPU leg of BASELINE config 5 (tools/inversion_bench.py --cpu): the oracle's restatement of
+    one stage-1 inversion step (objective, backward to the latent, Adam) on the host cores for a
+    bounded sample (the batch handed in); best of two steps."""
+    import torch
+
+    from oracle import dusty_oracle as O
+    t_depth, t_inv = O.inversion_targets(depth, mask, min_depth, max_depth)
+    z = torch.nn.Parameter(z0.clone())
+    opt = torch.optim.Adam([z], lr=5e-2)
+    times = []
+    for _ in range(2):
+        t0 = time.perf_counter()
+        _, loss = O.inversion_forward(sdG, z, angle, t_depth, t_inv, mask, min_depth, max_depth, latent_type)
+        opt.zero_grad(set_to_none=True)
+        loss.backward(gradient=torch.ones_like(loss))
+        opt.step()
+        times.append(time.perf_counter() - t0)
+    n = int(z0.shape[0])
+    return {"target_iterations_per_s": n / min(times), "batch": n, "cores": torch.get_num_threads(),
+            "kind": "port"}
+
+
 def main():
     args = parse()
     rank = int(os.environ.get("RANK", "0"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
+
+    if args.ref_kernels_only:
+        if rank == 0:
+            print(json.dumps(reference_kernel_baseline()))
+        return
 
     if args.impl == "reference":
         if rank != 0:
@@ -573,6 +712,15 @@ def main():
             ips, spt, cores, desc = cpu_reference_run(args, 2, 1, args.cpu_batch)
             line["cpu_baseline"] = {"value": ips, "unit": UNIT, "cores": cores, "kind": "port",
                                     "sample": desc}
+        if not args.no_ref_kernels and not args.no_roofline:
+            # kernel-level reference arm in a child process with a hard time limit: nothing it
+            # does (a failed graph capture, a missing oracle/_ref) can cost the line above
+            try:
+                cp = subprocess.run([sys.executable, os.path.abspath(__file__), "--ref-kernels-only"],
+                                    capture_output=True, text=True, timeout=120, cwd=ROOT)
+                line["ref_kernels"] = json.loads(cp.stdout.strip().splitlines()[-1])
+            except Exception as e:
+                line["ref_kernels"] = {"unavailable": f"{type(e).__name__}: {str(e)[:120]}"}
     if rank == 0:
         print(json.dumps(line))
     if world > 1:

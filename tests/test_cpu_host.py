@@ -207,3 +207,21 @@ def test_ncu_window_summary_tool():
                          check=True, capture_output=True, text=True).stdout
     head = out.splitlines()[0]
     assert "2500 launches" in head and "dusty:: kernels" in head
+
+
+def test_bench_reference_legs_on_cpu(g_gen, g_invloop):
+    """bench.py is the one measurement entry that executes oracle/: its kernel-level reference arm
+    reports `unavailable` without a GPU (never raises into the bench line), the config-5 CPU leg
+    runs the oracle's inversion step."""
+    import bench
+    res = bench.reference_kernel_baseline()
+    assert "unavailable" in res
+    cp = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--ref-kernels-only"],
+                        capture_output=True, text=True, timeout=300, cwd=ROOT)
+    import json
+    assert "unavailable" in json.loads(cp.stdout.strip().splitlines()[-1])
+    sd = {k[3:]: torch.from_numpy(v) for k, v in g_gen.items() if k.startswith("sd_")}
+    T = torch.from_numpy
+    out = bench.inversion_cpu_baseline(sd, T(g_invloop["w+_z0"]), T(g_invloop["angle"]), T(g_invloop["depth"]),
+                                       T(g_invloop["mask"]), "w+")
+    assert out["batch"] == 3 and out["target_iterations_per_s"] > 0 and out["kind"] == "port"

@@ -12,7 +12,6 @@ import argparse
 import json
 import os
 import sys
-import time
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
@@ -84,24 +83,11 @@ def main():
         "last_chunk_point_set_shape": list(pts.shape),
     }
     if args.cpu:
-        from oracle import dusty_oracle as O
         sd = {k: v.detach().float().cpu() for k, v in G.state_dict().items()}
         b = {k: v[:2].cpu() for k, v in pool[0].items()}
-        t_depth, t_inv = O.inversion_targets(b["depth"] * b["mask"], b["mask"], 1.45, 80.0)
-        z = torch.nn.Parameter(jobs[0].z.detach()[:2].float().cpu().clone())
-        opt = torch.optim.Adam([z], lr=5e-2)
-        ang = coord.angle.cpu()
-        times = []
-        for _ in range(2):
-            t0 = time.perf_counter()
-            _, loss = O.inversion_forward(sd, z, ang, t_depth, t_inv, b["mask"], 1.45, 80.0,
-                                          args.latent_type)
-            opt.zero_grad(set_to_none=True)
-            loss.backward(gradient=torch.ones_like(loss))
-            opt.step()
-            times.append(time.perf_counter() - t0)
-        res["cpu_oracle"] = {"target_iterations_per_s": 2 / min(times), "batch": 2,
-                             "cores": torch.get_num_threads(), "kind": "port"}
+        res["cpu_oracle"] = bench.inversion_cpu_baseline(sd, jobs[0].z.detach()[:2].float().cpu(),
+                                                         coord.angle.cpu(), b["depth"] * b["mask"], b["mask"],
+                                                         args.latent_type)
     os.makedirs(os.path.dirname(args.json), exist_ok=True)
     json.dump(res, open(args.json, "w"), indent=1)
     print(json.dumps(res))

@@ -1,0 +1,133 @@
+"""Live cross-checks of the oracle against the UNMODIFIED reference imported from /root/reference
+(CPU tensors), on fresh random inputs and random module configurations -- beyond the committed
+golden fixtures.  Runs only in the build container: skipped where the reference tree is absent
+(the GPU box) or where its `fused` extension has not been built yet (importing the reference's
+ops compiles it; tests/golden/make_golden.py does that once)."""
+import os
+
+import numpy as np
+import pytest
+import torch
+
+from oracle import dusty_oracle as O
+from oracle import ref_import
+
+_EXT = os.path.join(os.environ.get("TORCH_EXTENSIONS_DIR", "/tmp/torch_ext"), "fused", "fused.so")
+pytestmark = pytest.mark.skipif(
+    not (ref_import.available() and os.path.exists(_EXT)),
+    reason="needs /root/reference and its prebuilt `fused` extension (build container only)")
+
+
+@pytest.fixture(scope="module")
+def rops():
+    ref_import.install()
+    from gans.models import ops
+    return ops
+
+
+def close(a, b, rtol=1e-5, atol=1e-6):
+    np.testing.assert_allclose(a.detach().numpy(), b.detach().numpy(), rtol=rtol, atol=atol)
+
+
+@pytest.mark.parametrize("seed", range(4))
+def test_resample_family_random(rops, seed):
+    g = torch.Generator().manual_seed(100 + seed)
+    C, H, W = int(torch.randint(1, 5, (1,), generator=g)), 2 * int(torch.randint(2, 9, (1,), generator=g)), \
+        4 * int(torch.randint(2, 9, (1,), generator=g))
+    x = torch.randn(2, C, H, W, generator=g)
+    for kw in (dict(up=2), dict(down=2), dict(), dict(window=[1, 2, 1]), dict(window=[1, 2, 1], direction="h"),
+               dict(window=[1, 2, 1], direction="w")):
+        ref = rops.Resample(**kw)(x)
+        got = O.resample(x, up=kw.get("up", 1), down=kw.get("down", 1), window=kw.get("window", (1, 3, 3, 1)),
+                         direction=kw.get("direction", "hw"))
+        assert got.shape == ref.shape, kw
+        close(got, ref, rtol=1e-5, atol=1e-6)
+    close(O.blur_vh(x[:, :1]), rops.BlurVH()(x[:, :1]))
+    for pad, ring, mode in ((1, True, "replicate"), (2, True, "reflect"), ((1, 2, 0, 1), False, "replicate")):
+        close(O.pad2d(x, pad, ring=ring, mode=mode), rops.Pad(pad, ring=ring, mode=mode)(x), rtol=0, atol=0)
+
+
+@pytest.mark.parametrize("seed", range(4))
+def test_fused_leaky_relu_and_modconv_random(rops, seed):
+    g = torch.Generator().manual_seed(200 + seed)
+    C = int(torch.randint(2, 9, (1,), generator=g))
+    x = torch.randn(3, C, 4, 8, generator=g, requires_grad=True)
+    b = torch.randn(C, generator=g)
+    act = rops.FusedLeakyReLU(C)
+    with torch.no_grad():
+        act.bias.copy_(b)
+    ref = act(x)
+    close(O.bias_act(x, b), ref)
+    (gr,) = torch.autograd.grad(ref.square().sum(), x)
+    (go,) = torch.autograd.grad(O.bias_act(x, b).square().sum(), x)
+    close(go, gr)
+    # modulated 1x1 convolution, eval and training (EMA side effect)
+    O_ch, M = int(torch.randint(1, 7, (1,), generator=g)), 8
+    torch.manual_seed(300 + seed)
+    for demod, bias, ema in ((True, False, True), (False, True, True), (True, False, False)):
+        m = rops.ModConv2d(in_ch=C, out_ch=O_ch, mod_ch=M, ksize=1, stride=1, padding=0, demod=demod,
+                           bias=bias, ema=ema)
+        with torch.no_grad():
+            m.ema_var.fill_(0.7)
+            if bias:
+                m.bias.normal_()
+        style = torch.randn(3, M, generator=g)
+        xin = torch.randn(3, C, 4, 8, generator=g)
+        ev = m.ema_var.clone() if ema else torch.tensor(1.0)
+        m.eval()
+        ref = m(xin, style)
+        got, _ = O.modconv(xin, style, m.weight, m.mod.module.weight, m.mod.module.bias, ev, demod=demod,
+                           bias=m.bias if bias else None)
+        close(got, ref, rtol=1e-4, atol=1e-5)
+        if ema:                     # training mode: the EMA is updated before it is used
+            m.train()
+            ref_t = m(xin, style)
+            got_t, new_ev = O.modconv(xin, style, m.weight, m.mod.module.weight, m.mod.module.bias, ev,
+                                      demod=demod, bias=m.bias if bias else None, training=True,
+                                      ema_decay=m.ema_decay)
+            close(got_t, ref_t, rtol=1e-4, atol=1e-5)
+            close(new_ev, m.ema_var, rtol=1e-6, atol=0)
+
+
+@pytest.mark.parametrize("seed", range(2))
+def test_small_generator_eval_random_weights(rops, seed):
+    """A freshly initialised small dusty_v2 generator (new seed, new Fourier basis) in eval mode
+    against the oracle driven by its state_dict."""
+    from gans.models.builder import build_generator
+    from small_cfgs import G_SMALL
+    torch.manual_seed(400 + seed)
+    np.random.seed(400 + seed)
+    G = build_generator(ref_import.to_attr(G_SMALL)).eval()
+    sd = {k: v.clone() for k, v in G.state_dict().items()}
+    B = 2
+    z = torch.randn(B, 16)
+    el = torch.linspace(0.05, -0.41, 16)[:, None].expand(16, 64)
+    az = -((torch.arange(64) + 0.5) / 64 * 2 * np.pi - np.pi)[None].expand(16, 64)
+    angle = torch.stack([el, az], 0)[None].repeat(B, 1, 1, 1).contiguous()
+    torch.manual_seed(500 + seed)
+    with torch.no_grad():
+        ref = G(z, angle=angle)
+    torch.manual_seed(500 + seed)
+    u = torch.rand(B, 1, 16, 64)
+    with torch.no_grad():
+        got = O.generator(sd, z, angle, u)
+    for k in ("image_orig", "raydrop_logit", "image"):
+        close(got[k], ref[k], rtol=1e-4, atol=1e-5)
+    assert torch.equal(got["raydrop_mask"], ref["raydrop_mask"])
+    assert int(got["raydrop_mask"].sum()) == int(ref["raydrop_mask"].sum())
+
+
+def test_inversion_losses_random(rops):
+    from gans import inversion as rinv
+    import torch.nn.functional as F
+    g = torch.Generator().manual_seed(600)
+    for H, W, level in ((8, 32, None), (16, 64, 2), (32, 32, 3)):
+        gen = (torch.rand(2, 1, H, W, generator=g) * 0.8 + 0.1).requires_grad_()
+        ref = torch.rand(2, 1, H, W, generator=g) * 0.8 + 0.1
+        mask = (torch.rand(2, 1, H, W, generator=g) < 0.6).float()
+        for loss_fn, name, rel in ((F.l1_loss, "l1", True), (F.mse_loss, "l2", False)):
+            r = rinv.MultiScaleMaskedLoss(loss_fn, level=level, relative=rel)(gen, ref, mask)
+            o = O.multiscale_masked_loss(gen, ref, mask, level=level, loss=name, relative=rel)
+            close(o, r, rtol=1e-5, atol=1e-6)
+    lat = torch.randn(3, 10, 16, generator=g)
+    close(O.geocross_loss(lat), rinv.geocross_loss(lat), rtol=1e-5, atol=1e-7)

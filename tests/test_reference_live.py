@@ -131,3 +131,52 @@ def test_inversion_losses_random(rops):
             close(o, r, rtol=1e-5, atol=1e-6)
     lat = torch.randn(3, 10, 16, generator=g)
     close(O.geocross_loss(lat), rinv.geocross_loss(lat), rtol=1e-5, atol=1e-7)
+
+
+@pytest.mark.parametrize("seed", range(2))
+def test_small_discriminator_and_r1_random_weights(rops, seed):
+    from gans.models.builder import build_discriminator
+    from gans.models.loss import GANLoss
+    from small_cfgs import D_SMALL
+    torch.manual_seed(700 + seed)
+    D = build_discriminator(ref_import.to_attr(D_SMALL))
+    with torch.no_grad():
+        for n, p in D.named_parameters():
+            if "bias" in n:
+                p.normal_(0, 0.3)
+    sd = {k: v.clone() for k, v in D.state_dict().items()}
+    x = torch.tanh(torch.randn(4, 1, 16, 64)).requires_grad_()
+    y_ref = D(x)
+    xo = x.detach().clone().requires_grad_()
+    y_got = O.discriminator(sd, xo)
+    close(y_got, y_ref, rtol=1e-4, atol=1e-5)
+    # R1 penalty (trainer.py:426-447) and the non-saturating losses (loss.py:39-41,68-69)
+    (g_ref,) = torch.autograd.grad(y_ref.sum(), x, create_graph=True)
+    (g_got,) = torch.autograd.grad(y_got.sum(), xo, create_graph=True)
+    r1_ref = g_ref.pow(2).sum(dim=[1, 2, 3]).mean()
+    close(O.r1_penalty(g_got), r1_ref, rtol=1e-4, atol=1e-7)
+    crit = GANLoss("nsgan")
+    y_fake = torch.randn(4, 1)
+    close(O.nsgan_g(y_fake), crit(None, y_fake, "G"), rtol=1e-6, atol=1e-7)
+    close(O.nsgan_d(y_ref.detach(), y_fake), crit(y_ref.detach(), y_fake, "D"), rtol=1e-6, atol=1e-7)
+
+
+def test_coord_bridge_random(rops):
+    from gans.coords import CoordBridge
+    angle_file = os.path.join(ref_import.REFERENCE_ROOT, "data/coords/kitti_raw.npy")
+    for H, W in ((16, 64), (64, 512)):
+        cb = CoordBridge(H, W, 1.45, 80.0, angle_file)
+        assert torch.equal(O.angle_grid(np.load(angle_file), H, W), cb.angle)
+        g = torch.Generator().manual_seed(800 + H)
+        depth = 80.0 * torch.rand(2, 1, H, W, generator=g) ** 2
+        x = cb.convert(depth.clone(), "depth", "inv_depth_norm")
+        close(O.depth_to_inv_depth_norm(depth, 1.45, 80.0), x, rtol=0, atol=0)
+        pm = cb.convert(x.clone(), "inv_depth_norm", "point_map")
+        ps = cb.convert(x.clone(), "inv_depth_norm", "point_set")
+        opm, ops_, cnt = O.inv_depth_norm_to_points(x.clone(), cb.angle, 1.45, 80.0)
+        close(opm, pm, rtol=0, atol=0)
+        close(ops_, ps, rtol=0, atol=0)
+        valid = (x > 1e-11).float() * cb.get_mask(x / 1.45, "inv_depth").float()
+        assert cnt == int(valid.sum().item())
+        close(O.inv_depth_norm_to_depth_norm(x.clone(), 1.45, 80.0), cb.convert(x.clone(), "inv_depth_norm", "depth_norm"),
+              rtol=0, atol=0)

@@ -8,7 +8,7 @@ Layout:
   gans/...                   host-side mirror of the reference modules: same names, ctor
                              arguments, state_dict keys (gans.models.ops, gans.models.*,
                              gans.coords.CoordBridge, gans.augment.adaptive_augment,
-                             gans.trainer)
+                             gans.trainer, gans.inversion, gans.utils)
 
 There is no CPU or pure-PyTorch fallback: ops raise on CPU tensors and the package fails
 loudly when the shared library is missing.
@@ -28,7 +28,7 @@ _MIRRORED = [
     "gans.models.ops.gumbel", "gans.models.ops.fused_act", "gans.models.ops.fused_act.fused_act",
     "gans.models.ops.upfirdn2d", "gans.models.ops.upfirdn2d.upfirdn2d", "gans.models.base",
     "gans.models.dusty_v1", "gans.models.dusty_v2", "gans.models.vanilla", "gans.models.builder",
-    "gans.models.loss", "gans.augment", "gans.augment.adaptive_augment", "gans.inversion",
+    "gans.models.loss", "gans.augment", "gans.augment.adaptive_augment", "gans.inversion", "gans.utils",
 ]
 
 

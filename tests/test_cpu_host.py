@@ -225,3 +225,27 @@ def test_bench_reference_legs_on_cpu(g_gen, g_invloop):
     out = bench.inversion_cpu_baseline(sd, T(g_invloop["w+_z0"]), T(g_invloop["angle"]), T(g_invloop["depth"]),
                                        T(g_invloop["mask"]), "w+")
     assert out["batch"] == 3 and out["target_iterations_per_s"] > 0 and out["kind"] == "port"
+
+
+def test_utils_mirror_host_helpers():
+    """gans/utils.py mirror: the sampler's stream is reproducible and rank-disjoint, the
+    visualisation helpers refuse, and the module is registered by install_as_gans."""
+    import dusty_gan_v2_b200 as pkg
+    from dusty_gan_v2_b200.gans import utils as U
+    assert "gans.utils" in pkg._MIRRORED and "gans.inversion" in pkg._MIRRORED
+    data = list(range(10))
+    streams = []
+    for rank in range(2):
+        it = iter(U.InfiniteSampler(data, rank=rank, num_replicas=2, seed=4))
+        streams.append([int(next(it)) for _ in range(40)])
+    it = iter(U.InfiniteSampler(data, rank=0, num_replicas=2, seed=4))
+    assert streams[0] == [int(next(it)) for _ in range(40)]
+    assert streams[0] != streams[1]
+    it = iter(U.InfiniteSampler(data, shuffle=False))
+    assert [int(next(it)) for _ in range(12)] == list(range(10)) + [0, 1]
+    with pytest.raises(NotImplementedError):
+        U.colorize(torch.zeros(1))
+    lin = torch.nn.Linear(2, 2)
+    U.set_requires_grad(lin, False)
+    assert not any(p.requires_grad for p in lin.parameters())
+    assert torch.equal(U.sigmoid_to_tanh(U.tanh_to_sigmoid(torch.tensor([-1.0, 0.25]))), torch.tensor([-1.0, 0.25]))

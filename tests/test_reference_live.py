@@ -180,3 +180,36 @@ def test_coord_bridge_random(rops):
         assert cnt == int(valid.sum().item())
         close(O.inv_depth_norm_to_depth_norm(x.clone(), 1.45, 80.0), cb.convert(x.clone(), "inv_depth_norm", "depth_norm"),
               rtol=0, atol=0)
+
+
+def test_utils_sampler_and_seeding_match_reference(rops):
+    """gans/utils.py host helpers: the infinite windowed-shuffle sampler yields the reference's
+    index stream for every (seed, rank, replicas, window); init_random_seed leaves every RNG in the
+    same state."""
+    import random
+    import gans.utils as rutils
+    from dusty_gan_v2_b200.gans import utils as mine
+    data = list(range(37))
+    for seed, rank, reps, win, shuffle in ((0, 0, 1, 0.5, True), (3, 1, 4, 0.5, True), (7, 2, 3, 0.1, True),
+                                           (1, 0, 2, 0.0, True), (5, 1, 2, 0.5, False)):
+        # the reference's constructor calls Sampler.__init__(dataset), which torch 2.11 rejects:
+        # fill the attributes it would set and run the reference's own __iter__
+        ref_s = object.__new__(rutils.InfiniteSampler)
+        ref_s.__dict__.update(dataset=data, rank=rank, num_replicas=reps, shuffle=shuffle, seed=seed,
+                              window_size=win)
+        a = iter(ref_s)
+        b = iter(mine.InfiniteSampler(data, rank=rank, num_replicas=reps, shuffle=shuffle, seed=seed,
+                                      window_size=win))
+        assert [int(next(a)) for _ in range(150)] == [int(next(b)) for _ in range(150)]
+    draws = []
+    for mod in (rutils, mine):
+        mod.init_random_seed(11, rank=2)
+        draws.append((random.random(), float(np.random.rand()), float(torch.rand(1))))
+    assert draws[0] == draws[1]
+    x = torch.linspace(-1, 1, 9)
+    assert torch.equal(mine.tanh_to_sigmoid(x), rutils.tanh_to_sigmoid(x))
+    assert torch.equal(mine.sigmoid_to_tanh(x), rutils.sigmoid_to_tanh(x))
+    g = torch.Generator().manual_seed(1)
+    a, b, m = torch.rand(2, 1, 4, 4, generator=g), torch.rand(2, 1, 4, 4, generator=g), torch.ones(2, 1, 4, 4)
+    for d in ("l1", "l2"):
+        assert torch.allclose(mine.masked_loss(a, b, m, d), rutils.masked_loss(a, b, m, d))

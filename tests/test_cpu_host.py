@@ -249,3 +249,26 @@ def test_utils_mirror_host_helpers():
     U.set_requires_grad(lin, False)
     assert not any(p.requires_grad for p in lin.parameters())
     assert torch.equal(U.sigmoid_to_tanh(U.tanh_to_sigmoid(torch.tensor([-1.0, 0.25]))), torch.tensor([-1.0, 0.25]))
+
+
+def test_install_as_gans_resolves_reference_import_lines():
+    """after install_as_gans() the reference's own import lines
+    (trainer.py:13-27, demo_inversion.py:11-28) resolve to the mirror."""
+    code = "\n".join([
+        "import sys; sys.path.insert(0, %r)" % ROOT,
+        "import dusty_gan_v2_b200 as b200; b200.install_as_gans()",
+        "import gans.models.ops as ops",
+        "from gans.coords import CoordBridge",
+        "from gans.augment.adaptive_augment import AdaptiveAugment",
+        "from gans.inversion import MultiScaleMaskedLoss, SphericalOptimizer, geocross_loss, normalize_noise_",
+        "from gans.models.builder import build_discriminator, build_generator",
+        "from gans.models.loss import GANLoss",
+        "from gans.models.ops.common import filter2d",
+        "from gans.utils import InfiniteSampler, set_requires_grad, sigmoid_to_tanh, tanh_to_sigmoid, "
+        "init_random_seed, cycle",
+        "from gans.models.ops.upfirdn2d.upfirdn2d import upfirdn2d",
+        "from gans.models.ops.fused_act.fused_act import FusedLeakyReLU, fused_leaky_relu",
+        "assert ops.ModConv2d.__module__.startswith('dusty_gan_v2_b200')",
+        "assert CoordBridge.__module__.startswith('dusty_gan_v2_b200')",
+    ])
+    subprocess.run([sys.executable, "-c", code], check=True, timeout=300)

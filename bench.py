@@ -193,14 +193,25 @@ def cpu_reference_run(args, steps, warmup, batch):
 
     for i in range(warmup):
         one(i + 1)
-    t0 = time.perf_counter()
+    per_it = []
     for i in range(steps):
+        t0 = time.perf_counter()
         one(i)
-    dt = time.perf_counter() - t0
+        per_it.append((i % 16 == 0, time.perf_counter() - t0))
+    r1 = [t for is_r1, t in per_it if is_r1]
+    plain = [t for is_r1, t in per_it if not is_r1]
+    if steps % 16 == 0 or not r1 or not plain:
+        spt = sum(t for _, t in per_it) / steps          # the sample already holds R1 at its 1/16 share
+        mix = f"{steps} steps"
+    else:
+        # short sample: iteration 0 carries the lazy R1 pass; weight it as the training loop does
+        spt = (15 * sum(plain) / len(plain) + sum(r1) / len(r1)) / 16
+        mix = (f"{len(plain)} plain + {len(r1)} R1 iteration(s) timed, combined at the training loop's "
+               f"15:1 ratio ({sum(plain) / len(plain):.2f} s / {sum(r1) / len(r1):.2f} s)")
     desc = (f"oracle port of Trainer.step (G step + D step + R1 on every 16th step, ADA p="
-            f"{args.ada_p or 0.0}, warm-up dropout 0.5), fp32, batch {batch}, {steps} steps, "
+            f"{args.ada_p or 0.0}, warm-up dropout 0.5), fp32, batch {batch}, {mix}, "
             f"Adam updates included (all three phases use the pre-step weights)")
-    return steps * batch / dt, dt / steps, cores, desc
+    return batch / spt, spt, cores, desc
 
 
 # ------------------------------------------------------------------------------ kernel roofline
@@ -527,6 +538,25 @@ def reference_kernel_baseline():
            "reference's own .cu files (oracle/_ref); median of 6 graph replays of 4 launches (device time, no host "
            "wrapper cost), L2 flushed before each replay", "rows": rows}
     return res
+
+
+def generator_forward_cpu_baseline(sdG, z, angle, batch, reps=3):
+    """CPU leg of BASELINE config 1 (tools/config1_bench.py --cpu): the oracle's generator forward
+    (eval, psi = 1) on the host cores, best of `reps` after one warm-up."""
+    import torch
+
+    from oracle import dusty_oracle as O
+    ang = angle.expand(batch, -1, -1, -1) if angle.shape[0] != batch else angle
+    u = torch.rand(batch, 1, ang.shape[-2], ang.shape[-1], generator=torch.Generator().manual_seed(3))
+    times = []
+    with torch.no_grad():
+        for _ in range(reps + 1):
+            t0 = time.perf_counter()
+            O.generator(sdG, z, ang, u)
+            times.append(time.perf_counter() - t0)
+    best = min(times[1:])
+    return {"images_per_s": batch / best, "ms_per_forward": best * 1e3, "batch": batch,
+            "cores": torch.get_num_threads(), "kind": "port"}
 
 
 def inversion_cpu_baseline(sdG, z0, angle, depth, mask, latent_type, min_depth=1.45, max_depth=80.0):

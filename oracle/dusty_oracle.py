@@ -119,9 +119,40 @@ def _fir_axis(x: Tensor, taps: Tensor, up: int, down: int, p0: int, p1: int,
               axis: int, circular: bool) -> Tensor:
     """One separable pass: out[m] = sum_t taps[t] * xu[m*down + t - p0], where
     xu[q] = X(q/up) if up | q else 0 and X() extends x circularly (ring, W axis)
-    or by edge replication (H axis).  This is the closed form of
-    margin-pad -> zero-insert -> crop -> depthwise correlate -> stride
-    (common.py:105-135)."""
+    or by edge replication (H axis) -- the closed form of margin-pad -> zero-insert ->
+    crop -> depthwise correlate -> stride (common.py:105-135).
+
+    Evaluated the way the reference's CPU path spends its time (a depthwise library
+    correlation over the extended, zero-stuffed signal), so that the oracle is a fair CPU
+    baseline too; `_fir_axis_gather` below is the literal tap-by-tap form, kept as the
+    cross-check (tests/test_oracle_golden.py::test_fir_axis_forms_agree)."""
+    if x.ndim != 4:
+        return _fir_axis_gather(x, taps, up, down, p0, p1, axis, circular)
+    n = x.shape[axis]
+    k = taps.numel()
+    n_out = (n * up + p0 + p1 - k) // down + 1
+    # source samples q = -p0 .. (n_out-1)*down + k-1 - p0 of the zero-stuffed, extended signal
+    q_lo, q_hi = -p0, (n_out - 1) * down + k - 1 - p0
+    i_lo, i_hi = -((-q_lo) // up) if q_lo < 0 else (q_lo + up - 1) // up, q_hi // up   # ceil / floor
+    idx = _boundary_index(torch.arange(i_lo, i_hi + 1), n, circular)
+    ext = x.index_select(axis, idx) if (i_lo < 0 or i_hi >= n) else x.narrow(axis, i_lo, i_hi - i_lo + 1)
+    if up > 1:
+        shape = list(ext.shape)
+        shape[axis] = q_hi - q_lo + 1
+        stuffed = x.new_zeros(shape)
+        first = i_lo * up - q_lo                       # position of sample i_lo inside [q_lo, q_hi]
+        stuffed.narrow(axis, first, (i_hi - i_lo) * up + 1).index_copy_(
+            axis, torch.arange(0, (i_hi - i_lo) * up + 1, up), ext)
+        ext = stuffed
+    C = x.shape[1]
+    w = taps.to(x.dtype).reshape((1, 1, k, 1) if axis == 2 else (1, 1, 1, k)).repeat(C, 1, 1, 1)
+    stride = (down, 1) if axis == 2 else (1, down)
+    return F.conv2d(ext, w, stride=stride, groups=C)
+
+
+def _fir_axis_gather(x: Tensor, taps: Tensor, up: int, down: int, p0: int, p1: int,
+                     axis: int, circular: bool) -> Tensor:
+    """The literal form of `_fir_axis`: one gathered, weighted term per tap."""
     n = x.shape[axis]
     k = taps.numel()
     n_out = (n * up + p0 + p1 - k) // down + 1

@@ -299,3 +299,21 @@ def test_inversion_loop_against_reference(g_gen, g_invloop, latent_type):
         close(z.grad, ref_g, rtol=2e-3, atol=2e-4 * np.abs(ref_g).max())
         opt.step()
         close(z, g[f"{latent_type}_z{step + 1}"], rtol=1e-3, atol=2e-3)
+
+
+def test_fir_axis_forms_agree():
+    """The oracle's library-correlation FIR against its literal tap-by-tap form over the whole
+    Resample family (up / down / blur, both axes, ring and replicate boundaries)."""
+    g = torch.Generator().manual_seed(5)
+    for up, down, win, ring in ((2, 1, (1, 3, 3, 1), True), (1, 2, (1, 3, 3, 1), True), (1, 1, (1, 3, 3, 1), True),
+                                (1, 1, (1, 2, 1), True), (2, 1, (1, 3, 3, 1), False), (2, 1, (1, 2, 1), True)):
+        taps = torch.tensor(win, dtype=torch.float32)
+        taps = taps / taps.sum()
+        p0, p1 = O.resample_geometry(len(win), up, down)
+        for H, W in ((4, 8), (6, 20), (16, 64)):
+            x = torch.randn(2, 3, H, W, generator=g)
+            for axis, circ in ((3, ring), (2, False)):
+                a = O._fir_axis(x, taps, up, down, p0, p1, axis, circ)
+                b = O._fir_axis_gather(x, taps, up, down, p0, p1, axis, circ)
+                assert a.shape == b.shape
+                close(a, b, rtol=1e-5, atol=1e-6)

@@ -133,6 +133,12 @@ def cycle(pool):
 def cpu_reference_run(args, steps, warmup, batch):
     """Times the oracle's restatement of Trainer.step on the host cores.  Returns
     (images_per_s, seconds_per_step, cores, description)."""
+    from oracle import dusty_oracle as O
+    with O.fir_impl("library"):      # the reference's CPU path runs its FIRs as depthwise convolutions
+        return _cpu_reference_run(args, steps, warmup, batch)
+
+
+def _cpu_reference_run(args, steps, warmup, batch):
     import numpy as np
     import torch
 
@@ -549,7 +555,7 @@ def generator_forward_cpu_baseline(sdG, z, angle, batch, reps=3):
     ang = angle.expand(batch, -1, -1, -1) if angle.shape[0] != batch else angle
     u = torch.rand(batch, 1, ang.shape[-2], ang.shape[-1], generator=torch.Generator().manual_seed(3))
     times = []
-    with torch.no_grad():
+    with torch.no_grad(), O.fir_impl("library"):
         for _ in range(reps + 1):
             t0 = time.perf_counter()
             O.generator(sdG, z, ang, u)
@@ -572,9 +578,11 @@ def inversion_cpu_baseline(sdG, z0, angle, depth, mask, latent_type, min_depth=1
     times = []
     for _ in range(2):
         t0 = time.perf_counter()
-        _, loss = O.inversion_forward(sdG, z, angle, t_depth, t_inv, mask, min_depth, max_depth, latent_type)
-        opt.zero_grad(set_to_none=True)
-        loss.backward(gradient=torch.ones_like(loss))
+        with O.fir_impl("library"):
+            _, loss = O.inversion_forward(sdG, z, angle, t_depth, t_inv, mask, min_depth, max_depth,
+                                          latent_type)
+            opt.zero_grad(set_to_none=True)
+            loss.backward(gradient=torch.ones_like(loss))
         opt.step()
         times.append(time.perf_counter() - t0)
     n = int(z0.shape[0])

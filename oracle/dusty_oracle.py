@@ -115,6 +115,38 @@ def _boundary_index(idx: Tensor, n: int, circular: bool) -> Tensor:
     return torch.remainder(idx, n) if circular else idx.clamp(0, n - 1)
 
 
+# Two evaluations of the same separable pass.  "gather" (default: what every parity test and
+# smoke() check against) is the literal tap-by-tap form; "library" runs it as a depthwise
+# library correlation over the extended, zero-stuffed signal -- the way the reference's CPU path
+# spends its time -- and is what bench.py's CPU baseline legs select, so that the port is a fair
+# stand-in for the reference's speed (tests/golden/calibrate_cpu_port.py).  The two agree to
+# 1-2 ulp (tests/test_oracle_golden.py::test_fir_axis_forms_agree runs the goldens under both).
+_FIR_IMPL = {"mode": "gather"}
+
+
+def set_fir_impl(mode: str) -> str:
+    """Select the FIR evaluation ("gather" | "library"); returns the previous mode."""
+    if mode not in ("gather", "library"):
+        raise ValueError(mode)
+    prev, _FIR_IMPL["mode"] = _FIR_IMPL["mode"], mode
+    return prev
+
+
+class fir_impl:
+    """`with fir_impl("library"): ...` -- scoped `set_fir_impl`."""
+
+    def __init__(self, mode: str):
+        self.mode = mode
+
+    def __enter__(self):
+        self.prev = set_fir_impl(self.mode)
+        return self
+
+    def __exit__(self, *exc):
+        set_fir_impl(self.prev)
+        return False
+
+
 def _fir_axis(x: Tensor, taps: Tensor, up: int, down: int, p0: int, p1: int,
               axis: int, circular: bool) -> Tensor:
     """One separable pass: out[m] = sum_t taps[t] * xu[m*down + t - p0], where
@@ -122,11 +154,9 @@ def _fir_axis(x: Tensor, taps: Tensor, up: int, down: int, p0: int, p1: int,
     or by edge replication (H axis) -- the closed form of margin-pad -> zero-insert ->
     crop -> depthwise correlate -> stride (common.py:105-135).
 
-    Evaluated the way the reference's CPU path spends its time (a depthwise library
-    correlation over the extended, zero-stuffed signal), so that the oracle is a fair CPU
-    baseline too; `_fir_axis_gather` below is the literal tap-by-tap form, kept as the
-    cross-check (tests/test_oracle_golden.py::test_fir_axis_forms_agree)."""
-    if x.ndim != 4:
+    Dispatches on `set_fir_impl`: the literal form (`_fir_axis_gather`) or the depthwise
+    library correlation below."""
+    if x.ndim != 4 or _FIR_IMPL["mode"] != "library":
         return _fir_axis_gather(x, taps, up, down, p0, p1, axis, circular)
     n = x.shape[axis]
     k = taps.numel()

@@ -37,6 +37,7 @@ def best(fn, reps=3):
 
 
 def main():
+    O.set_fir_impl("library")          # what bench.py's CPU legs run
     torch.manual_seed(0)
     np.random.seed(0)
     cfg = preset("dusty_v2").model

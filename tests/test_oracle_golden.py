@@ -301,9 +301,19 @@ def test_inversion_loop_against_reference(g_gen, g_invloop, latent_type):
         close(z, g[f"{latent_type}_z{step + 1}"], rtol=1e-3, atol=2e-3)
 
 
-def test_fir_axis_forms_agree():
-    """The oracle's library-correlation FIR against its literal tap-by-tap form over the whole
-    Resample family (up / down / blur, both axes, ring and replicate boundaries)."""
+def test_fir_axis_forms_agree(g_ops, g_gen):
+    """The oracle's library-correlation FIR (what bench.py's CPU baseline legs run) against its
+    literal tap-by-tap form (what the parity tests check against) over the whole Resample family
+    (up / down / blur, both axes, ring and replicate boundaries), and the golden checks that
+    lean on the FIR re-run under the library form."""
+    prev = O.set_fir_impl("library")
+    try:
+        assert O._FIR_IMPL["mode"] == "library"
+        test_resample_family(g_ops)
+        test_generator_eval(g_gen)
+    finally:
+        O.set_fir_impl(prev)
+    assert O._FIR_IMPL["mode"] == "gather"
     g = torch.Generator().manual_seed(5)
     for up, down, win, ring in ((2, 1, (1, 3, 3, 1), True), (1, 2, (1, 3, 3, 1), True), (1, 1, (1, 3, 3, 1), True),
                                 (1, 1, (1, 2, 1), True), (2, 1, (1, 3, 3, 1), False), (2, 1, (1, 2, 1), True)):
@@ -313,7 +323,9 @@ def test_fir_axis_forms_agree():
         for H, W in ((4, 8), (6, 20), (16, 64)):
             x = torch.randn(2, 3, H, W, generator=g)
             for axis, circ in ((3, ring), (2, False)):
+                O.set_fir_impl("library")
                 a = O._fir_axis(x, taps, up, down, p0, p1, axis, circ)
+                O.set_fir_impl("gather")
                 b = O._fir_axis_gather(x, taps, up, down, p0, p1, axis, circ)
                 assert a.shape == b.shape
                 close(a, b, rtol=1e-5, atol=1e-6)

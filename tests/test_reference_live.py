@@ -213,3 +213,39 @@ def test_utils_sampler_and_seeding_match_reference(rops):
     a, b, m = torch.rand(2, 1, 4, 4, generator=g), torch.rand(2, 1, 4, 4, generator=g), torch.ones(2, 1, 4, 4)
     for d in ("l1", "l2"):
         assert torch.allclose(mine.masked_loss(a, b, m, d), rutils.masked_loss(a, b, m, d))
+
+
+_EXT_UFD = os.path.join(os.environ.get("TORCH_EXTENSIONS_DIR", "/tmp/torch_ext"), "upfirdn2d", "upfirdn2d.so")
+
+
+@pytest.mark.skipif(not os.path.exists(_EXT_UFD), reason="reference `upfirdn2d` extension not prebuilt")
+@pytest.mark.parametrize("seed,hw", [(0, (16, 64)), (1, (16, 64)), (2, (32, 128))])
+def test_ada_pipeline_random_transforms(rops, seed, hw):
+    """AdaptiveAugment.forward (adaptive_augment.py:471-545) with freshly sampled affine / colour
+    transforms pinned on both sides: value, gradient, and the gradient of a gradient-norm penalty
+    (the path the R1 step takes through ADA), oracle vs the live reference."""
+    from gans.augment import adaptive_augment as ra
+    torch.manual_seed(900 + seed)
+    np.random.seed(900 + seed)
+    ada = ra.AdaptiveAugment(p_init=0.8, lr_flip=1, ud_flip=1, int_trans=1, iso_scale=1, frac_trans=1,
+                             brightness=1, contrast=1, luma_flip=1, hue=1, saturation=1)
+    B, (H, W) = 3, hw
+    G = ada.sample_affine(B, H, W)
+    C = ada.sample_color(B)
+    ada.sample_affine = lambda *a, **k: G.clone()
+    ada.sample_color = lambda *a, **k: C.clone()
+    x = torch.tanh(torch.randn(B, 1, H, W))
+    xr = x.clone().requires_grad_()
+    yr = ada(xr)
+    xo = x.clone().requires_grad_()
+    yo = O.ada_apply(xo, torch.inverse(G), C)
+    close(yo, yr, rtol=1e-4, atol=2e-5)
+    gy = torch.randn_like(yr)
+    (gr,) = torch.autograd.grad(yr, xr, gy, create_graph=True)
+    (go,) = torch.autograd.grad(yo, xo, gy, create_graph=True)
+    close(go, gr, rtol=1e-4, atol=2e-5)
+    v = torch.randn_like(x)
+    # second order: d/d(gy-direction) is linear, so probe d<grad, v>/dx through a nonlinearity in y
+    (g2r,) = torch.autograd.grad((torch.autograd.grad(yr.square().sum(), xr, create_graph=True)[0] * v).sum(), xr)
+    (g2o,) = torch.autograd.grad((torch.autograd.grad(yo.square().sum(), xo, create_graph=True)[0] * v).sum(), xo)
+    close(g2o, g2r, rtol=1e-3, atol=1e-4)

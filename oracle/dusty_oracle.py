@@ -14,7 +14,10 @@ Parity pinning: the reference ships no tests or golden vectors (SURVEY.md
 section 4/8c).  The oracle is therefore pinned against outputs of the reference
 itself, imported in the build container from /root/reference by
 tests/golden/make_golden.py; the resulting small fixtures are committed under
-tests/golden/ and checked by tests/test_oracle_golden.py on every CPU run.
+tests/golden/ and checked by tests/test_oracle_golden.py on every CPU run.  Where
+/root/reference is present (the build container) tests/test_reference_live.py also
+cross-checks it against the live reference on fresh random inputs, up to the
+reference's real Trainer.step against `train_iteration`.
 """
 from __future__ import annotations
 

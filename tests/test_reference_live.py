@@ -249,3 +249,170 @@ def test_ada_pipeline_random_transforms(rops, seed, hw):
     (g2r,) = torch.autograd.grad((torch.autograd.grad(yr.square().sum(), xr, create_graph=True)[0] * v).sum(), xr)
     (g2o,) = torch.autograd.grad((torch.autograd.grad(yo.square().sum(), xo, create_graph=True)[0] * v).sum(), xo)
     close(g2o, g2r, rtol=1e-3, atol=1e-4)
+
+
+@pytest.mark.skipif(not os.path.exists(_EXT_UFD), reason="reference `upfirdn2d` extension not prebuilt")
+def test_reference_trainer_step_vs_oracle(rops, tmp_path):
+    """The reference's REAL `Trainer.step` (gans/trainer.py:247-482) run on CPU -- the object is
+    assembled without `__init__` (which needs a CUDA rank and KITTI files), DDP over gloo with one
+    rank, small G / D -- against `O.train_iteration`, the restatement bench.py times as the CPU
+    baseline.  Every random draw of the step (z, azimuth shift, Gumbel uniforms, warm-up dropout,
+    ADA transforms) is recorded on the way and replayed into the oracle; the oracle is advanced
+    phase by phase with the reference's Adam settings (G step -> D step -> lazy R1)."""
+    import copy
+    import torch.distributed as dist
+    from torch.nn.parallel import DistributedDataParallel as DDP
+    from gans import trainer as rtr
+    from gans.augment.adaptive_augment import AdaptiveAugment
+    from gans.coords import CoordBridge
+    from gans.models.builder import build_discriminator, build_generator
+    from gans.models.loss import GANLoss
+    from small_cfgs import D_SMALL, G_SMALL
+
+    own_group = not dist.is_initialized()
+    if own_group:
+        dist.init_process_group("gloo", init_method=f"file://{tmp_path}/pg", rank=0, world_size=1)
+    try:
+        _trainer_step_vs_oracle(rops, dist, DDP, rtr, AdaptiveAugment, CoordBridge, build_discriminator,
+                                build_generator, GANLoss, D_SMALL, G_SMALL, copy)
+    finally:
+        if own_group:
+            dist.destroy_process_group()
+
+
+def _trainer_step_vs_oracle(rops, dist, DDP, rtr, AdaptiveAugment, CoordBridge, build_discriminator,
+                            build_generator, GANLoss, D_SMALL, G_SMALL, copy):
+    B, H, W = 4, 16, 64
+    torch.manual_seed(1000)
+    np.random.seed(1000)
+    cfg = ref_import.to_attr(dict(
+        training=dict(batch_size_per_gpu=B, batch_size=B, num_gpus=1, gan_objective="nsgan",
+                      amp=dict(main=False, reg=False), loss=dict(gan=1.0, gp=16.0, pl=0.0),
+                      lazy=dict(gp=16, pl=4, ada=4), ema_kimg=10, ema_rampup=0.05,
+                      warmup=dict(fade_kimg=200, blur_init_sigma=0, dropout_init_ratio=0.5)),
+        dataset=dict(raydrop_const=-1, min_depth=1.45, max_depth=80.0),
+        model=dict(generator=dict(arch="dusty_v2", mapping_kwargs=dict(in_ch=16)))))
+    G = build_generator(ref_import.to_attr(G_SMALL))
+    D = build_discriminator(ref_import.to_attr(D_SMALL))
+    T = object.__new__(rtr.Trainer)
+    T.cfg, T.device = cfg, torch.device("cpu")
+    T.G_ema = copy.deepcopy(G).eval()
+    T.A = AdaptiveAugment(p_init=0.5, p_target=0.6, kimg=500, lr_flip=1, ud_flip=1, int_trans=1, iso_scale=1,
+                          frac_trans=1, brightness=1, contrast=1, luma_flip=1, hue=1, saturation=1)
+    T.coord = CoordBridge(H, W, 1.45, 80.0, os.path.join(ref_import.REFERENCE_ROOT, "data/coords/kitti_raw.npy")).eval()
+    T.G, T.D = DDP(G, broadcast_buffers=True), DDP(D, broadcast_buffers=False)
+    T.ddp_models = (T.G, T.D)
+    for m in (T.G, T.G_ema, T.D, T.A, T.coord):
+        m.requires_grad_(False)
+    T.auxin = {"angle": T.coord.angle.repeat_interleave(B, dim=0)}
+    g = torch.Generator().manual_seed(1001)
+    batch = {"depth": 1.45 + 78.55 * torch.rand(B, 1, H, W, generator=g),
+             "mask": (torch.rand(B, 1, H, W, generator=g) < 0.85).float()}
+    T.iter_train_loader = iter([batch])
+    T.adversarial_loss = GANLoss("nsgan")
+    lazy = 16 / 17.0
+    T.optim_G = torch.optim.Adam(T.G.parameters(), lr=0.002, betas=(0.0, 0.99))
+    T.optim_D = torch.optim.Adam(T.D.parameters(), lr=0.002 * lazy, betas=(0.0, 0.99 ** lazy))
+    for name in ("scaler_D", "scaler_G", "scaler_r1", "scaler_pl"):
+        setattr(T, name, rtr.GradScaler(enabled=False))
+    T.warmup_fade_kimg, T.blur_sigma, T.dropout_ratio = 200e3, 0, 0
+    T.iters_to_imgs = lambda i: int(i * B)
+
+    sdG0 = {k: v.clone() for k, v in G.state_dict().items()}
+    sdD0 = {k: v.clone() for k, v in D.state_dict().items()}
+
+    # ---- record every random draw of the step
+    log = {"randn": [], "rand": [], "uniform_": [], "bernoulli": [], "affine": [], "color": []}
+    quiet = [0]
+    real = dict(randn=torch.randn, rand=torch.rand, bernoulli=torch.bernoulli, uniform_=torch.Tensor.uniform_)
+
+    def recorder(name):
+        def fn(*a, **k):
+            out = real[name](*a, **k)
+            if not quiet[0]:
+                log[name].append(out.detach().clone())
+            return out
+        return fn
+
+    def sampler(name, orig):
+        def fn(*a, **k):
+            quiet[0] += 1
+            try:
+                out = orig(*a, **k)
+            finally:
+                quiet[0] -= 1
+            log[name].append(out.detach().clone())
+            return out
+        return fn
+
+    T.A.sample_affine = sampler("affine", T.A.sample_affine)
+    T.A.sample_color = sampler("color", T.A.sample_color)
+    d_grads = []
+    d_step = T.optim_D.step
+
+    def recording_step(*a, **k):
+        d_grads.append({n: p.grad.detach().clone() for n, p in D.named_parameters() if p.grad is not None})
+        return d_step(*a, **k)
+
+    T.optim_D.step = recording_step
+    torch.randn, torch.rand, torch.bernoulli = recorder("randn"), recorder("rand"), recorder("bernoulli")
+    torch.Tensor.uniform_ = recorder("uniform_")
+    try:
+        scalars = T.step(0)
+    finally:
+        torch.randn, torch.rand, torch.bernoulli = real["randn"], real["rand"], real["bernoulli"]
+        torch.Tensor.uniform_ = real["uniform_"]
+    assert [len(log[k]) for k in ("randn", "uniform_", "rand", "bernoulli", "affine", "color")] == [2, 2, 2, 4, 4, 4]
+    rnd = dict(z_g=log["randn"][0], z_d=log["randn"][1], shift_g=log["uniform_"][0], shift_d=log["uniform_"][1],
+               u_g=log["rand"][0], u_d=log["rand"][1])
+    for i, tag in enumerate(("g_fake", "d_real", "d_fake", "r1")):
+        rnd[f"keep_{tag}"] = log["bernoulli"][i]
+        rnd[f"Ginv_{tag}"] = torch.inverse(log["affine"][i])
+        rnd[f"C_{tag}"] = log["color"][i]
+
+    # ---- the oracle, phase by phase
+    nograd = ("ema_var", "w_avg", "kernel", "pe.", "raydrop_const")
+    sdG = {k: v.clone().requires_grad_(not any(t in k for t in nograd)) for k, v in sdG0.items()}
+    sdD = {k: v.clone().requires_grad_("kernel" not in k) for k, v in sdD0.items()}
+    angle = T.auxin["angle"]
+    x_real = O.fetch_reals(batch["depth"], batch["mask"], 1.45, 80.0)
+    optG = torch.optim.Adam([v for v in sdG.values() if v.requires_grad], lr=0.002, betas=(0.0, 0.99))
+    optD = torch.optim.Adam([v for v in sdD.values() if v.requires_grad], lr=0.002 * lazy, betas=(0.0, 0.99 ** lazy))
+
+    def apply(opt, sd, grads):
+        for k, gr in grads.items():
+            sd[k].grad = gr
+        opt.step()
+        opt.zero_grad(set_to_none=True)
+
+    def check_grads(got, ref, min_n):
+        n = 0
+        for k, gr in got.items():
+            if gr is None or k not in ref:
+                continue
+            r = ref[k]
+            np.testing.assert_allclose(gr.numpy(), r.numpy(), rtol=5e-3, atol=2e-3 * max(float(r.abs().max()), 1e-7))
+            n += 1
+        assert n >= min_n, n
+
+    # G step (pre-step weights on both sides)
+    r = O.train_iteration(sdG, sdD, x_real, angle, rnd, with_r1=False)
+    assert float(r["loss_G"]) == pytest.approx(scalars["loss/G/adversarial"], rel=1e-4, abs=1e-6)
+    check_grads(r["grads_G"], {n: p.grad for n, p in G.named_parameters() if p.grad is not None}, 40)
+    # the G-step forward also moved the EMA buffers; the D step sees them and the updated weights
+    nb = {}
+    with torch.no_grad():
+        O.generator(sdG, rnd["z_g"], angle, rnd["u_g"], training=True,
+                    shifts_rad=rnd["shift_g"] * (2 * np.pi), new_buffers=nb)
+    apply(optG, sdG, r["grads_G"])
+    for k, v in nb.items():
+        sdG[k] = v.detach().clone()
+    # D step
+    r = O.train_iteration(sdG, sdD, x_real, angle, rnd, with_r1=False)
+    assert float(r["loss_D"]) == pytest.approx(scalars["loss/D/adversarial"], rel=2e-3, abs=1e-5)
+    check_grads(r["grads_D"], d_grads[0], 10)
+    apply(optD, sdD, r["grads_D"])
+    # lazy R1 step on the updated discriminator
+    r = O.train_iteration(sdG, sdD, x_real, angle, rnd, with_r1=True)
+    assert float(r["r1"]) == pytest.approx(scalars["loss/D/gradient_penalty"], rel=5e-3, abs=1e-7)
+    check_grads(r["grads_R1"], d_grads[1], 10)

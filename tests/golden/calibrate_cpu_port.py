@@ -36,6 +36,39 @@ def best(fn, reps=3):
     return min(ts[1:])
 
 
+def full_step_row(batch=2):
+    """Full-size dusty_v2 training iteration (no R1: iteration 1) at `batch`: the reference's real
+    Trainer.step (assembled for CPU by tests/ref_trainer_harness.py) vs the port exactly as
+    bench.py's CPU baseline runs it."""
+    import tempfile
+    from types import SimpleNamespace
+
+    import torch.distributed as dist
+
+    import bench
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    from ref_trainer_harness import build_reference_trainer
+    cfg = preset("dusty_v2").model
+    pool = bench.synthetic_batches(3, batch, seed=2)
+    own = not dist.is_initialized()
+    if own:
+        dist.init_process_group("gloo", init_method=f"file://{tempfile.mkdtemp()}/pg", rank=0, world_size=1)
+    try:
+        T, _, _ = build_reference_trainer(dict(cfg.generator), dict(cfg.discriminator), batch, (64, 512), pool)
+        T.step(1)                                    # warm-up (plain iteration)
+        t0 = time.perf_counter()
+        T.step(2)
+        t_ref = time.perf_counter() - t0
+    finally:
+        if own:
+            dist.destroy_process_group()
+    args = SimpleNamespace(arch="dusty_v2", ada_p=None)
+    _, spt, _, desc = bench.cpu_reference_run(args, 2, 1, batch)      # iterations 0 (R1) and 1 (plain)
+    # the description carries the plain / R1 split: "... ratio (P s / R s)"
+    plain = float(desc.split("ratio (")[1].split(" s")[0])
+    return (f"training iteration (G + D step), batch {batch}", t_ref, plain)
+
+
 def main():
     O.set_fir_impl("library")          # what bench.py's CPU legs run
     torch.manual_seed(0)
@@ -74,7 +107,9 @@ def main():
 
     rows.append(("D forward + backward, batch 4", best(lambda: ref_d(False)), best(lambda: port_d(False))))
     rows.append(("D forward + R1 double backward, batch 4", best(lambda: ref_d(True)), best(lambda: port_d(True))))
-    print(f"# host threads: {torch.get_num_threads()}; seconds, best of 3 after one warm-up")
+    rows.append(full_step_row())
+    print(f"# host threads: {torch.get_num_threads()}; seconds, best of 3 after one warm-up "
+          f"(training step: one plain iteration after one warm-up iteration)")
     print(f"{'case':42s} {'reference':>10s} {'port':>10s} {'port/ref':>9s}")
     for name, r, p in rows:
         print(f"{name:42s} {r:10.3f} {p:10.3f} {p / r:9.2f}")

@@ -259,64 +259,28 @@ def test_reference_trainer_step_vs_oracle(rops, tmp_path):
     baseline.  Every random draw of the step (z, azimuth shift, Gumbel uniforms, warm-up dropout,
     ADA transforms) is recorded on the way and replayed into the oracle; the oracle is advanced
     phase by phase with the reference's Adam settings (G step -> D step -> lazy R1)."""
-    import copy
     import torch.distributed as dist
-    from torch.nn.parallel import DistributedDataParallel as DDP
-    from gans import trainer as rtr
-    from gans.augment.adaptive_augment import AdaptiveAugment
-    from gans.coords import CoordBridge
-    from gans.models.builder import build_discriminator, build_generator
-    from gans.models.loss import GANLoss
-    from small_cfgs import D_SMALL, G_SMALL
-
     own_group = not dist.is_initialized()
     if own_group:
         dist.init_process_group("gloo", init_method=f"file://{tmp_path}/pg", rank=0, world_size=1)
     try:
-        _trainer_step_vs_oracle(rops, dist, DDP, rtr, AdaptiveAugment, CoordBridge, build_discriminator,
-                                build_generator, GANLoss, D_SMALL, G_SMALL, copy)
+        _trainer_step_vs_oracle()
     finally:
         if own_group:
             dist.destroy_process_group()
 
 
-def _trainer_step_vs_oracle(rops, dist, DDP, rtr, AdaptiveAugment, CoordBridge, build_discriminator,
-                            build_generator, GANLoss, D_SMALL, G_SMALL, copy):
+def _trainer_step_vs_oracle():
+    from small_cfgs import D_SMALL, G_SMALL
     B, H, W = 4, 16, 64
     torch.manual_seed(1000)
     np.random.seed(1000)
-    cfg = ref_import.to_attr(dict(
-        training=dict(batch_size_per_gpu=B, batch_size=B, num_gpus=1, gan_objective="nsgan",
-                      amp=dict(main=False, reg=False), loss=dict(gan=1.0, gp=16.0, pl=0.0),
-                      lazy=dict(gp=16, pl=4, ada=4), ema_kimg=10, ema_rampup=0.05,
-                      warmup=dict(fade_kimg=200, blur_init_sigma=0, dropout_init_ratio=0.5)),
-        dataset=dict(raydrop_const=-1, min_depth=1.45, max_depth=80.0),
-        model=dict(generator=dict(arch="dusty_v2", mapping_kwargs=dict(in_ch=16)))))
-    G = build_generator(ref_import.to_attr(G_SMALL))
-    D = build_discriminator(ref_import.to_attr(D_SMALL))
-    T = object.__new__(rtr.Trainer)
-    T.cfg, T.device = cfg, torch.device("cpu")
-    T.G_ema = copy.deepcopy(G).eval()
-    T.A = AdaptiveAugment(p_init=0.5, p_target=0.6, kimg=500, lr_flip=1, ud_flip=1, int_trans=1, iso_scale=1,
-                          frac_trans=1, brightness=1, contrast=1, luma_flip=1, hue=1, saturation=1)
-    T.coord = CoordBridge(H, W, 1.45, 80.0, os.path.join(ref_import.REFERENCE_ROOT, "data/coords/kitti_raw.npy")).eval()
-    T.G, T.D = DDP(G, broadcast_buffers=True), DDP(D, broadcast_buffers=False)
-    T.ddp_models = (T.G, T.D)
-    for m in (T.G, T.G_ema, T.D, T.A, T.coord):
-        m.requires_grad_(False)
-    T.auxin = {"angle": T.coord.angle.repeat_interleave(B, dim=0)}
     g = torch.Generator().manual_seed(1001)
     batch = {"depth": 1.45 + 78.55 * torch.rand(B, 1, H, W, generator=g),
              "mask": (torch.rand(B, 1, H, W, generator=g) < 0.85).float()}
-    T.iter_train_loader = iter([batch])
-    T.adversarial_loss = GANLoss("nsgan")
+    from ref_trainer_harness import build_reference_trainer
+    T, G, D = build_reference_trainer(G_SMALL, D_SMALL, B, (H, W), [batch], p_init=0.5)
     lazy = 16 / 17.0
-    T.optim_G = torch.optim.Adam(T.G.parameters(), lr=0.002, betas=(0.0, 0.99))
-    T.optim_D = torch.optim.Adam(T.D.parameters(), lr=0.002 * lazy, betas=(0.0, 0.99 ** lazy))
-    for name in ("scaler_D", "scaler_G", "scaler_r1", "scaler_pl"):
-        setattr(T, name, rtr.GradScaler(enabled=False))
-    T.warmup_fade_kimg, T.blur_sigma, T.dropout_ratio = 200e3, 0, 0
-    T.iters_to_imgs = lambda i: int(i * B)
 
     sdG0 = {k: v.clone() for k, v in G.state_dict().items()}
     sdD0 = {k: v.clone() for k, v in D.state_dict().items()}

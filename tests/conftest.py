@@ -72,3 +72,8 @@ def g_inv():
 @pytest.fixture(scope="session")
 def g_invloop():
     return load_golden("inversion_loop.npz")
+
+
+@pytest.fixture(scope="session")
+def g_step():
+    return load_golden("trainer_step.npz")

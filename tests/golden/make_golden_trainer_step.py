@@ -1,0 +1,70 @@
+"""Golden vectors of ONE FULL TRAINING ITERATION produced by the reference's real
+`gans.trainer.Trainer.step` (gans/trainer.py:247-482) on CPU: the trainer object is assembled by
+tests/ref_trainer_harness.py (no `__init__`: that needs a CUDA rank and the KITTI files; one-rank
+gloo DDP), small G / D, iteration 0 (G step, D step, lazy R1 step, ADA p = 0.5, warm-up dropout
+0.5).  Every random draw of the step is recorded and stored, together with the losses and the
+gradients each optimiser step consumed.
+
+    python tests/golden/make_golden_trainer_step.py      ->  tests/golden/trainer_step.npz
+"""
+import os
+import sys
+import tempfile
+
+import numpy as np
+import torch
+import torch.distributed as dist
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+ROOT = os.path.dirname(os.path.dirname(HERE))
+sys.path.insert(0, ROOT)
+sys.path.insert(0, os.path.join(ROOT, "tests"))
+
+from ref_trainer_harness import build_reference_trainer, record_step  # noqa: E402
+from small_cfgs import D_SMALL, G_SMALL  # noqa: E402
+
+npy = lambda t: t.detach().cpu().numpy().copy()  # noqa: E731
+
+
+def main():
+    dist.init_process_group("gloo", init_method=f"file://{tempfile.mkdtemp()}/pg", rank=0, world_size=1)
+    B, H, W = 4, 16, 64
+    torch.manual_seed(1100)
+    np.random.seed(1100)
+    g = torch.Generator().manual_seed(1101)
+    batch = {"depth": 1.45 + 78.55 * torch.rand(B, 1, H, W, generator=g),
+             "mask": (torch.rand(B, 1, H, W, generator=g) < 0.85).float()}
+    T, G, D = build_reference_trainer(G_SMALL, D_SMALL, B, (H, W), [batch], p_init=0.5)
+    with torch.no_grad():                         # de-trivialise the zero-initialised biases
+        for net in (G, D):
+            for n, p in net.named_parameters():
+                if "bias" in n:
+                    p.normal_(0, 0.2)
+    out = {f"sdG_{k}": npy(v) for k, v in G.state_dict().items()}
+    out.update({f"sdD_{k}": npy(v) for k, v in D.state_dict().items()})
+    scalars, log, g_grads, d_grads = record_step(T, G, D, 0)
+    assert [len(log[k]) for k in ("randn", "uniform_", "rand", "bernoulli", "affine", "color")] == [2, 2, 2, 4, 4, 4]
+    out.update(depth=npy(batch["depth"]), mask=npy(batch["mask"]), angle=npy(T.auxin["angle"]),
+               z_g=npy(log["randn"][0]), z_d=npy(log["randn"][1]), shift_g=npy(log["uniform_"][0]),
+               shift_d=npy(log["uniform_"][1]), u_g=npy(log["rand"][0]), u_d=npy(log["rand"][1]))
+    for i, tag in enumerate(("g_fake", "d_real", "d_fake", "r1")):
+        out[f"keep_{tag}"] = npy(log["bernoulli"][i])
+        out[f"G_{tag}"] = npy(log["affine"][i])
+        out[f"C_{tag}"] = npy(log["color"][i])
+    out.update(loss_G=np.array(scalars["loss/G/adversarial"]), loss_D=np.array(scalars["loss/D/adversarial"]),
+               r1=np.array(scalars["loss/D/gradient_penalty"]), ada_rt=np.array(scalars["stats/ada_rt"]),
+               ada_p_after=npy(T.A.p), ema_decay=np.array(scalars["stats/ema_decay"]))
+    out.update({f"gG_{k}": npy(v) for k, v in g_grads.items()})
+    out.update({f"gD_{k}": npy(v) for k, v in d_grads[0].items()})
+    out.update({f"gR1_{k}": npy(v) for k, v in d_grads[1].items()})
+    out.update({f"afterG_{k}": npy(v) for k, v in G.state_dict().items() if "kernel" not in k and "pe." not in k})
+    out.update({f"afterD_{k}": npy(v) for k, v in D.state_dict().items() if "kernel" not in k})
+    out.update({f"afterGema_{k}": npy(v) for k, v in T.G_ema.state_dict().items() if k.endswith("ema_var") or k == "w_avg"})
+    path = os.path.join(HERE, "trainer_step.npz")
+    np.savez_compressed(path, **out)
+    print(f"trainer_step.npz: {os.path.getsize(path) / 1024:.1f} KiB, {len(out)} arrays")
+    dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

@@ -56,3 +56,49 @@ def build_reference_trainer(g_cfg, d_cfg, batch_size, resolution, batches, p_ini
     T.warmup_fade_kimg, T.blur_sigma, T.dropout_ratio = 200e3, 0, 0
     T.iters_to_imgs = lambda i: int(i * B)
     return T, G, D
+
+
+def record_step(T, G, D, iteration):
+    """Runs T.step(iteration) with every random draw logged; returns (scalars, log, g_grads, d_grads)."""
+    log = {"randn": [], "rand": [], "uniform_": [], "bernoulli": [], "affine": [], "color": []}
+    quiet = [0]
+    real = dict(randn=torch.randn, rand=torch.rand, bernoulli=torch.bernoulli, uniform_=torch.Tensor.uniform_)
+
+    def recorder(name):
+        def fn(*a, **k):
+            out = real[name](*a, **k)
+            if not quiet[0]:
+                log[name].append(out.detach().clone())
+            return out
+        return fn
+
+    def sampler(name, orig):
+        def fn(*a, **k):
+            quiet[0] += 1
+            try:
+                out = orig(*a, **k)
+            finally:
+                quiet[0] -= 1
+            log[name].append(out.detach().clone())
+            return out
+        return fn
+
+    T.A.sample_affine = sampler("affine", T.A.sample_affine)
+    T.A.sample_color = sampler("color", T.A.sample_color)
+    d_grads = []
+    d_step = T.optim_D.step
+
+    def recording_step(*a, **k):
+        d_grads.append({n: p.grad.detach().clone() for n, p in D.named_parameters() if p.grad is not None})
+        return d_step(*a, **k)
+
+    T.optim_D.step = recording_step
+    torch.randn, torch.rand, torch.bernoulli = recorder("randn"), recorder("rand"), recorder("bernoulli")
+    torch.Tensor.uniform_ = recorder("uniform_")
+    try:
+        scalars = T.step(iteration)
+    finally:
+        torch.randn, torch.rand, torch.bernoulli = real["randn"], real["rand"], real["bernoulli"]
+        torch.Tensor.uniform_ = real["uniform_"]
+    g_grads = {n: p.grad.detach().clone() for n, p in G.named_parameters() if p.grad is not None}
+    return scalars, log, g_grads, d_grads

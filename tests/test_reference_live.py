@@ -278,54 +278,15 @@ def _trainer_step_vs_oracle():
     g = torch.Generator().manual_seed(1001)
     batch = {"depth": 1.45 + 78.55 * torch.rand(B, 1, H, W, generator=g),
              "mask": (torch.rand(B, 1, H, W, generator=g) < 0.85).float()}
-    from ref_trainer_harness import build_reference_trainer
+    from ref_trainer_harness import build_reference_trainer, record_step
     T, G, D = build_reference_trainer(G_SMALL, D_SMALL, B, (H, W), [batch], p_init=0.5)
     lazy = 16 / 17.0
 
     sdG0 = {k: v.clone() for k, v in G.state_dict().items()}
     sdD0 = {k: v.clone() for k, v in D.state_dict().items()}
 
-    # ---- record every random draw of the step
-    log = {"randn": [], "rand": [], "uniform_": [], "bernoulli": [], "affine": [], "color": []}
-    quiet = [0]
-    real = dict(randn=torch.randn, rand=torch.rand, bernoulli=torch.bernoulli, uniform_=torch.Tensor.uniform_)
-
-    def recorder(name):
-        def fn(*a, **k):
-            out = real[name](*a, **k)
-            if not quiet[0]:
-                log[name].append(out.detach().clone())
-            return out
-        return fn
-
-    def sampler(name, orig):
-        def fn(*a, **k):
-            quiet[0] += 1
-            try:
-                out = orig(*a, **k)
-            finally:
-                quiet[0] -= 1
-            log[name].append(out.detach().clone())
-            return out
-        return fn
-
-    T.A.sample_affine = sampler("affine", T.A.sample_affine)
-    T.A.sample_color = sampler("color", T.A.sample_color)
-    d_grads = []
-    d_step = T.optim_D.step
-
-    def recording_step(*a, **k):
-        d_grads.append({n: p.grad.detach().clone() for n, p in D.named_parameters() if p.grad is not None})
-        return d_step(*a, **k)
-
-    T.optim_D.step = recording_step
-    torch.randn, torch.rand, torch.bernoulli = recorder("randn"), recorder("rand"), recorder("bernoulli")
-    torch.Tensor.uniform_ = recorder("uniform_")
-    try:
-        scalars = T.step(0)
-    finally:
-        torch.randn, torch.rand, torch.bernoulli = real["randn"], real["rand"], real["bernoulli"]
-        torch.Tensor.uniform_ = real["uniform_"]
+    # ---- run the reference's step with every random draw recorded
+    scalars, log, g_grads, d_grads = record_step(T, G, D, 0)
     assert [len(log[k]) for k in ("randn", "uniform_", "rand", "bernoulli", "affine", "color")] == [2, 2, 2, 4, 4, 4]
     rnd = dict(z_g=log["randn"][0], z_d=log["randn"][1], shift_g=log["uniform_"][0], shift_d=log["uniform_"][1],
                u_g=log["rand"][0], u_d=log["rand"][1])
@@ -362,7 +323,7 @@ def _trainer_step_vs_oracle():
     # G step (pre-step weights on both sides)
     r = O.train_iteration(sdG, sdD, x_real, angle, rnd, with_r1=False)
     assert float(r["loss_G"]) == pytest.approx(scalars["loss/G/adversarial"], rel=1e-4, abs=1e-6)
-    check_grads(r["grads_G"], {n: p.grad for n, p in G.named_parameters() if p.grad is not None}, 40)
+    check_grads(r["grads_G"], g_grads, 40)
     # the G-step forward also moved the EMA buffers; the D step sees them and the updated weights
     nb = {}
     with torch.no_grad():

@@ -191,7 +191,7 @@ def _cpu_reference_run(args, steps, warmup, batch):
     def one(it):
         b = pool[it % len(pool)]
         x_real = O.fetch_reals(b["depth"], b["mask"], 1.45, 80.0)
-        r = O.train_iteration(sdG, sdD, x_real, angle, draws(), with_r1=(it % 16 == 0))
+        r = O.train_iteration(sdG, sdD, x_real, angle, draws(), with_r1=(it % 16 == 0), arch=args.arch)
         apply(optG, sdG, r["grads_G"])
         apply(optD, sdD, r["grads_D"])
         if "grads_R1" in r:
@@ -214,7 +214,7 @@ def _cpu_reference_run(args, steps, warmup, batch):
         spt = (15 * sum(plain) / len(plain) + sum(r1) / len(r1)) / 16
         mix = (f"{len(plain)} plain + {len(r1)} R1 iteration(s) timed, combined at the training loop's "
                f"15:1 ratio ({sum(plain) / len(plain):.2f} s / {sum(r1) / len(r1):.2f} s)")
-    desc = (f"oracle port of Trainer.step (G step + D step + R1 on every 16th step, ADA p="
+    desc = (f"oracle port of {args.arch} Trainer.step (G step + D step + R1 on every 16th step, ADA p="
             f"{args.ada_p or 0.0}, warm-up dropout 0.5), fp32, batch {batch}, {mix}, "
             f"Adam updates included (all three phases use the pre-step weights)")
     return batch / spt, spt, cores, desc
@@ -605,7 +605,7 @@ def main():
         if rank != 0:
             return
         ips, spt, cores, desc = cpu_reference_run(args, args.steps, args.warmup, args.cpu_batch)
-        line = {"impl": "reference", "metric": METRIC, "value": ips, "unit": UNIT, "n_gpus": args.gpus,
+        line = {"impl": "reference", "metric": METRIC.replace("dusty_v2", args.arch), "value": ips, "unit": UNIT, "n_gpus": args.gpus,
                 "steps": args.steps, "warmup": args.warmup, "ms_per_step": spt * 1e3,
                 "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
                 "data": "synthetic",

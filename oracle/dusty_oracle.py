@@ -719,12 +719,24 @@ def warmup_dropout(x: Tensor, keep: Optional[Tensor], raydrop_const: float = -1.
 
 
 def train_iteration(sdG: Dict[str, Tensor], sdD: Dict[str, Tensor], x_real: Tensor, angle: Tensor,
-                    rnd: Dict[str, Tensor], with_r1: bool = True, gp_weight: float = 16.0):
+                    rnd: Dict[str, Tensor], with_r1: bool = True, gp_weight: float = 16.0,
+                    arch: str = "dusty_v2"):
     """Losses and gradients of one iteration: G step, D step and (optionally) the R1 step,
     with every random draw supplied in `rnd` (z_g, z_d, shift_g, shift_d, u_g, u_d, keep_*,
-    Ginv_*, C_*).  Returns dict(loss_G, loss_D, r1, grads_G, grads_D, grads_R1)."""
+    Ginv_*, C_*).  Returns dict(loss_G, loss_D, r1, grads_G, grads_D, grads_R1).
+    arch "dusty_v2" (default) or "dusty_v1" / "vanilla" (BASELINE config 3: transposed-conv
+    generator, strided-conv discriminator; no angle input, no azimuth shift; the Gumbel uniforms
+    are used by dusty_v1 only)."""
     def aug(x, tag):
         return ada_apply(warmup_dropout(x, rnd.get(f"keep_{tag}")), rnd[f"Ginv_{tag}"], rnd[f"C_{tag}"])
+
+    if arch != "dusty_v2":
+        def generator(sd, z, _angle, u, training=True, shifts_rad=None):      # noqa: F811
+            return vanilla_generator(sd, z, u if arch == "dusty_v1" else None)
+
+        discriminator = vanilla_discriminator                                # noqa: F811
+    else:
+        generator, discriminator = globals()["generator"], globals()["discriminator"]
 
     import time
     pG = {k: v for k, v in sdG.items() if v.requires_grad}

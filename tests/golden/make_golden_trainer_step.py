@@ -21,20 +21,27 @@ sys.path.insert(0, ROOT)
 sys.path.insert(0, os.path.join(ROOT, "tests"))
 
 from ref_trainer_harness import build_reference_trainer, record_step  # noqa: E402
-from small_cfgs import D_SMALL, G_SMALL  # noqa: E402
+from small_cfgs import D_SMALL, G_SMALL, V1_SMALL, VD_SMALL  # noqa: E402
 
 npy = lambda t: t.detach().cpu().numpy().copy()  # noqa: E731
 
 
 def main():
     dist.init_process_group("gloo", init_method=f"file://{tempfile.mkdtemp()}/pg", rank=0, world_size=1)
-    B, H, W = 4, 16, 64
-    torch.manual_seed(1100)
-    np.random.seed(1100)
-    g = torch.Generator().manual_seed(1101)
+    one(G_SMALL, D_SMALL, (16, 64), "trainer_step.npz", 1100)
+    one(V1_SMALL, VD_SMALL, (32, 64), "trainer_step_dusty_v1.npz", 1200)       # BASELINE config 3
+    dist.destroy_process_group()
+
+
+def one(g_cfg, d_cfg, res, fname, seed):
+    B, (H, W) = 4, res
+    v2 = g_cfg["arch"] == "dusty_v2"
+    torch.manual_seed(seed)
+    np.random.seed(seed)
+    g = torch.Generator().manual_seed(seed + 1)
     batch = {"depth": 1.45 + 78.55 * torch.rand(B, 1, H, W, generator=g),
              "mask": (torch.rand(B, 1, H, W, generator=g) < 0.85).float()}
-    T, G, D = build_reference_trainer(G_SMALL, D_SMALL, B, (H, W), [batch], p_init=0.5)
+    T, G, D = build_reference_trainer(g_cfg, d_cfg, B, (H, W), [batch], p_init=0.5)
     with torch.no_grad():                         # de-trivialise the zero-initialised biases
         for net in (G, D):
             for n, p in net.named_parameters():
@@ -43,10 +50,12 @@ def main():
     out = {f"sdG_{k}": npy(v) for k, v in G.state_dict().items()}
     out.update({f"sdD_{k}": npy(v) for k, v in D.state_dict().items()})
     scalars, log, g_grads, d_grads = record_step(T, G, D, 0)
-    assert [len(log[k]) for k in ("randn", "uniform_", "rand", "bernoulli", "affine", "color")] == [2, 2, 2, 4, 4, 4]
-    out.update(depth=npy(batch["depth"]), mask=npy(batch["mask"]), angle=npy(T.auxin["angle"]),
-               z_g=npy(log["randn"][0]), z_d=npy(log["randn"][1]), shift_g=npy(log["uniform_"][0]),
-               shift_d=npy(log["uniform_"][1]), u_g=npy(log["rand"][0]), u_d=npy(log["rand"][1]))
+    assert [len(log[k]) for k in ("randn", "uniform_", "rand", "bernoulli", "affine", "color")] == \
+        [2, 2 if v2 else 0, 2, 4, 4, 4]
+    out.update(depth=npy(batch["depth"]), mask=npy(batch["mask"]), z_g=npy(log["randn"][0]),
+               z_d=npy(log["randn"][1]), u_g=npy(log["rand"][0]), u_d=npy(log["rand"][1]))
+    if v2:
+        out.update(angle=npy(T.auxin["angle"]), shift_g=npy(log["uniform_"][0]), shift_d=npy(log["uniform_"][1]))
     for i, tag in enumerate(("g_fake", "d_real", "d_fake", "r1")):
         out[f"keep_{tag}"] = npy(log["bernoulli"][i])
         out[f"G_{tag}"] = npy(log["affine"][i])
@@ -60,10 +69,9 @@ def main():
     out.update({f"afterG_{k}": npy(v) for k, v in G.state_dict().items() if "kernel" not in k and "pe." not in k})
     out.update({f"afterD_{k}": npy(v) for k, v in D.state_dict().items() if "kernel" not in k})
     out.update({f"afterGema_{k}": npy(v) for k, v in T.G_ema.state_dict().items() if k.endswith("ema_var") or k == "w_avg"})
-    path = os.path.join(HERE, "trainer_step.npz")
+    path = os.path.join(HERE, fname)
     np.savez_compressed(path, **out)
-    print(f"trainer_step.npz: {os.path.getsize(path) / 1024:.1f} KiB, {len(out)} arrays")
-    dist.destroy_process_group()
+    print(f"{fname}: {os.path.getsize(path) / 1024:.1f} KiB, {len(out)} arrays")
 
 
 if __name__ == "__main__":

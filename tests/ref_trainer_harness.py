@@ -29,8 +29,8 @@ def build_reference_trainer(g_cfg, d_cfg, batch_size, resolution, batches, p_ini
                       lazy=dict(gp=16, pl=4, ada=4), ema_kimg=10, ema_rampup=0.05,
                       warmup=dict(fade_kimg=200, blur_init_sigma=0, dropout_init_ratio=0.5)),
         dataset=dict(raydrop_const=-1, min_depth=1.45, max_depth=80.0),
-        model=dict(generator=dict(arch=g_cfg["arch"],
-                                  mapping_kwargs=dict(in_ch=g_cfg["mapping_kwargs"]["in_ch"])))))
+        model=dict(generator=dict(arch=g_cfg["arch"], mapping_kwargs=dict(
+            in_ch=g_cfg.get("mapping_kwargs", g_cfg["synthesis_kwargs"])["in_ch"])))))
     G = build_generator(ref_import.to_attr(g_cfg))
     D = build_discriminator(ref_import.to_attr(d_cfg))
     T = object.__new__(rtr.Trainer)
@@ -45,7 +45,9 @@ def build_reference_trainer(g_cfg, d_cfg, batch_size, resolution, batches, p_ini
     T.ddp_models = (T.G, T.D)
     for m in (T.G, T.G_ema, T.D, T.A, T.coord):
         m.requires_grad_(False)
-    T.auxin = {"angle": T.coord.angle.repeat_interleave(B, dim=0)}
+    T.auxin = {}
+    if "dusty_v2" in g_cfg["arch"]:
+        T.auxin["angle"] = T.coord.angle.repeat_interleave(B, dim=0)
     T.iter_train_loader = iter(batches)
     T.adversarial_loss = GANLoss("nsgan")
     lazy = 16 / 17.0

@@ -395,3 +395,52 @@ def test_train_iteration_against_reference_trainer_step(g_step):
             near += int((d < 2e-4).sum())
             total += d.numel()
     assert total > 1000 and near / total > 0.98, (near, total)
+
+
+def test_train_iteration_dusty_v1_against_reference_trainer_step(g_step_v1):
+    """BASELINE config 3: `O.train_iteration(arch="dusty_v1")` against one full iteration of the
+    reference's real `Trainer.step` with the dusty_v1 generator / vanilla discriminator."""
+    g = g_step_v1
+    sdG = {k[4:]: T(v).clone() for k, v in g.items() if k.startswith("sdG_")}
+    sdD = {k[4:]: T(v).clone() for k, v in g.items() if k.startswith("sdD_")}
+    sdG = {k: v.requires_grad_(v.dtype.is_floating_point and not any(t in k for t in ("kernel", "raydrop_const", "w_avg")))
+           for k, v in sdG.items()}
+    sdD = {k: v.requires_grad_("kernel" not in k) for k, v in sdD.items()}
+    rnd = {k: T(g[k]) for k in ("z_g", "z_d", "u_g", "u_d")}
+    rnd["shift_g"] = rnd["shift_d"] = torch.zeros(4)
+    for tag in ("g_fake", "d_real", "d_fake", "r1"):
+        rnd[f"keep_{tag}"] = T(g[f"keep_{tag}"])
+        rnd[f"Ginv_{tag}"] = torch.inverse(T(g[f"G_{tag}"]))
+        rnd[f"C_{tag}"] = T(g[f"C_{tag}"])
+    x_real = O.fetch_reals(T(g["depth"]), T(g["mask"]), 1.45, 80.0)
+    lazy = 16 / 17.0
+    optG = torch.optim.Adam([v for v in sdG.values() if v.requires_grad], lr=0.002, betas=(0.0, 0.99))
+    optD = torch.optim.Adam([v for v in sdD.values() if v.requires_grad], lr=0.002 * lazy, betas=(0.0, 0.99 ** lazy))
+
+    def apply(opt, sd, grads):
+        for k, gr in grads.items():
+            sd[k].grad = gr
+        opt.step()
+        opt.zero_grad(set_to_none=True)
+
+    def check_grads(got, prefix, min_n):
+        n = 0
+        for k, gr in got.items():
+            if gr is None or prefix + k not in g:
+                continue
+            ref = g[prefix + k]
+            close(gr, ref, rtol=5e-3, atol=2e-3 * max(float(np.abs(ref).max()), 1e-7))
+            n += 1
+        assert n >= min_n, n
+
+    r = O.train_iteration(sdG, sdD, x_real, None, rnd, with_r1=False, arch="dusty_v1")
+    close(r["loss_G"], g["loss_G"], rtol=1e-4, atol=1e-6)
+    check_grads(r["grads_G"], "gG_", 8)
+    apply(optG, sdG, r["grads_G"])
+    r = O.train_iteration(sdG, sdD, x_real, None, rnd, with_r1=False, arch="dusty_v1")
+    close(r["loss_D"], g["loss_D"], rtol=2e-3, atol=1e-5)
+    check_grads(r["grads_D"], "gD_", 8)
+    apply(optD, sdD, r["grads_D"])
+    r = O.train_iteration(sdG, sdD, x_real, None, rnd, with_r1=True, arch="dusty_v1")
+    close(r["r1"], g["r1"], rtol=5e-3, atol=1e-7)
+    check_grads(r["grads_R1"], "gR1_", 8)

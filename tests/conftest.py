@@ -77,8 +77,3 @@ def g_invloop():
 @pytest.fixture(scope="session")
 def g_step():
     return load_golden("trainer_step.npz")
-
-
-@pytest.fixture(scope="session")
-def g_step_v1():
-    return load_golden("trainer_step_dusty_v1.npz")

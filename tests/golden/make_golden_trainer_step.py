@@ -21,7 +21,7 @@ sys.path.insert(0, ROOT)
 sys.path.insert(0, os.path.join(ROOT, "tests"))
 
 from ref_trainer_harness import build_reference_trainer, record_step  # noqa: E402
-from small_cfgs import D_SMALL, G_SMALL, V1_SMALL, VD_SMALL  # noqa: E402
+from small_cfgs import D_SMALL, G_SMALL, V1_SMALL, V_SMALL, VD_SMALL  # noqa: E402
 
 npy = lambda t: t.detach().cpu().numpy().copy()  # noqa: E731
 
@@ -30,6 +30,7 @@ def main():
     dist.init_process_group("gloo", init_method=f"file://{tempfile.mkdtemp()}/pg", rank=0, world_size=1)
     one(G_SMALL, D_SMALL, (16, 64), "trainer_step.npz", 1100)
     one(V1_SMALL, VD_SMALL, (32, 64), "trainer_step_dusty_v1.npz", 1200)       # BASELINE config 3
+    one(V_SMALL, VD_SMALL, (32, 64), "trainer_step_vanilla.npz", 1300)
     dist.destroy_process_group()
 
 
@@ -50,10 +51,13 @@ def one(g_cfg, d_cfg, res, fname, seed):
     out = {f"sdG_{k}": npy(v) for k, v in G.state_dict().items()}
     out.update({f"sdD_{k}": npy(v) for k, v in D.state_dict().items()})
     scalars, log, g_grads, d_grads = record_step(T, G, D, 0)
+    gumbel = g_cfg["arch"] != "vanilla"
     assert [len(log[k]) for k in ("randn", "uniform_", "rand", "bernoulli", "affine", "color")] == \
-        [2, 2 if v2 else 0, 2, 4, 4, 4]
+        [2, 2 if v2 else 0, 2 if gumbel else 0, 4, 4, 4]
     out.update(depth=npy(batch["depth"]), mask=npy(batch["mask"]), z_g=npy(log["randn"][0]),
-               z_d=npy(log["randn"][1]), u_g=npy(log["rand"][0]), u_d=npy(log["rand"][1]))
+               z_d=npy(log["randn"][1]))
+    if gumbel:
+        out.update(u_g=npy(log["rand"][0]), u_d=npy(log["rand"][1]))
     if v2:
         out.update(angle=npy(T.auxin["angle"]), shift_g=npy(log["uniform_"][0]), shift_d=npy(log["uniform_"][1]))
     for i, tag in enumerate(("g_fake", "d_real", "d_fake", "r1")):

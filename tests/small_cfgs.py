@@ -20,3 +20,5 @@ V1_SMALL = dict(arch="dusty_v1", synthesis_kwargs=dict(V_SYN, out_ch=[
     measurement_kwargs=dict(raydrop_const=-1, gumbel_temperature=1))
 VD_SMALL = dict(arch="vanilla", layer_kwargs=dict(in_ch=1, ring=True, ch_base=4, ch_max=16,
                                                   resolution=[32, 64]))
+V_SMALL = dict(arch="vanilla", synthesis_kwargs=dict(V_SYN, out_ch=[dict(name="image", ch=1, act=None)]),
+               measurement_kwargs={})

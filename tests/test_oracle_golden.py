@@ -397,17 +397,21 @@ def test_train_iteration_against_reference_trainer_step(g_step):
     assert total > 1000 and near / total > 0.98, (near, total)
 
 
-def test_train_iteration_dusty_v1_against_reference_trainer_step(g_step_v1):
-    """BASELINE config 3: `O.train_iteration(arch="dusty_v1")` against one full iteration of the
-    reference's real `Trainer.step` with the dusty_v1 generator / vanilla discriminator."""
-    g = g_step_v1
+@pytest.mark.parametrize("arch", ["dusty_v1", "vanilla"])
+def test_train_iteration_config3_against_reference_trainer_step(arch):
+    """BASELINE config 3: `O.train_iteration(arch=...)` against one full iteration of the reference's
+    real `Trainer.step` with the dusty_v1 / vanilla generator and the vanilla discriminator."""
+    g = dict(np.load(os.path.join(ROOT, "tests", "golden", f"trainer_step_{arch}.npz")))
     sdG = {k[4:]: T(v).clone() for k, v in g.items() if k.startswith("sdG_")}
     sdD = {k[4:]: T(v).clone() for k, v in g.items() if k.startswith("sdD_")}
     sdG = {k: v.requires_grad_(v.dtype.is_floating_point and not any(t in k for t in ("kernel", "raydrop_const", "w_avg")))
            for k, v in sdG.items()}
     sdD = {k: v.requires_grad_("kernel" not in k) for k, v in sdD.items()}
-    rnd = {k: T(g[k]) for k in ("z_g", "z_d", "u_g", "u_d")}
+    rnd = {k: T(g[k]) for k in ("z_g", "z_d", "u_g", "u_d") if k in g}
     rnd["shift_g"] = rnd["shift_d"] = torch.zeros(4)
+    if arch == "vanilla":
+        assert "u_g" not in g                        # no Gumbel draw: the vanilla generator has no raydrop head
+        rnd["u_g"] = rnd["u_d"] = None
     for tag in ("g_fake", "d_real", "d_fake", "r1"):
         rnd[f"keep_{tag}"] = T(g[f"keep_{tag}"])
         rnd[f"Ginv_{tag}"] = torch.inverse(T(g[f"G_{tag}"]))
@@ -433,14 +437,14 @@ def test_train_iteration_dusty_v1_against_reference_trainer_step(g_step_v1):
             n += 1
         assert n >= min_n, n
 
-    r = O.train_iteration(sdG, sdD, x_real, None, rnd, with_r1=False, arch="dusty_v1")
+    r = O.train_iteration(sdG, sdD, x_real, None, rnd, with_r1=False, arch=arch)
     close(r["loss_G"], g["loss_G"], rtol=1e-4, atol=1e-6)
     check_grads(r["grads_G"], "gG_", 8)
     apply(optG, sdG, r["grads_G"])
-    r = O.train_iteration(sdG, sdD, x_real, None, rnd, with_r1=False, arch="dusty_v1")
+    r = O.train_iteration(sdG, sdD, x_real, None, rnd, with_r1=False, arch=arch)
     close(r["loss_D"], g["loss_D"], rtol=2e-3, atol=1e-5)
     check_grads(r["grads_D"], "gD_", 8)
     apply(optD, sdD, r["grads_D"])
-    r = O.train_iteration(sdG, sdD, x_real, None, rnd, with_r1=True, arch="dusty_v1")
+    r = O.train_iteration(sdG, sdD, x_real, None, rnd, with_r1=True, arch=arch)
     close(r["r1"], g["r1"], rtol=5e-3, atol=1e-7)
     check_grads(r["grads_R1"], "gR1_", 8)

@@ -156,6 +156,19 @@ def test_c_abi_argument_errors_are_status_codes_not_crashes():
     assert rc != 0 and "shape" in K.last_error()
     with pytest.raises(RuntimeError, match="status"):
         K.call("dusty_pad2d_cl", p, p, 1, 8, 8, 8, 9, 0, 0, 0, K.PAD_REPLICATE, K.PAD_CIRCULAR, 0, K.BF16, None)
+    # entries added late in round 1
+    rc = lib.dusty_residual_fork_bwd_cl(p, None, p, 0.125, 0.375, 0.375, 0.125, 1, 8, 8, 8, K.BF16, None)
+    assert rc != 0 and "null" in K.last_error()
+    rc = lib.dusty_residual_fork_bwd_cl(p, p, p, 0.125, 0.375, 0.375, 0.125, 1, 7, 8, 8, K.BF16, None)     # odd H
+    assert rc != 0 and "shape" in K.last_error()
+    rc = lib.dusty_residual_fork_bwd_cl(p, p, p, 0.125, 0.375, 0.375, 0.125, 1, 8, 8, 12, K.BF16, None)    # C % 8
+    assert rc != 0 and "vector" in K.last_error()
+    rc = lib.dusty_up2_sumsq(p, p, None, 0.25, 0.75, 0.75, 0.25, 1, 8, 8, K.BF16, None)
+    assert rc != 0 and "null" in K.last_error()
+    rc = lib.dusty_up2_sumsq(p, p, p, 0.25, 0.75, 0.75, 0.25, 1, 8, 12, K.BF16, None)                      # W % 8
+    assert rc != 0 and "multiple" in K.last_error()
+    rc = lib.dusty_fir1d(p, p, p, 65, 1, 1, 8, 8, 1, 2, 1, 6, 5, None)                                     # > 64 taps
+    assert rc != 0 and "tap count" in K.last_error()
 
 
 def test_inversion_host_logic_and_no_cpu_fallback():

@@ -285,3 +285,20 @@ def test_install_as_gans_resolves_reference_import_lines():
         "assert CoordBridge.__module__.startswith('dusty_gan_v2_b200')",
     ])
     subprocess.run([sys.executable, "-c", code], check=True, timeout=300)
+
+
+def test_ada_controller_matches_reference_trainer_step(g_step):
+    """ADA's probability controller (adaptive_augment.py:368-384, host logic of the mirror) against
+    what the reference's real Trainer.step did in the recorded iteration: rt = mean sign of D(real),
+    p moves by sign(rt - p_target) * n_pred / (kimg * 1000)."""
+    from dusty_gan_v2_b200.gans.augment.adaptive_augment import AdaptiveAugment
+    ada = AdaptiveAugment(p_init=0.5, p_target=0.6, kimg=500, lr_flip=1, ud_flip=1, int_trans=1, iso_scale=1,
+                          frac_trans=1, brightness=1, contrast=1, luma_flip=1, hue=1, saturation=1)
+    rt_ref = float(g_step["ada_rt"])
+    n_pos = int(round((rt_ref + 1) / 2 * 4))
+    y_real = torch.tensor([1.0] * n_pos + [-1.0] * (4 - n_pos)).reshape(4, 1)
+    ada.cumulate(y_real)
+    rt = ada.update_p()
+    assert float(rt) == pytest.approx(rt_ref)
+    assert float(ada.p) == pytest.approx(float(g_step["ada_p_after"].reshape(-1)[0]), abs=1e-7)
+    assert float(ada.sign_cum) == 0.0 and float(ada.n_pred_cum) == 0.0

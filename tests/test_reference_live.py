@@ -341,3 +341,49 @@ def _trainer_step_vs_oracle():
     r = O.train_iteration(sdG, sdD, x_real, angle, rnd, with_r1=True)
     assert float(r["r1"]) == pytest.approx(scalars["loss/D/gradient_penalty"], rel=5e-3, abs=1e-7)
     check_grads(r["grads_R1"], d_grads[1], 10)
+
+
+@pytest.mark.skipif(not os.path.exists(_EXT_UFD), reason="reference `upfirdn2d` extension not prebuilt")
+@pytest.mark.parametrize("p", [1.0, 0.3])
+def test_ada_host_samplers_match_reference_distribution(rops, p):
+    """The mirror samples ADA's transforms on the host (no device sync); their distribution must be
+    the reference's (adaptive_augment.py:386-469): per-entry mean and standard deviation of the
+    affine (3x3) and colour (4x4) matrices over 40 000 draws, within 5 standard errors."""
+    from gans.augment import adaptive_augment as ra
+    from dusty_gan_v2_b200.gans.augment.adaptive_augment import AdaptiveAugment as Mine
+    kw = dict(p_init=p, lr_flip=1, ud_flip=1, int_trans=1, iso_scale=1, frac_trans=1, brightness=1, contrast=1,
+              luma_flip=1, hue=1, saturation=1)
+    N, H, W = 40000, 64, 512
+    torch.manual_seed(1234)
+    ref = ra.AdaptiveAugment(**kw)
+    Gr, Cr = ref.sample_affine(N, H, W), ref.sample_color(N)
+    mine = Mine(**kw)
+    mine.generator = torch.Generator().manual_seed(4321)
+    Gm, Cm = mine.sample_affine(N, H, W), mine.sample_color(N)
+    for a, b, name in ((Gr, Gm, "affine"), (Cr, Cm, "color")):
+        assert a.shape == b.shape, name
+        a, b = a.double(), b.double()
+        se = (a.std(0) + b.std(0)) / np.sqrt(N) + 1e-9
+        assert bool(((a.mean(0) - b.mean(0)).abs() <= 5 * se + 1e-6).all()), (name, a.mean(0), b.mean(0))
+        # standard deviations: relative agreement (heavy-tailed entries: log-normal scales)
+        assert bool(((a.std(0) - b.std(0)).abs() <= 0.05 * (a.std(0) + b.std(0)) / 2 + 1e-6).all()), (
+            name, a.std(0), b.std(0))
+
+
+@pytest.mark.skipif(not os.path.exists(_EXT_UFD), reason="reference `upfirdn2d` extension not prebuilt")
+def test_ada_padding_and_filter_bank_match_reference(rops):
+    """`padding_for` (host ints, no device sync) against the reference's `get_padding`
+    (adaptive_augment.py:271-291) on sampled transforms, and the wavelet filter bank buffer."""
+    from gans.augment import adaptive_augment as ra
+    from dusty_gan_v2_b200.gans.augment import adaptive_augment as ma
+    kw = dict(p_init=0.9, lr_flip=1, ud_flip=1, int_trans=1, iso_scale=1, frac_trans=1, brightness=1, contrast=1,
+              luma_flip=1, hue=1, saturation=1)
+    torch.manual_seed(77)
+    ref = ra.AdaptiveAugment(**kw)
+    for H, W, n in ((64, 512, 64), (16, 64, 8), (32, 64, 128)):
+        G_inv = torch.inverse(ref.sample_affine(n, H, W))
+        want = tuple(int(v) for v in ra.get_padding(G_inv, H, W, 12))
+        assert tuple(int(v) for v in ma.padding_for(G_inv, H, W, 12)) == want
+    mine = ma.AdaptiveAugment(**kw)
+    assert torch.allclose(mine.Hz_fbank, ref.Hz_fbank, rtol=0, atol=1e-7)
+    assert sorted(mine.state_dict().keys()) == sorted(ref.state_dict().keys())

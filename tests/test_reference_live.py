@@ -387,3 +387,73 @@ def test_ada_padding_and_filter_bank_match_reference(rops):
     mine = ma.AdaptiveAugment(**kw)
     assert torch.allclose(mine.Hz_fbank, ref.Hz_fbank, rtol=0, atol=1e-7)
     assert sorted(mine.state_dict().keys()) == sorted(ref.state_dict().keys())
+
+
+@pytest.mark.skipif(not os.path.exists(_EXT_UFD), reason="reference `upfirdn2d` extension not prebuilt")
+def test_trainer_host_methods_match_reference(rops, tmp_path):
+    """Host-side pieces of the mirror Trainer against the reference's own methods executed on the
+    CPU-assembled reference trainer: warm-up schedule (trainer.py:219-232), `fetch_reals`
+    (211-217), the warm-up dropout (234-245, same Bernoulli draw on both sides), `sample_z`."""
+    import torch.distributed as dist
+    from ref_trainer_harness import build_reference_trainer
+    from small_cfgs import D_SMALL, G_SMALL
+    from dusty_gan_v2_b200.config import to_attr
+    from dusty_gan_v2_b200.gans.trainer import Trainer
+    from dusty_gan_v2_b200.presets import preset
+    own_group = not dist.is_initialized()
+    if own_group:
+        dist.init_process_group("gloo", init_method=f"file://{tmp_path}/pg", rank=0, world_size=1)
+    try:
+        B, H, W = 4, 16, 64
+        R, _, _ = build_reference_trainer(G_SMALL, D_SMALL, B, (H, W), [], p_init=0.0)
+    finally:
+        if own_group:
+            dist.destroy_process_group()
+    cfg = preset("dusty_v2", batch_size=B)
+    cfg.model.generator, cfg.model.discriminator = to_attr(G_SMALL), to_attr(D_SMALL)
+    M = Trainer(cfg, iter([]), device="cpu", precision="fp32",
+                angle_file=os.path.join(ref_import.REFERENCE_ROOT, "data/coords/kitti_raw.npy"))
+    assert torch.equal(M.coord.angle, R.coord.angle)
+    for it in (0, 1, 999, 12500, 25000, 49999, 50000, 80000):
+        R.set_warmup_params(it)
+        M.set_warmup_params(it)
+        assert float(M.blur_sigma) == pytest.approx(float(R.blur_sigma), abs=0)
+        assert float(M.dropout_ratio) == pytest.approx(float(R.dropout_ratio), abs=1e-15), it
+    g = torch.Generator().manual_seed(5)
+    batch = {"depth": 90.0 * torch.rand(B, 1, H, W, generator=g), "mask": (torch.rand(B, 1, H, W, generator=g) < 0.8).float()}
+    r, m = R.fetch_reals(batch), M.fetch_reals(batch)
+    assert torch.equal(m["image"], r["image"]) and torch.equal(m["raydrop_mask"], r["raydrop_mask"])
+    for it in (0, 30000):
+        R.set_warmup_params(it)
+        M.set_warmup_params(it)
+        torch.manual_seed(9)
+        xr = R.warmup(r["image"].clone())
+        torch.manual_seed(9)
+        xm = M.warmup(m["image"].clone())
+        assert torch.equal(xm, xr)
+    torch.manual_seed(3)
+    zr = R.sample_z(B)
+    torch.manual_seed(3)
+    assert torch.equal(M.sample_z(B), zr)
+    # ema_inplace (trainer.py:28-41): parameters lerp, buffers copy
+    from gans import trainer as rtr
+    from dusty_gan_v2_b200.gans import trainer as mtr
+    import copy
+    src = torch.nn.Sequential(torch.nn.Linear(3, 4), torch.nn.BatchNorm1d(4))
+    with torch.no_grad():
+        src[1].running_mean.normal_()
+    a, b = copy.deepcopy(src), copy.deepcopy(src)
+    with torch.no_grad():
+        for p_ in list(a.parameters()) + list(a.buffers()):
+            if p_.is_floating_point():
+                p_.add_(1.0)
+        b.load_state_dict(a.state_dict())
+    rtr.ema_inplace(a, src, 0.9)
+    mtr.ema_inplace(b, src, 0.9)
+    for (k, va), vb in zip(a.state_dict().items(), b.state_dict().values()):
+        assert torch.allclose(va.float(), vb.float(), rtol=1e-6, atol=1e-7), k
+    # optimiser settings the mirror derives from the config (trainer.py:137-171: lazy regularisation)
+    lazy = 16 / 17.0
+    assert M.optim_D.param_groups[0]["lr"] == pytest.approx(0.002 * lazy, rel=1e-12)
+    assert M.optim_D.param_groups[0]["betas"] == pytest.approx((0.0, 0.99 ** lazy), rel=1e-12)
+    assert M.optim_G.param_groups[0]["lr"] == pytest.approx(0.002) and M.gp_weight == 16 and M.gp_every == 16

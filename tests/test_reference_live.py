@@ -457,3 +457,27 @@ def test_trainer_host_methods_match_reference(rops, tmp_path):
     assert M.optim_D.param_groups[0]["lr"] == pytest.approx(0.002 * lazy, rel=1e-12)
     assert M.optim_D.param_groups[0]["betas"] == pytest.approx((0.0, 0.99 ** lazy), rel=1e-12)
     assert M.optim_G.param_groups[0]["lr"] == pytest.approx(0.002) and M.gp_weight == 16 and M.gp_every == 16
+
+
+def test_gan_loss_all_objectives_match_reference(rops):
+    """gans/models/loss.py mirror: every objective the reference implements (loss.py:37-88), both
+    modes, values and gradients."""
+    from gans.models.loss import GANLoss as Ref
+    from dusty_gan_v2_b200.gans.models.loss import GANLoss as Mine
+    g = torch.Generator().manual_seed(42)
+    for metric in Mine.METRICS:
+        for smoothing in (1.0, 0.9):
+            ref, mine = Ref(metric, smoothing), Mine(metric, smoothing)
+            for mode in ("G", "D"):
+                r0, f0 = torch.randn(6, 1, generator=g), torch.randn(6, 1, generator=g)
+                outs = []
+                for crit in (ref, mine):
+                    r, f = r0.clone().requires_grad_(), f0.clone().requires_grad_()
+                    loss = crit(r, f, mode)
+                    grads = torch.autograd.grad(loss, [r, f], allow_unused=True)
+                    outs.append((loss.detach(), grads))
+                assert torch.allclose(outs[0][0], outs[1][0], rtol=1e-6, atol=1e-7), (metric, mode)
+                for ga, gb in zip(outs[0][1], outs[1][1]):
+                    assert (ga is None) == (gb is None), (metric, mode)
+                    if ga is not None:
+                        assert torch.allclose(ga, gb, rtol=1e-6, atol=1e-7), (metric, mode)

@@ -481,3 +481,38 @@ def test_gan_loss_all_objectives_match_reference(rops):
                     assert (ga is None) == (gb is None), (metric, mode)
                     if ga is not None:
                         assert torch.allclose(ga, gb, rtol=1e-6, atol=1e-7), (metric, mode)
+
+
+@pytest.mark.parametrize("arch", ["dusty_v2", "dusty_v1", "vanilla"])
+def test_presets_equal_reference_yaml(arch):
+    """`presets.preset(arch)` against the reference's own `configs/gans/<arch>.yaml` read by the
+    mirror's `load_config`: every model / training / dataset value on the hot path is identical;
+    only out-of-scope keys (dataset paths and splits, checkpoint cadence, validation) are absent."""
+    from dusty_gan_v2_b200 import load_config
+    from dusty_gan_v2_b200.presets import preset
+
+    def plain(x):
+        if isinstance(x, dict):
+            return {k: plain(v) for k, v in x.items()}
+        if isinstance(x, (list, tuple)):
+            return [plain(v) for v in x]
+        return x
+
+    y = plain(load_config(os.path.join(ref_import.REFERENCE_ROOT, "configs", "gans", f"{arch}.yaml")))
+    p = plain(preset(arch, batch_size=y["training"]["batch_size"],
+                     resolution=tuple(y["model"]["generator"]["synthesis_kwargs"]["resolution"])))
+
+    def diff(a, b, path=""):
+        if isinstance(a, dict) and isinstance(b, dict):
+            out = []
+            for k in sorted(set(a) | set(b)):
+                if k not in a or k not in b:
+                    out.append(f"{path}/{k}")
+                else:
+                    out += diff(a[k], b[k], f"{path}/{k}")
+            return out
+        return [] if a == b else [path]
+
+    allowed = {"/dataset/flip", "/dataset/root", "/dataset/test", "/dataset/train", "/dataset/val",
+               "/training/checkpoint", "/training/pin_memory", "/validation"}
+    assert set(diff(y, p)) <= allowed, sorted(set(diff(y, p)) - allowed)

@@ -394,3 +394,16 @@ class Trainer:
                 "G": self.G_module.state_dict(), "D": self.D_module.state_dict(),
                 "G_ema": self.G_ema.state_dict(), "A": self.A.state_dict(),
                 "optim_G": self.optim_G.state_dict(), "optim_D": self.optim_D.state_dict()}
+
+    def load_state_dict(self, state, strict=True):
+        """Resume from a checkpoint payload with the reference's keys -- one written by
+        `state_dict(step)` here or by the reference's `Trainer.save_checkpoint`
+        (trainer.py:184-196, 551-567).  Weights are copied into the existing tensors, so captured
+        CUDA graphs stay valid.  Returns the iteration to continue from (`step // batch_size`)."""
+        self.G_module.load_state_dict(state["G"], strict=strict)
+        self.D_module.load_state_dict(state["D"], strict=strict)
+        self.G_ema.load_state_dict(state["G_ema"], strict=strict)
+        self.A.load_state_dict(state["A"])
+        self.optim_G.load_state_dict(state["optim_G"])
+        self.optim_D.load_state_dict(state["optim_D"])
+        return int(state["step"]) // int(self.cfg.training.batch_size)

@@ -302,3 +302,39 @@ def test_ada_controller_matches_reference_trainer_step(g_step):
     assert float(rt) == pytest.approx(rt_ref)
     assert float(ada.p) == pytest.approx(float(g_step["ada_p_after"].reshape(-1)[0]), abs=1e-7)
     assert float(ada.sign_cum) == 0.0 and float(ada.n_pred_cum) == 0.0
+
+
+def test_trainer_checkpoint_round_trip_on_host():
+    """`Trainer.state_dict(step)` (the reference's checkpoint keys, trainer.py:551-567) ->
+    `Trainer.load_state_dict` (resume, trainer.py:184-196): weights, EMA copy, ADA state, both Adam
+    states and the start iteration survive; host-only (construction needs no GPU)."""
+    from small_cfgs import D_SMALL, G_SMALL
+    from dusty_gan_v2_b200.config import to_attr
+    from dusty_gan_v2_b200.gans.trainer import Trainer
+    from dusty_gan_v2_b200.presets import preset
+
+    def make(seed):
+        torch.manual_seed(seed)
+        np.random.seed(seed)
+        cfg = preset("dusty_v2", batch_size=4)
+        cfg.model.generator, cfg.model.discriminator = to_attr(G_SMALL), to_attr(D_SMALL)
+        return Trainer(cfg, iter([]), device="cpu", precision="fp32",
+                       angle_file=os.path.join(ROOT, "data/coords/kitti_raw.npy"))
+
+    a, b = make(1), make(2)
+    for opt, net in ((a.optim_G, a.G_module), (a.optim_D, a.D_module)):      # give Adam some state
+        for p in net.parameters():
+            p.requires_grad_(True)
+            p.grad = torch.randn_like(p)
+        opt.step()
+    a.A.p.fill_(0.25)
+    payload = a.state_dict(step=7 * 4)
+    assert set(payload) == {"cfg", "step", "angle", "G", "D", "G_ema", "A", "optim_G", "optim_D"}
+    assert b.load_state_dict(payload) == 7
+    for x, y in ((a.G_module, b.G_module), (a.D_module, b.D_module), (a.G_ema, b.G_ema), (a.A, b.A)):
+        for (k, u), v in zip(x.state_dict().items(), y.state_dict().values()):
+            assert torch.equal(u, v), k
+    for oa, na, ob, nb in ((a.optim_G, a.G_module, b.optim_G, b.G_module), (a.optim_D, a.D_module, b.optim_D, b.D_module)):
+        for pa, pb in zip(na.parameters(), nb.parameters()):
+            assert torch.equal(oa.state[pa]["exp_avg"], ob.state[pb]["exp_avg"])
+            assert torch.equal(oa.state[pa]["exp_avg_sq"], ob.state[pb]["exp_avg_sq"])

@@ -516,3 +516,77 @@ def test_presets_equal_reference_yaml(arch):
     allowed = {"/dataset/flip", "/dataset/root", "/dataset/test", "/dataset/train", "/dataset/val",
                "/training/checkpoint", "/training/pin_memory", "/validation"}
     assert set(diff(y, p)) <= allowed, sorted(set(diff(y, p)) - allowed)
+
+
+@pytest.mark.skipif(not os.path.exists(_EXT_UFD), reason="reference `upfirdn2d` extension not prebuilt")
+def test_checkpoint_written_by_reference_resumes_in_mirror(rops, tmp_path):
+    """A checkpoint written by the reference's own `Trainer.save_checkpoint` (trainer.py:551-567)
+    after one real training iteration resumes in the mirror Trainer: weights, EMA copy, ADA state
+    and both Adam states land on the parameters of the same name (the optimiser state is indexed
+    by parameter ORDER, so this also pins the module registration order); and the payload the
+    mirror writes loads back into the reference's modules."""
+    import pathlib
+    import torch.distributed as dist
+    from ref_trainer_harness import build_reference_trainer
+    from small_cfgs import D_SMALL, G_SMALL
+    from dusty_gan_v2_b200.config import to_attr
+    from dusty_gan_v2_b200.gans.trainer import Trainer
+    from dusty_gan_v2_b200.presets import preset
+    B, H, W = 4, 16, 64
+    g = torch.Generator().manual_seed(21)
+    batch = {"depth": 1.45 + 78.55 * torch.rand(B, 1, H, W, generator=g),
+             "mask": (torch.rand(B, 1, H, W, generator=g) < 0.85).float()}
+    own_group = not dist.is_initialized()
+    if own_group:
+        dist.init_process_group("gloo", init_method=f"file://{tmp_path}/pg", rank=0, world_size=1)
+    try:
+        torch.manual_seed(22)
+        np.random.seed(22)
+        R, RG, RD = build_reference_trainer(G_SMALL, D_SMALL, B, (H, W), [batch], p_init=0.3)
+        R.step(0)
+        path = pathlib.Path(tmp_path) / "ckpt" / "0000000004.pth"
+        R.save_checkpoint(path, step=3 * B)
+    finally:
+        if own_group:
+            dist.destroy_process_group()
+    state = torch.load(path, map_location="cpu", weights_only=False)
+    cfg = preset("dusty_v2", batch_size=B)
+    cfg.model.generator, cfg.model.discriminator = to_attr(G_SMALL), to_attr(D_SMALL)
+    M = Trainer(cfg, iter([]), device="cpu", precision="fp32",
+                angle_file=os.path.join(ref_import.REFERENCE_ROOT, "data/coords/kitti_raw.npy"))
+    assert [n for n, _ in M.G_module.named_parameters()] == [n for n, _ in RG.named_parameters()]
+    assert [n for n, _ in M.D_module.named_parameters()] == [n for n, _ in RD.named_parameters()]
+    assert M.load_state_dict(state) == 3
+    for mine, ref in ((M.G_module, RG), (M.D_module, RD), (M.G_ema, R.G_ema), (M.A, R.A)):
+        rs = ref.state_dict()
+        ms = mine.state_dict()
+        assert list(ms.keys()) == list(rs.keys())
+        for k in rs:
+            assert torch.equal(ms[k].float().reshape(-1), rs[k].float().reshape(-1)), k
+    for m_opt, m_net, r_opt, r_net in ((M.optim_G, M.G_module, R.optim_G, RG), (M.optim_D, M.D_module, R.optim_D, RD)):
+        r_by_name = dict(r_net.named_parameters())
+        n = 0
+        for name, p in m_net.named_parameters():
+            rst = r_opt.state.get(r_by_name[name])
+            if not rst:
+                continue
+            mst = m_opt.state[p]
+            assert torch.equal(mst["exp_avg"], rst["exp_avg"]) and torch.equal(mst["exp_avg_sq"], rst["exp_avg_sq"]), name
+            assert float(mst["step"]) == float(rst["step"])
+            n += 1
+        assert n >= 10
+        assert m_opt.param_groups[0]["lr"] == r_opt.param_groups[0]["lr"]
+        assert tuple(m_opt.param_groups[0]["betas"]) == tuple(r_opt.param_groups[0]["betas"])
+    # and back: the mirror's payload loads into the reference's modules
+    back = M.state_dict(step=3 * B)
+    assert set(back.keys()) == set(state.keys())
+    RG.load_state_dict(back["G"], strict=True)
+    RD.load_state_dict(back["D"], strict=True)
+    R.G_ema.load_state_dict(back["G_ema"], strict=True)
+    # (the reference's own `p` buffer turns from 0-dim into shape [1] at its first update_p, so a
+    # running reference trainer cannot even reload its own initial state; a fresh one takes ours)
+    from gans.augment.adaptive_augment import AdaptiveAugment as RefADA
+    RefADA(p_init=0.3, p_target=0.6, kimg=500, lr_flip=1, ud_flip=1, int_trans=1, iso_scale=1, frac_trans=1,
+           brightness=1, contrast=1, luma_flip=1, hue=1, saturation=1).load_state_dict(back["A"])
+    R.optim_G.load_state_dict(back["optim_G"])
+    R.optim_D.load_state_dict(back["optim_D"])

@@ -590,3 +590,35 @@ def test_checkpoint_written_by_reference_resumes_in_mirror(rops, tmp_path):
            brightness=1, contrast=1, luma_flip=1, hue=1, saturation=1).load_state_dict(back["A"])
     R.optim_G.load_state_dict(back["optim_G"])
     R.optim_D.load_state_dict(back["optim_D"])
+
+
+def test_mapping_network_style_mixing_truncation_match_reference(rops):
+    """base.Generator host-side paths that run without a kernel (base.py:26-114): mapping network,
+    style mixing (same `random.randint` / `torch.randn_like` consumption), truncation trick and the
+    w_avg moving average -- mirror against the reference with the same weights and seeds."""
+    import random
+    from gans.models.builder import build_generator as ref_build
+    from small_cfgs import G_SMALL
+    from dusty_gan_v2_b200.gans.models.builder import build_generator as my_build
+    torch.manual_seed(7)
+    np.random.seed(7)
+    R = ref_build(ref_import.to_attr(G_SMALL))
+    M = my_build(G_SMALL)
+    M.load_state_dict(R.state_dict(), strict=True)
+    z = torch.randn(5, 16)
+    assert torch.allclose(M.mapping_network(z), R.mapping_network(z), rtol=1e-6, atol=1e-7)
+    for seed in (0, 1, 2):
+        outs = []
+        for net in (R, M):
+            random.seed(seed)
+            torch.manual_seed(seed)
+            outs.append(net.forward_mapping(z, style_mixing=True))
+        assert outs[0].shape == outs[1].shape and torch.allclose(outs[0], outs[1], rtol=1e-6, atol=1e-7)
+    w = R.forward_mapping(z, False)
+    with torch.no_grad():
+        R.w_avg.normal_()
+        M.w_avg.copy_(R.w_avg)
+    assert torch.allclose(M.truncation_trick(w, 0.6), R.truncation_trick(w, 0.6), rtol=1e-6, atol=1e-7)
+    R.moving_average_w(w)
+    M.moving_average_w(w)
+    assert torch.allclose(M.w_avg, R.w_avg, rtol=1e-6, atol=1e-8)

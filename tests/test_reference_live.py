@@ -622,3 +622,24 @@ def test_mapping_network_style_mixing_truncation_match_reference(rops):
     R.moving_average_w(w)
     M.moving_average_w(w)
     assert torch.allclose(M.w_avg, R.w_avg, rtol=1e-6, atol=1e-8)
+
+
+@pytest.mark.parametrize("demod,ema", [(True, True), (False, True), (True, False)])
+def test_modconv_composite_weights_match_reference_forward(rops, demod, ema):
+    """`ModConv2d._effective_weights_composite` (the plain-tensor statement of the fused
+    dusty_modprep kernel, which the GPU tests hold that kernel to) against the reference module:
+    bmm(wb, x) equals the reference's grouped-convolution forward (style.py:68-126)."""
+    from dusty_gan_v2_b200.gans.models.ops.style import ModConv2d as Mine
+    torch.manual_seed(11)
+    C, Oc, Mch = 12, 7, 16
+    ref = rops.ModConv2d(in_ch=C, out_ch=Oc, mod_ch=Mch, ksize=1, stride=1, padding=0, demod=demod, bias=False,
+                         ema=ema).eval()
+    mine = Mine(in_ch=C, out_ch=Oc, mod_ch=Mch, ksize=1, stride=1, padding=0, demod=demod, bias=False, ema=ema)
+    mine.load_state_dict(ref.state_dict(), strict=True)
+    with torch.no_grad():
+        ref.ema_var.fill_(0.8)
+        mine.ema_var.fill_(0.8)
+    x, style = torch.randn(3, C, 4, 8), torch.randn(3, Mch)
+    wb = mine._effective_weights_composite(mine.mod(style))
+    y = torch.bmm(wb, x.flatten(2)).reshape(3, Oc, 4, 8)
+    assert torch.allclose(y, ref(x, style), rtol=1e-4, atol=1e-5)

@@ -1,5 +1,9 @@
-"""Drop-in for gans/models/loss.py: GANLoss (reference 22-88).  Thin scalar math on [B,1]
-logits -- stays in PyTorch."""
+"""Drop-in for gans/models/loss.py: `GANLoss(metric, smoothing)(pred_real, pred_fake, mode)`
+(reference 22-88) for the seven objectives the reference implements.  Scalar math on [B, 1]
+logits: stays in PyTorch.  Each objective is a pair (discriminator loss, generator loss) of
+functions of (real logits, fake logits); the relativistic-average ones see each side relative to
+the batch mean of the other (reference 7-18).
+"""
 import torch
 import torch.nn as nn
 import torch.nn.functional as F
@@ -8,6 +12,32 @@ import torch.nn.functional as F
 def _rel(a, b):
     """a - mean(b) over the batch (relativistic average)."""
     return a - b.mean(0, keepdim=True)
+
+
+def _sq(x):
+    return (x ** 2).mean()
+
+
+def _objectives(crit):
+    one = lambda t: crit.label_real.expand_as(t)            # noqa: E731
+    zero = lambda t: crit.label_fake.expand_as(t)           # noqa: E731
+    sp, relu = F.softplus, F.relu
+    return {
+        "nsgan": (lambda r, f: sp(-r).mean() + sp(f).mean(),
+                  lambda r, f: sp(-f).mean()),
+        "wgan": (lambda r, f: -r.mean() + f.mean(),
+                 lambda r, f: -f.mean()),
+        "lsgan": (lambda r, f: F.mse_loss(r, one(r) * crit.smoothing) + F.mse_loss(f, zero(f)),
+                  lambda r, f: F.mse_loss(f, one(f))),
+        "hinge": (lambda r, f: relu(1 - r).mean() + relu(1 + f).mean(),
+                  lambda r, f: -f.mean()),
+        "ragan": (lambda r, f: sp(-_rel(r, f)).mean() + sp(_rel(f, r)).mean(),
+                  lambda r, f: sp(_rel(r, f)).mean() + sp(-_rel(f, r)).mean()),
+        "rahinge": (lambda r, f: relu(1 - _rel(r, f)).mean() + relu(1 + _rel(f, r)).mean(),
+                    lambda r, f: relu(1 + _rel(r, f)).mean() + relu(1 - _rel(f, r)).mean()),
+        "ralsgan": (lambda r, f: _sq(_rel(r, f) - 1.0) + _sq(_rel(f, r) + 1.0),
+                    lambda r, f: _sq(_rel(r, f) + 1.0) + _sq(_rel(f, r) - 1.0)),
+    }
 
 
 class GANLoss(nn.Module):
@@ -20,44 +50,19 @@ class GANLoss(nn.Module):
         self.metric = metric
         self.smoothing = smoothing
 
+    def _pair(self):
+        table = _objectives(self)
+        if self.metric not in table:
+            raise NotImplementedError(self.metric)
+        return table[self.metric]
+
+    def loss_D(self, pred_real, pred_fake):
+        return self._pair()[0](pred_real, pred_fake)
+
+    def loss_G(self, pred_real, pred_fake):
+        return self._pair()[1](pred_real, pred_fake)
+
     def forward(self, pred_real, pred_fake, mode):
-        if mode == "G":
-            return self.loss_G(pred_real, pred_fake)
-        if mode == "D":
-            return self.loss_D(pred_real, pred_fake)
-        raise ValueError(mode)
-
-    def loss_D(self, r, f):
-        m = self.metric
-        if m == "nsgan":
-            return F.softplus(-r).mean() + F.softplus(f).mean()
-        if m == "wgan":
-            return -r.mean() + f.mean()
-        if m == "lsgan":
-            return (F.mse_loss(r, self.label_real.expand_as(r) * self.smoothing)
-                    + F.mse_loss(f, self.label_fake.expand_as(f)))
-        if m == "hinge":
-            return F.relu(1 - r).mean() + F.relu(1 + f).mean()
-        if m == "ragan":
-            return F.softplus(-_rel(r, f)).mean() + F.softplus(_rel(f, r)).mean()
-        if m == "rahinge":
-            return F.relu(1 - _rel(r, f)).mean() + F.relu(1 + _rel(f, r)).mean()
-        if m == "ralsgan":
-            return ((_rel(r, f) - 1.0) ** 2).mean() + ((_rel(f, r) + 1.0) ** 2).mean()
-        raise NotImplementedError(m)
-
-    def loss_G(self, r, f):
-        m = self.metric
-        if m == "nsgan":
-            return F.softplus(-f).mean()
-        if m in ("wgan", "hinge"):
-            return -f.mean()
-        if m == "lsgan":
-            return F.mse_loss(f, self.label_real.expand_as(f))
-        if m == "ragan":
-            return F.softplus(_rel(r, f)).mean() + F.softplus(-_rel(f, r)).mean()
-        if m == "rahinge":
-            return F.relu(1 + _rel(r, f)).mean() + F.relu(1 - _rel(f, r)).mean()
-        if m == "ralsgan":
-            return ((_rel(r, f) + 1.0) ** 2).mean() + ((_rel(f, r) - 1.0) ** 2).mean()
-        raise NotImplementedError(m)
+        if mode not in ("G", "D"):
+            raise ValueError(mode)
+        return (self.loss_G if mode == "G" else self.loss_D)(pred_real, pred_fake)

@@ -136,6 +136,14 @@ class LatentInversion:
                  num_z_samples=10_000):
         if latent_type not in ("z", "w", "w+"):
             raise ValueError(f"{latent_type=}")
+        if optimize_phase:
+            # demo_inversion.py's --optimize_phase needs d(image)/d(angle): the Fourier operand of
+            # the modulated contraction is a non-differentiable input of our kernels
+            # (functional.fourier_features / modconv_bmm detach it), so the option would
+            # silently optimise nothing.  Refuse it instead.
+            raise NotImplementedError(
+                "LatentInversion(optimize_phase=True): the gradient w.r.t. the angle grid is not "
+                "implemented by the B200 kernels (Fourier features are a constant operand)")
         if not depth.is_cuda:
             raise RuntimeError("LatentInversion: CUDA tensors only (no CPU fallback)")
         self.G, self.coord = G, coord

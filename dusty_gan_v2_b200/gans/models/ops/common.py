@@ -386,7 +386,9 @@ class EqualLR(nn.Module):
         by the same launch when our tcgen05 convolutions are in use, else None)."""
         m = self.module
         if m.weight.is_cuda and m.weight.dim() == 4:
-            want = with_tco and DF._CONV_IMPL["mode"] != "library" and m.weight.requires_grad is not None
+            # the [R*S][C][O] copy feeds the data-gradient kernels only: skip it when no
+            # backward pass can follow
+            want = with_tco and DF._CONV_IMPL["mode"] != "library" and torch.is_grad_enabled()
             r = DF.prep_conv_weight(m.weight, self.scale * self.gain_, dtype, want)
             if with_tco:
                 return r if want else (r, None)

@@ -122,9 +122,15 @@ class Trainer:
             if not self.cuda_graphs:
                 self.G = DDP(self.G, broadcast_buffers=True, **kw)
                 self.D = DDP(self.D, broadcast_buffers=False, **kw)
-            # graphed path: gradients of G (17.5 MB) and D (154 MB) are all-reduced as flat
-            # NCCL buckets right after each backward, G buffers broadcast before its forward
-            # -- the same collectives DDP would issue (graph replays bypass DDP's hooks)
+            else:
+                # graphed path: no DDP wrapper (graph replays bypass its hooks), so do what its
+                # constructor does -- every rank starts from rank 0's parameters and buffers
+                # (ranks seed differently: reference utils.init_random_seed(seed, rank)) -- and
+                # re-derive G_ema from the synchronised G.  Gradients of G (17.5 MB) and D
+                # (154 MB) are all-reduced as flat NCCL buckets after each backward, G's
+                # buffers broadcast before its forward: the collectives DDP would issue.
+                self._broadcast_module_states(self.G, self.D)
+                self.G_ema.load_state_dict(self.G.state_dict())
         for m in (self.G, self.G_ema, self.D, self.A, self.coord):
             m.requires_grad_(False)
 
@@ -167,6 +173,21 @@ class Trainer:
         self.dropout_ratio = 0.0
         self.scalar_names = []
 
+    @staticmethod
+    @torch.no_grad()
+    def _broadcast_module_states(*modules, src=0):
+        """Rank `src`'s parameters and buffers to every rank (what DDP's constructor does),
+        as one flat broadcast per dtype."""
+        by_dtype = {}
+        for m in modules:
+            for t in list(m.parameters()) + list(m.buffers()):
+                by_dtype.setdefault(t.dtype, []).append(t.data)
+        for tensors in by_dtype.values():
+            flat = torch.cat([t.reshape(-1) for t in tensors])
+            dist.broadcast(flat, src)
+            torch._foreach_copy_(tensors, [c.reshape(t.shape) for t, c in
+                                           zip(tensors, flat.split([t.numel() for t in tensors]))])
+
     # ------------------------------------------------------------------ inputs
     def sample_z(self, batch_size):
         return torch.randn(batch_size, self.z_dim, device=self.device)
@@ -207,6 +228,27 @@ class Trainer:
             torch._foreach_copy_(bufs, [c.reshape(b.shape).to(b.dtype)
                                         for b, c in zip(bufs, flat.split([b.numel() for b in bufs]))])
 
+    class _KeepState:
+        """Graph warm-up and capture run extra real forwards of the live train-mode generator:
+        each one moves `ema_var` / `w_avg` and consumes device RNG.  Snapshot the buffers and
+        the RNG state, restore them afterwards, so that a graphed trainer starts from exactly
+        the state an eager one (or the reference) has for the same seed."""
+
+        def __init__(self, module, device):
+            self.module, self.device = module, device
+
+        def __enter__(self):
+            self.bufs = [b.detach().clone() for b in self.module.buffers()]
+            self.rng = torch.cuda.get_rng_state(self.device)
+
+        def __exit__(self, *exc):
+            torch.cuda.synchronize(self.device)
+            with torch.no_grad():
+                for b, c in zip(self.module.buffers(), self.bufs):
+                    b.copy_(c)
+            torch.cuda.set_rng_state(self.rng, self.device)
+            return False
+
     def _G_train_forward(self, z):
         """x_fake for the G step, with autograd.  With CUDA graphs: forward and backward of
         the whole generator are two graph launches (torch.cuda.make_graphed_callables)."""
@@ -218,7 +260,8 @@ class Trainer:
             wrapper = _GImage(self.G_module, self.auxin)
             n0 = _cabi.launch_count()
             try:
-                self._G_train_callable = torch.cuda.make_graphed_callables(wrapper, (z.clone(),))
+                with self._KeepState(self.G_module, self.device):
+                    self._G_train_callable = torch.cuda.make_graphed_callables(wrapper, (z.clone(),))
                 # 3 warm-up passes + 1 capture, each forward + backward
                 self._G_train_launches = (_cabi.launch_count() - n0) // 4
             except Exception as exc:           # capture not possible: stay eager, loudly
@@ -285,17 +328,18 @@ class Trainer:
         from .. import _cabi
         self._sync_G_buffers()
         if self._g_graph is None:
-            side = torch.cuda.Stream(device=self.device)
-            side.wait_stream(torch.cuda.current_stream(self.device))
-            with torch.cuda.stream(side), torch.no_grad():
-                for _ in range(2):          # warm-up outside capture (lazy inits, autotune)
-                    self.G_module(self.sample_z(B), **self.auxin)
-            torch.cuda.current_stream(self.device).wait_stream(side)
-            graph = torch.cuda.CUDAGraph()
-            n0 = _cabi.launch_count()
-            with torch.no_grad(), torch.cuda.graph(graph):
-                out = self.G_module(self.sample_z(B), **self.auxin)["image"]
-            self._g_graph_launches = _cabi.launch_count() - n0
+            with self._KeepState(self.G_module, self.device):
+                side = torch.cuda.Stream(device=self.device)
+                side.wait_stream(torch.cuda.current_stream(self.device))
+                with torch.cuda.stream(side), torch.no_grad():
+                    for _ in range(2):          # warm-up outside capture (lazy inits, autotune)
+                        self.G_module(self.sample_z(B), **self.auxin)
+                torch.cuda.current_stream(self.device).wait_stream(side)
+                graph = torch.cuda.CUDAGraph()
+                n0 = _cabi.launch_count()
+                with torch.no_grad(), torch.cuda.graph(graph):
+                    out = self.G_module(self.sample_z(B), **self.auxin)["image"]
+                self._g_graph_launches = _cabi.launch_count() - n0
             self._g_graph, self._g_graph_out = graph, out
         self._g_graph.replay()
         self.graph_replayed_launches += self._g_graph_launches
@@ -316,7 +360,10 @@ class Trainer:
         self.optim_G.zero_grad(set_to_none=True)
         x_fake = self._G_train_forward(self.sample_z(B))
         y_fake = self._D_forward(self.A(self.warmup(x_fake)), "frozen")
-        loss_gan = self.adversarial_loss(None, y_fake, "G")
+        y_real = None
+        if tr.gan_objective in ("ragan", "rahinge", "ralsgan"):      # trainer.py:263,281-286
+            y_real = _DLogits(self.D, 1)(self.A(self.warmup(x_real)).detach())
+        loss_gan = self.adversarial_loss(y_real, y_fake, "G")
         (tr.loss.gan * loss_gan).backward()
         self._allreduce_G_grads()
         self.optim_G.step()

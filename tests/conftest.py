@@ -77,3 +77,8 @@ def g_invloop():
 @pytest.fixture(scope="session")
 def g_step():
     return load_golden("trainer_step.npz")
+
+
+@pytest.fixture(scope="session")
+def g_step_mid():
+    return load_golden("trainer_step_mid.npz")

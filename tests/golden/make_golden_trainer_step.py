@@ -21,7 +21,7 @@ sys.path.insert(0, ROOT)
 sys.path.insert(0, os.path.join(ROOT, "tests"))
 
 from ref_trainer_harness import build_reference_trainer, record_step  # noqa: E402
-from small_cfgs import D_SMALL, G_SMALL, V1_SMALL, V_SMALL, VD_SMALL  # noqa: E402
+from small_cfgs import D_MID, D_SMALL, G_MID, G_SMALL, V1_SMALL, V_SMALL, VD_SMALL, sample_flat  # noqa: E402
 
 npy = lambda t: t.detach().cpu().numpy().copy()  # noqa: E731
 
@@ -31,10 +31,13 @@ def main():
     one(G_SMALL, D_SMALL, (16, 64), "trainer_step.npz", 1100)
     one(V1_SMALL, VD_SMALL, (32, 64), "trainer_step_dusty_v1.npz", 1200)       # BASELINE config 3
     one(V_SMALL, VD_SMALL, (32, 64), "trainer_step_vanilla.npz", 1300)
+    # channel counts that qualify for the tcgen05 kernels (bf16 / CUDA-graph twin of the replay
+    # test); gradients and updated weights stored as fixed-stride samples + norms to stay small
+    one(G_MID, D_MID, (32, 128), "trainer_step_mid.npz", 1400, compact=True, logit_gain=True)
     dist.destroy_process_group()
 
 
-def one(g_cfg, d_cfg, res, fname, seed):
+def one(g_cfg, d_cfg, res, fname, seed, compact=False, logit_gain=False):
     B, (H, W) = 4, res
     v2 = g_cfg["arch"] == "dusty_v2"
     torch.manual_seed(seed)
@@ -48,6 +51,15 @@ def one(g_cfg, d_cfg, res, fname, seed):
             for n, p in net.named_parameters():
                 if "bias" in n:
                     p.normal_(0, 0.2)
+    if logit_gain:
+        # a state with O(1) logits (random-init logits are ~0.05: a bf16 comparison of them would
+        # measure rounding noise): widen D's last linear until std(D(x)) ~ 1 on the real batch
+        with torch.no_grad():
+            x = T.fetch_reals(batch)["image"]
+            last = D.epilogue[-1].module
+            s0 = float(D(x).std())
+            last.weight.mul_(1.0 / max(s0, 1e-6))
+            print(f"{fname}: logit std {s0:.4f} -> {float(D(x).std()):.4f}")
     out = {f"sdG_{k}": npy(v) for k, v in G.state_dict().items()}
     out.update({f"sdD_{k}": npy(v) for k, v in D.state_dict().items()})
     scalars, log, g_grads, d_grads = record_step(T, G, D, 0)
@@ -67,11 +79,19 @@ def one(g_cfg, d_cfg, res, fname, seed):
     out.update(loss_G=np.array(scalars["loss/G/adversarial"]), loss_D=np.array(scalars["loss/D/adversarial"]),
                r1=np.array(scalars["loss/D/gradient_penalty"]), ada_rt=np.array(scalars["stats/ada_rt"]),
                ada_p_after=npy(T.A.p), ema_decay=np.array(scalars["stats/ema_decay"]))
-    out.update({f"gG_{k}": npy(v) for k, v in g_grads.items()})
-    out.update({f"gD_{k}": npy(v) for k, v in d_grads[0].items()})
-    out.update({f"gR1_{k}": npy(v) for k, v in d_grads[1].items()})
-    out.update({f"afterG_{k}": npy(v) for k, v in G.state_dict().items() if "kernel" not in k and "pe." not in k})
-    out.update({f"afterD_{k}": npy(v) for k, v in D.state_dict().items() if "kernel" not in k})
+    def put(prefix, items):
+        for k, v in items:
+            if compact:
+                out[f"{prefix}_{k}"] = npy(sample_flat(v))
+                out[f"n{prefix}_{k}"] = np.array(float(v.detach().double().norm()))
+            else:
+                out[f"{prefix}_{k}"] = npy(v)
+
+    put("gG", g_grads.items())
+    put("gD", d_grads[0].items())
+    put("gR1", d_grads[1].items())
+    put("afterG", [(k, v) for k, v in G.state_dict().items() if "kernel" not in k and "pe." not in k])
+    put("afterD", [(k, v) for k, v in D.state_dict().items() if "kernel" not in k])
     out.update({f"afterGema_{k}": npy(v) for k, v in T.G_ema.state_dict().items() if k.endswith("ema_var") or k == "w_avg"})
     path = os.path.join(HERE, fname)
     np.savez_compressed(path, **out)

@@ -22,3 +22,31 @@ VD_SMALL = dict(arch="vanilla", layer_kwargs=dict(in_ch=1, ring=True, ch_base=4,
                                                   resolution=[32, 64]))
 V_SMALL = dict(arch="vanilla", synthesis_kwargs=dict(V_SYN, out_ch=[dict(name="image", ch=1, act=None)]),
                measurement_kwargs={})
+
+# Mid-size dusty_v2 pair whose channel counts qualify for the tcgen05 kernels (G: 64-wide
+# features so a 64-channel K block never straddles the feature / Fourier sources, 256-pixel
+# lowest level; D: 16..32 channels, multiples of 8) -- tests/golden/trainer_step_mid.npz.
+G_MID = dict(
+    arch="dusty_v2",
+    mapping_kwargs=dict(in_ch=64, out_ch=64, depth=2),
+    synthesis_kwargs=dict(
+        in_ch=64,
+        out_ch=[dict(name="image", ch=1, act="nn.Tanh"), dict(name="raydrop_logit", ch=1, act=None)],
+        ch_base=32, ch_max=64, resolution=[32, 128], layers=[2, 2], ring=True,
+        num_fp16_layers=-1, use_noise=False, pe_type="random", pe_scale_offset=[3, -1],
+        aug_coords=True, aug_coords_blitting=False),
+    measurement_kwargs=dict(raydrop_const=-1, gumbel_temperature=1),
+)
+D_MID = dict(arch="dusty_v2", layer_kwargs=dict(in_ch=1, ring=True, ch_base=16, ch_max=32,
+                                                resolution=[32, 128], mbdis_group=4, mbdis_feat=1,
+                                                num_fp16_layers=-1, pre_blur=True))
+
+
+def sample_flat(t, n=2048):
+    """Fixed-stride sample of a tensor (all of it when it has at most `n` elements): what the
+    compact fixtures store of large gradient / weight tensors, next to their L2 norm."""
+    f = t.detach().reshape(-1)
+    if f.numel() <= n:
+        return f.clone()
+    stride = f.numel() // n
+    return f[::stride][:n].clone()

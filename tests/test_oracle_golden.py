@@ -331,70 +331,30 @@ def test_fir_axis_forms_agree(g_ops, g_gen):
                 close(a, b, rtol=1e-5, atol=1e-6)
 
 
-def test_train_iteration_against_reference_trainer_step(g_step):
+@pytest.mark.parametrize("which", ["small", "mid"])
+def test_train_iteration_against_reference_trainer_step(g_step, g_step_mid, which):
     """`O.train_iteration` (what bench.py times as the CPU baseline) against ONE FULL ITERATION of
     the reference's real `Trainer.step` (tests/golden/make_golden_trainer_step.py): the recorded
     random draws are replayed, the oracle advanced phase by phase with the reference's Adam
-    settings -- G step, D step on the updated generator, lazy R1 step on the updated discriminator."""
-    g = g_step
-    nograd = ("ema_var", "w_avg", "kernel", "pe.", "raydrop_const")
+    settings -- G step, D step on the updated generator, lazy R1 step on the updated
+    discriminator.  "mid": the fixture of the bf16 / CUDA-graph GPU twin (tcgen05-sized channel
+    counts, gradients stored as samples + norms)."""
+    from step_replay import (check, check_grads, check_updated_weights, fixture_draws, oracle_iteration,
+                             oracle_rnd)
+    g = g_step if which == "small" else g_step_mid
     sdG = {k[4:]: T(v).clone() for k, v in g.items() if k.startswith("sdG_")}
     sdD = {k[4:]: T(v).clone() for k, v in g.items() if k.startswith("sdD_")}
-    sdG = {k: v.requires_grad_(v.dtype.is_floating_point and not any(t in k for t in nograd)) for k, v in sdG.items()}
-    sdD = {k: v.requires_grad_("kernel" not in k) for k, v in sdD.items()}
-    rnd = {k: T(g[k]) for k in ("z_g", "z_d", "shift_g", "shift_d", "u_g", "u_d")}
-    for tag in ("g_fake", "d_real", "d_fake", "r1"):
-        rnd[f"keep_{tag}"] = T(g[f"keep_{tag}"])
-        rnd[f"Ginv_{tag}"] = torch.inverse(T(g[f"G_{tag}"]))
-        rnd[f"C_{tag}"] = T(g[f"C_{tag}"])
-    angle = T(g["angle"])
     x_real = O.fetch_reals(T(g["depth"]), T(g["mask"]), 1.45, 80.0)
-    lazy = 16 / 17.0
-    optG = torch.optim.Adam([v for v in sdG.values() if v.requires_grad], lr=0.002, betas=(0.0, 0.99))
-    optD = torch.optim.Adam([v for v in sdD.values() if v.requires_grad], lr=0.002 * lazy, betas=(0.0, 0.99 ** lazy))
-
-    def apply(opt, sd, grads):
-        for k, gr in grads.items():
-            sd[k].grad = gr
-        opt.step()
-        opt.zero_grad(set_to_none=True)
-
-    def check_grads(got, prefix, min_n):
-        n = 0
-        for k, gr in got.items():
-            if gr is None or prefix + k not in g:
-                continue
-            ref = g[prefix + k]
-            close(gr, ref, rtol=5e-3, atol=2e-3 * max(float(np.abs(ref).max()), 1e-7))
-            n += 1
-        assert n >= min_n, n
-
-    r = O.train_iteration(sdG, sdD, x_real, angle, rnd, with_r1=False)
+    r = oracle_iteration(O, sdG, sdD, x_real, T(g["angle"]), oracle_rnd(fixture_draws(g)))
     close(r["loss_G"], g["loss_G"], rtol=1e-4, atol=1e-6)
-    check_grads(r["grads_G"], "gG_", 40)
-    nb = {}
-    with torch.no_grad():
-        O.generator(sdG, rnd["z_g"], angle, rnd["u_g"], training=True,
-                    shifts_rad=rnd["shift_g"] * (2 * np.pi), new_buffers=nb)
-    apply(optG, sdG, r["grads_G"])
-    for k, v in nb.items():
-        sdG[k] = v.detach().clone()
-    r = O.train_iteration(sdG, sdD, x_real, angle, rnd, with_r1=False)
     close(r["loss_D"], g["loss_D"], rtol=2e-3, atol=1e-5)
-    check_grads(r["grads_D"], "gD_", 10)
-    apply(optD, sdD, r["grads_D"])
-    r = O.train_iteration(sdG, sdD, x_real, angle, rnd, with_r1=True)
     close(r["r1"], g["r1"], rtol=5e-3, atol=1e-7)
-    check_grads(r["grads_R1"], "gR1_", 10)
-    # the generator's weights after its Adam step (first step: lr * g / (|g| + eps): entries whose
-    # gradient is ~0 may differ in sign, hence the fraction)
-    near, total = 0, 0
-    for k, v in sdG.items():
-        if v.requires_grad and f"afterG_{k}" in g:
-            d = (v.detach() - T(g[f"afterG_{k}"])).abs()
-            near += int((d < 2e-4).sum())
-            total += d.numel()
-    assert total > 1000 and near / total > 0.98, (near, total)
+    check_grads(r["grads_G"], g, "gG_", 5e-3, 2e-3, 20)
+    check_grads(r["grads_D"], g, "gD_", 5e-3, 2e-3, 10)
+    check_grads(r["grads_R1"], g, "gR1_", 5e-3, 2e-3, 10)
+    check_updated_weights({k: v for k, v in r["sdG"].items() if v.requires_grad}, g, "afterG_", 0.002)
+    check_updated_weights({k: v for k, v in r["sdD"].items() if v.requires_grad}, g, "afterD_", 0.004,
+                          min_total=500)
 
 
 @pytest.mark.parametrize("arch", ["dusty_v1", "vanilla"])

@@ -11,7 +11,8 @@ import os
 import torch
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libdusty_b200.so")
+# DUSTY_LIB: tools may point at an instrumented build of the same library (csrc/Makefile `prof`)
+LIB_PATH = os.environ.get("DUSTY_LIB") or os.path.join(_HERE, "libdusty_b200.so")
 
 F32, BF16 = 0, 1
 PAD_ZERO, PAD_CIRCULAR, PAD_REPLICATE, PAD_REFLECT = 0, 1, 2, 3
@@ -66,6 +67,8 @@ SIGNATURES = {
     "dusty_stem_dx": [_vp, _vp, _i, _i, _i, _f, _f, _f, _vp],
     "dusty_conv2d_tc": [_vp, _vp, _vp, _vp] + [_i] * 9 + [_vp, _vp, _i, _i, _i]
                        + [C.c_longlong] * 4 + [_i, _f, _f, C.c_longlong, C.c_longlong, _vp, _i, _vp],
+    "dusty_conv2d_tc_classes": [_vp, _vp, _vp] + [_i] * 6 + [_vp] * 7 + [C.c_longlong] * 5 + [_i, _vp],
+    "dusty_conv_role_prof": [_vp, _i],
     "dusty_conv2d_wgrad_tc_workspace": [_i] * 7,
     "dusty_conv2d_halo_supported": [_i] * 4,
     "dusty_conv2d_halo_tc": [_vp, _vp, _vp, _vp] + [_i] * 11 + [C.c_longlong] * 4

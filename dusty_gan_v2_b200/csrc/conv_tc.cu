@@ -43,19 +43,55 @@ constexpr int kCABytes = kCM * kCK * 2;  // 16 KiB
 constexpr int kCThreads = 64 + 256;   // TMA warp, MMA warp, 8 epilogue warps (fprop / dgrad)
 constexpr int kWgThreads = 192;        // wgrad: one epilogue pass per CTA, 4 warps
 constexpr int kMaxGroups = 16;
+constexpr int kMaxClasses = 4;            // output parity classes of a stride-2 data gradient
+
+// Role profiling (tools only; libdusty_b200_prof.so is built with -DDUSTY_ROLE_PROF): cycles the
+// three warp roles spend waiting on each other, summed over CTAs.  slots: 0 producer waits for
+// a free ring slot, 1 MMA warp waits for operands, 2 MMA warp waits for a free accumulator,
+// 3 epilogue warp 2 waits for a finished accumulator, 4 lifetime of the producer warp, 5 of
+// the MMA warp, 6 of epilogue warp 2, 7 CTAs.
+#ifdef DUSTY_ROLE_PROF
+__device__ unsigned long long s_role_prof[8];
+#define PROF_DECL long long prof_acc__[2] = {0, 0}; const long long prof_t0__ = clock64()
+#define PROF_WAIT(i, stmt) do { const long long t__ = clock64(); stmt; prof_acc__[i] += clock64() - t__; } while (0)
+#define PROF_FLUSH(slot_a, slot_b, slot_life)                                              \
+  do {                                                                                     \
+    if ((threadIdx.x & 31) == 0) {                                                         \
+      atomicAdd(&s_role_prof[slot_a], (unsigned long long)prof_acc__[0]);                  \
+      if ((slot_b) >= 0) atomicAdd(&s_role_prof[(slot_b) < 0 ? 0 : (slot_b)], (unsigned long long)prof_acc__[1]); \
+      atomicAdd(&s_role_prof[slot_life], (unsigned long long)(clock64() - prof_t0__));     \
+      if ((slot_life) == 4) atomicAdd(&s_role_prof[7], 1ull);                              \
+    }                                                                                      \
+  } while (0)
+#else
+#define PROF_DECL
+#define PROF_WAIT(i, stmt) stmt
+#define PROF_FLUSH(a, b, c)
+#endif
 
 struct ConvMaps {
   CUtensorMap a[4];
   CUtensorMap w;
 };
 
-struct ConvParams {
-  int G, KC;                               // groups, 64-wide chunks per group
-  int amap[kMaxGroups], aw[kMaxGroups], ah[kMaxGroups];
+// A launch covers `ncls` classes (1 except for a strided data gradient, whose output parity
+// classes each have their own taps, output origin and extent); a CTA walks tiles with the class
+// as the fastest index, so every CTA sees the same mix of cheap and expensive classes.
+struct ConvClass {
+  int G;                                   // groups (taps / filter rows)
+  int aw[kMaxGroups], ah[kMaxGroups];      // coordinate offset of group g's box
   int wtap[kMaxGroups];                    // index of group g's filter block in the weight tensor
+  int H_out, W_out;                        // extent of this class's output view
+  long long y_off;                         // element offset of its origin
+};
+
+struct ConvParams {
+  int ncls, KC;                            // classes, 64-wide chunks per group
+  ConvClass cls[kMaxClasses];
+  int amap[kMaxGroups];                    // window mode: tensor map of group g (class 0 only)
   int TW, TH, tiles_w, tiles_h, NT, total_tiles, tiles_per_cta;
-  int H_out, W_out, O;
-  long long y_off, y_sb, y_sh, y_sw;       // element strides of the output view
+  int O;
+  long long y_sb, y_sh, y_sw;              // element strides of the output view
   const float *bias;
   __nv_bfloat16 *y;
   int act;
@@ -78,7 +114,6 @@ conv_fwd_tc_kernel(const __grid_constant__ ConvMaps maps, const __grid_constant_
   uint32_t *tmem_slot = (uint32_t *)(acc_empty + 2);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int num_kb = prm.G * prm.KC;
   const int t_begin = blockIdx.x * prm.tiles_per_cta;
   const int t_end = min(t_begin + prm.tiles_per_cta, prm.total_tiles);
 
@@ -98,9 +133,13 @@ conv_fwd_tc_kernel(const __grid_constant__ ConvMaps maps, const __grid_constant_
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
+  PROF_DECL;
 
-  // tile -> (sample, patch row, patch column, channel tile); channel tiles of a patch adjacent
-  auto decode = [&](int tile, int &b, int &oh0, int &ow0, int &n0) {
+  // tile -> (class, channel tile, sample, patch row, patch column); the classes and channel
+  // tiles of a patch are adjacent (same activation patch: L2-resident across them)
+  auto decode = [&](int tile, int &c, int &b, int &oh0, int &ow0, int &n0) {
+    c = tile % prm.ncls;
+    tile /= prm.ncls;
     n0 = (tile % prm.NT) * BN;
     int r = tile / prm.NT;
     ow0 = (r % prm.tiles_w) * prm.TW;
@@ -113,24 +152,26 @@ conv_fwd_tc_kernel(const __grid_constant__ ConvMaps maps, const __grid_constant_
     // warp-uniform loop, elected lane issues (see elect_one_sync)
     RingPos r;
     for (int tile = t_begin; tile < t_end; ++tile) {
-      int b, oh0, ow0, n0;
-      decode(tile, b, oh0, ow0, n0);
-      for (int g = 0; g < prm.G; ++g) {
+      int ci, b, oh0, ow0, n0;
+      decode(tile, ci, b, oh0, ow0, n0);
+      const ConvClass &cl = prm.cls[ci];
+      for (int g = 0; g < cl.G; ++g) {
         const CUtensorMap *am = &maps.a[prm.amap[g]];
-        const int cw = ow0 + prm.aw[g], ch = oh0 + prm.ah[g];
+        const int cw = ow0 + cl.aw[g], ch = oh0 + cl.ah[g];
         for (int kc = 0; kc < prm.KC; ++kc) {
           const int s = r.s;
-          mbar_wait(&empty[s], r.ph ^ 1);
+          PROF_WAIT(0, mbar_wait(&empty[s], r.ph ^ 1));
           if (elect_one_sync()) {
             mbar_expect_tx(&full[s], kStageBytes);
             tma_load_4d(a_base + s * kCABytes, am, &full[s], kc * kCK, cw, ch, b);
-            tma_load_3d(b_base + s * kBBytes, &maps.w, &full[s], kc * kCK, n0, prm.wtap[g]);
+            tma_load_3d(b_base + s * kBBytes, &maps.w, &full[s], kc * kCK, n0, cl.wtap[g]);
           }
           __syncwarp();
           r.template advance<STAGES>();
         }
       }
     }
+    PROF_FLUSH(0, -1, 4);
   } else if (warp == 1) {
     constexpr uint32_t idesc = make_idesc(kCM, BN, false, false);
     // K-major SW128 on both sides: 32 bytes per UMMA_K step inside the swizzle atom, SBO =
@@ -142,12 +183,13 @@ conv_fwd_tc_kernel(const __grid_constant__ ConvMaps maps, const __grid_constant_
     int lt = 0;
     for (int tile = t_begin; tile < t_end; ++tile, ++lt) {
       const int a = lt & 1;
-      mbar_wait(&acc_empty[a], ((lt >> 1) & 1) ^ 1);
+      const int num_kb = prm.cls[tile % prm.ncls].G * prm.KC;
+      PROF_WAIT(1, mbar_wait(&acc_empty[a], ((lt >> 1) & 1) ^ 1));
       tc_fence_after();
       const uint32_t tmem_acc = tmem_base + (uint32_t)(a * BN);
       for (int kb = 0; kb < num_kb; ++kb) {
         const int s = r.s;
-        mbar_wait(&full[s], r.ph);
+        PROF_WAIT(0, mbar_wait(&full[s], r.ph));
         tc_fence_after();
         if (elect_one_sync()) {
           const uint32_t a_lo = a_lo0 + (uint32_t)s * (kCABytes >> 4);
@@ -164,6 +206,7 @@ conv_fwd_tc_kernel(const __grid_constant__ ConvMaps maps, const __grid_constant_
       if (elect_one_sync()) umma_commit(&acc_full[a]);
       __syncwarp();
     }
+    PROF_FLUSH(1, 2, 5);
   } else {
     const int q = warp & 3;
     const int grp = (warp - 2) >> 2;
@@ -171,15 +214,16 @@ conv_fwd_tc_kernel(const __grid_constant__ ConvMaps maps, const __grid_constant_
     const int th = row / prm.TW, tw = row % prm.TW;
     int lt = 0;
     for (int tile = t_begin; tile < t_end; ++tile, ++lt) {
-      int b, oh0, ow0, n0;
-      decode(tile, b, oh0, ow0, n0);
+      int ci, b, oh0, ow0, n0;
+      decode(tile, ci, b, oh0, ow0, n0);
+      const ConvClass &cl = prm.cls[ci];
       const int a = lt & 1;
-      mbar_wait(&acc_full[a], (lt >> 1) & 1);
+      PROF_WAIT(0, mbar_wait(&acc_full[a], (lt >> 1) & 1));
       tc_fence_after();
       const uint32_t tmem_acc = tmem_base + (uint32_t)(a * BN) + ((uint32_t)(q * 32) << 16);
       const int oh = oh0 + th, ow = ow0 + tw;
-      const bool pix_ok = oh < prm.H_out && ow < prm.W_out;
-      __nv_bfloat16 *yp = prm.y + prm.y_off + (long long)b * prm.y_sb + (long long)oh * prm.y_sh +
+      const bool pix_ok = oh < cl.H_out && ow < cl.W_out;
+      __nv_bfloat16 *yp = prm.y + cl.y_off + (long long)b * prm.y_sb + (long long)oh * prm.y_sh +
                           (long long)ow * prm.y_sw + n0;
       // the two groups of four epilogue warps take alternate 16-column chunks
       constexpr int kLastMine = BN - 32;      // + 16 * grp: last chunk a group reads (BN >= 32)
@@ -221,6 +265,7 @@ conv_fwd_tc_kernel(const __grid_constant__ ConvMaps maps, const __grid_constant_
         }
       }
     }
+    if (warp == 2) PROF_FLUSH(3, -1, 6);
   }
   tc_fence_before();
   __syncthreads();
@@ -303,6 +348,7 @@ conv_halo_tc_kernel(const __grid_constant__ HaloMaps maps, const __grid_constant
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
+  PROF_DECL;
 
   auto decode = [&](int tile, int &b, int &oh0, int &ow0) {
     ow0 = (tile % prm.tiles_w) * prm.TWo;
@@ -323,7 +369,7 @@ conv_halo_tc_kernel(const __grid_constant__ HaloMaps maps, const __grid_constant
       int b, oh0, ow0;
       decode(tile, b, oh0, ow0);
       const int s = r.s;
-      mbar_wait(&empty[s], r.ph ^ 1);
+      PROF_WAIT(0, mbar_wait(&empty[s], r.ph ^ 1));
       if (elect_one_sync()) {
         mbar_expect_tx(&full[s], prm.patch_bytes);
         tma_load_4d(p_base + s * buf_stride, &maps.x, &full[s], 0, ow0 + prm.org_w, oh0 + prm.org_h, b);
@@ -331,6 +377,7 @@ conv_halo_tc_kernel(const __grid_constant__ HaloMaps maps, const __grid_constant
       __syncwarp();
       r.template advance<NBUF>();
     }
+    PROF_FLUSH(0, -1, 4);
   } else if (warp == 1) {
     constexpr uint32_t idesc = make_idesc(kCM, BN, false, false);
     mbar_wait(w_full, 0);
@@ -342,12 +389,12 @@ conv_halo_tc_kernel(const __grid_constant__ HaloMaps maps, const __grid_constant
     int lt = 0;
     for (int tile = t_begin; tile < t_end; ++tile) {
       const int s = r.s;
-      mbar_wait(&full[s], r.ph);
+      PROF_WAIT(0, mbar_wait(&full[s], r.ph));
       tc_fence_after();
       const uint32_t p_lo = p_lo0 + (uint32_t)s * (uint32_t)(buf_stride >> 4);
       for (int mb = 0; mb < prm.MB; ++mb, ++lt) {
         const int a = lt & 1;
-        mbar_wait(&acc_empty[a], ((lt >> 1) & 1) ^ 1);
+        PROF_WAIT(1, mbar_wait(&acc_empty[a], ((lt >> 1) & 1) ^ 1));
         tc_fence_after();
         if (elect_one_sync()) {
           const uint32_t tmem_acc = tmem_base + (uint32_t)(a * BN);
@@ -374,6 +421,7 @@ conv_halo_tc_kernel(const __grid_constant__ HaloMaps maps, const __grid_constant
       __syncwarp();
       r.template advance<NBUF>();
     }
+    PROF_FLUSH(1, 2, 5);
   } else {
     const int q = warp & 3;
     const int grp = (warp - 2) >> 2;
@@ -384,7 +432,7 @@ conv_halo_tc_kernel(const __grid_constant__ HaloMaps maps, const __grid_constant
       decode(tile, b, oh0, ow0);
       for (int mb = 0; mb < prm.MB; ++mb, ++lt) {
         const int a = lt & 1;
-        mbar_wait(&acc_full[a], (lt >> 1) & 1);
+        PROF_WAIT(0, mbar_wait(&acc_full[a], (lt >> 1) & 1));
         tc_fence_after();
         const uint32_t tmem_acc = tmem_base + (uint32_t)(a * BN) + ((uint32_t)(q * 32) << 16);
         const int m = mb * kCM + row;                 // virtual pixel inside the patch
@@ -433,6 +481,7 @@ conv_halo_tc_kernel(const __grid_constant__ HaloMaps maps, const __grid_constant
         }
       }
     }
+    if (warp == 2) PROF_FLUSH(3, -1, 6);
   }
   tc_fence_before();
   __syncthreads();
@@ -500,6 +549,7 @@ conv_wgrad_tc_kernel(const __grid_constant__ WgMaps maps, const __grid_constant_
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_acc = *tmem_slot;
+  PROF_DECL;
 
   if (warp == 0) {
     RingPos rp;
@@ -510,7 +560,7 @@ conv_wgrad_tc_kernel(const __grid_constant__ WgMaps maps, const __grid_constant_
       t /= prm.tiles_w;
       const int oh0 = (t % prm.tiles_h) * prm.TH;
       const int b = t / prm.tiles_h;
-      mbar_wait(&empty[s], rp.ph ^ 1);
+      PROF_WAIT(0, mbar_wait(&empty[s], rp.ph ^ 1));
       if (elect_one_sync()) {
         mbar_expect_tx(&full[s], kStageBytes);
 #pragma unroll
@@ -527,6 +577,7 @@ conv_wgrad_tc_kernel(const __grid_constant__ WgMaps maps, const __grid_constant_
       __syncwarp();
       rp.template advance<STAGES>();
     }
+    PROF_FLUSH(0, -1, 4);
   } else if (warp == 1) {
     constexpr uint32_t idesc = make_idesc(kCM, BN, true, true);
     // MN-major SW128: 16 pixel rows = 2 KiB per UMMA_K step; LBO = next 64-channel block
@@ -537,7 +588,7 @@ conv_wgrad_tc_kernel(const __grid_constant__ WgMaps maps, const __grid_constant_
     RingPos rp;
     for (int pb = pb_begin; pb < pb_end; ++pb) {
       const int s = rp.s;
-      mbar_wait(&full[s], rp.ph);
+      PROF_WAIT(0, mbar_wait(&full[s], rp.ph));
       tc_fence_after();
       if (elect_one_sync()) {
         const uint32_t b_lo = b_lo0 + (uint32_t)s * (kBBytes >> 4);
@@ -556,10 +607,11 @@ conv_wgrad_tc_kernel(const __grid_constant__ WgMaps maps, const __grid_constant_
     }
     if (elect_one_sync()) umma_commit(acc_full);
     __syncwarp();
+    PROF_FLUSH(1, 2, 5);
   } else {
     const int q = warp & 3;
     const int m = m0 + q * 32 + lane;
-    mbar_wait(acc_full, 0);
+    PROF_WAIT(0, mbar_wait(acc_full, 0));
     tc_fence_after();
     const bool have = pb_end > pb_begin;
     const bool atomic = prm.atomic != 0;    // split-K partials meet in the (zeroed) result
@@ -591,6 +643,7 @@ conv_wgrad_tc_kernel(const __grid_constant__ WgMaps maps, const __grid_constant_
         }
       }
     }
+    if (warp == 2) PROF_FLUSH(3, -1, 6);
   }
   tc_fence_before();
   __syncthreads();
@@ -727,6 +780,102 @@ void pick_patch(int W, int H, int n, int *TW, int *TH) {
 
 using namespace dusty;
 
+// One launch of the implicit-GEMM kernel over `ncls` classes.  Host-side description of a class:
+struct HostClass {
+  int G;
+  const int *dh, *dw, *wtap;
+  int H_out, W_out;
+  long long y_off;
+};
+
+static int conv_launch(const char *who, const void *x, const void *wpk, const float *bias, void *y,
+                       int B, int H_in, int W_in, int C, int O, int mode, int ncls,
+                       const HostClass *hc, int S, int stride_h, int stride_w, long long y_sb,
+                       long long y_sh, long long y_sw, int act, float alpha, float scale,
+                       long long w_sn, long long w_sg, int w_taps, cudaStream_t st) {
+  const int Kg = mode == 1 ? S * C : C;
+  ConvMaps maps;
+  ConvParams prm;
+  prm.ncls = ncls;
+  prm.KC = (Kg + kCK - 1) / kCK;
+  int H_max = 0, W_max = 0;
+  for (int c = 0; c < ncls; ++c) {
+    H_max = hc[c].H_out > H_max ? hc[c].H_out : H_max;
+    W_max = hc[c].W_out > W_max ? hc[c].W_out : W_max;
+  }
+  pick_patch(W_max, H_max, kCM, &prm.TW, &prm.TH);
+  const uint32_t box[4] = {(uint32_t)kCK, (uint32_t)prm.TW, (uint32_t)prm.TH, 1u};
+  const __nv_bfloat16 *xb = (const __nv_bfloat16 *)x;
+  bool ok = true;
+  for (int g = 0; g < kMaxGroups; ++g) prm.amap[g] = 0;
+  if (mode == 1) {
+    const HostClass &h = hc[0];
+    for (int g = 0; g < h.G; ++g) {
+      const int dh = h.dh[g], dw = h.dw[g];
+      if (!(dh >= 0 && dw >= 0 && (long long)(h.H_out - 1) * stride_h + dh < H_in &&
+            (long long)(h.W_out - 1) * stride_w + dw + S <= W_in)) {
+        set_error("%s: window outside the input", who);
+        return DUSTY_EINVAL;
+      }
+      const uint64_t dims[4] = {(uint64_t)Kg, (uint64_t)h.W_out, (uint64_t)h.H_out, (uint64_t)B};
+      const uint64_t strides[3] = {(uint64_t)stride_w * C * 2, (uint64_t)stride_h * W_in * C * 2,
+                                   (uint64_t)H_in * W_in * C * 2};
+      ok = ok && make_map4(&maps.a[g], xb + ((long long)dh * W_in + dw) * C, dims, strides, box);
+      prm.amap[g] = g;
+    }
+    for (int g = h.G; g < 4; ++g) maps.a[g] = maps.a[0];
+  } else {
+    const uint64_t dims[4] = {(uint64_t)C, (uint64_t)W_in, (uint64_t)H_in, (uint64_t)B};
+    const uint64_t strides[3] = {(uint64_t)C * 2, (uint64_t)W_in * C * 2, (uint64_t)H_in * W_in * C * 2};
+    ok = make_map4(&maps.a[0], xb, dims, strides, box);
+    for (int g = 1; g < 4; ++g) maps.a[g] = maps.a[0];
+  }
+  int Gw = w_taps;
+  for (int c = 0; c < kMaxClasses; ++c) {
+    ConvClass &cl = prm.cls[c];
+    const HostClass &h = hc[c < ncls ? c : 0];
+    cl.G = h.G; cl.H_out = h.H_out; cl.W_out = h.W_out; cl.y_off = h.y_off;
+    for (int g = 0; g < kMaxGroups; ++g) {
+      const bool in = g < h.G;
+      cl.aw[g] = (in && mode == 0) ? h.dw[g] : 0;
+      cl.ah[g] = (in && mode == 0) ? h.dh[g] : 0;
+      cl.wtap[g] = in ? (h.wtap ? h.wtap[g] : g) : 0;
+    }
+    if (!h.wtap && c < ncls && h.G > Gw) Gw = h.G;
+  }
+  for (int c = 0; c < ncls; ++c)
+    for (int g = 0; g < hc[c].G; ++g)
+      if (prm.cls[c].wtap[g] < 0 || prm.cls[c].wtap[g] >= Gw) {
+        set_error("%s: wtap out of range", who);
+        return DUSTY_EINVAL;
+      }
+  const int BN = O > 128 ? 256 : (O > 64 ? 128 : (O > 32 ? 64 : 32));
+  ok = ok && make_map3w(&maps.w, wpk, (uint64_t)Kg, (uint64_t)O, (uint64_t)Gw, kCK, (uint32_t)BN,
+                        (uint64_t)w_sn, (uint64_t)w_sg);
+  if (!ok) {
+    set_error("%s: cuTensorMapEncodeTiled failed", who);
+    return DUSTY_ECUDA;
+  }
+  prm.tiles_w = (W_max + prm.TW - 1) / prm.TW;
+  prm.tiles_h = (H_max + prm.TH - 1) / prm.TH;
+  prm.NT = (O + BN - 1) / BN;
+  const long long total = (long long)prm.tiles_w * prm.tiles_h * prm.NT * B * ncls;
+  if (total > 0x7fffffff) {
+    set_error("%s: too many tiles", who);
+    return DUSTY_EINVAL;
+  }
+  prm.total_tiles = (int)total;
+  prm.O = O;
+  prm.y_sb = y_sb; prm.y_sh = y_sh; prm.y_sw = y_sw;
+  prm.bias = bias; prm.y = (__nv_bfloat16 *)y; prm.act = act; prm.alpha = alpha; prm.scale = scale;
+  switch (BN) {
+    case 256: return launch_conv<256, 4>(maps, prm, st);
+    case 128: return launch_conv<128, 5>(maps, prm, st);
+    case 64: return launch_conv<64, 4>(maps, prm, st);
+    default: return launch_conv<32, 4>(maps, prm, st);
+  }
+}
+
 extern "C" int dusty_conv2d_tc(const void *x, const void *wpk, const float *bias, void *y, int B,
                                int H_in, int W_in, int C, int H_out, int W_out, int O, int mode,
                                int G, const int *tap_dh, const int *tap_dw, int S, int stride_h,
@@ -746,66 +895,64 @@ extern "C" int dusty_conv2d_tc(const void *x, const void *wpk, const float *bias
   DUSTY_CHECK_ARG(aligned16(x) && aligned16(wpk) && aligned16(y), "16-byte alignment");
   DUSTY_CHECK_ARG((y_off % 8 == 0) && (y_sb % 8 == 0) && (y_sh % 8 == 0) && (y_sw % 8 == 0),
                   "output strides must keep 16-byte alignment");
-  cudaStream_t st = (cudaStream_t)stream;
-  const int Kg = mode == 1 ? S * C : C;
-  ConvMaps maps;
-  ConvParams prm;
-  prm.G = G;
-  prm.KC = (Kg + kCK - 1) / kCK;
-  pick_patch(W_out, H_out, kCM, &prm.TW, &prm.TH);
-  const uint32_t box[4] = {(uint32_t)kCK, (uint32_t)prm.TW, (uint32_t)prm.TH, 1u};
-  const __nv_bfloat16 *xb = (const __nv_bfloat16 *)x;
-  bool ok = true;
-  if (mode == 1) {
-    for (int g = 0; g < G; ++g) {
-      const int dh = tap_dh[g], dw = tap_dw[g];
-      DUSTY_CHECK_ARG(dh >= 0 && dw >= 0 && (long long)(H_out - 1) * stride_h + dh < H_in &&
-                          (long long)(W_out - 1) * stride_w + dw + S <= W_in,
-                      "window outside the input");
-      const uint64_t dims[4] = {(uint64_t)Kg, (uint64_t)W_out, (uint64_t)H_out, (uint64_t)B};
-      const uint64_t strides[3] = {(uint64_t)stride_w * C * 2, (uint64_t)stride_h * W_in * C * 2,
-                                   (uint64_t)H_in * W_in * C * 2};
-      ok = ok && make_map4(&maps.a[g], xb + ((long long)dh * W_in + dw) * C, dims, strides, box);
-      prm.amap[g] = g; prm.aw[g] = 0; prm.ah[g] = 0;
-    }
-    for (int g = G; g < 4; ++g) maps.a[g] = maps.a[0];
-  } else {
-    const uint64_t dims[4] = {(uint64_t)C, (uint64_t)W_in, (uint64_t)H_in, (uint64_t)B};
-    const uint64_t strides[3] = {(uint64_t)C * 2, (uint64_t)W_in * C * 2, (uint64_t)H_in * W_in * C * 2};
-    ok = make_map4(&maps.a[0], xb, dims, strides, box);
-    for (int g = 1; g < 4; ++g) maps.a[g] = maps.a[0];
-    for (int g = 0; g < G; ++g) { prm.amap[g] = 0; prm.aw[g] = tap_dw[g]; prm.ah[g] = tap_dh[g]; }
-  }
-  for (int g = G; g < kMaxGroups; ++g) { prm.amap[g] = 0; prm.aw[g] = 0; prm.ah[g] = 0; }
-  const int BN = O > 128 ? 256 : (O > 64 ? 128 : (O > 32 ? 64 : 32));
-  const int Gw = wtap ? w_taps : G;          // filter blocks present in the weight tensor
-  for (int g = 0; g < kMaxGroups; ++g) prm.wtap[g] = (wtap && g < G) ? wtap[g] : (g < G ? g : 0);
-  for (int g = 0; g < G; ++g) DUSTY_CHECK_ARG(prm.wtap[g] >= 0 && prm.wtap[g] < Gw, "wtap out of range");
-  ok = ok && make_map3w(&maps.w, wpk, (uint64_t)Kg, (uint64_t)O, (uint64_t)Gw, kCK, (uint32_t)BN,
-                        (uint64_t)w_sn, (uint64_t)w_sg);
-  if (!ok) {
-    set_error("dusty_conv2d_tc: cuTensorMapEncodeTiled failed");
-    return DUSTY_ECUDA;
-  }
-  prm.tiles_w = (W_out + prm.TW - 1) / prm.TW;
-  prm.tiles_h = (H_out + prm.TH - 1) / prm.TH;
-  prm.NT = (O + BN - 1) / BN;
-  const long long total = (long long)prm.tiles_w * prm.tiles_h * prm.NT * B;
-  DUSTY_CHECK_ARG(total <= 0x7fffffff, "too many tiles");
-  prm.total_tiles = (int)total;
-  prm.H_out = H_out; prm.W_out = W_out; prm.O = O;
-  prm.y_off = y_off; prm.y_sb = y_sb; prm.y_sh = y_sh; prm.y_sw = y_sw;
-  prm.bias = bias; prm.y = (__nv_bfloat16 *)y; prm.act = act; prm.alpha = alpha; prm.scale = scale;
-  int rc;
-  switch (BN) {
-    case 256: rc = launch_conv<256, 4>(maps, prm, st); break;
-    case 128: rc = launch_conv<128, 5>(maps, prm, st); break;
-    case 64: rc = launch_conv<64, 4>(maps, prm, st); break;
-    default: rc = launch_conv<32, 4>(maps, prm, st); break;
-  }
-  if (rc) return rc;
+  const HostClass hc = {G, tap_dh, tap_dw, wtap, H_out, W_out, y_off};
+  if (int rc = conv_launch("dusty_conv2d_tc", x, wpk, bias, y, B, H_in, W_in, C, O, mode, 1, &hc, S,
+                           stride_h, stride_w, y_sb, y_sh, y_sw, act, alpha, scale, w_sn, w_sg,
+                           wtap ? w_taps : 0, (cudaStream_t)stream))
+    return rc;
   DUSTY_LAUNCH_CHECK();
   return DUSTY_OK;
+}
+
+extern "C" int dusty_conv2d_tc_classes(const void *x, const void *wpk, void *y, int B, int H_in,
+                                       int W_in, int C, int O, int ncls, const int *cls_G,
+                                       const int *tap_dh, const int *tap_dw, const int *wtap,
+                                       const int *cls_H_out, const int *cls_W_out,
+                                       const long long *cls_y_off, long long y_sb, long long y_sh,
+                                       long long y_sw, long long w_sn, long long w_sg, int w_taps,
+                                       void *stream) {
+  DUSTY_CHECK_ARG(x && wpk && y && cls_G && tap_dh && tap_dw && wtap && cls_H_out && cls_W_out && cls_y_off,
+                  "null pointer");
+  DUSTY_CHECK_ARG(get_encode() != nullptr, "cuTensorMapEncodeTiled unavailable");
+  DUSTY_CHECK_ARG(B > 0 && H_in > 0 && W_in > 0, "empty tensor");
+  DUSTY_CHECK_ARG(C % 8 == 0 && O % 8 == 0, "channel counts must be multiples of 8");
+  DUSTY_CHECK_ARG(ncls >= 1 && ncls <= kMaxClasses, "1..4 classes");
+  DUSTY_CHECK_ARG(w_sn >= 0 && w_sg >= 0 && w_sn % 8 == 0 && w_sg % 8 == 0, "weight strides: multiples of 8");
+  DUSTY_CHECK_ARG(w_taps >= 1, "w_taps: filter blocks in the weight tensor");
+  DUSTY_CHECK_ARG(aligned16(x) && aligned16(wpk) && aligned16(y), "16-byte alignment");
+  DUSTY_CHECK_ARG((y_sb % 8 == 0) && (y_sh % 8 == 0) && (y_sw % 8 == 0), "output strides must keep 16-byte alignment");
+  HostClass hc[kMaxClasses];
+  int at = 0;
+  for (int c = 0; c < ncls; ++c) {
+    DUSTY_CHECK_ARG(cls_G[c] >= 1 && cls_G[c] <= kMaxGroups, "1..16 taps per class");
+    DUSTY_CHECK_ARG(cls_H_out[c] > 0 && cls_W_out[c] > 0, "empty class");
+    DUSTY_CHECK_ARG(cls_y_off[c] % 8 == 0, "class origin must keep 16-byte alignment");
+    hc[c] = {cls_G[c], tap_dh + at, tap_dw + at, wtap + at, cls_H_out[c], cls_W_out[c], cls_y_off[c]};
+    at += cls_G[c];
+  }
+  if (int rc = conv_launch("dusty_conv2d_tc_classes", x, wpk, nullptr, y, B, H_in, W_in, C, O, 0, ncls,
+                           hc, 1, 1, 1, y_sb, y_sh, y_sw, 1, 0.f, 1.f, w_sn, w_sg, w_taps,
+                           (cudaStream_t)stream))
+    return rc;
+  DUSTY_LAUNCH_CHECK();
+  return DUSTY_OK;
+}
+
+extern "C" int dusty_conv_role_prof(double *out8, int reset) {
+#ifdef DUSTY_ROLE_PROF
+  unsigned long long h[8];
+  if (cudaMemcpyFromSymbol(h, s_role_prof, sizeof(h)) != cudaSuccess) return DUSTY_ECUDA;
+  for (int i = 0; i < 8; ++i) out8[i] = (double)h[i];
+  if (reset) {
+    unsigned long long z[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+    if (cudaMemcpyToSymbol(s_role_prof, z, sizeof(z)) != cudaSuccess) return DUSTY_ECUDA;
+  }
+  return DUSTY_OK;
+#else
+  (void)reset;
+  for (int i = 0; i < 8; ++i) out8[i] = 0.0;
+  return DUSTY_EUNSUPPORTED;
+#endif
 }
 
 // three filter rows per CTA (shared dY tile): 3-row filters whose N tile is at most 128 wide

@@ -1340,27 +1340,31 @@ def conv2d_dgrad_tc(gy, w, stride, in_hw, w_tco=None):
         K.call("dusty_conv2d_halo_tc", K.ptr(gy), K.ptr(w_tco), None, K.ptr(gx), B, Ho, Wo, O, H, W,
                C, R, S, -(R - 1), -(S - 1), 0, H * W * C, W * C, C, 1, 0.0, 1.0, 0, 0, 1, st)
         return gx
-    classes = []
+    # strided: one class per output parity (ph, pw), all of them in ONE launch
+    cls_G, dh, dw, wtap, cls_H, cls_W, cls_off = [], [], [], [], [], [], []
+    empty_class = False
     for ph in range(sh):
         rs = [r for r in range(R) if r % sh == ph]
         for pw in range(sw):
             ss = [s for s in range(S) if s % sw == pw]
-            classes.append((ph, pw, rs, ss))
-    if not all(rs and ss for _, _, rs, ss in classes):
+            Hc, Wc = (H - ph + sh - 1) // sh, (W - pw + sw - 1) // sw
+            if not (rs and ss) or Hc <= 0 or Wc <= 0:
+                empty_class = empty_class or (Hc > 0 and Wc > 0)
+                continue
+            taps = [(r, s) for r in rs for s in ss]
+            cls_G.append(len(taps))
+            dh += [(ph - r) // sh for r, _ in taps]
+            dw += [(pw - s) // sw for _, s in taps]
+            wtap += [r * S + s for r, s in taps]
+            cls_H.append(Hc)
+            cls_W.append(Wc)
+            cls_off.append((ph * W + pw) * C)
+    if empty_class:                      # positions no filter tap reaches (e.g. 1x1, stride 2)
         gx.zero_()
-    for ph, pw, rs, ss in classes:
-        if not (rs and ss):
-            continue
-        Hc, Wc = (H - ph + sh - 1) // sh, (W - pw + sw - 1) // sw
-        if Hc <= 0 or Wc <= 0:
-            continue
-        taps = [(r, s) for r in rs for s in ss]
-        dh = [(ph - r) // sh for r, _ in taps]
-        dw = [(pw - s) // sw for _, s in taps]
-        wtap = [r * S + s for r, s in taps]
-        K.call("dusty_conv2d_tc", K.ptr(gy), K.ptr(w_tco), None, K.ptr(gx),
-               B, Ho, Wo, O, Hc, Wc, C, 0, len(taps), _ints(dh), _ints(dw), 1, 1, 1,
-               (ph * W + pw) * C, H * W * C, sh * W * C, sw * C, 1, 0.0, 1.0, 0, 0, _ints(wtap), R * S, st)
+    if cls_G:
+        K.call("dusty_conv2d_tc_classes", K.ptr(gy), K.ptr(w_tco), K.ptr(gx), B, Ho, Wo, O, C,
+               len(cls_G), _ints(cls_G), _ints(dh), _ints(dw), _ints(wtap), _ints(cls_H), _ints(cls_W),
+               (K.C.c_longlong * len(cls_off))(*cls_off), H * W * C, sh * W * C, sw * C, 0, 0, R * S, st)
     return gx
 
 

@@ -344,6 +344,24 @@ int dusty_conv2d_tc(const void *x, const void *wpk, const float *bias, void *y, 
                     float alpha, float scale, long long w_sn, long long w_sg, const int *wtap,
                     int w_taps, void *stream);
 
+/* Tap mode over `ncls` classes in ONE launch: the data gradient of a strided convolution is one
+ * class per output parity (ph, pw), each with its own taps, output origin cls_y_off[c] and
+ * extent cls_H_out[c] x cls_W_out[c] (output strides y_sh / y_sw are the doubled ones, shared).
+ * tap_dh / tap_dw / wtap are the classes' tap lists concatenated (cls_G[c] entries each); the
+ * tiles of the classes interleave so that every CTA gets the same mix of 1-, 2- and 4-tap
+ * tiles.  Replaces aten::convolution_backward's input gradient for Conv2d(.., stride=2),
+ * gans/models/dusty_v2.py:303,305 (conv2 / skip of ResidualBlock). */
+int dusty_conv2d_tc_classes(const void *x, const void *wpk, void *y, int B, int H_in, int W_in,
+                            int C, int O, int ncls, const int *cls_G, const int *tap_dh,
+                            const int *tap_dw, const int *wtap, const int *cls_H_out,
+                            const int *cls_W_out, const long long *cls_y_off, long long y_sb,
+                            long long y_sh, long long y_sw, long long w_sn, long long w_sg,
+                            int w_taps, void *stream);
+
+/* Tools only: role-cycle counters of the tcgen05 convolution kernels (8 doubles; see
+ * conv_tc.cu).  DUSTY_EUNSUPPORTED unless the library was built with -DDUSTY_ROLE_PROF. */
+int dusty_conv_role_prof(double *out8, int reset);
+
 /* Filter gradient of the valid convolution above:
  *   dwp[r][s*C+c][n] = sum_{b,oh,ow} x[b, oh*stride_h + r, ow*stride_w + s, c] * dy[b,oh,ow,n]
  * fp32 output [R][S*C][O].  ws: caller-owned fp32 workspace of at least

@@ -51,7 +51,20 @@ constexpr int kMaxClasses = 4;            // output parity classes of a stride-2
 // 3 epilogue warp 2 waits for a finished accumulator, 4 lifetime of the producer warp, 5 of
 // the MMA warp, 6 of epilogue warp 2, 7 CTAs.
 #ifdef DUSTY_ROLE_PROF
-__device__ unsigned long long s_role_prof[8];
+__device__ unsigned long long s_role_prof[12];   // 8: MMA issue-loop cycles (halo), 9: blocks
+// event trace of CTA 0 (halo kernel): (tag << 56) | (index << 40) | clock
+__device__ unsigned long long s_trace[8192];
+__device__ unsigned int s_trace_n;
+// no atomics (an atomic with a return value stalls its thread for ~700 cycles): every role
+// appends to its own quarter of the buffer with a private counter
+__device__ __forceinline__ void trace_ev(unsigned role, unsigned &n, unsigned tag, unsigned idx) {
+  if (blockIdx.x != 0 || n >= 2048) return;
+  s_trace[role * 2048 + n++] = ((unsigned long long)tag << 56) | ((unsigned long long)(idx & 0xffff) << 40) |
+                               ((unsigned long long)clock64() & 0xffffffffffull);
+}
+#define TRACE_DECL unsigned trace_n__ = 0
+#define TRACE(role, tag, idx) trace_ev(role, trace_n__, tag, idx)
+#define TRACE0(role, tag, idx) do { if ((threadIdx.x & 31) == 0) trace_ev(role, trace_n__, tag, idx); } while (0)
 #define PROF_DECL long long prof_acc__[2] = {0, 0}; const long long prof_t0__ = clock64()
 #define PROF_WAIT(i, stmt) do { const long long t__ = clock64(); stmt; prof_acc__[i] += clock64() - t__; } while (0)
 #define PROF_FLUSH(slot_a, slot_b, slot_life)                                              \
@@ -67,6 +80,9 @@ __device__ unsigned long long s_role_prof[8];
 #define PROF_DECL
 #define PROF_WAIT(i, stmt) stmt
 #define PROF_FLUSH(a, b, c)
+#define TRACE_DECL
+#define TRACE(role, tag, idx)
+#define TRACE0(role, tag, idx)
 #endif
 
 struct ConvMaps {
@@ -291,7 +307,7 @@ conv_fwd_tc_kernel(const __grid_constant__ ConvMaps maps, const __grid_constant_
 // dY with the patch origin moved by -(R-1), -(S-1) (TMA zero-fills outside dY) and the filter
 // flipped / transposed by the host.
 struct HaloMaps {
-  CUtensorMap x, w;
+  CUtensorMap x, w, y;
 };
 
 struct HaloParams {
@@ -310,23 +326,42 @@ struct HaloParams {
   float alpha, scale;
 };
 
+// Pipeline.  The tensor pipe's queue is shallow (a handful of UMMAs: ~100-300 cycles of work at
+// N <= 64), so EVERY cycle the issuing thread spends between UMMAs on barrier round trips idles
+// it: with one acc_empty wait + fence + elect + commit per 128-pixel block the first version
+// measured ~1290 cycles per block for 720 cycles of MMA work (tools/conv_roles.py,
+// tools/debug/halo_trace.py; tools/experiments/umma_halo.cu shows the stream itself running at
+// 40 cycles per 128x32x16 UMMA next to tcgen05.ld traffic).  Here the unit of synchronisation is
+// the TILE: TMEM holds two SETS of MB accumulators (2 * MB * BN <= 512 columns), the MMA warp
+// waits once per tile (patch landed, set drained), then issues all MB * T * C/16 UMMAs back to
+// back with only a tcgen05.commit between blocks, so the epilogue of block 0 overlaps the MMAs
+// of blocks 1.. and of the next tile's set.  The two epilogue groups take alternate blocks, each
+// thread owning one pixel row (all BN channels: one tcgen05.wait, a full row of stores).
 template <int ROWB, int BN, int NBUF>
-__global__ void __launch_bounds__(kCThreads)
+__global__ void __launch_bounds__(kCThreads, 1)
 conv_halo_tc_kernel(const __grid_constant__ HaloMaps maps, const __grid_constant__ HaloParams prm,
                     int buf_stride) {
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   uint8_t *smem = (uint8_t *)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
   constexpr uint64_t kLayout = ROWB == 64 ? 4 : 2;          // SWIZZLE_64B : SWIZZLE_128B
   constexpr int kWTap = BN * ROWB;                          // bytes of one filter tap [BN][C]
+  constexpr int kSetBlocks = 256 / BN;                      // accumulators per set (MB <= this)
+  constexpr int kSubCh = BN > 64 ? 64 : BN;                 // channels of one staging sub-tile
+  constexpr int kSubs = BN / kSubCh;
+  constexpr int kSubBytes = kCM * kSubCh * 2;               // [128 rows][kSubCh] swizzled
   uint8_t *w_base = smem;
-  uint8_t *p_base = smem + ((prm.T * kWTap + 1023) & ~1023);
+  uint8_t *stage_base = smem + ((prm.T * kWTap + 1023) & ~1023);     // [2 groups][kSubs] sub-tiles
+  uint8_t *p_base = stage_base + 2 * kSubs * kSubBytes;
   uint64_t *full = (uint64_t *)(p_base + NBUF * buf_stride);
   uint64_t *empty = full + NBUF;
-  uint64_t *acc_full = empty + NBUF;
-  uint64_t *acc_empty = acc_full + 2;
-  uint64_t *w_full = acc_empty + 2;
+  uint64_t *acc_full = empty + NBUF;                        // [2][kSetBlocks]
+  uint64_t *set_empty = acc_full + 2 * kSetBlocks;          // [2]
+  uint64_t *w_full = set_empty + 2;
   uint32_t *tmem_slot = (uint32_t *)(w_full + 1);
+  float *bias_s = (float *)(((uintptr_t)(tmem_slot + 2) + 15) & ~(uintptr_t)15);   // BN floats
 
+  // warp roles: 0 = TMA producer, 1..8 = epilogue (two groups of four), 9 = MMA issuer
+  constexpr int kMmaWarp = 9;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int t_begin = blockIdx.x * prm.tiles_per_cta;
   const int t_end = min(t_begin + prm.tiles_per_cta, prm.total_tiles);
@@ -336,19 +371,22 @@ conv_halo_tc_kernel(const __grid_constant__ HaloMaps maps, const __grid_constant
       mbar_init(&full[s], 1);
       mbar_init(&empty[s], 1);
     }
-    for (int a = 0; a < 2; ++a) {
-      mbar_init(&acc_full[a], 1);
-      mbar_init(&acc_empty[a], 8);
-    }
+    for (int a = 0; a < 2 * kSetBlocks; ++a) mbar_init(&acc_full[a], 1);
+    for (int a = 0; a < 2; ++a) mbar_init(&set_empty[a], 8);      // every epilogue warp, once per tile
     mbar_init(w_full, 1);
     fence_barrier_init();
   }
-  if (warp == 1) tmem_alloc(tmem_slot, 2 * BN < 32 ? 32 : 2 * BN);
+  if (threadIdx.x >= 32 && threadIdx.x < 32 + BN) {
+    const int o = threadIdx.x - 32;
+    bias_s[o] = (prm.bias && o < prm.O) ? prm.bias[o] : 0.f;
+  }
+  if (warp == kMmaWarp) tmem_alloc(tmem_slot, 512);
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
   PROF_DECL;
+  TRACE_DECL;
 
   auto decode = [&](int tile, int &b, int &oh0, int &ow0) {
     ow0 = (tile % prm.tiles_w) * prm.TWo;
@@ -373,37 +411,40 @@ conv_halo_tc_kernel(const __grid_constant__ HaloMaps maps, const __grid_constant
       if (elect_one_sync()) {
         mbar_expect_tx(&full[s], prm.patch_bytes);
         tma_load_4d(p_base + s * buf_stride, &maps.x, &full[s], 0, ow0 + prm.org_w, oh0 + prm.org_h, b);
+        TRACE(0, 1, tile - t_begin);
       }
       __syncwarp();
       r.template advance<NBUF>();
     }
     PROF_FLUSH(0, -1, 4);
-  } else if (warp == 1) {
+  } else if (warp == kMmaWarp) {
     constexpr uint32_t idesc = make_idesc(kCM, BN, false, false);
     mbar_wait(w_full, 0);
     const uint32_t d_hi = desc_hi(8 * ROWB, (uint32_t)kLayout);
     const uint32_t p_lo0 = desc_lo(smem_u32(p_base), 16);
     const uint32_t w_lo0 = desc_lo(smem_u32(w_base), 16);
     constexpr uint32_t kRow16 = ROWB >> 4;            // descriptor units per pixel row
+    const int T = prm.T, S = prm.S, MB = prm.MB;
+    const uint32_t row_step = (uint32_t)prm.PW * kRow16;
     RingPos r;
     int lt = 0;
-    for (int tile = t_begin; tile < t_end; ++tile) {
-      const int s = r.s;
+    for (int tile = t_begin; tile < t_end; ++tile, ++lt) {
+      const int s = r.s, set = lt & 1;
       PROF_WAIT(0, mbar_wait(&full[s], r.ph));
+      PROF_WAIT(1, mbar_wait(&set_empty[set], ((lt >> 1) & 1) ^ 1));
+      TRACE0(1, 2, tile - t_begin);
       tc_fence_after();
-      const uint32_t p_lo = p_lo0 + (uint32_t)s * (uint32_t)(buf_stride >> 4);
-      for (int mb = 0; mb < prm.MB; ++mb, ++lt) {
-        const int a = lt & 1;
-        PROF_WAIT(1, mbar_wait(&acc_empty[a], ((lt >> 1) & 1) ^ 1));
-        tc_fence_after();
-        if (elect_one_sync()) {
-          const uint32_t tmem_acc = tmem_base + (uint32_t)(a * BN);
+      if (elect_one_sync()) {
+        const uint32_t p_lo = p_lo0 + (uint32_t)s * (uint32_t)(buf_stride >> 4);
+        uint32_t tmem_acc = tmem_base + (uint32_t)(set * 256);
+        uint64_t *af = &acc_full[set * kSetBlocks];
+        for (int mb = 0; mb < MB; ++mb) {
           uint32_t first = 0;
           // tap (r, s2): A = the patch read from pixel row mb*128 + r*PW + s2 onwards
           uint32_t a_row = p_lo + (uint32_t)(mb * kCM) * kRow16;
           uint32_t w_lo = w_lo0;
           int s2 = 0;
-          for (int t = 0; t < prm.T; ++t) {
+          for (int t = 0; t < T; ++t) {
 #pragma unroll
             for (int k16 = 0; k16 < ROWB / 32; ++k16) {
               umma_bf16_lh(tmem_acc, a_row + (uint32_t)s2 * kRow16 + k16 * 2, d_hi, w_lo + k16 * 2,
@@ -411,83 +452,119 @@ conv_halo_tc_kernel(const __grid_constant__ HaloMaps maps, const __grid_constant
               first = 1u;
             }
             w_lo += kWTap >> 4;
-            if (++s2 == prm.S) { s2 = 0; a_row += (uint32_t)prm.PW * kRow16; }
+            if (++s2 == S) { s2 = 0; a_row += row_step; }
           }
-          umma_commit(&acc_full[a]);
+          umma_commit(af + mb);
+          tmem_acc += BN;
         }
-        __syncwarp();
+        umma_commit(&empty[s]);            // patch buffer reusable once these MMAs retire
+        TRACE(1, 4, tile - t_begin);
       }
-      if (elect_one_sync()) umma_commit(&empty[s]);   // patch buffer reusable once these MMAs retire
       __syncwarp();
       r.template advance<NBUF>();
     }
     PROF_FLUSH(1, 2, 5);
   } else {
-    const int q = warp & 3;
-    const int grp = (warp - 2) >> 2;
+    // Output path: registers -> swizzled staging tile in shared memory -> ONE TMA store per
+    // block and 64-channel sub-tile.  (Per-thread 16-byte global stores of a pixel row each --
+    // 32 lanes x 16 B at a 64..256-byte stride per instruction -- kept the LSU busy for ~1300
+    // cycles per block: the epilogue, not the MMA stream, bounded the first versions.)
+    const int q = warp & 3;                           // TMEM lane quarter of this warp
+    const int grp = (warp - 1) >> 2;                  // epilogue group: blocks with (mb & 1) == grp ^ (lt & 1)
     const int row = q * 32 + lane;
+    const int pw_shift = prm.PW == 64 ? 6 : 5;        // patch pitch is 32 or 64 pixels
+    const int rows_pb = kCM >> pw_shift;              // image rows per 128-pixel block
+    const bool lrelu = prm.act == 3;
+    const bool has_bias = prm.bias != nullptr;
+    const float alpha = prm.alpha, scale = prm.scale;
+    const bool issuer = (q == 0 && lane == 0);
+    const uint32_t stage_u32 = smem_u32(stage_base) + (uint32_t)(grp * kSubs * kSubBytes);
+    // dense box order of the staging tile: row = (image row inside the block) * TWo + column
+    const int hh_l = row >> pw_shift, ww = row & (prm.PW - 1);
+    const bool col_ok = ww < prm.TWo;
+    const uint32_t srow = (uint32_t)(hh_l * prm.TWo + ww);
+    // 16-byte chunk c of staging row r lives at chunk c ^ swz(r) (64B / 128B TMA swizzle)
+    constexpr int kChunks = kSubCh / 8;               // 16-byte chunks per row: 4 or 8
+    const uint32_t swz = kSubCh == 32 ? ((srow >> 1) & 3u) : (srow & 7u);
+    const uint32_t srow_addr = stage_u32 + srow * (uint32_t)(kSubCh * 2);
     int lt = 0;
-    for (int tile = t_begin; tile < t_end; ++tile) {
+    for (int tile = t_begin; tile < t_end; ++tile, ++lt) {
       int b, oh0, ow0;
       decode(tile, b, oh0, ow0);
-      for (int mb = 0; mb < prm.MB; ++mb, ++lt) {
-        const int a = lt & 1;
-        PROF_WAIT(0, mbar_wait(&acc_full[a], (lt >> 1) & 1));
+      const int set = lt & 1;
+      const uint32_t set_parity = (lt >> 1) & 1;
+      // odd block counts: the group with the extra block alternates from tile to tile
+      for (int mb = (grp ^ (lt & 1)); mb < prm.MB; mb += 2) {
+        PROF_WAIT(0, mbar_wait(&acc_full[set * kSetBlocks + mb], set_parity));
+        if (q == 0) TRACE0(2 + grp, 5, lt * 8 + mb);
         tc_fence_after();
-        const uint32_t tmem_acc = tmem_base + (uint32_t)(a * BN) + ((uint32_t)(q * 32) << 16);
-        const int m = mb * kCM + row;                 // virtual pixel inside the patch
-        const int hh = m / prm.PW, ww = m - hh * prm.PW;
-        const int oh = oh0 + hh, ow = ow0 + ww;
-        const bool pix_ok = ww < prm.TWo && oh < prm.H_out && ow < prm.W_out;
-        __nv_bfloat16 *yp = prm.y + prm.y_off + (long long)b * prm.y_sb + (long long)oh * prm.y_sh +
-                            (long long)ow * prm.y_sw;
-        constexpr int kLastMine = BN - 32;    // + 16 * grp: last chunk a group reads (BN >= 32)
-#pragma unroll 1
-        for (int c = 16 * grp; c < BN; c += 32) {
-          uint32_t r[16];
-          tmem_ld16(tmem_acc + (uint32_t)c, r);
+        const uint32_t tmem_acc = tmem_base + (uint32_t)(set * 256 + mb * BN) + ((uint32_t)(q * 32) << 16);
+#pragma unroll
+        for (int sub = 0; sub < kSubs; ++sub) {
+          uint32_t v[kSubCh / 16][16];
+#pragma unroll
+          for (int c = 0; c < kSubCh / 16; ++c) tmem_ld16(tmem_acc + (uint32_t)(sub * kSubCh + c * 16), v[c]);
           tmem_ld_wait();
-          if (c >= kLastMine) {
-            tc_fence_before();
-            __syncwarp();
-            if (lane == 0) mbar_arrive(&acc_empty[a]);
-          }
-          if (pix_ok) {
+          uint4 pk[kChunks];
 #pragma unroll
-            for (int h8 = 0; h8 < 2; ++h8) {
-              const int o = c + h8 * 8;
-              if (o < prm.O) {
-                uint32_t pk[4];
+          for (int ch = 0; ch < kChunks; ++ch) {
+            uint32_t w4[4];
+            // bias as two 16-byte broadcast loads per 8 columns: a broadcast LDS.32 costs a whole
+            // shared-memory wavefront, and the UMMA operand reads saturate that port at N <= 64
+            const float4 b0 = has_bias ? *reinterpret_cast<const float4 *>(bias_s + sub * kSubCh + ch * 8) : make_float4(0.f, 0.f, 0.f, 0.f);
+            const float4 b1 = has_bias ? *reinterpret_cast<const float4 *>(bias_s + sub * kSubCh + ch * 8 + 4) : make_float4(0.f, 0.f, 0.f, 0.f);
 #pragma unroll
-                for (int j = 0; j < 4; ++j) {
-                  float v0 = __uint_as_float(r[h8 * 8 + 2 * j]);
-                  float v1 = __uint_as_float(r[h8 * 8 + 2 * j + 1]);
-                  if (prm.bias) {
-                    v0 += __ldg(prm.bias + o + 2 * j);
-                    v1 += __ldg(prm.bias + o + 2 * j + 1);
-                  }
-                  if (prm.act == 3) {
-                    v0 = v0 > 0.f ? v0 : v0 * prm.alpha;
-                    v1 = v1 > 0.f ? v1 : v1 * prm.alpha;
-                  }
-                  const uint32_t lo = __bfloat16_as_ushort(__float2bfloat16_rn(v0 * prm.scale));
-                  const uint32_t hi = __bfloat16_as_ushort(__float2bfloat16_rn(v1 * prm.scale));
-                  pk[j] = lo | (hi << 16);
-                }
-                *reinterpret_cast<uint4 *>(yp + o) = make_uint4(pk[0], pk[1], pk[2], pk[3]);
+            for (int j = 0; j < 4; ++j) {
+              const int e = ch * 8 + 2 * j;           // column inside the sub-tile
+              float v0 = __uint_as_float(v[e >> 4][e & 15]) + (j < 2 ? (j == 0 ? b0.x : b0.z) : (j == 2 ? b1.x : b1.z));
+              float v1 = __uint_as_float(v[e >> 4][(e & 15) + 1]) + (j < 2 ? (j == 0 ? b0.y : b0.w) : (j == 2 ? b1.y : b1.w));
+              if (lrelu) {
+                v0 = v0 > 0.f ? v0 : v0 * alpha;
+                v1 = v1 > 0.f ? v1 : v1 * alpha;
               }
+              const __nv_bfloat162 pr = __floats2bfloat162_rn(v0 * scale, v1 * scale);
+              w4[j] = *reinterpret_cast<const uint32_t *>(&pr);
+            }
+            pk[ch] = make_uint4(w4[0], w4[1], w4[2], w4[3]);
+          }
+          if (sub == 0) {                             // the previous store has left the staging tiles
+            if (issuer) tma_store_wait_read<0>();
+            named_bar_sync(1 + grp, 128);
+          }
+          if (col_ok) {
+#pragma unroll
+            for (int ch = 0; ch < kChunks; ++ch) {
+              const uint32_t a = srow_addr + (uint32_t)(sub * kSubBytes) + (((uint32_t)ch ^ swz) << 4);
+              asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(a), "r"(pk[ch].x), "r"(pk[ch].y),
+                           "r"(pk[ch].z), "r"(pk[ch].w)
+                           : "memory");
             }
           }
         }
+        fence_proxy_async();
+        named_bar_sync(1 + grp, 128);
+        if (issuer) {
+#pragma unroll
+          for (int sub = 0; sub < kSubs; ++sub)
+            tma_store_4d(&maps.y, stage_u32 + (uint32_t)(sub * kSubBytes), sub * kSubCh, ow0,
+                         oh0 + mb * rows_pb, b);
+          tma_store_commit();
+        }
+        if (q == 0) TRACE0(2 + grp, 7, lt * 8 + mb);
       }
+      // this warp is done reading the set's accumulators
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&set_empty[set]);
     }
-    if (warp == 2) PROF_FLUSH(3, -1, 6);
+    if (issuer) tma_store_wait_read<0>();             // staging must outlive the last store's read
+    if (warp == 3) PROF_FLUSH(3, -1, 6);
   }
   tc_fence_before();
   __syncthreads();
-  if (warp == 1) {
+  if (warp == kMmaWarp) {
     tc_fence_after();
-    tmem_dealloc(tmem_base, 2 * BN < 32 ? 32 : 2 * BN);
+    tmem_dealloc(tmem_base, 512);
   }
 }
 
@@ -710,9 +787,10 @@ bool make_map_sw(CUtensorMap *m, const void *ptr, int rank, const uint64_t *dims
              CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
 }
 
+// one CTA per SM: it owns all 512 TMEM columns (two sets of 256 / BN accumulators)
 template <int ROWB, int BN, int NBUF>
 int launch_halo(const HaloMaps &maps, HaloParams prm, int buf_stride, cudaStream_t st) {
-  const int smem = ((prm.T * BN * ROWB + 1023) & ~1023) + NBUF * buf_stride + 256 + 1024;
+  const int smem = ((prm.T * BN * ROWB + 1023) & ~1023) + 2 * kCM * BN * 2 + NBUF * buf_stride + 1024 + 1024;
   static int configured = 0;
   if (smem > configured) {
     if (cudaFuncSetAttribute(conv_halo_tc_kernel<ROWB, BN, NBUF>,
@@ -722,8 +800,7 @@ int launch_halo(const HaloMaps &maps, HaloParams prm, int buf_stride, cudaStream
     }
     configured = smem;
   }
-  const int per_sm = (2 * smem <= 225 * 1024 && 4 * BN <= 512) ? 2 : 1;
-  const int resident = num_sms() * per_sm;
+  const int resident = num_sms();
   int ctas = prm.total_tiles < resident ? prm.total_tiles : resident;
   prm.tiles_per_cta = (prm.total_tiles + ctas - 1) / ctas;
   ctas = (prm.total_tiles + prm.tiles_per_cta - 1) / prm.tiles_per_cta;
@@ -938,19 +1015,32 @@ extern "C" int dusty_conv2d_tc_classes(const void *x, const void *wpk, void *y, 
   return DUSTY_OK;
 }
 
-extern "C" int dusty_conv_role_prof(double *out8, int reset) {
+extern "C" int dusty_conv_trace(unsigned long long *out, int cap) {
 #ifdef DUSTY_ROLE_PROF
-  unsigned long long h[8];
+  if (cap < 8192) return -1;
+  if (cudaMemcpyFromSymbol(out, s_trace, sizeof(unsigned long long) * 8192) != cudaSuccess) return -1;
+  static unsigned long long zeros[8192];
+  cudaMemcpyToSymbol(s_trace, zeros, sizeof(zeros));
+  return 8192;
+#else
+  (void)out; (void)cap;
+  return -1;
+#endif
+}
+
+extern "C" int dusty_conv_role_prof(double *out8, int reset) {     // 12 doubles
+#ifdef DUSTY_ROLE_PROF
+  unsigned long long h[12];
   if (cudaMemcpyFromSymbol(h, s_role_prof, sizeof(h)) != cudaSuccess) return DUSTY_ECUDA;
-  for (int i = 0; i < 8; ++i) out8[i] = (double)h[i];
+  for (int i = 0; i < 12; ++i) out8[i] = (double)h[i];
   if (reset) {
-    unsigned long long z[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+    unsigned long long z[12] = {0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0};
     if (cudaMemcpyToSymbol(s_role_prof, z, sizeof(z)) != cudaSuccess) return DUSTY_ECUDA;
   }
   return DUSTY_OK;
 #else
   (void)reset;
-  for (int i = 0; i < 8; ++i) out8[i] = 0.0;
+  for (int i = 0; i < 12; ++i) out8[i] = 0.0;
   return DUSTY_EUNSUPPORTED;
 #endif
 }
@@ -1101,12 +1191,22 @@ extern "C" int dusty_conv2d_halo_tc(const void *x, const void *wpk, const float 
   auto cover = [&](int pw) { const int two = pw - (S - 1); return (long long)((W_out + two - 1) / two) * pw; };
   prm.PW = cover(32) < cover(64) ? 32 : 64;
   prm.TWo = prm.PW - (S - 1);
-  // rows per tile: as many as a 48 / 64 KiB patch allows, in multiples that make TH * PW % 128 == 0
+  // rows per tile: multiples that make TH * PW % 128 == 0, bounded by the shared memory left
+  // for two patches next to the resident filter and the staging tiles, by the accumulators of
+  // one TMEM set, and chosen to load the fewest rows (tile rows + halo) over the image
   const int th_step = 128 / prm.PW;
+  const int smem_left = 227 * 1024 - 2048 - ((prm.T * BN * ROWB + 1023) & ~1023) - 2 * kCM * BN * 2;
+  const int patch_cap = smem_left / 2 - 1024 < 64 * 1024 ? smem_left / 2 - 1024 : 64 * 1024;
+  const int mb_cap = 256 / BN;             // accumulators of one TMEM set
   int th = th_step;
-  const int patch_cap = ROWB == 64 ? 48 * 1024 : 64 * 1024;
-  while ((th + th_step + R - 1) * prm.PW * ROWB <= patch_cap && th + th_step <= 16 &&
-         th < H_out) th += th_step;
+  long long best_rows = -1;
+  for (int t = th_step; t <= 16 && t * prm.PW / 128 <= mb_cap; t += th_step) {
+    if ((t + R - 1) * prm.PW * ROWB + (S - 1) * ROWB > patch_cap || t + R - 1 > 256) break;
+    const long long rows = (long long)((H_out + t - 1) / t) * (t + R - 1);
+    if (best_rows < 0 || rows <= best_rows) { best_rows = rows; th = t; }
+    if (t >= H_out) break;
+  }
+  DUSTY_CHECK_ARG((th + R - 1) * prm.PW * ROWB + (S - 1) * ROWB <= patch_cap, "filter too large for the halo kernel");
   prm.TH = th;
   prm.MB = prm.TH * prm.PW / 128;
   prm.org_h = org_h; prm.org_w = org_w;
@@ -1131,8 +1231,14 @@ extern "C" int dusty_conv2d_halo_tc(const void *x, const void *wpk, const float 
     const uint64_t wdims[3] = {(uint64_t)C, (uint64_t)O, (uint64_t)prm.T};
     const uint64_t wstr[2] = {(uint64_t)(w_sn ? w_sn : C) * 2, (uint64_t)(w_sg ? w_sg : (long long)O * C) * 2};
     const uint32_t wbox[3] = {(uint32_t)C, (uint32_t)BN, 1u};
+    // output: NHWC view through the caller's strides; one box = the valid pixels of a block
+    const int sub_ch = BN > 64 ? 64 : BN;
+    const uint64_t ydims[4] = {(uint64_t)O, (uint64_t)W_out, (uint64_t)H_out, (uint64_t)B};
+    const uint64_t ystr[3] = {(uint64_t)y_sw * 2, (uint64_t)y_sh * 2, (uint64_t)y_sb * 2};
+    const uint32_t ybox[4] = {(uint32_t)sub_ch, (uint32_t)prm.TWo, (uint32_t)(kCM / prm.PW), 1u};
     if (!make_map_sw(&maps.x, x, 4, dims, strides, box, ROWB == 64) ||
-        !make_map_sw(&maps.w, wpk, 3, wdims, wstr, wbox, ROWB == 64)) {
+        !make_map_sw(&maps.w, wpk, 3, wdims, wstr, wbox, ROWB == 64) ||
+        !make_map_sw(&maps.y, (const __nv_bfloat16 *)y + y_off, 4, ydims, ystr, ybox, sub_ch == 32)) {
       set_error("dusty_conv2d_halo_tc: cuTensorMapEncodeTiled failed");
       return DUSTY_ECUDA;
     }

@@ -358,7 +358,7 @@ int dusty_conv2d_tc_classes(const void *x, const void *wpk, void *y, int B, int 
                             long long y_sh, long long y_sw, long long w_sn, long long w_sg,
                             int w_taps, void *stream);
 
-/* Tools only: role-cycle counters of the tcgen05 convolution kernels (8 doubles; see
+/* Tools only: role-cycle counters of the tcgen05 convolution kernels (12 doubles; see
  * conv_tc.cu).  DUSTY_EUNSUPPORTED unless the library was built with -DDUSTY_ROLE_PROF. */
 int dusty_conv_role_prof(double *out8, int reset);
 

@@ -19,7 +19,7 @@ from conv_once import layers  # noqa: E402
 
 
 def read(reset=True):
-    buf = (ctypes.c_double * 8)()
+    buf = (ctypes.c_double * 12)()
     K.call("dusty_conv_role_prof", ctypes.addressof(buf), 1 if reset else 0)
     return list(buf)
 
@@ -37,7 +37,9 @@ def report(tag, fn):
     life = [max(p[4], 1), max(p[5], 1), max(p[6], 1)]
     print(f"{tag:34s} {s.elapsed_time(e) * 1e3:7.1f} us  ctas {int(ctas):4d}  cyc/cta {life[1] / ctas:9.0f} | "
           f"producer waits slot {100 * p[0] / life[0]:5.1f}% | mma waits operands {100 * p[1] / life[1]:5.1f}% "
-          f"acc {100 * p[2] / life[1]:5.1f}% | epilogue waits acc {100 * p[3] / life[2]:5.1f}%", flush=True)
+          f"acc {100 * p[2] / life[1]:5.1f}% | epilogue waits acc {100 * p[3] / life[2]:5.1f}%"
+          + (f" | issue loop {p[8] / p[9]:6.0f} cyc/block x {int(p[9] / ctas)} blocks, fence+elect {p[10] / p[9]:5.0f}, "
+             f"commit {p[11] / p[9]:5.0f}" if p[9] else ""), flush=True)
 
 
 def main():

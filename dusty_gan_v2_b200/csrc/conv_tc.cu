@@ -291,6 +291,221 @@ conv_fwd_tc_kernel(const __grid_constant__ ConvMaps maps, const __grid_constant_
   }
 }
 
+// ------------------------------------------------------------------ CTA-pair implicit GEMM (C >= 128)
+// The deep layers are GEMM-shaped (K = 1152 .. 4608) and bound by the shared-memory port: a
+// 128 x N x 16 UMMA reads 4 KB of A and 32 N bytes of B, and the TMA writes of single-use
+// operands cross the same 128 B / cycle -- 256 B / cycle of demand at N = 128, 192 at N = 256
+// (measured: 47-57 % tensor-pipe activity for conv_fwd_tc_kernel<128 / 256>).  Here two CTAs of
+// a cluster (the two SMs of a TPC) run ONE 256 x N UMMA per k-step (cta_group::2): each CTA
+// lands its own 128-pixel A tile and HALF of the filter tile, the halves are exchanged by the
+// hardware, so per CTA the port carries 32 KB + 32 KB per 512 MMA cycles at N = 256.
+// Roles per CTA: warp 0 = TMA producer (both CTAs; all transaction bytes are counted on the
+// LEADER's full barrier), warp 1 = MMA issuer (leader only; commits multicast to the barriers of
+// both CTAs), warps 2-9 = epilogue (each CTA drains the 128 accumulator rows in its own TMEM
+// and reports to the leader's acc_empty barrier).  The MMA warp probes the next stage's barrier
+// BEFORE issuing the current stage's UMMAs (the tensor pipe's queue is a few instructions deep:
+// a blocking wait between stages is idle time, see the halo kernel's notes).  Output through a
+// swizzled staging tile and TMA stores, 64 channels at a time.
+struct PairMaps {
+  CUtensorMap a[4];
+  CUtensorMap w;
+  CUtensorMap y[kMaxClasses];
+};
+
+template <int BN, int STAGES>
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kCThreads, 1)
+conv_pair_tc_kernel(const __grid_constant__ PairMaps maps, const __grid_constant__ ConvParams prm,
+                    int patches) {
+  extern __shared__ __align__(1024) uint8_t smem_raw[];
+  uint8_t *smem = (uint8_t *)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
+  constexpr int kBHalf = (BN / 2) * kCK * 2;                // this CTA's half of the filter tile
+  constexpr int kStageBytes = kCABytes + kBHalf;
+  constexpr int kStageTile = kCM * 64 * 2;                  // [128 rows][64 channels] staging tile
+  uint8_t *a_base = smem;
+  uint8_t *b_base = smem + STAGES * kCABytes;
+  uint8_t *stage_base = smem + STAGES * kStageBytes;        // one staging tile per epilogue group
+  uint64_t *full = (uint64_t *)(stage_base + 2 * kStageTile);
+  uint64_t *empty = full + STAGES;
+  uint64_t *acc_full = empty + STAGES;
+  uint64_t *acc_empty = acc_full + 2;
+  uint32_t *tmem_slot = (uint32_t *)(acc_empty + 2);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const uint32_t rank = cluster_ctarank();
+  const int cluster_id = blockIdx.x >> 1;
+  const int t_begin = cluster_id * prm.tiles_per_cta;
+  const int t_end = min(t_begin + prm.tiles_per_cta, prm.total_tiles);
+
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < STAGES; ++s) {
+      mbar_init(&full[s], 1);            // the leader's arrive.expect_tx (+ both CTAs' bytes)
+      mbar_init(&empty[s], 1);           // the leader's multicast commit
+    }
+    for (int a = 0; a < 2; ++a) {
+      mbar_init(&acc_full[a], 1);        // multicast commit
+      mbar_init(&acc_empty[a], 16);      // 8 epilogue warps of each CTA (leader's copy is used)
+    }
+    fence_barrier_init();
+  }
+  if (warp == 1) tmem_alloc_pair(tmem_slot, 2 * BN);
+  tc_fence_before();
+  __syncthreads();
+  cluster_sync_all();                    // peer barriers initialised before anything remote
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+  PROF_DECL;
+
+  // pair tile -> (class, channel tile, patch pair); this CTA's patch -> (sample, row, column)
+  auto decode = [&](int pt, int &ci, int &n0, int &b, int &oh0, int &ow0, bool &valid) {
+    ci = pt % prm.ncls;
+    pt /= prm.ncls;
+    n0 = (pt % prm.NT) * BN;
+    const int patch = (pt / prm.NT) * 2 + (int)rank;
+    valid = patch < patches;
+    int r = patch;
+    ow0 = (r % prm.tiles_w) * prm.TW;
+    r /= prm.tiles_w;
+    oh0 = (r % prm.tiles_h) * prm.TH;
+    b = r / prm.tiles_h;                 // == B for the dummy patch of an odd count: zero-filled loads
+  };
+
+  if (warp == 0) {
+    uint32_t lead_full[STAGES];
+#pragma unroll
+    for (int s = 0; s < STAGES; ++s) lead_full[s] = mapa_u32(smem_u32(&full[s]), 0);
+    RingPos r;
+    for (int pt = t_begin; pt < t_end; ++pt) {
+      int ci, n0, b, oh0, ow0;
+      bool valid;
+      decode(pt, ci, n0, b, oh0, ow0, valid);
+      const ConvClass &cl = prm.cls[ci];
+      for (int g = 0; g < cl.G; ++g) {
+        const CUtensorMap *am = &maps.a[prm.amap[g]];
+        const int cw = ow0 + cl.aw[g], ch = oh0 + cl.ah[g];
+        for (int kc = 0; kc < prm.KC; ++kc) {
+          const int s = r.s;
+          PROF_WAIT(0, mbar_wait(&empty[s], r.ph ^ 1));
+          if (elect_one_sync()) {
+            if (rank == 0) mbar_expect_tx(&full[s], 2 * kStageBytes);
+            uint32_t lf = lead_full[0];
+#pragma unroll
+            for (int i = 1; i < STAGES; ++i) lf = (s == i) ? lead_full[i] : lf;
+            tma_load_4d_pair(a_base + s * kCABytes, am, lf, kc * kCK, cw, ch, b);
+            tma_load_3d_pair(b_base + s * kBHalf, &maps.w, lf, kc * kCK, n0 + (int)rank * (BN / 2), cl.wtap[g]);
+          }
+          __syncwarp();
+          r.template advance<STAGES>();
+        }
+      }
+    }
+    if (rank == 0) PROF_FLUSH(0, -1, 4);
+  } else if (warp == 1) {
+    if (rank == 0) {
+      constexpr uint32_t idesc = make_idesc(2 * kCM, BN, false, false);
+      const uint32_t d_hi = desc_hi(1024, 2);
+      const uint32_t a_lo0 = desc_lo(smem_u32(a_base), 16);
+      const uint32_t b_lo0 = desc_lo(smem_u32(b_base), 16);
+      RingPos r;
+      int lt = 0;
+      bool ready = false;                // stage r.s already known to be full (probed ahead)
+      for (int pt = t_begin; pt < t_end; ++pt, ++lt) {
+        const int a = lt & 1;
+        const int num_kb = prm.cls[pt % prm.ncls].G * prm.KC;
+        PROF_WAIT(1, mbar_wait(&acc_empty[a], ((lt >> 1) & 1) ^ 1));
+        const uint32_t tmem_acc = tmem_base + (uint32_t)(a * BN);
+        for (int kb = 0; kb < num_kb; ++kb) {
+          const int s = r.s;
+          if (!ready) PROF_WAIT(0, mbar_wait(&full[s], r.ph));
+          tc_fence_after();
+          RingPos nx = r;
+          nx.template advance<STAGES>();
+          const bool more = kb + 1 < num_kb || pt + 1 < t_end;
+          ready = more && mbar_try_wait(&full[nx.s], nx.ph);      // probe, consumed next iteration
+          if (elect_one_sync()) {
+            const uint32_t a_lo = a_lo0 + (uint32_t)s * (kCABytes >> 4);
+            const uint32_t b_lo = b_lo0 + (uint32_t)s * (kBHalf >> 4);
+#pragma unroll
+            for (int k16 = 0; k16 < kCK / 16; ++k16)
+              umma_bf16_lh_pair(tmem_acc, a_lo + k16 * 2, d_hi, b_lo + k16 * 2, d_hi, idesc,
+                                (kb > 0 || k16 > 0) ? 1u : 0u);
+            umma_commit_pair(&empty[s]);
+            if (kb == num_kb - 1) umma_commit_pair(&acc_full[a]);
+          }
+          __syncwarp();
+          r = nx;
+        }
+      }
+      PROF_FLUSH(1, 2, 5);
+    }
+  } else {
+    const int q = warp & 3;
+    const int grp = (warp - 2) >> 2;
+    const int row = q * 32 + lane;
+    const bool issuer = (warp - 2) % 4 == 0 && lane == 0;
+    const uint32_t lead_acc_empty[2] = {mapa_u32(smem_u32(&acc_empty[0]), 0), mapa_u32(smem_u32(&acc_empty[1]), 0)};
+    const uint32_t stage_u32 = smem_u32(stage_base) + (uint32_t)(grp * kStageTile);
+    const uint32_t srow_addr = stage_u32 + (uint32_t)row * 128u;
+    const uint32_t swz = (uint32_t)row & 7u;
+    constexpr int kNChunks = BN / 64;
+    int lt = 0;
+    for (int pt = t_begin; pt < t_end; ++pt, ++lt) {
+      int ci, n0, b, oh0, ow0;
+      bool valid;
+      decode(pt, ci, n0, b, oh0, ow0, valid);
+      const int a = lt & 1;
+      PROF_WAIT(0, mbar_wait(&acc_full[a], (lt >> 1) & 1));
+      tc_fence_after();
+      const uint32_t tmem_acc = tmem_base + (uint32_t)(a * BN) + ((uint32_t)(q * 32) << 16);
+#pragma unroll 1
+      for (int c = grp; c < kNChunks; c += 2) {
+        uint32_t v[4][16];
+#pragma unroll
+        for (int i = 0; i < 4; ++i) tmem_ld16(tmem_acc + (uint32_t)(c * 64 + i * 16), v[i]);
+        tmem_ld_wait();
+        if (c + 2 >= kNChunks) {           // this group's last chunk: the accumulator may be reused
+          tc_fence_before();
+          __syncwarp();
+          if (lane == 0) mbar_arrive_cluster(lead_acc_empty[a]);
+        }
+        if (valid && n0 + c * 64 < prm.O) {
+          if (issuer) tma_store_wait_read<0>();
+          named_bar_sync(1 + grp, 128);
+#pragma unroll
+          for (int ch = 0; ch < 8; ++ch) {
+            uint32_t w4[4];
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+              const int e = ch * 8 + 2 * j;
+              const __nv_bfloat162 pr = __floats2bfloat162_rn(__uint_as_float(v[e >> 4][e & 15]) * prm.scale,
+                                                              __uint_as_float(v[e >> 4][(e & 15) + 1]) * prm.scale);
+              w4[j] = *reinterpret_cast<const uint32_t *>(&pr);
+            }
+            const uint32_t addr = srow_addr + (((uint32_t)ch ^ swz) << 4);
+            asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(w4[0]), "r"(w4[1]), "r"(w4[2]),
+                         "r"(w4[3])
+                         : "memory");
+          }
+          fence_proxy_async();
+          named_bar_sync(1 + grp, 128);
+          if (issuer) {
+            tma_store_4d(&maps.y[ci], stage_u32, n0 + c * 64, ow0, oh0, b);
+            tma_store_commit();
+          }
+        }
+      }
+    }
+    if (issuer) tma_store_wait_read<0>();
+    if (warp == 2 && rank == 0) PROF_FLUSH(3, -1, 6);
+  }
+  tc_fence_before();
+  __syncthreads();
+  cluster_sync_all();                    // no CTA leaves while its peer may still signal it
+  if (warp == 1) {
+    tc_fence_after();
+    tmem_dealloc_pair(tmem_base, 2 * BN);
+  }
+}
+
 // ------------------------------------------------------------------ halo-resident 3x3 (C = 32 / 64)
 // The thin, wide layers (32 / 64 channels at 64x512 / 32x256) are bound by operand delivery, not
 // by the tensor pipe: an implicit GEMM that lands every filter tap as its own shared-memory tile
@@ -857,6 +1072,24 @@ void pick_patch(int W, int H, int n, int *TW, int *TH) {
 
 using namespace dusty;
 
+static bool pair_enabled() {
+  static const bool off = [] { const char *e = getenv("DUSTY_CONV_PAIR"); return e && atoi(e) == 0; }();
+  return !off;
+}
+
+template <int BN, int STAGES>
+int launch_pair(const PairMaps &maps, ConvParams prm, int patches, cudaStream_t st) {
+  constexpr int smem = STAGES * (kCABytes + (BN / 2) * kCK * 2) + 2 * kCM * 64 * 2 + 1024 + 1024;
+  static bool configured = false;
+  if (int rc = set_smem(conv_pair_tc_kernel<BN, STAGES>, smem, &configured)) return rc;
+  int clusters = num_sms() / 2;
+  if (prm.total_tiles < clusters) clusters = prm.total_tiles;
+  prm.tiles_per_cta = (prm.total_tiles + clusters - 1) / clusters;
+  clusters = (prm.total_tiles + prm.tiles_per_cta - 1) / prm.tiles_per_cta;
+  conv_pair_tc_kernel<BN, STAGES><<<2 * clusters, kCThreads, smem, st>>>(maps, prm, patches);
+  return 0;
+}
+
 // One launch of the implicit-GEMM kernel over `ncls` classes.  Host-side description of a class:
 struct HostClass {
   int G;
@@ -945,6 +1178,30 @@ static int conv_launch(const char *who, const void *x, const void *wpk, const fl
   prm.O = O;
   prm.y_sb = y_sb; prm.y_sh = y_sh; prm.y_sw = y_sw;
   prm.bias = bias; prm.y = (__nv_bfloat16 *)y; prm.act = act; prm.alpha = alpha; prm.scale = scale;
+  // deep layers: CTA pairs (plain output, no bias / activation epilogue)
+  if (pair_enabled() && BN >= 128 && Kg % kCK == 0 && prm.KC * hc[0].G >= 4 && bias == nullptr && act == 1 &&
+      O % 8 == 0) {
+    PairMaps pm;
+    for (int g = 0; g < 4; ++g) pm.a[g] = maps.a[g];
+    pm.w = maps.w;
+    // the pair kernel lands HALF of the filter tile per CTA
+    ok = make_map3w(&pm.w, wpk, (uint64_t)Kg, (uint64_t)O, (uint64_t)Gw, kCK, (uint32_t)(BN / 2),
+                    (uint64_t)w_sn, (uint64_t)w_sg);
+    const uint32_t ybox[4] = {64u, (uint32_t)prm.TW, (uint32_t)prm.TH, 1u};
+    for (int c = 0; c < kMaxClasses; ++c) {
+      const HostClass &h = hc[c < ncls ? c : 0];
+      const uint64_t ydims[4] = {(uint64_t)O, (uint64_t)h.W_out, (uint64_t)h.H_out, (uint64_t)B};
+      const uint64_t ystr[3] = {(uint64_t)y_sw * 2, (uint64_t)y_sh * 2, (uint64_t)y_sb * 2};
+      ok = ok && make_map_sw(&pm.y[c], (const __nv_bfloat16 *)y + h.y_off, 4, ydims, ystr, ybox, false);
+    }
+    if (!ok) {
+      set_error("%s: cuTensorMapEncodeTiled failed (pair kernel)", who);
+      return DUSTY_ECUDA;
+    }
+    const int patches = prm.tiles_w * prm.tiles_h * B;
+    prm.total_tiles = ((patches + 1) / 2) * prm.NT * ncls;
+    return BN == 256 ? launch_pair<256, 5>(pm, prm, patches, st) : launch_pair<128, 7>(pm, prm, patches, st);
+  }
   switch (BN) {
     case 256: return launch_conv<256, 4>(maps, prm, st);
     case 128: return launch_conv<128, 5>(maps, prm, st);

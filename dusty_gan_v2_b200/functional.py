@@ -1361,6 +1361,16 @@ def conv2d_dgrad_tc(gy, w, stride, in_hw, w_tco=None):
             cls_off.append((ph * W + pw) * C)
     if empty_class:                      # positions no filter tap reaches (e.g. 1x1, stride 2)
         gx.zero_()
+    if len(cls_G) > 2:
+        # a CTA walks the classes of a patch in order and its range may end between them: put
+        # the heaviest and the lightest class side by side (3x3 stride 2: 4, 1, 2, 2 taps)
+        order = sorted(range(len(cls_G)), key=lambda c: -cls_G[c])
+        order = [order[0], order[-1]] + order[1:-1]
+        starts = [sum(cls_G[:c]) for c in range(len(cls_G))]
+        pick = lambda v: [x for c in order for x in v[starts[c]:starts[c] + cls_G[c]]]   # noqa: E731
+        dh, dw, wtap = pick(dh), pick(dw), pick(wtap)
+        cls_H, cls_W, cls_off = [cls_H[c] for c in order], [cls_W[c] for c in order], [cls_off[c] for c in order]
+        cls_G = [cls_G[c] for c in order]
     if cls_G:
         K.call("dusty_conv2d_tc_classes", K.ptr(gy), K.ptr(w_tco), K.ptr(gx), B, Ho, Wo, O, C,
                len(cls_G), _ints(cls_G), _ints(dh), _ints(dw), _ints(wtap), _ints(cls_H), _ints(cls_W),

@@ -13,11 +13,16 @@ import dusty_gan_v2_b200.functional as DF  # noqa: E402
 
 
 def timeit(fn, flush, iters=8):
+    """Device time of one call: L2 flushed before EVERY timed launch, and a spin kernel between
+    the flush and the start event so that the host has finished enqueueing `fn` (tensor-map
+    encoding, Python) before the device reaches it -- otherwise the event interval of a 20 us
+    kernel measures the host wrapper."""
     fn()
     torch.cuda.synchronize()
     ts = []
     for _ in range(iters):
         flush.add_(1.0)
+        torch.cuda._sleep(1_000_000)           # ~0.5 ms of device time
         s, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         s.record()
         fn()

@@ -106,6 +106,7 @@ struct ConvParams {
   ConvClass cls[kMaxClasses];
   int amap[kMaxGroups];                    // window mode: tensor map of group g (class 0 only)
   int TW, TH, tiles_w, tiles_h, NT, total_tiles, tiles_per_cta;
+  int a_bytes;                             // bytes one activation box lands (TW * TH pixels x 64 k)
   int O;
   long long y_sb, y_sh, y_sw;              // element strides of the output view
   const float *bias;
@@ -178,7 +179,7 @@ conv_fwd_tc_kernel(const __grid_constant__ ConvMaps maps, const __grid_constant_
           const int s = r.s;
           PROF_WAIT(0, mbar_wait(&empty[s], r.ph ^ 1));
           if (elect_one_sync()) {
-            mbar_expect_tx(&full[s], kStageBytes);
+            mbar_expect_tx(&full[s], prm.a_bytes + kBBytes);
             tma_load_4d(a_base + s * kCABytes, am, &full[s], kc * kCK, cw, ch, b);
             tma_load_3d(b_base + s * kBBytes, &maps.w, &full[s], kc * kCK, n0, cl.wtap[g]);
           }
@@ -238,7 +239,7 @@ conv_fwd_tc_kernel(const __grid_constant__ ConvMaps maps, const __grid_constant_
       tc_fence_after();
       const uint32_t tmem_acc = tmem_base + (uint32_t)(a * BN) + ((uint32_t)(q * 32) << 16);
       const int oh = oh0 + th, ow = ow0 + tw;
-      const bool pix_ok = oh < cl.H_out && ow < cl.W_out;
+      const bool pix_ok = th < prm.TH && oh < cl.H_out && ow < cl.W_out;
       __nv_bfloat16 *yp = prm.y + cl.y_off + (long long)b * prm.y_sb + (long long)oh * prm.y_sh +
                           (long long)ow * prm.y_sw + n0;
       // the two groups of four epilogue warps take alternate 16-column chunks
@@ -386,7 +387,7 @@ conv_pair_tc_kernel(const __grid_constant__ PairMaps maps, const __grid_constant
           const int s = r.s;
           PROF_WAIT(0, mbar_wait(&empty[s], r.ph ^ 1));
           if (elect_one_sync()) {
-            if (rank == 0) mbar_expect_tx(&full[s], 2 * kStageBytes);
+            if (rank == 0) mbar_expect_tx(&full[s], 2 * (prm.a_bytes + kBHalf));
             uint32_t lf = lead_full[0];
 #pragma unroll
             for (int i = 1; i < STAGES; ++i) lf = (s == i) ? lead_full[i] : lf;
@@ -1053,6 +1054,33 @@ int launch_wgrad(const WgMaps &maps, const WgParams &prm, int splits, int R, cud
 
 // pixel patch of `n` pixels (n = 128 or 64): widest power-of-two row segment with the least
 // padding waste over a W x H output
+// Patch of AT MOST `n` pixels, any TW x TH (a TMA box need not be a power of two): the fewest
+// tiles over a W x H output, ties broken towards fuller tiles.  The operand tile keeps its
+// 128 rows; rows past TW * TH hold stale data whose products are never stored.  (A data
+// gradient is taken on the padded grid -- 66 x 10, 130 x 18, parity classes of 33 x 5 -- where
+// power-of-two patches waste up to half of every tile.)
+void pick_patch_any(int W, int H, int n, int *TW, int *TH) {
+  long long best_tiles = -1;
+  int best_fill = 0;
+  for (int tw = 1; tw <= n && tw <= 256; ++tw) {
+    if (tw > W && tw != 1) break;
+    int th = n / tw;
+    if (th > H) th = H;
+    if (th > 256) th = 256;
+    if (th < 1) continue;
+    // rows of a box land 8 to a swizzle atom; any count works, but keep boxes of >= 8 pixels
+    const long long tiles = (long long)((W + tw - 1) / tw) * ((H + th - 1) / th);
+    const int fill = tw * th;
+    // ties: fuller tiles, then wider rows (long contiguous runs per box row)
+    if (best_tiles < 0 || tiles < best_tiles || (tiles == best_tiles && fill >= best_fill)) {
+      best_tiles = tiles;
+      best_fill = fill;
+      *TW = tw;
+      *TH = th;
+    }
+  }
+}
+
 void pick_patch(int W, int H, int n, int *TW, int *TH) {
   long long best = -1;
   for (int tw = n; tw >= 1; tw >>= 1) {
@@ -1113,7 +1141,8 @@ static int conv_launch(const char *who, const void *x, const void *wpk, const fl
     H_max = hc[c].H_out > H_max ? hc[c].H_out : H_max;
     W_max = hc[c].W_out > W_max ? hc[c].W_out : W_max;
   }
-  pick_patch(W_max, H_max, kCM, &prm.TW, &prm.TH);
+  pick_patch_any(W_max, H_max, kCM, &prm.TW, &prm.TH);
+  prm.a_bytes = prm.TW * prm.TH * kCK * 2;
   const uint32_t box[4] = {(uint32_t)kCK, (uint32_t)prm.TW, (uint32_t)prm.TH, 1u};
   const __nv_bfloat16 *xb = (const __nv_bfloat16 *)x;
   bool ok = true;

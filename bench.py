@@ -50,9 +50,6 @@ def parse():
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cudnn-benchmark", action="store_true")
     ap.add_argument("--no-cuda-graphs", action="store_true")
-    ap.add_argument("--conv-impl", default="tc", choices=["tc", "auto", "library"],
-                    help="D convolutions: own tcgen05 kernels everywhere (default), own-or-cuDNN by "
-                         "measured speed, or cuDNN")
     ap.add_argument("--ref-kernels-only", action="store_true",
                     help="time the reference's own CUDA kernels (oracle/_ref) beside ours, print JSON, exit")
     ap.add_argument("--no-ref-kernels", action="store_true")
@@ -72,7 +69,7 @@ class ClockSampler:
         self.rows, self.proc = [], None
         try:
             self.proc = subprocess.Popen(
-                ["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "200",
+                ["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "50",
                  "-i", str(index)], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
             self.thread = threading.Thread(target=self._pump, daemon=True)
             self.thread.start()
@@ -224,7 +221,9 @@ def _cpu_reference_run(args, steps, warmup, batch):
 def kernel_rooflines(device, peaks):
     """Isolated CUDA-event timings of this repo's kernels at the step's real shapes (B=64,
     bf16), L2 flushed between launches.  `achieved` uses ALGORITHMIC bytes / flops (DESIGN.md
-    section 4).  Returns (dominant_contraction_entry, list_of_entries)."""
+    section 4).  Returns (dominant_entry, list_of_entries, conv_family_summary): the dominant
+    entry is the kernel with the largest share of the training step's device time (its isolated
+    duration x its launches per plain iteration) -- a discriminator convolution."""
     import torch
 
     import dusty_gan_v2_b200.functional as DF
@@ -233,12 +232,12 @@ def kernel_rooflines(device, peaks):
     B = 64
     flush = torch.empty(256 * 1024 * 1024, dtype=torch.uint8, device=device)
 
-    def timeit(fn, reps=6, inner=4):
-        """Mean duration of one launch: `inner` back-to-back launches per CUDA-event pair (a
-        single 50 us kernel between two events reads ~20 us too long), L2 flushed (256 MB
-        write) before every timed group; the first launch of a group is cold, later ones may
-        find part of a < 126 MB working set in L2 -- the ncu DRAM byte counts in profiles/
-        are the cross-check."""
+    def timeit(fn, reps=7):
+        """Median device time of ONE launch: L2 flushed (256 MB write) before EVERY timed launch,
+        so `achieved` is against DRAM-cold inputs like the ncu `traffic` figure; a spin kernel
+        between the flush and the start event gives the host time to finish enqueueing `fn`
+        (Python, tensor-map encoding) before the device reaches it -- without it a 20-50 us
+        kernel's event interval measures the host wrapper."""
         fn()
         torch.cuda.synchronize()
         if os.environ.get("DUSTY_KB_ONCE"):      # one launch per kernel: for `ncu --set full`
@@ -246,14 +245,15 @@ def kernel_rooflines(device, peaks):
         ts = []
         for _ in range(reps):
             flush.zero_()
+            torch.cuda._sleep(600_000)
             e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
             e0.record()
-            for _ in range(inner):
-                fn()
+            fn()
             e1.record()
             torch.cuda.synchronize()
-            ts.append(e0.elapsed_time(e1) * 1e-3 / inner)
-        return sum(ts) / len(ts)
+            ts.append(e0.elapsed_time(e1) * 1e-3)
+        ts.sort()
+        return ts[len(ts) // 2]
 
     bf = torch.bfloat16
     hbm = peaks.get("hbm_gbs", 6650.0)
@@ -430,11 +430,59 @@ def kernel_rooflines(device, peaks):
                  2.0 * B * O_ * C1 * P, (g.numel() + gx1.numel() + wb.numel()) * 2)
         return e
 
-    dom = contraction("L4.conv1", 32, 64, 512, H, W, True)
+    contraction("L4.conv1", 32, 64, 512, H, W, True)
     contraction("L4.conv1", 32, 64, 512, H, W, False)
     contraction("L1.conv1", 256, 512, 512, 8, 64, True)
     contraction("L2.conv1", 128, 256, 512, 16, 128, True)
-    return dom, out
+    torch.cuda.empty_cache()
+
+    # ---- discriminator convolutions (tcgen05 implicit GEMM): every layer x (fprop, dgrad, wgrad).
+    # Per plain training iteration the trunk runs 3 forward, 3 data-gradient and 2 filter-gradient
+    # passes in units of a 64-sample batch (G step: D frozen on 64 fakes; D step: 128 stacked
+    # real + fake with parameter gradients) -- the weights of the time shares below.
+    CLF = torch.channels_last
+    per_iter = {"fprop": 3, "dgrad": 3, "wgrad": 2}
+    layers = []
+    for i in range(4):
+        C_ = 32 << i
+        hh, ww = H >> i, W >> i
+        layers.append((f"RB{i}.conv1 3x3 s1 {C_}->{C_}", C_, C_, hh + 2, ww + 2, 3, 1))
+        layers.append((f"RB{i}.conv2 3x3 s2 {C_}->{2 * C_}", C_, 2 * C_, hh + 2, ww + 2, 3, 2))
+        layers.append((f"RB{i}.skip 1x1 s1 {C_}->{2 * C_} (decimated)", C_, 2 * C_, hh // 2, ww // 2, 1, 1))
+    layers.append(("EP.conv 3x3 s1 512->512", 512, 512, 6, 34, 3, 1))
+    conv_entries, fam_ms, fam_flops = [], 0.0, 0.0
+    for name, C_, O_, hh, ww, k_, s_ in layers:
+        xx = torch.randn(B, C_, hh, ww, device=device).to(bf).contiguous(memory_format=CLF)
+        wt = (torch.randn(O_, C_, k_, k_, device=device) / (C_ * k_ * k_) ** 0.5).to(bf)
+        st_ = (s_, s_)
+        ho, wo = (hh - k_) // s_ + 1, (ww - k_) // s_ + 1
+        yy = torch.empty((B, O_, ho, wo), dtype=bf, device=device, memory_format=CLF)
+        gy = torch.randn(B, O_, ho, wo, device=device).to(bf).contiguous(memory_format=CLF)
+        wtco = DF.filter_tco(wt)
+        flops = 2.0 * yy.numel() * C_ * k_ * k_
+        nb = {"fprop": (xx.numel() + yy.numel() + wt.numel()) * 2,
+              "dgrad": (xx.numel() + yy.numel() + wt.numel()) * 2,
+              "wgrad": (xx.numel() + yy.numel()) * 2 + wt.numel() * 4}
+        fns = {"fprop": lambda: DF.conv2d_fprop_tc(xx, wt, st_),
+               "dgrad": lambda: DF.conv2d_dgrad_tc(gy, wt, st_, (hh, ww), wtco),
+               "wgrad": lambda: DF.conv2d_wgrad_tc(gy, xx, st_, wt.shape, torch.float32)}
+        for op in ("fprop", "dgrad", "wgrad"):
+            e = tc_entry(f"conv_{op}[{name} @B=64]bf16", fns[op], flops, nb[op])
+            e["launches_per_iteration"] = per_iter[op]
+            e["step_ms_share"] = e["ms"] * per_iter[op]
+            conv_entries.append(e)
+            fam_ms += e["ms"] * per_iter[op]
+            fam_flops += flops * per_iter[op]
+        del xx, wt, yy, gy, wtco
+    sustained = peaks.get("bf16_tflops_sustained", 1400.0)
+    family = {"what": "all D convolutions of one plain training iteration (3 fprop + 3 dgrad + 2 wgrad passes "
+                      "in 64-sample units), isolated launches, L2 flushed before each",
+              "ms_per_iteration": fam_ms, "tflop_per_iteration": fam_flops / 1e12,
+              "tflops": fam_flops / (fam_ms * 1e-3) / 1e12,
+              "frac_of_bf16_sustained": fam_flops / (fam_ms * 1e-3) / 1e12 / sustained,
+              "frac_of_bf16_burst": fam_flops / (fam_ms * 1e-3) / 1e12 / tflops}
+    dom = max(conv_entries, key=lambda e: e["step_ms_share"])
+    return dom, out, family
 
 
 # ------------------------------------------------------------------------------ main
@@ -631,8 +679,6 @@ def main():
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
         dist.init_process_group("nccl", device_id=device)
     pkg.set_precision(args.precision)
-    import dusty_gan_v2_b200.functional as DFm
-    DFm.set_conv_impl(args.conv_impl)
     torch.backends.cudnn.benchmark = not args.no_cudnn_benchmark   # the reference sets it (gans/utils.py:29-30)
     if args.precision == "bf16":                 # fp32 epilogue GEMMs of D on the tensor cores
         torch.backends.cuda.matmul.allow_tf32 = True
@@ -693,12 +739,15 @@ def main():
         pool_host = synthetic_batches(4, B, seed=2 + rank, pinned=True)
         tr.batch_iter = cycle(pool_host)
         h2d = sum(t.numel() * t.element_size() for t in pool_host[0].values())
-        run(start + args.steps, 2)
+        # same R1 mix as the device-timed window: start on an R1 iteration too
+        first = start + args.steps
+        e2e_start = ((first + 2 + gp - 1) // gp) * gp
+        run(first, e2e_start - first)
         barrier()
         t0 = time.perf_counter()
         d2h = 0
         for i in range(args.steps):
-            packed = tr.step(start + args.steps + 2 + i)
+            packed = tr.step(e2e_start + i)
             host = packed.cpu()                       # device -> host read of the step's scalars
             d2h = host.numel() * host.element_size()
         barrier()
@@ -706,7 +755,9 @@ def main():
         if world > 1:
             dist.all_reduce(dt, op=dist.ReduceOp.MAX)
         e2e = {"value": args.steps * B * world / float(dt.item()), "unit": UNIT,
-               "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h}
+               "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
+               "r1_steps_timed": len([i for i in range(e2e_start, e2e_start + args.steps)
+                                      if tr.gp_every and i % tr.gp_every == 0])}
         tr.batch_iter = cycle(pool_dev)
 
     line = {"metric": METRIC.replace("dusty_v2", args.arch), "value": value, "unit": UNIT, "n_gpus": world,
@@ -719,16 +770,10 @@ def main():
                        "global_batch": B * world, "per_gpu_batch": B, "parallelism": f"dp{world}",
                        "r1_steps_timed": r1_steps, "ada_p": "adaptive from 0.0" if args.ada_p is None else args.ada_p,
                        "l2": "no flush: per-step working set (GBs) >> 126 MB L2",
-                       "dense_convs": {
-                           "tc": "all D residual-block / epilogue convolutions on own tcgen05 kernels "
-                                 "(fprop, dgrad, wgrad), fused stem kernel; cuBLAS for the two linears",
-                           "auto": "own tcgen05 kernels where they measured faster than cuDNN "
-                                   "(profiles/r01_conv_layers.json), cuDNN elsewhere; cuBLAS linears",
-                           "library": "cuDNN convolutions, cuBLAS linears"}[args.conv_impl]
-                       if args.arch == "dusty_v2" else
-                       "dense 4x4 (transposed) convolutions of the vanilla / dusty_v1 networks are cuDNN calls; "
-                       "pad, blur, bias_act, raydrop, ADA on own kernels",
-                       "conv_impl": args.conv_impl},
+                       "dense_convs": "every dense (transposed) convolution on own kernels: tcgen05 implicit GEMM "
+                                      "(fprop / dgrad / wgrad, CTA pairs for the deep layers) for bf16 NHWC, "
+                                      "CUDA-core family for fp32 and odd shapes; no library convolution; "
+                                      "cuBLAS for the linears"},
             "clocks": clk, "gpu_launches": launches, "e2e": e2e}
 
     if rank == 0 and world == 1:
@@ -740,11 +785,14 @@ def main():
         if not args.no_roofline:
             del tr
             torch.cuda.empty_cache()
-            dom, kernels = kernel_rooflines(device, peaks)
+            dom, kernels, family = kernel_rooflines(device, peaks)
             line["roofline"] = {k: dom[k] for k in ("bound", "achieved", "peak", "unit", "frac", "traffic")}
             for k in ("kernel", "peak_source", "algorithmic_bytes", "algorithmic_flops", "tflops",
-                      "tensor_frac", "hbm_gbs", "hbm_frac", "ms"):
+                      "tensor_frac", "hbm_gbs", "hbm_frac", "ms", "launches_per_iteration", "step_ms_share"):
                 line["roofline"][k] = dom[k]
+            line["roofline"]["selected_by"] = ("largest share of the step's device time among all kernels timed "
+                                               "below (isolated duration x launches per plain iteration)")
+            line["roofline"]["conv_family"] = family
             line["kernels"] = kernels
         if not args.no_cpu_baseline:
             ips, spt, cores, desc = cpu_reference_run(args, 2, 1, args.cpu_batch)

@@ -1,0 +1,223 @@
+// a11 / a15: dense 2-D convolution family on the CUDA cores (fp32 accumulation): forward, data
+// gradient (= transposed convolution) and filter gradient for ANY layout (element strides),
+// filter size, stride and zero padding, fp32 or bf16 tensors.  This is the path of fp32 parity
+// mode (exact fp32 FMAs: no TF32 rounding between the mirror and the CPU oracle) and of every
+// shape outside the tcgen05 kernels' domain (conv_tc.cu: bf16 NHWC, channel counts that are
+// multiples of 8) -- e.g. the 1- and 2-channel first layers, the 513-channel epilogue
+// convolution, the 4x4 (transposed) convolutions of the vanilla / dusty_v1 baselines in fp32.
+// The product never calls a library convolution.
+//
+// One implicit-GEMM kernel, C[m, n] = sum_k A(m, k) * B(n, k), 64 x 64 output tile per CTA,
+// 16-deep k slices staged in shared memory, 4 x 4 outputs per thread:
+//   fprop  m = (b, oh, ow)  n = o          k = (r, s, c)     A = x window,  B = w
+//   dgrad  m = (b, ih, iw)  n = c          k = (r, s, o)     A = dy taps,   B = w
+//   wgrad  m = o            n = (c, r, s)  k = (b, oh, ow)   A = dy,        B = x window
+#include "common.cuh"
+
+namespace dusty {
+namespace {
+
+struct SimtConv {
+  int B, C, H, W, O, Ho, Wo, R, S, sh, sw, ph, pw;
+  long long x_sb, x_sc, x_sh, x_sw;      // element strides of x  [B, C, H, W]
+  long long y_sb, y_sc, y_sh, y_sw;      // ... of y / dy          [B, O, Ho, Wo]
+  long long w_so, w_sc, w_sr, w_ss;      // ... of w               [O, C, R, S]
+  long long M, N, K;
+  float scale;
+};
+
+constexpr int kTile = 64, kSlice = 16;
+
+template <typename T, int MODE>
+__device__ __forceinline__ float fetch_a(const SimtConv &p, const T *__restrict__ x,
+                                         const T *__restrict__ dy, long long m, long long k) {
+  if (m >= p.M || k >= p.K) return 0.f;
+  if (MODE == 0) {                                   // x[b, oh*sh + r - ph, ow*sw + s - pw, c]
+    const int ow = (int)(m % p.Wo);
+    long long t = m / p.Wo;
+    const int oh = (int)(t % p.Ho), b = (int)(t / p.Ho);
+    const int c = (int)(k % p.C);
+    const int rs = (int)(k / p.C);
+    const int r = rs / p.S, s = rs % p.S;
+    const int ih = oh * p.sh + r - p.ph, iw = ow * p.sw + s - p.pw;
+    if (ih < 0 || ih >= p.H || iw < 0 || iw >= p.W) return 0.f;
+    return to_f(x[b * p.x_sb + c * p.x_sc + ih * p.x_sh + iw * p.x_sw]);
+  } else if (MODE == 1) {                            // dy[b, (ih + ph - r)/sh, (iw + pw - s)/sw, o]
+    const int iw = (int)(m % p.W);
+    long long t = m / p.W;
+    const int ih = (int)(t % p.H), b = (int)(t / p.H);
+    const int o = (int)(k % p.O);
+    const int rs = (int)(k / p.O);
+    const int r = rs / p.S, s = rs % p.S;
+    const int nh = ih + p.ph - r, nw = iw + p.pw - s;
+    if (nh < 0 || nw < 0 || nh % p.sh || nw % p.sw) return 0.f;
+    const int oh = nh / p.sh, ow = nw / p.sw;
+    if (oh >= p.Ho || ow >= p.Wo) return 0.f;
+    return to_f(dy[b * p.y_sb + o * p.y_sc + oh * p.y_sh + ow * p.y_sw]);
+  } else {                                           // dy[b, oh, ow, m]
+    const int ow = (int)(k % p.Wo);
+    long long t = k / p.Wo;
+    const int oh = (int)(t % p.Ho), b = (int)(t / p.Ho);
+    return to_f(dy[b * p.y_sb + m * p.y_sc + oh * p.y_sh + ow * p.y_sw]);
+  }
+}
+
+template <typename T, int MODE>
+__device__ __forceinline__ float fetch_b(const SimtConv &p, const T *__restrict__ x,
+                                         const T *__restrict__ w, long long n, long long k) {
+  if (n >= p.N || k >= p.K) return 0.f;
+  if (MODE == 0) {                                   // w[n, c, r, s], k = (r, s, c)
+    const int c = (int)(k % p.C);
+    const int rs = (int)(k / p.C);
+    return to_f(w[n * p.w_so + c * p.w_sc + (rs / p.S) * p.w_sr + (rs % p.S) * p.w_ss]);
+  } else if (MODE == 1) {                            // w[o, n, r, s], k = (r, s, o)
+    const int o = (int)(k % p.O);
+    const int rs = (int)(k / p.O);
+    return to_f(w[o * p.w_so + n * p.w_sc + (rs / p.S) * p.w_sr + (rs % p.S) * p.w_ss]);
+  } else {                                           // x window of (c, r, s) = n at pixel k
+    const int s = (int)(n % p.S);
+    long long t = n / p.S;
+    const int r = (int)(t % p.R), c = (int)(t / p.R);
+    const int ow = (int)(k % p.Wo);
+    long long u = k / p.Wo;
+    const int oh = (int)(u % p.Ho), b = (int)(u / p.Ho);
+    const int ih = oh * p.sh + r - p.ph, iw = ow * p.sw + s - p.pw;
+    if (ih < 0 || ih >= p.H || iw < 0 || iw >= p.W) return 0.f;
+    return to_f(x[b * p.x_sb + c * p.x_sc + ih * p.x_sh + iw * p.x_sw]);
+  }
+}
+
+// TO: output element type (T for fprop / dgrad, float for wgrad)
+template <typename T, typename TO, int MODE>
+__global__ void __launch_bounds__(256)
+conv_simt_kernel(const T *__restrict__ x, const T *__restrict__ dy, const T *__restrict__ w,
+                 TO *__restrict__ out, const SimtConv p, int k_splits) {
+  __shared__ float As[kSlice][kTile + 1];
+  __shared__ float Bs[kSlice][kTile + 1];
+  const long long m0 = (long long)blockIdx.x * kTile, n0 = (long long)blockIdx.y * kTile;
+  const int tx = threadIdx.x & 15, ty = threadIdx.x >> 4;       // 16 x 16 threads, 4 x 4 outputs each
+  // split-K (wgrad: K = all pixels): this CTA's slice range
+  const long long slices = (p.K + kSlice - 1) / kSlice;
+  const long long per = (slices + k_splits - 1) / k_splits;
+  const long long s_begin = (long long)blockIdx.z * per;
+  const long long s_end = s_begin + per < slices ? s_begin + per : slices;
+  float acc[4][4] = {};
+  const int lm = threadIdx.x & 63, lk = threadIdx.x >> 6;       // loader: row lm, k rows lk, lk+4, ..
+  for (long long sl = s_begin; sl < s_end; ++sl) {
+    const long long k0 = sl * kSlice;
+#pragma unroll
+    for (int i = 0; i < kSlice / 4; ++i) {
+      const int kk = lk + 4 * i;
+      As[kk][lm] = fetch_a<T, MODE>(p, x, dy, m0 + lm, k0 + kk);
+      Bs[kk][lm] = fetch_b<T, MODE>(p, x, w, n0 + lm, k0 + kk);
+    }
+    __syncthreads();
+#pragma unroll
+    for (int kk = 0; kk < kSlice; ++kk) {
+      float a[4], b[4];
+#pragma unroll
+      for (int i = 0; i < 4; ++i) { a[i] = As[kk][ty * 4 + i]; b[i] = Bs[kk][tx * 4 + i]; }
+#pragma unroll
+      for (int i = 0; i < 4; ++i)
+#pragma unroll
+        for (int j = 0; j < 4; ++j) acc[i][j] = fmaf(a[i], b[j], acc[i][j]);
+    }
+    __syncthreads();
+  }
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const long long m = m0 + ty * 4 + i;
+    if (m >= p.M) continue;
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const long long n = n0 + tx * 4 + j;
+      if (n >= p.N) continue;
+      const float v = acc[i][j] * p.scale;
+      if (MODE == 0) {
+        const int ow = (int)(m % p.Wo);
+        long long t = m / p.Wo;
+        const int oh = (int)(t % p.Ho), b = (int)(t / p.Ho);
+        out[b * p.y_sb + n * p.y_sc + oh * p.y_sh + ow * p.y_sw] = from_f<TO>(v);
+      } else if (MODE == 1) {
+        const int iw = (int)(m % p.W);
+        long long t = m / p.W;
+        const int ih = (int)(t % p.H), b = (int)(t / p.H);
+        out[b * p.x_sb + n * p.x_sc + ih * p.x_sh + iw * p.x_sw] = from_f<TO>(v);
+      } else {                                         // fp32 [O, C, R, S] contiguous
+        float *o = reinterpret_cast<float *>(out) + m * p.N + n;
+        if (k_splits > 1) atomicAdd(o, v); else *o = v;
+      }
+    }
+  }
+}
+
+template <typename T>
+int launch_simt(int mode, const void *x, const void *dy, const void *w, void *out, const SimtConv &p,
+                cudaStream_t st) {
+  const long long gm = (p.M + kTile - 1) / kTile, gn = (p.N + kTile - 1) / kTile;
+  if (gm > 0x7fffffffLL || gn > 65535) {
+    set_error("dusty_conv2d_simt: problem too large for the grid");
+    return DUSTY_EINVAL;
+  }
+  int splits = 1;
+  if (mode == 2) {                                    // few output tiles, long reduction
+    const long long want = (4LL * num_sms() + gm * gn - 1) / (gm * gn);
+    const long long slices = (p.K + kSlice - 1) / kSlice;
+    splits = (int)(want < 1 ? 1 : (want > slices ? slices : want));
+    if (splits > 1024) splits = 1024;
+    if (splits > 1 &&
+        cudaMemsetAsync(out, 0, sizeof(float) * (size_t)(p.M * p.N), st) != cudaSuccess) {
+      set_error("dusty_conv2d_simt: memset failed");
+      return DUSTY_ECUDA;
+    }
+  }
+  dim3 grid((unsigned)gm, (unsigned)gn, (unsigned)splits);
+  const T *xp = (const T *)x, *dp = (const T *)dy, *wp = (const T *)w;
+  if (mode == 0) conv_simt_kernel<T, T, 0><<<grid, 256, 0, st>>>(xp, dp, wp, (T *)out, p, 1);
+  else if (mode == 1) conv_simt_kernel<T, T, 1><<<grid, 256, 0, st>>>(xp, dp, wp, (T *)out, p, 1);
+  else conv_simt_kernel<T, float, 2><<<grid, 256, 0, st>>>(xp, dp, wp, (float *)out, p, splits);
+  return 0;
+}
+
+}  // namespace
+}  // namespace dusty
+
+using namespace dusty;
+
+// mode 0: y = conv2d(x, w) * scale; mode 1: dx = conv_transpose2d(dy, w) * scale (the data
+// gradient); mode 2: dw (fp32, [O, C, R, S] contiguous) = filter gradient * scale.
+// Tensors are addressed through element strides in logical (b, c, h, w) / (o, c, r, s) order:
+// NCHW, NHWC and OHWI memory all work without copies.  dtype: element type of x, dy, w and of
+// the output of modes 0 / 1.
+extern "C" int dusty_conv2d_simt(int mode, const void *x, const void *dy, const void *w, void *out,
+                                 int B, int C, int H, int W, int O, int Ho, int Wo, int R, int S,
+                                 int stride_h, int stride_w, int pad_h, int pad_w,
+                                 const long long *x_strides, const long long *y_strides,
+                                 const long long *w_strides, float scale, int dtype, void *stream) {
+  DUSTY_CHECK_ARG(mode >= 0 && mode <= 2, "mode: 0 fprop, 1 dgrad, 2 wgrad");
+  DUSTY_CHECK_ARG(out && x_strides && y_strides && w_strides, "null pointer");
+  DUSTY_CHECK_ARG((mode == 1 || x) && (mode == 0 || dy) && (mode == 2 || w), "missing operand");
+  DUSTY_CHECK_ARG(B > 0 && C > 0 && H > 0 && W > 0 && O > 0 && Ho > 0 && Wo > 0 && R > 0 && S > 0, "empty tensor");
+  DUSTY_CHECK_ARG(stride_h >= 1 && stride_w >= 1 && pad_h >= 0 && pad_w >= 0, "bad stride / padding");
+  // fprop / wgrad: every window lies inside the zero-padded input (the data gradient needs no
+  // such bound: positions no window reaches receive zero, a smaller dx is a cropped one)
+  DUSTY_CHECK_ARG(mode == 1 || ((long long)(Ho - 1) * stride_h + R <= H + 2LL * pad_h &&
+                                (long long)(Wo - 1) * stride_w + S <= W + 2LL * pad_w),
+                  "output larger than the convolution produces");
+  DUSTY_CHECK_ARG(dtype == DUSTY_F32 || dtype == DUSTY_BF16, "bad dtype");
+  SimtConv p;
+  p.B = B; p.C = C; p.H = H; p.W = W; p.O = O; p.Ho = Ho; p.Wo = Wo; p.R = R; p.S = S;
+  p.sh = stride_h; p.sw = stride_w; p.ph = pad_h; p.pw = pad_w;
+  p.x_sb = x_strides[0]; p.x_sc = x_strides[1]; p.x_sh = x_strides[2]; p.x_sw = x_strides[3];
+  p.y_sb = y_strides[0]; p.y_sc = y_strides[1]; p.y_sh = y_strides[2]; p.y_sw = y_strides[3];
+  p.w_so = w_strides[0]; p.w_sc = w_strides[1]; p.w_sr = w_strides[2]; p.w_ss = w_strides[3];
+  p.scale = scale;
+  if (mode == 0) { p.M = (long long)B * Ho * Wo; p.N = O; p.K = (long long)R * S * C; }
+  else if (mode == 1) { p.M = (long long)B * H * W; p.N = C; p.K = (long long)R * S * O; }
+  else { p.M = O; p.N = (long long)C * R * S; p.K = (long long)B * Ho * Wo; }
+  const int rc = dtype == DUSTY_F32 ? launch_simt<float>(mode, x, dy, w, out, p, (cudaStream_t)stream)
+                                    : launch_simt<__nv_bfloat16>(mode, x, dy, w, out, p, (cudaStream_t)stream);
+  if (rc) return rc;
+  DUSTY_LAUNCH_CHECK();
+  return DUSTY_OK;
+}

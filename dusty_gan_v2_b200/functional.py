@@ -1220,7 +1220,7 @@ def stem(x, w, bias, taps, composite, negative_slope: float = 0.2, scale: float 
 
 
 # ---- a11: dense NHWC convolutions on tcgen05 (conv_tc.cu) --------------------------------
-_CONV_IMPL = {"mode": "tc", "halo": True}
+_CONV_IMPL = {"halo": True}
 
 
 def set_conv_halo(enabled: bool):
@@ -1228,22 +1228,11 @@ def set_conv_halo(enabled: bool):
     _CONV_IMPL["halo"] = bool(enabled)
 
 
-def set_conv_impl(mode: str):
-    """'tc' (default): own tcgen05 kernels for every bf16 NHWC shape that qualifies (all of
-    D's residual-block convolutions); 'library': cuDNN; 'auto': own kernels where they measured
-    faster than cuDNN at the step's shapes (profiles/r01_conv_layers.json: the thin 64x512 /
-    32x256 layers), cuDNN elsewhere -- 6 % faster per training iteration than 'tc' today
-    (18.9 vs 20.0 ms, all-cuDNN 19.3 ms; profiles/r01_conv_impl_modes.json)."""
-    if mode not in ("auto", "tc", "library"):
-        raise ValueError(mode)
-    _CONV_IMPL["mode"] = mode
-
-
 def conv_tc_supported(x: torch.Tensor, w: torch.Tensor, stride, op: str = "fprop") -> bool:
-    """bf16 NHWC activations, channel counts multiples of 8 (16-byte TMA strides), filters of at
-    most 4x4 taps, strides 1 or 2."""
-    mode = _CONV_IMPL["mode"]
-    if mode == "library" or not x.is_cuda or x.dim() != 4:
+    """Domain of the tcgen05 kernels: bf16 NHWC activations, channel counts that are multiples
+    of 8 (16-byte TMA strides), filters of at most 4x4 taps, strides 1 or 2.  Everything else
+    runs on the CUDA-core kernels of the same family (conv_simt.cu); there is no library path."""
+    if not x.is_cuda or x.dim() != 4:
         return False
     if x.dtype != torch.bfloat16 or w.dtype != torch.bfloat16:
         return False
@@ -1254,11 +1243,6 @@ def conv_tc_supported(x: torch.Tensor, w: torch.Tensor, stride, op: str = "fprop
         return False
     if x.shape[2] < R or x.shape[3] < S:
         return False
-    if mode == "auto":
-        strided = stride[0] == 2 or stride[1] == 2
-        if not strided and op in ("fprop", "dgrad") and conv_halo_ok(w, op):
-            return True
-        return C <= 32 and ((op == "dgrad" and strided) or (op == "wgrad" and R * S > 1))
     return True
 
 
@@ -1398,3 +1382,65 @@ def conv2d_wgrad_tc(gy, x, stride, w_shape, out_dtype):
                K.stream_of(x))
         return gw
     return dwp.permute(3, 2, 0, 1).to(out_dtype).contiguous()
+
+
+# ---- a11 / a15: the same family on the CUDA cores (conv_simt.cu): fp32 parity mode, odd shapes --
+def _ll4(vals):
+    return (K.C.c_longlong * 4)(*[int(v) for v in vals])
+
+
+def _simt_dtype(*ts):
+    """Common element type of the operands: bf16 only if all are, else fp32."""
+    return torch.bfloat16 if all(t.dtype == torch.bfloat16 for t in ts) else torch.float32
+
+
+def _empty_like_layout(shape, ref, dtype):
+    fmt = torch.channels_last if _is_cl(ref) else torch.contiguous_format
+    return torch.empty(shape, dtype=dtype, device=ref.device, memory_format=fmt)
+
+
+def conv2d_fprop_simt(x, w, stride, padding=(0, 0)):
+    """y = conv2d(x, w, stride, zero padding); any layout, fp32 or bf16 (fp32 accumulation)."""
+    K.require_cuda(x, w)
+    dt = _simt_dtype(x, w)
+    x, w = x.detach().to(dt), w.detach().to(dt)
+    B, C, H, W = x.shape
+    O, _, R, S = w.shape
+    sh, sw = stride
+    ph, pw = padding
+    Ho, Wo = (H + 2 * ph - R) // sh + 1, (W + 2 * pw - S) // sw + 1
+    y = _empty_like_layout((B, O, Ho, Wo), x, dt)
+    K.call("dusty_conv2d_simt", 0, K.ptr(x), None, K.ptr(w), K.ptr(y), B, C, H, W, O, Ho, Wo, R, S, sh, sw,
+           ph, pw, _ll4(x.stride()), _ll4(y.stride()), _ll4(w.stride()), 1.0, K.dtype_code(y), K.stream_of(x))
+    return y
+
+
+def conv2d_dgrad_simt(gy, w, stride, padding, in_hw, like=None):
+    """Data gradient of the convolution above = conv_transpose2d(gy, w) cropped to in_hw."""
+    K.require_cuda(gy, w)
+    dt = _simt_dtype(gy, w)
+    gy, w = gy.detach().to(dt), w.detach().to(dt)
+    B, O, Ho, Wo = gy.shape
+    _, C, R, S = w.shape
+    H, W = in_hw
+    gx = _empty_like_layout((B, C, H, W), gy if like is None else like, dt)
+    K.call("dusty_conv2d_simt", 1, None, K.ptr(gy), K.ptr(w), K.ptr(gx), B, C, H, W, O, Ho, Wo, R, S,
+           stride[0], stride[1], padding[0], padding[1], _ll4(gx.stride()), _ll4(gy.stride()),
+           _ll4(w.stride()), 1.0, K.dtype_code(gx), K.stream_of(gy))
+    return gx
+
+
+def conv2d_wgrad_simt(gy, x, stride, padding, w_shape):
+    """Filter gradient, fp32 [O, C, R, S] contiguous."""
+    K.require_cuda(gy, x)
+    dt = _simt_dtype(gy, x)
+    gy, x = gy.detach().to(dt), x.detach().to(dt)
+    B, C, H, W = x.shape
+    O, _, R, S = w_shape
+    _, _, Ho, Wo = gy.shape
+    gw = torch.empty((O, C, R, S), dtype=torch.float32, device=x.device)
+    K.call("dusty_conv2d_simt", 2, K.ptr(x), K.ptr(gy), None, K.ptr(gw), B, C, H, W, O, Ho, Wo, R, S,
+           stride[0], stride[1], padding[0], padding[1], _ll4(x.stride()), _ll4(gy.stride()),
+           _ll4((C * R * S, R * S, S, 1)), 1.0, K.dtype_code(x), K.stream_of(x))
+    return gw
+

@@ -38,37 +38,6 @@ def reduce_sum(tensor):
     return tensor
 
 
-# ---- bilinear warp with analytic first and second order (linear in the image) -----------
-class _Warp(autograd.Function):
-    @staticmethod
-    def forward(ctx, img, grid):
-        ctx.save_for_backward(img, grid)
-        return F.grid_sample(img, grid, mode="bilinear", padding_mode="zeros", align_corners=False)
-
-    @staticmethod
-    def backward(ctx, g):
-        img, grid = ctx.saved_tensors
-        return _WarpAdjoint.apply(g, img, grid), None
-
-
-class _WarpAdjoint(autograd.Function):
-    @staticmethod
-    def forward(ctx, g, img, grid):
-        ctx.save_for_backward(grid)
-        g_img, _ = torch.ops.aten.grid_sampler_2d_backward(g.contiguous(), img, grid, 0, 0, False,
-                                                           (True, False))
-        return g_img
-
-    @staticmethod
-    def backward(ctx, gg):
-        (grid,) = ctx.saved_tensors
-        return _Warp.apply(gg, grid), None, None
-
-
-def grid_sample(img, grid):
-    return _Warp.apply(img, grid)
-
-
 # ---- host-side transform sampling -------------------------------------------------------
 def _eye(n, size):
     return torch.eye(n).repeat(size, 1, 1)

@@ -3,8 +3,9 @@ PixelNorm, MinibatchStdDev -- same constructor arguments, attribute and state_di
 
 All resampling / padding goes through one polyphase FIR kernel (dusty_fir2d) with the
 boundary extension folded into index math: no padded or zero-inserted tensor exists.
-The dense convolutions / linears themselves are library calls for now (cuDNN / cuBLAS via
-torch), with the EqualLR scale folded into the (small) weight instead of the activation.
+The dense convolutions run on this package's own kernels (tcgen05 implicit GEMM for bf16 NHWC,
+a CUDA-core family for fp32 / odd shapes); linears are cuBLAS GEMMs.  The EqualLR scale is folded
+into the (small) weight instead of the activation.
 """
 import math
 
@@ -155,30 +156,38 @@ class BlurVH(nn.Module):
 
 
 # ---- dense convolution with an explicit first / second order ------------------------------
-# bf16 NHWC shapes can run on our tcgen05 implicit-GEMM kernels (conv_tc.cu: fprop / dgrad /
-# wgrad; DF.set_conv_impl selects "tc" / "auto" / "library"); fp32 (parity mode), NCHW and odd
-# channel counts are library calls.  The autograd
-# wiring is ours either way: PyTorch's generic convolution double-backward falls onto slow grouped / SIMT conv
-# formulations (~100 ms per R1 step at B=64), whereas conv is bilinear in (x, w) so every
-# derivative of every order is again one of fprop / dgrad / wgrad.
-def _conv_fprop(x, w, stride):
-    if DF.conv_tc_supported(x, w, stride):
+# Every dense convolution of the path runs on this package's own kernels: bf16 NHWC shapes on the
+# tcgen05 implicit-GEMM family (conv_tc.cu: fprop / dgrad / wgrad), everything else -- fp32 parity
+# mode, NCHW, 1- / 2- / 513-channel layers, zero padding -- on the CUDA-core family
+# (conv_simt.cu).  There is no library convolution anywhere.  The autograd wiring is ours too:
+# conv is bilinear in (x, w), so every derivative of every order is again one of fprop / dgrad /
+# wgrad (PyTorch's generic convolution double-backward falls onto slow grouped formulations,
+# ~100 ms per R1 step at B=64).
+def _tc_ok(x, w, stride, padding, op="fprop"):
+    return tuple(padding) == (0, 0) and DF.conv_tc_supported(x, w, stride, op)
+
+
+def _conv_fprop(x, w, stride, padding=(0, 0)):
+    if _tc_ok(x, w, stride, padding):
         return DF.conv2d_fprop_tc(x, w, stride)
-    return F.conv2d(x, w, None, stride)
+    return DF.conv2d_fprop_simt(x, w, stride, padding).to(x.dtype)
 
 
-def _conv_grads(gy, x, w, stride, need_x, need_w, w_tco=None):
+def _conv_grads(gy, x, w, stride, need_x, need_w, w_tco=None, padding=(0, 0)):
     gx = gw = None
     same = gy.dtype == x.dtype
-    if need_x and same and DF.conv_tc_supported(x, w, stride, "dgrad"):
-        gx, need_x = DF.conv2d_dgrad_tc(gy, w, stride, x.shape[2:], w_tco), False
-    if need_w and same and DF.conv_tc_supported(x, w, stride, "wgrad"):
-        gw, need_w = DF.conv2d_wgrad_tc(gy, x, stride, w.shape, w.dtype), False
-    if need_x or need_w:
-        lx, lw, _ = torch.ops.aten.convolution_backward(
-            gy, x, w, None, stride, (0, 0), (1, 1), False, (0, 0), 1, (need_x, need_w, False))
-        gx = lx if need_x else gx
-        gw = lw if need_w else gw
+    if need_x:
+        if same and _tc_ok(x, w, stride, padding, "dgrad"):
+            gx = DF.conv2d_dgrad_tc(gy, w, stride, x.shape[2:], w_tco)
+        else:
+            gx = DF.conv2d_dgrad_simt(gy, w, stride, padding, x.shape[2:], like=x).to(x.dtype)
+    if need_w:
+        if same and _tc_ok(x, w, stride, padding, "wgrad"):
+            gw = DF.conv2d_wgrad_tc(gy, x, stride, w.shape, w.dtype)
+        else:
+            gw = DF.conv2d_wgrad_simt(gy, x, stride, padding, w.shape).to(w.dtype)
+            if w.is_contiguous(memory_format=torch.channels_last) and not w.is_contiguous():
+                gw = gw.contiguous(memory_format=torch.channels_last)
     return gx, gw
 
 
@@ -187,27 +196,27 @@ class _Conv2dFn(torch.autograd.Function):
     the same values, not a separate autograd input)."""
 
     @staticmethod
-    def forward(ctx, x, w, stride, w_tco=None):
+    def forward(ctx, x, w, stride, w_tco=None, padding=(0, 0)):
         ctx.save_for_backward(x, w)
-        ctx.stride = stride
+        ctx.stride, ctx.padding = stride, tuple(padding)
         ctx.w_tco = w_tco
-        return _conv_fprop(x, w, stride)
+        return _conv_fprop(x, w, stride, padding)
 
     @staticmethod
     def backward(ctx, gy):
         x, w = ctx.saved_tensors
         gx, gw = _Conv2dBwdFn.apply(gy, x, w, ctx.stride, ctx.needs_input_grad[0],
-                                    ctx.needs_input_grad[1], ctx.w_tco)
-        return gx, gw, None, None
+                                    ctx.needs_input_grad[1], ctx.w_tco, ctx.padding)
+        return gx, gw, None, None, None
 
 
 class _Conv2dBwdFn(torch.autograd.Function):
     @staticmethod
-    def forward(ctx, gy, x, w, stride, need_x, need_w, w_tco=None):
+    def forward(ctx, gy, x, w, stride, need_x, need_w, w_tco=None, padding=(0, 0)):
         ctx.save_for_backward(gy, x, w)
-        ctx.stride, ctx.need = stride, (need_x, need_w)
+        ctx.stride, ctx.need, ctx.padding = stride, (need_x, need_w), tuple(padding)
         gy = gy.contiguous(memory_format=torch.channels_last) if DF._is_cl(x) else gy.contiguous()
-        gx, gw = _conv_grads(gy, x, w, stride, need_x, need_w, w_tco)
+        gx, gw = _conv_grads(gy, x, w, stride, need_x, need_w, w_tco, padding)
         if (gw is not None and not gw.is_contiguous()
                 and not gw.is_contiguous(memory_format=torch.channels_last)):
             gw = gw.contiguous()           # odd strides -> dense (OHWI filter grads stay OHWI)
@@ -216,22 +225,84 @@ class _Conv2dBwdFn(torch.autograd.Function):
     @staticmethod
     def backward(ctx, ggx, ggw):
         gy, x, w = ctx.saved_tensors
-        s = ctx.stride
+        s, pad = ctx.stride, ctx.padding
         need_gy, need_x, need_w = ctx.needs_input_grad[:3]
         g_gy = g_x = g_w = None
         if ggx is not None:
             ggx = ggx.contiguous(memory_format=torch.channels_last) if DF._is_cl(x) else ggx.contiguous()
             if need_gy:
-                g_gy = _Conv2dFn.apply(ggx, w, s)                       # fprop
+                g_gy = _Conv2dFn.apply(ggx, w, s, None, pad)                      # fprop
             if need_w:
-                g_w = _conv_grads(gy, ggx, w, s, False, True)[1]        # wgrad(ggx, gy)
+                g_w = _conv_grads(gy, ggx, w, s, False, True, None, pad)[1]       # wgrad(ggx, gy)
         if ggw is not None:
             if need_gy:
-                t = _Conv2dFn.apply(x, ggw, s)
+                t = _Conv2dFn.apply(x, ggw, s, None, pad)
                 g_gy = t if g_gy is None else g_gy + t
             if need_x:
-                g_x = _conv_grads(gy, x, ggw.contiguous(), s, True, False)[0]   # dgrad(gy, ggw)
-        return g_gy, g_x, g_w, None, None, None, None
+                g_x = _conv_grads(gy, x, ggw.contiguous(), s, True, False, None, pad)[0]   # dgrad(gy, ggw)
+        return g_gy, g_x, g_w, None, None, None, None, None
+
+
+def _convT_tc_ok(x, w, stride):
+    O, C, R, S = w.shape
+    return (x.is_cuda and x.dtype == torch.bfloat16 and w.dtype == torch.bfloat16 and O % 8 == 0
+            and C % 8 == 0 and O >= 16 and C >= 16 and R <= 4 and S <= 4 and stride[0] in (1, 2)
+            and stride[1] in (1, 2))
+
+
+class _ConvTranspose2dFn(torch.autograd.Function):
+    """y = conv_transpose2d(x, w, stride, padding): the data-gradient kernel of the convolution
+    whose filter is w [in_ch, out_ch, R, S] (reference vanilla.py:18-27, the 4x4 stride-2
+    up-convolutions of the vanilla / dusty_v1 generators); its own gradients are that
+    convolution's forward and filter gradient.  bf16: the tcgen05 kernels (the un-cropped data
+    gradient, then the `padding` crop as a view; the backward zero-pads the incoming gradient
+    with the package's pad kernel); otherwise the CUDA-core family."""
+
+    @staticmethod
+    def forward(ctx, x, w, stride, padding, out_hw):
+        ctx.save_for_backward(x, w)
+        ctx.cfg = (stride, tuple(padding), tuple(out_hw))
+        ph, pw = padding
+        if _convT_tc_ok(x, w, stride):
+            full = (out_hw[0] + 2 * ph, out_hw[1] + 2 * pw)
+            y = DF.conv2d_dgrad_tc(x.contiguous(memory_format=torch.channels_last), w, stride, full)
+            return y[:, :, ph:ph + out_hw[0], pw:pw + out_hw[1]]
+        return DF.conv2d_dgrad_simt(x, w, stride, padding, out_hw, like=x).to(x.dtype)
+
+    @staticmethod
+    @torch.autograd.function.once_differentiable
+    def backward(ctx, gy):
+        x, w = ctx.saved_tensors
+        stride, padding, out_hw = ctx.cfg
+        ph, pw = padding
+        gx = gw = None
+        if _convT_tc_ok(x, w, stride) and gy.dtype == x.dtype:
+            gyp = gy.contiguous(memory_format=torch.channels_last)
+            if ph or pw:
+                cfg = DF.FirCfg(1, 1, pad=(ph, ph, pw, pw), mode=(K.PAD_ZERO, K.PAD_ZERO))
+                gyp = DF.fir2d(gyp, DF.device_taps([[1.0]], gyp.device), cfg)
+                gyp = gyp.contiguous(memory_format=torch.channels_last)
+            xc = x.contiguous(memory_format=torch.channels_last)
+            if ctx.needs_input_grad[0]:
+                gx = DF.conv2d_fprop_tc(gyp, w, stride)
+            if ctx.needs_input_grad[1]:
+                gw = DF.conv2d_wgrad_tc(xc, gyp, stride, w.shape, w.dtype)
+            return gx, gw, None, None, None
+        gy = gy.contiguous(memory_format=torch.channels_last) if DF._is_cl(x) else gy.contiguous()
+        if ctx.needs_input_grad[0]:
+            gx = DF.conv2d_fprop_simt(gy, w, stride, padding).to(x.dtype)
+        if ctx.needs_input_grad[1]:
+            gw = DF.conv2d_wgrad_simt(x, gy, stride, padding, w.shape).to(w.dtype)
+        return gx, gw, None, None, None
+
+
+def conv_transpose2d(x, w, bias, stride, padding, output_padding=(0, 0)):
+    stride, padding = tuple(stride), tuple(padding)
+    R, S = w.shape[2:]
+    out_hw = ((x.shape[2] - 1) * stride[0] - 2 * padding[0] + R + output_padding[0],
+              (x.shape[3] - 1) * stride[1] - 2 * padding[1] + S + output_padding[1])
+    y = _ConvTranspose2dFn.apply(x, w, stride, padding, out_hw)
+    return y if bias is None else y + bias.to(y.dtype).view(1, -1, 1, 1)
 
 
 class _ConvBiasActFn(torch.autograd.Function):
@@ -282,10 +353,19 @@ def conv_bias_act(x, w, bias, stride, negative_slope=0.2, gain=2 ** 0.5, w_tco=N
 
 def conv2d_valid(x, w, stride, w_tco=None):
     """Un-padded, bias-free 2-D convolution with analytic higher-order gradients."""
+    return conv2d(x, w, None, stride, (0, 0), w_tco)
+
+
+def conv2d(x, w, bias, stride, padding=(0, 0), w_tco=None):
+    """Dense convolution (zero padding, optional bias) on this package's kernels."""
     stride = tuple(stride) if isinstance(stride, (tuple, list)) else (stride, stride)
-    if x.is_cuda and w.shape[1] == x.shape[1]:
-        return _Conv2dFn.apply(x, w, stride, w_tco)
-    return F.conv2d(x, w, None, stride)
+    padding = tuple(padding) if isinstance(padding, (tuple, list)) else (padding, padding)
+    if not x.is_cuda:
+        raise RuntimeError("dusty_gan_v2_b200 convolutions run on CUDA tensors only (no CPU fallback)")
+    if w.shape[1] != x.shape[1]:
+        raise RuntimeError(f"conv2d: {x.shape[1]} input channels, filter expects {w.shape[1]} (groups unsupported)")
+    y = _Conv2dFn.apply(x, w, stride, w_tco, padding)
+    return y if bias is None else y + bias.to(y.dtype).view(1, -1, 1, 1)
 
 
 class _tf32_matmul:
@@ -368,15 +448,14 @@ class EqualLR(nn.Module):
         b = None if m.bias is None else (m.bias * self.gain_).to(x.dtype)
         if isinstance(m, nn.Linear):
             return F.linear(x, w, b)
-        if isinstance(m, nn.Conv2d):
-            if DF._is_cl(x):            # NHWC activations: hand cuDNN an NHWC filter too
-                w = w.contiguous(memory_format=torch.channels_last)
-            if b is None and m.padding == (0, 0) and m.dilation == (1, 1) and m.groups == 1:
-                return conv2d_valid(x, w, m.stride)
-            return F.conv2d(x, w, b, m.stride, m.padding, m.dilation, m.groups)
-        if isinstance(m, nn.ConvTranspose2d):
-            return F.conv_transpose2d(x, w, b, m.stride, m.padding, m.output_padding, m.groups,
-                                      m.dilation)
+        if isinstance(m, (nn.Conv2d, nn.ConvTranspose2d)):
+            if m.dilation != (1, 1) or m.groups != 1 or isinstance(m.padding, str):
+                raise NotImplementedError("dilated / grouped convolutions are not part of the path")
+            if isinstance(m, nn.Conv2d):
+                if DF._is_cl(x):        # NHWC activations: OHWI filter memory
+                    w = w.contiguous(memory_format=torch.channels_last)
+                return conv2d(x, w, b, m.stride, m.padding)
+            return conv_transpose2d(x, w, b, m.stride, m.padding, m.output_padding)
         return m(x * self.scale) * self.gain_
 
     def prepared_weight(self, dtype, with_tco=False):
@@ -388,7 +467,7 @@ class EqualLR(nn.Module):
         if m.weight.is_cuda and m.weight.dim() == 4:
             # the [R*S][C][O] copy feeds the data-gradient kernels only: skip it when no
             # backward pass can follow
-            want = with_tco and DF._CONV_IMPL["mode"] != "library" and torch.is_grad_enabled()
+            want = with_tco and torch.is_grad_enabled()
             r = DF.prep_conv_weight(m.weight, self.scale * self.gain_, dtype, want)
             if with_tco:
                 return r if want else (r, None)

@@ -358,6 +358,22 @@ int dusty_conv2d_tc_classes(const void *x, const void *wpk, void *y, int B, int 
                             long long y_sh, long long y_sw, long long w_sn, long long w_sg,
                             int w_taps, void *stream);
 
+/* The same convolution family on the CUDA cores, fp32 accumulation, for fp32 parity mode and
+ * every shape outside the tcgen05 kernels' domain (1- / 2- / 513-channel layers, 4x4 filters in
+ * fp32, NCHW tensors): replaces F.conv2d / F.conv_transpose2d / aten::convolution_backward behind
+ * gans/models/ops/common.py:158-210 (EqualLR + Conv2d) and gans/models/vanilla.py:7-105.
+ *   mode 0: y  [B,O,Ho,Wo] = conv2d(x, w, stride, zero padding) * scale
+ *   mode 1: dx [B,C,H,W]   = conv_transpose2d(dy, w, stride, padding) * scale  (data gradient)
+ *   mode 2: dw fp32 [O,C,R,S] contiguous = filter gradient * scale
+ * x_strides / y_strides / w_strides: HOST arrays of 4 element strides in logical (b,c,h,w) /
+ * (b,o,oh,ow) / (o,c,r,s) order -- any memory layout.  dtype: DUSTY_F32 / DUSTY_BF16 of x, dy, w
+ * and of the outputs of modes 0 and 1. */
+int dusty_conv2d_simt(int mode, const void *x, const void *dy, const void *w, void *out, int B,
+                      int C, int H, int W, int O, int Ho, int Wo, int R, int S, int stride_h,
+                      int stride_w, int pad_h, int pad_w, const long long *x_strides,
+                      const long long *y_strides, const long long *w_strides, float scale, int dtype,
+                      void *stream);
+
 /* Tools only: role-cycle counters of the tcgen05 convolution kernels (12 doubles; see
  * conv_tc.cu).  DUSTY_EUNSUPPORTED unless the library was built with -DDUSTY_ROLE_PROF. */
 int dusty_conv_role_prof(double *out8, int reset);

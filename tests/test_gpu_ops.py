@@ -751,13 +751,11 @@ def test_conv2d_tcgen05_fprop_dgrad_wgrad(DF, B, C, Oc, H, W, k, stride, halo):
     s2 = (stride, stride)
     if halo and not (stride == 1 and (DF.conv_halo_ok(wd, "fprop") or DF.conv_halo_ok(wd, "dgrad"))):
         pytest.skip("shape does not take the halo-resident kernel")
-    DF.set_conv_impl("tc")
     DF.set_conv_halo(halo)
     try:
         assert DF.conv_tc_supported(xd, wd, s2)
         _conv_checks(DF, xd, wd, w, s2, ref, gy, gx_ref, gw_ref, g, Oc, H, W)
     finally:
-        DF.set_conv_impl("tc")
         DF.set_conv_halo(True)
 
 
@@ -777,29 +775,87 @@ def _conv_checks(DF, xd, wd, w, s2, ref, gy, gx_ref, gw_ref, g, Oc, H, W):
 
 
 def test_conv2d_valid_autograd_routes_through_tcgen05(DF, ops):
-    """conv2d_valid: first and second order through the own kernels agree with the library path."""
+    """conv2d_valid: first and second order through the own tcgen05 kernels against fp32 CPU
+    autograd of the same bilinear map (bf16-rounded operands)."""
     from dusty_gan_v2_b200.gans.models.ops.common import conv2d_valid
     g = torch.Generator().manual_seed(34)
     bf = torch.bfloat16
-    x = torch.randn(2, 32, 12, 36, generator=g).to(bf).to(DEV).contiguous(memory_format=torch.channels_last)
-    w = (torch.randn(64, 32, 3, 3, generator=g) / 17.0).to(bf).to(DEV)
-    gy = torch.randn(2, 64, 5, 17, generator=g).to(bf).to(DEV)
-    res = {}
-    for mode in ("tc", "library"):
-        DF.set_conv_impl(mode)
-        try:
-            xg, wg = x.clone().requires_grad_(), w.clone().requires_grad_()
-            n0 = DF.K.launch_count()
-            y = conv2d_valid(xg, wg, (2, 2))
-            gx, gw = torch.autograd.grad(y, [xg, wg], gy, create_graph=True)
-            r1 = gx.float().pow(2).sum()
-            ggw, = torch.autograd.grad(r1, [wg])
-            res[mode] = (y.detach(), gx.detach(), gw.detach(), ggw.detach(), DF.K.launch_count() - n0)
-        finally:
-            DF.set_conv_impl("tc")
-    assert res["tc"][4] >= 6 and res["library"][4] == 0
-    for a, b in zip(res["tc"][:4], res["library"][:4]):
+    x = torch.randn(2, 32, 12, 36, generator=g).to(bf)
+    w = (torch.randn(64, 32, 3, 3, generator=g) / 17.0).to(bf)
+    gy = torch.randn(2, 64, 5, 17, generator=g).to(bf)
+    xr, wr = x.float().requires_grad_(), w.float().requires_grad_()
+    yr = torch.nn.functional.conv2d(xr, wr, None, 2)
+    gxr, gwr = torch.autograd.grad(yr, [xr, wr], gy.float(), create_graph=True)
+    ggwr, = torch.autograd.grad(gxr.pow(2).sum(), [wr])
+    xg = x.to(DEV).contiguous(memory_format=torch.channels_last).requires_grad_()
+    wg = w.to(DEV).requires_grad_()
+    n0 = DF.K.launch_count()
+    y = conv2d_valid(xg, wg, (2, 2))
+    gx, gw = torch.autograd.grad(y, [xg, wg], gy.to(DEV), create_graph=True)
+    ggw, = torch.autograd.grad(gx.float().pow(2).sum(), [wg])
+    assert DF.K.launch_count() - n0 >= 6
+    for a, b in ((y, yr), (gx, gxr), (gw, gwr), (ggw, ggwr)):
         close(a, b, rtol=3e-2, atol_rel=1e-2)
+
+
+@pytest.mark.parametrize("B,C,Oc,H,W,k,stride,pad", [
+    (2, 1, 8, 9, 20, 3, 1, 0),        # single-channel first layers
+    (2, 2, 4, 16, 64, 1, 1, 0),       # the discriminator stem's 1x1 convolution
+    (2, 9, 8, 6, 18, 3, 1, 1),        # odd channel count, zero padding (the 513-channel epilogue conv, small)
+    (3, 4, 8, 18, 34, 3, 2, 0),       # stride 2
+    (2, 6, 10, 12, 20, 4, 2, 1),      # 4x4 stride-2 padding-1 (vanilla discriminator)
+])
+@pytest.mark.parametrize("dtype,layout", [(torch.float32, "nchw"), (torch.float32, "nhwc"), (torch.bfloat16, "nhwc")])
+def test_conv2d_simt_family_vs_cpu_autograd(DF, B, C, Oc, H, W, k, stride, pad, dtype, layout):
+    """The CUDA-core convolution family (fp32 parity mode, shapes outside the tcgen05 domain):
+    forward, data gradient, filter gradient and the R1-style second order through conv2d()
+    against CPU autograd; exact fp32 FMAs -> rtol 1e-4 in fp32."""
+    from dusty_gan_v2_b200.gans.models.ops.common import conv2d
+    g = torch.Generator().manual_seed(35)
+    x = torch.randn(B, C, H, W, generator=g).to(dtype)
+    w = (torch.randn(Oc, C, k, k, generator=g) / np.sqrt(C * k * k)).to(dtype)
+    b = torch.randn(Oc, generator=g)
+    xr, wr = x.float().requires_grad_(), w.float().requires_grad_()
+    yr = torch.nn.functional.conv2d(xr, wr, b, stride, pad)
+    gy = torch.randn(yr.shape, generator=g).to(dtype)
+    gxr, gwr = torch.autograd.grad(yr, [xr, wr], gy.float(), create_graph=True)
+    ggwr, = torch.autograd.grad(gxr.pow(2).sum(), [wr])
+    fmt = torch.channels_last if layout == "nhwc" else torch.contiguous_format
+    xg = x.to(DEV).contiguous(memory_format=fmt).requires_grad_()
+    wg = w.to(DEV).requires_grad_()
+    assert not DF.conv_tc_supported(xg, wg, (stride, stride)) or pad
+    n0 = DF.K.launch_count()
+    y = conv2d(xg, wg, b.to(DEV), (stride, stride), (pad, pad))
+    gx, gw = torch.autograd.grad(y, [xg, wg], gy.to(DEV), create_graph=True)
+    ggw, = torch.autograd.grad(gx.float().pow(2).sum(), [wg])
+    assert DF.K.launch_count() - n0 >= 5
+    tol = (1e-4, 1e-5) if dtype == torch.float32 else (2e-2, 1e-2)
+    for a, r in ((y, yr), (gx, gxr), (gw, gwr), (ggw, ggwr)):
+        assert a.dtype == dtype
+        close(a, r, rtol=tol[0], atol_rel=tol[1])
+
+
+@pytest.mark.parametrize("dtype,C,Oc", [(torch.float32, 6, 5), (torch.bfloat16, 32, 16), (torch.bfloat16, 12, 6)])
+def test_conv_transpose2d_vs_cpu_autograd(DF, dtype, C, Oc):
+    """ConvTranspose2d(4x4, stride 2, padding 1) of the vanilla / dusty_v1 generators
+    (reference vanilla.py:18-27): the data-gradient kernels (tcgen05 for bf16 channel counts
+    that qualify, CUDA cores otherwise) against CPU autograd, first order."""
+    from dusty_gan_v2_b200.gans.models.ops.common import conv_transpose2d
+    g = torch.Generator().manual_seed(36)
+    x = torch.randn(2, C, 5, 9, generator=g).to(dtype)
+    w = (torch.randn(C, Oc, 4, 4, generator=g) / np.sqrt(C * 4)).to(dtype)
+    b = torch.randn(Oc, generator=g)
+    xr, wr = x.float().requires_grad_(), w.float().requires_grad_()
+    yr = torch.nn.functional.conv_transpose2d(xr, wr, b, 2, 1)
+    gy = torch.randn(yr.shape, generator=g).to(dtype)
+    gxr, gwr = torch.autograd.grad(yr, [xr, wr], gy.float())
+    xg, wg = x.to(DEV).requires_grad_(), w.to(DEV).requires_grad_()
+    y = conv_transpose2d(xg, wg, b.to(DEV), (2, 2), (1, 1))
+    assert tuple(y.shape) == tuple(yr.shape)
+    gx, gw = torch.autograd.grad(y, [xg, wg], gy.to(DEV))
+    tol = (1e-4, 1e-5) if dtype == torch.float32 else (2e-2, 1e-2)
+    for a, r in ((y, yr), (gx, gxr), (gw, gwr)):
+        close(a, r, rtol=tol[0], atol_rel=tol[1])
 
 
 # ----------------------------------------------------------------------------- a11 fused tails

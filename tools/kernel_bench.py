@@ -29,8 +29,8 @@ def main():
         peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
     except Exception:
         pass
-    dom, kernels = bench.kernel_rooflines(dev, peaks)
-    out = {"dominant": dom, "kernels": kernels}
+    dom, kernels, family = bench.kernel_rooflines(dev, peaks)
+    out = {"dominant": dom, "kernels": kernels, "conv_family": family}
     print(json.dumps(out, indent=1))
     if args.json:
         json.dump(out, open(args.json, "w"), indent=1)

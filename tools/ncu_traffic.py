@@ -30,6 +30,9 @@ HINTS = [  # bench entry prefix -> substring of the kernel name that carries the
     ("sumsq", "sumsq_rows_kernel"), ("gumbel_raydrop", "raydrop"), ("point_project", "point_project"),
     ("upfirdn2d_ada", "fir1d"), ("modconv_fwd", "modconv_fwd"), ("modconv_dw", "modconv_dw"),
     ("modconv_dx", "modconv_fwd_tc_kernel"),
+    ("conv_fprop", ("conv_halo_tc_kernel", "conv_fwd_tc_kernel", "conv_pair_tc_kernel")),
+    ("conv_dgrad", ("conv_halo_tc_kernel", "conv_fwd_tc_kernel", "conv_pair_tc_kernel")),
+    ("conv_wgrad", "conv_wgrad_tc_kernel"),
 ]
 
 
@@ -62,7 +65,8 @@ def main():
         hint = next((sub for pre, sub in HINTS if e.startswith(pre)), None)
         if hint is None:
             continue
-        j = next((i for i in range(pos, len(launches)) if hint in launches[i]["name"]), None)
+        hints = hint if isinstance(hint, tuple) else (hint,)
+        j = next((i for i in range(pos, len(launches)) if any(h_ in launches[i]["name"] for h_ in hints)), None)
         if j is None:
             continue
         pos = j + 1

@@ -27,12 +27,10 @@ def main():
     ap.add_argument("--steps", type=int, default=34)
     ap.add_argument("--batch", type=int, default=64)
     ap.add_argument("--json", default=None)
-    ap.add_argument("--conv-impl", default="auto", choices=["auto", "tc", "library"])
     args = ap.parse_args()
     dev = torch.device("cuda", 0)
     pkg.set_precision("bf16")
     import dusty_gan_v2_b200.functional as DF
-    DF.set_conv_impl(args.conv_impl)
     torch.backends.cudnn.benchmark = True
     cfg = preset("dusty_v2", batch_size=args.batch)
     pool = bench.synthetic_batches(4, args.batch, seed=2, device=dev)

@@ -69,6 +69,8 @@ SIGNATURES = {
                        + [C.c_longlong] * 4 + [_i, _f, _f, C.c_longlong, C.c_longlong, _vp, _i, _vp],
     "dusty_conv2d_tc_classes": [_vp, _vp, _vp] + [_i] * 6 + [_vp] * 7 + [C.c_longlong] * 5 + [_i, _vp],
     "dusty_conv_role_prof": [_vp, _i],
+    "dusty_multi_adam": [_vp, _vp, _vp, _vp, _vp, _vp, _i, _f, _f, _f, _f, _i, _f, _f, _vp],
+    "dusty_multi_copy": [_vp, _vp, _vp, _i, _f, _vp],
     "dusty_conv2d_simt": [_i, _vp, _vp, _vp, _vp] + [_i] * 13 + [_vp, _vp, _vp, _f, _i, _vp],
     "dusty_conv2d_wgrad_tc_workspace": [_i] * 7,
     "dusty_conv2d_halo_supported": [_i] * 4,

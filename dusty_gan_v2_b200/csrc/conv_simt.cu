@@ -151,9 +151,145 @@ conv_simt_kernel(const T *__restrict__ x, const T *__restrict__ dy, const T *__r
   }
 }
 
+// ---- pointwise (1x1, unit stride, no padding) convolutions with a handful of input channels:
+// the discriminator stem's 2 -> 32 convolution, which the R1 step differentiates twice through
+// the single ops (functional._Stem's composite).  With K = C <= 4 the tiled kernel above loads
+// 16 x 64 slices to use a 2 x 64 corner; these are plain streaming passes over the pixels.
+template <typename T, int C>
+__global__ void pw_fprop_kernel(const T *__restrict__ x, const T *__restrict__ w, T *__restrict__ y,
+                                const SimtConv p) {
+  __shared__ float ws[64 * C];
+  for (int i = threadIdx.x; i < p.O * C; i += blockDim.x)
+    ws[i] = to_f(w[(i / C) * p.w_so + (i % C) * p.w_sc]);
+  __syncthreads();
+  const long long P = (long long)p.B * p.H * p.W;
+  const int groups = (p.O + 7) / 8;
+  for (long long it = blockIdx.x * (long long)blockDim.x + threadIdx.x; it < P * groups;
+       it += (long long)gridDim.x * blockDim.x) {
+    const long long pix = it / groups;
+    const int o0 = (int)(it % groups) * 8;
+    const int wq = (int)(pix % p.W);
+    const long long t = pix / p.W;
+    const int h = (int)(t % p.H), b = (int)(t / p.H);
+    float xv[C];
+#pragma unroll
+    for (int c = 0; c < C; ++c) xv[c] = to_f(x[b * p.x_sb + c * p.x_sc + h * p.x_sh + wq * p.x_sw]);
+    T *yp = y + b * p.y_sb + h * p.y_sh + wq * p.y_sw;
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      const int o = o0 + j;
+      if (o >= p.O) break;
+      float acc = 0.f;
+#pragma unroll
+      for (int c = 0; c < C; ++c) acc = fmaf(xv[c], ws[o * C + c], acc);
+      yp[o * p.y_sc] = from_f<T>(acc * p.scale);
+    }
+  }
+}
+
+template <typename T, int C>
+__global__ void pw_dgrad_kernel(const T *__restrict__ dy, const T *__restrict__ w, T *__restrict__ dx,
+                                const SimtConv p) {
+  __shared__ float ws[64 * C];
+  for (int i = threadIdx.x; i < p.O * C; i += blockDim.x)
+    ws[i] = to_f(w[(i / C) * p.w_so + (i % C) * p.w_sc]);
+  __syncthreads();
+  const long long P = (long long)p.B * p.H * p.W;
+  for (long long pix = blockIdx.x * (long long)blockDim.x + threadIdx.x; pix < P;
+       pix += (long long)gridDim.x * blockDim.x) {
+    const int wq = (int)(pix % p.W);
+    const long long t = pix / p.W;
+    const int h = (int)(t % p.H), b = (int)(t / p.H);
+    const T *gp = dy + b * p.y_sb + h * p.y_sh + wq * p.y_sw;
+    float acc[C] = {};
+    for (int o = 0; o < p.O; ++o) {
+      const float g = to_f(gp[o * p.y_sc]);
+#pragma unroll
+      for (int c = 0; c < C; ++c) acc[c] = fmaf(g, ws[o * C + c], acc[c]);
+    }
+#pragma unroll
+    for (int c = 0; c < C; ++c)
+      dx[b * p.x_sb + c * p.x_sc + h * p.x_sh + wq * p.x_sw] = from_f<T>(acc[c] * p.scale);
+  }
+}
+
+// dw[o, c] = sum_pixels dy[pixel, o] * x[pixel, c]; blockIdx.y picks a 16-wide group of o
+template <typename T, int C>
+__global__ void __launch_bounds__(256)
+pw_wgrad_kernel(const T *__restrict__ dy, const T *__restrict__ x, float *__restrict__ dw, const SimtConv p) {
+  const int o0 = blockIdx.y * 16;
+  const long long P = (long long)p.B * p.H * p.W;
+  float acc[16][C] = {};
+  for (long long pix = blockIdx.x * (long long)blockDim.x + threadIdx.x; pix < P;
+       pix += (long long)gridDim.x * blockDim.x) {
+    const int wq = (int)(pix % p.W);
+    const long long t = pix / p.W;
+    const int h = (int)(t % p.H), b = (int)(t / p.H);
+    float xv[C];
+#pragma unroll
+    for (int c = 0; c < C; ++c) xv[c] = to_f(x[b * p.x_sb + c * p.x_sc + h * p.x_sh + wq * p.x_sw]);
+    const T *gp = dy + b * p.y_sb + h * p.y_sh + wq * p.y_sw;
+#pragma unroll
+    for (int j = 0; j < 16; ++j) {
+      const float g = (o0 + j < p.O) ? to_f(gp[(o0 + j) * p.y_sc]) : 0.f;
+#pragma unroll
+      for (int c = 0; c < C; ++c) acc[j][c] = fmaf(g, xv[c], acc[j][c]);
+    }
+  }
+  __shared__ float red[8][16 * C];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+#pragma unroll
+  for (int j = 0; j < 16; ++j)
+#pragma unroll
+    for (int c = 0; c < C; ++c) {
+      float v = acc[j][c];
+#pragma unroll
+      for (int d = 16; d > 0; d >>= 1) v += __shfl_xor_sync(0xffffffffu, v, d);
+      if (lane == 0) red[warp][j * C + c] = v;
+    }
+  __syncthreads();
+  if (threadIdx.x < 16 * C) {
+    float v = 0.f;
+#pragma unroll
+    for (int k = 0; k < 8; ++k) v += red[k][threadIdx.x];
+    const int j = threadIdx.x / C, c = threadIdx.x % C;
+    if (o0 + j < p.O) atomicAdd(dw + (long long)(o0 + j) * C + c, v * p.scale);
+  }
+}
+
+template <typename T, int C>
+int launch_pointwise(int mode, const void *x, const void *dy, const void *w, void *out, const SimtConv &p,
+                     cudaStream_t st) {
+  const long long P = (long long)p.B * p.H * p.W;
+  const int blocks = (int)(P / 256 + 1 < 16LL * num_sms() ? P / 256 + 1 : 16LL * num_sms());
+  if (mode == 0) {
+    pw_fprop_kernel<T, C><<<blocks, 256, 0, st>>>((const T *)x, (const T *)w, (T *)out, p);
+  } else if (mode == 1) {
+    pw_dgrad_kernel<T, C><<<blocks, 256, 0, st>>>((const T *)dy, (const T *)w, (T *)out, p);
+  } else {
+    if (cudaMemsetAsync(out, 0, sizeof(float) * (size_t)(p.O * C), st) != cudaSuccess) {
+      set_error("dusty_conv2d_simt: memset failed");
+      return DUSTY_ECUDA;
+    }
+    const int bx = blocks < 4 * num_sms() ? blocks : 4 * num_sms();
+    pw_wgrad_kernel<T, C><<<dim3((unsigned)bx, (unsigned)((p.O + 15) / 16)), 256, 0, st>>>(
+        (const T *)dy, (const T *)x, (float *)out, p);
+  }
+  return 0;
+}
+
 template <typename T>
 int launch_simt(int mode, const void *x, const void *dy, const void *w, void *out, const SimtConv &p,
                 cudaStream_t st) {
+  if (p.R == 1 && p.S == 1 && p.sh == 1 && p.sw == 1 && p.ph == 0 && p.pw == 0 && p.C <= 4 && p.O <= 64 &&
+      p.Ho == p.H && p.Wo == p.W) {
+    switch (p.C) {
+      case 1: return launch_pointwise<T, 1>(mode, x, dy, w, out, p, st);
+      case 2: return launch_pointwise<T, 2>(mode, x, dy, w, out, p, st);
+      case 3: return launch_pointwise<T, 3>(mode, x, dy, w, out, p, st);
+      default: return launch_pointwise<T, 4>(mode, x, dy, w, out, p, st);
+    }
+  }
   const long long gm = (p.M + kTile - 1) / kTile, gn = (p.N + kTile - 1) / kTile;
   if (gm > 0x7fffffffLL || gn > 65535) {
     set_error("dusty_conv2d_simt: problem too large for the grid");

@@ -25,6 +25,7 @@ from .coords import CoordBridge
 from .models.builder import build_discriminator, build_generator
 from .models.loss import GANLoss
 from .models.ops.common import filter2d
+from .optim import Adam, multi_copy
 
 
 def set_requires_grad(net, requires_grad: bool = True):
@@ -150,13 +151,20 @@ class Trainer:
             raise NotImplementedError("path-length regularisation is dead code in the reference "
                                       "(loss.pl = 0 in every config; the branch is broken)")
         lr_g, lr_d = tr.lr.generator, tr.lr.discriminator
-        self.optim_G = torch.optim.Adam(self.G.parameters(), lr=lr_g.alpha,
-                                        betas=(float(lr_g.beta1), float(lr_g.beta2)), fused=True)
-        self.optim_D = torch.optim.Adam(self.D.parameters(), lr=lr_d.alpha * lazy_D,
-                                        betas=(float(lr_d.beta1 ** lazy_D), float(lr_d.beta2 ** lazy_D)),
-                                        fused=True)
+        # own multi-tensor Adam (csrc/optim.cu); the generator's EMA lerp rides in its pass
+        self.optim_G = Adam(self.G.parameters(), lr=lr_g.alpha, betas=(float(lr_g.beta1), float(lr_g.beta2)),
+                            ema_params=self.G_ema.parameters())
+        self.optim_D = Adam(self.D.parameters(), lr=lr_d.alpha * lazy_D,
+                            betas=(float(lr_d.beta1 ** lazy_D), float(lr_d.beta2 ** lazy_D)))
         self._G_params = list(self.G.parameters())     # cached: no module-tree walk per step
         self._D_params = list(self.D.parameters())
+        # flat fp32 gradient buckets of the graphed multi-GPU path: packed by one kernel, reduced
+        # by one NCCL call, consumed in place by the optimiser (no cat / split / copy-back); the
+        # discriminator's exchange + update run on a side stream, under the next G forward
+        self._flat = {}
+        self._comm_stream = torch.cuda.Stream(device=self.device) if (world_size > 1 and self.cuda_graphs) else None
+        self._d_update_done = None
+        self._ema_bufs = None
         self.z_dim = cfg.model.generator.mapping_kwargs.in_ch
         # CUDA graphs for the static-shape segments (the step is launch-bound at B=64):
         #   * the no-grad generator forward of the D step (z drawn inside the graph)
@@ -302,23 +310,51 @@ class Trainer:
         self.graph_replayed_launches += self._D_launches[mode]
         return fn(x)
 
-    def _allreduce_grads(self, params):
-        if self.world_size > 1 and self.cuda_graphs:
-            grads = [p.grad for p in params if p.grad is not None]
-            flat = torch.cat([g.reshape(-1) for g in grads])
-            dist.all_reduce(flat)
-            flat /= self.world_size
-            torch._foreach_copy_(grads, [c.reshape(g.shape) for g, c in
-                                         zip(grads, flat.split([g.numel() for g in grads]))])
+    def _reduced_grads(self, name, params):
+        """Graphed multi-GPU path: (views of the summed flat bucket, 1 / world_size) for the
+        parameters that have a gradient; (None, 1.0) when there is nothing to exchange (one GPU,
+        or DDP already averaged the gradients in its hooks)."""
+        if not (self.world_size > 1 and self.cuda_graphs):
+            return None, 1.0
+        grads = [p.grad for p in params if p.grad is not None]
+        sizes = [g.numel() for g in grads]
+        entry = self._flat.get(name)
+        if entry is None or entry[2] != sizes:
+            flat = torch.empty(sum(sizes), dtype=torch.float32, device=self.device)
+            entry = (flat, [v.view_as(g) for v, g in zip(flat.split(sizes), grads)], sizes)
+            self._flat[name] = entry
+        flat, views, _ = entry
+        self._pack(views, [g if g.dtype == torch.float32 and g.is_contiguous() else g.float().contiguous()
+                           for g in grads])
+        dist.all_reduce(flat)
+        return views, 1.0 / self.world_size
 
-    def _allreduce_G_grads(self):
-        if self.world_size > 1 and self.G is self.G_module:
-            grads = [p.grad for p in self._G_params if p.grad is not None]
-            flat = torch.cat([g.reshape(-1) for g in grads])
-            dist.all_reduce(flat)
-            flat /= self.world_size
-            torch._foreach_copy_(grads, [c.reshape(g.shape) for g, c in
-                                         zip(grads, flat.split([g.numel() for g in grads]))])
+    _pack = staticmethod(multi_copy)        # the packing kernel (host-logic tests on gloo swap it)
+
+    def _update_D(self):
+        """Gradient exchange + Adam step of the discriminator.  Multi-GPU (graphed): on the side
+        stream, so that NCCL and the update overlap whatever the main stream does next that does
+        not read D's weights (the next iteration's generator forward); `_wait_D_update` is the
+        join."""
+        if self._comm_stream is None:
+            views, scale = self._reduced_grads("D", self._D_params)
+            self.optim_D.step(grads=views, grad_scale=scale)
+            return
+        main = torch.cuda.current_stream(self.device)
+        self._comm_stream.wait_stream(main)
+        with torch.cuda.stream(self._comm_stream):
+            for p in self._D_params:
+                if p.grad is not None:
+                    p.grad.record_stream(self._comm_stream)
+            views, scale = self._reduced_grads("D", self._D_params)
+            self.optim_D.step(grads=views, grad_scale=scale)
+            self._d_update_done = torch.cuda.Event()
+            self._d_update_done.record(self._comm_stream)
+
+    def _wait_D_update(self):
+        if self._d_update_done is not None:
+            torch.cuda.current_stream(self.device).wait_event(self._d_update_done)
+            self._d_update_done = None
 
     def _fake_images_nograd(self, B):
         """x_fake for the D step (no graph of G is needed: trainer.py:380-383)."""
@@ -354,19 +390,25 @@ class Trainer:
         B = self.B
         scalars = OrderedDict()
         x_real = self.fetch_reals(next(self.batch_iter))["image"]
+        ema_imgs = int(tr.ema_kimg * 1e3)                       # trainer.py:459-466
+        if tr.ema_rampup is not None:
+            ema_imgs = min(ema_imgs, iteration * tr.batch_size * tr.ema_rampup)
+        ema_decay = 0.5 ** (tr.batch_size / max(ema_imgs, 1e-8))
 
         # ---- G step (trainer.py:262-301)
         set_requires_grad(self._G_params, True)
         self.optim_G.zero_grad(set_to_none=True)
         x_fake = self._G_train_forward(self.sample_z(B))
+        self._wait_D_update()                       # D's weights of the previous iteration are final
         y_fake = self._D_forward(self.A(self.warmup(x_fake)), "frozen")
         y_real = None
         if tr.gan_objective in ("ragan", "rahinge", "ralsgan"):      # trainer.py:263,281-286
             y_real = _DLogits(self.D, 1)(self.A(self.warmup(x_real)).detach())
         loss_gan = self.adversarial_loss(y_real, y_fake, "G")
         (tr.loss.gan * loss_gan).backward()
-        self._allreduce_G_grads()
-        self.optim_G.step()
+        views, scale = self._reduced_grads("G", self._G_params)
+        # Adam + the EMA lerp of G_ema's parameters towards the new weights in one pass
+        self.optim_G.step(grads=views, grad_scale=scale, ema_weight=1.0 - ema_decay)
         scalars["loss/G/adversarial"] = loss_gan.detach()
         set_requires_grad(self._G_params, False)
 
@@ -381,14 +423,14 @@ class Trainer:
         self.A.cumulate(y_real)
         loss_gan = self.adversarial_loss(y_real, y_fake, "D")
         (tr.loss.gan * loss_gan).backward()
-        self._allreduce_grads(self._D_params)
-        self.optim_D.step()
+        self._update_D()
         scalars["loss/D/output/real"] = y_real.mean().detach()
         scalars["loss/D/output/fake"] = y_fake.mean().detach()
         scalars["loss/D/adversarial"] = loss_gan.detach()
 
         # ---- lazy R1 (trainer.py:419-451)
         if self.gp_weight > 0 and iteration % self.gp_every == 0:
+            self._wait_D_update()
             self.optim_D.zero_grad(set_to_none=True)
             x_gp = x_real.detach().requires_grad_()
             y_real = self.D(self.A(self.warmup(x_gp)))
@@ -396,17 +438,12 @@ class Trainer:
             r1 = DF.sumsq_rows(grads).mean()
             loss = (self.gp_weight / 2) * r1 + 0.0 * y_real.squeeze()[0]
             loss.backward()
-            self._allreduce_grads(self._D_params)
-            self.optim_D.step()
+            self._update_D()
             scalars["loss/D/gradient_penalty"] = r1.detach()
         set_requires_grad(self._D_params, False)
 
         # ---- exit (trainer.py:459-476)
-        ema_imgs = int(tr.ema_kimg * 1e3)
-        if tr.ema_rampup is not None:
-            ema_imgs = min(ema_imgs, iteration * tr.batch_size * tr.ema_rampup)
-        ema_decay = 0.5 ** (tr.batch_size / max(ema_imgs, 1e-8))
-        ema_inplace(self.G_ema, self.G_module, ema_decay)
+        self._copy_ema_buffers()          # parameters were lerped in the G step's Adam pass
         if iteration % tr.lazy.ada == 0:
             scalars["stats/ada_rt"] = self.A.update_p().detach().reshape(())
             scalars["stats/ada_p"] = self.A.p.detach().reshape(())
@@ -419,6 +456,20 @@ class Trainer:
         self.last_stats = dict(ema_decay=ema_decay, blur_sigma=self.blur_sigma,
                                dropout_ratio=self.dropout_ratio)
         return packed            # device tensor; names in self.scalar_names
+
+    @torch.no_grad()
+    def _copy_ema_buffers(self):
+        """The buffer half of ema_inplace (trainer.py:38-41): G_ema's buffers <- G's."""
+        if self._ema_bufs is None:
+            pairs = list(zip(self.G_ema.buffers(), self.G_module.buffers()))
+            own = [(a, b) for a, b in pairs if a.dtype == torch.float32 and b.dtype == torch.float32
+                   and a.is_contiguous() and b.is_contiguous() and a.numel() > 0]
+            rest = [(a, b) for a, b in pairs if not any(a is x for x, _ in own)]
+            self._ema_bufs = ([a for a, _ in own], [b for _, b in own], [a for a, _ in rest], [b for _, b in rest])
+        da, sa, db, sb = self._ema_bufs
+        multi_copy(da, sa)
+        if db:
+            torch._foreach_copy_(db, sb)
 
     def scalars_to_host(self, packed):
         vals = packed.detach().cpu().tolist()

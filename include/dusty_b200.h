@@ -374,6 +374,22 @@ int dusty_conv2d_simt(int mode, const void *x, const void *dy, const void *w, vo
                       const long long *y_strides, const long long *w_strides, float scale, int dtype,
                       void *stream);
 
+/* ---- f2: optimiser step and EMA (gans/trainer.py:30-41 ema_inplace, 128-171 Adam) ----------
+ * Multi-tensor Adam exactly as torch.optim.Adam (no weight decay / amsgrad) over `count` fp32
+ * tensors given as HOST arrays of device pointers: grads are multiplied by grad_scale first
+ * (1 / world_size after a summing all-reduce), `step` is the 1-based update count (bias
+ * corrections are computed on the host).  ema (array or NULL; entries may be NULL): after the
+ * update ema[i] += ema_weight * (param[i] - ema[i]) -- the generator's EMA lerp towards the new
+ * weights, folded into the same pass. */
+int dusty_multi_adam(void *const *params, const void *const *grads, void *const *exp_avg,
+                     void *const *exp_avg_sq, void *const *ema, const long long *numel, int count,
+                     float lr, float beta1, float beta2, float eps, int step, float ema_weight,
+                     float grad_scale, void *stream);
+/* dst[i] = src[i] * scale for `count` fp32 tensors (gradient bucket packing / unpacking, EMA
+ * buffer copies) in one launch per 32 tensors. */
+int dusty_multi_copy(void *const *dst, const void *const *src, const long long *numel, int count,
+                     float scale, void *stream);
+
 /* Tools only: role-cycle counters of the tcgen05 convolution kernels (12 doubles; see
  * conv_tc.cu).  DUSTY_EUNSUPPORTED unless the library was built with -DDUSTY_ROLE_PROF. */
 int dusty_conv_role_prof(double *out8, int reset);

@@ -323,10 +323,16 @@ def test_trainer_checkpoint_round_trip_on_host():
 
     a, b = make(1), make(2)
     for opt, net in ((a.optim_G, a.G_module), (a.optim_D, a.D_module)):      # give Adam some state
+        for p in net.parameters():              # (the update itself is a CUDA kernel: GPU tests)
+            st = opt._state_of(p)
+            st["step"] += 3
+            st["exp_avg"].normal_()
+            st["exp_avg_sq"].uniform_()
+        with pytest.raises(RuntimeError):       # no CPU fallback
+            next(iter(net.parameters())).grad = torch.zeros_like(next(iter(net.parameters())))
+            opt.step()
         for p in net.parameters():
-            p.requires_grad_(True)
-            p.grad = torch.randn_like(p)
-        opt.step()
+            p.grad = None
     a.A.p.fill_(0.25)
     payload = a.state_dict(step=7 * 4)
     assert set(payload) == {"cfg", "step", "angle", "G", "D", "G_ema", "A", "optim_G", "optim_D"}

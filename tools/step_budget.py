@@ -10,7 +10,7 @@ import sys
 from collections import OrderedDict
 
 GROUPS = OrderedDict([
-    ("D convolutions (own tcgen05: fprop / dgrad / wgrad, halo)", r"conv_(fwd|halo|wgrad)_tc_kernel"),
+    ("D convolutions (own tcgen05: fprop / dgrad / wgrad, halo)", r"conv_(fwd|halo|wgrad|pair)_tc_kernel|conv_simt"),
     ("D conv weight preparation / filter layout", r"weight_prep|filter_rsco|filter_tco"),
     ("NHWC stencils (blur, blur+pad, blur+decimate, pad, fork)", r"blur4_cl|blur4_down2|pad2d_cl|residual_fork"),
     ("bias_act / residual tail (NHWC + NCHW)", r"bias_act"),

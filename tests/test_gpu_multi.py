@@ -1,5 +1,4 @@
-"""Multi-GPU (`gpurun --gpus 2`) and optimiser tests: the flat NCCL gradient bucket + side-stream
-update of the graphed trainer against a single-GPU double batch, and the multi-tensor Adam / EMA
+"""Multi-GPU (`gpurun --gpus 2`) and optimiser tests: the flat NCCL gradient bucket + update of the graphed trainer against a single-GPU double batch, and the multi-tensor Adam / EMA
 kernel against torch.optim.Adam."""
 import os
 import tempfile
@@ -96,8 +95,7 @@ def _rank_main(rank, world, init_file, out_file):
         set_requires_grad(tr._D_params, True)
         y = tr.D(x_all[rank * B:(rank + 1) * B].to(dev))
         torch.nn.functional.softplus(-y).mean().backward()
-        tr._update_D()                                          # pack -> NCCL -> Adam, side stream
-        tr._wait_D_update()
+        tr._update_D()                                          # pack -> NCCL -> Adam on the bucket
         torch.cuda.synchronize()
         if rank == 0:
             # the same step on ONE GPU with the double batch and torch's Adam
@@ -108,7 +106,10 @@ def _rank_main(rank, world, init_file, out_file):
                     p.copy_(w)
             lazy = 16 / 17.0
             opt = torch.optim.Adam(D1.parameters(), lr=0.002 * lazy, betas=(0.0, 0.99 ** lazy))
-            torch.nn.functional.softplus(-D1(x_all.to(dev))).mean().backward()
+            # MinibatchStdDev groups the STRIDED sets {m, m + B/4, ..} (reference common.py:237-250):
+            # interleave the ranks' samples so that the double batch forms the same groups
+            x_single = x_all.view(world, B, 1, 32, 128).transpose(0, 1).reshape(world * B, 1, 32, 128)
+            torch.nn.functional.softplus(-D1(x_single.to(dev))).mean().backward()
             g_single = [p.grad.detach().clone() for p in D1.parameters()]
             opt.step()
             views = tr._flat["D"][1]
@@ -130,8 +131,8 @@ def _rank_main(rank, world, init_file, out_file):
 def test_two_gpu_flat_bucket_update_equals_single_gpu_double_batch():
     """gradients (and the Adam update) of a 2-rank data-parallel
     discriminator step through the trainer's own exchange path -- rank-0 weight broadcast, one
-    packed fp32 bucket, ONE NCCL all-reduce, optimiser reading the bucket with 1 / world_size, on
-    the side stream -- equal those of one GPU fed the double batch."""
+    packed fp32 bucket, ONE NCCL all-reduce, optimiser reading the bucket with 1 / world_size --
+    equal those of one GPU fed the double batch."""
     import torch.multiprocessing as mp
     with tempfile.TemporaryDirectory() as d:
         out = os.path.join(d, "result")

@@ -1444,3 +1444,89 @@ def conv2d_wgrad_simt(gy, x, stride, padding, w_shape):
            _ll4((C * R * S, R * S, S, 1)), 1.0, K.dtype_code(x), K.stream_of(x))
     return gw
 
+
+# ---- a11: linears of the discriminator epilogue on own GEMMs (linear_tc.cu) -----------------------
+def _major(t, mult):
+    """(mn_major flag, leading dimension) of a 2-D operand [rows, K] for the GEMM kernels, or None
+    when it has to be copied first (`mult`: leading dimensions are multiples of 16 bytes)."""
+    if t.stride(1) == 1 and t.stride(0) % mult == 0 and t.stride(0) >= t.shape[1]:
+        return 0, t.stride(0)
+    if t.stride(0) == 1 and t.stride(1) % mult == 0 and t.stride(1) >= t.shape[0]:
+        return 1, t.stride(1)
+    return None
+
+
+def matmul_nt(a: torch.Tensor, b: torch.Tensor, alpha: float = 1.0) -> torch.Tensor:
+    """alpha * a @ b.T -> fp32 [M, N] for CUDA matrices a [M, K], b [N, K] (either may be a
+    transposed view: both majors are read in place).  fp32 operands with K contiguous run on
+    tcgen05 kind::tf32 (the forward of the 65536 -> 512 linear: the fp32 master weight is read
+    once, uncast); any other combination on kind::f16 with bf16 operands (the gradients: the same
+    tensors as MN-major operands); tiny outputs on the CUDA-core kernel."""
+    K.require_cuda(a, b)
+    if a.dim() != 2 or b.dim() != 2 or a.shape[1] != b.shape[1]:
+        raise RuntimeError(f"matmul_nt: shapes {tuple(a.shape)} x {tuple(b.shape)}^T")
+    a, b = a.detach(), b.detach()
+    M, Kd = a.shape
+    N = b.shape[0]
+    c = torch.empty((M, N), dtype=torch.float32, device=a.device)
+    st = K.stream_of(a)
+    if min(M, N) < 16 or N % 4 or (M * N <= (1 << 16) and Kd < 1024):
+        a32 = a if a.dtype == torch.float32 else a.float()
+        b32 = b if b.dtype == torch.float32 else b.float()
+        K.call("dusty_gemm_simt", K.ptr(a32), K.ptr(b32), K.ptr(c), M, N, Kd, a32.stride(0), a32.stride(1),
+               b32.stride(0), b32.stride(1), N, 1, float(alpha), st)
+        return c
+    if a.dtype == torch.float32 and b.dtype == torch.float32:
+        ma, mb = _major(a, 4), _major(b, 4)
+        if ma is not None and mb is not None and ma[0] == 0 and mb[0] == 0 and a.data_ptr() % 16 == 0 \
+                and b.data_ptr() % 16 == 0:
+            K.call("dusty_gemm_tf32", K.ptr(a), K.ptr(b), K.ptr(c), M, N, Kd, ma[1], mb[1], N, float(alpha), 0, st)
+            return c
+    a16 = a if a.dtype == torch.bfloat16 else a.to(torch.bfloat16)      # strides are preserved
+    b16 = b if b.dtype == torch.bfloat16 else b.to(torch.bfloat16)
+    ma, mb = _major(a16, 8), _major(b16, 8)
+    if ma is None or a16.data_ptr() % 16:
+        a16 = a16.contiguous()
+        ma = _major(a16, 8) or (0, a16.stride(0))
+    if mb is None or b16.data_ptr() % 16:
+        b16 = b16.contiguous()
+        mb = _major(b16, 8) or (0, b16.stride(0))
+    if ma[1] % 8 or mb[1] % 8:
+        raise RuntimeError("matmul_nt: operand rows must be multiples of 8 elements for the bf16 GEMM")
+    K.call("dusty_gemm_bf16", K.ptr(a16), K.ptr(b16), K.ptr(c), M, N, Kd, ma[0], mb[0], ma[1], mb[1], N,
+           float(alpha), 0, st)
+    return c
+
+
+class _LinearNT(Function):
+    """y = x @ w.T (bilinear: every derivative of every order is again a product of this form,
+    so the R1 double backward runs on the same kernels)."""
+
+    @staticmethod
+    def forward(ctx, x, w):
+        ctx.save_for_backward(x, w)
+        if x.dtype != w.dtype and w.dtype == torch.float32:
+            return matmul_nt(x.float(), w)     # bf16 activations, fp32 master weight: TF32 on the weight as is
+        return matmul_nt(x, w)
+
+    @staticmethod
+    def backward(ctx, gy):
+        x, w = ctx.saved_tensors
+        gx = gw = None
+        if torch.is_grad_enabled():            # create_graph=True: keep it differentiable
+            if ctx.needs_input_grad[0]:
+                gx = _LinearNT.apply(gy, w.t()).to(x.dtype)
+            if ctx.needs_input_grad[1]:
+                gw = _LinearNT.apply(gy.t(), x.t()).to(w.dtype)
+            return gx, gw
+        if ctx.needs_input_grad[0]:
+            gx = matmul_nt(gy, w.t()).to(x.dtype)
+        if ctx.needs_input_grad[1]:
+            gw = matmul_nt(gy.t(), x.t()).to(w.dtype)
+        return gx, gw
+
+
+def linear_nt(x: torch.Tensor, w: torch.Tensor) -> torch.Tensor:
+    """x [B, K] @ w [N, K].T -> fp32 on this package's GEMM kernels, with autograd of any order."""
+    return _LinearNT.apply(x, w)
+

@@ -368,46 +368,6 @@ def conv2d(x, w, bias, stride, padding=(0, 0), w_tco=None):
     return y if bias is None else y + bias.to(y.dtype).view(1, -1, 1, 1)
 
 
-class _tf32_matmul:
-    """Scoped torch.backends.cuda.matmul.allow_tf32 = True (the flag is read when cuBLAS is
-    called, also during CUDA-graph capture)."""
-
-    def __enter__(self):
-        self.prev = torch.backends.cuda.matmul.allow_tf32
-        torch.backends.cuda.matmul.allow_tf32 = True
-
-    def __exit__(self, *exc):
-        torch.backends.cuda.matmul.allow_tf32 = self.prev
-
-
-class _TF32Linear(torch.autograd.Function):
-    """y = x @ w^T with TF32 tensor-core GEMMs in forward, backward and double backward
-    (bilinear: every derivative is again a matmul)."""
-
-    @staticmethod
-    def forward(ctx, x, w):
-        ctx.save_for_backward(x, w)
-        with _tf32_matmul():
-            return x @ w.t()
-
-    @staticmethod
-    def backward(ctx, gy):
-        x, w = ctx.saved_tensors
-        gx = gw = None
-        if torch.is_grad_enabled():            # create_graph=True: keep it differentiable
-            if ctx.needs_input_grad[0]:
-                gx = _TF32Linear.apply(gy, w.t())
-            if ctx.needs_input_grad[1]:
-                gw = _TF32Linear.apply(gy.t(), x.t())
-            return gx, gw
-        with _tf32_matmul():
-            if ctx.needs_input_grad[0]:
-                gx = gy @ w
-            if ctx.needs_input_grad[1]:
-                gw = gy.t() @ x
-        return gx, gw
-
-
 class EqualLR(nn.Module):
     """reference common.py:158-184.  y = module(x / sqrt(fan_in)) * gain * lr_mul, computed
     with the scale folded into the weight (a [O, fan_in] tensor) rather than applied to the
@@ -434,11 +394,17 @@ class EqualLR(nn.Module):
         if (isinstance(m, nn.Linear) and x.is_cuda and x.dtype in (torch.float32, torch.bfloat16)
                 and DF.act_dtype() == torch.bfloat16 and m.weight.numel() >= (1 << 22)):
             # the 65536 -> 512 linear of D's epilogue (33.5 M weights, 134 MB in fp32) in
-            # low-precision mode: a TF32 tensor-core GEMM straight on the fp32 master weight, the
-            # EqualLR scale applied to the [B, 512] result.  No weight-sized elementwise pass
-            # exists in either direction (scaling + casting the weight to bf16 cost four 134 MB
-            # passes per forward/backward pair); TF32 keeps 3 more mantissa bits than bf16.
-            y = _TF32Linear.apply(x.float(), m.weight) * (self.scale * self.gain_)
+            # low-precision mode: our tcgen05 kind::tf32 GEMM straight on the fp32 master weight
+            # (linear_tc.cu), the EqualLR scale applied to the [B, 512] result.  No weight-sized
+            # elementwise pass exists in either direction (scaling + casting the weight to bf16
+            # cost four 134 MB passes per forward/backward pair); TF32 keeps 3 more mantissa bits
+            # than bf16.  Data and weight gradient read the same two tensors in place.
+            y = DF.linear_nt(x, m.weight) * (self.scale * self.gain_)
+            return y if m.bias is None else y + m.bias * self.gain_
+        if (isinstance(m, nn.Linear) and x.is_cuda and x.dim() == 2 and x.dtype == torch.float32
+                and DF.act_dtype() == torch.bfloat16 and m.out_features <= 8):
+            # the 512 -> 1 head: tiny GEMMs on the CUDA-core kernel
+            y = DF.linear_nt(x, m.weight) * (self.scale * self.gain_)
             return y if m.bias is None else y + m.bias * self.gain_
         if (isinstance(m, nn.Conv2d) and x.is_cuda and x.dtype == torch.bfloat16 and DF._is_cl(x)
                 and m.bias is None and m.padding == (0, 0) and m.dilation == (1, 1) and m.groups == 1):

@@ -374,6 +374,28 @@ int dusty_conv2d_simt(int mode, const void *x, const void *dy, const void *w, vo
                       const long long *y_strides, const long long *w_strides, float scale, int dtype,
                       void *stream);
 
+/* ---- a11: linears of the discriminator epilogue (gans/models/dusty_v2.py:382-384:
+ * EqualLR(Linear(65536 -> 512)), EqualLR(Linear(512 -> 1)); replaces F.linear / cuBLAS) ---------
+ * C[M, N] (+)= alpha * A[M, K] * B[N, K]^T, fp32 accumulation, C fp32 row-major (leading
+ * dimension ldc); accumulate != 0 adds into C.  Few output tiles -> split-K with TMA reduce-add.
+ * dusty_gemm_tf32: tcgen05 kind::tf32 on fp32 operands read in place by TMA (the 134 MB weight
+ *   matrix is streamed once, no cast pass); both operands K-major: element (row, k) at
+ *   row * ld + k.
+ * dusty_gemm_bf16: kind::f16 on bf16 operands; a_mn / b_mn = 1: the operand is MN-major (element
+ *   (row, k) at k * ld + row), so data and weight gradient read the same tensors as the forward.
+ * Pointers 16-byte aligned, leading dimensions multiples of 16 bytes. */
+int dusty_gemm_tf32(const float *a, const float *b, float *c, int M, int N, int K, long long lda,
+                    long long ldb, long long ldc, float alpha, int accumulate, void *stream);
+int dusty_gemm_bf16(const void *a, const void *b, float *c, int M, int N, int K, int a_mn, int b_mn,
+                    long long lda, long long ldb, long long ldc, float alpha, int accumulate,
+                    void *stream);
+/* The same product for tiny outputs (the 512 -> 1 head and its gradients) on the CUDA cores,
+ * fp32, arbitrary element strides: A(m, k) at m * a_sm + k * a_sk, B(n, k) at n * b_sn + k * b_sk,
+ * C(m, n) at m * c_sm + n * c_sn. */
+int dusty_gemm_simt(const float *a, const float *b, float *c, int M, int N, int K, long long a_sm,
+                    long long a_sk, long long b_sn, long long b_sk, long long c_sm, long long c_sn,
+                    float alpha, void *stream);
+
 /* ---- f2: optimiser step and EMA (gans/trainer.py:30-41 ema_inplace, 128-171 Adam) ----------
  * Multi-tensor Adam exactly as torch.optim.Adam (no weight decay / amsgrad) over `count` fp32
  * tensors given as HOST arrays of device pointers: grads are multiplied by grad_scale first

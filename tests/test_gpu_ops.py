@@ -858,6 +858,37 @@ def test_conv_transpose2d_vs_cpu_autograd(DF, dtype, C, Oc):
         close(a, r, rtol=tol[0], atol_rel=tol[1])
 
 
+@pytest.mark.parametrize("M,N,Kd", [(64, 512, 65536), (128, 512, 4096), (100, 72, 200), (64, 1, 512), (3, 512, 1)])
+def test_linear_nt_forward_dgrad_wgrad_vs_cpu(DF, M, N, Kd):
+    """The epilogue linears on own GEMMs (linear_tc.cu): y = x @ W.T, the data gradient
+    dy @ W (W read as an MN-major operand) and the weight gradient dy.T @ x (both operands
+    MN-major) against fp64 CPU products; TF32 operand rounding (rtol 2e-3) for the forward GEMM
+    on the fp32 master weight, bf16 operands (2e-2) for the gradient GEMMs, exact fp32 on the
+    CUDA-core path; then first and second order through autograd."""
+    g = torch.Generator().manual_seed(50)
+    x = torch.randn(M, Kd, generator=g)
+    w = torch.randn(N, Kd, generator=g) / np.sqrt(Kd)
+    dy = torch.randn(M, N, generator=g)
+    xd, wd, dyd = x.to(DEV), w.to(DEV), dy.to(DEV)
+    tol = dict(rtol=2e-3, atol_rel=2e-3)                   # TF32 operands (forward)
+    tolg = dict(rtol=2e-2, atol_rel=1e-2)                 # bf16 operands (gradient GEMMs)
+    if min(M, N) < 16:
+        tolg = tol
+    close(DF.matmul_nt(xd, wd, 0.5), 0.5 * (x.double() @ w.double().t()), **tol)
+    close(DF.matmul_nt(dyd, wd.t()), dy.double() @ w.double(), **tolg)                 # dgrad: B MN-major
+    close(DF.matmul_nt(dyd.t(), xd.t()), dy.double().t() @ x.double(), **tolg)         # wgrad: both MN-major
+    xg, wg = xd.clone().requires_grad_(), wd.clone().requires_grad_()
+    y = DF.linear_nt(xg, wg)
+    gx, gw = torch.autograd.grad(y, [xg, wg], dyd, create_graph=True)
+    close(gx, dy.double() @ w.double(), **tolg)
+    close(gw, dy.double().t() @ x.double(), **tolg)
+    (ggw,) = torch.autograd.grad(gx.square().sum(), [wg])           # R1-style second order
+    xr, wr = x.double().requires_grad_(), w.double().requires_grad_()
+    (gxr,) = torch.autograd.grad(xr @ wr.t(), [xr], dy.double(), create_graph=True)
+    (ggwr,) = torch.autograd.grad(gxr.square().sum(), [wr])
+    close(ggw, ggwr, rtol=3e-2, atol_rel=2e-2)
+
+
 # ----------------------------------------------------------------------------- a11 fused tails
 @pytest.mark.parametrize("C,HW", [(64, (8, 16)), (256, (4, 8)), (32, (16, 64))])
 def test_residual_tail_vs_single_ops(DF, C, HW):

@@ -72,6 +72,7 @@ SIGNATURES = {
     "dusty_gemm_tf32": [_vp, _vp, _vp, _i, _i, _i, C.c_longlong, C.c_longlong, C.c_longlong, _f, _i, _vp],
     "dusty_gemm_bf16": [_vp, _vp, _vp, _i, _i, _i, _i, _i, C.c_longlong, C.c_longlong, C.c_longlong, _f, _i, _vp],
     "dusty_gemm_simt": [_vp, _vp, _vp, _i, _i, _i] + [C.c_longlong] * 6 + [_f, _vp],
+    "dusty_scan_project": [_vp, _vp, _vp, _vp, _vp, _vp, _i, _i, _i, _i, _f, _f, _vp],
     "dusty_multi_adam": [_vp, _vp, _vp, _vp, _vp, _vp, _i, _f, _f, _f, _f, _i, _f, _f, _vp],
     "dusty_multi_copy": [_vp, _vp, _vp, _i, _f, _vp],
     "dusty_conv2d_simt": [_i, _vp, _vp, _vp, _vp] + [_i] * 13 + [_vp, _vp, _vp, _f, _i, _vp],

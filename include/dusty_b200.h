@@ -396,6 +396,17 @@ int dusty_gemm_simt(const float *a, const float *b, float *c, int M, int N, int 
                     long long a_sk, long long b_sn, long long b_sk, long long c_sm, long long c_sn,
                     float alpha, void *stream);
 
+/* ---- f4: KITTI scan -> range image (gans/datasets/kitti.py:216-220 numba `scatter`, 275-279
+ * NEAREST resize + mask, 317-370 load_pts_as_img) -------------------------------------------------
+ * points: [N, 4] fp32 (x, y, z, reflectance); depth: fp32 [N] norms; cell_h / cell_w: int32 [N]
+ * image cell of every point (host-computed: ring index from scan unfolding, column from the azimuth; a ring index of -1
+ * wraps to H - 1 as numpy indexing does); keys: caller-owned scratch of H * W 64-bit words.
+ * out: fp32 [6, H, W_out] = (x, y, z, reflectance, depth, mask) of the NEAREST point of cell
+ * (h, w * W / W_out), times mask = (min_depth <= depth <= max_depth); empty cells are zero. */
+int dusty_scan_project(const float *points, const float *depth, const int *cell_h, const int *cell_w,
+                       unsigned long long *keys, float *out, int N, int H, int W, int W_out,
+                       float min_depth, float max_depth, void *stream);
+
 /* ---- f2: optimiser step and EMA (gans/trainer.py:30-41 ema_inplace, 128-171 Adam) ----------
  * Multi-tensor Adam exactly as torch.optim.Adam (no weight decay / amsgrad) over `count` fp32
  * tensors given as HOST arrays of device pointers: grads are multiplied by grad_scale first

@@ -939,3 +939,57 @@ def inversion_forward(sdG: Dict[str, Tensor], z: Tensor, angle: Tensor, t_depth:
                raydrop_prob=torch.sigmoid(imgs["raydrop_logit"]), g_depth=g_depth,
                raydrop_logit=imgs["raydrop_logit"], raydrop_mask=imgs["raydrop_mask"])
     return out, loss
+
+
+# --------------------------------------------------------------------------------------
+# f4  KITTI scan -> range image                        gans/datasets/kitti.py:216-220,275-279,317-370
+# --------------------------------------------------------------------------------------
+
+
+def scan_cells(points: np.ndarray, H: int = 64, W: int = 2048, scan_unfolding: bool = True):
+    """Per-point image cell and depth (kitti.py:319-363), ring assignment as the sequential walk
+    the reference does: rings are the runs between 4th->1st quadrant transitions, numbered from
+    the LAST run (H - 1) downwards; the walk assigns one run more than H (index -1) before it
+    stops; runs further down and the points before the first transition stay at 0."""
+    pts = np.asarray(points, dtype=np.float32).reshape(-1, 4)
+    x, y, z = pts[:, 0], pts[:, 1], pts[:, 2]
+    depth = np.linalg.norm(pts[:, :3], ord=2, axis=1)
+    n = len(pts)
+    if scan_unfolding:
+        quad = np.zeros(n, dtype=np.int32)
+        quad[(x < 0) & (y >= 0)] = 1
+        quad[(x < 0) & (y < 0)] = 2
+        quad[(x >= 0) & (y < 0)] = 3
+        starts = [i for i in range(n) if quad[i - 1] - quad[i] == 3]
+        bounds = starts + [n]
+        cell_h = np.zeros(n, dtype=np.int32)
+        ring = H - 1
+        for j in range(len(starts) - 1, -1, -1):
+            cell_h[bounds[j]:bounds[j + 1]] = ring
+            if ring < 0:
+                break
+            ring -= 1
+    else:
+        up, down = np.deg2rad(3), np.deg2rad(-25)
+        pitch = np.arcsin(z / depth) + abs(down)
+        cell_h = np.floor((1 - pitch / (up - down)) * H).clip(0, H - 1).astype(np.int32)
+    yaw = -np.arctan2(y, x)
+    cell_w = np.floor(((yaw / np.pi + 1) / 2 % 1) * W).clip(0, W - 1).astype(np.int32)
+    return cell_h, cell_w, depth
+
+
+def scan_to_image(points: np.ndarray, H: int = 64, W: int = 2048, W_out: int = 512, min_depth: float = 0.9,
+                  max_depth: float = 120.0, scan_unfolding: bool = True) -> np.ndarray:
+    """[6, H, W_out] (x, y, z, reflectance, depth, mask) * mask: points written far-to-near into
+    the [H, W] image (kitti.py:216-220,364-368: the nearest point of a cell survives), every
+    (W / W_out)-th column kept (NEAREST resize, 276-277), product with the mask channel (278)."""
+    pts = np.asarray(points, dtype=np.float32).reshape(-1, 4)
+    cell_h, cell_w, depth = scan_cells(pts, H, W, scan_unfolding)
+    mask = ((depth >= min_depth) & (depth <= max_depth)).astype(np.float32)
+    rows = np.concatenate([pts, depth[:, None].astype(np.float32), mask[:, None]], axis=1)
+    img = np.zeros((H, W, 6), dtype=np.float32)
+    for i in np.argsort(-depth, kind="stable"):
+        img[cell_h[i], cell_w[i]] = rows[i]
+    out = img[:, :: W // W_out].transpose(2, 0, 1).copy()
+    return out * out[5:6]
+

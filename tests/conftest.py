@@ -82,3 +82,8 @@ def g_step():
 @pytest.fixture(scope="session")
 def g_step_mid():
     return load_golden("trainer_step_mid.npz")
+
+
+@pytest.fixture(scope="session")
+def g_kitti():
+    return load_golden("kitti_scan.npz")

@@ -50,3 +50,20 @@ def sample_flat(t, n=2048):
         return f.clone()
     stride = f.numel() // n
     return f[::stride][:n].clone()
+
+
+def synthetic_scan(rings=66, per_ring=120, seed=0):
+    """Velodyne-like [N, 4] float32 scan: `rings` sweeps of increasing azimuth (a new ring starts
+    where the azimuth passes from the 4th to the 1st quadrant), elevation falling from +3 to -25
+    degrees, ranges 0.5 .. 130 m (some outside any [min_depth, max_depth]); the first points are
+    dropped so that the scan starts before any ring start."""
+    import numpy as np
+    g = np.random.default_rng(seed)
+    rows = []
+    for r in range(rings):
+        phi = np.sort(g.uniform(0, 2 * np.pi, per_ring))
+        rng = g.uniform(0.5, 130, per_ring)
+        el = np.deg2rad(3 - 28 * r / rings) + g.normal(0, 0.002, per_ring)
+        rows.append(np.stack([rng * np.cos(el) * np.cos(phi), rng * np.cos(el) * np.sin(phi), rng * np.sin(el),
+                              g.uniform(0, 1, per_ring)], 1))
+    return np.concatenate(rows).astype(np.float32)[5:]

@@ -976,3 +976,29 @@ def test_equal_lr_weight_prep_kernel(DF, shape):
     v = torch.randn(*shape, generator=g).to(DEV)
     (gg,) = torch.autograd.grad(gw, gyr, v)
     close(gg, (v * s).to(torch.bfloat16), rtol=1e-2, atol_rel=1e-3)
+
+
+@pytest.mark.parametrize("tag,unfold", [("unfold", True), ("elev", False)])
+def test_kitti_scan_to_image_exact(g_kitti, tag, unfold):
+    """f4: scan -> [6, 64, 512] range image on the device (depth-ordered scatter as an atomic
+    min, NEAREST column selection, mask product) against the reference's golden output and the
+    oracle: integer-exact pixel indexing, bit-equal values."""
+    from dusty_gan_v2_b200.gans.datasets.kitti import KITTIRaw, scan_to_image
+    pts = g_kitti["points"]
+    img = scan_to_image(pts, (64, 512), 1.45, 80.0, unfold)
+    assert img.shape == (6, 64, 512) and img.is_cuda
+    assert np.array_equal(img.cpu().numpy(), g_kitti[f"{tag}_image"])
+    full = scan_to_image(pts, (64, 2048), 1.45, 80.0, unfold)
+    assert np.array_equal(full.cpu().numpy(), O.scan_to_image(pts, 64, 2048, 2048, 1.45, 80.0, unfold))
+    import os, tempfile
+    with tempfile.TemporaryDirectory() as d:
+        f = os.path.join(d, "0000000000.bin")
+        pts.tofile(f)
+        ds = KITTIRaw(shape=(64, 512), min_depth=1.45, max_depth=80.0, scan_unfolding=unfold, files=[f])
+        item = ds[0]
+    assert len(ds) == 1 and set(item) == {"xyz", "reflectance", "depth", "mask"}
+    assert np.array_equal(item["depth"].cpu().numpy(), g_kitti[f"{tag}_image"][4:5])
+    assert int(item["mask"].sum()) == int(g_kitti[f"{tag}_image"][5].sum())          # valid-point count
+    with pytest.raises(RuntimeError):
+        scan_to_image(pts, (64, 512), device="cpu")
+

@@ -408,3 +408,20 @@ def test_train_iteration_config3_against_reference_trainer_step(arch):
     r = O.train_iteration(sdG, sdD, x_real, None, rnd, with_r1=True, arch=arch)
     close(r["r1"], g["r1"], rtol=5e-3, atol=1e-7)
     check_grads(r["grads_R1"], "gR1_", 8)
+
+
+@pytest.mark.parametrize("tag,unfold", [("unfold", True), ("elev", False)])
+def test_kitti_scan_projection_golden(g_kitti, tag, unfold):
+    """f4: the oracle's scan -> range image against the reference's `load_pts_as_img` + NEAREST
+    resize + mask product (tests/golden/make_golden_kitti.py), bit for bit; and the mirror's
+    loop-free cell computation (host side of `scan_to_image`) against the oracle's sequential
+    ring walk, including the ring index -1 the reference assigns to the 65th ring from the top."""
+    from dusty_gan_v2_b200.gans.datasets.kitti import scan_cells
+    pts = g_kitti["points"]
+    img = O.scan_to_image(pts, 64, 2048, 512, 1.45, 80.0, unfold)
+    assert np.array_equal(img, g_kitti[f"{tag}_image"])
+    a, b = scan_cells(pts, 64, 2048, unfold), O.scan_cells(pts, 64, 2048, unfold)
+    assert all(np.array_equal(u, v) for u, v in zip(a, b))
+    if unfold:
+        assert a[0].min() == -1 and a[0].max() == 63
+

@@ -643,3 +643,22 @@ def test_modconv_composite_weights_match_reference_forward(rops, demod, ema):
     wb = mine._effective_weights_composite(mine.mod(style))
     y = torch.bmm(wb, x.flatten(2)).reshape(3, Oc, 4, 8)
     assert torch.allclose(y, ref(x, style), rtol=1e-4, atol=1e-5)
+
+
+@pytest.mark.parametrize("unfold", [True, False])
+def test_kitti_scan_projection_matches_reference_live(rops, tmp_path, unfold):
+    """f4: the oracle's scan -> range image (and the mirror's host-side cell computation) against
+    the reference's own `KITTIRaw.load_pts_as_img` on a fresh synthetic scan."""
+    from gans.datasets.kitti import KITTIRaw
+    from dusty_gan_v2_b200.gans.datasets.kitti import scan_cells
+    from small_cfgs import synthetic_scan
+    pts = synthetic_scan(rings=70, per_ring=90, seed=11)
+    f = tmp_path / "scan.bin"
+    pts.tofile(str(f))
+    ds = object.__new__(KITTIRaw)
+    ds.min_depth, ds.max_depth = 1.45, 80.0
+    ref = ds.load_pts_as_img(str(f), unfold, 64, 2048).transpose(2, 0, 1)
+    ref = ref * ref[5:6]
+    assert np.array_equal(O.scan_to_image(pts, 64, 2048, 2048, 1.45, 80.0, unfold), ref)
+    a, b = scan_cells(pts, 64, 2048, unfold), O.scan_cells(pts, 64, 2048, unfold)
+    assert all(np.array_equal(u, v) for u, v in zip(a, b))

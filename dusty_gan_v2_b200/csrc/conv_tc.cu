@@ -788,6 +788,7 @@ conv_halo_tc_kernel(const __grid_constant__ HaloMaps maps, const __grid_constant
 struct WgMaps {
   CUtensorMap a[4];    // x window of filter row r
   CUtensorMap g;       // dY
+  CUtensorMap o;       // fp32 result [R][S*C][O] (split-K partial tiles are TMA-reduced into it)
 };
 
 struct WgParams {
@@ -908,27 +909,63 @@ conv_wgrad_tc_kernel(const __grid_constant__ WgMaps maps, const __grid_constant_
     tc_fence_after();
     const bool have = pb_end > pb_begin;
     const bool atomic = prm.atomic != 0;    // split-K partials meet in the (zeroed) result
+    if (atomic) {
+      // Partial tile -> swizzled staging tile (the operand ring is idle once acc_full has
+      // fired) -> ONE TMA reduce-add per 32 columns.  (Per-thread 16-byte reductions -- 8192
+      // per CTA at BN = 256 -- took half of the CTA's lifetime: tools/conv_roles.py.)
+      if (have) {
+        const int row = q * 32 + lane;
+        const bool issuer = threadIdx.x == 64;
+        const uint32_t stage_u32 = smem_u32(a_base);
+        const uint32_t srow = stage_u32 + (uint32_t)row * 128u;
+        const uint32_t swz = (uint32_t)row & 7u;
 #pragma unroll 1
-    for (int rr = 0; rr < NR; ++rr) {
-      float *op = prm.out + (long long)split * prm.split_stride +
-                  ((long long)(r_first + rr) * prm.SC + m) * prm.O + n0;
+        for (int rr = 0; rr < NR; ++rr) {
 #pragma unroll 1
-      for (int c = 0; c < BN; c += 16) {
-        uint32_t v[16];
-        tmem_ld16(tmem_acc + ((uint32_t)(q * 32) << 16) + (uint32_t)(rr * BN + c), v);
-        tmem_ld_wait();
-        if (m < prm.SC) {
+          for (int c = 0; c < BN; c += 32) {
+            uint32_t v[2][16];
+            tmem_ld16(tmem_acc + ((uint32_t)(q * 32) << 16) + (uint32_t)(rr * BN + c), v[0]);
+            tmem_ld16(tmem_acc + ((uint32_t)(q * 32) << 16) + (uint32_t)(rr * BN + c + 16), v[1]);
+            tmem_ld_wait();
+            if (issuer) tma_store_wait_read<0>();
+            named_bar_sync(1, 128);
 #pragma unroll
-          for (int j4 = 0; j4 < 4; ++j4) {
-            if (n0 + c + j4 * 4 < prm.O) {
-              float4 o4;
-              o4.x = have ? __uint_as_float(v[j4 * 4 + 0]) : 0.f;
-              o4.y = have ? __uint_as_float(v[j4 * 4 + 1]) : 0.f;
-              o4.z = have ? __uint_as_float(v[j4 * 4 + 2]) : 0.f;
-              o4.w = have ? __uint_as_float(v[j4 * 4 + 3]) : 0.f;
-              if (atomic) {
-                if (have) atomicAdd(reinterpret_cast<float4 *>(op + c + j4 * 4), o4);   // 16-byte red (sm_90+)
-              } else {
+            for (int ch = 0; ch < 8; ++ch) {
+              const uint32_t *src = &v[ch >> 2][(ch & 3) * 4];
+              const uint32_t addr = srow + (((uint32_t)ch ^ swz) << 4);
+              asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(src[0]), "r"(src[1]),
+                           "r"(src[2]), "r"(src[3])
+                           : "memory");
+            }
+            fence_proxy_async();
+            named_bar_sync(1, 128);
+            if (issuer) {
+              tma_reduce_add_3d(&maps.o, stage_u32, n0 + c, m0, r_first + rr);
+              tma_store_commit();
+            }
+          }
+        }
+        if (issuer) tma_store_wait_read<0>();
+      }
+    } else {
+#pragma unroll 1
+      for (int rr = 0; rr < NR; ++rr) {
+        float *op = prm.out + (long long)split * prm.split_stride +
+                    ((long long)(r_first + rr) * prm.SC + m) * prm.O + n0;
+#pragma unroll 1
+        for (int c = 0; c < BN; c += 16) {
+          uint32_t v[16];
+          tmem_ld16(tmem_acc + ((uint32_t)(q * 32) << 16) + (uint32_t)(rr * BN + c), v);
+          tmem_ld_wait();
+          if (m < prm.SC) {
+#pragma unroll
+            for (int j4 = 0; j4 < 4; ++j4) {
+              if (n0 + c + j4 * 4 < prm.O) {
+                float4 o4;
+                o4.x = have ? __uint_as_float(v[j4 * 4 + 0]) : 0.f;
+                o4.y = have ? __uint_as_float(v[j4 * 4 + 1]) : 0.f;
+                o4.z = have ? __uint_as_float(v[j4 * 4 + 2]) : 0.f;
+                o4.w = have ? __uint_as_float(v[j4 * 4 + 3]) : 0.f;
                 *reinterpret_cast<float4 *>(op + c + j4 * 4) = o4;
               }
             }
@@ -1391,6 +1428,15 @@ extern "C" int dusty_conv2d_wgrad_tc(const void *x, const void *dy, float *dwp, 
     const uint64_t dims[4] = {(uint64_t)O, (uint64_t)W_out, (uint64_t)H_out, (uint64_t)B};
     const uint64_t strides[3] = {(uint64_t)O * 2, (uint64_t)W_out * O * 2, (uint64_t)H_out * W_out * O * 2};
     ok = ok && make_map4(&maps.g, dy, dims, strides, box);
+  }
+  {
+    EncodeTiledFn enc = get_encode();
+    cuuint64_t od[3] = {(cuuint64_t)O, (cuuint64_t)SC, (cuuint64_t)R};
+    cuuint64_t os[2] = {(cuuint64_t)O * 4, (cuuint64_t)SC * O * 4};
+    cuuint32_t ob[3] = {32, 128, 1}, oe[3] = {1, 1, 1};
+    ok = ok && enc(&maps.o, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 3, dwp, od, os, ob, oe, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                   CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
   }
   if (!ok) {
     set_error("dusty_conv2d_wgrad_tc: cuTensorMapEncodeTiled failed");

@@ -97,6 +97,15 @@ __device__ __forceinline__ void tma_store_4d(const CUtensorMap *map, uint32_t sm
                "r"(smem_src), "r"(c0), "r"(c1), "r"(c2), "r"(c3)
                : "memory");
 }
+// element-wise ADD of a shared-memory tile into global memory (split-K partial sums): one bulk
+// operation resolved in L2 instead of thousands of per-thread atomics
+__device__ __forceinline__ void tma_reduce_add_3d(const CUtensorMap *map, uint32_t smem_src, int c0, int c1,
+                                                  int c2) {
+  asm volatile("cp.reduce.async.bulk.tensor.3d.global.shared::cta.add.bulk_group [%0, {%2, %3, %4}], [%1];" ::"l"(
+                   map),
+               "r"(smem_src), "r"(c0), "r"(c1), "r"(c2)
+               : "memory");
+}
 __device__ __forceinline__ void tma_store_commit() {
   asm volatile("cp.async.bulk.commit_group;" ::: "memory");
 }

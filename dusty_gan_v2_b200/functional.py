@@ -1237,7 +1237,7 @@ def conv_tc_supported(x: torch.Tensor, w: torch.Tensor, stride, op: str = "fprop
     if x.dtype != torch.bfloat16 or w.dtype != torch.bfloat16:
         return False
     O, C, R, S = w.shape
-    if C != x.shape[1] or C % 8 or O % 8 or C < 16 or R > 4 or S > 4:
+    if C != x.shape[1] or C % 8 or O % 8 or R > 4 or S > 4:
         return False
     if stride[0] not in (1, 2) or stride[1] not in (1, 2):
         return False
@@ -1470,7 +1470,7 @@ def matmul_nt(a: torch.Tensor, b: torch.Tensor, alpha: float = 1.0) -> torch.Ten
     N = b.shape[0]
     c = torch.empty((M, N), dtype=torch.float32, device=a.device)
     st = K.stream_of(a)
-    if min(M, N) < 16 or N % 4 or (M * N <= (1 << 16) and Kd < 1024):
+    if min(M, N) < 16 or N % 4 or Kd < 16 or (M * N <= (1 << 16) and Kd < 1024):
         a32 = a if a.dtype == torch.float32 else a.float()
         b32 = b if b.dtype == torch.float32 else b.float()
         K.call("dusty_gemm_simt", K.ptr(a32), K.ptr(b32), K.ptr(c), M, N, Kd, a32.stride(0), a32.stride(1),

@@ -246,8 +246,16 @@ class _Conv2dBwdFn(torch.autograd.Function):
 def _convT_tc_ok(x, w, stride):
     O, C, R, S = w.shape
     return (x.is_cuda and x.dtype == torch.bfloat16 and w.dtype == torch.bfloat16 and O % 8 == 0
-            and C % 8 == 0 and O >= 16 and C >= 16 and R <= 4 and S <= 4 and stride[0] in (1, 2)
-            and stride[1] in (1, 2))
+            and C % 8 == 0 and R <= 4 and S <= 4 and stride[0] in (1, 2) and stride[1] in (1, 2))
+
+
+def _pad_channels(t, dim, mult=8):
+    """Zero-pad dimension `dim` to a multiple of `mult` (the tcgen05 kernels address channels in
+    16-byte units); differentiable, the gradient of the padding is dropped by the slice."""
+    r = (-t.shape[dim]) % mult
+    if r == 0:
+        return t
+    return F.pad(t, [0, 0] * (t.dim() - dim - 1) + [0, r])
 
 
 class _ConvTranspose2dFn(torch.autograd.Function):
@@ -417,12 +425,44 @@ class EqualLR(nn.Module):
         if isinstance(m, (nn.Conv2d, nn.ConvTranspose2d)):
             if m.dilation != (1, 1) or m.groups != 1 or isinstance(m.padding, str):
                 raise NotImplementedError("dilated / grouped convolutions are not part of the path")
+            if x.is_cuda and DF.act_dtype() == torch.bfloat16:
+                return self._conv_low_precision(x, w, b)
             if isinstance(m, nn.Conv2d):
                 if DF._is_cl(x):        # NHWC activations: OHWI filter memory
                     w = w.contiguous(memory_format=torch.channels_last)
                 return conv2d(x, w, b, m.stride, m.padding)
             return conv_transpose2d(x, w, b, m.stride, m.padding, m.output_padding)
         return m(x * self.scale) * self.gain_
+
+    def _conv_low_precision(self, x, w, b):
+        """The dense (transposed) convolutions of the vanilla / dusty_v1 baselines (reference
+        vanilla.py:7-105) in bf16 mode: activations become bf16 NHWC and stay so, channel counts
+        are zero-padded to multiples of 8 (1-channel heads, the 2-channel BlurVH pair) so that
+        every layer runs on the tcgen05 kernels; a convolution whose kernel covers the whole map
+        (the generator's projection from [B, C, 1, 1], the discriminator's logit) is a GEMM."""
+        m = self.module
+        bf = torch.bfloat16
+        transposed = isinstance(m, nn.ConvTranspose2d)
+        B = x.shape[0]
+        if (transposed and tuple(x.shape[2:]) == (1, 1) and m.stride == (1, 1) and m.padding == (0, 0)):
+            cin, cout, R, S = w.shape
+            y = DF.linear_nt(x.reshape(B, cin).float(), w.float().reshape(cin, cout * R * S).t())
+            y = y.reshape(B, cout, R, S).to(bf).contiguous(memory_format=torch.channels_last)
+        elif (not transposed and tuple(x.shape[2:]) == tuple(m.kernel_size) and m.padding == (0, 0)):
+            O = w.shape[0]
+            y = DF.linear_nt(x.float().flatten(1), w.float().flatten(1)).reshape(B, O, 1, 1)
+        else:
+            xb = _pad_channels(x.to(bf), 1).contiguous(memory_format=torch.channels_last)
+            wb = _pad_channels(_pad_channels(w.to(bf), 0), 1)
+            if transposed:
+                cout = w.shape[1]
+                y = conv_transpose2d(xb, wb, None, m.stride, m.padding, m.output_padding)[:, :cout]
+            else:
+                O = w.shape[0]
+                y = conv2d(xb, wb.contiguous(memory_format=torch.channels_last), None, m.stride, m.padding)[:, :O]
+            if y.shape[1] % 8 == 0:
+                y = y.contiguous(memory_format=torch.channels_last)
+        return y if b is None else y + b.to(y.dtype).view(1, -1, 1, 1)
 
     def prepared_weight(self, dtype, with_tco=False):
         """Scaled conv filter in `dtype`, channels_last memory: one kernel (scale + cast + layout)

@@ -9,8 +9,10 @@ module tree and state_dict keys:
   discriminator {1..4}       Downsample   Pad(1) -> Conv 4x4 stride 2 -> bias + lrelu
   discriminator 5            Conv with the full-map kernel -> one logit
 
-The dense (transposed) convolutions are library calls; the padding, the blur pair, the fused
-bias + leaky-ReLU and everything downstream of the heads are dusty_b200 kernels.
+Every layer runs on dusty_b200 kernels: the dense (transposed) convolutions on the tcgen05
+implicit-GEMM family in bf16 mode (ops.EqualLR._conv_low_precision: a transposed convolution is
+the data-gradient kernel) and on the CUDA-core family in fp32 parity mode; the padding, the blur
+pair, the fused bias + leaky-ReLU and everything downstream of the heads likewise.
 """
 from torch import nn
 
@@ -70,7 +72,8 @@ class Head(nn.Module):
             for spec in out_ch if spec["ch"] != 0})
 
     def forward(self, x):
-        return {name: branch(x) for name, branch in self.heads.items()}
+        # head maps leave the network in fp32 whatever the trunk's precision (as dusty_v2's do)
+        return {name: branch(x).float().contiguous() for name, branch in self.heads.items()}
 
 
 class SynthesisNetwork(nn.Sequential):

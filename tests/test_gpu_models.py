@@ -560,6 +560,58 @@ def test_vanilla_and_dusty_v1_golden(g_vanilla):
     assert n >= 15
 
 
+@pytest.mark.parametrize("arch", ["dusty_v1", "vanilla"])
+def test_config3_full_size_bf16_on_tcgen05_vs_oracle(arch):
+    """BASELINE config 3 at full size in the benched precision: the 4x4 stride-2 (transposed)
+    convolutions of the vanilla / dusty_v1 generator and discriminator run on the tcgen05
+    implicit-GEMM kernels (a transposed convolution is the data-gradient kernel, 1- / 2-channel
+    layers zero-padded to 8 channels, full-map kernels as GEMMs) -- outputs and the input
+    gradient against the fp32 CPU oracle within the bf16 tolerance."""
+    import dusty_gan_v2_b200 as pkg
+    from dusty_gan_v2_b200.gans.models.builder import build_discriminator, build_generator
+    from dusty_gan_v2_b200.presets import preset
+    torch.manual_seed(0)
+    cfg = preset(arch)
+    G, D = build_generator(cfg.model.generator).eval(), build_discriminator(cfg.model.discriminator)
+    with torch.no_grad():
+        for net in (G, D):
+            for n, p in net.named_parameters():
+                if "bias" in n:
+                    p.normal_(0, 0.2, generator=torch.Generator().manual_seed(13))
+    sdG = {k: v.clone() for k, v in G.state_dict().items()}
+    sdD = {k: v.clone() for k, v in D.state_dict().items()}
+    B = 2
+    gen = torch.Generator().manual_seed(4)
+    z = torch.randn(B, 512, generator=gen)
+    u = torch.rand(B, 1, 64, 512, generator=gen)
+    x = torch.tanh(torch.randn(B, 1, 64, 512, generator=gen))
+    with torch.no_grad():
+        ref = O.vanilla_generator(sdG, z, u if arch == "dusty_v1" else None)
+        ref_y = O.vanilla_discriminator(sdD, x)
+    pkg.set_precision("bf16")
+    G, D = G.to(DEV), D.to(DEV)
+    n0 = pkg.launch_count()
+    real_rand = torch.rand
+    torch.rand = lambda *a, **k: u.to(k.get("device", "cpu"))
+    try:
+        with torch.no_grad():
+            out = G(z.to(DEV))
+    finally:
+        torch.rand = real_rand
+    key = "image_orig" if arch == "dusty_v1" else "image"
+    assert out[key].dtype == torch.float32
+    close(out[key], ref[key], rtol=3e-2, atol_rel=3e-2)
+    xg = x.to(DEV).requires_grad_()
+    for p in D.parameters():
+        p.requires_grad_(True)
+    y = D(xg)
+    close(y.reshape(B, -1), ref_y.reshape(B, -1), rtol=3e-2, atol_rel=3e-2)
+    torch.nn.functional.softplus(-y.float()).mean().backward()
+    assert torch.isfinite(xg.grad).all() and all(p.grad is not None and torch.isfinite(p.grad).all()
+                                                  for p in D.parameters())
+    assert pkg.launch_count() - n0 > 20
+
+
 def test_inversion_style_latent_gradient_vs_oracle(g_gen):
     """BASELINE config 5 (gans/inversion.py usage): eval-mode G driven by per-layer styles w
     (input_w=True), masked L1-type loss on the converted depth, gradient w.r.t. w only; plus

@@ -41,9 +41,9 @@ constexpr int kCM = 128;                 // UMMA M
 constexpr int kCK = 64;                  // K elements per stage
 constexpr int kCABytes = kCM * kCK * 2;  // 16 KiB
 constexpr int kCThreads = 64 + 256;   // TMA warp, MMA warp, 8 epilogue warps (fprop / dgrad)
+constexpr int kMaxClasses = 4;            // output parity classes of a stride-2 data gradient
 constexpr int kWgThreads = 192;        // wgrad: one epilogue pass per CTA, 4 warps
 constexpr int kMaxGroups = 16;
-constexpr int kMaxClasses = 4;            // output parity classes of a stride-2 data gradient
 
 // Role profiling (tools only; libdusty_b200_prof.so is built with -DDUSTY_ROLE_PROF): cycles the
 // three warp roles spend waiting on each other, summed over CTAs.  slots: 0 producer waits for
@@ -88,6 +88,7 @@ __device__ __forceinline__ void trace_ev(unsigned role, unsigned &n, unsigned ta
 struct ConvMaps {
   CUtensorMap a[4];
   CUtensorMap w;
+  CUtensorMap y[kMaxClasses];              // output view of every class (TMA stores)
 };
 
 // A launch covers `ncls` classes (1 except for a strided data gradient, whose output parity
@@ -115,20 +116,32 @@ struct ConvParams {
   float alpha, scale;
 };
 
+// Pipeline (see the halo kernel's notes on the shallow UMMA queue): NACC accumulators in TMEM
+// (4 up to BN = 128), the MMA warp probes the next stage's barrier before issuing the current
+// stage's UMMAs, and the output leaves through a swizzled staging tile + ONE TMA store per
+// 64-channel sub-tile (per-thread 16-byte stores at a 64..512-byte stride kept the LSU busy for
+// longer than the MMAs of a thin tile).  BN <= 64: the two epilogue groups take alternate
+// tiles; BN >= 128: they split a tile's 64-column sub-tiles.
 template <int BN, int STAGES>
-__global__ void __launch_bounds__(kCThreads)
+__global__ void __launch_bounds__(kCThreads, 1)
 conv_fwd_tc_kernel(const __grid_constant__ ConvMaps maps, const __grid_constant__ ConvParams prm) {
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   uint8_t *smem = (uint8_t *)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
   constexpr int kBBytes = BN * kCK * 2;
   constexpr int kStageBytes = kCABytes + kBBytes;
+  constexpr int NACC = 512 / BN >= 4 ? 4 : 2;
+  constexpr bool kSplitTile = BN >= 128;                    // both groups work on every tile
+  constexpr int kSubCh = BN > 64 ? 64 : BN;                 // channels of a staging sub-tile
+  constexpr int kSubs = BN / kSubCh;
+  constexpr int kSubBytes = kCM * kSubCh * 2;
   uint8_t *a_base = smem;
   uint8_t *b_base = smem + STAGES * kCABytes;
-  uint64_t *full = (uint64_t *)(smem + STAGES * kStageBytes);
+  uint8_t *stage_base = smem + STAGES * kStageBytes;        // one staging sub-tile per group
+  uint64_t *full = (uint64_t *)(stage_base + 2 * kSubBytes);
   uint64_t *empty = full + STAGES;
   uint64_t *acc_full = empty + STAGES;
-  uint64_t *acc_empty = acc_full + 2;
-  uint32_t *tmem_slot = (uint32_t *)(acc_empty + 2);
+  uint64_t *acc_empty = acc_full + NACC;
+  uint32_t *tmem_slot = (uint32_t *)(acc_empty + NACC);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int t_begin = blockIdx.x * prm.tiles_per_cta;
@@ -139,13 +152,13 @@ conv_fwd_tc_kernel(const __grid_constant__ ConvMaps maps, const __grid_constant_
       mbar_init(&full[s], 1);
       mbar_init(&empty[s], 1);
     }
-    for (int a = 0; a < 2; ++a) {
+    for (int a = 0; a < NACC; ++a) {
       mbar_init(&acc_full[a], 1);
-      mbar_init(&acc_empty[a], 8);
+      mbar_init(&acc_empty[a], kSplitTile ? 8 : 4);
     }
     fence_barrier_init();
   }
-  if (warp == 1) tmem_alloc(tmem_slot, 2 * BN);
+  if (warp == 1) tmem_alloc(tmem_slot, NACC * BN);
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
@@ -196,18 +209,21 @@ conv_fwd_tc_kernel(const __grid_constant__ ConvMaps maps, const __grid_constant_
     const uint32_t d_hi = desc_hi(1024, 2);
     const uint32_t a_lo0 = desc_lo(smem_u32(a_base), 16);
     const uint32_t b_lo0 = desc_lo(smem_u32(b_base), 16);
-    RingPos r;
-    int lt = 0;
-    for (int tile = t_begin; tile < t_end; ++tile, ++lt) {
-      const int a = lt & 1;
+    RingPos r, acc;
+    bool ready = false;                  // stage r.s already known to be full (probed ahead)
+    for (int tile = t_begin; tile < t_end; ++tile) {
+      const int a = acc.s;
       const int num_kb = prm.cls[tile % prm.ncls].G * prm.KC;
-      PROF_WAIT(1, mbar_wait(&acc_empty[a], ((lt >> 1) & 1) ^ 1));
-      tc_fence_after();
+      PROF_WAIT(1, mbar_wait(&acc_empty[a], acc.ph ^ 1));
       const uint32_t tmem_acc = tmem_base + (uint32_t)(a * BN);
       for (int kb = 0; kb < num_kb; ++kb) {
         const int s = r.s;
-        PROF_WAIT(0, mbar_wait(&full[s], r.ph));
+        if (!ready) PROF_WAIT(0, mbar_wait(&full[s], r.ph));
         tc_fence_after();
+        RingPos nx = r;
+        nx.template advance<STAGES>();
+        const bool more = kb + 1 < num_kb || tile + 1 < t_end;
+        ready = more && mbar_try_wait(&full[nx.s], nx.ph);
         if (elect_one_sync()) {
           const uint32_t a_lo = a_lo0 + (uint32_t)s * (kCABytes >> 4);
           const uint32_t b_lo = b_lo0 + (uint32_t)s * (kBBytes >> 4);
@@ -216,79 +232,92 @@ conv_fwd_tc_kernel(const __grid_constant__ ConvMaps maps, const __grid_constant_
             umma_bf16_lh(tmem_acc, a_lo + k16 * 2, d_hi, b_lo + k16 * 2, d_hi, idesc,
                          (kb > 0 || k16 > 0) ? 1u : 0u);
           umma_commit(&empty[s]);
+          if (kb == num_kb - 1) umma_commit(&acc_full[a]);
         }
         __syncwarp();
-        r.template advance<STAGES>();
+        r = nx;
       }
-      if (elect_one_sync()) umma_commit(&acc_full[a]);
-      __syncwarp();
+      acc.template advance<NACC>();
     }
     PROF_FLUSH(1, 2, 5);
   } else {
     const int q = warp & 3;
     const int grp = (warp - 2) >> 2;
     const int row = q * 32 + lane;
-    const int th = row / prm.TW, tw = row % prm.TW;
+    const bool issuer = (warp - 2) % 4 == 0 && lane == 0;
+    const bool lrelu = prm.act == 3;
+    const float alpha = prm.alpha, scale = prm.scale;
+    const uint32_t stage_u32 = smem_u32(stage_base) + (uint32_t)(grp * kSubBytes);
+    const uint32_t srow_addr = stage_u32 + (uint32_t)row * (uint32_t)(kSubCh * 2);
+    constexpr int kChunks = kSubCh / 8;                     // 16-byte chunks per staging row
+    const uint32_t swz = kSubCh == 32 ? (((uint32_t)row >> 1) & 3u) : ((uint32_t)row & 7u);
     int lt = 0;
     for (int tile = t_begin; tile < t_end; ++tile, ++lt) {
+      if (!kSplitTile && (lt & 1) != grp) continue;
       int ci, b, oh0, ow0, n0;
       decode(tile, ci, b, oh0, ow0, n0);
-      const ConvClass &cl = prm.cls[ci];
-      const int a = lt & 1;
-      PROF_WAIT(0, mbar_wait(&acc_full[a], (lt >> 1) & 1));
+      const int a = lt % NACC;
+      PROF_WAIT(0, mbar_wait(&acc_full[a], (lt / NACC) & 1));
       tc_fence_after();
       const uint32_t tmem_acc = tmem_base + (uint32_t)(a * BN) + ((uint32_t)(q * 32) << 16);
-      const int oh = oh0 + th, ow = ow0 + tw;
-      const bool pix_ok = th < prm.TH && oh < cl.H_out && ow < cl.W_out;
-      __nv_bfloat16 *yp = prm.y + cl.y_off + (long long)b * prm.y_sb + (long long)oh * prm.y_sh +
-                          (long long)ow * prm.y_sw + n0;
-      // the two groups of four epilogue warps take alternate 16-column chunks
-      constexpr int kLastMine = BN - 32;      // + 16 * grp: last chunk a group reads (BN >= 32)
 #pragma unroll 1
-      for (int c = 16 * grp; c < BN; c += 32) {
-        uint32_t r[16];
-        tmem_ld16(tmem_acc + (uint32_t)c, r);
+      for (int sub = kSplitTile ? grp : 0; sub < kSubs; sub += kSplitTile ? 2 : 1) {
+        uint32_t v[kSubCh / 16][16];
+#pragma unroll
+        for (int i = 0; i < kSubCh / 16; ++i) tmem_ld16(tmem_acc + (uint32_t)(sub * kSubCh + i * 16), v[i]);
         tmem_ld_wait();
-        if (c >= kLastMine) {
+        if (sub + (kSplitTile ? 2 : 1) >= kSubs) {          // this warp's last read of the accumulator
           tc_fence_before();
           __syncwarp();
           if (lane == 0) mbar_arrive(&acc_empty[a]);
         }
-        if (pix_ok) {
+        const int o0 = n0 + sub * kSubCh;
+        if (o0 < prm.O) {
+          if (issuer) tma_store_wait_read<0>();
+          named_bar_sync(1 + grp, 128);
 #pragma unroll
-          for (int h8 = 0; h8 < 2; ++h8) {
-            const int o = n0 + c + h8 * 8;
-            if (o < prm.O) {
-              uint32_t pk[4];
-#pragma unroll
-              for (int j = 0; j < 4; ++j) {
-                float v0 = __uint_as_float(r[h8 * 8 + 2 * j]);
-                float v1 = __uint_as_float(r[h8 * 8 + 2 * j + 1]);
-                if (prm.bias) {
-                  v0 += __ldg(prm.bias + o + 2 * j);
-                  v1 += __ldg(prm.bias + o + 2 * j + 1);
-                }
-                if (prm.act == 3) {
-                  v0 = v0 > 0.f ? v0 : v0 * prm.alpha;
-                  v1 = v1 > 0.f ? v1 : v1 * prm.alpha;
-                }
-                const uint32_t lo = __bfloat16_as_ushort(__float2bfloat16_rn(v0 * prm.scale));
-                const uint32_t hi = __bfloat16_as_ushort(__float2bfloat16_rn(v1 * prm.scale));
-                pk[j] = lo | (hi << 16);
-              }
-              *reinterpret_cast<uint4 *>(yp + c + h8 * 8) = make_uint4(pk[0], pk[1], pk[2], pk[3]);
+          for (int ch = 0; ch < kChunks; ++ch) {
+            uint32_t w4[4];
+            float4 b0 = make_float4(0.f, 0.f, 0.f, 0.f), b1 = b0;
+            if (prm.bias && o0 + ch * 8 < prm.O) {
+              b0 = __ldg(reinterpret_cast<const float4 *>(prm.bias + o0 + ch * 8));
+              b1 = __ldg(reinterpret_cast<const float4 *>(prm.bias + o0 + ch * 8 + 4));
             }
+            const float bb[8] = {b0.x, b0.y, b0.z, b0.w, b1.x, b1.y, b1.z, b1.w};
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+              const int e = ch * 8 + 2 * j;
+              float v0 = __uint_as_float(v[e >> 4][e & 15]) + bb[2 * j];
+              float v1 = __uint_as_float(v[e >> 4][(e & 15) + 1]) + bb[2 * j + 1];
+              if (lrelu) {
+                v0 = v0 > 0.f ? v0 : v0 * alpha;
+                v1 = v1 > 0.f ? v1 : v1 * alpha;
+              }
+              const __nv_bfloat162 pr = __floats2bfloat162_rn(v0 * scale, v1 * scale);
+              w4[j] = *reinterpret_cast<const uint32_t *>(&pr);
+            }
+            const uint32_t addr = srow_addr + (((uint32_t)ch ^ swz) << 4);
+            asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(w4[0]), "r"(w4[1]), "r"(w4[2]),
+                         "r"(w4[3])
+                         : "memory");
+          }
+          fence_proxy_async();
+          named_bar_sync(1 + grp, 128);
+          if (issuer) {
+            tma_store_4d(&maps.y[ci], stage_u32, o0, ow0, oh0, b);
+            tma_store_commit();
           }
         }
       }
     }
+    if (issuer) tma_store_wait_read<0>();
     if (warp == 2) PROF_FLUSH(3, -1, 6);
   }
   tc_fence_before();
   __syncthreads();
   if (warp == 1) {
     tc_fence_after();
-    tmem_dealloc(tmem_base, 2 * BN);
+    tmem_dealloc(tmem_base, NACC * BN);
   }
 }
 
@@ -1063,7 +1092,7 @@ int launch_halo(const HaloMaps &maps, HaloParams prm, int buf_stride, cudaStream
 
 template <int BN, int STAGES>
 constexpr int conv_smem_bytes() {
-  return STAGES * (kCABytes + BN * kCK * 2) + 128 + 1024;
+  return STAGES * (kCABytes + BN * kCK * 2) + 2 * kCM * (BN > 64 ? 64 : BN) * 2 + 256 + 1024;
 }
 
 template <int BN, int STAGES>
@@ -1071,7 +1100,7 @@ int launch_conv(const ConvMaps &maps, ConvParams prm, cudaStream_t st) {
   constexpr int smem = conv_smem_bytes<BN, STAGES>();
   static bool configured = false;
   if (int rc = set_smem(conv_fwd_tc_kernel<BN, STAGES>, smem, &configured)) return rc;
-  const int resident = num_sms() * ((2 * smem <= 225 * 1024 && 2 * BN * 2 <= 512) ? 2 : 1);
+  const int resident = num_sms();         // one CTA per SM: it owns the accumulator ring in TMEM
   int ctas = prm.total_tiles < resident ? prm.total_tiles : resident;
   prm.tiles_per_cta = (prm.total_tiles + ctas - 1) / ctas;
   ctas = (prm.total_tiles + prm.tiles_per_cta - 1) / prm.tiles_per_cta;
@@ -1268,11 +1297,25 @@ static int conv_launch(const char *who, const void *x, const void *wpk, const fl
     prm.total_tiles = ((patches + 1) / 2) * prm.NT * ncls;
     return BN == 256 ? launch_pair<256, 5>(pm, prm, patches, st) : launch_pair<128, 7>(pm, prm, patches, st);
   }
+  {
+    const int sub_ch = BN > 64 ? 64 : BN;
+    const uint32_t ybox[4] = {(uint32_t)sub_ch, (uint32_t)prm.TW, (uint32_t)prm.TH, 1u};
+    for (int c = 0; c < kMaxClasses; ++c) {
+      const HostClass &h = hc[c < ncls ? c : 0];
+      const uint64_t ydims[4] = {(uint64_t)O, (uint64_t)h.W_out, (uint64_t)h.H_out, (uint64_t)B};
+      const uint64_t ystr[3] = {(uint64_t)y_sw * 2, (uint64_t)y_sh * 2, (uint64_t)y_sb * 2};
+      ok = ok && make_map_sw(&maps.y[c], (const __nv_bfloat16 *)y + h.y_off, 4, ydims, ystr, ybox, sub_ch == 32);
+    }
+    if (!ok) {
+      set_error("%s: cuTensorMapEncodeTiled failed (output view)", who);
+      return DUSTY_ECUDA;
+    }
+  }
   switch (BN) {
-    case 256: return launch_conv<256, 4>(maps, prm, st);
+    case 256: return launch_conv<256, 3>(maps, prm, st);
     case 128: return launch_conv<128, 5>(maps, prm, st);
-    case 64: return launch_conv<64, 4>(maps, prm, st);
-    default: return launch_conv<32, 4>(maps, prm, st);
+    case 64: return launch_conv<64, 6>(maps, prm, st);
+    default: return launch_conv<32, 6>(maps, prm, st);
   }
 }
 

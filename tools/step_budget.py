@@ -19,8 +19,8 @@ GROUPS = OrderedDict([
     ("modprep (per-sample weights, styles)", r"modprep_"),
     ("G resampling / Fourier / raydrop / shift", r"up2_|blur4_fwd|blur4_adj|fourier|raydrop|circ|angle_down|ema_lerp|point_project"),
     ("ADA (FIR passes, warp, pad)", r"fir1d|fir2d|affine_warp|pad2d_(fwd|adj)_kernel"),
-    ("cuBLAS / CUTLASS linears", r"cutlass|gemm|sgemm|cublas|gemv"),
-    ("optimizer (fused Adam, EMA foreach)", r"Adam|multi_tensor|FusedOptimizer|lerp"),
+    ("linears (own GEMMs: epilogue; cuBLAS: mapping / styles)", r"cutlass|sgemm|cublas|gemv|gemm_tc_kernel|gemm_simt|nvjet"),
+    ("optimizer (fused Adam, EMA foreach)", r"Adam|multi_tensor|FusedOptimizer|lerp|multi_adam|multi_copy"),
     ("ATen glue: gradient accumulation adds", r"CUDAFunctor_add"),
     ("ATen glue: copies / casts", r"copy_kernel|direct_copy|bfloat16_copy|CatArray"),
     ("memset", r"Memset"),

@@ -66,8 +66,9 @@ SIGNATURES = {
     "dusty_stem_bwd": [_vp, _vp, _vp, _vp, _vp, _vp, _i, _i, _i, _i, _f, _f, _f, _f, _f, _i, _vp],
     "dusty_stem_dx": [_vp, _vp, _i, _i, _i, _f, _f, _f, _vp],
     "dusty_conv2d_tc": [_vp, _vp, _vp, _vp] + [_i] * 9 + [_vp, _vp, _i, _i, _i]
-                       + [C.c_longlong] * 4 + [_i, _f, _f, C.c_longlong, C.c_longlong, _vp, _i, _vp],
-    "dusty_conv2d_tc_classes": [_vp, _vp, _vp] + [_i] * 6 + [_vp] * 7 + [C.c_longlong] * 5 + [_i, _vp],
+                       + [C.c_longlong] * 4 + [_i, _f, _f, C.c_longlong, C.c_longlong, _vp, _i, _i, _vp],
+    "dusty_conv2d_tc_classes": [_vp, _vp, _vp] + [_i] * 6 + [_vp] * 7 + [C.c_longlong] * 5 + [_i, _i, _vp],
+    "dusty_split_bf16x3": [_vp, _vp, C.c_longlong, C.c_longlong, C.c_longlong, _vp, _vp, _i, _vp],
     "dusty_conv_role_prof": [_vp, _i],
     "dusty_gemm_tf32": [_vp, _vp, _vp, _i, _i, _i, C.c_longlong, C.c_longlong, C.c_longlong, _f, _i, _vp],
     "dusty_gemm_bf16": [_vp, _vp, _vp, _i, _i, _i, _i, _i, C.c_longlong, C.c_longlong, C.c_longlong, _f, _i, _vp],

@@ -122,8 +122,10 @@ struct ConvParams {
 // 64-channel sub-tile (per-thread 16-byte stores at a 64..512-byte stride kept the LSU busy for
 // longer than the MMAs of a thin tile).  BN <= 64: the two epilogue groups take alternate
 // tiles; BN >= 128: they split a tile's 64-column sub-tiles.
-template <int BN, int STAGES>
-__global__ void __launch_bounds__(kCThreads, 1)
+// OutT = float: fp32 output (the fp32 mode's split-bf16 contractions, see split_bf16x3 in
+// pointwise.cu) through 32-channel sub-tiles (one 128-byte swizzle row per pixel).
+template <int BN, int STAGES, typename OutT>
+__global__ void __launch_bounds__(kCThreads, BN == 32 ? 2 : 1)
 conv_fwd_tc_kernel(const __grid_constant__ ConvMaps maps, const __grid_constant__ ConvParams prm) {
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   uint8_t *smem = (uint8_t *)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
@@ -131,9 +133,10 @@ conv_fwd_tc_kernel(const __grid_constant__ ConvMaps maps, const __grid_constant_
   constexpr int kStageBytes = kCABytes + kBBytes;
   constexpr int NACC = 512 / BN >= 4 ? 4 : 2;
   constexpr bool kSplitTile = BN >= 128;                    // both groups work on every tile
-  constexpr int kSubCh = BN > 64 ? 64 : BN;                 // channels of a staging sub-tile
+  constexpr bool kF32 = sizeof(OutT) == 4;
+  constexpr int kSubCh = kF32 ? 32 : (BN > 64 ? 64 : BN);   // channels of a staging sub-tile
   constexpr int kSubs = BN / kSubCh;
-  constexpr int kSubBytes = kCM * kSubCh * 2;
+  constexpr int kSubBytes = kCM * kSubCh * (int)sizeof(OutT);
   uint8_t *a_base = smem;
   uint8_t *b_base = smem + STAGES * kCABytes;
   uint8_t *stage_base = smem + STAGES * kStageBytes;        // one staging sub-tile per group
@@ -248,9 +251,11 @@ conv_fwd_tc_kernel(const __grid_constant__ ConvMaps maps, const __grid_constant_
     const bool lrelu = prm.act == 3;
     const float alpha = prm.alpha, scale = prm.scale;
     const uint32_t stage_u32 = smem_u32(stage_base) + (uint32_t)(grp * kSubBytes);
-    const uint32_t srow_addr = stage_u32 + (uint32_t)row * (uint32_t)(kSubCh * 2);
-    constexpr int kChunks = kSubCh / 8;                     // 16-byte chunks per staging row
-    const uint32_t swz = kSubCh == 32 ? (((uint32_t)row >> 1) & 3u) : ((uint32_t)row & 7u);
+    constexpr int kRowBytes = kSubCh * (int)sizeof(OutT);   // 64 (64B swizzle) or 128
+    constexpr int kChunks = kRowBytes / 16;                 // 16-byte chunks per staging row
+    constexpr int kPerChunk = 16 / (int)sizeof(OutT);       // channels per chunk
+    const uint32_t srow_addr = stage_u32 + (uint32_t)row * (uint32_t)kRowBytes;
+    const uint32_t swz = kRowBytes == 64 ? (((uint32_t)row >> 1) & 3u) : ((uint32_t)row & 7u);
     int lt = 0;
     for (int tile = t_begin; tile < t_end; ++tile, ++lt) {
       if (!kSplitTile && (lt & 1) != grp) continue;
@@ -278,23 +283,33 @@ conv_fwd_tc_kernel(const __grid_constant__ ConvMaps maps, const __grid_constant_
 #pragma unroll
           for (int ch = 0; ch < kChunks; ++ch) {
             uint32_t w4[4];
-            float4 b0 = make_float4(0.f, 0.f, 0.f, 0.f), b1 = b0;
-            if (prm.bias && o0 + ch * 8 < prm.O) {
-              b0 = __ldg(reinterpret_cast<const float4 *>(prm.bias + o0 + ch * 8));
-              b1 = __ldg(reinterpret_cast<const float4 *>(prm.bias + o0 + ch * 8 + 4));
+            float bb[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+            if (prm.bias && o0 + ch * kPerChunk < prm.O) {
+              const float4 b0 = __ldg(reinterpret_cast<const float4 *>(prm.bias + o0 + ch * kPerChunk));
+              bb[0] = b0.x; bb[1] = b0.y; bb[2] = b0.z; bb[3] = b0.w;
+              if (!kF32) {
+                const float4 b1 = __ldg(reinterpret_cast<const float4 *>(prm.bias + o0 + ch * 8 + 4));
+                bb[4] = b1.x; bb[5] = b1.y; bb[6] = b1.z; bb[7] = b1.w;
+              }
             }
-            const float bb[8] = {b0.x, b0.y, b0.z, b0.w, b1.x, b1.y, b1.z, b1.w};
 #pragma unroll
             for (int j = 0; j < 4; ++j) {
-              const int e = ch * 8 + 2 * j;
-              float v0 = __uint_as_float(v[e >> 4][e & 15]) + bb[2 * j];
-              float v1 = __uint_as_float(v[e >> 4][(e & 15) + 1]) + bb[2 * j + 1];
-              if (lrelu) {
-                v0 = v0 > 0.f ? v0 : v0 * alpha;
-                v1 = v1 > 0.f ? v1 : v1 * alpha;
+              if (kF32) {
+                const int e = ch * 4 + j;
+                float v0 = __uint_as_float(v[e >> 4][e & 15]) + bb[j];
+                if (lrelu) v0 = v0 > 0.f ? v0 : v0 * alpha;
+                w4[j] = __float_as_uint(v0 * scale);
+              } else {
+                const int e = ch * 8 + 2 * j;
+                float v0 = __uint_as_float(v[e >> 4][e & 15]) + bb[2 * j];
+                float v1 = __uint_as_float(v[e >> 4][(e & 15) + 1]) + bb[2 * j + 1];
+                if (lrelu) {
+                  v0 = v0 > 0.f ? v0 : v0 * alpha;
+                  v1 = v1 > 0.f ? v1 : v1 * alpha;
+                }
+                const __nv_bfloat162 pr = __floats2bfloat162_rn(v0 * scale, v1 * scale);
+                w4[j] = *reinterpret_cast<const uint32_t *>(&pr);
               }
-              const __nv_bfloat162 pr = __floats2bfloat162_rn(v0 * scale, v1 * scale);
-              w4[j] = *reinterpret_cast<const uint32_t *>(&pr);
             }
             const uint32_t addr = srow_addr + (((uint32_t)ch ^ swz) << 4);
             asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(w4[0]), "r"(w4[1]), "r"(w4[2]),
@@ -1055,7 +1070,7 @@ bool make_map3w(CUtensorMap *m, const void *ptr, uint64_t d0, uint64_t d1, uint6
 }
 
 bool make_map_sw(CUtensorMap *m, const void *ptr, int rank, const uint64_t *dims,
-                 const uint64_t *strides_b, const uint32_t *box, bool sw64) {
+                 const uint64_t *strides_b, const uint32_t *box, bool sw64, bool f32 = false) {
   EncodeTiledFn enc = get_encode();
   if (!enc) return false;
   cuuint64_t d[4];
@@ -1063,8 +1078,8 @@ bool make_map_sw(CUtensorMap *m, const void *ptr, int rank, const uint64_t *dims
   cuuint32_t bx[4], es[4];
   for (int i = 0; i < rank; ++i) { d[i] = dims[i]; bx[i] = box[i]; es[i] = 1; }
   for (int i = 0; i + 1 < rank; ++i) s[i] = strides_b[i];
-  return enc(m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, rank, const_cast<void *>(ptr), d, s, bx, es,
-             CU_TENSOR_MAP_INTERLEAVE_NONE,
+  return enc(m, f32 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT32 : CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, rank,
+             const_cast<void *>(ptr), d, s, bx, es, CU_TENSOR_MAP_INTERLEAVE_NONE,
              sw64 ? CU_TENSOR_MAP_SWIZZLE_64B : CU_TENSOR_MAP_SWIZZLE_128B,
              CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
 }
@@ -1090,21 +1105,24 @@ int launch_halo(const HaloMaps &maps, HaloParams prm, int buf_stride, cudaStream
   return 0;
 }
 
-template <int BN, int STAGES>
+template <int BN, int STAGES, typename OutT>
 constexpr int conv_smem_bytes() {
-  return STAGES * (kCABytes + BN * kCK * 2) + 2 * kCM * (BN > 64 ? 64 : BN) * 2 + 256 + 1024;
+  return STAGES * (kCABytes + BN * kCK * 2) +
+         2 * kCM * (sizeof(OutT) == 4 ? 128 : (BN > 64 ? 128 : BN * 2)) + 256 + 1024;
 }
 
-template <int BN, int STAGES>
+template <int BN, int STAGES, typename OutT>
 int launch_conv(const ConvMaps &maps, ConvParams prm, cudaStream_t st) {
-  constexpr int smem = conv_smem_bytes<BN, STAGES>();
+  constexpr int smem = conv_smem_bytes<BN, STAGES, OutT>();
   static bool configured = false;
-  if (int rc = set_smem(conv_fwd_tc_kernel<BN, STAGES>, smem, &configured)) return rc;
-  const int resident = num_sms();         // one CTA per SM: it owns the accumulator ring in TMEM
+  if (int rc = set_smem(conv_fwd_tc_kernel<BN, STAGES, OutT>, smem, &configured)) return rc;
+  // BN = 32 tiles are epilogue-bound (1-4 k-blocks of 160 tensor cycles per 8 KB of output):
+  // two co-resident CTAs double the epilogue warps; wider tiles own the SM
+  const int resident = num_sms() * (BN == 32 ? 2 : 1);
   int ctas = prm.total_tiles < resident ? prm.total_tiles : resident;
   prm.tiles_per_cta = (prm.total_tiles + ctas - 1) / ctas;
   ctas = (prm.total_tiles + prm.tiles_per_cta - 1) / prm.tiles_per_cta;
-  conv_fwd_tc_kernel<BN, STAGES><<<ctas, kCThreads, smem, st>>>(maps, prm);
+  conv_fwd_tc_kernel<BN, STAGES, OutT><<<ctas, kCThreads, smem, st>>>(maps, prm);
   return 0;
 }
 
@@ -1196,7 +1214,7 @@ static int conv_launch(const char *who, const void *x, const void *wpk, const fl
                        int B, int H_in, int W_in, int C, int O, int mode, int ncls,
                        const HostClass *hc, int S, int stride_h, int stride_w, long long y_sb,
                        long long y_sh, long long y_sw, int act, float alpha, float scale,
-                       long long w_sn, long long w_sg, int w_taps, cudaStream_t st) {
+                       long long w_sn, long long w_sg, int w_taps, cudaStream_t st, bool out_f32 = false) {
   const int Kg = mode == 1 ? S * C : C;
   ConvMaps maps;
   ConvParams prm;
@@ -1274,8 +1292,8 @@ static int conv_launch(const char *who, const void *x, const void *wpk, const fl
   prm.y_sb = y_sb; prm.y_sh = y_sh; prm.y_sw = y_sw;
   prm.bias = bias; prm.y = (__nv_bfloat16 *)y; prm.act = act; prm.alpha = alpha; prm.scale = scale;
   // deep layers: CTA pairs (plain output, no bias / activation epilogue)
-  if (pair_enabled() && BN >= 128 && Kg % kCK == 0 && prm.KC * hc[0].G >= 4 && bias == nullptr && act == 1 &&
-      O % 8 == 0) {
+  if (pair_enabled() && !out_f32 && BN >= 128 && Kg % kCK == 0 && prm.KC * hc[0].G >= 4 && bias == nullptr &&
+      act == 1 && O % 8 == 0) {
     PairMaps pm;
     for (int g = 0; g < 4; ++g) pm.a[g] = maps.a[g];
     pm.w = maps.w;
@@ -1298,24 +1316,34 @@ static int conv_launch(const char *who, const void *x, const void *wpk, const fl
     return BN == 256 ? launch_pair<256, 5>(pm, prm, patches, st) : launch_pair<128, 7>(pm, prm, patches, st);
   }
   {
-    const int sub_ch = BN > 64 ? 64 : BN;
+    const int sub_ch = out_f32 ? 32 : (BN > 64 ? 64 : BN);
+    const uint64_t esz = out_f32 ? 4 : 2;
     const uint32_t ybox[4] = {(uint32_t)sub_ch, (uint32_t)prm.TW, (uint32_t)prm.TH, 1u};
     for (int c = 0; c < kMaxClasses; ++c) {
       const HostClass &h = hc[c < ncls ? c : 0];
       const uint64_t ydims[4] = {(uint64_t)O, (uint64_t)h.W_out, (uint64_t)h.H_out, (uint64_t)B};
-      const uint64_t ystr[3] = {(uint64_t)y_sw * 2, (uint64_t)y_sh * 2, (uint64_t)y_sb * 2};
-      ok = ok && make_map_sw(&maps.y[c], (const __nv_bfloat16 *)y + h.y_off, 4, ydims, ystr, ybox, sub_ch == 32);
+      const uint64_t ystr[3] = {(uint64_t)y_sw * esz, (uint64_t)y_sh * esz, (uint64_t)y_sb * esz};
+      ok = ok && make_map_sw(&maps.y[c], (const uint8_t *)y + h.y_off * (long long)esz, 4, ydims, ystr, ybox,
+                             sub_ch * esz == 64, out_f32);
     }
     if (!ok) {
       set_error("%s: cuTensorMapEncodeTiled failed (output view)", who);
       return DUSTY_ECUDA;
     }
   }
+  if (out_f32) {
+    switch (BN) {
+      case 256: return launch_conv<256, 3, float>(maps, prm, st);
+      case 128: return launch_conv<128, 5, float>(maps, prm, st);
+      case 64: return launch_conv<64, 6, float>(maps, prm, st);
+      default: return launch_conv<32, 4, float>(maps, prm, st);
+    }
+  }
   switch (BN) {
-    case 256: return launch_conv<256, 3>(maps, prm, st);
-    case 128: return launch_conv<128, 5>(maps, prm, st);
-    case 64: return launch_conv<64, 6>(maps, prm, st);
-    default: return launch_conv<32, 6>(maps, prm, st);
+    case 256: return launch_conv<256, 3, __nv_bfloat16>(maps, prm, st);
+    case 128: return launch_conv<128, 5, __nv_bfloat16>(maps, prm, st);
+    case 64: return launch_conv<64, 6, __nv_bfloat16>(maps, prm, st);
+    default: return launch_conv<32, 4, __nv_bfloat16>(maps, prm, st);
   }
 }
 
@@ -1324,8 +1352,10 @@ extern "C" int dusty_conv2d_tc(const void *x, const void *wpk, const float *bias
                                int G, const int *tap_dh, const int *tap_dw, int S, int stride_h,
                                int stride_w, long long y_off, long long y_sb, long long y_sh,
                                long long y_sw, int act, float alpha, float scale, long long w_sn,
-                               long long w_sg, const int *wtap, int w_taps, void *stream) {
+                               long long w_sg, const int *wtap, int w_taps, int out_dtype,
+                               void *stream) {
   DUSTY_CHECK_ARG(x && wpk && y, "null pointer");
+  DUSTY_CHECK_ARG(out_dtype == DUSTY_BF16 || out_dtype == DUSTY_F32, "output dtype: bf16 or fp32");
   DUSTY_CHECK_ARG(get_encode() != nullptr, "cuTensorMapEncodeTiled unavailable");
   DUSTY_CHECK_ARG(B > 0 && H_in > 0 && W_in > 0 && H_out > 0 && W_out > 0, "empty tensor");
   DUSTY_CHECK_ARG(C % 8 == 0 && O % 8 == 0, "channel counts must be multiples of 8");
@@ -1341,7 +1371,7 @@ extern "C" int dusty_conv2d_tc(const void *x, const void *wpk, const float *bias
   const HostClass hc = {G, tap_dh, tap_dw, wtap, H_out, W_out, y_off};
   if (int rc = conv_launch("dusty_conv2d_tc", x, wpk, bias, y, B, H_in, W_in, C, O, mode, 1, &hc, S,
                            stride_h, stride_w, y_sb, y_sh, y_sw, act, alpha, scale, w_sn, w_sg,
-                           wtap ? w_taps : 0, (cudaStream_t)stream))
+                           wtap ? w_taps : 0, (cudaStream_t)stream, out_dtype == DUSTY_F32))
     return rc;
   DUSTY_LAUNCH_CHECK();
   return DUSTY_OK;
@@ -1353,7 +1383,8 @@ extern "C" int dusty_conv2d_tc_classes(const void *x, const void *wpk, void *y, 
                                        const int *cls_H_out, const int *cls_W_out,
                                        const long long *cls_y_off, long long y_sb, long long y_sh,
                                        long long y_sw, long long w_sn, long long w_sg, int w_taps,
-                                       void *stream) {
+                                       int out_dtype, void *stream) {
+  DUSTY_CHECK_ARG(out_dtype == DUSTY_BF16 || out_dtype == DUSTY_F32, "output dtype: bf16 or fp32");
   DUSTY_CHECK_ARG(x && wpk && y && cls_G && tap_dh && tap_dw && wtap && cls_H_out && cls_W_out && cls_y_off,
                   "null pointer");
   DUSTY_CHECK_ARG(get_encode() != nullptr, "cuTensorMapEncodeTiled unavailable");
@@ -1375,7 +1406,7 @@ extern "C" int dusty_conv2d_tc_classes(const void *x, const void *wpk, void *y, 
   }
   if (int rc = conv_launch("dusty_conv2d_tc_classes", x, wpk, nullptr, y, B, H_in, W_in, C, O, 0, ncls,
                            hc, 1, 1, 1, y_sb, y_sh, y_sw, 1, 0.f, 1.f, w_sn, w_sg, w_taps,
-                           (cudaStream_t)stream))
+                           (cudaStream_t)stream, out_dtype == DUSTY_F32))
     return rc;
   DUSTY_LAUNCH_CHECK();
   return DUSTY_OK;

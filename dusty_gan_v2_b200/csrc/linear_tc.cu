@@ -368,7 +368,10 @@ extern "C" int dusty_gemm_simt(const float *a, const float *b, float *c, int M, 
                                long long c_sm, long long c_sn, float alpha, void *stream) {
   DUSTY_CHECK_ARG(a && b && c, "null pointer");
   DUSTY_CHECK_ARG(M > 0 && N > 0 && K > 0, "empty problem");
-  DUSTY_CHECK_ARG((long long)M * N <= (1LL << 24), "dusty_gemm_simt is for small outputs (<= 16 M elements)");
+  // one warp per output for long dot products, one thread per output for K < 64 (e.g. the
+  // weight gradient of the 65536 -> 512 linear at batch 8: 33.5 M outputs of 8 terms)
+  DUSTY_CHECK_ARG((long long)M * N <= (K >= 64 ? (1LL << 24) : (1LL << 31)),
+                  "dusty_gemm_simt is for small outputs (<= 16 M elements of K >= 64 terms)");
   cudaStream_t st = (cudaStream_t)stream;
   const long long outs = (long long)M * N;
   if (K >= 64) {

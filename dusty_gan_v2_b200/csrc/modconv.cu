@@ -13,10 +13,10 @@ int modconv_bwd_dw_simt(const void *dy, const void *x1, const void *x2, float *d
 // tensor-core path (modconv_tc.cu); returns DUSTY_EUNSUPPORTED when the shape does not fit
 int modconv_fwd_tc(const void *wb, const void *x1, const void *x2, const float *bias, void *y,
                    int B, int O, int C1, int C2, int B2, int64_t P, int act, float alpha,
-                   float scale, bool batch_fused, cudaStream_t st);
+                   float scale, bool batch_fused, cudaStream_t st, bool out_f32);
 bool modconv_fwd_tc_supported(int B, int O, int C1, int C2, int B2, int64_t P);
 int modconv_dx_tc(const void *wb, const void *dy, void *dx1, int B, int O, int C1, int K, int64_t P,
-                  cudaStream_t st);
+                  cudaStream_t st, bool out_f32);
 bool modconv_dx_tc_supported(int B, int O, int C1, int K, int64_t P);
 int modconv_dw_tc(const void *dy, const void *x1, const void *x2, float *dwb, int B, int O, int C1,
                   int C2, int B2, int64_t P, cudaStream_t st);
@@ -38,8 +38,9 @@ extern "C" int dusty_modconv_fwd(const void *wb, const void *x1, const void *x2,
   DUSTY_CHECK_ARG(C2 == 0 || B2 == B || B2 == 1, "x2 batch must be B or 1");
   DUSTY_CHECK_ARG(act == 1 || act == 3, "act must be 1 or 3");
   DUSTY_CHECK_ARG(dtype_ok(dtype) && dtype_ok(wdtype), "bad dtype");
-  DUSTY_CHECK_ARG(impl >= 0 && impl <= 3,
-                  "impl must be 0 (auto), 1 (simt), 2 (tcgen05) or 3 (tcgen05, per-sample tiles only)");
+  DUSTY_CHECK_ARG(impl >= 0 && impl <= 4,
+                  "impl must be 0 (auto), 1 (simt), 2 (tcgen05), 3 (tcgen05, per-sample tiles only) or "
+                  "4 (tcgen05, fp32 output)");
   cudaStream_t st = (cudaStream_t)stream;
   if (C1 == 0) x1 = x2;  // keep pointers valid for address arithmetic
   if (C2 == 0) { x2 = x1; B2 = B; }
@@ -51,7 +52,8 @@ extern "C" int dusty_modconv_fwd(const void *wb, const void *x1, const void *x2,
   }
   int rc;
   if (impl >= 2 || (impl == 0 && tc_ok))
-    rc = modconv_fwd_tc(wb, x1, x2, bias, y, B, O, C1, C2, B2, P, act, alpha, scale, impl != 3, st);
+    rc = modconv_fwd_tc(wb, x1, x2, bias, y, B, O, C1, C2, B2, P, act, alpha, scale, impl < 3, st,
+                        impl == 4);
   else
     rc = modconv_fwd_simt(wb, x1, x2, bias, y, B, O, C1, C2, B2, P, act, alpha, scale, dtype,
                           wdtype, st);
@@ -66,7 +68,7 @@ extern "C" int dusty_modconv_bwd_dx(const void *wb, const void *dy, void *dx1, i
   DUSTY_CHECK_ARG(wb && dy && dx1, "null pointer");
   DUSTY_CHECK_ARG(B >= 1 && B <= 65535 && O >= 1 && C1 >= 1 && K >= C1 && P >= 1, "bad shape");
   DUSTY_CHECK_ARG(dtype_ok(dtype) && dtype_ok(wdtype), "bad dtype");
-  DUSTY_CHECK_ARG(impl >= 0 && impl <= 3, "impl must be 0 (auto), 1 (simt), 2 or 3 (tcgen05)");
+  DUSTY_CHECK_ARG(impl >= 0 && impl <= 4, "impl must be 0 (auto), 1 (simt), 2 / 3 (tcgen05) or 4 (tcgen05, fp32 output)");
   const bool tc_ok = dtype == DUSTY_BF16 && wdtype == DUSTY_BF16 && modconv_dx_tc_supported(B, O, C1, K, P);
   if (impl >= 2 && !tc_ok) {
     set_error("dusty_modconv_bwd_dx: tcgen05 path does not support this shape/dtype");
@@ -74,7 +76,7 @@ extern "C" int dusty_modconv_bwd_dx(const void *wb, const void *dy, void *dx1, i
   }
   int rc;
   if (impl >= 2 || (impl == 0 && tc_ok))
-    rc = modconv_dx_tc(wb, dy, dx1, B, O, C1, K, P, (cudaStream_t)stream);
+    rc = modconv_dx_tc(wb, dy, dx1, B, O, C1, K, P, (cudaStream_t)stream, impl == 4);
   else
     rc = modconv_bwd_dx_simt(wb, dy, dx1, B, O, C1, K, P, dtype, wdtype, (cudaStream_t)stream);
   if (rc) return rc;

@@ -44,6 +44,7 @@ struct TcParams {
   __nv_bfloat16 *y;
   int act;
   float alpha, scale;
+  int out_f32;            // 1: fp32 output (split-bf16 operands of the fp32 mode, split3.cu)
 };
 
 
@@ -93,7 +94,7 @@ template <typename BiasAt>
 __device__ __forceinline__ void epi_drain_tile(const EpiThread &e, uint32_t tmem_acc, int BN, int &gc,
                                                uint64_t *acc_empty_bar, BiasAt bias_at, int act,
                                                float alpha, float scale, const CUtensorMap *map_y,
-                                               int p0, int row0, int b) {
+                                               int p0, int row0, int b, bool out_f32 = false) {
   const int nch = BN >> 5;
   int my_last = nch - 1;                               // last chunk of this tile this group reads
   if (((gc + my_last) & 1) != e.g) --my_last;
@@ -116,6 +117,30 @@ __device__ __forceinline__ void epi_drain_tile(const EpiThread &e, uint32_t tmem
       if (e.lane == 0) mbar_arrive(acc_empty_bar);
     }
     const float *bp = e.bias_s + bias_at(c);
+    if (out_f32) {
+      // fp32 output: the same 8 KiB staging tile holds [16 channels][128 pixels] fp32, so a
+      // 32-column chunk leaves as two TMA stores
+#pragma unroll
+      for (int hf = 0; hf < 2; ++hf) {
+        if (e.issuer) tma_store_wait_read<0>();
+        named_bar_sync(1 + e.g, 128);
+        const uint32_t dst = e.stage_u32 + (uint32_t)e.row * 4;
+#pragma unroll
+        for (int j = 0; j < 16; ++j) {
+          float v = __uint_as_float(hf == 0 ? r0[j] : r1[j]) + bp[hf * 16 + j];
+          if (act == 3) v = v > 0.f ? v : v * alpha;
+          asm volatile("st.shared.b32 [%0], %1;" ::"r"(dst + (uint32_t)j * (kBM * 4)), "r"(__float_as_uint(v * scale))
+                       : "memory");
+        }
+        fence_proxy_async();
+        named_bar_sync(1 + e.g, 128);
+        if (e.issuer) {
+          tma_store_3d(map_y, e.stage_u32, p0, row0 + c + hf * 16, b);
+          tma_store_commit();
+        }
+      }
+      continue;
+    }
     uint32_t h[16];
 #pragma unroll
     for (int j = 0; j < 16; ++j) {
@@ -306,7 +331,7 @@ modconv_fwd_tc_kernel(const __grid_constant__ CUtensorMap map_x1,
       tc_fence_after();
       const uint32_t tmem_acc = tmem_base + (uint32_t)(a * BN) + ((uint32_t)(e.q * 32) << 16);
       epi_drain_tile(e, tmem_acc, BN, gc, &acc_empty[a], [&](int c) { return n0 + c; }, prm.act,
-                     prm.alpha, prm.scale, &map_y, p0, n0, b);
+                     prm.alpha, prm.scale, &map_y, p0, n0, b, prm.out_f32 != 0);
     }
     if (e.issuer) tma_store_wait_read<0>();
   }
@@ -666,14 +691,16 @@ static bool make_map3(CUtensorMap *m, const void *ptr, uint64_t d0, uint64_t d1,
 
 // same tensor, dense (un-swizzled) box: destination of the epilogue's TMA stores
 static bool make_map3_plain(CUtensorMap *m, const void *ptr, uint64_t d0, uint64_t d1, uint64_t d2,
-                            uint32_t box0, uint32_t box1) {
+                            uint32_t box0, uint32_t box1, bool f32 = false) {
   EncodeTiledFn enc = get_encode();
   if (!enc) return false;
+  const uint64_t esz = f32 ? 4 : 2;
   cuuint64_t dims[3] = {d0, d1, d2};
-  cuuint64_t strides[2] = {d0 * 2, d0 * d1 * 2};
+  cuuint64_t strides[2] = {d0 * esz, d0 * d1 * esz};
   cuuint32_t box[3] = {box0, box1, 1};
   cuuint32_t estr[3] = {1, 1, 1};
-  CUresult r = enc(m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 3, const_cast<void *>(ptr), dims, strides,
+  CUresult r = enc(m, f32 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT32 : CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 3,
+                   const_cast<void *>(ptr), dims, strides,
                    box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE,
                    CU_TENSOR_MAP_L2_PROMOTION_NONE, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   return r == CUDA_SUCCESS;
@@ -789,9 +816,9 @@ static int modconv_fwd_shared_tc(const void *wb, const void *x1, const void *pe,
 
 int modconv_fwd_tc(const void *wb, const void *x1, const void *x2, const float *bias, void *y,
                    int B, int O, int C1, int C2, int B2, int64_t P, int act, float alpha,
-                   float scale, bool batch_fused, cudaStream_t st) {
+                   float scale, bool batch_fused, cudaStream_t st, bool out_f32) {
   const int K = C1 + C2;
-  if (batch_fused) {
+  if (batch_fused && !out_f32) {
     const int ns = modconv_shared_group(B, O, C1, C2, B2, P);
     if (ns) return modconv_fwd_shared_tc(wb, x1, x2, bias, y, B, O, C1, C2, ns, P, act, alpha, scale, st);
   }
@@ -803,7 +830,7 @@ int modconv_fwd_tc(const void *wb, const void *x1, const void *x2, const float *
                              64, kBK);
   const bool ok3 = make_map3(&mw, wb, (uint64_t)K, (uint64_t)O, (uint64_t)B, kBK, (uint32_t)BN);
   CUtensorMap my;
-  const bool ok4 = make_map3_plain(&my, y, (uint64_t)P, (uint64_t)O, (uint64_t)B, kBM, 32);
+  const bool ok4 = make_map3_plain(&my, y, (uint64_t)P, (uint64_t)O, (uint64_t)B, kBM, out_f32 ? 16 : 32, out_f32);
   if (!(ok1 && ok2 && ok3 && ok4)) {
     set_error("modconv_fwd_tc: cuTensorMapEncodeTiled failed");
     return DUSTY_ECUDA;
@@ -811,6 +838,7 @@ int modconv_fwd_tc(const void *wb, const void *x1, const void *x2, const float *
   TcParams prm;
   prm.O = O; prm.C1 = C1; prm.K = K; prm.B2 = B2; prm.P = P; prm.bias = bias;
   prm.y = (__nv_bfloat16 *)y; prm.act = act; prm.alpha = alpha; prm.scale = scale;
+  prm.out_f32 = out_f32 ? 1 : 0;
   switch (BN) {
     case 256: return launch_tc<256, 4, false>(mx1, mx2, mw, my, prm, B, st);
     case 128: return launch_tc<128, 5, false>(mx1, mx2, mw, my, prm, B, st);
@@ -821,14 +849,14 @@ int modconv_fwd_tc(const void *wb, const void *x1, const void *x2, const float *
 
 // dX1[b, c, p] = sum_o wb[b, o, c] * dY[b, o, p], c < C1
 int modconv_dx_tc(const void *wb, const void *dy, void *dx1, int B, int O, int C1, int K, int64_t P,
-                  cudaStream_t st) {
+                  cudaStream_t st, bool out_f32) {
   const int BN = C1 > 128 ? 256 : (C1 > 64 ? 128 : 64);
   CUtensorMap mg, mw;
   const bool ok1 = make_map3(&mg, dy, (uint64_t)P, (uint64_t)O, (uint64_t)B, 64, kBK);
   // wb viewed with the in-channel axis innermost: box = [64 out-channels x 64 in-channels]
   const bool ok2 = make_map3(&mw, wb, (uint64_t)K, (uint64_t)O, (uint64_t)B, 64, kBK);
   CUtensorMap my;
-  const bool ok3 = make_map3_plain(&my, dx1, (uint64_t)P, (uint64_t)C1, (uint64_t)B, kBM, 32);
+  const bool ok3 = make_map3_plain(&my, dx1, (uint64_t)P, (uint64_t)C1, (uint64_t)B, kBM, out_f32 ? 16 : 32, out_f32);
   if (!(ok1 && ok2 && ok3)) {
     set_error("modconv_dx_tc: cuTensorMapEncodeTiled failed");
     return DUSTY_ECUDA;
@@ -838,6 +866,7 @@ int modconv_dx_tc(const void *wb, const void *dy, void *dx1, int B, int O, int C
   prm.C1 = O;            // the whole contraction axis (out-channels) comes from the dY map
   prm.K = O; prm.B2 = B; prm.P = P; prm.bias = nullptr;
   prm.y = (__nv_bfloat16 *)dx1; prm.act = 1; prm.alpha = 0.f; prm.scale = 1.f;
+  prm.out_f32 = out_f32 ? 1 : 0;
   switch (BN) {
     case 256: return launch_tc<256, 4, true>(mg, mg, mw, my, prm, B, st);
     case 128: return launch_tc<128, 5, true>(mg, mg, mw, my, prm, B, st);

@@ -21,7 +21,7 @@ from torch.autograd.function import once_differentiable
 from . import _cabi as K
 
 # --------------------------------------------------------------------------- precision
-_PRECISION = {"act": torch.float32, "modconv_impl": 0}
+_PRECISION = {"act": torch.float32, "modconv_impl": 0, "fp32_tc": True}
 
 
 def set_precision(name: str):
@@ -34,6 +34,16 @@ def set_precision(name: str):
         _PRECISION["act"] = torch.bfloat16
     else:
         raise ValueError(f"unknown precision {name!r}")
+
+
+def set_fp32_tensor_cores(enabled: bool):
+    """fp32 mode: run the dense contractions on tcgen05 with split-bf16 operands (default), or
+    on the CUDA-core kernels (exact fp32 FMA order of the parity oracle)."""
+    _PRECISION["fp32_tc"] = bool(enabled)
+
+
+def fp32_on_tensor_cores() -> bool:
+    return _PRECISION["fp32_tc"]
 
 
 def act_dtype() -> torch.dtype:
@@ -718,6 +728,54 @@ def angle_down2(angle: torch.Tensor) -> torch.Tensor:
 
 
 # --------------------------------------------------------------------------- modulated 1x1 conv
+def _modconv_x3_ok(wb, src, O, c1, c2, P, op) -> bool:
+    """fp32 mode (g1): does the split-bf16 form of this contraction lie in the tcgen05 kernels'
+    domain (modconv_tc.cu: modconv_{fwd,dx,dw}_tc_supported on the tripled axis)?"""
+    if not (_PRECISION["fp32_tc"] and _PRECISION["modconv_impl"] in (0, 2, 3)):
+        return False
+    if src.dtype != torch.float32 or wb.dtype != torch.float32 or not src.is_cuda:
+        return False
+    if c1 % 8 or c2 % 8 or P % 128:
+        return False
+    if op == "dx":
+        return O % 8 == 0 and c1 >= 32
+    if O < 32 or O % 16:
+        return False
+    if op == "fwd":
+        return c2 == 0 or (3 * c1) % 64 == 0
+    return c2 == 0 or c1 % 64 == 0           # dw: 64-channel boxes must not straddle the sources
+
+
+def _split_planes(x: torch.Tensor, pattern: int) -> torch.Tensor:
+    """fp32 [B, C, H, W] (contiguous) -> bf16 [B, 3C, H, W]: parts stacked on the channel axis."""
+    x = _contig(x)
+    B, C = x.shape[:2]
+    P = x[0, 0].numel()
+    out = torch.empty((B, 3 * C) + tuple(x.shape[2:]), dtype=torch.bfloat16, device=x.device)
+    return split_bf16x3(x, out, B, C, P, (C * P, P, 1), (3 * C * P, P, 1), pattern)
+
+
+def _split_pixels(x: torch.Tensor, pattern: int) -> torch.Tensor:
+    """fp32 [B, C, P...] -> bf16 [B, C, 3P]: parts side by side on the pixel axis."""
+    x = _contig(x)
+    B, C = x.shape[:2]
+    P = x[0, 0].numel()
+    out = torch.empty((B, C, 3 * P), dtype=torch.bfloat16, device=x.device)
+    return split_bf16x3(x, out, B * C, 1, P, (P, 0, 1), (3 * P, P, 1), pattern)
+
+
+def _split_wb_k(wb: torch.Tensor, c1: int, c2: int) -> torch.Tensor:
+    """fp32 wb[B, O, c1 + c2] -> bf16 [B, O, 3*c1 + 3*c2], each source's columns tripled in place
+    ([hi|lo|hi] of the feature block, then of the Fourier block)."""
+    B, O, Kt = wb.shape
+    out = torch.empty(B, O, 3 * Kt, dtype=torch.bfloat16, device=wb.device)
+    if c1:
+        split_bf16x3(wb, out, B * O, c1, 1, (Kt, 1, 0), (3 * Kt, 1, 0), 1)
+    if c2:
+        split_bf16x3(wb[:, :, c1:], out[:, :, 3 * c1:], B * O, c2, 1, (Kt, 1, 0), (3 * Kt, 1, 0), 1)
+    return out
+
+
 class _ModConvBmm(Function):
     """y[b] = act(wb[b] @ cat(x1[b], x2[b or 0]) + bias) ; x2 (Fourier features) has no grad."""
 
@@ -733,9 +791,17 @@ class _ModConvBmm(Function):
         b2 = 1 if x2 is None else x2.shape[0]
         y = torch.empty(B, O, H, W, device=src.device, dtype=src.dtype)
         biasf = None if bias is None else _contig(bias.detach().float().reshape(-1))
-        K.call("dusty_modconv_fwd", K.ptr(wb), K.ptr(x1), K.ptr(x2), K.ptr(biasf), K.ptr(y), B, O,
-               c1, c2, b2, P, act, alpha, scale, K.dtype_code(src), K.dtype_code(wb),
-               _PRECISION["modconv_impl"], K.stream_of(src))
+        if _modconv_x3_ok(wb, src, O, c1, c2, P, "fwd"):
+            # fp32 mode on tcgen05: K axis tripled, [x_hi|x_hi|x_lo] . [w_hi|w_lo|w_hi]
+            x1s = None if x1 is None else _split_planes(x1, 0)
+            x2s = None if x2 is None else _split_planes(x2, 0)
+            wbs = _split_wb_k(wb, c1, c2)
+            K.call("dusty_modconv_fwd", K.ptr(wbs), K.ptr(x1s), K.ptr(x2s), K.ptr(biasf), K.ptr(y), B, O,
+                   3 * c1, 3 * c2, b2, P, act, alpha, scale, K.BF16, K.BF16, 4, K.stream_of(src))
+        else:
+            K.call("dusty_modconv_fwd", K.ptr(wb), K.ptr(x1), K.ptr(x2), K.ptr(biasf), K.ptr(y), B, O,
+                   c1, c2, b2, P, act, alpha, scale, K.dtype_code(src), K.dtype_code(wb),
+                   _PRECISION["modconv_impl"], K.stream_of(src))
         ctx.save_for_backward(wb, x1, x2, y if act == 3 else None)
         ctx.cfg = (act, alpha, scale, bias is not None, None if bias is None else bias.shape,
                    None if bias is None else bias.dtype)
@@ -769,13 +835,28 @@ class _ModConvBmm(Function):
         b2 = 1 if x2 is None else x2.shape[0]
         if x1 is not None and ctx.needs_input_grad[1]:
             gx1 = torch.empty_like(x1)
-            K.call("dusty_modconv_bwd_dx", K.ptr(wb), K.ptr(gpre), K.ptr(gx1), B, O, c1, Kt, P, dt,
-                   K.dtype_code(wb), _PRECISION["modconv_impl"], st)
+            if _modconv_x3_ok(wb, gpre, O, c1, c2, P, "dx"):
+                gs = _split_planes(gpre, 0)                       # [B, 3O, P]
+                wbo = torch.empty(B, 3 * O, Kt, device=wb.device, dtype=torch.bfloat16)
+                split_bf16x3(wb, wbo, B, O, Kt, (O * Kt, Kt, 1), (3 * O * Kt, Kt, 1), 1)
+                K.call("dusty_modconv_bwd_dx", K.ptr(wbo), K.ptr(gs), K.ptr(gx1), B, 3 * O, c1, Kt, P,
+                       K.BF16, K.BF16, 4, st)
+            else:
+                K.call("dusty_modconv_bwd_dx", K.ptr(wb), K.ptr(gpre), K.ptr(gx1), B, O, c1, Kt, P, dt,
+                       K.dtype_code(wb), _PRECISION["modconv_impl"], st)
         gwb = None
         if ctx.needs_input_grad[0]:
             gw32 = torch.empty(B, O, Kt, device=gy.device, dtype=torch.float32)
-            K.call("dusty_modconv_bwd_dw", K.ptr(gpre), K.ptr(x1), K.ptr(x2), K.ptr(gw32), B, O, c1,
-                   c2, b2, P, dt, _PRECISION["modconv_impl"], st)
+            if _modconv_x3_ok(wb, gpre, O, c1, c2, P, "dw"):
+                # contraction over pixels: the three terms side by side on the pixel axis
+                gp = _split_pixels(gpre, 0)
+                x1p = None if x1 is None else _split_pixels(x1, 1)
+                x2p = None if x2 is None else _split_pixels(x2, 1)
+                K.call("dusty_modconv_bwd_dw", K.ptr(gp), K.ptr(x1p), K.ptr(x2p), K.ptr(gw32), B, O, c1,
+                       c2, b2, 3 * P, K.BF16, 2, st)
+            else:
+                K.call("dusty_modconv_bwd_dw", K.ptr(gpre), K.ptr(x1), K.ptr(x2), K.ptr(gw32), B, O, c1,
+                       c2, b2, P, dt, _PRECISION["modconv_impl"], st)
             gwb = gw32.to(wb.dtype)
         if has_bias and ctx.needs_input_grad[3]:
             db = db.reshape(bshape).to(bdtype)
@@ -1280,19 +1361,22 @@ def filter_tco(w: torch.Tensor) -> torch.Tensor:
     return w.permute(2, 3, 1, 0).reshape(R * S, C, O).contiguous()
 
 
-def conv2d_fprop_tc(x, w, stride, bias=None, act: int = 1, alpha: float = 0.2, scale: float = 1.0):
+def conv2d_fprop_tc(x, w, stride, bias=None, act: int = 1, alpha: float = 0.2, scale: float = 1.0,
+                    out_dtype=None):
     """y = conv2d(x, w, stride) (valid, no padding) [+ bias, leaky-ReLU, scale]; NHWC in/out.
-    The filter is read in place from its OHWI memory through strided tensor maps."""
+    The filter is read in place from its OHWI memory through strided tensor maps.
+    out_dtype=torch.float32: fp32 output (split-bf16 operands of the fp32 mode)."""
     K.require_cuda(x, w)
     x = _nhwc(x)
     B, C, H, W = x.shape
     O, _, R, S = w.shape
     sh, sw = stride
     Ho, Wo = (H - R) // sh + 1, (W - S) // sw + 1
-    y = torch.empty((B, O, Ho, Wo), dtype=x.dtype, device=x.device,
+    out_dtype = out_dtype or x.dtype
+    y = torch.empty((B, O, Ho, Wo), dtype=out_dtype, device=x.device,
                     memory_format=torch.channels_last)
     wo = _ohwi(w)
-    if sh == 1 and sw == 1 and conv_halo_ok(w, "fprop"):
+    if sh == 1 and sw == 1 and out_dtype == x.dtype and conv_halo_ok(w, "fprop"):
         # element (t, n, c) at  n * (R*S*C) + t * C + c
         K.call("dusty_conv2d_halo_tc", K.ptr(x), K.ptr(wo), K.ptr(bias), K.ptr(y), B, H, W, C,
                Ho, Wo, O, R, S, 0, 0, 0, Ho * Wo * O, Wo * O, O, act, alpha, scale,
@@ -1301,26 +1385,28 @@ def conv2d_fprop_tc(x, w, stride, bias=None, act: int = 1, alpha: float = 0.2, s
     # window mode: group r, element (n, s*C + c) at  n * (R*S*C) + r * (S*C) + s*C + c
     K.call("dusty_conv2d_tc", K.ptr(x), K.ptr(wo), K.ptr(bias), K.ptr(y),
            B, H, W, C, Ho, Wo, O, 1, R, _ints(list(range(R))), _ints([0] * R), S, sh, sw,
-           0, Ho * Wo * O, Wo * O, O, act, alpha, scale, R * S * C, S * C, None, 0, K.stream_of(x))
+           0, Ho * Wo * O, Wo * O, O, act, alpha, scale, R * S * C, S * C, None, 0, K.dtype_code(y),
+           K.stream_of(x))
     return y
 
 
-def conv2d_dgrad_tc(gy, w, stride, in_hw, w_tco=None):
+def conv2d_dgrad_tc(gy, w, stride, in_hw, w_tco=None, out_dtype=None, w_shape=None):
     """Gradient of the valid convolution w.r.t. its input ([B, C, H, W] NHWC).  Every variant
     (halo-resident, unit stride, the parity classes of a strided convolution) reads the same
     [R*S][C][O] filter tensor `w_tco` through tap-index maps: no flipping / stacking copies."""
-    K.require_cuda(gy, w)
+    K.require_cuda(gy, w if w is not None else w_tco)
     gy = _nhwc(gy)
     B, O, Ho, Wo = gy.shape
-    _, C, R, S = w.shape
+    _, C, R, S = w_shape if w is None else w.shape        # w=None: only the [R*S][C][O] form exists
     H, W = in_hw
     sh, sw = stride
     if w_tco is None or w_tco.dtype != gy.dtype or tuple(w_tco.shape) != (R * S, C, O):
         w_tco = filter_tco(w)
-    gx = torch.empty((B, C, H, W), dtype=gy.dtype, device=gy.device,
+    out_dtype = out_dtype or gy.dtype
+    gx = torch.empty((B, C, H, W), dtype=out_dtype, device=gy.device,
                      memory_format=torch.channels_last)
     st = K.stream_of(gy)
-    if sh == 1 and sw == 1 and conv_halo_ok(w, "dgrad"):
+    if sh == 1 and sw == 1 and out_dtype == gy.dtype and w is not None and conv_halo_ok(w, "dgrad"):
         K.call("dusty_conv2d_halo_tc", K.ptr(gy), K.ptr(w_tco), None, K.ptr(gx), B, Ho, Wo, O, H, W,
                C, R, S, -(R - 1), -(S - 1), 0, H * W * C, W * C, C, 1, 0.0, 1.0, 0, 0, 1, st)
         return gx
@@ -1358,7 +1444,8 @@ def conv2d_dgrad_tc(gy, w, stride, in_hw, w_tco=None):
     if cls_G:
         K.call("dusty_conv2d_tc_classes", K.ptr(gy), K.ptr(w_tco), K.ptr(gx), B, Ho, Wo, O, C,
                len(cls_G), _ints(cls_G), _ints(dh), _ints(dw), _ints(wtap), _ints(cls_H), _ints(cls_W),
-               (K.C.c_longlong * len(cls_off))(*cls_off), H * W * C, sh * W * C, sw * C, 0, 0, R * S, st)
+               (K.C.c_longlong * len(cls_off))(*cls_off), H * W * C, sh * W * C, sw * C, 0, 0, R * S,
+               K.dtype_code(gx), st)
     return gx
 
 
@@ -1382,6 +1469,89 @@ def conv2d_wgrad_tc(gy, x, stride, w_shape, out_dtype):
                K.stream_of(x))
         return gw
     return dwp.permute(3, 2, 0, 1).to(out_dtype).contiguous()
+
+
+# ---- g1: fp32 convolutions on the tensor cores (split-bf16 operands, csrc/split3.cu) -----------
+def _ll3(vals):
+    return (K.C.c_longlong * 3)(*[int(v) for v in vals])
+
+
+def split_bf16x3(src: torch.Tensor, dst: torch.Tensor, outer, k, inner, src_strides, dst_strides,
+                 pattern: int):
+    """dst[o, p*K + k, i] = part p of src[o, k, i] (hi,hi,lo for pattern 0; hi,lo,hi for 1)."""
+    K.require_cuda(src, dst)
+    if src.dtype != torch.float32 or dst.dtype != torch.bfloat16:
+        raise RuntimeError("split_bf16x3: fp32 source, bf16 destination")
+    K.call("dusty_split_bf16x3", K.ptr(src), K.ptr(dst), outer, k, inner, _ll3(src_strides),
+           _ll3(dst_strides), pattern, K.stream_of(src))
+    return dst
+
+
+def _collapsible_hw(t: torch.Tensor) -> bool:
+    return t.stride(2) == t.shape[3] * t.stride(3)
+
+
+def _split_act(x: torch.Tensor, pattern: int) -> torch.Tensor:
+    """fp32 [B, C, H, W] (NCHW or NHWC memory) -> bf16 NHWC [B, 3C, H, W]."""
+    if not _collapsible_hw(x):
+        x = x.contiguous(memory_format=torch.channels_last)
+    B, C, H, W = x.shape
+    out = torch.empty((B, 3 * C, H, W), dtype=torch.bfloat16, device=x.device,
+                      memory_format=torch.channels_last)
+    return split_bf16x3(x, out, B, C, H * W, (x.stride(0), x.stride(1), x.stride(3)),
+                        (H * W * 3 * C, 1, 3 * C), pattern)
+
+
+def _split_batch(x: torch.Tensor, pattern: int) -> torch.Tensor:
+    """fp32 [B, C, H, W] -> bf16 NHWC [3B, C, H, W]: the three terms stacked on the batch axis
+    (the weight gradient contracts over batch x pixels)."""
+    x = x.contiguous(memory_format=torch.channels_last)
+    B, C, H, W = x.shape
+    out = torch.empty((3 * B, C, H, W), dtype=torch.bfloat16, device=x.device,
+                      memory_format=torch.channels_last)
+    n = x.numel()
+    return split_bf16x3(x, out, 1, 1, n, (0, 0, 1), (0, n, 1), pattern)
+
+
+def conv_x3_supported(x: torch.Tensor, w: torch.Tensor, stride) -> bool:
+    """fp32 tensors whose split form lies in the tcgen05 kernels' domain."""
+    if not (x.is_cuda and x.dim() == 4 and x.dtype == torch.float32 and w.dtype == torch.float32):
+        return False
+    O, C, R, S = w.shape
+    if C != x.shape[1] or C % 8 or O % 8 or R > 4 or S > 4:
+        return False
+    if stride[0] not in (1, 2) or stride[1] not in (1, 2):
+        return False
+    return x.shape[2] >= R and x.shape[3] >= S
+
+
+def conv2d_fprop_x3(x, w, stride):
+    """fp32 y = conv2d(x, w, stride) (valid) on tcgen05: [x_hi|x_hi|x_lo] * [w_hi|w_lo|w_hi]."""
+    O, C, R, S = w.shape
+    xs = _split_act(x, 0)
+    ws = torch.empty((O, 3 * C, R, S), dtype=torch.bfloat16, device=w.device,
+                     memory_format=torch.channels_last)
+    # w[o, c, r, s] -> OHWI [o][t][3C]: outer = O, K = C, inner = R*S taps
+    wc = w.contiguous()
+    split_bf16x3(wc, ws, O, C, R * S, (C * R * S, R * S, 1), (R * S * 3 * C, 1, 3 * C), 1)
+    return conv2d_fprop_tc(xs, ws, stride, out_dtype=torch.float32)
+
+
+def conv2d_dgrad_x3(gy, w, stride, in_hw):
+    """fp32 gradient w.r.t. the input: contraction over (tap, O) with the O axis tripled."""
+    O, C, R, S = w.shape
+    gs = _split_act(gy, 0)
+    # [R*S][C][3*O] from w[o, c, r, s]: outer = taps (stride 1), K = O, inner = C
+    wc = w.contiguous()
+    w_tco = torch.empty((R * S, C, 3 * O), dtype=torch.bfloat16, device=w.device)
+    split_bf16x3(wc, w_tco, R * S, O, C, (1, C * R * S, R * S), (C * 3 * O, 1, 3 * O), 1)
+    return conv2d_dgrad_tc(gs, None, stride, in_hw, w_tco, out_dtype=torch.float32,
+                           w_shape=(3 * O, C, R, S))
+
+
+def conv2d_wgrad_x3(gy, x, stride, w_shape):
+    """fp32 gradient w.r.t. the filter: the three products as three batches of one launch."""
+    return conv2d_wgrad_tc(_split_batch(gy, 0), _split_batch(x, 1), stride, w_shape, torch.float32)
 
 
 # ---- a11 / a15: the same family on the CUDA cores (conv_simt.cu): fp32 parity mode, odd shapes --

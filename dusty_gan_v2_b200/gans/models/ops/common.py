@@ -167,23 +167,37 @@ def _tc_ok(x, w, stride, padding, op="fprop"):
     return tuple(padding) == (0, 0) and DF.conv_tc_supported(x, w, stride, op)
 
 
+def _x3_ok(x, w, stride, padding):
+    """fp32 mode: the same tcgen05 kernels on split-bf16 operands (DF.conv2d_*_x3)."""
+    return (tuple(padding) == (0, 0) and DF.fp32_on_tensor_cores() and DF.conv_x3_supported(x, w, stride))
+
+
 def _conv_fprop(x, w, stride, padding=(0, 0)):
     if _tc_ok(x, w, stride, padding):
         return DF.conv2d_fprop_tc(x, w, stride)
+    if _x3_ok(x, w, stride, padding):
+        return DF.conv2d_fprop_x3(x, w, stride)
     return DF.conv2d_fprop_simt(x, w, stride, padding).to(x.dtype)
 
 
 def _conv_grads(gy, x, w, stride, need_x, need_w, w_tco=None, padding=(0, 0)):
     gx = gw = None
     same = gy.dtype == x.dtype
+    x3 = same and _x3_ok(x, w, stride, padding)
     if need_x:
         if same and _tc_ok(x, w, stride, padding, "dgrad"):
             gx = DF.conv2d_dgrad_tc(gy, w, stride, x.shape[2:], w_tco)
+        elif x3:
+            gx = DF.conv2d_dgrad_x3(gy, w, stride, x.shape[2:])
         else:
             gx = DF.conv2d_dgrad_simt(gy, w, stride, padding, x.shape[2:], like=x).to(x.dtype)
     if need_w:
         if same and _tc_ok(x, w, stride, padding, "wgrad"):
             gw = DF.conv2d_wgrad_tc(gy, x, stride, w.shape, w.dtype)
+        elif x3:
+            gw = DF.conv2d_wgrad_x3(gy, x, stride, w.shape)
+            if not (w.is_contiguous(memory_format=torch.channels_last) and not w.is_contiguous()):
+                gw = gw.contiguous()
         else:
             gw = DF.conv2d_wgrad_simt(gy, x, stride, padding, w.shape).to(w.dtype)
             if w.is_contiguous(memory_format=torch.channels_last) and not w.is_contiguous():

@@ -191,7 +191,10 @@ int dusty_angle_down2(const float *angle_in, float *angle_out, int Ba, int H, in
  * wb has dtype `wdtype`; x1/x2/y have dtype `dtype`.
  * impl: 0 = auto, 1 = SIMT fp32-FMA kernel, 2 = tcgen05 tensor-core kernel (bf16 only; with a
  * batch-shared x2 the Fourier half runs as one dense GEMM over the [(B*O), K] weight matrix,
- * several samples side by side in one accumulator), 3 = tcgen05 with per-sample tiles only. */
+ * several samples side by side in one accumulator), 3 = tcgen05 with per-sample tiles only,
+ * 4 = tcgen05 with fp32 OUTPUT (y / dx1 are fp32 while `dtype` = bf16 names the operands): the
+ * fp32 mode, whose operands are split-bf16 with a three times longer K axis
+ * (dusty_split_bf16x3). */
 int dusty_modconv_fwd(const void *wb, const void *x1, const void *x2, const float *bias, void *y,
                       int B, int O, int C1, int C2, int B2, int64_t P, int act, float alpha,
                       float scale, int dtype, int wdtype, int impl, void *stream);
@@ -336,13 +339,15 @@ int dusty_stem_dx(const float *dvh, float *dx, int B, int H, int W, float k0, fl
  * is read at wpk[wtap[g] * w_sg + n * w_sn + k]; w_sn = 0 / w_sg = 0 mean the dense strides
  * K_g / O * K_g, wtap = NULL means wtap[g] = g; w_taps = number of filter blocks in the tensor
  * (used with wtap).  E.g. window mode straight from an OHWI filter: w_sn = R*S*C, w_sg = S*C;
- * a dgrad parity class from a [R*S][C][O] tensor: wtap[g] = r*S + s of the class's taps. */
+ * a dgrad parity class from a [R*S][C][O] tensor: wtap[g] = r*S + s of the class's taps.
+ * out_dtype: DUSTY_BF16, or DUSTY_F32 (y and its strides / offsets in fp32 elements: the fp32
+ * mode's split-bf16 contractions, dusty_split_bf16x3). */
 int dusty_conv2d_tc(const void *x, const void *wpk, const float *bias, void *y, int B, int H_in,
                     int W_in, int C, int H_out, int W_out, int O, int mode, int G,
                     const int *tap_dh, const int *tap_dw, int S, int stride_h, int stride_w,
                     long long y_off, long long y_sb, long long y_sh, long long y_sw, int act,
                     float alpha, float scale, long long w_sn, long long w_sg, const int *wtap,
-                    int w_taps, void *stream);
+                    int w_taps, int out_dtype, void *stream);
 
 /* Tap mode over `ncls` classes in ONE launch: the data gradient of a strided convolution is one
  * class per output parity (ph, pw), each with its own taps, output origin cls_y_off[c] and
@@ -356,7 +361,7 @@ int dusty_conv2d_tc_classes(const void *x, const void *wpk, void *y, int B, int 
                             const int *tap_dw, const int *wtap, const int *cls_H_out,
                             const int *cls_W_out, const long long *cls_y_off, long long y_sb,
                             long long y_sh, long long y_sw, long long w_sn, long long w_sg,
-                            int w_taps, void *stream);
+                            int w_taps, int out_dtype, void *stream);
 
 /* The same convolution family on the CUDA cores, fp32 accumulation, for fp32 parity mode and
  * every shape outside the tcgen05 kernels' domain (1- / 2- / 513-channel layers, 4x4 filters in
@@ -406,6 +411,19 @@ int dusty_gemm_simt(const float *a, const float *b, float *c, int M, int N, int 
 int dusty_scan_project(const float *points, const float *depth, const int *cell_h, const int *cell_w,
                        unsigned long long *keys, float *out, int N, int H, int W, int W_out,
                        float min_depth, float max_depth, void *stream);
+
+/* ---- g1: fp32 mode on the tensor cores ------------------------------------------------------
+ * fp32 tensor -> three bf16 terms concatenated along the contracted axis, so that an fp32
+ * contraction runs on the bf16 tcgen05 kernels with ~2^-16 relative error per product:
+ *   sum_k a_k b_k ~= [a_hi | a_hi | a_lo] . [b_hi | b_lo | b_hi],   x = x_hi + x_lo in bf16.
+ * src is viewed as [outer][K][inner] through the element strides src_strides[3] (HOST array),
+ * dst (bf16) as [outer][3K][inner] through dst_strides[3]; pattern 0 writes hi,hi,lo (the "a"
+ * operand), pattern 1 hi,lo,hi (the "b" operand).  Serves Conv2d / ModConv2d in fp32 mode
+ * (gans/models/ops/common.py:187-210, ops/style.py:68-126; reference config
+ * configs/gans/dusty_v2.yaml:63-65 trains in fp32). */
+int dusty_split_bf16x3(const float *src, void *dst, long long outer, long long K, long long inner,
+                       const long long *src_strides, const long long *dst_strides, int pattern,
+                       void *stream);
 
 /* ---- f2: optimiser step and EMA (gans/trainer.py:30-41 ema_inplace, 128-171 Adam) ----------
  * Multi-tensor Adam exactly as torch.optim.Adam (no weight decay / amsgrad) over `count` fp32

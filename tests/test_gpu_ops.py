@@ -515,6 +515,58 @@ def test_modconv_tcgen05_vs_fp32_reference(DF, B, Oc, C1, C2, B2, HW):
         close(res[2][1][1], dx_ref, rtol=2e-2, atol_rel=1e-2)
 
 
+@pytest.mark.parametrize("B,Oc,C1,C2,B2,HW", [
+    (2, 32, 64, 512, 2, (16, 128)),      # level 4 conv1 family, per-sample Fourier block
+    (3, 32, 64, 512, 1, (8, 64)),        # batch-shared Fourier block
+    (2, 512, 0, 512, 1, (4, 32)),        # level 0 (Fourier only)
+    (2, 128, 256, 512, 1, (16, 128)),    # level 2 conv1
+    (2, 64, 64, 0, 1, (32, 256)),        # conv2 (no Fourier block)
+    (2, 32, 32, 0, 1, (16, 128)),        # 96-channel split operand: zero-filled K tail
+    (1, 48, 64, 0, 1, (2, 64)),          # O not a multiple of the N tile
+])
+def test_modconv_fp32_on_tensor_cores_split_bf16(DF, B, Oc, C1, C2, B2, HW):
+    """g1: the fp32 mode's modulated contraction (forward, dX, dW) on tcgen05 through split-bf16
+    operands and an fp32 epilogue, against an fp64 CPU bmm.  rtol 1e-4 (fp32 mode bound: 1e-3)."""
+    g = torch.Generator().manual_seed(22)
+    H, W = HW
+    K = C1 + C2
+    wb = torch.randn(B, Oc, K, generator=g) / np.sqrt(K)
+    x1 = torch.randn(B, C1, H, W, generator=g) if C1 else None
+    x2 = torch.randn(B2, C2, H, W, generator=g) if C2 else None
+    bias = torch.randn(Oc, generator=g)
+    parts = ([x1.double()] if C1 else []) + ([x2.double().expand(B, -1, -1, -1)] if C2 else [])
+    xin = torch.cat(parts, 1).reshape(B, K, H * W)
+    pre = torch.bmm(wb.double(), xin).reshape(B, Oc, H, W) + bias.double().view(1, -1, 1, 1)
+    ref = torch.where(pre > 0, pre, 0.2 * pre) * O.SQRT2
+    gy = torch.randn(B, Oc, H, W, generator=g)
+    names = []
+    orig = DF.K.call
+    DF.K.call = lambda name, *a: (names.append((name, a[-2] if name.startswith("dusty_modconv") else None)),
+                                  orig(name, *a))[1]
+    try:
+        wg = wb.to(DEV).requires_grad_()
+        x1g = None if x1 is None else x1.to(DEV).requires_grad_()
+        out = DF.modconv_bmm(wg, x1g, None if x2 is None else x2.to(DEV), bias.to(DEV), 3, 0.2, O.SQRT2)
+        grads = torch.autograd.grad(out, [wg] + ([x1g] if C1 else []), gy.to(DEV))
+    finally:
+        DF.K.call = orig
+    assert out.dtype == torch.float32
+    assert ("dusty_modconv_fwd", 4) in names and ("dusty_modconv_bwd_dw", 2) in names, names
+    assert not C1 or ("dusty_modconv_bwd_dx", 4) in names, names
+    close(out, ref.float(), rtol=1e-4, atol_rel=2e-5)
+    # gate from the device forward's own sign pattern (a pre-activation within 1e-5 of zero may
+    # land on either side of it)
+    gate = torch.where(out.detach().double().cpu() > 0, 1.0, 0.2) * O.SQRT2
+    gp = (gy.double() * gate).reshape(B, Oc, H * W)
+    # dW contracts over 3 * H * W pixels in ONE TMEM accumulator: the tensor core's fp32
+    # accumulation truncates, a bias of ~2^-24 per UMMA step that grows with the chain length
+    # (measured 1.7e-4 of the rms at 24576 terms, 6e-4 at 98304) -- inside the fp32 bound
+    close(grads[0], torch.bmm(gp, xin.transpose(1, 2)).float(), rtol=1e-3, atol_rel=2e-4)
+    if C1:
+        dx_ref = torch.bmm(wb.double().transpose(1, 2), gp)[:, :C1].reshape(B, C1, H, W)
+        close(grads[1], dx_ref.float(), rtol=1e-4, atol_rel=2e-5)
+
+
 @pytest.mark.parametrize("demod", [True, False])
 @pytest.mark.parametrize("B,Oc,I", [(3, 8, 12), (64, 32, 576), (5, 256, 1024), (4, 1, 32)])
 def test_modprep_fused_vs_composite(ops, demod, B, Oc, I):
@@ -772,6 +824,55 @@ def _conv_checks(DF, xd, wd, w, s2, ref, gy, gx_ref, gw_ref, g, Oc, H, W):
     bias = torch.randn(Oc, generator=g)
     yb = DF.conv2d_fprop_tc(xd, wd, s2, bias.to(DEV), 3, 0.2, O.SQRT2)
     close(yb, O_lrelu(ref.detach() + bias.view(1, -1, 1, 1)), rtol=2e-2, atol_rel=4e-3)
+
+
+@pytest.mark.parametrize("B,C,Oc,H,W,k,stride,layout", [
+    (2, 32, 32, 18, 66, 3, 1, "nhwc"),      # RB0 conv1 family
+    (2, 32, 64, 19, 67, 3, 2, "nhwc"),      # strided, odd padded size, four parity classes
+    (2, 64, 128, 18, 130, 3, 2, "nchw"),    # NCHW source through the strided split
+    (1, 256, 512, 10, 66, 3, 2, "nhwc"),    # 768-channel split operand, two N tiles
+    (2, 128, 128, 6, 34, 3, 1, "nhwc"),
+    (2, 32, 64, 16, 64, 1, 2, "nhwc"),      # 1x1 stride 2 (positions no tap reaches)
+    (2, 48, 40, 9, 21, 3, 1, "nhwc"),       # channel counts that are not powers of two
+])
+def test_conv2d_fp32_on_tensor_cores_split_bf16(DF, B, C, Oc, H, W, k, stride, layout):
+    """g1: fp32 convolutions as [hi|hi|lo] x [hi|lo|hi] bf16 contractions on the tcgen05 kernels
+    with an fp32 epilogue, against fp64 CPU autograd of the same map.  Held to rtol 1e-4 (the
+    fp32 mode's bound is 1e-3): the dropped terms are ~2^-16 per product."""
+    from dusty_gan_v2_b200.gans.models.ops.common import conv2d_valid
+    g = torch.Generator().manual_seed(36)
+    x = torch.randn(B, C, H, W, generator=g)
+    w = torch.randn(Oc, C, k, k, generator=g) / np.sqrt(C * k * k)
+    xr, wr = x.double().requires_grad_(), w.double().requires_grad_()
+    yr = torch.nn.functional.conv2d(xr, wr, None, stride)
+    gy = torch.randn(yr.shape, generator=g)
+    gxr, gwr = torch.autograd.grad(yr, [xr, wr], gy.double(), create_graph=True)
+    ggwr, = torch.autograd.grad(gxr.pow(2).sum(), [wr])
+    fmt = torch.channels_last if layout == "nhwc" else torch.contiguous_format
+    xg = x.to(DEV).contiguous(memory_format=fmt).requires_grad_()
+    wg = w.to(DEV).requires_grad_()
+    s2 = (stride, stride)
+    assert DF.fp32_on_tensor_cores() and DF.conv_x3_supported(xg, wg, s2)
+    # the three primitives
+    y0 = DF.conv2d_fprop_x3(xg.detach(), wg.detach(), s2)
+    assert y0.dtype == torch.float32 and y0.shape == yr.shape
+    close(y0, yr.float(), rtol=1e-4, atol_rel=2e-5)
+    close(DF.conv2d_dgrad_x3(gy.to(DEV), wg.detach(), s2, (H, W)), gxr.float(), rtol=1e-4, atol_rel=2e-5)
+    close(DF.conv2d_wgrad_x3(gy.to(DEV), xg.detach(), s2, w.shape), gwr.float(), rtol=1e-4, atol_rel=2e-5)
+    # first and second order through the module-level op (what Conv2d / R1 run in fp32 mode)
+    names = []
+    orig = DF.K.call
+    DF.K.call = lambda name, *a: (names.append(name), orig(name, *a))[1]
+    try:
+        y = conv2d_valid(xg, wg, s2)
+        gx, gw = torch.autograd.grad(y, [xg, wg], gy.to(DEV), create_graph=True)
+        ggw, = torch.autograd.grad(gx.pow(2).sum(), [wg])
+    finally:
+        DF.K.call = orig
+    assert "dusty_conv2d_simt" not in names and "dusty_split_bf16x3" in names, names
+    for a, r in ((y, yr), (gx, gxr), (gw, gwr), (ggw, ggwr)):
+        assert a.dtype == torch.float32
+        close(a, r.float(), rtol=1e-4, atol_rel=2e-5)
 
 
 def test_conv2d_valid_autograd_routes_through_tcgen05(DF, ops):

@@ -490,7 +490,12 @@ class Discriminator(nn.Module):
 
     def _fast_epilogue_ok(self, h, low):
         mb = self.epilogue[0]
-        return (h.is_cuda and low == torch.bfloat16 and h.dtype == torch.bfloat16 and mb.features == 1
+        # bf16 trunk, or the fp32 mode with its contractions on the tensor cores (split-bf16
+        # operands): either way the 513-channel filter would fall outside the tcgen05 domain
+        low_ok = (low == torch.bfloat16 and h.dtype == torch.bfloat16) or \
+                 (low == torch.float32 and h.dtype == torch.float32 and DF.fp32_on_tensor_cores()
+                  and h.shape[1] % 8 == 0)
+        return (h.is_cuda and low_ok and mb.features == 1
                 and h.shape[0] % (mb.sub_batches * min(h.shape[0] // mb.sub_batches, mb.group)) == 0)
 
     def _epilogue_low_precision(self, h):

@@ -843,6 +843,15 @@ struct WgParams {
   float *out;                     // [splits][R][SC][O], or the result itself when atomic
   long long split_stride;
   int atomic;                     // partial tiles are added into `out` with 16-byte reductions
+  // operand geometry of one stage (bytes).  Row-resident mode (rows = 1, NR = 3, unit row
+  // stride): ONE x patch of TH + 2 image rows is landed per stage (maps.a[3]) and filter row r
+  // reads it from pixel row r * TW onwards -- the three row windows are the same pixels shifted
+  // by whole image rows, a multiple of the 8-row swizzle atom when TW % 8 == 0 -- so x crosses
+  // L2->SM (TH + 2) / TH times per stage instead of three times.
+  int rows;
+  int ksteps;                     // UMMA K steps (16 pixels each) per stage
+  int a_half, a_rr, a_slot;       // between the two 64-element blocks / filter rows / stages of A
+  int b_blk, b_slot;              // between 64-channel blocks / stages of dY
 };
 
 // NR = filter rows accumulated by one CTA.  NR == 1: one row per CTA (grid.z = R), every CTA
@@ -855,10 +864,9 @@ __global__ void __launch_bounds__(kWgThreads)
 conv_wgrad_tc_kernel(const __grid_constant__ WgMaps maps, const __grid_constant__ WgParams prm) {
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   uint8_t *smem = (uint8_t *)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
-  constexpr int kBBytes = BN * kCK * 2;
-  constexpr int kASlot = NR * kCABytes;
-  constexpr int kStageBytes = kASlot + kBBytes;
   constexpr int kTmemCols = NR * BN <= 32 ? 32 : (NR * BN <= 64 ? 64 : (NR * BN <= 128 ? 128 : (NR * BN <= 256 ? 256 : 512)));
+  const int kASlot = prm.a_slot, kBBytes = prm.b_slot;
+  const int kStageBytes = kASlot + kBBytes;
   uint8_t *a_base = smem;
   uint8_t *b_base = smem + STAGES * kASlot;
   uint64_t *full = (uint64_t *)(smem + STAGES * kStageBytes);
@@ -901,16 +909,22 @@ conv_wgrad_tc_kernel(const __grid_constant__ WgMaps maps, const __grid_constant_
       PROF_WAIT(0, mbar_wait(&empty[s], rp.ph ^ 1));
       if (elect_one_sync()) {
         mbar_expect_tx(&full[s], kStageBytes);
+        if (NR == 3 && prm.rows) {
+          uint8_t *a_dst = a_base + s * kASlot;
+          tma_load_4d(a_dst, &maps.a[3], &full[s], m0, ow0, oh0, b);
+          tma_load_4d(a_dst + prm.a_half, &maps.a[3], &full[s], m0 + 64, ow0, oh0, b);
+        } else {
 #pragma unroll
-        for (int rr = 0; rr < NR; ++rr) {
-          const CUtensorMap *am = &maps.a[r_first + rr];
-          uint8_t *a_dst = a_base + s * kASlot + rr * kCABytes;
-          tma_load_4d(a_dst, am, &full[s], m0, ow0, oh0, b);
-          tma_load_4d(a_dst + 8192, am, &full[s], m0 + 64, ow0, oh0, b);
+          for (int rr = 0; rr < NR; ++rr) {
+            const CUtensorMap *am = &maps.a[r_first + rr];
+            uint8_t *a_dst = a_base + s * kASlot + rr * kCABytes;
+            tma_load_4d(a_dst, am, &full[s], m0, ow0, oh0, b);
+            tma_load_4d(a_dst + 8192, am, &full[s], m0 + 64, ow0, oh0, b);
+          }
         }
 #pragma unroll
         for (int j = 0; j < BN / 64; ++j)
-          tma_load_4d(b_base + s * kBBytes + j * 8192, &maps.g, &full[s], n0 + 64 * j, ow0, oh0, b);
+          tma_load_4d(b_base + s * kBBytes + j * prm.b_blk, &maps.g, &full[s], n0 + 64 * j, ow0, oh0, b);
       }
       __syncwarp();
       rp.template advance<STAGES>();
@@ -921,20 +935,21 @@ conv_wgrad_tc_kernel(const __grid_constant__ WgMaps maps, const __grid_constant_
     // MN-major SW128: 16 pixel rows = 2 KiB per UMMA_K step; LBO = next 64-channel block
     // (8 KiB), SBO = next group of 8 pixel rows (1 KiB)
     const uint32_t d_hi = desc_hi(1024, 2);
-    const uint32_t a_lo0 = desc_lo(smem_u32(a_base), 8192);
-    const uint32_t b_lo0 = desc_lo(smem_u32(b_base), 8192);
+    const uint32_t a_lo0 = desc_lo(smem_u32(a_base), (uint32_t)prm.a_half);
+    const uint32_t b_lo0 = desc_lo(smem_u32(b_base), (uint32_t)prm.b_blk);
+    const int ksteps = prm.ksteps;
     RingPos rp;
     for (int pb = pb_begin; pb < pb_end; ++pb) {
       const int s = rp.s;
       PROF_WAIT(0, mbar_wait(&full[s], rp.ph));
       tc_fence_after();
       if (elect_one_sync()) {
-        const uint32_t b_lo = b_lo0 + (uint32_t)s * (kBBytes >> 4);
+        const uint32_t b_lo = b_lo0 + (uint32_t)s * (uint32_t)(kBBytes >> 4);
 #pragma unroll
         for (int rr = 0; rr < NR; ++rr) {
-          const uint32_t a_lo = a_lo0 + (uint32_t)s * (kASlot >> 4) + (uint32_t)rr * (kCABytes >> 4);
-#pragma unroll
-          for (int k16 = 0; k16 < kCK / 16; ++k16)
+          const uint32_t a_lo = a_lo0 + (uint32_t)s * (uint32_t)(kASlot >> 4) + (uint32_t)rr * (uint32_t)(prm.a_rr >> 4);
+#pragma unroll 4
+          for (int k16 = 0; k16 < ksteps; ++k16)
             umma_bf16_lh(tmem_acc + (uint32_t)(rr * BN), a_lo + k16 * (2048 >> 4), d_hi,
                          b_lo + k16 * (2048 >> 4), d_hi, idesc, (pb > pb_begin || k16 > 0) ? 1u : 0u);
         }
@@ -1128,9 +1143,16 @@ int launch_conv(const ConvMaps &maps, ConvParams prm, cudaStream_t st) {
 
 template <int BN, int STAGES, int NR>
 int launch_wgrad(const WgMaps &maps, const WgParams &prm, int splits, int R, cudaStream_t st) {
-  constexpr int smem = STAGES * (NR * kCABytes + BN * kCK * 2) + 256 + 1024;
-  static bool configured = false;
-  if (int rc = set_smem(conv_wgrad_tc_kernel<BN, STAGES, NR>, smem, &configured)) return rc;
+  const int smem = STAGES * (prm.a_slot + prm.b_slot) + 256 + 1024;
+  static int configured = 0;
+  if (smem > configured) {
+    if (cudaFuncSetAttribute(conv_wgrad_tc_kernel<BN, STAGES, NR>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                             smem) != cudaSuccess) {
+      set_error("conv_wgrad_tc: cannot reserve %d bytes of shared memory", smem);
+      return DUSTY_ECUDA;
+    }
+    configured = smem;
+  }
   dim3 grid((unsigned)splits, (unsigned)(prm.MT * prm.NT), (unsigned)(NR == 1 ? R : 1));
   conv_wgrad_tc_kernel<BN, STAGES, NR><<<grid, kWgThreads, smem, st>>>(maps, prm);
   return 0;
@@ -1448,9 +1470,19 @@ static bool wgrad_rows_merged(int O, int R) {
   return !off && R == 3 && O <= 128;
 }
 
-static int wgrad_splits(int B, int H_out, int W_out, int C, int O, int R, int S) {
+static bool wgrad_rows_resident() {
+  static const bool off = [] { const char *e = getenv("DUSTY_WGRAD_RESIDENT"); return e && atoi(e) == 0; }();
+  return !off;
+}
+
+static int wgrad_splits(int B, int H_out, int W_out, int C, int O, int R, int S, bool rows) {
   int TW, TH;
-  pick_patch(W_out, H_out, kCK, &TW, &TH);
+  if (rows) {
+    TW = W_out >= 32 ? 32 : ((W_out + 7) / 8) * 8;
+    TH = 4;
+  } else {
+    pick_patch(W_out, H_out, kCK, &TW, &TH);
+  }
   const long long total_pb = (long long)((W_out + TW - 1) / TW) * ((H_out + TH - 1) / TH) * B;
   const int BN = O > 128 ? 256 : (O > 64 ? 128 : 64);
   const int tile_ctas = ((S * C + kCM - 1) / kCM) * ((O + BN - 1) / BN) * (wgrad_rows_merged(O, R) ? 1 : R);
@@ -1467,7 +1499,7 @@ static bool wgrad_use_workspace() {
 extern "C" long long dusty_conv2d_wgrad_tc_workspace(int B, int H_out, int W_out, int C, int O,
                                                      int R, int S) {
   if (!wgrad_use_workspace()) return 0;      // split-K partials are reduced in place (atomics)
-  const int splits = wgrad_splits(B, H_out, W_out, C, O, R, S);
+  const int splits = wgrad_splits(B, H_out, W_out, C, O, R, S, false);
   return splits > 1 ? (long long)R * S * C * O * splits : 0;
 }
 
@@ -1487,7 +1519,25 @@ extern "C" int dusty_conv2d_wgrad_tc(const void *x, const void *dy, float *dwp, 
   const int SC = S * C;
   WgMaps maps;
   WgParams prm;
-  pick_patch(W_out, H_out, kCK, &prm.TW, &prm.TH);
+  const int BN = O > 128 ? 256 : (O > 64 ? 128 : 64);
+  // row-resident x patches: 3x3 with unit row stride, TW a multiple of 8 (row shifts stay on the
+  // swizzle atom), four image rows per stage (+ 2 halo rows)
+  const bool rows = wgrad_rows_merged(O, R) && wgrad_rows_resident() && stride_h == 1 && BN == 64;   // 3 x 64 KiB stages
+  if (rows) {
+    prm.TW = W_out >= 32 ? 32 : ((W_out + 7) / 8) * 8;
+    prm.TH = 4;
+  } else {
+    pick_patch(W_out, H_out, kCK, &prm.TW, &prm.TH);
+  }
+  const int kpix = prm.TW * prm.TH;
+  prm.rows = rows ? 1 : 0;
+  prm.ksteps = kpix / 16;
+  const int nr = wgrad_rows_merged(O, R) ? 3 : 1;
+  prm.a_half = rows ? (prm.TH + 2) * prm.TW * 128 : 8192;
+  prm.a_rr = rows ? prm.TW * 128 : kCABytes;
+  prm.a_slot = rows ? 2 * prm.a_half : nr * kCABytes;
+  prm.b_blk = kpix * 128;
+  prm.b_slot = (BN / 64) * prm.b_blk;
   const uint32_t box[4] = {64u, (uint32_t)prm.TW, (uint32_t)prm.TH, 1u};
   const __nv_bfloat16 *xb = (const __nv_bfloat16 *)x;
   bool ok = true;
@@ -1498,6 +1548,12 @@ extern "C" int dusty_conv2d_wgrad_tc(const void *x, const void *dy, float *dwp, 
     ok = ok && make_map4(&maps.a[r], xb + (long long)r * W_in * C, dims, strides, box);
   }
   for (int r = R; r < 4; ++r) maps.a[r] = maps.a[0];
+  if (rows) {
+    const uint64_t dims[4] = {(uint64_t)SC, (uint64_t)W_out, (uint64_t)(H_out + 2), (uint64_t)B};
+    const uint64_t strides[3] = {(uint64_t)stride_w * C * 2, (uint64_t)W_in * C * 2, (uint64_t)H_in * W_in * C * 2};
+    const uint32_t rbox[4] = {64u, (uint32_t)prm.TW, (uint32_t)(prm.TH + 2), 1u};
+    ok = ok && make_map4(&maps.a[3], xb, dims, strides, rbox);
+  }
   {
     const uint64_t dims[4] = {(uint64_t)O, (uint64_t)W_out, (uint64_t)H_out, (uint64_t)B};
     const uint64_t strides[3] = {(uint64_t)O * 2, (uint64_t)W_out * O * 2, (uint64_t)H_out * W_out * O * 2};
@@ -1516,7 +1572,6 @@ extern "C" int dusty_conv2d_wgrad_tc(const void *x, const void *dy, float *dwp, 
     set_error("dusty_conv2d_wgrad_tc: cuTensorMapEncodeTiled failed");
     return DUSTY_ECUDA;
   }
-  const int BN = O > 128 ? 256 : (O > 64 ? 128 : 64);
   prm.tiles_w = (W_out + prm.TW - 1) / prm.TW;
   prm.tiles_h = (H_out + prm.TH - 1) / prm.TH;
   const long long total_pb = (long long)prm.tiles_w * prm.tiles_h * B;
@@ -1526,7 +1581,7 @@ extern "C" int dusty_conv2d_wgrad_tc(const void *x, const void *dy, float *dwp, 
   prm.NT = (O + BN - 1) / BN;
   prm.SC = SC; prm.O = O;
   const long long n = (long long)R * SC * O;
-  int splits = wgrad_splits(B, H_out, W_out, C, O, R, S);
+  int splits = wgrad_splits(B, H_out, W_out, C, O, R, S, rows);
   // Split-K partials are ADDED into dwp with vector reductions (fp32, 16 bytes each) instead of
   // going through a [splits] workspace and a second kernel: the reduce pass cost 19 us per
   // convolution, 0.45 ms per training iteration.  (Summation order is then unordered: results

@@ -13,10 +13,10 @@ int modconv_bwd_dw_simt(const void *dy, const void *x1, const void *x2, float *d
 // tensor-core path (modconv_tc.cu); returns DUSTY_EUNSUPPORTED when the shape does not fit
 int modconv_fwd_tc(const void *wb, const void *x1, const void *x2, const float *bias, void *y,
                    int B, int O, int C1, int C2, int B2, int64_t P, int act, float alpha,
-                   float scale, bool batch_fused, cudaStream_t st, bool out_f32);
+                   float scale, bool batch_fused, cudaStream_t st, bool out_f32, const float *ema);
 bool modconv_fwd_tc_supported(int B, int O, int C1, int C2, int B2, int64_t P);
 int modconv_dx_tc(const void *wb, const void *dy, void *dx1, int B, int O, int C1, int K, int64_t P,
-                  cudaStream_t st, bool out_f32);
+                  cudaStream_t st, bool out_f32, const float *ema);
 bool modconv_dx_tc_supported(int B, int O, int C1, int K, int64_t P);
 int modconv_dw_tc(const void *dy, const void *x1, const void *x2, float *dwb, int B, int O, int C1,
                   int C2, int B2, int64_t P, cudaStream_t st);
@@ -30,7 +30,7 @@ static bool dtype_ok(int d) { return d == DUSTY_F32 || d == DUSTY_BF16; }
 extern "C" int dusty_modconv_fwd(const void *wb, const void *x1, const void *x2, const float *bias,
                                  void *y, int B, int O, int C1, int C2, int B2, int64_t P, int act,
                                  float alpha, float scale, int dtype, int wdtype, int impl,
-                                 void *stream) {
+                                 const float *ema_var, void *stream) {
   DUSTY_CHECK_ARG(wb && y, "null pointer");
   DUSTY_CHECK_ARG(B >= 1 && B <= 65535 && O >= 1 && C1 >= 0 && C2 >= 0 && C1 + C2 >= 1 && P >= 1,
                   "bad shape");
@@ -51,9 +51,14 @@ extern "C" int dusty_modconv_fwd(const void *wb, const void *x1, const void *x2,
     return DUSTY_EUNSUPPORTED;
   }
   int rc;
-  if (impl >= 2 || (impl == 0 && tc_ok))
+  const bool use_tc = impl >= 2 || (impl == 0 && tc_ok);
+  if (ema_var && !use_tc) {
+    set_error("dusty_modconv_fwd: ema_var is applied by the tcgen05 epilogue only");
+    return DUSTY_EUNSUPPORTED;
+  }
+  if (use_tc)
     rc = modconv_fwd_tc(wb, x1, x2, bias, y, B, O, C1, C2, B2, P, act, alpha, scale, impl < 3, st,
-                        impl == 4);
+                        impl == 4, ema_var);
   else
     rc = modconv_fwd_simt(wb, x1, x2, bias, y, B, O, C1, C2, B2, P, act, alpha, scale, dtype,
                           wdtype, st);
@@ -64,7 +69,7 @@ extern "C" int dusty_modconv_fwd(const void *wb, const void *x1, const void *x2,
 
 extern "C" int dusty_modconv_bwd_dx(const void *wb, const void *dy, void *dx1, int B, int O, int C1,
                                     int K, int64_t P, int dtype, int wdtype, int impl,
-                                    void *stream) {
+                                    const float *ema_var, void *stream) {
   DUSTY_CHECK_ARG(wb && dy && dx1, "null pointer");
   DUSTY_CHECK_ARG(B >= 1 && B <= 65535 && O >= 1 && C1 >= 1 && K >= C1 && P >= 1, "bad shape");
   DUSTY_CHECK_ARG(dtype_ok(dtype) && dtype_ok(wdtype), "bad dtype");
@@ -75,8 +80,13 @@ extern "C" int dusty_modconv_bwd_dx(const void *wb, const void *dy, void *dx1, i
     return DUSTY_EUNSUPPORTED;
   }
   int rc;
-  if (impl >= 2 || (impl == 0 && tc_ok))
-    rc = modconv_dx_tc(wb, dy, dx1, B, O, C1, K, P, (cudaStream_t)stream, impl == 4);
+  const bool use_tc = impl >= 2 || (impl == 0 && tc_ok);
+  if (ema_var && !use_tc) {
+    set_error("dusty_modconv_bwd_dx: ema_var is applied by the tcgen05 epilogue only");
+    return DUSTY_EUNSUPPORTED;
+  }
+  if (use_tc)
+    rc = modconv_dx_tc(wb, dy, dx1, B, O, C1, K, P, (cudaStream_t)stream, impl == 4, ema_var);
   else
     rc = modconv_bwd_dx_simt(wb, dy, dx1, B, O, C1, K, P, dtype, wdtype, (cudaStream_t)stream);
   if (rc) return rc;

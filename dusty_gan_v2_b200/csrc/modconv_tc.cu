@@ -45,6 +45,7 @@ struct TcParams {
   int act;
   float alpha, scale;
   int out_f32;            // 1: fp32 output (split-bf16 operands of the fp32 mode, split3.cu)
+  const float *ema;       // optional device scalar ema_var: accumulator * 1 / (sqrt(ema_var) + 1e-8)
 };
 
 
@@ -67,10 +68,17 @@ struct EpiThread {
   bool issuer;
   uint32_t stage_u32;
   const float *bias_s;
+  float pre;              // accumulator factor ahead of the bias: ModConv2d's EMA normaliser
 };
 
-__device__ __forceinline__ EpiThread epi_setup(uint8_t *epi_base, const float *bias, int n_bias) {
+// ema: optional device scalar (ModConv2d.ema_var, style.py:99-103).  The reference divides the
+// per-sample weights by sqrt(ema_var) + 1e-8; applying that scalar to the accumulator instead
+// makes the weights independent of the activation statistics, so all layers' weights can be
+// prepared ahead of (and concurrently with) the activation chain.
+__device__ __forceinline__ EpiThread epi_setup(uint8_t *epi_base, const float *bias, int n_bias,
+                                               const float *ema = nullptr) {
   EpiThread e;
+  e.pre = ema ? 1.f / (sqrtf(__ldg(ema)) + 1e-8f) : 1.f;
   const int warp = threadIdx.x >> 5;
   e.lane = threadIdx.x & 31;
   e.g = (warp - 2) >> 2;
@@ -127,7 +135,7 @@ __device__ __forceinline__ void epi_drain_tile(const EpiThread &e, uint32_t tmem
         const uint32_t dst = e.stage_u32 + (uint32_t)e.row * 4;
 #pragma unroll
         for (int j = 0; j < 16; ++j) {
-          float v = __uint_as_float(hf == 0 ? r0[j] : r1[j]) + bp[hf * 16 + j];
+          float v = fmaf(__uint_as_float(hf == 0 ? r0[j] : r1[j]), e.pre, bp[hf * 16 + j]);
           if (act == 3) v = v > 0.f ? v : v * alpha;
           asm volatile("st.shared.b32 [%0], %1;" ::"r"(dst + (uint32_t)j * (kBM * 4)), "r"(__float_as_uint(v * scale))
                        : "memory");
@@ -144,8 +152,8 @@ __device__ __forceinline__ void epi_drain_tile(const EpiThread &e, uint32_t tmem
     uint32_t h[16];
 #pragma unroll
     for (int j = 0; j < 16; ++j) {
-      float v0 = __uint_as_float(j < 8 ? r0[2 * j] : r1[2 * j - 16]) + bp[2 * j];
-      float v1 = __uint_as_float(j < 8 ? r0[2 * j + 1] : r1[2 * j - 15]) + bp[2 * j + 1];
+      float v0 = fmaf(__uint_as_float(j < 8 ? r0[2 * j] : r1[2 * j - 16]), e.pre, bp[2 * j]);
+      float v1 = fmaf(__uint_as_float(j < 8 ? r0[2 * j + 1] : r1[2 * j - 15]), e.pre, bp[2 * j + 1]);
       if (act == 3) {
         v0 = v0 > 0.f ? v0 : v0 * alpha;
         v1 = v1 > 0.f ? v1 : v1 * alpha;
@@ -321,7 +329,7 @@ modconv_fwd_tc_kernel(const __grid_constant__ CUtensorMap map_x1,
     }
   } else {
     // ===================== epilogue (warps 2..9) =====================
-    const EpiThread e = epi_setup(epi_base, prm.bias, prm.O);
+    const EpiThread e = epi_setup(epi_base, prm.bias, prm.O, prm.ema);
     int lt = 0, gc = 0;
     for (int tile = t_begin; tile < t_end; ++tile, ++lt) {
       int b, n0, p0;
@@ -364,6 +372,7 @@ struct ShParams {
   __nv_bfloat16 *y;
   int act;
   float alpha, scale;
+  const float *ema;       // as TcParams::ema
 };
 
 constexpr int kShBBytes = 256 * kBK * 2;          // B slot: up to 256 weight rows x 64 k
@@ -529,7 +538,7 @@ modconv_fwd_shared_tc_kernel(const __grid_constant__ CUtensorMap map_x1,
     // ===================== epilogue (warps 2..9) =====================
     // y viewed as [(B*O), P]: accumulator column c of column tile nt is row nt*BN + c of that
     // matrix, its bias is bias[(nt*BN + c) % O] (O % 32 == 0: a chunk never straddles samples)
-    const EpiThread e = epi_setup(epi_base, prm.bias, prm.O);
+    const EpiThread e = epi_setup(epi_base, prm.bias, prm.O, prm.ema);
     int lt = 0, gc = 0;
     for (int tile = t_begin; tile < t_end; ++tile, ++lt) {
       const int p0 = (tile % prm.MT) * kBM;
@@ -778,7 +787,7 @@ int modconv_shared_group(int B, int O, int C1, int C2, int B2, int64_t P) {
 
 static int modconv_fwd_shared_tc(const void *wb, const void *x1, const void *pe, const float *bias,
                                  void *y, int B, int O, int C1, int C2, int NS, int64_t P, int act,
-                                 float alpha, float scale, cudaStream_t st) {
+                                 float alpha, float scale, cudaStream_t st, const float *ema) {
   const int K = C1 + C2;
   const int BN = NS * O;
   CUtensorMap mx1, mpe, mws, mwp;
@@ -798,6 +807,7 @@ static int modconv_fwd_shared_tc(const void *wb, const void *x1, const void *pe,
   ShParams prm;
   prm.O = O; prm.C1 = C1; prm.C2 = C2; prm.NS = NS; prm.BN = BN; prm.P = P; prm.bias = bias;
   prm.y = (__nv_bfloat16 *)y; prm.act = act; prm.alpha = alpha; prm.scale = scale;
+  prm.ema = ema;
   prm.MT = (int)(P / kBM);
   prm.NT = B / NS;
   prm.pf = g_tc_prefetch != 0;
@@ -816,11 +826,11 @@ static int modconv_fwd_shared_tc(const void *wb, const void *x1, const void *pe,
 
 int modconv_fwd_tc(const void *wb, const void *x1, const void *x2, const float *bias, void *y,
                    int B, int O, int C1, int C2, int B2, int64_t P, int act, float alpha,
-                   float scale, bool batch_fused, cudaStream_t st, bool out_f32) {
+                   float scale, bool batch_fused, cudaStream_t st, bool out_f32, const float *ema) {
   const int K = C1 + C2;
   if (batch_fused && !out_f32) {
     const int ns = modconv_shared_group(B, O, C1, C2, B2, P);
-    if (ns) return modconv_fwd_shared_tc(wb, x1, x2, bias, y, B, O, C1, C2, ns, P, act, alpha, scale, st);
+    if (ns) return modconv_fwd_shared_tc(wb, x1, x2, bias, y, B, O, C1, C2, ns, P, act, alpha, scale, st, ema);
   }
   const int BN = O >= 256 ? 256 : (O >= 128 ? 128 : (O >= 64 ? 64 : 32));
   CUtensorMap mx1, mx2, mw;
@@ -839,6 +849,7 @@ int modconv_fwd_tc(const void *wb, const void *x1, const void *x2, const float *
   prm.O = O; prm.C1 = C1; prm.K = K; prm.B2 = B2; prm.P = P; prm.bias = bias;
   prm.y = (__nv_bfloat16 *)y; prm.act = act; prm.alpha = alpha; prm.scale = scale;
   prm.out_f32 = out_f32 ? 1 : 0;
+  prm.ema = ema;
   switch (BN) {
     case 256: return launch_tc<256, 4, false>(mx1, mx2, mw, my, prm, B, st);
     case 128: return launch_tc<128, 5, false>(mx1, mx2, mw, my, prm, B, st);
@@ -849,7 +860,7 @@ int modconv_fwd_tc(const void *wb, const void *x1, const void *x2, const float *
 
 // dX1[b, c, p] = sum_o wb[b, o, c] * dY[b, o, p], c < C1
 int modconv_dx_tc(const void *wb, const void *dy, void *dx1, int B, int O, int C1, int K, int64_t P,
-                  cudaStream_t st, bool out_f32) {
+                  cudaStream_t st, bool out_f32, const float *ema) {
   const int BN = C1 > 128 ? 256 : (C1 > 64 ? 128 : 64);
   CUtensorMap mg, mw;
   const bool ok1 = make_map3(&mg, dy, (uint64_t)P, (uint64_t)O, (uint64_t)B, 64, kBK);
@@ -867,6 +878,7 @@ int modconv_dx_tc(const void *wb, const void *dy, void *dx1, int B, int O, int C
   prm.K = O; prm.B2 = B; prm.P = P; prm.bias = nullptr;
   prm.y = (__nv_bfloat16 *)dx1; prm.act = 1; prm.alpha = 0.f; prm.scale = 1.f;
   prm.out_f32 = out_f32 ? 1 : 0;
+  prm.ema = ema;
   switch (BN) {
     case 256: return launch_tc<256, 4, true>(mg, mg, mw, my, prm, B, st);
     case 128: return launch_tc<128, 5, true>(mg, mg, mw, my, prm, B, st);

@@ -60,10 +60,15 @@ struct PrepCtx {
   // [C1+F, C1+2F) the cos block.  rot == nullptr: none.
   const float *rot;
   int C1, F;
+  // backward only: ema_var read at backward time (the forward prepared the weights WITHOUT the
+  // EMA normaliser, which the contraction's epilogue applied; d(loss)/d(wb * g) arrives here)
+  const float *g_late;
   __device__ __forceinline__ bool rotated(int i) const { return rot != nullptr && i >= C1; }
   __device__ __forceinline__ float smax(int b) const { return stats[b]; }
   __device__ __forceinline__ float wmax() const { return demod ? stats[B] : 1.f; }
-  __device__ __forceinline__ float g() const { return stats[B + 1]; }
+  __device__ __forceinline__ float g() const {
+    return g_late ? 1.f / (sqrtf(__ldg(g_late)) + 1e-8f) : stats[B + 1];
+  }
   __device__ __forceinline__ float d(int b, int o) const { return stats[B + 2 + (int64_t)b * O + o]; }
   __device__ __forceinline__ float wp(int o, int i, float inv_wmax) const {
     return W[(int64_t)o * I + i] * scale * inv_wmax;
@@ -277,7 +282,7 @@ extern "C" int dusty_modprep_fwd(const float *slin, const float *weight, const f
   if (nw > 64) nw = 64;
   if (nw < 1) nw = 1;
   modprep_stats_kernel<<<B + nw, 256, 0, st>>>(slin, weight, ema_var, stats, B, O, I, scale, demod);
-  PrepCtx c{slin, weight, stats, B, O, I, demod, scale, rot, C1, F};
+  PrepCtx c{slin, weight, stats, B, O, I, demod, scale, rot, C1, F, nullptr};
   dim3 grid((unsigned)((O + 3) / 4), (unsigned)B);
   if (wdtype == DUSTY_F32) modprep_wb_kernel<float><<<grid, 128, 0, st>>>(c, stats, (float *)wb);
   else modprep_wb_kernel<__nv_bfloat16><<<grid, 128, 0, st>>>(c, stats, (__nv_bfloat16 *)wb);
@@ -289,12 +294,12 @@ extern "C" int dusty_modprep_fwd(const float *slin, const float *weight, const f
 extern "C" int dusty_modprep_bwd(const float *gwb, const float *slin, const float *weight,
                                  const float *stats, float *dslin, float *dweight, float *work,
                                  int B, int O, int I, float scale, int demod, const float *rot,
-                                 int C1, int F, void *stream) {
+                                 int C1, int F, const float *ema_late, void *stream) {
   DUSTY_CHECK_ARG(gwb && slin && weight && stats && dslin && dweight && work, "null pointer");
   DUSTY_CHECK_ARG(rot == nullptr || (C1 >= 0 && F >= 1 && C1 + 2 * F == I), "bad rotation layout");
   DUSTY_CHECK_ARG(B >= 1 && B <= 65535 && O >= 1 && O <= 65535 && I >= 1, "bad shape");
   cudaStream_t st = (cudaStream_t)stream;
-  PrepCtx c{slin, weight, stats, B, O, I, demod, scale, rot, C1, F};
+  PrepCtx c{slin, weight, stats, B, O, I, demod, scale, rot, C1, F, ema_late};
   float *cbo = work;                         // [B*O]
   float *dsp = work + (int64_t)B * O;        // [B*I]
   float *dwp = dsp + (int64_t)B * I;         // [O*I]

@@ -780,7 +780,7 @@ class _ModConvBmm(Function):
     """y[b] = act(wb[b] @ cat(x1[b], x2[b or 0]) + bias) ; x2 (Fourier features) has no grad."""
 
     @staticmethod
-    def forward(ctx, wb, x1, x2, bias, act, alpha, scale):
+    def forward(ctx, wb, x1, x2, bias, act, alpha, scale, ema_var=None):
         B, O, Kt = wb.shape
         c1 = 0 if x1 is None else x1.shape[1]
         c2 = 0 if x2 is None else x2.shape[1]
@@ -791,17 +791,21 @@ class _ModConvBmm(Function):
         b2 = 1 if x2 is None else x2.shape[0]
         y = torch.empty(B, O, H, W, device=src.device, dtype=src.dtype)
         biasf = None if bias is None else _contig(bias.detach().float().reshape(-1))
-        if _modconv_x3_ok(wb, src, O, c1, c2, P, "fwd"):
+        ev = None if ema_var is None else ema_var.detach().float().reshape(1)
+        ctx.ema = ev
+        if ev is not None and not modconv_tc_domain(wb, src, O, c1, c2, P):
+            raise RuntimeError("modconv_bmm: ema_var is applied by the tcgen05 kernels only")
+        if ev is None and _modconv_x3_ok(wb, src, O, c1, c2, P, "fwd"):
             # fp32 mode on tcgen05: K axis tripled, [x_hi|x_hi|x_lo] . [w_hi|w_lo|w_hi]
             x1s = None if x1 is None else _split_planes(x1, 0)
             x2s = None if x2 is None else _split_planes(x2, 0)
             wbs = _split_wb_k(wb, c1, c2)
             K.call("dusty_modconv_fwd", K.ptr(wbs), K.ptr(x1s), K.ptr(x2s), K.ptr(biasf), K.ptr(y), B, O,
-                   3 * c1, 3 * c2, b2, P, act, alpha, scale, K.BF16, K.BF16, 4, K.stream_of(src))
+                   3 * c1, 3 * c2, b2, P, act, alpha, scale, K.BF16, K.BF16, 4, None, K.stream_of(src))
         else:
             K.call("dusty_modconv_fwd", K.ptr(wb), K.ptr(x1), K.ptr(x2), K.ptr(biasf), K.ptr(y), B, O,
                    c1, c2, b2, P, act, alpha, scale, K.dtype_code(src), K.dtype_code(wb),
-                   _PRECISION["modconv_impl"], K.stream_of(src))
+                   _PRECISION["modconv_impl"], K.ptr(ev), K.stream_of(src))
         ctx.save_for_backward(wb, x1, x2, y if act == 3 else None)
         ctx.cfg = (act, alpha, scale, bias is not None, None if bias is None else bias.shape,
                    None if bias is None else bias.dtype)
@@ -835,15 +839,15 @@ class _ModConvBmm(Function):
         b2 = 1 if x2 is None else x2.shape[0]
         if x1 is not None and ctx.needs_input_grad[1]:
             gx1 = torch.empty_like(x1)
-            if _modconv_x3_ok(wb, gpre, O, c1, c2, P, "dx"):
+            if ctx.ema is None and _modconv_x3_ok(wb, gpre, O, c1, c2, P, "dx"):
                 gs = _split_planes(gpre, 0)                       # [B, 3O, P]
                 wbo = torch.empty(B, 3 * O, Kt, device=wb.device, dtype=torch.bfloat16)
                 split_bf16x3(wb, wbo, B, O, Kt, (O * Kt, Kt, 1), (3 * O * Kt, Kt, 1), 1)
                 K.call("dusty_modconv_bwd_dx", K.ptr(wbo), K.ptr(gs), K.ptr(gx1), B, 3 * O, c1, Kt, P,
-                       K.BF16, K.BF16, 4, st)
+                       K.BF16, K.BF16, 4, None, st)
             else:
                 K.call("dusty_modconv_bwd_dx", K.ptr(wb), K.ptr(gpre), K.ptr(gx1), B, O, c1, Kt, P, dt,
-                       K.dtype_code(wb), _PRECISION["modconv_impl"], st)
+                       K.dtype_code(wb), _PRECISION["modconv_impl"], K.ptr(ctx.ema), st)
         gwb = None
         if ctx.needs_input_grad[0]:
             gw32 = torch.empty(B, O, Kt, device=gy.device, dtype=torch.float32)
@@ -862,20 +866,52 @@ class _ModConvBmm(Function):
             db = db.reshape(bshape).to(bdtype)
         else:
             db = None
-        return gwb, gx1, None, db, None, None, None
+        return gwb, gx1, None, db, None, None, None, None
 
 
-def modconv_bmm(wb, x1, x2=None, bias=None, act: int = 1, alpha: float = 0.2, scale: float = 1.0):
+def set_late_ema(enabled: bool):
+    """ModConv2d: apply the EMA normaliser in the contraction's epilogue (default) or fold it into
+    the per-sample weights as the reference does (the two differ by bf16 rounding of wb only)."""
+    _PRECISION["late_ema"] = bool(enabled)
+
+
+def late_ema_enabled() -> bool:
+    return _PRECISION.get("late_ema", True)
+
+
+def modconv_tc_domain(wb, src, O, c1, c2, P) -> bool:
+    return src.is_cuda and wb.dtype == src.dtype and modconv_tc_domain_of(src.dtype, O, c1, c2, P)
+
+
+def modconv_tc_domain_of(dtype, O, c1, c2, P) -> bool:
+    """Will dusty_modconv_fwd (and, with x1, dusty_modconv_bwd_dx) take the tcgen05 kernels for
+    this contraction?  Mirrors modconv_{fwd,dx}_tc_supported (modconv_tc.cu) and the dispatch of
+    modconv.cu; needed where a caller relies on an epilogue only those kernels have (ema_var)."""
+    if _PRECISION["modconv_impl"] == 1:
+        return False
+    if dtype != torch.bfloat16:
+        return False
+    if O < 32 or O % 16 or O > 768 or P % 128 or c1 % 8 or c2 % 8:
+        return False
+    if c1 % 64 and c2:
+        return False
+    return c1 == 0 or c1 >= 32
+
+
+def modconv_bmm(wb, x1, x2=None, bias=None, act: int = 1, alpha: float = 0.2, scale: float = 1.0,
+                ema_var=None):
+    """ema_var: apply the layer's EMA normaliser 1 / (sqrt(ema_var) + 1e-8) to the product (the
+    weights wb then carry none: modprep(..., ema_var=None, ema_late=ema_var))."""
     K.require_cuda(wb, x1, x2, bias)
     wb = _contig(wb)
     x1 = None if x1 is None else _contig(x1)
     x2 = None if x2 is None else _contig(x2.detach())
-    return _ModConvBmm.apply(wb, x1, x2, bias, int(act), float(alpha), float(scale))
+    return _ModConvBmm.apply(wb, x1, x2, bias, int(act), float(alpha), float(scale), ema_var)
 
 
 class _ModPrep(Function):
     @staticmethod
-    def forward(ctx, slin, weight, ema_var, scale, demod, out_dtype, rot, c1):
+    def forward(ctx, slin, weight, ema_var, scale, demod, out_dtype, rot, c1, ema_late=None):
         slin = _contig(slin.float())
         w2 = _contig(weight.float().reshape(weight.shape[-4], weight.shape[-3]) if weight.ndim == 5
                      else weight.float())
@@ -894,6 +930,9 @@ class _ModPrep(Function):
                I, scale, 1 if demod else 0, K.dtype_code(wb), K.ptr(rot), c1, nf, K.stream_of(slin))
         ctx.save_for_backward(slin, w2, stats, rot)
         ctx.cfg = (scale, demod, tuple(weight.shape), weight.dtype, c1, nf)
+        # the buffer itself, read at backward time (no forward runs between a layer's forward
+        # and its backward, so the value is the one the contraction used)
+        ctx.ema_late = None if ema_late is None else ema_late.detach()
         return wb
 
     @staticmethod
@@ -909,16 +948,21 @@ class _ModPrep(Function):
         work = torch.empty(B * O + B * I + O * I + B + 1, device=slin.device, dtype=torch.float32)
         K.call("dusty_modprep_bwd", K.ptr(gwb), K.ptr(slin), K.ptr(w2), K.ptr(stats), K.ptr(dslin),
                K.ptr(dw), K.ptr(work), B, O, I, scale, 1 if demod else 0, K.ptr(rot), c1, nf,
-               K.stream_of(slin))
-        return dslin, dw.reshape(wshape).to(wdtype), None, None, None, None, None, None
+               K.ptr(ctx.ema_late), K.stream_of(slin))
+        return dslin, dw.reshape(wshape).to(wdtype), None, None, None, None, None, None, None
 
 
 def modprep(slin, weight, ema_var, scale: float, demod: bool, out_dtype=torch.float32, rot=None,
-            c1: int = 0):
+            c1: int = 0, ema_late=None):
     """Per-sample effective weights wb[B,O,I] of a modulated 1x1 conv (see dusty_modprep_fwd).
-    rot: optional [B, 2F] (cos | sin) rotation of the Fourier columns starting at c1."""
+    rot: optional [B, 2F] (cos | sin) rotation of the Fourier columns starting at c1.
+    ema_late: the layer's ema_var buffer when the EMA normaliser is applied by the contraction
+    (modconv_bmm(ema_var=...)) instead of being folded into wb (then ema_var must be None)."""
     K.require_cuda(slin, weight, ema_var, rot)
-    return _ModPrep.apply(slin, weight, ema_var, float(scale), bool(demod), out_dtype, rot, int(c1))
+    if ema_late is not None and ema_var is not None:
+        raise RuntimeError("modprep: ema_var and ema_late are exclusive")
+    return _ModPrep.apply(slin, weight, ema_var, float(scale), bool(demod), out_dtype, rot, int(c1),
+                          ema_late)
 
 
 def sumsq_total(x: torch.Tensor) -> torch.Tensor:

@@ -47,11 +47,16 @@ class ModConv2d(nn.Module):
         self.register_buffer("ema_var", torch.tensor(1.0))
 
     # -- small fp32 tensors: [B, O, I] at most 64 MiB for the widest layer, usually < 1 MiB
-    def effective_weights(self, style, out_dtype=torch.float32, pe_rot=None, c1=0):
+    def effective_weights(self, style, out_dtype=torch.float32, pe_rot=None, c1=0, late_ema=False):
         """wb[B,O,I]: one fused kernel pair (dusty_modprep_fwd/bwd) on CUDA.  pe_rot [B, 2F]
-        rotates the Fourier columns (batch-shared Fourier block under an azimuth shift)."""
+        rotates the Fourier columns (batch-shared Fourier block under an azimuth shift).
+        late_ema: leave the EMA normaliser out of wb (the contraction's epilogue applies it), so
+        that wb depends on the style and the parameters only."""
         s = self.mod(style.float())
         if s.is_cuda:
+            if late_ema and self.ema:
+                return DF.modprep(s, self.weight, None, self.scale, self.demod, out_dtype, pe_rot, c1,
+                                  ema_late=self.ema_var)
             return DF.modprep(s, self.weight, self.ema_var if self.ema else None, self.scale,
                               self.demod, out_dtype, pe_rot, c1)
         if pe_rot is not None:
@@ -87,10 +92,18 @@ class ModConv2d(nn.Module):
             numel += pe.numel() * rep
         DF.ema_lerp_(self.ema_var, sa, sb, rep, numel, 1 - self.ema_decay)
 
-    def forward(self, x, style, pe=None, fused_act=None, pe_rot=None, x_sumsq=None):
+    def ema_in_epilogue(self, src, c1, c2) -> bool:
+        """Can this layer's EMA normaliser be applied by the contraction's epilogue?  (tcgen05
+        kernels only: the bf16 production path.)"""
+        P = src.shape[-2] * src.shape[-1]
+        return bool(self.ema and src.is_cuda and DF.late_ema_enabled()
+                    and DF.modconv_tc_domain_of(src.dtype, self.out_ch, c1, c2, P))
+
+    def forward(self, x, style, pe=None, fused_act=None, pe_rot=None, x_sumsq=None, wb=None):
         """x: [B, C1, H, W] (or None when the input is `pe` alone); pe: optional Fourier
         block [B or 1, C2, H, W] appended on the channel axis; fused_act: a FusedLeakyReLU
-        module to apply in the epilogue."""
+        module to apply in the epilogue; wb: weights prepared ahead by
+        effective_weights(..., late_ema=True) (SynthesisNetwork's weight bank)."""
         c1 = 0 if x is None else x.shape[1]
         c2 = 0 if pe is None else pe.shape[1]
         if c1 + c2 != self.in_ch:
@@ -98,7 +111,9 @@ class ModConv2d(nn.Module):
         if self.ema and self.training:
             self.update_ema(x, pe, x_sumsq)
         src = x if x is not None else pe
-        wb = self.effective_weights(style, src.dtype, pe_rot, c1)
+        late = wb is not None or self.ema_in_epilogue(src, c1, c2)
+        if wb is None:
+            wb = self.effective_weights(style, src.dtype, pe_rot, c1, late_ema=late)
         bias = self.bias
         act, alpha, scale = 1, 0.0, float(self.gain)
         if fused_act is not None:
@@ -107,7 +122,8 @@ class ModConv2d(nn.Module):
             alpha, scale = float(fused_act.negative_slope), float(fused_act.scale)
         elif bias is not None and self.gain != 1.0:
             bias = bias * self.gain          # (h + b) * gain == h*gain + b*gain
-        return DF.modconv_bmm(wb, x, pe, bias, act, alpha, scale)
+        return DF.modconv_bmm(wb, x, pe, bias, act, alpha, scale,
+                              ema_var=self.ema_var if (late and self.ema) else None)
 
     def extra_repr(self):
         return (f"in_ch={self.in_ch}, out_ch={self.out_ch}, mod_ch={self.mod_ch}, "

@@ -194,13 +194,20 @@ int dusty_angle_down2(const float *angle_in, float *angle_out, int Ba, int H, in
  * several samples side by side in one accumulator), 3 = tcgen05 with per-sample tiles only,
  * 4 = tcgen05 with fp32 OUTPUT (y / dx1 are fp32 while `dtype` = bf16 names the operands): the
  * fp32 mode, whose operands are split-bf16 with a three times longer K axis
- * (dusty_split_bf16x3). */
+ * (dusty_split_bf16x3).
+ * ema_var (optional device scalar, ModConv2d.ema_var): the accumulator is multiplied by
+ * 1 / (sqrt(ema_var) + 1e-8) ahead of the bias -- the EMA normaliser of style.py:99-103 applied to
+ * the product instead of to the weights, so that wb does not depend on the activation statistics
+ * (all layers' weights can then be prepared ahead of the activation chain).  tcgen05 path only. */
 int dusty_modconv_fwd(const void *wb, const void *x1, const void *x2, const float *bias, void *y,
                       int B, int O, int C1, int C2, int B2, int64_t P, int act, float alpha,
-                      float scale, int dtype, int wdtype, int impl, void *stream);
-/* dX1[b,k,p] = sum_o wb[b,o,k] * dY[b,o,p]  for k < C1 (Fourier channels carry no grad). */
+                      float scale, int dtype, int wdtype, int impl, const float *ema_var,
+                      void *stream);
+/* dX1[b,k,p] = sum_o wb[b,o,k] * dY[b,o,p]  for k < C1 (Fourier channels carry no grad);
+ * ema_var as above (the same scalar on the way back). */
 int dusty_modconv_bwd_dx(const void *wb, const void *dy, void *dx1, int B, int O, int C1, int K,
-                         int64_t P, int dtype, int wdtype, int impl, void *stream);
+                         int64_t P, int dtype, int wdtype, int impl, const float *ema_var,
+                         void *stream);
 /* dwb[b,o,k] = sum_p dY[b,o,p] * X(b,k,p)  (fp32 output, overwritten). */
 int dusty_modconv_bwd_dw(const void *dy, const void *x1, const void *x2, float *dwb, int B, int O,
                          int C1, int C2, int B2, int64_t P, int dtype, int impl, void *stream);
@@ -219,10 +226,14 @@ int dusty_modprep_fwd(const float *slin, const float *weight, const float *ema_v
                       float *stats, int B, int O, int I, float scale, int demod, int wdtype,
                       const float *rot, int C1, int F, void *stream);
 /* Analytic backward: gwb fp32 [B, O, I] -> dslin [B, I], dweight [O, I].
- * work: fp32 workspace of B*O + B*I + O*I + B + 1 floats. */
+ * work: fp32 workspace of B*O + B*I + O*I + B + 1 floats.
+ * ema_late (optional device scalar): the forward ran with ema_var = NULL and the contraction
+ * applied the EMA normaliser (dusty_modconv_fwd's ema_var); gwb is then the gradient w.r.t. the
+ * NORMALISED weights and the factor is read here, at backward time. */
 int dusty_modprep_bwd(const float *gwb, const float *slin, const float *weight, const float *stats,
                       float *dslin, float *dweight, float *work, int B, int O, int I, float scale,
-                      int demod, const float *rot, int C1, int F, void *stream);
+                      int demod, const float *rot, int C1, int F, const float *ema_late,
+                      void *stream);
 
 /* ---- a10: Gumbel-sigmoid raydrop -------------------------------------------------------
  * Replaces GumbelSigmoid.forward gans/models/ops/gumbel.py:23-29 (RelaxedBernoulli.rsample

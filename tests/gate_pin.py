@@ -53,8 +53,8 @@ class GateRecorder:
             keep((pre.detach().float() + b) > 0)
             return o_tail(pre, bias, skip, *a, **k)
 
-        def modconv_bmm(wb, x1, x2=None, bias=None, act=1, alpha=0.2, scale=1.0):
-            y = o_bmm(wb, x1, x2, bias, act, alpha, scale)
+        def modconv_bmm(wb, x1, x2=None, bias=None, act=1, alpha=0.2, scale=1.0, **kw):
+            y = o_bmm(wb, x1, x2, bias, act, alpha, scale, **kw)
             if act == 3:
                 keep(y > 0)
             return y

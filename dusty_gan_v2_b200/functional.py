@@ -942,6 +942,9 @@ class _ModPrep(Function):
         scale, demod, wshape, wdtype, c1, nf = ctx.cfg
         B, I = slin.shape
         O = w2.shape[0]
+        # this node may run on the weight bank's side stream while gwb was produced (and its
+        # memory is owned) by the stream of the contraction's backward
+        gwb.record_stream(torch.cuda.current_stream())
         gwb = _contig(gwb.float())
         dslin = torch.empty_like(slin)
         dw = torch.empty_like(w2)

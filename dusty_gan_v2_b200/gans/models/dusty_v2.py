@@ -14,6 +14,7 @@ dtype (bf16 in production, fp32 in parity mode); head outputs and everything aft
 are fp32 like the reference (dusty_v2.py:174-178).
 """
 import math
+import os
 
 import numpy as np
 import torch
@@ -116,10 +117,39 @@ class SynthesisBlock(nn.Module):
         per = self.downsample(torch.cat([angle.sin(), angle.cos()], dim=1))
         return torch.atan2(per[:, :c], per[:, c:])
 
-    def _conv(self, conv, noise, act, h, style, pe=None, pe_rot=None, x_sumsq=None):
+    def _conv(self, conv, noise, act, h, style, pe=None, pe_rot=None, x_sumsq=None, ready=None):
+        wb = None
+        if ready is not None:                  # weights prepared ahead on the side stream
+            wb, event = ready
+            main = torch.cuda.current_stream()
+            main.wait_event(event)
+            # wb was allocated on the side stream and is read here (and, saved by autograd, in this
+            # stream's backward): its memory must not return to the side stream's pool before
+            wb.record_stream(main)
         if noise is None:
-            return conv(h, style, pe=pe, fused_act=act, pe_rot=pe_rot, x_sumsq=x_sumsq)
-        return act(noise(conv(h, style, pe=pe, pe_rot=pe_rot, x_sumsq=x_sumsq)))
+            return conv(h, style, pe=pe, fused_act=act, pe_rot=pe_rot, x_sumsq=x_sumsq, wb=wb)
+        return act(noise(conv(h, style, pe=pe, pe_rot=pe_rot, x_sumsq=x_sumsq, wb=wb)))
+
+    def prepare_weights(self, ws, dtype, P, shift_rad, side):
+        """Per-sample weights of conv1 / conv2 for this block, computed on the stream `side`
+        (they depend on the styles and the parameters only once the EMA normaliser lives in the
+        contraction epilogue).  Returns {name: (wb, event)} for the layers that qualify."""
+        out = {}
+        pe_ch = self.pe.out_ch if self.use_pe else 0
+        plan = [("conv1", self.conv1, ws[0], self.conv1.in_ch - pe_ch, pe_ch)]
+        if not self.is_first:
+            plan.append(("conv2", self.conv2, ws[1], self.conv2.in_ch, 0))
+        for name, conv, style, c1, c2 in plan:
+            if not conv.ema_in_epilogue_for(dtype, P, c1, c2):
+                continue
+            rot = None
+            if name == "conv1" and shift_rad is not None and self.use_pe:
+                rot = self.pe_rotation(shift_rad)
+            wb = conv.effective_weights(style, dtype, rot, c1, late_ema=True)
+            event = torch.cuda.Event()
+            event.record(side)
+            out[name] = (wb, event)
+        return out
 
     def pe_rotation(self, shift_rad):
         """[B, 2F] table (cos | sin) of psi[b,f] = f_w[f] * shift_b for this block's basis."""
@@ -127,8 +157,9 @@ class SynthesisBlock(nn.Module):
         psi = shift_rad.reshape(-1, 1).float() * f_w
         return torch.cat([psi.cos(), psi.sin()], dim=1)
 
-    def forward(self, h, skip, ws, angle, shift_rad=None):
+    def forward(self, h, skip, ws, angle, shift_rad=None, ready=None):
         ws = iter(ws)
+        ready = ready or {}
         dtype = DF.act_dtype() if (self.use_fp16 and angle.is_cuda) else torch.float32
         h_ss = None
         if h is not None:
@@ -138,10 +169,12 @@ class SynthesisBlock(nn.Module):
             else:
                 h = self.resample(h.to(dtype))
         pe = self.pe(angle, out_dtype=dtype) if self.use_pe else None
-        rot = self.pe_rotation(shift_rad) if (shift_rad is not None and pe is not None) else None
-        h = self._conv(self.conv1, self.noise1, self.bias_act1, h, next(ws), pe, rot, h_ss)
+        rot = self.pe_rotation(shift_rad) if (shift_rad is not None and pe is not None
+                                              and "conv1" not in ready) else None
+        h = self._conv(self.conv1, self.noise1, self.bias_act1, h, next(ws), pe, rot, h_ss,
+                       ready.get("conv1"))
         if not self.is_first:
-            h = self._conv(self.conv2, self.noise2, self.bias_act2, h, next(ws))
+            h = self._conv(self.conv2, self.noise2, self.bias_act2, h, next(ws), ready=ready.get("conv2"))
         o = self.head(h, next(ws))
         y = o.stacked.float()
         if skip is not None:
@@ -156,6 +189,18 @@ class SynthesisBlock(nn.Module):
 
     def extra_repr(self):
         return f"use_fp16={self.use_fp16}"
+
+
+_SIDE_STREAMS = {}
+
+
+def _side_stream(device) -> "torch.cuda.Stream":
+    """One side stream per device for the weight bank (module-level: streams do not deep-copy)."""
+    key = torch.device(device).index if torch.device(device).index is not None else torch.cuda.current_device()
+    st = _SIDE_STREAMS.get(key)
+    if st is None:
+        st = _SIDE_STREAMS[key] = torch.cuda.Stream(device=key)
+    return st
 
 
 def _batch_shared(angle: torch.Tensor, cache: dict) -> bool:
@@ -208,6 +253,24 @@ class SynthesisNetwork(nn.Module):
         self._shared_cache = {}
         self._int_freq_cache = {}
         self.shared_pe_in_training = "auto"     # "auto" (bf16 mode only) | True | False
+        self.weight_bank = os.environ.get("DUSTY_WEIGHT_BANK", "1") != "0"
+
+    def _weight_bank(self, ws, pyramid, shift_rad):
+        if not (ws.is_cuda and self.weight_bank and DF.late_ema_enabled()):
+            return None
+        side, main = _side_stream(ws.device), torch.cuda.current_stream()
+        side.wait_stream(main)
+        bank, i = [], 0
+        with torch.cuda.stream(side):
+            for blk, ang in zip(self.layers, pyramid):
+                dtype = DF.act_dtype() if blk.use_fp16 else torch.float32
+                P = ang.shape[-2] * ang.shape[-1]
+                bank.append(blk.prepare_weights((ws[:, i], ws[:, i + 1]), dtype, P, shift_rad, side))
+                i += blk.num_conv
+        if not any(bank):
+            main.wait_stream(side)
+            return None
+        return bank
 
     def _can_rotate(self, angle):
         """Shared-Fourier-block training path: low-precision mode, batch-shared angle grid and
@@ -265,10 +328,20 @@ class SynthesisNetwork(nn.Module):
                 angle = blk.downsample_angle(angle)
             pyramid.insert(0, angle)
 
+        # Weight bank: every layer's per-sample weights are functions of the styles and the
+        # parameters alone (the EMA normaliser is applied by the contraction), so they are
+        # prepared up-front on a side stream and overlap with the activation chain instead of
+        # sitting in it as ~40 latency-bound launches (and ~100 more on the way back: autograd
+        # runs their backward on the same side stream).
+        bank = self._weight_bank(ws, pyramid, shift_rad)
         h, skip, i = None, None, 0
-        for blk, ang in zip(self.layers, pyramid):
-            h, skip = blk(h, skip, (ws[:, i], ws[:, i + 1], ws[:, i + 2]), ang, shift_rad)
+        for bi, (blk, ang) in enumerate(zip(self.layers, pyramid)):
+            h, skip = blk(h, skip, (ws[:, i], ws[:, i + 1], ws[:, i + 2]), ang, shift_rad,
+                          None if bank is None else bank[bi])
             i += blk.num_conv
+        if bank is not None:
+            torch.cuda.current_stream().wait_stream(_side_stream(ws.device))     # rejoin (graph capture)
+            del bank        # the weights stay alive through autograd only
 
         y = skip.stacked
         if aug:      # cancel the azimuth shift in image space, output_scale folded in

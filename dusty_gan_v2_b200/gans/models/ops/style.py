@@ -95,9 +95,11 @@ class ModConv2d(nn.Module):
     def ema_in_epilogue(self, src, c1, c2) -> bool:
         """Can this layer's EMA normaliser be applied by the contraction's epilogue?  (tcgen05
         kernels only: the bf16 production path.)"""
-        P = src.shape[-2] * src.shape[-1]
-        return bool(self.ema and src.is_cuda and DF.late_ema_enabled()
-                    and DF.modconv_tc_domain_of(src.dtype, self.out_ch, c1, c2, P))
+        return src.is_cuda and self.ema_in_epilogue_for(src.dtype, src.shape[-2] * src.shape[-1], c1, c2)
+
+    def ema_in_epilogue_for(self, dtype, P, c1, c2) -> bool:
+        return bool(self.ema and DF.late_ema_enabled()
+                    and DF.modconv_tc_domain_of(dtype, self.out_ch, c1, c2, P))
 
     def forward(self, x, style, pe=None, fused_act=None, pe_rot=None, x_sumsq=None, wb=None):
         """x: [B, C1, H, W] (or None when the input is `pe` alone); pe: optional Fourier

@@ -464,7 +464,7 @@ def kernel_rooflines(device, peaks):
         gx1 = torch.empty_like(x1)
         tc_entry(f"modconv_dx[{tag},pe={pe_tag}]bf16",
                  lambda: K.call("dusty_modconv_bwd_dx", K.ptr(wb), K.ptr(g), K.ptr(gx1), B, O_, C1, C1 + C2, P,
-                                K.BF16, K.BF16, 0, None, K.stream_of(g)),
+                                K.BF16, K.BF16, 0, None, None, K.stream_of(g)),
                  2.0 * B * O_ * C1 * P, (g.numel() + gx1.numel() + wb.numel()) * 2)
         return e
 

@@ -5,9 +5,9 @@
 namespace dusty {
 int modconv_fwd_simt(const void *wb, const void *x1, const void *x2, const float *bias, void *y,
                      int B, int O, int C1, int C2, int B2, int64_t P, int act, float alpha,
-                     float scale, int dtype, int wdtype, cudaStream_t st);
+                     float scale, int dtype, int wdtype, cudaStream_t st, const float *const *ema_rows);
 int modconv_bwd_dx_simt(const void *wb, const void *dy, void *dx1, int B, int O, int C1, int K,
-                        int64_t P, int dtype, int wdtype, cudaStream_t st);
+                        int64_t P, int dtype, int wdtype, cudaStream_t st, const float *const *ema_rows);
 int modconv_bwd_dw_simt(const void *dy, const void *x1, const void *x2, float *dwb, int B, int O,
                         int C1, int C2, int B2, int64_t P, int dtype, cudaStream_t st);
 // tensor-core path (modconv_tc.cu); returns DUSTY_EUNSUPPORTED when the shape does not fit
@@ -30,8 +30,9 @@ static bool dtype_ok(int d) { return d == DUSTY_F32 || d == DUSTY_BF16; }
 extern "C" int dusty_modconv_fwd(const void *wb, const void *x1, const void *x2, const float *bias,
                                  void *y, int B, int O, int C1, int C2, int B2, int64_t P, int act,
                                  float alpha, float scale, int dtype, int wdtype, int impl,
-                                 const float *ema_var, void *stream) {
+                                 const float *ema_var, const float *const *ema_rows, void *stream) {
   DUSTY_CHECK_ARG(wb && y, "null pointer");
+  DUSTY_CHECK_ARG(!(ema_var && ema_rows), "ema_var and ema_rows are exclusive");
   DUSTY_CHECK_ARG(B >= 1 && B <= 65535 && O >= 1 && C1 >= 0 && C2 >= 0 && C1 + C2 >= 1 && P >= 1,
                   "bad shape");
   DUSTY_CHECK_ARG((C1 == 0 || x1) && (C2 == 0 || x2), "missing source tensor");
@@ -52,8 +53,8 @@ extern "C" int dusty_modconv_fwd(const void *wb, const void *x1, const void *x2,
   }
   int rc;
   const bool use_tc = impl >= 2 || (impl == 0 && tc_ok);
-  if (ema_var && !use_tc) {
-    set_error("dusty_modconv_fwd: ema_var is applied by the tcgen05 epilogue only");
+  if ((ema_var && !use_tc) || (ema_rows && use_tc)) {
+    set_error("dusty_modconv_fwd: ema_var is applied by the tcgen05 epilogue, ema_rows by the small-O kernel");
     return DUSTY_EUNSUPPORTED;
   }
   if (use_tc)
@@ -61,7 +62,7 @@ extern "C" int dusty_modconv_fwd(const void *wb, const void *x1, const void *x2,
                         impl == 4, ema_var);
   else
     rc = modconv_fwd_simt(wb, x1, x2, bias, y, B, O, C1, C2, B2, P, act, alpha, scale, dtype,
-                          wdtype, st);
+                          wdtype, st, ema_rows);
   if (rc) return rc;
   DUSTY_LAUNCH_CHECK();
   return DUSTY_OK;
@@ -69,8 +70,9 @@ extern "C" int dusty_modconv_fwd(const void *wb, const void *x1, const void *x2,
 
 extern "C" int dusty_modconv_bwd_dx(const void *wb, const void *dy, void *dx1, int B, int O, int C1,
                                     int K, int64_t P, int dtype, int wdtype, int impl,
-                                    const float *ema_var, void *stream) {
+                                    const float *ema_var, const float *const *ema_rows, void *stream) {
   DUSTY_CHECK_ARG(wb && dy && dx1, "null pointer");
+  DUSTY_CHECK_ARG(!(ema_var && ema_rows), "ema_var and ema_rows are exclusive");
   DUSTY_CHECK_ARG(B >= 1 && B <= 65535 && O >= 1 && C1 >= 1 && K >= C1 && P >= 1, "bad shape");
   DUSTY_CHECK_ARG(dtype_ok(dtype) && dtype_ok(wdtype), "bad dtype");
   DUSTY_CHECK_ARG(impl >= 0 && impl <= 4, "impl must be 0 (auto), 1 (simt), 2 / 3 (tcgen05) or 4 (tcgen05, fp32 output)");
@@ -81,14 +83,14 @@ extern "C" int dusty_modconv_bwd_dx(const void *wb, const void *dy, void *dx1, i
   }
   int rc;
   const bool use_tc = impl >= 2 || (impl == 0 && tc_ok);
-  if (ema_var && !use_tc) {
-    set_error("dusty_modconv_bwd_dx: ema_var is applied by the tcgen05 epilogue only");
+  if ((ema_var && !use_tc) || (ema_rows && use_tc)) {
+    set_error("dusty_modconv_bwd_dx: ema_var is applied by the tcgen05 epilogue, ema_rows by the small-O kernel");
     return DUSTY_EUNSUPPORTED;
   }
   if (use_tc)
     rc = modconv_dx_tc(wb, dy, dx1, B, O, C1, K, P, (cudaStream_t)stream, impl == 4, ema_var);
   else
-    rc = modconv_bwd_dx_simt(wb, dy, dx1, B, O, C1, K, P, dtype, wdtype, (cudaStream_t)stream);
+    rc = modconv_bwd_dx_simt(wb, dy, dx1, B, O, C1, K, P, dtype, wdtype, (cudaStream_t)stream, ema_rows);
   if (rc) return rc;
   DUSTY_LAUNCH_CHECK();
   return DUSTY_OK;

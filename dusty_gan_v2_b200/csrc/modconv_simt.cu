@@ -36,6 +36,13 @@ struct GemmNN {
   const float *bias;
   int M, K; int64_t N;
   int act; float alpha, scale;
+  // optional per-row EMA normalisers (heads: one ModConv2d per output row, each with its own
+  // ema_var): row r of the weights is multiplied by 1 / (sqrt(*ema_rows[r]) + 1e-8) as it is
+  // staged in shared memory (small-O kernels only)
+  const float *ema_rows[4];
+  __device__ __forceinline__ float row_scale(int r) const {
+    return (r < 4 && ema_rows[r]) ? 1.f / (sqrtf(__ldg(ema_rows[r])) + 1e-8f) : 1.f;
+  }
 };
 
 // C[b] (M x N) = A[b] (M x K) * B[b] (K x N), fp32 accumulate, fused bias + lrelu epilogue.
@@ -137,7 +144,7 @@ small_o_kernel(GemmNN g, int PG) {
   const TA *A = (const TA *)g.a + (int64_t)b * g.a_bs;
   for (int i = threadIdx.x; i < g.M * g.K; i += blockDim.x) {
     const int m = i / g.K, k = i - m * g.K;
-    sw[i] = to_f(A[(int64_t)m * g.a_ms + (int64_t)k * g.a_ks]);
+    sw[i] = to_f(A[(int64_t)m * g.a_ms + (int64_t)k * g.a_ks]) * g.row_scale(m);
   }
   __syncthreads();
   const int64_t p0 = ((int64_t)blockIdx.x * PG + tx) * V;
@@ -245,7 +252,7 @@ small_o_dx_kernel(GemmNN g, int c_chunk) {
   const TA *A = (const TA *)g.a + (int64_t)b * g.a_bs;
   for (int i = threadIdx.x; i < g.K * nc; i += blockDim.x) {
     const int o = i / nc, c = i - o * nc;
-    sw[o * c_chunk + c] = to_f(A[(int64_t)(c0 + c) * g.a_ms + (int64_t)o * g.a_ks]);
+    sw[o * c_chunk + c] = to_f(A[(int64_t)(c0 + c) * g.a_ms + (int64_t)o * g.a_ks]) * g.row_scale(o);
   }
   __syncthreads();
   const int64_t p0 = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) * V;
@@ -548,11 +555,23 @@ static int run_nn(const GemmNN &g, int B, bool a_kcontig, cudaStream_t st) {
   return 0;
 }
 
+static bool set_rows(GemmNN &g, const float *const *ema_rows, int rows, bool small_o) {
+  for (int r = 0; r < 4; ++r) g.ema_rows[r] = nullptr;
+  if (!ema_rows) return true;
+  if (!small_o || rows > 4) return false;
+  for (int r = 0; r < rows; ++r) g.ema_rows[r] = ema_rows[r];
+  return true;
+}
+
 int modconv_fwd_simt(const void *wb, const void *x1, const void *x2, const float *bias, void *y,
                      int B, int O, int C1, int C2, int B2, int64_t P, int act, float alpha,
-                     float scale, int dtype, int wdtype, cudaStream_t st) {
+                     float scale, int dtype, int wdtype, cudaStream_t st, const float *const *ema_rows) {
   GemmNN g;
   const int K = C1 + C2;
+  if (!set_rows(g, ema_rows, O, O <= 4 && (size_t)O * K * sizeof(float) <= 48 * 1024)) {
+    set_error("modconv_fwd_simt: ema_rows needs the small-O kernel (O <= 4)");
+    return DUSTY_EUNSUPPORTED;
+  }
   g.a = wb; g.a_bs = (int64_t)O * K; g.a_ms = K; g.a_ks = 1;
   g.b1 = x1; g.b2 = x2; g.b1_bs = (int64_t)C1 * P; g.b2_bs = (B2 == 1) ? 0 : (int64_t)C2 * P;
   g.K1 = C1; g.c = y; g.c_bs = (int64_t)O * P; g.bias = bias;
@@ -566,8 +585,12 @@ int modconv_fwd_simt(const void *wb, const void *x1, const void *x2, const float
 }
 
 int modconv_bwd_dx_simt(const void *wb, const void *dy, void *dx1, int B, int O, int C1, int K,
-                        int64_t P, int dtype, int wdtype, cudaStream_t st) {
+                        int64_t P, int dtype, int wdtype, cudaStream_t st, const float *const *ema_rows) {
   GemmNN g;
+  if (!set_rows(g, ema_rows, O, O <= 4)) {
+    set_error("modconv_bwd_dx_simt: ema_rows needs the small-O kernel (O <= 4)");
+    return DUSTY_EUNSUPPORTED;
+  }
   // A(m = k, kk = o) = wb[b, o, k]
   g.a = wb; g.a_bs = (int64_t)O * K; g.a_ms = 1; g.a_ks = K;
   g.b1 = dy; g.b2 = dy; g.b1_bs = (int64_t)O * P; g.b2_bs = 0; g.K1 = O;

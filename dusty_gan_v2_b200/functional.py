@@ -780,7 +780,7 @@ class _ModConvBmm(Function):
     """y[b] = act(wb[b] @ cat(x1[b], x2[b or 0]) + bias) ; x2 (Fourier features) has no grad."""
 
     @staticmethod
-    def forward(ctx, wb, x1, x2, bias, act, alpha, scale, ema_var=None):
+    def forward(ctx, wb, x1, x2, bias, act, alpha, scale, ema_var=None, ema_rows=None):
         B, O, Kt = wb.shape
         c1 = 0 if x1 is None else x1.shape[1]
         c2 = 0 if x2 is None else x2.shape[1]
@@ -795,17 +795,25 @@ class _ModConvBmm(Function):
         ctx.ema = ev
         if ev is not None and not modconv_tc_domain(wb, src, O, c1, c2, P):
             raise RuntimeError("modconv_bmm: ema_var is applied by the tcgen05 kernels only")
-        if ev is None and _modconv_x3_ok(wb, src, O, c1, c2, P, "fwd"):
+        # heads: one device scalar per output row (kept alive by ctx; read again by dX)
+        rows = None
+        if ema_rows is not None:
+            if len(ema_rows) != O or O > 4 or ev is not None:
+                raise RuntimeError("modconv_bmm: ema_rows is one scalar per output row, O <= 4")
+            rows = [r.detach().float().reshape(1) for r in ema_rows]
+        ctx.ema_rows = rows
+        rows_p = None if rows is None else (K.C.c_void_p * O)(*[r.data_ptr() for r in rows])
+        if ev is None and rows is None and _modconv_x3_ok(wb, src, O, c1, c2, P, "fwd"):
             # fp32 mode on tcgen05: K axis tripled, [x_hi|x_hi|x_lo] . [w_hi|w_lo|w_hi]
             x1s = None if x1 is None else _split_planes(x1, 0)
             x2s = None if x2 is None else _split_planes(x2, 0)
             wbs = _split_wb_k(wb, c1, c2)
             K.call("dusty_modconv_fwd", K.ptr(wbs), K.ptr(x1s), K.ptr(x2s), K.ptr(biasf), K.ptr(y), B, O,
-                   3 * c1, 3 * c2, b2, P, act, alpha, scale, K.BF16, K.BF16, 4, None, K.stream_of(src))
+                   3 * c1, 3 * c2, b2, P, act, alpha, scale, K.BF16, K.BF16, 4, None, None, K.stream_of(src))
         else:
             K.call("dusty_modconv_fwd", K.ptr(wb), K.ptr(x1), K.ptr(x2), K.ptr(biasf), K.ptr(y), B, O,
                    c1, c2, b2, P, act, alpha, scale, K.dtype_code(src), K.dtype_code(wb),
-                   _PRECISION["modconv_impl"], K.ptr(ev), K.stream_of(src))
+                   _PRECISION["modconv_impl"], K.ptr(ev), rows_p, K.stream_of(src))
         ctx.save_for_backward(wb, x1, x2, y if act == 3 else None)
         ctx.cfg = (act, alpha, scale, bias is not None, None if bias is None else bias.shape,
                    None if bias is None else bias.dtype)
@@ -839,15 +847,17 @@ class _ModConvBmm(Function):
         b2 = 1 if x2 is None else x2.shape[0]
         if x1 is not None and ctx.needs_input_grad[1]:
             gx1 = torch.empty_like(x1)
-            if ctx.ema is None and _modconv_x3_ok(wb, gpre, O, c1, c2, P, "dx"):
+            if ctx.ema is None and ctx.ema_rows is None and _modconv_x3_ok(wb, gpre, O, c1, c2, P, "dx"):
                 gs = _split_planes(gpre, 0)                       # [B, 3O, P]
                 wbo = torch.empty(B, 3 * O, Kt, device=wb.device, dtype=torch.bfloat16)
                 split_bf16x3(wb, wbo, B, O, Kt, (O * Kt, Kt, 1), (3 * O * Kt, Kt, 1), 1)
                 K.call("dusty_modconv_bwd_dx", K.ptr(wbo), K.ptr(gs), K.ptr(gx1), B, 3 * O, c1, Kt, P,
-                       K.BF16, K.BF16, 4, None, st)
+                       K.BF16, K.BF16, 4, None, None, st)
             else:
+                rows = ctx.ema_rows
+                rows_p = None if rows is None else (K.C.c_void_p * O)(*[r.data_ptr() for r in rows])
                 K.call("dusty_modconv_bwd_dx", K.ptr(wb), K.ptr(gpre), K.ptr(gx1), B, O, c1, Kt, P, dt,
-                       K.dtype_code(wb), _PRECISION["modconv_impl"], K.ptr(ctx.ema), st)
+                       K.dtype_code(wb), _PRECISION["modconv_impl"], K.ptr(ctx.ema), rows_p, st)
         gwb = None
         if ctx.needs_input_grad[0]:
             gw32 = torch.empty(B, O, Kt, device=gy.device, dtype=torch.float32)
@@ -866,7 +876,7 @@ class _ModConvBmm(Function):
             db = db.reshape(bshape).to(bdtype)
         else:
             db = None
-        return gwb, gx1, None, db, None, None, None, None
+        return gwb, gx1, None, db, None, None, None, None, None
 
 
 def set_late_ema(enabled: bool):
@@ -899,14 +909,16 @@ def modconv_tc_domain_of(dtype, O, c1, c2, P) -> bool:
 
 
 def modconv_bmm(wb, x1, x2=None, bias=None, act: int = 1, alpha: float = 0.2, scale: float = 1.0,
-                ema_var=None):
+                ema_var=None, ema_rows=None):
     """ema_var: apply the layer's EMA normaliser 1 / (sqrt(ema_var) + 1e-8) to the product (the
-    weights wb then carry none: modprep(..., ema_var=None, ema_late=ema_var))."""
+    weights wb then carry none: modprep(..., ema_var=None, ema_late=ema_var)).  ema_rows: the
+    same per output row (heads: O <= 4 rows, each its own ModConv2d), a list of O buffers."""
     K.require_cuda(wb, x1, x2, bias)
     wb = _contig(wb)
     x1 = None if x1 is None else _contig(x1)
     x2 = None if x2 is None else _contig(x2.detach())
-    return _ModConvBmm.apply(wb, x1, x2, bias, int(act), float(alpha), float(scale), ema_var)
+    return _ModConvBmm.apply(wb, x1, x2, bias, int(act), float(alpha), float(scale), ema_var,
+                             None if ema_rows is None else list(ema_rows))
 
 
 class _ModPrep(Function):

@@ -56,16 +56,37 @@ class Head(nn.Module):
                                                   ksize=1, stride=1, padding=0, demod=False,
                                                   ema=True)
 
-    def forward(self, x, style):
+    def late_ema_ok(self, is_cuda=True) -> bool:
+        """Per-row EMA normalisers applied by the small-O contraction kernels (weights then depend
+        on the style and the parameters only: SynthesisNetwork's weight bank)."""
+        mods = list(self.heads.values())
+        return bool(is_cuda and DF.late_ema_enabled() and 1 <= len(mods) <= 4 and all(m.ema for m in mods)
+                    and DF._PRECISION["modconv_impl"] in (0, 1) and self.in_ch * len(mods) * 4 <= 48 * 1024)
+
+    def prepare_weights(self, style, dtype, side):
+        mods = list(self.heads.values())
+        wb = torch.cat([m.effective_weights(style, dtype, late_ema=True) for m in mods], dim=1)
+        event = torch.cuda.Event()
+        event.record(side)
+        return wb, event
+
+    def forward(self, x, style, ready=None):
         """All heads share x and the style: one contraction with O = number of heads."""
         mods = list(self.heads.values())
         if self.training:
             total = DF.sumsq_buffer(x)
             for m in mods:
                 DF.ema_lerp_(m.ema_var, total, None, 1, x.numel(), 1 - m.ema_decay)
-        wb = torch.cat([m.effective_weights(style, x.dtype) for m in mods], dim=1)
         bias = torch.cat([m.bias.reshape(-1) for m in mods])
-        y = DF.modconv_bmm(wb, x, None, bias, 1, 0.0, 1.0)
+        if ready is not None:
+            wb, event = ready
+            main = torch.cuda.current_stream()
+            main.wait_event(event)
+            wb.record_stream(main)
+            y = DF.modconv_bmm(wb, x, None, bias, 1, 0.0, 1.0, ema_rows=[m.ema_var for m in mods])
+        else:
+            wb = torch.cat([m.effective_weights(style, x.dtype) for m in mods], dim=1)
+            y = DF.modconv_bmm(wb, x, None, bias, 1, 0.0, 1.0)
         out = _HeadOut()
         out.stacked = y
         for i, name in enumerate(self.heads.keys()):
@@ -149,6 +170,8 @@ class SynthesisBlock(nn.Module):
             event = torch.cuda.Event()
             event.record(side)
             out[name] = (wb, event)
+        if self.head.late_ema_ok() and (dtype == torch.bfloat16 or dtype == torch.float32):
+            out["head"] = self.head.prepare_weights(ws[-1], dtype, side)
         return out
 
     def pe_rotation(self, shift_rad):
@@ -175,7 +198,7 @@ class SynthesisBlock(nn.Module):
                        ready.get("conv1"))
         if not self.is_first:
             h = self._conv(self.conv2, self.noise2, self.bias_act2, h, next(ws), ready=ready.get("conv2"))
-        o = self.head(h, next(ws))
+        o = self.head(h, next(ws), ready.get("head"))
         y = o.stacked.float()
         if skip is not None:
             prev = skip.stacked if isinstance(skip, _HeadOut) else torch.cat(
@@ -265,7 +288,8 @@ class SynthesisNetwork(nn.Module):
             for blk, ang in zip(self.layers, pyramid):
                 dtype = DF.act_dtype() if blk.use_fp16 else torch.float32
                 P = ang.shape[-2] * ang.shape[-1]
-                bank.append(blk.prepare_weights((ws[:, i], ws[:, i + 1]), dtype, P, shift_rad, side))
+                styles = (ws[:, i], ws[:, i + 1]) + (() if blk.is_first else (ws[:, i + 2],))
+                bank.append(blk.prepare_weights(styles, dtype, P, shift_rad, side))
                 i += blk.num_conv
         if not any(bank):
             main.wait_stream(side)

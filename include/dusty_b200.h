@@ -198,16 +198,19 @@ int dusty_angle_down2(const float *angle_in, float *angle_out, int Ba, int H, in
  * ema_var (optional device scalar, ModConv2d.ema_var): the accumulator is multiplied by
  * 1 / (sqrt(ema_var) + 1e-8) ahead of the bias -- the EMA normaliser of style.py:99-103 applied to
  * the product instead of to the weights, so that wb does not depend on the activation statistics
- * (all layers' weights can then be prepared ahead of the activation chain).  tcgen05 path only. */
+ * (all layers' weights can then be prepared ahead of the activation chain).  tcgen05 path only.
+ * ema_rows (optional HOST array of O device scalars, O <= 4; exclusive with ema_var): the same
+ * per OUTPUT ROW for the heads, where every row belongs to its own ModConv2d (dusty_v2.py:48-60);
+ * applied by the small-O CUDA-core kernels to the weight rows as they are staged. */
 int dusty_modconv_fwd(const void *wb, const void *x1, const void *x2, const float *bias, void *y,
                       int B, int O, int C1, int C2, int B2, int64_t P, int act, float alpha,
                       float scale, int dtype, int wdtype, int impl, const float *ema_var,
-                      void *stream);
+                      const float *const *ema_rows, void *stream);
 /* dX1[b,k,p] = sum_o wb[b,o,k] * dY[b,o,p]  for k < C1 (Fourier channels carry no grad);
- * ema_var as above (the same scalar on the way back). */
+ * ema_var / ema_rows as above (the same factors on the way back). */
 int dusty_modconv_bwd_dx(const void *wb, const void *dy, void *dx1, int B, int O, int C1, int K,
                          int64_t P, int dtype, int wdtype, int impl, const float *ema_var,
-                         void *stream);
+                         const float *const *ema_rows, void *stream);
 /* dwb[b,o,k] = sum_p dY[b,o,p] * X(b,k,p)  (fp32 output, overwritten). */
 int dusty_modconv_bwd_dw(const void *dy, const void *x1, const void *x2, float *dwb, int B, int O,
                          int C1, int C2, int B2, int64_t P, int dtype, int impl, void *stream);

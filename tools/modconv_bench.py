@@ -101,7 +101,7 @@ def main():
         row["fwd_us"] = timeit(lambda: DF.modconv_bmm(wb, x1, None, bias, 3, 0.2, 1.41))
         row["fwd_hbm_frac"] = row["hbm_mbytes_fwd"] / row["fwd_us"] / 6554.9 * 1e3
         row["dx_us"] = timeit(lambda: K.call("dusty_modconv_bwd_dx", K.ptr(wb), K.ptr(gy), K.ptr(gx), B, O_, C1, C1,
-                                             P, K.BF16, K.BF16, 0, None, K.stream_of(gy)))
+                                             P, K.BF16, K.BF16, 0, None, None, K.stream_of(gy)))
         sub = [0, B - 1]
         ref = torch.bmm(wb[sub].float().transpose(1, 2), gy[sub].float().reshape(2, O_, P)).reshape(2, C1, hh, ww)
         row["dx_relerr"] = float((gx[sub].float() - ref).abs().max() / ref.abs().max())

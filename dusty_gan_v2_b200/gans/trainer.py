@@ -106,6 +106,8 @@ class Trainer:
         self.resolution = cfg.model.generator.synthesis_kwargs.resolution
         self.B = tr.batch_size // world_size
         self.batch_iter = batch_iter
+        self._prefetched = None          # (iterator, device batch, event): next step's H2D copy in flight
+        self._copy_stream = None
 
         self.G = build_generator(cfg.model.generator).to(self.device)
         self.G_ema = copy.deepcopy(self.G).eval()
@@ -196,6 +198,38 @@ class Trainer:
     # ------------------------------------------------------------------ inputs
     def sample_z(self, batch_size):
         return torch.randn(batch_size, self.z_dim, device=self.device)
+
+    # -- input pipeline: the NEXT step's host -> device copy runs on a copy stream under this step
+    def _issue_copy(self, raw):
+        if self.device.type != "cuda" or all((not torch.is_tensor(v)) or v.is_cuda for v in raw.values()):
+            return raw, None
+        if self._copy_stream is None:
+            self._copy_stream = torch.cuda.Stream(device=self.device)
+        with torch.cuda.stream(self._copy_stream):
+            dev = {k: (v.to(self.device, non_blocking=True) if torch.is_tensor(v) else v) for k, v in raw.items()}
+            event = torch.cuda.Event()
+            event.record(self._copy_stream)
+        return dev, event
+
+    def _next_batch(self):
+        """next(self.batch_iter) with the following batch's pinned-memory upload already issued
+        (a batch prefetched from an iterator that has since been replaced is dropped)."""
+        pre = self._prefetched
+        if pre is not None and pre[0] is self.batch_iter:
+            cur, event = pre[1], pre[2]
+        else:
+            cur, event = self._issue_copy(next(self.batch_iter))
+        try:
+            self._prefetched = (self.batch_iter,) + self._issue_copy(next(self.batch_iter))
+        except StopIteration:
+            self._prefetched = None
+        if event is not None:
+            main = torch.cuda.current_stream()
+            main.wait_event(event)
+            for v in cur.values():
+                if torch.is_tensor(v):
+                    v.record_stream(main)
+        return cur
 
     def fetch_reals(self, raw_batch):
         """trainer.py:211-217: depth -> inverse depth in [-1, 1], dropped rays -> raydrop_const."""
@@ -369,7 +403,7 @@ class Trainer:
         self.set_warmup_params(iteration)
         B = self.B
         scalars = OrderedDict()
-        x_real = self.fetch_reals(next(self.batch_iter))["image"]
+        x_real = self.fetch_reals(self._next_batch())["image"]
         ema_imgs = int(tr.ema_kimg * 1e3)                       # trainer.py:459-466
         if tr.ema_rampup is not None:
             ema_imgs = min(ema_imgs, iteration * tr.batch_size * tr.ema_rampup)

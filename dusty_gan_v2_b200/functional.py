@@ -780,8 +780,10 @@ class _ModConvBmm(Function):
     """y[b] = act(wb[b] @ cat(x1[b], x2[b or 0]) + bias) ; x2 (Fourier features) has no grad."""
 
     @staticmethod
-    def forward(ctx, wb, x1, x2, bias, act, alpha, scale, ema_var=None, ema_rows=None):
+    def forward(ctx, wb, x1, x2, bias, act, alpha, scale, ema_var=None, ema_rows=None, parts=None,
+                *handles):
         B, O, Kt = wb.shape
+        ctx.parts = parts            # [(slot, row0, row1)] matching `handles` (see _ModPrep)
         c1 = 0 if x1 is None else x1.shape[1]
         c2 = 0 if x2 is None else x2.shape[1]
         assert c1 + c2 == Kt, (c1, c2, Kt)
@@ -859,7 +861,9 @@ class _ModConvBmm(Function):
                 K.call("dusty_modconv_bwd_dx", K.ptr(wb), K.ptr(gpre), K.ptr(gx1), B, O, c1, Kt, P, dt,
                        K.dtype_code(wb), _PRECISION["modconv_impl"], K.ptr(ctx.ema), rows_p, st)
         gwb = None
-        if ctx.needs_input_grad[0]:
+        n_fixed = 10
+        want_h = [bool(f) for f in ctx.needs_input_grad[n_fixed:]]
+        if ctx.needs_input_grad[0] or any(want_h):
             gw32 = torch.empty(B, O, Kt, device=gy.device, dtype=torch.float32)
             if _modconv_x3_ok(wb, gpre, O, c1, c2, P, "dw"):
                 # contraction over pixels: the three terms side by side on the pixel axis
@@ -871,12 +875,21 @@ class _ModConvBmm(Function):
             else:
                 K.call("dusty_modconv_bwd_dw", K.ptr(gpre), K.ptr(x1), K.ptr(x2), K.ptr(gw32), B, O, c1,
                        c2, b2, P, dt, _PRECISION["modconv_impl"], st)
-            gwb = gw32.to(wb.dtype)
+            if ctx.needs_input_grad[0]:
+                gwb = gw32.to(wb.dtype)
+        gh = []
+        if ctx.parts:
+            for (slot, r0, r1), want in zip(ctx.parts, want_h):
+                if want:
+                    slot["gw32"] = gw32 if (r0, r1) == (0, O) else gw32[:, r0:r1]
+                    gh.append(gw32.reshape(-1)[:1])        # the edge's token; its value is unused
+                else:
+                    gh.append(None)
         if has_bias and ctx.needs_input_grad[3]:
             db = db.reshape(bshape).to(bdtype)
         else:
             db = None
-        return gwb, gx1, None, db, None, None, None, None, None
+        return (gwb, gx1, None, db, None, None, None, None, None, None) + tuple(gh)
 
 
 def set_late_ema(enabled: bool):
@@ -914,16 +927,19 @@ def modconv_bmm(wb, x1, x2=None, bias=None, act: int = 1, alpha: float = 0.2, sc
     weights wb then carry none: modprep(..., ema_var=None, ema_late=ema_var)).  ema_rows: the
     same per output row (heads: O <= 4 rows, each its own ModConv2d), a list of O buffers."""
     K.require_cuda(wb, x1, x2, bias)
+    parts = getattr(wb, "_dusty_parts", None)
     wb = _contig(wb)
     x1 = None if x1 is None else _contig(x1)
     x2 = None if x2 is None else _contig(x2.detach())
+    handles = () if not parts else tuple(h for _, h, _, _ in parts)
     return _ModConvBmm.apply(wb, x1, x2, bias, int(act), float(alpha), float(scale), ema_var,
-                             None if ema_rows is None else list(ema_rows))
+                             None if ema_rows is None else list(ema_rows),
+                             None if not parts else [(s_, a, b) for s_, _, a, b in parts], *handles)
 
 
 class _ModPrep(Function):
     @staticmethod
-    def forward(ctx, slin, weight, ema_var, scale, demod, out_dtype, rot, c1, ema_late=None):
+    def forward(ctx, slin, weight, ema_var, scale, demod, out_dtype, rot, c1, ema_late=None, slot=None):
         slin = _contig(slin.float())
         w2 = _contig(weight.float().reshape(weight.shape[-4], weight.shape[-3]) if weight.ndim == 5
                      else weight.float())
@@ -945,15 +961,28 @@ class _ModPrep(Function):
         # the buffer itself, read at backward time (no forward runs between a layer's forward
         # and its backward, so the value is the one the contraction used)
         ctx.ema_late = None if ema_late is None else ema_late.detach()
+        ctx.slot = slot
+        if slot is not None:
+            # Gradient hand-over outside autograd's dtype rules: wb (bf16) is marked
+            # non-differentiable and a 1-element fp32 HANDLE carries the graph edge; the
+            # contraction's backward leaves the fp32 weight gradient in `slot` (modconv_bmm), this
+            # node picks it up.  (Through autograd the gradient of a bf16 tensor must be bf16:
+            # an fp32 -> bf16 -> fp32 round trip of [B, O, K] per layer.)
+            handle = torch.empty(1, device=slin.device, dtype=torch.float32)
+            ctx.mark_non_differentiable(wb)
+            ctx.set_materialize_grads(False)       # no zero-filled stand-in for wb's (absent) gradient
+            return wb, handle
         return wb
 
     @staticmethod
     @once_differentiable
-    def backward(ctx, gwb):
+    def backward(ctx, gwb, ghandle=None):
         slin, w2, stats, rot = ctx.saved_tensors
         scale, demod, wshape, wdtype, c1, nf = ctx.cfg
         B, I = slin.shape
         O = w2.shape[0]
+        if ctx.slot is not None:
+            gwb = ctx.slot.pop("gw32")
         # this node may run on the weight bank's side stream while gwb was produced (and its
         # memory is owned) by the stream of the contraction's backward
         gwb.record_stream(torch.cuda.current_stream())
@@ -964,11 +993,25 @@ class _ModPrep(Function):
         K.call("dusty_modprep_bwd", K.ptr(gwb), K.ptr(slin), K.ptr(w2), K.ptr(stats), K.ptr(dslin),
                K.ptr(dw), K.ptr(work), B, O, I, scale, 1 if demod else 0, K.ptr(rot), c1, nf,
                K.ptr(ctx.ema_late), K.stream_of(slin))
-        return dslin, dw.reshape(wshape).to(wdtype), None, None, None, None, None, None, None
+        return dslin, dw.reshape(wshape).to(wdtype), None, None, None, None, None, None, None, None
+
+
+def cat_wb(wbs):
+    """torch.cat(wbs, dim=1) for weights made with modprep(via_handle=True): the row ranges keep
+    their gradient slots."""
+    out = torch.cat(wbs, dim=1)
+    parts, o0 = [], 0
+    for w in wbs:
+        for slot, handle, a, b in getattr(w, "_dusty_parts", []):
+            parts.append((slot, handle, o0 + a, o0 + b))
+        o0 += w.shape[1]
+    if parts:
+        out._dusty_parts = parts
+    return out
 
 
 def modprep(slin, weight, ema_var, scale: float, demod: bool, out_dtype=torch.float32, rot=None,
-            c1: int = 0, ema_late=None):
+            c1: int = 0, ema_late=None, via_handle=False):
     """Per-sample effective weights wb[B,O,I] of a modulated 1x1 conv (see dusty_modprep_fwd).
     rot: optional [B, 2F] (cos | sin) rotation of the Fourier columns starting at c1.
     ema_late: the layer's ema_var buffer when the EMA normaliser is applied by the contraction
@@ -976,6 +1019,13 @@ def modprep(slin, weight, ema_var, scale: float, demod: bool, out_dtype=torch.fl
     K.require_cuda(slin, weight, ema_var, rot)
     if ema_late is not None and ema_var is not None:
         raise RuntimeError("modprep: ema_var and ema_late are exclusive")
+    if via_handle:
+        # wb for modconv_bmm only: its gradient reaches this node through a slot, in fp32
+        slot = {}
+        wb, handle = _ModPrep.apply(slin, weight, ema_var, float(scale), bool(demod), out_dtype, rot,
+                                    int(c1), ema_late, slot)
+        wb._dusty_parts = [(slot, handle, 0, wb.shape[1])]
+        return wb
     return _ModPrep.apply(slin, weight, ema_var, float(scale), bool(demod), out_dtype, rot, int(c1),
                           ema_late)
 

@@ -65,7 +65,7 @@ class Head(nn.Module):
 
     def prepare_weights(self, style, dtype, side):
         mods = list(self.heads.values())
-        wb = torch.cat([m.effective_weights(style, dtype, late_ema=True) for m in mods], dim=1)
+        wb = DF.cat_wb([m.effective_weights(style, dtype, late_ema=True, via_handle=True) for m in mods])
         event = torch.cuda.Event()
         event.record(side)
         return wb, event
@@ -85,7 +85,7 @@ class Head(nn.Module):
             wb.record_stream(main)
             y = DF.modconv_bmm(wb, x, None, bias, 1, 0.0, 1.0, ema_rows=[m.ema_var for m in mods])
         else:
-            wb = torch.cat([m.effective_weights(style, x.dtype) for m in mods], dim=1)
+            wb = DF.cat_wb([m.effective_weights(style, x.dtype, via_handle=x.is_cuda) for m in mods])
             y = DF.modconv_bmm(wb, x, None, bias, 1, 0.0, 1.0)
         out = _HeadOut()
         out.stacked = y
@@ -166,7 +166,7 @@ class SynthesisBlock(nn.Module):
             rot = None
             if name == "conv1" and shift_rad is not None and self.use_pe:
                 rot = self.pe_rotation(shift_rad)
-            wb = conv.effective_weights(style, dtype, rot, c1, late_ema=True)
+            wb = conv.effective_weights(style, dtype, rot, c1, late_ema=True, via_handle=True)
             event = torch.cuda.Event()
             event.record(side)
             out[name] = (wb, event)

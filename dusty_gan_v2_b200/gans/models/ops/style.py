@@ -47,7 +47,8 @@ class ModConv2d(nn.Module):
         self.register_buffer("ema_var", torch.tensor(1.0))
 
     # -- small fp32 tensors: [B, O, I] at most 64 MiB for the widest layer, usually < 1 MiB
-    def effective_weights(self, style, out_dtype=torch.float32, pe_rot=None, c1=0, late_ema=False):
+    def effective_weights(self, style, out_dtype=torch.float32, pe_rot=None, c1=0, late_ema=False,
+                          via_handle=False):
         """wb[B,O,I]: one fused kernel pair (dusty_modprep_fwd/bwd) on CUDA.  pe_rot [B, 2F]
         rotates the Fourier columns (batch-shared Fourier block under an azimuth shift).
         late_ema: leave the EMA normaliser out of wb (the contraction's epilogue applies it), so
@@ -56,9 +57,9 @@ class ModConv2d(nn.Module):
         if s.is_cuda:
             if late_ema and self.ema:
                 return DF.modprep(s, self.weight, None, self.scale, self.demod, out_dtype, pe_rot, c1,
-                                  ema_late=self.ema_var)
+                                  ema_late=self.ema_var, via_handle=via_handle)
             return DF.modprep(s, self.weight, self.ema_var if self.ema else None, self.scale,
-                              self.demod, out_dtype, pe_rot, c1)
+                              self.demod, out_dtype, pe_rot, c1, via_handle=via_handle)
         if pe_rot is not None:
             raise RuntimeError("pe_rot needs the CUDA path")
         return self._effective_weights_composite(s).to(out_dtype)
@@ -115,7 +116,7 @@ class ModConv2d(nn.Module):
         src = x if x is not None else pe
         late = wb is not None or self.ema_in_epilogue(src, c1, c2)
         if wb is None:
-            wb = self.effective_weights(style, src.dtype, pe_rot, c1, late_ema=late)
+            wb = self.effective_weights(style, src.dtype, pe_rot, c1, late_ema=late, via_handle=True)
         bias = self.bias
         act, alpha, scale = 1, 0.0, float(self.gain)
         if fused_act is not None:

@@ -513,6 +513,8 @@ class Discriminator(nn.Module):
         self.channels_last = True
         self.fused_stem = True          # BlurVH + 1x1 conv + bias/lrelu as one kernel (bf16 mode)
         self._stem_taps = None
+        self.weight_bank = os.environ.get("DUSTY_WEIGHT_BANK", "1") != "0"
+        self._bank_convs = None
         in_ch = in_ch * 2 if pre_blur else in_ch
         stack = [ops.BlurVH(ring=ring)] if pre_blur else []
         stack += [ops.Conv2d(in_ch, ch(0), 1, 1, 0, **kw), ops.FusedLeakyReLU(ch(0))]
@@ -566,13 +568,45 @@ class Discriminator(nn.Module):
 
         return DF.stem(x, w, act.bias, self._stem_taps, composite, act.negative_slope, act.scale)
 
+    def _prepare_conv_weights(self, device, dtype):
+        """Filter bank: the scaled / cast / re-laid-out filters of every residual-block convolution
+        depend on the parameters only, so they are prepared up-front on the side stream (one
+        launch each, ~50 per pass with their adjoints) instead of inside the activation chain."""
+        if not self.weight_bank:
+            return None
+        if self._bank_convs is None:
+            self._bank_convs = [eq for blk in self.layers if isinstance(blk, ResidualBlock)
+                                for conv in (blk.conv1, blk.conv2, blk.skip)
+                                for eq in conv if isinstance(eq, ops.EqualLR) and isinstance(eq.module, nn.Conv2d)
+                                and eq.module.bias is None and eq.module.padding == (0, 0)]
+        side, main = _side_stream(device), torch.cuda.current_stream()
+        side.wait_stream(main)
+        with torch.cuda.stream(side):
+            for eq in self._bank_convs:
+                eq._ready = None
+                w, w_tco = eq.prepared_weight(dtype, with_tco=True)
+                event = torch.cuda.Event()
+                event.record(side)
+                eq._ready = (w, w_tco, event)
+        return side
+
+    def _release_conv_weights(self, side):
+        if side is not None:
+            torch.cuda.current_stream().wait_stream(side)        # rejoin (graph capture)
+            for eq in self._bank_convs:
+                eq._ready = None
+
     def forward(self, h):
         low = DF.act_dtype()
         y = self._fused_stem(h, low) if h.dim() == 4 and h.shape[1] == 1 else None
         if y is not None:
             h = y
-            for layer in self.layers[3:]:
-                h = layer(h)
+            side = self._prepare_conv_weights(h.device, low)
+            try:
+                for layer in self.layers[3:]:
+                    h = layer(h)
+            finally:
+                self._release_conv_weights(side)
             if self._fast_epilogue_ok(h, low):
                 return self._epilogue_low_precision(h)
             return self.epilogue(h.to(torch.float32).contiguous())

@@ -484,6 +484,18 @@ class EqualLR(nn.Module):
         with_tco=True: (w, w_tco) with the [R*S][C][O] form the data-gradient kernels read (made
         by the same launch when our tcgen05 convolutions are in use, else None)."""
         m = self.module
+        ready = getattr(self, "_ready", None)
+        if ready is not None and with_tco and ready[0].dtype == dtype:
+            # prepared ahead on the discriminator's side stream (filter bank, dusty_v2.py): wait
+            # for it, and keep its memory out of the side stream's pool while this stream reads it
+            w, w_tco, event = ready
+            self._ready = None
+            main = torch.cuda.current_stream()
+            main.wait_event(event)
+            w.record_stream(main)
+            if w_tco is not None:
+                w_tco.record_stream(main)
+            return w, w_tco
         if m.weight.is_cuda and m.weight.dim() == 4:
             # the [R*S][C][O] copy feeds the data-gradient kernels only: skip it when no
             # backward pass can follow

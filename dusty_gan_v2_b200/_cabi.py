@@ -68,6 +68,9 @@ SIGNATURES = {
     "dusty_conv2d_tc": [_vp, _vp, _vp, _vp] + [_i] * 9 + [_vp, _vp, _i, _i, _i]
                        + [C.c_longlong] * 4 + [_i, _f, _f, C.c_longlong, C.c_longlong, _vp, _i, _i, _vp],
     "dusty_conv2d_tc_classes": [_vp, _vp, _vp] + [_i] * 6 + [_vp] * 7 + [C.c_longlong] * 5 + [_i, _i, _vp],
+    "dusty_ada_apply": [_vp, _vp, _vp, _i, _i, _i, _i, _vp],
+    "dusty_ada_apply_smem": [_i, _i],
+    "dusty_ada_sample": [_vp, _vp, C.c_ulonglong, _vp, _i, _i, _i, _vp, _vp],
     "dusty_split_bf16x3": [_vp, _vp, C.c_longlong, C.c_longlong, C.c_longlong, _vp, _vp, _i, _vp],
     "dusty_conv_role_prof": [_vp, _i],
     "dusty_gemm_tf32": [_vp, _vp, _vp, _i, _i, _i, C.c_longlong, C.c_longlong, C.c_longlong, _f, _i, _vp],
@@ -84,7 +87,7 @@ SIGNATURES = {
     "dusty_conv2d_wgrad_tc": [_vp, _vp, _vp, _vp, C.c_longlong] + [_i] * 11 + [_vp],
 }
 _RESTYPE = {"dusty_last_error": C.c_char_p, "dusty_launch_count": C.c_int64,
-            "dusty_conv2d_wgrad_tc_workspace": C.c_longlong}
+            "dusty_conv2d_wgrad_tc_workspace": C.c_longlong, "dusty_ada_apply_smem": C.c_longlong}
 
 _lib = None
 _fns = {}

@@ -601,6 +601,53 @@ def fir1d(x, kernel, up, down, pad):
     return _Fir1d.apply(x, taps, 0, int(up[1]), int(down[1]), int(pad[2]), int(pad[3]), 1)
 
 
+# ---- f1: AdaptiveAugment as one device-side op (csrc/ada_fused.cu) ------------------------------
+class _AdaApply(Function):
+    """out = gain * A(img) + offset for per-sample axis-aligned transforms (params [B, 8]); linear
+    in img: the backward is the adjoint kernel, the backward of that the forward without offset."""
+
+    @staticmethod
+    def forward(ctx, img, params, mode):
+        img = _contig(img.float())
+        B, ch, H, W = img.shape
+        out = torch.empty_like(img)
+        K.call("dusty_ada_apply", K.ptr(img), K.ptr(out), K.ptr(params), B * ch, H, W, mode, K.stream_of(img))
+        ctx.save_for_backward(params)
+        ctx.mode = mode
+        return out
+
+    @staticmethod
+    def backward(ctx, g):
+        (params,) = ctx.saved_tensors
+        return _AdaApply.apply(g, params, 2 if ctx.mode == 1 else 1), None, None
+
+
+def ada_fused_supported(img: torch.Tensor) -> bool:
+    if not (img.is_cuda and img.dim() == 4 and img.shape[1] == 1):
+        return False
+    return int(K.load().dusty_ada_apply_smem(int(img.shape[2]), int(img.shape[3]))) <= 227 * 1024
+
+
+def ada_apply(img: torch.Tensor, params: torch.Tensor) -> torch.Tensor:
+    """params: fp32 CUDA [B, 8] = ax, tx, dy, ty of the inverse transform, colour gain, offset."""
+    K.require_cuda(img, params)
+    if params.dtype != torch.float32 or tuple(params.shape) != (img.shape[0], 8):
+        raise RuntimeError("ada_apply: params must be fp32 [B, 8]")
+    return _AdaApply.apply(img, _contig(params), 0)
+
+
+def ada_sample(params: torch.Tensor, p: torch.Tensor, seed: int, counter: torch.Tensor, H: int, W: int,
+               policy):
+    """Draw B transforms on the device into params [B, 8] (see dusty_ada_sample)."""
+    K.require_cuda(params, p, counter)
+    if counter.dtype != torch.int64 or p.dtype != torch.float32:
+        raise RuntimeError("ada_sample: int64 counter, fp32 p")
+    pol = (K.C.c_float * 11)(*[float(v) for v in policy])
+    K.call("dusty_ada_sample", K.ptr(params), K.ptr(p), int(seed) & 0xFFFFFFFFFFFFFFFF, K.ptr(counter),
+           params.shape[0], H, W, pol, K.stream_of(params))
+    return params
+
+
 class _AffineWarp(Function):
     @staticmethod
     def forward(ctx, img, theta, out_hw, in_hw, adjoint):

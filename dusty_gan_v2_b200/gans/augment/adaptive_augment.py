@@ -12,6 +12,7 @@ transform):
   * `p` keeps a host mirror refreshed in update_p() (one sync every `lazy.ada` iterations).
 """
 import math
+import os
 
 import numpy as np
 import torch
@@ -112,6 +113,11 @@ class AdaptiveAugment(torch.nn.Module):
         self.register_buffer("Hz_fbank", torch.as_tensor(self._filter_bank(), dtype=torch.float32))
         self._p_host = float(p_init)
         self.generator = None           # optional torch.Generator (CPU) for reproducible draws
+        # one-channel images + axis-aligned policies: the whole augmentation as one kernel, the
+        # transforms drawn on the device (csrc/ada_fused.cu); no host work, graph-capturable
+        self.fused = os.environ.get("DUSTY_ADA_FUSED", "1") != "0"
+        self._seed = None
+        self.register_buffer("_calls", torch.zeros(1, dtype=torch.int64), persistent=False)
 
     @staticmethod
     def _filter_bank():
@@ -145,12 +151,17 @@ class AdaptiveAugment(torch.nn.Module):
             self.p = (self.p + adjust).clamp_(0, self.p_max).reshape(())
         self.sign_cum *= 0
         self.n_pred_cum *= 0
-        self._p_host = float(self.p)       # the one host sync of the controller
+        self._p_host = None                # read back lazily, only if the host samplers run
         return rt
+
+    def _p(self) -> float:
+        if self._p_host is None:
+            self._p_host = float(self.p)   # the one host sync of the controller (host sampling only)
+        return self._p_host
 
     # -- sampling (reference 386-469), on the host
     def sample_affine(self, size, height, width, device="cpu"):
-        g, p = self.generator, self._p_host
+        g, p = self.generator, self._p()
         G = _eye(3, size)
         ones = torch.ones(size)
         if self.mul_lr_flip > 0:
@@ -172,7 +183,7 @@ class AdaptiveAugment(torch.nn.Module):
         return G.to(device)
 
     def sample_color(self, size, device="cpu"):
-        g, p = self.generator, self._p_host
+        g, p = self.generator, self._p()
         C = _eye(4, size)
         v = 1 / math.sqrt(3)
         axis = torch.tensor([v, v, v, 0.0])
@@ -205,11 +216,34 @@ class AdaptiveAugment(torch.nn.Module):
         return C.to(device)
 
     # -- the deterministic part: image, inverse transform, colour matrix -> image
+    def policy_vector(self):
+        return [self.mul_lr_flip, self.mul_ud_flip, self.mul_int_trans, self.mul_iso_scale,
+                self.mul_frac_trans, self.mul_brightness, self.mul_contrast, self.mul_luma_flip,
+                self.mul_hue, self.mul_saturation, self.h_trans_factor]
+
+    @staticmethod
+    def fused_params(G_inv, C):
+        """[B, 8] parameter rows of the fused kernel from an inverse transform / colour matrix
+        pair, or None when a transform is not axis-aligned."""
+        G_inv, C = G_inv.detach().float().cpu(), C.detach().float().cpu()
+        if bool((G_inv[:, 0, 1] != 0).any()) or bool((G_inv[:, 1, 0] != 0).any()):
+            return None
+        Cm = C[:, :3, :].mean(dim=1)
+        out = torch.zeros(G_inv.shape[0], 8)
+        out[:, 0], out[:, 1] = G_inv[:, 0, 0], G_inv[:, 0, 2]
+        out[:, 2], out[:, 3] = G_inv[:, 1, 1], G_inv[:, 1, 2]
+        out[:, 4], out[:, 5] = Cm[:, :3].sum(dim=1), Cm[:, 3]
+        return out
+
     def apply(self, img, G_inv, C):
         """img [B,C,H,W] fp32 CUDA; G_inv [B,3,3], C [B,4,4] host or device tensors."""
         img = img.float()
         device = img.device
         B, ch, H, W = img.shape
+        if self.fused and DF.ada_fused_supported(img):
+            params = self.fused_params(G_inv, C)
+            if params is not None:
+                return DF.ada_apply(img, params.to(device, non_blocking=True))
         nk = len(SYM6)
         k = DF.device_taps([list(SYM6)], device)[0]
         k_flip = DF.device_taps([list(SYM6[::-1])], device)[0]
@@ -257,5 +291,14 @@ class AdaptiveAugment(torch.nn.Module):
         if not img.is_cuda:
             raise RuntimeError("AdaptiveAugment runs on CUDA tensors only (no CPU fallback)")
         B, _, H, W = img.shape
+        overridden = "sample_affine" in self.__dict__ or "sample_color" in self.__dict__   # pinned draws
+        if self.fused and not overridden and DF.ada_fused_supported(img):
+            # transforms drawn on the device: no host tensors, no sync, CUDA-graph safe
+            params = torch.empty(B, 8, device=img.device, dtype=torch.float32)
+            if self._seed is None:
+                self._seed = int(self.generator.initial_seed() if self.generator is not None
+                                 else torch.initial_seed())
+            DF.ada_sample(params, self.p.reshape(1), self._seed, self._calls, H, W, self.policy_vector())
+            return DF.ada_apply(img, params)
         G_inv = torch.inverse(self.sample_affine(B, H, W))
         return self.apply(img, G_inv, self.sample_color(B))

@@ -439,6 +439,30 @@ int dusty_split_bf16x3(const float *src, void *dst, long long outer, long long K
                        const long long *src_strides, const long long *dst_strides, int pattern,
                        void *stream);
 
+/* ---- f1: AdaptiveAugment as one device-side op ------------------------------------------------
+ * Replaces AdaptiveAugment.forward for one-channel images and the axis-aligned geometric policies
+ * of the shipped configs (gans/augment/adaptive_augment.py:271-291 get_padding, 386-469 sampling,
+ * 471-545 pad -> up -> affine grid_sample -> down -> colour).
+ * params: fp32 [B, 8] = ax, tx, dy, ty (the INVERSE transform [[ax,0,tx],[0,dy,ty]]), colour gain,
+ * colour offset, 2 unused.
+ * dusty_ada_apply: img / out fp32 [B, H, W]; one CTA per sample, the image resident in shared
+ * memory (dusty_ada_apply_smem(H, W) bytes must fit in 227 KB), rows then columns through the 1-D
+ * pad / up / interpolate / down pipeline; fixed maximum padding (W-1 / H-1, index arithmetic).
+ *   mode 0: out = gain * A(img) + offset;  mode 1: the adjoint, out = gain * A^T(img);
+ *   mode 2: mode 0 without the offset (the backward of the adjoint: R1 differentiates twice).
+ * dusty_ada_sample: draws the transforms on the device with probability *p (device scalar,
+ * AdaptiveAugment.p) per policy; Philox seeded by `seed`, one subsequence per sample, advanced by
+ * the device-resident call counter `counter` (so that a captured graph draws fresh transforms at
+ * every replay).  policy: HOST array of 11 floats = the multipliers lr_flip, ud_flip, int_trans,
+ * iso_scale, frac_trans, brightness, contrast, luma_flip, hue, saturation, and the vertical
+ * translation factor (0 with wonly_trans). */
+long long dusty_ada_apply_smem(int H, int W);
+int dusty_ada_apply(const float *img, float *out, const float *params, int B, int H, int W, int mode,
+                    void *stream);
+int dusty_ada_sample(float *params, const float *p, unsigned long long seed,
+                     unsigned long long *counter, int B, int H, int W, const float *policy,
+                     void *stream);
+
 /* ---- f2: optimiser step and EMA (gans/trainer.py:30-41 ema_inplace, 128-171 Adam) ----------
  * Multi-tensor Adam exactly as torch.optim.Adam (no weight decay / amsgrad) over `count` fp32
  * tensors given as HOST arrays of device pointers: grads are multiplied by grad_scale first

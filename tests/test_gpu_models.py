@@ -351,6 +351,96 @@ def test_ada_apply_golden_first_and_second_order(g_ada):
     assert out.shape == x.shape and torch.isfinite(out).all()
 
 
+@pytest.mark.parametrize("H,W", [(64, 512), (16, 64)])
+def test_ada_fused_kernel_vs_oracle_and_composite(H, W):
+    """f1: the whole augmentation as ONE kernel (csrc/ada_fused.cu: per-sample CTA, image resident
+    in shared memory, separable pad / up / interpolate / down pipelines, fixed maximum padding)
+    against the CPU oracle's stage-by-stage restatement and the mirror's composite path, for
+    axis-aligned transforms incl. flips, large translations (padding clamp) and y scales; first
+    order (adjoint kernel) and the R1-style second order."""
+    from dusty_gan_v2_b200.gans.augment.adaptive_augment import AdaptiveAugment
+    g = torch.Generator().manual_seed(8)
+    B = 6
+    ada = AdaptiveAugment(p_init=1.0, lr_flip=1, ud_flip=1, int_trans=1, iso_scale=1, frac_trans=1,
+                          brightness=1, contrast=1, luma_flip=1, hue=1, saturation=1).to(DEV)
+    ada.generator = torch.Generator().manual_seed(3)
+    G = ada.sample_affine(B, H, W)
+    # hand-made extremes: identity, pure flips, a translation beyond the padding clamp, strong scales
+    eye = torch.eye(3)
+    G[0] = eye
+    G[1] = torch.tensor([[-1.0, 0, 0], [0, -1.0, 0], [0, 0, 1]])
+    G[2] = torch.tensor([[1.0, 0, 0.9 * W], [0, 1.0, 0.45 * H], [0, 0, 1]])
+    G[3] = torch.tensor([[1.0, 0, -3.25], [0, 1.6, 2.5], [0, 0, 1]])
+    G_inv = torch.inverse(G)
+    C = ada.sample_color(B)
+    x = torch.randn(B, 1, H, W, generator=g)
+    ref = O.ada_apply(x, G_inv, C)
+    assert DF_mod().ada_fused_supported(x.to(DEV))
+    names = []
+    K = DF_mod().K
+    orig = K.call
+    K.call = lambda name, *a: (names.append(name), orig(name, *a))[1]
+    try:
+        xg = x.to(DEV).requires_grad_()
+        y = ada.apply(xg, G_inv, C)
+        gy = torch.randn(y.shape, generator=g).to(DEV).requires_grad_()
+        (gx,) = torch.autograd.grad(y, xg, gy, create_graph=True)
+        v = torch.randn(x.shape, generator=g)
+        (gg,) = torch.autograd.grad((gx * v.to(DEV)).sum(), gy)
+    finally:
+        K.call = orig
+    assert names.count("dusty_ada_apply") == 3 and "dusty_fir2d" not in names and "dusty_affine_warp" not in names
+    close(y, ref, rtol=1e-3, atol_rel=2e-4)
+    xr = x.clone().requires_grad_()
+    (gx_ref,) = torch.autograd.grad(O.ada_apply(xr, G_inv, C), xr, gy.detach().cpu())
+    close(gx, gx_ref, rtol=1e-3, atol_rel=2e-4)
+    C0 = C.clone()
+    C0[:, :3, 3] = 0
+    close(gg, O.ada_apply(v, G_inv, C0), rtol=1e-3, atol_rel=2e-4)
+    # the composite (stage-by-stage) path of the mirror gives the same image
+    ada.fused = False
+    close(ada.apply(x.to(DEV), G_inv, C), y.detach(), rtol=1e-3, atol_rel=2e-4)
+
+
+def test_ada_device_sampler_statistics():
+    """dusty_ada_sample against the host samplers (the reference's distributions, pinned live in
+    tests/test_reference_live.py): gate frequencies, flip signs, translation and scale moments of
+    the INVERSE transform rows and the colour gain / offset, over 1024 samples x 8 calls; fresh
+    draws at every call (device-resident call counter)."""
+    from dusty_gan_v2_b200.gans.augment.adaptive_augment import AdaptiveAugment
+    H, W, B = 64, 512, 1024
+    ada = AdaptiveAugment(p_init=0.7, lr_flip=1, ud_flip=1, int_trans=1, iso_scale=1, frac_trans=1,
+                          brightness=1, contrast=1, luma_flip=1, hue=1, saturation=1).to(DEV)
+    DFm = DF_mod()
+    dev_rows = []
+    for _ in range(8):
+        prm = torch.empty(B, 8, device=DEV)
+        DFm.ada_sample(prm, ada.p.reshape(1), 1234, ada._calls, H, W, ada.policy_vector())
+        dev_rows.append(prm.cpu())
+    assert int(ada._calls) == 8 and not torch.equal(dev_rows[0], dev_rows[1])
+    dev = torch.cat(dev_rows)
+    ada.generator = torch.Generator().manual_seed(0)
+    host = torch.cat([ada.fused_params(torch.inverse(ada.sample_affine(B, H, W)), ada.sample_color(B))
+                      for _ in range(8)])
+    n = dev.shape[0]
+    for col, name in enumerate(["ax", "tx", "dy", "ty", "gain", "offset"]):
+        a, b = dev[:, col], host[:, col]
+        se = float(b.std()) / np.sqrt(n) * 5 + 1e-3
+        assert abs(float(a.mean()) - float(b.mean())) < se * 2, (name, float(a.mean()), float(b.mean()))
+        assert abs(float(a.std()) - float(b.std())) < 0.08 * float(b.std()) + 1e-3, (name, float(a.std()), float(b.std()))
+    # discrete structure: flips are exactly +-1 (x) and the share of untouched samples matches
+    assert set(torch.unique(dev[:, 0]).tolist()) <= {-1.0, 1.0}
+    for col in (0, 1, 3):
+        fa = float((dev[:, col] == host[0, col] * 0 + (1.0 if col == 0 else 0.0)).float().mean())
+        fb = float((host[:, col] == (1.0 if col == 0 else 0.0)).float().mean())
+        assert abs(fa - fb) < 0.03, (col, fa, fb)
+
+
+def DF_mod():
+    import dusty_gan_v2_b200.functional as DFm
+    return DFm
+
+
 def test_training_step_runs_and_matches_oracle_losses(monkeypatch):
     """One full iteration (G step, D step, R1, EMA) of the drop-in Trainer at a small size with
     FRESH random draws: every draw the mirror makes is recorded and the CPU oracle is advanced

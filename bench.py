@@ -418,7 +418,7 @@ def kernel_rooflines(device, peaks):
     gwh_ = torch.empty(B, 2, 32, device=device)
     mem_entry("heads_dw[O=2,C=32,64x512]bf16",
               lambda: K.call("dusty_modconv_bwd_dw", K.ptr(gh_), K.ptr(hd), None, K.ptr(gwh_), B, 2, 32, 0, 1,
-                             H * W, K.BF16, 0, K.stream_of(hd)), (hd.numel() + gh_.numel()) * 2)
+                             H * W, K.BF16, 0, 0, K.stream_of(hd)), (hd.numel() + gh_.numel()) * 2)
     del gh_
     del hd
     ang = torch.rand(B, 2, H, W, device=device)
@@ -459,7 +459,7 @@ def kernel_rooflines(device, peaks):
         pe_tag = "shared" if shared else "per-sample"
         tc_entry(f"modconv_dw[{tag},pe={pe_tag}]bf16",
                  lambda: K.call("dusty_modconv_bwd_dw", K.ptr(g), K.ptr(x1), K.ptr(x2), K.ptr(gw), B, O_, C1, C2,
-                                x2.shape[0], P, K.BF16, 0, K.stream_of(g)),
+                                x2.shape[0], P, K.BF16, 0, 0, K.stream_of(g)),
                  flops, (x1.numel() + g.numel() + x2.numel() * (1 if shared else 1)) * 2 + gw.numel() * 4)
         gx1 = torch.empty_like(x1)
         tc_entry(f"modconv_dx[{tag},pe={pe_tag}]bf16",

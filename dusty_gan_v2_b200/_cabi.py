@@ -48,7 +48,7 @@ SIGNATURES = {
     "dusty_angle_down2": [_vp, _vp, _i, _i, _i, _vp],
     "dusty_modconv_fwd": [_vp, _vp, _vp, _vp, _vp, _i, _i, _i, _i, _i, _i64, _i, _f, _f, _i, _i, _i, _vp, _vp, _vp],
     "dusty_modconv_bwd_dx": [_vp, _vp, _vp, _i, _i, _i, _i, _i64, _i, _i, _i, _vp, _vp, _vp],
-    "dusty_modconv_bwd_dw": [_vp, _vp, _vp, _vp, _i, _i, _i, _i, _i, _i64, _i, _i, _vp],
+    "dusty_modconv_bwd_dw": [_vp, _vp, _vp, _vp, _i, _i, _i, _i, _i, _i64, _i, _i, C.c_longlong, _vp],
     "dusty_modprep_fwd": [_vp, _vp, _vp, _vp, _vp, _i, _i, _i, _f, _i, _i, _vp, _i, _i, _vp],
     "dusty_modprep_bwd": [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _i, _i, _i, _f, _i, _vp, _i, _i, _vp, _vp],
     "dusty_gumbel_raydrop_fwd": [_vp] * 7 + [_i64, _f, _f, _vp],

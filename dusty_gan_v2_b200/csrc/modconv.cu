@@ -19,7 +19,7 @@ int modconv_dx_tc(const void *wb, const void *dy, void *dx1, int B, int O, int C
                   cudaStream_t st, bool out_f32, const float *ema);
 bool modconv_dx_tc_supported(int B, int O, int C1, int K, int64_t P);
 int modconv_dw_tc(const void *dy, const void *x1, const void *x2, float *dwb, int B, int O, int C1,
-                  int C2, int B2, int64_t P, cudaStream_t st);
+                  int C2, int B2, int64_t P, cudaStream_t st, int64_t ld);
 bool modconv_dw_tc_supported(int B, int O, int C1, int C2, int B2, int64_t P);
 }  // namespace dusty
 
@@ -98,8 +98,9 @@ extern "C" int dusty_modconv_bwd_dx(const void *wb, const void *dy, void *dx1, i
 
 extern "C" int dusty_modconv_bwd_dw(const void *dy, const void *x1, const void *x2, float *dwb,
                                     int B, int O, int C1, int C2, int B2, int64_t P, int dtype,
-                                    int impl, void *stream) {
+                                    int impl, long long dw_ld, void *stream) {
   DUSTY_CHECK_ARG(dy && dwb, "null pointer");
+  DUSTY_CHECK_ARG(dw_ld == 0 || dw_ld >= C1 + C2, "dw_ld: row pitch of dwb, 0 = dense");
   DUSTY_CHECK_ARG(B >= 1 && B <= 65535 && O >= 1 && C1 >= 0 && C2 >= 0 && C1 + C2 >= 1 && P >= 1,
                   "bad shape");
   DUSTY_CHECK_ARG((C1 == 0 || x1) && (C2 == 0 || x2), "missing source tensor");
@@ -114,8 +115,13 @@ extern "C" int dusty_modconv_bwd_dw(const void *dy, const void *x1, const void *
     return DUSTY_EUNSUPPORTED;
   }
   int rc;
-  if (impl >= 2 || (impl == 0 && tc_ok))
-    rc = modconv_dw_tc(dy, x1, x2, dwb, B, O, C1, C2, B2, P, (cudaStream_t)stream);
+  const bool dw_tc = impl >= 2 || (impl == 0 && tc_ok);
+  if (dw_ld > C1 + C2 && !dw_tc) {
+    set_error("dusty_modconv_bwd_dw: a strided result needs the tcgen05 path");
+    return DUSTY_EUNSUPPORTED;
+  }
+  if (dw_tc)
+    rc = modconv_dw_tc(dy, x1, x2, dwb, B, O, C1, C2, B2, P, (cudaStream_t)stream, dw_ld);
   else
     rc = modconv_bwd_dw_simt(dy, x1, x2, dwb, B, O, C1, C2, B2, P, dtype, (cudaStream_t)stream);
   if (rc) return rc;

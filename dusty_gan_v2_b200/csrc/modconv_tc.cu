@@ -570,6 +570,7 @@ struct DwParams {
   int O, C1, K, B2;
   int64_t P;
   float *dw;
+  int64_t ld;            // row pitch of dw (floats): K, or the pitch of a wider [B, O, ld] tensor
 };
 
 template <int BN, int STAGES>
@@ -662,7 +663,7 @@ modconv_dw_tc_kernel(const __grid_constant__ CUtensorMap map_x1,
     const int k = m0 + q * 32 + lane;      // in-channel index of this thread's accumulator row
     mbar_wait(acc_full, 0);
     tc_fence_after();
-    float *dwb = prm.dw + (int64_t)b * prm.O * prm.K + k;
+    float *dwb = prm.dw + (int64_t)b * prm.O * prm.ld + k;
 #pragma unroll 1
     for (int c = 0; c < BN; c += 16) {
       uint32_t r[16];
@@ -671,7 +672,7 @@ modconv_dw_tc_kernel(const __grid_constant__ CUtensorMap map_x1,
 #pragma unroll
       for (int j = 0; j < 16; ++j) {
         const int o = n0 + c + j;
-        if (o < prm.O && k < prm.K) dwb[(int64_t)o * prm.K] = __uint_as_float(r[j]);
+        if (o < prm.O && k < prm.K) dwb[(int64_t)o * prm.ld] = __uint_as_float(r[j]);
       }
     }
   }
@@ -898,7 +899,7 @@ static int launch_dw(const CUtensorMap &mx1, const CUtensorMap &mx2, const CUten
 }
 
 int modconv_dw_tc(const void *dy, const void *x1, const void *x2, float *dwb, int B, int O, int C1,
-                  int C2, int B2, int64_t P, cudaStream_t st) {
+                  int C2, int B2, int64_t P, cudaStream_t st, int64_t ld) {
   const int BN = O >= 256 ? 256 : (O >= 128 ? 128 : (O >= 64 ? 64 : 32));
   CUtensorMap mx1, mx2, mg;
   const bool ok1 = make_map3(&mx1, x1, (uint64_t)P, (uint64_t)(C1 ? C1 : C2), (uint64_t)(C1 ? B : B2),
@@ -912,6 +913,7 @@ int modconv_dw_tc(const void *dy, const void *x1, const void *x2, float *dwb, in
   }
   DwParams prm;
   prm.O = O; prm.C1 = C1; prm.K = C1 + C2; prm.B2 = B2; prm.P = P; prm.dw = dwb;
+  prm.ld = ld > 0 ? ld : C1 + C2;
   switch (BN) {
     case 256: return launch_dw<256, 4>(mx1, mx2, mg, prm, B, st);
     case 128: return launch_dw<128, 4>(mx1, mx2, mg, prm, B, st);

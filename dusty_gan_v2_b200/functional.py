@@ -793,6 +793,22 @@ def _modconv_x3_ok(wb, src, O, c1, c2, P, op) -> bool:
     return c2 == 0 or c1 % 64 == 0           # dw: 64-channel boxes must not straddle the sources
 
 
+def _dw_fused_ok(gpre, x1, x2, O, c1, c2, b2, P) -> bool:
+    """dW of a contraction whose Fourier block is batch-shared: dense-GEMM formulation (bf16
+    tcgen05 kernels; shapes inside both kernels' domains)."""
+    if not (_PRECISION.get("dw_fused", True) and _PRECISION["modconv_impl"] in (0, 2)):
+        return False
+    if x2 is None or b2 != 1 or c2 < 64 or gpre.dtype != torch.bfloat16 or x2.dtype != torch.bfloat16:
+        return False
+    if P % 128 or c2 % 8 or c1 % 4 or (c1 + c2) % 4 or O < 32 or O % 16:
+        return False
+    return c1 == 0 or (x1 is not None and x1.dtype == torch.bfloat16 and c1 % 8 == 0)
+
+
+def set_dw_fused(enabled: bool):
+    _PRECISION["dw_fused"] = bool(enabled)
+
+
 def _split_planes(x: torch.Tensor, pattern: int) -> torch.Tensor:
     """fp32 [B, C, H, W] (contiguous) -> bf16 [B, 3C, H, W]: parts stacked on the channel axis."""
     x = _contig(x)
@@ -918,10 +934,19 @@ class _ModConvBmm(Function):
                 x1p = None if x1 is None else _split_pixels(x1, 1)
                 x2p = None if x2 is None else _split_pixels(x2, 1)
                 K.call("dusty_modconv_bwd_dw", K.ptr(gp), K.ptr(x1p), K.ptr(x2p), K.ptr(gw32), B, O, c1,
-                       c2, b2, 3 * P, K.BF16, 2, st)
+                       c2, b2, 3 * P, K.BF16, 2, 0, st)
+            elif _dw_fused_ok(gpre, x1, x2, O, c1, c2, b2, P):
+                # batch-shared Fourier block: its columns of dW for ALL samples are one dense GEMM
+                # [(B*O), P] x [P, C2] (the block crosses L2 -> SM once instead of once per sample);
+                # the feature columns stay per sample, written at the pitch of the full tensor
+                K.call("dusty_gemm_bf16", K.ptr(gpre), K.ptr(x2), gw32.data_ptr() + 4 * c1, B * O, c2, P, 0, 0,
+                       P, P, Kt, 1.0, 0, st)
+                if c1:
+                    K.call("dusty_modconv_bwd_dw", K.ptr(gpre), K.ptr(x1), None, K.ptr(gw32), B, O, c1, 0, 1, P,
+                           dt, 2, Kt, st)
             else:
                 K.call("dusty_modconv_bwd_dw", K.ptr(gpre), K.ptr(x1), K.ptr(x2), K.ptr(gw32), B, O, c1,
-                       c2, b2, P, dt, _PRECISION["modconv_impl"], st)
+                       c2, b2, P, dt, _PRECISION["modconv_impl"], 0, st)
             if ctx.needs_input_grad[0]:
                 gwb = gw32.to(wb.dtype)
         gh = []

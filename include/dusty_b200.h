@@ -211,9 +211,14 @@ int dusty_modconv_fwd(const void *wb, const void *x1, const void *x2, const floa
 int dusty_modconv_bwd_dx(const void *wb, const void *dy, void *dx1, int B, int O, int C1, int K,
                          int64_t P, int dtype, int wdtype, int impl, const float *ema_var,
                          const float *const *ema_rows, void *stream);
-/* dwb[b,o,k] = sum_p dY[b,o,p] * X(b,k,p)  (fp32 output, overwritten). */
+/* dwb[b,o,k] = sum_p dY[b,o,p] * X(b,k,p)  (fp32 output, overwritten).
+ * dw_ld: row pitch of dwb in floats (0 = C1 + C2); a wider pitch writes the columns of one source
+ * into a [B, O, dw_ld] tensor whose other columns come from elsewhere: with a batch-SHARED x2 the
+ * Fourier columns of all samples are ONE dense GEMM, dusty_gemm_bf16 over dY viewed [(B*O), P]
+ * (the Fourier block is then read once instead of once per sample). */
 int dusty_modconv_bwd_dw(const void *dy, const void *x1, const void *x2, float *dwb, int B, int O,
-                         int C1, int C2, int B2, int64_t P, int dtype, int impl, void *stream);
+                         int C1, int C2, int B2, int64_t P, int dtype, int impl, long long dw_ld,
+                         void *stream);
 
 /* Per-sample effective weights (modulation, pre-normalisation, demodulation, EMA
  * normaliser) -- the part of ModConv2d.forward before the grouped conv, style.py:72-103.

@@ -541,8 +541,8 @@ def test_modconv_fp32_on_tensor_cores_split_bf16(DF, B, Oc, C1, C2, B2, HW):
     gy = torch.randn(B, Oc, H, W, generator=g)
     names = []
     orig = DF.K.call
-    # impl argument: (..., impl, ema_var, ema_rows, stream) for fwd / dx, (..., impl, stream) for dw
-    impl_of = lambda name, a: a[-2] if name == "dusty_modconv_bwd_dw" else (a[-4] if name.startswith("dusty_modconv") else None)  # noqa: E731
+    # impl argument: (..., impl, ema_var, ema_rows, stream) for fwd / dx, (..., impl, dw_ld, stream) for dw
+    impl_of = lambda name, a: a[-3] if name == "dusty_modconv_bwd_dw" else (a[-4] if name.startswith("dusty_modconv") else None)  # noqa: E731
     DF.K.call = lambda name, *a: (names.append((name, impl_of(name, a))), orig(name, *a))[1]
     try:
         wg = wb.to(DEV).requires_grad_()

@@ -17,7 +17,7 @@ for (B, Oc, C1, H, W) in [(2, 64, 64, 32, 256), (2, 64, 64, 16, 256), (2, 64, 64
         xp = DF._split_pixels(x1d, 1)
         gw = torch.empty(B, Oc, C1, device=dev)
         K.call("dusty_modconv_bwd_dw", K.ptr(gp), K.ptr(xp), None, K.ptr(gw), B, Oc, C1, 0, 1, 3 * P, K.BF16, 2,
-               K.stream_of(gw))
+               0, K.stream_of(gw))
         torch.cuda.synchronize()
         d = (gw.cpu() - ref).abs()
         bad = (d > 2e-5 * ref.abs().max() + 1e-4 * ref.abs()).nonzero()

@@ -78,7 +78,7 @@ def main():
 
             def dw():
                 K.call("dusty_modconv_bwd_dw", K.ptr(gy), K.ptr(x1), K.ptr(x2), K.ptr(gw), B, O_, C1, C2, 1, P,
-                       K.BF16, impl, K.stream_of(gy))
+                       K.BF16, impl, 0, K.stream_of(gy))
             dw()
             errw = float((gw[sub] - dw_ref).abs().max() / dw_ref.abs().max())
             row[f"dw_{name}_us"] = timeit(dw)

@@ -827,8 +827,11 @@ def main():
                        "l2": "no flush: per-step working set (GBs) >> 126 MB L2",
                        "dense_convs": "every dense (transposed) convolution on own kernels: tcgen05 implicit GEMM "
                                       "(fprop / dgrad / wgrad, CTA pairs for the deep layers) for bf16 NHWC, "
-                                      "CUDA-core family for fp32 and odd shapes; no library convolution; "
-                                      "cuBLAS for the linears"},
+                                      "split-bf16 operands on the same kernels in fp32 mode, CUDA-core family "
+                                      "for odd shapes; no library convolution; D's linears on own GEMMs "
+                                      "(cuBLAS only for the mapping / style linears)",
+                       "augment": "AdaptiveAugment as a device-side op (transforms drawn on the device)",
+                       "side_streams": "generator weight bank, discriminator filter bank, next batch's upload"},
             "clocks": clk, "gpu_launches": launches, "e2e": e2e}
 
     if rank == 0 and world == 1:

@@ -48,6 +48,7 @@ def parse():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-roofline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--per-step", action="store_true", help="print the device time of every timed step (stderr)")
     ap.add_argument("--no-cudnn-benchmark", action="store_true")
     ap.add_argument("--no-cuda-graphs", action="store_true")
     ap.add_argument("--ref-kernels-only", action="store_true",
@@ -740,29 +741,50 @@ def main():
             dist.barrier()
         torch.cuda.synchronize()
 
-    def run(first_it, n):
+    step_events = []
+
+    def run(first_it, n, trace=False):
+        last = None
         for i in range(n):
             last = tr.step(first_it + i)
+            if trace:
+                ev = torch.cuda.Event(enable_timing=True)
+                ev.record()
+                step_events.append(ev)
         return last
 
     # warm-up: iteration 0 carries an R1 step, so every phase is warmed
     run(0, args.warmup)
     gp = max(tr.gp_every, 1)
     start = ((args.warmup + gp - 1) // gp) * gp          # timed region starts on an R1 iteration
-    barrier()
+    # the iterations between the requested warm-up and that R1 iteration run untimed as well (they
+    # would otherwise be skipped): lazily created handles, allocator growth and NCCL channel set-up
+    # of a young process otherwise land in the timed window (seen at N = 2: 15.4-17.6 ms / step for
+    # the same build, while the later end-to-end window was stable at 15.4)
+    run(args.warmup, start - args.warmup)
+    # (the sampler is started BEFORE the barrier: NVML initialisation on rank 0 alone, between the
+    # barrier and the first timed step, made the other ranks wait for it inside their first
+    # collective -- up to 80 ms inside their timed window, and the window is the max over ranks)
     clocks = ClockSampler(local_rank) if rank == 0 else None
+    barrier()
     n0 = pkg.launch_count()
     g0 = tr.graph_replayed_launches
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     if args.ncu_window:
         torch.cuda.profiler.start()
     e0.record()
-    run(start, args.steps)
+    run(start, args.steps, trace=args.per_step)
     e1.record()
     barrier()
     if args.ncu_window:
         torch.cuda.profiler.stop()
     launches = pkg.launch_count() - n0 + (tr.graph_replayed_launches - g0)
+    if args.per_step and rank == 0:
+        prev, per = e0, []
+        for ev in step_events:
+            per.append(round(prev.elapsed_time(ev), 2))
+            prev = ev
+        print("device ms per timed step:", per, file=sys.stderr)
     ms = torch.tensor([e0.elapsed_time(e1)], device=device)
     if world > 1:
         dist.all_reduce(ms, op=dist.ReduceOp.MAX)
@@ -825,6 +847,8 @@ def main():
                        "global_batch": B * world, "per_gpu_batch": B, "parallelism": f"dp{world}",
                        "r1_steps_timed": r1_steps, "ada_p": "adaptive from 0.0" if args.ada_p is None else args.ada_p,
                        "l2": "no flush: per-step working set (GBs) >> 126 MB L2",
+                       "warmup_extra": f"{start - args.warmup} further untimed iterations up to the R1 iteration the "
+                                       "timed window starts on",
                        "dense_convs": "every dense (transposed) convolution on own kernels: tcgen05 implicit GEMM "
                                       "(fprop / dgrad / wgrad, CTA pairs for the deep layers) for bf16 NHWC, "
                                       "split-bf16 operands on the same kernels in fp32 mode, CUDA-core family "

@@ -28,13 +28,20 @@ def main():
     ap.add_argument("--batch", type=int, default=64)
     ap.add_argument("--json", default=None)
     args = ap.parse_args()
-    dev = torch.device("cuda", 0)
+    # under torchrun: one process per GPU, per-GPU batch `--batch` (rank 0 reports)
+    rank, world = int(os.environ.get("RANK", 0)), int(os.environ.get("WORLD_SIZE", 1))
+    local = int(os.environ.get("LOCAL_RANK", 0))
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        import torch.distributed as dist
+        dist.init_process_group("nccl", device_id=dev)
     pkg.set_precision("bf16")
-    import dusty_gan_v2_b200.functional as DF
     torch.backends.cudnn.benchmark = True
-    cfg = preset("dusty_v2", batch_size=args.batch)
-    pool = bench.synthetic_batches(4, args.batch, seed=2, device=dev)
-    tr = Trainer(cfg, bench.cycle(pool), device=dev, angle_file=os.path.join(ROOT, "data/coords/kitti_raw.npy"))
+    cfg = preset("dusty_v2", batch_size=args.batch * world)
+    pool = bench.synthetic_batches(4, args.batch, seed=2 + rank, device=dev)
+    tr = Trainer(cfg, bench.cycle(pool), device=dev, rank=rank, world_size=world,
+                 angle_file=os.path.join(ROOT, "data/coords/kitti_raw.npy"))
     for i in range(4):
         tr.step(i)
     torch.cuda.synchronize()
@@ -55,8 +62,10 @@ def main():
     out = {"plain_ms_median": sorted(plain)[len(plain) // 2], "r1_ms": r1,
            "host_plain_ms_median": sorted(r["host_ms"] for r in rows if not r["r1"])[len(plain) // 2],
            "host_r1_ms": [r["host_ms"] for r in rows if r["r1"]], "rows": rows}
-    print(json.dumps({k: v for k, v in out.items() if k != "rows"}))
-    if args.json:
+    if rank == 0:
+        print(json.dumps({k: v for k, v in out.items() if k != "rows"}))
+        print("device ms per iteration:", [r["device_ms"] for r in rows])
+    if args.json and rank == 0:
         json.dump(out, open(args.json, "w"), indent=1)
 
 

@@ -18,7 +18,7 @@ GROUPS = OrderedDict([
     ("modulated contractions (tcgen05) + heads", r"modconv_|small_o_kernel|heads_dw|gemm_n"),
     ("modprep (per-sample weights, styles)", r"modprep_"),
     ("G resampling / Fourier / raydrop / shift", r"up2_|blur4_fwd|blur4_adj|fourier|raydrop|circ|angle_down|ema_lerp|point_project"),
-    ("ADA (FIR passes, warp, pad)", r"fir1d|fir2d|affine_warp|pad2d_(fwd|adj)_kernel"),
+    ("ADA (device-side op: sample, row pass, column pass)", r"ada_rows|ada_cols|ada_sample|fir1d|fir2d|affine_warp|pad2d_(fwd|adj)_kernel"),
     ("linears (own GEMMs: epilogue; cuBLAS: mapping / styles)", r"cutlass|sgemm|cublas|gemv|gemm_tc_kernel|gemm_simt|nvjet"),
     ("optimizer (fused Adam, EMA foreach)", r"Adam|multi_tensor|FusedOptimizer|lerp|multi_adam|multi_copy"),
     ("ATen glue: gradient accumulation adds", r"CUDAFunctor_add"),

@@ -235,14 +235,35 @@ struct Taps4CL { float k[4]; };
 // PAD == true fuses the ring padding (1 pixel, circular W / replicate H) that follows the blur
 // in the residual blocks (conv2 input): forward writes the blurred image straight into the
 // padded [H+2, W+2] tensor; the adjoint reads the padded gradient and folds the halo on load.
-template <typename T, bool ADJ, bool PAD>
+// GATE (ADJ && PAD only): the adjoint's result is the gradient w.r.t. an ACTIVATED tensor
+// yact = lrelu(pre + bias) * scale that fed the blur; it is multiplied by the activation's gate
+// on the way out and the bias gradient is accumulated (shared memory -> one atomic per CTA and
+// channel): the separate bias_act backward pass over the same tensor disappears.
+constexpr int kGateReplicas = 64;
+struct GateArgs {
+  const void *yact;
+  float *db;
+  float pos, neg;         // gate value for yact > 0 / otherwise: scale, alpha * scale
+};
+
+template <typename T, bool ADJ, bool PAD, bool GATE = false>
 __global__ void __launch_bounds__(128, (ADJ && PAD) ? 4 : 5)
 blur4_cl_kernel(const T *__restrict__ x, T *__restrict__ y, Taps4CL t, int H, int W, int cv,
-                int strip, int64_t n_threads) {
+                int strip, int64_t n_threads, GateArgs ga = GateArgs{nullptr, nullptr, 1.f, 1.f}) {
   constexpr int V = Vec16<T>::N;      // 16-byte channel groups
   const int Wx = (PAD && !ADJ) ? W + 2 : W;      // columns covered by threads
   const int64_t tid = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-  if (tid >= n_threads) return;
+  __shared__ float s_db[GATE ? 512 : 1];
+  if (GATE) {
+    for (int c = threadIdx.x; c < cv * V; c += blockDim.x) s_db[c] = 0.f;
+    __syncthreads();
+  }
+  const bool active = tid < n_threads;
+  if (!GATE && !active) return;
+  if (GATE && !active) {             // keep the block barriers below convergent
+    __syncthreads();
+    return;
+  }
   const int j = (int)(tid % cv);
   const int64_t q = tid / cv;
   const int xo = (int)(q % Wx);                  // output column (padded coordinates if PAD fwd)
@@ -366,10 +387,17 @@ blur4_cl_kernel(const T *__restrict__ x, T *__restrict__ y, Taps4CL t, int H, in
     issue(e_lo + 2, nxt);
     reduce(cur, c);
     float2 acc[VP];
+    float dbs[GATE ? V : 1] = {};
 #pragma unroll
     for (int k = 0; k < VP; ++k) acc[k] = make_float2(0.f, 0.f);
 #pragma unroll 4
     for (int e = e_lo; e <= e_hi; ++e) {
+      const int i = e < 0 ? 0 : (e >= H ? H - 1 : e);
+      const int i_next = (e + 1) < 0 ? 0 : ((e + 1) >= H ? H - 1 : (e + 1));
+      const bool store = e == e_hi || i_next != i;
+      const int64_t off = (((int64_t)i * W + xx) * cv + j) * V;
+      Vec16<T> ya;
+      if (GATE && store) ya = ld16(reinterpret_cast<const T *>(ga.yact) + b * out_img + off);   // in flight under the row's math
       cur = nxt;                         // row e+2
       issue(e + 3, nxt);
       reduce(cur, d);
@@ -378,14 +406,31 @@ blur4_cl_kernel(const T *__restrict__ x, T *__restrict__ y, Taps4CL t, int H, in
         acc[k] = fma2(t.k[0], d[k], fma2(t.k[1], c[k], fma2(t.k[2], bb[k], fma2(t.k[3], a[k], acc[k]))));
         a[k] = bb[k]; bb[k] = c[k]; c[k] = d[k];
       }
-      const int i = e < 0 ? 0 : (e >= H ? H - 1 : e);
-      const int i_next = (e + 1) < 0 ? 0 : ((e + 1) >= H ? H - 1 : (e + 1));
-      if (e == e_hi || i_next != i) {
+      if (store) {
         Vec16<T> o;
+        if (GATE) {
+#pragma unroll
+          for (int k = 0; k < VP; ++k) {
+            const float2 yy = get2(ya, k);
+            acc[k].x *= yy.x > 0.f ? ga.pos : ga.neg;
+            acc[k].y *= yy.y > 0.f ? ga.pos : ga.neg;
+            dbs[2 * k] += acc[k].x;
+            dbs[2 * k + 1] += acc[k].y;
+          }
+        }
 #pragma unroll
         for (int k = 0; k < VP; ++k) { set2(o, k, acc[k]); acc[k] = make_float2(0.f, 0.f); }
-        st16(out + (((int64_t)i * W + xx) * cv + j) * V, o);
+        st16(out + off, o);
       }
+    }
+    if (GATE) {
+#pragma unroll
+      for (int k = 0; k < V; ++k) atomicAdd(&s_db[j * V + k], dbs[k]);
+      __syncthreads();
+      // kGateReplicas copies of db (the caller sums them): 8192 CTAs adding into the same 32
+      // addresses serialised in L2 for ~80 us at [64, 32, 64, 512]
+      float *dbr = ga.db + (size_t)((blockIdx.x + blockIdx.y * gridDim.x) % kGateReplicas) * (cv * V);
+      for (int c = threadIdx.x; c < cv * V; c += blockDim.x) atomicAdd(dbr + c, s_db[c]);
     }
   }
 }
@@ -1068,6 +1113,37 @@ extern "C" int dusty_blur4_cl(const void *x, void *y, float k0, float k1, float 
   else BLUR_CL_DISPATCH(__nv_bfloat16);
 #undef BLUR_CL_DISPATCH
 #undef BLUR_CL
+  DUSTY_LAUNCH_CHECK();
+  return DUSTY_OK;
+}
+
+extern "C" int dusty_blur4_cl_adj_act(const void *gpad, const void *yact, void *gpre, float *db, float k0,
+                                     float k1, float k2, float k3, int B, int H, int W, int C,
+                                     float alpha, float scale, int dtype, void *stream) {
+  DUSTY_CHECK_ARG(gpad && yact && gpre && db, "null pointer");
+  DUSTY_CHECK_ARG(B >= 1 && H >= 2 && W >= 4, "bad shape");
+  DUSTY_CHECK_ARG(dtype == DUSTY_F32 || dtype == DUSTY_BF16, "bad dtype");
+  const int V = dtype == DUSTY_F32 ? 4 : 8;
+  DUSTY_CHECK_ARG(C % V == 0 && C <= 512, "C: a multiple of the 16-byte vector width, at most 512");
+  // db: [64][C] partial sums (zero-filled by the caller, who adds the 64 rows up)
+  Taps4CL t;
+  t.k[0] = k0; t.k[1] = k1; t.k[2] = k2; t.k[3] = k3;
+  const int cv = C / V;
+  cudaStream_t st = (cudaStream_t)stream;
+  const int64_t n_threads = (int64_t)B * W * cv;
+  int strip = H;
+  const int64_t ctas_x = (n_threads + 127) / 128;
+  // a CTA must hold whole channel groups of ONE set of columns: 128 % cv == 0 keeps j = tid % cv aligned
+  while (strip > 8 && ctas_x * ((H + strip - 1) / strip) < (int64_t)num_sms() * 8) strip = (strip + 1) / 2;
+  DUSTY_CHECK_ARG(ctas_x <= 0x7fffffff, "tensor too large");
+  dim3 grid((unsigned)ctas_x, (unsigned)((H + strip - 1) / strip));
+  GateArgs ga{yact, db, scale, alpha * scale};
+  if (dtype == DUSTY_F32)
+    blur4_cl_kernel<float, true, true, true><<<grid, 128, 0, st>>>((const float *)gpad, (float *)gpre, t, H, W, cv,
+                                                                  strip, n_threads, ga);
+  else
+    blur4_cl_kernel<__nv_bfloat16, true, true, true><<<grid, 128, 0, st>>>(
+        (const __nv_bfloat16 *)gpad, (__nv_bfloat16 *)gpre, t, H, W, cv, strip, n_threads, ga);
   DUSTY_LAUNCH_CHECK();
   return DUSTY_OK;
 }

@@ -414,6 +414,24 @@ def blur_pad_cl_supported(x: torch.Tensor) -> bool:
             and x.shape[-2] >= 2 and x.shape[-1] >= 4)
 
 
+def blur_pad_adj_act(g_pad: torch.Tensor, y_act: torch.Tensor, taps4, alpha: float, scale: float):
+    """(d loss / d pre, d loss / d bias) for  pre -> y = lrelu(pre + bias) * scale -> blur -> ring pad,
+    given the gradient of the PADDED blurred tensor: blur adjoint + ring fold + activation gate +
+    bias-gradient reduction in one kernel (no autograd: the caller's backward owns the chain)."""
+    K.require_cuda(g_pad, y_act)
+    g_pad = g_pad if _is_cl(g_pad) else g_pad.contiguous(memory_format=_CL)
+    if g_pad.dtype != y_act.dtype:
+        g_pad = g_pad.to(y_act.dtype)
+    B, C, H, W = y_act.shape
+    if tuple(g_pad.shape) != (B, C, H + 2, W + 2) or not _is_cl(y_act):
+        raise RuntimeError("blur_pad_adj_act: gradient must be [B, C, H+2, W+2], activation NHWC [B, C, H, W]")
+    gpre = torch.empty((B, C, H, W), device=y_act.device, dtype=y_act.dtype, memory_format=_CL)
+    db = torch.zeros(64, C, device=y_act.device, dtype=torch.float32)      # 64 replicas, see the header
+    K.call("dusty_blur4_cl_adj_act", K.ptr(g_pad), K.ptr(y_act), K.ptr(gpre), K.ptr(db), taps4[0], taps4[1],
+           taps4[2], taps4[3], B, H, W, C, alpha, scale, K.dtype_code(y_act), K.stream_of(y_act))
+    return gpre, db.sum(dim=0)
+
+
 def blur_pad_cl(x: torch.Tensor, taps4) -> torch.Tensor:
     """Pad(1, ring)(Resample([k0..k3], ring)(x)) for an NHWC tensor."""
     return _BlurPadCL.apply(x, tuple(float(t) for t in taps4), False)

@@ -401,6 +401,7 @@ class ResidualBlock(nn.Module):
         self.bias_act2 = ops.FusedLeakyReLU(out_ch)
         self.skip = ops.Conv2d(in_ch, out_ch, 1, 2, 0, **kw)
         self.fused_fork = True          # one backward kernel for the input's two consumers (NHWC)
+        self.fused_act_blur = True      # conv1 + bias_act1 + blur + pad as one autograd node
 
     def _blur_pad_conv2(self, h):
         """conv2(resample(h)) with the blur and conv2's ring padding as one kernel (NHWC)."""
@@ -477,10 +478,40 @@ class ResidualBlock(nn.Module):
             return DF.residual_fork(x, rs._taps_host)
         return None, None
 
+    def _conv1_act_blur_pad(self, x, xp):
+        """pad(blur(bias_act1(conv1(x)))) as ONE autograd node on the halo-resident kernel's layers:
+        bias / leaky ReLU in the convolution's epilogue, then the blur + pad kernel; backward: blur
+        adjoint + ring fold + activation gate + bias gradient in one kernel.  None when the block
+        is not on that path (the caller then runs the stages one by one)."""
+        seq, act, rs = self.conv1, self.bias_act1, self.resample
+        pad2 = self.conv2[0] if len(self.conv2) == 2 else None
+        if not (self.fused_act_blur and (xp is not None or self._conv1_fast(x))
+                and isinstance(pad2, ops.Pad) and pad2.padding == (1, 1, 1, 1)
+                and pad2.horizontal == "circular" and pad2.vertical == "replicate"
+                and getattr(rs, "_fast_up", None) == 1):
+            return None
+        eq = seq[-1]
+        if xp is None:
+            xp = seq[0](x)
+        w_like = torch.empty(eq.module.weight.shape, dtype=xp.dtype, device="meta")
+        out_like = x if x.shape[1] == w_like.shape[0] else None
+        if not (ops.conv_bias_act_supported(xp, w_like, (1, 1)) and out_like is not None
+                and DF.blur_pad_cl_supported(out_like)):
+            return None
+        if rs._taps_host is None:
+            rs._taps_host = tuple(rs.kernel.detach().float().cpu().tolist())
+        w, w_tco = eq.prepared_weight(x.dtype, with_tco=True)
+        return ops.conv_bias_act(xp, w, act.bias, (1, 1), act.negative_slope, act.scale, w_tco,
+                                 blur_taps=rs._taps_host)
+
     def forward(self, x):
         xp, xd = self._fork(x)
         skip = self._skip(x, xd)
-        pre = self._blur_pad_conv2(self._conv1_act(x, xp))            # conv2 output, before bias_act2
+        hp = self._conv1_act_blur_pad(x, xp)
+        if hp is not None:
+            pre = self.conv2[1](hp)
+        else:
+            pre = self._blur_pad_conv2(self._conv1_act(x, xp))        # conv2 output, before bias_act2
         act = self.bias_act2
         if DF.residual_tail_supported(pre, skip):
             # bias_act2, the residual sum and the 1/sqrt(2) as one NHWC pass

@@ -334,31 +334,40 @@ class _ConvBiasActFn(torch.autograd.Function):
     is re-expressed through the differentiable single ops."""
 
     @staticmethod
-    def forward(ctx, x, w, bias, stride, alpha, gain, w_tco=None):
+    def forward(ctx, x, w, bias, stride, alpha, gain, w_tco=None, blur_taps=None):
+        """blur_taps: also apply the ring blur + Pad(1, ring) that follows in a ResidualBlock
+        (DF.blur_pad_cl) and return ITS output; the backward then runs the blur's adjoint, the
+        activation gate and the bias-gradient reduction as ONE kernel (dusty_blur4_cl_adj_act)
+        instead of the blur adjoint followed by a bias_act backward pass over the same tensor."""
         bf = None if bias is None else bias.detach().float().contiguous()
         y = DF.conv2d_fprop_tc(x, w, stride, bf, 3, alpha, gain)
         ctx.save_for_backward(x, w, bias, y)
-        ctx.cfg = (stride, alpha, gain)
+        ctx.cfg = (stride, alpha, gain, blur_taps)
         ctx.w_tco = w_tco
-        return y
+        return y if blur_taps is None else DF.blur_pad_cl(y, blur_taps)
 
     @staticmethod
     def backward(ctx, gy):
         x, w, bias, y = ctx.saved_tensors
-        stride, alpha, gain = ctx.cfg
+        stride, alpha, gain, blur_taps = ctx.cfg
         need_x, need_w, need_b = ctx.needs_input_grad[:3]
         if torch.is_grad_enabled():
             with torch.enable_grad():
                 yc = DF.bias_act(conv2d_valid(x, w, stride), bias, alpha, gain)
+                if blur_taps is not None:
+                    yc = DF.blur_pad_cl(yc, blur_taps)
                 wanted = [t for t, n in ((x, need_x), (w, need_w), (bias, need_b)) if n and t is not None]
                 grads = list(torch.autograd.grad(yc, wanted, gy, create_graph=True, allow_unused=True))
             out = [grads.pop(0) if (n and t is not None) else None
                    for t, n in ((x, need_x), (w, need_w), (bias, need_b))]
-            return out[0], out[1], out[2], None, None, None, None
-        gpre, db = DF._BiasActBackward.apply(gy, y, bias is not None, alpha, gain)
+            return out[0], out[1], out[2], None, None, None, None, None
+        if blur_taps is not None:
+            gpre, db = DF.blur_pad_adj_act(gy, y, blur_taps, alpha, gain)
+        else:
+            gpre, db = DF._BiasActBackward.apply(gy, y, bias is not None, alpha, gain)
         gx, gw = _Conv2dBwdFn.apply(gpre, x, w, stride, need_x, need_w, ctx.w_tco)
         gb = db.to(bias.dtype) if (need_b and bias is not None) else None
-        return gx, gw, gb, None, None, None, None
+        return gx, gw, gb, None, None, None, None, None
 
 
 def conv_bias_act_supported(x, w, stride) -> bool:
@@ -368,9 +377,10 @@ def conv_bias_act_supported(x, w, stride) -> bool:
             and DF.conv_halo_ok(w, "fprop"))
 
 
-def conv_bias_act(x, w, bias, stride, negative_slope=0.2, gain=2 ** 0.5, w_tco=None):
+def conv_bias_act(x, w, bias, stride, negative_slope=0.2, gain=2 ** 0.5, w_tco=None, blur_taps=None):
     stride = tuple(stride) if isinstance(stride, (tuple, list)) else (stride, stride)
-    return _ConvBiasActFn.apply(x, w, bias, stride, float(negative_slope), float(gain), w_tco)
+    taps = None if blur_taps is None else tuple(float(t) for t in blur_taps)
+    return _ConvBiasActFn.apply(x, w, bias, stride, float(negative_slope), float(gain), w_tco, taps)
 
 
 def conv2d_valid(x, w, stride, w_tco=None):

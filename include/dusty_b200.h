@@ -136,6 +136,17 @@ int dusty_pad2d_cl(const void *x, void *y, int B, int H, int W, int C, int pt, i
 int dusty_blur4_cl(const void *x, void *y, float k0, float k1, float k2, float k3, int B, int H,
                    int W, int C, int adjoint, int pad, int dtype, void *stream);
 
+/* Backward of  pre -> yact = lrelu(pre + bias, alpha) * scale -> dusty_blur4_cl(pad = 1)  as ONE
+ * kernel: gpad [B, H+2, W+2, C] is the gradient of the padded blurred tensor, yact [B, H, W, C] the
+ * activation's output; gpre = blur_pad^T(gpad) * gate(yact) * scale; db: fp32 [64][C] partial sums of
+ * gpre over pixels (caller zero-fills and adds the 64 rows: spread over replicas, the CTAs' atomics
+ * do not serialise on C addresses).  Replaces UpFirDn2dBackward of the ResidualBlock's Resample + the Pad adjoint +
+ * FusedLeakyReLUFunctionBackward over the same tensor (gans/models/dusty_v2.py:300-315,
+ * ops/fused_act/fused_act.py:34-66). */
+int dusty_blur4_cl_adj_act(const void *gpad, const void *yact, void *gpre, float *db, float k0,
+                           float k1, float k2, float k3, int B, int H, int W, int C, float alpha,
+                           float scale, int dtype, void *stream);
+
 /* Skip branch of ResidualBlock (dusty_v2.py:387-396): conv1x1_stride2(Resample(x)) only reads
  * the blurred image at even rows / columns.  y[b,i,j,:] = blur4(x)[b,2i,2j,:], y is
  * [B,H/2,W/2,C]; adjoint != 0: x is the [B,H/2,W/2,C] gradient, y the [B,H,W,C] result.

@@ -65,9 +65,13 @@ class GateRecorder:
             return y
 
         def conv_bias_act(*a, **k):
+            # the gate is read off the ACTIVATION's output: with blur_taps the op would return the
+            # blurred / padded tensor, so the recorder runs the two stages separately (the fused
+            # backward kernel has its own test, test_conv_bias_act_blur_pad_fused_backward)
+            taps = k.pop("blur_taps", None)
             y = o_cba(*a, **k)
             keep(y > 0)
-            return y
+            return y if taps is None else DF.blur_pad_cl(y, taps)
 
         self._patch(DF, "bias_act", bias_act)
         self._patch(DF, "residual_tail", residual_tail)

@@ -1025,6 +1025,56 @@ def test_residual_tail_vs_single_ops(DF, C, HW):
     close(res[0][1][1], (gs.bfloat16().float() * gate).sum((0, 2, 3)), rtol=2e-2, atol_rel=1e-2)   # d/dbias
 
 
+@pytest.mark.parametrize("B,C,H,W", [(2, 32, 16, 64), (3, 64, 10, 36), (2, 32, 64, 512)])
+def test_conv_bias_act_blur_pad_fused_backward(ops, DF, B, C, H, W):
+    """conv1 + bias / leaky ReLU epilogue + blur + ring pad as ONE autograd node whose backward runs
+    the blur adjoint, the ring fold, the activation gate and the bias-gradient reduction in one
+    kernel (dusty_blur4_cl_adj_act), against the same chain run stage by stage on the device (same
+    bf16 roundings up to the intermediate the fused kernel never writes) and, at 2e-2, against fp32
+    CPU autograd through the oracle's restatement; second order goes through the composite."""
+    g = torch.Generator().manual_seed(41)
+    bf = torch.bfloat16
+    taps = (0.125, 0.375, 0.375, 0.125)
+    x = torch.randn(B, C, H + 2, W + 2, generator=g).to(bf)
+    w = (torch.randn(C, C, 3, 3, generator=g) / np.sqrt(9 * C)).to(bf)
+    bias = torch.randn(C, generator=g) * 0.2
+    gy = torch.randn(B, C, H + 2, W + 2, generator=g).to(bf)
+    xd = x.to(DEV).contiguous(memory_format=torch.channels_last)
+    res = {}
+    for fused in (True, False):
+        xg, wg, bg = xd.clone().requires_grad_(), w.to(DEV).requires_grad_(), bias.to(DEV).requires_grad_()
+        names = []
+        orig = DF.K.call
+        DF.K.call = lambda name, *a: (names.append(name), orig(name, *a))[1]
+        try:
+            if fused:
+                out = ops.conv_bias_act(xg, wg, bg, (1, 1), 0.2, O.SQRT2, None, blur_taps=taps)
+            else:
+                out = DF.blur_pad_cl(ops.conv_bias_act(xg, wg, bg, (1, 1), 0.2, O.SQRT2), taps)
+            grads = torch.autograd.grad(out, [xg, wg, bg], gy.to(DEV))
+        finally:
+            DF.K.call = orig
+        assert ("dusty_blur4_cl_adj_act" in names) == fused and (("dusty_bias_act_bwd_cl" in names) != fused), names
+        res[fused] = (out.detach(), grads)
+    assert torch.equal(res[True][0], res[False][0])
+    for a, b_ in zip(res[True][1], res[False][1]):
+        # the unfused chain rounds the blur adjoint's output to bf16 before the gate
+        close(a, b_, rtol=2e-2, atol_rel=6e-3)
+    # fp32 reference of the whole chain
+    xr, wr, br = x.float().requires_grad_(), w.float().requires_grad_(), bias.clone().requires_grad_()
+    pre = torch.nn.functional.conv2d(xr, wr) + br.view(1, -1, 1, 1)
+    yact = torch.where(pre > 0, pre, 0.2 * pre) * O.SQRT2
+    ref = O.pad2d(O.resample(yact), 1, ring=True, mode="replicate")
+    close(res[True][0], ref, rtol=2e-2, atol_rel=6e-3)
+    # gradients in the linear region the device took (gate of ITS activation output)
+    y_dev = ops.conv_bias_act(xd, w.to(DEV), bias.to(DEV), (1, 1), 0.2, O.SQRT2).float().cpu()
+    gate = torch.where(y_dev > 0, 1.0, 0.2) * O.SQRT2
+    gblur, = torch.autograd.grad(O.pad2d(O.resample(yact), 1, ring=True, mode="replicate"), yact, gy.float())
+    gx_ref, gw_ref, gb_ref = torch.autograd.grad(pre, [xr, wr, br], gblur * gate)
+    for a, r in zip(res[True][1], (gx_ref, gw_ref, gb_ref)):
+        close(a, r, rtol=3e-2, atol_rel=1e-2)
+
+
 def test_conv_bias_act_epilogue_vs_single_ops(ops, DF):
     """3x3 unit-stride convolution of a thin NHWC layer with bias + leaky ReLU in the tcgen05
     kernel's epilogue against conv2d_valid followed by bias_act."""

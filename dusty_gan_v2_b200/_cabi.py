@@ -68,6 +68,7 @@ SIGNATURES = {
     "dusty_conv2d_tc": [_vp, _vp, _vp, _vp] + [_i] * 9 + [_vp, _vp, _i, _i, _i]
                        + [C.c_longlong] * 4 + [_i, _f, _f, C.c_longlong, C.c_longlong, _vp, _i, _i, _vp],
     "dusty_conv2d_tc_classes": [_vp, _vp, _vp] + [_i] * 6 + [_vp] * 7 + [C.c_longlong] * 5 + [_i, _i, _vp],
+    "dusty_residual_fork_fwd_cl": [_vp, _vp, _vp, _f, _f, _f, _f, _i, _i, _i, _i, _i, _vp],
     "dusty_blur4_cl_adj_act": [_vp, _vp, _vp, _vp, _f, _f, _f, _f, _i, _i, _i, _i, _f, _f, _i, _vp],
     "dusty_ada_apply": [_vp, _vp, _vp, _i, _i, _i, _i, _vp],
     "dusty_ada_apply_smem": [_i, _i],

@@ -655,10 +655,13 @@ blur4_ring_cl_kernel(const T *__restrict__ x, T *__restrict__ y, Taps4CL t, int 
 // (input read once, a quarter written; the 1x1 convolution then runs at unit stride).
 // thread -> (b, j, channel vector), slides over a strip of output rows; two new input rows per
 // step, the next two already in flight.
-template <typename T>
+// PADOUT: the thread's own two input columns (2 xo, 2 xo + 1) of the two rows it lands per step
+// are also written into xp = Pad(1, circular W / replicate H)(x), the other consumer of a
+// ResidualBlock's input: the separate pad kernel (a full read + write of x) disappears.
+template <typename T, bool PADOUT = false>
 __global__ void __launch_bounds__(128, 4)
 blur4_down2_cl_kernel(const T *__restrict__ x, T *__restrict__ y, Taps4CL t, int H, int W, int cv,
-                      int strip, int64_t n_threads) {
+                      int strip, int64_t n_threads, T *__restrict__ xp = nullptr) {
   constexpr int V = Vec16<T>::N;
   const int H2 = H >> 1, W2 = W >> 1;
   const int64_t tid = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
@@ -703,8 +706,24 @@ blur4_down2_cl_kernel(const T *__restrict__ x, T *__restrict__ y, Taps4CL t, int
   issue(2 * i0, r0);
   reduce(r1, bb);
   issue(2 * i0 + 1, r1);
+  const int Wp = W + 2;
+  T *pimg = PADOUT ? xp + b * (int64_t)(H + 2) * Wp * cv * V : nullptr;
+  // padded row `pr` <- the thread's columns of input row data (+ the circular halo columns)
+  auto put_row = [&](int pr, const Row &row) {
+    T *dst = pimg + (int64_t)pr * Wp * cv * V;
+    st16(dst + ((int64_t)(2 * xo + 1) * cv + j) * V, row.v[2]);
+    st16(dst + ((int64_t)(2 * xo + 2) * cv + j) * V, row.v[3]);
+    if (xo == 0) st16(dst + ((int64_t)(W + 1) * cv + j) * V, row.v[2]);          // x[.., 0] -> right halo
+    if (2 * xo + 2 == W) st16(dst + (int64_t)j * V, row.v[3]);                    // x[.., W-1] -> left halo
+  };
 #pragma unroll 2
   for (int i = i0; i < i1; ++i) {
+    if (PADOUT) {                        // r0 = input row 2i, r1 = row 2i + 1 (never clamped)
+      put_row(2 * i + 1, r0);
+      put_row(2 * i + 2, r1);
+      if (i == 0) put_row(0, r0);
+      if (2 * i + 2 == H) put_row(H + 1, r1);
+    }
     reduce(r0, c);
     issue(2 * i + 2, r0);
     reduce(r1, d);
@@ -1180,6 +1199,33 @@ extern "C" int dusty_blur4_down2_cl(const void *x, void *y, float k0, float k1, 
     else
       blur4_down2_cl_adj_kernel<__nv_bfloat16><<<(unsigned)blocks, 256, 0, st>>>((const __nv_bfloat16 *)x, (__nv_bfloat16 *)y, t, H, W, cv, n_threads);
   }
+  DUSTY_LAUNCH_CHECK();
+  return DUSTY_OK;
+}
+
+extern "C" int dusty_residual_fork_fwd_cl(const void *x, void *xp, void *xd, float k0, float k1, float k2,
+                                          float k3, int B, int H, int W, int C, int dtype, void *stream) {
+  DUSTY_CHECK_ARG(x && xp && xd, "null pointer");
+  DUSTY_CHECK_ARG(B >= 1 && H >= 2 && W >= 4 && H % 2 == 0 && W % 2 == 0, "bad shape");
+  DUSTY_CHECK_ARG(dtype == DUSTY_F32 || dtype == DUSTY_BF16, "bad dtype");
+  const int V = dtype == DUSTY_F32 ? 4 : 8;
+  DUSTY_CHECK_ARG(C % V == 0, "C must be a multiple of the 16-byte vector width");
+  Taps4CL t;
+  t.k[0] = k0; t.k[1] = k1; t.k[2] = k2; t.k[3] = k3;
+  const int cv = C / V;
+  cudaStream_t st = (cudaStream_t)stream;
+  const int H2 = H / 2;
+  const int64_t n_threads = (int64_t)B * (W / 2) * cv;
+  int strip = H2;
+  const int64_t ctas_x = (n_threads + 127) / 128;
+  while (strip > 4 && ctas_x * ((H2 + strip - 1) / strip) < (int64_t)num_sms() * 8) strip = (strip + 1) / 2;
+  dim3 grid((unsigned)ctas_x, (unsigned)((H2 + strip - 1) / strip));
+  if (dtype == DUSTY_F32)
+    blur4_down2_cl_kernel<float, true><<<grid, 128, 0, st>>>((const float *)x, (float *)xd, t, H, W, cv, strip,
+                                                            n_threads, (float *)xp);
+  else
+    blur4_down2_cl_kernel<__nv_bfloat16, true><<<grid, 128, 0, st>>>(
+        (const __nv_bfloat16 *)x, (__nv_bfloat16 *)xd, t, H, W, cv, strip, n_threads, (__nv_bfloat16 *)xp);
   DUSTY_LAUNCH_CHECK();
   return DUSTY_OK;
 }

@@ -481,10 +481,11 @@ class _ResidualFork(Function):
     def forward(ctx, x, taps4):
         x = x if _is_cl(x) else x.contiguous(memory_format=_CL)
         B, C, H, W = x.shape
-        xp = _pad_raw(x, _FORK_PADS, _FORK_MODES, False)
+        # one pass over x writes both consumers' inputs (the pad is a by-product of the blur's loads)
+        xp = torch.empty((B, C, H + 2, W + 2), device=x.device, dtype=x.dtype, memory_format=_CL)
         xd = torch.empty((B, C, H // 2, W // 2), device=x.device, dtype=x.dtype, memory_format=_CL)
-        K.call("dusty_blur4_down2_cl", K.ptr(x), K.ptr(xd), taps4[0], taps4[1], taps4[2], taps4[3],
-               B, H, W, C, 0, K.dtype_code(x), K.stream_of(x))
+        K.call("dusty_residual_fork_fwd_cl", K.ptr(x), K.ptr(xp), K.ptr(xd), taps4[0], taps4[1], taps4[2],
+               taps4[3], B, H, W, C, K.dtype_code(x), K.stream_of(x))
         ctx.cfg = (taps4, (H, W))
         ctx.set_materialize_grads(False)
         return xp, xd

@@ -154,6 +154,12 @@ int dusty_blur4_cl_adj_act(const void *gpad, const void *yact, void *gpre, float
 int dusty_blur4_down2_cl(const void *x, void *y, float k0, float k1, float k2, float k3, int B,
                          int H, int W, int C, int adjoint, int dtype, void *stream);
 
+/* Forward of the ResidualBlock's input fork in one pass over x (NHWC): xp = Pad(1, circular W /
+ * replicate H)(x) [B, H+2, W+2, C] for conv1 and xd = blur(x)[::2, ::2] [B, H/2, W/2, C] for the skip
+ * branch (gans/models/dusty_v2.py:300-315: conv1's Pad, the skip's Resample + stride-2 conv). */
+int dusty_residual_fork_fwd_cl(const void *x, void *xp, void *xd, float k0, float k1, float k2, float k3,
+                               int B, int H, int W, int C, int dtype, void *stream);
+
 /* Backward of the ResidualBlock input fork (dusty_v2.py:387-396: x feeds conv1 = Pad(1, ring) +
  * conv AND skip = conv1x1_stride2(Resample(x))): dx = pad_adjoint(g_pad) + blur4_down2_adjoint(
  * g_down) in one pass, replacing two adjoint launches plus the autograd accumulation add.

@@ -1,5 +1,7 @@
 """GPU parity of the assembled models against golden outputs of the unmodified reference
 (same state_dict loaded into both) and against the CPU oracle at full size."""
+import os
+
 import numpy as np
 import pytest
 import torch
@@ -221,6 +223,8 @@ def close_l2(a, b, tol, what=""):
     nb = float(b.norm())
     rel = float((a - b).norm()) / max(nb, 1e-20)
     worst = float((a - b).abs().max()) / max(float(b.abs().max()), 1e-20)
+    if os.environ.get("DUSTY_TEST_VERBOSE"):
+        print(f"close_l2 {what}: rel_l2 {rel:.4f} worst {worst:.4f} (tol {tol})")
     assert rel <= tol and worst <= 3 * tol, f"{what}: rel_l2 {rel:.4f}, worst element {worst:.4f} of max (tol {tol})"
 
 

@@ -84,6 +84,10 @@ class Head(nn.Module):
             main.wait_event(event)
             wb.record_stream(main)
             y = DF.modconv_bmm(wb, x, None, bias, 1, 0.0, 1.0, ema_rows=[m.ema_var for m in mods])
+        elif self.late_ema_ok(x.is_cuda):
+            # the same formulation as the weight bank's (results do not depend on the bank)
+            wb = DF.cat_wb([m.effective_weights(style, x.dtype, late_ema=True, via_handle=True) for m in mods])
+            y = DF.modconv_bmm(wb, x, None, bias, 1, 0.0, 1.0, ema_rows=[m.ema_var for m in mods])
         else:
             wb = DF.cat_wb([m.effective_weights(style, x.dtype, via_handle=x.is_cuda) for m in mods])
             y = DF.modconv_bmm(wb, x, None, bias, 1, 0.0, 1.0)

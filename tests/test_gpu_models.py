@@ -270,6 +270,60 @@ def test_full_size_discriminator_bf16_vs_oracle():
         close_l2(params[k].grad, gr, 2e-2, k)
 
 
+def test_weight_and_filter_banks_do_not_change_results():
+    """The side-stream banks (generator per-sample weights, discriminator filters) only move work
+    off the activation chain: with the banks on and off, a train-mode generator forward + backward
+    and a discriminator forward + backward give bit-identical outputs and EMA buffers, and
+    gradients that are identical up to the arrival order of the split-K weight-gradient sums
+    (same kernels, same arithmetic; only the stream they run on differs).  The graphed form of the
+    same paths is held to the reference by the step-replay tests."""
+    import dusty_gan_v2_b200 as pkg
+    from dusty_gan_v2_b200.gans.coords import CoordBridge
+    from dusty_gan_v2_b200.gans.models.builder import build_discriminator, build_generator
+    from dusty_gan_v2_b200.presets import preset
+    pkg.set_precision("bf16")
+    cfg = preset("dusty_v2")
+    torch.manual_seed(7)
+    G = build_generator(cfg.model.generator).train().to(DEV)
+    D = build_discriminator(cfg.model.discriminator).to(DEV)
+    cb = CoordBridge(64, 512, 1.45, 80.0, "data/coords/kitti_raw.npy")
+    B = 4
+    z = torch.randn(B, 512, device=DEV)
+    angle = cb.angle.to(DEV).expand(B, -1, -1, -1)
+    ct = torch.randn(B, 1, 64, 512, device=DEV)
+    state = {k: v.clone() for k, v in G.state_dict().items()}
+
+    def run(bank):
+        G.load_state_dict(state)
+        G.synthesis_network.weight_bank = bank
+        D.weight_bank = bank
+        for p in list(G.parameters()) + list(D.parameters()):
+            p.grad = None
+        torch.manual_seed(11)
+        torch.cuda.manual_seed(11)
+        img = G(z, angle=angle)["image"]
+        logit = D(img)
+        (img * ct).sum().backward(retain_graph=True)
+        torch.nn.functional.softplus(-logit).mean().backward()
+        torch.cuda.synchronize()
+        grads = {n: p.grad.detach().clone() for n, p in list(G.named_parameters()) + list(D.named_parameters())
+                 if p.grad is not None}
+        bufs = {k: v.clone() for k, v in G.state_dict().items() if k.endswith("ema_var")}
+        return img.detach().clone(), logit.detach().clone(), grads, bufs
+
+    ref = run(False)
+    assert len(ref[2]) > 60 and len(ref[3]) >= 19
+    for _ in range(2):
+        got = run(True)
+        assert torch.equal(got[0], ref[0]) and torch.equal(got[1], ref[1])
+        for k, v in ref[3].items():
+            assert torch.equal(got[3][k], v), k
+        for k, v in ref[2].items():
+            if not torch.equal(got[2][k], v):
+                rel = float((got[2][k].float() - v.float()).norm() / v.float().norm().clamp_min(1e-20))
+                assert rel < 1e-4, (k, rel)
+
+
 def test_full_size_generator_bf16_gradients_vs_oracle():
     """Model-level gradient check of the benched generator path (bf16: batch-shared Fourier
     block, tcgen05 modconv fwd / dX / dW, modprep backward, fused resampling) against the fp32

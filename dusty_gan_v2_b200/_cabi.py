@@ -46,7 +46,7 @@ SIGNATURES = {
     "dusty_affine_warp": [_vp, _vp, _vp] + [_i] * 7 + [_vp],
     "dusty_fourier": [_vp, _vp, _vp, _vp, _i, _i, _i64, _i, _vp],
     "dusty_angle_down2": [_vp, _vp, _i, _i, _i, _vp],
-    "dusty_modconv_fwd": [_vp, _vp, _vp, _vp, _vp, _i, _i, _i, _i, _i, _i64, _i, _f, _f, _i, _i, _i, _vp, _vp, _vp],
+    "dusty_modconv_fwd": [_vp, _vp, _vp, _vp, _vp, _i, _i, _i, _i, _i, _i64, _i, _f, _f, _i, _i, _i, _vp, _vp, _vp, _vp],
     "dusty_modconv_bwd_dx": [_vp, _vp, _vp, _i, _i, _i, _i, _i64, _i, _i, _i, _vp, _vp, _vp],
     "dusty_modconv_bwd_dw": [_vp, _vp, _vp, _vp, _i, _i, _i, _i, _i, _i64, _i, _i, C.c_longlong, _vp],
     "dusty_modprep_fwd": [_vp, _vp, _vp, _vp, _vp, _i, _i, _i, _f, _i, _i, _vp, _i, _i, _vp],

@@ -13,7 +13,7 @@ int modconv_bwd_dw_simt(const void *dy, const void *x1, const void *x2, float *d
 // tensor-core path (modconv_tc.cu); returns DUSTY_EUNSUPPORTED when the shape does not fit
 int modconv_fwd_tc(const void *wb, const void *x1, const void *x2, const float *bias, void *y,
                    int B, int O, int C1, int C2, int B2, int64_t P, int act, float alpha,
-                   float scale, bool batch_fused, cudaStream_t st, bool out_f32, const float *ema);
+                   float scale, bool batch_fused, cudaStream_t st, bool out_f32, const float *ema, float *sumsq);
 bool modconv_fwd_tc_supported(int B, int O, int C1, int C2, int B2, int64_t P);
 int modconv_dx_tc(const void *wb, const void *dy, void *dx1, int B, int O, int C1, int K, int64_t P,
                   cudaStream_t st, bool out_f32, const float *ema);
@@ -30,7 +30,8 @@ static bool dtype_ok(int d) { return d == DUSTY_F32 || d == DUSTY_BF16; }
 extern "C" int dusty_modconv_fwd(const void *wb, const void *x1, const void *x2, const float *bias,
                                  void *y, int B, int O, int C1, int C2, int B2, int64_t P, int act,
                                  float alpha, float scale, int dtype, int wdtype, int impl,
-                                 const float *ema_var, const float *const *ema_rows, void *stream) {
+                                 const float *ema_var, const float *const *ema_rows, float *sumsq,
+                                 void *stream) {
   DUSTY_CHECK_ARG(wb && y, "null pointer");
   DUSTY_CHECK_ARG(!(ema_var && ema_rows), "ema_var and ema_rows are exclusive");
   DUSTY_CHECK_ARG(B >= 1 && B <= 65535 && O >= 1 && C1 >= 0 && C2 >= 0 && C1 + C2 >= 1 && P >= 1,
@@ -53,13 +54,14 @@ extern "C" int dusty_modconv_fwd(const void *wb, const void *x1, const void *x2,
   }
   int rc;
   const bool use_tc = impl >= 2 || (impl == 0 && tc_ok);
-  if ((ema_var && !use_tc) || (ema_rows && use_tc)) {
-    set_error("dusty_modconv_fwd: ema_var is applied by the tcgen05 epilogue, ema_rows by the small-O kernel");
+  if ((ema_var && !use_tc) || (ema_rows && use_tc) || (sumsq && (!use_tc || impl == 4))) {
+    set_error("dusty_modconv_fwd: ema_var / sumsq belong to the tcgen05 (bf16 output) epilogue, ema_rows to "
+              "the small-O kernel");
     return DUSTY_EUNSUPPORTED;
   }
   if (use_tc)
     rc = modconv_fwd_tc(wb, x1, x2, bias, y, B, O, C1, C2, B2, P, act, alpha, scale, impl < 3, st,
-                        impl == 4, ema_var);
+                        impl == 4, ema_var, sumsq);
   else
     rc = modconv_fwd_simt(wb, x1, x2, bias, y, B, O, C1, C2, B2, P, act, alpha, scale, dtype,
                           wdtype, st, ema_rows);

@@ -46,6 +46,7 @@ struct TcParams {
   float alpha, scale;
   int out_f32;            // 1: fp32 output (split-bf16 operands of the fp32 mode, split3.cu)
   const float *ema;       // optional device scalar ema_var: accumulator * 1 / (sqrt(ema_var) + 1e-8)
+  float *sumsq;           // optional: += sum of the squares of the STORED (bf16-rounded) outputs
 };
 
 
@@ -94,6 +95,14 @@ __device__ __forceinline__ EpiThread epi_setup(uint8_t *epi_base, const float *b
   return e;
 }
 
+// one atomic per epilogue warp and CTA (persistent CTAs: a few thousand adds per launch)
+__device__ __forceinline__ void epi_flush_sumsq(float ss, float *out, int lane) {
+  if (out == nullptr) return;
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) ss += __shfl_xor_sync(0xffffffffu, ss, o);
+  if (lane == 0) atomicAdd(out, ss);
+}
+
 // Drains the 32-column chunks of one accumulator that belong to this thread's group.
 // gc: running chunk counter (same sequence in every epilogue thread); bias_at(c): index of the
 // bias entry of accumulator column c; (p0, row0, b): TMA coordinates of the tile's first
@@ -102,7 +111,7 @@ template <typename BiasAt>
 __device__ __forceinline__ void epi_drain_tile(const EpiThread &e, uint32_t tmem_acc, int BN, int &gc,
                                                uint64_t *acc_empty_bar, BiasAt bias_at, int act,
                                                float alpha, float scale, const CUtensorMap *map_y,
-                                               int p0, int row0, int b, bool out_f32 = false) {
+                                               int p0, int row0, int b, bool out_f32, float &ss) {
   const int nch = BN >> 5;
   int my_last = nch - 1;                               // last chunk of this tile this group reads
   if (((gc + my_last) & 1) != e.g) --my_last;
@@ -160,6 +169,9 @@ __device__ __forceinline__ void epi_drain_tile(const EpiThread &e, uint32_t tmem
       }
       const __nv_bfloat162 pk = __floats2bfloat162_rn(v0 * scale, v1 * scale);
       h[j] = *reinterpret_cast<const uint32_t *>(&pk);
+      // statistic of the tensor as the next layer will read it (ModConv2d's ema_var, style.py:99-102)
+      const float2 f = __bfloat1622float2(pk);
+      ss = fmaf(f.x, f.x, fmaf(f.y, f.y, ss));
     }
     if (e.issuer) tma_store_wait_read<0>();            // previous store has left the staging tile
     named_bar_sync(1 + e.g, 128);
@@ -331,6 +343,7 @@ modconv_fwd_tc_kernel(const __grid_constant__ CUtensorMap map_x1,
     // ===================== epilogue (warps 2..9) =====================
     const EpiThread e = epi_setup(epi_base, prm.bias, prm.O, prm.ema);
     int lt = 0, gc = 0;
+    float ss = 0.f;
     for (int tile = t_begin; tile < t_end; ++tile, ++lt) {
       int b, n0, p0;
       decode(tile, b, n0, p0);
@@ -339,9 +352,10 @@ modconv_fwd_tc_kernel(const __grid_constant__ CUtensorMap map_x1,
       tc_fence_after();
       const uint32_t tmem_acc = tmem_base + (uint32_t)(a * BN) + ((uint32_t)(e.q * 32) << 16);
       epi_drain_tile(e, tmem_acc, BN, gc, &acc_empty[a], [&](int c) { return n0 + c; }, prm.act,
-                     prm.alpha, prm.scale, &map_y, p0, n0, b, prm.out_f32 != 0);
+                     prm.alpha, prm.scale, &map_y, p0, n0, b, prm.out_f32 != 0, ss);
     }
     if (e.issuer) tma_store_wait_read<0>();
+    epi_flush_sumsq(ss, prm.sumsq, e.lane);
   }
   tc_fence_before();
   __syncthreads();
@@ -373,6 +387,7 @@ struct ShParams {
   int act;
   float alpha, scale;
   const float *ema;       // as TcParams::ema
+  float *sumsq;           // as TcParams::sumsq
 };
 
 constexpr int kShBBytes = 256 * kBK * 2;          // B slot: up to 256 weight rows x 64 k
@@ -540,6 +555,7 @@ modconv_fwd_shared_tc_kernel(const __grid_constant__ CUtensorMap map_x1,
     // matrix, its bias is bias[(nt*BN + c) % O] (O % 32 == 0: a chunk never straddles samples)
     const EpiThread e = epi_setup(epi_base, prm.bias, prm.O, prm.ema);
     int lt = 0, gc = 0;
+    float ss = 0.f;
     for (int tile = t_begin; tile < t_end; ++tile, ++lt) {
       const int p0 = (tile % prm.MT) * kBM;
       const int n0 = (tile / prm.MT) * prm.BN;
@@ -548,9 +564,10 @@ modconv_fwd_shared_tc_kernel(const __grid_constant__ CUtensorMap map_x1,
       tc_fence_after();
       const uint32_t tmem_acc = tmem_base + (uint32_t)(a * 256) + ((uint32_t)(e.q * 32) << 16);
       epi_drain_tile(e, tmem_acc, prm.BN, gc, &acc_empty[a], [&](int c) { return (n0 + c) % prm.O; },
-                     prm.act, prm.alpha, prm.scale, &map_y, p0, n0, 0);
+                     prm.act, prm.alpha, prm.scale, &map_y, p0, n0, 0, false, ss);
     }
     if (e.issuer) tma_store_wait_read<0>();
+    epi_flush_sumsq(ss, prm.sumsq, e.lane);
   }
   tc_fence_before();
   __syncthreads();
@@ -788,7 +805,7 @@ int modconv_shared_group(int B, int O, int C1, int C2, int B2, int64_t P) {
 
 static int modconv_fwd_shared_tc(const void *wb, const void *x1, const void *pe, const float *bias,
                                  void *y, int B, int O, int C1, int C2, int NS, int64_t P, int act,
-                                 float alpha, float scale, cudaStream_t st, const float *ema) {
+                                 float alpha, float scale, cudaStream_t st, const float *ema, float *sumsq) {
   const int K = C1 + C2;
   const int BN = NS * O;
   CUtensorMap mx1, mpe, mws, mwp;
@@ -809,6 +826,7 @@ static int modconv_fwd_shared_tc(const void *wb, const void *x1, const void *pe,
   prm.O = O; prm.C1 = C1; prm.C2 = C2; prm.NS = NS; prm.BN = BN; prm.P = P; prm.bias = bias;
   prm.y = (__nv_bfloat16 *)y; prm.act = act; prm.alpha = alpha; prm.scale = scale;
   prm.ema = ema;
+  prm.sumsq = sumsq;
   prm.MT = (int)(P / kBM);
   prm.NT = B / NS;
   prm.pf = g_tc_prefetch != 0;
@@ -827,11 +845,11 @@ static int modconv_fwd_shared_tc(const void *wb, const void *x1, const void *pe,
 
 int modconv_fwd_tc(const void *wb, const void *x1, const void *x2, const float *bias, void *y,
                    int B, int O, int C1, int C2, int B2, int64_t P, int act, float alpha,
-                   float scale, bool batch_fused, cudaStream_t st, bool out_f32, const float *ema) {
+                   float scale, bool batch_fused, cudaStream_t st, bool out_f32, const float *ema, float *sumsq) {
   const int K = C1 + C2;
   if (batch_fused && !out_f32) {
     const int ns = modconv_shared_group(B, O, C1, C2, B2, P);
-    if (ns) return modconv_fwd_shared_tc(wb, x1, x2, bias, y, B, O, C1, C2, ns, P, act, alpha, scale, st, ema);
+    if (ns) return modconv_fwd_shared_tc(wb, x1, x2, bias, y, B, O, C1, C2, ns, P, act, alpha, scale, st, ema, sumsq);
   }
   const int BN = O >= 256 ? 256 : (O >= 128 ? 128 : (O >= 64 ? 64 : 32));
   CUtensorMap mx1, mx2, mw;
@@ -851,6 +869,7 @@ int modconv_fwd_tc(const void *wb, const void *x1, const void *x2, const float *
   prm.y = (__nv_bfloat16 *)y; prm.act = act; prm.alpha = alpha; prm.scale = scale;
   prm.out_f32 = out_f32 ? 1 : 0;
   prm.ema = ema;
+  prm.sumsq = out_f32 ? nullptr : sumsq;
   switch (BN) {
     case 256: return launch_tc<256, 4, false>(mx1, mx2, mw, my, prm, B, st);
     case 128: return launch_tc<128, 5, false>(mx1, mx2, mw, my, prm, B, st);
@@ -880,6 +899,7 @@ int modconv_dx_tc(const void *wb, const void *dy, void *dx1, int B, int O, int C
   prm.y = (__nv_bfloat16 *)dx1; prm.act = 1; prm.alpha = 0.f; prm.scale = 1.f;
   prm.out_f32 = out_f32 ? 1 : 0;
   prm.ema = ema;
+  prm.sumsq = nullptr;
   switch (BN) {
     case 256: return launch_tc<256, 4, true>(mg, mg, mw, my, prm, B, st);
     case 128: return launch_tc<128, 5, true>(mg, mg, mw, my, prm, B, st);

@@ -866,6 +866,7 @@ class _ModConvBmm(Function):
                 *handles):
         B, O, Kt = wb.shape
         ctx.parts = parts            # [(slot, row0, row1)] matching `handles` (see _ModPrep)
+        want_ss, ctx_ss = _SUMSQ_REQUEST.pop("want", False), None
         c1 = 0 if x1 is None else x1.shape[1]
         c2 = 0 if x2 is None else x2.shape[1]
         assert c1 + c2 == Kt, (c1, c2, Kt)
@@ -893,11 +894,15 @@ class _ModConvBmm(Function):
             x2s = None if x2 is None else _split_planes(x2, 0)
             wbs = _split_wb_k(wb, c1, c2)
             K.call("dusty_modconv_fwd", K.ptr(wbs), K.ptr(x1s), K.ptr(x2s), K.ptr(biasf), K.ptr(y), B, O,
-                   3 * c1, 3 * c2, b2, P, act, alpha, scale, K.BF16, K.BF16, 4, None, None, K.stream_of(src))
+                   3 * c1, 3 * c2, b2, P, act, alpha, scale, K.BF16, K.BF16, 4, None, None, None,
+                   K.stream_of(src))
         else:
+            if want_ss and rows is None and modconv_tc_domain(wb, src, O, c1, c2, P):
+                ctx_ss = torch.zeros(1, device=src.device, dtype=torch.float32)
             K.call("dusty_modconv_fwd", K.ptr(wb), K.ptr(x1), K.ptr(x2), K.ptr(biasf), K.ptr(y), B, O,
                    c1, c2, b2, P, act, alpha, scale, K.dtype_code(src), K.dtype_code(wb),
-                   _PRECISION["modconv_impl"], K.ptr(ev), rows_p, K.stream_of(src))
+                   _PRECISION["modconv_impl"], K.ptr(ev), rows_p, K.ptr(ctx_ss), K.stream_of(src))
+        _SUMSQ_REQUEST["got"] = ctx_ss
         ctx.save_for_backward(wb, x1, x2, y if act == 3 else None)
         ctx.cfg = (act, alpha, scale, bias is not None, None if bias is None else bias.shape,
                    None if bias is None else bias.dtype)
@@ -1012,9 +1017,13 @@ def modconv_tc_domain_of(dtype, O, c1, c2, P) -> bool:
     return c1 == 0 or c1 >= 32
 
 
+_SUMSQ_REQUEST = {}      # side channel of modconv_bmm(want_sumsq=True): not an autograd output
+
+
 def modconv_bmm(wb, x1, x2=None, bias=None, act: int = 1, alpha: float = 0.2, scale: float = 1.0,
-                ema_var=None, ema_rows=None):
-    """ema_var: apply the layer's EMA normaliser 1 / (sqrt(ema_var) + 1e-8) to the product (the
+                ema_var=None, ema_rows=None, want_sumsq=False):
+    """want_sumsq: also accumulate sum(y^2) in the epilogue (tcgen05 path; y._dusty_sumsq).
+    ema_var: apply the layer's EMA normaliser 1 / (sqrt(ema_var) + 1e-8) to the product (the
     weights wb then carry none: modprep(..., ema_var=None, ema_late=ema_var)).  ema_rows: the
     same per output row (heads: O <= 4 rows, each its own ModConv2d), a list of O buffers."""
     K.require_cuda(wb, x1, x2, bias)
@@ -1023,9 +1032,17 @@ def modconv_bmm(wb, x1, x2=None, bias=None, act: int = 1, alpha: float = 0.2, sc
     x1 = None if x1 is None else _contig(x1)
     x2 = None if x2 is None else _contig(x2.detach())
     handles = () if not parts else tuple(h for _, h, _, _ in parts)
-    return _ModConvBmm.apply(wb, x1, x2, bias, int(act), float(alpha), float(scale), ema_var,
-                             None if ema_rows is None else list(ema_rows),
-                             None if not parts else [(s_, a, b) for s_, _, a, b in parts], *handles)
+    _SUMSQ_REQUEST["want"] = bool(want_sumsq)
+    _SUMSQ_REQUEST["got"] = None
+    y = _ModConvBmm.apply(wb, x1, x2, bias, int(act), float(alpha), float(scale), ema_var,
+                          None if ema_rows is None else list(ema_rows),
+                          None if not parts else [(s_, a, b) for s_, _, a, b in parts], *handles)
+    ss = _SUMSQ_REQUEST.pop("got", None)
+    if ss is not None:
+        # sum(y^2) accumulated by the contraction's epilogue: the next ModConv2d's EMA statistic
+        # (a plain attribute: it rides along with this tensor object only)
+        y._dusty_sumsq = ss
+    return y
 
 
 class _ModPrep(Function):

@@ -74,7 +74,9 @@ class Head(nn.Module):
         """All heads share x and the style: one contraction with O = number of heads."""
         mods = list(self.heads.values())
         if self.training:
-            total = DF.sumsq_buffer(x)
+            total = getattr(x, "_dusty_sumsq", None)
+            if total is None:
+                total = DF.sumsq_buffer(x)
             for m in mods:
                 DF.ema_lerp_(m.ema_var, total, None, 1, x.numel(), 1 - m.ema_decay)
         bias = torch.cat([m.bias.reshape(-1) for m in mods])
@@ -152,7 +154,10 @@ class SynthesisBlock(nn.Module):
             # stream's backward): its memory must not return to the side stream's pool before
             wb.record_stream(main)
         if noise is None:
-            return conv(h, style, pe=pe, fused_act=act, pe_rot=pe_rot, x_sumsq=x_sumsq, wb=wb)
+            # the output feeds another ModConv2d (conv2 / the heads): its EMA statistic comes out
+            # of this contraction's epilogue
+            return conv(h, style, pe=pe, fused_act=act, pe_rot=pe_rot, x_sumsq=x_sumsq, wb=wb,
+                        want_sumsq=True)
         return act(noise(conv(h, style, pe=pe, pe_rot=pe_rot, x_sumsq=x_sumsq, wb=wb)))
 
     def prepare_weights(self, ws, dtype, P, shift_rad, side):

@@ -102,7 +102,8 @@ class ModConv2d(nn.Module):
         return bool(self.ema and DF.late_ema_enabled()
                     and DF.modconv_tc_domain_of(dtype, self.out_ch, c1, c2, P))
 
-    def forward(self, x, style, pe=None, fused_act=None, pe_rot=None, x_sumsq=None, wb=None):
+    def forward(self, x, style, pe=None, fused_act=None, pe_rot=None, x_sumsq=None, wb=None,
+                want_sumsq=False):
         """x: [B, C1, H, W] (or None when the input is `pe` alone); pe: optional Fourier
         block [B or 1, C2, H, W] appended on the channel axis; fused_act: a FusedLeakyReLU
         module to apply in the epilogue; wb: weights prepared ahead by
@@ -112,6 +113,8 @@ class ModConv2d(nn.Module):
         if c1 + c2 != self.in_ch:
             raise RuntimeError(f"expected {self.in_ch} input channels, got {c1}+{c2}")
         if self.ema and self.training:
+            if x_sumsq is None and x is not None:
+                x_sumsq = getattr(x, "_dusty_sumsq", None)     # left by the producing contraction
             self.update_ema(x, pe, x_sumsq)
         src = x if x is not None else pe
         late = wb is not None or self.ema_in_epilogue(src, c1, c2)
@@ -126,7 +129,8 @@ class ModConv2d(nn.Module):
         elif bias is not None and self.gain != 1.0:
             bias = bias * self.gain          # (h + b) * gain == h*gain + b*gain
         return DF.modconv_bmm(wb, x, pe, bias, act, alpha, scale,
-                              ema_var=self.ema_var if (late and self.ema) else None)
+                              ema_var=self.ema_var if (late and self.ema) else None,
+                              want_sumsq=want_sumsq and self.training)
 
     def extra_repr(self):
         return (f"in_ch={self.in_ch}, out_ch={self.out_ch}, mod_ch={self.mod_ch}, "

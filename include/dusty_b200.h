@@ -218,11 +218,14 @@ int dusty_angle_down2(const float *angle_in, float *angle_out, int Ba, int H, in
  * (all layers' weights can then be prepared ahead of the activation chain).  tcgen05 path only.
  * ema_rows (optional HOST array of O device scalars, O <= 4; exclusive with ema_var): the same
  * per OUTPUT ROW for the heads, where every row belongs to its own ModConv2d (dusty_v2.py:48-60);
- * applied by the small-O CUDA-core kernels to the weight rows as they are staged. */
+ * applied by the small-O CUDA-core kernels to the weight rows as they are staged.
+ * sumsq (optional device scalar, caller zero-fills; tcgen05 bf16-output path): += sum of the
+ * squares of the stored outputs -- the statistic the NEXT ModConv2d takes of its input
+ * (style.py:99-102), accumulated in the epilogue instead of by a pass over the tensor. */
 int dusty_modconv_fwd(const void *wb, const void *x1, const void *x2, const float *bias, void *y,
                       int B, int O, int C1, int C2, int B2, int64_t P, int act, float alpha,
                       float scale, int dtype, int wdtype, int impl, const float *ema_var,
-                      const float *const *ema_rows, void *stream);
+                      const float *const *ema_rows, float *sumsq, void *stream);
 /* dX1[b,k,p] = sum_o wb[b,o,k] * dY[b,o,p]  for k < C1 (Fourier channels carry no grad);
  * ema_var / ema_rows as above (the same factors on the way back). */
 int dusty_modconv_bwd_dx(const void *wb, const void *dy, void *dx1, int B, int O, int C1, int K,

@@ -150,7 +150,7 @@ def test_c_abi_argument_errors_are_status_codes_not_crashes():
     assert rc != 0 and "null" in K.last_error()
     rc = lib.dusty_bias_act_add_cl(p, None, p, p, 64, 12, 0.2, 1.41, 0.7, K.BF16, None)           # C % 8 != 0
     assert rc != 0 and "channel" in K.last_error()
-    rc = lib.dusty_modconv_fwd(p, p, p, None, p, 2, 32, 64, 0, 1, 128, 3, 0.2, 1.0, K.BF16, K.BF16, 7, None, None, None)
+    rc = lib.dusty_modconv_fwd(p, p, p, None, p, 2, 32, 64, 0, 1, 128, 3, 0.2, 1.0, K.BF16, K.BF16, 7, None, None, None, None)
     assert rc != 0 and "impl" in K.last_error()
     rc = lib.dusty_filter_rsco_to_ohwi(p, p, 0, 4, 9, K.BF16, None)
     assert rc != 0 and "shape" in K.last_error()

@@ -541,8 +541,10 @@ def test_modconv_fp32_on_tensor_cores_split_bf16(DF, B, Oc, C1, C2, B2, HW):
     gy = torch.randn(B, Oc, H, W, generator=g)
     names = []
     orig = DF.K.call
-    # impl argument: (..., impl, ema_var, ema_rows, stream) for fwd / dx, (..., impl, dw_ld, stream) for dw
-    impl_of = lambda name, a: a[-3] if name == "dusty_modconv_bwd_dw" else (a[-4] if name.startswith("dusty_modconv") else None)  # noqa: E731
+    # impl argument: (..., impl, ema_var, ema_rows, sumsq, stream) for fwd, (..., impl, ema_var, ema_rows, stream)
+    # for dx, (..., impl, dw_ld, stream) for dw
+    impl_of = lambda name, a: {"dusty_modconv_bwd_dw": -3, "dusty_modconv_bwd_dx": -4, "dusty_modconv_fwd": -5}.get(name)  # noqa: E731
+    impl_of = (lambda f: (lambda name, a: a[f(name, a)] if f(name, a) is not None else None))(impl_of)
     DF.K.call = lambda name, *a: (names.append((name, impl_of(name, a))), orig(name, *a))[1]
     try:
         wg = wb.to(DEV).requires_grad_()
@@ -1154,3 +1156,24 @@ def test_kitti_scan_to_image_exact(g_kitti, tag, unfold):
     with pytest.raises(RuntimeError):
         scan_to_image(pts, (64, 512), device="cpu")
 
+
+
+def test_modconv_epilogue_sumsq_matches_separate_pass(DF):
+    """sum(y^2) accumulated by the tcgen05 contraction's epilogue (the next ModConv2d's EMA
+    statistic) against the stand-alone reduction over the stored tensor, per-sample tiles and
+    batch-fused tiles."""
+    g = torch.Generator().manual_seed(23)
+    bf = torch.bfloat16
+    for (B, Oc, C1, C2, B2, HW) in [(3, 64, 64, 0, 1, (16, 128)), (8, 32, 64, 512, 1, (16, 128)),
+                                     (2, 48, 64, 0, 1, (2, 64))]:
+        K_ = C1 + C2
+        wb = (torch.randn(B, Oc, K_, generator=g) / np.sqrt(K_)).to(bf).to(DEV)
+        x1 = torch.randn(B, C1, *HW, generator=g).to(bf).to(DEV)
+        x2 = torch.randn(B2, C2, *HW, generator=g).to(bf).to(DEV) if C2 else None
+        bias = torch.randn(Oc, generator=g).to(DEV)
+        y = DF.modconv_bmm(wb, x1, x2, bias, 3, 0.2, O.SQRT2, want_sumsq=True)
+        assert hasattr(y, "_dusty_sumsq")
+        ref = float(y.float().pow(2).sum())
+        assert abs(float(y._dusty_sumsq) - ref) <= 2e-4 * ref, (float(y._dusty_sumsq), ref)
+        y2 = DF.modconv_bmm(wb, x1, x2, bias, 3, 0.2, O.SQRT2)
+        assert torch.equal(y, y2) and not hasattr(y2, "_dusty_sumsq")

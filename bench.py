@@ -773,18 +773,33 @@ def main():
     if args.ncu_window:
         torch.cuda.profiler.start()
     e0.record()
-    run(start, args.steps, trace=args.per_step)
+    run(start, args.steps, trace=True)
     e1.record()
     barrier()
     if args.ncu_window:
         torch.cuda.profiler.stop()
     launches = pkg.launch_count() - n0 + (tr.graph_replayed_launches - g0)
+    prev, per = e0, []
+    for ev in step_events:
+        per.append(prev.elapsed_time(ev))
+        prev = ev
     if args.per_step and rank == 0:
-        prev, per = e0, []
-        for ev in step_events:
-            per.append(round(prev.elapsed_time(ev), 2))
-            prev = ev
-        print("device ms per timed step:", per, file=sys.stderr)
+        print("device ms per timed step:", [round(v, 2) for v in per], file=sys.stderr)
+    # the training loop's long-run mix (one R1 iteration in `gp_every`) from this rank's per-step
+    # device times: the timed window starts ON an R1 iteration, so a window that is not a multiple
+    # of gp_every steps carries more than its share of them (e.g. 2 in 20) -- `value` is the
+    # window's own throughput, this is what the same step times give at the 15:1 mix
+    is_r1 = [bool(tr.gp_every) and (start + i) % gp == 0 for i in range(args.steps)]
+    plain = sorted(v for v, r in zip(per, is_r1) if not r)
+    r1t = sorted(v for v, r in zip(per, is_r1) if r)
+    mix = None
+    if plain:
+        p_med = plain[len(plain) // 2]
+        r_med = r1t[len(r1t) // 2] if r1t else p_med
+        mix_ms = ((gp - 1) * p_med + r_med) / gp if tr.gp_every else p_med
+        mix = {"plain_ms": round(p_med, 3), "r1_ms": round(r_med, 3), "ms_per_step": round(mix_ms, 3),
+               "images_per_s_per_gpu": round(B / (mix_ms * 1e-3), 1),
+               "what": f"rank-0 median step times combined at the loop's {gp - 1}:1 plain : R1 mix"}
     ms = torch.tensor([e0.elapsed_time(e1)], device=device)
     if world > 1:
         dist.all_reduce(ms, op=dist.ReduceOp.MAX)
@@ -845,7 +860,7 @@ def main():
             "config": {"workload": f"{args.arch} full G+D training step (nsgan + R1 every 16th step, ADA, "
                                    f"warm-up dropout, EMA, Adam), 64x512 range images, random-init weights",
                        "global_batch": B * world, "per_gpu_batch": B, "parallelism": f"dp{world}",
-                       "r1_steps_timed": r1_steps, "ada_p": "adaptive from 0.0" if args.ada_p is None else args.ada_p,
+                       "r1_steps_timed": r1_steps, "steady_state_mix": mix, "ada_p": "adaptive from 0.0" if args.ada_p is None else args.ada_p,
                        "l2": "no flush: per-step working set (GBs) >> 126 MB L2",
                        "warmup_extra": f"{start - args.warmup} further untimed iterations up to the R1 iteration the "
                                        "timed window starts on",

@@ -42,6 +42,8 @@ def parse():
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--precision", default="bf16", choices=["bf16", "fp32"])
     ap.add_argument("--batch-per-gpu", type=int, default=64)
+    ap.add_argument("--global-batch", type=int, default=None,
+                    help="strong scaling: fix the job's batch and give each GPU global/N of it")
     ap.add_argument("--arch", default="dusty_v2", choices=["dusty_v2", "dusty_v1", "vanilla"])
     ap.add_argument("--ada-p", type=float, default=None, help="pin the ADA probability")
     ap.add_argument("--cpu-batch", type=int, default=2, help="batch of the CPU baseline sample")
@@ -726,6 +728,10 @@ def main():
     np.random.seed(0 + rank)
 
     B = args.batch_per_gpu
+    if args.global_batch is not None:
+        if args.global_batch % world:
+            raise SystemExit(f"--global-batch {args.global_batch} does not divide over {world} GPUs")
+        B = args.global_batch // world
     cfg = preset(args.arch, batch_size=B * world)
     if args.ada_p is not None:
         cfg.training.augment.p_init = args.ada_p
@@ -855,7 +861,8 @@ def main():
     line = {"metric": METRIC.replace("dusty_v2", args.arch), "value": value, "unit": UNIT, "n_gpus": world,
             "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": ms / args.steps, "higher_is_better": True,
-            "scaling": "weak", "vs_baseline": None, "dtype": "bf16" if args.precision == "bf16" else "f32",
+            "scaling": "weak" if args.global_batch is None else "strong", "vs_baseline": None,
+            "dtype": "bf16" if args.precision == "bf16" else "f32",
             "data": "synthetic",
             "config": {"workload": f"{args.arch} full G+D training step (nsgan + R1 every 16th step, ADA, "
                                    f"warm-up dropout, EMA, Adam), 64x512 range images, random-init weights",

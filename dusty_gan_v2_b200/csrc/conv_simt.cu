@@ -155,6 +155,14 @@ conv_simt_kernel(const T *__restrict__ x, const T *__restrict__ dy, const T *__r
 // the discriminator stem's 2 -> 32 convolution, which the R1 step differentiates twice through
 // the single ops (functional._Stem's composite).  With K = C <= 4 the tiled kernel above loads
 // 16 x 64 slices to use a 2 x 64 corner; these are plain streaming passes over the pixels.
+// channel-contiguous (NHWC) y / dy: 16-byte accesses along o (same arithmetic, same order)
+template <typename T>
+__device__ __forceinline__ bool pw_vec_ok(const SimtConv &p, const void *y) {
+  constexpr int V = Vec16<T>::N;
+  return p.y_sc == 1 && p.O % V == 0 && p.y_sb % V == 0 && p.y_sh % V == 0 && p.y_sw % V == 0 &&
+         (reinterpret_cast<uintptr_t>(y) & 15) == 0;
+}
+
 template <typename T, int C>
 __global__ void pw_fprop_kernel(const T *__restrict__ x, const T *__restrict__ w, T *__restrict__ y,
                                 const SimtConv p) {
@@ -164,6 +172,7 @@ __global__ void pw_fprop_kernel(const T *__restrict__ x, const T *__restrict__ w
   __syncthreads();
   const long long P = (long long)p.B * p.H * p.W;
   const int groups = (p.O + 7) / 8;
+  const bool vec = pw_vec_ok<T>(p, y) && p.O % 8 == 0;
   for (long long it = blockIdx.x * (long long)blockDim.x + threadIdx.x; it < P * groups;
        it += (long long)gridDim.x * blockDim.x) {
     const long long pix = it / groups;
@@ -175,6 +184,22 @@ __global__ void pw_fprop_kernel(const T *__restrict__ x, const T *__restrict__ w
 #pragma unroll
     for (int c = 0; c < C; ++c) xv[c] = to_f(x[b * p.x_sb + c * p.x_sc + h * p.x_sh + wq * p.x_sw]);
     T *yp = y + b * p.y_sb + h * p.y_sh + wq * p.y_sw;
+    if (vec) {                                         // O % 8 == 0 here: the whole group exists
+      constexpr int V = Vec16<T>::N;
+#pragma unroll
+      for (int j0 = 0; j0 < 8; j0 += V) {
+        Vec16<T> out;
+#pragma unroll
+        for (int j = 0; j < V; ++j) {
+          float acc = 0.f;
+#pragma unroll
+          for (int c = 0; c < C; ++c) acc = fmaf(xv[c], ws[(o0 + j0 + j) * C + c], acc);
+          out.set(j, to_f(from_f<T>(acc * p.scale)));
+        }
+        st16(yp + o0 + j0, out);
+      }
+      continue;
+    }
 #pragma unroll
     for (int j = 0; j < 8; ++j) {
       const int o = o0 + j;
@@ -195,6 +220,7 @@ __global__ void pw_dgrad_kernel(const T *__restrict__ dy, const T *__restrict__ 
     ws[i] = to_f(w[(i / C) * p.w_so + (i % C) * p.w_sc]);
   __syncthreads();
   const long long P = (long long)p.B * p.H * p.W;
+  const bool vec = pw_vec_ok<T>(p, dy);
   for (long long pix = blockIdx.x * (long long)blockDim.x + threadIdx.x; pix < P;
        pix += (long long)gridDim.x * blockDim.x) {
     const int wq = (int)(pix % p.W);
@@ -202,10 +228,23 @@ __global__ void pw_dgrad_kernel(const T *__restrict__ dy, const T *__restrict__ 
     const int h = (int)(t % p.H), b = (int)(t / p.H);
     const T *gp = dy + b * p.y_sb + h * p.y_sh + wq * p.y_sw;
     float acc[C] = {};
-    for (int o = 0; o < p.O; ++o) {
-      const float g = to_f(gp[o * p.y_sc]);
+    if (vec) {
+      constexpr int V = Vec16<T>::N;
+      for (int o0 = 0; o0 < p.O; o0 += V) {
+        const Vec16<T> gv = ld16(gp + o0);
 #pragma unroll
-      for (int c = 0; c < C; ++c) acc[c] = fmaf(g, ws[o * C + c], acc[c]);
+        for (int j = 0; j < V; ++j) {
+          const float g = gv.get(j);
+#pragma unroll
+          for (int c = 0; c < C; ++c) acc[c] = fmaf(g, ws[(o0 + j) * C + c], acc[c]);
+        }
+      }
+    } else {
+      for (int o = 0; o < p.O; ++o) {
+        const float g = to_f(gp[o * p.y_sc]);
+#pragma unroll
+        for (int c = 0; c < C; ++c) acc[c] = fmaf(g, ws[o * C + c], acc[c]);
+      }
     }
 #pragma unroll
     for (int c = 0; c < C; ++c)
@@ -219,6 +258,7 @@ __global__ void __launch_bounds__(256)
 pw_wgrad_kernel(const T *__restrict__ dy, const T *__restrict__ x, float *__restrict__ dw, const SimtConv p) {
   const int o0 = blockIdx.y * 16;
   const long long P = (long long)p.B * p.H * p.W;
+  const bool vec = pw_vec_ok<T>(p, dy) && p.O % 16 == 0;
   float acc[16][C] = {};
   for (long long pix = blockIdx.x * (long long)blockDim.x + threadIdx.x; pix < P;
        pix += (long long)gridDim.x * blockDim.x) {
@@ -229,6 +269,20 @@ pw_wgrad_kernel(const T *__restrict__ dy, const T *__restrict__ x, float *__rest
 #pragma unroll
     for (int c = 0; c < C; ++c) xv[c] = to_f(x[b * p.x_sb + c * p.x_sc + h * p.x_sh + wq * p.x_sw]);
     const T *gp = dy + b * p.y_sb + h * p.y_sh + wq * p.y_sw;
+    if (vec) {                                          // O % 16 == 0: no partial group
+      constexpr int V = Vec16<T>::N;
+#pragma unroll
+      for (int j0 = 0; j0 < 16; j0 += V) {
+        const Vec16<T> gv = ld16(gp + o0 + j0);
+#pragma unroll
+        for (int j = 0; j < V; ++j) {
+          const float g = gv.get(j);
+#pragma unroll
+          for (int c = 0; c < C; ++c) acc[j0 + j][c] = fmaf(g, xv[c], acc[j0 + j][c]);
+        }
+      }
+      continue;
+    }
 #pragma unroll
     for (int j = 0; j < 16; ++j) {
       const float g = (o0 + j < p.O) ? to_f(gp[(o0 + j) * p.y_sc]) : 0.f;

@@ -1786,17 +1786,32 @@ def _empty_like_layout(shape, ref, dtype):
     return torch.empty(shape, dtype=dtype, device=ref.device, memory_format=fmt)
 
 
+def conv_fans_out_to_nhwc(x, w) -> bool:
+    """The 1x1 convolution that lifts a few-channel NCHW image into the NHWC bf16 feature stack
+    (the discriminator stem's 2 -> C0 layer as single ops: functional._Stem's composite, which
+    the R1 double backward runs): its OUTPUT and the gradients w.r.t. that output are NHWC like
+    every tensor downstream -- the strided CUDA-core kernels read / write either layout, and an
+    NCHW result here cost four 134 MB layout copies per R1 iteration further down the chain."""
+    return (x.dim() == 4 and w.dim() == 4 and x.dtype == torch.bfloat16 and w.dtype == torch.bfloat16
+            and x.shape[1] <= 4 and w.shape[2] == 1 and w.shape[3] == 1 and w.shape[0] % 8 == 0
+            and _PRECISION["act"] == torch.bfloat16)
+
+
 def conv2d_fprop_simt(x, w, stride, padding=(0, 0)):
     """y = conv2d(x, w, stride, zero padding); any layout, fp32 or bf16 (fp32 accumulation)."""
     K.require_cuda(x, w)
     dt = _simt_dtype(x, w)
+    fan_out = conv_fans_out_to_nhwc(x, w)
     x, w = x.detach().to(dt), w.detach().to(dt)
     B, C, H, W = x.shape
     O, _, R, S = w.shape
     sh, sw = stride
     ph, pw = padding
     Ho, Wo = (H + 2 * ph - R) // sh + 1, (W + 2 * pw - S) // sw + 1
-    y = _empty_like_layout((B, O, Ho, Wo), x, dt)
+    if fan_out:
+        y = torch.empty((B, O, Ho, Wo), dtype=dt, device=x.device, memory_format=torch.channels_last)
+    else:
+        y = _empty_like_layout((B, O, Ho, Wo), x, dt)
     K.call("dusty_conv2d_simt", 0, K.ptr(x), None, K.ptr(w), K.ptr(y), B, C, H, W, O, Ho, Wo, R, S, sh, sw,
            ph, pw, _ll4(x.stride()), _ll4(y.stride()), _ll4(w.stride()), 1.0, K.dtype_code(y), K.stream_of(x))
     return y

@@ -229,7 +229,10 @@ class _Conv2dBwdFn(torch.autograd.Function):
     def forward(ctx, gy, x, w, stride, need_x, need_w, w_tco=None, padding=(0, 0)):
         ctx.save_for_backward(gy, x, w)
         ctx.stride, ctx.need, ctx.padding = stride, (need_x, need_w), tuple(padding)
-        gy = gy.contiguous(memory_format=torch.channels_last) if DF._is_cl(x) else gy.contiguous()
+        if DF._is_cl(x):
+            gy = gy.contiguous(memory_format=torch.channels_last)
+        elif not (DF.conv_fans_out_to_nhwc(x, w) and DF._is_cl(gy)):   # that layer's gy stays NHWC
+            gy = gy.contiguous()
         gx, gw = _conv_grads(gy, x, w, stride, need_x, need_w, w_tco, padding)
         if (gw is not None and not gw.is_contiguous()
                 and not gw.is_contiguous(memory_format=torch.channels_last)):

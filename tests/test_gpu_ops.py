@@ -939,6 +939,42 @@ def test_conv2d_simt_family_vs_cpu_autograd(DF, B, C, Oc, H, W, k, stride, pad, 
         close(a, r, rtol=tol[0], atol_rel=tol[1])
 
 
+@pytest.mark.parametrize("C,Oc", [(2, 32), (1, 16), (4, 64)])
+def test_pointwise_fan_out_conv_writes_nhwc_and_takes_nhwc_gradients(DF, C, Oc):
+    """The stem's 1x1 convolution as a single op (functional._Stem's composite under
+    create_graph, i.e. the R1 double backward): a few-channel NCHW bf16 image goes in, the
+    feature tensor comes out NHWC, an NHWC gradient is consumed in place (no layout copy) and
+    the second-order terms come back NHWC too; values against CPU autograd."""
+    from dusty_gan_v2_b200.gans.models.ops.common import conv2d_valid
+    prev = "bf16" if DF.act_dtype() == torch.bfloat16 else "fp32"
+    DF.set_precision("bf16")                     # the rule belongs to the bf16 NHWC feature stack
+    g = torch.Generator().manual_seed(77)
+    B, H, W = 3, 10, 24
+    x = torch.randn(B, C, H, W, generator=g).bfloat16()
+    w = (torch.randn(Oc, C, 1, 1, generator=g) / np.sqrt(C)).bfloat16()
+    xr, wr = x.float().requires_grad_(), w.float().requires_grad_()
+    yr = torch.nn.functional.conv2d(xr, wr)
+    gy = torch.randn(yr.shape, generator=g).bfloat16()
+    gxr, gwr = torch.autograd.grad(yr, [xr, wr], gy.float(), create_graph=True)
+    ggyr_src = gxr.pow(2).sum()
+    ggwr, = torch.autograd.grad(ggyr_src, [wr], retain_graph=True)
+    xg, wg = x.to(DEV).requires_grad_(), w.to(DEV).requires_grad_()
+    gyg = gy.to(DEV).contiguous(memory_format=torch.channels_last).requires_grad_()
+    try:
+        y = conv2d_valid(xg, wg, (1, 1))
+        assert DF._is_cl(y), "fan-out convolution must produce NHWC"
+        gx, gw = torch.autograd.grad(y, [xg, wg], gyg, create_graph=True)
+        ggw, ggy = torch.autograd.grad(gx.float().pow(2).sum(), [wg, gyg])
+        assert DF._is_cl(ggy), "the gradient w.r.t. the incoming gradient must stay NHWC"
+    finally:
+        DF.set_precision(prev)
+    gyr = gy.float().requires_grad_()
+    gxr2, = torch.autograd.grad(yr, [xr], gyr, create_graph=True)
+    ggyr, = torch.autograd.grad(gxr2.pow(2).sum(), [gyr])
+    for a, r in ((y, yr), (gx, gxr), (gw, gwr), (ggw, ggwr), (ggy, ggyr)):
+        close(a, r, rtol=2e-2, atol_rel=1e-2)
+
+
 @pytest.mark.parametrize("dtype,C,Oc", [(torch.float32, 6, 5), (torch.bfloat16, 32, 16), (torch.bfloat16, 12, 6)])
 def test_conv_transpose2d_vs_cpu_autograd(DF, dtype, C, Oc):
     """ConvTranspose2d(4x4, stride 2, padding 1) of the vanilla / dusty_v1 generators

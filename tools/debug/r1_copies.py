@@ -24,10 +24,19 @@ def where():
     fr = [f for f in traceback.extract_stack()[:-2] if "dusty_gan_v2_b200" in f.filename]
     return " <- ".join(f"{os.path.basename(f.filename)}:{f.lineno}" for f in fr[-3:])
 
+def producer(t):
+    """Name of the autograd node that made t (set under create_graph) and of its inputs' nodes."""
+    fn = t.grad_fn
+    if fn is None:
+        return "leaf/no-graph"
+    ups = ",".join(type(u[0]).__name__ if u[0] is not None else "None" for u in fn.next_functions[:3])
+    return f"{type(fn).__name__}({ups})"
+
+
 def contiguous(self, *a, **k):
     out = orig_contig(self, *a, **k)
     if self.is_cuda and self.numel() >= (1 << 22) and out.data_ptr() != self.data_ptr():
-        log[("contiguous", tuple(self.shape), tuple(self.stride()), str(self.dtype), where())] += 1
+        log[("contiguous", tuple(self.shape), tuple(self.stride()), str(self.dtype), where(), producer(self))] += 1
     return out
 
 def to(self, *a, **k):

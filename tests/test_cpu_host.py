@@ -127,6 +127,37 @@ def test_ada_host_sampling_and_padding():
     assert tuple(ada.Hz_fbank.shape) == (4, 43)
 
 
+def test_ada_fused_parameter_rows_and_policy_vector():
+    """Host side of the fused ADA op (adaptive_augment.py:271-291,386-545 as two launches): the
+    [B, 8] parameter rows carry the axis-aligned inverse transform and the one-channel colour
+    gain / offset of the sampled matrices; anything with shear / rotation is refused (None ->
+    the single-op path); the policy vector the device sampler reads lists the eleven multipliers
+    in the kernel's order."""
+    from dusty_gan_v2_b200.gans.augment import adaptive_augment as A
+    ada = A.AdaptiveAugment(p_init=0.0, lr_flip=1, ud_flip=1, int_trans=1, iso_scale=1, frac_trans=1,
+                            brightness=1, contrast=1, luma_flip=1, hue=1, saturation=1)
+    ada.generator = torch.Generator().manual_seed(3)
+    ada._p_host = 0.8
+    G_inv = torch.inverse(ada.sample_affine(16, 64, 512))
+    C = ada.sample_color(16)
+    rows = A.AdaptiveAugment.fused_params(G_inv, C)
+    assert rows.shape == (16, 8)
+    # x' = a x + tx, y' = d y + ty of the inverse map
+    rebuilt = torch.eye(3).repeat(16, 1, 1)
+    rebuilt[:, 0, 0], rebuilt[:, 0, 2], rebuilt[:, 1, 1], rebuilt[:, 1, 2] = rows[:, 0], rows[:, 1], rows[:, 2], rows[:, 3]
+    assert torch.allclose(rebuilt, G_inv, atol=1e-6)
+    # one-channel images: the colour matrix collapses to a gain and an offset (mean over the RGB rows)
+    x = torch.rand(16, 1, 7)
+    full = (C[:, :3, :3] @ x.expand(16, 3, 7) + C[:, :3, 3:]).mean(dim=1, keepdim=True)
+    assert torch.allclose(x * rows[:, 4].view(-1, 1, 1) + rows[:, 5].view(-1, 1, 1), full, atol=1e-5)
+    assert torch.equal(rows[:, 6:], torch.zeros(16, 2))
+    sheared = G_inv.clone()
+    sheared[3, 0, 1] = 0.1
+    assert A.AdaptiveAugment.fused_params(sheared, C) is None
+    pv = ada.policy_vector()
+    assert len(pv) == 11 and pv[:10] == [1] * 10 and pv[10] == ada.h_trans_factor
+
+
 def test_fir_geometry_matches_oracle_sizes():
     from dusty_gan_v2_b200.functional import FirCfg
     from oracle import dusty_oracle as O

@@ -158,6 +158,32 @@ def test_ada_fused_parameter_rows_and_policy_vector():
     assert len(pv) == 11 and pv[:10] == [1] * 10 and pv[10] == ada.h_trans_factor
 
 
+def test_split_bf16x3_scheme_error_bound():
+    """The arithmetic behind fp32 mode on the tensor cores (csrc/split3.cu), restated
+    on the host: a = a_hi + a_lo in bf16, the K axis tripled as [a_hi|a_hi|a_lo] . [b_hi|b_lo|b_hi]
+    with fp32 accumulation reproduces the fp32 dot product to ~2^-16 relative to sum |a||b| --
+    two orders below the rtol 1e-3 the mode is held to -- while plain bf16 operands do not."""
+    g = torch.Generator().manual_seed(11)
+    a = torch.randn(64, 1536, generator=g)
+    b = torch.randn(1536, 48, generator=g)
+
+    def split(t):
+        hi = t.bfloat16()
+        lo = (t - hi.float()).bfloat16()
+        return hi.float(), lo.float()
+
+    ah, al = split(a)
+    bh, bl = split(b)
+    a3 = torch.cat([ah, ah, al], dim=1)                   # pattern 0 (the "a" side)
+    b3 = torch.cat([bh, bl, bh], dim=0)                   # pattern 1 (the "b" side)
+    ref = a.double() @ b.double()
+    scale = (a.abs().double() @ b.abs().double())
+    err3 = ((a3 @ b3).double() - ref).abs() / scale
+    err1 = ((ah @ bh).double() - ref).abs() / scale
+    assert float(err3.max()) < 4e-5, float(err3.max())    # dropped lo*lo + residuals: ~2^-16
+    assert float(err1.max()) > 20 * float(err3.max())      # bf16 operands alone: ~2^-9
+
+
 def test_fir_geometry_matches_oracle_sizes():
     from dusty_gan_v2_b200.functional import FirCfg
     from oracle import dusty_oracle as O
